@@ -1,0 +1,1185 @@
+// fluidgym_b200 -- batched PISO solver step for B200 (sm_100a).  See include/fluidgym_b200.h for the ABI
+// and DESIGN.md for the data layout and the per-kernel rooflines.
+//
+// All kernels are table driven: the multi-block / curvilinear / boundary-condition logic the reference
+// re-derives per cell at run time (K.cu = extensions/PISO_multiblock_cuda_kernel.cu) is resolved once on
+// the host (fluidgym_b200/domain.py) into neighbour and coefficient tables shared by every environment
+// of the batch.  Fields are [B][C][N] float32 with the cell index contiguous, so every access that is
+// not a neighbour gather is fully coalesced; the shared tables stay L2 resident across environments.
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+
+#include "fluidgym_b200.h"
+
+namespace cg = cooperative_groups;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char *msg, cudaError_t ce = cudaSuccess) {
+    if (ce != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", msg, cudaGetErrorString(ce));
+    else snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+extern "C" const char *fgb_last_error(void) { return g_err; }
+extern "C" int fgb_version(void) { return 1; }
+
+#define LAUNCH_CHECK(name)                                                       \
+    do {                                                                         \
+        cudaError_t e_ = cudaGetLastError();                                     \
+        if (e_ != cudaSuccess) return set_err(FGB_E_CUDA, name, e_);             \
+    } while (0)
+
+typedef fgb_tables Tab;
+
+struct fgb_batch {
+    Tab t;
+    int B;
+    fgb_options opt;
+    char *ws;
+    size_t ws_bytes;
+    // carved buffers
+    float *Coff, *A, *rhs, *ures, *Poff, *Pdiag, *hbya, *div, *pres, *kry;
+    float *resid, *dt, *maxvel, *fluxbal;
+    double *remaining;
+    int32_t *iters, *active, *nsub, *counters;
+    int32_t *h_counters;  // pinned host mirror
+    int cluster_ok;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Carver {
+    char *base; size_t off;
+    template <typename T> T *take(size_t n) { T *p = (T *)(base + off); off = align_up(off + n * sizeof(T)); return p; }
+};
+static const int KRY_VECS = 12;
+
+static void carve(fgb_batch *b, char *base, size_t *total) {
+    Carver c{base, 0};
+    size_t BN = (size_t)b->B * b->t.N;
+    b->Coff = c.take<float>(4 * BN); b->A = c.take<float>(BN); b->rhs = c.take<float>(2 * BN);
+    b->ures = c.take<float>(2 * BN); b->Poff = c.take<float>(4 * BN); b->Pdiag = c.take<float>(BN);
+    b->hbya = c.take<float>(2 * BN); b->div = c.take<float>(BN); b->pres = c.take<float>(BN);
+    b->kry = c.take<float>(KRY_VECS * BN);
+    b->resid = c.take<float>(8 * (size_t)b->B); b->dt = c.take<float>(b->B); b->maxvel = c.take<float>(b->B);
+    b->fluxbal = c.take<float>(b->B); b->remaining = c.take<double>(b->B);
+    b->iters = c.take<int32_t>(8 * (size_t)b->B); b->active = c.take<int32_t>(b->B); b->nsub = c.take<int32_t>(b->B);
+    b->counters = c.take<int32_t>(64);
+    *total = c.off;
+}
+
+extern "C" size_t fgb_workspace_bytes(const fgb_tables *t, int32_t B) {
+    fgb_batch tmp; memset(&tmp, 0, sizeof(tmp)); tmp.t = *t; tmp.B = B;
+    size_t total = 0; carve(&tmp, nullptr, &total);
+    return total;
+}
+
+static fgb_options default_options() {
+    fgb_options o; o.corrector_steps = 2; o.adv_nonortho_steps = 1; o.p_nonortho_steps = 1; o.nonortho = 1;
+    o.adv_tol = 1e-5f; o.p_tol = 1e-5f; o.max_iter = 5000; o.cg_impl = 0; return o;
+}
+
+extern "C" int fgb_batch_create(const fgb_tables *t, int32_t B, void *workspace, size_t workspace_bytes,
+                                const fgb_options *opt, fgb_batch **out) {
+    if (!t || !out || B <= 0 || t->N <= 0) return set_err(FGB_E_ARG, "fgb_batch_create: bad argument");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) return set_err(FGB_E_CUDA, "fgb_batch_create: no CUDA device (there is no CPU fallback)", ce);
+    size_t need = fgb_workspace_bytes(t, B);
+    if (!workspace || workspace_bytes < need) return set_err(FGB_E_WORKSPACE, "fgb_batch_create: workspace too small");
+    fgb_batch *b = new (std::nothrow) fgb_batch();
+    if (!b) return set_err(FGB_E_ARG, "fgb_batch_create: out of host memory");
+    memset(b, 0, sizeof(*b));
+    b->t = *t; b->B = B; b->opt = opt ? *opt : default_options();
+    b->ws = (char *)workspace; b->ws_bytes = workspace_bytes;
+    size_t total; carve(b, b->ws, &total);
+    ce = cudaMallocHost(&b->h_counters, 64 * sizeof(int32_t));
+    if (ce != cudaSuccess) { delete b; return set_err(FGB_E_CUDA, "cudaMallocHost", ce); }
+    ce = cudaMemset(b->ws, 0, need);
+    if (ce != cudaSuccess) { cudaFreeHost(b->h_counters); delete b; return set_err(FGB_E_CUDA, "cudaMemset workspace", ce); }
+    *out = b;
+    return FGB_OK;
+}
+extern "C" void fgb_batch_destroy(fgb_batch *b) {
+    if (!b) return;
+    if (b->h_counters) cudaFreeHost(b->h_counters);
+    delete b;
+}
+extern "C" int fgb_batch_set_options(fgb_batch *b, const fgb_options *opt) {
+    if (!b || !opt) return set_err(FGB_E_ARG, "fgb_batch_set_options: bad argument");
+    b->opt = *opt; return FGB_OK;
+}
+extern "C" void *fgb_batch_buffer(fgb_batch *b, const char *name) {
+    if (!b || !name) return nullptr;
+#define BUF(n) if (!strcmp(name, #n)) return (void *)b->n;
+    BUF(Coff) BUF(A) BUF(rhs) BUF(ures) BUF(Poff) BUF(Pdiag) BUF(hbya) BUF(div) BUF(pres) BUF(kry)
+    BUF(iters) BUF(resid) BUF(dt) BUF(active) BUF(remaining) BUF(nsub) BUF(maxvel) BUF(fluxbal) BUF(counters)
+#undef BUF
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float contra_cell(const Tab &t, int k, int g, float u, float v) {
+    // det * (Minv[k] . vel)   (K.cu:495-510)
+    const int N = t.N;
+    return t.det[g] * (t.minv[(2 * k) * N + g] * u + t.minv[(2 * k + 1) * N + g] * v);
+}
+__device__ __forceinline__ float bflux(const Tab &t, int j, int ax, float bu, float bv) {
+    const int NB = t.NB;
+    return t.b_det[j] * (t.b_minv[(2 * ax) * NB + j] * bu + t.b_minv[(2 * ax + 1) * NB + j] * bv);
+}
+
+// face fluxes of a cell-centred vector field (K.cu:1567-1645): F_f = 1/2 (U_P + +-U_N), boundary: U_b
+__device__ __forceinline__ void face_fluxes(const Tab &t, int g, const float *__restrict__ vel, const float *__restrict__ bv,
+                                            const int nb[4], float fl[4]) {
+    const int N = t.N, NB = t.NB;
+    const float ux = vel[g], uy = vel[N + g];
+    const float Uc[2] = {contra_cell(t, 0, g, ux, uy), contra_cell(t, 1, g, ux, uy)};
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        if (nb[f] >= 0) {
+            const int fc = t.fl_comp[f * N + g];
+            float velN = contra_cell(t, fc & 1, nb[f], vel[nb[f]], vel[N + nb[f]]);
+            if (fc & 2) velN = -velN;
+            fl[f] = (velN + Uc[f >> 1]) * 0.5f;
+        } else {
+            const int j = -1 - nb[f];
+            fl[f] = bflux(t, j, f >> 1, bv[j], bv[NB + j]);
+        }
+    }
+}
+
+// Dirichlet boundary advection + diffusion sources of a cell (K.cu:4321-4380), before the division by det
+__device__ __forceinline__ void boundary_source(const Tab &t, const float *__restrict__ bv, const int nb[4], float S[2]) {
+    const int NB = t.NB;
+    S[0] = 0.f; S[1] = 0.f;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        if (nb[f] < 0) {
+            const int j = -1 - nb[f];
+            const float bu = bv[j], bw = bv[NB + j];
+            const float flux = bflux(t, j, f >> 1, bu, bw) * ((f & 1) ? 1.f : -1.f);
+            const float visc2a = t.viscosity * 2.f * t.b_alpha[j];
+            S[0] -= bu * flux; S[0] += bu * visc2a;
+            S[1] -= bw * flux; S[1] += bw * visc2a;
+        }
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void block_reduce_sum(float (&v)[K], double *sm /* [32*K + K] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sm[warp * K + k] = (double)x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double x = lane < nw ? sm[lane * K + k] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) sm[32 * K + k] = x;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = (float)sm[32 * K + k];
+    __syncthreads();
+}
+__device__ __forceinline__ float block_reduce_max(float v, float *sm /*[33]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float x = lane < nw ? sm[lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+        if (lane == 0) sm[32] = x;
+    }
+    __syncthreads();
+    float r = sm[32];
+    __syncthreads();
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// assembly kernels: one thread per (cell, environment), grid = (ceil(N/256), B)
+// ------------------------------------------------------------------------------------------------
+// SetupAdvectionMatrix + SetupAdvectionVelocity fused (K.cu:3617-3880, 4296-4400).
+__global__ void __launch_bounds__(256) k_setup_advection(Tab t, const float *__restrict__ U, const float *__restrict__ Ures,
+                                                          const float *__restrict__ Bvel, const float *__restrict__ Src,
+                                                          const float *__restrict__ dtv, const int32_t *__restrict__ active,
+                                                          float *__restrict__ Coff, float *__restrict__ A, float *__restrict__ Rhs,
+                                                          int with_matrix) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N, NB = t.NB;
+    if (g >= N) return;
+    const float *u = U + (size_t)b * 2 * N, *ur = Ures + (size_t)b * 2 * N, *bv = Bvel + (size_t)b * 2 * NB;
+    const float dt = dtv[b];
+    const float det = t.det[g];
+    int nb[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) nb[f] = t.nbr[f * N + g];
+    if (with_matrix) {
+        float fl[4];
+        face_fluxes(t, g, u, bv, nb, fl);
+        float diag = det / dt + t.Cd[g];
+        float *co = Coff + (size_t)b * 4 * N;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            float o = 0.f;
+            if (nb[f] >= 0) {
+                const float ff = ((f & 1) ? 0.5f : -0.5f) * fl[f];
+                diag += ff;
+                o = (ff + t.Cd[(f + 1) * N + g]) / det;
+            }
+            co[f * N + g] = o;
+        }
+        A[(size_t)b * N + g] = diag / det;
+    }
+    float S[2];
+    boundary_source(t, bv, nb, S);
+    float no0 = 0.f, no1 = 0.f;
+    for (int k = 0; k < t.K_no; ++k) {
+        const float w = t.no_wv[k * N + g];
+        if (w != 0.f) { const int j = t.no_idx[k * N + g]; no0 += w * ur[j]; no1 += w * ur[N + j]; }
+    }
+    for (int k = 0; k < t.K_nob; ++k) {
+        const float w = t.nob_w[k * N + g];
+        if (w != 0.f) { const int j = t.nob_idx[k * N + g]; no0 += w * bv[j]; no1 += w * bv[NB + j]; }
+    }
+    float r0 = (det * u[g] / dt + S[0] - no0) / det;
+    float r1 = (det * u[N + g] / dt + S[1] - no1) / det;
+    if (Src) { r0 += Src[(size_t)b * 2 * N + g]; r1 += Src[(size_t)b * 2 * N + N + g]; }
+    Rhs[(size_t)b * 2 * N + g] = r0;
+    Rhs[(size_t)b * 2 * N + N + g] = r1;
+}
+
+// SetupPressureMatrix (K.cu:4812-4978): P_e = sum_j Wp[e][j] * (1/A)_j
+__global__ void __launch_bounds__(256) k_setup_pressure_matrix(Tab t, const float *__restrict__ A, const int32_t *__restrict__ active,
+                                                                float *__restrict__ Poff, float *__restrict__ Pdiag) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N;
+    if (g >= N) return;
+    const float *a = A + (size_t)b * N;
+    float rA[5];
+    rA[0] = 1.0f / a[g];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) { const int nb = t.nbr[f * N + g]; rA[f + 1] = nb >= 0 ? 1.0f / a[nb] : rA[0]; }
+    float P[5];
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) s += t.Wp[(5 * e + j) * N + g] * rA[j];
+        P[e] = s;
+    }
+    Pdiag[(size_t)b * N + g] = P[0];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) Poff[(size_t)b * 4 * N + f * N + g] = P[f + 1];
+}
+
+// PISO_build_pressure_rhs (K.cu:5136-5255): HbyA = (u^n/dt - sum_nb C_nb u*_nb + S_bnd/det + src) / A
+__global__ void __launch_bounds__(256) k_hbya(Tab t, const float *__restrict__ U, const float *__restrict__ Ures,
+                                               const float *__restrict__ Bvel, const float *__restrict__ Src,
+                                               const float *__restrict__ Coff, const float *__restrict__ A,
+                                               const float *__restrict__ dtv, const int32_t *__restrict__ active,
+                                               float *__restrict__ Hbya) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N, NB = t.NB;
+    if (g >= N) return;
+    const float *u = U + (size_t)b * 2 * N, *ur = Ures + (size_t)b * 2 * N, *bv = Bvel + (size_t)b * 2 * NB;
+    const float *co = Coff + (size_t)b * 4 * N;
+    const float dt = dtv[b];
+    int nb[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) nb[f] = t.nbr[f * N + g];
+    float H0 = 0.f, H1 = 0.f;
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+        if (nb[f] >= 0) { const float c = co[f * N + g]; H0 += c * ur[nb[f]]; H1 += c * ur[N + nb[f]]; }
+    float S[2];
+    boundary_source(t, bv, nb, S);
+    const float det = t.det[g];
+    float s0 = S[0] / det, s1 = S[1] / det;
+    if (Src) { s0 += Src[(size_t)b * 2 * N + g]; s1 += Src[(size_t)b * 2 * N + N + g]; }
+    const float rD = 1.0f / A[(size_t)b * N + g];
+    Hbya[(size_t)b * 2 * N + g] = rD * (u[g] / dt - H0 + s0);
+    Hbya[(size_t)b * 2 * N + N + g] = rD * (u[N + g] / dt - H1 + s1);
+}
+
+// k_computePressureRHSdivergenceFromFlux + k_pressureRHSaddNonOrthoComponents (K.cu:5389-5492)
+__global__ void __launch_bounds__(256) k_pressure_div(Tab t, const float *__restrict__ Hbya, const float *__restrict__ Bvel,
+                                                       const float *__restrict__ Pprev, const float *__restrict__ A,
+                                                       const int32_t *__restrict__ active, int nonortho, float *__restrict__ Div) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N, NB = t.NB;
+    if (g >= N) return;
+    const float *h = Hbya + (size_t)b * 2 * N, *bv = Bvel + (size_t)b * 2 * NB;
+    int nb[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) nb[f] = t.nbr[f * N + g];
+    float fl[4];
+    face_fluxes(t, g, h, bv, nb, fl);
+    float d = (fl[1] - fl[0]) + (fl[3] - fl[2]);
+    if (nonortho) {
+        const float *a = A + (size_t)b * N, *pp = Pprev + (size_t)b * N;
+        float rA[5];
+        rA[0] = 1.0f / a[g];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) rA[f + 1] = nb[f] >= 0 ? 1.0f / a[nb[f]] : rA[0];
+        float S = 0.f;
+        for (int k = 0; k < t.K_no; ++k) {
+            const float gP = t.no_gP[k * N + g], gN = t.no_gN[k * N + g];
+            if (gP != 0.f || gN != 0.f) {
+                const int fc = t.no_face[k * N + g];
+                const float rn = fc == 0 ? rA[1] : fc == 1 ? rA[2] : fc == 2 ? rA[3] : rA[4];
+                S += (gP * rA[0] + gN * rn) * pp[t.no_idx[k * N + g]];
+            }
+        }
+        d += S;
+    }
+    Div[(size_t)b * N + g] = d;
+}
+
+// PISO_update_velocity (K.cu:816-849, 5962-5995)
+__global__ void __launch_bounds__(256) k_correct_velocity(Tab t, const float *__restrict__ Hbya, const float *__restrict__ P,
+                                                           const float *__restrict__ A, const int32_t *__restrict__ active,
+                                                           float *__restrict__ Uout) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N;
+    if (g >= N) return;
+    const float *p = P + (size_t)b * N;
+    const float pc = p[g];
+    float pg[2];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        const int nl = t.nbr[(2 * d) * N + g], nu = t.nbr[(2 * d + 1) * N + g];
+        const float fac = (nl < 0 || nu < 0) ? 1.0f : 0.5f;
+        const float vl = nl >= 0 ? p[nl] : pc, vu = nu >= 0 ? p[nu] : pc;
+        pg[d] = (vu - vl) * fac;
+    }
+    const float gx = pg[0] * t.minv[g] + pg[1] * t.minv[2 * N + g];
+    const float gy = pg[0] * t.minv[N + g] + pg[1] * t.minv[3 * N + g];
+    const float rD = 1.0f / A[(size_t)b * N + g];
+    Uout[(size_t)b * 2 * N + g] = -rD * gx + Hbya[(size_t)b * 2 * N + g];
+    Uout[(size_t)b * 2 * N + N + g] = -rD * gy + Hbya[(size_t)b * 2 * N + N + g];
+}
+
+__global__ void k_fill(float *p, float v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_copy_active(const float *__restrict__ src, float *__restrict__ dst, int per_env, const int32_t *__restrict__ active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < per_env) dst[(size_t)b * per_env + i] = src[(size_t)b * per_env + i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Krylov solvers, implementation 0: one CTA per environment, vectors in global memory (L2 resident)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ell_row(const Tab &t, int g, const float *__restrict__ off, const float *__restrict__ diag,
+                                         const float *__restrict__ x) {
+    const int N = t.N;
+    float s = diag[g] * x[g];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) { const int nb = t.nbr[f * N + g]; if (nb >= 0) s += off[f * N + g] * x[nb]; }
+    return s;
+}
+
+// BiCGStab without preconditioner (BICG.cu:237-376), both velocity components in lock step.
+template <int T>
+__global__ void __launch_bounds__(T) k_bicgstab(Tab t, const float *__restrict__ Coff, const float *__restrict__ Adiag,
+                                                 const float *__restrict__ Rhs, float *__restrict__ X, float *__restrict__ work,
+                                                 int maxit, float tol, int zero_init, const int32_t *__restrict__ active,
+                                                 int32_t *__restrict__ iters, float *__restrict__ resid) {
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    __shared__ double red[32 * 4 + 4];
+    const int N = t.N;
+    const float *off = Coff + (size_t)b * 4 * N, *dg = Adiag + (size_t)b * N;
+    const float norm = 1.0f / sqrtf((float)N);
+    float *wb = work + (size_t)b * KRY_VECS * N;
+    // per component c: r, rw, p, v, tt
+    float *r[2] = {wb, wb + 5 * (size_t)N}, *rw[2] = {wb + N, wb + 6 * (size_t)N}, *p[2] = {wb + 2 * (size_t)N, wb + 7 * (size_t)N};
+    float *v[2] = {wb + 3 * (size_t)N, wb + 8 * (size_t)N}, *tt[2] = {wb + 4 * (size_t)N, wb + 9 * (size_t)N};
+    float *x[2] = {X + (size_t)b * 2 * N, X + (size_t)b * 2 * N + N};
+    const float *f[2] = {Rhs + (size_t)b * 2 * N, Rhs + (size_t)b * 2 * N + N};
+
+    if (zero_init) { for (int c = 0; c < 2; ++c) for (int g = threadIdx.x; g < N; g += T) x[c][g] = 0.f; }
+    __syncthreads();
+    float acc[4];
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    for (int c = 0; c < 2; ++c)
+        for (int g = threadIdx.x; g < N; g += T) {
+            const float rr = f[c][g] - (zero_init ? 0.f : ell_row(t, g, off, dg, x[c]));
+            r[c][g] = rr; rw[c][g] = rr; p[c][g] = rr;
+            acc[c] += rr * rr;
+        }
+    block_reduce_sum<4>(acc, red);
+    bool done[2]; int used[2]; float fin[2]; float rho[2] = {1.f, 1.f}, alpha[2] = {1.f, 1.f}, omega[2] = {1.f, 1.f};
+    for (int c = 0; c < 2; ++c) {
+        fin[c] = sqrtf(acc[c]) * norm; used[c] = -1; done[c] = fin[c] < tol;
+    }
+    for (int i = 0; i < maxit && !(done[0] && done[1]); ++i) {
+        // rho = <rw, r>
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+        for (int c = 0; c < 2; ++c) if (!done[c])
+            for (int g = threadIdx.x; g < N; g += T) acc[c] += rw[c][g] * r[c][g];
+        block_reduce_sum<4>(acc, red);
+        for (int c = 0; c < 2; ++c) if (!done[c]) {
+            const float rhop = rho[c]; rho[c] = acc[c];
+            if (i > 0) {
+                const float beta = (rho[c] / rhop) * (alpha[c] / omega[c]);
+                for (int g = threadIdx.x; g < N; g += T) p[c][g] = r[c][g] + beta * (p[c][g] - omega[c] * v[c][g]);
+            }
+        }
+        __syncthreads();
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+        for (int c = 0; c < 2; ++c) if (!done[c])
+            for (int g = threadIdx.x; g < N; g += T) { const float vv = ell_row(t, g, off, dg, p[c]); v[c][g] = vv; acc[c] += rw[c][g] * vv; }
+        block_reduce_sum<4>(acc, red);
+        float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < 2; ++c) if (!done[c]) {
+            alpha[c] = rho[c] / acc[c];
+            for (int g = threadIdx.x; g < N; g += T) {
+                const float rr = r[c][g] - alpha[c] * v[c][g];
+                r[c][g] = rr; x[c][g] += alpha[c] * p[c][g];
+                acc2[c] += rr * rr;
+            }
+        }
+        block_reduce_sum<4>(acc2, red);
+        for (int c = 0; c < 2; ++c) if (!done[c]) {
+            const float nr = sqrtf(acc2[c]) * norm;
+            used[c] = i; fin[c] = nr;
+            if (!isfinite(nr) || nr < tol) done[c] = true;
+        }
+        // t = C r (s = r)
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+        for (int c = 0; c < 2; ++c) if (!done[c])
+            for (int g = threadIdx.x; g < N; g += T) {
+                const float tv = ell_row(t, g, off, dg, r[c]); tt[c][g] = tv;
+                acc[c] += tv * r[c][g]; acc[2 + c] += tv * tv;
+            }
+        block_reduce_sum<4>(acc, red);
+        acc2[0] = acc2[1] = acc2[2] = acc2[3] = 0.f;
+        for (int c = 0; c < 2; ++c) if (!done[c]) {
+            omega[c] = acc[c] / acc[2 + c];
+            for (int g = threadIdx.x; g < N; g += T) {
+                const float rg = r[c][g];
+                x[c][g] += omega[c] * rg;
+                const float rr = rg - omega[c] * tt[c][g];
+                acc2[c] += rr * rr;
+                r[c][g] = rr;   // all rows of t = C r are complete (the reduction above synchronised the block)
+            }
+        }
+        block_reduce_sum<4>(acc2, red);
+        for (int c = 0; c < 2; ++c) if (!done[c]) {
+            const float nr = sqrtf(acc2[c]) * norm;
+            fin[c] = nr;
+            if (nr < tol) { done[c] = true; used[c] = i + 1; }
+        }
+    }
+    if (threadIdx.x == 0) {
+        iters[b * 8 + 0] = used[0]; iters[b * 8 + 1] = used[1];
+        resid[b * 8 + 0] = fin[0]; resid[b * 8 + 1] = fin[1];
+    }
+}
+
+// Conjugate gradients (CG.cu:225-446) with residual reset, best-iterate tracking and mean removal.
+template <int T>
+__global__ void __launch_bounds__(T) k_cg(Tab t, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
+                                           const float *__restrict__ Rhs, float *__restrict__ Xout, float *__restrict__ work,
+                                           int maxit, float tol, int zero_init, int reset_steps, int slot,
+                                           const int32_t *__restrict__ active, int32_t *__restrict__ iters, float *__restrict__ resid) {
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    __shared__ double red[32 * 2 + 2];
+    const int N = t.N;
+    const float *off = Poff + (size_t)b * 4 * N, *dg = Pdiag + (size_t)b * N, *f = Rhs + (size_t)b * N;
+    float *wb = work + (size_t)b * KRY_VECS * N;
+    float *r = wb, *p = wb + N, *ap = wb + 2 * (size_t)N, *best = wb + 3 * (size_t)N, *x = wb + 4 * (size_t)N;
+    float *xo = Xout + (size_t)b * N;
+    const float norm = 1.0f / sqrtf((float)N);
+    float acc[2] = {0.f, 0.f};
+    int allzero_local = 1;
+    for (int g = threadIdx.x; g < N; g += T) {
+        const float x0 = zero_init ? 0.f : xo[g];
+        x[g] = x0;
+        if (f[g] != 0.f) allzero_local = 0;
+    }
+    __syncthreads();
+    const int nonzero = __syncthreads_or(!allzero_local);
+    int used = -1; float fin = 0.f;
+    if (!nonzero) {   // all-zero right-hand side -> zero result (DIFF.py:392, 489-490)
+        for (int g = threadIdx.x; g < N; g += T) x[g] = 0.f;
+    } else {
+        for (int g = threadIdx.x; g < N; g += T) {
+            const float rr = f[g] - (zero_init ? 0.f : ell_row(t, g, off, dg, x));
+            r[g] = rr; p[g] = rr; acc[0] += rr * rr;
+        }
+        block_reduce_sum<2>(acc, red);
+        float rho = acc[0];
+        float bestc = 0.f, lastc = 0.f; int best_it = -1, rising = 0;
+        for (int i = 0; i < maxit; ++i) {
+            if (reset_steps > 0 && (i + 1) % reset_steps == 0) {
+                __syncthreads();
+                acc[0] = 0.f;
+                for (int g = threadIdx.x; g < N; g += T) {
+                    const float rr = f[g] - ell_row(t, g, off, dg, x);
+                    r[g] = rr; acc[0] += rr * rr;
+                }
+                __syncthreads();
+                for (int g = threadIdx.x; g < N; g += T) p[g] = r[g];
+                acc[1] = 0.f;
+                block_reduce_sum<2>(acc, red);
+                rho = acc[0];
+            }
+            __syncthreads();
+            acc[0] = acc[1] = 0.f;
+            for (int g = threadIdx.x; g < N; g += T) { const float a = ell_row(t, g, off, dg, p); ap[g] = a; acc[0] += p[g] * a; }
+            block_reduce_sum<2>(acc, red);
+            const float alpha = rho / acc[0];
+            acc[0] = acc[1] = 0.f;
+            for (int g = threadIdx.x; g < N; g += T) {
+                x[g] += alpha * p[g];
+                const float rr = r[g] - alpha * ap[g];
+                r[g] = rr; acc[0] += rr * rr;
+            }
+            block_reduce_sum<2>(acc, red);
+            const float crit = sqrtf(acc[0]) * norm;
+            if (!isfinite(crit)) { used = i; fin = crit; break; }
+            if (i == 0 || crit < bestc) {
+                bestc = crit; best_it = i;
+                for (int g = threadIdx.x; g < N; g += T) best[g] = x[g];
+            }
+            if (i > 0 && crit >= lastc) ++rising; else rising = 0;
+            lastc = crit;
+            used = i; fin = crit;
+            if (crit < tol) break;
+            if (i == maxit - 1 || rising >= 100) {
+                __syncthreads();
+                for (int g = threadIdx.x; g < N; g += T) x[g] = best[g];
+                used = best_it; fin = bestc;
+                break;
+            }
+            const float rhop = rho; rho = acc[0];
+            const float beta = rho / rhop;
+            for (int g = threadIdx.x; g < N; g += T) p[g] = r[g] + beta * p[g];
+        }
+    }
+    __syncthreads();
+    // mean removal (SIM.py:1922-1925)
+    acc[0] = acc[1] = 0.f;
+    for (int g = threadIdx.x; g < N; g += T) acc[0] += x[g];
+    block_reduce_sum<2>(acc, red);
+    const float mean = acc[0] / (float)N;
+    for (int g = threadIdx.x; g < N; g += T) xo[g] = x[g] - mean;
+    if (threadIdx.x == 0) { iters[b * 8 + 2 + slot] = used; resid[b * 8 + 2 + slot] = fin; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Krylov solvers, implementation 1: one thread-block cluster per environment, everything on chip.
+// Each CTA of the cluster owns a contiguous range of cells; the search direction p lives in shared
+// memory (neighbour gathers hit local smem or a peer CTA's smem through DSMEM), x / r / best and the
+// five stencil coefficients of the owned cells live in registers; the two dot products per iteration
+// are reduced inside the cluster through DSMEM + one cluster barrier each.  HBM traffic per solve is
+// one read of P, rhs and one write of p.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_dsmem_f64x2(uint32_t addr, double a, double b) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+
+template <int T, int CPT, int CS>
+__global__ void __launch_bounds__(T, 1) k_cg_cluster(Tab t, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
+                                                      const float *__restrict__ Rhs, float *__restrict__ Xout,
+                                                      int maxit, float tol, int zero_init, int reset_steps, int slot,
+                                                      const int32_t *__restrict__ active, int32_t *__restrict__ iters,
+                                                      float *__restrict__ resid) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int b = blockIdx.x / CS;
+    const int rank = (int)cluster.block_rank();
+    if (active && !active[b]) return;  // uniform over the cluster
+    extern __shared__ __align__(16) float smem[];
+    const int N = t.N;
+    const int per = (N + CS - 1) / CS;          // cells owned per CTA
+    const int per_pad = (per + 3) & ~3;
+    const int start = rank * per;
+    const int cnt = max(0, min(per, N - start));
+    float *ps = smem;                            // [per_pad] search direction of the owned cells
+    float *bs = smem + per_pad;                  // [per_pad] best iterate of the owned cells
+    double *red = (double *)(smem + 2 * per_pad);        // [2 parity][CS][2] partial sums written by the peers
+    double *wred = red + 2 * CS * 2;                      // [32*2+2] intra-block reduction scratch
+    const float *off = Poff + (size_t)b * 4 * N, *dg = Pdiag + (size_t)b * N, *f = Rhs + (size_t)b * N;
+    float *xo = Xout + (size_t)b * N;
+    const float norm = 1.0f / sqrtf((float)N);
+    const uint32_t ps_addr = smem_u32(ps), red_addr = smem_u32(red);
+
+    // registers: stencil coefficients, cluster-shared addresses of the 4 neighbours, x, r
+    float cd[CPT], co[CPT][4], xr[CPT], rr[CPT];
+    uint32_t na[CPT][4];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int l = threadIdx.x + k * T;
+        const int g = start + l;
+        const bool ok = l < cnt;
+        cd[k] = ok ? dg[g] : 0.f;
+        xr[k] = (ok && !zero_init) ? xo[g] : 0.f;
+#pragma unroll
+        for (int ff = 0; ff < 4; ++ff) {
+            const int nb = ok ? t.nbr[ff * N + g] : -1;
+            co[k][ff] = (ok && nb >= 0) ? off[ff * N + g] : 0.f;
+            const int gi = nb >= 0 ? nb : (ok ? g : start);   // coefficient is 0 for absent neighbours
+            const int c = gi / per;
+            na[k][ff] = mapa_u32(ps_addr + 4u * (uint32_t)(gi - c * per), (uint32_t)c);
+        }
+    }
+    int parity = 0;
+    // cluster-wide sum of two values: block reduction, DSMEM scatter of the partials, one cluster barrier
+    auto cluster_sum2 = [&](float a0, float a1, float &o0, float &o1) {
+        float v[2] = {a0, a1};
+        block_reduce_sum<2>(v, wred);
+        if (threadIdx.x < CS)
+            st_dsmem_f64x2(mapa_u32(red_addr + 16u * (uint32_t)(parity * CS + rank), threadIdx.x), (double)v[0], (double)v[1]);
+        cluster.sync();
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < CS; ++c) { s0 += red[(parity * CS + c) * 2]; s1 += red[(parity * CS + c) * 2 + 1]; }
+        parity ^= 1;
+        o0 = (float)s0; o1 = (float)s1;
+    };
+    auto apply = [&](int k) -> float {   // row k of P times the vector currently held in ps (cluster wide)
+        const int l = threadIdx.x + k * T;
+        float s = cd[k] * ps[l < cnt ? l : 0];
+#pragma unroll
+        for (int ff = 0; ff < 4; ++ff) s += co[k][ff] * ld_dsmem_f32(na[k][ff]);
+        return l < cnt ? s : 0.f;
+    };
+
+    // all-zero right-hand side -> result zero (DIFF.py:392, 489-490)
+    float nz = 0.f, dummy;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; nz += (l < cnt && f[start + l] != 0.f) ? 1.f : 0.f; }
+    float nzt;
+    cluster_sum2(nz, 0.f, nzt, dummy);
+    int used = -1; float fin = 0.f;
+    if (!(nzt > 0.f)) {
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) xr[k] = 0.f;
+    } else {
+        // r0 = f - P x0
+        if (!zero_init) {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) ps[l] = xr[k]; }
+            cluster.sync();
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; rr[k] = (l < cnt ? f[start + l] : 0.f) - apply(k); }
+            cluster.sync();
+        } else {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; rr[k] = l < cnt ? f[start + l] : 0.f; }
+        }
+        float a0 = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) { ps[l] = rr[k]; bs[l] = xr[k]; } a0 += rr[k] * rr[k]; }
+        float rho;
+        cluster_sum2(a0, 0.f, rho, dummy);   // the barrier inside also publishes ps
+        float bestc = 0.f, lastc = 0.f; int best_it = -1, rising = 0;
+        for (int i = 0; i < maxit; ++i) {
+            if (reset_steps > 0 && (i + 1) % reset_steps == 0) {
+                // r = f - P x ; p = r ; rho = <r,r>   (CG.cu:281-302)
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) ps[l] = xr[k]; }
+                cluster.sync();
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; rr[k] = (l < cnt ? f[start + l] : 0.f) - apply(k); }
+                cluster.sync();
+                a0 = 0.f;
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) ps[l] = rr[k]; a0 += rr[k] * rr[k]; }
+                cluster_sum2(a0, 0.f, rho, dummy);
+            }
+            float apk[CPT];
+            a0 = 0.f;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const int l = threadIdx.x + k * T;
+                apk[k] = apply(k);
+                a0 += (l < cnt ? ps[l] : 0.f) * apk[k];
+            }
+            float pap;
+            cluster_sum2(a0, 0.f, pap, dummy);   // after this barrier every CTA has finished reading ps
+            const float alpha = rho / pap;
+            a0 = 0.f;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const int l = threadIdx.x + k * T;
+                const float pk = l < cnt ? ps[l] : 0.f;
+                xr[k] += alpha * pk;
+                rr[k] -= alpha * apk[k];
+                a0 += rr[k] * rr[k];
+            }
+            float rr2;
+            cluster_sum2(a0, 0.f, rr2, dummy);
+            const float crit = sqrtf(rr2) * norm;
+            if (!isfinite(crit)) { used = i; fin = crit; break; }
+            if (i == 0 || crit < bestc) {
+                bestc = crit; best_it = i;
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) bs[l] = xr[k]; }
+            }
+            if (i > 0 && crit >= lastc) ++rising; else rising = 0;
+            lastc = crit; used = i; fin = crit;
+            if (crit < tol) break;
+            if (i == maxit - 1 || rising >= 100) {
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; xr[k] = l < cnt ? bs[l] : 0.f; }
+                used = best_it; fin = bestc;
+                break;
+            }
+            const float beta = rr2 / rho;
+            rho = rr2;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) ps[l] = rr[k] + beta * ps[l]; }
+            cluster.sync();   // new p visible cluster wide
+        }
+    }
+    // mean removal
+    float sx = 0.f, mean_sum;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; sx += l < cnt ? xr[k] : 0.f; }
+    cluster_sum2(sx, 0.f, mean_sum, dummy);
+    const float mean = mean_sum / (float)N;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) xo[start + l] = xr[k] - mean; }
+    if (threadIdx.x == 0 && rank == 0) { iters[b * 8 + 2 + slot] = used; resid[b * 8 + 2 + slot] = fin; }
+    cluster.sync();   // keep peer shared memory alive until everyone is done
+}
+
+// ------------------------------------------------------------------------------------------------
+// boundary / stepping kernels: one CTA per environment
+// ------------------------------------------------------------------------------------------------
+// Domain.getMaxVelocity(True, True) (DS.cpp:1360-1367, 1580-1611): max |M^-1 u| over cells and fixed faces
+template <int T>
+__device__ float env_max_velocity(const Tab &t, const float *u, const float *bv, float *sm) {
+    const int N = t.N, NB = t.NB;
+    float m = 0.f;
+    for (int g = threadIdx.x; g < N; g += T) {
+        const float a = u[g], c = u[N + g];
+        m = fmaxf(m, fabsf(t.minv[g] * a + t.minv[N + g] * c));
+        m = fmaxf(m, fabsf(t.minv[2 * N + g] * a + t.minv[3 * N + g] * c));
+    }
+    for (int j = threadIdx.x; j < NB; j += T) {
+        const float a = bv[j], c = bv[NB + j];
+        m = fmaxf(m, fabsf(t.b_minv[j] * a + t.b_minv[NB + j] * c));
+        m = fmaxf(m, fabsf(t.b_minv[2 * NB + j] * a + t.b_minv[3 * NB + j] * c));
+    }
+    return block_reduce_max(m, sm);
+}
+template <int T>
+__global__ void __launch_bounds__(T) k_max_velocity(Tab t, const float *__restrict__ U, const float *__restrict__ Bvel, float *__restrict__ out) {
+    __shared__ float sm[33];
+    const int b = blockIdx.x;
+    const float m = env_max_velocity<T>(t, U + (size_t)b * 2 * t.N, Bvel + (size_t)b * 2 * t.NB, sm);
+    if (threadIdx.x == 0) out[b] = m;
+}
+
+// signed boundary flux sums; which: 0 = faces with b_out==0, 1 = faces with b_out==1, 2 = all
+template <int T>
+__device__ void env_flux_sums(const Tab &t, const float *bv, float &fixed, float &var, double *red) {
+    const int NB = t.NB;
+    float acc[2] = {0.f, 0.f};
+    for (int j = threadIdx.x; j < NB; j += T) {
+        const int f = t.b_face[j];
+        float fl = bflux(t, j, f >> 1, bv[j], bv[NB + j]);
+        if (!(f & 1)) fl = -fl;
+        if (t.b_out && t.b_out[j]) acc[1] += fl; else acc[0] += fl;
+    }
+    block_reduce_sum<2>(acc, red);
+    fixed = acc[0]; var = acc[1];
+}
+template <int T>
+__global__ void __launch_bounds__(T) k_flux_balance(Tab t, const float *__restrict__ Bvel, float *__restrict__ out) {
+    __shared__ double red[32 * 2 + 2];
+    const int b = blockIdx.x;
+    float fx, vr;
+    env_flux_sums<T>(t, Bvel + (size_t)b * 2 * t.NB, fx, vr, red);
+    if (threadIdx.x == 0) out[b] = fx + vr;
+}
+
+// advective outflow boundary relaxation and global flux rescale (SIM.py:188-224, 282-393)
+template <int T>
+__device__ void env_update_outflow(const Tab &t, const float *u, float *bv, float dt, float cvx, float cvy, float bc_tol, double *red) {
+    const int N = t.N, NB = t.NB;
+    for (int j = threadIdx.x; j < NB; j += T) {
+        if (t.b_out[j]) {
+            const int ax = t.b_face[j] >> 1;
+            const float adv = t.b_minv[(2 * ax) * NB + j] * cvx + t.b_minv[(2 * ax + 1) * NB + j] * cvy;
+            const float al = dt * 2.f * adv;
+            const float w = 1.f - 1.f / (1.f + al);
+            const int c = t.b_cell[j];
+            const float b0 = bv[j], b1 = bv[NB + j];
+            bv[j] = b0 - w * (b0 - u[c]);
+            bv[NB + j] = b1 - w * (b1 - u[N + c]);
+        }
+    }
+    __syncthreads();
+    float fx, vr;
+    env_flux_sums<T>(t, bv, fx, vr, red);
+    if (!(fabsf(fx + vr) <= bc_tol * 0.01f)) {
+        const float sc = -fx / vr;
+        for (int j = threadIdx.x; j < NB; j += T)
+            if (t.b_out[j]) { bv[j] *= sc; bv[NB + j] *= sc; }
+    }
+    __syncthreads();
+}
+
+// Adaptive sub-stepping plan (SIM.py:2004-2031) + advective outflow boundary update and global flux
+// balancing (SIM.py:188-224, 228-393), fused: one CTA per environment.
+template <int T>
+__global__ void __launch_bounds__(T) k_plan_substep(Tab t, const float *__restrict__ U, float *__restrict__ Bvel,
+                                                     double *__restrict__ remaining, float *__restrict__ dtv,
+                                                     int32_t *__restrict__ active, int32_t *__restrict__ nsub,
+                                                     float *__restrict__ maxvel, int32_t *__restrict__ counters,
+                                                     float cfl, float cvx, float cvy, float bc_tol, int do_outflow) {
+    __shared__ float smf[33];
+    __shared__ double red[32 * 2 + 2];
+    __shared__ float s_dt; __shared__ int s_active;
+    const int b = blockIdx.x;
+    const int N = t.N, NB = t.NB;
+    const float *u = U + (size_t)b * 2 * N;
+    float *bv = Bvel + (size_t)b * 2 * NB;
+    const float mv = env_max_velocity<T>(t, u, bv, smf);
+    if (threadIdx.x == 0) {
+        double rem = remaining[b];
+        int act = (rem > 0.0) && !(fabs(rem) <= 1e-8);
+        float dt = 0.f;
+        if (act) {
+            double ts;
+            if (fabsf(mv) <= 1e-8f) ts = rem;
+            else {
+                const float mts = cfl / mv;
+                if ((double)mts >= rem) ts = rem;
+                else { const int k = (int)ceilf((float)rem / mts); ts = rem / (double)k; }
+            }
+            rem -= ts;
+            dt = (float)ts;
+            remaining[b] = rem;
+            nsub[b] += 1;
+            atomicAdd(&counters[0], 1);
+        }
+        dtv[b] = dt; active[b] = act; maxvel[b] = mv;
+        s_dt = dt; s_active = act;
+    }
+    __syncthreads();
+    if (!s_active || !do_outflow || !t.b_out) return;
+    env_update_outflow<T>(t, u, bv, s_dt, cvx, cvy, bc_tol, red);
+}
+template <int T>
+__global__ void __launch_bounds__(T) k_update_outflow(Tab t, const float *__restrict__ U, float *__restrict__ Bvel,
+                                                       const float *__restrict__ dtv, float cvx, float cvy, float bc_tol) {
+    __shared__ double red[32 * 2 + 2];
+    const int b = blockIdx.x;
+    env_update_outflow<T>(t, U + (size_t)b * 2 * t.N, Bvel + (size_t)b * 2 * t.NB, dtv[b], cvx, cvy, bc_tol, red);
+}
+__global__ void k_set_remaining(double *remaining, int32_t *nsub, int32_t *counters, double v, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) { remaining[i] = v; nsub[i] = 0; }
+    if (i == 0) counters[0] = 0;
+}
+__global__ void k_zero_counter(int32_t *counters) { counters[0] = 0; }
+
+// jet actuation
+__global__ void k_apply_jet(float *__restrict__ Bvel, float *__restrict__ last, const float *__restrict__ action, float smoothing,
+                            const int32_t *__restrict__ faces, const float *__restrict__ templ, int nf, int NB, int B) {
+    const int b = blockIdx.x;
+    const float l = last[b];
+    const float c = l + smoothing * (action[b] - l);
+    for (int k = threadIdx.x; k < nf; k += blockDim.x) {
+        const int j = faces[k];
+        Bvel[(size_t)b * 2 * NB + j] = templ[k] * c;
+        Bvel[(size_t)b * 2 * NB + NB + j] = templ[nf + k] * c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last[b] = c;
+}
+
+// wall forces (forces.py:193-275)
+__global__ void __launch_bounds__(128) k_wall_forces(fgb_wall w, float visc, int N, int NB, const float *__restrict__ U,
+                                                      const float *__restrict__ P, const float *__restrict__ Bvel, float *__restrict__ acc) {
+    __shared__ double red[32 * 2 + 2];
+    const int b = blockIdx.x;
+    const float *u = U + (size_t)b * 2 * N, *p = P + (size_t)b * N, *bv = Bvel + (size_t)b * 2 * NB;
+    const int n = w.n_wall;
+    float f[2] = {0.f, 0.f};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = w.cell[i], j = w.bface[i];
+        const int il = w.cell[(i + 1) % n], ir = w.cell[(i + n - 1) % n];   // roll(-1) / roll(+1)
+        const float nx = w.normal[i], ny = w.normal[n + i];
+        const float tx = ny, ty = -nx;
+        const float du_dn = (u[c] - bv[j]) / w.dist[i], dv_dn = (u[N + c] - bv[NB + j]) / w.dist[i];
+        const float du_dt = (u[ir] - u[il]) / (2.f * w.tlen[i]), dv_dt = (u[N + ir] - u[N + il]) / (2.f * w.tlen[i]);
+        const float du_dx = du_dn * nx + du_dt * tx, du_dy = du_dn * ny + du_dt * ty;
+        const float dv_dx = dv_dn * nx + dv_dt * tx, dv_dy = dv_dn * ny + dv_dt * ty;
+        const float sxx = 2.f * visc * du_dx - p[c], syy = 2.f * visc * dv_dy - p[c];
+        const float sxy = 2.f * visc * (0.5f * (du_dy + dv_dx));
+        f[0] += (sxx * nx + sxy * ny) * w.flen[i];
+        f[1] += (sxy * nx + syy * ny) * w.flen[i];
+    }
+    block_reduce_sum<2>(f, red);
+    if (threadIdx.x == 0) { acc[b * 2] += f[0] * w.scale; acc[b * 2 + 1] += f[1] * w.scale; }
+}
+
+// sensors: out[b][c][s] = sum_k w[k][s] * field[b][c][idx[k][s]]
+__global__ void k_sample_sensors(const float *__restrict__ field, int C, int N, const int32_t *__restrict__ idx,
+                                 const float *__restrict__ w, int K, int ns, float *__restrict__ out) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * ns) return;
+    const int c = i / ns, s = i - c * ns;
+    const float *fl = field + ((size_t)b * C + c) * N;
+    float v = 0.f;
+    for (int k = 0; k < K; ++k) { const float ww = w[k * ns + s]; if (ww != 0.f) v += ww * fl[idx[k * ns + s]]; }
+    out[((size_t)b * C + c) * ns + s] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static inline dim3 cell_grid(const fgb_batch *b) { return dim3((b->t.N + 255) / 256, b->B); }
+#define STREAM(s) ((cudaStream_t)(s))
+
+extern "C" int fgb_setup_advection(fgb_batch *b, const float *u, const float *ures, const float *bvel, const float *src,
+                                   const float *dt, const int32_t *active, fgb_stream_t s) {
+    if (!b || !u || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_setup_advection: null argument");
+    k_setup_advection<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, u, ures ? ures : u, bvel, src, dt, active, b->Coff, b->A, b->rhs, 1);
+    LAUNCH_CHECK("k_setup_advection");
+    return FGB_OK;
+}
+extern "C" int fgb_solve_advection(fgb_batch *b, int zero_init, const int32_t *active, fgb_stream_t s) {
+    if (!b) return set_err(FGB_E_ARG, "fgb_solve_advection: null argument");
+    k_bicgstab<1024><<<b->B, 1024, 0, STREAM(s)>>>(b->t, b->Coff, b->A, b->rhs, b->ures, b->kry, b->opt.max_iter, b->opt.adv_tol,
+                                                   zero_init, active, b->iters, b->resid);
+    LAUNCH_CHECK("k_bicgstab");
+    return FGB_OK;
+}
+extern "C" int fgb_setup_pressure_matrix(fgb_batch *b, const int32_t *active, fgb_stream_t s) {
+    if (!b) return set_err(FGB_E_ARG, "fgb_setup_pressure_matrix: null argument");
+    k_setup_pressure_matrix<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, b->A, active, b->Poff, b->Pdiag);
+    LAUNCH_CHECK("k_setup_pressure_matrix");
+    return FGB_OK;
+}
+extern "C" int fgb_setup_pressure_rhs(fgb_batch *b, const float *u, const float *bvel, const float *src, const float *p_prev,
+                                      const float *dt, int with_hbya, const int32_t *active, fgb_stream_t s) {
+    if (!b || !bvel) return set_err(FGB_E_ARG, "fgb_setup_pressure_rhs: null argument");
+    if (with_hbya) {
+        if (!u || !dt) return set_err(FGB_E_ARG, "fgb_setup_pressure_rhs: u/dt required with_hbya");
+        k_hbya<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, u, b->ures, bvel, src, b->Coff, b->A, dt, active, b->hbya);
+        LAUNCH_CHECK("k_hbya");
+    }
+    const int no = b->opt.nonortho && p_prev;
+    k_pressure_div<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, b->hbya, bvel, p_prev, b->A, active, no, b->div);
+    LAUNCH_CHECK("k_pressure_div");
+    return FGB_OK;
+}
+
+template <int CS, int CPT>
+static int launch_cg_cluster(fgb_batch *b, float *p_out, int zero_init, int reset_steps, int max_iter, int slot,
+                             const int32_t *active, cudaStream_t st) {
+    constexpr int T = 512;
+    const int N = b->t.N;
+    const int per = (N + CS - 1) / CS;
+    if (per > T * CPT) return 1;  // does not fit this instantiation
+    const size_t smem = (size_t)((per + 3) & ~3) * 2 * 4 + (2 * CS * 2 + 32 * 2 + 2 + 2) * sizeof(double);
+    auto kern = k_cg_cluster<T, CPT, CS>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_cg_cluster)", ce);
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(b->B * CS); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ce = cudaLaunchKernelEx(&cfg, kern, b->t, (const float *)b->Poff, (const float *)b->Pdiag, (const float *)b->div, p_out,
+                            max_iter, b->opt.p_tol, zero_init, reset_steps, slot, active, b->iters, b->resid);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchKernelEx(k_cg_cluster)", ce);
+    return FGB_OK;
+}
+
+static int solve_pressure_slot(fgb_batch *b, float *p_out, int zero_init, int reset_steps, int max_iter, int slot,
+                               const int32_t *active, fgb_stream_t s) {
+    if (!b || !p_out) return set_err(FGB_E_ARG, "fgb_solve_pressure: null argument");
+    if (slot < 0 || slot > 5) slot = 5;
+    if (b->opt.cg_impl == 1) {
+        int rc = launch_cg_cluster<2, 6>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        if (rc == 1) rc = launch_cg_cluster<4, 7>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        if (rc == 1) rc = launch_cg_cluster<8, 7>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        if (rc <= 0) return rc;
+        // too large for the on-chip variant: fall through to the global-memory kernel
+    }
+    k_cg<1024><<<b->B, 1024, 0, STREAM(s)>>>(b->t, b->Poff, b->Pdiag, b->div, p_out, b->kry, max_iter, b->opt.p_tol, zero_init,
+                                             reset_steps, slot, active, b->iters, b->resid);
+    LAUNCH_CHECK("k_cg");
+    return FGB_OK;
+}
+extern "C" int fgb_solve_pressure(fgb_batch *b, float *p_out, int zero_init, int reset_steps, int max_iter,
+                                  const int32_t *active, fgb_stream_t s) {
+    return solve_pressure_slot(b, p_out, zero_init, reset_steps, max_iter, 0, active, s);
+}
+extern "C" int fgb_correct_velocity(fgb_batch *b, const float *p, float *u_out, const int32_t *active, fgb_stream_t s) {
+    if (!b || !p || !u_out) return set_err(FGB_E_ARG, "fgb_correct_velocity: null argument");
+    k_correct_velocity<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, b->hbya, p, b->A, active, u_out);
+    LAUNCH_CHECK("k_correct_velocity");
+    return FGB_OK;
+}
+
+extern "C" int fgb_piso_substep(fgb_batch *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
+                                const int32_t *active, fgb_stream_t s) {
+    if (!b || !u || !p || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_piso_substep: null argument");
+    int rc;
+    const fgb_options &o = b->opt;
+    cudaStream_t st = STREAM(s);
+    const int N = b->t.N;
+    // predictor (SIM.py:1662-1757)
+    for (int ns = 0; ns < o.adv_nonortho_steps; ++ns) {
+        k_setup_advection<<<cell_grid(b), 256, 0, st>>>(b->t, u, ns == 0 ? u : b->ures, bvel, src, dt, active, b->Coff, b->A, b->rhs, ns == 0);
+        LAUNCH_CHECK("k_setup_advection");
+        if ((rc = fgb_solve_advection(b, ns == 0, active, s))) return rc;
+    }
+    // correctors (SIM.py:1777-1972)
+    int slot = 0;
+    for (int cs = 0; cs < o.corrector_steps; ++cs) {
+        if (cs == 0) { if ((rc = fgb_setup_pressure_matrix(b, active, s))) return rc; }   // A is unchanged between correctors
+        for (int ps = 0; ps < o.p_nonortho_steps; ++ps) {
+            if ((rc = fgb_setup_pressure_rhs(b, u, bvel, src, p, dt, ps == 0, active, s))) return rc;
+            if ((rc = solve_pressure_slot(b, p, ps == 0, 100, o.max_iter, slot++, active, s))) return rc;
+        }
+        float *uo = (cs == o.corrector_steps - 1) ? u : b->ures;
+        if ((rc = fgb_correct_velocity(b, p, uo, active, s))) return rc;
+    }
+    (void)N;
+    return FGB_OK;
+}
+
+extern "C" int fgb_make_divergence_free(fgb_batch *b, float *u, float *p, const float *bvel, int max_iter, fgb_stream_t s) {
+    if (!b || !u || !p || !bvel) return set_err(FGB_E_ARG, "fgb_make_divergence_free: null argument");
+    cudaStream_t st = STREAM(s);
+    const size_t BN = (size_t)b->B * b->t.N;
+    int rc;
+    k_fill<<<(unsigned)((BN + 255) / 256), 256, 0, st>>>(b->A, 1.0f, BN);
+    LAUNCH_CHECK("k_fill");
+    cudaError_t ce = cudaMemcpyAsync(b->hbya, u, 2 * BN * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "memcpy hbya", ce);
+    if ((rc = fgb_setup_pressure_matrix(b, nullptr, s))) return rc;
+    for (int ps = 0; ps < b->opt.p_nonortho_steps; ++ps) {
+        if ((rc = fgb_setup_pressure_rhs(b, nullptr, bvel, nullptr, p, nullptr, 0, nullptr, s))) return rc;
+        if ((rc = solve_pressure_slot(b, p, ps == 0, 0, max_iter, ps, nullptr, s))) return rc;
+    }
+    return fgb_correct_velocity(b, p, u, nullptr, s);
+}
+
+extern "C" int fgb_sim_step(fgb_batch *b, float *u, float *p, float *bvel, const float *src, float dt_target, float cfl,
+                            const float *char_vel, float bc_tol, int32_t *substeps_max, fgb_stream_t s) {
+    if (!b || !u || !p || !bvel) return set_err(FGB_E_ARG, "fgb_sim_step: null argument");
+    cudaStream_t st = STREAM(s);
+    k_set_remaining<<<(b->B + 255) / 256, 256, 0, st>>>(b->remaining, b->nsub, b->counters, (double)dt_target, b->B);
+    LAUNCH_CHECK("k_set_remaining");
+    const int do_out = (char_vel != nullptr) && (b->t.b_out != nullptr);
+    int rounds = 0;
+    for (;; ++rounds) {
+        if (rounds > 1000) return set_err(FGB_E_ARG, "fgb_sim_step: more than 1000 adaptive substeps");
+        k_zero_counter<<<1, 1, 0, st>>>(b->counters);
+        k_plan_substep<512><<<b->B, 512, 0, st>>>(b->t, u, bvel, b->remaining, b->dt, b->active, b->nsub, b->maxvel, b->counters,
+                                                  cfl, do_out ? char_vel[0] : 0.f, do_out ? char_vel[1] : 0.f, bc_tol, do_out);
+        LAUNCH_CHECK("k_plan_substep");
+        cudaError_t ce = cudaMemcpyAsync(b->h_counters, b->counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "memcpy counters", ce);
+        ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "fgb_sim_step: stream sync", ce);
+        if (b->h_counters[0] == 0) break;
+        int rc = fgb_piso_substep(b, u, p, bvel, src, b->dt, b->active, s);
+        if (rc) return rc;
+    }
+    if (substeps_max) *substeps_max = rounds;
+    return FGB_OK;
+}
+
+extern "C" int fgb_update_outflow(fgb_batch *b, const float *u, float *bvel, const float *dt, const float *char_vel, float bc_tol,
+                                  fgb_stream_t s) {
+    if (!b || !u || !bvel || !dt || !char_vel) return set_err(FGB_E_ARG, "fgb_update_outflow: null argument");
+    if (!b->t.b_out) return FGB_OK;
+    k_update_outflow<512><<<b->B, 512, 0, STREAM(s)>>>(b->t, u, bvel, dt, char_vel[0], char_vel[1], bc_tol);
+    LAUNCH_CHECK("k_update_outflow");
+    return FGB_OK;
+}
+extern "C" int fgb_flux_balance(fgb_batch *b, const float *bvel, float *out, fgb_stream_t s) {
+    if (!b || !bvel || !out) return set_err(FGB_E_ARG, "fgb_flux_balance: null argument");
+    k_flux_balance<256><<<b->B, 256, 0, STREAM(s)>>>(b->t, bvel, out);
+    LAUNCH_CHECK("k_flux_balance");
+    return FGB_OK;
+}
+extern "C" int fgb_max_velocity(fgb_batch *b, const float *u, const float *bvel, float *out, fgb_stream_t s) {
+    if (!b || !u || !bvel || !out) return set_err(FGB_E_ARG, "fgb_max_velocity: null argument");
+    k_max_velocity<512><<<b->B, 512, 0, STREAM(s)>>>(b->t, u, bvel, out);
+    LAUNCH_CHECK("k_max_velocity");
+    return FGB_OK;
+}
+extern "C" int fgb_apply_jet_action(fgb_batch *b, float *bvel, float *last_control, const float *action, float smoothing,
+                                    const int32_t *faces, const float *templ, int32_t n_faces, fgb_stream_t s) {
+    if (!b || !bvel || !last_control || !action || !faces || !templ) return set_err(FGB_E_ARG, "fgb_apply_jet_action: null argument");
+    k_apply_jet<<<b->B, 64, 0, STREAM(s)>>>(bvel, last_control, action, smoothing, faces, templ, n_faces, b->t.NB, b->B);
+    LAUNCH_CHECK("k_apply_jet");
+    return FGB_OK;
+}
+extern "C" int fgb_wall_forces(fgb_batch *b, const fgb_wall *w, const float *u, const float *p, const float *bvel, float *acc,
+                               fgb_stream_t s) {
+    if (!b || !w || !u || !p || !bvel || !acc) return set_err(FGB_E_ARG, "fgb_wall_forces: null argument");
+    k_wall_forces<<<b->B, 128, 0, STREAM(s)>>>(*w, b->t.viscosity, b->t.N, b->t.NB, u, p, bvel, acc);
+    LAUNCH_CHECK("k_wall_forces");
+    return FGB_OK;
+}
+extern "C" int fgb_sample_sensors(fgb_batch *b, const float *field, int32_t channels, const int32_t *idx, const float *w,
+                                  int32_t K, int32_t n_sensors, float *out, fgb_stream_t s) {
+    if (!b || !field || !idx || !w || !out) return set_err(FGB_E_ARG, "fgb_sample_sensors: null argument");
+    dim3 grid((channels * n_sensors + 127) / 128, b->B);
+    k_sample_sensors<<<grid, 128, 0, STREAM(s)>>>(field, channels, b->t.N, idx, w, K, n_sensors, out);
+    LAUNCH_CHECK("k_sample_sensors");
+    return FGB_OK;
+}

@@ -1,0 +1,308 @@
+"""Batched ``CylinderJet2D`` environment: B independent environments advanced by one launch sequence.
+
+Public surface mirrors the reference's ``FluidEnv`` / ``CylinderJetEnv2D``
+(``envs/fluid_env.py:749-917``, ``envs/cylinder/cylinder_env_base.py``, ``jet_cylinder_env_2d.py``):
+``reset(seed, randomize)``, ``step(action)``, ``sample_action``, ``n_agents``, ``observation_space`` /
+``action_space`` shapes, ``get_state/set_state``, and the error strings of
+``tests/env_utils/test_fluid_env.py``.  Every tensor gains a leading environment dimension, exactly like
+the reference's ``ParallelFluidEnv`` (``envs/parallel_env.py:233-287``) -- but the B environments live in
+one process / one CUDA context and never leave the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import native
+from ..domain import FIXED
+from ..sensors import cell_centres, sensor_tables
+from ..solver import BatchedPISO, _ptr
+from .cylinder_domain import BOTTOM, LEFT, RIGHT, TOP, WAKE, jet_profile, make_cylinder_domain
+
+CYLINDER_JET_2D_DEFAULT_CONFIG = {
+    "reynolds_number": 1e2, "resolution": 24, "dt": 1e-2, "adaptive_cfl": 0.8, "step_length": 0.25,
+    "episode_length": 80, "lift_penalty": 1.0,
+}
+
+
+class CylinderJet2DEnv:
+    H, L, cylinder_diameter, U_mean, cylinder_offset_y = 4.1, 22.0, 1.0, 1.0, 0.05
+    n_sensors = 151
+    action_smoothing_alpha = 0.1
+    jet_angle = 10.0
+    metrics = ["drag", "lift"]
+
+    def __init__(self, n_envs: int = 1, reynolds_number=1e2, resolution=24, dt=1e-2, adaptive_cfl=0.8, step_length=0.25,
+                 episode_length=80, lift_penalty=1.0, device="cuda:0", cg_impl=1, compiled=None, cd_ref=0.0,
+                 randomize_initial_state=False, enable_actions=True):
+        self.n_envs = int(n_envs)
+        self.resolution, self.dt, self.cfl = int(resolution), float(dt), float(adaptive_cfl)
+        self.step_length, self.episode_length = float(step_length), int(episode_length)
+        self.lift_penalty, self.cd_ref = float(lift_penalty), float(cd_ref)
+        self.randomize_initial_state = randomize_initial_state
+        self.enable_actions = enable_actions
+        self.device = torch.device(device)
+        if compiled is None:
+            spec = make_cylinder_domain(resolution, reynolds_number, self.U_mean, self.H, self.L, self.cylinder_offset_y)
+            cd = spec.prepare()
+        else:
+            spec, cd = compiled
+        self.spec, self.cd = spec, cd
+        out_mask = np.zeros(cd.NB, dtype=np.int8)
+        o = cd.boff[WAKE, 1]
+        out_mask[o:o + spec.blocks[WAKE].ny] = 1
+        self.solver = BatchedPISO(cd, self.n_envs, device=device, corrector_steps=2, advect_non_ortho_steps=1,
+                                  pressure_non_ortho_steps=1, non_orthogonal=True, pressure_tol=1e-5, cg_impl=cg_impl,
+                                  out_mask=out_mask)
+        self.lib = self.solver.lib
+        self.char_vel = (self.U_mean, 0.0)
+        self._setup_jets()
+        self._setup_wall()
+        self._setup_sensors()
+        B, dev = self.n_envs, self.device
+        self.last_control = torch.zeros(B, device=dev)
+        self._acc = torch.zeros(B, 2, device=dev)
+        self._zero_action = torch.zeros(B, 1, device=dev)
+        self._reset_called = False
+        self._seed = None
+        self._n_steps = 0
+        self.last_substeps = 0
+
+    # ---- static tables ---------------------------------------------------------------------------
+    def _setup_jets(self):
+        """Jet velocity templates on the cylinder faces of the top / bottom blocks
+        (jet_cylinder_env_2d.py:136-183)."""
+        cd, spec = self.cd, self.spec
+
+        def coords_to_velocities(coords_boundary, direction):
+            cb = torch.from_numpy(np.ascontiguousarray(coords_boundary))
+            centers = 0.5 * (cb[:, :-1] + cb[:, 1:])
+            if direction == "top":
+                angles = torch.pi / 2 - torch.atan2(centers[1, :], centers[0, :])
+            else:
+                angles = -torch.pi / 2 - torch.atan2(centers[1, :], centers[0, :])
+            angles_deg = torch.rad2deg(angles)
+            angles_deg_abs = torch.abs(angles_deg)
+            angles_deg_abs[angles_deg_abs > self.jet_angle] = 0.0
+            min_idx, max_idx = torch.where(angles_deg_abs > 0.0)[0][[0, -1]]
+            min_idx, max_idx = int(min_idx) - 1, int(max_idx) + 1
+            prof = torch.from_numpy(jet_profile(max_idx - min_idx + 1))
+            vel = torch.zeros_like(centers)
+            for i, um in zip(range(min_idx, max_idx + 1), prof):
+                a = angles_deg[i]
+                vel[0, i] = um * torch.sin(torch.deg2rad(a))
+                vel[1, i] = um * torch.cos(torch.deg2rad(a))
+            return vel.numpy()
+
+        top_v = coords_to_velocities(spec.blocks[TOP].vertex[:, 0, :], "top")
+        bot_v = coords_to_velocities(spec.blocks[BOTTOM].vertex[:, -1, :], "bottom")
+        nx = spec.blocks[TOP].nx
+        faces = np.concatenate([cd.boff[TOP, 2] + np.arange(nx), cd.boff[BOTTOM, 3] + np.arange(nx)]).astype(np.int32)
+        templ = np.concatenate([top_v, bot_v], axis=1).astype(np.float32)
+        self.jet_faces = torch.from_numpy(faces).to(self.device)
+        self.jet_templ = torch.from_numpy(np.ascontiguousarray(templ)).to(self.device)
+
+    def _setup_wall(self):
+        """Ring of wall-adjacent cells around the cylinder and its geometry (CYL.py:548-655,
+        forces.py:12-39, 42-107)."""
+        cd, spec = self.cd, self.spec
+        ring = [(LEFT, 1, False), (TOP, 2, False), (RIGHT, 0, True), (BOTTOM, 3, True)]
+        vc_list, cc_list, cells, bfaces = [], [], [], []
+        for k, (bi, f, flip) in enumerate(ring):
+            b = spec.blocks[bi]
+            v = torch.from_numpy(b.vertex)
+            cc = torch.from_numpy(cell_centres(b.vertex))
+            ax = f >> 1
+            if ax == 0:
+                col = -1 if (f & 1) else 0
+                bc, ce = v[:, :, col], cc[:, :, col]
+                idx = [cd.gidx(bi, [b.nx - 1 if (f & 1) else 0, y]) for y in range(b.ny)]
+            else:
+                row = -1 if (f & 1) else 0
+                bc, ce = v[:, row, :], cc[:, row, :]
+                idx = [cd.gidx(bi, [x, b.ny - 1 if (f & 1) else 0]) for x in range(b.nx)]
+            bf = [cd.boff[bi, f] + i for i in range(len(idx))]
+            if flip:
+                bc, ce = torch.flip(bc, dims=[-1]), torch.flip(ce, dims=[-1])
+                idx, bf = idx[::-1], bf[::-1]
+            if k != len(ring) - 1:
+                bc = bc[..., :-1]
+            vc_list.append(bc)
+            cc_list.append(ce)
+            cells += idx
+            bfaces += bf
+        vc = torch.cat(vc_list, dim=-1)
+        centers = torch.cat(cc_list, dim=-1)
+        left = torch.roll(centers, shifts=-1, dims=-1)
+        right = torch.roll(centers, shifts=1, dims=-1)
+        tlen = torch.sqrt(torch.sum((left - right) ** 2, dim=0))
+        v0, v1 = vc[:, :-1], vc[:, 1:]
+        e = v1 - v0
+        eps = 1e-20
+        t = e / (torch.linalg.norm(e, dim=0, keepdim=True) + eps)
+        n = torch.stack([t[1], -t[0]], dim=0)
+        m = 0.5 * (v0 + v1)
+        d = torch.clamp(((centers - m) * n).sum(dim=0).abs(), min=eps)
+        n = n * -1
+        flen = torch.sqrt((vc[0, 1:] - vc[0, :-1]) ** 2 + (vc[1, 1:] - vc[1, :-1]) ** 2)
+        dev = self.device
+        self._wall_t = dict(cell=torch.tensor(cells, dtype=torch.int32, device=dev),
+                            bface=torch.tensor(bfaces, dtype=torch.int32, device=dev),
+                            normal=n.contiguous().float().to(dev), dist=d.float().to(dev), tlen=tlen.float().to(dev),
+                            flen=flen.float().to(dev))
+        w = native.Wall()
+        w.n_wall = len(cells)
+        for k2 in ("cell", "bface", "normal", "dist", "tlen", "flen"):
+            setattr(w, k2, self._wall_t[k2].data_ptr())
+        w.scale = 1.0 / (0.5 * self.U_mean ** 2 * self.cylinder_diameter)
+        self.wall = w
+
+    @property
+    def render_shape(self):
+        z = self.resolution * 4
+        return (int(z / self.H * self.L), z)
+
+    def sensor_locations_physical(self) -> torch.Tensor:
+        """CYL.py:457-516"""
+        x_idx = torch.arange(1.0, 5.0, step=0.5)
+        y_idx = torch.arange(-1.5, 1.75, step=0.5)
+        xy = torch.meshgrid(x_idx, y_idx, indexing="ij")
+        loc = torch.stack([xy[0].ravel(), xy[1].ravel()], dim=0)
+        x_1 = torch.arange(-0.25, 1, 0.25)
+        y_1a, y_1b = torch.full_like(x_1, -1.5), torch.full_like(x_1, 1.5)
+        x_2 = torch.concatenate([torch.tensor([-0.25]), torch.arange(0.25, 1.25, 0.25)])
+        y_2a, y_2b = torch.full_like(x_2, self.cylinder_diameter), torch.full_like(x_2, -self.cylinder_diameter)
+        x_3, y_3 = torch.tensor([0.75] * 3), torch.tensor([-0.5, 0, 0.5])
+        add = torch.stack([torch.concatenate([x_1, x_1, x_2, x_2, x_3]), torch.concatenate([y_1a, y_1b, y_2a, y_2b, y_3])], dim=0)
+        ang = torch.linspace(0, 2 * torch.pi, steps=36)
+        r1, r2 = 2 * 0.5, 1.25 * 0.5
+        c1 = torch.stack([r1 * torch.cos(ang), r1 * torch.sin(ang)], dim=0)
+        c2 = torch.stack([r2 * torch.cos(ang), r2 * torch.sin(ang)], dim=0)
+        return torch.concatenate([loc, c1, c2, add], dim=1)
+
+    def _setup_sensors(self):
+        pc = self.sensor_locations_physical()
+        rs = self.render_shape
+        pc[0, :] += 2.0
+        pc[0, :] *= (rs[0] - 1) / (self.L - 2.0)
+        pc[1, :] += self.H / 2
+        pc[1, :] *= (rs[1] - 1) / self.H
+        self.sensor_px = torch.round(pc).to(torch.int32).numpy()
+        idx, w = sensor_tables([b.vertex for b in self.spec.blocks], rs, self.sensor_px, fill_max_steps=16)
+        self.sens_idx = torch.from_numpy(idx).to(self.device)
+        self.sens_w = torch.from_numpy(w).to(self.device)
+
+    # ---- reference-shaped API ---------------------------------------------------------------------
+    @property
+    def n_agents(self):
+        return 1
+
+    @property
+    def n_sim_steps(self):
+        return max(1, int(self.step_length / self.dt))
+
+    def seed(self, seed: int):
+        self._seed = seed
+        self._np_rng = np.random.default_rng(seed)
+        self._torch_rng = torch.Generator(device=self.device).manual_seed(seed)
+
+    def sample_action(self):
+        if self._seed is None:
+            raise RuntimeError("Environment must be seeded before sampling actions")
+        return torch.rand(self.n_envs, 1, device=self.device, generator=self._torch_rng) * 2 - 1
+
+    def set_state(self, u, p, bvel, last_control=None):
+        s = self.solver
+        for dst, src in ((s.u, u), (s.p, p), (s.bvel, bvel)):
+            src = torch.as_tensor(src, dtype=torch.float32, device=self.device)
+            dst.copy_(src if src.dim() == dst.dim() else src.unsqueeze(0).expand_as(dst))
+        if last_control is not None:
+            self.last_control.copy_(torch.as_tensor(last_control, device=self.device).expand_as(self.last_control))
+        self._reset_called = True
+
+    def get_state(self):
+        s = self.solver
+        return dict(u=s.u.clone(), p=s.p.clone(), bvel=s.bvel.clone(), last_control=self.last_control.clone())
+
+    def reset(self, seed: int | None = None, randomize: bool | None = None):
+        if seed is None:
+            if self._seed is None:
+                raise ValueError("Seed must be provided either during reset or by calling seed().")
+        else:
+            self.seed(seed)
+        s = self.solver
+        s.u.zero_()
+        s.p.zero_()
+        s.bvel.copy_(torch.from_numpy(self.cd.bvel0[:, :self.cd.NB].copy()).to(self.device).unsqueeze(0).expand_as(s.bvel))
+        # Simulation.make_divergence_free incl. its "PRE" hook with time step 1 (SIM.py:1335-1347)
+        s.update_outflow(1.0, self.char_vel, tol=5e-6)
+        s.make_divergence_free(max_iter=1000)
+        self.last_control.zero_()
+        randomize = self.randomize_initial_state if randomize is None else randomize
+        if randomize:
+            self._randomize_domain()
+        self._apply_action(self._zero_action, smooth=False)
+        self._reset_called = True
+        self._n_steps = 0
+        return self._get_obs(), {}
+
+    def _randomize_domain(self):
+        """CYL.py:364-404 (per-environment noise, common number of settling steps)."""
+        period = 1 / (0.3 * self.U_mean / self.cylinder_diameter)
+        max_n = 2 * int(period / self.step_length) - 1
+        n_steps = int(self._np_rng.integers(int(0.5 * max_n), max_n)) + 1
+        s = self.solver
+        s.u += torch.randn(s.u.shape, device=self.device, generator=self._torch_rng) * 0.025
+        s.p += torch.randn(s.p.shape, device=self.device, generator=self._torch_rng) * 0.025
+        for _ in range(n_steps):
+            s.single_step(self.dt, self.cfl, char_vel=self.char_vel)
+
+    def _apply_action(self, action, smooth=True):
+        """jet_cylinder_env_2d.py:185-188 with the exponential smoothing of CYL.py:748-751."""
+        a = torch.as_tensor(action, dtype=torch.float32, device=self.device).reshape(self.n_envs).contiguous()
+        if not smooth:
+            self.last_control.copy_(a)
+        native.check(self.lib.fgb_apply_jet_action(self.solver.handle, _ptr(self.solver.bvel), _ptr(self.last_control), _ptr(a),
+                                                   self.action_smoothing_alpha if smooth else 0.0, _ptr(self.jet_faces),
+                                                   _ptr(self.jet_templ), int(self.jet_faces.numel()), self.solver.stream),
+                     "fgb_apply_jet_action")
+
+    def _get_obs(self):
+        s = self.solver
+        B, ns = self.n_envs, self.sens_idx.shape[1]
+        K = self.sens_idx.shape[0]
+        vel = torch.empty(B, 2, ns, device=self.device)
+        prs = torch.empty(B, 1, ns, device=self.device)
+        native.check(self.lib.fgb_sample_sensors(s.handle, _ptr(s.u), 2, _ptr(self.sens_idx), _ptr(self.sens_w), K, ns, _ptr(vel),
+                                                 s.stream), "fgb_sample_sensors")
+        native.check(self.lib.fgb_sample_sensors(s.handle, _ptr(s.p), 1, _ptr(self.sens_idx), _ptr(self.sens_w), K, ns, _ptr(prs),
+                                                 s.stream), "fgb_sample_sensors")
+        return {"velocity": vel.permute(0, 2, 1).contiguous(), "pressure": prs[:, 0]}
+
+    def step(self, action):
+        if not self._reset_called:
+            raise RuntimeError("Environment must be reset before stepping. Call 'reset()' before'step()'.")
+        action = torch.as_tensor(action, dtype=torch.float32, device=self.device)
+        if action.shape != self._zero_action.shape:
+            raise ValueError(f"Action shape {action.shape} does not match expected shape {self._zero_action.shape}.")
+        if self._n_steps >= self.episode_length:
+            raise RuntimeError("Episode has already terminated. Call 'reset()' first.")
+        s = self.solver
+        self._acc.zero_()
+        nsub = 0
+        for _ in range(self.n_sim_steps):
+            if self.enable_actions:
+                self._apply_action(action)
+            nsub += s.single_step(self.dt, self.cfl, char_vel=self.char_vel)
+            native.check(self.lib.fgb_wall_forces(s.handle, C.byref(self.wall), _ptr(s.u), _ptr(s.p), _ptr(s.bvel), _ptr(self._acc),
+                                                  s.stream), "fgb_wall_forces")
+        self.last_substeps = nsub
+        obs = self._get_obs()
+        mean = self._acc / self.n_sim_steps
+        cd, cl = mean[:, 0], mean[:, 1]
+        reward = self.cd_ref - cd - self.lift_penalty * torch.abs(cl)
+        self._n_steps += 1
+        truncated = self._n_steps >= self.episode_length
+        return obs, reward, False, truncated, {"drag": cd.detach(), "lift": cl.detach()}

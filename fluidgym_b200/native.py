@@ -1,0 +1,90 @@
+"""ctypes binding of the C ABI in include/fluidgym_b200.h (no torch types cross the boundary).
+
+The product path has NO CPU fallback: if the shared library is missing or no CUDA device is
+present, loading / creating a batch raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_lib = None
+
+
+class FGBError(RuntimeError):
+    pass
+
+
+class Tables(C.Structure):
+    _fields_ = [("N", C.c_int32), ("NB", C.c_int32), ("K_no", C.c_int32), ("K_nob", C.c_int32),
+                ("viscosity", C.c_float)] + [(n, C.c_void_p) for n in (
+                    "nbr", "fl_comp", "minv", "det", "Cd", "Wp", "no_idx", "no_face", "no_gP", "no_gN", "no_wv",
+                    "nob_idx", "nob_w", "b_minv", "b_det", "b_alpha", "b_cell", "b_face", "b_out")]
+
+
+class Options(C.Structure):
+    _fields_ = [("corrector_steps", C.c_int32), ("adv_nonortho_steps", C.c_int32), ("p_nonortho_steps", C.c_int32),
+                ("nonortho", C.c_int32), ("adv_tol", C.c_float), ("p_tol", C.c_float), ("max_iter", C.c_int32),
+                ("cg_impl", C.c_int32)]
+
+
+class Wall(C.Structure):
+    _fields_ = [("n_wall", C.c_int32), ("cell", C.c_void_p), ("bface", C.c_void_p), ("normal", C.c_void_p),
+                ("dist", C.c_void_p), ("tlen", C.c_void_p), ("flen", C.c_void_p), ("scale", C.c_float)]
+
+
+EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_create", "fgb_batch_destroy",
+           "fgb_batch_set_options", "fgb_batch_buffer", "fgb_setup_advection", "fgb_solve_advection",
+           "fgb_setup_pressure_matrix", "fgb_setup_pressure_rhs", "fgb_solve_pressure", "fgb_correct_velocity",
+           "fgb_piso_substep", "fgb_make_divergence_free", "fgb_sim_step", "fgb_update_outflow", "fgb_flux_balance",
+           "fgb_max_velocity", "fgb_apply_jet_action", "fgb_wall_forces", "fgb_sample_sensors"]
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load libfluidgym_b200.so (built in-tree by fluidgym_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise FGBError(f"{path} is missing: run `python -m fluidgym_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+    L.fgb_last_error.restype = C.c_char_p
+    L.fgb_workspace_bytes.restype = C.c_size_t
+    L.fgb_workspace_bytes.argtypes = [C.POINTER(Tables), i32]
+    L.fgb_batch_create.argtypes = [C.POINTER(Tables), i32, vp, C.c_size_t, C.POINTER(Options), C.POINTER(vp)]
+    L.fgb_batch_destroy.argtypes = [vp]
+    L.fgb_batch_destroy.restype = None
+    L.fgb_batch_set_options.argtypes = [vp, C.POINTER(Options)]
+    L.fgb_batch_buffer.restype = vp
+    L.fgb_batch_buffer.argtypes = [vp, C.c_char_p]
+    L.fgb_setup_advection.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.fgb_solve_advection.argtypes = [vp, i32, vp, vp]
+    L.fgb_setup_pressure_matrix.argtypes = [vp, vp, vp]
+    L.fgb_setup_pressure_rhs.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    L.fgb_solve_pressure.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.fgb_correct_velocity.argtypes = [vp, vp, vp, vp, vp]
+    L.fgb_piso_substep.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.fgb_make_divergence_free.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.fgb_sim_step.argtypes = [vp, vp, vp, vp, vp, f32, f32, C.POINTER(f32), f32, C.POINTER(i32), vp]
+    L.fgb_update_outflow.argtypes = [vp, vp, vp, vp, C.POINTER(f32), f32, vp]
+    L.fgb_flux_balance.argtypes = [vp, vp, vp, vp]
+    L.fgb_max_velocity.argtypes = [vp, vp, vp, vp, vp]
+    L.fgb_apply_jet_action.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32, vp]
+    L.fgb_wall_forces.argtypes = [vp, C.POINTER(Wall), vp, vp, vp, vp, vp]
+    L.fgb_sample_sensors.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().fgb_last_error().decode()
+        raise FGBError(f"{what}: error {rc}: {msg}")

@@ -1,0 +1,117 @@
+"""Sensor sampling as a static sparse linear map (host-side setup).
+
+The reference renders *all* cells onto a uniform grid every observation (bilinear splat with atomics,
+weight normalisation, up to ``fill_max_steps`` neighbour-mean hole-filling sweeps) and then reads a few
+sensor pixels (``envs/util/obs_extraction.py:10-57`` -> ``simulation/pict/data/resample.py:300-358`` ->
+``extensions/resampling.cu:191-243, 296-364, 526-609``).  Geometry and output grid never change, so the
+value at every pixel is a fixed linear combination of cell values; this module computes those
+combinations once for the sensor pixels and hands them to ``fgb_sample_sensors`` as ELL tables.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+f32 = np.float32
+
+
+def cell_centres(vertex: np.ndarray) -> np.ndarray:
+    """2x2 average pooling of the vertices (shapes.py:216-225) -> [2, ny, nx] float32."""
+    v = vertex.astype(f32)
+    return ((v[:, :-1, :-1] + v[:, :-1, 1:] + v[:, 1:, :-1] + v[:, 1:, 1:]) * f32(0.25)).astype(f32)
+
+
+def uniform_grid_transform(vertex_list, out_shape):
+    """AABB_OUTER mapping world -> pixel coordinates (resample.py:66-96): returns (scale, offset[2])
+    with pixel = (world - centre) / scale + out_shape / 2 - 0.5."""
+    allv = np.concatenate([v.reshape(2, -1) for v in vertex_list], axis=1).astype(f32)
+    lower, upper = allv.min(axis=1), allv.max(axis=1)
+    size = (upper - lower).astype(f32)
+    centre = (lower + size * f32(0.5)).astype(f32)
+    os_ = np.asarray(out_shape, dtype=f32)
+    scale = f32(np.max(size / os_))
+    return scale, centre, os_
+
+
+def splat_matrix(vertex_list, out_shape):
+    """Sparse [n_pixels, N] bilinear splat weights and per-pixel weight sums (resampling.cu:296-344)."""
+    scale, centre, os_ = uniform_grid_transform(vertex_list, out_shape)
+    W, H = int(out_shape[0]), int(out_shape[1])
+    centres = np.concatenate([cell_centres(v).reshape(2, -1) for v in vertex_list], axis=1)
+    N = centres.shape[1]
+    sc = ((centres - centre[:, None]) / scale + (os_ * f32(0.5) - f32(0.5))[:, None]).astype(f32)
+    fl, ce = np.floor(sc), np.ceil(sc)
+    fr = (sc - fl).astype(f32)
+    rows, cols, vals = [], [], []
+    for ux in (0, 1):
+        for uy in (0, 1):
+            px = (ce[0] if ux else fl[0]).astype(np.int64)
+            py = (ce[1] if uy else fl[1]).astype(np.int64)
+            w = (fr[0] if ux else 1 - fr[0]) * (fr[1] if uy else 1 - fr[1])
+            ok = (px >= 0) & (px < W) & (py >= 0) & (py < H)
+            rows.append((py * W + px)[ok])
+            cols.append(np.arange(N)[ok])
+            vals.append(w[ok].astype(np.float64))
+    S = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(W * H, N))
+    return S, np.asarray(S.sum(axis=1)).ravel()
+
+
+def fill_levels(valid0: np.ndarray, fill_max_steps: int) -> np.ndarray:
+    """Sweep index at which every pixel becomes valid in ``_FillEmptyCells`` (resampling.cu:246-293):
+    0 = has splat weight, k = filled from neighbours in sweep k, -1 = never."""
+    H, W = valid0.shape
+    level = np.where(valid0, 0, -1).astype(np.int32)
+    valid = valid0.copy()
+    for k in range(1, int(fill_max_steps) + 1):
+        if valid.all():
+            break
+        nb = np.zeros_like(valid)
+        nb[:, 1:] |= valid[:, :-1]
+        nb[:, :-1] |= valid[:, 1:]
+        nb[1:, :] |= valid[:-1, :]
+        nb[:-1, :] |= valid[1:, :]
+        newly = nb & ~valid
+        level[newly] = k
+        valid = valid | newly
+    return level
+
+
+def sensor_tables(vertex_list, out_shape, sensor_px: np.ndarray, fill_max_steps: int):
+    """ELL tables (idx [K, n_s] int32, w [K, n_s] float32) of the rendered-pixel map at the sensor
+    pixels ``sensor_px`` = [2, n_s] integer (x, y) pixel coordinates: normalised splat row where the
+    pixel received weight, otherwise the mean of the neighbours that were valid one sweep earlier."""
+    W, H = int(out_shape[0]), int(out_shape[1])
+    S, wsum = splat_matrix(vertex_list, out_shape)
+    level = fill_levels((wsum > 1e-8).reshape(H, W), fill_max_steps)
+    memo = {}
+
+    def row(y, x):
+        key = (y, x)
+        if key in memo:
+            return memo[key]
+        lv = level[y, x]
+        if lv == 0:
+            a, b = S.indptr[y * W + x], S.indptr[y * W + x + 1]
+            r = dict(zip(S.indices[a:b].tolist(), (S.data[a:b] / wsum[y * W + x]).tolist()))
+        elif lv < 0:
+            r = {}
+        else:
+            nb = [(y + dy, x + dx) for dx, dy in ((-1, 0), (1, 0), (0, -1), (0, 1))
+                  if 0 <= x + dx < W and 0 <= y + dy < H and 0 <= level[y + dy, x + dx] < lv]
+            r = {}
+            for (yy, xx) in nb:
+                for c, v in row(yy, xx).items():
+                    r[c] = r.get(c, 0.0) + v / len(nb)
+        memo[key] = r
+        return r
+
+    rows = [row(int(y), int(x)) for x, y in zip(sensor_px[0], sensor_px[1])]
+    ns = len(rows)
+    K = max(1, max(len(r) for r in rows))
+    idx = np.zeros((K, ns), dtype=np.int32)
+    w = np.zeros((K, ns), dtype=f32)
+    for s_, r in enumerate(rows):
+        for k, (c, v) in enumerate(sorted(r.items())):
+            idx[k, s_] = c
+            w[k, s_] = v
+    return idx, w

@@ -1,0 +1,172 @@
+"""Batched PISO solver: host-side mirror of ``fluidgym.simulation.Simulation`` for B environments.
+
+Keeps the reference's vocabulary (``single_step``, ``make_divergence_free``, ``corrector_steps``,
+``pressure_tol`` ...; FGSIM.py:125-280, SIM.py:489-1037) but advances a whole batch of environments
+that share one geometry with the sm_100a kernels behind ``include/fluidgym_b200.h``.  torch is used
+only to own device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import native
+from .domain import CompiledDomain
+
+_TABLE_FIELDS = ["nbr", "fl_comp", "minv", "det", "Cd", "Wp", "no_idx", "no_face", "no_gP", "no_gN", "no_wv",
+                 "nob_idx", "nob_w", "b_minv", "b_det", "b_alpha", "b_cell", "b_face"]
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class BatchedPISO:
+    """State + solver for ``n_envs`` environments on one GPU.
+
+    State tensors (device, float32): ``u [B,2,N]``, ``p [B,N]``, ``bvel [B,2,NB]``.
+    """
+
+    def __init__(self, cd: CompiledDomain, n_envs: int, device="cuda:0", corrector_steps=2, advect_non_ortho_steps=1,
+                 pressure_non_ortho_steps=1, non_orthogonal=True, advection_tol=1e-5, pressure_tol=1e-5,
+                 max_iter=5000, cg_impl=1, out_mask=None):
+        if not torch.cuda.is_available():
+            raise native.FGBError("fluidgym_b200 needs a CUDA device (there is no CPU fallback)")
+        self.lib = native.load()
+        self.cd = cd
+        self.B = int(n_envs)
+        self.N, self.NB = cd.N, cd.NB
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        dev = self.device
+        self._tab = {}
+        for name in _TABLE_FIELDS:
+            arr = getattr(cd, name)
+            if name == "b_face":
+                arr = arr.astype(np.int8)
+            self._tab[name] = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+        self._tab["b_out"] = torch.from_numpy(np.ascontiguousarray(out_mask, dtype=np.int8)).to(dev) if out_mask is not None else None
+        self.tables = native.Tables()
+        self.tables.N, self.tables.NB, self.tables.K_no, self.tables.K_nob = cd.N, cd.NB, cd.K_no, cd.K_nob
+        self.tables.viscosity = float(cd.visc)
+        for name in _TABLE_FIELDS + ["b_out"]:
+            t = self._tab[name]
+            setattr(self.tables, name, t.data_ptr() if t is not None else None)
+        self.options = native.Options(corrector_steps, advect_non_ortho_steps, pressure_non_ortho_steps,
+                                      int(bool(non_orthogonal)), advection_tol, pressure_tol, max_iter, cg_impl)
+        nbytes = self.lib.fgb_workspace_bytes(C.byref(self.tables), self.B)
+        self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        self._ws_off = (-self.workspace.data_ptr()) % 256
+        handle = C.c_void_p()
+        native.check(self.lib.fgb_batch_create(C.byref(self.tables), self.B, C.c_void_p(self.workspace.data_ptr() + self._ws_off),
+                                               nbytes, C.byref(self.options), C.byref(handle)), "fgb_batch_create")
+        self.handle = handle
+        B, N, NB = self.B, self.N, self.NB
+        self.u = torch.zeros(B, 2, N, device=dev)
+        self.p = torch.zeros(B, N, device=dev)
+        self.bvel = torch.from_numpy(cd.bvel0[:, :NB].copy()).to(dev).unsqueeze(0).repeat(B, 1, 1).contiguous()
+        self.src = None
+        self.ones_dt = torch.ones(B, device=dev)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.fgb_batch_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_options(self, **kw):
+        for k, v in kw.items():
+            setattr(self.options, k, v)
+        native.check(self.lib.fgb_batch_set_options(self.handle, C.byref(self.options)), "fgb_batch_set_options")
+
+    def buffer(self, name: str) -> torch.Tensor:
+        """Zero-copy view of a named workspace buffer (see fgb_batch_buffer)."""
+        B, N = self.B, self.N
+        shapes = {"Coff": ((B, 4, N), torch.float32), "A": ((B, N), torch.float32), "rhs": ((B, 2, N), torch.float32),
+                  "ures": ((B, 2, N), torch.float32), "Poff": ((B, 4, N), torch.float32), "Pdiag": ((B, N), torch.float32),
+                  "hbya": ((B, 2, N), torch.float32), "div": ((B, N), torch.float32), "pres": ((B, N), torch.float32),
+                  "iters": ((B, 8), torch.int32), "resid": ((B, 8), torch.float32), "dt": ((B,), torch.float32),
+                  "active": ((B,), torch.int32), "remaining": ((B,), torch.float64), "nsub": ((B,), torch.int32),
+                  "maxvel": ((B,), torch.float32), "fluxbal": ((B,), torch.float32)}
+        shape, dtype = shapes[name]
+        ptr = self.lib.fgb_batch_buffer(self.handle, name.encode())
+        off = ptr - self.workspace.data_ptr()
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        return self.workspace[off:off + n].view(dtype).view(shape)
+
+    # ---- individual ops (names follow the PISOtorch free functions) --------------------------------
+    def _dt(self, dt):
+        if isinstance(dt, torch.Tensor):
+            return dt.to(self.device, torch.float32).contiguous()
+        return torch.full((self.B,), float(dt), device=self.device)
+
+    def setup_advection(self, dt, ures=None, active=None):
+        self._dtc = self._dt(dt)
+        native.check(self.lib.fgb_setup_advection(self.handle, _ptr(self.u), _ptr(ures), _ptr(self.bvel), _ptr(self.src),
+                                                  _ptr(self._dtc), _ptr(active), self.stream), "fgb_setup_advection")
+
+    def solve_advection(self, zero_init=True, active=None):
+        native.check(self.lib.fgb_solve_advection(self.handle, int(zero_init), _ptr(active), self.stream), "fgb_solve_advection")
+
+    def setup_pressure_matrix(self, active=None):
+        native.check(self.lib.fgb_setup_pressure_matrix(self.handle, _ptr(active), self.stream), "fgb_setup_pressure_matrix")
+
+    def setup_pressure_rhs(self, dt, p_prev=None, with_hbya=True, active=None):
+        self._dtc = self._dt(dt)
+        p_prev = self.p if p_prev is None else p_prev
+        native.check(self.lib.fgb_setup_pressure_rhs(self.handle, _ptr(self.u), _ptr(self.bvel), _ptr(self.src), _ptr(p_prev),
+                                                     _ptr(self._dtc), int(with_hbya), _ptr(active), self.stream), "fgb_setup_pressure_rhs")
+
+    def solve_pressure(self, p_out=None, zero_init=True, reset_steps=100, max_iter=None, active=None):
+        p_out = self.p if p_out is None else p_out
+        native.check(self.lib.fgb_solve_pressure(self.handle, _ptr(p_out), int(zero_init), reset_steps,
+                                                 max_iter or self.options.max_iter, _ptr(active), self.stream), "fgb_solve_pressure")
+
+    def correct_velocity(self, p=None, u_out=None, active=None):
+        p = self.p if p is None else p
+        u_out = self.buffer("ures") if u_out is None else u_out
+        native.check(self.lib.fgb_correct_velocity(self.handle, _ptr(p), _ptr(u_out), _ptr(active), self.stream), "fgb_correct_velocity")
+
+    # ---- fused level ------------------------------------------------------------------------------
+    def piso_substep(self, dt, active=None):
+        """``Simulation._PISO_split_step(iterations=1, time_step=dt)`` for every (active) environment."""
+        self._dtc = self._dt(dt)
+        native.check(self.lib.fgb_piso_substep(self.handle, _ptr(self.u), _ptr(self.p), _ptr(self.bvel), _ptr(self.src),
+                                               _ptr(self._dtc), _ptr(active), self.stream), "fgb_piso_substep")
+
+    def make_divergence_free(self, max_iter=1000):
+        native.check(self.lib.fgb_make_divergence_free(self.handle, _ptr(self.u), _ptr(self.p), _ptr(self.bvel), max_iter,
+                                                       self.stream), "fgb_make_divergence_free")
+
+    def update_outflow(self, dt, char_vel, tol=5e-6):
+        self._dtc = self._dt(dt)
+        cv = (C.c_float * 2)(*[float(x) for x in char_vel])
+        native.check(self.lib.fgb_update_outflow(self.handle, _ptr(self.u), _ptr(self.bvel), _ptr(self._dtc), cv, tol, self.stream),
+                     "fgb_update_outflow")
+
+    def single_step(self, dt, cfl=0.8, char_vel=None, bc_tol=5e-6) -> int:
+        """``Simulation.single_step()`` with adaptive CFL sub-stepping; returns the substep rounds used."""
+        cv = (C.c_float * 2)(*[float(x) for x in char_vel]) if char_vel is not None else None
+        n = C.c_int32(0)
+        native.check(self.lib.fgb_sim_step(self.handle, _ptr(self.u), _ptr(self.p), _ptr(self.bvel), _ptr(self.src), float(dt),
+                                           float(cfl), cv, float(bc_tol), C.byref(n), self.stream), "fgb_sim_step")
+        return n.value
+
+    def flux_balance(self) -> torch.Tensor:
+        out = torch.empty(self.B, device=self.device)
+        native.check(self.lib.fgb_flux_balance(self.handle, _ptr(self.bvel), _ptr(out), self.stream), "fgb_flux_balance")
+        return out
+
+    def max_velocity(self) -> torch.Tensor:
+        out = torch.empty(self.B, device=self.device)
+        native.check(self.lib.fgb_max_velocity(self.handle, _ptr(self.u), _ptr(self.bvel), _ptr(out), self.stream), "fgb_max_velocity")
+        return out

@@ -1,0 +1,170 @@
+/*
+ * fluidgym_b200 -- C ABI of the batched B200 (sm_100a) PISO solver step.
+ *
+ * This is the drop-in boundary for the fluid-solver step of FluidGym.  Each entry point names the
+ * reference interface it replaces (paths relative to /root/reference/src/fluidgym/):
+ *   BIND.cpp  = simulation/extensions/PISOtorch.cpp        (pybind11 module `PISOtorch`)
+ *   K.cu      = simulation/extensions/PISO_multiblock_cuda_kernel.cu
+ *   SIM.py    = simulation/pict/PISOtorch_simulation.py
+ *
+ * Differences by design: the reference ops work on ONE mutable Domain object (batch size 1,
+ * DS.cpp:1136) and synchronise the device around every launch; here every op advances B independent
+ * environments that share one geometry, takes raw device pointers + a CUDA stream, never synchronises
+ * and never allocates.  All arrays are float32 / int32, structure-of-arrays, environment-major:
+ *   u    [B][2][N]    cell velocity            (Block.velocity, all blocks concatenated)
+ *   p    [B][N]       cell pressure            (Block.pressure == Domain.pressureResult)
+ *   bvel [B][2][NB]   Dirichlet boundary velocity of every fixed-boundary face (FixedBoundary.velocity)
+ * plus per-environment scalars dt[B] (float) and active[B] (int32: 0 = skip this environment).
+ *
+ * Error handling: every function returns 0 on success, a negative FGB_E_* code otherwise;
+ * fgb_last_error() returns a static message for the calling thread.  No exceptions cross the ABI.
+ * There is NO CPU fallback: without a CUDA device every launch returns FGB_E_CUDA.
+ */
+#ifndef FLUIDGYM_B200_H
+#define FLUIDGYM_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGB_OK 0
+#define FGB_E_ARG -1
+#define FGB_E_CUDA -2
+#define FGB_E_WORKSPACE -3
+
+typedef void *fgb_stream_t; /* cudaStream_t */
+
+/* Geometry tables of one domain, produced on the host by fluidgym_b200.domain.CompiledDomain and
+ * uploaded by the caller.  ALL pointers are DEVICE pointers owned by the caller and must outlive the
+ * handle.  Replaces the packed DomainGPU/BlockGPU/BoundaryGPU atlas (DSG.h:160-397, DS.cpp:3055-3282). */
+typedef struct fgb_tables {
+    int32_t N, NB, K_no, K_nob;
+    float viscosity;
+    const int32_t *nbr;     /* [4][N]   neighbour cell across face f, or -1-j for boundary face j      */
+    const int8_t *fl_comp;  /* [4][N]   bit0: contravariant component of the neighbour, bit1: negate   */
+    const float *minv;      /* [4][N]   M^-1 row-major                                                  */
+    const float *det;       /* [N]                                                                      */
+    const float *Cd;        /* [5][N]   constant (diffusive + non-orthogonal) part of C, before /det    */
+    const float *Wp;        /* [25][N]  P_e = sum_j Wp[5e+j] * (1/A)_j, j=0 self, 1..4 face neighbours  */
+    const int32_t *no_idx;  /* [K_no][N] deferred non-orthogonal terms: cell index                      */
+    const int8_t *no_face;  /* [K_no][N] face whose neighbour 1/A enters the pressure weight           */
+    const float *no_gP;     /* [K_no][N]                                                                */
+    const float *no_gN;     /* [K_no][N] pressure weight = gP*(1/A)_P + gN*(1/A)_nbr(face)              */
+    const float *no_wv;     /* [K_no][N] velocity weight (viscosity folded in)                          */
+    const int32_t *nob_idx; /* [K_nob][N] boundary-face index                                           */
+    const float *nob_w;     /* [K_nob][N] weight of that boundary velocity in the velocity correction  */
+    const float *b_minv;    /* [4][NB]  boundary-face M^-1                                              */
+    const float *b_det;     /* [NB]                                                                     */
+    const float *b_alpha;   /* [NB]     det*|M^-1 row(axis)|^2 of the boundary face                     */
+    const int32_t *b_cell;  /* [NB]     cell adjacent to the boundary face                              */
+    const int8_t *b_face;   /* [NB]     face direction 0..3                                             */
+    const int8_t *b_out;    /* [NB]     1 = advective-outflow face (SIM.py:228-393), may be NULL        */
+} fgb_tables;
+
+typedef struct fgb_batch fgb_batch; /* opaque: tables + workspace carving for B environments */
+
+/* Solver options (Simulation ctor arguments, SIM.py:489-1037; defaults of CylinderEnvBase, CYL.py:303-332) */
+typedef struct fgb_options {
+    int32_t corrector_steps;        /* 2 */
+    int32_t adv_nonortho_steps;     /* 1 */
+    int32_t p_nonortho_steps;       /* 1 */
+    int32_t nonortho;               /* 1: flags CENTER_MATRIX|DIRECT_MATRIX|DIAGONAL_RHS, 0: orthogonal */
+    float adv_tol, p_tol;           /* 1e-5, 1e-5 : ||r||_2/sqrt(N) absolute (SIM.py:1096-1098)          */
+    int32_t max_iter;               /* 5000 */
+    int32_t cg_impl;                /* 0: one CTA per environment, vectors in global memory
+                                       1: thread-block cluster per environment, vectors on chip        */
+} fgb_options;
+
+const char *fgb_last_error(void);
+int fgb_version(void);
+
+/* bytes of device workspace fgb_batch_create needs for B environments */
+size_t fgb_workspace_bytes(const fgb_tables *t, int32_t B);
+/* workspace: device memory (>= fgb_workspace_bytes, 256-byte aligned) owned by the caller */
+int fgb_batch_create(const fgb_tables *t, int32_t B, void *workspace, size_t workspace_bytes,
+                     const fgb_options *opt, fgb_batch **out);
+void fgb_batch_destroy(fgb_batch *b);
+int fgb_batch_set_options(fgb_batch *b, const fgb_options *opt);
+
+/* Device pointer of a named intermediate inside the workspace (for parity tests and autograd glue):
+ * "Coff"[B][4][N] "A"[B][N] "rhs"[B][2][N] "ures"[B][2][N] "Poff"[B][4][N] "Pdiag"[B][N]
+ * "hbya"[B][2][N] "div"[B][N] "pres"[B][N] "iters"[B][8] int32 "resid"[B][8] "dt"[B] "active"[B] int32
+ * "remaining"[B] double "nsub"[B] int32 "maxvel"[B] "fluxbal"[B] */
+void *fgb_batch_buffer(fgb_batch *b, const char *name);
+
+/* ---- individual native ops (each replaces one PISOtorch free function) ------------------------- */
+/* SetupAdvectionMatrix + SetupAdvectionVelocity (BIND.cpp:518-579, K.cu:3617-3880, 4296-4400):
+ * C off-diagonals, A = diag(C), predictor right-hand side.  ures = velocity used in the deferred
+ * non-orthogonal term (u itself on the first non-orthogonal step). */
+int fgb_setup_advection(fgb_batch *b, const float *u, const float *ures, const float *bvel, const float *src,
+                        const float *dt, const int32_t *active, fgb_stream_t s);
+/* SolveLinear(C, velocityRHS, BiCG) (K.cu:7085-7118, BICG.cu:64-411) for both components; x=ures */
+int fgb_solve_advection(fgb_batch *b, int zero_init, const int32_t *active, fgb_stream_t s);
+/* SetupPressureMatrix (K.cu:4812-4978) */
+int fgb_setup_pressure_matrix(fgb_batch *b, const int32_t *active, fgb_stream_t s);
+/* SetupPressureRHS / SetupPressureRHSdiv (K.cu:5136-5255, 5389-5492); p_prev = pressureResult used
+ * by the deferred non-orthogonal correction; with_hbya=0 rebuilds only the divergence */
+int fgb_setup_pressure_rhs(fgb_batch *b, const float *u, const float *bvel, const float *src, const float *p_prev,
+                           const float *dt, int with_hbya, const int32_t *active, fgb_stream_t s);
+/* SolveLinear(P, pressureRHSdiv, CG, residual reset 100, best result) + mean removal (CG.cu:130-471,
+ * SIM.py:1908-1925). p_out may alias p_prev. */
+int fgb_solve_pressure(fgb_batch *b, float *p_out, int zero_init, int reset_steps, int max_iter,
+                       const int32_t *active, fgb_stream_t s);
+/* CorrectVelocity version 1 "FD" (K.cu:816-849, 5962-5995): u_out = HbyA - 1/A * M^-T grad p */
+int fgb_correct_velocity(fgb_batch *b, const float *p, float *u_out, const int32_t *active, fgb_stream_t s);
+
+/* ---- fused driver level (replaces the python loops of SIM.py) ----------------------------------- */
+/* Simulation._PISO_split_step(iterations=1) (SIM.py:1431-2002): one PISO substep of dt[e] for every
+ * active environment; u, p updated in place. */
+int fgb_piso_substep(fgb_batch *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
+                     const int32_t *active, fgb_stream_t s);
+/* Simulation.make_divergence_free (SIM.py:1320-1429): A=1, dt=1 projection of u (max_iter 1000). */
+int fgb_make_divergence_free(fgb_batch *b, float *u, float *p, const float *bvel, int max_iter, fgb_stream_t s);
+/* Simulation.single_step with substeps="ADAPTIVE" (FGSIM.py:210-280, SIM.py:2004-2064) including the
+ * advective-outflow "PRE" hook of the cylinder / airfoil environments (CYL.py:289-295, SIM.py:228-393)
+ * when the tables carry b_out and char_vel (HOST pointer, 2 floats) is given.  Returns in *substeps_max the largest number of substeps any
+ * environment needed (one small device->host read per substep round). */
+int fgb_sim_step(fgb_batch *b, float *u, float *p, float *bvel, const float *src, float dt_target, float cfl,
+                 const float *char_vel, float bc_tol, int32_t *substeps_max, fgb_stream_t s);
+
+/* update_advective_boundaries + balance_boundary_fluxes (SIM.py:188-224, 228-393) for the faces marked in
+ * tables.b_out, with the per-environment time step dt[B] (device).  char_vel: HOST pointer to the two
+ * components of the characteristic velocity (CYL.py:279-295). */
+int fgb_update_outflow(fgb_batch *b, const float *u, float *bvel, const float *dt, const float *char_vel, float bc_tol,
+                       fgb_stream_t s);
+/* Domain.GetBoundaryFluxBalance (DS.cpp:2476-2510): signed sum of boundary fluxes per environment */
+int fgb_flux_balance(fgb_batch *b, const float *bvel, float *out, fgb_stream_t s);
+/* Domain.getMaxVelocity(True, True) (DS.cpp:1580-1611, 2403-2411) */
+int fgb_max_velocity(fgb_batch *b, const float *u, const float *bvel, float *out, fgb_stream_t s);
+
+/* ---- environment glue ---------------------------------------------------------------------------- */
+/* jet actuation (CYL.py:748-753, jet_cylinder_env_2d.py:185-188): control = last + smoothing*(action-last);
+ * bvel[:, faces] = template * control.  faces/template are device arrays of n_faces entries. */
+int fgb_apply_jet_action(fgb_batch *b, float *bvel, float *last_control, const float *action, float smoothing,
+                         const int32_t *faces, const float *templ /*[2][n_faces]*/, int32_t n_faces, fgb_stream_t s);
+/* wall forces (CYL.py:657-698, forces.py:193-275): drag/lift coefficients of one sim step accumulated
+ * into acc[B][2].  Ring tables have n_wall entries (ordered around the body). */
+typedef struct fgb_wall {
+    int32_t n_wall;
+    const int32_t *cell;   /* [n] wall-adjacent cell   */
+    const int32_t *bface;  /* [n] boundary face index  */
+    const float *normal;   /* [2][n] into the fluid    */
+    const float *dist;     /* [n] wall distance        */
+    const float *tlen;     /* [n] tangent length       */
+    const float *flen;     /* [n] wall face length     */
+    float scale;           /* 1 / (0.5 U^2 D)          */
+} fgb_wall;
+int fgb_wall_forces(fgb_batch *b, const fgb_wall *w, const float *u, const float *p, const float *bvel,
+                    float *acc, fgb_stream_t s);
+/* sensor sampling (obs_extraction.py:10-57 -> resampling.cu:296-364): out[B][C][n_s] =
+ * sum_k w[k][s] * field[B][C][idx[k][s]] (the static splat+normalise+fill map evaluated at the sensors) */
+int fgb_sample_sensors(fgb_batch *b, const float *field, int32_t channels, const int32_t *idx, const float *w,
+                       int32_t K, int32_t n_sensors, float *out, fgb_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,89 @@
+"""Reduces the raw reference dumps of oracle/ref_harness.py (gpurun_out/golden/, produced by the
+UNMODIFIED reference on a B200) to the small flat fixtures committed next to this script.
+
+    python tests/golden/extract_fixtures.py [gpurun_out/golden] [CylinderJet2D_easy_v0]
+
+Layout of the fixtures = layout of the product: cells of all blocks concatenated (x fastest),
+fields component-major ``[2, N]``, boundary faces concatenated in (block, face) order ``[2, NB]``.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from fluidgym_b200.domain import FIXED  # noqa: E402
+from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain  # noqa: E402
+
+
+def main():
+    src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden"
+    tag = sys.argv[2] if len(sys.argv) > 2 else "CylinderJet2D_easy_v0"
+    out = "cyl24"
+    spec = make_cylinder_domain(24)
+    nb = len(spec.blocks)
+    faces = [(bi, f) for bi, b in enumerate(spec.blocks) for f in range(4) if b.bounds[f].type == FIXED]
+
+    def cells(d, key, comps):
+        return np.concatenate([d[key.format(bi)].reshape(comps, -1) for bi in range(nb)], axis=1).astype(np.float32)
+
+    def bfaces(d, key):
+        outv = []
+        for bi, f in faces:
+            v = d[key.format(bi, f)]
+            n = spec.blocks[bi].size(1 - (f >> 1))
+            v = v.reshape(2, -1)
+            outv.append(np.broadcast_to(v, (2, n)) if v.shape[1] == 1 else v)
+        return np.concatenate(outv, axis=1).astype(np.float32)
+
+    g = np.load(os.path.join(src, f"{tag}_geometry.npz"))
+    T = np.concatenate([g[f"b{bi}_transform"].reshape(-1, 9) for bi in range(nb)])
+    bT = np.concatenate([g[f"b{bi}_f{f}_transform"].reshape(-1, 9) for bi, f in faces])
+    np.savez_compressed(os.path.join(HERE, f"{out}_geometry.npz"), T=T, bT=bT)
+
+    tr = np.load(os.path.join(src, f"{tag}_trace.npz"))
+    meta = json.load(open(os.path.join(src, f"{tag}_meta.json")))
+    for s in (0, 1):
+        k = f"s{s}_"
+        fx = dict(
+            dt=tr[k + "dt"], u_in=cells(tr, k + "in_b{}_u", 2), p_in=cells(tr, k + "in_b{}_p", 1)[0],
+            bvel_in=bfaces(tr, k + "in_b{}_f{}_velocity"), presres_in=tr[k + "in_pressureResult"].ravel(),
+            C_value=tr[k + "C_value"], C_index=tr[k + "C_index"], C_row=tr[k + "C_row"], A=tr[k + "A"].ravel(),
+            rhs=tr[k + "velocityRHS0"].reshape(2, -1), ustar=tr[k + "solve0_x"].reshape(2, -1),
+            P_value=tr[k + "P_value0"], P_index=tr[k + "P_index"], P_row=tr[k + "P_row"],
+            hbya0=tr[k + "pressureRHS0"].reshape(2, -1), div0=tr[k + "pressureRHSdiv0"].ravel(),
+            p0=tr[k + "pressureResult0"].ravel(), u0=tr[k + "velocityResult0"].reshape(2, -1),
+            hbya1=tr[k + "pressureRHS1"].reshape(2, -1), div1=tr[k + "pressureRHSdiv1"].ravel(),
+            p1=tr[k + "pressureResult1"].ravel(), u1=tr[k + "velocityResult1"].reshape(2, -1),
+        )
+        its = [m for m in meta["trace_meta"] if m["substep"] == s]
+        fx["bicg_iters"] = np.array([i[1] for i in its[0]["infos"]])
+        fx["cg_iters"] = np.array([its[1]["infos"][0][1], its[2]["infos"][0][1]])
+        if s == 0:  # keep the first substep small: inputs + final outputs only
+            fx = {k2: fx[k2] for k2 in ("dt", "u_in", "p_in", "bvel_in", "presres_in", "u1", "p1", "bicg_iters", "cg_iters")}
+        np.savez_compressed(os.path.join(HERE, f"{out}_substep{s}.npz"), **fx)
+
+    rs = np.load(os.path.join(src, f"{tag}_state_reset.npz"))
+    np.savez_compressed(os.path.join(HERE, f"{out}_reset.npz"), u=cells(rs, "b{}_u", 2), p=cells(rs, "b{}_p", 1)[0],
+                        bvel=bfaces(rs, "b{}_f{}_velocity"), presres=rs["pressureResult"].ravel(),
+                        obs_velocity=rs["obs_velocity"], obs_pressure=rs["obs_pressure"])
+    st = np.load(os.path.join(src, f"{tag}_steps.npz"))
+    s0 = np.load(os.path.join(src, f"{tag}_simstep0.npz"))
+    e0 = np.load(os.path.join(src, f"{tag}_state_step0.npz"))
+    e3 = np.load(os.path.join(src, f"{tag}_state_step3.npz"))
+    fx = {k2: st[k2] for k2 in st.files}
+    fx.update(sim0_u=cells(s0, "b{}_u", 2), sim0_p=cells(s0, "b{}_p", 1)[0],
+              env0_u=cells(e0, "b{}_u", 2), env0_p=cells(e0, "b{}_p", 1)[0], env0_bvel=bfaces(e0, "b{}_f{}_velocity"),
+              env3_u=cells(e3, "b{}_u", 2), env3_p=cells(e3, "b{}_p", 1)[0])
+    np.savez_compressed(os.path.join(HERE, f"{out}_steps.npz"), **fx)
+    keep = {k2: meta[k2] for k2 in ("env", "seed", "torch", "gpu", "n_sim_steps", "dt", "viscosity", "timing",
+                                    "mean_iters", "max_iters", "n_solves", "substeps_in_env_steps", "reset_seconds")}
+    json.dump(keep, open(os.path.join(HERE, f"{out}_meta.json"), "w"), indent=1)
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()
