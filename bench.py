@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Benchmark of the fluid-solver step (BASELINE.json: env-steps/sec = PISO solver steps x envs per second).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (hand-written sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the unmodified reference on the same box
+
+One bench "step" = one RL ``env.step()`` of the whole batch = 25 solver (PISO) steps per environment incl.
+jet actuation, advective outflow update, drag/lift integration and sensor sampling.
+Workload (BASELINE.json configs[1]): CylinderJet2D-easy-v0 (5-block O-grid, 14 232 cells, fp32), 256
+environments per GPU, synthetic initial state = projected initial field + per-environment Gaussian noise,
+random jet actions.  Environments are independent -> weak scaling over GPUs with no collective on the
+data path.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENV_ID = "CylinderJet2D-easy-v0"
+METRIC = "env-steps/sec (solver steps x envs)"
+UNIT = "env-steps/s"
+CG_BYTES_PER_CELL_ITER = 64      # K_cg = S + 11 floats = 64 B per cell and iteration in 2-D
+BICG_BYTES_PER_CELL_ITER = 248   # K_bicg = D (2S + 21) floats
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            self.f.close()
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = [float(r[1]) for r in rows]
+            reasons = set()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for r in rows:
+                for k, nme in enumerate(names):
+                    if len(r) > 5 + k and r[5 + k].strip().lower() == "active":
+                        reasons.add(nme)
+            if sm:
+                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                       "samples": len(sm), "power_w_max": max(float(r[3]) for r in rows)}
+        except Exception as e:  # pragma: no cover
+            out["error"] = str(e)
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+def dist_setup(n_gpus):
+    import torch
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    return rank, world, local
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world, device):
+    import torch
+    if world == 1:
+        return float(x)
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world, device):
+    import torch
+    if world == 1:
+        return float(x)
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(env, n_sim_steps=12):
+    """CPU restatement (oracle/piso_oracle.c, single thread) timed on the host cores, starting from the state
+    of environment 0 after the GPU warm-up: a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import Oracle
+    cd = env.cd
+    s = env.solver
+    u = s.u[0].cpu().numpy().copy()
+    p = s.p[0].cpu().numpy().copy()
+    orc = Oracle(cd.sizes, cd.btype, cd.bconn, cd.T, cd.bT, s.bvel[0].cpu().numpy(), float(cd.visc))
+    out_mask = env.solver._tab["b_out"].cpu().numpy().astype(np.uint8)
+    t0 = time.perf_counter()
+    nsub = 0
+    for _ in range(n_sim_steps):
+        n, _, _ = orc.sim_step(u, p, env.dt, env.cfl, out_mask=out_mask, adj=cd.b_cell, char_vel=[1.0, 0.0])
+        nsub += n
+    el = time.perf_counter() - t0
+    return {"value": nsub / el, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n_sim_steps} solver steps of 1 environment (same grid/state as env 0 after warm-up), "
+                      f"oracle/piso_oracle.c single thread, {os.cpu_count()} host cores present"}
+
+
+def run_ours(args):
+    import torch
+    import fluidgym_b200
+    from fluidgym_b200 import native
+
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    B = args.envs
+    env = fluidgym_b200.make(ENV_ID, n_envs=B, device=str(dev), cg_impl=args.cg_impl)
+    N = env.cd.N
+    env.reset(seed=42 + rank)
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    env.solver.u += 0.025 * torch.randn(env.solver.u.shape, device=dev, generator=gen)
+    env.solver.p += 0.025 * torch.randn(env.solver.p.shape, device=dev, generator=gen)
+    cpu_gen = torch.Generator().manual_seed(7 + rank)
+    total = args.warmup + 2 * args.steps
+    actions_host = (torch.rand(total, B, 1, generator=cpu_gen) * 2 - 1).pin_memory()
+    actions_dev = actions_host.to(dev)
+    env.episode_length = 10 ** 9
+
+    for i in range(args.warmup):
+        env.step(actions_dev[i])
+    torch.cuda.synchronize()
+    lib, h = env.lib, env.solver.handle
+
+    # ---- kernel-resident timing: inputs already in HBM ------------------------------------------
+    it0 = env.solver.buffer("iter_total").view(torch.int64).clone()
+    l0 = lib.fgb_launch_count(h)
+    native.check(lib.fgb_profile_enable(h, 1), "profile_enable")
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    nsub = 0
+    for i in range(args.steps):
+        env.step(actions_dev[args.warmup + i])
+        nsub += env.last_substeps
+    e1.record()
+    barrier(world)
+    ms_local = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    ms_prof = (C.c_double * 4)()
+    cnt_prof = (C.c_int64 * 4)()
+    native.check(lib.fgb_profile_read(h, ms_prof, cnt_prof, 1), "profile_read")
+    native.check(lib.fgb_profile_enable(h, 0), "profile_enable")
+    launches = lib.fgb_launch_count(h) - l0
+    it1 = env.solver.buffer("iter_total").view(torch.int64).clone()
+    d_it = (it1 - it0).cpu().numpy().reshape(B, 2)
+    ms = max_over_ranks(ms_local, world, dev)
+    env_substeps = sum_over_ranks(B * nsub, world, dev)
+    value = env_substeps / (ms / 1e3)
+
+    # ---- end-to-end through the public API with host buffers --------------------------------------
+    obs_host = {"velocity": torch.empty(B, 151, 2).pin_memory(), "pressure": torch.empty(B, 151).pin_memory()}
+    rew_host = torch.empty(B).pin_memory()
+    barrier(world)
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    nsub_e = 0
+    for i in range(args.steps):
+        a = actions_host[args.warmup + args.steps + i].to(dev, non_blocking=True)
+        obs, rew, _, _, info = env.step(a)
+        obs_host["velocity"].copy_(obs["velocity"], non_blocking=True)
+        obs_host["pressure"].copy_(obs["pressure"], non_blocking=True)
+        rew_host.copy_(rew, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        nsub_e += env.last_substeps
+    t1.record()
+    barrier(world)
+    ms_e = max_over_ranks(t0.elapsed_time(t1), world, dev)
+    e2e_value = sum_over_ranks(B * nsub_e, world, dev) / (ms_e / 1e3)
+    h2d = B * 4
+    d2h = B * (151 * 2 + 151 + 1) * 4
+
+    # ---- roofline of the dominant kernel (pressure CG) ---------------------------------------------
+    peak, peak_src = peaks()
+    cg_ms, cg_launches = ms_prof[0], int(cnt_prof[0])
+    cg_bytes = float(d_it[:, 0].sum()) * N * CG_BYTES_PER_CELL_ITER
+    achieved = cg_bytes / (cg_ms / 1e3) / 1e9 if cg_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "cg_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roof = {"bound": "hbm", "kernel": "k_cg_cluster" if args.cg_impl == 1 else "k_cg", "achieved": achieved, "peak": peak,
+            "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "algorithmic_bytes_per_launch": cg_bytes / max(cg_launches, 1), "avg_launch_ms": cg_ms / max(cg_launches, 1),
+            "launches": cg_launches, "share_of_step": cg_ms / ms_local,
+            "note": "on-chip (cluster-resident) CG: algorithmic bytes are the SURVEY 8(d) streaming figure; measured DRAM "
+                    "traffic is far lower because x/r/p and the stencil stay in registers/shared memory"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{ENV_ID} x{B} envs per GPU (BASELINE.json configs[1]); step = env.step() = 25 PISO solver steps",
+                   "cells_per_env": N, "envs_per_gpu": B, "parallelism": f"env-batch x{world} (no collective)",
+                   "l2_policy": "working set 256 envs x 2.3 MB = 590 MB > 126 MB L2 (inputs larger than L2)",
+                   "cg_impl": args.cg_impl},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "solver": {"cg_iters_per_solve": float(d_it[:, 0].sum()) / max(B * nsub * 2, 1),
+                   "bicg_iters_per_rhs": float(d_it[:, 1].sum()) / max(B * nsub * 2, 1),
+                   "substeps_per_sim_step": nsub / (args.steps * env.n_sim_steps),
+                   "rl_env_steps_per_s": value / (env.n_sim_steps * max(nsub / (args.steps * env.n_sim_steps), 1e-9)),
+                   "time_share_ms": {"cg": ms_prof[0], "bicgstab": ms_prof[1], "assembly": ms_prof[2], "total": ms_local}},
+        "clocks": clk,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(env, args.cpu_steps)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """Reference arm.  The reference has NO CPU implementation of this path (FluidEnv.reset raises without
+    CUDA, envs/fluid_env.py:885-886): when the unmodified reference (baseline/_ref, built by
+    oracle/build_ref.sh) and a GPU are present it is run through its own public API (fluidgym.make ->
+    reset -> step, batch size 1: its native ops assert N == 1); otherwise the CPU oracle port is timed."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    kind = args.ref_kind
+    have_ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "fluidgym"))
+    import torch
+    if kind == "auto":
+        kind = "cuda" if (have_ref and torch.cuda.is_available()) else "cpu"
+    if kind == "cuda":
+        import ref_shims
+        ref_shims.install()
+        import fluidgym
+        from fluidgym.simulation.extensions import PISOtorch
+        env = fluidgym.make(ENV_ID, load_initial_domain=False, load_domain_statistics=False, randomize_initial_state=False)
+        env.reset(seed=42)
+        cnt = {"n": 0}
+        orig = PISOtorch.SetupAdvectionMatrix
+
+        def counted(*a, **k):
+            cnt["n"] += 1
+            return orig(*a, **k)
+
+        PISOtorch.SetupAdvectionMatrix = counted
+        g = torch.Generator().manual_seed(7)
+        acts = torch.rand(args.warmup + args.steps, 1, 1, generator=g) * 2 - 1
+        env._episode_length = 10 ** 9
+        for i in range(args.warmup):
+            env.step(acts[i, 0].to(env._cuda_device))
+        torch.cuda.synchronize()
+        cnt["n"] = 0
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            env.step(acts[args.warmup + i, 0].to(env._cuda_device))
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        value = cnt["n"] / el
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{ENV_ID} x1 env (the reference's native ops assert batch size 1; more envs = more "
+                                       f"OS processes, envs/parallel_env.py:162-175); step = env.step() = 25 PISO solver steps",
+                           "reference_kind": "unmodified reference CUDA extension compiled for sm_100 (baseline/_ref)"},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                                 "sample": f"{args.steps} env.step() of 1 environment through fluidgym.make/reset/step; the "
+                                           f"reference has no CPU solver, this is its CUDA path driven by its python loop"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+    # CPU oracle port
+    from fluidgym_b200.envs.cylinder_domain import WAKE, make_cylinder_domain
+    from oracle import Oracle
+    spec = make_cylinder_domain(24)
+    cd = spec.prepare()
+    orc = Oracle.from_compiled(cd)
+    u = np.zeros((2, cd.N), np.float32)
+    p = np.zeros(cd.N, np.float32)
+    out = np.zeros(cd.NB, np.uint8)
+    o = cd.boff[WAKE, 1]
+    out[o:o + spec.blocks[WAKE].ny] = 1
+    orc.update_outflow(u, out, cd.b_cell, [1.0, 0.0], 1.0, 5e-6)
+    orc.make_divergence_free(u, p, 1000)
+    per_step = max(1, args.cpu_steps // max(args.steps, 1))
+    for _ in range(args.warmup):
+        orc.sim_step(u, p, 0.01, 0.8, out_mask=out, adj=cd.b_cell, char_vel=[1.0, 0.0])
+    t0 = time.perf_counter()
+    nsub = 0
+    for _ in range(args.steps * per_step):
+        n, _, _ = orc.sim_step(u, p, 0.01, 0.8, out_mask=out, adj=cd.b_cell, char_vel=[1.0, 0.0])
+        nsub += n
+    el = time.perf_counter() - t0
+    value = nsub / el
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{ENV_ID} x1 env, {per_step} solver steps per bench step (bounded sample)",
+                       "reference_kind": "CPU oracle port (oracle/piso_oracle.c), the reference has no CPU path"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{args.steps * per_step} solver steps of 1 environment"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=256, help="environments per GPU")
+    ap.add_argument("--cg-impl", type=int, default=1)
+    ap.add_argument("--ref-kind", default="auto", choices=["auto", "cuda", "cpu"])
+    ap.add_argument("--cpu-steps", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,40 @@
+"""fluidgym_b200 -- B200-native (sm_100a) batched implementation of FluidGym's PISO solver step.
+
+Drop-in scope: the fluid-solver step behind ``fluidgym.make(...).step()`` --
+assembly, BiCGStab predictor, pressure CG, velocity correction, outflow / jet boundary conditions,
+drag-lift reward and sensor sampling -- for whole batches of environments per launch.
+"""
+from __future__ import annotations
+
+__version__ = "0.1.0"
+
+_REGISTRY = {}
+
+
+def register(env_id: str, entry_point, **defaults):
+    _REGISTRY[env_id] = (entry_point, defaults)
+
+
+def make(env_id: str, n_envs: int = 1, **kwargs):
+    """``fluidgym.make`` (registry.py:101-116) with an extra ``n_envs``: the returned environment steps
+    ``n_envs`` independent copies at once (the reference needs one OS process per copy,
+    envs/parallel_env.py:162-175)."""
+    if env_id not in _REGISTRY:
+        _register_defaults()
+    if env_id not in _REGISTRY:
+        raise KeyError(f"unknown environment id {env_id!r}; available: {sorted(_REGISTRY)}")
+    entry, defaults = _REGISTRY[env_id]
+    cfg = dict(defaults)
+    # reference-only constructor flags that have no meaning here are accepted and ignored
+    for k in ("load_initial_domain", "load_domain_statistics", "use_marl", "dtype", "differentiable"):
+        kwargs.pop(k, None)
+    cfg.update(kwargs)
+    return entry(n_envs=n_envs, **cfg)
+
+
+def _register_defaults():
+    from .envs.cylinder import CYLINDER_JET_2D_DEFAULT_CONFIG, CylinderJet2DEnv
+    # fluidgym/__init__.py:28-60: easy = Re 100 / res 24, medium = Re 250 / res 32, hard = Re 500 / res 32
+    register("CylinderJet2D-easy-v0", CylinderJet2DEnv, **CYLINDER_JET_2D_DEFAULT_CONFIG)
+    register("CylinderJet2D-medium-v0", CylinderJet2DEnv, **{**CYLINDER_JET_2D_DEFAULT_CONFIG, "reynolds_number": 250.0, "resolution": 32})
+    register("CylinderJet2D-hard-v0", CylinderJet2DEnv, **{**CYLINDER_JET_2D_DEFAULT_CONFIG, "reynolds_number": 500.0, "resolution": 32})

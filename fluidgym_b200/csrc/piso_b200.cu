@@ -48,7 +48,27 @@ struct fgb_batch {
     double *remaining;
     int32_t *iters, *active, *nsub, *counters;
     int32_t *h_counters;  // pinned host mirror
-    int cluster_ok;
+    unsigned long long *iter_total;   // [B][2] accumulated Krylov iterations (cg, bicgstab)
+    long long launches;               // kernels launched through this handle
+    // optional CUDA-event profiling of the solver launches (bench.py roofline)
+    int prof_on;
+    static const int PROF_MAX = 8192;
+    cudaEvent_t *prof_ev;             // [PROF_MAX][2]
+    int *prof_cls;                    // class of each recorded pair
+    int prof_n;
+};
+enum { CLS_CG = 0, CLS_BICG = 1, CLS_ASM = 2, CLS_OTHER = 3 };
+struct ProfScope {
+    fgb_batch *b; cudaStream_t st; int idx;
+    ProfScope(fgb_batch *b_, int cls, cudaStream_t st_) : b(b_), st(st_), idx(-1) {
+        b->launches++;
+        if (b->prof_on && b->prof_n < fgb_batch::PROF_MAX) {
+            idx = b->prof_n++;
+            b->prof_cls[idx] = cls;
+            cudaEventRecord(b->prof_ev[2 * idx], st);
+        }
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(b->prof_ev[2 * idx + 1], st); }
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -70,6 +90,7 @@ static void carve(fgb_batch *b, char *base, size_t *total) {
     b->fluxbal = c.take<float>(b->B); b->remaining = c.take<double>(b->B);
     b->iters = c.take<int32_t>(8 * (size_t)b->B); b->active = c.take<int32_t>(b->B); b->nsub = c.take<int32_t>(b->B);
     b->counters = c.take<int32_t>(64);
+    b->iter_total = c.take<unsigned long long>(2 * (size_t)b->B);
     *total = c.off;
 }
 
@@ -108,8 +129,37 @@ extern "C" int fgb_batch_create(const fgb_tables *t, int32_t B, void *workspace,
 extern "C" void fgb_batch_destroy(fgb_batch *b) {
     if (!b) return;
     if (b->h_counters) cudaFreeHost(b->h_counters);
+    if (b->prof_ev) { for (int i = 0; i < 2 * fgb_batch::PROF_MAX; ++i) cudaEventDestroy(b->prof_ev[i]); delete[] b->prof_ev; delete[] b->prof_cls; }
     delete b;
 }
+extern "C" int fgb_profile_enable(fgb_batch *b, int on) {
+    if (!b) return set_err(FGB_E_ARG, "fgb_profile_enable: null argument");
+    if (on && !b->prof_ev) {
+        b->prof_ev = new cudaEvent_t[2 * fgb_batch::PROF_MAX];
+        b->prof_cls = new int[fgb_batch::PROF_MAX];
+        for (int i = 0; i < 2 * fgb_batch::PROF_MAX; ++i) {
+            cudaError_t ce = cudaEventCreate(&b->prof_ev[i]);
+            if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaEventCreate", ce);
+        }
+    }
+    b->prof_on = on; b->prof_n = 0;
+    return FGB_OK;
+}
+extern "C" int fgb_profile_read(fgb_batch *b, double *ms_out, int64_t *count_out, int reset) {
+    if (!b || !ms_out || !count_out) return set_err(FGB_E_ARG, "fgb_profile_read: null argument");
+    for (int k = 0; k < 4; ++k) { ms_out[k] = 0.0; count_out[k] = 0; }
+    cudaError_t ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "fgb_profile_read: sync", ce);
+    for (int i = 0; i < b->prof_n; ++i) {
+        float ms = 0.f;
+        ce = cudaEventElapsedTime(&ms, b->prof_ev[2 * i], b->prof_ev[2 * i + 1]);
+        if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaEventElapsedTime", ce);
+        ms_out[b->prof_cls[i]] += ms; count_out[b->prof_cls[i]] += 1;
+    }
+    if (reset) b->prof_n = 0;
+    return FGB_OK;
+}
+extern "C" long long fgb_launch_count(fgb_batch *b) { return b ? b->launches : 0; }
 extern "C" int fgb_batch_set_options(fgb_batch *b, const fgb_options *opt) {
     if (!b || !opt) return set_err(FGB_E_ARG, "fgb_batch_set_options: bad argument");
     b->opt = *opt; return FGB_OK;
@@ -118,7 +168,7 @@ extern "C" void *fgb_batch_buffer(fgb_batch *b, const char *name) {
     if (!b || !name) return nullptr;
 #define BUF(n) if (!strcmp(name, #n)) return (void *)b->n;
     BUF(Coff) BUF(A) BUF(rhs) BUF(ures) BUF(Poff) BUF(Pdiag) BUF(hbya) BUF(div) BUF(pres) BUF(kry)
-    BUF(iters) BUF(resid) BUF(dt) BUF(active) BUF(remaining) BUF(nsub) BUF(maxvel) BUF(fluxbal) BUF(counters)
+    BUF(iter_total) BUF(iters) BUF(resid) BUF(dt) BUF(active) BUF(remaining) BUF(nsub) BUF(maxvel) BUF(fluxbal) BUF(counters)
 #undef BUF
     return nullptr;
 }
@@ -418,7 +468,8 @@ template <int T>
 __global__ void __launch_bounds__(T) k_bicgstab(Tab t, const float *__restrict__ Coff, const float *__restrict__ Adiag,
                                                  const float *__restrict__ Rhs, float *__restrict__ X, float *__restrict__ work,
                                                  int maxit, float tol, int zero_init, const int32_t *__restrict__ active,
-                                                 int32_t *__restrict__ iters, float *__restrict__ resid) {
+                                                 int32_t *__restrict__ iters, float *__restrict__ resid,
+                                                 unsigned long long *__restrict__ iter_total) {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     __shared__ double red[32 * 4 + 4];
@@ -509,6 +560,7 @@ __global__ void __launch_bounds__(T) k_bicgstab(Tab t, const float *__restrict__
     if (threadIdx.x == 0) {
         iters[b * 8 + 0] = used[0]; iters[b * 8 + 1] = used[1];
         resid[b * 8 + 0] = fin[0]; resid[b * 8 + 1] = fin[1];
+        iter_total[b * 2 + 1] += (unsigned long long)(used[0] + 1 + used[1] + 1);
     }
 }
 
@@ -517,7 +569,8 @@ template <int T>
 __global__ void __launch_bounds__(T) k_cg(Tab t, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
                                            const float *__restrict__ Rhs, float *__restrict__ Xout, float *__restrict__ work,
                                            int maxit, float tol, int zero_init, int reset_steps, int slot,
-                                           const int32_t *__restrict__ active, int32_t *__restrict__ iters, float *__restrict__ resid) {
+                                           const int32_t *__restrict__ active, int32_t *__restrict__ iters, float *__restrict__ resid,
+                                           unsigned long long *__restrict__ iter_total) {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     __shared__ double red[32 * 2 + 2];
@@ -601,7 +654,7 @@ __global__ void __launch_bounds__(T) k_cg(Tab t, const float *__restrict__ Poff,
     block_reduce_sum<2>(acc, red);
     const float mean = acc[0] / (float)N;
     for (int g = threadIdx.x; g < N; g += T) xo[g] = x[g] - mean;
-    if (threadIdx.x == 0) { iters[b * 8 + 2 + slot] = used; resid[b * 8 + 2 + slot] = fin; }
+    if (threadIdx.x == 0) { iters[b * 8 + 2 + slot] = used; resid[b * 8 + 2 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -627,30 +680,45 @@ __device__ __forceinline__ void st_dsmem_f64x2(uint32_t addr, double a, double b
     asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
 }
 
-template <int T, int CPT, int CS>
+__device__ __forceinline__ void st_dsmem_f32x2(uint32_t addr, float a, float b) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() { cluster_arrive_release(); cluster_wait_acquire(); }
+
+// VARIANT: 0 = textbook recurrence of the reference (A*p applied to the search direction, 3 cluster
+// barriers per iteration); 1 = A*p obtained from the recurrence Ap <- A*r + beta*Ap (mathematically
+// identical, 2 cluster barriers per iteration, p and Ap never leave registers).
+// Cells are padded to T*CPT per CTA: padding cells carry zero coefficients / zero data so the inner loops
+// need no bounds predicates.
+template <int T, int CPT, int CS, int VARIANT>
 __global__ void __launch_bounds__(T, 1) k_cg_cluster(Tab t, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
                                                       const float *__restrict__ Rhs, float *__restrict__ Xout,
                                                       int maxit, float tol, int zero_init, int reset_steps, int slot,
                                                       const int32_t *__restrict__ active, int32_t *__restrict__ iters,
-                                                      float *__restrict__ resid) {
-    cg::cluster_group cluster = cg::this_cluster();
+                                                      float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
+    constexpr int NW = T / 32;                  // warps per CTA
+    constexpr int NP = NW * CS;                 // warp partials per cluster-wide reduction
+    constexpr int PAD = T * CPT;                // padded cells per CTA
+    static_assert(NP <= 64, "final reduction reads two partials per lane");
     const int b = blockIdx.x / CS;
-    const int rank = (int)cluster.block_rank();
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     if (active && !active[b]) return;  // uniform over the cluster
     extern __shared__ __align__(16) float smem[];
     const int N = t.N;
     const int per = (N + CS - 1) / CS;          // cells owned per CTA
-    const int per_pad = (per + 3) & ~3;
-    const int start = rank * per;
+    const int start = (int)rank * per;
     const int cnt = max(0, min(per, N - start));
-    float *ps = smem;                            // [per_pad] search direction of the owned cells
-    float *bs = smem + per_pad;                  // [per_pad] best iterate of the owned cells
-    double *red = (double *)(smem + 2 * per_pad);        // [2 parity][CS][2] partial sums written by the peers
-    double *wred = red + 2 * CS * 2;                      // [32*2+2] intra-block reduction scratch
+    float *vs = smem;                            // [PAD] vector exposed to the neighbours (p, or r in variant 1)
+    float *bs = smem + PAD;                      // [PAD] best iterate of the owned cells
+    float *red = smem + 2 * PAD;                 // [2 parity][NP] warp partials written by every warp of the cluster
     const float *off = Poff + (size_t)b * 4 * N, *dg = Pdiag + (size_t)b * N, *f = Rhs + (size_t)b * N;
     float *xo = Xout + (size_t)b * N;
     const float norm = 1.0f / sqrtf((float)N);
-    const uint32_t ps_addr = smem_u32(ps), red_addr = smem_u32(red);
+    const uint32_t vs_addr = smem_u32(vs), red_addr = smem_u32(red);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // registers: stencil coefficients, cluster-shared addresses of the 4 neighbours, x, r
     float cd[CPT], co[CPT][4], xr[CPT], rr[CPT];
@@ -662,43 +730,49 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster(Tab t, const float *__restr
         const bool ok = l < cnt;
         cd[k] = ok ? dg[g] : 0.f;
         xr[k] = (ok && !zero_init) ? xo[g] : 0.f;
+        vs[l] = 0.f; bs[l] = 0.f;
 #pragma unroll
         for (int ff = 0; ff < 4; ++ff) {
             const int nb = ok ? t.nbr[ff * N + g] : -1;
             co[k][ff] = (ok && nb >= 0) ? off[ff * N + g] : 0.f;
             const int gi = nb >= 0 ? nb : (ok ? g : start);   // coefficient is 0 for absent neighbours
             const int c = gi / per;
-            na[k][ff] = mapa_u32(ps_addr + 4u * (uint32_t)(gi - c * per), (uint32_t)c);
+            na[k][ff] = mapa_u32(vs_addr + 4u * (uint32_t)(gi - c * per), (uint32_t)c);
         }
     }
     int parity = 0;
-    // cluster-wide sum of two values: block reduction, DSMEM scatter of the partials, one cluster barrier
-    auto cluster_sum2 = [&](float a0, float a1, float &o0, float &o1) {
-        float v[2] = {a0, a1};
-        block_reduce_sum<2>(v, wred);
-        if (threadIdx.x < CS)
-            st_dsmem_f64x2(mapa_u32(red_addr + 16u * (uint32_t)(parity * CS + rank), threadIdx.x), (double)v[0], (double)v[1]);
-        cluster.sync();
-        double s0 = 0.0, s1 = 0.0;
+    // Cluster-wide sum with ONE cluster barrier and no block barrier: every warp pushes its partial into
+    // the reduction slots of all CTAs through DSMEM; after the barrier every warp folds the NP partials
+    // with the same butterfly, so all threads of the cluster obtain bit-identical totals.
+    auto cluster_sum = [&](float a0) -> float {
 #pragma unroll
-        for (int c = 0; c < CS; ++c) { s0 += red[(parity * CS + c) * 2]; s1 += red[(parity * CS + c) * 2 + 1]; }
+        for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        if (lane < CS) {
+            const uint32_t ra = mapa_u32(red_addr + 4u * (uint32_t)(parity * NP + (int)rank * NW + warp), (uint32_t)lane);
+            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(a0) : "memory");
+        }
+        cluster_sync_all();
+        const float *rp = red + parity * NP;
+        float s0 = lane < NP ? rp[lane] : 0.f;
+        if (NP > 32) s0 += (lane + 32 < NP) ? rp[lane + 32] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
         parity ^= 1;
-        o0 = (float)s0; o1 = (float)s1;
+        return s0;
     };
-    auto apply = [&](int k) -> float {   // row k of P times the vector currently held in ps (cluster wide)
-        const int l = threadIdx.x + k * T;
-        float s = cd[k] * ps[l < cnt ? l : 0];
+    auto apply = [&](int k) -> float {   // row k of P times the vector currently exposed in vs (cluster wide)
+        float s = cd[k] * vs[threadIdx.x + k * T];
 #pragma unroll
         for (int ff = 0; ff < 4; ++ff) s += co[k][ff] * ld_dsmem_f32(na[k][ff]);
-        return l < cnt ? s : 0.f;
+        return s;
     };
+    auto load_f = [&](int k) -> float { const int l = threadIdx.x + k * T; return l < cnt ? f[start + l] : 0.f; };
 
     // all-zero right-hand side -> result zero (DIFF.py:392, 489-490)
-    float nz = 0.f, dummy;
+    float nz = 0.f;
 #pragma unroll
-    for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; nz += (l < cnt && f[start + l] != 0.f) ? 1.f : 0.f; }
-    float nzt;
-    cluster_sum2(nz, 0.f, nzt, dummy);
+    for (int k = 0; k < CPT; ++k) nz += (load_f(k) != 0.f) ? 1.f : 0.f;
+    const float nzt = cluster_sum(nz);           // the barrier also orders the zero-fill of vs/bs
     int used = -1; float fin = 0.f;
     if (!(nzt > 0.f)) {
 #pragma unroll
@@ -707,90 +781,102 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster(Tab t, const float *__restr
         // r0 = f - P x0
         if (!zero_init) {
 #pragma unroll
-            for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) ps[l] = xr[k]; }
-            cluster.sync();
+            for (int k = 0; k < CPT; ++k) vs[threadIdx.x + k * T] = xr[k];
+            cluster_sync_all();
 #pragma unroll
-            for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; rr[k] = (l < cnt ? f[start + l] : 0.f) - apply(k); }
-            cluster.sync();
+            for (int k = 0; k < CPT; ++k) rr[k] = load_f(k) - apply(k);
+            cluster_sync_all();
         } else {
 #pragma unroll
-            for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; rr[k] = l < cnt ? f[start + l] : 0.f; }
+            for (int k = 0; k < CPT; ++k) rr[k] = load_f(k);
         }
         float a0 = 0.f;
 #pragma unroll
-        for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) { ps[l] = rr[k]; bs[l] = xr[k]; } a0 += rr[k] * rr[k]; }
-        float rho;
-        cluster_sum2(a0, 0.f, rho, dummy);   // the barrier inside also publishes ps
+        for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; vs[l] = rr[k]; bs[l] = xr[k]; a0 += rr[k] * rr[k]; }
+        float rho = cluster_sum(a0);             // the barrier inside also publishes vs (= r0 = p0)
         float bestc = 0.f, lastc = 0.f; int best_it = -1, rising = 0;
+        float pk[CPT], apk[CPT];                 // search direction and A*p of the owned cells
+        float beta = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) { pk[k] = 0.f; apk[k] = 0.f; }
         for (int i = 0; i < maxit; ++i) {
             if (reset_steps > 0 && (i + 1) % reset_steps == 0) {
                 // r = f - P x ; p = r ; rho = <r,r>   (CG.cu:281-302)
+                cluster_sync_all();              // everyone is done reading vs
 #pragma unroll
-                for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) ps[l] = xr[k]; }
-                cluster.sync();
+                for (int k = 0; k < CPT; ++k) vs[threadIdx.x + k * T] = xr[k];
+                cluster_sync_all();
 #pragma unroll
-                for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; rr[k] = (l < cnt ? f[start + l] : 0.f) - apply(k); }
-                cluster.sync();
+                for (int k = 0; k < CPT; ++k) rr[k] = load_f(k) - apply(k);
+                cluster_sync_all();
                 a0 = 0.f;
 #pragma unroll
-                for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) ps[l] = rr[k]; a0 += rr[k] * rr[k]; }
-                cluster_sum2(a0, 0.f, rho, dummy);
+                for (int k = 0; k < CPT; ++k) { vs[threadIdx.x + k * T] = rr[k]; a0 += rr[k] * rr[k]; }
+                rho = cluster_sum(a0);
+                beta = 0.f;
             }
-            float apk[CPT];
             a0 = 0.f;
+            if (VARIANT == 0) {
 #pragma unroll
-            for (int k = 0; k < CPT; ++k) {
-                const int l = threadIdx.x + k * T;
-                apk[k] = apply(k);
-                a0 += (l < cnt ? ps[l] : 0.f) * apk[k];
+                for (int k = 0; k < CPT; ++k) {
+                    apk[k] = apply(k);
+                    pk[k] = vs[threadIdx.x + k * T];
+                    a0 += pk[k] * apk[k];
+                }
+            } else {
+                // vs holds r:  Ap <- A r + beta Ap ,  p <- r + beta p   (beta = 0 right after (re)starts)
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    apk[k] = apply(k) + beta * apk[k];
+                    pk[k] = rr[k] + beta * pk[k];
+                    a0 += pk[k] * apk[k];
+                }
             }
-            float pap;
-            cluster_sum2(a0, 0.f, pap, dummy);   // after this barrier every CTA has finished reading ps
+            const float pap = cluster_sum(a0);   // after this barrier every CTA has finished reading vs
             const float alpha = rho / pap;
             a0 = 0.f;
 #pragma unroll
             for (int k = 0; k < CPT; ++k) {
-                const int l = threadIdx.x + k * T;
-                const float pk = l < cnt ? ps[l] : 0.f;
-                xr[k] += alpha * pk;
+                xr[k] += alpha * pk[k];
                 rr[k] -= alpha * apk[k];
                 a0 += rr[k] * rr[k];
+                if (VARIANT == 1) vs[threadIdx.x + k * T] = rr[k];   // published by the barrier of the next reduction
             }
-            float rr2;
-            cluster_sum2(a0, 0.f, rr2, dummy);
+            const float rr2 = cluster_sum(a0);
             const float crit = sqrtf(rr2) * norm;
             if (!isfinite(crit)) { used = i; fin = crit; break; }
             if (i == 0 || crit < bestc) {
                 bestc = crit; best_it = i;
 #pragma unroll
-                for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) bs[l] = xr[k]; }
+                for (int k = 0; k < CPT; ++k) bs[threadIdx.x + k * T] = xr[k];
             }
             if (i > 0 && crit >= lastc) ++rising; else rising = 0;
             lastc = crit; used = i; fin = crit;
             if (crit < tol) break;
             if (i == maxit - 1 || rising >= 100) {
 #pragma unroll
-                for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; xr[k] = l < cnt ? bs[l] : 0.f; }
+                for (int k = 0; k < CPT; ++k) xr[k] = bs[threadIdx.x + k * T];
                 used = best_it; fin = bestc;
                 break;
             }
-            const float beta = rr2 / rho;
+            beta = rr2 / rho;
             rho = rr2;
+            if (VARIANT == 0) {
 #pragma unroll
-            for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) ps[l] = rr[k] + beta * ps[l]; }
-            cluster.sync();   // new p visible cluster wide
+                for (int k = 0; k < CPT; ++k) vs[threadIdx.x + k * T] = rr[k] + beta * pk[k];
+                cluster_sync_all();   // new p visible cluster wide
+            }
         }
     }
     // mean removal
-    float sx = 0.f, mean_sum;
+    float sx = 0.f;
 #pragma unroll
-    for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; sx += l < cnt ? xr[k] : 0.f; }
-    cluster_sum2(sx, 0.f, mean_sum, dummy);
-    const float mean = mean_sum / (float)N;
+    for (int k = 0; k < CPT; ++k) sx += xr[k];
+    const float mean = cluster_sum(sx) / (float)N;
 #pragma unroll
     for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) xo[start + l] = xr[k] - mean; }
-    if (threadIdx.x == 0 && rank == 0) { iters[b * 8 + 2 + slot] = used; resid[b * 8 + 2 + slot] = fin; }
-    cluster.sync();   // keep peer shared memory alive until everyone is done
+    if (threadIdx.x == 0 && rank == 0) { iters[b * 8 + 2 + slot] = used; resid[b * 8 + 2 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1); }
+    cluster_sync_all();   // keep peer shared memory alive until everyone is done
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -989,19 +1075,22 @@ static inline dim3 cell_grid(const fgb_batch *b) { return dim3((b->t.N + 255) / 
 extern "C" int fgb_setup_advection(fgb_batch *b, const float *u, const float *ures, const float *bvel, const float *src,
                                    const float *dt, const int32_t *active, fgb_stream_t s) {
     if (!b || !u || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_setup_advection: null argument");
+    ProfScope ps(b, CLS_ASM, STREAM(s));
     k_setup_advection<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, u, ures ? ures : u, bvel, src, dt, active, b->Coff, b->A, b->rhs, 1);
     LAUNCH_CHECK("k_setup_advection");
     return FGB_OK;
 }
 extern "C" int fgb_solve_advection(fgb_batch *b, int zero_init, const int32_t *active, fgb_stream_t s) {
     if (!b) return set_err(FGB_E_ARG, "fgb_solve_advection: null argument");
+    ProfScope ps(b, CLS_BICG, STREAM(s));
     k_bicgstab<1024><<<b->B, 1024, 0, STREAM(s)>>>(b->t, b->Coff, b->A, b->rhs, b->ures, b->kry, b->opt.max_iter, b->opt.adv_tol,
-                                                   zero_init, active, b->iters, b->resid);
+                                                   zero_init, active, b->iters, b->resid, b->iter_total);
     LAUNCH_CHECK("k_bicgstab");
     return FGB_OK;
 }
 extern "C" int fgb_setup_pressure_matrix(fgb_batch *b, const int32_t *active, fgb_stream_t s) {
     if (!b) return set_err(FGB_E_ARG, "fgb_setup_pressure_matrix: null argument");
+    ProfScope ps(b, CLS_ASM, STREAM(s));
     k_setup_pressure_matrix<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, b->A, active, b->Poff, b->Pdiag);
     LAUNCH_CHECK("k_setup_pressure_matrix");
     return FGB_OK;
@@ -1009,8 +1098,10 @@ extern "C" int fgb_setup_pressure_matrix(fgb_batch *b, const int32_t *active, fg
 extern "C" int fgb_setup_pressure_rhs(fgb_batch *b, const float *u, const float *bvel, const float *src, const float *p_prev,
                                       const float *dt, int with_hbya, const int32_t *active, fgb_stream_t s) {
     if (!b || !bvel) return set_err(FGB_E_ARG, "fgb_setup_pressure_rhs: null argument");
+    ProfScope ps(b, CLS_ASM, STREAM(s));
     if (with_hbya) {
         if (!u || !dt) return set_err(FGB_E_ARG, "fgb_setup_pressure_rhs: u/dt required with_hbya");
+        b->launches++;
         k_hbya<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, u, b->ures, bvel, src, b->Coff, b->A, dt, active, b->hbya);
         LAUNCH_CHECK("k_hbya");
     }
@@ -1020,15 +1111,15 @@ extern "C" int fgb_setup_pressure_rhs(fgb_batch *b, const float *u, const float 
     return FGB_OK;
 }
 
-template <int CS, int CPT>
+template <int CS, int CPT, int VARIANT>
 static int launch_cg_cluster(fgb_batch *b, float *p_out, int zero_init, int reset_steps, int max_iter, int slot,
                              const int32_t *active, cudaStream_t st) {
     constexpr int T = 512;
     const int N = b->t.N;
     const int per = (N + CS - 1) / CS;
     if (per > T * CPT) return 1;  // does not fit this instantiation
-    const size_t smem = (size_t)((per + 3) & ~3) * 2 * 4 + (2 * CS * 2 + 32 * 2 + 2 + 2) * sizeof(double);
-    auto kern = k_cg_cluster<T, CPT, CS>;
+    const size_t smem = ((size_t)2 * T * CPT + (size_t)2 * (T / 32) * CS) * sizeof(float) + 16;
+    auto kern = k_cg_cluster<T, CPT, CS, VARIANT>;
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_cg_cluster)", ce);
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
@@ -1038,7 +1129,7 @@ static int launch_cg_cluster(fgb_batch *b, float *p_out, int zero_init, int rese
     attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     ce = cudaLaunchKernelEx(&cfg, kern, b->t, (const float *)b->Poff, (const float *)b->Pdiag, (const float *)b->div, p_out,
-                            max_iter, b->opt.p_tol, zero_init, reset_steps, slot, active, b->iters, b->resid);
+                            max_iter, b->opt.p_tol, zero_init, reset_steps, slot, active, b->iters, b->resid, b->iter_total);
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchKernelEx(k_cg_cluster)", ce);
     return FGB_OK;
 }
@@ -1047,15 +1138,21 @@ static int solve_pressure_slot(fgb_batch *b, float *p_out, int zero_init, int re
                                const int32_t *active, fgb_stream_t s) {
     if (!b || !p_out) return set_err(FGB_E_ARG, "fgb_solve_pressure: null argument");
     if (slot < 0 || slot > 5) slot = 5;
-    if (b->opt.cg_impl == 1) {
-        int rc = launch_cg_cluster<2, 6>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
-        if (rc == 1) rc = launch_cg_cluster<4, 7>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
-        if (rc == 1) rc = launch_cg_cluster<8, 7>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+    ProfScope ps(b, CLS_CG, STREAM(s));
+    if (b->opt.cg_impl == 1 || b->opt.cg_impl == 2) {
+        int rc;
+        if (b->opt.cg_impl == 1) {
+            rc = launch_cg_cluster<2, 6, 0>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+            if (rc == 1) rc = launch_cg_cluster<4, 7, 0>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        } else {
+            rc = launch_cg_cluster<2, 6, 1>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+            if (rc == 1) rc = launch_cg_cluster<4, 7, 1>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        }
         if (rc <= 0) return rc;
-        // too large for the on-chip variant: fall through to the global-memory kernel
+        // too large for the on-chip variants: fall through to the global-memory kernel
     }
     k_cg<1024><<<b->B, 1024, 0, STREAM(s)>>>(b->t, b->Poff, b->Pdiag, b->div, p_out, b->kry, max_iter, b->opt.p_tol, zero_init,
-                                             reset_steps, slot, active, b->iters, b->resid);
+                                             reset_steps, slot, active, b->iters, b->resid, b->iter_total);
     LAUNCH_CHECK("k_cg");
     return FGB_OK;
 }
@@ -1065,6 +1162,7 @@ extern "C" int fgb_solve_pressure(fgb_batch *b, float *p_out, int zero_init, int
 }
 extern "C" int fgb_correct_velocity(fgb_batch *b, const float *p, float *u_out, const int32_t *active, fgb_stream_t s) {
     if (!b || !p || !u_out) return set_err(FGB_E_ARG, "fgb_correct_velocity: null argument");
+    ProfScope ps(b, CLS_ASM, STREAM(s));
     k_correct_velocity<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, b->hbya, p, b->A, active, u_out);
     LAUNCH_CHECK("k_correct_velocity");
     return FGB_OK;
@@ -1079,6 +1177,7 @@ extern "C" int fgb_piso_substep(fgb_batch *b, float *u, float *p, const float *b
     const int N = b->t.N;
     // predictor (SIM.py:1662-1757)
     for (int ns = 0; ns < o.adv_nonortho_steps; ++ns) {
+        b->launches++;
         k_setup_advection<<<cell_grid(b), 256, 0, st>>>(b->t, u, ns == 0 ? u : b->ures, bvel, src, dt, active, b->Coff, b->A, b->rhs, ns == 0);
         LAUNCH_CHECK("k_setup_advection");
         if ((rc = fgb_solve_advection(b, ns == 0, active, s))) return rc;
@@ -1103,6 +1202,7 @@ extern "C" int fgb_make_divergence_free(fgb_batch *b, float *u, float *p, const 
     cudaStream_t st = STREAM(s);
     const size_t BN = (size_t)b->B * b->t.N;
     int rc;
+    b->launches += 2;
     k_fill<<<(unsigned)((BN + 255) / 256), 256, 0, st>>>(b->A, 1.0f, BN);
     LAUNCH_CHECK("k_fill");
     cudaError_t ce = cudaMemcpyAsync(b->hbya, u, 2 * BN * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -1119,12 +1219,14 @@ extern "C" int fgb_sim_step(fgb_batch *b, float *u, float *p, float *bvel, const
                             const float *char_vel, float bc_tol, int32_t *substeps_max, fgb_stream_t s) {
     if (!b || !u || !p || !bvel) return set_err(FGB_E_ARG, "fgb_sim_step: null argument");
     cudaStream_t st = STREAM(s);
+    b->launches++;
     k_set_remaining<<<(b->B + 255) / 256, 256, 0, st>>>(b->remaining, b->nsub, b->counters, (double)dt_target, b->B);
     LAUNCH_CHECK("k_set_remaining");
     const int do_out = (char_vel != nullptr) && (b->t.b_out != nullptr);
     int rounds = 0;
     for (;; ++rounds) {
         if (rounds > 1000) return set_err(FGB_E_ARG, "fgb_sim_step: more than 1000 adaptive substeps");
+        b->launches += 2;
         k_zero_counter<<<1, 1, 0, st>>>(b->counters);
         k_plan_substep<512><<<b->B, 512, 0, st>>>(b->t, u, bvel, b->remaining, b->dt, b->active, b->nsub, b->maxvel, b->counters,
                                                   cfl, do_out ? char_vel[0] : 0.f, do_out ? char_vel[1] : 0.f, bc_tol, do_out);
@@ -1145,18 +1247,21 @@ extern "C" int fgb_update_outflow(fgb_batch *b, const float *u, float *bvel, con
                                   fgb_stream_t s) {
     if (!b || !u || !bvel || !dt || !char_vel) return set_err(FGB_E_ARG, "fgb_update_outflow: null argument");
     if (!b->t.b_out) return FGB_OK;
+    b->launches++;
     k_update_outflow<512><<<b->B, 512, 0, STREAM(s)>>>(b->t, u, bvel, dt, char_vel[0], char_vel[1], bc_tol);
     LAUNCH_CHECK("k_update_outflow");
     return FGB_OK;
 }
 extern "C" int fgb_flux_balance(fgb_batch *b, const float *bvel, float *out, fgb_stream_t s) {
     if (!b || !bvel || !out) return set_err(FGB_E_ARG, "fgb_flux_balance: null argument");
+    b->launches++;
     k_flux_balance<256><<<b->B, 256, 0, STREAM(s)>>>(b->t, bvel, out);
     LAUNCH_CHECK("k_flux_balance");
     return FGB_OK;
 }
 extern "C" int fgb_max_velocity(fgb_batch *b, const float *u, const float *bvel, float *out, fgb_stream_t s) {
     if (!b || !u || !bvel || !out) return set_err(FGB_E_ARG, "fgb_max_velocity: null argument");
+    b->launches++;
     k_max_velocity<512><<<b->B, 512, 0, STREAM(s)>>>(b->t, u, bvel, out);
     LAUNCH_CHECK("k_max_velocity");
     return FGB_OK;
@@ -1164,6 +1269,7 @@ extern "C" int fgb_max_velocity(fgb_batch *b, const float *u, const float *bvel,
 extern "C" int fgb_apply_jet_action(fgb_batch *b, float *bvel, float *last_control, const float *action, float smoothing,
                                     const int32_t *faces, const float *templ, int32_t n_faces, fgb_stream_t s) {
     if (!b || !bvel || !last_control || !action || !faces || !templ) return set_err(FGB_E_ARG, "fgb_apply_jet_action: null argument");
+    b->launches++;
     k_apply_jet<<<b->B, 64, 0, STREAM(s)>>>(bvel, last_control, action, smoothing, faces, templ, n_faces, b->t.NB, b->B);
     LAUNCH_CHECK("k_apply_jet");
     return FGB_OK;
@@ -1171,6 +1277,7 @@ extern "C" int fgb_apply_jet_action(fgb_batch *b, float *bvel, float *last_contr
 extern "C" int fgb_wall_forces(fgb_batch *b, const fgb_wall *w, const float *u, const float *p, const float *bvel, float *acc,
                                fgb_stream_t s) {
     if (!b || !w || !u || !p || !bvel || !acc) return set_err(FGB_E_ARG, "fgb_wall_forces: null argument");
+    b->launches++;
     k_wall_forces<<<b->B, 128, 0, STREAM(s)>>>(*w, b->t.viscosity, b->t.N, b->t.NB, u, p, bvel, acc);
     LAUNCH_CHECK("k_wall_forces");
     return FGB_OK;
@@ -1179,6 +1286,7 @@ extern "C" int fgb_sample_sensors(fgb_batch *b, const float *field, int32_t chan
                                   int32_t K, int32_t n_sensors, float *out, fgb_stream_t s) {
     if (!b || !field || !idx || !w || !out) return set_err(FGB_E_ARG, "fgb_sample_sensors: null argument");
     dim3 grid((channels * n_sensors + 127) / 128, b->B);
+    b->launches++;
     k_sample_sensors<<<grid, 128, 0, STREAM(s)>>>(field, channels, b->t.N, idx, w, K, n_sensors, out);
     LAUNCH_CHECK("k_sample_sensors");
     return FGB_OK;

@@ -39,7 +39,8 @@ EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_cr
            "fgb_batch_set_options", "fgb_batch_buffer", "fgb_setup_advection", "fgb_solve_advection",
            "fgb_setup_pressure_matrix", "fgb_setup_pressure_rhs", "fgb_solve_pressure", "fgb_correct_velocity",
            "fgb_piso_substep", "fgb_make_divergence_free", "fgb_sim_step", "fgb_update_outflow", "fgb_flux_balance",
-           "fgb_max_velocity", "fgb_apply_jet_action", "fgb_wall_forces", "fgb_sample_sensors"]
+           "fgb_max_velocity", "fgb_apply_jet_action", "fgb_wall_forces", "fgb_sample_sensors", "fgb_profile_enable",
+           "fgb_profile_read", "fgb_launch_count"]
 
 
 def lib_path() -> str:
@@ -80,6 +81,10 @@ def load():
     L.fgb_apply_jet_action.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32, vp]
     L.fgb_wall_forces.argtypes = [vp, C.POINTER(Wall), vp, vp, vp, vp, vp]
     L.fgb_sample_sensors.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp]
+    L.fgb_profile_enable.argtypes = [vp, i32]
+    L.fgb_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), i32]
+    L.fgb_launch_count.argtypes = [vp]
+    L.fgb_launch_count.restype = C.c_longlong
     _lib = L
     return L
 

@@ -94,7 +94,7 @@ class BatchedPISO:
         shapes = {"Coff": ((B, 4, N), torch.float32), "A": ((B, N), torch.float32), "rhs": ((B, 2, N), torch.float32),
                   "ures": ((B, 2, N), torch.float32), "Poff": ((B, 4, N), torch.float32), "Pdiag": ((B, N), torch.float32),
                   "hbya": ((B, 2, N), torch.float32), "div": ((B, N), torch.float32), "pres": ((B, N), torch.float32),
-                  "iters": ((B, 8), torch.int32), "resid": ((B, 8), torch.float32), "dt": ((B,), torch.float32),
+                  "iters": ((B, 8), torch.int32), "iter_total": ((B, 2), torch.int64), "resid": ((B, 8), torch.float32), "dt": ((B,), torch.float32),
                   "active": ((B,), torch.int32), "remaining": ((B,), torch.float64), "nsub": ((B,), torch.int32),
                   "maxvel": ((B,), torch.float32), "fluxbal": ((B,), torch.float32)}
         shape, dtype = shapes[name]

@@ -75,7 +75,10 @@ typedef struct fgb_options {
     float adv_tol, p_tol;           /* 1e-5, 1e-5 : ||r||_2/sqrt(N) absolute (SIM.py:1096-1098)          */
     int32_t max_iter;               /* 5000 */
     int32_t cg_impl;                /* 0: one CTA per environment, vectors in global memory
-                                       1: thread-block cluster per environment, vectors on chip        */
+                                       1: thread-block cluster per environment, vectors on chip,
+                                          textbook recurrence (3 cluster barriers / iteration)
+                                       2: as 1 with A*p from the recurrence Ap <- A*r + beta*Ap
+                                          (mathematically identical, 2 cluster barriers / iteration)    */
 } fgb_options;
 
 const char *fgb_last_error(void);
@@ -92,7 +95,7 @@ int fgb_batch_set_options(fgb_batch *b, const fgb_options *opt);
 /* Device pointer of a named intermediate inside the workspace (for parity tests and autograd glue):
  * "Coff"[B][4][N] "A"[B][N] "rhs"[B][2][N] "ures"[B][2][N] "Poff"[B][4][N] "Pdiag"[B][N]
  * "hbya"[B][2][N] "div"[B][N] "pres"[B][N] "iters"[B][8] int32 "resid"[B][8] "dt"[B] "active"[B] int32
- * "remaining"[B] double "nsub"[B] int32 "maxvel"[B] "fluxbal"[B] */
+ * "iter_total"[B][2] uint64 (cg, bicgstab) "remaining"[B] double "nsub"[B] int32 "maxvel"[B] "fluxbal"[B] */
 void *fgb_batch_buffer(fgb_batch *b, const char *name);
 
 /* ---- individual native ops (each replaces one PISOtorch free function) ------------------------- */
@@ -163,6 +166,15 @@ int fgb_wall_forces(fgb_batch *b, const fgb_wall *w, const float *u, const float
  * sum_k w[k][s] * field[B][C][idx[k][s]] (the static splat+normalise+fill map evaluated at the sensors) */
 int fgb_sample_sensors(fgb_batch *b, const float *field, int32_t channels, const int32_t *idx, const float *w,
                        int32_t K, int32_t n_sensors, float *out, fgb_stream_t s);
+
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------------ */
+/* Record CUDA events around the solver launches on their own stream.  fgb_profile_read synchronises the
+ * device and returns accumulated milliseconds / launch counts per class {0: pressure CG, 1: BiCGStab,
+ * 2: assembly kernels, 3: other}. */
+int fgb_profile_enable(fgb_batch *b, int on);
+int fgb_profile_read(fgb_batch *b, double *ms_out /*[4]*/, int64_t *count_out /*[4]*/, int reset);
+/* number of kernel launches issued through this handle since creation */
+long long fgb_launch_count(fgb_batch *b);
 
 #ifdef __cplusplus
 }
