@@ -880,6 +880,230 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster(Tab t, const float *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Krylov solvers, implementation 3: as implementation 1 (cluster per environment, textbook CG
+// recurrence) but WITHOUT cluster-wide barriers in the iteration.  All cross-CTA synchronisation is
+// point-to-point through shared-memory mbarriers:
+//   * reductions: every warp pushes its partial into every CTA's slot array with
+//     st.async ... mbarrier::complete_tx (data and completion signal travel together, no fence);
+//     consumers wait on their local transaction barrier;
+//   * search-direction visibility: after a CTA has rewritten its part of p, one thread arrives
+//     (release.cluster) on every peer's "p ready" mbarrier; consumers acquire it before the gathers.
+// Write-after-read safety of p and of the slot arrays follows from the data flow: a reduction can only
+// complete once every warp of every CTA has contributed, i.e. has finished the preceding phase.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t a, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P1;\n\t"
+                 "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+                 "selp.b32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) { while (!mbar_try_wait(a, parity)) {} }
+__device__ __forceinline__ void st_async_f32(uint32_t cluster_addr, float v, uint32_t cluster_mbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];"
+                 ::"r"(cluster_addr), "r"(__float_as_uint(v)), "r"(cluster_mbar) : "memory");
+}
+
+template <int T, int CPT, int CS>
+__global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
+                                                         const float *__restrict__ Rhs, float *__restrict__ Xout,
+                                                         int maxit, float tol, int zero_init, int reset_steps, int slot,
+                                                         const int32_t *__restrict__ active, int32_t *__restrict__ iters,
+                                                         float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
+    constexpr int NW = T / 32;
+    constexpr int NP = NW * CS;
+    constexpr int PAD = T * CPT;
+    static_assert(NP <= 64, "final reduction reads two partials per lane");
+    const int b = blockIdx.x / CS;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if (active && !active[b]) return;
+    extern __shared__ __align__(16) float smem[];
+    const int N = t.N;
+    const int per = (N + CS - 1) / CS;
+    const int start = (int)rank * per;
+    const int cnt = max(0, min(per, N - start));
+    float *vs = smem;                            // [PAD] search direction of the owned cells
+    float *bs = smem + PAD;                      // [PAD] best iterate
+    float *red = smem + 2 * PAD;                 // [2][NP] reduction slots (alternating)
+    unsigned long long *mb = (unsigned long long *)(smem + 2 * PAD + 2 * NP);   // [0],[1]: reductions, [2]: p ready
+    const float *off = Poff + (size_t)b * 4 * N, *dg = Pdiag + (size_t)b * N, *f = Rhs + (size_t)b * N;
+    float *xo = Xout + (size_t)b * N;
+    const float norm = 1.0f / sqrtf((float)N);
+    const uint32_t vs_addr = smem_u32(vs), red_addr = smem_u32(red), mb_addr = smem_u32(mb);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        mbar_init(mb_addr, 1); mbar_init(mb_addr + 8, 1); mbar_init(mb_addr + 16, CS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arrive_expect_tx(mb_addr, NP * 4);          // arm both reduction barriers for their first use
+        mbar_arrive_expect_tx(mb_addr + 8, NP * 4);
+    }
+    float cd[CPT], co[CPT][4], xr[CPT], rr[CPT];
+    uint32_t na[CPT][4];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int l = threadIdx.x + k * T;
+        const int g = start + l;
+        const bool ok = l < cnt;
+        cd[k] = ok ? dg[g] : 0.f;
+        xr[k] = (ok && !zero_init) ? xo[g] : 0.f;
+        vs[l] = 0.f; bs[l] = 0.f;
+#pragma unroll
+        for (int ff = 0; ff < 4; ++ff) {
+            const int nb = ok ? t.nbr[ff * N + g] : -1;
+            co[k][ff] = (ok && nb >= 0) ? off[ff * N + g] : 0.f;
+            const int gi = nb >= 0 ? nb : (ok ? g : start);
+            const int c = gi / per;
+            na[k][ff] = mapa_u32(vs_addr + 4u * (uint32_t)(gi - c * per), (uint32_t)c);
+        }
+    }
+    // addresses this lane pushes partials to (lane < CS): slot array and barriers of CTA `lane`
+    const uint32_t peer_red = mapa_u32(red_addr, (uint32_t)(lane < CS ? lane : 0));
+    const uint32_t peer_mb = mapa_u32(mb_addr, (uint32_t)(lane < CS ? lane : 0));
+    cluster_sync_all();                          // barriers initialised and vs/bs zero-filled everywhere
+
+    uint32_t rcount = 0;                         // reductions issued so far (slot array / barrier = rcount & 1)
+    uint32_t pphase = 0;                         // phase parity of the "p ready" barrier
+    auto cluster_sum = [&](float a0) -> float {
+        const uint32_t w = rcount & 1u, par = (rcount >> 1) & 1u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        if (lane < CS) st_async_f32(peer_red + 4u * (w * NP + rank * NW + (uint32_t)warp), a0, peer_mb + 8u * w);
+        mbar_wait(mb_addr + 8u * w, par);
+        const float *rp = red + w * NP;
+        float s0 = lane < NP ? rp[lane] : 0.f;
+        if (NP > 32) s0 += (lane + 32 < NP) ? rp[lane + 32] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        // re-arm this barrier for its next use (two reductions from now); every warp of this CTA has to be
+        // past the wait first, which the CTA-wide barrier of the following publish()/sync guarantees only
+        // loosely -- the arm may trail the first complete_tx of the next phase, which mbarrier semantics allow
+        // (the phase cannot complete before the pending arrival of the arm itself).
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(mb_addr + 8u * w, NP * 4);
+        ++rcount;
+        return s0;
+    };
+    auto publish = [&]() {                       // my part of vs is written: tell every CTA of the cluster
+        __syncthreads();
+        if (threadIdx.x < CS) mbar_arrive_remote_release(mapa_u32(mb_addr + 16, threadIdx.x));
+    };
+    auto acquire_p = [&]() { mbar_wait(mb_addr + 16, pphase); pphase ^= 1u; };
+    auto apply = [&](int k) -> float {
+        float s = cd[k] * vs[threadIdx.x + k * T];
+#pragma unroll
+        for (int ff = 0; ff < 4; ++ff) s += co[k][ff] * ld_dsmem_f32(na[k][ff]);
+        return s;
+    };
+    auto load_f = [&](int k) -> float { const int l = threadIdx.x + k * T; return l < cnt ? f[start + l] : 0.f; };
+
+    float nz = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) nz += (load_f(k) != 0.f) ? 1.f : 0.f;
+    const float nzt = cluster_sum(nz);
+    int used = -1; float fin = 0.f;
+    if (!(nzt > 0.f)) {
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) xr[k] = 0.f;
+    } else {
+        if (!zero_init) {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) vs[threadIdx.x + k * T] = xr[k];
+            publish(); acquire_p();
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) rr[k] = load_f(k) - apply(k);
+            (void)cluster_sum(0.f);              // everyone is done reading vs (= x)
+        } else {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) rr[k] = load_f(k);
+        }
+        float a0 = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; vs[l] = rr[k]; bs[l] = xr[k]; a0 += rr[k] * rr[k]; }
+        publish();
+        float rho = cluster_sum(a0);
+        float bestc = 0.f, lastc = 0.f; int best_it = -1, rising = 0;
+        float pk[CPT], apk[CPT];
+        for (int i = 0; i < maxit; ++i) {
+            if (reset_steps > 0 && (i + 1) % reset_steps == 0) {
+                // r = f - P x ; p = r ; rho = <r,r>   (CG.cu:281-302).  The pending "p ready" phase is consumed
+                // first so that the barrier phases stay aligned.
+                acquire_p();
+                (void)cluster_sum(0.f);          // nobody reads vs any more
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) vs[threadIdx.x + k * T] = xr[k];
+                publish(); acquire_p();
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) rr[k] = load_f(k) - apply(k);
+                (void)cluster_sum(0.f);
+                a0 = 0.f;
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) { vs[threadIdx.x + k * T] = rr[k]; a0 += rr[k] * rr[k]; }
+                publish();
+                rho = cluster_sum(a0);
+            }
+            acquire_p();                         // p of every CTA is visible
+            a0 = 0.f;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                apk[k] = apply(k);
+                pk[k] = vs[threadIdx.x + k * T];
+                a0 += pk[k] * apk[k];
+            }
+            const float pap = cluster_sum(a0);   // completes only after every warp of the cluster finished its gathers
+            const float alpha = rho / pap;
+            a0 = 0.f;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                xr[k] += alpha * pk[k];
+                rr[k] -= alpha * apk[k];
+                a0 += rr[k] * rr[k];
+            }
+            const float rr2 = cluster_sum(a0);
+            const float crit = sqrtf(rr2) * norm;
+            if (!isfinite(crit)) { used = i; fin = crit; break; }
+            if (i == 0 || crit < bestc) {
+                bestc = crit; best_it = i;
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) bs[threadIdx.x + k * T] = xr[k];
+            }
+            if (i > 0 && crit >= lastc) ++rising; else rising = 0;
+            lastc = crit; used = i; fin = crit;
+            if (crit < tol) break;
+            if (i == maxit - 1 || rising >= 100) {
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) xr[k] = bs[threadIdx.x + k * T];
+                used = best_it; fin = bestc;
+                break;
+            }
+            const float beta = rr2 / rho;
+            rho = rr2;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) vs[threadIdx.x + k * T] = rr[k] + beta * pk[k];
+            publish();
+        }
+    }
+    float sx = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) sx += xr[k];
+    const float mean = cluster_sum(sx) / (float)N;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) xo[start + l] = xr[k] - mean; }
+    if (threadIdx.x == 0 && rank == 0) { iters[b * 8 + 2 + slot] = used; resid[b * 8 + 2 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1); }
+    cluster_sync_all();   // keep peer shared memory (and in-flight st.async targets) alive until everyone is done
+}
+
+// ------------------------------------------------------------------------------------------------
 // boundary / stepping kernels: one CTA per environment
 // ------------------------------------------------------------------------------------------------
 // Domain.getMaxVelocity(True, True) (DS.cpp:1360-1367, 1580-1611): max |M^-1 u| over cells and fixed faces
@@ -1134,11 +1358,39 @@ static int launch_cg_cluster(fgb_batch *b, float *p_out, int zero_init, int rese
     return FGB_OK;
 }
 
+template <int CS, int CPT>
+static int launch_cg_cluster_mb(fgb_batch *b, float *p_out, int zero_init, int reset_steps, int max_iter, int slot,
+                                const int32_t *active, cudaStream_t st) {
+    constexpr int T = 512;
+    const int N = b->t.N;
+    const int per = (N + CS - 1) / CS;
+    if (per > T * CPT) return 1;
+    const size_t smem = ((size_t)2 * T * CPT + (size_t)2 * (T / 32) * CS) * sizeof(float) + 3 * 8 + 16;
+    auto kern = k_cg_cluster_mb<T, CPT, CS>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_cg_cluster_mb)", ce);
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(b->B * CS); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ce = cudaLaunchKernelEx(&cfg, kern, b->t, (const float *)b->Poff, (const float *)b->Pdiag, (const float *)b->div, p_out,
+                            max_iter, b->opt.p_tol, zero_init, reset_steps, slot, active, b->iters, b->resid, b->iter_total);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchKernelEx(k_cg_cluster_mb)", ce);
+    return FGB_OK;
+}
+
 static int solve_pressure_slot(fgb_batch *b, float *p_out, int zero_init, int reset_steps, int max_iter, int slot,
                                const int32_t *active, fgb_stream_t s) {
     if (!b || !p_out) return set_err(FGB_E_ARG, "fgb_solve_pressure: null argument");
     if (slot < 0 || slot > 5) slot = 5;
     ProfScope ps(b, CLS_CG, STREAM(s));
+    if (b->opt.cg_impl == 3) {
+        int rc = launch_cg_cluster_mb<2, 6>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        if (rc == 1) rc = launch_cg_cluster_mb<4, 7>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        if (rc <= 0) return rc;
+    }
     if (b->opt.cg_impl == 1 || b->opt.cg_impl == 2) {
         int rc;
         if (b->opt.cg_impl == 1) {
