@@ -900,10 +900,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t a, uint32_t bytes
 __device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// CTA-scope acquire (the default): everything exchanged here lives in shared memory (st.async payloads, or
+// st.shared data published with a release.cluster arrive and read back with ld.shared::cluster), which is
+// never cached in L1, so the cluster-scope acquire -- a CCTL.IVALL L1 invalidation per waiting warp, 10 % of
+// all stall samples in profiles/r01_ncu_cg_cluster_impl3.txt -- buys nothing.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t a, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred P1;\n\t"
-                 "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
                  "selp.b32 %0, 1, 0, P1;\n\t}"
                  : "=r"(ok) : "r"(a), "r"(parity) : "memory");
     return ok != 0;
@@ -965,6 +969,8 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__re
             co[k][ff] = (ok && nb >= 0) ? off[ff * N + g] : 0.f;
             const int gi = nb >= 0 ? nb : (ok ? g : start);
             const int c = gi / per;
+            // (measured: splitting local neighbours onto plain ld.shared with a per-gather predicate is SLOWER,
+            //  10.8 vs 8.3 ms per substep -- the cluster-window load of an own-CTA address is not the bottleneck)
             na[k][ff] = mapa_u32(vs_addr + 4u * (uint32_t)(gi - c * per), (uint32_t)c);
         }
     }
@@ -1101,6 +1107,218 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__re
     for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) xo[start + l] = xr[k] - mean; }
     if (threadIdx.x == 0 && rank == 0) { iters[b * 8 + 2 + slot] = used; resid[b * 8 + 2 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1); }
     cluster_sync_all();   // keep peer shared memory (and in-flight st.async targets) alive until everyone is done
+}
+
+// ------------------------------------------------------------------------------------------------
+// Krylov solvers, implementation 4: "fat CTA" variant of implementation 3.  Twice the cells per CTA
+// (cluster of 2 for the 14k-cell cylinder grid -> every SM of the chip is usable, 74 environments in
+// flight) so that the cross-CTA latency of the two reductions and of the p hand-shake is amortised over
+// twice the work.  To fit, only the stencil coefficients, A*p and p of the owned cells stay in
+// registers; x, r, the best iterate, p and the neighbour table (16 bit: 3 bits CTA rank, 13 bits slot)
+// live in shared memory (172 KB per CTA).  Same textbook recurrence, same mbarrier protocol.
+// ------------------------------------------------------------------------------------------------
+template <int T, int CPT, int CS, int MINB>
+__global__ void __launch_bounds__(T, MINB) k_cg_smem(Tab t, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
+                                                   const float *__restrict__ Rhs, float *__restrict__ Xout,
+                                                   int maxit, float tol, int zero_init, int reset_steps, int slot,
+                                                   const int32_t *__restrict__ active, int32_t *__restrict__ iters,
+                                                   float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
+    constexpr int NW = T / 32;
+    constexpr int NP = NW * CS;
+    constexpr int PAD = T * CPT;
+    static_assert(PAD <= 8192, "13-bit slot index");
+    const int b = blockIdx.x / CS;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if (active && !active[b]) return;
+    extern __shared__ __align__(16) float smem[];
+    const int N = t.N;
+    const int per = (N + CS - 1) / CS;
+    const int start = (int)rank * per;
+    const int cnt = max(0, min(per, N - start));
+    float *ps = smem;                            // [PAD] search direction
+    float *xs = smem + PAD;                      // [PAD] iterate
+    float *rs = smem + 2 * PAD;                  // [PAD] residual
+    float *bs = smem + 3 * PAD;                  // [PAD] best iterate
+    uint2 *nbs = (uint2 *)(smem + 4 * PAD);      // [PAD] 4 x 16-bit neighbour codes
+    float *red = smem + 6 * PAD;                 // [2][NP]
+    unsigned long long *mb = (unsigned long long *)(smem + 6 * PAD + 2 * NP);
+    const float *off = Poff + (size_t)b * 4 * N, *dg = Pdiag + (size_t)b * N, *f = Rhs + (size_t)b * N;
+    float *xo = Xout + (size_t)b * N;
+    const float norm = 1.0f / sqrtf((float)N);
+    const uint32_t ps_addr = smem_u32(ps), red_addr = smem_u32(red), mb_addr = smem_u32(mb);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        mbar_init(mb_addr, 1); mbar_init(mb_addr + 8, 1); mbar_init(mb_addr + 16, CS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arrive_expect_tx(mb_addr, NP * 4);
+        mbar_arrive_expect_tx(mb_addr + 8, NP * 4);
+    }
+    float cd[CPT], co[CPT][4];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int l = threadIdx.x + k * T;
+        const int g = start + l;
+        const bool ok = l < cnt;
+        cd[k] = ok ? dg[g] : 0.f;
+        xs[l] = (ok && !zero_init) ? xo[g] : 0.f;
+        ps[l] = 0.f; bs[l] = 0.f; rs[l] = 0.f;
+        uint32_t code[4];
+#pragma unroll
+        for (int ff = 0; ff < 4; ++ff) {
+            const int nb = ok ? t.nbr[ff * N + g] : -1;
+            co[k][ff] = (ok && nb >= 0) ? off[ff * N + g] : 0.f;
+            const int gi = nb >= 0 ? nb : (ok ? g : start);
+            const int c = gi / per;
+            code[ff] = ((uint32_t)c << 13) | (uint32_t)(gi - c * per);
+        }
+        nbs[l] = make_uint2(code[0] | (code[1] << 16), code[2] | (code[3] << 16));
+    }
+    const uint32_t peer_red = mapa_u32(red_addr, (uint32_t)(lane < CS ? lane : 0));
+    const uint32_t peer_mb = mapa_u32(mb_addr, (uint32_t)(lane < CS ? lane : 0));
+    cluster_sync_all();
+
+    uint32_t rcount = 0, pphase = 0;
+    auto cluster_sum = [&](float a0) -> float {
+        const uint32_t w = rcount & 1u, par = (rcount >> 1) & 1u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        if (lane < CS) st_async_f32(peer_red + 4u * (w * NP + rank * NW + (uint32_t)warp), a0, peer_mb + 8u * w);
+        mbar_wait(mb_addr + 8u * w, par);
+        const float *rp = red + w * NP;
+        float s0 = 0.f;
+#pragma unroll
+        for (int q = 0; q < (NP + 31) / 32; ++q) s0 += (lane + 32 * q < NP) ? rp[lane + 32 * q] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(mb_addr + 8u * w, NP * 4);
+        ++rcount;
+        return s0;
+    };
+    auto publish = [&]() {
+        __syncthreads();
+        if (threadIdx.x < CS) mbar_arrive_remote_release(mapa_u32(mb_addr + 16, threadIdx.x));
+    };
+    auto acquire_p = [&]() { mbar_wait(mb_addr + 16, pphase); pphase ^= 1u; };
+    auto gather = [&](uint32_t code) -> float {
+        return ld_dsmem_f32(mapa_u32(ps_addr + ((code & 0x1fffu) << 2), (code >> 13) & 7u));
+    };
+    auto apply = [&](int k, float &own) -> float {   // row k of P times the vector exposed in ps
+        const int l = threadIdx.x + k * T;
+        const uint2 nb = nbs[l];
+        own = ps[l];
+        float s = cd[k] * own;
+        s += co[k][0] * gather(nb.x & 0xffffu);
+        s += co[k][1] * gather(nb.x >> 16);
+        s += co[k][2] * gather(nb.y & 0xffffu);
+        s += co[k][3] * gather(nb.y >> 16);
+        return s;
+    };
+    auto load_f = [&](int k) -> float { const int l = threadIdx.x + k * T; return l < cnt ? f[start + l] : 0.f; };
+
+    float nz = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) nz += (load_f(k) != 0.f) ? 1.f : 0.f;
+    const float nzt = cluster_sum(nz);
+    int used = -1; float fin = 0.f;
+    bool result_in_best = false;
+    if (!(nzt > 0.f)) {
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) xs[threadIdx.x + k * T] = 0.f;
+    } else {
+        float a0 = 0.f, own;
+        if (!zero_init) {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) ps[threadIdx.x + k * T] = xs[threadIdx.x + k * T];
+            publish(); acquire_p();
+            float tmp[CPT];
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) tmp[k] = load_f(k) - apply(k, own);
+            (void)cluster_sum(0.f);
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; rs[l] = tmp[k]; ps[l] = tmp[k]; a0 += tmp[k] * tmp[k]; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; const float r0 = load_f(k); rs[l] = r0; ps[l] = r0; a0 += r0 * r0; }
+        }
+        publish();
+        float rho = cluster_sum(a0);
+        float bestc = 0.f, lastc = 0.f; int best_it = -1, rising = 0;
+        bool copy_best = false;                  // x of the previous iteration still has to be saved into bs
+        float pk[CPT], apk[CPT];
+        for (int i = 0; i < maxit; ++i) {
+            if (reset_steps > 0 && (i + 1) % reset_steps == 0) {
+                acquire_p();
+                (void)cluster_sum(0.f);
+                if (copy_best) {
+#pragma unroll
+                    for (int k = 0; k < CPT; ++k) bs[threadIdx.x + k * T] = xs[threadIdx.x + k * T];
+                    copy_best = false;
+                }
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) ps[threadIdx.x + k * T] = xs[threadIdx.x + k * T];
+                publish(); acquire_p();
+                float tmp[CPT];
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) tmp[k] = load_f(k) - apply(k, own);
+                (void)cluster_sum(0.f);
+                a0 = 0.f;
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; rs[l] = tmp[k]; ps[l] = tmp[k]; a0 += tmp[k] * tmp[k]; }
+                publish();
+                rho = cluster_sum(a0);
+            }
+            acquire_p();
+            a0 = 0.f;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                apk[k] = apply(k, pk[k]);
+                a0 += pk[k] * apk[k];
+            }
+            const float pap = cluster_sum(a0);
+            const float alpha = rho / pap;
+            a0 = 0.f;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const int l = threadIdx.x + k * T;
+                const float xo_ = xs[l];
+                if (copy_best) bs[l] = xo_;      // deferred copy of the previous (best so far) iterate
+                xs[l] = xo_ + alpha * pk[k];
+                const float rn = rs[l] - alpha * apk[k];
+                rs[l] = rn;
+                a0 += rn * rn;
+            }
+            copy_best = false;
+            const float rr2 = cluster_sum(a0);
+            const float crit = sqrtf(rr2) * norm;
+            if (!isfinite(crit)) { used = i; fin = crit; break; }
+            if (i == 0 || crit < bestc) { bestc = crit; best_it = i; copy_best = true; }
+            if (i > 0 && crit >= lastc) ++rising; else rising = 0;
+            lastc = crit; used = i; fin = crit;
+            if (crit < tol) break;
+            if (i == maxit - 1 || rising >= 100) {
+                // the best iterate is the current x if it was flagged this very iteration, else what bs holds
+                result_in_best = !copy_best;
+                used = best_it; fin = bestc;
+                break;
+            }
+            const float beta = rr2 / rho;
+            rho = rr2;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; ps[l] = rs[l] + beta * pk[k]; }
+            publish();
+        }
+    }
+    const float *res = result_in_best ? bs : xs;
+    float sx = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) sx += res[threadIdx.x + k * T];
+    const float mean = cluster_sum(sx) / (float)N;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) xo[start + l] = res[l] - mean; }
+    if (threadIdx.x == 0 && rank == 0) { iters[b * 8 + 2 + slot] = used; resid[b * 8 + 2 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1); }
+    cluster_sync_all();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1381,11 +1599,46 @@ static int launch_cg_cluster_mb(fgb_batch *b, float *p_out, int zero_init, int r
     return FGB_OK;
 }
 
+template <int CS, int CPT, int MINB>
+static int launch_cg_smem(fgb_batch *b, float *p_out, int zero_init, int reset_steps, int max_iter, int slot,
+                          const int32_t *active, cudaStream_t st) {
+    constexpr int T = 512;
+    const int N = b->t.N;
+    const int per = (N + CS - 1) / CS;
+    if (per > T * CPT) return 1;
+    const size_t smem = ((size_t)6 * T * CPT + (size_t)2 * (T / 32) * CS) * sizeof(float) + 3 * 8 + 16;
+    auto kern = k_cg_smem<T, CPT, CS, MINB>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_cg_smem)", ce);
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(b->B * CS); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ce = cudaLaunchKernelEx(&cfg, kern, b->t, (const float *)b->Poff, (const float *)b->Pdiag, (const float *)b->div, p_out,
+                            max_iter, b->opt.p_tol, zero_init, reset_steps, slot, active, b->iters, b->resid, b->iter_total);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchKernelEx(k_cg_smem)", ce);
+    return FGB_OK;
+}
+
 static int solve_pressure_slot(fgb_batch *b, float *p_out, int zero_init, int reset_steps, int max_iter, int slot,
                                const int32_t *active, fgb_stream_t s) {
     if (!b || !p_out) return set_err(FGB_E_ARG, "fgb_solve_pressure: null argument");
     if (slot < 0 || slot > 5) slot = 5;
     ProfScope ps(b, CLS_CG, STREAM(s));
+    if (b->opt.cg_impl == 4) {
+        int rc = launch_cg_smem<1, 12, 1>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        if (rc == 1) rc = launch_cg_smem<2, 14, 1>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        if (rc == 1) rc = launch_cg_smem<4, 12, 1>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        if (rc <= 0) return rc;
+    }
+    if (b->opt.cg_impl == 5) {   // two co-resident CTAs per SM (64 registers per thread): twice the environments in flight
+        int rc = launch_cg_smem<2, 6, 2>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        if (rc == 1) rc = launch_cg_smem<4, 7, 2>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        if (rc == 1) rc = launch_cg_smem<8, 7, 2>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        if (rc <= 0) return rc;
+    }
     if (b->opt.cg_impl == 3) {
         int rc = launch_cg_cluster_mb<2, 6>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
         if (rc == 1) rc = launch_cg_cluster_mb<4, 7>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));

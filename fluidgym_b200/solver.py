@@ -31,7 +31,7 @@ class BatchedPISO:
 
     def __init__(self, cd: CompiledDomain, n_envs: int, device="cuda:0", corrector_steps=2, advect_non_ortho_steps=1,
                  pressure_non_ortho_steps=1, non_orthogonal=True, advection_tol=1e-5, pressure_tol=1e-5,
-                 max_iter=5000, cg_impl=1, out_mask=None):
+                 max_iter=5000, cg_impl=3, out_mask=None):
         if not torch.cuda.is_available():
             raise native.FGBError("fluidgym_b200 needs a CUDA device (there is no CPU fallback)")
         self.lib = native.load()

@@ -78,7 +78,12 @@ typedef struct fgb_options {
                                        1: thread-block cluster per environment, vectors on chip,
                                           textbook recurrence (3 cluster barriers / iteration)
                                        2: as 1 with A*p from the recurrence Ap <- A*r + beta*Ap
-                                          (mathematically identical, 2 cluster barriers / iteration)    */
+                                          (mathematically identical, 2 cluster barriers / iteration)
+                                       3: as 1 without cluster barriers: st.async + mbarrier transactions
+                                          for the reductions, remote mbarrier arrive for the p hand-shake
+                                          (default, fastest)
+                                       4: as 3 with x/r/p/neighbour table in shared memory, 2x cells per CTA
+                                       5: as 4 with two co-resident CTAs per SM                            */
 } fgb_options;
 
 const char *fgb_last_error(void);
