@@ -26,7 +26,7 @@ def make(env_id: str, n_envs: int = 1, **kwargs):
     entry, defaults = _REGISTRY[env_id]
     cfg = dict(defaults)
     # reference-only constructor flags that have no meaning here are accepted and ignored
-    for k in ("load_initial_domain", "load_domain_statistics", "use_marl", "dtype", "differentiable"):
+    for k in ("load_initial_domain", "load_domain_statistics", "dtype", "differentiable"):
         kwargs.pop(k, None)
     cfg.update(kwargs)
     return entry(n_envs=n_envs, **cfg)
@@ -37,4 +37,10 @@ def _register_defaults():
     # fluidgym/__init__.py:28-60: easy = Re 100 / res 24, medium = Re 250 / res 32, hard = Re 500 / res 32
     register("CylinderJet2D-easy-v0", CylinderJet2DEnv, **CYLINDER_JET_2D_DEFAULT_CONFIG)
     register("CylinderJet2D-medium-v0", CylinderJet2DEnv, **{**CYLINDER_JET_2D_DEFAULT_CONFIG, "reynolds_number": 250.0, "resolution": 32})
+    from .envs.rbc import RBC_2D_DEFAULT_CONFIG, RBC2DEnv
+    # fluidgym/__init__.py:106-157
+    register("RBC2D-easy-v0", RBC2DEnv, **{**RBC_2D_DEFAULT_CONFIG, "rayleigh_number": 8e4, "adaptive_cfl": 0.8})
+    register("RBC2D-medium-v0", RBC2DEnv, **{**RBC_2D_DEFAULT_CONFIG, "rayleigh_number": 4e5, "adaptive_cfl": 0.5})
+    register("RBC2D-hard-v0", RBC2DEnv, **{**RBC_2D_DEFAULT_CONFIG, "rayleigh_number": 8e5, "adaptive_cfl": 0.5})
+    register("RBC2D-wide-easy-v0", RBC2DEnv, **{**RBC_2D_DEFAULT_CONFIG, "aspect_ratio": 2, "n_heaters": 24, "rayleigh_number": 8e4})
     register("CylinderJet2D-hard-v0", CylinderJet2DEnv, **{**CYLINDER_JET_2D_DEFAULT_CONFIG, "reynolds_number": 500.0, "resolution": 32})

@@ -440,6 +440,78 @@ __global__ void __launch_bounds__(256) k_correct_velocity(Tab t, const float *__
     Uout[(size_t)b * 2 * N + N + g] = -rD * gy + Hbya[(size_t)b * 2 * N + N + g];
 }
 
+// Passive-scalar transport: SetupAdvectionMatrix(forPassiveScalar) + SetupAdvectionScalar fused
+// (K.cu:3617-3880 with the scalar diffusivity, K.cu:4094-4198), orthogonal path.
+__global__ void __launch_bounds__(256) k_setup_scalar(Tab t, const float *__restrict__ U, const float *__restrict__ Tin,
+                                                       const float *__restrict__ Bvel, const float *__restrict__ Sbval,
+                                                       const float *__restrict__ dtv, const int32_t *__restrict__ active,
+                                                       float *__restrict__ Coff, float *__restrict__ A, float *__restrict__ Rhs) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N, NB = t.NB;
+    if (g >= N) return;
+    const float *u = U + (size_t)b * 2 * N, *bv = Bvel + (size_t)b * 2 * NB, *sb = Sbval + (size_t)b * NB;
+    const float dt = dtv[b];
+    const float det = t.det[g];
+    int nb[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) nb[f] = t.nbr[f * N + g];
+    float fl[4];
+    face_fluxes(t, g, u, bv, nb, fl);
+    float diag = det / dt + t.Cd_s[g];
+    float r = det * Tin[(size_t)b * N + g] / dt;
+    float *co = Coff + (size_t)b * 4 * N;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        float o = 0.f;
+        if (nb[f] >= 0) {
+            const float ff = ((f & 1) ? 0.5f : -0.5f) * fl[f];
+            diag += ff;
+            o = (ff + t.Cd_s[(f + 1) * N + g]) / det;
+        } else {
+            const int j = -1 - nb[f];
+            const float sc = sb[j];
+            const float flux = fl[f] * ((f & 1) ? 1.f : -1.f);   // fl[f] is the boundary flux on prescribed faces
+            r -= sc * flux;
+            if (t.sb_neumann[j] == 0) r += sc * t.scalar_viscosity * 2.f * t.b_alpha[j];
+            else r += sc * t.scalar_viscosity;
+        }
+        co[f * N + g] = o;
+    }
+    A[(size_t)b * N + g] = diag / det;
+    Rhs[(size_t)b * N + g] = r / det;
+}
+
+// buoyancy hook of the RBC environments (rbc_env_base.py:280-304): velocity source = (0, beta * T)
+__global__ void k_buoyancy(const float *__restrict__ Tin, float beta, int N, const int32_t *__restrict__ active, float *__restrict__ src) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    src[(size_t)b * 2 * N + g] = 0.f;
+    src[(size_t)b * 2 * N + N + g] = Tin[(size_t)b * N + g] * beta;
+}
+
+// column sums of a * b * det and of det over a single structured block of nx x ny cells (Nusselt number,
+// rbc_env_base.py:491-539, rbc_env_2d.py:328-357): out[b][0][x] = sum_y a*b*det, out[b][1][x] = sum_y det
+__global__ void k_column_sums(Tab t, const float *__restrict__ Afield, const float *__restrict__ Bfield, int nx, int ny,
+                              float *__restrict__ out) {
+    const int b = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nx) return;
+    const int N = t.N;
+    float s = 0.f, v = 0.f;
+    for (int y = 0; y < ny; ++y) {
+        const int g = x + nx * y;
+        const float d = t.det[g];
+        s += Afield[(size_t)b * N + g] * Bfield[(size_t)b * N + g] * d;
+        v += d;
+    }
+    out[(size_t)b * 2 * nx + x] = s;
+    out[(size_t)b * 2 * nx + nx + x] = v;
+}
+
 __global__ void k_fill(float *p, float v, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -463,8 +535,8 @@ __device__ __forceinline__ float ell_row(const Tab &t, int g, const float *__res
     return s;
 }
 
-// BiCGStab without preconditioner (BICG.cu:237-376), both velocity components in lock step.
-template <int T>
+// BiCGStab without preconditioner (BICG.cu:237-376); NC right-hand sides (velocity components) in lock step.
+template <int T, int NC>
 __global__ void __launch_bounds__(T) k_bicgstab(Tab t, const float *__restrict__ Coff, const float *__restrict__ Adiag,
                                                  const float *__restrict__ Rhs, float *__restrict__ X, float *__restrict__ work,
                                                  int maxit, float tol, int zero_init, const int32_t *__restrict__ active,
@@ -480,31 +552,32 @@ __global__ void __launch_bounds__(T) k_bicgstab(Tab t, const float *__restrict__
     // per component c: r, rw, p, v, tt
     float *r[2] = {wb, wb + 5 * (size_t)N}, *rw[2] = {wb + N, wb + 6 * (size_t)N}, *p[2] = {wb + 2 * (size_t)N, wb + 7 * (size_t)N};
     float *v[2] = {wb + 3 * (size_t)N, wb + 8 * (size_t)N}, *tt[2] = {wb + 4 * (size_t)N, wb + 9 * (size_t)N};
-    float *x[2] = {X + (size_t)b * 2 * N, X + (size_t)b * 2 * N + N};
-    const float *f[2] = {Rhs + (size_t)b * 2 * N, Rhs + (size_t)b * 2 * N + N};
+    float *x[2] = {X + (size_t)b * NC * N, X + (size_t)b * NC * N + (NC - 1) * N};
+    const float *f[2] = {Rhs + (size_t)b * NC * N, Rhs + (size_t)b * NC * N + (NC - 1) * N};
 
-    if (zero_init) { for (int c = 0; c < 2; ++c) for (int g = threadIdx.x; g < N; g += T) x[c][g] = 0.f; }
+    if (zero_init) { for (int c = 0; c < NC; ++c) for (int g = threadIdx.x; g < N; g += T) x[c][g] = 0.f; }
     __syncthreads();
     float acc[4];
     acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-    for (int c = 0; c < 2; ++c)
+    for (int c = 0; c < NC; ++c)
         for (int g = threadIdx.x; g < N; g += T) {
             const float rr = f[c][g] - (zero_init ? 0.f : ell_row(t, g, off, dg, x[c]));
             r[c][g] = rr; rw[c][g] = rr; p[c][g] = rr;
             acc[c] += rr * rr;
         }
     block_reduce_sum<4>(acc, red);
-    bool done[2]; int used[2]; float fin[2]; float rho[2] = {1.f, 1.f}, alpha[2] = {1.f, 1.f}, omega[2] = {1.f, 1.f};
-    for (int c = 0; c < 2; ++c) {
+    bool done[2] = {true, true}; int used[2] = {-1, -1}; float fin[2] = {0.f, 0.f};
+    float rho[2] = {1.f, 1.f}, alpha[2] = {1.f, 1.f}, omega[2] = {1.f, 1.f};
+    for (int c = 0; c < NC; ++c) {
         fin[c] = sqrtf(acc[c]) * norm; used[c] = -1; done[c] = fin[c] < tol;
     }
-    for (int i = 0; i < maxit && !(done[0] && done[1]); ++i) {
+    for (int i = 0; i < maxit && !(done[0] && done[NC - 1]); ++i) {
         // rho = <rw, r>
         acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-        for (int c = 0; c < 2; ++c) if (!done[c])
+        for (int c = 0; c < NC; ++c) if (!done[c])
             for (int g = threadIdx.x; g < N; g += T) acc[c] += rw[c][g] * r[c][g];
         block_reduce_sum<4>(acc, red);
-        for (int c = 0; c < 2; ++c) if (!done[c]) {
+        for (int c = 0; c < NC; ++c) if (!done[c]) {
             const float rhop = rho[c]; rho[c] = acc[c];
             if (i > 0) {
                 const float beta = (rho[c] / rhop) * (alpha[c] / omega[c]);
@@ -513,11 +586,11 @@ __global__ void __launch_bounds__(T) k_bicgstab(Tab t, const float *__restrict__
         }
         __syncthreads();
         acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-        for (int c = 0; c < 2; ++c) if (!done[c])
+        for (int c = 0; c < NC; ++c) if (!done[c])
             for (int g = threadIdx.x; g < N; g += T) { const float vv = ell_row(t, g, off, dg, p[c]); v[c][g] = vv; acc[c] += rw[c][g] * vv; }
         block_reduce_sum<4>(acc, red);
         float acc2[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int c = 0; c < 2; ++c) if (!done[c]) {
+        for (int c = 0; c < NC; ++c) if (!done[c]) {
             alpha[c] = rho[c] / acc[c];
             for (int g = threadIdx.x; g < N; g += T) {
                 const float rr = r[c][g] - alpha[c] * v[c][g];
@@ -526,21 +599,21 @@ __global__ void __launch_bounds__(T) k_bicgstab(Tab t, const float *__restrict__
             }
         }
         block_reduce_sum<4>(acc2, red);
-        for (int c = 0; c < 2; ++c) if (!done[c]) {
+        for (int c = 0; c < NC; ++c) if (!done[c]) {
             const float nr = sqrtf(acc2[c]) * norm;
             used[c] = i; fin[c] = nr;
             if (!isfinite(nr) || nr < tol) done[c] = true;
         }
         // t = C r (s = r)
         acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-        for (int c = 0; c < 2; ++c) if (!done[c])
+        for (int c = 0; c < NC; ++c) if (!done[c])
             for (int g = threadIdx.x; g < N; g += T) {
                 const float tv = ell_row(t, g, off, dg, r[c]); tt[c][g] = tv;
                 acc[c] += tv * r[c][g]; acc[2 + c] += tv * tv;
             }
         block_reduce_sum<4>(acc, red);
         acc2[0] = acc2[1] = acc2[2] = acc2[3] = 0.f;
-        for (int c = 0; c < 2; ++c) if (!done[c]) {
+        for (int c = 0; c < NC; ++c) if (!done[c]) {
             omega[c] = acc[c] / acc[2 + c];
             for (int g = threadIdx.x; g < N; g += T) {
                 const float rg = r[c][g];
@@ -551,16 +624,21 @@ __global__ void __launch_bounds__(T) k_bicgstab(Tab t, const float *__restrict__
             }
         }
         block_reduce_sum<4>(acc2, red);
-        for (int c = 0; c < 2; ++c) if (!done[c]) {
+        for (int c = 0; c < NC; ++c) if (!done[c]) {
             const float nr = sqrtf(acc2[c]) * norm;
             fin[c] = nr;
             if (nr < tol) { done[c] = true; used[c] = i + 1; }
         }
     }
     if (threadIdx.x == 0) {
-        iters[b * 8 + 0] = used[0]; iters[b * 8 + 1] = used[1];
-        resid[b * 8 + 0] = fin[0]; resid[b * 8 + 1] = fin[1];
-        iter_total[b * 2 + 1] += (unsigned long long)(used[0] + 1 + used[1] + 1);
+        if (NC == 2) {
+            iters[b * 8 + 0] = used[0]; iters[b * 8 + 1] = used[1];
+            resid[b * 8 + 0] = fin[0]; resid[b * 8 + 1] = fin[1];
+            iter_total[b * 2 + 1] += (unsigned long long)(used[0] + 1 + used[1] + 1);
+        } else {
+            iters[b * 8 + 7] = used[0]; resid[b * 8 + 7] = fin[0];
+            iter_total[b * 2 + 1] += (unsigned long long)(used[0] + 1);
+        }
     }
 }
 
@@ -1525,8 +1603,8 @@ extern "C" int fgb_setup_advection(fgb_batch *b, const float *u, const float *ur
 extern "C" int fgb_solve_advection(fgb_batch *b, int zero_init, const int32_t *active, fgb_stream_t s) {
     if (!b) return set_err(FGB_E_ARG, "fgb_solve_advection: null argument");
     ProfScope ps(b, CLS_BICG, STREAM(s));
-    k_bicgstab<1024><<<b->B, 1024, 0, STREAM(s)>>>(b->t, b->Coff, b->A, b->rhs, b->ures, b->kry, b->opt.max_iter, b->opt.adv_tol,
-                                                   zero_init, active, b->iters, b->resid, b->iter_total);
+    k_bicgstab<1024, 2><<<b->B, 1024, 0, STREAM(s)>>>(b->t, b->Coff, b->A, b->rhs, b->ures, b->kry, b->opt.max_iter, b->opt.adv_tol,
+                                                      zero_init, active, b->iters, b->resid, b->iter_total);
     LAUNCH_CHECK("k_bicgstab");
     return FGB_OK;
 }
@@ -1674,31 +1752,57 @@ extern "C" int fgb_correct_velocity(fgb_batch *b, const float *p, float *u_out, 
 }
 
 extern "C" int fgb_piso_substep(fgb_batch *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
-                                const int32_t *active, fgb_stream_t s) {
+                                const int32_t *active, const fgb_scalar *sc, fgb_stream_t s) {
     if (!b || !u || !p || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_piso_substep: null argument");
     int rc;
     const fgb_options &o = b->opt;
     cudaStream_t st = STREAM(s);
     const int N = b->t.N;
-    // predictor (SIM.py:1662-1757)
-    for (int ns = 0; ns < o.adv_nonortho_steps; ++ns) {
+    // passive scalar first, with the velocity of the previous step (SIM.py:1471-1644), then the buoyancy hook
+    if (sc) {
+        if (!sc->T || !sc->sbval || !sc->src || !b->t.Cd_s || !b->t.sb_neumann)
+            return set_err(FGB_E_ARG, "fgb_piso_substep: incomplete scalar description / tables");
+        {
+            ProfScope ps(b, CLS_ASM, st);
+            k_setup_scalar<<<cell_grid(b), 256, 0, st>>>(b->t, u, sc->T, bvel, sc->sbval, dt, active, b->Coff, b->A, b->rhs);
+            LAUNCH_CHECK("k_setup_scalar");
+        }
+        {
+            ProfScope ps(b, CLS_BICG, st);
+            k_bicgstab<1024, 1><<<b->B, 1024, 0, st>>>(b->t, b->Coff, b->A, b->rhs, sc->T, b->kry, o.max_iter, o.adv_tol, 1, active,
+                                                        b->iters, b->resid, b->iter_total);
+            LAUNCH_CHECK("k_bicgstab<1>");
+        }
+        b->launches++;
+        k_buoyancy<<<cell_grid(b), 256, 0, st>>>(sc->T, sc->beta, N, active, sc->src);
+        LAUNCH_CHECK("k_buoyancy");
+        src = sc->src;
+    }
+    // predictor (SIM.py:1662-1757).  Orthogonal path: one solve started from the previous velocityResult
+    // (which is kept in the workspace buffer "ures"); non-orthogonal path: zero start, deferred corrections.
+    const int n_adv = o.nonortho ? o.adv_nonortho_steps : 1;
+    for (int ns = 0; ns < n_adv; ++ns) {
         b->launches++;
         k_setup_advection<<<cell_grid(b), 256, 0, st>>>(b->t, u, ns == 0 ? u : b->ures, bvel, src, dt, active, b->Coff, b->A, b->rhs, ns == 0);
         LAUNCH_CHECK("k_setup_advection");
-        if ((rc = fgb_solve_advection(b, ns == 0, active, s))) return rc;
+        if ((rc = fgb_solve_advection(b, o.nonortho ? (ns == 0) : 0, active, s))) return rc;
     }
     // correctors (SIM.py:1777-1972)
     int slot = 0;
+    const int n_p = o.nonortho ? o.p_nonortho_steps : 1;
+    const int reset = o.nonortho ? 100 : 0;
     for (int cs = 0; cs < o.corrector_steps; ++cs) {
         if (cs == 0) { if ((rc = fgb_setup_pressure_matrix(b, active, s))) return rc; }   // A is unchanged between correctors
-        for (int ps = 0; ps < o.p_nonortho_steps; ++ps) {
+        for (int ps = 0; ps < n_p; ++ps) {
             if ((rc = fgb_setup_pressure_rhs(b, u, bvel, src, p, dt, ps == 0, active, s))) return rc;
-            if ((rc = solve_pressure_slot(b, p, ps == 0, 100, o.max_iter, slot++, active, s))) return rc;
+            if ((rc = solve_pressure_slot(b, p, ps == 0, reset, o.max_iter, slot++, active, s))) return rc;
         }
-        float *uo = (cs == o.corrector_steps - 1) ? u : b->ures;
-        if ((rc = fgb_correct_velocity(b, p, uo, active, s))) return rc;
+        if ((rc = fgb_correct_velocity(b, p, b->ures, active, s))) return rc;
     }
-    (void)N;
+    // CopyVelocityResultToBlocks (SIM.py:1974): "ures" keeps domain.velocityResult for the next predictor
+    b->launches++;
+    k_copy_active<<<dim3((2 * N + 255) / 256, b->B), 256, 0, st>>>(b->ures, u, 2 * N, active);
+    LAUNCH_CHECK("k_copy_active");
     return FGB_OK;
 }
 
@@ -1721,7 +1825,7 @@ extern "C" int fgb_make_divergence_free(fgb_batch *b, float *u, float *p, const 
 }
 
 extern "C" int fgb_sim_step(fgb_batch *b, float *u, float *p, float *bvel, const float *src, float dt_target, float cfl,
-                            const float *char_vel, float bc_tol, int32_t *substeps_max, fgb_stream_t s) {
+                            const float *char_vel, float bc_tol, const fgb_scalar *sc, int32_t *substeps_max, fgb_stream_t s) {
     if (!b || !u || !p || !bvel) return set_err(FGB_E_ARG, "fgb_sim_step: null argument");
     cudaStream_t st = STREAM(s);
     b->launches++;
@@ -1741,7 +1845,7 @@ extern "C" int fgb_sim_step(fgb_batch *b, float *u, float *p, float *bvel, const
         ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "fgb_sim_step: stream sync", ce);
         if (b->h_counters[0] == 0) break;
-        int rc = fgb_piso_substep(b, u, p, bvel, src, b->dt, b->active, s);
+        int rc = fgb_piso_substep(b, u, p, bvel, src, b->dt, b->active, sc, s);
         if (rc) return rc;
     }
     if (substeps_max) *substeps_max = rounds;
@@ -1785,6 +1889,13 @@ extern "C" int fgb_wall_forces(fgb_batch *b, const fgb_wall *w, const float *u, 
     b->launches++;
     k_wall_forces<<<b->B, 128, 0, STREAM(s)>>>(*w, b->t.viscosity, b->t.N, b->t.NB, u, p, bvel, acc);
     LAUNCH_CHECK("k_wall_forces");
+    return FGB_OK;
+}
+extern "C" int fgb_column_sums(fgb_batch *b, const float *fa, const float *fb, int32_t nx, int32_t ny, float *out, fgb_stream_t s) {
+    if (!b || !fa || !fb || !out || nx * ny != b->t.N) return set_err(FGB_E_ARG, "fgb_column_sums: bad argument (single nx*ny block expected)");
+    b->launches++;
+    k_column_sums<<<dim3((nx + 63) / 64, b->B), 64, 0, STREAM(s)>>>(b->t, fa, fb, nx, ny, out);
+    LAUNCH_CHECK("k_column_sums");
     return FGB_OK;
 }
 extern "C" int fgb_sample_sensors(fgb_batch *b, const float *field, int32_t channels, const int32_t *idx, const float *w,

@@ -35,6 +35,8 @@ class Boundary:
     other: int = -1
     axes: tuple = (0, 0)
     velocity: np.ndarray | None = None  # [2, n] Dirichlet values along the face (fixed only)
+    scalar: np.ndarray | None = None    # [n] passive-scalar boundary value (fixed only)
+    scalar_neumann: bool = False        # passive-scalar boundary condition type (False = Dirichlet)
 
 
 @dataclass
@@ -59,8 +61,10 @@ class DomainSpec:
     """Host-side mirror of the subset of ``PISOtorch.Domain`` the environments use to *describe* a
     domain (``CreateBlock``, ``CloseBoundary``, ``ConnectBlock``, ``MakePeriodic``; BIND.cpp:214-360)."""
 
-    def __init__(self, viscosity: float, name: str = "domain"):
+    def __init__(self, viscosity: float, name: str = "domain", scalar_viscosity: float | None = None):
         self.viscosity = float(np.float32(viscosity))
+        # one passive scalar channel (Domain(passiveScalarChannels=1) + setScalarViscosity, BIND.cpp:362-504)
+        self.scalar_viscosity = None if scalar_viscosity is None else float(np.float32(scalar_viscosity))
         self.name = name
         self.blocks: list[Block] = []
 
@@ -72,7 +76,7 @@ class DomainSpec:
         self.blocks.append(Block(v, name))
         return len(self.blocks) - 1
 
-    def close_boundary(self, block: int, face, velocity=None):
+    def close_boundary(self, block: int, face, velocity=None, scalar=None, scalar_neumann=False):
         f = _face(face)
         b = self.blocks[block]
         n = b.size(1 - (f >> 1))
@@ -80,7 +84,10 @@ class DomainSpec:
         if velocity is not None:
             velocity = np.asarray(velocity, dtype=np.float32).reshape(2, -1)
             vel[:] = velocity  # broadcasts a static [2,1] value
-        b.bounds[f] = Boundary(FIXED, velocity=vel)
+        sc = np.zeros(n, dtype=np.float32)
+        if scalar is not None:
+            sc[:] = np.asarray(scalar, dtype=np.float32).reshape(-1)
+        b.bounds[f] = Boundary(FIXED, velocity=vel, scalar=sc, scalar_neumann=bool(scalar_neumann))
 
     def connect(self, block1: int, face1, block2: int, face2, axis1):
         """``ConnectBlocks`` (domain_structs.cpp:1080-1113), 2-D case."""
@@ -187,6 +194,9 @@ class CompiledDomain:
         bvel = np.zeros((2, max(self.NB, 1)), dtype=f32)
         self.b_cell = np.zeros(max(self.NB, 1), dtype=np.int32)
         self.b_face = np.zeros(max(self.NB, 1), dtype=np.int32)
+        self.sb_val0 = np.zeros(max(self.NB, 1), dtype=f32)
+        self.sb_neumann = np.zeros(max(self.NB, 1), dtype=np.int8)
+        self.scalar_visc = None if spec.scalar_viscosity is None else f32(spec.scalar_viscosity)
         for bi, b in enumerate(blocks):
             for f in range(4):
                 if b.bounds[f].type != FIXED:
@@ -198,6 +208,9 @@ class CompiledDomain:
                 else:
                     bT[o:o + n] = boundary_transforms(b.vertex, f)
                 bvel[:, o:o + n] = b.bounds[f].velocity
+                if b.bounds[f].scalar is not None:
+                    self.sb_val0[o:o + n] = b.bounds[f].scalar
+                    self.sb_neumann[o:o + n] = 1 if b.bounds[f].scalar_neumann else 0
                 for k in range(n):
                     pos = [0, 0]
                     pos[1 - (f >> 1)] = k
@@ -490,6 +503,21 @@ class CompiledDomain:
                                 for j in items:
                                     s = f32(-fs * tfs * inv)
                                     no_entries[g].append((j, f, f32(s * half * aP), f32(s * half * aN), 0))
+        # constant part of the passive-scalar transport matrix (K.cu:3692-3750, 3816-3848 with
+        # forPassiveScalar): orthogonal diffusion with the scalar diffusivity, Dirichlet faces add 2*kappa*alpha.
+        # (The deferred non-orthogonal scalar terms are not tabulated: the only scalar environments, RBC, run
+        # with non_orthogonal=False on an orthogonal grid, rbc_env_base.py:306-329.)
+        kap = self.scalar_visc if self.scalar_visc is not None else f32(0.0)
+        Cd_s = np.zeros((5, N), dtype=f32)
+        for f in range(4):
+            dim = f >> 1
+            inner = nbr[f] >= 0
+            vc = ((alpha[dim] * kap + nalpha[f] * kap) * half).astype(f32)
+            j = np.where(inner, 0, -1 - nbr[f])
+            dirichlet = (self.sb_neumann[j] == 0)
+            Cd_s[0] += np.where(inner, vc, np.where(dirichlet, f32(2.0) * kap * alpha[dim], f32(0.0))).astype(f32)
+            Cd_s[f + 1] = np.where(inner, -vc, f32(0.0))
+        self.Cd_s = Cd_s
         self.nbr = nbr
         self.fl_comp = fl_comp
         self.nalpha = nalpha

@@ -36,7 +36,9 @@ class CylinderJet2DEnv:
 
     def __init__(self, n_envs: int = 1, reynolds_number=1e2, resolution=24, dt=1e-2, adaptive_cfl=0.8, step_length=0.25,
                  episode_length=80, lift_penalty=1.0, device="cuda:0", cg_impl=3, compiled=None, cd_ref=0.0,
-                 randomize_initial_state=False, enable_actions=True):
+                 randomize_initial_state=False, enable_actions=True, use_marl=False):
+        if use_marl:
+            raise ValueError("CylinderJet2D is a single-agent environment (n_agents == 1)")
         self.n_envs = int(n_envs)
         self.resolution, self.dt, self.cfl = int(resolution), float(dt), float(adaptive_cfl)
         self.step_length, self.episode_length = float(step_length), int(episode_length)

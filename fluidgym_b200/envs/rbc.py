@@ -1,0 +1,239 @@
+"""Batched ``RBC2D`` (Rayleigh-Benard convection with bottom-plate heaters) environment.
+
+Mirrors ``envs/rbc/rbc_env_base.py`` / ``rbc_env_2d.py`` of the reference: temperature as passive scalar,
+buoyancy source after the scalar advection of every substep, heater actuation on the bottom plate
+(zero-mean, clamped, cubic-blended profile, ``rbc_env_2d.py:210-282``), Nusselt-number reward
+(``rbc_env_base.py:491-539``), 48 x 8 sensor grid on the rendered field, and the multi-agent interface
+(``use_marl``: one agent per heater, circular moving observation windows ``obs_extraction.py:206-252`` and
+local Nusselt rewards ``rbc_env_2d.py:328-357``).  All tensors carry a leading environment dimension.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import native
+from ..sensors import sensor_tables
+from ..solver import BatchedPISO, _ptr
+from .rbc_domain import make_rbc_domain
+
+RBC_2D_DEFAULT_CONFIG = {
+    "rayleigh_number": 8e4, "prandtl_number": 0.7, "n_heaters": 12, "resolution": 8, "dt": 0.05, "adaptive_cfl": 0.8,
+    "step_length": 1.0, "episode_length": 200, "local_obs_window": 11, "local_reward_weight": 0.2, "uniform_grid": False,
+    "aspect_ratio": 1.0, "use_marl": False,
+}
+
+
+def extract_moving_window_2d(field: torch.Tensor, n_agents: int, agent_width: int, n_agents_per_window: int) -> torch.Tensor:
+    """[..., Y, X] -> [..., n_agents, Y, window*agent_width] circular windows centred on each agent
+    (obs_extraction.py:206-252, batched)."""
+    *lead, Y, X = field.shape
+    assert X == n_agents * agent_width
+    fa = field.reshape(*lead, Y, n_agents, agent_width)
+    pad = n_agents_per_window // 2
+    idx = (torch.arange(n_agents, device=field.device)[:, None] + torch.arange(n_agents_per_window, device=field.device)[None, :] - pad) % n_agents
+    win = fa[..., idx, :]                       # [..., Y, n_agents, window, agent_width]
+    win = win.movedim(-3, -4)                   # [..., n_agents, Y, window, agent_width]
+    return win.reshape(*lead, n_agents, Y, n_agents_per_window * agent_width)
+
+
+class RBC2DEnv:
+    T_cold, T_hot, heater_limit = 0.0, 1.0, 0.75
+    n_sensors_y, n_sensors_per_heater = 8, 4
+    buoyancy_factor = 1.0
+    metrics = ["nusselt"]
+
+    def __init__(self, n_envs: int = 1, rayleigh_number=8e4, prandtl_number=0.7, n_heaters=12, resolution=8, dt=0.05,
+                 adaptive_cfl=0.8, step_length=1.0, episode_length=200, local_obs_window=11, local_reward_weight=0.2,
+                 uniform_grid=False, aspect_ratio=1.0, use_marl=False, device="cuda:0", cg_impl=3, nu_ref=0.0,
+                 randomize_initial_state=False, enable_actions=True):
+        self.n_envs = int(n_envs)
+        self.Ra, self.Pr = float(rayleigh_number), float(prandtl_number)
+        self.n_heaters, self.heater_width = int(n_heaters), int(resolution)
+        self.dt, self.cfl = float(dt), float(adaptive_cfl)
+        self.step_length, self.episode_length = float(step_length), int(episode_length)
+        self.local_obs_window, self.local_reward_weight = int(local_obs_window), local_reward_weight
+        self.use_marl, self.nu_ref = bool(use_marl), float(nu_ref)
+        self.enable_actions = enable_actions
+        self.device = torch.device(device)
+        self.aspect = aspect_ratio * torch.pi
+        spec, info = make_rbc_domain(rayleigh_number, prandtl_number, n_heaters, resolution, aspect_ratio, uniform_grid)
+        self.spec, self.info = spec, info
+        self.cd = spec.prepare()
+        self.nx, self.ny = info["nx"], info["ny"]
+        self.solver = BatchedPISO(self.cd, self.n_envs, device=device, corrector_steps=2, advect_non_ortho_steps=1,
+                                  pressure_non_ortho_steps=1, non_orthogonal=False, pressure_tol=1e-5, cg_impl=cg_impl)
+        self.solver.set_buoyancy(self.buoyancy_factor)
+        self.lib = self.solver.lib
+        self._bottom = slice(int(self.cd.boff[0, 2]), int(self.cd.boff[0, 2]) + self.nx)
+        self._setup_sensors()
+        self._zero_action = torch.zeros(self.n_envs, self.n_heaters, 1, device=self.device)
+        self._reset_called, self._seed, self._n_steps = False, None, 0
+        self.last_substeps = 0
+
+    # ---- static tables ---------------------------------------------------------------------------
+    @property
+    def render_shape(self):
+        nx = self.n_heaters * 20
+        return (nx, round(nx / self.aspect))
+
+    @property
+    def n_sensors_x(self):
+        return self.n_heaters * self.n_sensors_per_heater
+
+    def _setup_sensors(self):
+        nx, ny = self.render_shape
+        sx = torch.linspace(0, nx, self.n_sensors_x + 1)[:-1] + nx / (2 * self.n_sensors_x)
+        sy = torch.linspace(0, ny, self.n_sensors_y + 1)[:-1] + ny / (2 * self.n_sensors_y)
+        gx, gy = torch.meshgrid(sx, sy, indexing="ij")
+        loc = torch.stack([gx, gy], dim=-1).reshape(-1, 2).T
+        self.sensor_px = loc.round().to(torch.int).numpy()       # [2, n_sx * n_sy], x-major (rbc_env_base.py:445-470)
+        idx, w = sensor_tables([b.vertex for b in self.spec.blocks], (nx, ny), self.sensor_px, fill_max_steps=16)
+        self.sens_idx = torch.from_numpy(idx).to(self.device)
+        self.sens_w = torch.from_numpy(w).to(self.device)
+
+    # ---- reference-shaped API ---------------------------------------------------------------------
+    @property
+    def n_agents(self):
+        return self.n_heaters if self.use_marl else 1
+
+    @property
+    def n_sim_steps(self):
+        return max(1, int(self.step_length / self.dt))
+
+    def seed(self, seed: int):
+        self._seed = seed
+        self._np_rng = np.random.default_rng(seed)
+        self._torch_rng = torch.Generator(device=self.device).manual_seed(seed)
+
+    def sample_action(self):
+        if self._seed is None:
+            raise RuntimeError("Environment must be seeded before sampling actions")
+        return torch.rand(self._zero_action.shape, device=self.device, generator=self._torch_rng) * 2 - 1
+
+    def set_state(self, u, p, T, sbval=None, ures=None):
+        s = self.solver
+        for dst, src in ((s.u, u), (s.p, p), (s.T, T)):
+            src = torch.as_tensor(src, dtype=torch.float32, device=self.device)
+            dst.copy_(src if src.dim() == dst.dim() else src.unsqueeze(0).expand_as(dst))
+        if sbval is not None:
+            sb = torch.as_tensor(sbval, dtype=torch.float32, device=self.device)
+            s.sbval.copy_(sb if sb.dim() == 2 else sb.unsqueeze(0).expand_as(s.sbval))
+        ur = s.buffer("ures")
+        if ures is None:
+            ur.zero_()
+        else:
+            ures = torch.as_tensor(ures, dtype=torch.float32, device=self.device)
+            ur.copy_(ures if ures.dim() == 3 else ures.unsqueeze(0).expand_as(ur))
+        self._reset_called = True
+
+    def reset(self, seed: int | None = None, randomize: bool | None = None):
+        """rbc_env_base.py:190-278: linear temperature profile + 0.1 N(0,1) clamped to [T_cold, T_hot],
+        velocity 0.05 N(0,1) (per environment streams of one generator)."""
+        if seed is None:
+            if self._seed is None:
+                raise ValueError("Seed must be provided either during reset or by calling seed().")
+        else:
+            self.seed(seed)
+        s = self.solver
+        B, nx, ny = self.n_envs, self.nx, self.ny
+        grad = torch.linspace(self.T_hot, self.T_cold, steps=ny, device=self.device)[:, None].expand(ny, nx)
+        T0 = grad[None] + torch.randn(B, ny, nx, device=self.device, generator=self._torch_rng) * 0.1 * (self.T_hot - self.T_cold)
+        s.T.copy_(torch.clamp(T0, self.T_cold, self.T_hot).reshape(B, -1))
+        s.u.copy_(torch.randn(B, 2, ny * nx, device=self.device, generator=self._torch_rng) * 0.05)
+        s.p.zero_()
+        s.buffer("ures").zero_()
+        s.sbval.copy_(torch.from_numpy(self.cd.sb_val0[:self.cd.NB].copy()).to(self.device).unsqueeze(0).expand_as(s.sbval))
+        self._apply_action(self._zero_action)
+        self._reset_called, self._n_steps = True, 0
+        return (self._get_local_obs() if self.use_marl else self._get_global_obs()), {}
+
+    def _action_to_control(self, action: torch.Tensor) -> torch.Tensor:
+        """[B, n_heaters] -> bottom-plate temperature [B, nx] (rbc_env_2d.py:210-270)."""
+        hw = self.heater_width
+        T_shifted = action - action.mean(dim=1, keepdim=True)
+        T_action = T_shifted / (torch.clamp(T_shifted.abs(), min=1.0) / self.heater_limit) + self.T_hot
+        bw = round(hw * 0.1)
+        T_left, T_right = torch.roll(T_action, 1, dims=1), torch.roll(T_action, -1, dims=1)
+        x_idx = torch.arange(self.nx, device=action.device)
+        seg, xpos = x_idx // hw, x_idx % hw
+        T0, T1, T2 = T_left[:, seg], T_action[:, seg], T_right[:, seg]
+        left_zone, right_zone = xpos < bw, xpos >= hw - bw
+        tL = (xpos.to(torch.float32) / bw + 0.5).clamp(0.0, 1.0) if bw > 0 else torch.ones_like(xpos, dtype=torch.float32)
+        tR = 1 - torch.roll(tL, shifts=hw - bw + 1, dims=0)
+
+        def blend(t, A, Bv):
+            sm = t * t * (3 - 2 * t)
+            return (1 - sm) * A + sm * Bv
+
+        return torch.where(left_zone, blend(tL, T0, T1), torch.where(right_zone, blend(tR, T1, T2), T1))
+
+    def _apply_action(self, action):
+        a = torch.as_tensor(action, dtype=torch.float32, device=self.device).reshape(self.n_envs, self.n_heaters)
+        self.solver.sbval[:, self._bottom] = self._action_to_control(a)
+
+    def _sample(self, field, channels):
+        s = self.solver
+        ns, K = self.sens_idx.shape[1], self.sens_idx.shape[0]
+        out = torch.empty(self.n_envs, channels, ns, device=self.device)
+        native.check(self.lib.fgb_sample_sensors(s.handle, _ptr(field), channels, _ptr(self.sens_idx), _ptr(self.sens_w), K, ns,
+                                                 _ptr(out), s.stream), "fgb_sample_sensors")
+        # sensors are enumerated x-major; the reference reshapes to [n_sx, n_sy] and transposes to [n_sy, n_sx]
+        return out.reshape(self.n_envs, channels, self.n_sensors_x, self.n_sensors_y).transpose(-1, -2).contiguous()
+
+    def _get_global_obs(self):
+        s = self.solver
+        return {"temperature": self._sample(s.T, 1)[:, 0], "velocity": self._sample(s.u, 2), "pressure": self._sample(s.p, 1)[:, 0]}
+
+    def _get_local_obs(self):
+        g = self._get_global_obs()
+        w = dict(n_agents=self.n_heaters, agent_width=self.n_sensors_per_heater, n_agents_per_window=self.local_obs_window)
+        T = extract_moving_window_2d(g["temperature"], **w)
+        ux = extract_moving_window_2d(g["velocity"][:, 0], **w)
+        uy = extract_moving_window_2d(g["velocity"][:, 1], **w)
+        p = extract_moving_window_2d(g["pressure"], **w)
+        return {"temperature": T, "velocity": torch.stack([ux, uy], dim=2), "pressure": p}
+
+    def _column_sums(self):
+        s = self.solver
+        return s.column_sums(s.u[:, 1].contiguous(), s.T, self.nx, self.ny)     # [B, 2, nx]: sum_y u_y T dV, sum_y dV
+
+    def compute_global_nusselt(self, cs=None):
+        cs = self._column_sums() if cs is None else cs
+        return 1.0 + (self.Ra * self.Pr) ** 0.5 * cs[:, 0].sum(dim=1) / cs[:, 1].sum(dim=1)
+
+    def _get_local_rewards(self, cs=None):
+        """rbc_env_2d.py:328-357: Nusselt number over each agent's moving window.  NB the reference divides by
+        the cell volume of the FIRST window*heater_width columns for every agent -- reproduced."""
+        cs = self._column_sums() if cs is None else cs
+        w = dict(n_agents=self.n_heaters, agent_width=self.heater_width, n_agents_per_window=self.local_obs_window)
+        num = extract_moving_window_2d(cs[:, 0:1], **w).sum(dim=(-1, -2))            # [B, n_agents]
+        vol = cs[:, 1, : self.local_obs_window * self.heater_width].sum(dim=1, keepdim=True)
+        return self.nu_ref - (1.0 + (self.Ra * self.Pr) ** 0.5 * num / vol)
+
+    def step(self, action):
+        if not self._reset_called:
+            raise RuntimeError("Environment must be reset before stepping. Call 'reset()' before'step()'.")
+        action = torch.as_tensor(action, dtype=torch.float32, device=self.device)
+        if action.shape != self._zero_action.shape:
+            raise ValueError(f"Action shape {action.shape} does not match expected shape {self._zero_action.shape}.")
+        if self._n_steps >= self.episode_length:
+            raise RuntimeError("Episode has already terminated. Call 'reset()' first.")
+        if self.enable_actions:
+            self._apply_action(action)
+        nsub = 0
+        for _ in range(self.n_sim_steps):
+            nsub += self.solver.single_step(self.dt, self.cfl)
+        self.last_substeps = nsub
+        cs = self._column_sums()
+        nu = self.compute_global_nusselt(cs)
+        reward = self.nu_ref - nu
+        info = {"nusselt": nu.detach()}
+        self._n_steps += 1
+        truncated = self._n_steps >= self.episode_length
+        if not self.use_marl:
+            return self._get_global_obs(), reward, False, truncated, info
+        lw = self.local_reward_weight
+        local = self._get_local_rewards(cs) if lw > 0 else torch.zeros(self.n_envs, self.n_heaters, device=self.device)
+        info["global_reward"] = reward
+        return self._get_local_obs(), lw * local + (1 - lw) * reward[:, None], False, truncated, info

@@ -21,7 +21,12 @@ class Tables(C.Structure):
     _fields_ = [("N", C.c_int32), ("NB", C.c_int32), ("K_no", C.c_int32), ("K_nob", C.c_int32),
                 ("viscosity", C.c_float)] + [(n, C.c_void_p) for n in (
                     "nbr", "fl_comp", "minv", "det", "Cd", "Wp", "no_idx", "no_face", "no_gP", "no_gN", "no_wv",
-                    "nob_idx", "nob_w", "b_minv", "b_det", "b_alpha", "b_cell", "b_face", "b_out")]
+                    "nob_idx", "nob_w", "b_minv", "b_det", "b_alpha", "b_cell", "b_face", "b_out")] + [
+                    ("scalar_viscosity", C.c_float), ("Cd_s", C.c_void_p), ("sb_neumann", C.c_void_p)]
+
+
+class Scalar(C.Structure):
+    _fields_ = [("T", C.c_void_p), ("sbval", C.c_void_p), ("beta", C.c_float), ("src", C.c_void_p)]
 
 
 class Options(C.Structure):
@@ -39,7 +44,8 @@ EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_cr
            "fgb_batch_set_options", "fgb_batch_buffer", "fgb_setup_advection", "fgb_solve_advection",
            "fgb_setup_pressure_matrix", "fgb_setup_pressure_rhs", "fgb_solve_pressure", "fgb_correct_velocity",
            "fgb_piso_substep", "fgb_make_divergence_free", "fgb_sim_step", "fgb_update_outflow", "fgb_flux_balance",
-           "fgb_max_velocity", "fgb_apply_jet_action", "fgb_wall_forces", "fgb_sample_sensors", "fgb_profile_enable",
+           "fgb_max_velocity", "fgb_apply_jet_action", "fgb_wall_forces", "fgb_column_sums", "fgb_sample_sensors",
+           "fgb_profile_enable",
            "fgb_profile_read", "fgb_launch_count"]
 
 
@@ -72,9 +78,10 @@ def load():
     L.fgb_setup_pressure_rhs.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp]
     L.fgb_solve_pressure.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.fgb_correct_velocity.argtypes = [vp, vp, vp, vp, vp]
-    L.fgb_piso_substep.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.fgb_piso_substep.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(Scalar), vp]
     L.fgb_make_divergence_free.argtypes = [vp, vp, vp, vp, i32, vp]
-    L.fgb_sim_step.argtypes = [vp, vp, vp, vp, vp, f32, f32, C.POINTER(f32), f32, C.POINTER(i32), vp]
+    L.fgb_sim_step.argtypes = [vp, vp, vp, vp, vp, f32, f32, C.POINTER(f32), f32, C.POINTER(Scalar), C.POINTER(i32), vp]
+    L.fgb_column_sums.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.fgb_update_outflow.argtypes = [vp, vp, vp, vp, C.POINTER(f32), f32, vp]
     L.fgb_flux_balance.argtypes = [vp, vp, vp, vp]
     L.fgb_max_velocity.argtypes = [vp, vp, vp, vp, vp]

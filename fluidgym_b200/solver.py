@@ -51,7 +51,14 @@ class BatchedPISO:
         self.tables = native.Tables()
         self.tables.N, self.tables.NB, self.tables.K_no, self.tables.K_nob = cd.N, cd.NB, cd.K_no, cd.K_nob
         self.tables.viscosity = float(cd.visc)
-        for name in _TABLE_FIELDS + ["b_out"]:
+        self.has_scalar = cd.scalar_visc is not None
+        if self.has_scalar:
+            self._tab["Cd_s"] = torch.from_numpy(np.ascontiguousarray(cd.Cd_s)).to(dev)
+            self._tab["sb_neumann"] = torch.from_numpy(np.ascontiguousarray(cd.sb_neumann[:max(cd.NB, 1)], dtype=np.int8)).to(dev)
+            self.tables.scalar_viscosity = float(cd.scalar_visc)
+        else:
+            self._tab["Cd_s"] = self._tab["sb_neumann"] = None
+        for name in _TABLE_FIELDS + ["b_out", "Cd_s", "sb_neumann"]:
             t = self._tab[name]
             setattr(self.tables, name, t.data_ptr() if t is not None else None)
         self.options = native.Options(corrector_steps, advect_non_ortho_steps, pressure_non_ortho_steps,
@@ -68,7 +75,16 @@ class BatchedPISO:
         self.p = torch.zeros(B, N, device=dev)
         self.bvel = torch.from_numpy(cd.bvel0[:, :NB].copy()).to(dev).unsqueeze(0).repeat(B, 1, 1).contiguous()
         self.src = None
+        self.scalar = None           # native.Scalar when the domain carries a passive scalar
+        if self.has_scalar:
+            self.T = torch.zeros(B, N, device=dev)
+            self.sbval = torch.from_numpy(cd.sb_val0[:NB].copy()).to(dev).unsqueeze(0).repeat(B, 1).contiguous()
+            self.vsrc = torch.zeros(B, 2, N, device=dev)
+            self.set_buoyancy(1.0)
         self.ones_dt = torch.ones(B, device=dev)
+
+    def set_buoyancy(self, beta: float):
+        self.scalar = native.Scalar(self.T.data_ptr(), self.sbval.data_ptr(), float(beta), self.vsrc.data_ptr())
 
     def __del__(self):
         try:
@@ -140,8 +156,9 @@ class BatchedPISO:
     def piso_substep(self, dt, active=None):
         """``Simulation._PISO_split_step(iterations=1, time_step=dt)`` for every (active) environment."""
         self._dtc = self._dt(dt)
+        sc = C.byref(self.scalar) if self.scalar is not None else None
         native.check(self.lib.fgb_piso_substep(self.handle, _ptr(self.u), _ptr(self.p), _ptr(self.bvel), _ptr(self.src),
-                                               _ptr(self._dtc), _ptr(active), self.stream), "fgb_piso_substep")
+                                               _ptr(self._dtc), _ptr(active), sc, self.stream), "fgb_piso_substep")
 
     def make_divergence_free(self, max_iter=1000):
         native.check(self.lib.fgb_make_divergence_free(self.handle, _ptr(self.u), _ptr(self.p), _ptr(self.bvel), max_iter,
@@ -157,13 +174,19 @@ class BatchedPISO:
         """``Simulation.single_step()`` with adaptive CFL sub-stepping; returns the substep rounds used."""
         cv = (C.c_float * 2)(*[float(x) for x in char_vel]) if char_vel is not None else None
         n = C.c_int32(0)
+        sc = C.byref(self.scalar) if self.scalar is not None else None
         native.check(self.lib.fgb_sim_step(self.handle, _ptr(self.u), _ptr(self.p), _ptr(self.bvel), _ptr(self.src), float(dt),
-                                           float(cfl), cv, float(bc_tol), C.byref(n), self.stream), "fgb_sim_step")
+                                           float(cfl), cv, float(bc_tol), sc, C.byref(n), self.stream), "fgb_sim_step")
         return n.value
 
     def flux_balance(self) -> torch.Tensor:
         out = torch.empty(self.B, device=self.device)
         native.check(self.lib.fgb_flux_balance(self.handle, _ptr(self.bvel), _ptr(out), self.stream), "fgb_flux_balance")
+        return out
+
+    def column_sums(self, fa: torch.Tensor, fb: torch.Tensor, nx: int, ny: int) -> torch.Tensor:
+        out = torch.empty(self.B, 2, nx, device=self.device)
+        native.check(self.lib.fgb_column_sums(self.handle, _ptr(fa), _ptr(fb), nx, ny, _ptr(out), self.stream), "fgb_column_sums")
         return out
 
     def max_velocity(self) -> torch.Tensor:

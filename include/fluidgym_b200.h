@@ -62,7 +62,21 @@ typedef struct fgb_tables {
     const int32_t *b_cell;  /* [NB]     cell adjacent to the boundary face                              */
     const int8_t *b_face;   /* [NB]     face direction 0..3                                             */
     const int8_t *b_out;    /* [NB]     1 = advective-outflow face (SIM.py:228-393), may be NULL        */
+    /* passive scalar (temperature) transport, NULL / 0 when the domain has none */
+    float scalar_viscosity; /*          scalar diffusivity (Domain.setScalarViscosity)                     */
+    const float *Cd_s;      /* [5][N]   constant part of the scalar transport matrix, before /det          */
+    const int8_t *sb_neumann; /* [NB]   scalar boundary condition type: 0 Dirichlet, 1 Neumann             */
 } fgb_tables;
+
+/* Passive scalar + buoyancy coupling of one batch (RBC: temperature; rbc_env_base.py:190-304).  With the
+ * reference's ordering: the scalar is advected first with the old velocity (SIM.py:1471-1644), then
+ * the velocity source (0, beta*T_new) is built ("PRE_VELOCITY_SETUP" hook) and used by the predictor / HbyA. */
+typedef struct fgb_scalar {
+    float *T;             /* [B][N]   scalar field, updated in place                                   */
+    const float *sbval;   /* [B][NB]  boundary values (FixedBoundary.passiveScalar)                    */
+    float beta;           /*          buoyancy factor                                                    */
+    float *src;           /* [B][2][N] velocity-source buffer written by the step                       */
+} fgb_scalar;
 
 typedef struct fgb_batch fgb_batch; /* opaque: tables + workspace carving for B environments */
 
@@ -128,7 +142,7 @@ int fgb_correct_velocity(fgb_batch *b, const float *p, float *u_out, const int32
 /* Simulation._PISO_split_step(iterations=1) (SIM.py:1431-2002): one PISO substep of dt[e] for every
  * active environment; u, p updated in place. */
 int fgb_piso_substep(fgb_batch *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
-                     const int32_t *active, fgb_stream_t s);
+                     const int32_t *active, const fgb_scalar *sc /* may be NULL */, fgb_stream_t s);
 /* Simulation.make_divergence_free (SIM.py:1320-1429): A=1, dt=1 projection of u (max_iter 1000). */
 int fgb_make_divergence_free(fgb_batch *b, float *u, float *p, const float *bvel, int max_iter, fgb_stream_t s);
 /* Simulation.single_step with substeps="ADAPTIVE" (FGSIM.py:210-280, SIM.py:2004-2064) including the
@@ -136,7 +150,8 @@ int fgb_make_divergence_free(fgb_batch *b, float *u, float *p, const float *bvel
  * when the tables carry b_out and char_vel (HOST pointer, 2 floats) is given.  Returns in *substeps_max the largest number of substeps any
  * environment needed (one small device->host read per substep round). */
 int fgb_sim_step(fgb_batch *b, float *u, float *p, float *bvel, const float *src, float dt_target, float cfl,
-                 const float *char_vel, float bc_tol, int32_t *substeps_max, fgb_stream_t s);
+                 const float *char_vel, float bc_tol, const fgb_scalar *sc /* may be NULL */, int32_t *substeps_max,
+                 fgb_stream_t s);
 
 /* update_advective_boundaries + balance_boundary_fluxes (SIM.py:188-224, 228-393) for the faces marked in
  * tables.b_out, with the per-environment time step dt[B] (device).  char_vel: HOST pointer to the two
@@ -167,6 +182,9 @@ typedef struct fgb_wall {
 } fgb_wall;
 int fgb_wall_forces(fgb_batch *b, const fgb_wall *w, const float *u, const float *p, const float *bvel,
                     float *acc, fgb_stream_t s);
+/* column sums over y of fa*fb*det and of det for a single structured nx x ny block (Nusselt number,
+ * rbc_env_base.py:491-539; local rewards rbc_env_2d.py:328-357): out[B][2][nx] */
+int fgb_column_sums(fgb_batch *b, const float *fa, const float *fb, int32_t nx, int32_t ny, float *out, fgb_stream_t s);
 /* sensor sampling (obs_extraction.py:10-57 -> resampling.cu:296-364): out[B][C][n_s] =
  * sum_k w[k][s] * field[B][C][idx[k][s]] (the static splat+normalise+fill map evaluated at the sensors) */
 int fgb_sample_sensors(fgb_batch *b, const float *field, int32_t channels, const int32_t *idx, const float *w,

@@ -152,6 +152,30 @@ class Oracle:
         it = self.lib.orc_bicgstab(self.N, _fp(val), _ip(idx), _fp(f), _fp(x), maxit, C.c_float(tol), C.byref(res), C.byref(conv))
         return x, it, res.value, bool(conv.value)
 
+    def set_scalar(self, scal_visc, sb_neumann, sbval):
+        self.lib.orc_sbval.restype = C.POINTER(C.c_float)
+        t = np.ascontiguousarray(sb_neumann, np.int32)
+        v = np.ascontiguousarray(sbval, np.float32)
+        self.lib.orc_set_scalar(self.dom, C.c_float(scal_visc), _ip(t), _fp(v))
+        self.sbval = np.ctypeslib.as_array(self.lib.orc_sbval(self.dom), shape=(self.NB,))
+
+    def scalar_rhs(self, u, T, dt):
+        rhs = np.zeros(self.N, np.float32)
+        u = np.ascontiguousarray(u, np.float32)
+        T = np.ascontiguousarray(T, np.float32)
+        self.lib.orc_scalar_rhs(self.dom, _fp(u), _fp(T), C.c_float(dt), _fp(rhs))
+        return rhs
+
+    def substep_scalar(self, u, p, T, ures, dt, beta=1.0):
+        """Orthogonal-path substep with passive scalar + buoyancy, in place on u, p, T, ures."""
+        self.lib.orc_substep_ortho_scalar(self.dom, self.work, C.byref(self.cfg), _fp(u), _fp(p), _fp(T), _fp(ures),
+                                          C.c_float(dt), C.c_float(beta))
+        return list(self.cfg.bicg_iters), list(self.cfg.cg_iters)[: self.cfg.n_cg], self.cfg.cg_iters[7]
+
+    def sim_step_scalar(self, u, p, T, ures, dt_target, cfl, beta=1.0):
+        return self.lib.orc_sim_step_scalar(self.dom, self.work, C.byref(self.cfg), _fp(u), _fp(p), _fp(T), _fp(ures),
+                                            C.c_float(dt_target), C.c_float(cfl), C.c_float(beta))
+
     def max_velocity(self, u):
         u = np.ascontiguousarray(u, np.float32)
         return float(self.lib.orc_max_velocity(self.dom, _fp(u)))

@@ -56,10 +56,14 @@ def snapshot_state(env):
     for bi, blk in enumerate(dom.getBlocks()):
         st[f"b{bi}_u"] = t2n(blk.velocity)
         st[f"b{bi}_p"] = t2n(blk.pressure)
+        if dom.hasPassiveScalar():
+            st[f"b{bi}_s"] = t2n(blk.passiveScalar)
         for f in range(2 * dom.getSpatialDims()):
             bnd = blk.getBoundary(f)
             if type(bnd).__name__ == "FixedBoundary":
                 st[f"b{bi}_f{f}_velocity"] = t2n(bnd.velocity)
+                if dom.hasPassiveScalar() and bnd.passiveScalar is not None:
+                    st[f"b{bi}_f{f}_scalar"] = t2n(bnd.passiveScalar)
     st["pressureResult"] = t2n(dom.pressureResult)
     st["velocityResult"] = t2n(dom.velocityResult)
     return st
@@ -103,7 +107,9 @@ class OpTracer:
         orig = self._orig[name]
 
         def wrapper(*a, **k):
-            if name == "SetupAdvectionMatrix" and not (k.get("forPassiveScalar", False) or (len(a) > 3 and a[3])):
+            is_scalar_mat = name == "SetupAdvectionMatrix" and bool(k.get("forPassiveScalar", False) or (len(a) > 3 and a[3]))
+            starts = name == "SetupAdvectionMatrix" and (is_scalar_mat or not a[0].hasPassiveScalar())
+            if starts:
                 self.substep += 1
                 self.n_substeps_total += 1
                 self.count = {}
@@ -113,10 +119,15 @@ class OpTracer:
                     for bi, blk in enumerate(dom.getBlocks()):
                         self._rec(f"in_b{bi}_u", blk.velocity)
                         self._rec(f"in_b{bi}_p", blk.pressure)
+                        if dom.hasPassiveScalar():
+                            self._rec(f"in_b{bi}_s", blk.passiveScalar)
                         for f in range(2 * dom.getSpatialDims()):
                             bnd = blk.getBoundary(f)
                             if type(bnd).__name__ == "FixedBoundary":
                                 self._rec(f"in_b{bi}_f{f}_velocity", bnd.velocity)
+                                if dom.hasPassiveScalar() and bnd.passiveScalar is not None:
+                                    self._rec(f"in_b{bi}_f{f}_scalar", bnd.passiveScalar)
+                    self._rec("in_velocityResult", dom.velocityResult)
                     self._rec("in_pressureResult", dom.pressureResult)
             res = orig(*a, **k)
             rec = self.substep < self.max_substeps and self.substep >= 0
@@ -133,13 +144,29 @@ class OpTracer:
                     self.meta.append({"substep": self.substep, "solve": c, "bicg": use_bicg, "infos": infos})
             elif rec:
                 dom = a[0]
-                if name == "SetupAdvectionMatrix":
+                if name == "SetupAdvectionMatrix" and is_scalar_mat:
+                    self._rec("Cs_value", dom.C.value)
+                    self._rec("Cs_index", dom.C.index)
+                    self._rec("Cs_row", dom.C.row)
+                elif name == "SetupAdvectionScalar":
+                    self._rec(f"scalarRHS{c}", dom.scalarRHS)
+                elif name == "SetupPressureCorrection":
+                    self._rec(f"P_value{c}", dom.P.value)
+                    if c == 0:
+                        self._rec("P_index", dom.P.index)
+                        self._rec("P_row", dom.P.row)
+                    self._rec(f"pressureRHS{c}", dom.pressureRHS)
+                    self._rec(f"pressureRHSdiv{c}", dom.pressureRHSdiv)
+                elif name == "SetupAdvectionMatrix":
                     self._rec("C_value", dom.C.value)
                     self._rec("C_index", dom.C.index)
                     self._rec("C_row", dom.C.row)
                     self._rec("A", dom.A)
                 elif name == "SetupAdvectionVelocity":
                     self._rec(f"velocityRHS{c}", dom.velocityRHS)
+                    for bi, blk in enumerate(dom.getBlocks()):
+                        if blk.velocitySource is not None:
+                            self._rec(f"b{bi}_velocitySource", blk.velocitySource)
                 elif name == "SetupPressureMatrix":
                     self._rec(f"P_value{c}", dom.P.value)
                     if c == 0:
@@ -191,7 +218,13 @@ def main():
     np.savez_compressed(os.path.join(args.out, f"{tag}_state_reset.npz"), **st)
     meta["n_sim_steps"] = int(env._n_sim_steps)
     meta["dt"] = float(env._dt)
-    meta["viscosity"] = float(env._viscosity.cpu().item())
+    visc = getattr(env, "_viscosity", None)
+    if visc is None:
+        visc = getattr(env, "_kinematic_viscosity", None)
+    meta["viscosity"] = float(visc.cpu().item()) if visc is not None else None
+    for k2 in ("_thermal_diffusivity",):
+        if hasattr(env, k2):
+            meta[k2.strip("_")] = float(getattr(env, k2).cpu().item())
 
     tracer = OpTracer(PISOtorch, args.trace_substeps)
     tracer.install()
@@ -208,6 +241,8 @@ def main():
             for bi, blk in enumerate(env._domain.getBlocks()):
                 s[f"b{bi}_u"] = t2n(blk.velocity)
                 s[f"b{bi}_p"] = t2n(blk.pressure)
+                if env._domain.hasPassiveScalar():
+                    s[f"b{bi}_s"] = t2n(blk.passiveScalar)
             s["substeps_so_far"] = np.array(tracer.n_substeps_total)
             per_sim.append(s)
         return r
@@ -218,6 +253,9 @@ def main():
     actions = []
     for i in range(args.env_steps):
         act = torch.full_like(env._zero_action, args.action * float(np.cos(0.7 * i)))
+        if act.numel() > 1:
+            ramp = torch.linspace(-1.0, 1.0, act.numel(), device=act.device).reshape(act.shape)
+            act = act * torch.sin(3.0 * ramp + 0.5 * i)
         actions.append(t2n(act))
         obs, reward, term, trunc, info = env.step(act)
         step_out[f"step{i}_reward"] = t2n(reward)

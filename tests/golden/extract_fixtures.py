@@ -18,9 +18,49 @@ from fluidgym_b200.domain import FIXED  # noqa: E402
 from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain  # noqa: E402
 
 
+def rbc(src, tag="RBC2D_easy_v0", out="rbc"):
+    """Single block [61 x 96]: cells are already in product order; boundary faces = (-y: 96, +y: 96)."""
+    g = np.load(os.path.join(src, f"{tag}_geometry.npz"))
+    np.savez_compressed(os.path.join(HERE, f"{out}_geometry.npz"), T=g["b0_transform"].reshape(-1, 9),
+                        bT=np.concatenate([g["b0_f2_transform"].reshape(-1, 9), g["b0_f3_transform"].reshape(-1, 9)]))
+    tr = np.load(os.path.join(src, f"{tag}_trace.npz"))
+    meta = json.load(open(os.path.join(src, f"{tag}_meta.json")))
+
+    def sb(d, pre):
+        return np.concatenate([np.broadcast_to(d[pre + "f2_scalar"].ravel(), (96,)), np.broadcast_to(d[pre + "f3_scalar"].ravel(), (96,))]).astype(np.float32)
+
+    k = "s0_"
+    its = [m for m in meta["trace_meta"] if m["substep"] == 0]
+    fx = dict(dt=tr[k + "dt"], u_in=tr[k + "in_b0_u"].reshape(2, -1), p_in=tr[k + "in_pressureResult"].ravel(),
+              T_in=tr[k + "in_b0_s"].ravel(), sbval_in=sb(tr, k + "in_b0_"), ures_in=tr[k + "in_velocityResult"].reshape(2, -1),
+              Cs_value=tr[k + "Cs_value"], Cs_index=tr[k + "Cs_index"], Cs_row=tr[k + "Cs_row"], srhs=tr[k + "scalarRHS0"],
+              T_out=tr[k + "solve0_x"], A=tr[k + "A"], rhs=tr[k + "velocityRHS0"].reshape(2, -1), ustar=tr[k + "solve1_x"].reshape(2, -1),
+              hbya0=tr[k + "pressureRHS0"].reshape(2, -1), div0=tr[k + "pressureRHSdiv0"], p0=tr[k + "pressureResult0"],
+              u1=tr[k + "velocityResult1"].reshape(2, -1), p1=tr[k + "pressureResult1"],
+              scalar_iters=np.array([its[0]["infos"][0][1]]), bicg_iters=np.array([i[1] for i in its[1]["infos"]]),
+              cg_iters=np.array([its[2]["infos"][0][1], its[3]["infos"][0][1]]))
+    np.savez_compressed(os.path.join(HERE, f"{out}_substep0.npz"), **fx)
+    rs = np.load(os.path.join(src, f"{tag}_state_reset.npz"))
+    st = np.load(os.path.join(src, f"{tag}_steps.npz"))
+    e0 = np.load(os.path.join(src, f"{tag}_state_step0.npz"))
+    s0 = np.load(os.path.join(src, f"{tag}_simstep0.npz"))
+    fx = {k2: st[k2] for k2 in st.files if not k2.startswith("step2")}
+    fx.update(reset_u=rs["b0_u"].reshape(2, -1), reset_p=rs["pressureResult"], reset_T=rs["b0_s"].ravel(), reset_sbval=sb(rs, "b0_"),
+              reset_ures=rs["velocityResult"].reshape(2, -1), reset_obs_temperature=rs["obs_temperature"],
+              reset_obs_velocity=rs["obs_velocity"], reset_obs_pressure=rs["obs_pressure"],
+              sim0_u=s0["b0_u"].reshape(2, -1), sim0_T=s0["b0_s"].ravel(), sim0_substeps=s0["substeps_so_far"],
+              env0_u=e0["b0_u"].reshape(2, -1), env0_p=e0["b0_p"].ravel(), env0_T=e0["b0_s"].ravel(), env0_sbval=sb(e0, "b0_"))
+    np.savez_compressed(os.path.join(HERE, f"{out}_steps.npz"), **fx)
+    keep = {k2: meta[k2] for k2 in ("env", "seed", "gpu", "n_sim_steps", "dt", "viscosity", "thermal_diffusivity", "timing",
+                                    "mean_iters", "max_iters", "n_solves", "substeps_in_env_steps")}
+    json.dump(keep, open(os.path.join(HERE, f"{out}_meta.json"), "w"), indent=1)
+
+
 def main():
     src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden"
     tag = sys.argv[2] if len(sys.argv) > 2 else "CylinderJet2D_easy_v0"
+    if os.path.exists(os.path.join(src, "RBC2D_easy_v0_trace.npz")):
+        rbc(src)
     out = "cyl24"
     spec = make_cylinder_domain(24)
     nb = len(spec.blocks)

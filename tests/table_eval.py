@@ -158,3 +158,24 @@ def max_velocity(cd, u, bvel):
     c = np.abs(bm[0] * bvel[0] + bm[1] * bvel[1]).max()
     d = np.abs(bm[2] * bvel[0] + bm[3] * bvel[1]).max()
     return float(max(a, b, c, d))
+
+
+def scalar_setup(cd, u, T, bvel, sbval, dt):
+    """Scalar transport matrix (off [4,N], diag [N]) and right-hand side, as k_setup_scalar computes them."""
+    fl = face_fluxes(cd, u, bvel)
+    diag = cd.det / f32(dt) + cd.Cd_s[0]
+    r = cd.det * T / f32(dt)
+    off = np.zeros((4, cd.N), f32)
+    kap = cd.scalar_visc
+    for f in range(4):
+        nb = cd.nbr[f]
+        inner = nb >= 0
+        fs = f32((f & 1) * 2 - 1)
+        ff = fs * f32(0.5) * fl[f]
+        diag = diag + np.where(inner, ff, 0)
+        off[f] = np.where(inner, (ff + cd.Cd_s[f + 1]) / cd.det, 0)
+        j = np.where(inner, 0, -1 - nb)
+        sc = sbval[j]
+        visc = np.where(cd.sb_neumann[j] == 0, sc * kap * 2 * cd.b_alpha[j], sc * kap)
+        r = r + np.where(inner, 0, -sc * (fl[f] * fs) + visc)
+    return off.astype(f32), (diag / cd.det).astype(f32), (r / cd.det).astype(f32)
