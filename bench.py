@@ -163,7 +163,9 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     B = args.envs
-    env = fluidgym_b200.make(ENV_ID, n_envs=B, device=str(dev), cg_impl=args.cg_impl)
+    env_id = ENV_ID if args.workload == "cylinder" else "RBC2D-easy-v0"
+    kw = {} if args.workload == "cylinder" else {"use_marl": True}
+    env = fluidgym_b200.make(env_id, n_envs=B, device=str(dev), cg_impl=args.cg_impl, **kw)
     N = env.cd.N
     env.reset(seed=42 + rank)
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
@@ -171,7 +173,7 @@ def run_ours(args):
     env.solver.p += 0.025 * torch.randn(env.solver.p.shape, device=dev, generator=gen)
     cpu_gen = torch.Generator().manual_seed(7 + rank)
     total = args.warmup + 2 * args.steps
-    actions_host = (torch.rand(total, B, 1, generator=cpu_gen) * 2 - 1).pin_memory()
+    actions_host = (torch.rand(total, *env._zero_action.shape, generator=cpu_gen) * 2 - 1).pin_memory()
     actions_dev = actions_host.to(dev)
     env.episode_length = 10 ** 9
 
@@ -210,8 +212,9 @@ def run_ours(args):
     value = env_substeps / (ms / 1e3)
 
     # ---- end-to-end through the public API with host buffers --------------------------------------
-    obs_host = {"velocity": torch.empty(B, 151, 2).pin_memory(), "pressure": torch.empty(B, 151).pin_memory()}
-    rew_host = torch.empty(B).pin_memory()
+    obs_probe, rew_probe, _, _, _ = env.step(actions_dev[args.warmup])
+    obs_host = {k2: torch.empty(v.shape).pin_memory() for k2, v in obs_probe.items()}
+    rew_host = torch.empty(rew_probe.shape).pin_memory()
     barrier(world)
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
@@ -220,8 +223,8 @@ def run_ours(args):
     for i in range(args.steps):
         a = actions_host[args.warmup + args.steps + i].to(dev, non_blocking=True)
         obs, rew, _, _, info = env.step(a)
-        obs_host["velocity"].copy_(obs["velocity"], non_blocking=True)
-        obs_host["pressure"].copy_(obs["pressure"], non_blocking=True)
+        for k2, v in obs.items():
+            obs_host[k2].copy_(v, non_blocking=True)
         rew_host.copy_(rew, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         nsub_e += env.last_substeps
@@ -229,8 +232,8 @@ def run_ours(args):
     barrier(world)
     ms_e = max_over_ranks(t0.elapsed_time(t1), world, dev)
     e2e_value = sum_over_ranks(B * nsub_e, world, dev) / (ms_e / 1e3)
-    h2d = B * 4
-    d2h = B * (151 * 2 + 151 + 1) * 4
+    h2d = actions_host[0].numel() * 4
+    d2h = (sum(v.numel() for v in obs_host.values()) + rew_host.numel()) * 4
 
     # ---- roofline of the dominant kernel (pressure CG) ---------------------------------------------
     peak, peak_src = peaks()
@@ -254,9 +257,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{ENV_ID} x{B} envs per GPU (BASELINE.json configs[1]); step = env.step() = 25 PISO solver steps",
+        "config": {"workload": f"{env_id} x{B} envs per GPU (BASELINE.json configs[{1 if args.workload == 'cylinder' else 2}]); "
+                               f"step = env.step() = {env.n_sim_steps} solver steps (adaptive CFL substeps)",
                    "cells_per_env": N, "envs_per_gpu": B, "parallelism": f"env-batch x{world} (no collective)",
-                   "l2_policy": "working set 256 envs x 2.3 MB = 590 MB > 126 MB L2 (inputs larger than L2)",
+                   "l2_policy": f"working set {B} envs x {N * 45 * 4 / 1e6:.1f} MB > 126 MB L2 (inputs larger than L2)",
                    "cg_impl": args.cg_impl},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e / args.steps},
@@ -269,7 +273,7 @@ def run_ours(args):
                    "time_share_ms": {"cg": ms_prof[0], "bicgstab": ms_prof[1], "assembly": ms_prof[2], "total": ms_local}},
         "clocks": clk,
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "cylinder":
         line["cpu_baseline"] = cpu_baseline(env, args.cpu_steps)
     if rank == 0:
         print(json.dumps(line))
@@ -374,6 +378,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=256, help="environments per GPU")
+    ap.add_argument("--workload", default="cylinder", choices=["cylinder", "rbc"])
     ap.add_argument("--cg-impl", type=int, default=3)
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "cuda", "cpu"])
     ap.add_argument("--cpu-steps", type=int, default=12)
