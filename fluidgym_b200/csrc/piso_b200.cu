@@ -1188,6 +1188,284 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__re
 }
 
 // ------------------------------------------------------------------------------------------------
+// BiCGStab on chip: one cluster per environment, same mbarrier protocol as the CG above.  r, p, x and the
+// shadow residual live in shared memory (r and p are the two vectors the neighbours gather), v, t and the
+// stencil in registers.  Operation order follows BICG.cu:276-366; rho of the next iteration is reduced
+// together with the residual norm of the second half step (same operands, one reduction less).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_async_f32x4(uint32_t cluster_addr, float a, float b, float c, float d, uint32_t cluster_mbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_mbar) : "memory");
+}
+
+template <int T, int CPT, int CS, int NC>
+__global__ void __launch_bounds__(T, 1) k_bicgstab_cluster(Tab t, const float *__restrict__ Coff, const float *__restrict__ Adiag,
+                                                            const float *__restrict__ Rhs, float *__restrict__ X,
+                                                            int maxit, float tol, int zero_init, const int32_t *__restrict__ active,
+                                                            int32_t *__restrict__ iters, float *__restrict__ resid,
+                                                            unsigned long long *__restrict__ iter_total) {
+    constexpr int NW = T / 32;
+    constexpr int NP = NW * CS;
+    constexpr int PAD = T * CPT;
+    const int b = blockIdx.x / CS;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if (active && !active[b]) return;
+    extern __shared__ __align__(16) float smem[];
+    const int N = t.N;
+    const int per = (N + CS - 1) / CS;
+    const int start = (int)rank * per;
+    const int cnt = max(0, min(per, N - start));
+    float *rs = smem;                            // [NC][PAD] residual            (exposed to the neighbours)
+    float *ps = smem + NC * PAD;                 // [NC][PAD] search direction    (exposed)
+    float *ws = smem + 2 * NC * PAD;             // [NC][PAD] shadow residual r^_0
+    float *xs = smem + 3 * NC * PAD;             // [NC][PAD] iterate
+    float4 *red = (float4 *)(smem + 4 * NC * PAD);       // [2][NP] partials
+    unsigned long long *mb = (unsigned long long *)(smem + 4 * NC * PAD + 2 * NP * 4);
+    const float *off = Coff + (size_t)b * 4 * N, *dg = Adiag + (size_t)b * N;
+    const float norm = 1.0f / sqrtf((float)N);
+    const uint32_t rs_addr = smem_u32(rs), red_addr = smem_u32(red), mb_addr = smem_u32(mb);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        mbar_init(mb_addr, 1); mbar_init(mb_addr + 8, 1); mbar_init(mb_addr + 16, CS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arrive_expect_tx(mb_addr, NP * 16);
+        mbar_arrive_expect_tx(mb_addr + 8, NP * 16);
+    }
+    float cd[CPT], co[CPT][4], vv[NC][CPT], tt[NC][CPT];
+    uint32_t na[CPT][4];                          // cluster address of the neighbour's slot in rs, component 0
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int l = threadIdx.x + k * T;
+        const int g = start + l;
+        const bool ok = l < cnt;
+        cd[k] = ok ? dg[g] : 0.f;
+#pragma unroll
+        for (int ff = 0; ff < 4; ++ff) {
+            const int nb = ok ? t.nbr[ff * N + g] : -1;
+            co[k][ff] = (ok && nb >= 0) ? off[ff * N + g] : 0.f;
+            const int gi = nb >= 0 ? nb : (ok ? g : start);
+            const int c = gi / per;
+            na[k][ff] = mapa_u32(rs_addr + 4u * (uint32_t)(gi - c * per), (uint32_t)c);
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            xs[c * PAD + l] = (ok && !zero_init) ? X[(size_t)b * NC * N + (size_t)c * N + g] : 0.f;
+            rs[c * PAD + l] = 0.f; ps[c * PAD + l] = 0.f; ws[c * PAD + l] = 0.f;
+            vv[c][k] = 0.f; tt[c][k] = 0.f;
+        }
+    }
+    const uint32_t peer_red = mapa_u32(red_addr, (uint32_t)(lane < CS ? lane : 0));
+    const uint32_t peer_mb = mapa_u32(mb_addr, (uint32_t)(lane < CS ? lane : 0));
+    cluster_sync_all();
+
+    uint32_t rcount = 0, pphase = 0;
+    auto cluster_sum4 = [&](float (&a)[4]) {
+        const uint32_t w = rcount & 1u, par = (rcount >> 1) & 1u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+        }
+        if (lane < CS) st_async_f32x4(peer_red + 16u * (w * NP + rank * NW + (uint32_t)warp), a[0], a[1], a[2], a[3], peer_mb + 8u * w);
+        mbar_wait(mb_addr + 8u * w, par);
+        const float4 *rp = red + w * NP;
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < (NP + 31) / 32; ++q)
+            if (lane + 32 * q < NP) { const float4 v = rp[lane + 32 * q]; s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0.x += __shfl_xor_sync(0xffffffffu, s0.x, o); s0.y += __shfl_xor_sync(0xffffffffu, s0.y, o);
+            s0.z += __shfl_xor_sync(0xffffffffu, s0.z, o); s0.w += __shfl_xor_sync(0xffffffffu, s0.w, o);
+        }
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(mb_addr + 8u * w, NP * 16);
+        ++rcount;
+        a[0] = s0.x; a[1] = s0.y; a[2] = s0.z; a[3] = s0.w;
+    };
+    auto publish = [&]() {
+        __syncthreads();
+        if (threadIdx.x < CS) mbar_arrive_remote_release(mapa_u32(mb_addr + 16, threadIdx.x));
+    };
+    auto acquire = [&]() { mbar_wait(mb_addr + 16, pphase); pphase ^= 1u; };
+    // row k of C times an exposed array: `arr` = local base of the array, aoff = its byte offset from rs
+    auto apply = [&](int k, const float *arr, uint32_t aoff) -> float {
+        float s = cd[k] * arr[threadIdx.x + k * T];
+#pragma unroll
+        for (int ff = 0; ff < 4; ++ff) s += co[k][ff] * ld_dsmem_f32(na[k][ff] + aoff);
+        return s;
+    };
+    auto load_f = [&](int c, int k) -> float { const int l = threadIdx.x + k * T; return l < cnt ? Rhs[(size_t)b * NC * N + (size_t)c * N + start + l] : 0.f; };
+
+    float acc[4];
+    // r0 = f - C x0 ; shadow = r0 ; p = r0
+    if (!zero_init) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) ps[c * PAD + threadIdx.x + k * T] = xs[c * PAD + threadIdx.x + k * T];
+        publish(); acquire();
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) tt[c][k] = load_f(c, k) - apply(k, ps + c * PAD, (uint32_t)((NC + c) * PAD * 4));
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+        cluster_sum4(acc);                       // everyone is done reading ps (= x)
+    } else {
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) tt[c][k] = load_f(c, k);
+    }
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const int l = c * PAD + threadIdx.x + k * T;
+            rs[l] = tt[c][k]; ws[l] = tt[c][k]; ps[l] = tt[c][k];
+            acc[c] += tt[c][k] * tt[c][k];
+        }
+    publish();                                   // p0 (= r0) exposed
+    cluster_sum4(acc);                           // ||r0||^2 = <shadow, r0> = rho of the first iteration
+    bool done[2] = {true, true}; int used[2] = {-1, -1}; float fin[2] = {0.f, 0.f};
+    float rho[2] = {1.f, 1.f}, rho_next[2] = {1.f, 1.f}, alpha[2] = {1.f, 1.f}, omega[2] = {1.f, 1.f};
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { fin[c] = sqrtf(acc[c]) * norm; done[c] = fin[c] < tol; rho_next[c] = acc[c]; }
+    for (int i = 0; i < maxit && !(done[0] && done[NC - 1]); ++i) {
+        // rho = <shadow, r> ; p = r + beta (p - omega v)      (ps already holds p - omega v from the last half step)
+        if (i > 0) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) if (!done[c]) {
+                const float beta = (rho_next[c] / rho[c]) * (alpha[c] / omega[c]);
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) { const int l = c * PAD + threadIdx.x + k * T; ps[l] = rs[l] + beta * ps[l]; }
+            }
+            publish();
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) if (!done[c]) rho[c] = rho_next[c];
+        acquire();                               // p of every CTA visible
+        // v = C p ; alpha = rho / <shadow, v>
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) if (!done[c])
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                vv[c][k] = apply(k, ps + c * PAD, (uint32_t)((NC + c) * PAD * 4));
+                acc[c] += ws[c * PAD + threadIdx.x + k * T] * vv[c][k];
+            }
+        cluster_sum4(acc);                       // completes only when every warp has finished gathering p
+        float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < NC; ++c) if (!done[c]) {
+            alpha[c] = rho[c] / acc[c];
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const int l = c * PAD + threadIdx.x + k * T;
+                const float rn = rs[l] - alpha[c] * vv[c][k];
+                rs[l] = rn; xs[l] += alpha[c] * ps[l];
+                acc2[c] += rn * rn;
+            }
+        }
+        publish();                               // r exposed for t = C r; the hand-shake overlaps the reduction
+        cluster_sum4(acc2);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) if (!done[c]) {
+            const float nr = sqrtf(acc2[c]) * norm;
+            used[c] = i; fin[c] = nr;
+            if (!isfinite(nr) || nr < tol) done[c] = true;
+        }
+        acquire();
+        // t = C r ; omega = <t,r>/<t,t>
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) if (!done[c])
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                tt[c][k] = apply(k, rs + c * PAD, (uint32_t)(c * PAD * 4));
+                const float rv = rs[c * PAD + threadIdx.x + k * T];
+                acc[c] += tt[c][k] * rv; acc[2 + c] += tt[c][k] * tt[c][k];
+            }
+        cluster_sum4(acc);                       // every warp has finished gathering r
+        acc2[0] = acc2[1] = acc2[2] = acc2[3] = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) if (!done[c]) {
+            omega[c] = acc[c] / acc[2 + c];
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const int l = c * PAD + threadIdx.x + k * T;
+                const float rg = rs[l];
+                xs[l] += omega[c] * rg;
+                const float rn = rg - omega[c] * tt[c][k];
+                rs[l] = rn;
+                ps[l] = ps[l] - omega[c] * vv[c][k];          // p - omega v, finished into the new p at the top of the loop
+                acc2[c] += rn * rn; acc2[2 + c] += ws[l] * rn;  // ||r||^2 and rho of the next iteration
+            }
+        }
+        cluster_sum4(acc2);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) if (!done[c]) {
+            const float nr = sqrtf(acc2[c]) * norm;
+            fin[c] = nr; rho_next[c] = acc2[2 + c];
+            if (nr < tol) { done[c] = true; used[c] = i + 1; }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) X[(size_t)b * NC * N + (size_t)c * N + start + l] = xs[c * PAD + l]; }
+    if (threadIdx.x == 0 && rank == 0) {
+        if (NC == 2) {
+            iters[b * 8 + 0] = used[0]; iters[b * 8 + 1] = used[1];
+            resid[b * 8 + 0] = fin[0]; resid[b * 8 + 1] = fin[1];
+            iter_total[b * 2 + 1] += (unsigned long long)(used[0] + 1 + used[1] + 1);
+        } else {
+            iters[b * 8 + 7] = used[0]; resid[b * 8 + 7] = fin[0];
+            iter_total[b * 2 + 1] += (unsigned long long)(used[0] + 1);
+        }
+    }
+    cluster_sync_all();
+}
+
+template <int CS, int CPT, int NC>
+static int launch_bicgstab_cluster(fgb_batch *b, const float *rhs, float *x, int zero_init, const int32_t *active, cudaStream_t st) {
+    constexpr int T = 512;
+    const int N = b->t.N;
+    const int per = (N + CS - 1) / CS;
+    if (per > T * CPT) return 1;
+    const size_t smem = ((size_t)4 * NC * T * CPT + (size_t)2 * (T / 32) * CS * 4) * sizeof(float) + 3 * 8 + 16;
+    if (smem > 227 * 1024) return 1;
+    auto kern = k_bicgstab_cluster<T, CPT, CS, NC>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_bicgstab_cluster)", ce);
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(b->B * CS); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ce = cudaLaunchKernelEx(&cfg, kern, b->t, (const float *)b->Coff, (const float *)b->A, rhs, x, b->opt.max_iter, b->opt.adv_tol,
+                            zero_init, active, b->iters, b->resid, b->iter_total);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchKernelEx(k_bicgstab_cluster)", ce);
+    return FGB_OK;
+}
+// BiCGStab dispatcher: on-chip cluster kernel when the grid fits, else one CTA per environment in global memory
+template <int NC>
+static int run_bicgstab(fgb_batch *b, const float *rhs, float *x, int zero_init, const int32_t *active, cudaStream_t st) {
+    if (b->opt.cg_impl >= 1) {
+        int rc = launch_bicgstab_cluster<2, 6, NC>(b, rhs, x, zero_init, active, st);
+        if (rc == 1) rc = launch_bicgstab_cluster<4, 7, NC>(b, rhs, x, zero_init, active, st);
+        if (rc <= 0) return rc;
+    }
+    k_bicgstab<1024, NC><<<b->B, 1024, 0, st>>>(b->t, b->Coff, b->A, rhs, x, b->kry, b->opt.max_iter, b->opt.adv_tol, zero_init, active,
+                                                 b->iters, b->resid, b->iter_total);
+    LAUNCH_CHECK("k_bicgstab");
+    return FGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Krylov solvers, implementation 4: "fat CTA" variant of implementation 3.  Twice the cells per CTA
 // (cluster of 2 for the 14k-cell cylinder grid -> every SM of the chip is usable, 74 environments in
 // flight) so that the cross-CTA latency of the two reductions and of the p hand-shake is amortised over
@@ -1603,10 +1881,7 @@ extern "C" int fgb_setup_advection(fgb_batch *b, const float *u, const float *ur
 extern "C" int fgb_solve_advection(fgb_batch *b, int zero_init, const int32_t *active, fgb_stream_t s) {
     if (!b) return set_err(FGB_E_ARG, "fgb_solve_advection: null argument");
     ProfScope ps(b, CLS_BICG, STREAM(s));
-    k_bicgstab<1024, 2><<<b->B, 1024, 0, STREAM(s)>>>(b->t, b->Coff, b->A, b->rhs, b->ures, b->kry, b->opt.max_iter, b->opt.adv_tol,
-                                                      zero_init, active, b->iters, b->resid, b->iter_total);
-    LAUNCH_CHECK("k_bicgstab");
-    return FGB_OK;
+    return run_bicgstab<2>(b, b->rhs, b->ures, zero_init, active, STREAM(s));
 }
 extern "C" int fgb_setup_pressure_matrix(fgb_batch *b, const int32_t *active, fgb_stream_t s) {
     if (!b) return set_err(FGB_E_ARG, "fgb_setup_pressure_matrix: null argument");
@@ -1769,9 +2044,7 @@ extern "C" int fgb_piso_substep(fgb_batch *b, float *u, float *p, const float *b
         }
         {
             ProfScope ps(b, CLS_BICG, st);
-            k_bicgstab<1024, 1><<<b->B, 1024, 0, st>>>(b->t, b->Coff, b->A, b->rhs, sc->T, b->kry, o.max_iter, o.adv_tol, 1, active,
-                                                        b->iters, b->resid, b->iter_total);
-            LAUNCH_CHECK("k_bicgstab<1>");
+            if ((rc = run_bicgstab<1>(b, b->rhs, sc->T, 1, active, st))) return rc;
         }
         b->launches++;
         k_buoyancy<<<cell_grid(b), 256, 0, st>>>(sc->T, sc->beta, N, active, sc->src);
