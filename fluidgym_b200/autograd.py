@@ -1,0 +1,67 @@
+"""torch.autograd integration of the batched PISO substep.
+
+The reference wraps every native op in its own ``torch.autograd.Function`` and re-installs saved tensors
+into the shared mutable ``Domain`` for each backward call (``simulation/pict/PISOtorch_diff.py:624-1808``).
+Here one ``Function`` covers a whole substep: the forward call records a compact tape on the device
+(``fgb_piso_substep_record``), the backward call runs the hand-written adjoint kernels and two transposed
+on-chip Krylov solves (``fgb_piso_substep_backward``).  Differentiable inputs: cell velocity ``u``, previous
+pressure ``p`` (enters through the deferred non-orthogonal correction) and the Dirichlet boundary velocities
+``bvel`` (jets / inflow); geometry and viscosity are constants, like the transforms in the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import native
+from .solver import BatchedPISO, _ptr
+
+
+class PISOSubstep(torch.autograd.Function):
+    """(u [B,2,N], p [B,N], bvel [B,2,NB]) -> (u_next, p_next) for one substep of ``dt`` (tensor [B] or float)."""
+
+    @staticmethod
+    def forward(ctx, u, p, bvel, solver: BatchedPISO, dt):
+        B, N, NB = solver.B, solver.N, solver.NB
+        dev = solver.device
+        dtc = solver._dt(dt)
+        f32 = dict(device=dev, dtype=torch.float32)
+        tape = dict(u_in=torch.empty(B, 2, N, **f32), p_in=torch.empty(B, N, **f32), bvel_in=torch.empty(B, 2, NB, **f32),
+                    dt=torch.empty(B, **f32), Coff=torch.empty(B, 4, N, **f32), A=torch.empty(B, N, **f32),
+                    ustar=torch.empty(B, 2, N, **f32), hb=torch.empty(2, B, 2, N, **f32), p=torch.empty(2, B, N, **f32),
+                    pmean=torch.empty(2, B, **f32), u1=torch.empty(B, 2, N, **f32))
+        ct = native.Tape(*[tape[k].data_ptr() for k, _ in native.Tape._fields_])
+        u_out = u.detach().clone().contiguous()
+        p_out = p.detach().clone().contiguous()
+        bv = bvel.detach().contiguous()
+        native.check(solver.lib.fgb_piso_substep_record(solver.handle, _ptr(u_out), _ptr(p_out), _ptr(bv), _ptr(dtc), C.byref(ct),
+                                                        solver.stream), "fgb_piso_substep_record")
+        ctx.solver, ctx.tape = solver, tape
+        return u_out, p_out
+
+    @staticmethod
+    def backward(ctx, u_out_bar, p_out_bar):
+        solver, tape = ctx.solver, ctx.tape
+        B, N, NB = solver.B, solver.N, solver.NB
+        f32 = dict(device=solver.device, dtype=torch.float32)
+        ct = native.Tape(*[tape[k].data_ptr() for k, _ in native.Tape._fields_])
+        ub = torch.empty(B, 2, N, **f32)
+        pb = torch.empty(B, N, **f32)
+        bvb = torch.empty(B, 2, NB, **f32)
+        nbytes = solver.lib.fgb_adjoint_workspace_bytes(C.byref(solver.tables), B)
+        ws = getattr(solver, "_adj_ws", None)
+        if ws is None or ws.numel() < nbytes + 256:
+            ws = solver._adj_ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=solver.device)
+        off = (-ws.data_ptr()) % 256
+        uo = (u_out_bar if u_out_bar is not None else torch.zeros(B, 2, N, **f32)).contiguous()
+        po = (p_out_bar if p_out_bar is not None else torch.zeros(B, N, **f32)).contiguous()
+        native.check(solver.lib.fgb_piso_substep_backward(solver.handle, C.byref(ct), _ptr(uo), _ptr(po), _ptr(ub), _ptr(pb), _ptr(bvb),
+                                                          C.c_void_p(ws.data_ptr() + off), nbytes, solver.stream),
+                     "fgb_piso_substep_backward")
+        return ub, pb, bvb, None, None
+
+
+def piso_substep(solver: BatchedPISO, u, p, bvel, dt):
+    """Differentiable PISO substep (functional form: inputs are not modified)."""
+    return PISOSubstep.apply(u, p, bvel, solver, dt)

@@ -44,7 +44,7 @@ struct fgb_batch {
     size_t ws_bytes;
     // carved buffers
     float *Coff, *A, *rhs, *ures, *Poff, *Pdiag, *hbya, *div, *pres, *kry;
-    float *resid, *dt, *maxvel, *fluxbal;
+    float *resid, *dt, *maxvel, *fluxbal, *pmean;
     double *remaining;
     int32_t *iters, *active, *nsub, *counters;
     int32_t *h_counters;  // pinned host mirror
@@ -87,7 +87,7 @@ static void carve(fgb_batch *b, char *base, size_t *total) {
     b->hbya = c.take<float>(2 * BN); b->div = c.take<float>(BN); b->pres = c.take<float>(BN);
     b->kry = c.take<float>(KRY_VECS * BN);
     b->resid = c.take<float>(8 * (size_t)b->B); b->dt = c.take<float>(b->B); b->maxvel = c.take<float>(b->B);
-    b->fluxbal = c.take<float>(b->B); b->remaining = c.take<double>(b->B);
+    b->fluxbal = c.take<float>(b->B); b->pmean = c.take<float>(8 * (size_t)b->B); b->remaining = c.take<double>(b->B);
     b->iters = c.take<int32_t>(8 * (size_t)b->B); b->active = c.take<int32_t>(b->B); b->nsub = c.take<int32_t>(b->B);
     b->counters = c.take<int32_t>(64);
     b->iter_total = c.take<unsigned long long>(2 * (size_t)b->B);
@@ -168,7 +168,7 @@ extern "C" void *fgb_batch_buffer(fgb_batch *b, const char *name) {
     if (!b || !name) return nullptr;
 #define BUF(n) if (!strcmp(name, #n)) return (void *)b->n;
     BUF(Coff) BUF(A) BUF(rhs) BUF(ures) BUF(Poff) BUF(Pdiag) BUF(hbya) BUF(div) BUF(pres) BUF(kry)
-    BUF(iter_total) BUF(iters) BUF(resid) BUF(dt) BUF(active) BUF(remaining) BUF(nsub) BUF(maxvel) BUF(fluxbal) BUF(counters)
+    BUF(pmean) BUF(iter_total) BUF(iters) BUF(resid) BUF(dt) BUF(active) BUF(remaining) BUF(nsub) BUF(maxvel) BUF(fluxbal) BUF(counters)
 #undef BUF
     return nullptr;
 }
@@ -1001,7 +1001,11 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__re
                                                          const float *__restrict__ Rhs, float *__restrict__ Xout,
                                                          int maxit, float tol, int zero_init, int reset_steps, int slot,
                                                          const int32_t *__restrict__ active, int32_t *__restrict__ iters,
-                                                         float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
+                                                         float *__restrict__ resid, unsigned long long *__restrict__ iter_total,
+                                                         int flags, float *__restrict__ mean_out) {
+    // flags bit 0: apply the TRANSPOSED operator (adjoint solve, DIFF.py:572-590): the coefficient of neighbour
+    //              j in row i is the one stored in row j for the face that points back to i (tables.rev)
+    //       bit 1: do not remove the mean of the result
     constexpr int NW = T / 32;
     constexpr int NP = NW * CS;
     constexpr int PAD = T * CPT;
@@ -1044,7 +1048,8 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__re
 #pragma unroll
         for (int ff = 0; ff < 4; ++ff) {
             const int nb = ok ? t.nbr[ff * N + g] : -1;
-            co[k][ff] = (ok && nb >= 0) ? off[ff * N + g] : 0.f;
+            if (flags & 1) co[k][ff] = (ok && nb >= 0) ? off[(int)t.rev[ff * N + g] * N + nb] : 0.f;
+            else co[k][ff] = (ok && nb >= 0) ? off[ff * N + g] : 0.f;
             const int gi = nb >= 0 ? nb : (ok ? g : start);
             const int c = gi / per;
             // (measured: splitting local neighbours onto plain ld.shared with a per-gather predicate is SLOWER,
@@ -1180,7 +1185,8 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__re
     float sx = 0.f;
 #pragma unroll
     for (int k = 0; k < CPT; ++k) sx += xr[k];
-    const float mean = cluster_sum(sx) / (float)N;
+    const float mean = (flags & 2) ? 0.f : cluster_sum(sx) / (float)N;
+    if (mean_out && threadIdx.x == 0 && rank == 0) mean_out[b] = mean;
 #pragma unroll
     for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) xo[start + l] = xr[k] - mean; }
     if (threadIdx.x == 0 && rank == 0) { iters[b * 8 + 2 + slot] = used; resid[b * 8 + 2 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1); }
@@ -1203,7 +1209,7 @@ __global__ void __launch_bounds__(T, 1) k_bicgstab_cluster(Tab t, const float *_
                                                             const float *__restrict__ Rhs, float *__restrict__ X,
                                                             int maxit, float tol, int zero_init, const int32_t *__restrict__ active,
                                                             int32_t *__restrict__ iters, float *__restrict__ resid,
-                                                            unsigned long long *__restrict__ iter_total) {
+                                                            unsigned long long *__restrict__ iter_total, int transposed) {
     constexpr int NW = T / 32;
     constexpr int NP = NW * CS;
     constexpr int PAD = T * CPT;
@@ -1244,7 +1250,8 @@ __global__ void __launch_bounds__(T, 1) k_bicgstab_cluster(Tab t, const float *_
 #pragma unroll
         for (int ff = 0; ff < 4; ++ff) {
             const int nb = ok ? t.nbr[ff * N + g] : -1;
-            co[k][ff] = (ok && nb >= 0) ? off[ff * N + g] : 0.f;
+            if (transposed) co[k][ff] = (ok && nb >= 0) ? off[(int)t.rev[ff * N + g] * N + nb] : 0.f;
+            else co[k][ff] = (ok && nb >= 0) ? off[ff * N + g] : 0.f;
             const int gi = nb >= 0 ? nb : (ok ? g : start);
             const int c = gi / per;
             na[k][ff] = mapa_u32(rs_addr + 4u * (uint32_t)(gi - c * per), (uint32_t)c);
@@ -1430,7 +1437,8 @@ __global__ void __launch_bounds__(T, 1) k_bicgstab_cluster(Tab t, const float *_
 }
 
 template <int CS, int CPT, int NC>
-static int launch_bicgstab_cluster(fgb_batch *b, const float *rhs, float *x, int zero_init, const int32_t *active, cudaStream_t st) {
+static int launch_bicgstab_cluster(fgb_batch *b, const float *coff, const float *adiag, const float *rhs, float *x, int zero_init,
+                                   const int32_t *active, int transposed, cudaStream_t st) {
     constexpr int T = 512;
     const int N = b->t.N;
     const int per = (N + CS - 1) / CS;
@@ -1446,8 +1454,8 @@ static int launch_bicgstab_cluster(fgb_batch *b, const float *rhs, float *x, int
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    ce = cudaLaunchKernelEx(&cfg, kern, b->t, (const float *)b->Coff, (const float *)b->A, rhs, x, b->opt.max_iter, b->opt.adv_tol,
-                            zero_init, active, b->iters, b->resid, b->iter_total);
+    ce = cudaLaunchKernelEx(&cfg, kern, b->t, coff, adiag, rhs, x, b->opt.max_iter, b->opt.adv_tol,
+                            zero_init, active, b->iters, b->resid, b->iter_total, transposed);
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchKernelEx(k_bicgstab_cluster)", ce);
     return FGB_OK;
 }
@@ -1455,8 +1463,8 @@ static int launch_bicgstab_cluster(fgb_batch *b, const float *rhs, float *x, int
 template <int NC>
 static int run_bicgstab(fgb_batch *b, const float *rhs, float *x, int zero_init, const int32_t *active, cudaStream_t st) {
     if (b->opt.cg_impl >= 1) {
-        int rc = launch_bicgstab_cluster<2, 6, NC>(b, rhs, x, zero_init, active, st);
-        if (rc == 1) rc = launch_bicgstab_cluster<4, 7, NC>(b, rhs, x, zero_init, active, st);
+        int rc = launch_bicgstab_cluster<2, 6, NC>(b, b->Coff, b->A, rhs, x, zero_init, active, 0, st);
+        if (rc == 1) rc = launch_bicgstab_cluster<4, 7, NC>(b, b->Coff, b->A, rhs, x, zero_init, active, 0, st);
         if (rc <= 0) return rc;
     }
     k_bicgstab<1024, NC><<<b->B, 1024, 0, st>>>(b->t, b->Coff, b->A, rhs, x, b->kry, b->opt.max_iter, b->opt.adv_tol, zero_init, active,
@@ -1865,6 +1873,241 @@ __global__ void k_sample_sensors(const float *__restrict__ field, int C, int N, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Reverse-mode adjoint of one PISO substep (replaces the *_GRAD kernels K.cu:3884-4090, 4403-4491,
+// 4982-5130, 5258-5385, 5438-5509, 6265-6309 and the python glue DIFF.py:516-1808).  Specification:
+// tests/adjoint_eval.py (float64 numpy, validated against finite differences).  Every forward gather
+// y_i += w * x[j] becomes the scatter xbar[j] += w * ybar_i with red.global.add.f32; the two linear solves
+// become solves with the transposed operator by the same on-chip Krylov kernels.
+// All kernels: one thread per (cell, environment).
+// ------------------------------------------------------------------------------------------------
+// scatter of a flux-divergence adjoint: flb[f] = adjoint of face flux f of this cell
+__device__ __forceinline__ void fluxes_adjoint(const Tab &t, int g, const int nb[4], const float flb[4], float *__restrict__ vb /*[2][N]*/,
+                                               float *__restrict__ Fbb /*[NB]*/) {
+    const int N = t.N;
+    float Ub[2] = {0.f, 0.f};
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        if (nb[f] >= 0) {
+            const float gq = 0.5f * flb[f];
+            Ub[f >> 1] += gq;
+            const int fc = t.fl_comp[f * N + g];
+            const int cn = fc & 1, n = nb[f];
+            const float w = ((fc & 2) ? -gq : gq) * t.det[n];
+            atomicAdd(&vb[n], w * t.minv[(2 * cn) * N + n]);
+            atomicAdd(&vb[N + n], w * t.minv[(2 * cn + 1) * N + n]);
+        } else if (Fbb) {
+            atomicAdd(&Fbb[-1 - nb[f]], flb[f]);
+        }
+    }
+    const float d = t.det[g];
+    atomicAdd(&vb[g], d * (t.minv[g] * Ub[0] + t.minv[2 * N + g] * Ub[1]));
+    atomicAdd(&vb[N + g], d * (t.minv[N + g] * Ub[0] + t.minv[3 * N + g] * Ub[1]));
+}
+
+// adjoint of the corrector u_next = hb - rA * Minv^T grad(p):  hbb += unb ; rAb += -(g . unb) ; pb += grad^T(...)
+__global__ void __launch_bounds__(256) k_adj_correct(Tab t, const float *__restrict__ Unb, const float *__restrict__ P, const float *__restrict__ A,
+                                                      float *__restrict__ Hbb, float *__restrict__ rAb, float *__restrict__ Pb) {
+    const int b = blockIdx.y;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N;
+    if (g >= N) return;
+    const float *p = P + (size_t)b * N;
+    const float ub0 = Unb[(size_t)b * 2 * N + g], ub1 = Unb[(size_t)b * 2 * N + N + g];
+    Hbb[(size_t)b * 2 * N + g] = ub0; Hbb[(size_t)b * 2 * N + N + g] = ub1;
+    const float rA = 1.0f / A[(size_t)b * N + g];
+    const float pc = p[g];
+    float pg[2]; int nl[2], nu[2]; float fac[2];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        nl[d] = t.nbr[(2 * d) * N + g]; nu[d] = t.nbr[(2 * d + 1) * N + g];
+        fac[d] = (nl[d] < 0 || nu[d] < 0) ? 1.0f : 0.5f;
+        pg[d] = ((nu[d] >= 0 ? p[nu[d]] : pc) - (nl[d] >= 0 ? p[nl[d]] : pc)) * fac[d];
+    }
+    const float m00 = t.minv[g], m01 = t.minv[N + g], m10 = t.minv[2 * N + g], m11 = t.minv[3 * N + g];
+    const float gx = pg[0] * m00 + pg[1] * m10, gy = pg[0] * m01 + pg[1] * m11;
+    atomicAdd(&rAb[(size_t)b * N + g], -(gx * ub0 + gy * ub1));
+    const float gb0 = -rA * ub0, gb1 = -rA * ub1;
+    const float pgb[2] = {gb0 * m00 + gb1 * m01, gb0 * m10 + gb1 * m11};
+    float *pb = Pb + (size_t)b * N;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        const float w = pgb[d] * fac[d];
+        atomicAdd(&pb[nu[d] >= 0 ? nu[d] : g], w);
+        atomicAdd(&pb[nl[d] >= 0 ? nl[d] : g], -w);
+    }
+}
+
+// x_bar = p_bar - mean(p_bar)   (adjoint of the mean removal), one CTA per environment
+template <int T>
+__global__ void __launch_bounds__(T) k_adj_remove_mean(int N, const float *__restrict__ Pb, float *__restrict__ Xb) {
+    __shared__ double red[32 * 2 + 2];
+    const int b = blockIdx.x;
+    float acc[2] = {0.f, 0.f};
+    for (int g = threadIdx.x; g < N; g += T) acc[0] += Pb[(size_t)b * N + g];
+    block_reduce_sum<2>(acc, red);
+    const float m = acc[0] / (float)N;
+    for (int g = threadIdx.x; g < N; g += T) Xb[(size_t)b * N + g] = Pb[(size_t)b * N + g] - m;
+}
+
+// adjoint of  div = fluxdiv(hb) + NOp(p_prev, rA)  and of  x = P^-1 div  w.r.t. P:   given lam = P^-T x_bar
+__global__ void __launch_bounds__(256) k_adj_pressure_rhs(Tab t, const float *__restrict__ Lam, const float *__restrict__ Pm /*p of this corrector*/,
+                                                           const float *__restrict__ Pmean, const float *__restrict__ Pprev,
+                                                           const float *__restrict__ A, float *__restrict__ Hbb, float *__restrict__ Fbb,
+                                                           float *__restrict__ rAb, float *__restrict__ Pprevb) {
+    const int b = blockIdx.y;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N, NB = t.NB;
+    if (g >= N) return;
+    const float lam = Lam[(size_t)b * N + g];
+    const float *px = Pm + (size_t)b * N;
+    const float mean = Pmean[b];
+    int nb[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) nb[f] = t.nbr[f * N + g];
+    // P_bar_e = -lam_i * x_j on the pattern (x = p + mean); rA_bar_j += Wp[e][j] * P_bar_e
+    float Pb[5];
+    Pb[0] = -lam * (px[g] + mean);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) Pb[f + 1] = nb[f] >= 0 ? -lam * (px[nb[f]] + mean) : 0.f;
+    float rb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 5; ++e)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) rb[j] += t.Wp[(5 * e + j) * N + g] * Pb[e];
+    // deferred non-orthogonal pressure term: div += sum_k (gP rA_P + gN rA_nbr(face)) * pprev[idx]
+    const float *a = A + (size_t)b * N, *pp = Pprev + (size_t)b * N;
+    float rA[5];
+    rA[0] = 1.0f / a[g];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) rA[f + 1] = nb[f] >= 0 ? 1.0f / a[nb[f]] : rA[0];
+    for (int k = 0; k < t.K_no; ++k) {
+        const float gP = t.no_gP[k * N + g], gN = t.no_gN[k * N + g];
+        if (gP != 0.f || gN != 0.f) {
+            const int fc = t.no_face[k * N + g], j = t.no_idx[k * N + g];
+            const float wb = lam * pp[j];
+            rb[0] += gP * wb; rb[1 + fc] += gN * wb;
+            atomicAdd(&Pprevb[(size_t)b * N + j], (gP * rA[0] + gN * rA[1 + fc]) * lam);
+        }
+    }
+    float *ra = rAb + (size_t)b * N;
+    atomicAdd(&ra[g], rb[0]);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) atomicAdd(&ra[nb[f] >= 0 ? nb[f] : g], rb[f + 1]);
+    const float flb[4] = {-lam, lam, -lam, lam};
+    fluxes_adjoint(t, g, nb, flb, Hbb + (size_t)b * 2 * N, Fbb + (size_t)b * NB);
+}
+
+// adjoint of  hb = rA * (u/dt - H + Sb/det),  H_c = sum_f Coff_f * uprev_c[nb_f]
+__global__ void __launch_bounds__(256) k_adj_hbya(Tab t, const float *__restrict__ Hbb, const float *__restrict__ Hb /*saved hb*/,
+                                                   const float *__restrict__ A, const float *__restrict__ Coff, const float *__restrict__ Uprev,
+                                                   const float *__restrict__ dtv, float *__restrict__ rAb, float *__restrict__ Ub,
+                                                   float *__restrict__ Sbb, float *__restrict__ Coffb, float *__restrict__ Uprevb) {
+    const int b = blockIdx.y;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N;
+    if (g >= N) return;
+    const float dt = dtv[b];
+    const float Ag = A[(size_t)b * N + g];
+    const float rA = 1.0f / Ag;
+    const float det = t.det[g];
+    float accr = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const size_t o = (size_t)b * 2 * N + (size_t)c * N;
+        const float hbb = Hbb[o + g];
+        accr += hbb * (Hb[o + g] * Ag);
+        const float ib = rA * hbb;
+        Ub[o + g] += ib / dt;
+        Sbb[o + g] += ib / det;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const int nb = t.nbr[f * N + g];
+            if (nb >= 0) {
+                Coffb[(size_t)b * 4 * N + f * N + g] += -ib * Uprev[o + nb];
+                atomicAdd(&Uprevb[o + nb], -ib * Coff[(size_t)b * 4 * N + f * N + g]);
+            }
+        }
+    }
+    atomicAdd(&rAb[(size_t)b * N + g], accr);
+}
+
+// adjoint of the predictor: given mu = C^-T ustar_bar
+__global__ void __launch_bounds__(256) k_adj_advection(Tab t, const float *__restrict__ Mu, const float *__restrict__ Ustar, const float *__restrict__ rAb,
+                                                        const float *__restrict__ A, const float *__restrict__ dtv, float *__restrict__ Ab,
+                                                        float *__restrict__ Coffb, float *__restrict__ Ub, float *__restrict__ Sbb, float *__restrict__ Bvb) {
+    const int b = blockIdx.y;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N, NB = t.NB;
+    if (g >= N) return;
+    const float dt = dtv[b];
+    const float det = t.det[g];
+    const float Ag = A[(size_t)b * N + g];
+    float ab = -rAb[(size_t)b * N + g] / (Ag * Ag);          // A_bar from rA_bar (rA = 1/A)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const size_t o = (size_t)b * 2 * N + (size_t)c * N;
+        const float mu = Mu[o + g];
+        ab += -mu * Ustar[o + g];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const int nb = t.nbr[f * N + g];
+            if (nb >= 0) Coffb[(size_t)b * 4 * N + f * N + g] += -mu * Ustar[o + nb];
+        }
+        atomicAdd(&Ub[o + g], mu / dt);  // rhs = (det u/dt + Sb - NOv)/det  (other threads scatter into Ub in this kernel)
+        Sbb[o + g] += mu / det;
+        const float nob = -mu / det;
+        for (int k = 0; k < t.K_no; ++k) { const float w = t.no_wv[k * N + g]; if (w != 0.f) atomicAdd(&Ub[o + t.no_idx[k * N + g]], w * nob); }
+        for (int k = 0; k < t.K_nob; ++k) {
+            const float w = t.nob_w[k * N + g];
+            if (w != 0.f) atomicAdd(&Bvb[(size_t)b * 2 * NB + (size_t)c * NB + t.nob_idx[k * N + g]], w * nob);
+        }
+    }
+    Ab[(size_t)b * N + g] = ab;
+}
+
+// adjoint of the assembly (A, Coff from the face fluxes) and of the boundary sources
+__global__ void __launch_bounds__(256) k_adj_assemble(Tab t, const float *__restrict__ Ab, const float *__restrict__ Coffb, const float *__restrict__ Sbb,
+                                                       const float *__restrict__ Bvel, float *__restrict__ Ub, float *__restrict__ Bvb, float *__restrict__ Fbb) {
+    const int b = blockIdx.y;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N, NB = t.NB;
+    if (g >= N) return;
+    const float det = t.det[g];
+    const float diagb = Ab[(size_t)b * N + g] / det;
+    const float *bv = Bvel + (size_t)b * 2 * NB;
+    int nb[4]; float flb[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        nb[f] = t.nbr[f * N + g];
+        const float sig = (f & 1) ? 1.f : -1.f;
+        flb[f] = 0.f;
+        if (nb[f] >= 0) flb[f] = 0.5f * sig * (Coffb[(size_t)b * 4 * N + f * N + g] / det + diagb);
+        else {
+            const int j = -1 - nb[f];
+            const float Fb = bflux(t, j, f >> 1, bv[j], bv[NB + j]);
+            const float s0 = Sbb[(size_t)b * 2 * N + g], s1 = Sbb[(size_t)b * 2 * N + N + g];
+            const float k = -(sig * Fb) + 2.f * t.viscosity * t.b_alpha[j];
+            atomicAdd(&Bvb[(size_t)b * 2 * NB + j], s0 * k);
+            atomicAdd(&Bvb[(size_t)b * 2 * NB + NB + j], s1 * k);
+            atomicAdd(&Fbb[(size_t)b * NB + j], -(s0 * bv[j] + s1 * bv[NB + j]) * sig);
+        }
+    }
+    fluxes_adjoint(t, g, nb, flb, Ub + (size_t)b * 2 * N, nullptr);
+}
+
+// adjoint of Fb(bvel): one thread per (boundary face, environment)
+__global__ void k_adj_bflux(Tab t, const float *__restrict__ Fbb, float *__restrict__ Bvb) {
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int NB = t.NB;
+    if (j >= NB) return;
+    const int ax = t.b_face[j] >> 1;
+    const float f = Fbb[(size_t)b * NB + j] * t.b_det[j];
+    Bvb[(size_t)b * 2 * NB + j] += f * t.b_minv[(2 * ax) * NB + j];
+    Bvb[(size_t)b * 2 * NB + NB + j] += f * t.b_minv[(2 * ax + 1) * NB + j];
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static inline dim3 cell_grid(const fgb_batch *b) { return dim3((b->t.N + 255) / 256, b->B); }
@@ -1930,8 +2173,9 @@ static int launch_cg_cluster(fgb_batch *b, float *p_out, int zero_init, int rese
 }
 
 template <int CS, int CPT>
-static int launch_cg_cluster_mb(fgb_batch *b, float *p_out, int zero_init, int reset_steps, int max_iter, int slot,
-                                const int32_t *active, cudaStream_t st) {
+static int launch_cg_cluster_mb(fgb_batch *b, const float *poff, const float *pdiag, const float *rhs, float *p_out, int zero_init,
+                                int reset_steps, int max_iter, int slot, const int32_t *active, int flags, float *mean_out,
+                                cudaStream_t st) {
     constexpr int T = 512;
     const int N = b->t.N;
     const int per = (N + CS - 1) / CS;
@@ -1946,8 +2190,8 @@ static int launch_cg_cluster_mb(fgb_batch *b, float *p_out, int zero_init, int r
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    ce = cudaLaunchKernelEx(&cfg, kern, b->t, (const float *)b->Poff, (const float *)b->Pdiag, (const float *)b->div, p_out,
-                            max_iter, b->opt.p_tol, zero_init, reset_steps, slot, active, b->iters, b->resid, b->iter_total);
+    ce = cudaLaunchKernelEx(&cfg, kern, b->t, poff, pdiag, rhs, p_out, max_iter, b->opt.p_tol, zero_init, reset_steps, slot, active,
+                            b->iters, b->resid, b->iter_total, flags, mean_out);
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchKernelEx(k_cg_cluster_mb)", ce);
     return FGB_OK;
 }
@@ -1993,8 +2237,10 @@ static int solve_pressure_slot(fgb_batch *b, float *p_out, int zero_init, int re
         if (rc <= 0) return rc;
     }
     if (b->opt.cg_impl == 3) {
-        int rc = launch_cg_cluster_mb<2, 6>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
-        if (rc == 1) rc = launch_cg_cluster_mb<4, 7>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
+        int rc = launch_cg_cluster_mb<2, 6>(b, b->Poff, b->Pdiag, b->div, p_out, zero_init, reset_steps, max_iter, slot, active, 0,
+                                            b->pmean + (size_t)slot * b->B, STREAM(s));
+        if (rc == 1) rc = launch_cg_cluster_mb<4, 7>(b, b->Poff, b->Pdiag, b->div, p_out, zero_init, reset_steps, max_iter, slot, active, 0,
+                                                     b->pmean + (size_t)slot * b->B, STREAM(s));
         if (rc <= 0) return rc;
     }
     if (b->opt.cg_impl == 1 || b->opt.cg_impl == 2) {
@@ -2076,6 +2322,118 @@ extern "C" int fgb_piso_substep(fgb_batch *b, float *u, float *p, const float *b
     b->launches++;
     k_copy_active<<<dim3((2 * N + 255) / 256, b->B), 256, 0, st>>>(b->ures, u, 2 * N, active);
     LAUNCH_CHECK("k_copy_active");
+    return FGB_OK;
+}
+
+static int copy_async(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    cudaError_t ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st);
+    return ce == cudaSuccess ? FGB_OK : set_err(FGB_E_CUDA, "cudaMemcpyAsync (tape)", ce);
+}
+
+// fgb_piso_substep that additionally records the tape the backward pass needs (non-orthogonal path with
+// corrector_steps = 2, advect_non_ortho_steps = pressure_non_ortho_steps = 1, no passive scalar).
+extern "C" int fgb_piso_substep_record(fgb_batch *b, float *u, float *p, const float *bvel, const float *dt, const fgb_tape *tp,
+                                       fgb_stream_t s) {
+    if (!b || !u || !p || !bvel || !dt || !tp) return set_err(FGB_E_ARG, "fgb_piso_substep_record: null argument");
+    const fgb_options &o = b->opt;
+    if (!o.nonortho || o.corrector_steps != 2 || o.adv_nonortho_steps != 1 || o.p_nonortho_steps != 1 || o.cg_impl != 3)
+        return set_err(FGB_E_ARG, "fgb_piso_substep_record: supports the non-orthogonal path with 2 correctors, 1 non-ortho step, cg_impl 3");
+    cudaStream_t st = STREAM(s);
+    const size_t B = b->B, N = b->t.N, NB = b->t.NB;
+    int rc;
+    if ((rc = copy_async(tp->u_in, u, 2 * B * N * 4, st))) return rc;
+    if ((rc = copy_async(tp->p_in, p, B * N * 4, st))) return rc;
+    if ((rc = copy_async(tp->bvel_in, bvel, 2 * B * NB * 4, st))) return rc;
+    if ((rc = copy_async(tp->dt, dt, B * 4, st))) return rc;
+    if ((rc = fgb_setup_advection(b, u, u, bvel, nullptr, dt, nullptr, s))) return rc;
+    if ((rc = fgb_solve_advection(b, 1, nullptr, s))) return rc;
+    if ((rc = copy_async(tp->Coff, b->Coff, 4 * B * N * 4, st))) return rc;
+    if ((rc = copy_async(tp->A, b->A, B * N * 4, st))) return rc;
+    if ((rc = copy_async(tp->ustar, b->ures, 2 * B * N * 4, st))) return rc;
+    if ((rc = fgb_setup_pressure_matrix(b, nullptr, s))) return rc;
+    for (int cs = 0; cs < 2; ++cs) {
+        if ((rc = fgb_setup_pressure_rhs(b, u, bvel, nullptr, p, dt, 1, nullptr, s))) return rc;
+        if ((rc = solve_pressure_slot(b, p, 1, 100, o.max_iter, cs, nullptr, s))) return rc;
+        if ((rc = copy_async(tp->hb + cs * 2 * B * N, b->hbya, 2 * B * N * 4, st))) return rc;
+        if ((rc = copy_async(tp->p + cs * B * N, p, B * N * 4, st))) return rc;
+        if ((rc = copy_async(tp->pmean + cs * B, b->pmean + cs * B, B * 4, st))) return rc;
+        if ((rc = fgb_correct_velocity(b, p, b->ures, nullptr, s))) return rc;
+        if (cs == 0 && (rc = copy_async(tp->u1, b->ures, 2 * B * N * 4, st))) return rc;
+    }
+    return copy_async(u, b->ures, 2 * B * N * 4, st);
+}
+
+extern "C" size_t fgb_adjoint_workspace_bytes(const fgb_tables *t, int32_t B) {
+    const size_t BN = (size_t)B * t->N, BNB = (size_t)B * (t->NB > 0 ? t->NB : 1);
+    return (size_t)(2 + 2 + 1 + 4 + 2 + 1 + 1 + 1 + 2 + 1 + 2) * align_up(BN * 4) + align_up(BNB * 4) + 4096;
+}
+
+// Reverse pass of fgb_piso_substep_record.  u_out_bar / p_out_bar: incoming gradients; u_bar, p_prev_bar, bvel_bar
+// are OVERWRITTEN with the gradients w.r.t. the inputs of the substep.  ws: >= fgb_adjoint_workspace_bytes.
+extern "C" int fgb_piso_substep_backward(fgb_batch *b, const fgb_tape *tp, const float *u_out_bar, const float *p_out_bar,
+                                         float *u_bar, float *p_prev_bar, float *bvel_bar, void *ws, size_t ws_bytes, fgb_stream_t s) {
+    if (!b || !tp || !u_out_bar || !p_out_bar || !u_bar || !p_prev_bar || !bvel_bar || !ws)
+        return set_err(FGB_E_ARG, "fgb_piso_substep_backward: null argument");
+    if (ws_bytes < fgb_adjoint_workspace_bytes(&b->t, b->B)) return set_err(FGB_E_WORKSPACE, "fgb_piso_substep_backward: workspace too small");
+    if (!b->t.rev) return set_err(FGB_E_ARG, "fgb_piso_substep_backward: tables.rev missing");
+    cudaStream_t st = STREAM(s);
+    const size_t B = b->B, N = b->t.N, NB = b->t.NB, BN = B * N;
+    Carver c{(char *)ws, 0};
+    float *unb = c.take<float>(2 * BN), *hbb = c.take<float>(2 * BN), *rAb = c.take<float>(BN), *Coffb = c.take<float>(4 * BN);
+    float *Sbb = c.take<float>(2 * BN), *pb = c.take<float>(BN), *xb = c.take<float>(BN), *lam = c.take<float>(BN);
+    float *uprevb = c.take<float>(2 * BN), *Ab = c.take<float>(BN), *mu = c.take<float>(2 * BN), *Fbb = c.take<float>(B * NB);
+    const dim3 grid = cell_grid(b);
+    cudaError_t ce;
+#define ZERO(ptr, n) do { ce = cudaMemsetAsync(ptr, 0, (n) * sizeof(float), st); if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "memset", ce); } while (0)
+    ZERO(rAb, BN); ZERO(Coffb, 4 * BN); ZERO(Sbb, 2 * BN); ZERO(Fbb, B * NB); ZERO(u_bar, 2 * BN); ZERO(bvel_bar, 2 * B * NB);
+    int rc;
+    if ((rc = copy_async(unb, u_out_bar, 2 * BN * 4, st))) return rc;
+    if ((rc = copy_async(pb, p_out_bar, BN * 4, st))) return rc;
+    // the pressure matrix of this substep (function of A only)
+    b->launches++;
+    k_setup_pressure_matrix<<<grid, 256, 0, st>>>(b->t, tp->A, nullptr, b->Poff, b->Pdiag);
+    LAUNCH_CHECK("k_setup_pressure_matrix (backward)");
+    for (int cs = 1; cs >= 0; --cs) {
+        const float *p_c = tp->p + cs * BN, *hb_c = tp->hb + cs * 2 * BN;
+        const float *pprev = cs == 0 ? tp->p_in : tp->p;            // p of corrector 0 is the previous pressure of corrector 1
+        const float *uprev = cs == 0 ? tp->ustar : tp->u1;
+        b->launches += 2;
+        k_adj_correct<<<grid, 256, 0, st>>>(b->t, unb, p_c, tp->A, hbb, rAb, pb);
+        LAUNCH_CHECK("k_adj_correct");
+        k_adj_remove_mean<256><<<b->B, 256, 0, st>>>((int)N, pb, xb);
+        LAUNCH_CHECK("k_adj_remove_mean");
+        {   // lam = P^-T x_bar
+            ProfScope ps(b, CLS_CG, st);
+            rc = launch_cg_cluster_mb<2, 6>(b, b->Poff, b->Pdiag, xb, lam, 1, 100, b->opt.max_iter, 4 + cs, nullptr, 1 | 2, nullptr, st);
+            if (rc == 1) rc = launch_cg_cluster_mb<4, 7>(b, b->Poff, b->Pdiag, xb, lam, 1, 100, b->opt.max_iter, 4 + cs, nullptr, 1 | 2, nullptr, st);
+            if (rc == 1) return set_err(FGB_E_ARG, "fgb_piso_substep_backward: grid too large for the on-chip transposed solve");
+            if (rc) return rc;
+        }
+        ZERO(uprevb, 2 * BN);
+        ZERO(pb, BN);                  // becomes p_prev_bar of this corrector
+        b->launches += 2;
+        k_adj_pressure_rhs<<<grid, 256, 0, st>>>(b->t, lam, p_c, tp->pmean + cs * B, pprev, tp->A, hbb, Fbb, rAb, pb);
+        LAUNCH_CHECK("k_adj_pressure_rhs");
+        k_adj_hbya<<<grid, 256, 0, st>>>(b->t, hbb, hb_c, tp->A, tp->Coff, uprev, tp->dt, rAb, u_bar, Sbb, Coffb, uprevb);
+        LAUNCH_CHECK("k_adj_hbya");
+        if ((rc = copy_async(unb, uprevb, 2 * BN * 4, st))) return rc;      // gradient w.r.t. the velocity entering this corrector
+    }
+    if ((rc = copy_async(p_prev_bar, pb, BN * 4, st))) return rc;
+    {   // mu = C^-T ustar_bar   (unb now holds ustar_bar)
+        ProfScope ps(b, CLS_BICG, st);
+        rc = launch_bicgstab_cluster<2, 6, 2>(b, tp->Coff, tp->A, unb, mu, 1, nullptr, 1, st);
+        if (rc == 1) rc = launch_bicgstab_cluster<4, 7, 2>(b, tp->Coff, tp->A, unb, mu, 1, nullptr, 1, st);
+        if (rc == 1) return set_err(FGB_E_ARG, "fgb_piso_substep_backward: grid too large for the on-chip transposed solve");
+        if (rc) return rc;
+    }
+    b->launches += 3;
+    k_adj_advection<<<grid, 256, 0, st>>>(b->t, mu, tp->ustar, rAb, tp->A, tp->dt, Ab, Coffb, u_bar, Sbb, bvel_bar);
+    LAUNCH_CHECK("k_adj_advection");
+    k_adj_assemble<<<grid, 256, 0, st>>>(b->t, Ab, Coffb, Sbb, tp->bvel_in, u_bar, bvel_bar, Fbb);
+    LAUNCH_CHECK("k_adj_assemble");
+    k_adj_bflux<<<dim3((unsigned)((NB + 127) / 128), b->B), 128, 0, st>>>(b->t, Fbb, bvel_bar);
+    LAUNCH_CHECK("k_adj_bflux");
+#undef ZERO
     return FGB_OK;
 }
 

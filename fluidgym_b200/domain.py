@@ -518,6 +518,17 @@ class CompiledDomain:
             Cd_s[0] += np.where(inner, vc, np.where(dirichlet, f32(2.0) * kap * alpha[dim], f32(0.0))).astype(f32)
             Cd_s[f + 1] = np.where(inner, -vc, f32(0.0))
         self.Cd_s = Cd_s
+        # reverse faces: rev[f][g] = face f' of the neighbour n = nbr[f][g] with nbr[f'][n] == g
+        rev = np.full((4, N), -1, dtype=np.int8)
+        cells = np.arange(N)
+        for f in range(4):
+            inner = nbr[f] >= 0
+            nn = np.where(inner, nbr[f], 0)
+            for f2 in range(4):
+                hit = inner & (nbr[f2][nn] == cells) & (rev[f] < 0)
+                rev[f][hit] = f2
+            assert (rev[f][inner] >= 0).all(), "neighbour relation is not symmetric"
+        self.rev = rev
         self.nbr = nbr
         self.fl_comp = fl_comp
         self.nalpha = nalpha

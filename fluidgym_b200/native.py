@@ -22,7 +22,11 @@ class Tables(C.Structure):
                 ("viscosity", C.c_float)] + [(n, C.c_void_p) for n in (
                     "nbr", "fl_comp", "minv", "det", "Cd", "Wp", "no_idx", "no_face", "no_gP", "no_gN", "no_wv",
                     "nob_idx", "nob_w", "b_minv", "b_det", "b_alpha", "b_cell", "b_face", "b_out")] + [
-                    ("scalar_viscosity", C.c_float), ("Cd_s", C.c_void_p), ("sb_neumann", C.c_void_p)]
+                    ("scalar_viscosity", C.c_float), ("Cd_s", C.c_void_p), ("sb_neumann", C.c_void_p), ("rev", C.c_void_p)]
+
+
+class Tape(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("u_in", "p_in", "bvel_in", "dt", "Coff", "A", "ustar", "hb", "p", "pmean", "u1")]
 
 
 class Scalar(C.Structure):
@@ -46,7 +50,8 @@ EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_cr
            "fgb_piso_substep", "fgb_make_divergence_free", "fgb_sim_step", "fgb_update_outflow", "fgb_flux_balance",
            "fgb_max_velocity", "fgb_apply_jet_action", "fgb_wall_forces", "fgb_column_sums", "fgb_sample_sensors",
            "fgb_profile_enable",
-           "fgb_profile_read", "fgb_launch_count"]
+           "fgb_profile_read", "fgb_launch_count", "fgb_piso_substep_record", "fgb_adjoint_workspace_bytes",
+           "fgb_piso_substep_backward"]
 
 
 def lib_path() -> str:
@@ -92,6 +97,10 @@ def load():
     L.fgb_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), i32]
     L.fgb_launch_count.argtypes = [vp]
     L.fgb_launch_count.restype = C.c_longlong
+    L.fgb_piso_substep_record.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Tape), vp]
+    L.fgb_adjoint_workspace_bytes.restype = C.c_size_t
+    L.fgb_adjoint_workspace_bytes.argtypes = [C.POINTER(Tables), i32]
+    L.fgb_piso_substep_backward.argtypes = [vp, C.POINTER(Tape), vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     _lib = L
     return L
 

@@ -16,7 +16,7 @@ from . import native
 from .domain import CompiledDomain
 
 _TABLE_FIELDS = ["nbr", "fl_comp", "minv", "det", "Cd", "Wp", "no_idx", "no_face", "no_gP", "no_gN", "no_wv",
-                 "nob_idx", "nob_w", "b_minv", "b_det", "b_alpha", "b_cell", "b_face"]
+                 "nob_idx", "nob_w", "b_minv", "b_det", "b_alpha", "b_cell", "b_face", "rev"]
 
 
 def _ptr(t):
@@ -112,7 +112,7 @@ class BatchedPISO:
                   "hbya": ((B, 2, N), torch.float32), "div": ((B, N), torch.float32), "pres": ((B, N), torch.float32),
                   "iters": ((B, 8), torch.int32), "iter_total": ((B, 2), torch.int64), "resid": ((B, 8), torch.float32), "dt": ((B,), torch.float32),
                   "active": ((B,), torch.int32), "remaining": ((B,), torch.float64), "nsub": ((B,), torch.int32),
-                  "maxvel": ((B,), torch.float32), "fluxbal": ((B,), torch.float32)}
+                  "maxvel": ((B,), torch.float32), "fluxbal": ((B,), torch.float32), "pmean": ((8, B), torch.float32)}
         shape, dtype = shapes[name]
         ptr = self.lib.fgb_batch_buffer(self.handle, name.encode())
         off = ptr - self.workspace.data_ptr()

@@ -66,6 +66,8 @@ typedef struct fgb_tables {
     float scalar_viscosity; /*          scalar diffusivity (Domain.setScalarViscosity)                     */
     const float *Cd_s;      /* [5][N]   constant part of the scalar transport matrix, before /det          */
     const int8_t *sb_neumann; /* [NB]   scalar boundary condition type: 0 Dirichlet, 1 Neumann             */
+    const int8_t *rev;      /* [4][N]   face of the neighbour nbr[f] that points back to this cell (adjoint /
+                                        transposed solves), -1 on boundary faces                        */
 } fgb_tables;
 
 /* Passive scalar + buoyancy coupling of one batch (RBC: temperature; rbc_env_base.py:190-304).  With the
@@ -189,6 +191,33 @@ int fgb_column_sums(fgb_batch *b, const float *fa, const float *fb, int32_t nx, 
  * sum_k w[k][s] * field[B][C][idx[k][s]] (the static splat+normalise+fill map evaluated at the sensors) */
 int fgb_sample_sensors(fgb_batch *b, const float *field, int32_t channels, const int32_t *idx, const float *w,
                        int32_t K, int32_t n_sensors, float *out, fgb_stream_t s);
+
+/* ---- differentiability (torch.autograd is layered on top in fluidgym_b200/autograd.py) ----------------- */
+/* Tape of one substep: device buffers owned by the caller, filled by fgb_piso_substep_record.  Replaces the
+ * tensors the reference's autograd.Functions save per native op (DIFF.py:624-1808). */
+typedef struct fgb_tape {
+    float *u_in;     /* [B][2][N]   */
+    float *p_in;     /* [B][N]      */
+    float *bvel_in;  /* [B][2][NB]  */
+    float *dt;       /* [B]         */
+    float *Coff;     /* [B][4][N]   */
+    float *A;        /* [B][N]      */
+    float *ustar;    /* [B][2][N]   predictor result                    */
+    float *hb;       /* [2][B][2][N] HbyA of the two correctors          */
+    float *p;        /* [2][B][N]   pressure of the two correctors (mean removed) */
+    float *pmean;    /* [2][B]      the removed means                    */
+    float *u1;       /* [B][2][N]   velocity after the first corrector   */
+} fgb_tape;
+/* forward substep (non-orthogonal path, 2 correctors, no passive scalar, all environments active) + tape */
+int fgb_piso_substep_record(fgb_batch *b, float *u, float *p, const float *bvel, const float *dt, const fgb_tape *tape,
+                            fgb_stream_t s);
+size_t fgb_adjoint_workspace_bytes(const fgb_tables *t, int32_t B);
+/* vector-Jacobian product of that substep: (u_out_bar, p_out_bar) -> (u_bar, p_prev_bar, bvel_bar), all overwritten.
+ * Linear-solve adjoints are solves with the transposed operator (DIFF.py:572-590) by the same on-chip kernels;
+ * replaces SetupAdvectionMatrixGrad ... CorrectVelocityGrad (BIND.cpp:582-608). */
+int fgb_piso_substep_backward(fgb_batch *b, const fgb_tape *tape, const float *u_out_bar, const float *p_out_bar,
+                              float *u_bar, float *p_prev_bar, float *bvel_bar, void *workspace, size_t workspace_bytes,
+                              fgb_stream_t s);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------ */
 /* Record CUDA events around the solver launches on their own stream.  fgb_profile_read synchronises the

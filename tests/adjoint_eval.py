@@ -1,0 +1,248 @@
+"""float64 numpy statement of one PISO substep on the compiled tables and of its hand-derived reverse-mode
+adjoint (test helper, CPU only).
+
+This is the *specification* of the adjoint CUDA kernels (fluidgym_b200/csrc, fgb_*_adjoint): the same
+table-driven formulas as tests/table_eval.py, in float64 with exact dense linear solves so that the VJP can
+be validated against central finite differences to ~1e-7 (tests/test_adjoint_cpu.py).  The CUDA adjoint
+kernels are then compared op by op against these functions on the GPU.
+
+Substep (non-orthogonal path of SIM.py:1431-2002, advect_non_ortho_steps = pressure_non_ortho_steps = 1):
+    (u, p_prev, bvel)  ->  (u_out, p_out)
+"""
+import numpy as np
+
+
+class T64:
+    """float64 copy of the tables of a CompiledDomain plus a few index helpers."""
+
+    def __init__(self, cd):
+        self.N, self.NB = cd.N, cd.NB
+        self.nbr = cd.nbr.astype(np.int64)
+        self.inner = self.nbr >= 0
+        self.nb_safe = np.where(self.inner, self.nbr, 0)
+        self.bj = np.where(self.inner, 0, -1 - self.nbr)
+        self.comp = (cd.fl_comp & 1).astype(np.int64)
+        self.sgn = np.where(cd.fl_comp & 2, -1.0, 1.0)
+        for k in ("minv", "det", "Cd", "Wp", "no_gP", "no_gN", "no_wv", "nob_w", "b_minv", "b_det", "b_alpha"):
+            setattr(self, k, np.asarray(getattr(cd, k), dtype=np.float64))
+        self.b_minv = self.b_minv[:, :cd.NB]
+        self.b_det, self.b_alpha = self.b_det[:cd.NB], self.b_alpha[:cd.NB]
+        self.no_idx, self.no_face = cd.no_idx.astype(np.int64), cd.no_face.astype(np.int64)
+        self.nob_idx = cd.nob_idx.astype(np.int64)
+        self.b_face = cd.b_face[:cd.NB].astype(np.int64)
+        self.visc = float(cd.visc)
+        self.K_no, self.K_nob = cd.K_no, cd.K_nob
+        self.fac = [np.where((~self.inner[2 * d]) | (~self.inner[2 * d + 1]), 1.0, 0.5) for d in range(2)]
+        self.cells = np.arange(cd.N)
+
+
+# ---- elementary pieces ------------------------------------------------------------------------------
+def contra(t, v):
+    return np.stack([t.det * (t.minv[0] * v[0] + t.minv[1] * v[1]), t.det * (t.minv[2] * v[0] + t.minv[3] * v[1])])
+
+
+def contra_T(t, Ub):
+    """adjoint of contra: v_bar from U_bar"""
+    return np.stack([t.det * (t.minv[0] * Ub[0] + t.minv[2] * Ub[1]), t.det * (t.minv[1] * Ub[0] + t.minv[3] * Ub[1])])
+
+
+def bflux(t, bv):
+    ax = t.b_face >> 1
+    r0 = np.where(ax == 0, t.b_minv[0], t.b_minv[2])
+    r1 = np.where(ax == 0, t.b_minv[1], t.b_minv[3])
+    return t.b_det * (r0 * bv[0] + r1 * bv[1]), (t.b_det * r0, t.b_det * r1)
+
+
+def fluxes(t, v, Fb):
+    U = contra(t, v)
+    fl = np.zeros((4, t.N))
+    for f in range(4):
+        velN = t.sgn[f] * U[t.comp[f], t.nb_safe[f]]
+        fl[f] = np.where(t.inner[f], 0.5 * (velN + U[f >> 1]), Fb[t.bj[f]])
+    return fl
+
+
+def fluxes_T(t, flb):
+    """adjoint of fluxes: (v_bar [2,N], Fb_bar [NB]) from fl_bar [4,N]"""
+    Ub = np.zeros((2, t.N))
+    Fbb = np.zeros(t.NB)
+    for f in range(4):
+        g = np.where(t.inner[f], 0.5 * flb[f], 0.0)
+        Ub[f >> 1] += g
+        np.add.at(Ub, (t.comp[f], t.nb_safe[f]), g * t.sgn[f])
+        np.add.at(Fbb, t.bj[f], np.where(t.inner[f], 0.0, flb[f]))
+    return contra_T(t, Ub), Fbb
+
+
+def spmv(t, off, diag, x):
+    y = diag * x
+    for f in range(4):
+        y = y + np.where(t.inner[f], off[f] * x[t.nb_safe[f]], 0.0)
+    return y
+
+
+def dense(t, off, diag):
+    M = np.zeros((t.N, t.N))
+    M[t.cells, t.cells] = diag
+    for f in range(4):
+        m = t.inner[f]
+        np.add.at(M, (t.cells[m], t.nbr[f][m]), off[f][m])
+    return M
+
+
+def nbr_vals(t, x):
+    return np.stack([x] + [np.where(t.inner[f], x[t.nb_safe[f]], x) for f in range(4)])
+
+
+def nbr_vals_T(t, vb):
+    """adjoint of nbr_vals: x_bar from [5,N]"""
+    xb = vb[0].copy()
+    for f in range(4):
+        np.add.at(xb, np.where(t.inner[f], t.nb_safe[f], t.cells), vb[f + 1])
+    return xb
+
+
+# ---- forward substep with a tape ---------------------------------------------------------------------
+def substep(t, u, p_prev, bvel, dt, correctors=2):
+    tape = {}
+    Fb, (br0, br1) = bflux(t, bvel)
+    fl = fluxes(t, u, Fb)
+    sig = np.array([-1.0, 1.0, -1.0, 1.0])
+    ff = np.where(t.inner, 0.5 * sig[:, None] * fl, 0.0)
+    diag = t.det / dt + t.Cd[0] + ff.sum(0)
+    A = diag / t.det
+    Coff = np.where(t.inner, (ff + t.Cd[1:]) / t.det, 0.0)
+    # boundary sources
+    Sb = np.zeros((2, t.N))
+    for f in range(4):
+        m = ~t.inner[f]
+        j = t.bj[f]
+        for c in range(2):
+            Sb[c] += np.where(m, -bvel[c, j] * (sig[f] * Fb[j]) + bvel[c, j] * 2 * t.visc * t.b_alpha[j], 0.0)
+    NOv = np.zeros((2, t.N))
+    for c in range(2):
+        for k in range(t.K_no):
+            NOv[c] += t.no_wv[k] * u[c][t.no_idx[k]]
+        for k in range(t.K_nob):
+            NOv[c] += t.nob_w[k] * bvel[c][t.nob_idx[k]]
+    rhs = (t.det * u / dt + Sb - NOv) / t.det
+    C = dense(t, Coff, A)
+    ustar = np.stack([np.linalg.solve(C, rhs[c]) for c in range(2)])
+    rA = 1.0 / A
+    rAn = nbr_vals(t, rA)
+    Pm = np.einsum("ejn,jn->en", t.Wp, rAn)
+    P = dense(t, Pm[1:], Pm[0])
+    tape.update(Fb=Fb, fl=fl, A=A, Coff=Coff, Sb=Sb, C=C, ustar=ustar, rA=rA, rAn=rAn, Pm=Pm, P=P, cor=[])
+    uprev, pprev = ustar, p_prev
+    for _ in range(correctors):
+        H = np.stack([sum(np.where(t.inner[f], Coff[f] * uprev[c][t.nb_safe[f]], 0.0) for f in range(4)) for c in range(2)])
+        hb = rA * (u / dt - H + Sb / t.det)
+        flh = fluxes(t, hb, Fb)
+        wno = np.stack([t.no_gP[k] * rAn[0] + t.no_gN[k] * rAn[1 + t.no_face[k], t.cells] for k in range(t.K_no)])
+        NOp = sum(wno[k] * pprev[t.no_idx[k]] for k in range(t.K_no))
+        div = (flh[1] - flh[0]) + (flh[3] - flh[2]) + NOp
+        x = np.linalg.solve(P, div)
+        p = x - x.mean()
+        pv = nbr_vals(t, p)
+        pg = np.stack([(pv[2] - pv[1]) * t.fac[0], (pv[4] - pv[3]) * t.fac[1]])
+        g = np.stack([pg[0] * t.minv[0] + pg[1] * t.minv[2], pg[0] * t.minv[1] + pg[1] * t.minv[3]])
+        unext = hb - rA * g
+        tape["cor"].append(dict(uprev=uprev, pprev=pprev, H=H, hb=hb, x=x, p=p, g=g, wno=wno))
+        uprev, pprev = unext, p
+    return uprev, pprev, tape
+
+
+# ---- reverse pass --------------------------------------------------------------------------------------
+def substep_vjp(t, u, p_prev, bvel, dt, tape, u_out_bar, p_out_bar):
+    """returns (u_bar, p_prev_bar, bvel_bar)"""
+    N = t.N
+    sig = np.array([-1.0, 1.0, -1.0, 1.0])
+    Coff, A, rA, rAn, Sb, Fb = tape["Coff"], tape["A"], tape["rA"], tape["rAn"], tape["Sb"], tape["Fb"]
+    ub = np.zeros((2, N)); bvb = np.zeros((2, t.NB)); Fbb = np.zeros(t.NB)
+    Coffb = np.zeros((4, N)); rAb = np.zeros(N); rAnb = np.zeros((5, N)); Sbb = np.zeros((2, N)); Pmb = np.zeros((5, N))
+    unb, pb = u_out_bar.copy(), p_out_bar.copy()
+    ustarb = np.zeros((2, N)); pprevb_in = np.zeros(N)
+    for ci in reversed(range(len(tape["cor"]))):
+        cr = tape["cor"][ci]
+        # unext = hb - rA * g
+        hbb = unb.copy()
+        rAb += -(cr["g"] * unb).sum(0)
+        gb = -rA * unb
+        pgb = np.stack([gb[0] * t.minv[0] + gb[1] * t.minv[1], gb[0] * t.minv[2] + gb[1] * t.minv[3]])
+        pvb = np.zeros((5, N))
+        pvb[2] += pgb[0] * t.fac[0]; pvb[1] -= pgb[0] * t.fac[0]
+        pvb[4] += pgb[1] * t.fac[1]; pvb[3] -= pgb[1] * t.fac[1]
+        pb = pb + nbr_vals_T(t, pvb)
+        # p = x - mean(x) ; x = P^-1 div
+        xb = pb - pb.mean()
+        lam = np.linalg.solve(tape["P"].T, xb)
+        divb = lam
+        # P_bar on the pattern: P_ij_bar = -lam_i x_j
+        Pmb[0] += -lam * cr["x"]
+        for f in range(4):
+            Pmb[f + 1] += np.where(t.inner[f], -lam * cr["x"][t.nb_safe[f]], 0.0)
+        # div = flux divergence of hb + NOp
+        flhb = np.stack([-divb, divb, -divb, divb])
+        hb_b2, Fbb2 = fluxes_T(t, flhb)
+        hbb += hb_b2; Fbb += Fbb2
+        pprevb = np.zeros(N)
+        for k in range(t.K_no):
+            wb = divb * cr["pprev"][t.no_idx[k]]
+            rAnb[0] += t.no_gP[k] * wb
+            np.add.at(rAnb, (1 + t.no_face[k], t.cells), t.no_gN[k] * wb)
+            np.add.at(pprevb, t.no_idx[k], cr["wno"][k] * divb)
+        # hb = rA (u/dt - H + Sb/det)
+        rAb += (hbb * (cr["hb"] / rA)).sum(0)
+        inner_b = rA * hbb
+        ub += inner_b / dt
+        Sbb += inner_b / t.det
+        Hb = -inner_b
+        uprevb = np.zeros((2, N))
+        for f in range(4):
+            m = t.inner[f]
+            for c in range(2):
+                Coffb[f] += np.where(m, Hb[c] * cr["uprev"][c][t.nb_safe[f]], 0.0)
+                np.add.at(uprevb[c], t.nb_safe[f], np.where(m, Hb[c] * Coff[f], 0.0))
+        if ci > 0:
+            unb, pb = uprevb, pprevb
+        else:
+            ustarb, pprevb_in = uprevb, pprevb
+    # P = Wp . rAn
+    rAnb += np.einsum("ejn,en->jn", t.Wp, Pmb)
+    rAb += nbr_vals_T(t, rAnb)
+    Ab = -rAb * rA * rA
+    # ustar = C^-1 rhs
+    rhsb = np.zeros((2, N))
+    for c in range(2):
+        mu = np.linalg.solve(tape["C"].T, ustarb[c])
+        rhsb[c] = mu
+        Ab += -mu * tape["ustar"][c]
+        for f in range(4):
+            Coffb[f] += np.where(t.inner[f], -mu * tape["ustar"][c][t.nb_safe[f]], 0.0)
+    # rhs = (det u/dt + Sb - NOv)/det
+    ub += rhsb / dt
+    Sbb += rhsb / t.det
+    NOvb = -rhsb / t.det
+    for c in range(2):
+        for k in range(t.K_no):
+            np.add.at(ub[c], t.no_idx[k], t.no_wv[k] * NOvb[c])
+        for k in range(t.K_nob):
+            np.add.at(bvb[c], t.nob_idx[k], t.nob_w[k] * NOvb[c])
+    # Sb(bvel, Fb)
+    for f in range(4):
+        m = ~t.inner[f]
+        j = t.bj[f]
+        for c in range(2):
+            np.add.at(bvb[c], j, np.where(m, Sbb[c] * (-(sig[f] * Fb[j]) + 2 * t.visc * t.b_alpha[j]), 0.0))
+            np.add.at(Fbb, j, np.where(m, Sbb[c] * (-bvel[c, j] * sig[f]), 0.0))
+    # A = diag/det, Coff = (ff + Cd)/det, diag = det/dt + Cd0 + sum ff
+    diagb = Ab / t.det
+    ffb = np.where(t.inner, Coffb / t.det + diagb[None, :], 0.0)
+    flb = 0.5 * sig[:, None] * ffb
+    ub2, Fbb3 = fluxes_T(t, flb)
+    ub += ub2; Fbb += Fbb3
+    # Fb(bvel)
+    _, (br0, br1) = bflux(t, bvel)
+    bvb[0] += br0 * Fbb
+    bvb[1] += br1 * Fbb
+    return ub, pprevb_in, bvb

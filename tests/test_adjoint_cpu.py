@@ -1,0 +1,43 @@
+"""The hand-derived reverse-mode adjoint of one PISO substep (tests/adjoint_eval.py, the float64 numpy
+specification of the CUDA adjoint kernels) against central finite differences: directional derivatives of a
+random linear functional of (u_out, p_out) w.r.t. u, p_prev and the boundary velocities."""
+import numpy as np
+import pytest
+
+import adjoint_eval as ae
+
+
+@pytest.fixture(scope="module")
+def small():
+    from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
+    cd = make_cylinder_domain(8).prepare()
+    return cd, ae.T64(cd)
+
+
+def test_substep_vjp_matches_finite_differences(small):
+    cd, t = small
+    rng = np.random.default_rng(1)
+    u = 0.3 * rng.standard_normal((2, t.N)); u[0] += 1.0
+    p0 = 0.1 * rng.standard_normal(t.N)
+    bvel = cd.bvel0[:, :t.NB].astype(np.float64) + 0.05 * rng.standard_normal((2, t.NB))
+    dt = 0.01
+    wu, wp = rng.standard_normal((2, t.N)), rng.standard_normal(t.N)
+
+    def J(u_, p_, b_):
+        uo, po, _ = ae.substep(t, u_, p_, b_, dt)
+        return float((wu * uo).sum() + (wp * po).sum())
+
+    uo, po, tape = ae.substep(t, u, p0, bvel, dt)
+    ub, pb, bb = ae.substep_vjp(t, u, p0, bvel, dt, tape, wu, wp)
+    for name, grad, shape in (("u", ub, u.shape), ("p_prev", pb, p0.shape), ("bvel", bb, bvel.shape)):
+        for trial in range(2):
+            d = rng.standard_normal(shape)
+            eps = 1e-6
+            if name == "u":
+                fd = (J(u + eps * d, p0, bvel) - J(u - eps * d, p0, bvel)) / (2 * eps)
+            elif name == "p_prev":
+                fd = (J(u, p0 + eps * d, bvel) - J(u, p0 - eps * d, bvel)) / (2 * eps)
+            else:
+                fd = (J(u, p0, bvel + eps * d) - J(u, p0, bvel - eps * d)) / (2 * eps)
+            an = float((grad * d).sum())
+            assert abs(fd - an) <= 2e-5 * max(abs(fd), abs(an)) + 1e-7, (name, trial, fd, an)

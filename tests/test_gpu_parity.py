@@ -184,3 +184,38 @@ def test_env_step_matches_reference(cyl24, golden):
     assert obs["velocity"].shape == (2, 151, 2) and obs["pressure"].shape == (2, 151)
     assert np.abs(obs["velocity"][0].cpu().numpy() - st["step0_obs_velocity"]).max() < 2e-3
     assert np.abs(obs["pressure"][0].cpu().numpy() - st["step0_obs_pressure"]).max() < 2e-3
+
+
+def test_parallel_fluid_env_api():
+    """ParallelFluidEnv(env_id, cuda_ids): one environment per entry, results stacked on the CPU
+    (envs/parallel_env.py:162-287 of the reference)."""
+    from fluidgym_b200.envs.parallel_env import ParallelFluidEnv
+    env = ParallelFluidEnv("CylinderJet2D-easy-v0", cuda_ids=[0, 0, 0])
+    obs, info = env.reset(seed=11)
+    assert obs["velocity"].shape == (3, 151, 2) and obs["velocity"].device.type == "cpu"
+    a = env.sample_action()
+    assert a.shape == (3, 1)
+    obs, reward, term, trunc, info = env.step(a)
+    assert reward.shape == (3,) and set(info) == {"drag", "lift"} and isinstance(term, bool) and isinstance(trunc, bool)
+    with pytest.raises(NotImplementedError):
+        env.get_state()
+    env.close()
+
+
+def test_batch_entries_are_independent(cyl24):
+    """Environment e of a batch evolves exactly as it would alone (no cross-talk through shared workspaces)."""
+    spec, cd = cyl24
+    from fluidgym_b200.envs.cylinder import CylinderJet2DEnv
+    big = CylinderJet2DEnv(n_envs=5, compiled=(spec, cd))
+    one = CylinderJet2DEnv(n_envs=1, compiled=(spec, cd))
+    big.reset(seed=3)
+    one.reset(seed=3)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    big.solver.u += 0.02 * torch.randn(big.solver.u.shape, device="cuda", generator=gen)
+    one.solver.u.copy_(big.solver.u[3:4])
+    act = torch.linspace(-1, 1, 5, device="cuda").reshape(5, 1)
+    big.n_sim_steps_override = None
+    ob, rb, *_ = big.step(act)
+    oo, ro, *_ = one.step(act[3:4])
+    assert torch.equal(big.solver.u[3], one.solver.u[0]) and torch.equal(big.solver.p[3], one.solver.p[0])
+    assert torch.equal(rb[3], ro[0]) and torch.equal(ob["pressure"][3], oo["pressure"][0])
