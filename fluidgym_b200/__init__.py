@@ -26,8 +26,13 @@ def make(env_id: str, n_envs: int = 1, **kwargs):
     entry, defaults = _REGISTRY[env_id]
     cfg = dict(defaults)
     # reference-only constructor flags that have no meaning here are accepted and ignored
-    for k in ("load_initial_domain", "load_domain_statistics", "dtype", "differentiable"):
+    for k in ("load_initial_domain", "load_domain_statistics", "dtype"):
         kwargs.pop(k, None)
+    if "differentiable" in kwargs:
+        import inspect
+        if "differentiable" not in inspect.signature(entry.__init__).parameters:
+            if kwargs.pop("differentiable"):
+                raise NotImplementedError(f"{env_id}: differentiable=True is not available for this environment family yet")
     cfg.update(kwargs)
     return entry(n_envs=n_envs, **cfg)
 

@@ -36,7 +36,7 @@ class CylinderJet2DEnv:
 
     def __init__(self, n_envs: int = 1, reynolds_number=1e2, resolution=24, dt=1e-2, adaptive_cfl=0.8, step_length=0.25,
                  episode_length=80, lift_penalty=1.0, device="cuda:0", cg_impl=3, compiled=None, cd_ref=0.0,
-                 randomize_initial_state=False, enable_actions=True, use_marl=False):
+                 randomize_initial_state=False, enable_actions=True, use_marl=False, differentiable=False):
         if use_marl:
             raise ValueError("CylinderJet2D is a single-agent environment (n_agents == 1)")
         self.n_envs = int(n_envs)
@@ -45,6 +45,8 @@ class CylinderJet2DEnv:
         self.lift_penalty, self.cd_ref = float(lift_penalty), float(cd_ref)
         self.randomize_initial_state = randomize_initial_state
         self.enable_actions = enable_actions
+        self.differentiable = bool(differentiable)
+        self._dstate = None
         self.device = torch.device(device)
         if compiled is None:
             spec = make_cylinder_domain(resolution, reynolds_number, self.U_mean, self.H, self.L, self.cylinder_offset_y)
@@ -222,6 +224,7 @@ class CylinderJet2DEnv:
             dst.copy_(src if src.dim() == dst.dim() else src.unsqueeze(0).expand_as(dst))
         if last_control is not None:
             self.last_control.copy_(torch.as_tensor(last_control, device=self.device).expand_as(self.last_control))
+        self._dstate = None
         self._reset_called = True
 
     def get_state(self):
@@ -246,6 +249,7 @@ class CylinderJet2DEnv:
         if randomize:
             self._randomize_domain()
         self._apply_action(self._zero_action, smooth=False)
+        self._dstate = None
         self._reset_called = True
         self._n_steps = 0
         return self._get_obs(), {}
@@ -291,6 +295,8 @@ class CylinderJet2DEnv:
             raise ValueError(f"Action shape {action.shape} does not match expected shape {self._zero_action.shape}.")
         if self._n_steps >= self.episode_length:
             raise RuntimeError("Episode has already terminated. Call 'reset()' first.")
+        if self.differentiable:
+            return self._step_differentiable(action)
         s = self.solver
         self._acc.zero_()
         nsub = 0
@@ -303,6 +309,121 @@ class CylinderJet2DEnv:
         self.last_substeps = nsub
         obs = self._get_obs()
         mean = self._acc / self.n_sim_steps
+        cd, cl = mean[:, 0], mean[:, 1]
+        reward = self.cd_ref - cd - self.lift_penalty * torch.abs(cl)
+        self._n_steps += 1
+        truncated = self._n_steps >= self.episode_length
+        return obs, reward, False, truncated, {"drag": cd.detach(), "lift": cl.detach()}
+
+    # ---- differentiable mode (fluid_env.py:154,232; examples/interfaces/gradient_based_methods.py) -----------------
+    # The PISO substep is one autograd node backed by the CUDA adjoint (fluidgym_b200.autograd); the few boundary
+    # and reward formulas around it are tiny torch expressions over the same static tables the kernels use, so
+    # gradients flow from the reward to the action, the block velocities and the boundary values exactly as in
+    # the reference, where those parts are torch code as well (SIM.py:188-393, forces.py:193-275).
+    def detach(self):
+        """fluid_env.py `detach()`: cut the autograd graph at the current state."""
+        if self._dstate is not None:
+            self._dstate = tuple(t.detach() for t in self._dstate)
+
+    def _diff_tables(self):
+        if getattr(self, "_dt_tab", None) is None:
+            cd, dev = self.cd, self.device
+            NB = cd.NB
+            out = np.nonzero(np.asarray(self.solver._tab["b_out"].cpu()))[0]
+            face = np.asarray(cd.b_face[:NB]).astype(np.int64)
+            ax = face >> 1
+            bminv = np.asarray(cd.b_minv)[:, :NB]
+            bdet = np.asarray(cd.b_det)[:NB]
+            j = np.arange(NB)
+            sign = np.where(face & 1, 1.0, -1.0)
+            fw = np.stack([bdet * bminv[2 * ax, j] * sign, bdet * bminv[2 * ax + 1, j] * sign]).astype(np.float32)   # signed flux weights
+            adv = bminv[2 * ax[out], out] * self.char_vel[0] + bminv[2 * ax[out] + 1, out] * self.char_vel[1]
+            is_out = np.zeros(NB, dtype=bool)
+            is_out[out] = True
+            tt = lambda a, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+            self._dt_tab = dict(out=tt(out, torch.int64), out_cell=tt(np.asarray(cd.b_cell)[out], torch.int64), adv=tt(adv),
+                                fw=tt(fw), is_out=tt(is_out, torch.bool))
+        return self._dt_tab
+
+    def _outflow_torch(self, u, bv, dt, bc_tol=5e-6):
+        """k_plan_substep's boundary part (SIM.py:188-224, 282-393) as differentiable torch ops."""
+        tb = self._diff_tables()
+        w = 1.0 - 1.0 / (1.0 + 2.0 * dt * tb["adv"])
+        bo = bv[:, :, tb["out"]]
+        bo = bo - w * (bo - u[:, :, tb["out_cell"]])
+        bv = bv.index_copy(2, tb["out"], bo)
+        fl = (bv * tb["fw"]).sum(dim=1)
+        fx = (fl * (~tb["is_out"])).sum(dim=1)
+        vr = (fl * tb["is_out"]).sum(dim=1)
+        need = ~((fx + vr).abs() <= bc_tol * 0.01)
+        sc = torch.where(need, -fx / vr, torch.ones_like(fx))
+        scale = torch.where(tb["is_out"][None, :], sc[:, None], torch.ones_like(fl))
+        return bv * scale[:, None, :]
+
+    def _forces_torch(self, u, p, bv):
+        """k_wall_forces (forces.py:193-275) as differentiable torch ops -> [B,2] (drag, lift coefficients)."""
+        w = self._wall_t
+        c, j = w["cell"].long(), w["bface"].long()
+        il, ir = torch.roll(c, -1), torch.roll(c, 1)
+        n = w["normal"]
+        nx, ny = n[0], n[1]
+        tx, ty = ny, -nx
+        visc = float(self.cd.visc)
+        dn = (u[:, :, c] - bv[:, :, j]) / w["dist"]
+        dt_ = (u[:, :, ir] - u[:, :, il]) / (2.0 * w["tlen"])
+        du_dx, du_dy = dn[:, 0] * nx + dt_[:, 0] * tx, dn[:, 0] * ny + dt_[:, 0] * ty
+        dv_dx, dv_dy = dn[:, 1] * nx + dt_[:, 1] * tx, dn[:, 1] * ny + dt_[:, 1] * ty
+        pc = p[:, c]
+        sxx, syy = 2.0 * visc * du_dx - pc, 2.0 * visc * dv_dy - pc
+        sxy = visc * (du_dy + dv_dx)
+        fxx = ((sxx * nx + sxy * ny) * w["flen"]).sum(dim=1)
+        fyy = ((sxy * nx + syy * ny) * w["flen"]).sum(dim=1)
+        return torch.stack([fxx, fyy], dim=1) * self.wall.scale
+
+    def _single_step_differentiable(self, u, p, bv):
+        """Simulation.single_step with the adaptive CFL plan of SIM.py:2004-2031; the plan itself is not
+        differentiated (the reference computes it from detached maxima as well).  One common substep size is
+        used for the batch (the most restrictive environment decides)."""
+        from ..autograd import piso_substep
+        s = self.solver
+        remaining, nsub = float(self.dt), 0
+        mvb = torch.empty(self.n_envs, device=self.device)
+        while remaining > 0.0 and not abs(remaining) <= 1e-8:
+            native.check(self.lib.fgb_max_velocity(s.handle, _ptr(u.detach().contiguous()), _ptr(bv.detach().contiguous()), _ptr(mvb),
+                                                   s.stream), "fgb_max_velocity")
+            mv = float(mvb.max())
+            if abs(mv) <= 1e-8:
+                ts = remaining
+            else:
+                mts = np.float32(self.cfl) / np.float32(mv)
+                ts = remaining if float(mts) >= remaining else remaining / float(np.ceil(np.float32(remaining) / mts))
+            remaining -= ts
+            bv = self._outflow_torch(u, bv, float(np.float32(ts)))
+            u, p = piso_substep(s, u, p, bv, float(np.float32(ts)))
+            nsub += 1
+        return u, p, bv, nsub
+
+    def _step_differentiable(self, action):
+        s = self.solver
+        if self._dstate is None:
+            self._dstate = (s.u.clone(), s.p.clone(), s.bvel.clone(), self.last_control.clone())
+        u, p, bv, last = self._dstate
+        a = action.reshape(self.n_envs)
+        acc = torch.zeros(self.n_envs, 2, device=self.device)
+        nsub = 0
+        for _ in range(self.n_sim_steps):
+            if self.enable_actions:
+                last = last + self.action_smoothing_alpha * (a - last)
+                bv = bv.index_copy(2, self.jet_faces.long(), self.jet_templ[None] * last[:, None, None])
+            u, p, bv, k = self._single_step_differentiable(u, p, bv)
+            nsub += k
+            acc = acc + self._forces_torch(u, p, bv)
+        self._dstate = (u, p, bv, last)
+        with torch.no_grad():                      # keep the solver's own state in step for obs / get_state
+            s.u.copy_(u); s.p.copy_(p); s.bvel.copy_(bv); self.last_control.copy_(last)
+        self.last_substeps = nsub
+        obs = self._get_obs()
+        mean = acc / self.n_sim_steps
         cd, cl = mean[:, 0], mean[:, 1]
         reward = self.cd_ref - cd - self.lift_penalty * torch.abs(cl)
         self._n_steps += 1

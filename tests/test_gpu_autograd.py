@@ -87,3 +87,58 @@ def test_vjp_matches_finite_differences_of_the_cuda_forward(setup):
         an = float((grad[0].double() * d.double()).sum())
         print('fd', name, fd, an)
         assert abs(fd - an) < 3e-2 * max(abs(fd), abs(an)) + 1e-3, (name, fd, an)
+
+
+# ---- environment level (examples/interfaces/gradient_based_methods.py) ------------------------------------
+@pytest.fixture(scope="module")
+def developed_state():
+    """A short spin-up of the easy cylinder so that drag/lift respond to the jets."""
+    import fluidgym_b200 as fg
+    env = fg.make("CylinderJet2D-easy-v0", n_envs=1)
+    env.reset(seed=0)
+    for _ in range(3):
+        env.step(torch.zeros(1, 1, device="cuda"))
+    return env.get_state()
+
+
+def test_differentiable_step_equals_plain_step(developed_state):
+    import fluidgym_b200 as fg
+    a = torch.full((2, 1), 0.6, device="cuda")
+    out = []
+    for diff in (False, True):
+        env = fg.make("CylinderJet2D-easy-v0", n_envs=2, differentiable=diff)
+        env.reset(seed=0)
+        st = developed_state
+        env.set_state(st["u"][0], st["p"][0], st["bvel"][0], st["last_control"][0])
+        obs, r, term, trunc, info = env.step(a)
+        out.append((r.detach().cpu().numpy(), env.solver.u.clone(), info["drag"].cpu().numpy()))
+    assert np.allclose(out[0][0], out[1][0], rtol=2e-4, atol=2e-4), (out[0][0], out[1][0])
+    assert float((out[0][1] - out[1][1]).abs().max()) < 5e-4
+
+
+def test_reward_gradient_wrt_action_matches_finite_differences(developed_state):
+    """d reward / d action through 25 sim steps of the easy cylinder (one env.step), checked against a central
+    difference of the non-differentiable environment."""
+    import fluidgym_b200 as fg
+    st = developed_state
+
+    def run(a0, diff):
+        env = fg.make("CylinderJet2D-easy-v0", n_envs=1, differentiable=diff)
+        env.reset(seed=0)
+        env.set_state(st["u"][0], st["p"][0], st["bvel"][0], st["last_control"][0])
+        # tight solves so that the difference quotient is not dominated by the CG tolerance ball
+        env.solver.set_options(pressure_tol=1e-7, advection_tol=1e-7)
+        a = torch.full((1, 1), a0, device="cuda", requires_grad=diff)
+        obs, r, *_ = env.step(a)
+        return a, r, env
+
+    a, r, env = run(0.3, True)
+    r.sum().backward()
+    g = float(a.grad)
+    env.detach()
+    eps = 0.1
+    rp = float(run(0.3 + eps, False)[1])
+    rm = float(run(0.3 - eps, False)[1])
+    fd = (rp - rm) / (2 * eps)
+    print("d reward / d action: autograd", g, "central difference", fd)
+    assert abs(g - fd) < 0.05 * max(abs(g), abs(fd)) + 1e-4
