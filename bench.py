@@ -348,7 +348,7 @@ def run_reference(args):
     out = np.zeros(cd.NB, np.uint8)
     o = cd.boff[WAKE, 1]
     out[o:o + spec.blocks[WAKE].ny] = 1
-    orc.update_outflow(u, out, cd.b_cell, [1.0, 0.0], 1.0, 5e-6)
+    orc.update_outflow(u, out, cd.b_cell, [1.0, 0.0], 1.0, 1e-5)
     orc.make_divergence_free(u, p, 1000)
     per_step = max(1, args.cpu_steps // max(args.steps, 1))
     for _ in range(args.warmup):

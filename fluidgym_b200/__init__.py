@@ -42,6 +42,16 @@ def _register_defaults():
     # fluidgym/__init__.py:28-60: easy = Re 100 / res 24, medium = Re 250 / res 32, hard = Re 500 / res 32
     register("CylinderJet2D-easy-v0", CylinderJet2DEnv, **CYLINDER_JET_2D_DEFAULT_CONFIG)
     register("CylinderJet2D-medium-v0", CylinderJet2DEnv, **{**CYLINDER_JET_2D_DEFAULT_CONFIG, "reynolds_number": 250.0, "resolution": 32})
+    from .envs.cylinder import CYLINDER_ROT_2D_DEFAULT_CONFIG, CylinderRot2DEnv
+    # fluidgym/__init__.py:52-74
+    register("CylinderRot2D-easy-v0", CylinderRot2DEnv, **CYLINDER_ROT_2D_DEFAULT_CONFIG)
+    register("CylinderRot2D-medium-v0", CylinderRot2DEnv, **{**CYLINDER_ROT_2D_DEFAULT_CONFIG, "reynolds_number": 250.0, "resolution": 32})
+    register("CylinderRot2D-hard-v0", CylinderRot2DEnv, **{**CYLINDER_ROT_2D_DEFAULT_CONFIG, "reynolds_number": 500.0, "resolution": 32})
+    from .envs.airfoil import AIRFOIL_2D_DEFAULT_CONFIG, Airfoil2DEnv
+    # fluidgym/__init__.py:306-328
+    register("Airfoil2D-easy-v0", Airfoil2DEnv, **{**AIRFOIL_2D_DEFAULT_CONFIG, "reynolds_number": 1e3})
+    register("Airfoil2D-medium-v0", Airfoil2DEnv, **{**AIRFOIL_2D_DEFAULT_CONFIG, "reynolds_number": 3e3})
+    register("Airfoil2D-hard-v0", Airfoil2DEnv, **{**AIRFOIL_2D_DEFAULT_CONFIG, "reynolds_number": 5e3})
     from .envs.rbc import RBC_2D_DEFAULT_CONFIG, RBC2DEnv
     # fluidgym/__init__.py:106-157
     register("RBC2D-easy-v0", RBC2DEnv, **{**RBC_2D_DEFAULT_CONFIG, "rayleigh_number": 8e4, "adaptive_cfl": 0.8})

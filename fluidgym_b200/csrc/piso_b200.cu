@@ -1009,7 +1009,6 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__re
     constexpr int NW = T / 32;
     constexpr int NP = NW * CS;
     constexpr int PAD = T * CPT;
-    static_assert(NP <= 64, "final reduction reads two partials per lane");
     const int b = blockIdx.x / CS;
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -1071,8 +1070,9 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__re
         if (lane < CS) st_async_f32(peer_red + 4u * (w * NP + rank * NW + (uint32_t)warp), a0, peer_mb + 8u * w);
         mbar_wait(mb_addr + 8u * w, par);
         const float *rp = red + w * NP;
-        float s0 = lane < NP ? rp[lane] : 0.f;
-        if (NP > 32) s0 += (lane + 32 < NP) ? rp[lane + 32] : 0.f;
+        float s0 = 0.f;
+#pragma unroll
+        for (int q = 0; q < (NP + 31) / 32; ++q) s0 += (lane + 32 * q < NP) ? rp[lane + 32 * q] : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
         // re-arm this barrier for its next use (two reductions from now); every warp of this CTA has to be
@@ -1448,6 +1448,10 @@ static int launch_bicgstab_cluster(fgb_batch *b, const float *coff, const float 
     auto kern = k_bicgstab_cluster<T, CPT, CS, NC>;
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_bicgstab_cluster)", ce);
+    if (CS > 8) {   // 16-CTA clusters are a non-portable size: opt in (one cluster then occupies most of a GPC)
+        ce = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_bicgstab_cluster, non-portable cluster)", ce);
+    }
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(b->B * CS); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1459,12 +1463,21 @@ static int launch_bicgstab_cluster(fgb_batch *b, const float *coff, const float 
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchKernelEx(k_bicgstab_cluster)", ce);
     return FGB_OK;
 }
+// smallest cluster that holds the grid on chip: 2 x 3072, 4 x 3584, 8 x 3584 or 16 x 3072 cells (returns 1 if none does)
+template <int NC>
+static int bicgstab_cluster_any(fgb_batch *b, const float *coff, const float *adiag, const float *rhs, float *x, int zero_init,
+                                const int32_t *active, int transposed, cudaStream_t st) {
+    int rc = launch_bicgstab_cluster<2, 6, NC>(b, coff, adiag, rhs, x, zero_init, active, transposed, st);
+    if (rc == 1) rc = launch_bicgstab_cluster<4, 7, NC>(b, coff, adiag, rhs, x, zero_init, active, transposed, st);
+    if (rc == 1) rc = launch_bicgstab_cluster<8, 7, NC>(b, coff, adiag, rhs, x, zero_init, active, transposed, st);
+    if (rc == 1) rc = launch_bicgstab_cluster<16, 6, NC>(b, coff, adiag, rhs, x, zero_init, active, transposed, st);
+    return rc;
+}
 // BiCGStab dispatcher: on-chip cluster kernel when the grid fits, else one CTA per environment in global memory
 template <int NC>
 static int run_bicgstab(fgb_batch *b, const float *rhs, float *x, int zero_init, const int32_t *active, cudaStream_t st) {
     if (b->opt.cg_impl >= 1) {
-        int rc = launch_bicgstab_cluster<2, 6, NC>(b, b->Coff, b->A, rhs, x, zero_init, active, 0, st);
-        if (rc == 1) rc = launch_bicgstab_cluster<4, 7, NC>(b, b->Coff, b->A, rhs, x, zero_init, active, 0, st);
+        int rc = bicgstab_cluster_any<NC>(b, b->Coff, b->A, rhs, x, zero_init, active, 0, st);
         if (rc <= 0) return rc;
     }
     k_bicgstab<1024, NC><<<b->B, 1024, 0, st>>>(b->t, b->Coff, b->A, rhs, x, b->kry, b->opt.max_iter, b->opt.adv_tol, zero_init, active,
@@ -1715,14 +1728,15 @@ __global__ void __launch_bounds__(T) k_max_velocity(Tab t, const float *__restri
 
 // signed boundary flux sums; which: 0 = faces with b_out==0, 1 = faces with b_out==1, 2 = all
 template <int T>
-__device__ void env_flux_sums(const Tab &t, const float *bv, float &fixed, float &var, double *red) {
+__device__ void env_flux_sums(const Tab &t, const float *bv, float &fixed, float &var, double *red, const int8_t *mask = nullptr) {
+    if (!mask) mask = t.b_out;
     const int NB = t.NB;
     float acc[2] = {0.f, 0.f};
     for (int j = threadIdx.x; j < NB; j += T) {
         const int f = t.b_face[j];
         float fl = bflux(t, j, f >> 1, bv[j], bv[NB + j]);
         if (!(f & 1)) fl = -fl;
-        if (t.b_out && t.b_out[j]) acc[1] += fl; else acc[0] += fl;
+        if (mask && mask[j]) acc[1] += fl; else acc[0] += fl;
     }
     block_reduce_sum<2>(acc, red);
     fixed = acc[0]; var = acc[1];
@@ -1810,6 +1824,21 @@ __global__ void __launch_bounds__(T) k_update_outflow(Tab t, const float *__rest
     __shared__ double red[32 * 2 + 2];
     const int b = blockIdx.x;
     env_update_outflow<T>(t, U + (size_t)b * 2 * t.N, Bvel + (size_t)b * 2 * t.NB, dtv[b], cvx, cvy, bc_tol, red);
+}
+// balance_boundary_fluxes (SIM.py:188-224) with an explicit set of free faces: all their velocities are scaled by
+// -(flux through the other prescribed faces) / (flux through the free faces)
+template <int T>
+__global__ void __launch_bounds__(T) k_balance_fluxes(Tab t, float *__restrict__ Bvel, const int8_t *__restrict__ free_mask, float bc_tol) {
+    __shared__ double red[32 * 2 + 2];
+    const int b = blockIdx.x, NB = t.NB;
+    float *bv = Bvel + (size_t)b * 2 * NB;
+    float fx, vr;
+    env_flux_sums<T>(t, bv, fx, vr, red, free_mask);
+    if (!(fabsf(fx + vr) <= bc_tol * 0.01f)) {
+        const float sc = -fx / vr;
+        for (int j = threadIdx.x; j < NB; j += T)
+            if (free_mask[j]) { bv[j] *= sc; bv[NB + j] *= sc; }
+    }
 }
 __global__ void k_set_remaining(double *remaining, int32_t *nsub, int32_t *counters, double v, int B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2184,6 +2213,10 @@ static int launch_cg_cluster_mb(fgb_batch *b, const float *poff, const float *pd
     auto kern = k_cg_cluster_mb<T, CPT, CS>;
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_cg_cluster_mb)", ce);
+    if (CS > 8) {   // 16-CTA clusters are a non-portable size: opt in (one cluster then occupies most of a GPC)
+        ce = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_cg_cluster_mb, non-portable cluster)", ce);
+    }
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(b->B * CS); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -2194,6 +2227,15 @@ static int launch_cg_cluster_mb(fgb_batch *b, const float *poff, const float *pd
                             b->iters, b->resid, b->iter_total, flags, mean_out);
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchKernelEx(k_cg_cluster_mb)", ce);
     return FGB_OK;
+}
+
+static int cg_cluster_mb_any(fgb_batch *b, const float *poff, const float *pdiag, const float *rhs, float *p_out, int zero_init,
+                             int reset_steps, int max_iter, int slot, const int32_t *active, int flags, float *mean_out, cudaStream_t st) {
+    int rc = launch_cg_cluster_mb<2, 6>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    if (rc == 1) rc = launch_cg_cluster_mb<4, 7>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    if (rc == 1) rc = launch_cg_cluster_mb<8, 7>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    if (rc == 1) rc = launch_cg_cluster_mb<16, 6>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    return rc;
 }
 
 template <int CS, int CPT, int MINB>
@@ -2237,10 +2279,8 @@ static int solve_pressure_slot(fgb_batch *b, float *p_out, int zero_init, int re
         if (rc <= 0) return rc;
     }
     if (b->opt.cg_impl == 3) {
-        int rc = launch_cg_cluster_mb<2, 6>(b, b->Poff, b->Pdiag, b->div, p_out, zero_init, reset_steps, max_iter, slot, active, 0,
-                                            b->pmean + (size_t)slot * b->B, STREAM(s));
-        if (rc == 1) rc = launch_cg_cluster_mb<4, 7>(b, b->Poff, b->Pdiag, b->div, p_out, zero_init, reset_steps, max_iter, slot, active, 0,
-                                                     b->pmean + (size_t)slot * b->B, STREAM(s));
+        int rc = cg_cluster_mb_any(b, b->Poff, b->Pdiag, b->div, p_out, zero_init, reset_steps, max_iter, slot, active, 0,
+                                   b->pmean + (size_t)slot * b->B, STREAM(s));
         if (rc <= 0) return rc;
     }
     if (b->opt.cg_impl == 1 || b->opt.cg_impl == 2) {
@@ -2404,8 +2444,7 @@ extern "C" int fgb_piso_substep_backward(fgb_batch *b, const fgb_tape *tp, const
         LAUNCH_CHECK("k_adj_remove_mean");
         {   // lam = P^-T x_bar
             ProfScope ps(b, CLS_CG, st);
-            rc = launch_cg_cluster_mb<2, 6>(b, b->Poff, b->Pdiag, xb, lam, 1, 100, b->opt.max_iter, 4 + cs, nullptr, 1 | 2, nullptr, st);
-            if (rc == 1) rc = launch_cg_cluster_mb<4, 7>(b, b->Poff, b->Pdiag, xb, lam, 1, 100, b->opt.max_iter, 4 + cs, nullptr, 1 | 2, nullptr, st);
+            rc = cg_cluster_mb_any(b, b->Poff, b->Pdiag, xb, lam, 1, 100, b->opt.max_iter, 4 + cs, nullptr, 1 | 2, nullptr, st);
             if (rc == 1) return set_err(FGB_E_ARG, "fgb_piso_substep_backward: grid too large for the on-chip transposed solve");
             if (rc) return rc;
         }
@@ -2421,8 +2460,7 @@ extern "C" int fgb_piso_substep_backward(fgb_batch *b, const fgb_tape *tp, const
     if ((rc = copy_async(p_prev_bar, pb, BN * 4, st))) return rc;
     {   // mu = C^-T ustar_bar   (unb now holds ustar_bar)
         ProfScope ps(b, CLS_BICG, st);
-        rc = launch_bicgstab_cluster<2, 6, 2>(b, tp->Coff, tp->A, unb, mu, 1, nullptr, 1, st);
-        if (rc == 1) rc = launch_bicgstab_cluster<4, 7, 2>(b, tp->Coff, tp->A, unb, mu, 1, nullptr, 1, st);
+        rc = bicgstab_cluster_any<2>(b, tp->Coff, tp->A, unb, mu, 1, nullptr, 1, st);
         if (rc == 1) return set_err(FGB_E_ARG, "fgb_piso_substep_backward: grid too large for the on-chip transposed solve");
         if (rc) return rc;
     }
@@ -2499,6 +2537,14 @@ extern "C" int fgb_flux_balance(fgb_batch *b, const float *bvel, float *out, fgb
     LAUNCH_CHECK("k_flux_balance");
     return FGB_OK;
 }
+extern "C" int fgb_balance_fluxes(fgb_batch *b, float *bvel, const int8_t *free_mask, float bc_tol, fgb_stream_t s) {
+    if (!b || !bvel || !free_mask) return set_err(FGB_E_ARG, "fgb_balance_fluxes: null argument");
+    b->launches++;
+    k_balance_fluxes<256><<<b->B, 256, 0, STREAM(s)>>>(b->t, bvel, free_mask, bc_tol);
+    LAUNCH_CHECK("k_balance_fluxes");
+    return FGB_OK;
+}
+
 extern "C" int fgb_max_velocity(fgb_batch *b, const float *u, const float *bvel, float *out, fgb_stream_t s) {
     if (!b || !u || !bvel || !out) return set_err(FGB_E_ARG, "fgb_max_velocity: null argument");
     b->launches++;

@@ -79,6 +79,19 @@ class DomainSpec:
     def close_boundary(self, block: int, face, velocity=None, scalar=None, scalar_neumann=False):
         f = _face(face)
         b = self.blocks[block]
+        # CloseConnectedBoudary (domain_structs.cpp:1789-1823): closing one side of a periodic pair (the default
+        # state of every face) or of a block connection also closes its partner face with a zero Dirichlet value
+        prev = b.bounds[f]
+        if prev.type == PERIODIC:
+            n_ = b.size(1 - (f >> 1))
+            b.bounds[f ^ 1] = Boundary(FIXED, velocity=np.zeros((2, n_), dtype=np.float32),
+                                       scalar=np.zeros(n_, dtype=np.float32), scalar_neumann=False)
+        elif prev.type == CONNECTED:
+            ob = self.blocks[prev.other]
+            of = prev.axes[0]
+            n_ = ob.size(1 - (of >> 1))
+            ob.bounds[of] = Boundary(FIXED, velocity=np.zeros((2, n_), dtype=np.float32), scalar=np.zeros(n_, dtype=np.float32),
+                                     scalar_neumann=False)
         n = b.size(1 - (f >> 1))
         vel = np.zeros((2, n), dtype=np.float32)
         if velocity is not None:

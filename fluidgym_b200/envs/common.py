@@ -1,0 +1,159 @@
+"""Pieces shared by the bluff-body environments (cylinder, airfoil): wall-force tables, and the differentiable
+rollout in which the PISO substep is one autograd node backed by the CUDA adjoint (``fluidgym_b200.autograd``)
+while the few boundary / reward formulas around it are tiny torch expressions over the same static tables the
+kernels use -- so gradients flow from the reward to the action, the cell velocities and the boundary values as in
+the reference, where those parts are torch code as well (SIM.py:188-393, forces.py:193-275)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import native
+from ..sensors import cell_centres
+from ..solver import _ptr
+
+
+def build_wall_tables(cd, spec, ring, device, scale: float):
+    """Wall-adjacent cells of a body described by ``ring = [(block, face, flip), ...]`` walked as one closed loop
+    (forces.py:12-107; cylinder_env_base.py:548-655; airfoil_env_base.py:341-441).  Returns the tensor dict and
+    the ``fgb_wall`` descriptor for ``fgb_wall_forces``."""
+    vc_list, cc_list, cells, bfaces = [], [], [], []
+    for k, (bi, f, flip) in enumerate(ring):
+        b = spec.blocks[bi]
+        v = torch.from_numpy(b.vertex)
+        cc = torch.from_numpy(cell_centres(b.vertex))
+        if (f >> 1) == 0:
+            col = -1 if (f & 1) else 0
+            bc, ce = v[:, :, col], cc[:, :, col]
+            idx = [cd.gidx(bi, [b.nx - 1 if (f & 1) else 0, y]) for y in range(b.ny)]
+        else:
+            row = -1 if (f & 1) else 0
+            bc, ce = v[:, row, :], cc[:, row, :]
+            idx = [cd.gidx(bi, [x, b.ny - 1 if (f & 1) else 0]) for x in range(b.nx)]
+        bf = [cd.boff[bi, f] + i for i in range(len(idx))]
+        if flip:
+            bc, ce = torch.flip(bc, dims=[-1]), torch.flip(ce, dims=[-1])
+            idx, bf = idx[::-1], bf[::-1]
+        if k != len(ring) - 1:
+            bc = bc[..., :-1]          # shared vertex with the next block
+        vc_list.append(bc)
+        cc_list.append(ce)
+        cells += idx
+        bfaces += bf
+    vc = torch.cat(vc_list, dim=-1)
+    centers = torch.cat(cc_list, dim=-1)
+    left = torch.roll(centers, shifts=-1, dims=-1)
+    right = torch.roll(centers, shifts=1, dims=-1)
+    tlen = torch.sqrt(torch.sum((left - right) ** 2, dim=0))
+    v0, v1 = vc[:, :-1], vc[:, 1:]
+    e = v1 - v0
+    eps = 1e-20
+    t = e / (torch.linalg.norm(e, dim=0, keepdim=True) + eps)
+    n = torch.stack([t[1], -t[0]], dim=0)
+    m = 0.5 * (v0 + v1)
+    d = torch.clamp(((centers - m) * n).sum(dim=0).abs(), min=eps)
+    n = n * -1
+    flen = torch.sqrt((vc[0, 1:] - vc[0, :-1]) ** 2 + (vc[1, 1:] - vc[1, :-1]) ** 2)
+    tab = dict(cell=torch.tensor(cells, dtype=torch.int32, device=device), bface=torch.tensor(bfaces, dtype=torch.int32, device=device),
+               normal=n.contiguous().float().to(device), dist=d.float().to(device), tlen=tlen.float().to(device),
+               flen=flen.float().to(device))
+    w = native.Wall()
+    w.n_wall = len(cells)
+    for k2 in ("cell", "bface", "normal", "dist", "tlen", "flen"):
+        setattr(w, k2, tab[k2].data_ptr())
+    w.scale = float(scale)
+    return tab, w
+
+
+class DifferentiableRollout:
+    """Mixin: needs ``solver, cd, device, lib, n_envs, dt, cfl, char_vel, wall, _wall_t, _dstate``."""
+
+    def detach(self):
+        """fluid_env.py ``detach()``: cut the autograd graph at the current state."""
+        if self._dstate is not None:
+            self._dstate = tuple(t.detach() for t in self._dstate)
+
+    def _diff_tables(self):
+        if getattr(self, "_dt_tab", None) is None:
+            cd, dev = self.cd, self.device
+            NB = cd.NB
+            out = np.nonzero(np.asarray(self.solver._tab["b_out"].cpu()))[0]
+            face = np.asarray(cd.b_face[:NB]).astype(np.int64)
+            ax = face >> 1
+            bminv = np.asarray(cd.b_minv)[:, :NB]
+            bdet = np.asarray(cd.b_det)[:NB]
+            j = np.arange(NB)
+            sign = np.where(face & 1, 1.0, -1.0)
+            fw = np.stack([bdet * bminv[2 * ax, j] * sign, bdet * bminv[2 * ax + 1, j] * sign]).astype(np.float32)   # signed flux weights
+            adv = bminv[2 * ax[out], out] * self.char_vel[0] + bminv[2 * ax[out] + 1, out] * self.char_vel[1]
+            is_out = np.zeros(NB, dtype=bool)
+            is_out[out] = True
+
+            def tt(a, dt=torch.float32):
+                return torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+            self._dt_tab = dict(out=tt(out, torch.int64), out_cell=tt(np.asarray(cd.b_cell)[out], torch.int64), adv=tt(adv),
+                                fw=tt(fw), is_out=tt(is_out, torch.bool))
+        return self._dt_tab
+
+    def _balance_torch(self, bv, free, bc_tol=1e-5):
+        """balance_boundary_fluxes (SIM.py:188-224): ``free`` is a bool mask [NB] of the faces that are rescaled."""
+        tb = self._diff_tables()
+        fl = (bv * tb["fw"]).sum(dim=1)
+        fx = (fl * (~free)).sum(dim=1)
+        vr = (fl * free).sum(dim=1)
+        need = ~((fx + vr).abs() <= bc_tol * 0.01)
+        sc = torch.where(need, -fx / vr, torch.ones_like(fx))
+        scale = torch.where(free[None, :], sc[:, None], torch.ones_like(fl))
+        return bv * scale[:, None, :]
+
+    def _outflow_torch(self, u, bv, dt, bc_tol=1e-5):
+        """k_plan_substep's boundary part (SIM.py:188-224, 282-393) as differentiable torch ops."""
+        tb = self._diff_tables()
+        w = 1.0 - 1.0 / (1.0 + 2.0 * dt * tb["adv"])
+        bo = bv[:, :, tb["out"]]
+        bo = bo - w * (bo - u[:, :, tb["out_cell"]])
+        bv = bv.index_copy(2, tb["out"], bo)
+        return self._balance_torch(bv, tb["is_out"], bc_tol)
+
+    def _forces_torch(self, u, p, bv):
+        """k_wall_forces (forces.py:193-275) as differentiable torch ops -> [B,2] (drag, lift coefficients)."""
+        w = self._wall_t
+        c, j = w["cell"].long(), w["bface"].long()
+        il, ir = torch.roll(c, -1), torch.roll(c, 1)
+        n = w["normal"]
+        nx, ny = n[0], n[1]
+        tx, ty = ny, -nx
+        visc = float(self.cd.visc)
+        dn = (u[:, :, c] - bv[:, :, j]) / w["dist"]
+        dt_ = (u[:, :, ir] - u[:, :, il]) / (2.0 * w["tlen"])
+        du_dx, du_dy = dn[:, 0] * nx + dt_[:, 0] * tx, dn[:, 0] * ny + dt_[:, 0] * ty
+        dv_dx, dv_dy = dn[:, 1] * nx + dt_[:, 1] * tx, dn[:, 1] * ny + dt_[:, 1] * ty
+        pc = p[:, c]
+        sxx, syy = 2.0 * visc * du_dx - pc, 2.0 * visc * dv_dy - pc
+        sxy = visc * (du_dy + dv_dx)
+        fxx = ((sxx * nx + sxy * ny) * w["flen"]).sum(dim=1)
+        fyy = ((sxy * nx + syy * ny) * w["flen"]).sum(dim=1)
+        return torch.stack([fxx, fyy], dim=1) * self.wall.scale
+
+    def _single_step_differentiable(self, u, p, bv):
+        """Simulation.single_step with the adaptive CFL plan of SIM.py:2004-2031; the plan itself is not
+        differentiated (the reference computes it from detached maxima as well).  One common substep size is
+        used for the batch (the most restrictive environment decides)."""
+        from ..autograd import piso_substep
+        s = self.solver
+        remaining, nsub = float(self.dt), 0
+        mvb = torch.empty(self.n_envs, device=self.device)
+        while remaining > 0.0 and not abs(remaining) <= 1e-8:
+            native.check(self.lib.fgb_max_velocity(s.handle, _ptr(u.detach().contiguous()), _ptr(bv.detach().contiguous()), _ptr(mvb),
+                                                   s.stream), "fgb_max_velocity")
+            mv = float(mvb.max())
+            if abs(mv) <= 1e-8:
+                ts = remaining
+            else:
+                mts = np.float32(self.cfl) / np.float32(mv)
+                ts = remaining if float(mts) >= remaining else remaining / float(np.ceil(np.float32(remaining) / mts))
+            remaining -= ts
+            bv = self._outflow_torch(u, bv, float(np.float32(ts)))
+            u, p = piso_substep(s, u, p, bv, float(np.float32(ts)))
+            nsub += 1
+        return u, p, bv, nsub

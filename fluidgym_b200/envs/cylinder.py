@@ -17,17 +17,22 @@ import torch
 
 from .. import native
 from ..domain import FIXED
-from ..sensors import cell_centres, sensor_tables
+from ..sensors import sensor_tables
 from ..solver import BatchedPISO, _ptr
+from .common import DifferentiableRollout, build_wall_tables
 from .cylinder_domain import BOTTOM, LEFT, RIGHT, TOP, WAKE, jet_profile, make_cylinder_domain
 
+CYLINDER_ROT_2D_DEFAULT_CONFIG = {
+    "reynolds_number": 1e2, "resolution": 24, "dt": 1e-2, "adaptive_cfl": 0.8, "step_length": 0.25,
+    "episode_length": 80, "lift_penalty": 1.0,
+}
 CYLINDER_JET_2D_DEFAULT_CONFIG = {
     "reynolds_number": 1e2, "resolution": 24, "dt": 1e-2, "adaptive_cfl": 0.8, "step_length": 0.25,
     "episode_length": 80, "lift_penalty": 1.0,
 }
 
 
-class CylinderJet2DEnv:
+class CylinderJet2DEnv(DifferentiableRollout):
     H, L, cylinder_diameter, U_mean, cylinder_offset_y = 4.1, 22.0, 1.0, 1.0, 0.05
     n_sensors = 151
     action_smoothing_alpha = 0.1
@@ -111,57 +116,9 @@ class CylinderJet2DEnv:
     def _setup_wall(self):
         """Ring of wall-adjacent cells around the cylinder and its geometry (CYL.py:548-655,
         forces.py:12-39, 42-107)."""
-        cd, spec = self.cd, self.spec
         ring = [(LEFT, 1, False), (TOP, 2, False), (RIGHT, 0, True), (BOTTOM, 3, True)]
-        vc_list, cc_list, cells, bfaces = [], [], [], []
-        for k, (bi, f, flip) in enumerate(ring):
-            b = spec.blocks[bi]
-            v = torch.from_numpy(b.vertex)
-            cc = torch.from_numpy(cell_centres(b.vertex))
-            ax = f >> 1
-            if ax == 0:
-                col = -1 if (f & 1) else 0
-                bc, ce = v[:, :, col], cc[:, :, col]
-                idx = [cd.gidx(bi, [b.nx - 1 if (f & 1) else 0, y]) for y in range(b.ny)]
-            else:
-                row = -1 if (f & 1) else 0
-                bc, ce = v[:, row, :], cc[:, row, :]
-                idx = [cd.gidx(bi, [x, b.ny - 1 if (f & 1) else 0]) for x in range(b.nx)]
-            bf = [cd.boff[bi, f] + i for i in range(len(idx))]
-            if flip:
-                bc, ce = torch.flip(bc, dims=[-1]), torch.flip(ce, dims=[-1])
-                idx, bf = idx[::-1], bf[::-1]
-            if k != len(ring) - 1:
-                bc = bc[..., :-1]
-            vc_list.append(bc)
-            cc_list.append(ce)
-            cells += idx
-            bfaces += bf
-        vc = torch.cat(vc_list, dim=-1)
-        centers = torch.cat(cc_list, dim=-1)
-        left = torch.roll(centers, shifts=-1, dims=-1)
-        right = torch.roll(centers, shifts=1, dims=-1)
-        tlen = torch.sqrt(torch.sum((left - right) ** 2, dim=0))
-        v0, v1 = vc[:, :-1], vc[:, 1:]
-        e = v1 - v0
-        eps = 1e-20
-        t = e / (torch.linalg.norm(e, dim=0, keepdim=True) + eps)
-        n = torch.stack([t[1], -t[0]], dim=0)
-        m = 0.5 * (v0 + v1)
-        d = torch.clamp(((centers - m) * n).sum(dim=0).abs(), min=eps)
-        n = n * -1
-        flen = torch.sqrt((vc[0, 1:] - vc[0, :-1]) ** 2 + (vc[1, 1:] - vc[1, :-1]) ** 2)
-        dev = self.device
-        self._wall_t = dict(cell=torch.tensor(cells, dtype=torch.int32, device=dev),
-                            bface=torch.tensor(bfaces, dtype=torch.int32, device=dev),
-                            normal=n.contiguous().float().to(dev), dist=d.float().to(dev), tlen=tlen.float().to(dev),
-                            flen=flen.float().to(dev))
-        w = native.Wall()
-        w.n_wall = len(cells)
-        for k2 in ("cell", "bface", "normal", "dist", "tlen", "flen"):
-            setattr(w, k2, self._wall_t[k2].data_ptr())
-        w.scale = 1.0 / (0.5 * self.U_mean ** 2 * self.cylinder_diameter)
-        self.wall = w
+        self._wall_t, self.wall = build_wall_tables(self.cd, self.spec, ring, self.device,
+                                                    1.0 / (0.5 * self.U_mean ** 2 * self.cylinder_diameter))
 
     @property
     def render_shape(self):
@@ -207,6 +164,21 @@ class CylinderJet2DEnv:
     def n_sim_steps(self):
         return max(1, int(self.step_length / self.dt))
 
+    use_marl = False
+
+    @property
+    def observation_space(self):
+        """cylinder_env_base.py:203-233 (per environment)."""
+        from .. import spaces
+        inf = float("inf")
+        ns = int(self.sens_idx.shape[1])
+        return spaces.Dict({"velocity": spaces.Box(-inf, inf, shape=(ns, 2)), "pressure": spaces.Box(-inf, inf, shape=(ns,))})
+
+    @property
+    def action_space(self):
+        from .. import spaces
+        return spaces.Box(-1.0, 1.0, shape=(1,))
+
     def seed(self, seed: int):
         self._seed = seed
         self._np_rng = np.random.default_rng(seed)
@@ -242,7 +214,7 @@ class CylinderJet2DEnv:
         s.p.zero_()
         s.bvel.copy_(torch.from_numpy(self.cd.bvel0[:, :self.cd.NB].copy()).to(self.device).unsqueeze(0).expand_as(s.bvel))
         # Simulation.make_divergence_free incl. its "PRE" hook with time step 1 (SIM.py:1335-1347)
-        s.update_outflow(1.0, self.char_vel, tol=5e-6)
+        s.update_outflow(1.0, self.char_vel, tol=1e-5)
         s.make_divergence_free(max_iter=1000)
         self.last_control.zero_()
         randomize = self.randomize_initial_state if randomize is None else randomize
@@ -320,89 +292,6 @@ class CylinderJet2DEnv:
     # and reward formulas around it are tiny torch expressions over the same static tables the kernels use, so
     # gradients flow from the reward to the action, the block velocities and the boundary values exactly as in
     # the reference, where those parts are torch code as well (SIM.py:188-393, forces.py:193-275).
-    def detach(self):
-        """fluid_env.py `detach()`: cut the autograd graph at the current state."""
-        if self._dstate is not None:
-            self._dstate = tuple(t.detach() for t in self._dstate)
-
-    def _diff_tables(self):
-        if getattr(self, "_dt_tab", None) is None:
-            cd, dev = self.cd, self.device
-            NB = cd.NB
-            out = np.nonzero(np.asarray(self.solver._tab["b_out"].cpu()))[0]
-            face = np.asarray(cd.b_face[:NB]).astype(np.int64)
-            ax = face >> 1
-            bminv = np.asarray(cd.b_minv)[:, :NB]
-            bdet = np.asarray(cd.b_det)[:NB]
-            j = np.arange(NB)
-            sign = np.where(face & 1, 1.0, -1.0)
-            fw = np.stack([bdet * bminv[2 * ax, j] * sign, bdet * bminv[2 * ax + 1, j] * sign]).astype(np.float32)   # signed flux weights
-            adv = bminv[2 * ax[out], out] * self.char_vel[0] + bminv[2 * ax[out] + 1, out] * self.char_vel[1]
-            is_out = np.zeros(NB, dtype=bool)
-            is_out[out] = True
-            tt = lambda a, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
-            self._dt_tab = dict(out=tt(out, torch.int64), out_cell=tt(np.asarray(cd.b_cell)[out], torch.int64), adv=tt(adv),
-                                fw=tt(fw), is_out=tt(is_out, torch.bool))
-        return self._dt_tab
-
-    def _outflow_torch(self, u, bv, dt, bc_tol=5e-6):
-        """k_plan_substep's boundary part (SIM.py:188-224, 282-393) as differentiable torch ops."""
-        tb = self._diff_tables()
-        w = 1.0 - 1.0 / (1.0 + 2.0 * dt * tb["adv"])
-        bo = bv[:, :, tb["out"]]
-        bo = bo - w * (bo - u[:, :, tb["out_cell"]])
-        bv = bv.index_copy(2, tb["out"], bo)
-        fl = (bv * tb["fw"]).sum(dim=1)
-        fx = (fl * (~tb["is_out"])).sum(dim=1)
-        vr = (fl * tb["is_out"]).sum(dim=1)
-        need = ~((fx + vr).abs() <= bc_tol * 0.01)
-        sc = torch.where(need, -fx / vr, torch.ones_like(fx))
-        scale = torch.where(tb["is_out"][None, :], sc[:, None], torch.ones_like(fl))
-        return bv * scale[:, None, :]
-
-    def _forces_torch(self, u, p, bv):
-        """k_wall_forces (forces.py:193-275) as differentiable torch ops -> [B,2] (drag, lift coefficients)."""
-        w = self._wall_t
-        c, j = w["cell"].long(), w["bface"].long()
-        il, ir = torch.roll(c, -1), torch.roll(c, 1)
-        n = w["normal"]
-        nx, ny = n[0], n[1]
-        tx, ty = ny, -nx
-        visc = float(self.cd.visc)
-        dn = (u[:, :, c] - bv[:, :, j]) / w["dist"]
-        dt_ = (u[:, :, ir] - u[:, :, il]) / (2.0 * w["tlen"])
-        du_dx, du_dy = dn[:, 0] * nx + dt_[:, 0] * tx, dn[:, 0] * ny + dt_[:, 0] * ty
-        dv_dx, dv_dy = dn[:, 1] * nx + dt_[:, 1] * tx, dn[:, 1] * ny + dt_[:, 1] * ty
-        pc = p[:, c]
-        sxx, syy = 2.0 * visc * du_dx - pc, 2.0 * visc * dv_dy - pc
-        sxy = visc * (du_dy + dv_dx)
-        fxx = ((sxx * nx + sxy * ny) * w["flen"]).sum(dim=1)
-        fyy = ((sxy * nx + syy * ny) * w["flen"]).sum(dim=1)
-        return torch.stack([fxx, fyy], dim=1) * self.wall.scale
-
-    def _single_step_differentiable(self, u, p, bv):
-        """Simulation.single_step with the adaptive CFL plan of SIM.py:2004-2031; the plan itself is not
-        differentiated (the reference computes it from detached maxima as well).  One common substep size is
-        used for the batch (the most restrictive environment decides)."""
-        from ..autograd import piso_substep
-        s = self.solver
-        remaining, nsub = float(self.dt), 0
-        mvb = torch.empty(self.n_envs, device=self.device)
-        while remaining > 0.0 and not abs(remaining) <= 1e-8:
-            native.check(self.lib.fgb_max_velocity(s.handle, _ptr(u.detach().contiguous()), _ptr(bv.detach().contiguous()), _ptr(mvb),
-                                                   s.stream), "fgb_max_velocity")
-            mv = float(mvb.max())
-            if abs(mv) <= 1e-8:
-                ts = remaining
-            else:
-                mts = np.float32(self.cfl) / np.float32(mv)
-                ts = remaining if float(mts) >= remaining else remaining / float(np.ceil(np.float32(remaining) / mts))
-            remaining -= ts
-            bv = self._outflow_torch(u, bv, float(np.float32(ts)))
-            u, p = piso_substep(s, u, p, bv, float(np.float32(ts)))
-            nsub += 1
-        return u, p, bv, nsub
-
     def _step_differentiable(self, action):
         s = self.solver
         if self._dstate is None:
@@ -429,3 +318,24 @@ class CylinderJet2DEnv:
         self._n_steps += 1
         truncated = self._n_steps >= self.episode_length
         return obs, reward, False, truncated, {"drag": cd.detach(), "lift": cl.detach()}
+
+
+class CylinderRot2DEnv(CylinderJet2DEnv):
+    """``CylinderRotEnv2D`` (envs/cylinder/rotating_cylinder_env_2d.py:20-182): the action is the rotation speed of
+    the cylinder wall.  Same solver, forces, sensors and smoothing as the jet environment; only the boundary
+    template differs -- unit tangential velocity ``(sin theta, -cos theta)`` on all four cylinder faces
+    (:131-139) instead of the two jet slots, so the same ``fgb_apply_jet_action`` kernel drives it."""
+
+    def _setup_jets(self):
+        cd, spec = self.cd, self.spec
+        faces, templ = [], []
+        # (block, face, boundary vertex line) in the reference's order: left +x, top -y, right -x, bottom +y
+        for bi, f, line in ((LEFT, 1, spec.blocks[LEFT].vertex[:, :, -1]), (TOP, 2, spec.blocks[TOP].vertex[:, 0, :]),
+                            (RIGHT, 0, spec.blocks[RIGHT].vertex[:, :, 0]), (BOTTOM, 3, spec.blocks[BOTTOM].vertex[:, -1, :])):
+            cb = torch.from_numpy(np.ascontiguousarray(line))
+            centers = 0.5 * (cb[:, :-1] + cb[:, 1:])
+            theta = torch.atan2(centers[1, :], centers[0, :])
+            templ.append(torch.stack([torch.sin(theta), -torch.cos(theta)]).numpy())
+            faces.append(cd.boff[bi, f] + np.arange(centers.shape[1]))
+        self.jet_faces = torch.from_numpy(np.concatenate(faces).astype(np.int32)).to(self.device)
+        self.jet_templ = torch.from_numpy(np.ascontiguousarray(np.concatenate(templ, axis=1).astype(np.float32))).to(self.device)

@@ -101,6 +101,21 @@ class RBC2DEnv:
     def n_sim_steps(self):
         return max(1, int(self.step_length / self.dt))
 
+    @property
+    def observation_space(self):
+        """Per-environment (per-agent in MARL mode) space, rbc_env_2d.py:131-166."""
+        from .. import spaces
+        width = self.n_sensors_per_heater * (self.local_obs_window if self.use_marl else self.n_heaters)
+        shape = (self.n_sensors_y, width)
+        inf = float("inf")
+        return spaces.Dict({"temperature": spaces.Box(self.T_cold, self.T_hot + self.heater_limit, shape=shape),
+                            "velocity": spaces.Box(-inf, inf, shape=(2,) + shape), "pressure": spaces.Box(-inf, inf, shape=shape)})
+
+    @property
+    def action_space(self):
+        from .. import spaces
+        return spaces.Box(-1.0, 1.0, shape=(1,) if self.use_marl else (self.n_heaters, 1))
+
     def seed(self, seed: int):
         self._seed = seed
         self._np_rng = np.random.default_rng(seed)

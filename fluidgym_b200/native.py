@@ -47,7 +47,7 @@ class Wall(C.Structure):
 EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_create", "fgb_batch_destroy",
            "fgb_batch_set_options", "fgb_batch_buffer", "fgb_setup_advection", "fgb_solve_advection",
            "fgb_setup_pressure_matrix", "fgb_setup_pressure_rhs", "fgb_solve_pressure", "fgb_correct_velocity",
-           "fgb_piso_substep", "fgb_make_divergence_free", "fgb_sim_step", "fgb_update_outflow", "fgb_flux_balance",
+           "fgb_piso_substep", "fgb_make_divergence_free", "fgb_sim_step", "fgb_update_outflow", "fgb_flux_balance", "fgb_balance_fluxes",
            "fgb_max_velocity", "fgb_apply_jet_action", "fgb_wall_forces", "fgb_column_sums", "fgb_sample_sensors",
            "fgb_profile_enable",
            "fgb_profile_read", "fgb_launch_count", "fgb_piso_substep_record", "fgb_adjoint_workspace_bytes",
@@ -89,6 +89,7 @@ def load():
     L.fgb_column_sums.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.fgb_update_outflow.argtypes = [vp, vp, vp, vp, C.POINTER(f32), f32, vp]
     L.fgb_flux_balance.argtypes = [vp, vp, vp, vp]
+    L.fgb_balance_fluxes.argtypes = [vp, vp, vp, C.c_float, vp]
     L.fgb_max_velocity.argtypes = [vp, vp, vp, vp, vp]
     L.fgb_apply_jet_action.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32, vp]
     L.fgb_wall_forces.argtypes = [vp, C.POINTER(Wall), vp, vp, vp, vp, vp]

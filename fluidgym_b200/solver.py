@@ -164,13 +164,13 @@ class BatchedPISO:
         native.check(self.lib.fgb_make_divergence_free(self.handle, _ptr(self.u), _ptr(self.p), _ptr(self.bvel), max_iter,
                                                        self.stream), "fgb_make_divergence_free")
 
-    def update_outflow(self, dt, char_vel, tol=5e-6):
+    def update_outflow(self, dt, char_vel, tol=1e-5):
         self._dtc = self._dt(dt)
         cv = (C.c_float * 2)(*[float(x) for x in char_vel])
         native.check(self.lib.fgb_update_outflow(self.handle, _ptr(self.u), _ptr(self.bvel), _ptr(self._dtc), cv, tol, self.stream),
                      "fgb_update_outflow")
 
-    def single_step(self, dt, cfl=0.8, char_vel=None, bc_tol=5e-6) -> int:
+    def single_step(self, dt, cfl=0.8, char_vel=None, bc_tol=1e-5) -> int:
         """``Simulation.single_step()`` with adaptive CFL sub-stepping; returns the substep rounds used."""
         cv = (C.c_float * 2)(*[float(x) for x in char_vel]) if char_vel is not None else None
         n = C.c_int32(0)

@@ -162,6 +162,10 @@ int fgb_update_outflow(fgb_batch *b, const float *u, float *bvel, const float *d
                        fgb_stream_t s);
 /* Domain.GetBoundaryFluxBalance (DS.cpp:2476-2510): signed sum of boundary fluxes per environment */
 int fgb_flux_balance(fgb_batch *b, const float *bvel, float *out, fgb_stream_t s);
+/* balance_boundary_fluxes(domain, free_bounds) (SIM.py:188-224) for an explicit set of free faces
+ * (free_mask[NB], device, int8): their velocities are scaled so that the net boundary flux vanishes.  Used
+ * by the airfoil actuation, whose free set is outflow + jet wall (airfoil_env_base.py:709-718). */
+int fgb_balance_fluxes(fgb_batch *b, float *bvel, const int8_t *free_mask, float bc_tol, fgb_stream_t s);
 /* Domain.getMaxVelocity(True, True) (DS.cpp:1580-1611, 2403-2411) */
 int fgb_max_velocity(fgb_batch *b, const float *u, const float *bvel, float *out, fgb_stream_t s);
 

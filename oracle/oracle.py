@@ -201,7 +201,7 @@ class Oracle:
         self.lib.orc_make_divergence_free(self.dom, self.work, C.byref(self.cfg), _fp(u), _fp(p), maxit)
         return list(self.cfg.cg_iters)[: self.cfg.n_cg]
 
-    def sim_step(self, u, p, dt_target, cfl, out_mask=None, adj=None, char_vel=None, bc_tol=5e-6):
+    def sim_step(self, u, p, dt_target, cfl, out_mask=None, adj=None, char_vel=None, bc_tol=1e-5):
         tcg, tb = C.c_int(0), C.c_int(0)
         if out_mask is not None:
             m = np.ascontiguousarray(out_mask, np.uint8)

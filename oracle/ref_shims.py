@@ -79,8 +79,34 @@ class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
             import importlib
 
             module.spaces = importlib.import_module("gymnasium.spaces")
+        if module.__name__ == "matplotlib.path":
+            module.Path = PolygonPath
         if module.__name__ == "seaborn":
             module.color_palette = lambda *a, **k: [(0.0, 0.0, 0.0)] * 10
+
+
+class PolygonPath:
+    """Stand-in for ``matplotlib.path.Path`` as used by ``airfoil_env_base.py:174-208`` (point-in-polygon mask of
+    the render grid, which decides which sensor pixels are dropped): even-odd crossing rule."""
+
+    def __init__(self, vertices, *a, **k):
+        self.vertices = np.asarray(vertices, dtype=np.float64)
+
+    def contains_points(self, points, *a, **k):
+        pts = np.asarray(points, dtype=np.float64)
+        x, y = pts[:, 0], pts[:, 1]
+        v = self.vertices
+        inside = np.zeros(len(pts), dtype=bool)
+        n = len(v)
+        for i in range(n):
+            x0, y0 = v[i]
+            x1, y1 = v[(i + 1) % n]
+            if y0 == y1:
+                continue
+            cond = (y0 > y) != (y1 > y)
+            xi = x0 + (y - y0) * (x1 - x0) / (y1 - y0)
+            inside ^= cond & (x < xi)
+        return inside
 
 
 class Space:

@@ -62,3 +62,31 @@ def cyl24_own():
 
     spec = make_cylinder_domain(24)
     return spec, spec.prepare()
+
+
+def _with_reference_transforms(spec, geometry_file):
+    from fluidgym_b200.domain import CompiledDomain, FIXED
+    g = np.load(os.path.join(GOLDEN, geometry_file))
+    T, bT = g["T"], g["bT"]
+    transforms, btr = [], {}
+    o = 0
+    for b in spec.blocks:
+        n = b.nx * b.ny
+        transforms.append(T[o:o + n].reshape(b.ny, b.nx, 9))
+        o += n
+    o = 0
+    for bi, b in enumerate(spec.blocks):
+        for f in range(4):
+            if b.bounds[f].type == FIXED:
+                n = b.size(1 - (f >> 1))
+                btr[(bi, f)] = bT[o:o + n]
+                o += n
+    return CompiledDomain(spec, transforms=transforms, btransforms=btr)
+
+
+@pytest.fixture(scope="session")
+def airfoil():
+    """Compiled Airfoil2D-medium domain (6 blocks, 46 806 cells) with the REFERENCE's transforms."""
+    from fluidgym_b200.envs.airfoil_domain import make_airfoil_domain
+    spec = make_airfoil_domain()
+    return spec, _with_reference_transforms(spec, "airfoil_geometry.npz")

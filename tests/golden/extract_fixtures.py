@@ -56,8 +56,78 @@ def rbc(src, tag="RBC2D_easy_v0", out="rbc"):
     json.dump(keep, open(os.path.join(HERE, f"{out}_meta.json"), "w"), indent=1)
 
 
+def _multiblock_helpers(spec):
+    nb = len(spec.blocks)
+    faces = [(bi, f) for bi, b in enumerate(spec.blocks) for f in range(4) if b.bounds[f].type == FIXED]
+
+    def cells(d, key, comps):
+        return np.concatenate([d[key.format(bi)].reshape(comps, -1) for bi in range(nb)], axis=1).astype(np.float32)
+
+    def bfaces(d, key):
+        outv = []
+        for bi, f in faces:
+            v = d[key.format(bi, f)].reshape(2, -1)
+            n = spec.blocks[bi].size(1 - (f >> 1))
+            outv.append(np.broadcast_to(v, (2, n)) if v.shape[1] == 1 else v)
+        return np.concatenate(outv, axis=1).astype(np.float32)
+    return nb, faces, cells, bfaces
+
+
+def rotating_cylinder(src, tag="CylinderRot2D_easy_v0", out="rot24"):
+    """First env.step of CylinderRot2D-easy from its reset state (same domain as cyl24)."""
+    spec = make_cylinder_domain(24)
+    nb, faces, cells, bfaces = _multiblock_helpers(spec)
+    rs = np.load(os.path.join(src, f"{tag}_state_reset.npz"))
+    st = np.load(os.path.join(src, f"{tag}_steps.npz"))
+    e0 = np.load(os.path.join(src, f"{tag}_state_step0.npz"))
+    fx = {k2: st[k2] for k2 in st.files if k2.startswith("step0") or k2 == "actions"}
+    fx.update(reset_u=cells(rs, "b{}_u", 2), reset_p=rs["pressureResult"].ravel(), reset_bvel=bfaces(rs, "b{}_f{}_velocity"),
+              env0_u=cells(e0, "b{}_u", 2), env0_bvel=bfaces(e0, "b{}_f{}_velocity"))
+    np.savez_compressed(os.path.join(HERE, f"{out}_steps.npz"), **fx)
+
+
+def airfoil(src, tag="Airfoil2D_medium_v0", out="airfoil"):
+    """Airfoil2D-medium: vertices of the six blocks, the first traced substep (2 advection and 2 x 4 pressure
+    non-orthogonal iterations) and the first env.step from the reset state."""
+    from fluidgym_b200.envs.airfoil_domain import make_airfoil_domain
+    spec = make_airfoil_domain()
+    nb, faces, cells, bfaces = _multiblock_helpers(spec)
+    g = np.load(os.path.join(src, f"{tag}_geometry.npz"))
+    np.savez_compressed(os.path.join(HERE, f"{out}_vertices.npz"), **{f"b{bi}": g[f"b{bi}_vertex"][0] for bi in range(nb)})
+    T = np.concatenate([g[f"b{bi}_transform"].reshape(-1, 9) for bi in range(nb)])
+    bT = np.concatenate([g[f"b{bi}_f{f}_transform"].reshape(-1, 9) for bi, f in faces])
+    np.savez_compressed(os.path.join(HERE, f"{out}_geometry.npz"), T=T, bT=bT)
+    tr = np.load(os.path.join(src, f"{tag}_trace.npz"))
+    meta = json.load(open(os.path.join(src, f"{tag}_meta.json")))
+    k = "s0_"
+    its = [m for m in meta["trace_meta"] if m["substep"] == 0]
+    fx = dict(dt=tr[k + "dt"], u_in=cells(tr, k + "in_b{}_u", 2), p_in=cells(tr, k + "in_b{}_p", 1)[0],
+              bvel_in=bfaces(tr, k + "in_b{}_f{}_velocity"), presres_in=tr[k + "in_pressureResult"].ravel(),
+              A=tr[k + "A"].ravel(), rhs0=tr[k + "velocityRHS0"].reshape(2, -1), rhs1=tr[k + "velocityRHS1"].reshape(2, -1),
+              ustar=tr[k + "solve1_x"].reshape(2, -1), div0=tr[k + "pressureRHSdiv0"].ravel(), div3=tr[k + "pressureRHSdiv3"].ravel(),
+              p_c0=tr[k + "pressureResult0"].ravel(), u1=tr[k + "velocityResult1"].reshape(2, -1), p1=tr[k + "pressureResult1"].ravel(),
+              bicg_iters=np.array([[i[1] for i in m["infos"]] for m in its[:2]]),
+              cg_iters=np.array([m["infos"][0][1] for m in its[2:10]]), cg_resid=np.array([m["infos"][0][0] for m in its[2:10]]))
+    np.savez_compressed(os.path.join(HERE, f"{out}_substep0.npz"), **fx)
+    rs = np.load(os.path.join(src, f"{tag}_state_reset.npz"))
+    st = np.load(os.path.join(src, f"{tag}_steps.npz"))
+    e0 = np.load(os.path.join(src, f"{tag}_state_step0.npz"))
+    fx = {k2: st[k2] for k2 in st.files if k2.startswith("step0") or k2 == "actions"}
+    fx.update(reset_u=cells(rs, "b{}_u", 2), reset_p=rs["pressureResult"].ravel(), reset_bvel=bfaces(rs, "b{}_f{}_velocity"),
+              reset_obs_velocity=rs["obs_velocity"], reset_obs_pressure=rs["obs_pressure"],
+              env0_u=cells(e0, "b{}_u", 2), env0_p=cells(e0, "b{}_p", 1)[0], env0_bvel=bfaces(e0, "b{}_f{}_velocity"))
+    np.savez_compressed(os.path.join(HERE, f"{out}_steps.npz"), **fx)
+    keep = {k2: meta[k2] for k2 in ("env", "seed", "torch", "gpu", "n_sim_steps", "dt", "viscosity", "timing",
+                                    "mean_iters", "max_iters", "n_solves", "substeps_in_env_steps", "reset_seconds")}
+    json.dump(keep, open(os.path.join(HERE, f"{out}_meta.json"), "w"), indent=1)
+
+
 def main():
     src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden"
+    if os.path.exists(os.path.join(src, "Airfoil2D_medium_v0_trace.npz")):
+        return airfoil(src)
+    if os.path.exists(os.path.join(src, "CylinderRot2D_easy_v0_steps.npz")):
+        return rotating_cylinder(src)
     tag = sys.argv[2] if len(sys.argv) > 2 else "CylinderJet2D_easy_v0"
     if os.path.exists(os.path.join(src, "RBC2D_easy_v0_trace.npz")):
         rbc(src)
