@@ -27,10 +27,12 @@ class PISOSubstep(torch.autograd.Function):
         dev = solver.device
         dtc = solver._dt(dt)
         f32 = dict(device=dev, dtype=torch.float32)
+        o = solver.options
+        C_, n_adv, n_p = int(o.corrector_steps), int(o.adv_nonortho_steps), int(o.p_nonortho_steps)
         tape = dict(u_in=torch.empty(B, 2, N, **f32), p_in=torch.empty(B, N, **f32), bvel_in=torch.empty(B, 2, NB, **f32),
                     dt=torch.empty(B, **f32), Coff=torch.empty(B, 4, N, **f32), A=torch.empty(B, N, **f32),
-                    ustar=torch.empty(B, 2, N, **f32), hb=torch.empty(2, B, 2, N, **f32), p=torch.empty(2, B, N, **f32),
-                    pmean=torch.empty(2, B, **f32), u1=torch.empty(B, 2, N, **f32))
+                    ustar=torch.empty(n_adv, B, 2, N, **f32), hb=torch.empty(C_, B, 2, N, **f32), p=torch.empty(C_ * n_p, B, N, **f32),
+                    pmean=torch.empty(C_ * n_p, B, **f32), u1=torch.empty(max(C_ - 1, 1), B, 2, N, **f32))
         ct = native.Tape(*[tape[k].data_ptr() for k, _ in native.Tape._fields_])
         u_out = u.detach().clone().contiguous()
         p_out = p.detach().clone().contiguous()

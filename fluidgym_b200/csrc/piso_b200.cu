@@ -2063,7 +2063,9 @@ __global__ void __launch_bounds__(256) k_adj_hbya(Tab t, const float *__restrict
 // adjoint of the predictor: given mu = C^-T ustar_bar
 __global__ void __launch_bounds__(256) k_adj_advection(Tab t, const float *__restrict__ Mu, const float *__restrict__ Ustar, const float *__restrict__ rAb,
                                                         const float *__restrict__ A, const float *__restrict__ dtv, float *__restrict__ Ab,
-                                                        float *__restrict__ Coffb, float *__restrict__ Ub, float *__restrict__ Sbb, float *__restrict__ Bvb) {
+                                                        float *__restrict__ Coffb, float *__restrict__ Ub, float *__restrict__ Sbb, float *__restrict__ Bvb,
+                                                        float *__restrict__ NoTarget /* adjoint of the field the deferred term read: u_bar (first
+                                                        iteration) or the previous iterate's bar */, int first /* initialise A_bar from rA_bar */) {
     const int b = blockIdx.y;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int N = t.N, NB = t.NB;
@@ -2071,7 +2073,7 @@ __global__ void __launch_bounds__(256) k_adj_advection(Tab t, const float *__res
     const float dt = dtv[b];
     const float det = t.det[g];
     const float Ag = A[(size_t)b * N + g];
-    float ab = -rAb[(size_t)b * N + g] / (Ag * Ag);          // A_bar from rA_bar (rA = 1/A)
+    float ab = first ? -rAb[(size_t)b * N + g] / (Ag * Ag) : Ab[(size_t)b * N + g];   // A_bar from rA_bar (rA = 1/A)
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         const size_t o = (size_t)b * 2 * N + (size_t)c * N;
@@ -2085,7 +2087,7 @@ __global__ void __launch_bounds__(256) k_adj_advection(Tab t, const float *__res
         atomicAdd(&Ub[o + g], mu / dt);  // rhs = (det u/dt + Sb - NOv)/det  (other threads scatter into Ub in this kernel)
         Sbb[o + g] += mu / det;
         const float nob = -mu / det;
-        for (int k = 0; k < t.K_no; ++k) { const float w = t.no_wv[k * N + g]; if (w != 0.f) atomicAdd(&Ub[o + t.no_idx[k * N + g]], w * nob); }
+        for (int k = 0; k < t.K_no; ++k) { const float w = t.no_wv[k * N + g]; if (w != 0.f) atomicAdd(&NoTarget[o + t.no_idx[k * N + g]], w * nob); }
         for (int k = 0; k < t.K_nob; ++k) {
             const float w = t.nob_w[k * N + g];
             if (w != 0.f) atomicAdd(&Bvb[(size_t)b * 2 * NB + (size_t)c * NB + t.nob_idx[k * N + g]], w * nob);
@@ -2264,6 +2266,7 @@ static int launch_cg_smem(fgb_batch *b, float *p_out, int zero_init, int reset_s
 static int solve_pressure_slot(fgb_batch *b, float *p_out, int zero_init, int reset_steps, int max_iter, int slot,
                                const int32_t *active, fgb_stream_t s) {
     if (!b || !p_out) return set_err(FGB_E_ARG, "fgb_solve_pressure: null argument");
+    const int mean_slot = slot < 0 ? 7 : (slot > 7 ? 7 : slot);      // pmean has 8 rows; iteration counters only 6
     if (slot < 0 || slot > 5) slot = 5;
     ProfScope ps(b, CLS_CG, STREAM(s));
     if (b->opt.cg_impl == 4) {
@@ -2280,7 +2283,7 @@ static int solve_pressure_slot(fgb_batch *b, float *p_out, int zero_init, int re
     }
     if (b->opt.cg_impl == 3) {
         int rc = cg_cluster_mb_any(b, b->Poff, b->Pdiag, b->div, p_out, zero_init, reset_steps, max_iter, slot, active, 0,
-                                   b->pmean + (size_t)slot * b->B, STREAM(s));
+                                   b->pmean + (size_t)mean_slot * b->B, STREAM(s));
         if (rc <= 0) return rc;
     }
     if (b->opt.cg_impl == 1 || b->opt.cg_impl == 2) {
@@ -2370,14 +2373,15 @@ static int copy_async(void *dst, const void *src, size_t bytes, cudaStream_t st)
     return ce == cudaSuccess ? FGB_OK : set_err(FGB_E_CUDA, "cudaMemcpyAsync (tape)", ce);
 }
 
-// fgb_piso_substep that additionally records the tape the backward pass needs (non-orthogonal path with
-// corrector_steps = 2, advect_non_ortho_steps = pressure_non_ortho_steps = 1, no passive scalar).
+// fgb_piso_substep that additionally records the tape the backward pass needs (non-orthogonal path, no passive
+// scalar, every environment active).  C = corrector_steps, n_adv / n_p = advect / pressure non-orthogonal iterations.
 extern "C" int fgb_piso_substep_record(fgb_batch *b, float *u, float *p, const float *bvel, const float *dt, const fgb_tape *tp,
                                        fgb_stream_t s) {
     if (!b || !u || !p || !bvel || !dt || !tp) return set_err(FGB_E_ARG, "fgb_piso_substep_record: null argument");
     const fgb_options &o = b->opt;
-    if (!o.nonortho || o.corrector_steps != 2 || o.adv_nonortho_steps != 1 || o.p_nonortho_steps != 1 || o.cg_impl != 3)
-        return set_err(FGB_E_ARG, "fgb_piso_substep_record: supports the non-orthogonal path with 2 correctors, 1 non-ortho step, cg_impl 3");
+    const int C = o.corrector_steps, n_adv = o.adv_nonortho_steps, n_p = o.p_nonortho_steps;
+    if (!o.nonortho || o.cg_impl != 3 || C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8)
+        return set_err(FGB_E_ARG, "fgb_piso_substep_record: needs the non-orthogonal path, cg_impl 3 and correctors x pressure iterations <= 8");
     cudaStream_t st = STREAM(s);
     const size_t B = b->B, N = b->t.N, NB = b->t.NB;
     int rc;
@@ -2385,27 +2389,32 @@ extern "C" int fgb_piso_substep_record(fgb_batch *b, float *u, float *p, const f
     if ((rc = copy_async(tp->p_in, p, B * N * 4, st))) return rc;
     if ((rc = copy_async(tp->bvel_in, bvel, 2 * B * NB * 4, st))) return rc;
     if ((rc = copy_async(tp->dt, dt, B * 4, st))) return rc;
-    if ((rc = fgb_setup_advection(b, u, u, bvel, nullptr, dt, nullptr, s))) return rc;
-    if ((rc = fgb_solve_advection(b, 1, nullptr, s))) return rc;
+    for (int k = 0; k < n_adv; ++k) {
+        if ((rc = fgb_setup_advection(b, u, k == 0 ? u : b->ures, bvel, nullptr, dt, nullptr, s))) return rc;
+        if ((rc = fgb_solve_advection(b, k == 0, nullptr, s))) return rc;
+        if ((rc = copy_async(tp->ustar + (size_t)k * 2 * B * N, b->ures, 2 * B * N * 4, st))) return rc;
+    }
     if ((rc = copy_async(tp->Coff, b->Coff, 4 * B * N * 4, st))) return rc;
     if ((rc = copy_async(tp->A, b->A, B * N * 4, st))) return rc;
-    if ((rc = copy_async(tp->ustar, b->ures, 2 * B * N * 4, st))) return rc;
     if ((rc = fgb_setup_pressure_matrix(b, nullptr, s))) return rc;
-    for (int cs = 0; cs < 2; ++cs) {
-        if ((rc = fgb_setup_pressure_rhs(b, u, bvel, nullptr, p, dt, 1, nullptr, s))) return rc;
-        if ((rc = solve_pressure_slot(b, p, 1, 100, o.max_iter, cs, nullptr, s))) return rc;
-        if ((rc = copy_async(tp->hb + cs * 2 * B * N, b->hbya, 2 * B * N * 4, st))) return rc;
-        if ((rc = copy_async(tp->p + cs * B * N, p, B * N * 4, st))) return rc;
-        if ((rc = copy_async(tp->pmean + cs * B, b->pmean + cs * B, B * 4, st))) return rc;
+    for (int cs = 0; cs < C; ++cs) {
+        for (int ps = 0; ps < n_p; ++ps) {
+            const int q = cs * n_p + ps;
+            if ((rc = fgb_setup_pressure_rhs(b, u, bvel, nullptr, p, dt, ps == 0, nullptr, s))) return rc;
+            if ((rc = solve_pressure_slot(b, p, ps == 0, 100, o.max_iter, q, nullptr, s))) return rc;
+            if ((rc = copy_async(tp->p + (size_t)q * B * N, p, B * N * 4, st))) return rc;
+            if ((rc = copy_async(tp->pmean + (size_t)q * B, b->pmean + (size_t)q * B, B * 4, st))) return rc;
+        }
+        if ((rc = copy_async(tp->hb + (size_t)cs * 2 * B * N, b->hbya, 2 * B * N * 4, st))) return rc;
         if ((rc = fgb_correct_velocity(b, p, b->ures, nullptr, s))) return rc;
-        if (cs == 0 && (rc = copy_async(tp->u1, b->ures, 2 * B * N * 4, st))) return rc;
+        if (cs + 1 < C && (rc = copy_async(tp->u1 + (size_t)cs * 2 * B * N, b->ures, 2 * B * N * 4, st))) return rc;
     }
     return copy_async(u, b->ures, 2 * B * N * 4, st);
 }
 
 extern "C" size_t fgb_adjoint_workspace_bytes(const fgb_tables *t, int32_t B) {
     const size_t BN = (size_t)B * t->N, BNB = (size_t)B * (t->NB > 0 ? t->NB : 1);
-    return (size_t)(2 + 2 + 1 + 4 + 2 + 1 + 1 + 1 + 2 + 1 + 2) * align_up(BN * 4) + align_up(BNB * 4) + 4096;
+    return (size_t)(2 + 2 + 1 + 4 + 2 + 1 + 1 + 1 + 2 + 1 + 2 + 1 + 2) * align_up(BN * 4) + align_up(BNB * 4) + 8192;
 }
 
 // Reverse pass of fgb_piso_substep_record.  u_out_bar / p_out_bar: incoming gradients; u_bar, p_prev_bar, bvel_bar
@@ -2422,6 +2431,10 @@ extern "C" int fgb_piso_substep_backward(fgb_batch *b, const fgb_tape *tp, const
     float *unb = c.take<float>(2 * BN), *hbb = c.take<float>(2 * BN), *rAb = c.take<float>(BN), *Coffb = c.take<float>(4 * BN);
     float *Sbb = c.take<float>(2 * BN), *pb = c.take<float>(BN), *xb = c.take<float>(BN), *lam = c.take<float>(BN);
     float *uprevb = c.take<float>(2 * BN), *Ab = c.take<float>(BN), *mu = c.take<float>(2 * BN), *Fbb = c.take<float>(B * NB);
+    float *pb2 = c.take<float>(BN), *xkb = c.take<float>(2 * BN);
+    const fgb_options &o = b->opt;
+    const int C = o.corrector_steps, n_adv = o.adv_nonortho_steps, n_p = o.p_nonortho_steps;
+    if (C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8) return set_err(FGB_E_ARG, "fgb_piso_substep_backward: unsupported iteration counts");
     const dim3 grid = cell_grid(b);
     cudaError_t ce;
 #define ZERO(ptr, n) do { ce = cudaMemsetAsync(ptr, 0, (n) * sizeof(float), st); if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "memset", ce); } while (0)
@@ -2433,40 +2446,56 @@ extern "C" int fgb_piso_substep_backward(fgb_batch *b, const fgb_tape *tp, const
     b->launches++;
     k_setup_pressure_matrix<<<grid, 256, 0, st>>>(b->t, tp->A, nullptr, b->Poff, b->Pdiag);
     LAUNCH_CHECK("k_setup_pressure_matrix (backward)");
-    for (int cs = 1; cs >= 0; --cs) {
-        const float *p_c = tp->p + cs * BN, *hb_c = tp->hb + cs * 2 * BN;
-        const float *pprev = cs == 0 ? tp->p_in : tp->p;            // p of corrector 0 is the previous pressure of corrector 1
-        const float *uprev = cs == 0 ? tp->ustar : tp->u1;
-        b->launches += 2;
-        k_adj_correct<<<grid, 256, 0, st>>>(b->t, unb, p_c, tp->A, hbb, rAb, pb);
+    for (int cs = C - 1; cs >= 0; --cs) {
+        const float *hb_c = tp->hb + (size_t)cs * 2 * BN;
+        const float *uprev = cs == 0 ? tp->ustar + (size_t)(n_adv - 1) * 2 * BN : tp->u1 + (size_t)(cs - 1) * 2 * BN;
+        b->launches++;
+        // u_next = hb - rA grad(p of the last pressure iteration): hbb = unb, rAb +=, pb += grad^T
+        k_adj_correct<<<grid, 256, 0, st>>>(b->t, unb, tp->p + (size_t)(cs * n_p + n_p - 1) * BN, tp->A, hbb, rAb, pb);
         LAUNCH_CHECK("k_adj_correct");
-        k_adj_remove_mean<256><<<b->B, 256, 0, st>>>((int)N, pb, xb);
-        LAUNCH_CHECK("k_adj_remove_mean");
-        {   // lam = P^-T x_bar
-            ProfScope ps(b, CLS_CG, st);
-            rc = cg_cluster_mb_any(b, b->Poff, b->Pdiag, xb, lam, 1, 100, b->opt.max_iter, 4 + cs, nullptr, 1 | 2, nullptr, st);
+        for (int ps = n_p - 1; ps >= 0; --ps) {
+            const int q = cs * n_p + ps;
+            // the pressure the deferred term of this solve read: previous iteration, previous corrector, or the input
+            const float *pprev = q == 0 ? tp->p_in : tp->p + (size_t)(q - 1) * BN;
+            b->launches++;
+            k_adj_remove_mean<256><<<b->B, 256, 0, st>>>((int)N, pb, xb);
+            LAUNCH_CHECK("k_adj_remove_mean");
+            {   // lam = P^-T x_bar
+                ProfScope psc(b, CLS_CG, st);
+                rc = cg_cluster_mb_any(b, b->Poff, b->Pdiag, xb, lam, 1, 100, b->opt.max_iter, 5, nullptr, 1 | 2, nullptr, st);
+                if (rc == 1) return set_err(FGB_E_ARG, "fgb_piso_substep_backward: grid too large for the on-chip transposed solve");
+                if (rc) return rc;
+            }
+            ZERO(pb2, BN);                 // becomes the gradient w.r.t. pprev
+            b->launches++;
+            k_adj_pressure_rhs<<<grid, 256, 0, st>>>(b->t, lam, tp->p + (size_t)q * BN, tp->pmean + (size_t)q * B, pprev, tp->A, hbb, Fbb, rAb, pb2);
+            LAUNCH_CHECK("k_adj_pressure_rhs");
+            float *tmp = pb; pb = pb2; pb2 = tmp;      // the previous iterate enters only through that deferred term
+        }
+        ZERO(uprevb, 2 * BN);
+        b->launches++;
+        k_adj_hbya<<<grid, 256, 0, st>>>(b->t, hbb, hb_c, tp->A, tp->Coff, uprev, tp->dt, rAb, u_bar, Sbb, Coffb, uprevb);
+        LAUNCH_CHECK("k_adj_hbya");
+        float *tmp = unb; unb = uprevb; uprevb = tmp;   // gradient w.r.t. the velocity entering this corrector
+    }
+    if ((rc = copy_async(p_prev_bar, pb, BN * 4, st))) return rc;
+    // predictor iterations x_k = C^-1 rhs(u, x_{k-1}), x_{-1} = u, in reverse; unb holds the gradient w.r.t. the last one
+    float *xb_cur = unb, *xb_prev = xkb;
+    for (int k = n_adv - 1; k >= 0; --k) {
+        {   // mu = C^-T x_k_bar
+            ProfScope psc(b, CLS_BICG, st);
+            rc = bicgstab_cluster_any<2>(b, tp->Coff, tp->A, xb_cur, mu, 1, nullptr, 1, st);
             if (rc == 1) return set_err(FGB_E_ARG, "fgb_piso_substep_backward: grid too large for the on-chip transposed solve");
             if (rc) return rc;
         }
-        ZERO(uprevb, 2 * BN);
-        ZERO(pb, BN);                  // becomes p_prev_bar of this corrector
-        b->launches += 2;
-        k_adj_pressure_rhs<<<grid, 256, 0, st>>>(b->t, lam, p_c, tp->pmean + cs * B, pprev, tp->A, hbb, Fbb, rAb, pb);
-        LAUNCH_CHECK("k_adj_pressure_rhs");
-        k_adj_hbya<<<grid, 256, 0, st>>>(b->t, hbb, hb_c, tp->A, tp->Coff, uprev, tp->dt, rAb, u_bar, Sbb, Coffb, uprevb);
-        LAUNCH_CHECK("k_adj_hbya");
-        if ((rc = copy_async(unb, uprevb, 2 * BN * 4, st))) return rc;      // gradient w.r.t. the velocity entering this corrector
+        if (k > 0) ZERO(xb_prev, 2 * BN);
+        b->launches++;
+        k_adj_advection<<<grid, 256, 0, st>>>(b->t, mu, tp->ustar + (size_t)k * 2 * BN, rAb, tp->A, tp->dt, Ab, Coffb, u_bar, Sbb, bvel_bar,
+                                              k > 0 ? xb_prev : u_bar, k == n_adv - 1);
+        LAUNCH_CHECK("k_adj_advection");
+        float *tmp = xb_cur; xb_cur = xb_prev; xb_prev = tmp;
     }
-    if ((rc = copy_async(p_prev_bar, pb, BN * 4, st))) return rc;
-    {   // mu = C^-T ustar_bar   (unb now holds ustar_bar)
-        ProfScope ps(b, CLS_BICG, st);
-        rc = bicgstab_cluster_any<2>(b, tp->Coff, tp->A, unb, mu, 1, nullptr, 1, st);
-        if (rc == 1) return set_err(FGB_E_ARG, "fgb_piso_substep_backward: grid too large for the on-chip transposed solve");
-        if (rc) return rc;
-    }
-    b->launches += 3;
-    k_adj_advection<<<grid, 256, 0, st>>>(b->t, mu, tp->ustar, rAb, tp->A, tp->dt, Ab, Coffb, u_bar, Sbb, bvel_bar);
-    LAUNCH_CHECK("k_adj_advection");
+    b->launches += 2;
     k_adj_assemble<<<grid, 256, 0, st>>>(b->t, Ab, Coffb, Sbb, tp->bvel_in, u_bar, bvel_bar, Fbb);
     LAUNCH_CHECK("k_adj_assemble");
     k_adj_bflux<<<dim3((unsigned)((NB + 127) / 128), b->B), 128, 0, st>>>(b->t, Fbb, bvel_bar);

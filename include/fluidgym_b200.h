@@ -199,20 +199,20 @@ int fgb_sample_sensors(fgb_batch *b, const float *field, int32_t channels, const
 /* ---- differentiability (torch.autograd is layered on top in fluidgym_b200/autograd.py) ----------------- */
 /* Tape of one substep: device buffers owned by the caller, filled by fgb_piso_substep_record.  Replaces the
  * tensors the reference's autograd.Functions save per native op (DIFF.py:624-1808). */
-typedef struct fgb_tape {
+typedef struct fgb_tape {      /* C = corrector_steps, n_adv / n_p = advect / pressure non-orthogonal iterations (fgb_options) */
     float *u_in;     /* [B][2][N]   */
     float *p_in;     /* [B][N]      */
     float *bvel_in;  /* [B][2][NB]  */
     float *dt;       /* [B]         */
     float *Coff;     /* [B][4][N]   */
     float *A;        /* [B][N]      */
-    float *ustar;    /* [B][2][N]   predictor result                    */
-    float *hb;       /* [2][B][2][N] HbyA of the two correctors          */
-    float *p;        /* [2][B][N]   pressure of the two correctors (mean removed) */
-    float *pmean;    /* [2][B]      the removed means                    */
-    float *u1;       /* [B][2][N]   velocity after the first corrector   */
+    float *ustar;    /* [n_adv][B][2][N]  predictor iterates (the last one is the predictor result) */
+    float *hb;       /* [C][B][2][N]      HbyA of every corrector */
+    float *p;        /* [C*n_p][B][N]     pressure after every solve (mean removed) */
+    float *pmean;    /* [C*n_p][B]        the removed means */
+    float *u1;       /* [max(C-1,1)][B][2][N]  velocity after every corrector but the last */
 } fgb_tape;
-/* forward substep (non-orthogonal path, 2 correctors, no passive scalar, all environments active) + tape */
+/* forward substep (non-orthogonal path, no passive scalar, all environments active, C * n_p <= 8) + tape */
 int fgb_piso_substep_record(fgb_batch *b, float *u, float *p, const float *bvel, const float *dt, const fgb_tape *tape,
                             fgb_stream_t s);
 size_t fgb_adjoint_workspace_bytes(const fgb_tables *t, int32_t B);

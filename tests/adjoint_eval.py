@@ -6,7 +6,7 @@ table-driven formulas as tests/table_eval.py, in float64 with exact dense linear
 be validated against central finite differences to ~1e-7 (tests/test_adjoint_cpu.py).  The CUDA adjoint
 kernels are then compared op by op against these functions on the GPU.
 
-Substep (non-orthogonal path of SIM.py:1431-2002, advect_non_ortho_steps = pressure_non_ortho_steps = 1):
+Substep (non-orthogonal path of SIM.py:1431-2002, any number of advect / pressure non-orthogonal iterations):
     (u, p_prev, bvel)  ->  (u_out, p_out)
 """
 import numpy as np
@@ -103,7 +103,8 @@ def nbr_vals_T(t, vb):
 
 
 # ---- forward substep with a tape ---------------------------------------------------------------------
-def substep(t, u, p_prev, bvel, dt, correctors=2):
+def substep(t, u, p_prev, bvel, dt, correctors=2, n_adv=1, n_p=1):
+    """n_adv / n_p: advect_non_ortho_steps / pressure_non_ortho_steps (deferred-correction iterations)."""
     tape = {}
     Fb, (br0, br1) = bflux(t, bvel)
     fl = fluxes(t, u, Fb)
@@ -119,36 +120,44 @@ def substep(t, u, p_prev, bvel, dt, correctors=2):
         j = t.bj[f]
         for c in range(2):
             Sb[c] += np.where(m, -bvel[c, j] * (sig[f] * Fb[j]) + bvel[c, j] * 2 * t.visc * t.b_alpha[j], 0.0)
-    NOv = np.zeros((2, t.N))
-    for c in range(2):
-        for k in range(t.K_no):
-            NOv[c] += t.no_wv[k] * u[c][t.no_idx[k]]
-        for k in range(t.K_nob):
-            NOv[c] += t.nob_w[k] * bvel[c][t.nob_idx[k]]
-    rhs = (t.det * u / dt + Sb - NOv) / t.det
     C = dense(t, Coff, A)
-    ustar = np.stack([np.linalg.solve(C, rhs[c]) for c in range(2)])
+    xs, xprev = [], u
+    for _ in range(n_adv):
+        NOv = np.zeros((2, t.N))
+        for c in range(2):
+            for k in range(t.K_no):
+                NOv[c] += t.no_wv[k] * xprev[c][t.no_idx[k]]
+            for k in range(t.K_nob):
+                NOv[c] += t.nob_w[k] * bvel[c][t.nob_idx[k]]
+        rhs = (t.det * u / dt + Sb - NOv) / t.det
+        xprev = np.stack([np.linalg.solve(C, rhs[c]) for c in range(2)])
+        xs.append(xprev)
+    ustar = xs[-1]
     rA = 1.0 / A
     rAn = nbr_vals(t, rA)
     Pm = np.einsum("ejn,jn->en", t.Wp, rAn)
     P = dense(t, Pm[1:], Pm[0])
-    tape.update(Fb=Fb, fl=fl, A=A, Coff=Coff, Sb=Sb, C=C, ustar=ustar, rA=rA, rAn=rAn, Pm=Pm, P=P, cor=[])
+    tape.update(Fb=Fb, fl=fl, A=A, Coff=Coff, Sb=Sb, C=C, ustar=ustar, xs=xs, rA=rA, rAn=rAn, Pm=Pm, P=P, cor=[])
     uprev, pprev = ustar, p_prev
+    wno = np.stack([t.no_gP[k] * rAn[0] + t.no_gN[k] * rAn[1 + t.no_face[k], t.cells] for k in range(t.K_no)])
     for _ in range(correctors):
         H = np.stack([sum(np.where(t.inner[f], Coff[f] * uprev[c][t.nb_safe[f]], 0.0) for f in range(4)) for c in range(2)])
         hb = rA * (u / dt - H + Sb / t.det)
         flh = fluxes(t, hb, Fb)
-        wno = np.stack([t.no_gP[k] * rAn[0] + t.no_gN[k] * rAn[1 + t.no_face[k], t.cells] for k in range(t.K_no)])
-        NOp = sum(wno[k] * pprev[t.no_idx[k]] for k in range(t.K_no))
-        div = (flh[1] - flh[0]) + (flh[3] - flh[2]) + NOp
-        x = np.linalg.solve(P, div)
-        p = x - x.mean()
+        sols = []
+        for _ps in range(n_p):
+            NOp = sum(wno[k] * pprev[t.no_idx[k]] for k in range(t.K_no))
+            div = (flh[1] - flh[0]) + (flh[3] - flh[2]) + NOp
+            x = np.linalg.solve(P, div)
+            p = x - x.mean()
+            sols.append(dict(pprev=pprev, x=x, p=p))
+            pprev = p
         pv = nbr_vals(t, p)
         pg = np.stack([(pv[2] - pv[1]) * t.fac[0], (pv[4] - pv[3]) * t.fac[1]])
         g = np.stack([pg[0] * t.minv[0] + pg[1] * t.minv[2], pg[0] * t.minv[1] + pg[1] * t.minv[3]])
         unext = hb - rA * g
-        tape["cor"].append(dict(uprev=uprev, pprev=pprev, H=H, hb=hb, x=x, p=p, g=g, wno=wno))
-        uprev, pprev = unext, p
+        tape["cor"].append(dict(uprev=uprev, H=H, hb=hb, sols=sols, g=g, wno=wno))
+        uprev = unext
     return uprev, pprev, tape
 
 
@@ -161,6 +170,7 @@ def substep_vjp(t, u, p_prev, bvel, dt, tape, u_out_bar, p_out_bar):
     ub = np.zeros((2, N)); bvb = np.zeros((2, t.NB)); Fbb = np.zeros(t.NB)
     Coffb = np.zeros((4, N)); rAb = np.zeros(N); rAnb = np.zeros((5, N)); Sbb = np.zeros((2, N)); Pmb = np.zeros((5, N))
     unb, pb = u_out_bar.copy(), p_out_bar.copy()
+    pprevb = np.zeros(N)
     ustarb = np.zeros((2, N)); pprevb_in = np.zeros(N)
     for ci in reversed(range(len(tape["cor"]))):
         cr = tape["cor"][ci]
@@ -173,24 +183,26 @@ def substep_vjp(t, u, p_prev, bvel, dt, tape, u_out_bar, p_out_bar):
         pvb[2] += pgb[0] * t.fac[0]; pvb[1] -= pgb[0] * t.fac[0]
         pvb[4] += pgb[1] * t.fac[1]; pvb[3] -= pgb[1] * t.fac[1]
         pb = pb + nbr_vals_T(t, pvb)
-        # p = x - mean(x) ; x = P^-1 div
-        xb = pb - pb.mean()
-        lam = np.linalg.solve(tape["P"].T, xb)
-        divb = lam
-        # P_bar on the pattern: P_ij_bar = -lam_i x_j
-        Pmb[0] += -lam * cr["x"]
-        for f in range(4):
-            Pmb[f + 1] += np.where(t.inner[f], -lam * cr["x"][t.nb_safe[f]], 0.0)
-        # div = flux divergence of hb + NOp
-        flhb = np.stack([-divb, divb, -divb, divb])
-        hb_b2, Fbb2 = fluxes_T(t, flhb)
-        hbb += hb_b2; Fbb += Fbb2
-        pprevb = np.zeros(N)
-        for k in range(t.K_no):
-            wb = divb * cr["pprev"][t.no_idx[k]]
-            rAnb[0] += t.no_gP[k] * wb
-            np.add.at(rAnb, (1 + t.no_face[k], t.cells), t.no_gN[k] * wb)
-            np.add.at(pprevb, t.no_idx[k], cr["wno"][k] * divb)
+        for so in reversed(cr["sols"]):
+            # p = x - mean(x) ; x = P^-1 div
+            xb = pb - pb.mean()
+            lam = np.linalg.solve(tape["P"].T, xb)
+            divb = lam
+            # P_bar on the pattern: P_ij_bar = -lam_i x_j
+            Pmb[0] += -lam * so["x"]
+            for f in range(4):
+                Pmb[f + 1] += np.where(t.inner[f], -lam * so["x"][t.nb_safe[f]], 0.0)
+            # div = flux divergence of hb + NOp(previous pressure iterate)
+            flhb = np.stack([-divb, divb, -divb, divb])
+            hb_b2, Fbb2 = fluxes_T(t, flhb)
+            hbb += hb_b2; Fbb += Fbb2
+            pprevb = np.zeros(N)
+            for k in range(t.K_no):
+                wb = divb * so["pprev"][t.no_idx[k]]
+                rAnb[0] += t.no_gP[k] * wb
+                np.add.at(rAnb, (1 + t.no_face[k], t.cells), t.no_gN[k] * wb)
+                np.add.at(pprevb, t.no_idx[k], cr["wno"][k] * divb)
+            pb = pprevb       # the previous iterate enters only through the deferred term of this solve
         # hb = rA (u/dt - H + Sb/det)
         rAb += (hbb * (cr["hb"] / rA)).sum(0)
         inner_b = rA * hbb
@@ -204,30 +216,35 @@ def substep_vjp(t, u, p_prev, bvel, dt, tape, u_out_bar, p_out_bar):
                 Coffb[f] += np.where(m, Hb[c] * cr["uprev"][c][t.nb_safe[f]], 0.0)
                 np.add.at(uprevb[c], t.nb_safe[f], np.where(m, Hb[c] * Coff[f], 0.0))
         if ci > 0:
-            unb, pb = uprevb, pprevb
+            unb = uprevb
         else:
-            ustarb, pprevb_in = uprevb, pprevb
+            ustarb, pprevb_in = uprevb, pb
     # P = Wp . rAn
     rAnb += np.einsum("ejn,en->jn", t.Wp, Pmb)
     rAb += nbr_vals_T(t, rAnb)
     Ab = -rAb * rA * rA
-    # ustar = C^-1 rhs
-    rhsb = np.zeros((2, N))
-    for c in range(2):
-        mu = np.linalg.solve(tape["C"].T, ustarb[c])
-        rhsb[c] = mu
-        Ab += -mu * tape["ustar"][c]
-        for f in range(4):
-            Coffb[f] += np.where(t.inner[f], -mu * tape["ustar"][c][t.nb_safe[f]], 0.0)
-    # rhs = (det u/dt + Sb - NOv)/det
-    ub += rhsb / dt
-    Sbb += rhsb / t.det
-    NOvb = -rhsb / t.det
-    for c in range(2):
-        for k in range(t.K_no):
-            np.add.at(ub[c], t.no_idx[k], t.no_wv[k] * NOvb[c])
-        for k in range(t.K_nob):
-            np.add.at(bvb[c], t.nob_idx[k], t.nob_w[k] * NOvb[c])
+    # x_k = C^-1 rhs(u, x_{k-1}),  x_{-1} = u,  ustar = x_{n_adv-1}
+    xb = ustarb
+    for kk in reversed(range(len(tape["xs"]))):
+        xk = tape["xs"][kk]
+        rhsb = np.zeros((2, N))
+        for c in range(2):
+            mu = np.linalg.solve(tape["C"].T, xb[c])
+            rhsb[c] = mu
+            Ab += -mu * xk[c]
+            for f in range(4):
+                Coffb[f] += np.where(t.inner[f], -mu * xk[c][t.nb_safe[f]], 0.0)
+        # rhs = (det u/dt + Sb - NOv(x_{k-1}))/det
+        ub += rhsb / dt
+        Sbb += rhsb / t.det
+        NOvb = -rhsb / t.det
+        target = ub if kk == 0 else np.zeros((2, N))
+        for c in range(2):
+            for k in range(t.K_no):
+                np.add.at(target[c], t.no_idx[k], t.no_wv[k] * NOvb[c])
+            for k in range(t.K_nob):
+                np.add.at(bvb[c], t.nob_idx[k], t.nob_w[k] * NOvb[c])
+        xb = target
     # Sb(bvel, Fb)
     for f in range(4):
         m = ~t.inner[f]

@@ -14,7 +14,8 @@ def small():
     return cd, ae.T64(cd)
 
 
-def test_substep_vjp_matches_finite_differences(small):
+@pytest.mark.parametrize("n_adv,n_p", [(1, 1), (2, 3)])
+def test_substep_vjp_matches_finite_differences(small, n_adv, n_p):
     cd, t = small
     rng = np.random.default_rng(1)
     u = 0.3 * rng.standard_normal((2, t.N)); u[0] += 1.0
@@ -24,10 +25,10 @@ def test_substep_vjp_matches_finite_differences(small):
     wu, wp = rng.standard_normal((2, t.N)), rng.standard_normal(t.N)
 
     def J(u_, p_, b_):
-        uo, po, _ = ae.substep(t, u_, p_, b_, dt)
+        uo, po, _ = ae.substep(t, u_, p_, b_, dt, n_adv=n_adv, n_p=n_p)
         return float((wu * uo).sum() + (wp * po).sum())
 
-    uo, po, tape = ae.substep(t, u, p0, bvel, dt)
+    uo, po, tape = ae.substep(t, u, p0, bvel, dt, n_adv=n_adv, n_p=n_p)
     ub, pb, bb = ae.substep_vjp(t, u, p0, bvel, dt, tape, wu, wp)
     for name, grad, shape in (("u", ub, u.shape), ("p_prev", pb, p0.shape), ("bvel", bb, bvel.shape)):
         for trial in range(2):
@@ -40,4 +41,6 @@ def test_substep_vjp_matches_finite_differences(small):
             else:
                 fd = (J(u, p0, bvel + eps * d) - J(u, p0, bvel - eps * d)) / (2 * eps)
             an = float((grad * d).sum())
-            assert abs(fd - an) <= 2e-5 * max(abs(fd), abs(an)) + 1e-7, (name, trial, fd, an)
+            # the absolute term covers the round-off of the finite difference itself: the pressure operator is
+            # nearly singular, so J carries ~1e-12 noise that eps = 1e-6 amplifies to ~1e-6
+            assert abs(fd - an) <= 2e-5 * max(abs(fd), abs(an)) + 5e-6, (name, trial, fd, an)

@@ -142,3 +142,26 @@ def test_reward_gradient_wrt_action_matches_finite_differences(developed_state):
     fd = (rp - rm) / (2 * eps)
     print("d reward / d action: autograd", g, "central difference", fd)
     assert abs(g - fd) < 0.05 * max(abs(g), abs(fd)) + 1e-4
+
+
+def test_vjp_with_several_nonorthogonal_iterations(setup):
+    """advect_non_ortho_steps = 2, pressure_non_ortho_steps = 3 (the airfoil runs 2 / 4): CUDA adjoint against the
+    float64 specification."""
+    cd, sol0, u, p0, bvel = setup
+    from fluidgym_b200.solver import BatchedPISO
+    sol = BatchedPISO(cd, 2, cg_impl=3, advection_tol=1e-7, pressure_tol=1e-7, advect_non_ortho_steps=2, pressure_non_ortho_steps=3)
+    t = ae.T64(cd)
+    rng = np.random.default_rng(5)
+    wu, wp = rng.standard_normal((2, cd.N)), np.zeros(cd.N)
+    tu, tp, tb, uo, po, J = _run(sol, u, p0, bvel, 0.01, wu, wp)
+    J.sum().backward()
+    torch.cuda.synchronize()
+    uo64, po64, tape = ae.substep(t, u, p0, bvel, 0.01, n_adv=2, n_p=3)
+    assert rel_l2(uo[0].detach().cpu().numpy(), uo64) < 1e-4
+    ub, pb, bb = ae.substep_vjp(t, u, p0, bvel, 0.01, tape, wu, wp)
+    print("multi-iteration adjoint vs spec: u_bar", rel_l2(tu.grad[0].cpu().numpy(), ub), "bvel_bar", rel_l2(tb.grad[0].cpu().numpy(), bb),
+          "p_bar", rel_l2(tp.grad[0].cpu().numpy(), pb), np.abs(pb).max())
+    assert rel_l2(tu.grad[0].cpu().numpy(), ub) < 1e-3
+    assert rel_l2(tb.grad[0].cpu().numpy(), bb) < 3e-3
+    # the previous pressure only enters through three nested deferred corrections: its gradient is tiny, compare absolutely
+    assert np.abs(tp.grad[0].cpu().numpy() - pb).max() < 3e-3 * max(np.abs(ub).max(), 1e-3)
