@@ -272,7 +272,7 @@ def run_ours(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roof = {"bound": "hbm", "kernel": {0: "k_cg", 1: "k_cg_cluster", 2: "k_cg_cluster", 3: "k_cg_cluster_mb", 4: "k_cg_smem", 5: "k_cg_smem"}[args.cg_impl], "achieved": achieved, "peak": peak,
+    roof = {"bound": "hbm", "kernel": {0: "k_cg", 1: "k_cg_cluster", 2: "k_cg_cluster", 3: "k_cg_cluster_mb", 4: "k_cg_smem", 5: "k_cg_smem", 6: "k_cg_cluster_mb<PUSH>", 7: "k_cg_cluster_mb<PUSH,256x14>"}[args.cg_impl], "achieved": achieved, "peak": peak,
             "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "algorithmic_bytes_per_launch": cg_bytes / max(cg_launches, 1), "avg_launch_ms": cg_ms / max(cg_launches, 1),
             "launches": cg_launches, "share_of_step": cg_ms / ms_local,
@@ -404,7 +404,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=256, help="environments per GPU")
     ap.add_argument("--workload", default="cylinder", choices=["cylinder", "rbc"])
-    ap.add_argument("--cg-impl", type=int, default=3)
+    ap.add_argument("--cg-impl", type=int, default=6)
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "cuda", "cpu"])
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -678,8 +678,11 @@ __global__ void __launch_bounds__(T) k_cg(Tab t, const float *__restrict__ Poff,
         block_reduce_sum<2>(acc, red);
         float rho = acc[0];
         float bestc = 0.f, lastc = 0.f; int best_it = -1, rising = 0;
+        int until_reset = reset_steps > 0 ? reset_steps - 1 : -1;     // (i + 1) % reset_steps == 0 without the division
         for (int i = 0; i < maxit; ++i) {
-            if (reset_steps > 0 && (i + 1) % reset_steps == 0) {
+            const bool do_reset = until_reset == 0;
+            if (until_reset >= 0) until_reset = do_reset ? reset_steps - 1 : until_reset - 1;
+            if (do_reset) {
                 __syncthreads();
                 acc[0] = 0.f;
                 for (int g = threadIdx.x; g < N; g += T) {
@@ -996,7 +999,19 @@ __device__ __forceinline__ void st_async_f32(uint32_t cluster_addr, float v, uin
                  ::"r"(cluster_addr), "r"(__float_as_uint(v)), "r"(cluster_mbar) : "memory");
 }
 
-template <int T, int CPT, int CS>
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// PUSH = false: neighbours are gathered from the owning CTA's shared memory through the cluster window (DSMEM).
+// PUSH = true : halo plan of tables.cg_* -- after every update of the exposed vector each CTA pushes the cells its
+//               neighbours need into THEIR shared memory (st.async, completing the receiver's mbarrier transaction
+//               count), so every stencil gather is a plain ld.shared and the hand-shake carries the data itself
+//               (no release fence, no remote arrive).  ncu on the PUSH=false kernel: each DSMEM gather costs an
+//               LD.E on a generic address plus two MOVs to assemble it, 84 of 391 instructions per iteration.
+template <int T, int CPT, int CS, bool PUSH>
 __global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
                                                          const float *__restrict__ Rhs, float *__restrict__ Xout,
                                                          int maxit, float tol, int zero_init, int reset_steps, int slot,
@@ -1019,20 +1034,36 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__re
     const int start = (int)rank * per;
     const int cnt = max(0, min(per, N - start));
     float *vs = smem;                            // [PAD] search direction of the owned cells
-    float *bs = smem + PAD;                      // [PAD] best iterate
-    float *red = smem + 2 * PAD;                 // [2][NP] reduction slots (alternating)
-    unsigned long long *mb = (unsigned long long *)(smem + 2 * PAD + 2 * NP);   // [0],[1]: reductions, [2]: p ready
+    const int HM = PUSH ? t.cg_hmax : 0;         // halo slots follow the owned cells: vs[PAD .. PAD + HM)
+    float *bs = smem + PAD + HM;                 // [PAD] best iterate
+    float *red = bs + PAD;                       // [2][NP] reduction slots (alternating)
+    unsigned long long *mb = (unsigned long long *)(red + 2 * NP);   // [0],[1]: reductions, [2]: p ready
+    uint2 *exps = (uint2 *)(mb + 4);             // [cg_emax] export list (PUSH)
     const float *off = Poff + (size_t)b * 4 * N, *dg = Pdiag + (size_t)b * N, *f = Rhs + (size_t)b * N;
     float *xo = Xout + (size_t)b * N;
     const float norm = 1.0f / sqrtf((float)N);
     const uint32_t vs_addr = smem_u32(vs), red_addr = smem_u32(red), mb_addr = smem_u32(mb);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+    const int n_exp = PUSH ? t.cg_cnt[2 * rank] : 0;
+    const uint32_t halo_bytes = PUSH ? 4u * (uint32_t)t.cg_cnt[2 * rank + 1] : 0u;
     if (threadIdx.x == 0) {
-        mbar_init(mb_addr, 1); mbar_init(mb_addr + 8, 1); mbar_init(mb_addr + 16, CS);
+        mbar_init(mb_addr, 1); mbar_init(mb_addr + 8, 1); mbar_init(mb_addr + 16, PUSH ? 1 : CS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_arrive_expect_tx(mb_addr, NP * 4);          // arm both reduction barriers for their first use
         mbar_arrive_expect_tx(mb_addr + 8, NP * 4);
+        if (PUSH) mbar_arrive_expect_tx(mb_addr + 16, halo_bytes);
+    }
+    if (PUSH) {
+        for (int e = threadIdx.x; e < n_exp; e += T) {
+            const int32_t a = t.cg_exp[((size_t)rank * t.cg_emax + e) * 2], d = t.cg_exp[((size_t)rank * t.cg_emax + e) * 2 + 1];
+            const uint32_t dst_rank = (uint32_t)a >> 24;
+            // x: byte offset of the own slot in vs | dest rank << 24 ; y: cluster address of the destination slot
+            // (a shared::cta address carries the CTA's position in the cluster window in its high bits, so the
+            //  byte OFFSET is packed, not the address)
+            exps[e] = make_uint2((4u * ((uint32_t)a & 0xffffffu)) | (dst_rank << 24), mapa_u32(vs_addr + 4u * (uint32_t)d, dst_rank));
+        }
+        for (int h = threadIdx.x; h < HM; h += T) vs[PAD + h] = 0.f;
     }
     float cd[CPT], co[CPT][4], xr[CPT], rr[CPT];
     uint32_t na[CPT][4];
@@ -1053,7 +1084,8 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__re
             const int c = gi / per;
             // (measured: splitting local neighbours onto plain ld.shared with a per-gather predicate is SLOWER,
             //  10.8 vs 8.3 ms per substep -- the cluster-window load of an own-CTA address is not the bottleneck)
-            na[k][ff] = mapa_u32(vs_addr + 4u * (uint32_t)(gi - c * per), (uint32_t)c);
+            if (PUSH) na[k][ff] = vs_addr + 4u * (uint32_t)(ok ? t.cg_slot[ff * N + g] : 0);
+            else na[k][ff] = mapa_u32(vs_addr + 4u * (uint32_t)(gi - c * per), (uint32_t)c);
         }
     }
     // addresses this lane pushes partials to (lane < CS): slot array and barriers of CTA `lane`
@@ -1085,13 +1117,24 @@ __global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__re
     };
     auto publish = [&]() {                       // my part of vs is written: tell every CTA of the cluster
         __syncthreads();
-        if (threadIdx.x < CS) mbar_arrive_remote_release(mapa_u32(mb_addr + 16, threadIdx.x));
+        if (PUSH) {
+            for (int e = threadIdx.x; e < n_exp; e += T) {
+                const uint2 ex = exps[e];
+                st_async_f32(ex.y, ld_shared_f32(vs_addr + (ex.x & 0xffffffu)), mapa_u32(mb_addr + 16, ex.x >> 24));
+            }
+        } else if (threadIdx.x < CS) mbar_arrive_remote_release(mapa_u32(mb_addr + 16, threadIdx.x));
     };
-    auto acquire_p = [&]() { mbar_wait(mb_addr + 16, pphase); pphase ^= 1u; };
+    auto acquire_p = [&]() {
+        mbar_wait(mb_addr + 16, pphase); pphase ^= 1u;
+        // PUSH: re-arm for the next hand-shake.  Its data cannot complete the phase before this arrival, and no
+        // sender can start the next push before every warp of this CTA has passed the wait above (the senders
+        // first need this CTA's partials of the following reduction).
+        if (PUSH && threadIdx.x == 0) mbar_arrive_expect_tx(mb_addr + 16, halo_bytes);
+    };
     auto apply = [&](int k) -> float {
         float s = cd[k] * vs[threadIdx.x + k * T];
 #pragma unroll
-        for (int ff = 0; ff < 4; ++ff) s += co[k][ff] * ld_dsmem_f32(na[k][ff]);
+        for (int ff = 0; ff < 4; ++ff) s += co[k][ff] * (PUSH ? ld_shared_f32(na[k][ff]) : ld_dsmem_f32(na[k][ff]));
         return s;
     };
     auto load_f = [&](int k) -> float { const int l = threadIdx.x + k * T; return l < cnt ? f[start + l] : 0.f; };
@@ -2203,16 +2246,19 @@ static int launch_cg_cluster(fgb_batch *b, float *p_out, int zero_init, int rese
     return FGB_OK;
 }
 
-template <int CS, int CPT>
+template <int CS, int CPT, bool PUSH = false, int T = 512>
 static int launch_cg_cluster_mb(fgb_batch *b, const float *poff, const float *pdiag, const float *rhs, float *p_out, int zero_init,
                                 int reset_steps, int max_iter, int slot, const int32_t *active, int flags, float *mean_out,
                                 cudaStream_t st) {
-    constexpr int T = 512;
     const int N = b->t.N;
     const int per = (N + CS - 1) / CS;
     if (per > T * CPT) return 1;
-    const size_t smem = ((size_t)2 * T * CPT + (size_t)2 * (T / 32) * CS) * sizeof(float) + 3 * 8 + 16;
-    auto kern = k_cg_cluster_mb<T, CPT, CS>;
+    if (PUSH && (!b->t.cg_slot || !b->t.cg_exp || !b->t.cg_cnt || b->t.cg_cs != CS || b->t.cg_pad != T * CPT))
+        return set_err(FGB_E_ARG, "cg_impl 6: tables.cg_* (halo plan) missing or built for another cluster size");
+    const size_t smem = ((size_t)2 * T * CPT + (size_t)2 * (T / 32) * CS + (PUSH ? (size_t)b->t.cg_hmax : 0)) * sizeof(float) + 4 * 8 + 16 +
+                        (PUSH ? (size_t)b->t.cg_emax * 8 : 0);
+    if (smem > 227 * 1024) return set_err(FGB_E_ARG, "cg_impl 6: halo plan does not fit in shared memory");
+    auto kern = k_cg_cluster_mb<T, CPT, CS, PUSH>;
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_cg_cluster_mb)", ce);
     if (CS > 8) {   // 16-CTA clusters are a non-portable size: opt in (one cluster then occupies most of a GPC)
@@ -2233,6 +2279,20 @@ static int launch_cg_cluster_mb(fgb_batch *b, const float *poff, const float *pd
 
 static int cg_cluster_mb_any(fgb_batch *b, const float *poff, const float *pdiag, const float *rhs, float *p_out, int zero_init,
                              int reset_steps, int max_iter, int slot, const int32_t *active, int flags, float *mean_out, cudaStream_t st) {
+    if (b->opt.cg_impl == 7) {       // as 6 with half the threads and twice the cells per thread (same padding per CTA)
+        int rc = launch_cg_cluster_mb<2, 12, true, 256>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        if (rc == 1) rc = launch_cg_cluster_mb<4, 14, true, 256>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        if (rc == 1) rc = launch_cg_cluster_mb<8, 14, true, 256>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        if (rc == 1) rc = launch_cg_cluster_mb<16, 12, true, 256>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        return rc;
+    }
+    if (b->opt.cg_impl == 6) {       // pushed halos: same cluster-size rule, gathers from local shared memory
+        int rc = launch_cg_cluster_mb<2, 6, true>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        if (rc == 1) rc = launch_cg_cluster_mb<4, 7, true>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        if (rc == 1) rc = launch_cg_cluster_mb<8, 7, true>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        if (rc == 1) rc = launch_cg_cluster_mb<16, 6, true>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        return rc;
+    }
     int rc = launch_cg_cluster_mb<2, 6>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
     if (rc == 1) rc = launch_cg_cluster_mb<4, 7>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
     if (rc == 1) rc = launch_cg_cluster_mb<8, 7>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
@@ -2281,7 +2341,7 @@ static int solve_pressure_slot(fgb_batch *b, float *p_out, int zero_init, int re
         if (rc == 1) rc = launch_cg_smem<8, 7, 2>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
         if (rc <= 0) return rc;
     }
-    if (b->opt.cg_impl == 3) {
+    if (b->opt.cg_impl == 3 || b->opt.cg_impl == 6 || b->opt.cg_impl == 7) {
         int rc = cg_cluster_mb_any(b, b->Poff, b->Pdiag, b->div, p_out, zero_init, reset_steps, max_iter, slot, active, 0,
                                    b->pmean + (size_t)mean_slot * b->B, STREAM(s));
         if (rc <= 0) return rc;
@@ -2380,8 +2440,8 @@ extern "C" int fgb_piso_substep_record(fgb_batch *b, float *u, float *p, const f
     if (!b || !u || !p || !bvel || !dt || !tp) return set_err(FGB_E_ARG, "fgb_piso_substep_record: null argument");
     const fgb_options &o = b->opt;
     const int C = o.corrector_steps, n_adv = o.adv_nonortho_steps, n_p = o.p_nonortho_steps;
-    if (!o.nonortho || o.cg_impl != 3 || C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8)
-        return set_err(FGB_E_ARG, "fgb_piso_substep_record: needs the non-orthogonal path, cg_impl 3 and correctors x pressure iterations <= 8");
+    if (!o.nonortho || (o.cg_impl != 3 && o.cg_impl != 6 && o.cg_impl != 7) || C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8)
+        return set_err(FGB_E_ARG, "fgb_piso_substep_record: needs the non-orthogonal path, cg_impl 3 or 6 and correctors x pressure iterations <= 8");
     cudaStream_t st = STREAM(s);
     const size_t B = b->B, N = b->t.N, NB = b->t.NB;
     int rc;

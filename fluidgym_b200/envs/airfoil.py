@@ -50,7 +50,7 @@ class Airfoil2DEnv(DifferentiableRollout):
     use_marl = False
 
     def __init__(self, n_envs: int = 1, reynolds_number=3e3, dt=0.05, step_length=0.25, adaptive_cfl=0.8, episode_length=300,
-                 attack_angle_deg=10.0, device="cuda:0", cg_impl=3, compiled=None, cl_cd_ref=0.0, randomize_initial_state=False,
+                 attack_angle_deg=10.0, device="cuda:0", cg_impl=6, compiled=None, cl_cd_ref=0.0, randomize_initial_state=False,
                  enable_actions=True, use_marl=False, differentiable=False):
         if attack_angle_deg < 0.0 or attack_angle_deg > 20.0:
             raise ValueError("Attack angle must be between 0 and 20 degrees.")

@@ -45,7 +45,7 @@ class RBC2DEnv:
 
     def __init__(self, n_envs: int = 1, rayleigh_number=8e4, prandtl_number=0.7, n_heaters=12, resolution=8, dt=0.05,
                  adaptive_cfl=0.8, step_length=1.0, episode_length=200, local_obs_window=11, local_reward_weight=0.2,
-                 uniform_grid=False, aspect_ratio=1.0, use_marl=False, device="cuda:0", cg_impl=3, nu_ref=0.0,
+                 uniform_grid=False, aspect_ratio=1.0, use_marl=False, device="cuda:0", cg_impl=6, nu_ref=0.0,
                  randomize_initial_state=False, enable_actions=True):
         self.n_envs = int(n_envs)
         self.Ra, self.Pr = float(rayleigh_number), float(prandtl_number)

@@ -22,7 +22,9 @@ class Tables(C.Structure):
                 ("viscosity", C.c_float)] + [(n, C.c_void_p) for n in (
                     "nbr", "fl_comp", "minv", "det", "Cd", "Wp", "no_idx", "no_face", "no_gP", "no_gN", "no_wv",
                     "nob_idx", "nob_w", "b_minv", "b_det", "b_alpha", "b_cell", "b_face", "b_out")] + [
-                    ("scalar_viscosity", C.c_float), ("Cd_s", C.c_void_p), ("sb_neumann", C.c_void_p), ("rev", C.c_void_p)]
+                    ("scalar_viscosity", C.c_float), ("Cd_s", C.c_void_p), ("sb_neumann", C.c_void_p), ("rev", C.c_void_p),
+                    ("cg_slot", C.c_void_p), ("cg_exp", C.c_void_p), ("cg_cnt", C.c_void_p),
+                    ("cg_cs", C.c_int32), ("cg_emax", C.c_int32), ("cg_hmax", C.c_int32), ("cg_pad", C.c_int32)]
 
 
 class Tape(C.Structure):

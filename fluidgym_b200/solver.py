@@ -23,6 +23,64 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def cluster_shape(N: int):
+    """(cluster size, cells per CTA incl. padding) the on-chip Krylov launchers pick for a grid of N cells
+    (cg_cluster_mb_any in csrc/piso_b200.cu): smallest cluster whose CTAs hold ceil(N/CS) cells."""
+    for cs, cpt in ((2, 6), (4, 7), (8, 7), (16, 6)):
+        if -(-N // cs) <= 512 * cpt:
+            return cs, 512 * cpt
+    return None
+
+
+def halo_plan(nbr: np.ndarray, N: int):
+    """Static communication plan of the pushed-halo CG (cg_impl 6, tables.cg_*): CTA r of the cluster owns cells
+    [r*per, (r+1)*per) in slots [0, per); every remote cell one of its stencils touches gets a halo slot
+    pad + h.  Returns dict(cs, pad, slot[4][N], exp[cs][emax][2], cnt[cs][2], emax, hmax) or None."""
+    shape = cluster_shape(N)
+    if shape is None:
+        return None
+    cs, pad = shape
+    per = -(-N // cs)
+    cells = np.arange(N)
+    owner = cells // per
+    slot = np.zeros((4, N), dtype=np.int32)
+    halos = []                                    # per CTA: sorted unique remote cells
+    for r in range(cs):
+        mine = owner == r
+        remote = []
+        for f in range(4):
+            n = nbr[f][mine]
+            ok = n >= 0
+            remote.append(n[ok][(n[ok] // per) != r])
+        halos.append(np.unique(np.concatenate(remote)) if remote else np.zeros(0, dtype=np.int64))
+    for f in range(4):
+        n = nbr[f]
+        inner = n >= 0
+        nn = np.where(inner, n, cells)
+        local = (nn // per) == owner
+        s = np.where(local, nn - owner * per, 0)
+        for r in range(cs):
+            sel = (~local) & (owner == r)
+            if sel.any():
+                s[sel] = pad + np.searchsorted(halos[r], nn[sel])
+        slot[f] = s
+    exports = [[] for _ in range(cs)]
+    for r in range(cs):
+        for h, g in enumerate(halos[r]):
+            src = int(g // per)
+            exports[src].append((int(g - src * per) | (r << 24), pad + h))
+    emax = max(1, max(len(e) for e in exports))
+    exp = np.zeros((cs, emax, 2), dtype=np.int32)
+    cnt = np.zeros((cs, 2), dtype=np.int32)
+    for r in range(cs):
+        if exports[r]:
+            exp[r, :len(exports[r])] = np.asarray(exports[r], dtype=np.int64).astype(np.int32)
+        cnt[r] = (len(exports[r]), len(halos[r]))
+    hmax = int(max(len(h) for h in halos))
+    hmax += hmax & 1                              # keeps the mbarriers behind the halo slots 8-byte aligned
+    return dict(cs=cs, pad=pad, slot=slot, exp=exp, cnt=cnt, emax=emax, hmax=hmax)
+
+
 class BatchedPISO:
     """State + solver for ``n_envs`` environments on one GPU.
 
@@ -31,7 +89,7 @@ class BatchedPISO:
 
     def __init__(self, cd: CompiledDomain, n_envs: int, device="cuda:0", corrector_steps=2, advect_non_ortho_steps=1,
                  pressure_non_ortho_steps=1, non_orthogonal=True, advection_tol=1e-5, pressure_tol=1e-5,
-                 max_iter=5000, cg_impl=3, out_mask=None):
+                 max_iter=5000, cg_impl=6, out_mask=None):
         if not torch.cuda.is_available():
             raise native.FGBError("fluidgym_b200 needs a CUDA device (there is no CPU fallback)")
         self.lib = native.load()
@@ -58,6 +116,14 @@ class BatchedPISO:
             self.tables.scalar_viscosity = float(cd.scalar_visc)
         else:
             self._tab["Cd_s"] = self._tab["sb_neumann"] = None
+        plan = halo_plan(np.asarray(cd.nbr), cd.N)
+        self.halo = plan
+        if plan is not None:
+            self._tab["cg_slot"] = torch.from_numpy(plan["slot"]).to(dev)
+            self._tab["cg_exp"] = torch.from_numpy(plan["exp"]).to(dev)
+            self._tab["cg_cnt"] = torch.from_numpy(plan["cnt"]).to(dev)
+            self.tables.cg_slot, self.tables.cg_exp, self.tables.cg_cnt = (self._tab[k].data_ptr() for k in ("cg_slot", "cg_exp", "cg_cnt"))
+            self.tables.cg_cs, self.tables.cg_emax, self.tables.cg_hmax, self.tables.cg_pad = plan["cs"], plan["emax"], plan["hmax"], plan["pad"]
         for name in _TABLE_FIELDS + ["b_out", "Cd_s", "sb_neumann"]:
             t = self._tab[name]
             setattr(self.tables, name, t.data_ptr() if t is not None else None)

@@ -68,6 +68,14 @@ typedef struct fgb_tables {
     const int8_t *sb_neumann; /* [NB]   scalar boundary condition type: 0 Dirichlet, 1 Neumann             */
     const int8_t *rev;      /* [4][N]   face of the neighbour nbr[f] that points back to this cell (adjoint /
                                         transposed solves), -1 on boundary faces                        */
+    /* optional halo plan of the on-chip Krylov kernels (cg_impl 6), built for ONE cluster size cg_cs by
+     * fluidgym_b200/solver.py::halo_plan: every CTA of a cluster owns ceil(N/cg_cs) consecutive cells, keeps the
+     * exposed vector of its own cells in shared-memory slots [0, cells) and receives the remote cells its stencils
+     * touch into slots [pad, pad + n_halo).  NULL = not available (kernels gather through DSMEM instead). */
+    const int32_t *cg_slot; /* [4][N]   shared-memory slot (in floats) holding the neighbour across face f      */
+    const int32_t *cg_exp;  /* [cg_cs][cg_emax][2]  export list of each CTA: {own slot | dest rank << 24, dest slot} */
+    const int32_t *cg_cnt;  /* [cg_cs][2]  {exports, halo cells} of each CTA                                     */
+    int32_t cg_cs, cg_emax, cg_hmax, cg_pad;
 } fgb_tables;
 
 /* Passive scalar + buoyancy coupling of one batch (RBC: temperature; rbc_env_base.py:190-304).  With the
@@ -99,7 +107,10 @@ typedef struct fgb_options {
                                           for the reductions, remote mbarrier arrive for the p hand-shake
                                           (default, fastest)
                                        4: as 3 with x/r/p/neighbour table in shared memory, 2x cells per CTA
-                                       5: as 4 with two co-resident CTAs per SM                            */
+                                       5: as 4 with two co-resident CTAs per SM
+                                       6: as 3 with PUSHED halos (tables.cg_slot/cg_exp): after updating the
+                                          search direction every CTA st.async-es the cells its neighbours need into
+                                          their shared memory, all stencil gathers become plain ld.shared      */
 } fgb_options;
 
 const char *fgb_last_error(void);

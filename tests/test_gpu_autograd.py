@@ -16,7 +16,7 @@ def setup():
     from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
     from fluidgym_b200.solver import BatchedPISO
     cd = make_cylinder_domain(8).prepare()
-    sol = BatchedPISO(cd, 2, cg_impl=3, advection_tol=1e-7, pressure_tol=1e-7)
+    sol = BatchedPISO(cd, 2, cg_impl=6, advection_tol=1e-7, pressure_tol=1e-7)
     rng = np.random.default_rng(1)
     u = 0.3 * rng.standard_normal((2, cd.N)); u[0] += 1.0
     p0 = 0.1 * rng.standard_normal(cd.N)
@@ -149,7 +149,7 @@ def test_vjp_with_several_nonorthogonal_iterations(setup):
     float64 specification."""
     cd, sol0, u, p0, bvel = setup
     from fluidgym_b200.solver import BatchedPISO
-    sol = BatchedPISO(cd, 2, cg_impl=3, advection_tol=1e-7, pressure_tol=1e-7, advect_non_ortho_steps=2, pressure_non_ortho_steps=3)
+    sol = BatchedPISO(cd, 2, cg_impl=6, advection_tol=1e-7, pressure_tol=1e-7, advect_non_ortho_steps=2, pressure_non_ortho_steps=3)
     t = ae.T64(cd)
     rng = np.random.default_rng(5)
     wu, wp = rng.standard_normal((2, cd.N)), np.zeros(cd.N)

@@ -75,7 +75,7 @@ def test_ops_match_reference_trace(cyl24, golden):
     assert rel_l2(sol.buffer("ures")[1].cpu().numpy(), fx["u0"]) < 2e-6
 
 
-@pytest.mark.parametrize("cg_impl", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("cg_impl", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_pressure_solve_matches_oracle(cyl24, golden, cg_impl):
     """CG: same algorithm, same stopping rule -> iteration count within 2% of the oracle's and of the
     reference's, residual below tolerance, solution within the tolerance ball (5e-4 relative; the
@@ -107,7 +107,7 @@ def test_pressure_solve_matches_oracle(cyl24, golden, cg_impl):
     del div
 
 
-@pytest.mark.parametrize("cg_impl", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("cg_impl", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_substep_matches_reference(cyl24, golden, cg_impl):
     """One full PISO substep from the reference's state.  u: 2e-4, p: 1e-3 relative L2 (bounded by the
     CG tolerance ball, see DESIGN.md 'parity'); batch entries with perturbed states are checked against
@@ -219,3 +219,19 @@ def test_batch_entries_are_independent(cyl24):
     oo, ro, *_ = one.step(act[3:4])
     assert torch.equal(big.solver.u[3], one.solver.u[0]) and torch.equal(big.solver.p[3], one.solver.p[0])
     assert torch.equal(rb[3], ro[0]) and torch.equal(ob["pressure"][3], oo["pressure"][0])
+
+
+def test_pushed_halo_cg_is_bit_identical_to_dsmem_gather_cg(cyl24, golden):
+    """cg_impl 6 (halo cells pushed into the consumer's shared memory, plain ld.shared gathers) performs exactly the
+    arithmetic of cg_impl 3 (gathers through the cluster window): same iterates, bit for bit."""
+    spec, cd = cyl24
+    fx = golden("cyl24_substep1.npz")
+    out = []
+    for impl in (3, 6):
+        sol = _solver(cd, 2, cg_impl=impl)
+        for dst, src in ((sol.u, fx["u_in"]), (sol.p, fx["presres_in"]), (sol.bvel, fx["bvel_in"])):
+            dst.copy_(torch.from_numpy(np.ascontiguousarray(src)).cuda().unsqueeze(0).expand_as(dst))
+        sol.piso_substep(float(fx["dt"][0]))
+        torch.cuda.synchronize()
+        out.append((sol.u.clone(), sol.p.clone(), sol.buffer("iters").clone()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
