@@ -52,6 +52,12 @@ def _register_defaults():
     register("Airfoil2D-easy-v0", Airfoil2DEnv, **{**AIRFOIL_2D_DEFAULT_CONFIG, "reynolds_number": 1e3})
     register("Airfoil2D-medium-v0", Airfoil2DEnv, **{**AIRFOIL_2D_DEFAULT_CONFIG, "reynolds_number": 3e3})
     register("Airfoil2D-hard-v0", Airfoil2DEnv, **{**AIRFOIL_2D_DEFAULT_CONFIG, "reynolds_number": 5e3})
+    from .envs.tcf import LARGE_TCF_3D_DEFAULT_CONFIG, SMALL_TCF_3D_DEFAULT_CONFIG, TCF3DBothEnv, TCF3DBottomEnv
+    # fluidgym/__init__.py:216-300
+    for size, cfg in (("Small", SMALL_TCF_3D_DEFAULT_CONFIG), ("Large", LARGE_TCF_3D_DEFAULT_CONFIG)):
+        for walls, entry in (("bottom", TCF3DBottomEnv), ("both", TCF3DBothEnv)):
+            for level, re_w in (("easy", 180), ("medium", 330), ("hard", 550)):
+                register(f"TCF{size}3D-{walls}-{level}-v0", entry, **{**cfg, "reynolds_number_wall": re_w})
     from .envs.rbc import RBC_2D_DEFAULT_CONFIG, RBC2DEnv
     # fluidgym/__init__.py:106-157
     register("RBC2D-easy-v0", RBC2DEnv, **{**RBC_2D_DEFAULT_CONFIG, "rayleigh_number": 8e4, "adaptive_cfl": 0.8})

@@ -1,0 +1,668 @@
+// D = 3 instantiation of the PISO substep for ORTHOGONAL grids (turbulent channel flow, SURVEY.md section 8 config 5;
+// reference: the same K.cu kernels with DIMS = 3).  Included at the end of piso_b200.cu (one translation unit, shared
+// error handling / reductions).  On a rectilinear grid every off-diagonal metric coefficient is exactly zero, so the
+// deferred non-orthogonal corrections of the 2-D path vanish (`if (alpha != 0)`, K.cu:3772) and the matrices are
+// plain ELL(7) on a 6-face neighbour table.  Specification: tests/box3d_eval.py (validated against a trace of the
+// reference on a 32 x 32 x 32 channel to 1e-7 per operator).
+//
+// Large single environments do not fit a thread-block cluster, so the Krylov solvers here are persistent
+// COOPERATIVE kernels: the whole GPU works on one system, vectors stay in L2 (266 k cells x 5 vectors = 5 MB of
+// the 126 MB L2), grid-wide reductions are a fixed-order two-stage sum (deterministic) separated by grid.sync().
+
+typedef fgb_ortho3_tables T3;
+
+struct fgb_ortho3 {
+    T3 t;
+    int B;
+    fgb_options opt;
+    float *Coff, *A, *rhs, *ures, *Poff, *Pdiag, *hbya, *div, *kry, *part;
+    int32_t *iters; float *resid; float *dt; int32_t *active; double *remaining; int32_t *nsub; float *maxvel;
+    int32_t *counters; int32_t *h_counters; float *src; float *rowmean;
+    unsigned long long *iter_total;
+    int grid_blocks;
+    long long launches;
+};
+
+static constexpr int O3_T = 256;          // threads per CTA of every ortho3 kernel
+static constexpr int O3_KRY = 15;         // Krylov work vectors per environment (BiCGStab: 5 per component)
+static constexpr int O3_PART = 8;         // floats per CTA per reduction slot
+
+extern "C" size_t fgb_ortho3_workspace_bytes(const fgb_ortho3_tables *t, int32_t B) {
+    const size_t BN = (size_t)B * t->N;
+    size_t n = 0;
+    n += align_up(6 * BN * 4) * 2 + align_up(BN * 4) * 4 + align_up(3 * BN * 4) * 3 + align_up((size_t)O3_KRY * BN * 4);
+    n += align_up((size_t)2 * 4096 * O3_PART * 4);
+    n += align_up((size_t)B * 64) * 16 + 8192;        // per-environment scalars (iteration counters, dt, flags, forcing ...)
+    return n;
+}
+
+extern "C" int fgb_ortho3_create(const fgb_ortho3_tables *t, int32_t B, void *workspace, size_t workspace_bytes, const fgb_options *opt,
+                                 fgb_ortho3 **out) {
+    if (!t || !out || B <= 0 || t->N <= 0 || !t->nbr || !t->minv || !t->det) return set_err(FGB_E_ARG, "fgb_ortho3_create: bad argument");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) return set_err(FGB_E_CUDA, "fgb_ortho3_create: no CUDA device (there is no CPU fallback)", ce);
+    if (!workspace || workspace_bytes < fgb_ortho3_workspace_bytes(t, B)) return set_err(FGB_E_WORKSPACE, "fgb_ortho3_create: workspace too small");
+    fgb_ortho3 *b = new (std::nothrow) fgb_ortho3();
+    if (!b) return set_err(FGB_E_ARG, "fgb_ortho3_create: out of host memory");
+    b->t = *t; b->B = B; b->launches = 0;
+    if (opt) b->opt = *opt; else { b->opt.corrector_steps = 2; b->opt.adv_nonortho_steps = 1; b->opt.p_nonortho_steps = 1; b->opt.nonortho = 1;
+                                   b->opt.adv_tol = 1e-6f; b->opt.p_tol = 1e-6f; b->opt.max_iter = 5000; b->opt.cg_impl = 0; }
+    const size_t BN = (size_t)B * t->N;
+    Carver c{(char *)workspace, 0};
+    b->Coff = c.take<float>(6 * BN); b->Poff = c.take<float>(6 * BN);
+    b->A = c.take<float>(BN); b->Pdiag = c.take<float>(BN); b->div = c.take<float>(BN);
+    (void)c.take<float>(BN);
+    b->rhs = c.take<float>(3 * BN); b->ures = c.take<float>(3 * BN); b->hbya = c.take<float>(3 * BN);
+    b->kry = c.take<float>((size_t)O3_KRY * BN);
+    b->part = c.take<float>((size_t)2 * 4096 * O3_PART);
+    b->iters = c.take<int32_t>((size_t)B * 8); b->resid = c.take<float>((size_t)B * 8);
+    b->remaining = c.take<double>(B); b->iter_total = c.take<unsigned long long>((size_t)B * 2);
+    (void)c.take<double>(B);
+    b->dt = c.take<float>(B); b->active = c.take<int32_t>(B); b->nsub = c.take<int32_t>(B); b->maxvel = c.take<float>(B);
+    b->counters = c.take<int32_t>(4); (void)c.take<float>(B);
+    b->src = c.take<float>((size_t)B * 4); b->rowmean = c.take<float>((size_t)B * 4);
+    ce = cudaMallocHost((void **)&b->h_counters, 16);
+    if (ce != cudaSuccess) { delete b; return set_err(FGB_E_CUDA, "cudaMallocHost", ce); }
+    ce = cudaMemset(workspace, 0, fgb_ortho3_workspace_bytes(t, B));
+    if (ce != cudaSuccess) { cudaFreeHost(b->h_counters); delete b; return set_err(FGB_E_CUDA, "cudaMemset workspace", ce); }
+    b->grid_blocks = 0;
+    *out = b;
+    return FGB_OK;
+}
+extern "C" void fgb_ortho3_destroy(fgb_ortho3 *b) {
+    if (!b) return;
+    if (b->h_counters) cudaFreeHost(b->h_counters);
+    delete b;
+}
+extern "C" int fgb_ortho3_set_options(fgb_ortho3 *b, const fgb_options *opt) {
+    if (!b || !opt) return set_err(FGB_E_ARG, "fgb_ortho3_set_options: bad argument");
+    b->opt = *opt;
+    return FGB_OK;
+}
+extern "C" void *fgb_ortho3_buffer(fgb_ortho3 *b, const char *name) {
+    if (!b || !name) return nullptr;
+    struct { const char *n; void *p; } tab[] = {
+        {"Coff", b->Coff}, {"A", b->A}, {"rhs", b->rhs}, {"ures", b->ures}, {"Poff", b->Poff}, {"Pdiag", b->Pdiag}, {"hbya", b->hbya},
+        {"div", b->div}, {"iters", b->iters}, {"resid", b->resid}, {"dt", b->dt}, {"active", b->active}, {"nsub", b->nsub},
+        {"maxvel", b->maxvel}, {"src", b->src}, {"rowmean", b->rowmean}, {"iter_total", b->iter_total}, {"remaining", b->remaining}};
+    for (auto &e : tab) if (!strcmp(e.n, name)) return e.p;
+    return nullptr;
+}
+extern "C" long long fgb_ortho3_launch_count(fgb_ortho3 *b) { return b ? b->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// one thread per (cell, environment): blockIdx.y = environment
+// ------------------------------------------------------------------------------------------------
+static inline dim3 o3_grid(const fgb_ortho3 *b) { return dim3((unsigned)((b->t.N + O3_T - 1) / O3_T), (unsigned)b->B); }
+
+__device__ __forceinline__ float o3_bflux(const T3 &t, int j, int d, const float *bv /* [3][NB] of this env */) {
+    return t.b_det[j] * t.b_minv[d * t.NB + j] * bv[d * t.NB + j];
+}
+
+// C = (det/dt I + convection + diffusion)/det as ELL(7), A = diag(C), predictor RHS (K.cu:3617-3880, 4296-4400)
+__global__ void __launch_bounds__(O3_T) k3_setup_advection(T3 t, const float *__restrict__ U, const float *__restrict__ Bvel,
+                                                           const float *__restrict__ Src /* [B][4] or null */, const float *__restrict__ dtv,
+                                                           const int32_t *__restrict__ active, float *__restrict__ Coff, float *__restrict__ A,
+                                                           float *__restrict__ Rhs) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NB = t.NB;
+    if (g >= N || (active && !active[b])) return;
+    const float *u = U + (size_t)b * 3 * N, *bv = Bvel + (size_t)b * 3 * NB;
+    const float dt = dtv[b], det = t.det[g], visc = t.viscosity;
+    float uo[3], mi[3], al[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { uo[d] = u[d * N + g]; mi[d] = t.minv[d * N + g]; al[d] = det * mi[d] * mi[d]; }
+    float diag = det / dt, Sb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const int d = f >> 1, n = t.nbr[f * N + g];
+        const float sig = (f & 1) ? 1.f : -1.f;
+        float off = 0.f;
+        if (n >= 0) {
+            const float dn = t.det[n], mn = t.minv[d * N + n];
+            const float fl = 0.5f * (det * mi[d] * uo[d] + dn * mn * u[d * N + n]);
+            const float vc = (al[d] * visc + (dn * mn * mn) * visc) * 0.5f;
+            const float ff = sig * 0.5f * fl;
+            diag += ff + vc;
+            off = (ff - vc) / det;
+        } else {
+            const int j = -1 - n;
+            diag += 2.f * visc * al[d];
+            const float bm = t.b_minv[d * NB + j];
+            const float k = -(sig * o3_bflux(t, j, d, bv)) + 2.f * visc * (t.b_det[j] * bm * bm);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Sb[c] += bv[c * NB + j] * k;
+        }
+        Coff[((size_t)b * 6 + f) * N + g] = off;
+    }
+    A[(size_t)b * N + g] = diag / det;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        Rhs[((size_t)b * 3 + c) * N + g] = (det * uo[c] / dt + Sb[c]) / det + (Src ? Src[b * 4 + c] : 0.f);
+}
+
+// P: off = 1/2 (alpha_P / A_P + alpha_N / A_N), diag = -sum (K.cu:4812-4978)
+__global__ void __launch_bounds__(O3_T) k3_pressure_matrix(T3 t, const float *__restrict__ A, const int32_t *__restrict__ active,
+                                                           float *__restrict__ Poff, float *__restrict__ Pdiag) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N;
+    if (g >= N || (active && !active[b])) return;
+    const float *a = A + (size_t)b * N;
+    const float det = t.det[g], rA = 1.0f / a[g];
+    float diag = 0.f;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const int d = f >> 1, n = t.nbr[f * N + g];
+        float c = 0.f;
+        if (n >= 0) {
+            const float mi = t.minv[d * N + g], mn = t.minv[d * N + n];
+            c = 0.5f * ((det * mi * mi) * rA + (t.det[n] * mn * mn) * (1.0f / a[n]));
+        }
+        Poff[((size_t)b * 6 + f) * N + g] = c;
+        diag -= c;
+    }
+    Pdiag[(size_t)b * N + g] = diag;
+}
+
+// HbyA = (u/dt - H(u_prev) + S_b/det + source) / A (K.cu:5136-5255)
+__global__ void __launch_bounds__(O3_T) k3_hbya(T3 t, const float *__restrict__ U, const float *__restrict__ Uprev, const float *__restrict__ Bvel,
+                                                const float *__restrict__ Src, const float *__restrict__ dtv, const int32_t *__restrict__ active,
+                                                const float *__restrict__ Coff, const float *__restrict__ A, float *__restrict__ Hb) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NB = t.NB;
+    if (g >= N || (active && !active[b])) return;
+    const float *u = U + (size_t)b * 3 * N, *up = Uprev + (size_t)b * 3 * N, *bv = Bvel + (size_t)b * 3 * NB;
+    const float dt = dtv[b], det = t.det[g], visc = t.viscosity, Ag = A[(size_t)b * N + g];
+    float H[3] = {0.f, 0.f, 0.f}, Sb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const int d = f >> 1, n = t.nbr[f * N + g];
+        if (n >= 0) {
+            const float c = Coff[((size_t)b * 6 + f) * N + g];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) H[k] += c * up[k * N + n];
+        } else {
+            const int j = -1 - n;
+            const float sig = (f & 1) ? 1.f : -1.f, bm = t.b_minv[d * NB + j];
+            const float k = -(sig * o3_bflux(t, j, d, bv)) + 2.f * visc * (t.b_det[j] * bm * bm);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Sb[c] += bv[c * NB + j] * k;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        Hb[((size_t)b * 3 + c) * N + g] = (u[c * N + g] / dt - H[c] + Sb[c] / det + (Src ? Src[b * 4 + c] : 0.f)) / Ag;
+}
+
+// divergence of the contravariant face fluxes of a cell-centred field (K.cu:1567-1645, 5389-5434)
+__global__ void __launch_bounds__(O3_T) k3_divergence(T3 t, const float *__restrict__ V, const float *__restrict__ Bvel,
+                                                      const int32_t *__restrict__ active, float *__restrict__ Div) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NB = t.NB;
+    if (g >= N || (active && !active[b])) return;
+    const float *v = V + (size_t)b * 3 * N, *bv = Bvel + (size_t)b * 3 * NB;
+    const float det = t.det[g];
+    float fl[6];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const int d = f >> 1, n = t.nbr[f * N + g];
+        if (n >= 0) fl[f] = 0.5f * (det * t.minv[d * N + g] * v[d * N + g] + t.det[n] * t.minv[d * N + n] * v[d * N + n]);
+        else fl[f] = o3_bflux(t, -1 - n, d, bv);
+    }
+    Div[(size_t)b * N + g] = (fl[1] - fl[0]) + (fl[3] - fl[2]) + (fl[5] - fl[4]);
+}
+
+// u = HbyA - (1/A) M^-T grad(p), central differences, one-sided at prescribed boundaries (K.cu:816-849, 5962-5995)
+__global__ void __launch_bounds__(O3_T) k3_correct(T3 t, const float *__restrict__ Hb, const float *__restrict__ P, const float *__restrict__ A,
+                                                   const int32_t *__restrict__ active, float *__restrict__ Uout) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N;
+    if (g >= N || (active && !active[b])) return;
+    const float *p = P + (size_t)b * N;
+    const float pc = p[g], rA = 1.0f / A[(size_t)b * N + g];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int nl = t.nbr[(2 * d) * N + g], nu = t.nbr[(2 * d + 1) * N + g];
+        const float fac = (nl < 0 || nu < 0) ? 1.0f : 0.5f;
+        const float pg = ((nu >= 0 ? p[nu] : pc) - (nl >= 0 ? p[nl] : pc)) * fac;
+        Uout[((size_t)b * 3 + d) * N + g] = Hb[((size_t)b * 3 + d) * N + g] - pg * t.minv[d * N + g] * rA;
+    }
+}
+
+__global__ void k3_copy_active(const float *__restrict__ src, float *__restrict__ dst, size_t n, const int32_t *__restrict__ active) {
+    const int b = blockIdx.y;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (active && !active[b])) return;
+    dst[(size_t)b * n + i] = src[(size_t)b * n + i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// cooperative Krylov kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float o3_row(const T3 &t, int g, const float *__restrict__ off, const float *__restrict__ dg, const float *x) {
+    const int N = t.N;
+    float s = dg[g] * x[g];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) { const int n = t.nbr[f * N + g]; if (n >= 0) s += off[f * N + g] * __ldcg(&x[n]); }
+    return s;
+}
+
+// deterministic grid-wide sum of K values: block sums -> part[slot][cta][k] -> grid.sync -> fixed-order sum in every CTA
+template <int K>
+__device__ __forceinline__ void o3_grid_sum(cg::grid_group &grid, float (&v)[K], float *part, unsigned &rcount, double *sm) {
+    static_assert(K <= O3_PART, "partials per CTA");
+    block_reduce_sum<K>(v, sm);
+    float *slot = part + (size_t)(rcount & 1u) * 4096 * O3_PART;
+#pragma unroll
+    for (int k = 0; k < K; ++k) if (threadIdx.x == k) slot[blockIdx.x * O3_PART + k] = v[k];
+    __threadfence();
+    grid.sync();
+    const int nb = gridDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp < K) {
+        double s = 0.0;
+        for (int i = lane; i < nb; i += 32) s += (double)__ldcg(&slot[i * O3_PART + warp]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sm[warp] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = (float)sm[k];
+    __syncthreads();
+    ++rcount;
+}
+
+// BiCGStab for the three velocity components in lock step (BICG.cu:237-376; same operation order as k_bicgstab)
+__global__ void __launch_bounds__(O3_T) k3_bicgstab(T3 t, int B, const float *__restrict__ Coff, const float *__restrict__ Adiag,
+                                                    const float *__restrict__ Rhs, float *X, float *work, float *part, int maxit, float tol,
+                                                    int zero_init, const int32_t *__restrict__ active, int32_t *__restrict__ iters,
+                                                    float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red[32 * 6 + 8];
+    const int N = t.N;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const float norm = 1.0f / sqrtf((float)N);
+    unsigned rcount = 0;
+    for (int b = 0; b < B; ++b) {
+        if (active && !active[b]) continue;
+        const float *off = Coff + (size_t)b * 6 * N, *dg = Adiag + (size_t)b * N;
+        float *wb = work + (size_t)b * O3_KRY * N;
+        float *r[3], *rw[3], *p[3], *v[3], *tt[3], *x[3];
+        const float *f[3];
+        for (int c = 0; c < 3; ++c) {
+            r[c] = wb + (size_t)(5 * c) * N; rw[c] = r[c] + N; p[c] = r[c] + 2 * (size_t)N; v[c] = r[c] + 3 * (size_t)N; tt[c] = r[c] + 4 * (size_t)N;
+            x[c] = X + ((size_t)b * 3 + c) * N; f[c] = Rhs + ((size_t)b * 3 + c) * N;
+        }
+        if (zero_init) { for (int c = 0; c < 3; ++c) for (int g = tid; g < N; g += nth) x[c][g] = 0.f; }
+        else grid.sync();
+        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < 3; ++c)
+            for (int g = tid; g < N; g += nth) {
+                const float rr = f[c][g] - (zero_init ? 0.f : o3_row(t, g, off, dg, x[c]));
+                r[c][g] = rr; rw[c][g] = rr; p[c][g] = rr;
+                acc[c] += rr * rr;
+            }
+        o3_grid_sum<6>(grid, acc, part, rcount, red);
+        bool done[3]; int used[3]; float fin[3], rho[3] = {1.f, 1.f, 1.f}, alpha[3] = {1.f, 1.f, 1.f}, omega[3] = {1.f, 1.f, 1.f};
+        for (int c = 0; c < 3; ++c) { fin[c] = sqrtf(acc[c]) * norm; used[c] = -1; done[c] = fin[c] < tol; }
+        for (int i = 0; i < maxit && !(done[0] && done[1] && done[2]); ++i) {
+            for (int k = 0; k < 6; ++k) acc[k] = 0.f;
+            for (int c = 0; c < 3; ++c) if (!done[c])
+                for (int g = tid; g < N; g += nth) acc[c] += rw[c][g] * r[c][g];
+            o3_grid_sum<6>(grid, acc, part, rcount, red);
+            for (int c = 0; c < 3; ++c) if (!done[c]) {
+                const float rhop = rho[c]; rho[c] = acc[c];
+                if (i > 0) {
+                    const float beta = (rho[c] / rhop) * (alpha[c] / omega[c]);
+                    for (int g = tid; g < N; g += nth) p[c][g] = r[c][g] + beta * (p[c][g] - omega[c] * v[c][g]);
+                }
+            }
+            __threadfence(); grid.sync();
+            for (int k = 0; k < 6; ++k) acc[k] = 0.f;
+            for (int c = 0; c < 3; ++c) if (!done[c])
+                for (int g = tid; g < N; g += nth) { const float vv = o3_row(t, g, off, dg, p[c]); v[c][g] = vv; acc[c] += rw[c][g] * vv; }
+            o3_grid_sum<6>(grid, acc, part, rcount, red);
+            float acc2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int c = 0; c < 3; ++c) if (!done[c]) {
+                alpha[c] = rho[c] / acc[c];
+                for (int g = tid; g < N; g += nth) {
+                    const float rr = r[c][g] - alpha[c] * v[c][g];
+                    r[c][g] = rr; x[c][g] += alpha[c] * p[c][g];
+                    acc2[c] += rr * rr;
+                }
+            }
+            o3_grid_sum<6>(grid, acc2, part, rcount, red);     // (its grid.sync also publishes r for the next product)
+            for (int c = 0; c < 3; ++c) if (!done[c]) {
+                const float nr = sqrtf(acc2[c]) * norm;
+                used[c] = i; fin[c] = nr;
+                if (!isfinite(nr) || nr < tol) done[c] = true;
+            }
+            for (int k = 0; k < 6; ++k) acc[k] = 0.f;
+            for (int c = 0; c < 3; ++c) if (!done[c])
+                for (int g = tid; g < N; g += nth) {
+                    const float tv = o3_row(t, g, off, dg, r[c]); tt[c][g] = tv;
+                    acc[c] += tv * r[c][g]; acc[3 + c] += tv * tv;
+                }
+            o3_grid_sum<6>(grid, acc, part, rcount, red);      // every row of t = C r is complete before r is overwritten
+            for (int k = 0; k < 6; ++k) acc2[k] = 0.f;
+            for (int c = 0; c < 3; ++c) if (!done[c]) {
+                omega[c] = acc[c] / acc[3 + c];
+                for (int g = tid; g < N; g += nth) {
+                    const float rg = r[c][g];
+                    x[c][g] += omega[c] * rg;
+                    const float rr = rg - omega[c] * tt[c][g];
+                    acc2[c] += rr * rr;
+                    r[c][g] = rr;
+                }
+            }
+            o3_grid_sum<6>(grid, acc2, part, rcount, red);
+            for (int c = 0; c < 3; ++c) if (!done[c]) {
+                const float nr = sqrtf(acc2[c]) * norm;
+                fin[c] = nr;
+                if (nr < tol) { done[c] = true; used[c] = i + 1; }
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long tot = 0;
+            for (int c = 0; c < 3; ++c) { iters[b * 8 + c] = used[c]; resid[b * 8 + c] = fin[c]; tot += (unsigned long long)(used[c] + 1); }
+            iter_total[b * 2 + 1] += tot;
+        }
+        grid.sync();
+    }
+}
+
+// CG with residual reset, best-iterate tracking, 100-rising-steps cut-off and mean removal (CG.cu:225-446, SIM.py:1908-1925)
+__global__ void __launch_bounds__(O3_T) k3_cg(T3 t, int B, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
+                                              const float *__restrict__ Rhs, float *Xout, float *work, float *part, int maxit, float tol,
+                                              int zero_init, int reset_steps, int slot, const int32_t *__restrict__ active,
+                                              int32_t *__restrict__ iters, float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red[32 * 2 + 8];
+    const int N = t.N;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const float norm = 1.0f / sqrtf((float)N);
+    unsigned rcount = 0;
+    for (int b = 0; b < B; ++b) {
+        if (active && !active[b]) continue;
+        const float *off = Poff + (size_t)b * 6 * N, *dg = Pdiag + (size_t)b * N, *f = Rhs + (size_t)b * N;
+        float *wb = work + (size_t)b * O3_KRY * N;
+        float *r = wb, *p = wb + N, *ap = wb + 2 * (size_t)N, *best = wb + 3 * (size_t)N, *x = wb + 4 * (size_t)N;
+        float *xo = Xout + (size_t)b * N;
+        float acc[2] = {0.f, 0.f};
+        for (int g = tid; g < N; g += nth) { x[g] = zero_init ? 0.f : xo[g]; acc[1] += (f[g] != 0.f) ? 1.f : 0.f; }
+        o3_grid_sum<2>(grid, acc, part, rcount, red);
+        int used = -1; float fin = 0.f;
+        if (!(acc[1] > 0.f)) {            // all-zero right-hand side -> zero result (DIFF.py:392, 489-490)
+            for (int g = tid; g < N; g += nth) x[g] = 0.f;
+        } else {
+            acc[0] = acc[1] = 0.f;
+            for (int g = tid; g < N; g += nth) {
+                const float rr = f[g] - (zero_init ? 0.f : o3_row(t, g, off, dg, x));
+                r[g] = rr; p[g] = rr; acc[0] += rr * rr;
+            }
+            o3_grid_sum<2>(grid, acc, part, rcount, red);
+            float rho = acc[0], bestc = 0.f, lastc = 0.f; int best_it = -1, rising = 0;
+            int until_reset = reset_steps > 0 ? reset_steps - 1 : -1;
+            for (int i = 0; i < maxit; ++i) {
+                const bool do_reset = until_reset == 0;
+                if (until_reset >= 0) until_reset = do_reset ? reset_steps - 1 : until_reset - 1;
+                if (do_reset) {
+                    __threadfence(); grid.sync();
+                    acc[0] = acc[1] = 0.f;
+                    for (int g = tid; g < N; g += nth) { const float rr = f[g] - o3_row(t, g, off, dg, x); r[g] = rr; p[g] = rr; acc[0] += rr * rr; }
+                    o3_grid_sum<2>(grid, acc, part, rcount, red);
+                    rho = acc[0];
+                }
+                acc[0] = acc[1] = 0.f;
+                for (int g = tid; g < N; g += nth) { const float a = o3_row(t, g, off, dg, p); ap[g] = a; acc[0] += p[g] * a; }
+                o3_grid_sum<2>(grid, acc, part, rcount, red);
+                const float alpha = rho / acc[0];
+                acc[0] = acc[1] = 0.f;
+                for (int g = tid; g < N; g += nth) {
+                    x[g] += alpha * p[g];
+                    const float rr = r[g] - alpha * ap[g];
+                    r[g] = rr; acc[0] += rr * rr;
+                }
+                o3_grid_sum<2>(grid, acc, part, rcount, red);
+                const float crit = sqrtf(acc[0]) * norm;
+                if (!isfinite(crit)) { used = i; fin = crit; break; }
+                if (i == 0 || crit < bestc) {
+                    bestc = crit; best_it = i;
+                    for (int g = tid; g < N; g += nth) best[g] = x[g];
+                }
+                if (i > 0 && crit >= lastc) ++rising; else rising = 0;
+                lastc = crit; used = i; fin = crit;
+                if (crit < tol) break;
+                if (i == maxit - 1 || rising >= 100) {
+                    for (int g = tid; g < N; g += nth) x[g] = best[g];
+                    used = best_it; fin = bestc;
+                    break;
+                }
+                const float rhop = rho; rho = acc[0];
+                const float beta = rho / rhop;
+                for (int g = tid; g < N; g += nth) p[g] = r[g] + beta * p[g];
+                __threadfence(); grid.sync();        // p complete before the next product gathers it
+            }
+        }
+        acc[0] = acc[1] = 0.f;
+        for (int g = tid; g < N; g += nth) acc[0] += x[g];
+        o3_grid_sum<2>(grid, acc, part, rcount, red);
+        const float mean = acc[0] / (float)N;
+        for (int g = tid; g < N; g += nth) xo[g] = x[g] - mean;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            iters[b * 8 + 3 + slot] = used; resid[b * 8 + 3 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1);
+        }
+        grid.sync();
+    }
+}
+
+static int o3_coop_blocks(fgb_ortho3 *b) {
+    if (b->grid_blocks > 0) return b->grid_blocks;
+    int dev = 0, sms = 0, per_a = 0, per_b = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_a, k3_cg, O3_T, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_b, k3_bicgstab, O3_T, 0);
+    int per = per_a < per_b ? per_a : per_b;
+    if (per > 4) per = 4;
+    int blocks = sms * (per > 0 ? per : 1);
+    const int need = (b->t.N + O3_T - 1) / O3_T;          // no point in more CTAs than cells / 256
+    if (blocks > need) blocks = need;
+    if (blocks > 4096) blocks = 4096;
+    if (blocks < 1) blocks = 1;
+    b->grid_blocks = blocks;
+    return blocks;
+}
+
+extern "C" int fgb_ortho3_setup_advection(fgb_ortho3 *b, const float *u, const float *bvel, const float *src, const float *dt,
+                                          const int32_t *active, fgb_stream_t s) {
+    if (!b || !u || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_ortho3_setup_advection: null argument");
+    b->launches++;
+    k3_setup_advection<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, u, bvel, src, dt, active, b->Coff, b->A, b->rhs);
+    LAUNCH_CHECK("k3_setup_advection");
+    return FGB_OK;
+}
+
+extern "C" int fgb_ortho3_solve_advection(fgb_ortho3 *b, int zero_init, const int32_t *active, fgb_stream_t s) {
+    if (!b) return set_err(FGB_E_ARG, "fgb_ortho3_solve_advection: null argument");
+    T3 t = b->t; int B = b->B; const float *coff = b->Coff, *a = b->A, *rhs = b->rhs; float *x = b->ures, *work = b->kry, *part = b->part;
+    int maxit = b->opt.max_iter; float tol = b->opt.adv_tol;
+    int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
+    void *args[] = {&t, &B, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot};
+    b->launches++;
+    cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab, dim3(o3_coop_blocks(b)), dim3(O3_T), args, 0, STREAM(s));
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab)", ce);
+    return FGB_OK;
+}
+
+extern "C" int fgb_ortho3_setup_pressure(fgb_ortho3 *b, const float *u, const float *bvel, const float *src, const float *dt,
+                                         int with_matrix, const int32_t *active, fgb_stream_t s) {
+    if (!b || !u || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_ortho3_setup_pressure: null argument");
+    cudaStream_t st = STREAM(s);
+    if (with_matrix) {
+        b->launches++;
+        k3_pressure_matrix<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->A, active, b->Poff, b->Pdiag);
+        LAUNCH_CHECK("k3_pressure_matrix");
+    }
+    b->launches += 2;
+    k3_hbya<<<o3_grid(b), O3_T, 0, st>>>(b->t, u, b->ures, bvel, src, dt, active, b->Coff, b->A, b->hbya);
+    LAUNCH_CHECK("k3_hbya");
+    k3_divergence<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->hbya, bvel, active, b->div);
+    LAUNCH_CHECK("k3_divergence");
+    return FGB_OK;
+}
+
+extern "C" int fgb_ortho3_solve_pressure(fgb_ortho3 *b, float *p_out, int zero_init, int reset_steps, int max_iter, int slot,
+                                         const int32_t *active, fgb_stream_t s) {
+    if (!b || !p_out) return set_err(FGB_E_ARG, "fgb_ortho3_solve_pressure: null argument");
+    if (slot < 0 || slot > 4) slot = 4;
+    T3 t = b->t; int B = b->B; const float *poff = b->Poff, *pd = b->Pdiag, *rhs = b->div; float *work = b->kry, *part = b->part;
+    float tol = b->opt.p_tol;
+    int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
+    void *args[] = {&t, &B, &poff, &pd, &rhs, &p_out, &work, &part, &max_iter, &tol, &zero_init, &reset_steps, &slot, &active, &iters, &resid, &itot};
+    b->launches++;
+    cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_cg, dim3(o3_coop_blocks(b)), dim3(O3_T), args, 0, STREAM(s));
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_cg)", ce);
+    return FGB_OK;
+}
+
+extern "C" int fgb_ortho3_correct_velocity(fgb_ortho3 *b, const float *p, float *u_out, const int32_t *active, fgb_stream_t s) {
+    if (!b || !p || !u_out) return set_err(FGB_E_ARG, "fgb_ortho3_correct_velocity: null argument");
+    b->launches++;
+    k3_correct<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, b->hbya, p, b->A, active, u_out);
+    LAUNCH_CHECK("k3_correct");
+    return FGB_OK;
+}
+
+// Simulation._PISO_split_step for D = 3 (SIM.py:1431-2002; orthogonal grid: one predictor and one pressure solve per corrector)
+extern "C" int fgb_ortho3_piso_substep(fgb_ortho3 *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
+                                       const int32_t *active, fgb_stream_t s) {
+    if (!b || !u || !p || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep: null argument");
+    int rc;
+    if ((rc = fgb_ortho3_setup_advection(b, u, bvel, src, dt, active, s))) return rc;
+    if ((rc = fgb_ortho3_solve_advection(b, 1, active, s))) return rc;
+    for (int cs = 0; cs < b->opt.corrector_steps; ++cs) {
+        if ((rc = fgb_ortho3_setup_pressure(b, u, bvel, src, dt, cs == 0, active, s))) return rc;
+        if ((rc = fgb_ortho3_solve_pressure(b, p, 1, b->opt.nonortho ? 100 : 0, b->opt.max_iter, cs, active, s))) return rc;
+        if ((rc = fgb_ortho3_correct_velocity(b, p, b->ures, active, s))) return rc;
+    }
+    b->launches++;
+    const size_t n = (size_t)3 * b->t.N;
+    k3_copy_active<<<dim3((unsigned)((n + 255) / 256), b->B), 256, 0, STREAM(s)>>>(b->ures, u, n, active);
+    LAUNCH_CHECK("k3_copy_active");
+    return FGB_OK;
+}
+
+// make_divergence_free (SIM.py:1320-1429): A = 1, one projection of the current velocity
+extern "C" int fgb_ortho3_make_divergence_free(fgb_ortho3 *b, float *u, float *p, const float *bvel, int max_iter, fgb_stream_t s) {
+    if (!b || !u || !p || !bvel) return set_err(FGB_E_ARG, "fgb_ortho3_make_divergence_free: null argument");
+    cudaStream_t st = STREAM(s);
+    const size_t BN = (size_t)b->B * b->t.N;
+    int rc;
+    b->launches += 3;
+    k_fill<<<(unsigned)((BN + 255) / 256), 256, 0, st>>>(b->A, 1.0f, BN);
+    LAUNCH_CHECK("k_fill");
+    cudaError_t ce = cudaMemcpyAsync(b->hbya, u, 3 * BN * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "memcpy hbya", ce);
+    k3_pressure_matrix<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->A, nullptr, b->Poff, b->Pdiag);
+    LAUNCH_CHECK("k3_pressure_matrix");
+    k3_divergence<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->hbya, bvel, nullptr, b->div);
+    LAUNCH_CHECK("k3_divergence");
+    if ((rc = fgb_ortho3_solve_pressure(b, p, 1, 0, max_iter, 0, nullptr, s))) return rc;
+    return fgb_ortho3_correct_velocity(b, p, u, nullptr, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stepping glue: CFL plan, channel forcing / wall shear (one CTA per environment)
+// ------------------------------------------------------------------------------------------------
+// Domain.getMaxVelocity(True, True): max |(M^-1 u)_d| over cells and prescribed faces, then the adaptive plan of
+// SIM.py:2004-2031 (same arithmetic as k_plan_substep)
+__global__ void __launch_bounds__(512) k3_plan_substep(T3 t, const float *__restrict__ U, const float *__restrict__ Bvel, double *__restrict__ remaining,
+                                                       float *__restrict__ dtv, int32_t *__restrict__ active, int32_t *__restrict__ nsub,
+                                                       float *__restrict__ maxvel, int32_t *__restrict__ counters, float cfl) {
+    __shared__ float smf[33];
+    const int b = blockIdx.x, N = t.N, NB = t.NB;
+    const float *u = U + (size_t)b * 3 * N, *bv = Bvel + (size_t)b * 3 * NB;
+    float m = 0.f;
+    for (int g = threadIdx.x; g < N; g += blockDim.x)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) m = fmaxf(m, fabsf(t.minv[d * N + g] * u[d * N + g]));
+    for (int j = threadIdx.x; j < NB; j += blockDim.x)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) m = fmaxf(m, fabsf(t.b_minv[d * NB + j] * bv[d * NB + j]));
+    const float mv = block_reduce_max(m, smf);
+    if (threadIdx.x == 0) {
+        double rem = remaining[b];
+        const int act = (rem > 0.0) && !(fabs(rem) <= 1e-8);
+        float dt = 0.f;
+        if (act) {
+            double ts;
+            if (fabsf(mv) <= 1e-8f) ts = rem;
+            else {
+                const float mts = cfl / mv;
+                if ((double)mts >= rem) ts = rem;
+                else { const int k = (int)ceilf((float)rem / mts); ts = rem / (double)k; }
+            }
+            rem -= ts;
+            dt = (float)ts;
+            remaining[b] = rem;
+            nsub[b] += 1;
+            atomicAdd(&counters[0], 1);
+        }
+        dtv[b] = dt; active[b] = act; maxvel[b] = mv;
+    }
+}
+
+// mean streamwise velocity of the first and last wall-normal cell layers -> wall shear stresses and the dynamic
+// forcing G_x = nu/2 (u_lo/d_lo + u_hi/d_hi) (envs/tcf/grid.py:128-163, tcf_env.py:564-584).  rows: [2][n_row] cell lists.
+__global__ void __launch_bounds__(512) k3_wall_rows(T3 t, const float *__restrict__ U, const int32_t *__restrict__ rows, int n_row, float d_lo, float d_hi,
+                                                    float *__restrict__ rowmean /* [B][4]: mean u lo, mean u hi, tau lo, tau hi */,
+                                                    float *__restrict__ src /* [B][4] or null */, float *__restrict__ acc /* [B][2] += tau, or null */) {
+    __shared__ double red[32 * 2 + 2];
+    const int b = blockIdx.x, N = t.N;
+    const float *u = U + (size_t)b * 3 * N;
+    float a[2] = {0.f, 0.f};
+    for (int i = threadIdx.x; i < n_row; i += blockDim.x) { a[0] += u[rows[i]]; a[1] += u[rows[n_row + i]]; }
+    block_reduce_sum<2>(a, red);
+    if (threadIdx.x == 0) {
+        const float mlo = a[0] / (float)n_row, mhi = a[1] / (float)n_row;
+        const float tlo = t.viscosity * mlo / d_lo, thi = t.viscosity * mhi / d_hi;
+        rowmean[b * 4 + 0] = mlo; rowmean[b * 4 + 1] = mhi; rowmean[b * 4 + 2] = tlo; rowmean[b * 4 + 3] = thi;
+        if (src) { src[b * 4 + 0] = (tlo + thi) * 0.5f; src[b * 4 + 1] = 0.f; src[b * 4 + 2] = 0.f; src[b * 4 + 3] = 0.f; }
+        if (acc) { acc[b * 2 + 0] += tlo; acc[b * 2 + 1] += thi; }
+    }
+}
+
+extern "C" int fgb_ortho3_wall_rows(fgb_ortho3 *b, const float *u, const int32_t *rows, int n_row, float d_lo, float d_hi, int set_forcing,
+                                    float *acc, fgb_stream_t s) {
+    if (!b || !u || !rows || n_row <= 0) return set_err(FGB_E_ARG, "fgb_ortho3_wall_rows: bad argument");
+    b->launches++;
+    k3_wall_rows<<<b->B, 512, 0, STREAM(s)>>>(b->t, u, rows, n_row, d_lo, d_hi, b->rowmean, set_forcing ? b->src : nullptr, acc);
+    LAUNCH_CHECK("k3_wall_rows");
+    return FGB_OK;
+}
+
+// Simulation.single_step with adaptive CFL sub-stepping; channel forcing (if rows != NULL) is refreshed before every
+// substep like the reference's "PRE" prep function.  Returns the number of substep rounds in *substeps_max.
+extern "C" int fgb_ortho3_sim_step(fgb_ortho3 *b, float *u, float *p, const float *bvel, float dt_target, float cfl, const int32_t *rows,
+                                   int n_row, float d_lo, float d_hi, int32_t *substeps_max, fgb_stream_t s) {
+    if (!b || !u || !p || !bvel) return set_err(FGB_E_ARG, "fgb_ortho3_sim_step: null argument");
+    cudaStream_t st = STREAM(s);
+    b->launches++;
+    k_set_remaining<<<(b->B + 255) / 256, 256, 0, st>>>(b->remaining, b->nsub, b->counters, (double)dt_target, b->B);
+    LAUNCH_CHECK("k_set_remaining");
+    int rounds = 0, rc;
+    for (;; ++rounds) {
+        if (rounds > 1000) return set_err(FGB_E_ARG, "fgb_ortho3_sim_step: more than 1000 adaptive substeps");
+        b->launches += 2;
+        k_zero_counter<<<1, 1, 0, st>>>(b->counters);
+        k3_plan_substep<<<b->B, 512, 0, st>>>(b->t, u, bvel, b->remaining, b->dt, b->active, b->nsub, b->maxvel, b->counters, cfl);
+        LAUNCH_CHECK("k3_plan_substep");
+        cudaError_t ce = cudaMemcpyAsync(b->h_counters, b->counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "memcpy counters", ce);
+        ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "fgb_ortho3_sim_step: sync", ce);
+        if (b->h_counters[0] == 0) break;
+        if (rows && (rc = fgb_ortho3_wall_rows(b, u, rows, n_row, d_lo, d_hi, 1, nullptr, s))) return rc;
+        if ((rc = fgb_ortho3_piso_substep(b, u, p, bvel, rows ? b->src : nullptr, b->dt, b->active, s))) return rc;
+    }
+    if (substeps_max) *substeps_max = rounds;
+    return FGB_OK;
+}

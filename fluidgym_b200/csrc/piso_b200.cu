@@ -2673,3 +2673,6 @@ extern "C" int fgb_sample_sensors(fgb_batch *b, const float *field, int32_t chan
     LAUNCH_CHECK("k_sample_sensors");
     return FGB_OK;
 }
+
+// D = 3 orthogonal-grid path (turbulent channel flow)
+#include "ortho3_b200.cuh"

@@ -182,3 +182,35 @@ def uniform_box_grid(res_x: int, res_y: int, lower, upper) -> np.ndarray:
     g[0] = xs[None, :]
     g[1] = ys[:, None]
     return g.astype(np.float32)
+
+
+def channel_y_weights(N: int = 1, ny_half: int = 48) -> list:
+    """Wall-normal vertex weights of the channel grid: geometric growth 1.2^(N/2) from both walls
+    (envs/tcf/grid.py:15-31)."""
+    ny = 2 * (ny_half // N)
+    r = 1.2 ** (N / 2)
+    h0 = 0.5 * (1 - r) / (1 - r ** (ny / 2))
+    h = 0
+    y = [0.0] * ny
+    for i in range((ny - 2) // 2):
+        h += h0 * (r ** i)
+        y[i] = h
+        y[ny - i - 2] = 1 - h
+    y[ny // 2 - 1] = 0.5
+    y[ny - 1] = 1.0
+    return [0] + y
+
+
+def channel_vertex_grid(H: float, L: float, D: float, x: int, y_half: int, yN: int, z: int) -> np.ndarray:
+    """[3, z+1, y+1, x+1] float32 vertices of the channel block: uniform in x and z, refined towards both walls in y
+    (envs/tcf/grid.py:34-72 + shapes.extrude_grid_z, shapes.py:641-680)."""
+    delta = H / 2
+    yw = channel_y_weights(N=yN, ny_half=y_half * yN)
+    ny = len(yw) - 1
+    g2 = transfinite_grid([ny + 1, x + 1], [(-L / 2, -delta), (L / 2, -delta), (-L / 2, delta), (L / 2, delta)], None, x_weights=yw)
+    zs = np.asarray([(-D / 2) * (1 - w) + (D / 2) * w for w in (k / z for k in range(z + 1))], dtype=np.float32)
+    out = np.zeros((3, z + 1, ny + 1, x + 1), dtype=np.float32)
+    out[0] = g2[0][None]
+    out[1] = g2[1][None]
+    out[2] = zs[:, None, None]
+    return out

@@ -41,6 +41,11 @@ class Options(C.Structure):
                 ("cg_impl", C.c_int32)]
 
 
+class Ortho3Tables(C.Structure):
+    _fields_ = [("N", C.c_int32), ("NB", C.c_int32), ("viscosity", C.c_float), ("nbr", C.c_void_p), ("minv", C.c_void_p),
+                ("det", C.c_void_p), ("b_minv", C.c_void_p), ("b_det", C.c_void_p)]
+
+
 class Wall(C.Structure):
     _fields_ = [("n_wall", C.c_int32), ("cell", C.c_void_p), ("bface", C.c_void_p), ("normal", C.c_void_p),
                 ("dist", C.c_void_p), ("tlen", C.c_void_p), ("flen", C.c_void_p), ("scale", C.c_float)]
@@ -53,7 +58,11 @@ EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_cr
            "fgb_max_velocity", "fgb_apply_jet_action", "fgb_wall_forces", "fgb_column_sums", "fgb_sample_sensors",
            "fgb_profile_enable",
            "fgb_profile_read", "fgb_launch_count", "fgb_piso_substep_record", "fgb_adjoint_workspace_bytes",
-           "fgb_piso_substep_backward"]
+           "fgb_piso_substep_backward",
+           "fgb_ortho3_workspace_bytes", "fgb_ortho3_create", "fgb_ortho3_destroy", "fgb_ortho3_set_options", "fgb_ortho3_buffer",
+           "fgb_ortho3_launch_count", "fgb_ortho3_setup_advection", "fgb_ortho3_solve_advection", "fgb_ortho3_setup_pressure",
+           "fgb_ortho3_solve_pressure", "fgb_ortho3_correct_velocity", "fgb_ortho3_piso_substep", "fgb_ortho3_make_divergence_free",
+           "fgb_ortho3_sim_step", "fgb_ortho3_wall_rows"]
 
 
 def lib_path() -> str:
@@ -104,6 +113,25 @@ def load():
     L.fgb_adjoint_workspace_bytes.restype = C.c_size_t
     L.fgb_adjoint_workspace_bytes.argtypes = [C.POINTER(Tables), i32]
     L.fgb_piso_substep_backward.argtypes = [vp, C.POINTER(Tape), vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.fgb_ortho3_workspace_bytes.restype = C.c_size_t
+    L.fgb_ortho3_workspace_bytes.argtypes = [C.POINTER(Ortho3Tables), i32]
+    L.fgb_ortho3_create.argtypes = [C.POINTER(Ortho3Tables), i32, vp, C.c_size_t, C.POINTER(Options), C.POINTER(vp)]
+    L.fgb_ortho3_destroy.argtypes = [vp]
+    L.fgb_ortho3_destroy.restype = None
+    L.fgb_ortho3_set_options.argtypes = [vp, C.POINTER(Options)]
+    L.fgb_ortho3_buffer.restype = vp
+    L.fgb_ortho3_buffer.argtypes = [vp, C.c_char_p]
+    L.fgb_ortho3_launch_count.argtypes = [vp]
+    L.fgb_ortho3_launch_count.restype = C.c_longlong
+    L.fgb_ortho3_setup_advection.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.fgb_ortho3_solve_advection.argtypes = [vp, i32, vp, vp]
+    L.fgb_ortho3_setup_pressure.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
+    L.fgb_ortho3_solve_pressure.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    L.fgb_ortho3_correct_velocity.argtypes = [vp, vp, vp, vp, vp]
+    L.fgb_ortho3_piso_substep.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.fgb_ortho3_make_divergence_free.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.fgb_ortho3_sim_step.argtypes = [vp, vp, vp, vp, f32, f32, vp, i32, f32, f32, C.POINTER(i32), vp]
+    L.fgb_ortho3_wall_rows.argtypes = [vp, vp, vp, i32, f32, f32, i32, vp, vp]
     _lib = L
     return L
 

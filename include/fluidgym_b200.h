@@ -234,6 +234,54 @@ int fgb_piso_substep_backward(fgb_batch *b, const fgb_tape *tape, const float *u
                               float *u_bar, float *p_prev_bar, float *bvel_bar, void *workspace, size_t workspace_bytes,
                               fgb_stream_t s);
 
+/* ---- D = 3, orthogonal grids (turbulent channel flow; the same K.cu kernels with DIMS = 3) ------------------ */
+/* Geometry tables of a 3-D domain whose metric tensors are diagonal (rectilinear blocks).  Fields are
+ * component-major [B][3][N]; faces 0..5 = -x,+x,-y,+y,-z,+z; prescribed (Dirichlet) faces are numbered 0..NB-1
+ * and carry boundary velocities bvel [B][3][NB].  On such grids every non-orthogonal coefficient is exactly zero, so
+ * one predictor solve and one pressure solve per corrector reproduce the reference's non-orthogonal code path. */
+typedef struct fgb_ortho3_tables {
+    int32_t N, NB;
+    float viscosity;
+    const int32_t *nbr;   /* [6][N]  neighbour cell across face f, or -1-j for prescribed face j                 */
+    const float *minv;    /* [3][N]  diagonal of M^-1                                                            */
+    const float *det;     /* [N]                                                                                 */
+    const float *b_minv;  /* [3][NB] diagonal of the boundary-face M^-1 (FixedBoundary.transform)                */
+    const float *b_det;   /* [NB]                                                                                */
+} fgb_ortho3_tables;
+typedef struct fgb_ortho3 fgb_ortho3;
+size_t fgb_ortho3_workspace_bytes(const fgb_ortho3_tables *t, int32_t B);
+int fgb_ortho3_create(const fgb_ortho3_tables *t, int32_t B, void *workspace, size_t workspace_bytes, const fgb_options *opt,
+                      fgb_ortho3 **out);
+void fgb_ortho3_destroy(fgb_ortho3 *b);
+int fgb_ortho3_set_options(fgb_ortho3 *b, const fgb_options *opt);
+/* named workspace buffers: "Coff" [B][6][N], "A", "rhs" [B][3][N], "ures", "Poff", "Pdiag", "hbya", "div", "iters" [B][8]
+ * (0..2 BiCGStab per component, 3.. CG per corrector), "resid", "dt", "active", "nsub", "maxvel", "src" [B][4], "rowmean" [B][4] */
+void *fgb_ortho3_buffer(fgb_ortho3 *b, const char *name);
+long long fgb_ortho3_launch_count(fgb_ortho3 *b);
+/* per-op entry points (SetupAdvectionMatrix + SetupAdvectionVelocity | SolveLinear(BiCGStab) | SetupPressureMatrix +
+ * SetupPressureRHS + SetupPressureRHSdiv | SolveLinear(CG) + mean removal | CorrectVelocity), cf. the 2-D table above.
+ * src: optional per-environment static velocity source [B][4] (Block.setVelocitySource, 3 used). */
+int fgb_ortho3_setup_advection(fgb_ortho3 *b, const float *u, const float *bvel, const float *src, const float *dt,
+                               const int32_t *active, fgb_stream_t s);
+int fgb_ortho3_solve_advection(fgb_ortho3 *b, int zero_init, const int32_t *active, fgb_stream_t s);
+int fgb_ortho3_setup_pressure(fgb_ortho3 *b, const float *u, const float *bvel, const float *src, const float *dt, int with_matrix,
+                              const int32_t *active, fgb_stream_t s);
+int fgb_ortho3_solve_pressure(fgb_ortho3 *b, float *p_out, int zero_init, int reset_steps, int max_iter, int slot,
+                              const int32_t *active, fgb_stream_t s);
+int fgb_ortho3_correct_velocity(fgb_ortho3 *b, const float *p, float *u_out, const int32_t *active, fgb_stream_t s);
+/* fused: Simulation._PISO_split_step / make_divergence_free / single_step (adaptive CFL) for D = 3 */
+int fgb_ortho3_piso_substep(fgb_ortho3 *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
+                            const int32_t *active, fgb_stream_t s);
+int fgb_ortho3_make_divergence_free(fgb_ortho3 *b, float *u, float *p, const float *bvel, int max_iter, fgb_stream_t s);
+/* rows: [2][n_row] cells of the first / last wall-normal layer; d_lo, d_hi their wall distances.  With rows != NULL the
+ * channel forcing G_x = nu/2 (<u>_lo/d_lo + <u>_hi/d_hi) (envs/tcf/grid.py:128-163) is refreshed before every substep. */
+int fgb_ortho3_sim_step(fgb_ortho3 *b, float *u, float *p, const float *bvel, float dt_target, float cfl, const int32_t *rows,
+                        int n_row, float d_lo, float d_hi, int32_t *substeps_max, fgb_stream_t s);
+/* wall shear stresses tau = nu <u>_row / d (tcf_env.py:564-584) into "rowmean"; set_forcing: also write "src";
+ * acc [B][2] (optional): += (tau_lo, tau_hi) */
+int fgb_ortho3_wall_rows(fgb_ortho3 *b, const float *u, const int32_t *rows, int n_row, float d_lo, float d_hi, int set_forcing,
+                         float *acc, fgb_stream_t s);
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------ */
 /* Record CUDA events around the solver launches on their own stream.  fgb_profile_read synchronises the
  * device and returns accumulated milliseconds / launch counts per class {0: pressure CG, 1: BiCGStab,

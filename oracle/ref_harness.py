@@ -100,7 +100,11 @@ class OpTracer:
         for name, fn in self._orig.items():
             setattr(self.P, name, fn)
 
+    lean = False
+
     def _rec(self, key, t):
+        if self.lean and key.split("_")[0] in ("C", "P", "Cs"):
+            return
         self.records[f"s{self.substep}_{key}"] = t2n(t)
 
     def _make(self, name):
@@ -194,6 +198,9 @@ def main():
     ap.add_argument("--env-steps", type=int, default=4)
     ap.add_argument("--time-steps", type=int, default=8)
     ap.add_argument("--action", type=float, default=0.5)
+    ap.add_argument("--kw", default="{}", help="JSON dict of extra fluidgym.make keyword arguments")
+    ap.add_argument("--perturb", type=float, default=0.0, help="std of Gaussian noise added to the block velocities after reset")
+    ap.add_argument("--lean", action="store_true", help="do not record the CSR matrices (large 3-D grids)")
     args = ap.parse_args()
     tag = args.tag or args.env.replace("-", "_")
     os.makedirs(args.out, exist_ok=True)
@@ -207,11 +214,18 @@ def main():
     meta = {"env": args.env, "seed": args.seed, "torch": torch.__version__, "gpu": torch.cuda.get_device_name(0)}
 
     env = fluidgym.make(args.env, load_initial_domain=False, load_domain_statistics=False,
-                        randomize_initial_state=False)
+                        randomize_initial_state=False, **json.loads(args.kw))
     t0 = time.time()
     obs0, _ = env.reset(seed=args.seed)
     torch.cuda.synchronize()
     meta["reset_seconds"] = time.time() - t0
+    if args.perturb > 0:
+        g = torch.Generator(device="cuda").manual_seed(args.seed)
+        for blk in env._domain.getBlocks():
+            u = blk.velocity
+            blk.setVelocity((u + args.perturb * torch.randn(u.shape, device=u.device, generator=g)).contiguous())
+        env._domain.UpdateDomainData()
+        meta["perturb"] = args.perturb
     dump_geometry(env, args.out, tag)
     st = snapshot_state(env)
     st.update({f"obs_{k}": t2n(v) for k, v in obs0.items()})
@@ -227,6 +241,7 @@ def main():
             meta[k2.strip("_")] = float(getattr(env, k2).cpu().item())
 
     tracer = OpTracer(PISOtorch, args.trace_substeps)
+    tracer.lean = args.lean
     tracer.install()
 
     # record the block state after every sim step of the first env.step

@@ -1,0 +1,87 @@
+"""D = 3 (turbulent channel flow): grid generator, box-domain tables and the float32 numpy specification of the 3-D
+orthogonal PISO operators (tests/box3d_eval.py) against a trace of the unmodified reference on a 32 x 32 x 32 channel
+(tests/golden/tcf32_*.npz: TCFSmall3D-both-easy-v0 with resolution 32/33, Reichardt profile + 5 % noise)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import box3d_eval as be
+from conftest import GOLDEN, rel_l2
+
+
+@pytest.fixture(scope="module")
+def tcf(golden):
+    g, fx = golden("tcf32_geometry.npz"), golden("tcf32_substep0.npz")
+    meta = json.load(open(os.path.join(GOLDEN, "tcf32_meta.json")))
+
+    def full(t7):                      # [.., 7] = (M00, M11, M22, Mi00, Mi11, Mi22, det) -> [.., 19]
+        T = np.zeros(t7.shape[:-1] + (19,), np.float32)
+        for k, c in enumerate((0, 4, 8, 9, 13, 17, 18)):
+            T[..., c] = t7[..., k]
+        return T
+    T = full(g["Tdiag"])
+    bT = {2: full(g["bT2"]).reshape(32, 1, 32, 19), 3: full(g["bT3"]).reshape(32, 1, 32, 19)}
+    box = be.Box3D(g["vertex"], closed=(False, True, False), viscosity=meta["viscosity"], T=T, bT=bT)
+    bvel = {2: fx["bvel2"].reshape(3, 32, 1, 32), 3: fx["bvel3"].reshape(3, 32, 1, 32)}
+    return box, fx, bvel, T, bT, meta
+
+
+def test_channel_grid_is_bit_identical(golden):
+    from fluidgym_b200.grids import channel_vertex_grid
+    v = channel_vertex_grid(2.0, np.pi, np.pi / 2, 32, 16, 2, 32)
+    assert np.array_equal(v, golden("tcf32_geometry.npz")["vertex"])
+
+
+def test_box_domain_metrics_and_tables(golden):
+    from fluidgym_b200.box3d import Box3DDomain
+    g = golden("tcf32_geometry.npz")
+    dom = Box3DDomain(g["vertex"], closed=(False, True, False), viscosity=1e-3)
+    T = g["Tdiag"]
+    for d in range(3):
+        assert np.array_equal(dom.h[d], T[..., d])
+        assert (np.abs(dom.minv[d] - T[..., 3 + d]) / T[..., 3 + d]).max() < 1e-6      # fast-math reciprocal in the reference
+    assert (np.abs(dom.det - T[..., 6]) / T[..., 6]).max() < 1e-6
+    # boundary faces: one-sided differences, different summation order -> cancellation error of the first cell height
+    assert (np.abs(dom.b_det[:1024] - g["bT2"][:, 6]) / g["bT2"][:, 6]).max() < 1e-5
+    assert dom.N == 32768 and dom.NB == 2048
+    cells = np.arange(dom.N).reshape(dom.shape)
+    assert np.array_equal(dom.nbr[1].reshape(dom.shape), np.roll(cells, -1, axis=2))          # +x periodic
+    assert np.array_equal(dom.nbr[2].reshape(dom.shape)[:, 0, :], -1 - np.arange(1024).reshape(32, 32))   # -y wall faces
+
+
+def test_specification_matches_reference_operators(tcf):
+    box, fx, bvel, *_ = tcf
+    dt, u = float(fx["dt"][0]), fx["u_in"]
+    off, A, fl = be.assemble(box, u, bvel, dt)
+    assert rel_l2(A, fx["A"]) < 5e-7
+    rhs, Sb = be.adv_rhs(box, u, bvel, dt, fx["src"])
+    assert rel_l2(rhs, fx["rhs"]) < 5e-7
+    ustar = fx["ustar"].reshape(3, *box.shape)
+    assert np.linalg.norm(be.spmv(box, off, A, ustar) - rhs) / np.sqrt(3 * box.N) < 5e-5   # reference solution solves our system
+    hb = be.hbya(box, u, ustar, off, A, Sb, dt, fx["src"])
+    assert rel_l2(hb, fx["hbya0"]) < 5e-7
+    div = be.divergence(box, hb, bvel)
+    assert rel_l2(div, fx["div0"]) < 5e-6                                                   # cancellation in the flux differences
+    Po, Pd = be.build_P(box, A)
+    r = be.spmv(box, Po, Pd, fx["p0"].reshape(1, *box.shape))[0] - fx["div0"].reshape(box.shape)
+    assert np.linalg.norm(r) / np.sqrt(box.N) < 2e-6                                        # reference pressure solves our system to its tol (1e-6)
+    u0 = be.correct(box, hb, fx["p0"].reshape(1, *box.shape), A)
+    assert rel_l2(u0, fx["u0"]) < 5e-7
+
+
+def test_agent_window_means_matches_loop_definition():
+    """extract_moving_window_2d_x_z (obs_extraction.py:255-343) restated without unfold: agent (ix, iz) sees the patch means
+    of agents (ix - pad_x + k, iz - pad_z + j), circular, ordered x-major."""
+    import torch
+    from fluidgym_b200.envs.tcf import agent_window_means
+    nax, naz, aw, wx, wz, px, pz = 4, 3, 2, 3, 2, 1, 1
+    f = torch.arange(naz * aw * nax * aw, dtype=torch.float32).reshape(naz * aw, nax * aw) ** 1.5
+    got = agent_window_means(f[None], nax, naz, aw, wx, wz, px, pz)[0]
+    means = f.reshape(naz, aw, nax, aw).mean(dim=(1, 3))
+    for ix in range(nax):
+        for iz in range(naz):
+            for j in range(wz):
+                for k in range(wx):
+                    assert got[ix * naz + iz, j, k] == means[(iz - pz + j) % naz, (ix - px + k) % nax]

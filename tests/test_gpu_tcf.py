@@ -1,0 +1,97 @@
+"""D = 3 orthogonal path on the GPU (fgb_ortho3_*) against the reference trace of a 32^3 channel and env-level checks."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_l2
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup(golden):
+    from fluidgym_b200.box3d import BatchedPISO3D, Box3DDomain
+    g, fx = golden("tcf32_geometry.npz"), golden("tcf32_substep0.npz")
+    meta = json.load(open(os.path.join(GOLDEN, "tcf32_meta.json")))
+
+    def full(t7):
+        T = np.zeros(t7.shape[:-1] + (19,), np.float32)
+        for k, c in enumerate((0, 4, 8, 9, 13, 17, 18)):
+            T[..., c] = t7[..., k]
+        return T
+    dom = Box3DDomain(g["vertex"], closed=(False, True, False), viscosity=meta["viscosity"], transforms=full(g["Tdiag"]),
+                      btransforms={2: full(g["bT2"]), 3: full(g["bT3"])})
+    sol = BatchedPISO3D(dom, 2)
+    return dom, sol, fx, meta
+
+
+def _load(sol, fx):
+    sol.u.copy_(torch.from_numpy(fx["u_in"]).cuda().unsqueeze(0).expand_as(sol.u))
+    sol.p.copy_(torch.from_numpy(fx["p_in"]).cuda().unsqueeze(0).expand_as(sol.p))
+    bv = np.concatenate([fx["bvel2"], fx["bvel3"]], axis=1)
+    sol.bvel.copy_(torch.from_numpy(bv).cuda().unsqueeze(0).expand_as(sol.bvel))
+    src = torch.zeros(sol.B, 4, device="cuda")
+    src[:, :3] = torch.from_numpy(fx["src"]).cuda()
+    return src
+
+
+def test_ops_match_reference_trace(setup):
+    dom, sol, fx, meta = setup
+    src = _load(sol, fx)
+    dt = float(fx["dt"][0])
+    sol.setup_advection(dt, src)
+    assert rel_l2(sol.buffer("A")[1].cpu().numpy(), fx["A"]) < 5e-7
+    assert rel_l2(sol.buffer("rhs")[1].cpu().numpy(), fx["rhs"]) < 5e-7
+    sol.solve_advection()
+    it = sol.buffer("iters")[0].cpu().numpy()
+    assert list(it[:3]) == list(fx["bicg_iters"])
+    assert rel_l2(sol.buffer("ures")[1].cpu().numpy(), fx["ustar"]) < 2e-6
+    sol.setup_pressure(dt, src, with_matrix=True)
+    assert rel_l2(sol.buffer("hbya")[0].cpu().numpy(), fx["hbya0"]) < 2e-6
+    assert rel_l2(sol.buffer("div")[0].cpu().numpy(), fx["div0"]) < 2e-4        # divergence of a nearly solenoidal field: cancellation
+    sol.solve_pressure(zero_init=True, slot=0)
+    it = sol.buffer("iters")[0].cpu().numpy()
+    assert abs(int(it[3]) - int(fx["cg_iters"][0])) <= 3
+    assert rel_l2(sol.p[0].cpu().numpy(), fx["p0"]) < 2e-3
+    sol.correct_velocity()
+    assert rel_l2(sol.buffer("ures")[0].cpu().numpy(), fx["u0"]) < 1e-5
+
+
+def test_substep_matches_reference(setup):
+    dom, sol, fx, meta = setup
+    src = _load(sol, fx)
+    sol.piso_substep(float(fx["dt"][0]), src)
+    torch.cuda.synchronize()
+    eu, ep = rel_l2(sol.u[0].cpu().numpy(), fx["u1"]), rel_l2(sol.p[0].cpu().numpy(), fx["p1"])
+    print("tcf32 substep: u", eu, "p", ep, "iters", sol.buffer("iters")[0].tolist(), "ref", fx["bicg_iters"], fx["cg_iters"])
+    assert eu < 1e-5 and ep < 2e-3
+    assert torch.equal(sol.u[0], sol.u[1])
+
+
+def test_env_step_matches_reference(golden):
+    """TCF 'both walls' MARL environment at the fixture resolution: one env.step (10 solver steps, dynamic forcing, wall
+    actuation on 2 x 16 x 16 patches) from the reference's perturbed reset state."""
+    import fluidgym_b200 as fg
+    st = golden("tcf32_steps.npz")
+    env = fg.make("TCFSmall3D-both-easy-v0", n_envs=2, resolution_x_z=32, resolution_y=33)
+    obs, _ = env.reset(seed=42)
+    assert obs["velocity"].shape == (2, 512, 1, 1, 2) and obs["pressure"].shape == (2, 512, 1, 1)
+    bvel = np.concatenate([st["reset_bvel2"], st["reset_bvel3"]], axis=1)
+    env.set_state(st["reset_u"], st["reset_p"], bvel)
+    action = torch.from_numpy(st["actions"][0]).cuda().reshape(1, 512, 1).repeat(2, 1, 1)
+    obs, reward, term, trunc, info = env.step(action)
+    torch.cuda.synchronize()
+    s = env.solver
+    print("tcf32 env.step: substeps", env.last_substeps, "u err", rel_l2(s.u[0].cpu().numpy(), st["env0_u"]),
+          "tau", float(info["wall_stress"][0]), float(st["step0_info_wall_stress"]), "bottom", float(info["wall_stress_bottom"][0]),
+          float(st["step0_info_wall_stress_bottom"]))
+    assert rel_l2(s.u[0].cpu().numpy(), st["env0_u"]) < 1e-3
+    for k in ("wall_stress", "wall_stress_bottom", "wall_stress_top"):
+        assert abs(float(info[k][0]) - float(st[f"step0_info_{k}"])) < 1e-3 * abs(float(st[f"step0_info_{k}"]))
+    assert reward.shape == (2, 512)
+    assert np.abs(reward[0].cpu().numpy() - st["step0_reward"]).max() < 1e-3 * np.abs(st["step0_reward"]).max() + 1e-6
+    assert np.abs(obs["velocity"][0].cpu().numpy() - st["step0_obs_velocity"]).max() < 2e-3 * np.abs(st["step0_obs_velocity"]).max()
+    assert np.abs(obs["pressure"][0].cpu().numpy() - st["step0_obs_pressure"]).max() < 5e-2 * np.abs(st["step0_obs_pressure"]).max()
