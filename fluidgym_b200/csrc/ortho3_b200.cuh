@@ -23,7 +23,9 @@ struct fgb_ortho3 {
     long long launches;
 };
 
-static constexpr int O3_T = 256;          // threads per CTA of every ortho3 kernel
+static constexpr int O3_T = 256;          // threads per CTA of the one-thread-per-cell kernels
+static constexpr int O3_CT = 1024;        // threads per CTA of the cooperative Krylov kernels (one CTA per SM: a grid.sync over
+                                          // 148 CTAs costs ~2 us, over 592 CTAs ~5 us, and there are 3-7 of them per iteration)
 static constexpr int O3_KRY = 15;         // Krylov work vectors per environment (BiCGStab: 5 per component)
 static constexpr int O3_PART = 8;         // floats per CTA per reduction slot
 
@@ -270,7 +272,7 @@ __device__ __forceinline__ void o3_grid_sum(cg::grid_group &grid, float (&v)[K],
 }
 
 // BiCGStab for the three velocity components in lock step (BICG.cu:237-376; same operation order as k_bicgstab)
-__global__ void __launch_bounds__(O3_T) k3_bicgstab(T3 t, int B, const float *__restrict__ Coff, const float *__restrict__ Adiag,
+__global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, int B, const float *__restrict__ Coff, const float *__restrict__ Adiag,
                                                     const float *__restrict__ Rhs, float *X, float *work, float *part, int maxit, float tol,
                                                     int zero_init, const int32_t *__restrict__ active, int32_t *__restrict__ iters,
                                                     float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(O3_T) k3_bicgstab(T3 t, int B, const float *__
 }
 
 // CG with residual reset, best-iterate tracking, 100-rising-steps cut-off and mean removal (CG.cu:225-446, SIM.py:1908-1925)
-__global__ void __launch_bounds__(O3_T) k3_cg(T3 t, int B, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
+__global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, int B, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
                                               const float *__restrict__ Rhs, float *Xout, float *work, float *part, int maxit, float tol,
                                               int zero_init, int reset_steps, int slot, const int32_t *__restrict__ active,
                                               int32_t *__restrict__ iters, float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
@@ -458,12 +460,10 @@ static int o3_coop_blocks(fgb_ortho3 *b) {
     int dev = 0, sms = 0, per_a = 0, per_b = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_a, k3_cg, O3_T, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_b, k3_bicgstab, O3_T, 0);
-    int per = per_a < per_b ? per_a : per_b;
-    if (per > 4) per = 4;
-    int blocks = sms * (per > 0 ? per : 1);
-    const int need = (b->t.N + O3_T - 1) / O3_T;          // no point in more CTAs than cells / 256
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_a, k3_cg, O3_CT, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_b, k3_bicgstab, O3_CT, 0);
+    int blocks = (per_a > 0 && per_b > 0) ? sms : 1;     // one CTA per SM (co-residency is what a cooperative launch needs)
+    const int need = (b->t.N + O3_CT - 1) / O3_CT;
     if (blocks > need) blocks = need;
     if (blocks > 4096) blocks = 4096;
     if (blocks < 1) blocks = 1;
@@ -487,7 +487,7 @@ extern "C" int fgb_ortho3_solve_advection(fgb_ortho3 *b, int zero_init, const in
     int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
     void *args[] = {&t, &B, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot};
     b->launches++;
-    cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab, dim3(o3_coop_blocks(b)), dim3(O3_T), args, 0, STREAM(s));
+    cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab)", ce);
     return FGB_OK;
 }
@@ -518,7 +518,7 @@ extern "C" int fgb_ortho3_solve_pressure(fgb_ortho3 *b, float *p_out, int zero_i
     int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
     void *args[] = {&t, &B, &poff, &pd, &rhs, &p_out, &work, &part, &max_iter, &tol, &zero_init, &reset_steps, &slot, &active, &iters, &resid, &itot};
     b->launches++;
-    cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_cg, dim3(o3_coop_blocks(b)), dim3(O3_T), args, 0, STREAM(s));
+    cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_cg, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_cg)", ce);
     return FGB_OK;
 }
@@ -572,42 +572,46 @@ extern "C" int fgb_ortho3_make_divergence_free(fgb_ortho3 *b, float *u, float *p
 // ------------------------------------------------------------------------------------------------
 // stepping glue: CFL plan, channel forcing / wall shear (one CTA per environment)
 // ------------------------------------------------------------------------------------------------
-// Domain.getMaxVelocity(True, True): max |(M^-1 u)_d| over cells and prescribed faces, then the adaptive plan of
-// SIM.py:2004-2031 (same arithmetic as k_plan_substep)
-__global__ void __launch_bounds__(512) k3_plan_substep(T3 t, const float *__restrict__ U, const float *__restrict__ Bvel, double *__restrict__ remaining,
-                                                       float *__restrict__ dtv, int32_t *__restrict__ active, int32_t *__restrict__ nsub,
-                                                       float *__restrict__ maxvel, int32_t *__restrict__ counters, float cfl) {
+// Domain.getMaxVelocity(True, True): max |(M^-1 u)_d| over cells and prescribed faces (many CTAs per environment,
+// combined with an integer atomicMax on the bit pattern of the non-negative float), then the adaptive plan of
+// SIM.py:2004-2031 (same arithmetic as k_plan_substep) by one thread per environment.
+__global__ void __launch_bounds__(256) k3_max_velocity(T3 t, const float *__restrict__ U, const float *__restrict__ Bvel, float *__restrict__ maxvel) {
     __shared__ float smf[33];
-    const int b = blockIdx.x, N = t.N, NB = t.NB;
+    const int b = blockIdx.y, N = t.N, NB = t.NB;
     const float *u = U + (size_t)b * 3 * N, *bv = Bvel + (size_t)b * 3 * NB;
     float m = 0.f;
-    for (int g = threadIdx.x; g < N; g += blockDim.x)
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x)
 #pragma unroll
         for (int d = 0; d < 3; ++d) m = fmaxf(m, fabsf(t.minv[d * N + g] * u[d * N + g]));
-    for (int j = threadIdx.x; j < NB; j += blockDim.x)
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < NB; j += gridDim.x * blockDim.x)
 #pragma unroll
         for (int d = 0; d < 3; ++d) m = fmaxf(m, fabsf(t.b_minv[d * NB + j] * bv[d * NB + j]));
     const float mv = block_reduce_max(m, smf);
-    if (threadIdx.x == 0) {
-        double rem = remaining[b];
-        const int act = (rem > 0.0) && !(fabs(rem) <= 1e-8);
-        float dt = 0.f;
-        if (act) {
-            double ts;
-            if (fabsf(mv) <= 1e-8f) ts = rem;
-            else {
-                const float mts = cfl / mv;
-                if ((double)mts >= rem) ts = rem;
-                else { const int k = (int)ceilf((float)rem / mts); ts = rem / (double)k; }
-            }
-            rem -= ts;
-            dt = (float)ts;
-            remaining[b] = rem;
-            nsub[b] += 1;
-            atomicAdd(&counters[0], 1);
+    if (threadIdx.x == 0) atomicMax((int *)&maxvel[b], __float_as_int(mv));
+}
+__global__ void k3_plan_substep(int B, double *__restrict__ remaining, float *__restrict__ dtv, int32_t *__restrict__ active,
+                                int32_t *__restrict__ nsub, const float *__restrict__ maxvel, int32_t *__restrict__ counters, float cfl) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float mv = maxvel[b];
+    double rem = remaining[b];
+    const int act = (rem > 0.0) && !(fabs(rem) <= 1e-8);
+    float dt = 0.f;
+    if (act) {
+        double ts;
+        if (fabsf(mv) <= 1e-8f) ts = rem;
+        else {
+            const float mts = cfl / mv;
+            if ((double)mts >= rem) ts = rem;
+            else { const int k = (int)ceilf((float)rem / mts); ts = rem / (double)k; }
         }
-        dtv[b] = dt; active[b] = act; maxvel[b] = mv;
+        rem -= ts;
+        dt = (float)ts;
+        remaining[b] = rem;
+        nsub[b] += 1;
+        atomicAdd(&counters[0], 1);
     }
+    dtv[b] = dt; active[b] = act;
 }
 
 // mean streamwise velocity of the first and last wall-normal cell layers -> wall shear stresses and the dynamic
@@ -651,9 +655,14 @@ extern "C" int fgb_ortho3_sim_step(fgb_ortho3 *b, float *u, float *p, const floa
     int rounds = 0, rc;
     for (;; ++rounds) {
         if (rounds > 1000) return set_err(FGB_E_ARG, "fgb_ortho3_sim_step: more than 1000 adaptive substeps");
-        b->launches += 2;
+        b->launches += 3;
         k_zero_counter<<<1, 1, 0, st>>>(b->counters);
-        k3_plan_substep<<<b->B, 512, 0, st>>>(b->t, u, bvel, b->remaining, b->dt, b->active, b->nsub, b->maxvel, b->counters, cfl);
+        cudaError_t ce0 = cudaMemsetAsync(b->maxvel, 0, (size_t)b->B * sizeof(float), st);
+        if (ce0 != cudaSuccess) return set_err(FGB_E_CUDA, "memset maxvel", ce0);
+        const int mv_blocks = (b->t.N + 256 * 8 - 1) / (256 * 8);
+        k3_max_velocity<<<dim3((unsigned)(mv_blocks < 1 ? 1 : mv_blocks), (unsigned)b->B), 256, 0, st>>>(b->t, u, bvel, b->maxvel);
+        LAUNCH_CHECK("k3_max_velocity");
+        k3_plan_substep<<<(b->B + 127) / 128, 128, 0, st>>>(b->B, b->remaining, b->dt, b->active, b->nsub, b->maxvel, b->counters, cfl);
         LAUNCH_CHECK("k3_plan_substep");
         cudaError_t ce = cudaMemcpyAsync(b->h_counters, b->counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
         if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "memcpy counters", ce);
