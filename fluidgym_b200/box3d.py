@@ -204,3 +204,206 @@ class BatchedPISO3D:
         native.check(self.lib.fgb_ortho3_wall_rows(self.handle, _ptr(self.u), _ptr(rows), int(rows.shape[1]), float(d_lo), float(d_hi),
                                                    int(set_forcing), _ptr(acc), self.stream), "fgb_ortho3_wall_rows")
         return self.buffer("rowmean")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# slab decomposition of one box over the GPUs of a node (BASELINE config 5): one process per GPU, z-slabs
+# ---------------------------------------------------------------------------------------------------------------------
+class _RawCuda:
+    """exposes a raw device pointer to torch through ``__cuda_array_interface__``"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class SlabTables:
+    """Tables of z-slab ``rank`` of ``world`` of a Box3DDomain: owned cells [0, N) in (z_local, y, x) order, lower halo plane
+    [N, N + P), upper halo plane [N + P, N + 2P) (P = nx ny); the -z / +z neighbours of the first / last owned plane are the
+    halo cells, whose metrics are copied from the neighbouring slabs (the grid is static)."""
+
+    def __init__(self, dom: Box3DDomain, rank: int, world: int):
+        if dom.closed[2]:
+            raise ValueError("slab decomposition runs along z, which must be periodic")
+        if dom.nz % world or dom.nz // world < 2:
+            raise ValueError(f"nz = {dom.nz} must be a multiple of the world size {world} with at least 2 planes per rank")
+        self.dom, self.rank, self.world = dom, rank, world
+        nx, ny, nz = dom.nx, dom.ny, dom.nz
+        self.nzl = nz // world
+        self.z0 = rank * self.nzl
+        P = self.P = nx * ny
+        N = self.N = P * self.nzl
+        NS = self.NS = N + 2 * P
+        zs = slice(self.z0, self.z0 + self.nzl)
+        zl, zu = (self.z0 - 1) % nz, (self.z0 + self.nzl) % nz
+        cells = np.arange(N, dtype=np.int64).reshape(self.nzl, ny, nx)
+        nbr = np.zeros((6, self.nzl, ny, nx), dtype=np.int64)
+        self.boff, nb = {}, 0
+        b_minv, b_det = [], []
+        for f in range(6):
+            d, up = f >> 1, f & 1
+            ax = 2 - d
+            nbr[f] = np.roll(cells, -1 if up else 1, axis=ax)
+            if d == 2:
+                off = np.arange(P).reshape(ny, nx)
+                if up:
+                    nbr[f][-1] = N + P + off
+                else:
+                    nbr[f][0] = N + off
+            elif dom.closed[d]:
+                sl = [slice(None)] * 3
+                sl[ax] = -1 if up else 0
+                layer = tuple(sl)
+                n_face = cells[layer].size
+                nbr[f][layer] = -1 - (nb + np.arange(n_face).reshape(cells[layer].shape))
+                self.boff[f] = nb
+                gl = dom.boff[f]
+                gshape = dom.bshape[f]                       # global face layer shape (z, tangential)
+                gm = dom.b_minv[:, gl:gl + int(np.prod(gshape))].reshape((3,) + gshape)
+                gd = dom.b_det[gl:gl + int(np.prod(gshape))].reshape(gshape)
+                b_minv.append(gm[:, zs].reshape(3, -1))
+                b_det.append(gd[zs].reshape(-1))
+                nb += n_face
+        self.NB = nb
+        self.nbr = np.full((6, NS), 0, dtype=np.int32)
+        self.nbr[:, :N] = nbr.reshape(6, N)
+
+        def with_halo(a):                                   # [nz, ny, nx] global -> [NS]
+            return np.concatenate([a[zs].reshape(-1), a[zl].reshape(-1), a[zu].reshape(-1)]).astype(f32)
+        self.minv = np.stack([with_halo(dom.minv[k]) for k in range(3)])
+        self.det = with_halo(dom.det)
+        self.b_minv = np.ascontiguousarray(np.concatenate(b_minv, axis=1)) if nb else np.zeros((3, 1), f32)
+        self.b_det = np.ascontiguousarray(np.concatenate(b_det)) if nb else np.zeros(1, f32)
+
+    def take_cells(self, a):
+        """[..., N_global] -> [..., NS] (owned part filled, halos zero)"""
+        a = np.asarray(a)
+        g = a.reshape(a.shape[:-1] + (self.dom.nz, self.P))[..., self.z0:self.z0 + self.nzl, :].reshape(a.shape[:-1] + (self.N,))
+        out = np.zeros(a.shape[:-1] + (self.NS,), dtype=a.dtype)
+        out[..., :self.N] = g
+        return out
+
+    def take_faces(self, a, f):
+        """boundary values of global face f [..., nz * tangential] -> this slab's faces"""
+        gshape = self.dom.bshape[f]
+        a = np.asarray(a)
+        lead = a.shape[:-1]
+        a = a.reshape(lead + gshape)
+        return a[..., self.z0:self.z0 + self.nzl, :].reshape(lead + (-1,))
+
+
+class SlabPISO3D:
+    """One rank of the slab-decomposed solver.  ``torch.distributed`` is used once, at construction, to exchange the CUDA IPC
+    handles of the symmetric regions; the solver path itself contains no collective call."""
+
+    PAD_BYTES = 4096
+
+    def __init__(self, dom: Box3DDomain, rank: int, world: int, device, group=None, corrector_steps=2, advection_tol=1e-6,
+                 pressure_tol=1e-6, max_iter=5000):
+        import torch.distributed as dist
+        self.lib = native.load()
+        self.tabs = tb = SlabTables(dom, rank, world)
+        self.rank, self.world = rank, world
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        dev = self.device
+        self._tab = {k: torch.from_numpy(np.ascontiguousarray(getattr(tb, k))).to(dev) for k in ("nbr", "minv", "det", "b_minv", "b_det")}
+        self.tables = native.Ortho3Tables(tb.N, tb.NB, dom.visc, *[self._tab[k].data_ptr() for k in ("nbr", "minv", "det", "b_minv", "b_det")],
+                                          tb.NS, dom.N, tb.P)
+        self.options = native.Options(corrector_steps, 1, 1, 1, advection_tol, pressure_tol, max_iter, 0)
+        ws_bytes = self.lib.fgb_ortho3_workspace_bytes(C.byref(self.tables), 1)
+
+        def al(n):
+            return (n + 255) // 256 * 256
+        NB = max(tb.NB, 1)
+        self._off = {"u": self.PAD_BYTES}
+        self._off["p"] = self._off["u"] + al(3 * tb.NS * 4)
+        self._off["bvel"] = self._off["p"] + al(tb.NS * 4)
+        self._off["ws"] = self._off["bvel"] + al(3 * NB * 4)
+        total = self._off["ws"] + al(ws_bytes)
+        base, handle = C.c_void_p(), C.create_string_buffer(64)
+        native.check(self.lib.fgb_ipc_alloc(total, C.byref(base), handle), "fgb_ipc_alloc")
+        self.base, self.total = base.value, total
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        peers = (C.c_void_p * world)()
+        self._opened = []
+        for q in range(world):
+            if q == rank:
+                peers[q] = self.base
+            else:
+                pp = C.c_void_p()
+                native.check(self.lib.fgb_ipc_open(handles[q], C.byref(pp)), "fgb_ipc_open")
+                peers[q] = pp.value
+                self._opened.append(pp.value)
+        raw = torch.as_tensor(_RawCuda(self.base, total), device=dev)
+        self._raw = raw
+
+        def view(name, shape):
+            n = int(np.prod(shape)) * 4
+            return raw[self._off[name]:self._off[name] + n].view(torch.float32).view(shape)
+        self.u, self.p, self.bvel = view("u", (1, 3, tb.NS)), view("p", (1, tb.NS)), view("bvel", (1, 3, NB))
+        h = C.c_void_p()
+        native.check(self.lib.fgb_ortho3_create(C.byref(self.tables), 1, C.c_void_p(self.base + self._off["ws"]), al(ws_bytes),
+                                                C.byref(self.options), C.byref(h)), "fgb_ortho3_create")
+        self.handle = h
+        native.check(self.lib.fgb_ortho3_set_slab(h, rank, world, C.c_void_p(self.base), peers), "fgb_ortho3_set_slab")
+        dist.barrier(group=group)          # every rank has mapped every region before the first kernel writes to a peer
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def buffer(self, name):
+        shapes = {"iters": ((1, 8), torch.int32), "resid": ((1, 8), torch.float32), "rowmean": ((1, 4), torch.float32),
+                  "src": ((1, 4), torch.float32), "dt": ((1,), torch.float32), "maxvel": ((1,), torch.float32),
+                  "iter_total": ((1, 2), torch.int64), "ures": ((1, 3, self.tabs.NS), torch.float32), "A": ((1, self.tabs.NS), torch.float32)}
+        shape, dtype = shapes[name]
+        ptr = self.lib.fgb_ortho3_buffer(self.handle, name.encode())
+        o = ptr - self.base
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        return self._raw[o:o + n].view(dtype).view(shape)
+
+    def load_global(self, u, p, bvel_faces=None):
+        """u [3, N_global], p [N_global] numpy; bvel_faces {face: [3, n_face_global]}"""
+        tb = self.tabs
+        self.u.copy_(torch.from_numpy(tb.take_cells(np.asarray(u, dtype=f32))).to(self.device).unsqueeze(0))
+        self.p.copy_(torch.from_numpy(tb.take_cells(np.asarray(p, dtype=f32))).to(self.device).unsqueeze(0))
+        self.bvel.zero_()
+        for f, v in (bvel_faces or {}).items():
+            loc = tb.take_faces(np.asarray(v, dtype=f32), f)
+            self.bvel[0, :, tb.boff[f]:tb.boff[f] + loc.shape[-1]] = torch.from_numpy(np.ascontiguousarray(loc)).to(self.device)
+
+    def owned(self, t):
+        return t[..., :self.tabs.N]
+
+    def piso_substep(self, dt, src=None):
+        dtc = torch.full((1,), float(dt), device=self.device)
+        native.check(self.lib.fgb_ortho3_piso_substep(self.handle, _ptr(self.u), _ptr(self.p), _ptr(self.bvel), _ptr(src), _ptr(dtc), None,
+                                                      self.stream), "fgb_ortho3_piso_substep")
+
+    def single_step(self, dt, cfl, rows=None, d_lo=1.0, d_hi=1.0) -> int:
+        n = C.c_int32(0)
+        n_row = 0 if rows is None else int(rows.shape[1])
+        native.check(self.lib.fgb_ortho3_sim_step(self.handle, _ptr(self.u), _ptr(self.p), _ptr(self.bvel), float(dt), float(cfl),
+                                                  _ptr(rows), n_row, float(d_lo), float(d_hi), C.byref(n), self.stream), "fgb_ortho3_sim_step")
+        return n.value
+
+    def wall_rows(self, rows, d_lo, d_hi, set_forcing=False, acc=None):
+        native.check(self.lib.fgb_ortho3_wall_rows(self.handle, _ptr(self.u), _ptr(rows), int(rows.shape[1]), float(d_lo), float(d_hi),
+                                                   int(set_forcing), _ptr(acc), self.stream), "fgb_ortho3_wall_rows")
+        return self.buffer("rowmean")
+
+    def error(self) -> int:
+        e = C.c_int32(0)
+        native.check(self.lib.fgb_ortho3_slab_error(self.handle, C.byref(e)), "fgb_ortho3_slab_error")
+        return e.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.fgb_ortho3_destroy(self.handle)
+            self.handle = None
+            for pp in self._opened:
+                self.lib.fgb_ipc_close(C.c_void_p(pp))
+            del self.u, self.p, self.bvel, self._raw
+            self.lib.fgb_ipc_free(C.c_void_p(self.base))

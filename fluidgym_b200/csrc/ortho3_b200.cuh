@@ -11,14 +11,54 @@
 
 typedef fgb_ortho3_tables T3;
 
+// ---- slab decomposition (one process per GPU, z-slabs, halos pushed over NVLink into the peer's memory) ----------
+// Every rank allocates ONE symmetric region with identical layout (fgb_ipc_alloc) and maps the peers' regions
+// (cudaIpcOpenMemHandle): the address of any buffer on rank q is peer_base[q] + (local address - local_base).
+// Cells: owned [0, N), lower halo plane [N, N + P), upper halo plane [N + P, N + 2P); arrays are strided by NS = N + 2P.
+static constexpr int O3_MAXR = 8;
+struct O3Pad {                                      // first bytes of the symmetric region of every rank
+    unsigned long long ar_seq[2][O3_MAXR];          // all-reduce arrival flags (parity double-buffered), per source rank
+    double ar_val[2][O3_MAXR][8];                   // all-reduce payloads
+    unsigned long long halo_seq[O3_MAXR];           // "my halo planes are in your memory" flags, per source rank
+    unsigned long long bar_seq[O3_MAXR];            // stream-level barrier flags, per source rank
+    int error;                                      // set when a wait timed out (a peer died): results are invalid
+};
+struct O3Slab {
+    int rank, world, lower, upper;                  // neighbours along z (periodic)
+    int on;                                         // slab protocol active (world == 1 exchanges with itself: periodic wrap)
+    char *local_base;
+    char *peer_base[O3_MAXR];
+    unsigned long long *ctr;                        // [3] local sequence counters: all-reduce, halo, barrier
+};
+template <typename T>
+__device__ __forceinline__ T *o3_peer(const O3Slab &sl, T *p, int q) { return (T *)(sl.peer_base[q] + ((char *)p - sl.local_base)); }
+__device__ __forceinline__ O3Pad *o3_pad(const O3Slab &sl, int q) { return (O3Pad *)sl.peer_base[q]; }
+__device__ __forceinline__ void o3_wait_ge(volatile unsigned long long *flag, unsigned long long s, O3Pad *mine) {
+    const long long t0 = clock64();
+    while (*flag < s) {
+        if (clock64() - t0 > 6000000000LL) { mine->error = 1; break; }      // ~3 s: a peer is gone, do not hang the GPU
+    }
+}
+
+// owned boundary planes -> the z-neighbours' halo planes (direct stores into peer memory over NVLink)
+__device__ __forceinline__ void o3_push(const O3Slab &sl, const T3 &t, float *vec, int g, float val) {
+    if (sl.on) {
+        const int P = t.plane, N = t.N;
+        if (g < P) o3_peer(sl, vec, sl.lower)[N + P + g] = val;               // my lowest plane = the lower neighbour's UPPER halo
+        if (g >= N - P) o3_peer(sl, vec, sl.upper)[N + (g - (N - P))] = val;  // my highest plane = the upper neighbour's LOWER halo
+    }
+}
+
 struct fgb_ortho3 {
     T3 t;
+    O3Slab slab;
     int B;
     fgb_options opt;
     float *Coff, *A, *rhs, *ures, *Poff, *Pdiag, *hbya, *div, *kry, *part;
     int32_t *iters; float *resid; float *dt; int32_t *active; double *remaining; int32_t *nsub; float *maxvel;
     int32_t *counters; int32_t *h_counters; float *src; float *rowmean;
     unsigned long long *iter_total;
+    unsigned long long *slab_ctr;     // [4] device-side sequence counters of the slab protocol
     int grid_blocks;
     long long launches;
 };
@@ -30,7 +70,7 @@ static constexpr int O3_KRY = 15;         // Krylov work vectors per environment
 static constexpr int O3_PART = 8;         // floats per CTA per reduction slot
 
 extern "C" size_t fgb_ortho3_workspace_bytes(const fgb_ortho3_tables *t, int32_t B) {
-    const size_t BN = (size_t)B * t->N;
+    const size_t BN = (size_t)B * (t->NS > 0 ? t->NS : t->N);
     size_t n = 0;
     n += align_up(6 * BN * 4) * 2 + align_up(BN * 4) * 4 + align_up(3 * BN * 4) * 3 + align_up((size_t)O3_KRY * BN * 4);
     n += align_up((size_t)2 * 4096 * O3_PART * 4);
@@ -50,7 +90,10 @@ extern "C" int fgb_ortho3_create(const fgb_ortho3_tables *t, int32_t B, void *wo
     b->t = *t; b->B = B; b->launches = 0;
     if (opt) b->opt = *opt; else { b->opt.corrector_steps = 2; b->opt.adv_nonortho_steps = 1; b->opt.p_nonortho_steps = 1; b->opt.nonortho = 1;
                                    b->opt.adv_tol = 1e-6f; b->opt.p_tol = 1e-6f; b->opt.max_iter = 5000; b->opt.cg_impl = 0; }
-    const size_t BN = (size_t)B * t->N;
+    if (b->t.NS <= 0) b->t.NS = b->t.N;
+    if (b->t.N_global <= 0) b->t.N_global = b->t.N;
+    memset(&b->slab, 0, sizeof(b->slab)); b->slab.world = 1;
+    const size_t BN = (size_t)B * b->t.NS;
     Carver c{(char *)workspace, 0};
     b->Coff = c.take<float>(6 * BN); b->Poff = c.take<float>(6 * BN);
     b->A = c.take<float>(BN); b->Pdiag = c.take<float>(BN); b->div = c.take<float>(BN);
@@ -64,6 +107,7 @@ extern "C" int fgb_ortho3_create(const fgb_ortho3_tables *t, int32_t B, void *wo
     b->dt = c.take<float>(B); b->active = c.take<int32_t>(B); b->nsub = c.take<int32_t>(B); b->maxvel = c.take<float>(B);
     b->counters = c.take<int32_t>(4); (void)c.take<float>(B);
     b->src = c.take<float>((size_t)B * 4); b->rowmean = c.take<float>((size_t)B * 4);
+    b->slab_ctr = c.take<unsigned long long>(4);
     ce = cudaMallocHost((void **)&b->h_counters, 16);
     if (ce != cudaSuccess) { delete b; return set_err(FGB_E_CUDA, "cudaMallocHost", ce); }
     ce = cudaMemset(workspace, 0, fgb_ortho3_workspace_bytes(t, B));
@@ -107,22 +151,22 @@ __global__ void __launch_bounds__(O3_T) k3_setup_advection(T3 t, const float *__
                                                            const float *__restrict__ Src /* [B][4] or null */, const float *__restrict__ dtv,
                                                            const int32_t *__restrict__ active, float *__restrict__ Coff, float *__restrict__ A,
                                                            float *__restrict__ Rhs) {
-    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NB = t.NB;
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS, NB = t.NB;
     if (g >= N || (active && !active[b])) return;
-    const float *u = U + (size_t)b * 3 * N, *bv = Bvel + (size_t)b * 3 * NB;
+    const float *u = U + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB;
     const float dt = dtv[b], det = t.det[g], visc = t.viscosity;
     float uo[3], mi[3], al[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) { uo[d] = u[d * N + g]; mi[d] = t.minv[d * N + g]; al[d] = det * mi[d] * mi[d]; }
+    for (int d = 0; d < 3; ++d) { uo[d] = u[d * NS + g]; mi[d] = t.minv[d * NS + g]; al[d] = det * mi[d] * mi[d]; }
     float diag = det / dt, Sb[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
-        const int d = f >> 1, n = t.nbr[f * N + g];
+        const int d = f >> 1, n = t.nbr[f * NS + g];
         const float sig = (f & 1) ? 1.f : -1.f;
         float off = 0.f;
         if (n >= 0) {
-            const float dn = t.det[n], mn = t.minv[d * N + n];
-            const float fl = 0.5f * (det * mi[d] * uo[d] + dn * mn * u[d * N + n]);
+            const float dn = t.det[n], mn = t.minv[d * NS + n];
+            const float fl = 0.5f * (det * mi[d] * uo[d] + dn * mn * u[d * NS + n]);
             const float vc = (al[d] * visc + (dn * mn * mn) * visc) * 0.5f;
             const float ff = sig * 0.5f * fl;
             diag += ff + vc;
@@ -135,52 +179,52 @@ __global__ void __launch_bounds__(O3_T) k3_setup_advection(T3 t, const float *__
 #pragma unroll
             for (int c = 0; c < 3; ++c) Sb[c] += bv[c * NB + j] * k;
         }
-        Coff[((size_t)b * 6 + f) * N + g] = off;
+        Coff[((size_t)b * 6 + f) * NS + g] = off;
     }
-    A[(size_t)b * N + g] = diag / det;
+    A[(size_t)b * NS + g] = diag / det;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-        Rhs[((size_t)b * 3 + c) * N + g] = (det * uo[c] / dt + Sb[c]) / det + (Src ? Src[b * 4 + c] : 0.f);
+        Rhs[((size_t)b * 3 + c) * NS + g] = (det * uo[c] / dt + Sb[c]) / det + (Src ? Src[b * 4 + c] : 0.f);
 }
 
 // P: off = 1/2 (alpha_P / A_P + alpha_N / A_N), diag = -sum (K.cu:4812-4978)
 __global__ void __launch_bounds__(O3_T) k3_pressure_matrix(T3 t, const float *__restrict__ A, const int32_t *__restrict__ active,
                                                            float *__restrict__ Poff, float *__restrict__ Pdiag) {
-    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N;
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS;
     if (g >= N || (active && !active[b])) return;
-    const float *a = A + (size_t)b * N;
+    const float *a = A + (size_t)b * NS;
     const float det = t.det[g], rA = 1.0f / a[g];
     float diag = 0.f;
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
-        const int d = f >> 1, n = t.nbr[f * N + g];
+        const int d = f >> 1, n = t.nbr[f * NS + g];
         float c = 0.f;
         if (n >= 0) {
-            const float mi = t.minv[d * N + g], mn = t.minv[d * N + n];
+            const float mi = t.minv[d * NS + g], mn = t.minv[d * NS + n];
             c = 0.5f * ((det * mi * mi) * rA + (t.det[n] * mn * mn) * (1.0f / a[n]));
         }
-        Poff[((size_t)b * 6 + f) * N + g] = c;
+        Poff[((size_t)b * 6 + f) * NS + g] = c;
         diag -= c;
     }
-    Pdiag[(size_t)b * N + g] = diag;
+    Pdiag[(size_t)b * NS + g] = diag;
 }
 
 // HbyA = (u/dt - H(u_prev) + S_b/det + source) / A (K.cu:5136-5255)
 __global__ void __launch_bounds__(O3_T) k3_hbya(T3 t, const float *__restrict__ U, const float *__restrict__ Uprev, const float *__restrict__ Bvel,
                                                 const float *__restrict__ Src, const float *__restrict__ dtv, const int32_t *__restrict__ active,
                                                 const float *__restrict__ Coff, const float *__restrict__ A, float *__restrict__ Hb) {
-    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NB = t.NB;
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS, NB = t.NB;
     if (g >= N || (active && !active[b])) return;
-    const float *u = U + (size_t)b * 3 * N, *up = Uprev + (size_t)b * 3 * N, *bv = Bvel + (size_t)b * 3 * NB;
-    const float dt = dtv[b], det = t.det[g], visc = t.viscosity, Ag = A[(size_t)b * N + g];
+    const float *u = U + (size_t)b * 3 * NS, *up = Uprev + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB;
+    const float dt = dtv[b], det = t.det[g], visc = t.viscosity, Ag = A[(size_t)b * NS + g];
     float H[3] = {0.f, 0.f, 0.f}, Sb[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
-        const int d = f >> 1, n = t.nbr[f * N + g];
+        const int d = f >> 1, n = t.nbr[f * NS + g];
         if (n >= 0) {
-            const float c = Coff[((size_t)b * 6 + f) * N + g];
+            const float c = Coff[((size_t)b * 6 + f) * NS + g];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) H[k] += c * up[k * N + n];
+            for (int k = 0; k < 3; ++k) H[k] += c * up[k * NS + n];
         } else {
             const int j = -1 - n;
             const float sig = (f & 1) ? 1.f : -1.f, bm = t.b_minv[d * NB + j];
@@ -191,39 +235,39 @@ __global__ void __launch_bounds__(O3_T) k3_hbya(T3 t, const float *__restrict__ 
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-        Hb[((size_t)b * 3 + c) * N + g] = (u[c * N + g] / dt - H[c] + Sb[c] / det + (Src ? Src[b * 4 + c] : 0.f)) / Ag;
+        Hb[((size_t)b * 3 + c) * NS + g] = (u[c * NS + g] / dt - H[c] + Sb[c] / det + (Src ? Src[b * 4 + c] : 0.f)) / Ag;
 }
 
 // divergence of the contravariant face fluxes of a cell-centred field (K.cu:1567-1645, 5389-5434)
 __global__ void __launch_bounds__(O3_T) k3_divergence(T3 t, const float *__restrict__ V, const float *__restrict__ Bvel,
                                                       const int32_t *__restrict__ active, float *__restrict__ Div) {
-    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NB = t.NB;
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS, NB = t.NB;
     if (g >= N || (active && !active[b])) return;
-    const float *v = V + (size_t)b * 3 * N, *bv = Bvel + (size_t)b * 3 * NB;
+    const float *v = V + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB;
     const float det = t.det[g];
     float fl[6];
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
-        const int d = f >> 1, n = t.nbr[f * N + g];
-        if (n >= 0) fl[f] = 0.5f * (det * t.minv[d * N + g] * v[d * N + g] + t.det[n] * t.minv[d * N + n] * v[d * N + n]);
+        const int d = f >> 1, n = t.nbr[f * NS + g];
+        if (n >= 0) fl[f] = 0.5f * (det * t.minv[d * NS + g] * v[d * NS + g] + t.det[n] * t.minv[d * NS + n] * v[d * NS + n]);
         else fl[f] = o3_bflux(t, -1 - n, d, bv);
     }
-    Div[(size_t)b * N + g] = (fl[1] - fl[0]) + (fl[3] - fl[2]) + (fl[5] - fl[4]);
+    Div[(size_t)b * NS + g] = (fl[1] - fl[0]) + (fl[3] - fl[2]) + (fl[5] - fl[4]);
 }
 
 // u = HbyA - (1/A) M^-T grad(p), central differences, one-sided at prescribed boundaries (K.cu:816-849, 5962-5995)
 __global__ void __launch_bounds__(O3_T) k3_correct(T3 t, const float *__restrict__ Hb, const float *__restrict__ P, const float *__restrict__ A,
                                                    const int32_t *__restrict__ active, float *__restrict__ Uout) {
-    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N;
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS;
     if (g >= N || (active && !active[b])) return;
-    const float *p = P + (size_t)b * N;
-    const float pc = p[g], rA = 1.0f / A[(size_t)b * N + g];
+    const float *p = P + (size_t)b * NS;
+    const float pc = p[g], rA = 1.0f / A[(size_t)b * NS + g];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        const int nl = t.nbr[(2 * d) * N + g], nu = t.nbr[(2 * d + 1) * N + g];
+        const int nl = t.nbr[(2 * d) * NS + g], nu = t.nbr[(2 * d + 1) * NS + g];
         const float fac = (nl < 0 || nu < 0) ? 1.0f : 0.5f;
         const float pg = ((nu >= 0 ? p[nu] : pc) - (nl >= 0 ? p[nl] : pc)) * fac;
-        Uout[((size_t)b * 3 + d) * N + g] = Hb[((size_t)b * 3 + d) * N + g] - pg * t.minv[d * N + g] * rA;
+        Uout[((size_t)b * 3 + d) * NS + g] = Hb[((size_t)b * 3 + d) * NS + g] - pg * t.minv[d * NS + g] * rA;
     }
 }
 
@@ -238,22 +282,27 @@ __global__ void k3_copy_active(const float *__restrict__ src, float *__restrict_
 // cooperative Krylov kernels
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float o3_row(const T3 &t, int g, const float *__restrict__ off, const float *__restrict__ dg, const float *x) {
-    const int N = t.N;
+    const int NS = t.NS;
     float s = dg[g] * x[g];
 #pragma unroll
-    for (int f = 0; f < 6; ++f) { const int n = t.nbr[f * N + g]; if (n >= 0) s += off[f * N + g] * __ldcg(&x[n]); }
+    for (int f = 0; f < 6; ++f) { const int n = t.nbr[f * NS + g]; if (n >= 0) s += off[f * NS + g] * __ldcg(&x[n]); }
     return s;
 }
 
-// deterministic grid-wide sum of K values: block sums -> part[slot][cta][k] -> grid.sync -> fixed-order sum in every CTA
+// deterministic grid-wide sum of K values: block sums -> part[slot][cta][k] -> grid.sync -> fixed-order sum in every CTA;
+// with slabs the per-GPU totals are then exchanged through the peers' pads (every rank adds them in rank order, so all
+// ranks hold bit-identical results and take identical branches).  Because every thread fences at system scope before
+// the grid.sync and the flag is written after it, a completed all-reduce also implies that all halo pushes issued
+// before it have landed: it doubles as the halo hand-shake.
 template <int K>
-__device__ __forceinline__ void o3_grid_sum(cg::grid_group &grid, float (&v)[K], float *part, unsigned &rcount, double *sm) {
+__device__ __forceinline__ void o3_grid_sum(cg::grid_group &grid, const O3Slab &sl, float (&v)[K], float *part, unsigned &rcount,
+                                            unsigned long long &arc, double *sm) {
     static_assert(K <= O3_PART, "partials per CTA");
     block_reduce_sum<K>(v, sm);
     float *slot = part + (size_t)(rcount & 1u) * 4096 * O3_PART;
 #pragma unroll
     for (int k = 0; k < K; ++k) if (threadIdx.x == k) slot[blockIdx.x * O3_PART + k] = v[k];
-    __threadfence();
+    if (sl.on) __threadfence_system(); else __threadfence();
     grid.sync();
     const int nb = gridDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -265,32 +314,68 @@ __device__ __forceinline__ void o3_grid_sum(cg::grid_group &grid, float (&v)[K],
         if (lane == 0) sm[warp] = s;
     }
     __syncthreads();
+    if (sl.on) {
+        const unsigned long long sq = ++arc;
+        const int par = (int)(sq & 1ull);
+        O3Pad *mine = (O3Pad *)sl.local_base;
+        if (blockIdx.x == 0 && threadIdx.x < sl.world) {
+            O3Pad *dst = o3_pad(sl, threadIdx.x);
+            for (int k = 0; k < K; ++k) ((volatile double *)dst->ar_val[par][sl.rank])[k] = sm[k];
+            __threadfence_system();
+            ((volatile unsigned long long *)dst->ar_seq[par])[sl.rank] = sq;
+        }
+        if (threadIdx.x < sl.world) o3_wait_ge(&mine->ar_seq[par][threadIdx.x], sq, mine);
+        __syncthreads();
+        __threadfence_system();
+        double tot = 0.0;
+        if (threadIdx.x < K) for (int q = 0; q < sl.world; ++q) tot += ((volatile double *)mine->ar_val[par][q])[threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x < K) sm[threadIdx.x] = tot;
+        __syncthreads();
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = (float)sm[k];
     __syncthreads();
     ++rcount;
 }
+// "the vector I just updated is complete everywhere": grid barrier + (slabs) flags to / from both z-neighbours
+__device__ __forceinline__ void o3_halo_sync(cg::grid_group &grid, const O3Slab &sl, unsigned long long &hc) {
+    if (sl.on) __threadfence_system(); else __threadfence();
+    grid.sync();
+    if (sl.on) {
+        const unsigned long long sq = ++hc;
+        O3Pad *mine = (O3Pad *)sl.local_base;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            ((volatile unsigned long long *)o3_pad(sl, sl.lower)->halo_seq)[sl.rank] = sq;
+            ((volatile unsigned long long *)o3_pad(sl, sl.upper)->halo_seq)[sl.rank] = sq;
+        }
+        if (threadIdx.x == 0) { o3_wait_ge(&mine->halo_seq[sl.lower], sq, mine); o3_wait_ge(&mine->halo_seq[sl.upper], sq, mine); }
+        __syncthreads();
+        __threadfence_system();
+    }
+}
 
 // BiCGStab for the three velocity components in lock step (BICG.cu:237-376; same operation order as k_bicgstab)
-__global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, int B, const float *__restrict__ Coff, const float *__restrict__ Adiag,
+__global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, const float *__restrict__ Coff, const float *__restrict__ Adiag,
                                                     const float *__restrict__ Rhs, float *X, float *work, float *part, int maxit, float tol,
                                                     int zero_init, const int32_t *__restrict__ active, int32_t *__restrict__ iters,
                                                     float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double red[32 * 6 + 8];
-    const int N = t.N;
+    const int N = t.N, NS = t.NS;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    const float norm = 1.0f / sqrtf((float)N);
+    const float norm = 1.0f / sqrtf((float)t.N_global);
     unsigned rcount = 0;
+    unsigned long long arc = sl.on ? sl.ctr[0] : 0ull, hc = sl.on ? sl.ctr[1] : 0ull;
     for (int b = 0; b < B; ++b) {
         if (active && !active[b]) continue;
-        const float *off = Coff + (size_t)b * 6 * N, *dg = Adiag + (size_t)b * N;
-        float *wb = work + (size_t)b * O3_KRY * N;
+        const float *off = Coff + (size_t)b * 6 * NS, *dg = Adiag + (size_t)b * NS;
+        float *wb = work + (size_t)b * O3_KRY * NS;
         float *r[3], *rw[3], *p[3], *v[3], *tt[3], *x[3];
         const float *f[3];
         for (int c = 0; c < 3; ++c) {
-            r[c] = wb + (size_t)(5 * c) * N; rw[c] = r[c] + N; p[c] = r[c] + 2 * (size_t)N; v[c] = r[c] + 3 * (size_t)N; tt[c] = r[c] + 4 * (size_t)N;
-            x[c] = X + ((size_t)b * 3 + c) * N; f[c] = Rhs + ((size_t)b * 3 + c) * N;
+            r[c] = wb + (size_t)(5 * c) * NS; rw[c] = r[c] + NS; p[c] = r[c] + 2 * (size_t)NS; v[c] = r[c] + 3 * (size_t)NS; tt[c] = r[c] + 4 * (size_t)NS;
+            x[c] = X + ((size_t)b * 3 + c) * NS; f[c] = Rhs + ((size_t)b * 3 + c) * NS;
         }
         if (zero_init) { for (int c = 0; c < 3; ++c) for (int g = tid; g < N; g += nth) x[c][g] = 0.f; }
         else grid.sync();
@@ -299,38 +384,40 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, int B, const float *_
             for (int g = tid; g < N; g += nth) {
                 const float rr = f[c][g] - (zero_init ? 0.f : o3_row(t, g, off, dg, x[c]));
                 r[c][g] = rr; rw[c][g] = rr; p[c][g] = rr;
+                o3_push(sl, t, p[c], g, rr);
                 acc[c] += rr * rr;
             }
-        o3_grid_sum<6>(grid, acc, part, rcount, red);
+        o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, red);
         bool done[3]; int used[3]; float fin[3], rho[3] = {1.f, 1.f, 1.f}, alpha[3] = {1.f, 1.f, 1.f}, omega[3] = {1.f, 1.f, 1.f};
         for (int c = 0; c < 3; ++c) { fin[c] = sqrtf(acc[c]) * norm; used[c] = -1; done[c] = fin[c] < tol; }
         for (int i = 0; i < maxit && !(done[0] && done[1] && done[2]); ++i) {
             for (int k = 0; k < 6; ++k) acc[k] = 0.f;
             for (int c = 0; c < 3; ++c) if (!done[c])
                 for (int g = tid; g < N; g += nth) acc[c] += rw[c][g] * r[c][g];
-            o3_grid_sum<6>(grid, acc, part, rcount, red);
+            o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, red);
             for (int c = 0; c < 3; ++c) if (!done[c]) {
                 const float rhop = rho[c]; rho[c] = acc[c];
                 if (i > 0) {
                     const float beta = (rho[c] / rhop) * (alpha[c] / omega[c]);
-                    for (int g = tid; g < N; g += nth) p[c][g] = r[c][g] + beta * (p[c][g] - omega[c] * v[c][g]);
+                    for (int g = tid; g < N; g += nth) { const float pn = r[c][g] + beta * (p[c][g] - omega[c] * v[c][g]); p[c][g] = pn; o3_push(sl, t, p[c], g, pn); }
                 }
             }
-            __threadfence(); grid.sync();
+            o3_halo_sync(grid, sl, hc);
             for (int k = 0; k < 6; ++k) acc[k] = 0.f;
             for (int c = 0; c < 3; ++c) if (!done[c])
                 for (int g = tid; g < N; g += nth) { const float vv = o3_row(t, g, off, dg, p[c]); v[c][g] = vv; acc[c] += rw[c][g] * vv; }
-            o3_grid_sum<6>(grid, acc, part, rcount, red);
+            o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, red);
             float acc2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int c = 0; c < 3; ++c) if (!done[c]) {
                 alpha[c] = rho[c] / acc[c];
                 for (int g = tid; g < N; g += nth) {
                     const float rr = r[c][g] - alpha[c] * v[c][g];
                     r[c][g] = rr; x[c][g] += alpha[c] * p[c][g];
+                    o3_push(sl, t, r[c], g, rr);
                     acc2[c] += rr * rr;
                 }
             }
-            o3_grid_sum<6>(grid, acc2, part, rcount, red);     // (its grid.sync also publishes r for the next product)
+            o3_grid_sum<6>(grid, sl, acc2, part, rcount, arc, red);     // (its grid.sync also publishes r for the next product)
             for (int c = 0; c < 3; ++c) if (!done[c]) {
                 const float nr = sqrtf(acc2[c]) * norm;
                 used[c] = i; fin[c] = nr;
@@ -342,7 +429,7 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, int B, const float *_
                     const float tv = o3_row(t, g, off, dg, r[c]); tt[c][g] = tv;
                     acc[c] += tv * r[c][g]; acc[3 + c] += tv * tv;
                 }
-            o3_grid_sum<6>(grid, acc, part, rcount, red);      // every row of t = C r is complete before r is overwritten
+            o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, red);      // every row of t = C r is complete before r is overwritten
             for (int k = 0; k < 6; ++k) acc2[k] = 0.f;
             for (int c = 0; c < 3; ++c) if (!done[c]) {
                 omega[c] = acc[c] / acc[3 + c];
@@ -354,7 +441,7 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, int B, const float *_
                     r[c][g] = rr;
                 }
             }
-            o3_grid_sum<6>(grid, acc2, part, rcount, red);
+            o3_grid_sum<6>(grid, sl, acc2, part, rcount, arc, red);
             for (int c = 0; c < 3; ++c) if (!done[c]) {
                 const float nr = sqrtf(acc2[c]) * norm;
                 fin[c] = nr;
@@ -368,28 +455,30 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, int B, const float *_
         }
         grid.sync();
     }
+    if (sl.on && blockIdx.x == 0 && threadIdx.x == 0) { sl.ctr[0] = arc; sl.ctr[1] = hc; }
 }
 
 // CG with residual reset, best-iterate tracking, 100-rising-steps cut-off and mean removal (CG.cu:225-446, SIM.py:1908-1925)
-__global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, int B, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
+__global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, O3Slab sl, int B, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
                                               const float *__restrict__ Rhs, float *Xout, float *work, float *part, int maxit, float tol,
                                               int zero_init, int reset_steps, int slot, const int32_t *__restrict__ active,
                                               int32_t *__restrict__ iters, float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double red[32 * 2 + 8];
-    const int N = t.N;
+    const int N = t.N, NS = t.NS;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    const float norm = 1.0f / sqrtf((float)N);
+    const float norm = 1.0f / sqrtf((float)t.N_global);
     unsigned rcount = 0;
+    unsigned long long arc = sl.on ? sl.ctr[0] : 0ull, hc = sl.on ? sl.ctr[1] : 0ull;
     for (int b = 0; b < B; ++b) {
         if (active && !active[b]) continue;
-        const float *off = Poff + (size_t)b * 6 * N, *dg = Pdiag + (size_t)b * N, *f = Rhs + (size_t)b * N;
-        float *wb = work + (size_t)b * O3_KRY * N;
-        float *r = wb, *p = wb + N, *ap = wb + 2 * (size_t)N, *best = wb + 3 * (size_t)N, *x = wb + 4 * (size_t)N;
-        float *xo = Xout + (size_t)b * N;
+        const float *off = Poff + (size_t)b * 6 * NS, *dg = Pdiag + (size_t)b * NS, *f = Rhs + (size_t)b * NS;
+        float *wb = work + (size_t)b * O3_KRY * NS;
+        float *r = wb, *p = wb + NS, *ap = wb + 2 * (size_t)NS, *best = wb + 3 * (size_t)NS, *x = wb + 4 * (size_t)NS;
+        float *xo = Xout + (size_t)b * NS;
         float acc[2] = {0.f, 0.f};
         for (int g = tid; g < N; g += nth) { x[g] = zero_init ? 0.f : xo[g]; acc[1] += (f[g] != 0.f) ? 1.f : 0.f; }
-        o3_grid_sum<2>(grid, acc, part, rcount, red);
+        o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, red);
         int used = -1; float fin = 0.f;
         if (!(acc[1] > 0.f)) {            // all-zero right-hand side -> zero result (DIFF.py:392, 489-490)
             for (int g = tid; g < N; g += nth) x[g] = 0.f;
@@ -398,23 +487,27 @@ __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, int B, const float *__restr
             for (int g = tid; g < N; g += nth) {
                 const float rr = f[g] - (zero_init ? 0.f : o3_row(t, g, off, dg, x));
                 r[g] = rr; p[g] = rr; acc[0] += rr * rr;
+                o3_push(sl, t, p, g, rr);
             }
-            o3_grid_sum<2>(grid, acc, part, rcount, red);
+            o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, red);
             float rho = acc[0], bestc = 0.f, lastc = 0.f; int best_it = -1, rising = 0;
             int until_reset = reset_steps > 0 ? reset_steps - 1 : -1;
             for (int i = 0; i < maxit; ++i) {
                 const bool do_reset = until_reset == 0;
                 if (until_reset >= 0) until_reset = do_reset ? reset_steps - 1 : until_reset - 1;
                 if (do_reset) {
-                    __threadfence(); grid.sync();
+                    if (sl.on) for (int g = tid; g < N; g += nth) o3_push(sl, t, x, g, x[g]);
+                    o3_halo_sync(grid, sl, hc);
                     acc[0] = acc[1] = 0.f;
-                    for (int g = tid; g < N; g += nth) { const float rr = f[g] - o3_row(t, g, off, dg, x); r[g] = rr; p[g] = rr; acc[0] += rr * rr; }
-                    o3_grid_sum<2>(grid, acc, part, rcount, red);
+                    for (int g = tid; g < N; g += nth) { const float rr = f[g] - o3_row(t, g, off, dg, x); r[g] = rr; acc[0] += rr * rr; }
+                    o3_halo_sync(grid, sl, hc);              // every row has read the old p halos before p is overwritten
+                    for (int g = tid; g < N; g += nth) { const float rr = r[g]; p[g] = rr; o3_push(sl, t, p, g, rr); }
+                    o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, red);
                     rho = acc[0];
                 }
                 acc[0] = acc[1] = 0.f;
                 for (int g = tid; g < N; g += nth) { const float a = o3_row(t, g, off, dg, p); ap[g] = a; acc[0] += p[g] * a; }
-                o3_grid_sum<2>(grid, acc, part, rcount, red);
+                o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, red);
                 const float alpha = rho / acc[0];
                 acc[0] = acc[1] = 0.f;
                 for (int g = tid; g < N; g += nth) {
@@ -422,7 +515,7 @@ __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, int B, const float *__restr
                     const float rr = r[g] - alpha * ap[g];
                     r[g] = rr; acc[0] += rr * rr;
                 }
-                o3_grid_sum<2>(grid, acc, part, rcount, red);
+                o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, red);
                 const float crit = sqrtf(acc[0]) * norm;
                 if (!isfinite(crit)) { used = i; fin = crit; break; }
                 if (i == 0 || crit < bestc) {
@@ -439,20 +532,139 @@ __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, int B, const float *__restr
                 }
                 const float rhop = rho; rho = acc[0];
                 const float beta = rho / rhop;
-                for (int g = tid; g < N; g += nth) p[g] = r[g] + beta * p[g];
-                __threadfence(); grid.sync();        // p complete before the next product gathers it
+                for (int g = tid; g < N; g += nth) { const float pn = r[g] + beta * p[g]; p[g] = pn; o3_push(sl, t, p, g, pn); }
+                o3_halo_sync(grid, sl, hc);          // p complete (incl. the neighbours' halo planes) before the next product gathers it
             }
         }
         acc[0] = acc[1] = 0.f;
         for (int g = tid; g < N; g += nth) acc[0] += x[g];
-        o3_grid_sum<2>(grid, acc, part, rcount, red);
-        const float mean = acc[0] / (float)N;
+        o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, red);
+        const float mean = acc[0] / (float)t.N_global;
         for (int g = tid; g < N; g += nth) xo[g] = x[g] - mean;
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             iters[b * 8 + 3 + slot] = used; resid[b * 8 + 3 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1);
         }
         grid.sync();
     }
+    if (sl.on && blockIdx.x == 0 && threadIdx.x == 0) { sl.ctr[0] = arc; sl.ctr[1] = hc; }
+}
+
+// ---- stream-level slab helpers ---------------------------------------------------------------------------------------
+// copy the two owned boundary planes of `ncomp` components of a field into the z-neighbours' halo planes
+__global__ void __launch_bounds__(256) k3_halo_push(O3Slab sl, T3 t, float *field, int ncomp) {
+    const int P = t.plane, N = t.N, NS = t.NS;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * P * ncomp) return;
+    const int c = i / (2 * P), r = i - c * 2 * P;
+    float *f = field + (size_t)c * NS;
+    if (r < P) o3_peer(sl, f, sl.lower)[N + P + r] = f[r];
+    else o3_peer(sl, f, sl.upper)[N + (r - P)] = f[N - P + (r - P)];
+}
+// all ranks reach this point of their streams; what every rank wrote before it is visible to all after it
+__global__ void k3_rank_barrier(O3Slab sl) {
+    O3Pad *mine = (O3Pad *)sl.local_base;
+    const unsigned long long sq = sl.ctr[2] + 1;
+    __threadfence_system();
+    if ((int)threadIdx.x < sl.world) {
+        ((volatile unsigned long long *)o3_pad(sl, threadIdx.x)->bar_seq)[sl.rank] = sq;
+        o3_wait_ge(&mine->bar_seq[threadIdx.x], sq, mine);
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (threadIdx.x == 0) sl.ctr[2] = sq;
+}
+// all-reduce of n <= 8 floats across ranks in place (op 0: sum, 1: max), fixed rank order
+__global__ void k3_rank_allreduce(O3Slab sl, float *buf, int n, int op) {
+    __shared__ double res[8];
+    O3Pad *mine = (O3Pad *)sl.local_base;
+    const unsigned long long sq = sl.ctr[0] + 1;
+    const int par = (int)(sq & 1ull);
+    if ((int)threadIdx.x < sl.world) {
+        O3Pad *dst = o3_pad(sl, threadIdx.x);
+        for (int k = 0; k < n; ++k) ((volatile double *)dst->ar_val[par][sl.rank])[k] = (double)buf[k];
+        __threadfence_system();
+        ((volatile unsigned long long *)dst->ar_seq[par])[sl.rank] = sq;
+        o3_wait_ge(&mine->ar_seq[par][threadIdx.x], sq, mine);
+    }
+    __syncthreads();
+    __threadfence_system();
+    if ((int)threadIdx.x < n) {
+        double a = ((volatile double *)mine->ar_val[par][0])[threadIdx.x];
+        for (int q = 1; q < sl.world; ++q) { const double v = ((volatile double *)mine->ar_val[par][q])[threadIdx.x]; a = op ? fmax(a, v) : a + v; }
+        res[threadIdx.x] = a;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < n) buf[threadIdx.x] = (float)res[threadIdx.x];
+    if (threadIdx.x == 0) sl.ctr[0] = sq;
+}
+static int o3_exchange(fgb_ortho3 *b, float *field, int ncomp, cudaStream_t st) {
+    if (!b->slab.on) return FGB_OK;
+    const int n = 2 * b->t.plane * ncomp;
+    b->launches += 2;
+    k3_halo_push<<<(n + 255) / 256, 256, 0, st>>>(b->slab, b->t, field, ncomp);
+    LAUNCH_CHECK("k3_halo_push");
+    k3_rank_barrier<<<1, 32, 0, st>>>(b->slab);
+    LAUNCH_CHECK("k3_rank_barrier");
+    return FGB_OK;
+}
+static int o3_allreduce(fgb_ortho3 *b, float *buf, int n, int op, cudaStream_t st) {
+    if (!b->slab.on || b->slab.world <= 1) return FGB_OK;
+    b->launches++;
+    k3_rank_allreduce<<<1, 32, 0, st>>>(b->slab, buf, n, op);
+    LAUNCH_CHECK("k3_rank_allreduce");
+    return FGB_OK;
+}
+
+// Slab decomposition: this handle owns z-slab `rank` of `world`; local_base / peer_bases = the symmetric regions (see O3Slab).
+// The tables must describe the slab (NS = N + 2 plane, halo neighbours), every field buffer passed to the fgb_ortho3_* calls
+// and the workspace must live inside the symmetric region, B must be 1.
+extern "C" int fgb_ortho3_set_slab(fgb_ortho3 *b, int32_t rank, int32_t world, void *local_base, void *const *peer_bases) {
+    if (!b || world < 1 || world > O3_MAXR || rank < 0 || rank >= world || !local_base || !peer_bases)
+        return set_err(FGB_E_ARG, "fgb_ortho3_set_slab: bad argument");
+    if (b->B != 1 || b->t.plane <= 0 || b->t.NS != b->t.N + 2 * b->t.plane)
+        return set_err(FGB_E_ARG, "fgb_ortho3_set_slab: slab tables need B == 1 and NS == N + 2 * plane");
+    b->slab.rank = rank; b->slab.world = world; b->slab.on = 1;
+    b->slab.lower = (rank + world - 1) % world; b->slab.upper = (rank + 1) % world;
+    b->slab.local_base = (char *)local_base;
+    for (int q = 0; q < world; ++q) b->slab.peer_base[q] = (char *)peer_bases[q];
+    b->slab.peer_base[rank] = (char *)local_base;
+    b->slab.ctr = (unsigned long long *)b->slab_ctr;
+    return FGB_OK;
+}
+extern "C" int fgb_ortho3_slab_error(fgb_ortho3 *b, int32_t *out) {
+    if (!b || !out) return set_err(FGB_E_ARG, "fgb_ortho3_slab_error: null argument");
+    *out = 0;
+    if (!b->slab.on) return FGB_OK;
+    cudaError_t ce = cudaMemcpy(out, &((O3Pad *)b->slab.local_base)->error, sizeof(int), cudaMemcpyDeviceToHost);
+    return ce == cudaSuccess ? FGB_OK : set_err(FGB_E_CUDA, "fgb_ortho3_slab_error", ce);
+}
+
+// ---- symmetric memory over CUDA IPC (one allocation per rank, mapped into every peer) -------------------------------
+extern "C" int fgb_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle_out /*[64]*/) {
+    if (!ptr || !handle_out || bytes == 0) return set_err(FGB_E_ARG, "fgb_ipc_alloc: bad argument");
+    cudaError_t ce = cudaMalloc(ptr, bytes);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "fgb_ipc_alloc: cudaMalloc", ce);
+    ce = cudaMemset(*ptr, 0, bytes);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "fgb_ipc_alloc: cudaMemset", ce);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    ce = cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle_out, *ptr);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "fgb_ipc_alloc: cudaIpcGetMemHandle", ce);
+    return FGB_OK;
+}
+extern "C" int fgb_ipc_open(const unsigned char *handle /*[64]*/, void **peer_ptr) {
+    if (!handle || !peer_ptr) return set_err(FGB_E_ARG, "fgb_ipc_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    cudaError_t ce = cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    return ce == cudaSuccess ? FGB_OK : set_err(FGB_E_CUDA, "fgb_ipc_open: cudaIpcOpenMemHandle", ce);
+}
+extern "C" int fgb_ipc_close(void *peer_ptr) {
+    cudaError_t ce = cudaIpcCloseMemHandle(peer_ptr);
+    return ce == cudaSuccess ? FGB_OK : set_err(FGB_E_CUDA, "fgb_ipc_close", ce);
+}
+extern "C" int fgb_ipc_free(void *ptr) {
+    cudaError_t ce = cudaFree(ptr);
+    return ce == cudaSuccess ? FGB_OK : set_err(FGB_E_CUDA, "fgb_ipc_free", ce);
 }
 
 static int o3_coop_blocks(fgb_ortho3 *b) {
@@ -482,10 +694,10 @@ extern "C" int fgb_ortho3_setup_advection(fgb_ortho3 *b, const float *u, const f
 
 extern "C" int fgb_ortho3_solve_advection(fgb_ortho3 *b, int zero_init, const int32_t *active, fgb_stream_t s) {
     if (!b) return set_err(FGB_E_ARG, "fgb_ortho3_solve_advection: null argument");
-    T3 t = b->t; int B = b->B; const float *coff = b->Coff, *a = b->A, *rhs = b->rhs; float *x = b->ures, *work = b->kry, *part = b->part;
+    T3 t = b->t; O3Slab sl = b->slab; int B = b->B; const float *coff = b->Coff, *a = b->A, *rhs = b->rhs; float *x = b->ures, *work = b->kry, *part = b->part;
     int maxit = b->opt.max_iter; float tol = b->opt.adv_tol;
     int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
-    void *args[] = {&t, &B, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot};
+    void *args[] = {&t, &sl, &B, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot};
     b->launches++;
     cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab)", ce);
@@ -504,6 +716,7 @@ extern "C" int fgb_ortho3_setup_pressure(fgb_ortho3 *b, const float *u, const fl
     b->launches += 2;
     k3_hbya<<<o3_grid(b), O3_T, 0, st>>>(b->t, u, b->ures, bvel, src, dt, active, b->Coff, b->A, b->hbya);
     LAUNCH_CHECK("k3_hbya");
+    { int rc = o3_exchange(b, b->hbya, 3, st); if (rc) return rc; }
     k3_divergence<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->hbya, bvel, active, b->div);
     LAUNCH_CHECK("k3_divergence");
     return FGB_OK;
@@ -513,10 +726,10 @@ extern "C" int fgb_ortho3_solve_pressure(fgb_ortho3 *b, float *p_out, int zero_i
                                          const int32_t *active, fgb_stream_t s) {
     if (!b || !p_out) return set_err(FGB_E_ARG, "fgb_ortho3_solve_pressure: null argument");
     if (slot < 0 || slot > 4) slot = 4;
-    T3 t = b->t; int B = b->B; const float *poff = b->Poff, *pd = b->Pdiag, *rhs = b->div; float *work = b->kry, *part = b->part;
+    T3 t = b->t; O3Slab sl = b->slab; int B = b->B; const float *poff = b->Poff, *pd = b->Pdiag, *rhs = b->div; float *work = b->kry, *part = b->part;
     float tol = b->opt.p_tol;
     int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
-    void *args[] = {&t, &B, &poff, &pd, &rhs, &p_out, &work, &part, &max_iter, &tol, &zero_init, &reset_steps, &slot, &active, &iters, &resid, &itot};
+    void *args[] = {&t, &sl, &B, &poff, &pd, &rhs, &p_out, &work, &part, &max_iter, &tol, &zero_init, &reset_steps, &slot, &active, &iters, &resid, &itot};
     b->launches++;
     cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_cg, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_cg)", ce);
@@ -531,20 +744,26 @@ extern "C" int fgb_ortho3_correct_velocity(fgb_ortho3 *b, const float *p, float 
     return FGB_OK;
 }
 
-// Simulation._PISO_split_step for D = 3 (SIM.py:1431-2002; orthogonal grid: one predictor and one pressure solve per corrector)
+// Simulation._PISO_split_step for D = 3 (SIM.py:1431-2002; orthogonal grid: one predictor and one pressure solve per corrector).
+// With slabs every field a stencil reads across the slab boundary is pushed into the neighbours' halo planes first.
 extern "C" int fgb_ortho3_piso_substep(fgb_ortho3 *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
                                        const int32_t *active, fgb_stream_t s) {
     if (!b || !u || !p || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep: null argument");
+    cudaStream_t st = STREAM(s);
     int rc;
+    if ((rc = o3_exchange(b, u, 3, st))) return rc;
     if ((rc = fgb_ortho3_setup_advection(b, u, bvel, src, dt, active, s))) return rc;
+    if ((rc = o3_exchange(b, b->A, 1, st))) return rc;
     if ((rc = fgb_ortho3_solve_advection(b, 1, active, s))) return rc;
     for (int cs = 0; cs < b->opt.corrector_steps; ++cs) {
+        if ((rc = o3_exchange(b, b->ures, 3, st))) return rc;
         if ((rc = fgb_ortho3_setup_pressure(b, u, bvel, src, dt, cs == 0, active, s))) return rc;
         if ((rc = fgb_ortho3_solve_pressure(b, p, 1, b->opt.nonortho ? 100 : 0, b->opt.max_iter, cs, active, s))) return rc;
+        if ((rc = o3_exchange(b, p, 1, st))) return rc;
         if ((rc = fgb_ortho3_correct_velocity(b, p, b->ures, active, s))) return rc;
     }
     b->launches++;
-    const size_t n = (size_t)3 * b->t.N;
+    const size_t n = (size_t)3 * b->t.NS;
     k3_copy_active<<<dim3((unsigned)((n + 255) / 256), b->B), 256, 0, STREAM(s)>>>(b->ures, u, n, active);
     LAUNCH_CHECK("k3_copy_active");
     return FGB_OK;
@@ -554,11 +773,12 @@ extern "C" int fgb_ortho3_piso_substep(fgb_ortho3 *b, float *u, float *p, const 
 extern "C" int fgb_ortho3_make_divergence_free(fgb_ortho3 *b, float *u, float *p, const float *bvel, int max_iter, fgb_stream_t s) {
     if (!b || !u || !p || !bvel) return set_err(FGB_E_ARG, "fgb_ortho3_make_divergence_free: null argument");
     cudaStream_t st = STREAM(s);
-    const size_t BN = (size_t)b->B * b->t.N;
+    const size_t BN = (size_t)b->B * b->t.NS;
     int rc;
     b->launches += 3;
     k_fill<<<(unsigned)((BN + 255) / 256), 256, 0, st>>>(b->A, 1.0f, BN);
     LAUNCH_CHECK("k_fill");
+    if ((rc = o3_exchange(b, u, 3, st))) return rc;
     cudaError_t ce = cudaMemcpyAsync(b->hbya, u, 3 * BN * sizeof(float), cudaMemcpyDeviceToDevice, st);
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "memcpy hbya", ce);
     k3_pressure_matrix<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->A, nullptr, b->Poff, b->Pdiag);
@@ -566,6 +786,7 @@ extern "C" int fgb_ortho3_make_divergence_free(fgb_ortho3 *b, float *u, float *p
     k3_divergence<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->hbya, bvel, nullptr, b->div);
     LAUNCH_CHECK("k3_divergence");
     if ((rc = fgb_ortho3_solve_pressure(b, p, 1, 0, max_iter, 0, nullptr, s))) return rc;
+    if ((rc = o3_exchange(b, p, 1, st))) return rc;
     return fgb_ortho3_correct_velocity(b, p, u, nullptr, s);
 }
 
@@ -577,12 +798,12 @@ extern "C" int fgb_ortho3_make_divergence_free(fgb_ortho3 *b, float *u, float *p
 // SIM.py:2004-2031 (same arithmetic as k_plan_substep) by one thread per environment.
 __global__ void __launch_bounds__(256) k3_max_velocity(T3 t, const float *__restrict__ U, const float *__restrict__ Bvel, float *__restrict__ maxvel) {
     __shared__ float smf[33];
-    const int b = blockIdx.y, N = t.N, NB = t.NB;
-    const float *u = U + (size_t)b * 3 * N, *bv = Bvel + (size_t)b * 3 * NB;
+    const int b = blockIdx.y, N = t.N, NS = t.NS, NB = t.NB;
+    const float *u = U + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB;
     float m = 0.f;
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x)
 #pragma unroll
-        for (int d = 0; d < 3; ++d) m = fmaxf(m, fabsf(t.minv[d * N + g] * u[d * N + g]));
+        for (int d = 0; d < 3; ++d) m = fmaxf(m, fabsf(t.minv[d * NS + g] * u[d * NS + g]));
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < NB; j += gridDim.x * blockDim.x)
 #pragma unroll
         for (int d = 0; d < 3; ++d) m = fmaxf(m, fabsf(t.b_minv[d * NB + j] * bv[d * NB + j]));
@@ -616,30 +837,39 @@ __global__ void k3_plan_substep(int B, double *__restrict__ remaining, float *__
 
 // mean streamwise velocity of the first and last wall-normal cell layers -> wall shear stresses and the dynamic
 // forcing G_x = nu/2 (u_lo/d_lo + u_hi/d_hi) (envs/tcf/grid.py:128-163, tcf_env.py:564-584).  rows: [2][n_row] cell lists.
-__global__ void __launch_bounds__(512) k3_wall_rows(T3 t, const float *__restrict__ U, const int32_t *__restrict__ rows, int n_row, float d_lo, float d_hi,
-                                                    float *__restrict__ rowmean /* [B][4]: mean u lo, mean u hi, tau lo, tau hi */,
-                                                    float *__restrict__ src /* [B][4] or null */, float *__restrict__ acc /* [B][2] += tau, or null */) {
+__global__ void __launch_bounds__(512) k3_wall_rows_sum(T3 t, const float *__restrict__ U, const int32_t *__restrict__ rows, int n_row,
+                                                        float *__restrict__ rowmean /* [B][4]: [0..1] = sums over this rank's rows */) {
     __shared__ double red[32 * 2 + 2];
-    const int b = blockIdx.x, N = t.N;
-    const float *u = U + (size_t)b * 3 * N;
+    const int b = blockIdx.x, NS = t.NS;
+    const float *u = U + (size_t)b * 3 * NS;
     float a[2] = {0.f, 0.f};
     for (int i = threadIdx.x; i < n_row; i += blockDim.x) { a[0] += u[rows[i]]; a[1] += u[rows[n_row + i]]; }
     block_reduce_sum<2>(a, red);
-    if (threadIdx.x == 0) {
-        const float mlo = a[0] / (float)n_row, mhi = a[1] / (float)n_row;
-        const float tlo = t.viscosity * mlo / d_lo, thi = t.viscosity * mhi / d_hi;
-        rowmean[b * 4 + 0] = mlo; rowmean[b * 4 + 1] = mhi; rowmean[b * 4 + 2] = tlo; rowmean[b * 4 + 3] = thi;
-        if (src) { src[b * 4 + 0] = (tlo + thi) * 0.5f; src[b * 4 + 1] = 0.f; src[b * 4 + 2] = 0.f; src[b * 4 + 3] = 0.f; }
-        if (acc) { acc[b * 2 + 0] += tlo; acc[b * 2 + 1] += thi; }
-    }
+    if (threadIdx.x == 0) { rowmean[b * 4 + 0] = a[0]; rowmean[b * 4 + 1] = a[1]; }
+}
+__global__ void k3_wall_rows_finish(int B, float visc, int n_row_global, float d_lo, float d_hi, float *__restrict__ rowmean,
+                                    float *__restrict__ src /* [B][4] or null */, float *__restrict__ acc /* [B][2] += tau, or null */) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float mlo = rowmean[b * 4 + 0] / (float)n_row_global, mhi = rowmean[b * 4 + 1] / (float)n_row_global;
+    const float tlo = visc * mlo / d_lo, thi = visc * mhi / d_hi;
+    rowmean[b * 4 + 0] = mlo; rowmean[b * 4 + 1] = mhi; rowmean[b * 4 + 2] = tlo; rowmean[b * 4 + 3] = thi;
+    if (src) { src[b * 4 + 0] = (tlo + thi) * 0.5f; src[b * 4 + 1] = 0.f; src[b * 4 + 2] = 0.f; src[b * 4 + 3] = 0.f; }
+    if (acc) { acc[b * 2 + 0] += tlo; acc[b * 2 + 1] += thi; }
 }
 
 extern "C" int fgb_ortho3_wall_rows(fgb_ortho3 *b, const float *u, const int32_t *rows, int n_row, float d_lo, float d_hi, int set_forcing,
                                     float *acc, fgb_stream_t s) {
     if (!b || !u || !rows || n_row <= 0) return set_err(FGB_E_ARG, "fgb_ortho3_wall_rows: bad argument");
-    b->launches++;
-    k3_wall_rows<<<b->B, 512, 0, STREAM(s)>>>(b->t, u, rows, n_row, d_lo, d_hi, b->rowmean, set_forcing ? b->src : nullptr, acc);
-    LAUNCH_CHECK("k3_wall_rows");
+    cudaStream_t st = STREAM(s);
+    int rc;
+    b->launches += 2;
+    k3_wall_rows_sum<<<b->B, 512, 0, st>>>(b->t, u, rows, n_row, b->rowmean);
+    LAUNCH_CHECK("k3_wall_rows_sum");
+    if ((rc = o3_allreduce(b, b->rowmean, 2, 0, st))) return rc;       // slabs: every rank holds a part of both wall layers
+    k3_wall_rows_finish<<<(b->B + 127) / 128, 128, 0, st>>>(b->B, b->t.viscosity, n_row * b->slab.world, d_lo, d_hi, b->rowmean,
+                                                           set_forcing ? b->src : nullptr, acc);
+    LAUNCH_CHECK("k3_wall_rows_finish");
     return FGB_OK;
 }
 
@@ -662,6 +892,7 @@ extern "C" int fgb_ortho3_sim_step(fgb_ortho3 *b, float *u, float *p, const floa
         const int mv_blocks = (b->t.N + 256 * 8 - 1) / (256 * 8);
         k3_max_velocity<<<dim3((unsigned)(mv_blocks < 1 ? 1 : mv_blocks), (unsigned)b->B), 256, 0, st>>>(b->t, u, bvel, b->maxvel);
         LAUNCH_CHECK("k3_max_velocity");
+        if ((rc = o3_allreduce(b, b->maxvel, 1, 1, st))) return rc;
         k3_plan_substep<<<(b->B + 127) / 128, 128, 0, st>>>(b->B, b->remaining, b->dt, b->active, b->nsub, b->maxvel, b->counters, cfl);
         LAUNCH_CHECK("k3_plan_substep");
         cudaError_t ce = cudaMemcpyAsync(b->h_counters, b->counters, sizeof(int32_t), cudaMemcpyDeviceToHost, st);

@@ -43,7 +43,8 @@ class Options(C.Structure):
 
 class Ortho3Tables(C.Structure):
     _fields_ = [("N", C.c_int32), ("NB", C.c_int32), ("viscosity", C.c_float), ("nbr", C.c_void_p), ("minv", C.c_void_p),
-                ("det", C.c_void_p), ("b_minv", C.c_void_p), ("b_det", C.c_void_p)]
+                ("det", C.c_void_p), ("b_minv", C.c_void_p), ("b_det", C.c_void_p), ("NS", C.c_int32), ("N_global", C.c_int32),
+                ("plane", C.c_int32)]
 
 
 class Wall(C.Structure):
@@ -62,7 +63,8 @@ EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_cr
            "fgb_ortho3_workspace_bytes", "fgb_ortho3_create", "fgb_ortho3_destroy", "fgb_ortho3_set_options", "fgb_ortho3_buffer",
            "fgb_ortho3_launch_count", "fgb_ortho3_setup_advection", "fgb_ortho3_solve_advection", "fgb_ortho3_setup_pressure",
            "fgb_ortho3_solve_pressure", "fgb_ortho3_correct_velocity", "fgb_ortho3_piso_substep", "fgb_ortho3_make_divergence_free",
-           "fgb_ortho3_sim_step", "fgb_ortho3_wall_rows"]
+           "fgb_ortho3_sim_step", "fgb_ortho3_wall_rows", "fgb_ipc_alloc", "fgb_ipc_open", "fgb_ipc_close", "fgb_ipc_free",
+           "fgb_ortho3_set_slab", "fgb_ortho3_slab_error"]
 
 
 def lib_path() -> str:
@@ -132,6 +134,12 @@ def load():
     L.fgb_ortho3_make_divergence_free.argtypes = [vp, vp, vp, vp, i32, vp]
     L.fgb_ortho3_sim_step.argtypes = [vp, vp, vp, vp, f32, f32, vp, i32, f32, f32, C.POINTER(i32), vp]
     L.fgb_ortho3_wall_rows.argtypes = [vp, vp, vp, i32, f32, f32, i32, vp, vp]
+    L.fgb_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
+    L.fgb_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.fgb_ipc_close.argtypes = [vp]
+    L.fgb_ipc_free.argtypes = [vp]
+    L.fgb_ortho3_set_slab.argtypes = [vp, i32, i32, vp, C.POINTER(vp)]
+    L.fgb_ortho3_slab_error.argtypes = [vp, C.POINTER(i32)]
     _lib = L
     return L
 

@@ -247,6 +247,9 @@ typedef struct fgb_ortho3_tables {
     const float *det;     /* [N]                                                                                 */
     const float *b_minv;  /* [3][NB] diagonal of the boundary-face M^-1 (FixedBoundary.transform)                */
     const float *b_det;   /* [NB]                                                                                */
+    /* slab decomposition (0 = single GPU): per-cell arrays are strided by NS = N + 2 * plane cells -- owned cells [0, N),
+     * lower halo plane [N, N + plane), upper halo plane [N + plane, NS); N_global = cells of the whole domain (norms) */
+    int32_t NS, N_global, plane;
 } fgb_ortho3_tables;
 typedef struct fgb_ortho3 fgb_ortho3;
 size_t fgb_ortho3_workspace_bytes(const fgb_ortho3_tables *t, int32_t B);
@@ -281,6 +284,19 @@ int fgb_ortho3_sim_step(fgb_ortho3 *b, float *u, float *p, const float *bvel, fl
  * acc [B][2] (optional): += (tau_lo, tau_hi) */
 int fgb_ortho3_wall_rows(fgb_ortho3 *b, const float *u, const int32_t *rows, int n_row, float d_lo, float d_hi, int set_forcing,
                          float *acc, fgb_stream_t s);
+
+/* ---- slab decomposition of one large 3-D domain over the GPUs of a node (one process per GPU) -------------------------
+ * Every rank owns nz/world z-planes.  All device memory the solver touches lives in ONE symmetric allocation per rank
+ * (fgb_ipc_alloc) that every peer maps with CUDA IPC (fgb_ipc_open): halo planes and reduction partials are written
+ * straight into the peer's memory over NVLink from inside the persistent Krylov kernels, sequence-numbered flags replace
+ * collectives (no NCCL call on the solver path).  The first 4 KiB of the region are reserved for the flag pad. */
+int fgb_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle_out /* [64] */);
+int fgb_ipc_open(const unsigned char *handle /* [64] */, void **peer_ptr);
+int fgb_ipc_close(void *peer_ptr);
+int fgb_ipc_free(void *ptr);
+int fgb_ortho3_set_slab(fgb_ortho3 *b, int32_t rank, int32_t world, void *local_base, void *const *peer_bases);
+/* non-zero in *out when a wait on a peer timed out (results invalid) */
+int fgb_ortho3_slab_error(fgb_ortho3 *b, int32_t *out);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------ */
 /* Record CUDA events around the solver launches on their own stream.  fgb_profile_read synchronises the

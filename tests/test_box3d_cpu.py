@@ -85,3 +85,33 @@ def test_agent_window_means_matches_loop_definition():
             for j in range(wz):
                 for k in range(wx):
                     assert got[ix * naz + iz, j, k] == means[(iz - pz + j) % naz, (ix - px + k) % nax]
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_slab_tables_reproduce_the_global_stencil(golden, world):
+    """Slab decomposition (host logic): with the halo planes filled from the z-neighbours, gathering through the local
+    neighbour table of every rank returns exactly what the global table returns; metrics incl. halos are copies."""
+    from fluidgym_b200.box3d import Box3DDomain, SlabTables
+    g = golden("tcf32_geometry.npz")
+    dom = Box3DDomain(g["vertex"], viscosity=1e-3)
+    x = np.random.default_rng(0).random(dom.N).astype(np.float32)
+    nz, P = dom.nz, dom.nx * dom.ny
+    xg = x.reshape(nz, P)
+    for r in range(world):
+        tb = SlabTables(dom, r, world)
+        assert tb.NS == tb.N + 2 * P and tb.N * world == dom.N
+        loc = tb.take_cells(x)
+        loc[tb.N:tb.N + P] = xg[(tb.z0 - 1) % nz]
+        loc[tb.N + P:] = xg[(tb.z0 + tb.nzl) % nz]
+        for f in range(6):
+            n = tb.nbr[f, :tb.N]
+            gn = dom.nbr[f].reshape(nz, P)[tb.z0:tb.z0 + tb.nzl].reshape(-1)
+            inner = n >= 0
+            assert np.array_equal(inner, gn >= 0)
+            assert np.array_equal(loc[n[inner]], x[gn[inner]])
+        assert np.array_equal(tb.det[:tb.N], dom.det.reshape(nz, P)[tb.z0:tb.z0 + tb.nzl].reshape(-1))
+        assert np.array_equal(tb.det[tb.N:tb.N + P], dom.det.reshape(nz, P)[(tb.z0 - 1) % nz])
+        faces = tb.take_faces(np.arange(3 * nz * dom.nx, dtype=np.float32).reshape(3, -1), 2)
+        assert faces.shape == (3, tb.nzl * dom.nx)
+    with pytest.raises(ValueError):
+        SlabTables(dom, 0, 5)
