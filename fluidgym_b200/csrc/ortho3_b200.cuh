@@ -41,11 +41,13 @@ __device__ __forceinline__ void o3_wait_ge(volatile unsigned long long *flag, un
 }
 
 // owned boundary planes -> the z-neighbours' halo planes (direct stores into peer memory over NVLink)
-__device__ __forceinline__ void o3_push(const O3Slab &sl, const T3 &t, float *vec, int g, float val) {
+// `dirty` records that this thread has peer stores in flight: only such threads need the (expensive) system-scope fence
+// before the next grid barrier; cumulativity carries their stores in front of the flag that CTA 0 writes after it.
+__device__ __forceinline__ void o3_push(const O3Slab &sl, const T3 &t, float *vec, int g, float val, bool &dirty) {
     if (sl.on) {
         const int P = t.plane, N = t.N;
-        if (g < P) o3_peer(sl, vec, sl.lower)[N + P + g] = val;               // my lowest plane = the lower neighbour's UPPER halo
-        if (g >= N - P) o3_peer(sl, vec, sl.upper)[N + (g - (N - P))] = val;  // my highest plane = the upper neighbour's LOWER halo
+        if (g < P) { o3_peer(sl, vec, sl.lower)[N + P + g] = val; dirty = true; }               // my lowest plane = the lower neighbour's UPPER halo
+        if (g >= N - P) { o3_peer(sl, vec, sl.upper)[N + (g - (N - P))] = val; dirty = true; }  // my highest plane = the upper neighbour's LOWER halo
     }
 }
 
@@ -147,7 +149,7 @@ __device__ __forceinline__ float o3_bflux(const T3 &t, int j, int d, const float
 }
 
 // C = (det/dt I + convection + diffusion)/det as ELL(7), A = diag(C), predictor RHS (K.cu:3617-3880, 4296-4400)
-__global__ void __launch_bounds__(O3_T) k3_setup_advection(T3 t, const float *__restrict__ U, const float *__restrict__ Bvel,
+__global__ void __launch_bounds__(O3_T) k3_setup_advection(T3 t, O3Slab sl, const float *__restrict__ U, const float *__restrict__ Bvel,
                                                            const float *__restrict__ Src /* [B][4] or null */, const float *__restrict__ dtv,
                                                            const int32_t *__restrict__ active, float *__restrict__ Coff, float *__restrict__ A,
                                                            float *__restrict__ Rhs) {
@@ -181,10 +183,14 @@ __global__ void __launch_bounds__(O3_T) k3_setup_advection(T3 t, const float *__
         }
         Coff[((size_t)b * 6 + f) * NS + g] = off;
     }
-    A[(size_t)b * NS + g] = diag / det;
+    const float Ag = diag / det;
+    A[(size_t)b * NS + g] = Ag;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
         Rhs[((size_t)b * 3 + c) * NS + g] = (det * uo[c] / dt + Sb[c]) / det + (Src ? Src[b * 4 + c] : 0.f);
+    bool dirty = false;
+    o3_push(sl, t, A, g, Ag, dirty);          // (slabs: B == 1) consumed after the predictor solve, whose reductions order it
+    if (dirty) __threadfence_system();
 }
 
 // P: off = 1/2 (alpha_P / A_P + alpha_N / A_N), diag = -sum (K.cu:4812-4978)
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(O3_T) k3_pressure_matrix(T3 t, const float *__
 }
 
 // HbyA = (u/dt - H(u_prev) + S_b/det + source) / A (K.cu:5136-5255)
-__global__ void __launch_bounds__(O3_T) k3_hbya(T3 t, const float *__restrict__ U, const float *__restrict__ Uprev, const float *__restrict__ Bvel,
+__global__ void __launch_bounds__(O3_T) k3_hbya(T3 t, O3Slab sl, const float *__restrict__ U, const float *__restrict__ Uprev, const float *__restrict__ Bvel,
                                                 const float *__restrict__ Src, const float *__restrict__ dtv, const int32_t *__restrict__ active,
                                                 const float *__restrict__ Coff, const float *__restrict__ A, float *__restrict__ Hb) {
     const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS, NB = t.NB;
@@ -233,9 +239,14 @@ __global__ void __launch_bounds__(O3_T) k3_hbya(T3 t, const float *__restrict__ 
             for (int c = 0; c < 3; ++c) Sb[c] += bv[c * NB + j] * k;
         }
     }
+    bool dirty = false;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-        Hb[((size_t)b * 3 + c) * NS + g] = (u[c * NS + g] / dt - H[c] + Sb[c] / det + (Src ? Src[b * 4 + c] : 0.f)) / Ag;
+    for (int c = 0; c < 3; ++c) {
+        const float hv = (u[c * NS + g] / dt - H[c] + Sb[c] / det + (Src ? Src[b * 4 + c] : 0.f)) / Ag;
+        Hb[((size_t)b * 3 + c) * NS + g] = hv;
+        o3_push(sl, t, Hb + (size_t)c * NS, g, hv, dirty);
+    }
+    if (dirty) __threadfence_system();
 }
 
 // divergence of the contravariant face fluxes of a cell-centred field (K.cu:1567-1645, 5389-5434)
@@ -256,19 +267,23 @@ __global__ void __launch_bounds__(O3_T) k3_divergence(T3 t, const float *__restr
 }
 
 // u = HbyA - (1/A) M^-T grad(p), central differences, one-sided at prescribed boundaries (K.cu:816-849, 5962-5995)
-__global__ void __launch_bounds__(O3_T) k3_correct(T3 t, const float *__restrict__ Hb, const float *__restrict__ P, const float *__restrict__ A,
+__global__ void __launch_bounds__(O3_T) k3_correct(T3 t, O3Slab sl, const float *__restrict__ Hb, const float *__restrict__ P, const float *__restrict__ A,
                                                    const int32_t *__restrict__ active, float *__restrict__ Uout) {
     const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS;
     if (g >= N || (active && !active[b])) return;
     const float *p = P + (size_t)b * NS;
     const float pc = p[g], rA = 1.0f / A[(size_t)b * NS + g];
+    bool dirty = false;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         const int nl = t.nbr[(2 * d) * NS + g], nu = t.nbr[(2 * d + 1) * NS + g];
         const float fac = (nl < 0 || nu < 0) ? 1.0f : 0.5f;
         const float pg = ((nu >= 0 ? p[nu] : pc) - (nl >= 0 ? p[nl] : pc)) * fac;
-        Uout[((size_t)b * 3 + d) * NS + g] = Hb[((size_t)b * 3 + d) * NS + g] - pg * t.minv[d * NS + g] * rA;
+        const float uv = Hb[((size_t)b * 3 + d) * NS + g] - pg * t.minv[d * NS + g] * rA;
+        Uout[((size_t)b * 3 + d) * NS + g] = uv;
+        o3_push(sl, t, Uout + (size_t)d * NS, g, uv, dirty);
     }
+    if (dirty) __threadfence_system();
 }
 
 __global__ void k3_copy_active(const float *__restrict__ src, float *__restrict__ dst, size_t n, const int32_t *__restrict__ active) {
@@ -296,13 +311,13 @@ __device__ __forceinline__ float o3_row(const T3 &t, int g, const float *__restr
 // before it have landed: it doubles as the halo hand-shake.
 template <int K>
 __device__ __forceinline__ void o3_grid_sum(cg::grid_group &grid, const O3Slab &sl, float (&v)[K], float *part, unsigned &rcount,
-                                            unsigned long long &arc, double *sm) {
+                                            unsigned long long &arc, bool &dirty, double *sm) {
     static_assert(K <= O3_PART, "partials per CTA");
     block_reduce_sum<K>(v, sm);
     float *slot = part + (size_t)(rcount & 1u) * 4096 * O3_PART;
 #pragma unroll
     for (int k = 0; k < K; ++k) if (threadIdx.x == k) slot[blockIdx.x * O3_PART + k] = v[k];
-    if (sl.on) __threadfence_system(); else __threadfence();
+    if (dirty) { __threadfence_system(); dirty = false; } else __threadfence();
     grid.sync();
     const int nb = gridDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -324,9 +339,8 @@ __device__ __forceinline__ void o3_grid_sum(cg::grid_group &grid, const O3Slab &
             __threadfence_system();
             ((volatile unsigned long long *)dst->ar_seq[par])[sl.rank] = sq;
         }
-        if (threadIdx.x < sl.world) o3_wait_ge(&mine->ar_seq[par][threadIdx.x], sq, mine);
+        if (threadIdx.x < sl.world) { o3_wait_ge(&mine->ar_seq[par][threadIdx.x], sq, mine); __threadfence_system(); }
         __syncthreads();
-        __threadfence_system();
         double tot = 0.0;
         if (threadIdx.x < K) for (int q = 0; q < sl.world; ++q) tot += ((volatile double *)mine->ar_val[par][q])[threadIdx.x];
         __syncthreads();
@@ -339,8 +353,8 @@ __device__ __forceinline__ void o3_grid_sum(cg::grid_group &grid, const O3Slab &
     ++rcount;
 }
 // "the vector I just updated is complete everywhere": grid barrier + (slabs) flags to / from both z-neighbours
-__device__ __forceinline__ void o3_halo_sync(cg::grid_group &grid, const O3Slab &sl, unsigned long long &hc) {
-    if (sl.on) __threadfence_system(); else __threadfence();
+__device__ __forceinline__ void o3_halo_sync(cg::grid_group &grid, const O3Slab &sl, unsigned long long &hc, bool &dirty) {
+    if (dirty) { __threadfence_system(); dirty = false; } else __threadfence();
     grid.sync();
     if (sl.on) {
         const unsigned long long sq = ++hc;
@@ -349,9 +363,8 @@ __device__ __forceinline__ void o3_halo_sync(cg::grid_group &grid, const O3Slab 
             ((volatile unsigned long long *)o3_pad(sl, sl.lower)->halo_seq)[sl.rank] = sq;
             ((volatile unsigned long long *)o3_pad(sl, sl.upper)->halo_seq)[sl.rank] = sq;
         }
-        if (threadIdx.x == 0) { o3_wait_ge(&mine->halo_seq[sl.lower], sq, mine); o3_wait_ge(&mine->halo_seq[sl.upper], sq, mine); }
+        if (threadIdx.x == 0) { o3_wait_ge(&mine->halo_seq[sl.lower], sq, mine); o3_wait_ge(&mine->halo_seq[sl.upper], sq, mine); __threadfence_system(); }
         __syncthreads();
-        __threadfence_system();
     }
 }
 
@@ -367,6 +380,7 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
     const float norm = 1.0f / sqrtf((float)t.N_global);
     unsigned rcount = 0;
     unsigned long long arc = sl.on ? sl.ctr[0] : 0ull, hc = sl.on ? sl.ctr[1] : 0ull;
+    bool dirty = false;
     for (int b = 0; b < B; ++b) {
         if (active && !active[b]) continue;
         const float *off = Coff + (size_t)b * 6 * NS, *dg = Adiag + (size_t)b * NS;
@@ -384,40 +398,40 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
             for (int g = tid; g < N; g += nth) {
                 const float rr = f[c][g] - (zero_init ? 0.f : o3_row(t, g, off, dg, x[c]));
                 r[c][g] = rr; rw[c][g] = rr; p[c][g] = rr;
-                o3_push(sl, t, p[c], g, rr);
+                o3_push(sl, t, p[c], g, rr, dirty);
                 acc[c] += rr * rr;
             }
-        o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, red);
+        o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, dirty, red);
         bool done[3]; int used[3]; float fin[3], rho[3] = {1.f, 1.f, 1.f}, alpha[3] = {1.f, 1.f, 1.f}, omega[3] = {1.f, 1.f, 1.f};
         for (int c = 0; c < 3; ++c) { fin[c] = sqrtf(acc[c]) * norm; used[c] = -1; done[c] = fin[c] < tol; }
         for (int i = 0; i < maxit && !(done[0] && done[1] && done[2]); ++i) {
             for (int k = 0; k < 6; ++k) acc[k] = 0.f;
             for (int c = 0; c < 3; ++c) if (!done[c])
                 for (int g = tid; g < N; g += nth) acc[c] += rw[c][g] * r[c][g];
-            o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, red);
+            o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, dirty, red);
             for (int c = 0; c < 3; ++c) if (!done[c]) {
                 const float rhop = rho[c]; rho[c] = acc[c];
                 if (i > 0) {
                     const float beta = (rho[c] / rhop) * (alpha[c] / omega[c]);
-                    for (int g = tid; g < N; g += nth) { const float pn = r[c][g] + beta * (p[c][g] - omega[c] * v[c][g]); p[c][g] = pn; o3_push(sl, t, p[c], g, pn); }
+                    for (int g = tid; g < N; g += nth) { const float pn = r[c][g] + beta * (p[c][g] - omega[c] * v[c][g]); p[c][g] = pn; o3_push(sl, t, p[c], g, pn, dirty); }
                 }
             }
-            o3_halo_sync(grid, sl, hc);
+            o3_halo_sync(grid, sl, hc, dirty);
             for (int k = 0; k < 6; ++k) acc[k] = 0.f;
             for (int c = 0; c < 3; ++c) if (!done[c])
                 for (int g = tid; g < N; g += nth) { const float vv = o3_row(t, g, off, dg, p[c]); v[c][g] = vv; acc[c] += rw[c][g] * vv; }
-            o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, red);
+            o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, dirty, red);
             float acc2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int c = 0; c < 3; ++c) if (!done[c]) {
                 alpha[c] = rho[c] / acc[c];
                 for (int g = tid; g < N; g += nth) {
                     const float rr = r[c][g] - alpha[c] * v[c][g];
                     r[c][g] = rr; x[c][g] += alpha[c] * p[c][g];
-                    o3_push(sl, t, r[c], g, rr);
+                    o3_push(sl, t, r[c], g, rr, dirty);
                     acc2[c] += rr * rr;
                 }
             }
-            o3_grid_sum<6>(grid, sl, acc2, part, rcount, arc, red);     // (its grid.sync also publishes r for the next product)
+            o3_grid_sum<6>(grid, sl, acc2, part, rcount, arc, dirty, red);     // (its grid.sync also publishes r for the next product)
             for (int c = 0; c < 3; ++c) if (!done[c]) {
                 const float nr = sqrtf(acc2[c]) * norm;
                 used[c] = i; fin[c] = nr;
@@ -429,7 +443,7 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
                     const float tv = o3_row(t, g, off, dg, r[c]); tt[c][g] = tv;
                     acc[c] += tv * r[c][g]; acc[3 + c] += tv * tv;
                 }
-            o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, red);      // every row of t = C r is complete before r is overwritten
+            o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, dirty, red);      // every row of t = C r is complete before r is overwritten
             for (int k = 0; k < 6; ++k) acc2[k] = 0.f;
             for (int c = 0; c < 3; ++c) if (!done[c]) {
                 omega[c] = acc[c] / acc[3 + c];
@@ -441,7 +455,7 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
                     r[c][g] = rr;
                 }
             }
-            o3_grid_sum<6>(grid, sl, acc2, part, rcount, arc, red);
+            o3_grid_sum<6>(grid, sl, acc2, part, rcount, arc, dirty, red);
             for (int c = 0; c < 3; ++c) if (!done[c]) {
                 const float nr = sqrtf(acc2[c]) * norm;
                 fin[c] = nr;
@@ -453,7 +467,8 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
             for (int c = 0; c < 3; ++c) { iters[b * 8 + c] = used[c]; resid[b * 8 + c] = fin[c]; tot += (unsigned long long)(used[c] + 1); }
             iter_total[b * 2 + 1] += tot;
         }
-        grid.sync();
+        if (sl.on) for (int c = 0; c < 3; ++c) for (int g = tid; g < N; g += nth) o3_push(sl, t, x[c], g, x[c][g], dirty);
+        o3_halo_sync(grid, sl, hc, dirty);       // the solution incl. the neighbours' halo planes is complete when the kernel ends
     }
     if (sl.on && blockIdx.x == 0 && threadIdx.x == 0) { sl.ctr[0] = arc; sl.ctr[1] = hc; }
 }
@@ -470,6 +485,7 @@ __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, O3Slab sl, int B, const flo
     const float norm = 1.0f / sqrtf((float)t.N_global);
     unsigned rcount = 0;
     unsigned long long arc = sl.on ? sl.ctr[0] : 0ull, hc = sl.on ? sl.ctr[1] : 0ull;
+    bool dirty = false;
     for (int b = 0; b < B; ++b) {
         if (active && !active[b]) continue;
         const float *off = Poff + (size_t)b * 6 * NS, *dg = Pdiag + (size_t)b * NS, *f = Rhs + (size_t)b * NS;
@@ -478,7 +494,7 @@ __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, O3Slab sl, int B, const flo
         float *xo = Xout + (size_t)b * NS;
         float acc[2] = {0.f, 0.f};
         for (int g = tid; g < N; g += nth) { x[g] = zero_init ? 0.f : xo[g]; acc[1] += (f[g] != 0.f) ? 1.f : 0.f; }
-        o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, red);
+        o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
         int used = -1; float fin = 0.f;
         if (!(acc[1] > 0.f)) {            // all-zero right-hand side -> zero result (DIFF.py:392, 489-490)
             for (int g = tid; g < N; g += nth) x[g] = 0.f;
@@ -487,27 +503,27 @@ __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, O3Slab sl, int B, const flo
             for (int g = tid; g < N; g += nth) {
                 const float rr = f[g] - (zero_init ? 0.f : o3_row(t, g, off, dg, x));
                 r[g] = rr; p[g] = rr; acc[0] += rr * rr;
-                o3_push(sl, t, p, g, rr);
+                o3_push(sl, t, p, g, rr, dirty);
             }
-            o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, red);
+            o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
             float rho = acc[0], bestc = 0.f, lastc = 0.f; int best_it = -1, rising = 0;
             int until_reset = reset_steps > 0 ? reset_steps - 1 : -1;
             for (int i = 0; i < maxit; ++i) {
                 const bool do_reset = until_reset == 0;
                 if (until_reset >= 0) until_reset = do_reset ? reset_steps - 1 : until_reset - 1;
                 if (do_reset) {
-                    if (sl.on) for (int g = tid; g < N; g += nth) o3_push(sl, t, x, g, x[g]);
-                    o3_halo_sync(grid, sl, hc);
+                    if (sl.on) for (int g = tid; g < N; g += nth) o3_push(sl, t, x, g, x[g], dirty);
+                    o3_halo_sync(grid, sl, hc, dirty);
                     acc[0] = acc[1] = 0.f;
                     for (int g = tid; g < N; g += nth) { const float rr = f[g] - o3_row(t, g, off, dg, x); r[g] = rr; acc[0] += rr * rr; }
-                    o3_halo_sync(grid, sl, hc);              // every row has read the old p halos before p is overwritten
-                    for (int g = tid; g < N; g += nth) { const float rr = r[g]; p[g] = rr; o3_push(sl, t, p, g, rr); }
-                    o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, red);
+                    o3_halo_sync(grid, sl, hc, dirty);              // every row has read the old p halos before p is overwritten
+                    for (int g = tid; g < N; g += nth) { const float rr = r[g]; p[g] = rr; o3_push(sl, t, p, g, rr, dirty); }
+                    o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
                     rho = acc[0];
                 }
                 acc[0] = acc[1] = 0.f;
                 for (int g = tid; g < N; g += nth) { const float a = o3_row(t, g, off, dg, p); ap[g] = a; acc[0] += p[g] * a; }
-                o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, red);
+                o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
                 const float alpha = rho / acc[0];
                 acc[0] = acc[1] = 0.f;
                 for (int g = tid; g < N; g += nth) {
@@ -515,7 +531,7 @@ __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, O3Slab sl, int B, const flo
                     const float rr = r[g] - alpha * ap[g];
                     r[g] = rr; acc[0] += rr * rr;
                 }
-                o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, red);
+                o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
                 const float crit = sqrtf(acc[0]) * norm;
                 if (!isfinite(crit)) { used = i; fin = crit; break; }
                 if (i == 0 || crit < bestc) {
@@ -532,19 +548,19 @@ __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, O3Slab sl, int B, const flo
                 }
                 const float rhop = rho; rho = acc[0];
                 const float beta = rho / rhop;
-                for (int g = tid; g < N; g += nth) { const float pn = r[g] + beta * p[g]; p[g] = pn; o3_push(sl, t, p, g, pn); }
-                o3_halo_sync(grid, sl, hc);          // p complete (incl. the neighbours' halo planes) before the next product gathers it
+                for (int g = tid; g < N; g += nth) { const float pn = r[g] + beta * p[g]; p[g] = pn; o3_push(sl, t, p, g, pn, dirty); }
+                o3_halo_sync(grid, sl, hc, dirty);          // p complete (incl. the neighbours' halo planes) before the next product gathers it
             }
         }
         acc[0] = acc[1] = 0.f;
         for (int g = tid; g < N; g += nth) acc[0] += x[g];
-        o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, red);
+        o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
         const float mean = acc[0] / (float)t.N_global;
-        for (int g = tid; g < N; g += nth) xo[g] = x[g] - mean;
+        for (int g = tid; g < N; g += nth) { const float xv = x[g] - mean; xo[g] = xv; o3_push(sl, t, xo, g, xv, dirty); }
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             iters[b * 8 + 3 + slot] = used; resid[b * 8 + 3 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1);
         }
-        grid.sync();
+        o3_halo_sync(grid, sl, hc, dirty);
     }
     if (sl.on && blockIdx.x == 0 && threadIdx.x == 0) { sl.ctr[0] = arc; sl.ctr[1] = hc; }
 }
@@ -603,6 +619,13 @@ static int o3_exchange(fgb_ortho3 *b, float *field, int ncomp, cudaStream_t st) 
     b->launches += 2;
     k3_halo_push<<<(n + 255) / 256, 256, 0, st>>>(b->slab, b->t, field, ncomp);
     LAUNCH_CHECK("k3_halo_push");
+    k3_rank_barrier<<<1, 32, 0, st>>>(b->slab);
+    LAUNCH_CHECK("k3_rank_barrier");
+    return FGB_OK;
+}
+static int o3_barrier(fgb_ortho3 *b, cudaStream_t st) {     // after a kernel that pushed its own output planes
+    if (!b->slab.on) return FGB_OK;
+    b->launches++;
     k3_rank_barrier<<<1, 32, 0, st>>>(b->slab);
     LAUNCH_CHECK("k3_rank_barrier");
     return FGB_OK;
@@ -687,7 +710,7 @@ extern "C" int fgb_ortho3_setup_advection(fgb_ortho3 *b, const float *u, const f
                                           const int32_t *active, fgb_stream_t s) {
     if (!b || !u || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_ortho3_setup_advection: null argument");
     b->launches++;
-    k3_setup_advection<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, u, bvel, src, dt, active, b->Coff, b->A, b->rhs);
+    k3_setup_advection<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, b->slab, u, bvel, src, dt, active, b->Coff, b->A, b->rhs);
     LAUNCH_CHECK("k3_setup_advection");
     return FGB_OK;
 }
@@ -714,9 +737,9 @@ extern "C" int fgb_ortho3_setup_pressure(fgb_ortho3 *b, const float *u, const fl
         LAUNCH_CHECK("k3_pressure_matrix");
     }
     b->launches += 2;
-    k3_hbya<<<o3_grid(b), O3_T, 0, st>>>(b->t, u, b->ures, bvel, src, dt, active, b->Coff, b->A, b->hbya);
+    k3_hbya<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->slab, u, b->ures, bvel, src, dt, active, b->Coff, b->A, b->hbya);
     LAUNCH_CHECK("k3_hbya");
-    { int rc = o3_exchange(b, b->hbya, 3, st); if (rc) return rc; }
+    { int rc = o3_barrier(b, st); if (rc) return rc; }          // k3_hbya pushed its boundary planes itself
     k3_divergence<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->hbya, bvel, active, b->div);
     LAUNCH_CHECK("k3_divergence");
     return FGB_OK;
@@ -739,7 +762,7 @@ extern "C" int fgb_ortho3_solve_pressure(fgb_ortho3 *b, float *p_out, int zero_i
 extern "C" int fgb_ortho3_correct_velocity(fgb_ortho3 *b, const float *p, float *u_out, const int32_t *active, fgb_stream_t s) {
     if (!b || !p || !u_out) return set_err(FGB_E_ARG, "fgb_ortho3_correct_velocity: null argument");
     b->launches++;
-    k3_correct<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, b->hbya, p, b->A, active, u_out);
+    k3_correct<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, b->slab, b->hbya, p, b->A, active, u_out);
     LAUNCH_CHECK("k3_correct");
     return FGB_OK;
 }
@@ -751,16 +774,17 @@ extern "C" int fgb_ortho3_piso_substep(fgb_ortho3 *b, float *u, float *p, const 
     if (!b || !u || !p || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep: null argument");
     cudaStream_t st = STREAM(s);
     int rc;
+    // slabs: u is exchanged explicitly (the caller may have changed it); every later field is pushed by the kernel that
+    // produces it -- A by the assembly (ordered by the predictor's reductions), u* and p by the Krylov kernels (hand-shake at
+    // their end), HbyA and the corrected velocity by their kernels followed by a flag-only barrier.
     if ((rc = o3_exchange(b, u, 3, st))) return rc;
     if ((rc = fgb_ortho3_setup_advection(b, u, bvel, src, dt, active, s))) return rc;
-    if ((rc = o3_exchange(b, b->A, 1, st))) return rc;
     if ((rc = fgb_ortho3_solve_advection(b, 1, active, s))) return rc;
     for (int cs = 0; cs < b->opt.corrector_steps; ++cs) {
-        if ((rc = o3_exchange(b, b->ures, 3, st))) return rc;
         if ((rc = fgb_ortho3_setup_pressure(b, u, bvel, src, dt, cs == 0, active, s))) return rc;
         if ((rc = fgb_ortho3_solve_pressure(b, p, 1, b->opt.nonortho ? 100 : 0, b->opt.max_iter, cs, active, s))) return rc;
-        if ((rc = o3_exchange(b, p, 1, st))) return rc;
         if ((rc = fgb_ortho3_correct_velocity(b, p, b->ures, active, s))) return rc;
+        if ((rc = o3_barrier(b, st))) return rc;
     }
     b->launches++;
     const size_t n = (size_t)3 * b->t.NS;
@@ -786,8 +810,8 @@ extern "C" int fgb_ortho3_make_divergence_free(fgb_ortho3 *b, float *u, float *p
     k3_divergence<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->hbya, bvel, nullptr, b->div);
     LAUNCH_CHECK("k3_divergence");
     if ((rc = fgb_ortho3_solve_pressure(b, p, 1, 0, max_iter, 0, nullptr, s))) return rc;
-    if ((rc = o3_exchange(b, p, 1, st))) return rc;
-    return fgb_ortho3_correct_velocity(b, p, u, nullptr, s);
+    if ((rc = fgb_ortho3_correct_velocity(b, p, u, nullptr, s))) return rc;
+    return o3_barrier(b, st);
 }
 
 // ------------------------------------------------------------------------------------------------

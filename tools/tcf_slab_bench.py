@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--nz-mult", type=int, default=1, help="repeat the domain along z (weak-scaling style sizes)")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--plain", action="store_true", help="world 1 only: the plain single-GPU solver on the same state (baseline of the protocol overhead)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -38,7 +39,26 @@ def main():
     u_wall = cfg["reynolds_number_wall"] / re_c
     vertex = channel_vertex_grid(2.0, cfg["L"], cfg["D"] * a.nz_mult, x, cfg["resolution_y"] // 2, 1, z)
     dom = Box3DDomain(vertex, closed=(False, True, False), viscosity=visc)
-    slab = SlabPISO3D(dom, rank, world, f"cuda:{local}")
+    if a.plain:
+        from fluidgym_b200.box3d import BatchedPISO3D
+
+        class _Plain(BatchedPISO3D):              # same surface as SlabPISO3D for this script
+            def load_global(self, u, p):
+                self.u.copy_(torch.from_numpy(u).cuda().unsqueeze(0)); self.p.copy_(torch.from_numpy(p).cuda().unsqueeze(0))
+
+            def owned(self, t):
+                return t
+
+            def error(self):
+                return 0
+
+            def close(self):
+                pass
+        assert world == 1
+        slab = _Plain(dom, 1, device=f"cuda:{local}")
+        slab.tabs = type("T", (), {"N": dom.N, "nzl": dom.nz})()
+    else:
+        slab = SlabPISO3D(dom, rank, world, f"cuda:{local}")
     tb = slab.tabs
     # state: Reichardt profile + 5 % noise, generated identically on every rank
     cc = dom.cell_centres()
@@ -74,7 +94,7 @@ def main():
     chk_t = torch.tensor([chk], device="cuda", dtype=torch.float64)
     dist.all_reduce(chk_t)
     if rank == 0:
-        print(json.dumps({"workload": f"TCF {'Large' if a.large else 'Small'} {dom.nx}x{dom.ny}x{dom.nz} = {dom.N} cells, 1 environment", "n_gpus": world,
+        print(json.dumps({"workload": f"TCF {'Large' if a.large else 'Small'} {dom.nx}x{dom.ny}x{dom.nz} = {dom.N} cells, 1 environment", "n_gpus": world, "mode": "plain" if a.plain else "slab",
                           "solver_steps": a.steps, "substeps": nsub, "ms_total": float(ms), "ms_per_substep": float(ms) / max(nsub, 1),
                           "substeps_per_s": nsub / (float(ms) / 1e3), "cg_iters_per_solve": it[0] / max(2 * nsub, 1),
                           "bicg_iters_per_rhs": it[1] / max(3 * nsub, 1), "slab_error": err, "checksum_u2": float(chk_t)}), flush=True)
