@@ -1011,8 +1011,8 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
 //               count), so every stencil gather is a plain ld.shared and the hand-shake carries the data itself
 //               (no release fence, no remote arrive).  ncu on the PUSH=false kernel: each DSMEM gather costs an
 //               LD.E on a generic address plus two MOVs to assemble it, 84 of 391 instructions per iteration.
-template <int T, int CPT, int CS, bool PUSH>
-__global__ void __launch_bounds__(T, 1) k_cg_cluster_mb(Tab t, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
+template <int T, int CPT, int CS, bool PUSH, int MINB = 1>
+__global__ void __launch_bounds__(T, MINB) k_cg_cluster_mb(Tab t, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
                                                          const float *__restrict__ Rhs, float *__restrict__ Xout,
                                                          int maxit, float tol, int zero_init, int reset_steps, int slot,
                                                          const int32_t *__restrict__ active, int32_t *__restrict__ iters,
@@ -2246,7 +2246,7 @@ static int launch_cg_cluster(fgb_batch *b, float *p_out, int zero_init, int rese
     return FGB_OK;
 }
 
-template <int CS, int CPT, bool PUSH = false, int T = 512>
+template <int CS, int CPT, bool PUSH = false, int T = 512, int MINB = 1>
 static int launch_cg_cluster_mb(fgb_batch *b, const float *poff, const float *pdiag, const float *rhs, float *p_out, int zero_init,
                                 int reset_steps, int max_iter, int slot, const int32_t *active, int flags, float *mean_out,
                                 cudaStream_t st) {
@@ -2258,7 +2258,7 @@ static int launch_cg_cluster_mb(fgb_batch *b, const float *poff, const float *pd
     const size_t smem = ((size_t)2 * T * CPT + (size_t)2 * (T / 32) * CS + (PUSH ? (size_t)b->t.cg_hmax : 0)) * sizeof(float) + 4 * 8 + 16 +
                         (PUSH ? (size_t)b->t.cg_emax * 8 : 0);
     if (smem > 227 * 1024) return set_err(FGB_E_ARG, "cg_impl 6: halo plan does not fit in shared memory");
-    auto kern = k_cg_cluster_mb<T, CPT, CS, PUSH>;
+    auto kern = k_cg_cluster_mb<T, CPT, CS, PUSH, MINB>;
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_cg_cluster_mb)", ce);
     if (CS > 8) {   // 16-CTA clusters are a non-portable size: opt in (one cluster then occupies most of a GPC)
@@ -2279,6 +2279,14 @@ static int launch_cg_cluster_mb(fgb_batch *b, const float *poff, const float *pd
 
 static int cg_cluster_mb_any(fgb_batch *b, const float *poff, const float *pdiag, const float *rhs, float *p_out, int zero_init,
                              int reset_steps, int max_iter, int slot, const int32_t *active, int flags, float *mean_out, cudaStream_t st) {
+    if (b->opt.cg_impl == 8) {       // as 6 with 256-thread CTAs of 1792 cells, TWO co-resident CTAs per SM (of different environments):
+                                     // while one waits for a cluster hand-shake the other one computes
+        int rc = launch_cg_cluster_mb<2, 7, true, 256, 2>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        if (rc == 1) rc = launch_cg_cluster_mb<4, 7, true, 256, 2>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        if (rc == 1) rc = launch_cg_cluster_mb<8, 7, true, 256, 2>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        if (rc == 1) rc = launch_cg_cluster_mb<16, 7, true, 256, 2>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        return rc;
+    }
     if (b->opt.cg_impl == 7) {       // as 6 with half the threads and twice the cells per thread (same padding per CTA)
         int rc = launch_cg_cluster_mb<2, 12, true, 256>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
         if (rc == 1) rc = launch_cg_cluster_mb<4, 14, true, 256>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
@@ -2341,7 +2349,7 @@ static int solve_pressure_slot(fgb_batch *b, float *p_out, int zero_init, int re
         if (rc == 1) rc = launch_cg_smem<8, 7, 2>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
         if (rc <= 0) return rc;
     }
-    if (b->opt.cg_impl == 3 || b->opt.cg_impl == 6 || b->opt.cg_impl == 7) {
+    if (b->opt.cg_impl == 3 || b->opt.cg_impl == 6 || b->opt.cg_impl == 7 || b->opt.cg_impl == 8) {
         int rc = cg_cluster_mb_any(b, b->Poff, b->Pdiag, b->div, p_out, zero_init, reset_steps, max_iter, slot, active, 0,
                                    b->pmean + (size_t)mean_slot * b->B, STREAM(s));
         if (rc <= 0) return rc;
@@ -2440,7 +2448,7 @@ extern "C" int fgb_piso_substep_record(fgb_batch *b, float *u, float *p, const f
     if (!b || !u || !p || !bvel || !dt || !tp) return set_err(FGB_E_ARG, "fgb_piso_substep_record: null argument");
     const fgb_options &o = b->opt;
     const int C = o.corrector_steps, n_adv = o.adv_nonortho_steps, n_p = o.p_nonortho_steps;
-    if (!o.nonortho || (o.cg_impl != 3 && o.cg_impl != 6 && o.cg_impl != 7) || C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8)
+    if (!o.nonortho || (o.cg_impl != 3 && o.cg_impl != 6 && o.cg_impl != 7 && o.cg_impl != 8) || C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8)
         return set_err(FGB_E_ARG, "fgb_piso_substep_record: needs the non-orthogonal path, cg_impl 3 or 6 and correctors x pressure iterations <= 8");
     cudaStream_t st = STREAM(s);
     const size_t B = b->B, N = b->t.N, NB = b->t.NB;

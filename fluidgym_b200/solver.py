@@ -23,20 +23,21 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def cluster_shape(N: int):
+def cluster_shape(N: int, cg_impl: int = 6):
     """(cluster size, cells per CTA incl. padding) the on-chip Krylov launchers pick for a grid of N cells
     (cg_cluster_mb_any in csrc/piso_b200.cu): smallest cluster whose CTAs hold ceil(N/CS) cells."""
-    for cs, cpt in ((2, 6), (4, 7), (8, 7), (16, 6)):
-        if -(-N // cs) <= 512 * cpt:
-            return cs, 512 * cpt
+    shapes = ((2, 1792), (4, 1792), (8, 1792), (16, 1792)) if cg_impl == 8 else ((2, 3072), (4, 3584), (8, 3584), (16, 3072))
+    for cs, pad in shapes:
+        if -(-N // cs) <= pad:
+            return cs, pad
     return None
 
 
-def halo_plan(nbr: np.ndarray, N: int):
+def halo_plan(nbr: np.ndarray, N: int, cg_impl: int = 6):
     """Static communication plan of the pushed-halo CG (cg_impl 6, tables.cg_*): CTA r of the cluster owns cells
     [r*per, (r+1)*per) in slots [0, per); every remote cell one of its stencils touches gets a halo slot
     pad + h.  Returns dict(cs, pad, slot[4][N], exp[cs][emax][2], cnt[cs][2], emax, hmax) or None."""
-    shape = cluster_shape(N)
+    shape = cluster_shape(N, cg_impl)
     if shape is None:
         return None
     cs, pad = shape
@@ -116,7 +117,7 @@ class BatchedPISO:
             self.tables.scalar_viscosity = float(cd.scalar_visc)
         else:
             self._tab["Cd_s"] = self._tab["sb_neumann"] = None
-        plan = halo_plan(np.asarray(cd.nbr), cd.N)
+        plan = halo_plan(np.asarray(cd.nbr), cd.N, cg_impl)
         self.halo = plan
         if plan is not None:
             self._tab["cg_slot"] = torch.from_numpy(plan["slot"]).to(dev)
