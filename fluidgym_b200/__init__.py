@@ -26,11 +26,13 @@ def make(env_id: str, n_envs: int = 1, **kwargs):
     entry, defaults = _REGISTRY[env_id]
     cfg = dict(defaults)
     # reference-only constructor flags that have no meaning here are accepted and ignored
+    import inspect
+    params = inspect.signature(entry.__init__).parameters
     for k in ("load_initial_domain", "load_domain_statistics", "dtype"):
-        kwargs.pop(k, None)
+        if k not in params:
+            kwargs.pop(k, None)
     if "differentiable" in kwargs:
-        import inspect
-        if "differentiable" not in inspect.signature(entry.__init__).parameters:
+        if "differentiable" not in params:
             if kwargs.pop("differentiable"):
                 raise NotImplementedError(f"{env_id}: differentiable=True is not available for this environment family yet")
     cfg.update(kwargs)

@@ -1,0 +1,127 @@
+"""Reader / writer of the reference's on-disk domain format (``simulation/pict/util/domain_io.py:64-327``): ``<path>.json``
+describes the block / boundary structure and refers to flat tensors stored under integer keys in ``<path>.npz``.  This is
+the format of the published initial-domain splits (``initial_domains/<env id>/<idx>/<mode>.{json,npz}``,
+``envs/fluid_env.py:1044-1112``), so states written by the reference load into the batched environments and vice versa.
+"""
+from __future__ import annotations
+
+import json
+
+import numpy as np
+
+from .domain import CONNECTED, FIXED, PERIODIC, Boundary, DomainSpec
+
+
+def load_domain(path: str):
+    """-> (DomainSpec, state) with state = dict(u [2,N], p [N], bvel [2,NB], T [N] | None, sbval [NB] | None) in the flat
+    layout of the solver (cells of all blocks concatenated, x fastest; prescribed faces in (block, face) order)."""
+    with open(path + ".json") as fh:
+        d = json.load(fh)
+    with np.load(path + ".npz") as z:
+        data = {k: z[k] for k in z.files}
+
+    def get(dct, name):
+        return data[dct[name]] if name in dct else None
+    if d["spatialDims"] != 2:
+        raise NotImplementedError("domain files of 3-D domains: use fluidgym_b200.box3d (only 2-D multi-block domains are read here)")
+    n_scalar = d.get("passiveScalarChannels", 0)
+    svisc = get(d, "passiveScalarViscosity")
+    spec = DomainSpec(float(np.asarray(get(d, "viscosity")).ravel()[0]), d.get("name", "domain"),
+                      scalar_viscosity=None if (n_scalar == 0 or svisc is None) else float(np.asarray(svisc).ravel()[0]))
+    for blk in d["blocks"]:
+        v = get(blk, "vertexCoordinates")
+        if v is None:
+            raise NotImplementedError("blocks stored by transform only (no vertex coordinates)")
+        spec.create_block(v[0], blk.get("name", ""))
+    us, ps, Ts = [], [], []
+    for bi, blk in enumerate(d["blocks"]):
+        b = spec.blocks[bi]
+        us.append(get(blk, "velocity")[0].reshape(2, -1))
+        ps.append(get(blk, "pressure")[0].reshape(-1))
+        if "scalar" in blk and n_scalar:
+            Ts.append(get(blk, "scalar")[0].reshape(-1))
+        for f, bd in enumerate(blk["boundaries"]):
+            kind = bd["type"]
+            if kind == "FIXED":
+                if bd.get("velocityType", "DIRICHLET") != "DIRICHLET":
+                    raise NotImplementedError(f"boundary velocity type {bd.get('velocityType')}")
+                vel = np.asarray(get(bd, "velocity"), dtype=np.float32)
+                vel = vel.reshape(2, -1) if vel.ndim > 2 else vel.reshape(2, 1)
+                sc, neumann = None, False
+                if "scalar" in bd and n_scalar:
+                    sc = np.asarray(get(bd, "scalar"), dtype=np.float32).reshape(-1)
+                    neumann = bd.get("passiveScalarType", ["DIRICHLET"])[0] == "NEUMANN"
+                # the file lists every face explicitly: set it directly (close_boundary would also re-close the partner face)
+                n = b.size(1 - (f >> 1))
+                vfull = np.zeros((2, n), dtype=np.float32)
+                vfull[:] = vel
+                sfull = np.zeros(n, dtype=np.float32)
+                if sc is not None:
+                    sfull[:] = sc
+                b.bounds[f] = Boundary(FIXED, velocity=vfull, scalar=sfull, scalar_neumann=neumann)
+            elif kind == "CONNECTED":
+                other, (of, axis) = int(bd["connectedBlock"]), bd["axes"]
+                b.bounds[f] = Boundary(CONNECTED, other, (int(of), int(axis)))
+            elif kind == "PERIODIC":
+                b.bounds[f] = Boundary(PERIODIC)
+            else:
+                raise NotImplementedError(f"boundary type {kind}")
+    bvel, sbval = [], []
+    for bi, b in enumerate(spec.blocks):
+        for f in range(4):
+            if b.bounds[f].type == FIXED:
+                bvel.append(np.asarray(b.bounds[f].velocity, dtype=np.float32).reshape(2, -1))
+                sbval.append(np.asarray(b.bounds[f].scalar, dtype=np.float32).reshape(-1))
+    state = dict(u=np.concatenate(us, axis=1).astype(np.float32), p=np.concatenate(ps).astype(np.float32),
+                 bvel=np.concatenate(bvel, axis=1) if bvel else np.zeros((2, 0), np.float32),
+                 T=np.concatenate(Ts).astype(np.float32) if Ts else None,
+                 sbval=np.concatenate(sbval) if (sbval and n_scalar) else None)
+    return spec, state
+
+
+def save_domain(spec: DomainSpec, state: dict, path: str):
+    """Write ``spec`` with the given flat state in the reference's format (load_domain of either implementation reads it)."""
+    data = []
+
+    def add(arr, dct, name):
+        dct[name] = str(len(data))
+        data.append(np.ascontiguousarray(arr, dtype=np.float32))
+    has_T = state.get("T") is not None and spec.scalar_viscosity is not None
+    d = {"name": spec.name, "spatialDims": 2}
+    add(np.array([spec.viscosity]), d, "viscosity")
+    d["passiveScalarChannels"] = 1 if has_T else 0
+    if has_T:
+        add(np.array([spec.scalar_viscosity]), d, "passiveScalarViscosity")
+    d["blocks"] = []
+    o = ob = 0
+    for bi, b in enumerate(spec.blocks):
+        n = b.nx * b.ny
+        bd = {"name": b.name}
+        add(state["u"][:, o:o + n].reshape(1, 2, b.ny, b.nx), bd, "velocity")
+        add(state["p"][o:o + n].reshape(1, 1, b.ny, b.nx), bd, "pressure")
+        if has_T:
+            add(state["T"][o:o + n].reshape(1, 1, b.ny, b.nx), bd, "scalar")
+        add(b.vertex[None], bd, "vertexCoordinates")
+        o += n
+        bd["boundaries"] = []
+        for f in range(4):
+            bn = b.bounds[f]
+            if bn.type == FIXED:
+                m = b.size(1 - (f >> 1))
+                e = {"type": "FIXED", "velocityType": "DIRICHLET"}
+                shape = (1, 2, m, 1) if (f >> 1) == 0 else (1, 2, 1, m)
+                add(state["bvel"][:, ob:ob + m].reshape(shape), e, "velocity")
+                if has_T:
+                    e["passiveScalarType"] = ["NEUMANN" if bn.scalar_neumann else "DIRICHLET"]
+                    add(state["sbval"][ob:ob + m].reshape((1, 1) + shape[2:]), e, "scalar")
+                ob += m
+            elif bn.type == CONNECTED:
+                e = {"type": "CONNECTED", "connectedBlock": int(bn.other), "axes": [int(bn.axes[0]), int(bn.axes[1])]}
+            else:
+                e = {"type": "PERIODIC"}
+            bd["boundaries"].append(e)
+        d["blocks"].append(bd)
+    d["data_info"] = {str(i): {"shape": list(a.shape), "dtype": "float32", "device": "cpu"} for i, a in enumerate(data)}
+    np.savez_compressed(path + ".npz", **{str(i): a for i, a in enumerate(data)})
+    with open(path + ".json", "w") as fh:
+        json.dump(d, fh)

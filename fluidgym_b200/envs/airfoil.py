@@ -16,7 +16,7 @@ from .. import native
 from ..sensors import sensor_tables
 from ..solver import BatchedPISO, _ptr
 from .airfoil_domain import BOT, FRONT, JET_CENTERS, JET_WIDTH, TAIL_LOWER, TAIL_UPPER, TOP, airfoil_polyline, make_airfoil_domain
-from .common import DifferentiableRollout, build_wall_tables
+from .common import DifferentiableRollout, InitialDomains, build_wall_tables
 from .cylinder_domain import jet_profile
 
 AIRFOIL_2D_DEFAULT_CONFIG = {
@@ -41,7 +41,7 @@ def polygon_mask(polygon_xy: np.ndarray, nx: int, ny: int) -> np.ndarray:
     return inside.reshape(ny, nx)
 
 
-class Airfoil2DEnv(DifferentiableRollout):
+class Airfoil2DEnv(DifferentiableRollout, InitialDomains):
     H, L, U_mean, airfoil_length = 1.4, 4.5, 0.3, 1.0
     n_jets = 3
     action_smoothing_alpha = 0.1
@@ -51,7 +51,7 @@ class Airfoil2DEnv(DifferentiableRollout):
 
     def __init__(self, n_envs: int = 1, reynolds_number=3e3, dt=0.05, step_length=0.25, adaptive_cfl=0.8, episode_length=300,
                  attack_angle_deg=10.0, device="cuda:0", cg_impl=6, compiled=None, cl_cd_ref=0.0, randomize_initial_state=False,
-                 enable_actions=True, use_marl=False, differentiable=False):
+                 enable_actions=True, use_marl=False, differentiable=False, load_initial_domain=False, initial_domains_path=None):
         if attack_angle_deg < 0.0 or attack_angle_deg > 20.0:
             raise ValueError("Attack angle must be between 0 and 20 degrees.")
         if use_marl:
@@ -64,6 +64,7 @@ class Airfoil2DEnv(DifferentiableRollout):
         self.randomize_initial_state, self.enable_actions = randomize_initial_state, enable_actions
         self.differentiable = bool(differentiable)
         self._dstate = None
+        self.load_domain_on_reset, self.initial_domains_path = bool(load_initial_domain), initial_domains_path
         self.device = torch.device(device)
         if compiled is None:
             spec = make_airfoil_domain(reynolds_number, self.U_mean, self.airfoil_length, self.H, self.L, attack_angle_deg)
@@ -153,6 +154,11 @@ class Airfoil2DEnv(DifferentiableRollout):
         return self.n_jets
 
     @property
+    def initial_domain_id(self):
+        """airfoil_env_base.py:829-831"""
+        return f"airfoil_2D_Re{int(self.reynolds_number)}"
+
+    @property
     def n_sim_steps(self):
         return max(1, int(self.step_length / self.dt))
 
@@ -198,9 +204,12 @@ class Airfoil2DEnv(DifferentiableRollout):
         else:
             self.seed(seed)
         s = self.solver
-        s.u.zero_()
-        s.p.zero_()
-        s.bvel.copy_(torch.from_numpy(self.cd.bvel0[:, :self.cd.NB].copy()).to(self.device).unsqueeze(0).expand_as(s.bvel))
+        if self.load_domain_on_reset:
+            self._load_initial_domains_on_reset(self.randomize_initial_state if randomize is None else randomize)
+        else:
+            s.u.zero_()
+            s.p.zero_()
+            s.bvel.copy_(torch.from_numpy(self.cd.bvel0[:, :self.cd.NB].copy()).to(self.device).unsqueeze(0).expand_as(s.bvel))
         s.update_outflow(1.0, self.char_vel, tol=1e-5)       # the "PRE" hook of make_divergence_free (SIM.py:1335-1347)
         s.make_divergence_free(max_iter=1000)
         self.last_control.zero_()

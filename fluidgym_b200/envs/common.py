@@ -157,3 +157,89 @@ class DifferentiableRollout:
             u, p = piso_substep(s, u, p, bv, float(np.float32(ts)))
             nsub += 1
         return u, p, bv, nsub
+
+
+N_INITIAL_DOMAINS = 10      # envs/fluid_env.py:58
+
+
+def default_initial_domains_path() -> str:
+    """``fluidgym.config.initial_domains_path`` (config.py:137-144: platformdirs user data dir / initial_domains); override
+    with the environment variable FLUIDGYM_INITIAL_DOMAINS."""
+    import os
+    return os.environ.get("FLUIDGYM_INITIAL_DOMAINS", os.path.join(os.path.expanduser("~"), ".local", "share", "FluidGym", "initial_domains"))
+
+
+class InitialDomains:
+    """Mixin: the published initial-domain splits (``initial_domains/<initial_domain_id>/<idx>/<mode>.{json,npz}``,
+    envs/fluid_env.py:507-551, 1040-1112) for batched environments.  Files are read once into a device-resident pool; every
+    environment of the batch draws its own index on ``reset`` (the reference draws one per process).
+    Needs ``spec, cd, solver, device, n_envs, initial_domain_id``."""
+
+    mode = "train"
+
+    def train(self):
+        self.mode = "train"
+
+    def val(self):
+        self.mode = "val"
+
+    def test(self):
+        self.mode = "test"
+
+    def initial_domain_file(self, idx: int, mode: str | None = None) -> str:
+        import os
+        root = getattr(self, "initial_domains_path", None) or default_initial_domains_path()
+        return os.path.join(root, self.initial_domain_id, str(idx), mode or self.mode)
+
+    def _pool_entry(self, idx: int, mode: str):
+        pool = self.__dict__.setdefault("_domain_pool", {})
+        key = (mode, idx)
+        if key not in pool:
+            import os
+            from ..domain_io import load_domain
+            path = self.initial_domain_file(idx, mode)
+            if not os.path.exists(path + ".json"):
+                raise RuntimeError("Initial domain not found. Please ensure it was downloaded.")
+            spec, st = load_domain(path)
+            if [b.vertex.shape for b in spec.blocks] != [b.vertex.shape for b in self.spec.blocks] or any(
+                    not np.array_equal(a.vertex, b.vertex) for a, b in zip(spec.blocks, self.spec.blocks)):
+                raise ValueError(f"{path}: the stored grid is not the grid of this environment")
+            pool[key] = {k: torch.from_numpy(np.ascontiguousarray(v)).to(self.device) for k, v in st.items() if v is not None}
+        return pool[key]
+
+    def load_initial_domain(self, idx: int, mode: str | None = None, env_index=None):
+        """fluid_env.py:1065-1086; ``env_index`` (int, list or None = all) selects which environments receive the state."""
+        st = self._pool_entry(int(idx), mode or self.mode)
+        s = self.solver
+        sel = slice(None) if env_index is None else env_index
+        s.u[sel] = st["u"]
+        s.p[sel] = st["p"]
+        s.bvel[sel] = st["bvel"]
+        if "T" in st and getattr(s, "has_scalar", False):
+            s.T[sel] = st["T"]
+            s.sbval[sel] = st["sbval"]
+        if getattr(self, "_dstate", None) is not None:
+            self._dstate = None
+
+    def save_initial_domain(self, idx: int, mode: str | None = None, env_index: int = 0):
+        """fluid_env.py:1047-1063: writes environment ``env_index`` in the reference's format."""
+        import os
+        from ..domain_io import save_domain
+        path = self.initial_domain_file(idx, mode)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        s = self.solver
+        st = dict(u=s.u[env_index].cpu().numpy(), p=s.p[env_index].cpu().numpy(), bvel=s.bvel[env_index].cpu().numpy())
+        if getattr(s, "has_scalar", False):
+            st.update(T=s.T[env_index].cpu().numpy(), sbval=s.sbval[env_index].cpu().numpy())
+        save_domain(self.spec, st, path)
+        return path
+
+    def _load_initial_domains_on_reset(self, randomize: bool):
+        """_set_initial_state with load_initial_domain=True: index 0, or one random index per environment."""
+        if randomize:
+            idxs = [int(self._np_rng.integers(0, N_INITIAL_DOMAINS)) for _ in range(self.n_envs)]
+        else:
+            idxs = [0] * self.n_envs
+        for idx in sorted(set(idxs)):
+            self.load_initial_domain(idx, env_index=[e for e, i in enumerate(idxs) if i == idx])
+        return idxs

@@ -19,7 +19,7 @@ from .. import native
 from ..domain import FIXED
 from ..sensors import sensor_tables
 from ..solver import BatchedPISO, _ptr
-from .common import DifferentiableRollout, build_wall_tables
+from .common import DifferentiableRollout, InitialDomains, build_wall_tables
 from .cylinder_domain import BOTTOM, LEFT, RIGHT, TOP, WAKE, jet_profile, make_cylinder_domain
 
 CYLINDER_ROT_2D_DEFAULT_CONFIG = {
@@ -32,7 +32,7 @@ CYLINDER_JET_2D_DEFAULT_CONFIG = {
 }
 
 
-class CylinderJet2DEnv(DifferentiableRollout):
+class CylinderJet2DEnv(DifferentiableRollout, InitialDomains):
     H, L, cylinder_diameter, U_mean, cylinder_offset_y = 4.1, 22.0, 1.0, 1.0, 0.05
     n_sensors = 151
     action_smoothing_alpha = 0.1
@@ -41,7 +41,8 @@ class CylinderJet2DEnv(DifferentiableRollout):
 
     def __init__(self, n_envs: int = 1, reynolds_number=1e2, resolution=24, dt=1e-2, adaptive_cfl=0.8, step_length=0.25,
                  episode_length=80, lift_penalty=1.0, device="cuda:0", cg_impl=6, compiled=None, cd_ref=0.0,
-                 randomize_initial_state=False, enable_actions=True, use_marl=False, differentiable=False):
+                 randomize_initial_state=False, enable_actions=True, use_marl=False, differentiable=False, load_initial_domain=False,
+                 initial_domains_path=None):
         if use_marl:
             raise ValueError("CylinderJet2D is a single-agent environment (n_agents == 1)")
         self.n_envs = int(n_envs)
@@ -52,6 +53,8 @@ class CylinderJet2DEnv(DifferentiableRollout):
         self.enable_actions = enable_actions
         self.differentiable = bool(differentiable)
         self._dstate = None
+        self.load_domain_on_reset, self.initial_domains_path = bool(load_initial_domain), initial_domains_path
+        self.reynolds_number = float(reynolds_number)
         self.device = torch.device(device)
         if compiled is None:
             spec = make_cylinder_domain(resolution, reynolds_number, self.U_mean, self.H, self.L, self.cylinder_offset_y)
@@ -161,6 +164,11 @@ class CylinderJet2DEnv(DifferentiableRollout):
         return 1
 
     @property
+    def initial_domain_id(self):
+        """cylinder_env_base.py:823-828"""
+        return f"cylinder_2D_Re{int(self.reynolds_number)}_Res{self.resolution}"
+
+    @property
     def n_sim_steps(self):
         return max(1, int(self.step_length / self.dt))
 
@@ -210,14 +218,17 @@ class CylinderJet2DEnv(DifferentiableRollout):
         else:
             self.seed(seed)
         s = self.solver
-        s.u.zero_()
-        s.p.zero_()
-        s.bvel.copy_(torch.from_numpy(self.cd.bvel0[:, :self.cd.NB].copy()).to(self.device).unsqueeze(0).expand_as(s.bvel))
+        randomize = self.randomize_initial_state if randomize is None else randomize
+        if self.load_domain_on_reset:
+            self._load_initial_domains_on_reset(randomize)          # fluid_env.py:519-539
+        else:
+            s.u.zero_()
+            s.p.zero_()
+            s.bvel.copy_(torch.from_numpy(self.cd.bvel0[:, :self.cd.NB].copy()).to(self.device).unsqueeze(0).expand_as(s.bvel))
         # Simulation.make_divergence_free incl. its "PRE" hook with time step 1 (SIM.py:1335-1347)
         s.update_outflow(1.0, self.char_vel, tol=1e-5)
         s.make_divergence_free(max_iter=1000)
         self.last_control.zero_()
-        randomize = self.randomize_initial_state if randomize is None else randomize
         if randomize:
             self._randomize_domain()
         self._apply_action(self._zero_action, smooth=False)

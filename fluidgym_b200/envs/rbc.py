@@ -15,6 +15,7 @@ import torch
 from .. import native
 from ..sensors import sensor_tables
 from ..solver import BatchedPISO, _ptr
+from .common import InitialDomains
 from .rbc_domain import make_rbc_domain
 
 RBC_2D_DEFAULT_CONFIG = {
@@ -37,7 +38,7 @@ def extract_moving_window_2d(field: torch.Tensor, n_agents: int, agent_width: in
     return win.reshape(*lead, n_agents, Y, n_agents_per_window * agent_width)
 
 
-class RBC2DEnv:
+class RBC2DEnv(InitialDomains):
     T_cold, T_hot, heater_limit = 0.0, 1.0, 0.75
     n_sensors_y, n_sensors_per_heater = 8, 4
     buoyancy_factor = 1.0
@@ -46,7 +47,7 @@ class RBC2DEnv:
     def __init__(self, n_envs: int = 1, rayleigh_number=8e4, prandtl_number=0.7, n_heaters=12, resolution=8, dt=0.05,
                  adaptive_cfl=0.8, step_length=1.0, episode_length=200, local_obs_window=11, local_reward_weight=0.2,
                  uniform_grid=False, aspect_ratio=1.0, use_marl=False, device="cuda:0", cg_impl=6, nu_ref=0.0,
-                 randomize_initial_state=False, enable_actions=True):
+                 randomize_initial_state=False, enable_actions=True, load_initial_domain=False, initial_domains_path=None):
         self.n_envs = int(n_envs)
         self.Ra, self.Pr = float(rayleigh_number), float(prandtl_number)
         self.n_heaters, self.heater_width = int(n_heaters), int(resolution)
@@ -55,6 +56,9 @@ class RBC2DEnv:
         self.local_obs_window, self.local_reward_weight = int(local_obs_window), local_reward_weight
         self.use_marl, self.nu_ref = bool(use_marl), float(nu_ref)
         self.enable_actions = enable_actions
+        self.randomize_initial_state = randomize_initial_state
+        self.load_domain_on_reset, self.initial_domains_path = bool(load_initial_domain), initial_domains_path
+        self.prandtl_number, self.rayleigh_number = prandtl_number, rayleigh_number
         self.device = torch.device(device)
         self.aspect = aspect_ratio * torch.pi
         spec, info = make_rbc_domain(rayleigh_number, prandtl_number, n_heaters, resolution, aspect_ratio, uniform_grid)
@@ -100,6 +104,11 @@ class RBC2DEnv:
     @property
     def n_sim_steps(self):
         return max(1, int(self.step_length / self.dt))
+
+    @property
+    def initial_domain_id(self):
+        """rbc_env_base.py:606-611"""
+        return f"rbc_2d_Ra{self.rayleigh_number}_Pr{self.prandtl_number}_NH{self.n_heaters}_HW{self.heater_width}"
 
     @property
     def observation_space(self):
@@ -152,6 +161,12 @@ class RBC2DEnv:
             self.seed(seed)
         s = self.solver
         B, nx, ny = self.n_envs, self.nx, self.ny
+        if self.load_domain_on_reset:                      # fluid_env.py:519-539
+            self._load_initial_domains_on_reset(self.randomize_initial_state if randomize is None else randomize)
+            s.buffer("ures").copy_(s.u)
+            self._apply_action(self._zero_action)
+            self._reset_called, self._n_steps = True, 0
+            return (self._get_local_obs() if self.use_marl else self._get_global_obs()), {}
         grad = torch.linspace(self.T_hot, self.T_cold, steps=ny, device=self.device)[:, None].expand(ny, nx)
         T0 = grad[None] + torch.randn(B, ny, nx, device=self.device, generator=self._torch_rng) * 0.1 * (self.T_hot - self.T_cold)
         s.T.copy_(torch.clamp(T0, self.T_cold, self.T_hot).reshape(B, -1))

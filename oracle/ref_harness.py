@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--kw", default="{}", help="JSON dict of extra fluidgym.make keyword arguments")
     ap.add_argument("--perturb", type=float, default=0.0, help="std of Gaussian noise added to the block velocities after reset")
     ap.add_argument("--lean", action="store_true", help="do not record the CSR matrices (large 3-D grids)")
+    ap.add_argument("--save-domain-only", action="store_true",
+                    help="reset, advance --env-steps steps, write the domain with the reference's own save_domain() and exit")
     args = ap.parse_args()
     tag = args.tag or args.env.replace("-", "_")
     os.makedirs(args.out, exist_ok=True)
@@ -226,6 +228,14 @@ def main():
             blk.setVelocity((u + args.perturb * torch.randn(u.shape, device=u.device, generator=g)).contiguous())
         env._domain.UpdateDomainData()
         meta["perturb"] = args.perturb
+    if args.save_domain_only:
+        from fluidgym.simulation.pict.util.domain_io import save_domain
+        for i in range(args.env_steps):
+            env.step(torch.full_like(env._zero_action, args.action))
+        save_domain(env._domain, os.path.join(args.out, f"{tag}_domain"))
+        np.savez_compressed(os.path.join(args.out, f"{tag}_domain_state.npz"), **snapshot_state(env))
+        print("saved", os.path.join(args.out, f"{tag}_domain"))
+        return
     dump_geometry(env, args.out, tag)
     st = snapshot_state(env)
     st.update({f"obs_{k}": t2n(v) for k, v in obs0.items()})

@@ -1,0 +1,50 @@
+"""On-disk domain format: files written by the reference's own save_domain() (tests/golden/{cyl24,rbc}_domain.*) load into
+the same tables the product compiles from scratch, and our writer round-trips."""
+import os
+
+import numpy as np
+
+from conftest import GOLDEN
+
+
+def test_reference_written_cylinder_domain_loads_into_identical_tables(cyl24_own, tmp_path):
+    from fluidgym_b200.domain_io import load_domain, save_domain
+    spec_own, cd_own = cyl24_own
+    spec, state = load_domain(os.path.join(GOLDEN, "cyl24_domain"))
+    assert [b.vertex.shape for b in spec.blocks] == [b.vertex.shape for b in spec_own.blocks]
+    for a, b in zip(spec.blocks, spec_own.blocks):
+        assert np.array_equal(a.vertex, b.vertex)
+        assert [x.type for x in a.bounds] == [x.type for x in b.bounds]
+        assert [(x.other, tuple(x.axes)) for x in a.bounds if x.type == 2] == [(x.other, tuple(x.axes)) for x in b.bounds if x.type == 2]
+    cd = spec.prepare()
+    for name in ("nbr", "fl_comp", "Cd", "Wp", "no_idx", "no_wv", "b_cell", "b_face", "rev"):
+        assert np.array_equal(getattr(cd, name), getattr(cd_own, name)), name
+    assert state["u"].shape == (2, cd.N) and state["p"].shape == (cd.N,) and state["bvel"].shape == (2, cd.NB)
+    assert np.abs(state["u"]).max() > 0.5 and state["T"] is None          # a developed flow after one env.step
+    # inflow profile is what the product builds itself; the outflow faces carry the advected values of the saved state
+    inflow = slice(0, 24)
+    assert np.allclose(state["bvel"][:, inflow], cd_own.bvel0[:, inflow], atol=1e-6)
+    # round trip through our writer
+    save_domain(spec, state, str(tmp_path / "rt"))
+    spec2, state2 = load_domain(str(tmp_path / "rt"))
+    for k in ("u", "p", "bvel"):
+        assert np.array_equal(state[k], state2[k])
+    assert np.array_equal(spec2.prepare().nbr, cd.nbr)
+
+
+def test_reference_written_rbc_domain_with_scalar(tmp_path):
+    from fluidgym_b200.domain_io import load_domain, save_domain
+    from fluidgym_b200.envs.rbc_domain import make_rbc_domain
+    spec, state = load_domain(os.path.join(GOLDEN, "rbc_domain"))
+    own, info = make_rbc_domain(8e4, 0.7, 12, 8, 1.0, False)
+    assert np.array_equal(spec.blocks[0].vertex, own.blocks[0].vertex)
+    assert abs(spec.viscosity - own.viscosity) < 1e-9 and abs(spec.scalar_viscosity - own.scalar_viscosity) < 1e-9
+    cd, cd_own = spec.prepare(), own.prepare()
+    for name in ("nbr", "Cd", "Cd_s", "sb_neumann"):
+        assert np.array_equal(getattr(cd, name), getattr(cd_own, name)), name
+    assert state["T"].shape == (cd.N,) and state["sbval"].shape == (cd.NB,)
+    assert state["sbval"][:96].min() >= 0.25 and state["sbval"][96:].max() == 0.0      # heated bottom, cold top
+    save_domain(spec, state, str(tmp_path / "rt"))
+    _, state2 = load_domain(str(tmp_path / "rt"))
+    for k in ("u", "p", "T", "sbval", "bvel"):
+        assert np.array_equal(state[k], state2[k])

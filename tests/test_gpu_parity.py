@@ -1,5 +1,6 @@
 """GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Every call goes through the C ABI
 (include/fluidgym_b200.h via ctypes); the checker is the CPU oracle and the reference golden trace."""
+import os
 import numpy as np
 import pytest
 
@@ -287,3 +288,37 @@ def test_wrappers_on_the_cuda_environment():
     assert obs.shape == (3, 8 * 48 + 2 * 8 * 48) and obs.is_cuda
     obs, r, term, trunc, info = env.step(env.sample_action())
     assert obs.shape == (3, 1152) and r.shape == (3,) and torch.isfinite(obs).all()
+
+
+def test_initial_domain_files_written_by_the_reference_drive_reset(tmp_path):
+    """load_initial_domain=True: reset() draws the state of every environment from files in the reference's on-disk format
+    (here: the domain the reference itself saved after one env.step, tests/golden/cyl24_domain.*), and a state written by
+    save_initial_domain() reads back bit-identically."""
+    import shutil
+    import fluidgym_b200 as fg
+    from conftest import GOLDEN
+    root = tmp_path / "initial_domains"
+    env = fg.make("CylinderJet2D-easy-v0", n_envs=3, load_initial_domain=True, initial_domains_path=str(root))
+    assert env.initial_domain_id == "cylinder_2D_Re100_Res24"
+    with pytest.raises(RuntimeError, match="Initial domain not found"):
+        env.reset(seed=1)
+    for idx in range(10):
+        d = root / env.initial_domain_id / str(idx)
+        d.mkdir(parents=True)
+        for ext in (".json", ".npz"):
+            shutil.copy(os.path.join(GOLDEN, "cyl24_domain" + ext), d / ("train" + ext))
+    obs, _ = env.reset(seed=1, randomize=False)
+    ref = np.load(os.path.join(GOLDEN, "cyl24_domain.npz"))
+    u_left = env.solver.u[0, :, :24 * 37].cpu().numpy().reshape(2, 24, 37)
+    # reset projects the loaded field again (make_divergence_free, as the reference's _get_simulation does): close, not equal
+    print("after reset (re-projected) vs stored", rel_l2(u_left, ref["1"][0]))
+    assert rel_l2(u_left, ref["1"][0]) < 0.5 and float(env.solver.u.abs().max()) > 0.5
+    env.load_initial_domain(0)
+    assert np.array_equal(env.solver.u[2, :, :24 * 37].cpu().numpy().reshape(2, 24, 37), ref["1"][0])
+    env.solver.u.mul_(0.5)
+    path = env.save_initial_domain(3, mode="val", env_index=1)
+    env.val()
+    env.solver.u.zero_()
+    env._domain_pool.clear()
+    env.load_initial_domain(3)
+    assert torch.equal(env.solver.u[0], env.solver.u[1]) and float(env.solver.u.abs().max()) > 0.2 and path.endswith("val")
