@@ -2181,6 +2181,53 @@ __global__ void k_adj_bflux(Tab t, const float *__restrict__ Fbb, float *__restr
     Bvb[(size_t)b * 2 * NB + NB + j] += f * t.b_minv[(2 * ax + 1) * NB + j];
 }
 
+// Passive scalar + buoyancy (RBC substep).  The velocity source enters the predictor right-hand side and HbyA next to
+// S_b / det, so its adjoint is det * S_b_bar; with src = (0, beta * T_new):
+//   T_new_bar = T_out_bar + beta * det * S_b_bar[1]
+__global__ void __launch_bounds__(256) k_adj_buoyancy(Tab t, const float *__restrict__ Sbb, const float *__restrict__ Toutb, float beta,
+                                                       float *__restrict__ Tnb) {
+    const int b = blockIdx.y;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N;
+    if (g >= N) return;
+    Tnb[(size_t)b * N + g] = Toutb[(size_t)b * N + g] + beta * t.det[g] * Sbb[(size_t)b * 2 * N + N + g];
+}
+
+// adjoint of k_setup_scalar + the scalar solve, given lam = C_s^-T T_new_bar:
+//   A_s_bar = -lam * T_new, Coff_s_bar[f] = -lam * T_new[nb_f]; rhs_s = r / det with
+//   r = det * T_in / dt + sum_{prescribed f} sb * (-(sig F_b) + kappa * (2 alpha_b | 1))
+__global__ void __launch_bounds__(256) k_adj_scalar(Tab t, const float *__restrict__ Lam, const float *__restrict__ Tnew,
+                                                     const float *__restrict__ Bvel, const float *__restrict__ Sbval,
+                                                     const float *__restrict__ dtv, float *__restrict__ Tinb, float *__restrict__ Sbvalb,
+                                                     float *__restrict__ Fbb, float *__restrict__ Ub) {
+    const int b = blockIdx.y;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N, NB = t.NB;
+    if (g >= N) return;
+    const float *tn = Tnew + (size_t)b * N, *bv = Bvel + (size_t)b * 2 * NB, *sb = Sbval + (size_t)b * NB;
+    const float lam = Lam[(size_t)b * N + g];
+    const float det = t.det[g];
+    const float rb = lam / det;
+    Tinb[(size_t)b * N + g] = lam / dtv[b];
+    const float diagb = -lam * tn[g] / det;                 // A_s = diag / det
+    int nb[4]; float flb[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        nb[f] = t.nbr[f * N + g];
+        const float sig = (f & 1) ? 1.f : -1.f;
+        flb[f] = 0.f;
+        if (nb[f] >= 0) flb[f] = 0.5f * sig * (-lam * tn[nb[f]] / det + diagb);
+        else {
+            const int j = -1 - nb[f];
+            const float Fb = bflux(t, j, f >> 1, bv[j], bv[NB + j]);
+            const float dif = t.scalar_viscosity * (t.sb_neumann[j] == 0 ? 2.f * t.b_alpha[j] : 1.f);
+            atomicAdd(&Sbvalb[(size_t)b * NB + j], rb * (-(sig * Fb) + dif));
+            atomicAdd(&Fbb[(size_t)b * NB + j], -rb * sb[j] * sig);
+        }
+    }
+    fluxes_adjoint(t, g, nb, flb, Ub + (size_t)b * 2 * N, nullptr);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -2441,15 +2488,16 @@ static int copy_async(void *dst, const void *src, size_t bytes, cudaStream_t st)
     return ce == cudaSuccess ? FGB_OK : set_err(FGB_E_CUDA, "cudaMemcpyAsync (tape)", ce);
 }
 
-// fgb_piso_substep that additionally records the tape the backward pass needs (non-orthogonal path, no passive
-// scalar, every environment active).  C = corrector_steps, n_adv / n_p = advect / pressure non-orthogonal iterations.
-extern "C" int fgb_piso_substep_record(fgb_batch *b, float *u, float *p, const float *bvel, const float *dt, const fgb_tape *tp,
-                                       fgb_stream_t s) {
-    if (!b || !u || !p || !bvel || !dt || !tp) return set_err(FGB_E_ARG, "fgb_piso_substep_record: null argument");
+// fgb_piso_substep that additionally records the tape the backward pass needs (every environment active).
+// C = corrector_steps, n_adv / n_p = advect / pressure non-orthogonal iterations (1 / 1 on the orthogonal path).
+// sc / stp: passive scalar + buoyancy (RBC), both or neither.
+static int record_impl(fgb_batch *b, float *u, float *p, const float *bvel, const float *dt, const fgb_tape *tp,
+                       const fgb_scalar *sc, const fgb_tape_scalar *stp, fgb_stream_t s) {
     const fgb_options &o = b->opt;
-    const int C = o.corrector_steps, n_adv = o.adv_nonortho_steps, n_p = o.p_nonortho_steps;
-    if (!o.nonortho || (o.cg_impl != 3 && o.cg_impl != 6 && o.cg_impl != 7 && o.cg_impl != 8) || C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8)
-        return set_err(FGB_E_ARG, "fgb_piso_substep_record: needs the non-orthogonal path, cg_impl 3 or 6 and correctors x pressure iterations <= 8");
+    const int C = o.corrector_steps, n_adv = o.nonortho ? o.adv_nonortho_steps : 1, n_p = o.nonortho ? o.p_nonortho_steps : 1;
+    const int reset = o.nonortho ? 100 : 0;
+    if ((o.cg_impl != 3 && o.cg_impl != 6 && o.cg_impl != 7 && o.cg_impl != 8) || C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8)
+        return set_err(FGB_E_ARG, "fgb_piso_substep_record: needs cg_impl 3 or 6 and correctors x pressure iterations <= 8");
     cudaStream_t st = STREAM(s);
     const size_t B = b->B, N = b->t.N, NB = b->t.NB;
     int rc;
@@ -2457,9 +2505,30 @@ extern "C" int fgb_piso_substep_record(fgb_batch *b, float *u, float *p, const f
     if ((rc = copy_async(tp->p_in, p, B * N * 4, st))) return rc;
     if ((rc = copy_async(tp->bvel_in, bvel, 2 * B * NB * 4, st))) return rc;
     if ((rc = copy_async(tp->dt, dt, B * 4, st))) return rc;
+    const float *src = nullptr;
+    if (sc) {   // scalar transport with the incoming velocity, then the buoyancy source from the new temperature (SIM.py:1471-1657)
+        if (!sc->T || !sc->sbval || !sc->src || !stp->T_in || !stp->T_out || !stp->sbval_in || !b->t.Cd_s || !b->t.sb_neumann)
+            return set_err(FGB_E_ARG, "fgb_piso_substep_record_scalar: incomplete scalar description / tables");
+        if ((rc = copy_async(stp->T_in, sc->T, B * N * 4, st))) return rc;
+        if ((rc = copy_async(stp->sbval_in, sc->sbval, B * NB * 4, st))) return rc;
+        {
+            ProfScope ps(b, CLS_ASM, st);
+            k_setup_scalar<<<cell_grid(b), 256, 0, st>>>(b->t, u, sc->T, bvel, sc->sbval, dt, nullptr, b->Coff, b->A, b->rhs);
+            LAUNCH_CHECK("k_setup_scalar");
+        }
+        {
+            ProfScope ps(b, CLS_BICG, st);
+            if ((rc = run_bicgstab<1>(b, b->rhs, sc->T, 1, nullptr, st))) return rc;
+        }
+        if ((rc = copy_async(stp->T_out, sc->T, B * N * 4, st))) return rc;
+        b->launches++;
+        k_buoyancy<<<cell_grid(b), 256, 0, st>>>(sc->T, sc->beta, (int)N, nullptr, sc->src);
+        LAUNCH_CHECK("k_buoyancy");
+        src = sc->src;
+    }
     for (int k = 0; k < n_adv; ++k) {
-        if ((rc = fgb_setup_advection(b, u, k == 0 ? u : b->ures, bvel, nullptr, dt, nullptr, s))) return rc;
-        if ((rc = fgb_solve_advection(b, k == 0, nullptr, s))) return rc;
+        if ((rc = fgb_setup_advection(b, u, k == 0 ? u : b->ures, bvel, src, dt, nullptr, s))) return rc;
+        if ((rc = fgb_solve_advection(b, o.nonortho ? (k == 0) : 0, nullptr, s))) return rc;
         if ((rc = copy_async(tp->ustar + (size_t)k * 2 * B * N, b->ures, 2 * B * N * 4, st))) return rc;
     }
     if ((rc = copy_async(tp->Coff, b->Coff, 4 * B * N * 4, st))) return rc;
@@ -2468,8 +2537,8 @@ extern "C" int fgb_piso_substep_record(fgb_batch *b, float *u, float *p, const f
     for (int cs = 0; cs < C; ++cs) {
         for (int ps = 0; ps < n_p; ++ps) {
             const int q = cs * n_p + ps;
-            if ((rc = fgb_setup_pressure_rhs(b, u, bvel, nullptr, p, dt, ps == 0, nullptr, s))) return rc;
-            if ((rc = solve_pressure_slot(b, p, ps == 0, 100, o.max_iter, q, nullptr, s))) return rc;
+            if ((rc = fgb_setup_pressure_rhs(b, u, bvel, src, p, dt, ps == 0, nullptr, s))) return rc;
+            if ((rc = solve_pressure_slot(b, p, ps == 0, reset, o.max_iter, q, nullptr, s))) return rc;
             if ((rc = copy_async(tp->p + (size_t)q * B * N, p, B * N * 4, st))) return rc;
             if ((rc = copy_async(tp->pmean + (size_t)q * B, b->pmean + (size_t)q * B, B * 4, st))) return rc;
         }
@@ -2479,6 +2548,17 @@ extern "C" int fgb_piso_substep_record(fgb_batch *b, float *u, float *p, const f
     }
     return copy_async(u, b->ures, 2 * B * N * 4, st);
 }
+extern "C" int fgb_piso_substep_record(fgb_batch *b, float *u, float *p, const float *bvel, const float *dt, const fgb_tape *tp,
+                                       fgb_stream_t s) {
+    if (!b || !u || !p || !bvel || !dt || !tp) return set_err(FGB_E_ARG, "fgb_piso_substep_record: null argument");
+    if (!b->opt.nonortho) return set_err(FGB_E_ARG, "fgb_piso_substep_record: needs the non-orthogonal path (use fgb_piso_substep_record_scalar for the orthogonal scalar path)");
+    return record_impl(b, u, p, bvel, dt, tp, nullptr, nullptr, s);
+}
+extern "C" int fgb_piso_substep_record_scalar(fgb_batch *b, float *u, float *p, const float *bvel, const float *dt, const fgb_scalar *sc,
+                                              const fgb_tape *tp, const fgb_tape_scalar *stp, fgb_stream_t s) {
+    if (!b || !u || !p || !bvel || !dt || !tp || !sc || !stp) return set_err(FGB_E_ARG, "fgb_piso_substep_record_scalar: null argument");
+    return record_impl(b, u, p, bvel, dt, tp, sc, stp, s);
+}
 
 extern "C" size_t fgb_adjoint_workspace_bytes(const fgb_tables *t, int32_t B) {
     const size_t BN = (size_t)B * t->N, BNB = (size_t)B * (t->NB > 0 ? t->NB : 1);
@@ -2487,10 +2567,13 @@ extern "C" size_t fgb_adjoint_workspace_bytes(const fgb_tables *t, int32_t B) {
 
 // Reverse pass of fgb_piso_substep_record.  u_out_bar / p_out_bar: incoming gradients; u_bar, p_prev_bar, bvel_bar
 // are OVERWRITTEN with the gradients w.r.t. the inputs of the substep.  ws: >= fgb_adjoint_workspace_bytes.
-extern "C" int fgb_piso_substep_backward(fgb_batch *b, const fgb_tape *tp, const float *u_out_bar, const float *p_out_bar,
-                                         float *u_bar, float *p_prev_bar, float *bvel_bar, void *ws, size_t ws_bytes, fgb_stream_t s) {
+static int backward_impl(fgb_batch *b, const fgb_tape *tp, const fgb_tape_scalar *stp, float beta, const float *u_out_bar,
+                         const float *p_out_bar, const float *T_out_bar, float *u_bar, float *p_prev_bar, float *bvel_bar,
+                         float *T_bar, float *sbval_bar, void *ws, size_t ws_bytes, fgb_stream_t s) {
     if (!b || !tp || !u_out_bar || !p_out_bar || !u_bar || !p_prev_bar || !bvel_bar || !ws)
         return set_err(FGB_E_ARG, "fgb_piso_substep_backward: null argument");
+    if (stp && (!T_out_bar || !T_bar || !sbval_bar || !stp->T_in || !stp->T_out || !stp->sbval_in || !b->t.Cd_s || !b->t.sb_neumann))
+        return set_err(FGB_E_ARG, "fgb_piso_substep_backward_scalar: incomplete scalar tape / tables");
     if (ws_bytes < fgb_adjoint_workspace_bytes(&b->t, b->B)) return set_err(FGB_E_WORKSPACE, "fgb_piso_substep_backward: workspace too small");
     if (!b->t.rev) return set_err(FGB_E_ARG, "fgb_piso_substep_backward: tables.rev missing");
     cudaStream_t st = STREAM(s);
@@ -2501,7 +2584,7 @@ extern "C" int fgb_piso_substep_backward(fgb_batch *b, const fgb_tape *tp, const
     float *uprevb = c.take<float>(2 * BN), *Ab = c.take<float>(BN), *mu = c.take<float>(2 * BN), *Fbb = c.take<float>(B * NB);
     float *pb2 = c.take<float>(BN), *xkb = c.take<float>(2 * BN);
     const fgb_options &o = b->opt;
-    const int C = o.corrector_steps, n_adv = o.adv_nonortho_steps, n_p = o.p_nonortho_steps;
+    const int C = o.corrector_steps, n_adv = o.nonortho ? o.adv_nonortho_steps : 1, n_p = o.nonortho ? o.p_nonortho_steps : 1;
     if (C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8) return set_err(FGB_E_ARG, "fgb_piso_substep_backward: unsupported iteration counts");
     const dim3 grid = cell_grid(b);
     cudaError_t ce;
@@ -2530,7 +2613,7 @@ extern "C" int fgb_piso_substep_backward(fgb_batch *b, const fgb_tape *tp, const
             LAUNCH_CHECK("k_adj_remove_mean");
             {   // lam = P^-T x_bar
                 ProfScope psc(b, CLS_CG, st);
-                rc = cg_cluster_mb_any(b, b->Poff, b->Pdiag, xb, lam, 1, 100, b->opt.max_iter, 5, nullptr, 1 | 2, nullptr, st);
+                rc = cg_cluster_mb_any(b, b->Poff, b->Pdiag, xb, lam, 1, o.nonortho ? 100 : 0, b->opt.max_iter, 5, nullptr, 1 | 2, nullptr, st);
                 if (rc == 1) return set_err(FGB_E_ARG, "fgb_piso_substep_backward: grid too large for the on-chip transposed solve");
                 if (rc) return rc;
             }
@@ -2566,10 +2649,41 @@ extern "C" int fgb_piso_substep_backward(fgb_batch *b, const fgb_tape *tp, const
     b->launches += 2;
     k_adj_assemble<<<grid, 256, 0, st>>>(b->t, Ab, Coffb, Sbb, tp->bvel_in, u_bar, bvel_bar, Fbb);
     LAUNCH_CHECK("k_adj_assemble");
+    if (stp) {
+        // buoyancy + scalar transport (they ran BEFORE the predictor): T_new_bar from the source adjoint, one transposed
+        // scalar solve, then the assembly adjoint.  xb / lam (pressure temporaries) are free again; the scalar matrix is
+        // rebuilt from the taped inputs into the forward workspace (Coff / A / rhs are not read by this pass).
+        float *Tnb = xb;
+        b->launches += 3;
+        k_adj_buoyancy<<<grid, 256, 0, st>>>(b->t, Sbb, T_out_bar, beta, Tnb);
+        LAUNCH_CHECK("k_adj_buoyancy");
+        k_setup_scalar<<<grid, 256, 0, st>>>(b->t, tp->u_in, stp->T_in, tp->bvel_in, stp->sbval_in, tp->dt, nullptr, b->Coff, b->A, b->rhs);
+        LAUNCH_CHECK("k_setup_scalar (backward)");
+        {
+            ProfScope psc(b, CLS_BICG, st);
+            rc = bicgstab_cluster_any<1>(b, b->Coff, b->A, Tnb, lam, 1, nullptr, 1, st);
+            if (rc == 1) return set_err(FGB_E_ARG, "fgb_piso_substep_backward_scalar: grid too large for the on-chip transposed solve");
+            if (rc) return rc;
+        }
+        ZERO(sbval_bar, B * NB);
+        k_adj_scalar<<<grid, 256, 0, st>>>(b->t, lam, stp->T_out, tp->bvel_in, stp->sbval_in, tp->dt, T_bar, sbval_bar, Fbb, u_bar);
+        LAUNCH_CHECK("k_adj_scalar");
+    }
     k_adj_bflux<<<dim3((unsigned)((NB + 127) / 128), b->B), 128, 0, st>>>(b->t, Fbb, bvel_bar);
     LAUNCH_CHECK("k_adj_bflux");
 #undef ZERO
     return FGB_OK;
+}
+extern "C" int fgb_piso_substep_backward(fgb_batch *b, const fgb_tape *tp, const float *u_out_bar, const float *p_out_bar,
+                                         float *u_bar, float *p_prev_bar, float *bvel_bar, void *ws, size_t ws_bytes, fgb_stream_t s) {
+    return backward_impl(b, tp, nullptr, 0.f, u_out_bar, p_out_bar, nullptr, u_bar, p_prev_bar, bvel_bar, nullptr, nullptr, ws, ws_bytes, s);
+}
+extern "C" int fgb_piso_substep_backward_scalar(fgb_batch *b, const fgb_tape *tp, const fgb_tape_scalar *stp, float beta,
+                                                const float *u_out_bar, const float *p_out_bar, const float *T_out_bar, float *u_bar,
+                                                float *p_prev_bar, float *bvel_bar, float *T_bar, float *sbval_bar, void *ws,
+                                                size_t ws_bytes, fgb_stream_t s) {
+    if (!stp) return set_err(FGB_E_ARG, "fgb_piso_substep_backward_scalar: null scalar tape");
+    return backward_impl(b, tp, stp, beta, u_out_bar, p_out_bar, T_out_bar, u_bar, p_prev_bar, bvel_bar, T_bar, sbval_bar, ws, ws_bytes, s);
 }
 
 extern "C" int fgb_make_divergence_free(fgb_batch *b, float *u, float *p, const float *bvel, int max_iter, fgb_stream_t s) {

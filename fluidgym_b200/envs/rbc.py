@@ -47,7 +47,8 @@ class RBC2DEnv(InitialDomains):
     def __init__(self, n_envs: int = 1, rayleigh_number=8e4, prandtl_number=0.7, n_heaters=12, resolution=8, dt=0.05,
                  adaptive_cfl=0.8, step_length=1.0, episode_length=200, local_obs_window=11, local_reward_weight=0.2,
                  uniform_grid=False, aspect_ratio=1.0, use_marl=False, device="cuda:0", cg_impl=6, nu_ref=0.0,
-                 randomize_initial_state=False, enable_actions=True, load_initial_domain=False, initial_domains_path=None):
+                 randomize_initial_state=False, enable_actions=True, load_initial_domain=False, initial_domains_path=None,
+                 differentiable=False):
         self.n_envs = int(n_envs)
         self.Ra, self.Pr = float(rayleigh_number), float(prandtl_number)
         self.n_heaters, self.heater_width = int(n_heaters), int(resolution)
@@ -56,6 +57,8 @@ class RBC2DEnv(InitialDomains):
         self.local_obs_window, self.local_reward_weight = int(local_obs_window), local_reward_weight
         self.use_marl, self.nu_ref = bool(use_marl), float(nu_ref)
         self.enable_actions = enable_actions
+        self.differentiable = bool(differentiable)
+        self._dstate = None          # (u, p, T, sbval) carried with their autograd history in differentiable mode
         self.randomize_initial_state = randomize_initial_state
         self.load_domain_on_reset, self.initial_domains_path = bool(load_initial_domain), initial_domains_path
         self.prandtl_number, self.rayleigh_number = prandtl_number, rayleigh_number
@@ -150,6 +153,7 @@ class RBC2DEnv(InitialDomains):
             ures = torch.as_tensor(ures, dtype=torch.float32, device=self.device)
             ur.copy_(ures if ures.dim() == 3 else ures.unsqueeze(0).expand_as(ur))
         self._reset_called = True
+        self._dstate = None
 
     def reset(self, seed: int | None = None, randomize: bool | None = None):
         """rbc_env_base.py:190-278: linear temperature profile + 0.1 N(0,1) clamped to [T_cold, T_hot],
@@ -161,6 +165,7 @@ class RBC2DEnv(InitialDomains):
             self.seed(seed)
         s = self.solver
         B, nx, ny = self.n_envs, self.nx, self.ny
+        self._dstate = None
         if self.load_domain_on_reset:                      # fluid_env.py:519-539
             self._load_initial_domains_on_reset(self.randomize_initial_state if randomize is None else randomize)
             s.buffer("ures").copy_(s.u)
@@ -241,6 +246,54 @@ class RBC2DEnv(InitialDomains):
         vol = cs[:, 1, : self.local_obs_window * self.heater_width].sum(dim=1, keepdim=True)
         return self.nu_ref - (1.0 + (self.Ra * self.Pr) ** 0.5 * num / vol)
 
+    # ---- differentiable mode (fluid_env.py:154,232; examples/interfaces/gradient_based_methods.py) -----------------
+    # One autograd node per substep (scalar transport + buoyancy + PISO, fluidgym_b200.autograd.PISOSubstepScalar backed by
+    # the CUDA adjoint); the heater profile (rbc_env_2d.py:210-282) and the Nusselt sums (rbc_env_base.py:491-539) around it
+    # are torch expressions, as in the reference.  The CFL plan is taken from detached maxima with one common substep size
+    # for the batch (the most restrictive environment decides), like envs/common.py::_single_step_differentiable.
+    def detach(self):
+        if self._dstate is not None:
+            self._dstate = tuple(t.detach() for t in self._dstate)
+
+    def _advance_differentiable(self, action):
+        from ..autograd import piso_substep_scalar
+        s = self.solver
+        if self._dstate is None:
+            self._dstate = (s.u.clone(), s.p.clone(), s.T.clone(), s.sbval.clone())
+        u, p, T, sb = self._dstate
+        if self.enable_actions:
+            ctrl = self._action_to_control(action.reshape(self.n_envs, self.n_heaters))
+            sb = sb.index_copy(1, torch.arange(self._bottom.start, self._bottom.stop, device=self.device), ctrl)
+        bv = s.bvel
+        mvb = torch.empty(self.n_envs, device=self.device)
+        nsub = 0
+        for _ in range(self.n_sim_steps):
+            remaining = float(self.dt)
+            while remaining > 0.0 and not abs(remaining) <= 1e-8:            # SIM.py:2004-2031
+                native.check(self.lib.fgb_max_velocity(s.handle, _ptr(u.detach().contiguous()), _ptr(bv), _ptr(mvb), s.stream),
+                             "fgb_max_velocity")
+                mv = float(mvb.max())
+                if abs(mv) <= 1e-8:
+                    ts = remaining
+                else:
+                    mts = np.float32(self.cfl) / np.float32(mv)
+                    ts = remaining if float(mts) >= remaining else remaining / float(np.ceil(np.float32(remaining) / mts))
+                remaining -= ts
+                u, p, T = piso_substep_scalar(s, u, p, bv, T, sb, float(np.float32(ts)), self.buoyancy_factor)
+                nsub += 1
+        self._dstate = (u, p, T, sb)
+        with torch.no_grad():                      # keep the solver's own state in step for observations / get_state
+            s.u.copy_(u); s.p.copy_(p); s.T.copy_(T); s.sbval.copy_(sb)
+        self.last_substeps = nsub
+        det = self._det_columns()
+        uyT = (u[:, 1] * T).reshape(self.n_envs, self.ny, self.nx) * det
+        return torch.stack([uyT.sum(dim=1), det.sum(dim=0)[None].expand(self.n_envs, self.nx)], dim=1)   # as k_column_sums
+
+    def _det_columns(self):
+        if getattr(self, "_det_t", None) is None:
+            self._det_t = torch.from_numpy(np.ascontiguousarray(self.cd.det, dtype=np.float32)).to(self.device).reshape(self.ny, self.nx)
+        return self._det_t
+
     def step(self, action):
         if not self._reset_called:
             raise RuntimeError("Environment must be reset before stepping. Call 'reset()' before'step()'.")
@@ -249,13 +302,16 @@ class RBC2DEnv(InitialDomains):
             raise ValueError(f"Action shape {action.shape} does not match expected shape {self._zero_action.shape}.")
         if self._n_steps >= self.episode_length:
             raise RuntimeError("Episode has already terminated. Call 'reset()' first.")
-        if self.enable_actions:
-            self._apply_action(action)
-        nsub = 0
-        for _ in range(self.n_sim_steps):
-            nsub += self.solver.single_step(self.dt, self.cfl)
-        self.last_substeps = nsub
-        cs = self._column_sums()
+        if self.differentiable:
+            cs = self._advance_differentiable(action)
+        else:
+            if self.enable_actions:
+                self._apply_action(action)
+            nsub = 0
+            for _ in range(self.n_sim_steps):
+                nsub += self.solver.single_step(self.dt, self.cfl)
+            self.last_substeps = nsub
+            cs = self._column_sums()
         nu = self.compute_global_nusselt(cs)
         reward = self.nu_ref - nu
         info = {"nusselt": nu.detach()}

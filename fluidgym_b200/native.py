@@ -31,6 +31,10 @@ class Tape(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("u_in", "p_in", "bvel_in", "dt", "Coff", "A", "ustar", "hb", "p", "pmean", "u1")]
 
 
+class ScalarTape(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("T_in", "T_out", "sbval_in")]
+
+
 class Scalar(C.Structure):
     _fields_ = [("T", C.c_void_p), ("sbval", C.c_void_p), ("beta", C.c_float), ("src", C.c_void_p)]
 
@@ -59,7 +63,7 @@ EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_cr
            "fgb_max_velocity", "fgb_apply_jet_action", "fgb_wall_forces", "fgb_column_sums", "fgb_sample_sensors",
            "fgb_profile_enable",
            "fgb_profile_read", "fgb_launch_count", "fgb_piso_substep_record", "fgb_adjoint_workspace_bytes",
-           "fgb_piso_substep_backward",
+           "fgb_piso_substep_backward", "fgb_piso_substep_record_scalar", "fgb_piso_substep_backward_scalar",
            "fgb_ortho3_workspace_bytes", "fgb_ortho3_create", "fgb_ortho3_destroy", "fgb_ortho3_set_options", "fgb_ortho3_buffer",
            "fgb_ortho3_launch_count", "fgb_ortho3_setup_advection", "fgb_ortho3_solve_advection", "fgb_ortho3_setup_pressure",
            "fgb_ortho3_solve_pressure", "fgb_ortho3_correct_velocity", "fgb_ortho3_piso_substep", "fgb_ortho3_make_divergence_free",
@@ -115,6 +119,9 @@ def load():
     L.fgb_adjoint_workspace_bytes.restype = C.c_size_t
     L.fgb_adjoint_workspace_bytes.argtypes = [C.POINTER(Tables), i32]
     L.fgb_piso_substep_backward.argtypes = [vp, C.POINTER(Tape), vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.fgb_piso_substep_record_scalar.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Scalar), C.POINTER(Tape), C.POINTER(ScalarTape), vp]
+    L.fgb_piso_substep_backward_scalar.argtypes = [vp, C.POINTER(Tape), C.POINTER(ScalarTape), f32, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                                   C.c_size_t, vp]
     L.fgb_ortho3_workspace_bytes.restype = C.c_size_t
     L.fgb_ortho3_workspace_bytes.argtypes = [C.POINTER(Ortho3Tables), i32]
     L.fgb_ortho3_create.argtypes = [C.POINTER(Ortho3Tables), i32, vp, C.c_size_t, C.POINTER(Options), C.POINTER(vp)]

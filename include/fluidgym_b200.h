@@ -234,6 +234,25 @@ int fgb_piso_substep_backward(fgb_batch *b, const fgb_tape *tape, const float *u
                               float *u_bar, float *p_prev_bar, float *bvel_bar, void *workspace, size_t workspace_bytes,
                               fgb_stream_t s);
 
+/* Passive scalar + buoyancy (RBC environments; the reference differentiates them through the same per-op
+ * autograd.Functions, DIFF.py:624-1808, with SetupAdvectionScalarGrad / SetupAdvectionMatrixGrad(forPassiveScalar),
+ * BIND.cpp:582-608).  Works on the orthogonal path (fgb_options.nonortho = 0: one predictor solve started from the
+ * previous result, one pressure solve per corrector) as well as on the non-orthogonal one. */
+typedef struct fgb_tape_scalar {
+    float *T_in;      /* [B][N]   temperature entering the substep                  */
+    float *T_out;     /* [B][N]   temperature after the scalar solve                */
+    float *sbval_in;  /* [B][NB]  boundary temperatures (heaters)                   */
+} fgb_tape_scalar;
+/* forward substep with scalar transport and buoyancy source (as fgb_piso_substep with sc != NULL) + tapes */
+int fgb_piso_substep_record_scalar(fgb_batch *b, float *u, float *p, const float *bvel, const float *dt, const fgb_scalar *sc,
+                                   const fgb_tape *tape, const fgb_tape_scalar *stape, fgb_stream_t s);
+/* (u_out_bar, p_out_bar, T_out_bar) -> (u_bar, p_prev_bar, bvel_bar, T_bar, sbval_bar), all overwritten.  beta = buoyancy factor
+ * of the forward call; workspace as fgb_piso_substep_backward. */
+int fgb_piso_substep_backward_scalar(fgb_batch *b, const fgb_tape *tape, const fgb_tape_scalar *stape, float beta,
+                                     const float *u_out_bar, const float *p_out_bar, const float *T_out_bar, float *u_bar,
+                                     float *p_prev_bar, float *bvel_bar, float *T_bar, float *sbval_bar, void *workspace,
+                                     size_t workspace_bytes, fgb_stream_t s);
+
 /* ---- D = 3, orthogonal grids (turbulent channel flow; the same K.cu kernels with DIMS = 3) ------------------ */
 /* Geometry tables of a 3-D domain whose metric tensors are diagonal (rectilinear blocks).  Fields are
  * component-major [B][3][N]; faces 0..5 = -x,+x,-y,+y,-z,+z; prescribed (Dirichlet) faces are numbered 0..NB-1

@@ -32,6 +32,10 @@ class T64:
         self.b_face = cd.b_face[:cd.NB].astype(np.int64)
         self.visc = float(cd.visc)
         self.K_no, self.K_nob = cd.K_no, cd.K_nob
+        if getattr(cd, "scalar_visc", None) is not None:     # passive scalar (RBC): diffusion table + boundary kinds
+            self.Cd_s = np.asarray(cd.Cd_s, dtype=np.float64)
+            self.sb_neumann = np.asarray(cd.sb_neumann[:cd.NB]).astype(np.int64)
+            self.kappa = float(cd.scalar_visc)
         self.fac = [np.where((~self.inner[2 * d]) | (~self.inner[2 * d + 1]), 1.0, 0.5) for d in range(2)]
         self.cells = np.arange(cd.N)
 
@@ -103,9 +107,12 @@ def nbr_vals_T(t, vb):
 
 
 # ---- forward substep with a tape ---------------------------------------------------------------------
-def substep(t, u, p_prev, bvel, dt, correctors=2, n_adv=1, n_p=1):
-    """n_adv / n_p: advect_non_ortho_steps / pressure_non_ortho_steps (deferred-correction iterations)."""
+def substep(t, u, p_prev, bvel, dt, correctors=2, n_adv=1, n_p=1, src=None):
+    """n_adv / n_p: advect_non_ortho_steps / pressure_non_ortho_steps (deferred-correction iterations);
+    src [2,N]: optional velocity source (buoyancy), added to the predictor right-hand side and to HbyA."""
     tape = {}
+    if src is None:
+        src = np.zeros((2, t.N))
     Fb, (br0, br1) = bflux(t, bvel)
     fl = fluxes(t, u, Fb)
     sig = np.array([-1.0, 1.0, -1.0, 1.0])
@@ -129,7 +136,7 @@ def substep(t, u, p_prev, bvel, dt, correctors=2, n_adv=1, n_p=1):
                 NOv[c] += t.no_wv[k] * xprev[c][t.no_idx[k]]
             for k in range(t.K_nob):
                 NOv[c] += t.nob_w[k] * bvel[c][t.nob_idx[k]]
-        rhs = (t.det * u / dt + Sb - NOv) / t.det
+        rhs = (t.det * u / dt + Sb - NOv) / t.det + src
         xprev = np.stack([np.linalg.solve(C, rhs[c]) for c in range(2)])
         xs.append(xprev)
     ustar = xs[-1]
@@ -142,7 +149,7 @@ def substep(t, u, p_prev, bvel, dt, correctors=2, n_adv=1, n_p=1):
     wno = np.stack([t.no_gP[k] * rAn[0] + t.no_gN[k] * rAn[1 + t.no_face[k], t.cells] for k in range(t.K_no)])
     for _ in range(correctors):
         H = np.stack([sum(np.where(t.inner[f], Coff[f] * uprev[c][t.nb_safe[f]], 0.0) for f in range(4)) for c in range(2)])
-        hb = rA * (u / dt - H + Sb / t.det)
+        hb = rA * (u / dt - H + Sb / t.det + src)
         flh = fluxes(t, hb, Fb)
         sols = []
         for _ps in range(n_p):
@@ -162,9 +169,10 @@ def substep(t, u, p_prev, bvel, dt, correctors=2, n_adv=1, n_p=1):
 
 
 # ---- reverse pass --------------------------------------------------------------------------------------
-def substep_vjp(t, u, p_prev, bvel, dt, tape, u_out_bar, p_out_bar):
-    """returns (u_bar, p_prev_bar, bvel_bar)"""
+def substep_vjp(t, u, p_prev, bvel, dt, tape, u_out_bar, p_out_bar, with_src=False):
+    """returns (u_bar, p_prev_bar, bvel_bar) [+ src_bar with_src]"""
     N = t.N
+    srcb = np.zeros((2, N))
     sig = np.array([-1.0, 1.0, -1.0, 1.0])
     Coff, A, rA, rAn, Sb, Fb = tape["Coff"], tape["A"], tape["rA"], tape["rAn"], tape["Sb"], tape["Fb"]
     ub = np.zeros((2, N)); bvb = np.zeros((2, t.NB)); Fbb = np.zeros(t.NB)
@@ -208,6 +216,7 @@ def substep_vjp(t, u, p_prev, bvel, dt, tape, u_out_bar, p_out_bar):
         inner_b = rA * hbb
         ub += inner_b / dt
         Sbb += inner_b / t.det
+        srcb += inner_b
         Hb = -inner_b
         uprevb = np.zeros((2, N))
         for f in range(4):
@@ -237,6 +246,7 @@ def substep_vjp(t, u, p_prev, bvel, dt, tape, u_out_bar, p_out_bar):
         # rhs = (det u/dt + Sb - NOv(x_{k-1}))/det
         ub += rhsb / dt
         Sbb += rhsb / t.det
+        srcb += rhsb
         NOvb = -rhsb / t.det
         target = ub if kk == 0 else np.zeros((2, N))
         for c in range(2):
@@ -262,4 +272,69 @@ def substep_vjp(t, u, p_prev, bvel, dt, tape, u_out_bar, p_out_bar):
     _, (br0, br1) = bflux(t, bvel)
     bvb[0] += br0 * Fbb
     bvb[1] += br1 * Fbb
+    if with_src:
+        return ub, pprevb_in, bvb, srcb
     return ub, pprevb_in, bvb
+
+
+# ---- passive scalar + buoyancy (RBC substep: SIM.py:1471-1657, rbc_env_base.py:280-304) -------------------------
+SIG = np.array([-1.0, 1.0, -1.0, 1.0])
+
+
+def scalar_step(t, u, bvel, T, sbval, dt):
+    """T_new = C_s(u)^-1 rhs_s(T, bvel, sbval) (k_setup_scalar + BiCGStab), with a tape."""
+    Fb, _ = bflux(t, bvel)
+    fl = fluxes(t, u, Fb)
+    ff = np.where(t.inner, 0.5 * SIG[:, None] * fl, 0.0)
+    diag = t.det / dt + t.Cd_s[0] + ff.sum(0)
+    As = diag / t.det
+    Coffs = np.where(t.inner, (ff + t.Cd_s[1:]) / t.det, 0.0)
+    r = t.det * T / dt
+    for f in range(4):
+        m = ~t.inner[f]
+        j = t.bj[f]
+        dif = t.kappa * np.where(t.sb_neumann[j] == 0, 2.0 * t.b_alpha[j], 1.0)
+        r = r + np.where(m, sbval[j] * (-(SIG[f] * Fb[j]) + dif), 0.0)
+    Cs = dense(t, Coffs, As)
+    Tn = np.linalg.solve(Cs, r / t.det)
+    return Tn, dict(Cs=Cs, Tn=Tn, Fb=Fb)
+
+
+def scalar_step_vjp(t, u, bvel, T, sbval, dt, tape, Tn_bar):
+    """returns (u_bar, bvel_bar, T_bar, sbval_bar)"""
+    N = t.N
+    Tn, Fb = tape["Tn"], tape["Fb"]
+    lam = np.linalg.solve(tape["Cs"].T, Tn_bar)
+    Asb = -lam * Tn
+    Coffsb = np.stack([np.where(t.inner[f], -lam * Tn[t.nb_safe[f]], 0.0) for f in range(4)])
+    rb = lam / t.det
+    Tb = rb * t.det / dt
+    sbb = np.zeros(t.NB); Fbb = np.zeros(t.NB)
+    for f in range(4):
+        m = ~t.inner[f]
+        j = t.bj[f]
+        dif = t.kappa * np.where(t.sb_neumann[j] == 0, 2.0 * t.b_alpha[j], 1.0)
+        np.add.at(sbb, j, np.where(m, rb * (-(SIG[f] * Fb[j]) + dif), 0.0))
+        np.add.at(Fbb, j, np.where(m, -rb * sbval[j] * SIG[f], 0.0))
+    diagb = Asb / t.det
+    ffb = np.where(t.inner, Coffsb / t.det + diagb[None, :], 0.0)
+    ub, Fbb2 = fluxes_T(t, 0.5 * SIG[:, None] * ffb)
+    Fbb += Fbb2
+    _, (br0, br1) = bflux(t, bvel)
+    return ub, np.stack([br0 * Fbb, br1 * Fbb]), Tb, sbb
+
+
+def substep_scalar(t, u, p_prev, bvel, T, sbval, dt, beta, correctors=2):
+    """RBC substep: scalar transport with the OLD velocity, buoyancy source from the NEW temperature, PISO substep."""
+    Tn, stape = scalar_step(t, u, bvel, T, sbval, dt)
+    src = np.stack([np.zeros(t.N), beta * Tn])
+    uo, po, tape = substep(t, u, p_prev, bvel, dt, correctors=correctors, src=src)
+    return uo, po, Tn, dict(piso=tape, scalar=stape)
+
+
+def substep_scalar_vjp(t, u, p_prev, bvel, T, sbval, dt, beta, tape, u_out_bar, p_out_bar, T_out_bar):
+    """returns (u_bar, p_prev_bar, bvel_bar, T_bar, sbval_bar)"""
+    ub, pb, bvb, srcb = substep_vjp(t, u, p_prev, bvel, dt, tape["piso"], u_out_bar, p_out_bar, with_src=True)
+    Tnb = T_out_bar + beta * srcb[1]
+    ub2, bvb2, Tb, sbb = scalar_step_vjp(t, u, bvel, T, sbval, dt, tape["scalar"], Tnb)
+    return ub + ub2, pb, bvb + bvb2, Tb, sbb

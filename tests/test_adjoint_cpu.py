@@ -44,3 +44,36 @@ def test_substep_vjp_matches_finite_differences(small, n_adv, n_p):
             # the absolute term covers the round-off of the finite difference itself: the pressure operator is
             # nearly singular, so J carries ~1e-12 noise that eps = 1e-6 amplifies to ~1e-6
             assert abs(fd - an) <= 2e-5 * max(abs(fd), abs(an)) + 5e-6, (name, trial, fd, an)
+
+
+def test_scalar_substep_vjp_matches_finite_differences():
+    """RBC substep (passive scalar with the old velocity, buoyancy from the new temperature, orthogonal PISO):
+    gradients w.r.t. u, the boundary velocities, the temperature and the heater (boundary) temperatures."""
+    from fluidgym_b200.envs.rbc_domain import make_rbc_domain
+    cd = make_rbc_domain(n_heaters=3, heater_width=4)[0].prepare()
+    t = ae.T64(cd)
+    rng = np.random.default_rng(2)
+    u = 0.05 * rng.standard_normal((2, t.N))
+    p0 = np.zeros(t.N)
+    bvel = 0.01 * rng.standard_normal((2, t.NB))
+    T = np.clip(0.5 + 0.3 * rng.standard_normal(t.N), 0, 1)
+    sb = cd.sb_val0[:t.NB].astype(np.float64) + 0.2 * rng.standard_normal(t.NB)
+    dt, beta = 0.05, 1.0
+    wu, wp, wT = rng.standard_normal((2, t.N)), rng.standard_normal(t.N), rng.standard_normal(t.N)
+
+    def J(u_, b_, T_, s_):
+        uo, po, Tn, _ = ae.substep_scalar(t, u_, p0, b_, T_, s_, dt, beta)
+        return float((wu * uo).sum() + (wp * po).sum() + (wT * Tn).sum())
+
+    uo, po, Tn, tape = ae.substep_scalar(t, u, p0, bvel, T, sb, dt, beta)
+    ub, pb, bb, Tb, sbb = ae.substep_scalar_vjp(t, u, p0, bvel, T, sb, dt, beta, tape, wu, wp, wT)
+    args = [u, bvel, T, sb]
+    for k, (name, grad) in enumerate((("u", ub), ("bvel", bb), ("T", Tb), ("sbval", sbb))):
+        for trial in range(2):
+            d = rng.standard_normal(args[k].shape)
+            eps = 1e-6 if name in ("u", "bvel") else 1e-3      # the substep is linear in T and in the boundary temperatures
+            hi = [a + eps * d if i == k else a for i, a in enumerate(args)]
+            lo = [a - eps * d if i == k else a for i, a in enumerate(args)]
+            fd = (J(*hi) - J(*lo)) / (2 * eps)
+            an = float((grad * d).sum())
+            assert abs(fd - an) <= 2e-5 * max(abs(fd), abs(an)) + 5e-6, (name, trial, fd, an)

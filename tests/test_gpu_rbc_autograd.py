@@ -1,0 +1,109 @@
+"""Differentiability of the Rayleigh-Benard path: the CUDA adjoint of the substep with passive scalar and buoyancy
+(fgb_piso_substep_backward_scalar through fluidgym_b200.autograd.PISOSubstepScalar) against (i) the float64 numpy
+specification (tests/adjoint_eval.py::substep_scalar_vjp, itself validated against finite differences on the CPU) and
+(ii) central finite differences of the CUDA forward through ``RBC2DEnv.step`` (reward w.r.t. the heater actions)."""
+import numpy as np
+import pytest
+
+import adjoint_eval as ae
+from conftest import rel_l2
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+DT, BETA = 0.05, 1.0
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from fluidgym_b200.envs.rbc_domain import make_rbc_domain
+    from fluidgym_b200.solver import BatchedPISO
+    cd = make_rbc_domain(n_heaters=4, heater_width=8)[0].prepare()
+    sol = BatchedPISO(cd, 2, cg_impl=6, non_orthogonal=False, advection_tol=1e-7, pressure_tol=1e-7)
+    rng = np.random.default_rng(5)
+    u = 0.05 * rng.standard_normal((2, cd.N))
+    p0 = np.zeros(cd.N)
+    bvel = np.zeros((2, cd.NB))
+    T = np.clip(0.5 + 0.3 * rng.standard_normal(cd.N), 0.0, 1.0)
+    sb = cd.sb_val0[:cd.NB].astype(np.float64) + 0.2 * rng.standard_normal(cd.NB)
+    return cd, sol, u, p0, bvel, T, sb
+
+
+def _tensors(arrs):
+    return [torch.tensor(np.stack([a, a]), dtype=torch.float32, device="cuda", requires_grad=True) for a in arrs]
+
+
+def test_forward_record_equals_plain_substep(setup):
+    from fluidgym_b200.autograd import piso_substep_scalar
+    cd, sol, u, p0, bvel, T, sb = setup
+    tu, tp, tb, tT, ts = _tensors((u, p0, bvel, T, sb))
+    sol.buffer("ures").copy_(tu.detach())
+    uo, po, To = piso_substep_scalar(sol, tu, tp, tb, tT, ts, DT, BETA)
+    sol.u.copy_(tu.detach()); sol.p.copy_(tp.detach()); sol.bvel.copy_(tb.detach()); sol.T.copy_(tT.detach()); sol.sbval.copy_(ts.detach())
+    sol.buffer("ures").copy_(tu.detach())
+    sol.set_buoyancy(BETA)
+    sol.piso_substep(DT)
+    torch.cuda.synchronize()
+    assert torch.equal(sol.T, To.detach())
+    assert torch.equal(sol.u, uo.detach()) and torch.equal(sol.p, po.detach())
+
+
+def test_vjp_matches_numpy_specification(setup):
+    from fluidgym_b200.autograd import piso_substep_scalar
+    cd, sol, u, p0, bvel, T, sb = setup
+    t = ae.T64(cd)
+    rng = np.random.default_rng(9)
+    wu, wT = rng.standard_normal((2, cd.N)), rng.standard_normal(cd.N)
+    tu, tp, tb, tT, ts = _tensors((u, p0, bvel, T, sb))
+    sol.buffer("ures").copy_(tu.detach())
+    uo, po, To = piso_substep_scalar(sol, tu, tp, tb, tT, ts, DT, BETA)
+    J = (uo * torch.tensor(wu, dtype=torch.float32, device="cuda")).sum() + (To * torch.tensor(wT, dtype=torch.float32, device="cuda")).sum()
+    J.backward()
+    torch.cuda.synchronize()
+    uo64, po64, Tn64, tape = ae.substep_scalar(t, u, p0, bvel, T, sb, DT, BETA)
+    e_fwd = (rel_l2(uo[0].detach().cpu().numpy(), uo64), rel_l2(To[0].detach().cpu().numpy(), Tn64))
+    ub, pb, bb, Tb, sbb = ae.substep_scalar_vjp(t, u, p0, bvel, T, sb, DT, BETA, tape, wu, np.zeros(cd.N), wT)
+    errs = dict(u=rel_l2(tu.grad[0].cpu().numpy(), ub), T=rel_l2(tT.grad[0].cpu().numpy(), Tb),
+                sbval=rel_l2(ts.grad[1].cpu().numpy(), sbb), bvel=rel_l2(tb.grad[1].cpu().numpy(), bb))
+    print("rbc adjoint vs spec: forward", e_fwd, "grads", errs)
+    assert e_fwd[0] < 1e-4 and e_fwd[1] < 1e-5
+    assert errs["u"] < 1e-3 and errs["T"] < 1e-3          # north_star: gradients within 1e-3 relative
+    assert errs["sbval"] < 3e-3 and errs["bvel"] < 3e-3
+    assert torch.allclose(tu.grad[0], tu.grad[1], rtol=1e-4, atol=1e-5)
+
+
+def test_reward_gradient_wrt_heater_actions_matches_finite_differences():
+    """d reward / d action through RBC2DEnv.step (4 solver steps incl. the cubic-blended heater profile) along a random
+    direction vs central differences of the same CUDA forward."""
+    import fluidgym_b200
+    env = fluidgym_b200.make("RBC2D-easy-v0", n_envs=2, n_heaters=4, resolution=8, step_length=0.2, differentiable=True)
+    env.solver.set_options(adv_tol=1e-7, p_tol=1e-7)
+    env.reset(seed=3)
+    s = env.solver
+    for _ in range(10):                                       # let the plumes start before differentiating
+        s.single_step(env.dt, env.cfl)
+    state = [x.clone() for x in (s.u, s.p, s.T, s.sbval, s.buffer("ures"))]
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    a0 = (torch.rand(2, 4, 1, device="cuda", generator=gen) * 2 - 1) * 0.5
+
+    def run(a):
+        env.set_state(*state)
+        env._n_steps = 0
+        return env.step(a)[1]
+
+    a = a0.clone().requires_grad_(True)
+    r = run(a)
+    assert r.requires_grad
+    r.sum().backward()
+    g = a.grad.clone()
+    d = torch.randn(a0.shape, device="cuda", generator=gen)
+    d = d / d.norm()
+    eps = 5e-2
+    with torch.no_grad():
+        fd = (run(a0 + eps * d) - run(a0 - eps * d)) / (2 * eps)
+    an = (g * d).sum(dim=(1, 2))
+    print("rbc d reward / d action: adjoint", an.tolist(), "finite differences", fd.tolist())
+    assert torch.all(fd.abs() > 1e-6)
+    assert torch.allclose(an, fd, rtol=5e-2, atol=1e-5)
+    env.detach()
+    assert all(not x.requires_grad for x in env._dstate)
