@@ -13,6 +13,7 @@ def main():
     spec = make_cylinder_domain(24)
     t0 = time.time(); cd = spec.prepare(); print("compile tables %.2fs" % (time.time() - t0))
     st = np.load(os.path.join(ROOT, "tests/golden", fixture))
+    first = None
     for impl in impls:
         sol = BatchedPISO(cd, B, cg_impl=impl)
         u = torch.from_numpy(st["env3_u"]).cuda(); p = torch.from_numpy(st["env3_p"]).cuda()
@@ -34,5 +35,12 @@ def main():
         print(json.dumps({"impl": impl, "B": B, "ms_per_substep": ms, "env_substeps_per_s": B / ms * 1e3,
                           "cg_iters_mean": float(its[:, 2:4].mean()) + 1, "cg_iters_max": int(its[:, 2:4].max()) + 1,
                           "bicg_iters_mean": float(its[:, :2].mean()) + 1}))
+        res = (sol.u.clone(), sol.p.clone())
+        if first is None:
+            first = res
+        else:   # same state, same number of substeps: distance to the first implementation of the list
+            print(json.dumps({"impl": impl, "rel_l2_u_vs_first": float((res[0] - first[0]).norm() / first[0].norm()),
+                              "rel_l2_p_vs_first": float((res[1] - first[1]).norm() / first[1].norm()),
+                              "resid_max": float(sol.buffer("resid")[:, 2:4].max())}))
         del sol
 main()
