@@ -66,4 +66,8 @@ def _register_defaults():
     register("RBC2D-medium-v0", RBC2DEnv, **{**RBC_2D_DEFAULT_CONFIG, "rayleigh_number": 4e5, "adaptive_cfl": 0.5})
     register("RBC2D-hard-v0", RBC2DEnv, **{**RBC_2D_DEFAULT_CONFIG, "rayleigh_number": 8e5, "adaptive_cfl": 0.5})
     register("RBC2D-wide-easy-v0", RBC2DEnv, **{**RBC_2D_DEFAULT_CONFIG, "aspect_ratio": 2, "n_heaters": 24, "rayleigh_number": 8e4})
+    register("RBC2D-wide-medium-v0", RBC2DEnv, **{**RBC_2D_DEFAULT_CONFIG, "aspect_ratio": 2, "n_heaters": 24, "rayleigh_number": 4e5,
+                                                   "adaptive_cfl": 0.5})
+    register("RBC2D-wide-hard-v0", RBC2DEnv, **{**RBC_2D_DEFAULT_CONFIG, "aspect_ratio": 2, "n_heaters": 24, "rayleigh_number": 8e5,
+                                                 "adaptive_cfl": 0.5})
     register("CylinderJet2D-hard-v0", CylinderJet2DEnv, **{**CYLINDER_JET_2D_DEFAULT_CONFIG, "reynolds_number": 500.0, "resolution": 32})

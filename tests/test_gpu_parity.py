@@ -187,6 +187,33 @@ def test_env_step_matches_reference(cyl24, golden):
     assert np.abs(obs["pressure"][0].cpu().numpy() - st["step0_obs_pressure"]).max() < 2e-3
 
 
+def test_100_solver_step_horizon_matches_reference(cyl24, golden):
+    """north_star: relative L2 <= 1e-3 on u over a 100-step horizon.  Four env.step calls (4 x 25 solver steps) with the
+    reference's recorded actions from the reference's reset state, compared with the reference's state, rewards and
+    sensors after every env step."""
+    spec, cd = cyl24
+    from fluidgym_b200.envs.cylinder import CylinderJet2DEnv
+    env = CylinderJet2DEnv(n_envs=2, compiled=(spec, cd))
+    rs = golden("cyl24_reset.npz")
+    st = golden("cyl24_steps.npz")
+    env.reset(seed=42)
+    env.set_state(rs["u"], rs["presres"], rs["bvel"])
+    errs = []
+    for k in range(4):
+        action = torch.tensor(st["actions"][k], device="cuda").reshape(1, 1).repeat(2, 1)
+        obs, reward, term, trunc, info = env.step(action)
+        drag_ref = float(st[f"step{k}_info_drag"])
+        errs.append((abs(float(reward[0]) - float(st[f"step{k}_reward"])), abs(float(info["drag"][0]) - drag_ref) / abs(drag_ref),
+                     float(np.abs(obs["velocity"][0].cpu().numpy() - st[f"step{k}_obs_velocity"]).max())))
+    e_u = rel_l2(env.solver.u[0].cpu().numpy(), st["env3_u"])
+    e_p = rel_l2(env.solver.p[0].cpu().numpy(), st["env3_p"])
+    print("100-step horizon: u", e_u, "p", e_p, "per env step (|d reward|, rel drag, max |d sensor velocity|)", errs)
+    assert e_u < 1e-3
+    assert e_p < 5e-3                  # p carries the tolerance ball of its last CG solve (DESIGN.md section 5)
+    for d_reward, d_drag, d_obs in errs:
+        assert d_reward < 1e-3 and d_drag < 1e-3 and d_obs < 2e-3
+
+
 def test_parallel_fluid_env_api():
     """ParallelFluidEnv(env_id, cuda_ids): one environment per entry, results stacked on the CPU
     (envs/parallel_env.py:162-287 of the reference)."""
