@@ -166,9 +166,12 @@ class RBC2DEnv(InitialDomains):
         s = self.solver
         B, nx, ny = self.n_envs, self.nx, self.ny
         self._dstate = None
+        randomize = self.randomize_initial_state if randomize is None else randomize
         if self.load_domain_on_reset:                      # fluid_env.py:519-539
-            self._load_initial_domains_on_reset(self.randomize_initial_state if randomize is None else randomize)
+            self._load_initial_domains_on_reset(randomize)
             s.buffer("ures").copy_(s.u)
+            if randomize:
+                self._randomize_domain()
             self._apply_action(self._zero_action)
             self._reset_called, self._n_steps = True, 0
             return (self._get_local_obs() if self.use_marl else self._get_global_obs()), {}
@@ -179,9 +182,37 @@ class RBC2DEnv(InitialDomains):
         s.p.zero_()
         s.buffer("ures").zero_()
         s.sbval.copy_(torch.from_numpy(self.cd.sb_val0[:self.cd.NB].copy()).to(self.device).unsqueeze(0).expand_as(s.sbval))
+        if randomize:                                      # fluid_env.py:549-551: also for a freshly built domain
+            self._randomize_domain()
         self._apply_action(self._zero_action)
         self._reset_called, self._n_steps = True, 0
         return (self._get_local_obs() if self.use_marl else self._get_global_obs()), {}
+
+    def _randomize_domain(self):
+        """rbc_env_base.py:336-393: mirror in x with probability 1/2 (the x velocity changes sign), periodic shift in x,
+        N(0, 0.05) noise on T (clamped) and u, then 1-2 time units of settling.  Flip and shift are drawn per environment;
+        the settling time is common to the batch (one launch sequence advances every environment)."""
+        s = self.solver
+        B, nx, ny = self.n_envs, self.nx, self.ny
+        flip = torch.from_numpy(self._np_rng.uniform(0.0, 1.0, size=B) > 0.5).to(self.device)
+        shift = torch.from_numpy(self._np_rng.integers(0, nx, size=B)).to(self.device)
+        T = s.T.reshape(B, ny, nx)
+        u = s.u.reshape(B, 2, ny, nx)
+        x = torch.arange(nx, device=self.device)
+        # flipped then rolled: out[x] = in_flipped[(x - shift) % nx], in_flipped[x'] = in[nx - 1 - x']
+        src = (x[None, :] - shift[:, None]) % nx
+        src = torch.where(flip[:, None], nx - 1 - src, src)                      # [B, nx]
+        T = torch.gather(T, 2, src[:, None, :].expand(B, ny, nx))
+        u = torch.gather(u, 3, src[:, None, None, :].expand(B, 2, ny, nx)).clone()
+        u[:, 0] = torch.where(flip[:, None, None], -u[:, 0], u[:, 0])
+        T = T + torch.randn(T.shape, device=self.device, generator=self._torch_rng) * 0.05
+        T = torch.clamp(T, self.T_cold, self.T_hot)
+        u = u + torch.randn(u.shape, device=self.device, generator=self._torch_rng) * 0.05
+        s.T.copy_(T.reshape(B, -1))
+        s.u.copy_(u.reshape(B, 2, -1))
+        n_steps = int(self._np_rng.uniform(1.0, 2.0) / self.dt)
+        for _ in range(n_steps):
+            s.single_step(self.dt, self.cfl)
 
     def _action_to_control(self, action: torch.Tensor) -> torch.Tensor:
         """[B, n_heaters] -> bottom-plate temperature [B, nx] (rbc_env_2d.py:210-270)."""

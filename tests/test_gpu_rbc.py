@@ -99,3 +99,19 @@ def test_error_strings_match_reference():
         env.sample_action()
     with pytest.raises(RuntimeError, match="Environment must be reset before stepping"):
         env.step(torch.zeros(1, 12, 1))
+
+
+def test_randomized_reset_is_per_environment_and_reproducible():
+    """reset(randomize=True) = rbc_env_base.py:336-393 per environment: mirror / periodic shift / noise, then 1-2 time units
+    of settling.  Seeded -> reproducible; environments of one batch differ from each other; temperature stays physical."""
+    env = _env(3, step_length=0.25)
+    env.reset(seed=5, randomize=True)
+    T1, u1 = env.solver.T.clone(), env.solver.u.clone()
+    env.reset(seed=5, randomize=True)
+    assert torch.equal(T1, env.solver.T) and torch.equal(u1, env.solver.u)
+    assert torch.isfinite(u1).all() and float(T1.min()) > -0.2 and float(T1.max()) < 1.2
+    assert not torch.allclose(T1[0], T1[1]) and not torch.allclose(T1[1], T1[2])
+    env.reset(seed=5, randomize=False)
+    assert not torch.allclose(T1, env.solver.T)
+    obs, reward, *_ = env.step(torch.zeros(3, 12, 1, device="cuda"))
+    assert torch.isfinite(reward).all()
