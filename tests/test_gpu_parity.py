@@ -349,3 +349,20 @@ def test_initial_domain_files_written_by_the_reference_drive_reset(tmp_path):
     env._domain_pool.clear()
     env.load_initial_domain(3)
     assert torch.equal(env.solver.u[0], env.solver.u[1]) and float(env.solver.u.abs().max()) > 0.2 and path.endswith("val")
+
+
+def test_vec_env_adapter_on_the_cuda_environments():
+    """integration.VecFluidEnv (SB3 VecEnv protocol) over the batched CUDA environments: single-agent cylinder batch and the
+    multi-agent RBC batch (slots = environments x agents)."""
+    import fluidgym_b200
+    from fluidgym_b200.integration import VecFluidEnv
+    v = VecFluidEnv(fluidgym_b200.make("CylinderJet2D-easy-v0", n_envs=3, step_length=0.02))
+    obs = v.reset(seed=0)
+    assert v.num_envs == 3 and obs["velocity"].shape == (3, 151, 2) and obs["pressure"].dtype == np.float32
+    obs, rew, dones, infos = v.step(np.zeros((3, 1), dtype=np.float32))
+    assert rew.shape == (3,) and np.isfinite(rew).all() and not dones.any() and "drag" in infos[0]
+    m = VecFluidEnv(fluidgym_b200.make("RBC2D-easy-v0", n_envs=2, use_marl=True, step_length=0.1))
+    obs = m.reset(seed=0)
+    assert m.num_envs == 24 and obs["temperature"].shape == (24, 8, 44)
+    obs, rew, dones, infos = m.step(np.zeros((24, 1), dtype=np.float32))
+    assert rew.shape == (24,) and np.isfinite(rew).all() and np.isfinite(infos[13]["nusselt"])
