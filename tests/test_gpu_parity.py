@@ -208,10 +208,12 @@ def test_100_solver_step_horizon_matches_reference(cyl24, golden):
     e_u = rel_l2(env.solver.u[0].cpu().numpy(), st["env3_u"])
     e_p = rel_l2(env.solver.p[0].cpu().numpy(), st["env3_p"])
     print("100-step horizon: u", e_u, "p", e_p, "per env step (|d reward|, rel drag, max |d sensor velocity|)", errs)
-    assert e_u < 1e-3
-    assert e_p < 5e-3                  # p carries the tolerance ball of its last CG solve
+    # north_star bars: u 1e-3 over 100 steps, rewards 1e-4.  Observed on B200: u 7.4e-6, p 2.6e-5, rewards <= 6.2e-5,
+    # drag <= 1.2e-5 relative, sensors <= 1.0e-4 -- the bars below leave one order of magnitude
+    assert e_u < 1e-4
+    assert e_p < 5e-4                  # p carries the tolerance ball of its last CG solve
     for d_reward, d_drag, d_obs in errs:
-        assert d_reward < 1e-3 and d_drag < 1e-3 and d_obs < 2e-3
+        assert d_reward < 1e-4 and d_drag < 1e-4 and d_obs < 1e-3
 
 
 def test_parallel_fluid_env_api():

@@ -106,6 +106,6 @@ def test_reward_gradient_wrt_heater_actions_matches_finite_differences():
     an = (g * d).sum(dim=(1, 2))
     print("rbc d reward / d action: adjoint", an.tolist(), "finite differences", fd.tolist())
     assert torch.all(fd.abs() > 1e-6)
-    assert torch.allclose(an, fd, rtol=5e-2, atol=2e-5)
+    assert torch.allclose(an, fd, rtol=2e-2, atol=1e-5)       # observed 0.25 % and 0.6 %
     env.detach()
     assert all(not x.requires_grad for x in env._dstate)
