@@ -104,7 +104,9 @@ class BatchedPISO3D:
     """State + solver for ``n_envs`` copies of one Box3DDomain: ``u [B,3,N]``, ``p [B,N]``, ``bvel [B,3,NB]``."""
 
     def __init__(self, dom: Box3DDomain, n_envs: int = 1, device="cuda:0", corrector_steps=2, advection_tol=1e-6, pressure_tol=1e-6,
-                 max_iter=5000):
+                 max_iter=5000, non_orthogonal=True):
+        """non_orthogonal: the reference's code path (Simulation(non_orthogonal=...)): True = zero-started predictor and CG with
+        residual reset every 100 iterations (TCF), False = predictor started from the previous result, no reset (RBC)."""
         if not torch.cuda.is_available():
             raise native.FGBError("fluidgym_b200 needs a CUDA device (there is no CPU fallback)")
         self.lib = native.load()
@@ -116,7 +118,7 @@ class BatchedPISO3D:
         self._tab["minv"] = torch.from_numpy(np.ascontiguousarray(dom.minv.reshape(3, -1))).to(dev)
         self._tab["det"] = torch.from_numpy(np.ascontiguousarray(dom.det.reshape(-1))).to(dev)
         self.tables = native.Ortho3Tables(dom.N, dom.NB, dom.visc, *[self._tab[k].data_ptr() for k in ("nbr", "minv", "det", "b_minv", "b_det")])
-        self.options = native.Options(corrector_steps, 1, 1, 1, advection_tol, pressure_tol, max_iter, 0)
+        self.options = native.Options(corrector_steps, 1, 1, int(bool(non_orthogonal)), advection_tol, pressure_tol, max_iter, 0)
         nbytes = self.lib.fgb_ortho3_workspace_bytes(C.byref(self.tables), self.B)
         self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
         off = (-self.workspace.data_ptr()) % 256
@@ -128,6 +130,25 @@ class BatchedPISO3D:
         self.u = torch.zeros(B, 3, N, device=dev)
         self.p = torch.zeros(B, N, device=dev)
         self.bvel = torch.zeros(B, 3, NB, device=dev)
+
+    # ---- passive scalar + buoyancy (RBC3D) ---------------------------------------------------------------------------
+    def attach_scalar(self, kappa: float, beta: float = 1.0, sbval0=None):
+        """Domain(passiveScalarChannels=1) + setScalarViscosity (rbc_env_base.py:206-216): adds ``T [B,N]`` and the Dirichlet
+        boundary values ``sbval [B,NB]``; every substep then transports T with the incoming velocity first and adds the
+        buoyancy source (0, beta T, 0)."""
+        dev = self.device
+        self.T = torch.zeros(self.B, self.N, device=dev)
+        self.sbval = torch.zeros(self.B, max(self.NB, 1), device=dev)
+        if sbval0 is not None:
+            self.sbval.copy_(torch.as_tensor(np.asarray(sbval0, dtype=np.float32), device=dev).expand_as(self.sbval))
+        self.kappa, self.beta = float(kappa), float(beta)
+        self._scalar = native.Ortho3Scalar(self.T.data_ptr(), self.sbval.data_ptr(), self.kappa, self.beta)
+        native.check(self.lib.fgb_ortho3_set_scalar(self.handle, C.byref(self._scalar)), "fgb_ortho3_set_scalar")
+
+    def advect_scalar(self, dt):
+        self._dtc = self._dt(dt)
+        native.check(self.lib.fgb_ortho3_advect_scalar(self.handle, _ptr(self.u), _ptr(self.bvel), _ptr(self._dtc), None, self.stream),
+                     "fgb_ortho3_advect_scalar")
 
     def __del__(self):
         try:

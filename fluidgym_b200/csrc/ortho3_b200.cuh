@@ -61,6 +61,7 @@ struct fgb_ortho3 {
     int32_t *counters; int32_t *h_counters; float *src; float *rowmean;
     unsigned long long *iter_total;
     unsigned long long *slab_ctr;     // [4] device-side sequence counters of the slab protocol
+    fgb_ortho3_scalar sc;             // passive scalar + buoyancy (RBC3D); sc.T == nullptr: none
     int grid_blocks;
     long long launches;
 };
@@ -95,6 +96,7 @@ extern "C" int fgb_ortho3_create(const fgb_ortho3_tables *t, int32_t B, void *wo
     if (b->t.NS <= 0) b->t.NS = b->t.N;
     if (b->t.N_global <= 0) b->t.N_global = b->t.N;
     memset(&b->slab, 0, sizeof(b->slab)); b->slab.world = 1;
+    memset(&b->sc, 0, sizeof(b->sc));
     const size_t BN = (size_t)B * b->t.NS;
     Carver c{(char *)workspace, 0};
     b->Coff = c.take<float>(6 * BN); b->Poff = c.take<float>(6 * BN);
@@ -152,7 +154,7 @@ __device__ __forceinline__ float o3_bflux(const T3 &t, int j, int d, const float
 __global__ void __launch_bounds__(O3_T) k3_setup_advection(T3 t, O3Slab sl, const float *__restrict__ U, const float *__restrict__ Bvel,
                                                            const float *__restrict__ Src /* [B][4] or null */, const float *__restrict__ dtv,
                                                            const int32_t *__restrict__ active, float *__restrict__ Coff, float *__restrict__ A,
-                                                           float *__restrict__ Rhs) {
+                                                           float *__restrict__ Rhs, const float *__restrict__ Tbuoy /* [B][NS] or null */, float beta) {
     const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS, NB = t.NB;
     if (g >= N || (active && !active[b])) return;
     const float *u = U + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB;
@@ -187,10 +189,47 @@ __global__ void __launch_bounds__(O3_T) k3_setup_advection(T3 t, O3Slab sl, cons
     A[(size_t)b * NS + g] = Ag;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-        Rhs[((size_t)b * 3 + c) * NS + g] = (det * uo[c] / dt + Sb[c]) / det + (Src ? Src[b * 4 + c] : 0.f);
+        Rhs[((size_t)b * 3 + c) * NS + g] = (det * uo[c] / dt + Sb[c]) / det + (Src ? Src[b * 4 + c] : 0.f) +
+                                            ((Tbuoy && c == 1) ? Tbuoy[(size_t)b * NS + g] * beta : 0.f);   // rbc_env_base.py:280-304
     bool dirty = false;
     o3_push(sl, t, A, g, Ag, dirty);          // (slabs: B == 1) consumed after the predictor solve, whose reductions order it
     if (dirty) __threadfence_system();
+}
+
+// Passive-scalar transport (SetupAdvectionMatrix(forPassiveScalar) + SetupAdvectionScalar, K.cu:3617-3880, 4094-4198):
+// the same convection with the scalar diffusivity kappa; Dirichlet boundary values sb on the prescribed faces.
+__global__ void __launch_bounds__(O3_T) k3_setup_scalar(T3 t, const float *__restrict__ U, const float *__restrict__ Tin, const float *__restrict__ Bvel,
+                                                        const float *__restrict__ Sbval, float kappa, const float *__restrict__ dtv,
+                                                        const int32_t *__restrict__ active, float *__restrict__ Coff, float *__restrict__ A,
+                                                        float *__restrict__ Rhs /* [B][NS] */) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS, NB = t.NB;
+    if (g >= N || (active && !active[b])) return;
+    const float *u = U + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB, *sb = Sbval + (size_t)b * NB;
+    const float dt = dtv[b], det = t.det[g];
+    float diag = det / dt, r = det * Tin[(size_t)b * NS + g] / dt;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const int d = f >> 1, n = t.nbr[f * NS + g];
+        const float sig = (f & 1) ? 1.f : -1.f;
+        const float mi = t.minv[d * NS + g], al = det * mi * mi;
+        float off = 0.f;
+        if (n >= 0) {
+            const float dn = t.det[n], mn = t.minv[d * NS + n];
+            const float fl = 0.5f * (det * mi * u[d * NS + g] + dn * mn * u[d * NS + n]);
+            const float vc = (al * kappa + (dn * mn * mn) * kappa) * 0.5f;
+            const float ff = sig * 0.5f * fl;
+            diag += ff + vc;
+            off = (ff - vc) / det;
+        } else {
+            const int j = -1 - n;
+            diag += 2.f * kappa * al;
+            const float bm = t.b_minv[d * NB + j];
+            r += sb[j] * (-(sig * o3_bflux(t, j, d, bv)) + 2.f * kappa * (t.b_det[j] * bm * bm));
+        }
+        Coff[((size_t)b * 6 + f) * NS + g] = off;
+    }
+    A[(size_t)b * NS + g] = diag / det;
+    Rhs[(size_t)b * NS + g] = r / det;
 }
 
 // P: off = 1/2 (alpha_P / A_P + alpha_N / A_N), diag = -sum (K.cu:4812-4978)
@@ -218,7 +257,8 @@ __global__ void __launch_bounds__(O3_T) k3_pressure_matrix(T3 t, const float *__
 // HbyA = (u/dt - H(u_prev) + S_b/det + source) / A (K.cu:5136-5255)
 __global__ void __launch_bounds__(O3_T) k3_hbya(T3 t, O3Slab sl, const float *__restrict__ U, const float *__restrict__ Uprev, const float *__restrict__ Bvel,
                                                 const float *__restrict__ Src, const float *__restrict__ dtv, const int32_t *__restrict__ active,
-                                                const float *__restrict__ Coff, const float *__restrict__ A, float *__restrict__ Hb) {
+                                                const float *__restrict__ Coff, const float *__restrict__ A, float *__restrict__ Hb,
+                                                const float *__restrict__ Tbuoy /* [B][NS] or null */, float beta) {
     const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS, NB = t.NB;
     if (g >= N || (active && !active[b])) return;
     const float *u = U + (size_t)b * 3 * NS, *up = Uprev + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB;
@@ -242,7 +282,8 @@ __global__ void __launch_bounds__(O3_T) k3_hbya(T3 t, O3Slab sl, const float *__
     bool dirty = false;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float hv = (u[c * NS + g] / dt - H[c] + Sb[c] / det + (Src ? Src[b * 4 + c] : 0.f)) / Ag;
+        const float srcv = (Src ? Src[b * 4 + c] : 0.f) + ((Tbuoy && c == 1) ? Tbuoy[(size_t)b * NS + g] * beta : 0.f);
+        const float hv = (u[c * NS + g] / dt - H[c] + Sb[c] / det + srcv) / Ag;
         Hb[((size_t)b * 3 + c) * NS + g] = hv;
         o3_push(sl, t, Hb + (size_t)c * NS, g, hv, dirty);
     }
@@ -370,7 +411,9 @@ __device__ __forceinline__ void o3_halo_sync(cg::grid_group &grid, const O3Slab 
     }
 }
 
-// BiCGStab for the three velocity components in lock step (BICG.cu:237-376; same operation order as k_bicgstab)
+// BiCGStab for NC right-hand sides in lock step (3 velocity components, or 1 passive scalar) (BICG.cu:237-376; same
+// operation order as k_bicgstab)
+template <int NC>
 __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, const float *__restrict__ Coff, const float *__restrict__ Adiag,
                                                     const float *__restrict__ Rhs, float *X, float *work, float *part, int maxit, float tol,
                                                     int zero_init, const int32_t *__restrict__ active, int32_t *__restrict__ iters,
@@ -389,14 +432,14 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
         float *wb = work + (size_t)b * O3_KRY * NS;
         float *r[3], *rw[3], *p[3], *v[3], *tt[3], *x[3];
         const float *f[3];
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < NC; ++c) {
             r[c] = wb + (size_t)(5 * c) * NS; rw[c] = r[c] + NS; p[c] = r[c] + 2 * (size_t)NS; v[c] = r[c] + 3 * (size_t)NS; tt[c] = r[c] + 4 * (size_t)NS;
-            x[c] = X + ((size_t)b * 3 + c) * NS; f[c] = Rhs + ((size_t)b * 3 + c) * NS;
+            x[c] = X + ((size_t)b * NC + c) * NS; f[c] = Rhs + ((size_t)b * NC + c) * NS;
         }
-        if (zero_init) { for (int c = 0; c < 3; ++c) for (int g = tid; g < N; g += nth) x[c][g] = 0.f; }
+        if (zero_init) { for (int c = 0; c < NC; ++c) for (int g = tid; g < N; g += nth) x[c][g] = 0.f; }
         else grid.sync();
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < NC; ++c)
             for (int g = tid; g < N; g += nth) {
                 const float rr = f[c][g] - (zero_init ? 0.f : o3_row(t, g, off, dg, x[c]));
                 r[c][g] = rr; rw[c][g] = rr; p[c][g] = rr;
@@ -404,14 +447,14 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
                 acc[c] += rr * rr;
             }
         o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, dirty, red);
-        bool done[3]; int used[3]; float fin[3], rho[3] = {1.f, 1.f, 1.f}, alpha[3] = {1.f, 1.f, 1.f}, omega[3] = {1.f, 1.f, 1.f};
-        for (int c = 0; c < 3; ++c) { fin[c] = sqrtf(acc[c]) * norm; used[c] = -1; done[c] = fin[c] < tol; }
+        bool done[3] = {true, true, true}; int used[3] = {-1, -1, -1}; float fin[3] = {0.f, 0.f, 0.f}, rho[3] = {1.f, 1.f, 1.f}, alpha[3] = {1.f, 1.f, 1.f}, omega[3] = {1.f, 1.f, 1.f};
+        for (int c = 0; c < NC; ++c) { fin[c] = sqrtf(acc[c]) * norm; used[c] = -1; done[c] = fin[c] < tol; }
         for (int i = 0; i < maxit && !(done[0] && done[1] && done[2]); ++i) {
             for (int k = 0; k < 6; ++k) acc[k] = 0.f;
-            for (int c = 0; c < 3; ++c) if (!done[c])
+            for (int c = 0; c < NC; ++c) if (!done[c])
                 for (int g = tid; g < N; g += nth) acc[c] += rw[c][g] * r[c][g];
             o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, dirty, red);
-            for (int c = 0; c < 3; ++c) if (!done[c]) {
+            for (int c = 0; c < NC; ++c) if (!done[c]) {
                 const float rhop = rho[c]; rho[c] = acc[c];
                 if (i > 0) {
                     const float beta = (rho[c] / rhop) * (alpha[c] / omega[c]);
@@ -420,11 +463,11 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
             }
             o3_halo_sync(grid, sl, hc, dirty);
             for (int k = 0; k < 6; ++k) acc[k] = 0.f;
-            for (int c = 0; c < 3; ++c) if (!done[c])
+            for (int c = 0; c < NC; ++c) if (!done[c])
                 for (int g = tid; g < N; g += nth) { const float vv = o3_row(t, g, off, dg, p[c]); v[c][g] = vv; acc[c] += rw[c][g] * vv; }
             o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, dirty, red);
             float acc2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int c = 0; c < 3; ++c) if (!done[c]) {
+            for (int c = 0; c < NC; ++c) if (!done[c]) {
                 alpha[c] = rho[c] / acc[c];
                 for (int g = tid; g < N; g += nth) {
                     const float rr = r[c][g] - alpha[c] * v[c][g];
@@ -434,20 +477,20 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
                 }
             }
             o3_grid_sum<6>(grid, sl, acc2, part, rcount, arc, dirty, red);     // (its grid.sync also publishes r for the next product)
-            for (int c = 0; c < 3; ++c) if (!done[c]) {
+            for (int c = 0; c < NC; ++c) if (!done[c]) {
                 const float nr = sqrtf(acc2[c]) * norm;
                 used[c] = i; fin[c] = nr;
                 if (!isfinite(nr) || nr < tol) done[c] = true;
             }
             for (int k = 0; k < 6; ++k) acc[k] = 0.f;
-            for (int c = 0; c < 3; ++c) if (!done[c])
+            for (int c = 0; c < NC; ++c) if (!done[c])
                 for (int g = tid; g < N; g += nth) {
                     const float tv = o3_row(t, g, off, dg, r[c]); tt[c][g] = tv;
                     acc[c] += tv * r[c][g]; acc[3 + c] += tv * tv;
                 }
             o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, dirty, red);      // every row of t = C r is complete before r is overwritten
             for (int k = 0; k < 6; ++k) acc2[k] = 0.f;
-            for (int c = 0; c < 3; ++c) if (!done[c]) {
+            for (int c = 0; c < NC; ++c) if (!done[c]) {
                 omega[c] = acc[c] / acc[3 + c];
                 for (int g = tid; g < N; g += nth) {
                     const float rg = r[c][g];
@@ -458,7 +501,7 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
                 }
             }
             o3_grid_sum<6>(grid, sl, acc2, part, rcount, arc, dirty, red);
-            for (int c = 0; c < 3; ++c) if (!done[c]) {
+            for (int c = 0; c < NC; ++c) if (!done[c]) {
                 const float nr = sqrtf(acc2[c]) * norm;
                 fin[c] = nr;
                 if (nr < tol) { done[c] = true; used[c] = i + 1; }
@@ -466,10 +509,11 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             unsigned long long tot = 0;
-            for (int c = 0; c < 3; ++c) { iters[b * 8 + c] = used[c]; resid[b * 8 + c] = fin[c]; tot += (unsigned long long)(used[c] + 1); }
+            const int slot0 = NC == 1 ? 7 : 0;       // the scalar solve reports in slot 7, like the 2-D path
+            for (int c = 0; c < NC; ++c) { iters[b * 8 + slot0 + c] = used[c]; resid[b * 8 + slot0 + c] = fin[c]; tot += (unsigned long long)(used[c] + 1); }
             iter_total[b * 2 + 1] += tot;
         }
-        if (sl.on) for (int c = 0; c < 3; ++c) for (int g = tid; g < N; g += nth) o3_push(sl, t, x[c], g, x[c][g], dirty);
+        if (sl.on) for (int c = 0; c < NC; ++c) for (int g = tid; g < N; g += nth) o3_push(sl, t, x[c], g, x[c][g], dirty);
         o3_halo_sync(grid, sl, hc, dirty);       // the solution incl. the neighbours' halo planes is complete when the kernel ends
     }
     if (sl.on && blockIdx.x == 0 && threadIdx.x == 0) { sl.ctr[0] = arc; sl.ctr[1] = hc; }
@@ -698,7 +742,7 @@ static int o3_coop_blocks(fgb_ortho3 *b) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_a, k3_cg, O3_CT, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_b, k3_bicgstab, O3_CT, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_b, k3_bicgstab<3>, O3_CT, 0);
     int blocks = (per_a > 0 && per_b > 0) ? sms : 1;     // one CTA per SM (co-residency is what a cooperative launch needs)
     const int need = (b->t.N + O3_CT - 1) / O3_CT;
     if (blocks > need) blocks = need;
@@ -712,7 +756,7 @@ extern "C" int fgb_ortho3_setup_advection(fgb_ortho3 *b, const float *u, const f
                                           const int32_t *active, fgb_stream_t s) {
     if (!b || !u || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_ortho3_setup_advection: null argument");
     b->launches++;
-    k3_setup_advection<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, b->slab, u, bvel, src, dt, active, b->Coff, b->A, b->rhs);
+    k3_setup_advection<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, b->slab, u, bvel, src, dt, active, b->Coff, b->A, b->rhs, b->sc.T, b->sc.beta);
     LAUNCH_CHECK("k3_setup_advection");
     return FGB_OK;
 }
@@ -724,8 +768,34 @@ extern "C" int fgb_ortho3_solve_advection(fgb_ortho3 *b, int zero_init, const in
     int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
     void *args[] = {&t, &sl, &B, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot};
     b->launches++;
-    cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
+    cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab<3>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab)", ce);
+    return FGB_OK;
+}
+
+// Passive scalar of a 3-D box (RBC3D): attach / detach the description; the substep then transports the scalar with the
+// incoming velocity first and adds the buoyancy source (0, beta T, 0) to the predictor and to HbyA (SIM.py:1471-1657).
+extern "C" int fgb_ortho3_set_scalar(fgb_ortho3 *b, const fgb_ortho3_scalar *sc) {
+    if (!b) return set_err(FGB_E_ARG, "fgb_ortho3_set_scalar: null argument");
+    if (!sc) { memset(&b->sc, 0, sizeof(b->sc)); return FGB_OK; }
+    if (!sc->T || !sc->sbval) return set_err(FGB_E_ARG, "fgb_ortho3_set_scalar: T and sbval are required");
+    b->sc = *sc;
+    return FGB_OK;
+}
+// SetupAdvectionMatrix(forPassiveScalar) + SetupAdvectionScalar + SolveLinear: T <- C_s(u)^-1 rhs_s(T) (zero start)
+extern "C" int fgb_ortho3_advect_scalar(fgb_ortho3 *b, const float *u, const float *bvel, const float *dt, const int32_t *active,
+                                        fgb_stream_t s) {
+    if (!b || !u || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_ortho3_advect_scalar: null argument");
+    if (!b->sc.T) return set_err(FGB_E_ARG, "fgb_ortho3_advect_scalar: no scalar attached (fgb_ortho3_set_scalar)");
+    b->launches += 2;
+    k3_setup_scalar<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, u, b->sc.T, bvel, b->sc.sbval, b->sc.kappa, dt, active, b->Coff, b->A, b->rhs);
+    LAUNCH_CHECK("k3_setup_scalar");
+    T3 t = b->t; O3Slab sl = b->slab; int B = b->B; const float *coff = b->Coff, *a = b->A, *rhs = b->rhs; float *x = b->sc.T, *work = b->kry, *part = b->part;
+    int maxit = b->opt.max_iter, zero_init = 1; float tol = b->opt.adv_tol;
+    int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
+    void *args[] = {&t, &sl, &B, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot};
+    cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab<1>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab<1>)", ce);
     return FGB_OK;
 }
 
@@ -739,7 +809,7 @@ extern "C" int fgb_ortho3_setup_pressure(fgb_ortho3 *b, const float *u, const fl
         LAUNCH_CHECK("k3_pressure_matrix");
     }
     b->launches += 2;
-    k3_hbya<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->slab, u, b->ures, bvel, src, dt, active, b->Coff, b->A, b->hbya);
+    k3_hbya<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->slab, u, b->ures, bvel, src, dt, active, b->Coff, b->A, b->hbya, b->sc.T, b->sc.beta);
     LAUNCH_CHECK("k3_hbya");
     { int rc = o3_barrier(b, st); if (rc) return rc; }          // k3_hbya pushed its boundary planes itself
     k3_divergence<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->hbya, bvel, active, b->div);
@@ -780,8 +850,10 @@ extern "C" int fgb_ortho3_piso_substep(fgb_ortho3 *b, float *u, float *p, const 
     // produces it -- A by the assembly (ordered by the predictor's reductions), u* and p by the Krylov kernels (hand-shake at
     // their end), HbyA and the corrected velocity by their kernels followed by a flag-only barrier.
     if ((rc = o3_exchange(b, u, 3, st))) return rc;
+    if (b->sc.T && (rc = fgb_ortho3_advect_scalar(b, u, bvel, dt, active, s))) return rc;
     if ((rc = fgb_ortho3_setup_advection(b, u, bvel, src, dt, active, s))) return rc;
-    if ((rc = fgb_ortho3_solve_advection(b, 1, active, s))) return rc;
+    // non-orthogonal code path (TCF): zero start; orthogonal path (RBC, non_orthogonal=False): previous velocityResult ("ures")
+    if ((rc = fgb_ortho3_solve_advection(b, b->opt.nonortho ? 1 : 0, active, s))) return rc;
     for (int cs = 0; cs < b->opt.corrector_steps; ++cs) {
         if ((rc = fgb_ortho3_setup_pressure(b, u, bvel, src, dt, cs == 0, active, s))) return rc;
         if ((rc = fgb_ortho3_solve_pressure(b, p, 1, b->opt.nonortho ? 100 : 0, b->opt.max_iter, cs, active, s))) return rc;

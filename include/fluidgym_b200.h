@@ -294,6 +294,17 @@ int fgb_ortho3_correct_velocity(fgb_ortho3 *b, const float *p, float *u_out, con
 /* fused: Simulation._PISO_split_step / make_divergence_free / single_step (adaptive CFL) for D = 3 */
 int fgb_ortho3_piso_substep(fgb_ortho3 *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
                             const int32_t *active, fgb_stream_t s);
+/* Passive scalar + buoyancy on a 3-D box (RBC3D: rbc_env_base.py:190-304 with ndims = 3).  Buffers are caller-owned device memory. */
+typedef struct fgb_ortho3_scalar {
+    float *T;             /* [B][NS]  scalar field, updated in place by the substep                        */
+    const float *sbval;   /* [B][NB]  Dirichlet values on the prescribed faces (FixedBoundary.passiveScalar) */
+    float kappa;          /*          scalar diffusivity (Domain.setScalarViscosity)                        */
+    float beta;           /*          buoyancy factor: velocity source (0, beta T, 0)                       */
+} fgb_ortho3_scalar;
+/* attach (or with NULL detach) the scalar: fgb_ortho3_piso_substep / _sim_step then run the scalar transport first */
+int fgb_ortho3_set_scalar(fgb_ortho3 *b, const fgb_ortho3_scalar *sc);
+/* SetupAdvectionMatrix(forPassiveScalar) + SetupAdvectionScalar + SolveLinear(BiCGStab, zero start): T <- C_s(u)^-1 rhs_s(T) */
+int fgb_ortho3_advect_scalar(fgb_ortho3 *b, const float *u, const float *bvel, const float *dt, const int32_t *active, fgb_stream_t s);
 int fgb_ortho3_make_divergence_free(fgb_ortho3 *b, float *u, float *p, const float *bvel, int max_iter, fgb_stream_t s);
 /* rows: [2][n_row] cells of the first / last wall-normal layer; d_lo, d_hi their wall distances.  With rows != NULL the
  * channel forcing G_x = nu/2 (<u>_lo/d_lo + <u>_hi/d_hi) (envs/tcf/grid.py:128-163) is refreshed before every substep. */

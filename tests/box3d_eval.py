@@ -164,7 +164,8 @@ def adv_rhs(g: Box3D, u, bvel, dt, src=None):
     Sb = boundary_source(g, bvel, fl)
     rhs = ((g.det * u / f32(dt) + Sb) / g.det).astype(f32)
     if src is not None:
-        rhs = rhs + np.asarray(src, dtype=f32).reshape(3, 1, 1, 1)
+        src = np.asarray(src, dtype=f32)
+        rhs = rhs + (src.reshape(3, 1, 1, 1) if src.size == 3 else src.reshape((3,) + g.shape))
     return rhs.astype(f32), Sb
 
 
@@ -197,7 +198,8 @@ def hbya(g: Box3D, u, ures, off, A, Sb, dt, src=None):
         H = H + off[f] * g.shift(ures, f >> 1, 1 if (f & 1) else -1)
     inner = u / f32(dt) - H + Sb / g.det
     if src is not None:
-        inner = inner + np.asarray(src, dtype=f32).reshape(3, 1, 1, 1)
+        src = np.asarray(src, dtype=f32)
+        inner = inner + (src.reshape(3, 1, 1, 1) if src.size == 3 else src.reshape((3,) + g.shape))
     return (inner / A).astype(f32)
 
 
@@ -215,3 +217,36 @@ def correct(g: Box3D, hb, p, A):
         fac = np.where(g.inner(2 * d + 1) & g.inner(2 * d), f32(0.5), f32(1.0))
         out[d] = hb[d] - (pu - pl) * fac * g.minv[d] / A
     return out.astype(f32)
+
+
+# ---- passive scalar + buoyancy (RBC3D) ---------------------------------------------------------------------
+def assemble_scalar(g: Box3D, u, bvel, T, sbval, dt, kappa):
+    """off [6, ...], A, rhs of the scalar transport (K.cu:3617-3880 with forPassiveScalar, K.cu:4094-4198);
+    sbval: {face: [face layer]} Dirichlet values on the closed faces."""
+    kappa = f32(kappa)
+    fl = face_fluxes(g, u, bvel)
+    T = g.field(T)[0]
+    diag = (g.det / f32(dt)).astype(f32)
+    r = (g.det * T / f32(dt)).astype(f32)
+    off = np.zeros((6,) + g.shape, dtype=f32)
+    for f in range(6):
+        d, up = f >> 1, f & 1
+        sig = f32(1.0 if up else -1.0)
+        inner = g.inner(f)
+        aN = g.shift(g.alpha[d], d, 1 if up else -1)
+        vc = ((g.alpha[d] * kappa + aN * kappa) * f32(0.5)).astype(f32)
+        ff = (sig * f32(0.5) * fl[f]).astype(f32)
+        diag = diag + np.where(inner, ff + vc, f32(2.0) * kappa * g.alpha[d])
+        off[f] = np.where(inner, (ff - vc) / g.det, 0).astype(f32)
+        if g.closed[d]:
+            b = g.b[f]
+            Fb = (b["det"] * b["minv"][d] * bvel[f][d]).astype(f32)
+            r = r + g.bexpand(f, (sbval[f] * (-(sig * Fb) + f32(2.0) * kappa * b["alpha"])).astype(f32))     # sbval[f]: face layer
+    return off.astype(f32), (diag / g.det).astype(f32), (r / g.det).astype(f32)
+
+
+def buoyancy_source(g: Box3D, T, beta):
+    """velocity source field (0, beta T, 0) [3, nz, ny, nx] (rbc_env_base.py:280-304)"""
+    T = g.field(T)[0]
+    z = np.zeros_like(T)
+    return np.stack([z, (f32(beta) * T).astype(f32), z])

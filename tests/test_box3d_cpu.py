@@ -115,3 +115,44 @@ def test_slab_tables_reproduce_the_global_stencil(golden, world):
         assert faces.shape == (3, tb.nzl * dom.nx)
     with pytest.raises(ValueError):
         SlabTables(dom, 0, 5)
+
+
+# ---- passive scalar + buoyancy on the 3-D box (RBC3D) -----------------------------------------------------------------
+def _full19(t7):
+    T = np.zeros(t7.shape[:-1] + (19,), np.float32)
+    for k, c in enumerate((0, 4, 8, 9, 13, 17, 18)):
+        T[..., c] = t7[..., k]
+    return T
+
+
+@pytest.fixture(scope="module")
+def rbc3d(golden):
+    g = golden("rbc3d_geometry.npz")
+    meta = json.load(open(os.path.join(GOLDEN, "rbc3d_meta.json")))
+    nz, ny, nx = g["Tdiag"].shape[:3]
+    bT = {2: _full19(g["bT2"]).reshape(nz, 1, nx, 19), 3: _full19(g["bT3"]).reshape(nz, 1, nx, 19)}
+    box = be.Box3D(g["vertex"], closed=(False, True, False), viscosity=meta["viscosity"], T=_full19(g["Tdiag"]), bT=bT)
+    return box, meta, (nz, ny, nx)
+
+
+@pytest.mark.parametrize("s", [0, 1])
+def test_scalar_specification_matches_reference_trace(rbc3d, golden, s):
+    """tests/box3d_eval.py::assemble_scalar / buoyancy_source and the operators fed by the buoyancy source field against
+    the op trace of the unmodified reference on RBC3D (16 x 10 x 16 cells, tests/golden/rbc3d_substep*.npz)."""
+    box, meta, (nz, ny, nx) = rbc3d
+    fx = golden(f"rbc3d_substep{s}.npz")
+    dt, u = float(fx["dt"][0]), fx["u_in"]
+    bvel = {2: np.zeros((3, nz, 1, nx), np.float32), 3: np.zeros((3, nz, 1, nx), np.float32)}
+    sb = {2: fx["sb2"].reshape(nz, 1, nx), 3: np.broadcast_to(fx["sb3"].reshape(1, 1, 1), (nz, 1, nx)).astype(np.float32)}
+    off, A, rhs = be.assemble_scalar(box, u, bvel, fx["T_in"], sb, dt, meta["thermal_diffusivity"])
+    assert rel_l2(rhs, fx["scalar_rhs"]) < 5e-7
+    assert rel_l2(be.spmv(box, off, A, fx["T_out"]), fx["scalar_rhs"]) < 2e-6      # C_s T_out = rhs up to the solver tolerance
+    src = be.buoyancy_source(box, fx["T_out"], 1.0)
+    assert np.array_equal(src.reshape(3, -1), fx["vsrc"])
+    offv, Av, _ = be.assemble(box, u, bvel, dt)
+    rhsv, Sb = be.adv_rhs(box, u, bvel, dt, src)
+    assert rel_l2(Av, fx["A"]) < 5e-7 and rel_l2(rhsv, fx["rhs"]) < 5e-7
+    hb = be.hbya(box, u, fx["ustar"], offv, Av, Sb, dt, src)
+    assert rel_l2(hb, fx["hbya0"]) < 1e-6
+    assert rel_l2(be.divergence(box, hb, bvel), fx["div0"]) < 1e-6
+    assert rel_l2(be.correct(box, hb, fx["p0"], Av), fx["u0"]) < 1e-6
