@@ -70,4 +70,10 @@ def _register_defaults():
                                                    "adaptive_cfl": 0.5})
     register("RBC2D-wide-hard-v0", RBC2DEnv, **{**RBC_2D_DEFAULT_CONFIG, "aspect_ratio": 2, "n_heaters": 24, "rayleigh_number": 8e5,
                                                  "adaptive_cfl": 0.5})
+    from .envs.rbc3d import RBC_3D_DEFAULT_CONFIG, RBC3DEnv
+    # fluidgym/__init__.py:159-214
+    for level, ra in (("easy", 6e3), ("medium", 8e3), ("hard", 1e4)):
+        register(f"RBC3D-{level}-v0", RBC3DEnv, **{**RBC_3D_DEFAULT_CONFIG, "rayleigh_number": ra, "adaptive_cfl": 0.5})
+        register(f"RBC3D-wide-{level}-v0", RBC3DEnv, **{**RBC_3D_DEFAULT_CONFIG, "aspect_ratio": 2, "n_heaters": 16, "rayleigh_number": ra,
+                                                        "adaptive_cfl": 0.5})
     register("CylinderJet2D-hard-v0", CylinderJet2DEnv, **{**CYLINDER_JET_2D_DEFAULT_CONFIG, "reynolds_number": 500.0, "resolution": 32})

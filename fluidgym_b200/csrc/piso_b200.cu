@@ -2796,5 +2796,15 @@ extern "C" int fgb_sample_sensors(fgb_batch *b, const float *field, int32_t chan
     return FGB_OK;
 }
 
+// handle-free variant (any field layout [B][channels][N]; used by the 3-D environments, whose solver handle is fgb_ortho3)
+extern "C" int fgb_sample_sensors_n(const float *field, int32_t B, int32_t channels, int32_t N, const int32_t *idx, const float *w,
+                                    int32_t K, int32_t n_sensors, float *out, fgb_stream_t s) {
+    if (!field || !idx || !w || !out || B <= 0 || channels <= 0 || N <= 0) return set_err(FGB_E_ARG, "fgb_sample_sensors_n: bad argument");
+    dim3 grid((channels * n_sensors + 127) / 128, B);
+    k_sample_sensors<<<grid, 128, 0, STREAM(s)>>>(field, channels, N, idx, w, K, n_sensors, out);
+    LAUNCH_CHECK("k_sample_sensors");
+    return FGB_OK;
+}
+
 // D = 3 orthogonal-grid path (turbulent channel flow)
 #include "ortho3_b200.cuh"

@@ -72,7 +72,7 @@ EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_cr
            "fgb_ortho3_launch_count", "fgb_ortho3_setup_advection", "fgb_ortho3_solve_advection", "fgb_ortho3_setup_pressure",
            "fgb_ortho3_solve_pressure", "fgb_ortho3_correct_velocity", "fgb_ortho3_piso_substep", "fgb_ortho3_make_divergence_free",
            "fgb_ortho3_sim_step", "fgb_ortho3_wall_rows", "fgb_ipc_alloc", "fgb_ipc_open", "fgb_ipc_close", "fgb_ipc_free",
-           "fgb_ortho3_set_slab", "fgb_ortho3_slab_error", "fgb_ortho3_set_scalar", "fgb_ortho3_advect_scalar"]
+           "fgb_ortho3_set_slab", "fgb_ortho3_slab_error", "fgb_ortho3_set_scalar", "fgb_ortho3_advect_scalar", "fgb_sample_sensors_n"]
 
 
 def lib_path() -> str:
@@ -115,6 +115,7 @@ def load():
     L.fgb_apply_jet_action.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32, vp]
     L.fgb_wall_forces.argtypes = [vp, C.POINTER(Wall), vp, vp, vp, vp, vp]
     L.fgb_sample_sensors.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp]
+    L.fgb_sample_sensors_n.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp, vp]
     L.fgb_profile_enable.argtypes = [vp, i32]
     L.fgb_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), i32]
     L.fgb_launch_count.argtypes = [vp]

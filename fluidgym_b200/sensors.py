@@ -115,3 +115,103 @@ def sensor_tables(vertex_list, out_shape, sensor_px: np.ndarray, fill_max_steps:
             idx[k, s_] = c
             w[k, s_] = v
     return idx, w
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# D = 3 (RBC3D): the same static map.  The reference's 3-D splat kernel loops over ``DIMS << 1`` = 6 of the 8 corner
+# pixels around a cell centre (resampling.cu:320: corners (x,y,z) = 000, 100, 010, 110, 001, 101 -- 011 and 111 are never
+# written); the observations are defined by that kernel, so the quirk is reproduced here.  Hole filling averages the valid
+# ones of the 6 face neighbours per sweep (resampling.cu:191-243).  Everything is built with sparse matrices, one sweep
+# at a time, so render grids of 10^6 pixels are fine.
+# ---------------------------------------------------------------------------------------------------------------------
+def cell_centres_3d(vertex: np.ndarray) -> np.ndarray:
+    """2x2x2 average pooling of the vertices [3, nz+1, ny+1, nx+1] -> [3, nz, ny, nx] float32."""
+    v = vertex.astype(f32)
+    c = 0
+    for i in (0, 1):
+        for j in (0, 1):
+            for k in (0, 1):
+                c = c + v[:, i:v.shape[1] - 1 + i, j:v.shape[2] - 1 + j, k:v.shape[3] - 1 + k]
+    return (c * f32(0.125)).astype(f32)
+
+
+def pixel_map_3d(vertex: np.ndarray, out_shape, fill_max_steps: int):
+    """Sparse [W*H*Z, N] matrix R with rendered[pixel] = R @ cells (pixel index = x + W (y + H z), cells in (z, y, x)
+    order) and the per-pixel fill level (0 = splat, k = filled in sweep k, -1 = never)."""
+    W, H, Z = (int(s) for s in out_shape)
+    allv = vertex.reshape(3, -1).astype(f32)
+    lower, upper = allv.min(axis=1), allv.max(axis=1)
+    size = (upper - lower).astype(f32)
+    centre = (lower + size * f32(0.5)).astype(f32)
+    os_ = np.asarray([W, H, Z], dtype=f32)
+    scale = f32(np.max(size / os_))
+    centres = cell_centres_3d(vertex).reshape(3, -1)
+    N = centres.shape[1]
+    sc = ((centres - centre[:, None]) / scale + (os_ * f32(0.5) - f32(0.5))[:, None]).astype(f32)
+    fl, ce = np.floor(sc), np.ceil(sc)
+    fr = (sc - fl).astype(f32)
+    dims = (W, H, Z)
+    rows, cols, vals = [], [], []
+    for idx in range(3 << 1):                                 # sic: 6 corners (resampling.cu:320)
+        ok = np.ones(N, dtype=bool)
+        w = np.ones(N, dtype=f32)
+        pos = []
+        for c in range(3):
+            up = (idx >> c) & 1
+            pc = (ce[c] if up else fl[c]).astype(np.int64)
+            ok &= (pc >= 0) & (pc < dims[c])
+            w = (w * (fr[c] if up else f32(1.0) - fr[c])).astype(f32)
+            pos.append(pc)
+        flat = pos[0] + W * (pos[1] + H * pos[2])
+        rows.append(flat[ok]); cols.append(np.arange(N)[ok]); vals.append(w[ok].astype(np.float64))
+    npx = W * H * Z
+    S = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(npx, N))
+    wsum = np.asarray(S.sum(axis=1)).ravel()
+    valid = wsum > 1e-8
+    level = np.where(valid, 0, -1).astype(np.int32)
+    inv = np.zeros(npx)
+    inv[valid] = 1.0 / wsum[valid]
+    R = sp.diags(inv) @ S
+    grid = np.arange(npx).reshape(Z, H, W)
+    for k in range(1, int(fill_max_steps) + 1):
+        if valid.all():
+            break
+        v3 = valid.reshape(Z, H, W)
+        src_l, dst_l = [], []
+        for ax in range(3):
+            for sh in (1, -1):
+                a = [slice(None)] * 3
+                b = [slice(None)] * 3
+                a[ax] = slice(1, None) if sh == 1 else slice(0, -1)       # destination pixels
+                b[ax] = slice(0, -1) if sh == 1 else slice(1, None)       # their neighbour in that direction
+                m = (~v3[tuple(a)]) & v3[tuple(b)]
+                dst_l.append(grid[tuple(a)][m]); src_l.append(grid[tuple(b)][m])
+        dst, src = np.concatenate(dst_l), np.concatenate(src_l)
+        if dst.size == 0:
+            break
+        cnt = np.bincount(dst, minlength=npx).astype(np.float64)
+        A = sp.csr_matrix((1.0 / cnt[dst], (dst, src)), shape=(npx, npx))
+        R = R + A @ R                                            # rows of valid pixels are untouched (A has no such rows)
+        newly = cnt > 0
+        level[newly] = k
+        valid = valid | newly
+    return R.tocsr(), level
+
+
+def sensor_tables_3d(vertex: np.ndarray, out_shape, sensor_px: np.ndarray, fill_max_steps: int):
+    """ELL tables (idx [K, n_s] int32, w [K, n_s] float32) of the rendered-voxel map at the sensor voxels
+    ``sensor_px`` = [3, n_s] integer (x, y, z) voxel coordinates (envs/rbc/rbc_env_3d.py:183-203)."""
+    W, H, Z = (int(s) for s in out_shape)
+    R, _ = pixel_map_3d(vertex, out_shape, fill_max_steps)
+    flat = sensor_px[0].astype(np.int64) + W * (sensor_px[1].astype(np.int64) + H * sensor_px[2].astype(np.int64))
+    Rs = R[flat]
+    ns = flat.size
+    nnz = np.diff(Rs.indptr)
+    K = max(1, int(nnz.max()))
+    idx = np.zeros((K, ns), dtype=np.int32)
+    w = np.zeros((K, ns), dtype=f32)
+    for s_ in range(ns):
+        a, b = Rs.indptr[s_], Rs.indptr[s_ + 1]
+        idx[:b - a, s_] = Rs.indices[a:b]
+        w[:b - a, s_] = Rs.data[a:b]
+    return idx, w

@@ -206,6 +206,10 @@ int fgb_column_sums(fgb_batch *b, const float *fa, const float *fb, int32_t nx, 
  * sum_k w[k][s] * field[B][C][idx[k][s]] (the static splat+normalise+fill map evaluated at the sensors) */
 int fgb_sample_sensors(fgb_batch *b, const float *field, int32_t channels, const int32_t *idx, const float *w,
                        int32_t K, int32_t n_sensors, float *out, fgb_stream_t s);
+/* the same map without a solver handle: field [B][channels][N] (3-D environments: rendered-voxel sensors of RBC3D,
+ * rbc_env_3d.py:183-203, 285-321) */
+int fgb_sample_sensors_n(const float *field, int32_t B, int32_t channels, int32_t N, const int32_t *idx, const float *w, int32_t K,
+                         int32_t n_sensors, float *out, fgb_stream_t s);
 
 /* ---- differentiability (torch.autograd is layered on top in fluidgym_b200/autograd.py) ----------------- */
 /* Tape of one substep: device buffers owned by the caller, filled by fgb_piso_substep_record.  Replaces the
