@@ -130,6 +130,7 @@ class BatchedPISO3D:
         self.u = torch.zeros(B, 3, N, device=dev)
         self.p = torch.zeros(B, N, device=dev)
         self.bvel = torch.zeros(B, 3, NB, device=dev)
+        self.has_scalar = False
 
     # ---- passive scalar + buoyancy (RBC3D) ---------------------------------------------------------------------------
     def attach_scalar(self, kappa: float, beta: float = 1.0, sbval0=None):
@@ -142,6 +143,7 @@ class BatchedPISO3D:
         if sbval0 is not None:
             self.sbval.copy_(torch.as_tensor(np.asarray(sbval0, dtype=np.float32), device=dev).expand_as(self.sbval))
         self.kappa, self.beta = float(kappa), float(beta)
+        self.has_scalar = True
         self._scalar = native.Ortho3Scalar(self.T.data_ptr(), self.sbval.data_ptr(), self.kappa, self.beta)
         native.check(self.lib.fgb_ortho3_set_scalar(self.handle, C.byref(self._scalar)), "fgb_ortho3_set_scalar")
 

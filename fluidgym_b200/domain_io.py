@@ -125,3 +125,111 @@ def save_domain(spec: DomainSpec, state: dict, path: str):
     np.savez_compressed(path + ".npz", **{str(i): a for i, a in enumerate(data)})
     with open(path + ".json", "w") as fh:
         json.dump(d, fh)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# D = 3: single-block rectilinear boxes (TCF, RBC3D).  Same file format; tensors carry one more spatial axis:
+# velocity [1,3,z,y,x], pressure / scalar [1,1,z,y,x], vertexCoordinates [1,3,z+1,y+1,x+1]; a FIXED boundary stores its
+# velocity as [1,3] (static) or with a singleton on the face-normal axis, e.g. [1,3,z,1,x] on a y face.
+# ---------------------------------------------------------------------------------------------------------------------
+def load_box_domain(path: str):
+    """-> dict(vertex [3,nz+1,ny+1,nx+1], closed (x,y,z), viscosity, scalar_viscosity | None, name,
+    state = dict(u [3,N], p [N], bvel [3,NB], T [N] | None, sbval [NB] | None)) in the layout of fluidgym_b200.box3d
+    (cell g = x + nx (y + ny z); prescribed faces face-major (-x, +x, -y, ...), tangential cells in (z, y, x) order)."""
+    with open(path + ".json") as fh:
+        d = json.load(fh)
+    with np.load(path + ".npz") as z:
+        data = {k: z[k] for k in z.files}
+
+    def get(dct, name):
+        return data[dct[name]] if name in dct else None
+    if d["spatialDims"] != 3 or len(d["blocks"]) != 1:
+        raise NotImplementedError("load_box_domain reads 3-D single-block domains (2-D multi-block domains: load_domain)")
+    blk = d["blocks"][0]
+    v = get(blk, "vertexCoordinates")
+    if v is None:
+        raise NotImplementedError("blocks stored by transform only (no vertex coordinates)")
+    vertex = np.ascontiguousarray(v[0], dtype=np.float32)
+    nz, ny, nx = (s - 1 for s in vertex.shape[1:])
+    N = nx * ny * nz
+    n_scalar = d.get("passiveScalarChannels", 0)
+    svisc = get(d, "passiveScalarViscosity")
+    u = np.asarray(get(blk, "velocity"), dtype=np.float32)[0].reshape(3, N)
+    p = np.asarray(get(blk, "pressure"), dtype=np.float32)[0].reshape(N)
+    T = np.asarray(get(blk, "scalar"), dtype=np.float32)[0].reshape(N) if ("scalar" in blk and n_scalar) else None
+    closed = [False, False, False]
+    bvel, sbval = [], []
+    for f, bd in enumerate(blk["boundaries"]):
+        kind, ax = bd["type"], f >> 1
+        if kind == "PERIODIC":
+            continue
+        if kind != "FIXED":
+            raise NotImplementedError(f"boundary type {kind} on a single-block box")
+        if bd.get("velocityType", "DIRICHLET") != "DIRICHLET":
+            raise NotImplementedError(f"boundary velocity type {bd.get('velocityType')}")
+        closed[ax] = True
+        n_face = N // (nx, ny, nz)[ax]
+        vel = np.asarray(get(bd, "velocity"), dtype=np.float32)
+        vfull = np.zeros((3, n_face), dtype=np.float32)
+        vfull[:] = vel.reshape(3, -1) if vel.ndim > 2 else vel.reshape(3, 1)
+        bvel.append(vfull)
+        sfull = np.zeros(n_face, dtype=np.float32)
+        if "scalar" in bd and n_scalar:
+            if bd.get("passiveScalarType", ["DIRICHLET"])[0] != "DIRICHLET":
+                raise NotImplementedError("Neumann scalar boundaries on the 3-D box")
+            sfull[:] = np.asarray(get(bd, "scalar"), dtype=np.float32).reshape(-1)
+        sbval.append(sfull)
+    for ax in range(3):
+        kinds = {blk["boundaries"][2 * ax]["type"], blk["boundaries"][2 * ax + 1]["type"]}
+        if len(kinds) != 1:
+            raise NotImplementedError("an axis of the box must be periodic or closed on both sides")
+    state = dict(u=u, p=p, bvel=np.concatenate(bvel, axis=1) if bvel else np.zeros((3, 0), np.float32), T=T,
+                 sbval=np.concatenate(sbval) if (sbval and n_scalar) else None)
+    return dict(vertex=vertex, closed=tuple(closed), viscosity=float(np.asarray(get(d, "viscosity")).ravel()[0]),
+                scalar_viscosity=None if (n_scalar == 0 or svisc is None) else float(np.asarray(svisc).ravel()[0]),
+                name=d.get("name", "domain"), state=state)
+
+
+def save_box_domain(vertex, closed, viscosity: float, state: dict, path: str, scalar_viscosity=None, name="domain"):
+    """Write a 3-D single-block box with the given flat state in the reference's format."""
+    vertex = np.ascontiguousarray(vertex, dtype=np.float32)
+    nz, ny, nx = (s - 1 for s in vertex.shape[1:])
+    data = []
+
+    def add(arr, dct, key):
+        dct[key] = str(len(data))
+        data.append(np.ascontiguousarray(arr, dtype=np.float32))
+    has_T = state.get("T") is not None and scalar_viscosity is not None
+    d = {"name": name, "spatialDims": 3}
+    add(np.array([viscosity]), d, "viscosity")
+    d["passiveScalarChannels"] = 1 if has_T else 0
+    if has_T:
+        add(np.array([scalar_viscosity]), d, "passiveScalarViscosity")
+    bd = {"name": "block"}
+    add(np.asarray(state["u"]).reshape(1, 3, nz, ny, nx), bd, "velocity")
+    add(np.asarray(state["p"]).reshape(1, 1, nz, ny, nx), bd, "pressure")
+    if has_T:
+        add(np.asarray(state["T"]).reshape(1, 1, nz, ny, nx), bd, "scalar")
+    add(vertex[None], bd, "vertexCoordinates")
+    bd["boundaries"] = []
+    ob = 0
+    for f in range(6):
+        ax = f >> 1
+        if not closed[ax]:
+            bd["boundaries"].append({"type": "PERIODIC"})
+            continue
+        shape = [nz, ny, nx]
+        shape[2 - ax] = 1
+        m = shape[0] * shape[1] * shape[2]
+        e = {"type": "FIXED", "velocityType": "DIRICHLET"}
+        add(np.asarray(state["bvel"])[:, ob:ob + m].reshape([1, 3] + shape), e, "velocity")
+        if has_T:
+            e["passiveScalarType"] = ["DIRICHLET"]
+            add(np.asarray(state["sbval"])[ob:ob + m].reshape([1, 1] + shape), e, "scalar")
+        ob += m
+        bd["boundaries"].append(e)
+    d["blocks"] = [bd]
+    d["data_info"] = {str(i): {"shape": list(a.shape), "dtype": "float32", "device": "cpu"} for i, a in enumerate(data)}
+    np.savez_compressed(path + ".npz", **{str(i): a for i, a in enumerate(data)})
+    with open(path + ".json", "w") as fh:
+        json.dump(d, fh)

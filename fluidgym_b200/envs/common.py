@@ -196,16 +196,21 @@ class InitialDomains:
         key = (mode, idx)
         if key not in pool:
             import os
-            from ..domain_io import load_domain
             path = self.initial_domain_file(idx, mode)
             if not os.path.exists(path + ".json"):
                 raise RuntimeError("Initial domain not found. Please ensure it was downloaded.")
-            spec, st = load_domain(path)
-            if [b.vertex.shape for b in spec.blocks] != [b.vertex.shape for b in self.spec.blocks] or any(
-                    not np.array_equal(a.vertex, b.vertex) for a, b in zip(spec.blocks, self.spec.blocks)):
-                raise ValueError(f"{path}: the stored grid is not the grid of this environment")
+            st = self._read_domain_file(path)
             pool[key] = {k: torch.from_numpy(np.ascontiguousarray(v)).to(self.device) for k, v in st.items() if v is not None}
         return pool[key]
+
+    def _read_domain_file(self, path: str) -> dict:
+        """2-D multi-block domains (``self.spec``); the 3-D box environments override this (InitialDomains3D)."""
+        from ..domain_io import load_domain
+        spec, st = load_domain(path)
+        if [b.vertex.shape for b in spec.blocks] != [b.vertex.shape for b in self.spec.blocks] or any(
+                not np.array_equal(a.vertex, b.vertex) for a, b in zip(spec.blocks, self.spec.blocks)):
+            raise ValueError(f"{path}: the stored grid is not the grid of this environment")
+        return st
 
     def load_initial_domain(self, idx: int, mode: str | None = None, env_index=None):
         """fluid_env.py:1065-1086; ``env_index`` (int, list or None = all) selects which environments receive the state."""
@@ -224,15 +229,18 @@ class InitialDomains:
     def save_initial_domain(self, idx: int, mode: str | None = None, env_index: int = 0):
         """fluid_env.py:1047-1063: writes environment ``env_index`` in the reference's format."""
         import os
-        from ..domain_io import save_domain
         path = self.initial_domain_file(idx, mode)
         os.makedirs(os.path.dirname(path), exist_ok=True)
         s = self.solver
         st = dict(u=s.u[env_index].cpu().numpy(), p=s.p[env_index].cpu().numpy(), bvel=s.bvel[env_index].cpu().numpy())
         if getattr(s, "has_scalar", False):
             st.update(T=s.T[env_index].cpu().numpy(), sbval=s.sbval[env_index].cpu().numpy())
-        save_domain(self.spec, st, path)
+        self._write_domain_file(st, path)
         return path
+
+    def _write_domain_file(self, st: dict, path: str):
+        from ..domain_io import save_domain
+        save_domain(self.spec, st, path)
 
     def _load_initial_domains_on_reset(self, randomize: bool):
         """_set_initial_state with load_initial_domain=True: index 0, or one random index per environment."""
@@ -243,3 +251,27 @@ class InitialDomains:
         for idx in sorted(set(idxs)):
             self.load_initial_domain(idx, env_index=[e for e, i in enumerate(idxs) if i == idx])
         return idxs
+
+
+class InitialDomains3D(InitialDomains):
+    """The same for the single-block 3-D box environments (TCF, RBC3D): needs ``dom`` (Box3DDomain) instead of ``spec``."""
+
+    def _read_domain_file(self, path: str) -> dict:
+        from ..domain_io import load_box_domain
+        d = load_box_domain(path)
+        if d["vertex"].shape != self.dom.vertex.shape or not np.array_equal(d["vertex"], self.dom.vertex) or d["closed"] != self.dom.closed:
+            raise ValueError(f"{path}: the stored grid is not the grid of this environment")
+        st = d["state"]
+        if st["bvel"].shape[1] == 0:
+            st["bvel"] = np.zeros((3, 1), np.float32)
+        return st
+
+    def _write_domain_file(self, st: dict, path: str):
+        from ..domain_io import save_box_domain
+        s = self.solver
+        st = dict(st, bvel=st["bvel"][:, :self.dom.NB])
+        if "sbval" in st:
+            st["sbval"] = st["sbval"][:self.dom.NB]
+        save_box_domain(self.dom.vertex, self.dom.closed, self.dom.visc, st, path,
+                        scalar_viscosity=getattr(s, "kappa", None) if getattr(s, "has_scalar", False) else None,
+                        name=type(self).__name__)

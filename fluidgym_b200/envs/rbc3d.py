@@ -18,6 +18,7 @@ from ..box3d import BatchedPISO3D, Box3DDomain
 from ..grids import wall_refined_ortho_grid
 from ..sensors import sensor_tables_3d
 from ..solver import _ptr
+from .common import InitialDomains3D
 
 RBC_3D_DEFAULT_CONFIG = {
     "rayleigh_number": 2e3, "prandtl_number": 0.7, "n_heaters": 8, "resolution": 8, "dt": 0.05, "adaptive_cfl": 0.8,
@@ -53,7 +54,7 @@ def extract_moving_window_3d(field: torch.Tensor, n_agents: int, agent_width: in
     return fzx.reshape(*lead, n_agents * n_agents, cells.shape[1], Y, cells.shape[1])
 
 
-class RBC3DEnv:
+class RBC3DEnv(InitialDomains3D):
     T_cold, T_hot, heater_limit = 0.0, 1.0, 0.75
     n_sensors_y, n_sensors_per_heater = 8, 4
     buoyancy_factor = 1.0
@@ -64,8 +65,10 @@ class RBC3DEnv:
     def __init__(self, n_envs: int = 1, rayleigh_number=2e3, prandtl_number=0.7, n_heaters=8, resolution=8, dt=0.05,
                  adaptive_cfl=0.8, step_length=1.0, episode_length=200, local_obs_window=3, local_reward_weight=0.0015,
                  uniform_grid=False, aspect_ratio=1.0, use_marl=True, device="cuda:0", nu_ref=0.0, randomize_initial_state=False,
-                 enable_actions=True, transforms=None, btransforms=None):
+                 enable_actions=True, load_initial_domain=False, initial_domains_path=None, transforms=None, btransforms=None):
         self.n_envs = int(n_envs)
+        self.load_domain_on_reset, self.initial_domains_path = bool(load_initial_domain), initial_domains_path
+        self.rayleigh_number, self.prandtl_number = rayleigh_number, prandtl_number
         self.Ra, self.Pr = float(rayleigh_number), float(prandtl_number)
         self.n_heaters, self.heater_width = int(n_heaters), int(resolution)
         self.dt, self.cfl = float(dt), float(adaptive_cfl)
@@ -136,7 +139,8 @@ class RBC3DEnv:
 
     @property
     def initial_domain_id(self):
-        return f"rbc_3d_Ra{self.Ra}_Pr{self.Pr}_NH{self.n_heaters}_HW{self.heater_width}"
+        """rbc_env_base.py:606-611"""
+        return f"rbc_3d_Ra{self.rayleigh_number}_Pr{self.prandtl_number}_NH{self.n_heaters}_HW{self.heater_width}"
 
     @property
     def observation_space(self):
@@ -188,6 +192,15 @@ class RBC3DEnv:
             self.seed(seed)
         s = self.solver
         B, nx, ny, nz = self.n_envs, self.nx, self.ny, self.nz
+        randomize = self.randomize_initial_state if randomize is None else randomize
+        if self.load_domain_on_reset:                      # fluid_env.py:519-551
+            self._load_initial_domains_on_reset(randomize)
+            s.buffer("ures").copy_(s.u)
+            if randomize:
+                self._randomize_domain()
+            self._apply_action(self._zero_action)
+            self._reset_called, self._n_steps = True, 0
+            return (self._get_local_obs() if self.use_marl else self._get_global_obs()), {}
         grad = torch.linspace(self.T_hot, self.T_cold, steps=ny, device=self.device)[None, :, None].expand(nz, ny, nx)
         T0 = grad[None] + torch.randn(B, nz, ny, nx, device=self.device, generator=self._torch_rng) * 0.1 * (self.T_hot - self.T_cold)
         s.T.copy_(torch.clamp(T0, self.T_cold, self.T_hot).reshape(B, -1))
@@ -195,7 +208,7 @@ class RBC3DEnv:
         s.p.zero_()
         s.buffer("ures").zero_()
         s.sbval.copy_(torch.from_numpy(self._sb0).to(self.device).unsqueeze(0).expand_as(s.sbval))
-        if self.randomize_initial_state if randomize is None else randomize:
+        if randomize:
             self._randomize_domain()
         self._apply_action(self._zero_action)
         self._reset_called, self._n_steps = True, 0

@@ -11,6 +11,7 @@ import torch
 
 from ..box3d import BatchedPISO3D, Box3DDomain
 from ..grids import channel_vertex_grid
+from .common import InitialDomains3D
 
 SMALL_TCF_3D_DEFAULT_CONFIG = {
     "resolution_y": 65, "resolution_x_z": 64, "actor_size": 2, "L": np.pi, "D": np.pi / 2, "reynolds_number_wall": 180,
@@ -38,7 +39,7 @@ def agent_window_means(field, n_agents_x, n_agents_z, agent_width, wx, wz, pad_x
     return win.reshape(*lead, n_agents_x * n_agents_z, wz, wx)
 
 
-class TCF3DEnv:
+class TCF3DEnv(InitialDomains3D):
     delta, H = 1.0, 2.0
     y_obs_wall = 15.0
     metrics = ["wall_stress", "wall_stress_bottom", "wall_stress_top"]
@@ -47,12 +48,13 @@ class TCF3DEnv:
     def __init__(self, n_envs: int = 1, resolution_y=65, resolution_x_z=64, actor_size=2, L=np.pi, D=np.pi / 2, reynolds_number_wall=180,
                  adaptive_cfl=0.1, step_length=0.6, episode_length=1000, local_obs_window=1, local_reward_weight=0.0, use_marl=True,
                  C_smag=0.0, use_van_driest=False, init_with_noise=False, device="cuda:0", tau_ref=1.0, randomize_initial_state=False,
-                 enable_actions=True, domain=None):
+                 enable_actions=True, domain=None, load_initial_domain=False, initial_domains_path=None):
         if C_smag != 0.0 or use_van_driest:
             raise NotImplementedError("sub-grid-scale viscosity (C_smag != 0) is not built; the registered TCF configurations use C_smag = 0")
         if init_with_noise:
             raise NotImplementedError("init_with_noise needs the reference's optional simplex-noise extension; start from a state instead")
         self.n_envs = int(n_envs)
+        self.load_domain_on_reset, self.initial_domains_path = bool(load_initial_domain), initial_domains_path
         self.L, self.D = float(L), float(D)
         self.re_wall = float(reynolds_number_wall)
         self.re_center = re_wall_to_cl(self.re_wall)
@@ -71,8 +73,8 @@ class TCF3DEnv:
         self.randomize_initial_state, self.enable_actions = randomize_initial_state, enable_actions
         self.scale_actions = True
         self.device = torch.device(device)
+        strength = self.grid_refinement_strength = 2 if resolution_x_z < 64 else 1          # tcf_env.py:252
         if domain is None:
-            strength = 2 if resolution_x_z < 64 else 1
             vertex = channel_vertex_grid(self.H, self.L, self.D, self.x, self.y // 2, strength, self.z)
             domain = Box3DDomain(vertex, closed=(False, True, False), viscosity=self.viscosity)
         self.dom = domain
@@ -110,6 +112,11 @@ class TCF3DEnv:
     @property
     def n_sim_steps(self):
         return max(1, int(self.step_length / self.dt))
+
+    @property
+    def initial_domain_id(self):
+        """tcf_env.py:866-872"""
+        return f"channel_flow3D_L{self.L:.2f}_Re{int(self.re_wall)}_Res{self.x}_Ref{self.grid_refinement_strength}"
 
     @property
     def observation_space(self):
@@ -153,13 +160,16 @@ class TCF3DEnv:
         else:
             self.seed(seed)
         s = self.solver
-        u0 = torch.zeros(3, self.z, self.ny, self.x)
-        u0[0] = self.u_init[None, :, None]
-        s.u.copy_(u0.reshape(1, 3, -1).to(self.device).expand_as(s.u))
-        s.p.zero_()
-        s.bvel.zero_()
-        s.make_divergence_free(max_iter=1000)
         randomize = self.randomize_initial_state if randomize is None else randomize
+        if self.load_domain_on_reset:                      # fluid_env.py:519-551
+            self._load_initial_domains_on_reset(randomize)
+        else:
+            u0 = torch.zeros(3, self.z, self.ny, self.x)
+            u0[0] = self.u_init[None, :, None]
+            s.u.copy_(u0.reshape(1, 3, -1).to(self.device).expand_as(s.u))
+            s.p.zero_()
+            s.bvel.zero_()
+            s.make_divergence_free(max_iter=1000)
         if randomize:
             self._randomize_domain()
         self._apply_action(self._zero_action)

@@ -48,3 +48,41 @@ def test_reference_written_rbc_domain_with_scalar(tmp_path):
     _, state2 = load_domain(str(tmp_path / "rt"))
     for k in ("u", "p", "T", "sbval", "bvel"):
         assert np.array_equal(state[k], state2[k])
+
+
+# ---- D = 3 single-block boxes (RBC3D, TCF) ---------------------------------------------------------------------------
+def test_reference_written_3d_domain_file_loads(golden):
+    """tests/golden/rbc3d_domain.{json,npz} was written by the UNMODIFIED reference's save_domain() (oracle/ref_harness.py
+    --env RBC3D-easy-v0 --save-domain-only, one env.step after reset); rbc3d_domain_state.npz is the reference's own view of
+    the same state."""
+    import os
+    from conftest import GOLDEN
+    from fluidgym_b200.domain_io import load_box_domain
+    d = load_box_domain(os.path.join(GOLDEN, "rbc3d_domain"))
+    st, ref = d["state"], golden("rbc3d_domain_state.npz")
+    assert d["closed"] == (False, True, False) and d["vertex"].shape == (3, 17, 11, 17)
+    assert np.array_equal(d["vertex"], golden("rbc3d_geometry.npz")["vertex"])
+    assert np.array_equal(st["u"], ref["u"]) and np.array_equal(st["p"], ref["p"]) and np.array_equal(st["T"], ref["T"])
+    assert st["bvel"].shape == (3, 512) and not st["bvel"].any()
+    assert np.array_equal(st["sbval"][:256], ref["sb2"]) and np.all(st["sbval"][256:] == ref["sb3"][0])
+    assert abs(d["scalar_viscosity"] - (6e3 * 0.7) ** -0.5) < 1e-7
+
+
+def test_3d_domain_file_round_trip(tmp_path):
+    from fluidgym_b200.domain_io import load_box_domain, save_box_domain
+    from fluidgym_b200.envs.rbc3d import rbc3d_vertex_grid
+    v = rbc3d_vertex_grid(8, 5, 3.14159, 1.0, 1.02)
+    N, NB = 8 * 5 * 8, 2 * 8 * 8
+    rng = np.random.default_rng(0)
+    st = dict(u=rng.standard_normal((3, N)).astype(np.float32), p=rng.standard_normal(N).astype(np.float32),
+              bvel=rng.standard_normal((3, NB)).astype(np.float32), T=rng.random(N).astype(np.float32), sbval=rng.random(NB).astype(np.float32))
+    path = str(tmp_path / "box")
+    save_box_domain(v, (False, True, False), 0.01, st, path, scalar_viscosity=0.02)
+    d = load_box_domain(path)
+    assert np.array_equal(d["vertex"], v) and abs(d["viscosity"] - 0.01) < 1e-9
+    for k, a in st.items():
+        assert np.array_equal(d["state"][k], a), k
+    # without a scalar (channel flow)
+    save_box_domain(v, (False, True, False), 0.01, dict(u=st["u"], p=st["p"], bvel=st["bvel"]), path)
+    d = load_box_domain(path)
+    assert d["state"]["T"] is None and d["state"]["sbval"] is None and np.array_equal(d["state"]["bvel"], st["bvel"])

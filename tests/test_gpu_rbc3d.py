@@ -125,3 +125,30 @@ def test_env_step_matches_reference(golden):
         assert d_nu < 1e-5 and d_r < 1e-5              # north_star: rewards within 1e-4
         assert d_oT < 2e-5 and d_ou < 1e-5
     assert reward.shape == (2, 16)
+
+
+def test_initial_domain_file_written_by_the_reference_drives_reset(golden, tmp_path):
+    """load_initial_domain=True with the reference's directory layout initial_domains/<id>/<idx>/<mode>.{json,npz}
+    (fluid_env.py:1044-1112): the file written by the unmodified reference becomes the reset state of every environment;
+    save_initial_domain writes a file the reader (and the reference) loads back."""
+    import shutil
+    import fluidgym_b200 as fg
+    T, bT = _ref_transforms(golden)
+    kw = dict(n_envs=2, n_heaters=4, resolution=4, step_length=0.25, transforms=T, btransforms=bT)
+    env = fg.make("RBC3D-easy-v0", load_initial_domain=True, initial_domains_path=str(tmp_path), **kw)
+    assert env.initial_domain_id == "rbc_3d_Ra6000.0_Pr0.7_NH4_HW4"
+    with pytest.raises(RuntimeError, match="Initial domain not found"):
+        env.reset(seed=0)
+    d = tmp_path / env.initial_domain_id / "0"
+    d.mkdir(parents=True)
+    for ext in ("json", "npz"):
+        shutil.copy(os.path.join(GOLDEN, f"rbc3d_domain.{ext}"), d / f"train.{ext}")
+    obs, _ = env.reset(seed=0, randomize=False)
+    ref = golden("rbc3d_domain_state.npz")
+    assert np.array_equal(env.solver.T[1].cpu().numpy(), ref["T"]) and np.array_equal(env.solver.u[0].cpu().numpy(), ref["u"])
+    obs, reward, *_ = env.step(torch.zeros(2, 16, 1, device="cuda"))
+    assert torch.isfinite(reward).all()
+    path = env.save_initial_domain(3, env_index=1)
+    from fluidgym_b200.domain_io import load_box_domain
+    back = load_box_domain(path)
+    assert np.array_equal(back["state"]["T"], env.solver.T[1].cpu().numpy())

@@ -101,3 +101,37 @@ def test_nusselt_rewards_match_reference(stub, golden):
     reward = e.local_reward_weight * local + (1 - e.local_reward_weight) * (e.nu_ref - nu)[:, None]
     assert np.abs(reward[0].numpy() - st["step0_reward"]).max() < 1e-5
     assert abs(float((e.nu_ref - nu)[0]) - float(st["step0_info_global_reward"][0])) < 1e-5
+
+
+def test_initial_domain_pool_glue_on_a_stand_in_solver(stub, golden, tmp_path):
+    """InitialDomains3D (envs/common.py) driven without a GPU: directory layout, per-environment state assignment from the
+    reference-written file, save_initial_domain round trip."""
+    import shutil
+    from fluidgym_b200.domain_io import load_box_domain
+    e, _ = stub
+
+    class S:
+        has_scalar, kappa = True, 0.0154
+        u, p, bvel = torch.zeros(3, 3, 2560), torch.zeros(3, 2560), torch.ones(3, 3, 512)
+        T, sbval = torch.zeros(3, 2560), torch.zeros(3, 512)
+    e.solver, e.n_envs = S, 3
+    e.rayleigh_number, e.prandtl_number = 6e3, 0.7
+    e.initial_domains_path = str(tmp_path)
+    e._np_rng = np.random.default_rng(0)
+    e.__dict__.pop("_domain_pool", None)
+    with pytest.raises(RuntimeError, match="Initial domain not found"):
+        e._load_initial_domains_on_reset(False)
+    d = tmp_path / e.initial_domain_id / "0"
+    d.mkdir(parents=True)
+    for ext in ("json", "npz"):
+        shutil.copy(os.path.join(GOLDEN, f"rbc3d_domain.{ext}"), d / f"train.{ext}")
+    assert e._load_initial_domains_on_reset(False) == [0, 0, 0]
+    ref = golden("rbc3d_domain_state.npz")
+    assert np.array_equal(S.T[2].numpy(), ref["T"]) and np.array_equal(S.u[1].numpy(), ref["u"]) and not S.bvel.any()
+    assert np.array_equal(S.sbval[0, :256].numpy(), ref["sb2"])
+    S.T[1] += 1.0
+    path = e.save_initial_domain(4, env_index=1)
+    assert path.endswith(os.path.join(e.initial_domain_id, "4", "train"))
+    back = load_box_domain(path)
+    assert np.array_equal(back["state"]["T"], S.T[1].numpy()) and np.array_equal(back["vertex"], e.dom.vertex)
+    e.n_envs = 1
