@@ -45,16 +45,8 @@ class PISOSubstep(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, u, p, bvel, solver: BatchedPISO, dt):
-        B, N, NB = solver.B, solver.N, solver.NB
-        dev = solver.device
         dtc = solver._dt(dt)
-        f32 = dict(device=dev, dtype=torch.float32)
-        o = solver.options
-        C_, n_adv, n_p = int(o.corrector_steps), int(o.adv_nonortho_steps), int(o.p_nonortho_steps)
-        tape = dict(u_in=torch.empty(B, 2, N, **f32), p_in=torch.empty(B, N, **f32), bvel_in=torch.empty(B, 2, NB, **f32),
-                    dt=torch.empty(B, **f32), Coff=torch.empty(B, 4, N, **f32), A=torch.empty(B, N, **f32),
-                    ustar=torch.empty(n_adv, B, 2, N, **f32), hb=torch.empty(C_, B, 2, N, **f32), p=torch.empty(C_ * n_p, B, N, **f32),
-                    pmean=torch.empty(C_ * n_p, B, **f32), u1=torch.empty(max(C_ - 1, 1), B, 2, N, **f32))
+        tape = _new_tape(solver)
         ct = native.Tape(*[tape[k].data_ptr() for k, _ in native.Tape._fields_])
         u_out = u.detach().clone().contiguous()
         p_out = p.detach().clone().contiguous()
@@ -70,19 +62,12 @@ class PISOSubstep(torch.autograd.Function):
         B, N, NB = solver.B, solver.N, solver.NB
         f32 = dict(device=solver.device, dtype=torch.float32)
         ct = native.Tape(*[tape[k].data_ptr() for k, _ in native.Tape._fields_])
-        ub = torch.empty(B, 2, N, **f32)
-        pb = torch.empty(B, N, **f32)
-        bvb = torch.empty(B, 2, NB, **f32)
-        nbytes = solver.lib.fgb_adjoint_workspace_bytes(C.byref(solver.tables), B)
-        ws = getattr(solver, "_adj_ws", None)
-        if ws is None or ws.numel() < nbytes + 256:
-            ws = solver._adj_ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=solver.device)
-        off = (-ws.data_ptr()) % 256
+        ub, pb, bvb = torch.empty(B, 2, N, **f32), torch.empty(B, N, **f32), torch.empty(B, 2, NB, **f32)
+        ws, nbytes = _adjoint_workspace(solver)
         uo = (u_out_bar if u_out_bar is not None else torch.zeros(B, 2, N, **f32)).contiguous()
         po = (p_out_bar if p_out_bar is not None else torch.zeros(B, N, **f32)).contiguous()
         native.check(solver.lib.fgb_piso_substep_backward(solver.handle, C.byref(ct), _ptr(uo), _ptr(po), _ptr(ub), _ptr(pb), _ptr(bvb),
-                                                          C.c_void_p(ws.data_ptr() + off), nbytes, solver.stream),
-                     "fgb_piso_substep_backward")
+                                                          ws, nbytes, solver.stream), "fgb_piso_substep_backward")
         return ub, pb, bvb, None, None
 
 
