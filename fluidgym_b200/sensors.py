@@ -135,9 +135,11 @@ def cell_centres_3d(vertex: np.ndarray) -> np.ndarray:
     return (c * f32(0.125)).astype(f32)
 
 
-def pixel_map_3d(vertex: np.ndarray, out_shape, fill_max_steps: int):
+def pixel_map_3d(vertex: np.ndarray, out_shape, fill_max_steps: int, n_corners: int = 3 << 1):
     """Sparse [W*H*Z, N] matrix R with rendered[pixel] = R @ cells (pixel index = x + W (y + H z), cells in (z, y, x)
-    order) and the per-pixel fill level (0 = splat, k = filled in sweep k, -1 = never)."""
+    order) and the per-pixel fill level (0 = splat, k = filled in sweep k, -1 = never).  ``n_corners`` = 6 is what the
+    reference's CUDA kernel does (and what its environments therefore observe); 8 is the full trilinear splat of its torch
+    re-implementation (resample.py:442-496), used by the tests to check everything but that quirk."""
     W, H, Z = (int(s) for s in out_shape)
     allv = vertex.reshape(3, -1).astype(f32)
     lower, upper = allv.min(axis=1), allv.max(axis=1)
@@ -152,7 +154,7 @@ def pixel_map_3d(vertex: np.ndarray, out_shape, fill_max_steps: int):
     fr = (sc - fl).astype(f32)
     dims = (W, H, Z)
     rows, cols, vals = [], [], []
-    for idx in range(3 << 1):                                 # sic: 6 corners (resampling.cu:320)
+    for idx in range(n_corners):                              # sic: 6 corners by default (resampling.cu:320)
         ok = np.ones(N, dtype=bool)
         w = np.ones(N, dtype=f32)
         pos = []
