@@ -1,0 +1,64 @@
+"""The reference's tests/envs/test_all_envs.py for the batched environments: every family (one id per distinct grid /
+variant) is built single-agent and -- where the family has agents -- multi-agent; observations match the declared
+observation space, sampled actions match the action space, rewards / flags / metrics have the reference's types.  All
+tensors carry the leading environment dimension (2 environments here)."""
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ENV_IDS = ["CylinderJet2D-easy-v0", "CylinderJet2D-medium-v0", "CylinderRot2D-easy-v0", "RBC2D-easy-v0", "RBC2D-wide-easy-v0",
+           "Airfoil2D-easy-v0", "TCFSmall3D-bottom-easy-v0", "TCFSmall3D-both-easy-v0", "RBC3D-easy-v0"]
+B = 2
+
+
+def _check_obs(env, obs, marl):
+    from fluidgym_b200 import spaces
+    space = env.observation_space
+    assert isinstance(space, spaces.Dict)
+    for key, sub in space.spaces.items():
+        assert key in obs, f"Observation missing key: {key}"
+        o = obs[key]
+        assert isinstance(o, torch.Tensor) and o.shape[0] == B
+        one = o[0][0] if marl else o[0]
+        assert tuple(one.shape) == tuple(sub.shape), f"{key}: {tuple(one.shape)} vs space {tuple(sub.shape)}"
+        assert torch.isfinite(o).all()
+
+
+def _check_action(env, action, marl):
+    from fluidgym_b200 import spaces
+    assert isinstance(env.action_space, spaces.Box) and isinstance(action, torch.Tensor) and action.shape[0] == B
+    one = action[0][0] if marl else action[0]
+    assert tuple(one.shape) == tuple(env.action_space.shape)
+
+
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_env_sarl(env_id):
+    import fluidgym_b200
+    env = fluidgym_b200.make(env_id, n_envs=B, use_marl=False)
+    env.seed(42)
+    obs, info = env.reset()
+    _check_obs(env, obs, marl=False)
+    _check_action(env, env.sample_action(), marl=False)
+    obs, reward, terminated, truncated, info = env.step(env.sample_action())
+    _check_obs(env, obs, marl=False)
+    assert isinstance(reward, torch.Tensor) and reward.shape[0] == B and torch.isfinite(reward).all()
+    assert isinstance(terminated, bool) and isinstance(truncated, bool) and isinstance(info, dict)
+    for metric in env.metrics:
+        assert metric in info and isinstance(info[metric], torch.Tensor)
+
+
+@pytest.mark.parametrize("env_id", ENV_IDS)
+def test_env_marl(env_id):
+    import fluidgym_b200
+    try:
+        env = fluidgym_b200.make(env_id, n_envs=B, use_marl=True)
+    except ValueError:
+        return                                     # single-agent family (cylinder, airfoil in 2-D), as in the reference
+    env.seed(42)
+    obs, info = env.reset()
+    _check_action(env, env.sample_action(), marl=True)
+    obs, reward, terminated, truncated, info = env.step(env.sample_action())
+    _check_obs(env, obs, marl=True)
+    assert reward.shape[:2] == (B, env.n_agents)
+    assert "global_reward" in info and isinstance(info["global_reward"], torch.Tensor)
