@@ -156,3 +156,34 @@ def test_scalar_specification_matches_reference_trace(rbc3d, golden, s):
     assert rel_l2(hb, fx["hbya0"]) < 1e-6
     assert rel_l2(be.divergence(box, hb, bvel), fx["div0"]) < 1e-6
     assert rel_l2(be.correct(box, hb, fx["p0"], Av), fx["u0"]) < 1e-6
+
+
+def test_channel_initial_domain_glue_without_a_gpu(tmp_path):
+    """InitialDomains3D for a box WITHOUT a passive scalar (turbulent channel): save -> directory layout -> pool -> per-environment
+    assignment, on a stand-in solver."""
+    import torch
+    from fluidgym_b200.box3d import Box3DDomain
+    from fluidgym_b200.envs.tcf import TCF3DEnv
+    from fluidgym_b200.grids import channel_vertex_grid
+    e = object.__new__(TCF3DEnv)
+    e.L, e.re_wall, e.x, e.grid_refinement_strength = float(np.pi), 180.0, 8, 2
+    e.dom = Box3DDomain(channel_vertex_grid(2.0, np.pi, np.pi / 2, 8, 4, 2, 8), closed=(False, True, False), viscosity=1e-3)
+    N, NB = e.dom.N, e.dom.NB
+    rng = np.random.default_rng(0)
+
+    class S:
+        u, p, bvel = torch.from_numpy(rng.standard_normal((2, 3, N)).astype(np.float32)), torch.zeros(2, N), torch.zeros(2, 3, NB)
+    e.solver, e.n_envs, e.device = S, 2, torch.device("cpu")
+    e.initial_domains_path = str(tmp_path)
+    e._np_rng = np.random.default_rng(1)
+    assert e.initial_domain_id == "channel_flow3D_L3.14_Re180_Res8_Ref2"
+    for idx in range(10):
+        S.u[0, 0, 0] = float(idx)
+        e.save_initial_domain(idx, env_index=0)
+    S.u.zero_()
+    idxs = e._load_initial_domains_on_reset(True)                  # one random index per environment
+    assert len(idxs) == 2 and all(0 <= i < 10 for i in idxs)
+    assert [float(S.u[k, 0, 0]) for k in range(2)] == [float(i) for i in idxs]
+    e.test()
+    with pytest.raises(RuntimeError, match="Initial domain not found"):
+        e._load_initial_domains_on_reset(False)                    # no "test" split was written
