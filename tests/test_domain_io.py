@@ -86,3 +86,35 @@ def test_3d_domain_file_round_trip(tmp_path):
     save_box_domain(v, (False, True, False), 0.01, dict(u=st["u"], p=st["p"], bvel=st["bvel"]), path)
     d = load_box_domain(path)
     assert d["state"]["T"] is None and d["state"]["sbval"] is None and np.array_equal(d["state"]["bvel"], st["bvel"])
+
+
+def test_2d_initial_domain_pool_glue_without_a_gpu(tmp_path):
+    """InitialDomains (envs/common.py) for the 2-D multi-block families on a stand-in solver: the file written by the reference
+    for CylinderJet2D-easy (tests/golden/cyl24_domain.*) is served from the directory layout of the published splits."""
+    import os
+    import shutil
+    import torch
+    from conftest import GOLDEN
+    from fluidgym_b200.envs.cylinder import CylinderJet2DEnv
+    from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
+    e = object.__new__(CylinderJet2DEnv)
+    e.spec = make_cylinder_domain(24)
+    cd = e.spec.prepare()
+    e.reynolds_number, e.resolution = 100.0, 24
+
+    class S:
+        has_scalar = False
+        u, p, bvel = torch.zeros(2, 2, cd.N), torch.zeros(2, cd.N), torch.zeros(2, 2, cd.NB)
+    e.solver, e.n_envs, e.device, e._dstate = S, 2, torch.device("cpu"), None
+    e.initial_domains_path = str(tmp_path)
+    e._np_rng = np.random.default_rng(0)
+    d = tmp_path / e.initial_domain_id / "0"
+    d.mkdir(parents=True)
+    for ext in ("json", "npz"):
+        shutil.copy(os.path.join(GOLDEN, f"cyl24_domain.{ext}"), d / f"train.{ext}")
+    assert e._load_initial_domains_on_reset(False) == [0, 0]
+    assert float(S.u.abs().max()) > 0.5 and torch.equal(S.u[0], S.u[1]) and float(S.bvel.abs().max()) > 0.5
+    path = e.save_initial_domain(7, env_index=1)
+    from fluidgym_b200.domain_io import load_domain
+    spec, st = load_domain(path)
+    assert np.array_equal(st["u"], S.u[1].numpy()) and len(spec.blocks) == 5
