@@ -272,7 +272,7 @@ def run_ours(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roof = {"bound": "hbm", "kernel": {0: "k_cg", 1: "k_cg_cluster", 2: "k_cg_cluster", 3: "k_cg_cluster_mb", 4: "k_cg_smem", 5: "k_cg_smem", 6: "k_cg_cluster_mb<PUSH>", 7: "k_cg_cluster_mb<PUSH,256x14>"}[args.cg_impl], "achieved": achieved, "peak": peak,
+    roof = {"bound": "hbm", "kernel": {0: "k_cg", 1: "k_cg_cluster", 2: "k_cg_cluster", 3: "k_cg_cluster_mb", 4: "k_cg_smem", 5: "k_cg_smem", 6: "k_cg_cluster_mb<PUSH>", 7: "k_cg_cluster_mb<PUSH,256x14>", 8: "k_cg_cluster_mb<PUSH,256x7,2 CTAs/SM>"}.get(args.cg_impl, f"cg_impl {args.cg_impl}"), "achieved": achieved, "peak": peak,
             "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "algorithmic_bytes_per_launch": cg_bytes / max(cg_launches, 1), "avg_launch_ms": cg_ms / max(cg_launches, 1),
             "launches": cg_launches, "share_of_step": cg_ms / ms_local,
