@@ -1,0 +1,288 @@
+// D = 3 operators on z-EXTRUDED multi-block domains (CylinderJet3D, Airfoil3D: the 2-D multi-block grid repeated over nz
+// uniform, periodic z planes; envs/cylinder/grid.py:298, shapes.py:641-676; reference: the K.cu kernels with DIMS = 3).
+//
+// STATUS: operator layer.  The per-cell functions below are __host__ __device__ so that tests/test_extruded_host.py can
+// execute exactly this code on the CPU (through tests/cpu_harness/extruded_host.cu) and compare it with the numpy
+// specification tests/extruded_eval.py, which is pinned to an op trace of the unmodified reference on CylinderJet3D-easy
+// (tests/golden/cyl3d_substep*.npz).  The launch glue at the end of this file has NOT run on a GPU yet: no environment is
+// registered on it and no GPU test depends on it.
+//
+// The metric tensor of an extruded cell is block diagonal, M3 = diag(M2, hz): every in-plane coefficient of a row / det3
+// equals the 2-D one from the compiled tables (fgb_tables), the z faces add  -+1/4 (u_z,P + u_z,N) / hz - nu / hz^2  off
+// the diagonal; all non-orthogonal (corner) terms stay in the x-y plane because alpha^{xz} = alpha^{yz} = 0.
+//
+// Layout: cell g3 = k * N2 + g (plane k, 2-D cell g); fields [B][3][N3]; boundary velocities [B][3][nz][NB2]; matrices
+// ELL(7) on a 6-face neighbour table (faces 0..3 in plane, 4 = -z, 5 = +z) so that the cooperative Krylov kernels of
+// ortho3_b200.cuh (k3_bicgstab, k3_cg) solve them unchanged.
+#pragma once
+
+#ifndef X3_HD
+#define X3_HD __host__ __device__ __forceinline__
+#endif
+
+struct X3Tab {
+    fgb_tables t;     // in-plane tables of the compiled 2-D domain
+    int nz;           // z planes (periodic)
+    float hz;         // plane spacing
+};
+
+X3_HD float x3_contra(const fgb_tables &t, int k, int g, float u, float v) {          // det2 * (Minv[k] . (u, v))   (K.cu:495-510)
+    const int N = t.N;
+    return t.det[g] * (t.minv[(2 * k) * N + g] * u + t.minv[(2 * k + 1) * N + g] * v);
+}
+X3_HD float x3_bflux(const fgb_tables &t, int j, int ax, float bu, float bv) {
+    const int NB = t.NB;
+    return t.b_det[j] * (t.b_minv[(2 * ax) * NB + j] * bu + t.b_minv[(2 * ax + 1) * NB + j] * bv);
+}
+// in-plane face fluxes / hz of plane-local fields ux, uy [N2] (K.cu:1567-1645)
+X3_HD void x3_face_fluxes(const fgb_tables &t, int g, const float *ux, const float *uy, const float *bx, const float *by,
+                          const int nb[4], float fl[4]) {
+    const int N = t.N;
+    const float Uc[2] = {x3_contra(t, 0, g, ux[g], uy[g]), x3_contra(t, 1, g, ux[g], uy[g])};
+    for (int f = 0; f < 4; ++f) {
+        if (nb[f] >= 0) {
+            const int fc = t.fl_comp[f * N + g];
+            float velN = x3_contra(t, fc & 1, nb[f], ux[nb[f]], uy[nb[f]]);
+            if (fc & 2) velN = -velN;
+            fl[f] = (velN + Uc[f >> 1]) * 0.5f;
+        } else {
+            const int j = -1 - nb[f];
+            fl[f] = x3_bflux(t, j, f >> 1, bx[j], by[j]);
+        }
+    }
+}
+// Dirichlet boundary advection + diffusion source of component values bc [NB2] (K.cu:4321-4380), before / det
+X3_HD float x3_boundary_source(const fgb_tables &t, const float *bx, const float *by, const float *bc, const int nb[4]) {
+    float S = 0.f;
+    for (int f = 0; f < 4; ++f)
+        if (nb[f] < 0) {
+            const int j = -1 - nb[f];
+            const float flux = x3_bflux(t, j, f >> 1, bx[j], by[j]) * ((f & 1) ? 1.f : -1.f);
+            S -= bc[j] * flux;
+            S += bc[j] * (t.viscosity * 2.f * t.b_alpha[j]);
+        }
+    return S;
+}
+
+// SetupAdvectionMatrix + SetupAdvectionVelocity (K.cu:3617-3880, 4296-4400) for cell (k, g) of one environment.
+// u, ures: [3][N3]; bvel: [3][nz][NB2]; outputs coff [6][N3], A [N3], rhs [3][N3]
+X3_HD void x3_setup_advection_cell(const X3Tab &x, int k, int g, const float *u, const float *ures, const float *bvel, float dt,
+                                   float *coff, float *A, float *rhs, int with_matrix) {
+    const fgb_tables &t = x.t;
+    const int N = t.N, NB = t.NB, nz = x.nz, N3 = N * nz, g3 = k * N + g;
+    const float det = t.det[g], hz = x.hz;
+    const float *ux = u + (size_t)k * N, *uy = u + (size_t)N3 + (size_t)k * N, *uz = u + 2 * (size_t)N3;
+    const float *bx = bvel + (size_t)k * NB, *by = bvel + (size_t)nz * NB + (size_t)k * NB;
+    int nb[4];
+    for (int f = 0; f < 4; ++f) nb[f] = t.nbr[f * N + g];
+    if (with_matrix) {
+        float fl[4];
+        x3_face_fluxes(t, g, ux, uy, bx, by, nb, fl);
+        float diag = det / dt + t.Cd[g];
+        for (int f = 0; f < 4; ++f) {
+            float o = 0.f;
+            if (nb[f] >= 0) {
+                const float ff = ((f & 1) ? 0.5f : -0.5f) * fl[f];
+                diag += ff;
+                o = (ff + t.Cd[(f + 1) * N + g]) / det;
+            }
+            coff[(size_t)f * N3 + g3] = o;
+        }
+        const int kl = (k + nz - 1) % nz, ku = (k + 1) % nz;
+        const float uzP = uz[g3], Fzm = 0.5f * (uzP + uz[(size_t)kl * N + g]), Fzp = 0.5f * (uzP + uz[(size_t)ku * N + g]);
+        const float dz = t.viscosity / (hz * hz);
+        coff[(size_t)4 * N3 + g3] = (-0.5f * Fzm) / hz - dz;
+        coff[(size_t)5 * N3 + g3] = (0.5f * Fzp) / hz - dz;
+        A[g3] = diag / det + 2.f * dz + 0.5f * (Fzp - Fzm) / hz;
+    }
+    for (int c = 0; c < 3; ++c) {
+        const float *bc = bvel + ((size_t)c * nz + k) * NB;
+        const float *ur = ures + (size_t)c * N3 + (size_t)k * N;
+        const float S = x3_boundary_source(t, bx, by, bc, nb);
+        float no = 0.f;
+        for (int q = 0; q < t.K_no; ++q) {
+            const float w = t.no_wv[q * N + g];
+            if (w != 0.f) no += w * ur[t.no_idx[q * N + g]];
+        }
+        for (int q = 0; q < t.K_nob; ++q) {
+            const float w = t.nob_w[q * N + g];
+            if (w != 0.f) no += w * bc[t.nob_idx[q * N + g]];
+        }
+        rhs[(size_t)c * N3 + g3] = (det * u[(size_t)c * N3 + g3] / dt + S - no) / det;
+    }
+}
+
+// SetupPressureMatrix (K.cu:4812-4978), NOT divided by det: in-plane  hz * sum_j Wp[e][j] (1/A)_j , z faces 1/2 (det2 / hz) (1/A_P + 1/A_N)
+X3_HD void x3_pressure_matrix_cell(const X3Tab &x, int k, int g, const float *A, float *poff, float *pdiag) {
+    const fgb_tables &t = x.t;
+    const int N = t.N, nz = x.nz, N3 = N * nz, g3 = k * N + g;
+    const float *a = A + (size_t)k * N;
+    float rA[5];
+    rA[0] = 1.0f / a[g];
+    for (int f = 0; f < 4; ++f) { const int nb = t.nbr[f * N + g]; rA[f + 1] = nb >= 0 ? 1.0f / a[nb] : rA[0]; }
+    float P[5];
+    for (int e = 0; e < 5; ++e) {
+        float s = 0.f;
+        for (int j = 0; j < 5; ++j) s += t.Wp[(5 * e + j) * N + g] * rA[j];
+        P[e] = s * x.hz;
+    }
+    const int kl = (k + nz - 1) % nz, ku = (k + 1) % nz;
+    const float az = t.det[g] / x.hz;
+    const float pl = 0.5f * az * (rA[0] + 1.0f / A[(size_t)kl * N + g]), pu = 0.5f * az * (rA[0] + 1.0f / A[(size_t)ku * N + g]);
+    for (int f = 0; f < 4; ++f) poff[(size_t)f * N3 + g3] = P[f + 1];
+    poff[(size_t)4 * N3 + g3] = pl;
+    poff[(size_t)5 * N3 + g3] = pu;
+    pdiag[g3] = P[0] - pl - pu;
+}
+
+// PISO_build_pressure_rhs (K.cu:5136-5255): HbyA = (u/dt - sum_nb C_nb u*_nb + S_b/det) / A for the three components
+X3_HD void x3_hbya_cell(const X3Tab &x, int k, int g, const float *u, const float *ures, const float *bvel, const float *coff,
+                        const float *A, float dt, float *hb) {
+    const fgb_tables &t = x.t;
+    const int N = t.N, NB = t.NB, nz = x.nz, N3 = N * nz, g3 = k * N + g;
+    const float *bx = bvel + (size_t)k * NB, *by = bvel + (size_t)nz * NB + (size_t)k * NB;
+    const int kl = (k + nz - 1) % nz, ku = (k + 1) % nz;
+    int nb[4];
+    for (int f = 0; f < 4; ++f) nb[f] = t.nbr[f * N + g];
+    const float rD = 1.0f / A[g3], det = t.det[g];
+    for (int c = 0; c < 3; ++c) {
+        const float *ur = ures + (size_t)c * N3;
+        float H = 0.f;
+        for (int f = 0; f < 4; ++f)
+            if (nb[f] >= 0) H += coff[(size_t)f * N3 + g3] * ur[(size_t)k * N + nb[f]];
+        H += coff[(size_t)4 * N3 + g3] * ur[(size_t)kl * N + g] + coff[(size_t)5 * N3 + g3] * ur[(size_t)ku * N + g];
+        const float S = x3_boundary_source(t, bx, by, bvel + ((size_t)c * nz + k) * NB, nb);
+        hb[(size_t)c * N3 + g3] = rD * (u[(size_t)c * N3 + g3] / dt - H + S / det);
+    }
+}
+
+// divergence of the face fluxes of HbyA (K.cu:5389-5434) + deferred non-orthogonal pressure term (K.cu:5470-5492)
+X3_HD void x3_divergence_cell(const X3Tab &x, int k, int g, const float *hb, const float *bvel, const float *pprev /* or null */,
+                              const float *A, float *div) {
+    const fgb_tables &t = x.t;
+    const int N = t.N, NB = t.NB, nz = x.nz, N3 = N * nz, g3 = k * N + g;
+    const float *hx = hb + (size_t)k * N, *hy = hb + (size_t)N3 + (size_t)k * N, *hzc = hb + 2 * (size_t)N3;
+    const float *bx = bvel + (size_t)k * NB, *by = bvel + (size_t)nz * NB + (size_t)k * NB;
+    int nb[4];
+    for (int f = 0; f < 4; ++f) nb[f] = t.nbr[f * N + g];
+    float fl[4];
+    x3_face_fluxes(t, g, hx, hy, bx, by, nb, fl);
+    float d = (fl[1] - fl[0]) + (fl[3] - fl[2]);
+    if (pprev) {
+        const float *a = A + (size_t)k * N, *pp = pprev + (size_t)k * N;
+        float rA[5];
+        rA[0] = 1.0f / a[g];
+        for (int f = 0; f < 4; ++f) rA[f + 1] = nb[f] >= 0 ? 1.0f / a[nb[f]] : rA[0];
+        float S = 0.f;
+        for (int q = 0; q < t.K_no; ++q) {
+            const float gP = t.no_gP[q * N + g], gN = t.no_gN[q * N + g];
+            if (gP != 0.f || gN != 0.f) S += (gP * rA[0] + gN * rA[1 + t.no_face[q * N + g]]) * pp[t.no_idx[q * N + g]];
+        }
+        d += S;
+    }
+    const int kl = (k + nz - 1) % nz, ku = (k + 1) % nz;
+    const float hP = hzc[g3];
+    div[g3] = d * x.hz + t.det[g] * (0.5f * (hP + hzc[(size_t)ku * N + g]) - 0.5f * (hP + hzc[(size_t)kl * N + g]));
+}
+
+// PISO_update_velocity (K.cu:816-849, 5962-5995)
+X3_HD void x3_correct_cell(const X3Tab &x, int k, int g, const float *hb, const float *p, const float *A, float *uout) {
+    const fgb_tables &t = x.t;
+    const int N = t.N, nz = x.nz, N3 = N * nz, g3 = k * N + g;
+    const float *pk = p + (size_t)k * N;
+    const float pc = pk[g];
+    float pg[2];
+    for (int d = 0; d < 2; ++d) {
+        const int nl = t.nbr[(2 * d) * N + g], nu = t.nbr[(2 * d + 1) * N + g];
+        const float fac = (nl < 0 || nu < 0) ? 1.0f : 0.5f;
+        pg[d] = ((nu >= 0 ? pk[nu] : pc) - (nl >= 0 ? pk[nl] : pc)) * fac;
+    }
+    const float gx = pg[0] * t.minv[g] + pg[1] * t.minv[2 * N + g];
+    const float gy = pg[0] * t.minv[N + g] + pg[1] * t.minv[3 * N + g];
+    const int kl = (k + nz - 1) % nz, ku = (k + 1) % nz;
+    const float gz = 0.5f * (p[(size_t)ku * N + g] - p[(size_t)kl * N + g]) / x.hz;
+    const float rD = 1.0f / A[g3];
+    uout[g3] = hb[g3] - rD * gx;
+    uout[(size_t)N3 + g3] = hb[(size_t)N3 + g3] - rD * gy;
+    uout[2 * (size_t)N3 + g3] = hb[2 * (size_t)N3 + g3] - rD * gz;
+}
+
+#ifdef __CUDACC__
+#ifndef X3_HOST_ONLY
+// ------------------------------------------------------------------------------------------------------------------
+// launch glue (one thread per (cell, plane, environment)); matrices / vectors live in the workspace of an fgb_ortho3
+// handle created on the 6-face neighbour table of the extruded domain, so fgb_ortho3_solve_advection / _solve_pressure
+// run the Krylov iterations.  NOT yet run on a GPU (see the header of this file).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kx3_setup_advection(X3Tab x, const float *U, const float *Ures, const float *Bvel, const float *dtv,
+                                                          float *Coff, float *A, float *Rhs, int with_matrix) {
+    const int b = blockIdx.z, k = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= x.t.N) return;
+    const size_t N3 = (size_t)x.t.N * x.nz;
+    x3_setup_advection_cell(x, k, g, U + b * 3 * N3, Ures + b * 3 * N3, Bvel + (size_t)b * 3 * x.nz * x.t.NB, dtv[b], Coff + b * 6 * N3,
+                            A + b * N3, Rhs + b * 3 * N3, with_matrix);
+}
+__global__ void __launch_bounds__(256) kx3_pressure_matrix(X3Tab x, const float *A, float *Poff, float *Pdiag) {
+    const int b = blockIdx.z, k = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= x.t.N) return;
+    const size_t N3 = (size_t)x.t.N * x.nz;
+    x3_pressure_matrix_cell(x, k, g, A + b * N3, Poff + b * 6 * N3, Pdiag + b * N3);
+}
+__global__ void __launch_bounds__(256) kx3_hbya(X3Tab x, const float *U, const float *Ures, const float *Bvel, const float *Coff, const float *A,
+                                               const float *dtv, float *Hb) {
+    const int b = blockIdx.z, k = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= x.t.N) return;
+    const size_t N3 = (size_t)x.t.N * x.nz;
+    x3_hbya_cell(x, k, g, U + b * 3 * N3, Ures + b * 3 * N3, Bvel + (size_t)b * 3 * x.nz * x.t.NB, Coff + b * 6 * N3, A + b * N3, dtv[b], Hb + b * 3 * N3);
+}
+__global__ void __launch_bounds__(256) kx3_divergence(X3Tab x, const float *Hb, const float *Bvel, const float *Pprev, const float *A, float *Div) {
+    const int b = blockIdx.z, k = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= x.t.N) return;
+    const size_t N3 = (size_t)x.t.N * x.nz;
+    x3_divergence_cell(x, k, g, Hb + b * 3 * N3, Bvel + (size_t)b * 3 * x.nz * x.t.NB, Pprev ? Pprev + b * N3 : nullptr, A + b * N3, Div + b * N3);
+}
+__global__ void __launch_bounds__(256) kx3_correct(X3Tab x, const float *Hb, const float *P, const float *A, float *Uout) {
+    const int b = blockIdx.z, k = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= x.t.N) return;
+    const size_t N3 = (size_t)x.t.N * x.nz;
+    x3_correct_cell(x, k, g, Hb + b * 3 * N3, P + b * N3, A + b * N3, Uout + b * 3 * N3);
+}
+
+// Simulation._PISO_split_step on an extruded domain (SIM.py:1431-2002, non-orthogonal path): b = fgb_ortho3 handle created on
+// the 6-face table (N = nz * N2); opt.adv_nonortho_steps / p_nonortho_steps deferred-correction iterations.
+extern "C" int fgb_extruded3_piso_substep(fgb_ortho3 *b, const fgb_extruded3_tables *xt, float *u, float *p, const float *bvel, const float *dt,
+                                          fgb_stream_t s) {
+    if (!b || !xt || !u || !p || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_extruded3_piso_substep: null argument");
+    if (b->t.N != xt->plane.N * xt->nz || b->slab.on) return set_err(FGB_E_ARG, "fgb_extruded3_piso_substep: handle / tables mismatch");
+    X3Tab x; x.t = xt->plane; x.nz = xt->nz; x.hz = xt->hz;
+    cudaStream_t st = STREAM(s);
+    const dim3 grid((unsigned)((x.t.N + 255) / 256), (unsigned)x.nz, (unsigned)b->B);
+    const fgb_options &o = b->opt;
+    int rc;
+    for (int ns = 0; ns < o.adv_nonortho_steps; ++ns) {
+        b->launches++;
+        kx3_setup_advection<<<grid, 256, 0, st>>>(x, u, ns == 0 ? u : b->ures, bvel, dt, b->Coff, b->A, b->rhs, ns == 0);
+        LAUNCH_CHECK("kx3_setup_advection");
+        if ((rc = fgb_ortho3_solve_advection(b, ns == 0, nullptr, s))) return rc;
+    }
+    for (int cs = 0; cs < o.corrector_steps; ++cs) {
+        b->launches += 2;
+        if (cs == 0) { kx3_pressure_matrix<<<grid, 256, 0, st>>>(x, b->A, b->Poff, b->Pdiag); LAUNCH_CHECK("kx3_pressure_matrix"); }
+        kx3_hbya<<<grid, 256, 0, st>>>(x, u, b->ures, bvel, b->Coff, b->A, dt, b->hbya);
+        LAUNCH_CHECK("kx3_hbya");
+        for (int ps = 0; ps < o.p_nonortho_steps; ++ps) {
+            b->launches++;
+            kx3_divergence<<<grid, 256, 0, st>>>(x, b->hbya, bvel, p, b->A, b->div);
+            LAUNCH_CHECK("kx3_divergence");
+            if ((rc = fgb_ortho3_solve_pressure(b, p, ps == 0, 100, o.max_iter, cs * o.p_nonortho_steps + ps, nullptr, s))) return rc;
+        }
+        b->launches++;
+        kx3_correct<<<grid, 256, 0, st>>>(x, b->hbya, p, b->A, b->ures);
+        LAUNCH_CHECK("kx3_correct");
+    }
+    cudaError_t ce = cudaMemcpyAsync(u, b->ures, (size_t)b->B * 3 * b->t.N * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "fgb_extruded3_piso_substep: copy", ce);
+    return FGB_OK;
+}
+#endif  // X3_HOST_ONLY
+#endif  // __CUDACC__

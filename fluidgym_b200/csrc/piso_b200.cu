@@ -2808,3 +2808,6 @@ extern "C" int fgb_sample_sensors_n(const float *field, int32_t B, int32_t chann
 
 // D = 3 orthogonal-grid path (turbulent channel flow)
 #include "ortho3_b200.cuh"
+
+// D = 3 operators on z-extruded multi-block domains (CylinderJet3D / Airfoil3D): 2-D tables + periodic z faces
+#include "extruded3_b200.cuh"

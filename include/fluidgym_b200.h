@@ -341,6 +341,21 @@ int fgb_profile_read(fgb_batch *b, double *ms_out /*[4]*/, int64_t *count_out /*
 /* number of kernel launches issued through this handle since creation */
 long long fgb_launch_count(fgb_batch *b);
 
+/* ---- D = 3, z-extruded multi-block domains (CylinderJet3D, Airfoil3D: envs/cylinder/grid.py:298, shapes.py:641-676) ----------
+ * The 2-D tables of the compiled plane + nz uniform periodic planes of spacing hz.  Fields [B][3][nz*N], cell = plane * N + g;
+ * boundary velocities [B][3][nz][NB].  The handle is an fgb_ortho3 created on the 6-face neighbour table of the extruded domain
+ * (faces 0..3 in plane, 4 = -z, 5 = +z), whose cooperative Krylov kernels solve the ELL(7) systems.  Operator arithmetic is
+ * verified on the CPU against a trace of the reference (tests/test_extruded_host.py); the launch path has not run on a GPU yet
+ * and no environment uses it. */
+typedef struct fgb_extruded3_tables {
+    fgb_tables plane;
+    int32_t nz;
+    float hz;
+} fgb_extruded3_tables;
+/* Simulation._PISO_split_step (SIM.py:1431-2002, non-orthogonal path; pressure_non_ortho_steps = 4 in 3-D, cylinder_env_base.py:317) */
+int fgb_extruded3_piso_substep(fgb_ortho3 *b, const fgb_extruded3_tables *x, float *u, float *p, const float *bvel, const float *dt,
+                               fgb_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

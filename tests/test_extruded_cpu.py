@@ -56,3 +56,25 @@ def test_extruded_matrices_match_reference_csr(cyl3d, golden):
         xg[glob] = x.reshape(-1)
         assert rel_l2(ee.spmv(cd, off, offz, A, x), (C @ xg)[glob].reshape(nz, N2)) < 5e-7
         assert rel_l2(ee.spmv(cd, Poff, Poffz, Pd, x), (P @ xg)[glob].reshape(nz, N2)) < 5e-7
+
+
+def test_six_face_neighbour_table_reproduces_the_extruded_matvec(cyl3d):
+    """fluidgym_b200.extruded3d.extruded_neighbours: the ELL(7) product the cooperative Krylov kernels form on that table (o3_row:
+    diag * x + sum_f off[f] * x[nbr[f]] for nbr >= 0) equals the specification's matvec."""
+    from fluidgym_b200.extruded3d import extruded_neighbours
+    cd = cyl3d
+    nz, hz = 8, 0.5
+    rng = np.random.default_rng(3)
+    u = rng.standard_normal((3, nz, cd.N)).astype(f32)
+    bvel = np.zeros((3, nz, cd.NB), f32)
+    bvel[:2] = cd.bvel0[:, None, :cd.NB]
+    off, offz, A = ee.assemble(cd, u, bvel, 0.01, hz)
+    nbr6 = extruded_neighbours(np.asarray(cd.nbr), nz)
+    assert nbr6.shape == (6, nz * cd.N) and (nbr6[4:] >= 0).all()
+    coff = np.concatenate([off, offz]).reshape(6, -1)
+    x = rng.standard_normal(nz * cd.N).astype(f32)
+    y = A.reshape(-1) * x
+    for f in range(6):
+        ok = nbr6[f] >= 0
+        y = y + np.where(ok, coff[f] * x[np.where(ok, nbr6[f], 0)], 0)
+    assert rel_l2(y.reshape(nz, cd.N), ee.spmv(cd, off, offz, A, x.reshape(nz, cd.N))) < 1e-6
