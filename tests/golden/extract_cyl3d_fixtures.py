@@ -66,6 +66,32 @@ def main(src):
                       C_row=t[p_ + "C_row"].astype(np.int32), P_value=t[p_ + "P_value0"], P_index=t[p_ + "P_index"].astype(np.int32),
                       P_row=t[p_ + "P_row"].astype(np.int32))
         np.savez_compressed(os.path.join(HERE, f"cyl3d_substep{s}.npz"), **fx)
+    # environment level (for the CylinderJet3D environment still to be built): reset state, state after the first env.step with
+    # the recorded action (25 solver steps), observations [8 jets, 2 sensor layers, ...], drag / lift / per-jet coefficients
+    st, rs, e0 = (np.load(os.path.join(src, f"cyl3d_{n}.npz")) for n in ("steps", "state_reset", "state_step0"))
+
+    def state(z):
+        u = np.zeros((3, nz, N2), f32)
+        p = np.zeros((nz, N2), f32)
+        for bi in range(len(spec.blocks)):
+            u[:, :, offs[bi]:offs[bi + 1]] = z[f"b{bi}_u"][0].reshape(3, nz, -1)
+            p[:, offs[bi]:offs[bi + 1]] = z[f"b{bi}_p"][0].reshape(nz, -1)
+        bv = np.zeros((3, nz, cd.NB), f32)
+        o = 0
+        for bi, b in enumerate(spec.blocks):
+            for f in range(4):
+                if b.bounds[f].type == FIXED:
+                    n = b.size(1 - (f >> 1))
+                    v = z[f"b{bi}_f{f}_velocity"][0]
+                    bv[:, :, o:o + n] = v.reshape(3, nz, n) if v.ndim > 1 else np.broadcast_to(v.reshape(3, 1, 1), (3, nz, n))
+                    o += n
+        return u, p, bv
+    ru, rp, rb = state(rs)
+    eu, ep, eb = state(e0)
+    env_fx = {k: st[k] for k in st.files}
+    env_fx.update(reset_u=ru, reset_p=rp, reset_bvel=rb, reset_obs_velocity=rs["obs_velocity"], reset_obs_pressure=rs["obs_pressure"],
+                  env0_u=eu, env0_p=ep, env0_bvel=eb)
+    np.savez_compressed(os.path.join(HERE, "cyl3d_env.npz"), **env_fx)
     keep = {k: meta[k] for k in ("env", "seed", "torch", "gpu", "n_sim_steps", "dt", "viscosity", "timing", "mean_iters", "max_iters",
                                  "n_solves", "substeps_in_env_steps", "reset_seconds")}
     keep["kw"] = {"resolution": 8, "n_jets": 8}
