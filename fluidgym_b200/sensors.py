@@ -142,19 +142,58 @@ def pixel_map_3d(vertex: np.ndarray, out_shape, fill_max_steps: int, n_corners: 
     re-implementation (resample.py:442-496), used by the tests to check everything but that quirk."""
     W, H, Z = (int(s) for s in out_shape)
     allv = vertex.reshape(3, -1).astype(f32)
-    lower, upper = allv.min(axis=1), allv.max(axis=1)
+    centres = cell_centres_3d(vertex).reshape(3, -1)
+    return _pixel_map_from_centres(centres, allv.min(axis=1), allv.max(axis=1), (W, H, Z), fill_max_steps, n_corners)
+
+
+def sensor_tables_3d(vertex: np.ndarray, out_shape, sensor_px: np.ndarray, fill_max_steps: int):
+    """ELL tables (idx [K, n_s] int32, w [K, n_s] float32) of the rendered-voxel map at the sensor voxels
+    ``sensor_px`` = [3, n_s] integer (x, y, z) voxel coordinates (envs/rbc/rbc_env_3d.py:183-203)."""
+    W, H, Z = (int(s) for s in out_shape)
+    R, _ = pixel_map_3d(vertex, out_shape, fill_max_steps)
+    flat = sensor_px[0].astype(np.int64) + W * (sensor_px[1].astype(np.int64) + H * sensor_px[2].astype(np.int64))
+    Rs = R[flat]
+    ns = flat.size
+    nnz = np.diff(Rs.indptr)
+    K = max(1, int(nnz.max()))
+    idx = np.zeros((K, ns), dtype=np.int32)
+    w = np.zeros((K, ns), dtype=f32)
+    for s_ in range(ns):
+        a, b = Rs.indptr[s_], Rs.indptr[s_ + 1]
+        idx[:b - a, s_] = Rs.indices[a:b]
+        w[:b - a, s_] = Rs.data[a:b]
+    return idx, w
+
+
+def pixel_map_extruded(vertex2d_list, z_vertices: np.ndarray, out_shape, fill_max_steps: int, n_corners: int = 3 << 1):
+    """pixel_map_3d for a z-extruded multi-block domain (CylinderJet3D / Airfoil3D): ``vertex2d_list`` = the 2-D vertex grids of
+    the blocks [2, ny+1, nx+1], ``z_vertices`` [nz+1].  Columns are the cells in plane-major order (plane * N2 + g, g = block-major
+    2-D cell index), the layout of fluidgym_b200/extruded3d.py."""
+    W, H, Z = (int(s) for s in out_shape)
+    z_vertices = np.asarray(z_vertices, dtype=f32)
+    allxy = np.concatenate([v.reshape(2, -1) for v in vertex2d_list], axis=1).astype(f32)
+    lower = np.array([allxy[0].min(), allxy[1].min(), z_vertices.min()], dtype=f32)
+    upper = np.array([allxy[0].max(), allxy[1].max(), z_vertices.max()], dtype=f32)
+    c2 = np.concatenate([cell_centres(v).reshape(2, -1) for v in vertex2d_list], axis=1)            # [2, N2]
+    zc = ((z_vertices[:-1] + z_vertices[1:]) * f32(0.5)).astype(f32)
+    nz, N2 = zc.size, c2.shape[1]
+    centres = np.stack([np.tile(c2[0], nz), np.tile(c2[1], nz), np.repeat(zc, N2)]).astype(f32)     # [3, nz * N2]
+    return _pixel_map_from_centres(centres, lower, upper, (W, H, Z), fill_max_steps, n_corners)
+
+
+def _pixel_map_from_centres(centres, lower, upper, out_shape, fill_max_steps, n_corners):
+    W, H, Z = out_shape
     size = (upper - lower).astype(f32)
     centre = (lower + size * f32(0.5)).astype(f32)
     os_ = np.asarray([W, H, Z], dtype=f32)
     scale = f32(np.max(size / os_))
-    centres = cell_centres_3d(vertex).reshape(3, -1)
     N = centres.shape[1]
     sc = ((centres - centre[:, None]) / scale + (os_ * f32(0.5) - f32(0.5))[:, None]).astype(f32)
     fl, ce = np.floor(sc), np.ceil(sc)
     fr = (sc - fl).astype(f32)
     dims = (W, H, Z)
     rows, cols, vals = [], [], []
-    for idx in range(n_corners):                              # sic: 6 corners by default (resampling.cu:320)
+    for idx in range(n_corners):
         ok = np.ones(N, dtype=bool)
         w = np.ones(N, dtype=f32)
         pos = []
@@ -184,8 +223,8 @@ def pixel_map_3d(vertex: np.ndarray, out_shape, fill_max_steps: int, n_corners: 
             for sh in (1, -1):
                 a = [slice(None)] * 3
                 b = [slice(None)] * 3
-                a[ax] = slice(1, None) if sh == 1 else slice(0, -1)       # destination pixels
-                b[ax] = slice(0, -1) if sh == 1 else slice(1, None)       # their neighbour in that direction
+                a[ax] = slice(1, None) if sh == 1 else slice(0, -1)
+                b[ax] = slice(0, -1) if sh == 1 else slice(1, None)
                 m = (~v3[tuple(a)]) & v3[tuple(b)]
                 dst_l.append(grid[tuple(a)][m]); src_l.append(grid[tuple(b)][m])
         dst, src = np.concatenate(dst_l), np.concatenate(src_l)
@@ -193,27 +232,8 @@ def pixel_map_3d(vertex: np.ndarray, out_shape, fill_max_steps: int, n_corners: 
             break
         cnt = np.bincount(dst, minlength=npx).astype(np.float64)
         A = sp.csr_matrix((1.0 / cnt[dst], (dst, src)), shape=(npx, npx))
-        R = R + A @ R                                            # rows of valid pixels are untouched (A has no such rows)
+        R = R + A @ R
         newly = cnt > 0
         level[newly] = k
         valid = valid | newly
     return R.tocsr(), level
-
-
-def sensor_tables_3d(vertex: np.ndarray, out_shape, sensor_px: np.ndarray, fill_max_steps: int):
-    """ELL tables (idx [K, n_s] int32, w [K, n_s] float32) of the rendered-voxel map at the sensor voxels
-    ``sensor_px`` = [3, n_s] integer (x, y, z) voxel coordinates (envs/rbc/rbc_env_3d.py:183-203)."""
-    W, H, Z = (int(s) for s in out_shape)
-    R, _ = pixel_map_3d(vertex, out_shape, fill_max_steps)
-    flat = sensor_px[0].astype(np.int64) + W * (sensor_px[1].astype(np.int64) + H * sensor_px[2].astype(np.int64))
-    Rs = R[flat]
-    ns = flat.size
-    nnz = np.diff(Rs.indptr)
-    K = max(1, int(nnz.max()))
-    idx = np.zeros((K, ns), dtype=np.int32)
-    w = np.zeros((K, ns), dtype=f32)
-    for s_ in range(ns):
-        a, b = Rs.indptr[s_], Rs.indptr[s_ + 1]
-        idx[:b - a, s_] = Rs.indices[a:b]
-        w[:b - a, s_] = Rs.data[a:b]
-    return idx, w

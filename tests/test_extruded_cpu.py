@@ -78,3 +78,45 @@ def test_six_face_neighbour_table_reproduces_the_extruded_matvec(cyl3d):
         ok = nbr6[f] >= 0
         y = y + np.where(ok, coff[f] * x[np.where(ok, nbr6[f], 0)], 0)
     assert rel_l2(y.reshape(nz, cd.N), ee.spmv(cd, off, offz, A, x.reshape(nz, cd.N))) < 1e-6
+
+
+def test_cylinder3d_observations_from_the_reference_state(golden):
+    """CylinderJet3D observation path (extract_global_3d_obs, obs_extraction.py:60-150): rendered-voxel map of the extruded
+    5-block domain (6-corner splat of the reference's 3-D kernel, 16 fill sweeps) read at 16 x 151 sensor voxels, incl. the
+    reference's raw ``view`` of the [sensor, component] axes; states and observations of the unmodified reference
+    (tests/golden/cyl3d_env.npz: after reset and after the first env.step)."""
+    import torch
+    from fluidgym_b200.envs.cylinder import CylinderJet2DEnv
+    from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
+    from fluidgym_b200.sensors import pixel_map_extruded
+    fx = golden("cyl3d_env.npz")
+    spec = make_cylinder_domain(8)
+    nz, n_jets, per_agent, H, L = 8, 8, 2, 4.1, 22.0
+    res = 8
+    rs = (int(res * 4 / H * L), res * 4, res * 4)                       # cylinder_env_base.py:235-240
+    R, level = pixel_map_extruded([b.vertex for b in spec.blocks], np.linspace(-2.0, 2.0, nz + 1, dtype=np.float32), rs, 16)
+    assert (level >= 0).all()
+    e = object.__new__(CylinderJet2DEnv)
+    e.cylinder_diameter = 1.0
+    xy = CylinderJet2DEnv.sensor_locations_physical(e)                  # [2, 151] physical sensor positions (shared with 2-D)
+    nsz = n_jets * per_agent
+    sz = torch.linspace(-H / 2, H / 2, nsz + 1)[:-1] + H / (2 * nsz)    # jet_cylinder_env_3d.py:289-301
+    pc = torch.stack([xy[0].unsqueeze(0).expand(nsz, -1).T, xy[1].unsqueeze(0).expand(nsz, -1).T, sz.unsqueeze(1).expand(-1, xy.shape[1]).T])
+    pc[0] = (pc[0] + 2.0) * ((rs[0] - 1) / (L - 2.0))
+    pc[1] = (pc[1] + H / 2) * ((rs[1] - 1) / H)
+    pc[2] = (pc[2] + H / 2) * ((rs[1] - 1) / H)                         # sic: render_shape[1] for z as well (cylinder_env_base.py:445-447)
+    gc = torch.round(pc).to(torch.int64)
+    gc = torch.stack([gc[c].reshape(-1, nsz).T for c in range(3)]).flatten(start_dim=1).numpy()      # z-major sensor order
+    flat = gc[0] + rs[0] * (gc[1] + rs[1] * gc[2])
+    Rs = R[flat]
+    for tag in ("reset", "env0"):
+        u, p = fx[f"{tag}_u"].reshape(3, -1), fx[f"{tag}_p"].reshape(-1)
+        us = (Rs @ u.T.astype(np.float64)).astype(np.float32)           # [sensors, 3]
+        ps = (Rs @ p.astype(np.float64)).astype(np.float32)
+        ov = torch.from_numpy(us).contiguous().view(nsz, 3, -1).view(n_jets, per_agent, 3, -1).numpy()
+        op = ps.reshape(nsz, -1).reshape(n_jets, per_agent, -1)
+        ref_v = fx["reset_obs_velocity"] if tag == "reset" else fx["step0_obs_velocity"]
+        ref_p = fx["reset_obs_pressure"] if tag == "reset" else fx["step0_obs_pressure"]
+        assert ov.shape == ref_v.shape == (8, 2, 3, 151)
+        assert np.abs(ov - ref_v).max() < 5e-5 * max(1.0, np.abs(ref_v).max())
+        assert np.abs(op - ref_p).max() < 5e-5 * max(1.0, np.abs(ref_p).max())
