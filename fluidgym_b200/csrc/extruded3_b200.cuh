@@ -3,7 +3,7 @@
 //
 // STATUS: operator layer.  The per-cell functions below are __host__ __device__ so that tests/test_extruded_host.py can
 // execute exactly this code on the CPU (through tests/cpu_harness/extruded_host.cu) and compare it with the numpy
-// specification tests/extruded_eval.py, which is pinned to an op trace of the unmodified reference on CylinderJet3D-easy
+// specification oracle/extruded_eval.py, which is pinned to an op trace of the unmodified reference on CylinderJet3D-easy
 // (tests/golden/cyl3d_substep*.npz).  The launch glue at the end of this file has NOT run on a GPU yet: no environment is
 // registered on it and no GPU test depends on it.
 //

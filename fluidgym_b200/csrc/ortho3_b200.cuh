@@ -2,7 +2,7 @@
 // reference: the same K.cu kernels with DIMS = 3).  Included at the end of piso_b200.cu (one translation unit, shared
 // error handling / reductions).  On a rectilinear grid every off-diagonal metric coefficient is exactly zero, so the
 // deferred non-orthogonal corrections of the 2-D path vanish (`if (alpha != 0)`, K.cu:3772) and the matrices are
-// plain ELL(7) on a 6-face neighbour table.  Specification: tests/box3d_eval.py (validated against a trace of the
+// plain ELL(7) on a 6-face neighbour table.  Specification: oracle/box3d_eval.py (validated against a trace of the
 // reference on a 32 x 32 x 32 channel to 1e-7 per operator).
 //
 // Large single environments do not fit a thread-block cluster, so the Krylov solvers here are persistent

@@ -1947,7 +1947,7 @@ __global__ void k_sample_sensors(const float *__restrict__ field, int C, int N, 
 // ------------------------------------------------------------------------------------------------
 // Reverse-mode adjoint of one PISO substep (replaces the *_GRAD kernels K.cu:3884-4090, 4403-4491,
 // 4982-5130, 5258-5385, 5438-5509, 6265-6309 and the python glue DIFF.py:516-1808).  Specification:
-// tests/adjoint_eval.py (float64 numpy, validated against finite differences).  Every forward gather
+// oracle/adjoint_eval.py (float64 numpy, validated against finite differences).  Every forward gather
 // y_i += w * x[j] becomes the scatter xbar[j] += w * ybar_i with red.global.add.f32; the two linear solves
 // become solves with the transposed operator by the same on-chip Krylov kernels.
 // All kernels: one thread per (cell, environment).

@@ -1,8 +1,10 @@
-"""float64 numpy statement of one PISO substep on the compiled tables and of its hand-derived reverse-mode
+"""TEST INFRASTRUCTURE ONLY (part of the CPU oracle; never imported by the product package fluidgym_b200).
+
+float64 numpy statement of one PISO substep on the compiled tables and of its hand-derived reverse-mode
 adjoint (test helper, CPU only).
 
 This is the *specification* of the adjoint CUDA kernels (fluidgym_b200/csrc, fgb_*_adjoint): the same
-table-driven formulas as tests/table_eval.py, in float64 with exact dense linear solves so that the VJP can
+table-driven formulas as oracle/table_eval.py, in float64 with exact dense linear solves so that the VJP can
 be validated against central finite differences to ~1e-7 (tests/test_adjoint_cpu.py).  The CUDA adjoint
 kernels are then compared op by op against these functions on the GPU.
 

@@ -1,6 +1,8 @@
-"""float32 numpy statement of the PISO substep on a 3-D single-block ORTHOGONAL box (periodic or wall-bounded per
+"""TEST INFRASTRUCTURE ONLY (part of the CPU oracle; never imported by the product package fluidgym_b200).
+
+float32 numpy statement of the PISO substep on a 3-D single-block ORTHOGONAL box (periodic or wall-bounded per
 axis) -- the specification of the D = 3 kernels (fluidgym_b200/csrc/piso3d_b200.cu), written against the same
-reference formulas as tests/table_eval.py (K.cu:495-537 contravariant fluxes, :1224-1466 Laplace coefficients,
+reference formulas as oracle/table_eval.py (K.cu:495-537 contravariant fluxes, :1224-1466 Laplace coefficients,
 :3617-3880 C, :4296-4400 RHS, :4812-4978 P, :5136-5255 HbyA, :5389-5434 divergence, :816-849 + :5962-5995
 corrector) with the metric tensors restricted to their diagonal: on a rectilinear grid every off-diagonal
 (non-orthogonal) coefficient is exactly zero, so the deferred corrections vanish (`if (alpha != 0)`, K.cu:3772).

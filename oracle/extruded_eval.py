@@ -1,11 +1,13 @@
-"""float32 numpy statement of the PISO operators on a z-EXTRUDED multi-block domain (CylinderJet3D, Airfoil3D: the 2-D
+"""TEST INFRASTRUCTURE ONLY (part of the CPU oracle; never imported by the product package fluidgym_b200).
+
+float32 numpy statement of the PISO operators on a z-EXTRUDED multi-block domain (CylinderJet3D, Airfoil3D: the 2-D
 multi-block grid repeated over nz uniform, periodic z planes; envs/cylinder/grid.py:298, shapes.py:641-676) -- test helper,
 CPU only, the specification for the D = 3 non-orthogonal kernels that are the next row of SURVEY section 8(f).
 
 The metric tensor of an extruded cell is block diagonal, M3 = diag(M2, hz): det3 = hz det2, alpha3^{ij} = hz alpha2^{ij} in
 the plane, alpha3^{zz} = det2 / hz and alpha3^{xz} = alpha3^{yz} = 0, so every non-orthogonal (corner) term of the reference's
 DIMS = 3 kernels lives in the x-y plane (`if (alpha != 0)`, K.cu:3772).  Rows are divided by det3, hence all in-plane
-coefficients equal the 2-D ones of tests/table_eval.py (compiled tables of fluidgym_b200.domain.CompiledDomain) and the
+coefficients equal the 2-D ones of oracle/table_eval.py (compiled tables of fluidgym_b200.domain.CompiledDomain) and the
 z faces add  +-1/4 (u_z,P + u_z,N) / hz - nu / hz^2  off the diagonal and  2 nu / hz^2 + 1/2 (F_z+ - F_z-) / (det2 hz)  on it.
 Validated against an op trace of the unmodified reference on CylinderJet3D-easy (resolution 8, 5 blocks x 8 planes,
 tests/golden/cyl3d_substep0.npz) in tests/test_extruded_cpu.py.

@@ -1,4 +1,6 @@
-"""numpy evaluation of the compiled domain tables (test helper, CPU only).
+"""TEST INFRASTRUCTURE ONLY (part of the CPU oracle; never imported by the product package fluidgym_b200).
+
+numpy evaluation of the compiled domain tables (test helper, CPU only).
 
 States, in vectorised numpy, exactly what each CUDA kernel in fluidgym_b200/csrc computes from the
 tables of ``fluidgym_b200.domain.CompiledDomain``.  Used by the CPU test-suite to check the table

@@ -2,7 +2,7 @@
 """Reduce the output of ``oracle/ref_harness.py --env CylinderJet3D-easy-v0 --tag cyl3d --kw '{"resolution":8,"n_jets":8}'
 --env-steps 1 --time-steps 1 --trace-substeps 2`` (the UNMODIFIED reference run on a B200: 5 blocks x 8 z-planes = 15 872
 cells, pressure_non_ortho_steps = 4) to ``tests/golden/cyl3d_substep{0,1}.npz``.  Fields are stored in the "planes" layout of
-tests/extruded_eval.py ([C, nz, N2], N2 = block-major 2-D cell index of make_cylinder_domain(8)); the CSR matrices of substep 0
+oracle/extruded_eval.py ([C, nz, N2], N2 = block-major 2-D cell index of make_cylinder_domain(8)); the CSR matrices of substep 0
 keep the reference's global ordering together with the permutation ``glob`` [nz, N2].  Test infrastructure only."""
 import json
 import os

@@ -1,4 +1,4 @@
-"""The hand-derived reverse-mode adjoint of one PISO substep (tests/adjoint_eval.py, the float64 numpy
+"""The hand-derived reverse-mode adjoint of one PISO substep (oracle/adjoint_eval.py, the float64 numpy
 specification of the CUDA adjoint kernels) against central finite differences: directional derivatives of a
 random linear functional of (u_out, p_out) w.r.t. u, p_prev and the boundary velocities."""
 import numpy as np

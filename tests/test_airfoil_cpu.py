@@ -60,7 +60,7 @@ def test_oracle_predictor_with_two_nonorthogonal_iterations(setup):
 
 
 def test_table_kernels_specification_matches_oracle_on_the_c_mesh(setup):
-    """The neighbour-table formulation the CUDA kernels implement (tests/table_eval.py) against the literal
+    """The neighbour-table formulation the CUDA kernels implement (oracle/table_eval.py) against the literal
     oracle on a domain with rotated block connections and a wake cut."""
     import table_eval as te
     cd, fx, orc = setup

@@ -1,5 +1,5 @@
 """D = 3 (turbulent channel flow): grid generator, box-domain tables and the float32 numpy specification of the 3-D
-orthogonal PISO operators (tests/box3d_eval.py) against a trace of the unmodified reference on a 32 x 32 x 32 channel
+orthogonal PISO operators (oracle/box3d_eval.py) against a trace of the unmodified reference on a 32 x 32 x 32 channel
 (tests/golden/tcf32_*.npz: TCFSmall3D-both-easy-v0 with resolution 32/33, Reichardt profile + 5 % noise)."""
 import json
 import os
@@ -137,7 +137,7 @@ def rbc3d(golden):
 
 @pytest.mark.parametrize("s", [0, 1])
 def test_scalar_specification_matches_reference_trace(rbc3d, golden, s):
-    """tests/box3d_eval.py::assemble_scalar / buoyancy_source and the operators fed by the buoyancy source field against
+    """oracle/box3d_eval.py::assemble_scalar / buoyancy_source and the operators fed by the buoyancy source field against
     the op trace of the unmodified reference on RBC3D (16 x 10 x 16 cells, tests/golden/rbc3d_substep*.npz)."""
     box, meta, (nz, ny, nx) = rbc3d
     fx = golden(f"rbc3d_substep{s}.npz")

@@ -1,5 +1,5 @@
 """z-extruded multi-block domains (CylinderJet3D / Airfoil3D): the float32 numpy specification
-tests/extruded_eval.py -- 2-D compiled tables + uniform periodic z faces -- against an op trace of the UNMODIFIED reference on
+oracle/extruded_eval.py -- 2-D compiled tables + uniform periodic z faces -- against an op trace of the UNMODIFIED reference on
 CylinderJet3D-easy-v0 with resolution 8 (tests/golden/cyl3d_substep*.npz, generated on a B200 by oracle/ref_harness.py and
 tests/golden/extract_cyl3d_fixtures.py).  This pins the operator the D = 3 non-orthogonal kernels have to implement."""
 import numpy as np

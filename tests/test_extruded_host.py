@@ -1,6 +1,6 @@
 """The per-cell code of the D = 3 extruded-domain kernels (fluidgym_b200/csrc/extruded3_b200.cuh, __host__ __device__) executed
 ON THE CPU through tests/cpu_harness/extruded_host.cu and compared with the op trace of the unmodified reference on
-CylinderJet3D-easy (tests/golden/cyl3d_substep*.npz) and with the numpy specification tests/extruded_eval.py.  This verifies
+CylinderJet3D-easy (tests/golden/cyl3d_substep*.npz) and with the numpy specification oracle/extruded_eval.py.  This verifies
 the arithmetic of the kernels without a GPU; their launch glue has not run on a GPU yet."""
 import ctypes as C
 import os

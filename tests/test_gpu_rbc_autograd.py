@@ -1,6 +1,6 @@
 """Differentiability of the Rayleigh-Benard path: the CUDA adjoint of the substep with passive scalar and buoyancy
 (fgb_piso_substep_backward_scalar through fluidgym_b200.autograd.PISOSubstepScalar) against (i) the float64 numpy
-specification (tests/adjoint_eval.py::substep_scalar_vjp, itself validated against finite differences on the CPU) and
+specification (oracle/adjoint_eval.py::substep_scalar_vjp, itself validated against finite differences on the CPU) and
 (ii) central finite differences of the CUDA forward through ``RBC2DEnv.step`` (reward w.r.t. the heater actions)."""
 import numpy as np
 import pytest

@@ -1,5 +1,5 @@
 """The table compiler (fluidgym_b200.domain) against the literal oracle: every table-driven op,
-evaluated in numpy exactly as the CUDA kernels evaluate it (tests/table_eval.py), must reproduce the
+evaluated in numpy exactly as the CUDA kernels evaluate it (oracle/table_eval.py), must reproduce the
 oracle's per-cell walk.  Bar: fp32 round-off (1e-6 relative)."""
 import numpy as np
 import pytest
