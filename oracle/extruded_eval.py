@@ -138,3 +138,57 @@ def correct(cd, hb, p, A, hz):
         out[:2, k] = te.correct(cd, hb[:2, k], p[k], A[k])
     out[2] = hb[2] - (f32(1) / A) * (f32(0.5) * (_zn(p, 1) - _zn(p, -1)) / hz)
     return out.astype(f32)
+
+
+# ---- boundary hooks of the 3-D cylinder (jets + outflow) --------------------------------------------------------------
+def _flux_weights(cd):
+    """signed in-plane boundary-flux weights [2, NB2] per unit plane spacing: F_b = hz * (fw[0] u_b + fw[1] v_b)"""
+    NB = cd.NB
+    face = cd.b_face[:NB].astype(np.int64)
+    ax = face >> 1
+    sign = np.where(face & 1, 1.0, -1.0).astype(f32)
+    j = np.arange(NB)
+    bm, bd = cd.b_minv[:, :NB], cd.b_det[:NB]
+    return np.stack([bd * bm[2 * ax, j] * sign, bd * bm[2 * ax + 1, j] * sign]).astype(f32)
+
+
+def balance_fluxes(cd, bvel, free, hz, tol):
+    """balance_boundary_fluxes (SIM.py:188-224) on [3, nz, NB2] boundary values: the velocities of the ``free`` faces (bool [NB2],
+    all planes) are scaled by -(flux through the other prescribed faces) / (flux through the free faces) unless the imbalance is
+    below 0.01 tol."""
+    fw = _flux_weights(cd)
+    fl = (bvel[0] * fw[0] + bvel[1] * fw[1]) * f32(hz)
+    fixed, var = fl[:, ~free].sum(dtype=np.float64), fl[:, free].sum(dtype=np.float64)
+    out = bvel.copy()
+    if not abs(fixed + var) <= tol * 0.01:
+        out[:, :, free] *= f32(-fixed / var)
+    return out
+
+
+def apply_jets(cd, bvel, control, jet_faces, jet_templ, out_mask, hz):
+    """CylinderJetEnv3D._apply_action (jet_cylinder_env_3d.py:399-424): control [nz] (the smoothed action of the jet that owns
+    the plane), jet faces take template * control in every plane (z component 0), then the jets AND the outflow are rescaled for a
+    zero net boundary flux (tol 1e-7)."""
+    out = bvel.copy()
+    for k in range(out.shape[1]):
+        out[:2, k][:, jet_faces] = jet_templ * f32(control[k])
+        out[2, k][jet_faces] = 0
+    free = out_mask.copy()
+    free[jet_faces] = True
+    return balance_fluxes(cd, out, free, hz, 1e-7)
+
+
+def update_outflow(cd, u, bvel, dt, out_mask, hz, char_vel=(1.0, 0.0), tol=1e-5):
+    """update_advective_boundaries + balance_boundary_fluxes (SIM.py:188-393) of the "PRE" hook: relaxation of the outflow values
+    towards the adjacent cell with weight 1 - 1 / (1 + 2 dt U_adv) for all three components, then the outflow alone is rescaled."""
+    NB = cd.NB
+    o = np.nonzero(out_mask)[0]
+    ax = (cd.b_face[:NB].astype(np.int64) >> 1)[o]
+    bm = cd.b_minv[:, :NB]
+    adv = bm[2 * ax, o] * f32(char_vel[0]) + bm[2 * ax + 1, o] * f32(char_vel[1])
+    w = f32(1) - f32(1) / (f32(1) + f32(2) * f32(dt) * adv)
+    cells = cd.b_cell[:NB][o]
+    out = bvel.copy()
+    for c in range(3):
+        out[c][:, o] = out[c][:, o] - w * (out[c][:, o] - u[c][:, cells])
+    return balance_fluxes(cd, out, out_mask, hz, tol)

@@ -160,3 +160,28 @@ def test_wall_forces_per_plane_equal_the_reference_force_function(golden):
     mine = torch.stack([DifferentiableRollout._forces_torch(env, u[:, k][None], p[k][None], bv[:, k][None])[0] for k in range(nz)], dim=1) * hz
     assert float(ref.abs().max()) > 1e-2
     assert torch.allclose(mine, ref, rtol=2e-5, atol=1e-6)
+
+
+def test_cylinder3d_boundary_hooks_reproduce_the_reference_boundary_values(cyl3d, golden):
+    """From the reference's reset state and its first action to the boundary velocities its first substep saw: action smoothing
+    (0.1), spanwise jets from the 2-D templates, flux balance over jets + outflow, advective outflow update + outflow balance."""
+    import torch
+    from fluidgym_b200.envs.cylinder import CylinderJet2DEnv
+    from fluidgym_b200.envs.cylinder_domain import WAKE, make_cylinder_domain
+    cd = cyl3d
+    spec = make_cylinder_domain(8)
+    env = object.__new__(CylinderJet2DEnv)
+    env.spec, env.cd, env.device, env.jet_angle = spec, cd, torch.device("cpu"), 10.0
+    CylinderJet2DEnv._setup_jets(env)
+    jf, jt = env.jet_faces.numpy().astype(np.int64), env.jet_templ.numpy()
+    fx, s0 = golden("cyl3d_env.npz"), golden("cyl3d_substep0.npz")
+    hz = float(s0["hz"][0])
+    out = np.zeros(cd.NB, bool)
+    o = cd.boff[WAKE, 1]
+    out[o:o + spec.blocks[WAKE].ny] = True
+    control = CylinderJet2DEnv.action_smoothing_alpha * fx["actions"][0].reshape(-1)          # last control = 0 after reset; one jet per plane
+    assert not fx["reset_bvel"][:, :, jf].any()
+    bv = ee.apply_jets(cd, fx["reset_bvel"], control, jf, jt, out, hz)
+    bv = ee.update_outflow(cd, s0["u_in"], bv, float(s0["dt"][0]), out, hz)
+    assert np.abs(bv[:, :, jf] - s0["bvel"][:, :, jf]).max() < 1e-7
+    assert np.abs(bv - s0["bvel"]).max() < 1e-6
