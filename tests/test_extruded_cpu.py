@@ -99,22 +99,17 @@ def test_cylinder3d_observations_from_the_reference_state(golden):
     e = object.__new__(CylinderJet2DEnv)
     e.cylinder_diameter = 1.0
     xy = CylinderJet2DEnv.sensor_locations_physical(e)                  # [2, 151] physical sensor positions (shared with 2-D)
+    from fluidgym_b200.envs.spanwise import global_obs_from_samples, spanwise_sensor_voxels
     nsz = n_jets * per_agent
-    sz = torch.linspace(-H / 2, H / 2, nsz + 1)[:-1] + H / (2 * nsz)    # jet_cylinder_env_3d.py:289-301
-    pc = torch.stack([xy[0].unsqueeze(0).expand(nsz, -1).T, xy[1].unsqueeze(0).expand(nsz, -1).T, sz.unsqueeze(1).expand(-1, xy.shape[1]).T])
-    pc[0] = (pc[0] + 2.0) * ((rs[0] - 1) / (L - 2.0))
-    pc[1] = (pc[1] + H / 2) * ((rs[1] - 1) / H)
-    pc[2] = (pc[2] + H / 2) * ((rs[1] - 1) / H)                         # sic: render_shape[1] for z as well (cylinder_env_base.py:445-447)
-    gc = torch.round(pc).to(torch.int64)
-    gc = torch.stack([gc[c].reshape(-1, nsz).T for c in range(3)]).flatten(start_dim=1).numpy()      # z-major sensor order
+    gc = spanwise_sensor_voxels(xy, nsz, H, L, rs).numpy()              # z-major sensor order
     flat = gc[0] + rs[0] * (gc[1] + rs[1] * gc[2])
     Rs = R[flat]
     for tag in ("reset", "env0"):
         u, p = fx[f"{tag}_u"].reshape(3, -1), fx[f"{tag}_p"].reshape(-1)
         us = (Rs @ u.T.astype(np.float64)).astype(np.float32)           # [sensors, 3]
         ps = (Rs @ p.astype(np.float64)).astype(np.float32)
-        ov = torch.from_numpy(us).contiguous().view(nsz, 3, -1).view(n_jets, per_agent, 3, -1).numpy()
-        op = ps.reshape(nsz, -1).reshape(n_jets, per_agent, -1)
+        g = global_obs_from_samples(torch.from_numpy(us)[None], torch.from_numpy(ps)[None], n_jets, per_agent)
+        ov, op = g["velocity"][0].numpy(), g["pressure"][0].numpy()
         ref_v = fx["reset_obs_velocity"] if tag == "reset" else fx["step0_obs_velocity"]
         ref_p = fx["reset_obs_pressure"] if tag == "reset" else fx["step0_obs_pressure"]
         assert ov.shape == ref_v.shape == (8, 2, 3, 151)

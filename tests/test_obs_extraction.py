@@ -91,3 +91,17 @@ def test_equal_to_the_reference_functions():
         mine = extract_moving_window_3d(f, n, w, k)
         for b in range(2):
             assert torch.equal(mine[b], ox.extract_moving_window_3d(f[b], n_agents=n, agent_width=w, n_agents_per_window=k))
+
+
+def test_spanwise_local_windows_equal_the_reference():
+    """transform_global_to_local_obs_3d (CylinderJet3D / Airfoil3D multi-agent observations)"""
+    ox = _reference()
+    from fluidgym_b200.envs.spanwise import local_obs_windows
+    torch.manual_seed(2)
+    for n_agents, window in ((8, 3), (8, 1), (6, 5)):
+        g = {"velocity": torch.rand(2, n_agents, 2, 3, 11), "pressure": torch.rand(2, n_agents, 2, 11)}
+        mine = local_obs_windows(g, window)
+        for b in range(2):
+            ref = ox.transform_global_to_local_obs_3d({k: v[b] for k, v in g.items()}, local_obs_window=window, n_agents=n_agents)
+            for k in g:
+                assert torch.equal(mine[k][b], ref[k]), (n_agents, window, k)
