@@ -76,4 +76,10 @@ def _register_defaults():
         register(f"RBC3D-{level}-v0", RBC3DEnv, **{**RBC_3D_DEFAULT_CONFIG, "rayleigh_number": ra, "adaptive_cfl": 0.5})
         register(f"RBC3D-wide-{level}-v0", RBC3DEnv, **{**RBC_3D_DEFAULT_CONFIG, "aspect_ratio": 2, "n_heaters": 16, "rayleigh_number": ra,
                                                         "adaptive_cfl": 0.5})
+    from .envs.cylinder3d import CYLINDER_JET_3D_DEFAULT_CONFIG, CylinderJet3DEnv
+    # fluidgym/__init__.py:79-101.  Host side verified on the CPU against the reference's env.step; the CUDA launch path of the
+    # extruded domains has not run on a GPU yet -- not part of tests/test_gpu_all_envs.py until it has.
+    register("CylinderJet3D-easy-v0", CylinderJet3DEnv, **{**CYLINDER_JET_3D_DEFAULT_CONFIG, "reynolds_number": 100.0, "resolution": 24})
+    register("CylinderJet3D-medium-v0", CylinderJet3DEnv, **{**CYLINDER_JET_3D_DEFAULT_CONFIG, "reynolds_number": 250.0, "resolution": 32})
+    register("CylinderJet3D-hard-v0", CylinderJet3DEnv, **{**CYLINDER_JET_3D_DEFAULT_CONFIG, "reynolds_number": 500.0, "resolution": 48})
     register("CylinderJet2D-hard-v0", CylinderJet2DEnv, **{**CYLINDER_JET_2D_DEFAULT_CONFIG, "reynolds_number": 500.0, "resolution": 32})

@@ -284,5 +284,37 @@ extern "C" int fgb_extruded3_piso_substep(fgb_ortho3 *b, const fgb_extruded3_tab
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "fgb_extruded3_piso_substep: copy", ce);
     return FGB_OK;
 }
+
+// Simulation.make_divergence_free on an extruded domain (SIM.py:1320-1430): A = 1, the velocity itself is the pressure right-hand
+// side vector; p_nonortho_steps x [divergence + deferred non-orthogonal term of the current pressure, CG (zero start in the first
+// iteration, then restarted from the previous result), mean removal], one velocity correction.  The "PRE" hook (outflow update
+// with time step 1) is the caller's.
+extern "C" int fgb_extruded3_make_divergence_free(fgb_ortho3 *b, const fgb_extruded3_tables *xt, float *u, float *p, const float *bvel,
+                                                  int max_iter, fgb_stream_t s) {
+    if (!b || !xt || !u || !p || !bvel) return set_err(FGB_E_ARG, "fgb_extruded3_make_divergence_free: null argument");
+    if (b->t.N != xt->plane.N * xt->nz || b->slab.on) return set_err(FGB_E_ARG, "fgb_extruded3_make_divergence_free: handle / tables mismatch");
+    X3Tab x; x.t = xt->plane; x.nz = xt->nz; x.hz = xt->hz;
+    cudaStream_t st = STREAM(s);
+    const dim3 grid((unsigned)((x.t.N + 255) / 256), (unsigned)x.nz, (unsigned)b->B);
+    const size_t BN = (size_t)b->B * b->t.N;
+    int rc;
+    b->launches += 2;
+    k_fill<<<(unsigned)((BN + 255) / 256), 256, 0, st>>>(b->A, 1.0f, BN);
+    LAUNCH_CHECK("k_fill");
+    kx3_pressure_matrix<<<grid, 256, 0, st>>>(x, b->A, b->Poff, b->Pdiag);
+    LAUNCH_CHECK("kx3_pressure_matrix");
+    for (int ps = 0; ps < b->opt.p_nonortho_steps; ++ps) {
+        b->launches++;
+        kx3_divergence<<<grid, 256, 0, st>>>(x, u, bvel, p, b->A, b->div);
+        LAUNCH_CHECK("kx3_divergence");
+        if ((rc = fgb_ortho3_solve_pressure(b, p, ps == 0, 0 /* no residual reset here, SIM.py:1387-1396 */, max_iter > 0 ? max_iter : b->opt.max_iter, ps, nullptr, s))) return rc;
+    }
+    b->launches++;
+    kx3_correct<<<grid, 256, 0, st>>>(x, u, p, b->A, b->ures);
+    LAUNCH_CHECK("kx3_correct");
+    cudaError_t ce = cudaMemcpyAsync(u, b->ures, 3 * BN * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "fgb_extruded3_make_divergence_free: copy", ce);
+    return FGB_OK;
+}
 #endif  // X3_HOST_ONLY
 #endif  // __CUDACC__

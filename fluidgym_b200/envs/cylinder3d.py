@@ -1,0 +1,273 @@
+"""Batched ``CylinderJet3D`` environment (``envs/cylinder/jet_cylinder_env_3d.py`` + ``cylinder_env_base.py`` with ``ndims = 3``):
+the 5-block cylinder grid extruded over ``resolution`` periodic z planes (span 4 D), ``n_jets`` pairs of synthetic jets lined up
+along the span -- one agent per jet with ``use_marl=True`` --, drag / lift per plane, sensors read from the rendered voxel grid.
+
+STATUS: every host-side piece of this class (jets, flux balances, outflow update, CFL plan, forces, observations, rewards,
+multi-agent windows) runs on the CPU in tests/test_cylinder3d_cpu.py on top of a stand-in solver that executes the per-cell code
+of the CUDA kernels on the host, and reproduces the unmodified reference's first ``env.step`` (tests/golden/cyl3d_env.npz).  The
+CUDA launch path underneath (``ExtrudedPISO3D`` -> ``fgb_extruded3_*``) has NOT run on a GPU yet; the
+boundary / reward formulas here are torch expressions over a few thousand boundary values, to be fused into kernels once that
+path is measured.  All tensors carry a leading environment dimension.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ..sensors import sensor_tables_extruded
+from .common import DifferentiableRollout, build_wall_tables
+from .cylinder import CylinderJet2DEnv
+from .cylinder_domain import BOTTOM, LEFT, RIGHT, TOP, WAKE, make_cylinder_domain
+from .spanwise import global_obs_from_samples, local_obs_windows, spanwise_sensor_voxels
+
+CYLINDER_JET_3D_DEFAULT_CONFIG = {
+    "n_jets": 8, "reynolds_number": 1e2, "resolution": 24, "dt": 1e-2, "adaptive_cfl": 0.8, "step_length": 0.25, "lift_penalty": 1.0,
+    "episode_length": 80, "local_obs_window": 3, "local_reward_weight": 0.8, "local_2d_obs": False, "use_marl": False,
+}
+
+
+class CylinderJet3DEnv:
+    H, L, D, cylinder_diameter, U_mean, cylinder_offset_y = 4.1, 22.0, 4.0, 1.0, 1.0, 0.05
+    action_smoothing_alpha = 0.1
+    jet_angle = 10.0
+    metrics = ["drag", "lift"]
+
+    def __init__(self, n_envs: int = 1, n_jets=8, reynolds_number=1e2, resolution=24, dt=1e-2, adaptive_cfl=0.8, step_length=0.25,
+                 episode_length=80, lift_penalty=1.0, local_obs_window=3, use_marl=False, local_reward_weight=0.8, local_2d_obs=False,
+                 device="cuda:0", cd_ref=0.0, randomize_initial_state=False, enable_actions=True, compiled=None, solver_cls=None):
+        if n_jets < 1 or resolution % n_jets != 0:
+            raise ValueError("n_agents must be a positive integer that evenly dividescircle_resolution_angular.")
+        if local_2d_obs and not use_marl:
+            raise ValueError("Local 2D observations are only supported in multi-agent mode.")
+        self.n_envs, self.n_jets = int(n_envs), int(n_jets)
+        self.resolution, self.dt, self.cfl = int(resolution), float(dt), float(adaptive_cfl)
+        self.step_length, self.episode_length = float(step_length), int(episode_length)
+        self.lift_penalty, self.cd_ref = float(lift_penalty), float(cd_ref)
+        self.use_marl, self.local_reward_weight, self.local_2d_obs = bool(use_marl), local_reward_weight, bool(local_2d_obs)
+        self.local_obs_window = 1 if local_2d_obs else int(local_obs_window)
+        self.n_sensors_per_agent = 1 if local_2d_obs else 2
+        self.randomize_initial_state, self.enable_actions = randomize_initial_state, enable_actions
+        self.reynolds_number = float(reynolds_number)
+        self.device = torch.device(device)
+        if compiled is None:
+            spec = make_cylinder_domain(resolution, reynolds_number, self.U_mean, self.H, self.L, self.cylinder_offset_y)
+            cd = spec.prepare()
+        else:
+            spec, cd = compiled
+        self.spec, self.cd = spec, cd
+        self.nz = self.resolution                                   # grid.py:291-298: res_z = angular resolution, z in [-2, 2]
+        self.hz = self.D / self.nz
+        self.nz_per_agent = self.nz // self.n_jets
+        if solver_cls is None:
+            from ..extruded3d import ExtrudedPISO3D as solver_cls   # raises without a CUDA device: there is no CPU path
+        # cylinder_env_base.py:305-323: 2 correctors, 1 + 4 deferred non-orthogonal iterations, tolerances 1e-5 / 5e-7
+        self.solver = solver_cls(cd, self.nz, self.hz, self.n_envs, device=device, corrector_steps=2, advect_non_ortho_steps=1,
+                                 pressure_non_ortho_steps=4, advection_tol=1e-5, pressure_tol=5e-7, max_iter=5000)
+        out_mask = np.zeros(cd.NB, dtype=bool)
+        o = cd.boff[WAKE, 1]
+        out_mask[o:o + spec.blocks[WAKE].ny] = True
+        self.solver.setup_stepping(out_mask, (self.U_mean, 0.0))
+        CylinderJet2DEnv._setup_jets(self)                          # the 2-D templates, repeated in every plane (:328-396)
+        free = out_mask.copy()
+        free[self.jet_faces.cpu().numpy()] = True
+        self._free_jets = torch.from_numpy(free).to(self.device)
+        ring = [(LEFT, 1, False), (TOP, 2, False), (RIGHT, 0, True), (BOTTOM, 3, True)]
+        self._wall_t, self.wall = build_wall_tables(cd, spec, ring, self.device, 1.0 / (0.5 * self.U_mean ** 2 * self.cylinder_diameter))
+        self._setup_sensors()
+        B, dev = self.n_envs, self.device
+        self.last_control = torch.zeros(B, self.n_jets, device=dev)
+        self._zero_action = torch.zeros(B, self.n_jets, 1, device=dev)
+        self._bvel0 = torch.from_numpy(np.ascontiguousarray(cd.bvel0[:, :cd.NB])).to(dev)
+        self._reset_called, self._seed, self._n_steps, self.last_substeps = False, None, 0, 0
+
+    # ---- static tables ---------------------------------------------------------------------------------------------------
+    @property
+    def render_shape(self):
+        z = self.resolution * 4
+        return (int(z / self.H * self.L), z, z)
+
+    @property
+    def n_sensors_z(self):
+        return self.n_jets * self.n_sensors_per_agent
+
+    def _setup_sensors(self):
+        xy = CylinderJet2DEnv.sensor_locations_physical(self)
+        self.n_sensors_xy = int(xy.shape[1])
+        rs = self.render_shape
+        self.sensor_px = spanwise_sensor_voxels(xy, self.n_sensors_z, self.H, self.L, rs).numpy()
+        zv = np.linspace(-2.0, 2.0, self.nz + 1, dtype=np.float32)
+        idx, w = sensor_tables_extruded([b.vertex for b in self.spec.blocks], zv, rs, self.sensor_px, fill_max_steps=16)
+        self.sens_idx = torch.from_numpy(idx.astype(np.int64)).to(self.device)
+        self.sens_w = torch.from_numpy(w).to(self.device)
+
+    # ---- reference-shaped API --------------------------------------------------------------------------------------------
+    @property
+    def n_agents(self):
+        return self.n_jets if self.use_marl else 1
+
+    @property
+    def id(self):
+        return f"JetCylinder3D_Re{self.reynolds_number}"
+
+    @property
+    def initial_domain_id(self):
+        return f"cylinder_3D_Re{int(self.reynolds_number)}_Res{self.resolution}"
+
+    @property
+    def n_sim_steps(self):
+        return max(1, int(self.step_length / self.dt))
+
+    @property
+    def observation_space(self):
+        """jet_cylinder_env_3d.py:205-258 (per environment, per agent with use_marl)"""
+        from .. import spaces
+        inf, nxy, spa = float("inf"), self.n_sensors_xy, self.n_sensors_per_agent
+        if self.use_marl and self.local_2d_obs:
+            vs, ps = (nxy, 2), (nxy,)
+        elif self.use_marl:
+            vs, ps = (self.local_obs_window, spa, 3, nxy), (self.local_obs_window, spa, nxy)
+        else:
+            vs, ps = (self.n_jets, spa, 3, nxy), (self.n_jets, spa, nxy)
+        return spaces.Dict({"velocity": spaces.Box(-inf, inf, shape=vs), "pressure": spaces.Box(-inf, inf, shape=ps)})
+
+    @property
+    def action_space(self):
+        from .. import spaces
+        return spaces.Box(-1.0, 1.0, shape=(1,) if self.use_marl else (self.n_jets, 1))
+
+    def seed(self, seed: int):
+        self._seed = seed
+        self._np_rng = np.random.default_rng(seed)
+        self._torch_rng = torch.Generator(device=self.device).manual_seed(seed)
+
+    def sample_action(self):
+        if self._seed is None:
+            raise RuntimeError("Environment must be seeded before sampling actions")
+        return torch.rand(self.n_envs, self.n_jets, 1, device=self.device, generator=self._torch_rng) * 2 - 1
+
+    def set_state(self, u, p, bvel, last_control=None):
+        s = self.solver
+        for dst, src in ((s.u, u), (s.p, p), (s.bvel, bvel)):
+            src = torch.as_tensor(src, dtype=torch.float32, device=self.device)
+            src = src.reshape(dst.shape[1:]) if src.numel() == dst[0].numel() else src.reshape(dst.shape)
+            dst.copy_(src if src.dim() == dst.dim() else src.unsqueeze(0).expand_as(dst))
+        if last_control is not None:
+            self.last_control.copy_(torch.as_tensor(last_control, device=self.device).expand_as(self.last_control))
+        self._reset_called = True
+
+    def get_state(self):
+        s = self.solver
+        return dict(u=s.u.clone(), p=s.p.clone(), bvel=s.bvel.clone(), last_control=self.last_control.clone())
+
+    def reset(self, seed: int | None = None, randomize: bool | None = None):
+        if seed is None:
+            if self._seed is None:
+                raise ValueError("Seed must be provided either during reset or by calling seed().")
+        else:
+            self.seed(seed)
+        s = self.solver
+        randomize = self.randomize_initial_state if randomize is None else randomize
+        s.u.zero_()
+        s.p.zero_()
+        s.bvel.zero_()
+        s.bvel[:, :2] = self._bvel0[None, :, None, :]
+        s.make_divergence_free_with_hook(max_iter=1000)              # cylinder_env_base.py:325; SIM.py:1320-1430
+        self.last_control.zero_()
+        if randomize:
+            self._randomize_domain()
+        self._apply_action(torch.zeros_like(self.last_control))     # fluid_env.py:909
+        self._n_steps = 0
+        self._reset_called = True
+        return self._get_obs(), {}
+
+    def _randomize_domain(self):
+        """cylinder_env_base.py:364-404 (per-environment noise, common number of settling steps)"""
+        period = 1 / (0.3 * self.U_mean / self.cylinder_diameter)
+        max_n = 2 * int(period / self.step_length) - 1
+        n_steps = int(self._np_rng.integers(int(0.5 * max_n), max_n)) + 1
+        s = self.solver
+        s.u += torch.randn(s.u.shape, device=self.device, generator=self._torch_rng) * 0.025
+        s.p += torch.randn(s.p.shape, device=self.device, generator=self._torch_rng) * 0.025
+        for _ in range(n_steps):
+            s.single_step(self.dt, self.cfl)
+
+    def _apply_action(self, control: torch.Tensor):
+        """jet_cylinder_env_3d.py:399-424: every jet drives its ``nz_per_agent`` planes with the 2-D template (no spanwise
+        component), then jets and outflow are rescaled for a zero net boundary flux (tol 1e-7)."""
+        s = self.solver
+        per_plane = control.repeat_interleave(self.nz_per_agent, dim=1)                           # [B, nz]
+        jf = self.jet_faces.long()
+        s.bvel[:, :2, :, jf] = self.jet_templ[None, :, None, :] * per_plane[:, None, :, None]
+        s.bvel[:, 2, :, jf] = 0.0
+        s.balance_fluxes(self._free_jets, 1e-7)
+
+    def _drag_and_lift(self):
+        """Per-plane drag / lift coefficients [B, nz] each (cylinder_env_base.py:657-700, forces.py:278-377: the 2-D wall
+        traction of every plane times the plane spacing)."""
+        s = self.solver
+        B, nz, N2 = self.n_envs, self.nz, s.N2
+        u2 = s.u.view(B, 3, nz, N2)[:, :2].permute(0, 2, 1, 3).reshape(B * nz, 2, N2)
+        p2 = s.p.view(B * nz, N2)
+        b2 = s.bvel[:, :2].permute(0, 2, 1, 3).reshape(B * nz, 2, -1)
+        f = DifferentiableRollout._forces_torch(self, u2, p2, b2).view(B, nz, 2) * self.hz
+        return f[:, :, 0], f[:, :, 1]
+
+    def _sample(self, field: torch.Tensor) -> torch.Tensor:
+        """[B, C, N3] -> [B, C, n_sensors]: the rendered-voxel map evaluated at the sensor voxels only (static ELL rows)"""
+        return (field[:, :, self.sens_idx] * self.sens_w).sum(dim=2)
+
+    def _get_global_obs(self):
+        s = self.solver
+        us = self._sample(s.u).permute(0, 2, 1)                                                   # [B, sensors, 3]
+        ps = self._sample(s.p[:, None])[:, 0]
+        return global_obs_from_samples(us, ps, self.n_jets, self.n_sensors_per_agent, local_2d_obs=self.local_2d_obs)
+
+    def _get_local_obs(self):
+        loc = local_obs_windows(self._get_global_obs(), self.local_obs_window)
+        if self.local_2d_obs:                                                                     # window.squeeze(), :313-314
+            loc = {k: v.reshape(v.shape[0], v.shape[1], *[d for d in v.shape[2:] if d != 1]) for k, v in loc.items()}
+        return loc
+
+    def _get_obs(self):
+        return self._get_local_obs() if self.use_marl else self._get_global_obs()
+
+    def step(self, action):
+        if not self._reset_called:
+            raise RuntimeError("Environment must be reset before stepping. Call 'reset()' before'step()'.")
+        action = torch.as_tensor(action, dtype=torch.float32, device=self.device)
+        if action.shape != self._zero_action.shape:
+            raise ValueError(f"Action shape {action.shape} does not match expected shape {self._zero_action.shape}.")
+        if self._n_steps >= self.episode_length:
+            raise RuntimeError("Episode has already terminated. Call 'reset()' first.")
+        if self.use_marl and self.local_reward_weight is None:
+            raise ValueError("local_reward_weight must be set for multi-agent step.")
+        s = self.solver
+        a = action.reshape(self.n_envs, self.n_jets)
+        cds = torch.zeros(self.n_envs, self.nz, device=self.device)
+        cls_ = torch.zeros_like(cds)
+        nsub = 0
+        for _ in range(self.n_sim_steps):                                                         # cylinder_env_base.py:741-776
+            self.last_control = self.last_control + self.action_smoothing_alpha * (a - self.last_control)
+            if self.enable_actions:
+                self._apply_action(self.last_control)
+            nsub += s.single_step(self.dt, self.cfl)
+            cd_k, cl_k = self._drag_and_lift()
+            cds += cd_k
+            cls_ += cl_k
+        self.last_substeps = nsub
+        all_cds, all_cls = cds / self.n_sim_steps, cls_ / self.n_sim_steps
+        cd, cl = all_cds.sum(dim=1) / self.D, all_cls.sum(dim=1) / self.D                        # jet_cylinder_env_3d.py:431-452
+        reward = self.cd_ref - cd - self.lift_penalty * torch.abs(cl)
+        self._n_steps += 1
+        truncated = self._n_steps >= self.episode_length
+        info = {"drag": cd, "lift": cl}
+        if not self.use_marl:
+            info["all_cds"], info["all_cls"] = all_cds, all_cls
+            return self._get_global_obs(), reward, False, truncated, info
+        per = self.D / self.n_jets                                                                # :454-486
+        local_cd = all_cds.view(self.n_envs, self.n_jets, -1).sum(dim=2) / per
+        local_cl = all_cls.view(self.n_envs, self.n_jets, -1).sum(dim=2) / per
+        local = self.cd_ref - local_cd - self.lift_penalty * torch.abs(local_cl)
+        lw = float(self.local_reward_weight)
+        info["global_reward"] = reward
+        return self._get_local_obs(), lw * local + (1 - lw) * reward[:, None], False, truncated, info

@@ -1,6 +1,6 @@
 """Helpers shared by the environments whose agents are lined up along the span (z) of an extruded domain (CylinderJet3D,
 Airfoil3D; ``envs/util/obs_extraction.py:60-205`` of the reference), batched over a leading environment dimension.  Host-side
-pieces only -- the environments themselves wait for the first GPU run of the extruded solver path."""
+pieces, used by ``envs/cylinder3d.py``."""
 from __future__ import annotations
 
 import torch
@@ -20,14 +20,17 @@ def spanwise_sensor_voxels(xy_physical: torch.Tensor, n_sensors_z: int, H: float
     return torch.stack([gc[c].reshape(-1, n_sensors_z).T for c in range(3)]).flatten(start_dim=1)
 
 
-def global_obs_from_samples(u_s: torch.Tensor, p_s: torch.Tensor, n_agents: int, n_sensors_per_agent: int):
+def global_obs_from_samples(u_s: torch.Tensor, p_s: torch.Tensor, n_agents: int, n_sensors_per_agent: int, local_2d_obs: bool = False):
     """u_s [B, n_sensors, 3], p_s [B, n_sensors] sampled at ``spanwise_sensor_voxels`` -> the reference's global observation
     {"velocity": [B, n_agents, per_agent, 3, n_xy], "pressure": [B, n_agents, per_agent, n_xy]}.  NB the reference reshapes the
     [sensor, component] axes with a raw ``view`` (obs_extraction.py:134-135), i.e. the axis labelled "component" does not hold the
     components; reproduced."""
     B = u_s.shape[0]
     nsz = n_agents * n_sensors_per_agent
-    v = u_s.contiguous().view(B, nsz, 3, -1).view(B, n_agents, n_sensors_per_agent, 3, -1)
+    nd = 2 if local_2d_obs else 3                                     # local_2d_obs: x / y velocity only (obs_extraction.py:121-139)
+    v = u_s[:, :, :nd].contiguous().view(B, nsz, nd, -1).view(B, n_agents, n_sensors_per_agent, nd, -1)
+    if local_2d_obs:
+        v = v.permute(0, 1, 2, 4, 3)
     p = p_s.contiguous().view(B, nsz, -1).view(B, n_agents, n_sensors_per_agent, -1)
     return {"velocity": v, "pressure": p}
 

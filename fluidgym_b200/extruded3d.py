@@ -34,7 +34,104 @@ def extruded_neighbours(nbr2: np.ndarray, nz: int) -> np.ndarray:
     return np.ascontiguousarray(out.reshape(6, nz * N2).astype(np.int32))
 
 
-class ExtrudedPISO3D:
+class ExtrudedStepping:
+    """``Simulation.single_step`` around the extruded substep: the adaptive CFL plan (SIM.py:2004-2031), the "PRE" hook of the
+    cylinder / airfoil environments (advective outflow relaxation + flux balance, SIM.py:188-393, cylinder_env_base.py:277-300) and
+    the boundary-flux balance used by the actuators -- small torch expressions over the boundary faces ([B, 3, nz, NB2], a few
+    thousand values), device agnostic so that the very same code is exercised on the CPU against the reference's boundary values
+    (tests/test_cylinder3d_cpu.py).  The class that mixes this in provides ``cd, nz, hz, B, N2, NB2, device, u, p, bvel`` and
+    ``piso_substep(dt)``."""
+
+    def setup_stepping(self, out_mask: np.ndarray, char_vel=(1.0, 0.0)):
+        cd, NB, dev = self.cd, self.cd.NB, self.device
+        face = cd.b_face[:NB].astype(np.int64)
+        ax = face >> 1
+        sign = np.where(face & 1, 1.0, -1.0).astype(np.float32)
+        j = np.arange(NB)
+        bm, bd = np.asarray(cd.b_minv)[:, :NB], np.asarray(cd.b_det)[:NB]
+        fw = np.stack([bd * bm[2 * ax, j] * sign, bd * bm[2 * ax + 1, j] * sign]).astype(np.float32)
+        o = np.nonzero(np.asarray(out_mask).astype(bool))[0]
+        adv = (bm[2 * ax[o], o] * np.float32(char_vel[0]) + bm[2 * ax[o] + 1, o] * np.float32(char_vel[1])).astype(np.float32)
+        self._st = dict(fw=torch.from_numpy(fw).to(dev), out=torch.from_numpy(o).to(dev), adv=torch.from_numpy(adv).to(dev),
+                        out_cells=torch.from_numpy(np.asarray(cd.b_cell)[:NB][o].astype(np.int64)).to(dev),
+                        is_out=torch.from_numpy(np.asarray(out_mask).astype(bool)).to(dev),
+                        minv=torch.from_numpy(np.ascontiguousarray(cd.minv)).to(dev),
+                        b_minv=torch.from_numpy(np.ascontiguousarray(bm)).to(dev))
+
+    def balance_fluxes(self, free: torch.Tensor, tol: float):
+        """balance_boundary_fluxes (SIM.py:188-224): all components of the ``free`` faces (bool [NB2], every plane) are scaled by
+        -(flux through the other prescribed faces) / (flux through the free faces) unless the imbalance is below 0.01 tol."""
+        bv = self.bvel
+        fw = self._st["fw"]
+        fl = (bv[:, 0] * fw[0] + bv[:, 1] * fw[1]) * self.hz                                  # [B, nz, NB2]
+        var = fl[:, :, free].double().sum(dim=(1, 2))
+        fixed = fl[:, :, ~free].double().sum(dim=(1, 2))
+        ok = (fixed + var).abs() <= tol * 0.01
+        scale = torch.where(ok, torch.ones_like(var), -fixed / torch.where(ok, torch.ones_like(var), var)).float()
+        bv[:, :, :, free] = bv[:, :, :, free] * scale[:, None, None, None]
+
+    def update_outflow(self, dt: torch.Tensor, tol: float = 5e-6):
+        """update_advective_boundaries (SIM.py:228-393): the outflow values relax towards the adjacent cell with weight
+        1 - 1 / (1 + 2 dt U_adv), all three components; then the outflow alone is rescaled for a zero net flux."""
+        st, bv = self._st, self.bvel
+        w = 1.0 - 1.0 / (1.0 + 2.0 * dt.to(self.device, torch.float32)[:, None] * st["adv"][None])       # [B, n_out]
+        u4 = self.u.view(self.B, 3, self.nz, self.N2)
+        bo = bv[:, :, :, st["out"]]
+        bv[:, :, :, st["out"]] = bo - w[:, None, None, :] * (bo - u4[:, :, :, st["out_cells"]])
+        self.balance_fluxes(st["is_out"], tol)
+
+    def max_velocity(self) -> torch.Tensor:
+        """Domain.getMaxVelocity(True, True) (DS.cpp:1580-1612) -> [B]: max |computational velocity component| over cells and
+        prescribed faces; the z component of an extruded cell is w / hz."""
+        st = self._st
+        u4, bv = self.u.view(self.B, 3, self.nz, self.N2), self.bvel
+        mi, bm = st["minv"], st["b_minv"]
+        m = torch.stack([(mi[0] * u4[:, 0] + mi[1] * u4[:, 1]).abs().amax(dim=(1, 2)), (mi[2] * u4[:, 0] + mi[3] * u4[:, 1]).abs().amax(dim=(1, 2)),
+                         u4[:, 2].abs().amax(dim=(1, 2)) / self.hz,
+                         (bm[0] * bv[:, 0] + bm[1] * bv[:, 1]).abs().amax(dim=(1, 2)), (bm[2] * bv[:, 0] + bm[3] * bv[:, 1]).abs().amax(dim=(1, 2)),
+                         bv[:, 2].abs().amax(dim=(1, 2)) / self.hz])
+        return m.amax(dim=0)
+
+    def single_step(self, dt: float, cfl: float = 0.8, bc_tol: float = 5e-6) -> int:
+        """One solver step of length ``dt`` for every environment, split into CFL-limited substeps per environment (same
+        arithmetic as k_plan_substep); environments that are already done keep their state.  Returns the substep rounds."""
+        B = self.B
+        remaining = np.full(B, float(dt), dtype=np.float64)
+        rounds = 0
+        while True:
+            act = (remaining > 0.0) & ~(np.abs(remaining) <= 1e-8)
+            if not act.any():
+                return rounds
+            mv = self.max_velocity().detach().cpu().numpy().astype(np.float32)
+            ts = np.zeros(B, dtype=np.float64)
+            for b in np.nonzero(act)[0]:
+                rem = remaining[b]
+                if abs(mv[b]) <= 1e-8:
+                    ts[b] = rem
+                else:
+                    mts = np.float32(cfl) / mv[b]
+                    ts[b] = rem if float(mts) >= rem else rem / float(np.ceil(np.float32(rem) / mts))
+                remaining[b] = rem - ts[b]
+            keep = None
+            if not act.all():                       # finished environments ride along with a dummy step and are restored afterwards
+                idle = torch.from_numpy(np.nonzero(~act)[0]).to(self.device)
+                keep = (idle, self.u[idle].clone(), self.p[idle].clone(), self.bvel[idle].clone())
+                ts[~act] = ts[act].max()
+            dtv = torch.from_numpy(ts.astype(np.float32)).to(self.device)
+            self.update_outflow(dtv, bc_tol)
+            self.piso_substep(dtv)
+            if keep is not None:
+                idle, u0, p0, b0 = keep
+                self.u[idle], self.p[idle], self.bvel[idle] = u0, p0, b0
+            rounds += 1
+
+    def make_divergence_free_with_hook(self, max_iter: int = 1000, bc_tol: float = 5e-6):
+        """Simulation.make_divergence_free incl. its "PRE" hook with time step 1 (SIM.py:1335-1347)."""
+        self.update_outflow(torch.ones(self.B), bc_tol)
+        self.make_divergence_free(max_iter)
+
+
+class ExtrudedPISO3D(ExtrudedStepping):
     """State + solver for ``n_envs`` copies of an extruded domain: ``u [B,3,nz*N2]``, ``p [B,nz*N2]``, ``bvel [B,3,nz,NB2]``."""
 
     def __init__(self, cd: CompiledDomain, nz: int, hz: float, n_envs: int = 1, device="cuda:0", corrector_steps=2,
@@ -92,3 +189,7 @@ class ExtrudedPISO3D:
         dtc = dt.to(self.device, torch.float32).contiguous() if isinstance(dt, torch.Tensor) else torch.full((self.B,), float(dt), device=self.device)
         native.check(self.lib.fgb_extruded3_piso_substep(self.handle, C.byref(self.xtables), _ptr(self.u), _ptr(self.p), _ptr(self.bvel),
                                                          _ptr(dtc), self.stream), "fgb_extruded3_piso_substep")
+
+    def make_divergence_free(self, max_iter: int = 1000):
+        native.check(self.lib.fgb_extruded3_make_divergence_free(self.handle, C.byref(self.xtables), _ptr(self.u), _ptr(self.p), _ptr(self.bvel),
+                                                                 int(max_iter), self.stream), "fgb_extruded3_make_divergence_free")

@@ -149,8 +149,12 @@ def pixel_map_3d(vertex: np.ndarray, out_shape, fill_max_steps: int, n_corners: 
 def sensor_tables_3d(vertex: np.ndarray, out_shape, sensor_px: np.ndarray, fill_max_steps: int):
     """ELL tables (idx [K, n_s] int32, w [K, n_s] float32) of the rendered-voxel map at the sensor voxels
     ``sensor_px`` = [3, n_s] integer (x, y, z) voxel coordinates (envs/rbc/rbc_env_3d.py:183-203)."""
-    W, H, Z = (int(s) for s in out_shape)
     R, _ = pixel_map_3d(vertex, out_shape, fill_max_steps)
+    return _ell_rows_at_voxels(R, out_shape, sensor_px)
+
+
+def _ell_rows_at_voxels(R, out_shape, sensor_px):
+    W, H, Z = (int(s) for s in out_shape)
     flat = sensor_px[0].astype(np.int64) + W * (sensor_px[1].astype(np.int64) + H * sensor_px[2].astype(np.int64))
     Rs = R[flat]
     ns = flat.size
@@ -163,6 +167,12 @@ def sensor_tables_3d(vertex: np.ndarray, out_shape, sensor_px: np.ndarray, fill_
         idx[:b - a, s_] = Rs.indices[a:b]
         w[:b - a, s_] = Rs.data[a:b]
     return idx, w
+
+
+def sensor_tables_extruded(vertex2d_list, z_vertices: np.ndarray, out_shape, sensor_px: np.ndarray, fill_max_steps: int):
+    """sensor_tables_3d for a z-extruded multi-block domain (columns = plane * N2 + g)."""
+    R, _ = pixel_map_extruded(vertex2d_list, z_vertices, out_shape, fill_max_steps)
+    return _ell_rows_at_voxels(R, out_shape, sensor_px)
 
 
 def pixel_map_extruded(vertex2d_list, z_vertices: np.ndarray, out_shape, fill_max_steps: int, n_corners: int = 3 << 1):

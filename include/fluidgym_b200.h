@@ -355,6 +355,10 @@ typedef struct fgb_extruded3_tables {
 /* Simulation._PISO_split_step (SIM.py:1431-2002, non-orthogonal path; pressure_non_ortho_steps = 4 in 3-D, cylinder_env_base.py:317) */
 int fgb_extruded3_piso_substep(fgb_ortho3 *b, const fgb_extruded3_tables *x, float *u, float *p, const float *bvel, const float *dt,
                                fgb_stream_t s);
+/* Simulation.make_divergence_free (SIM.py:1320-1430) on an extruded domain: projection with A = 1, p_nonortho_steps deferred
+ * corrections; max_iter <= 0 takes the handle's option.  The outflow update of its "PRE" hook is the caller's. */
+int fgb_extruded3_make_divergence_free(fgb_ortho3 *b, const fgb_extruded3_tables *x, float *u, float *p, const float *bvel, int max_iter,
+                                       fgb_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -4,31 +4,22 @@ CylinderJet3D-easy (tests/golden/cyl3d_substep*.npz) and with the numpy specific
 the arithmetic of the kernels without a GPU; their launch glue has not run on a GPU yet."""
 import ctypes as C
 import os
-import subprocess
+import sys
 
 import numpy as np
 import pytest
 
 import extruded_eval as ee
 from conftest import ROOT, rel_l2
-from fluidgym_b200 import native
 
 f32 = np.float32
-FIELDS = ["nbr", "fl_comp", "minv", "det", "Cd", "Wp", "no_idx", "no_face", "no_gP", "no_gN", "no_wv", "nob_idx", "nob_w", "b_minv", "b_det",
-          "b_alpha", "b_cell", "b_face"]
+sys.path.insert(0, os.path.join(ROOT, "tests", "cpu_harness"))
+from extruded_standin import bicgstab as _bicgstab, build_harness, cg as _cg, csr as _csr, host_tables  # noqa: E402
 
 
 @pytest.fixture(scope="module")
 def harness():
-    src = os.path.join(ROOT, "tests", "cpu_harness", "extruded_host.cu")
-    out = os.path.join(ROOT, "tests", "_build", "libextruded_host.so")
-    os.makedirs(os.path.dirname(out), exist_ok=True)
-    hdr = os.path.join(ROOT, "fluidgym_b200", "csrc", "extruded3_b200.cuh")
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        subprocess.check_call([nvcc, "-x", "cu", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared",
-                               "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "fluidgym_b200", "csrc"), "-o", out, src])
-    return C.CDLL(out)
+    return build_harness()
 
 
 @pytest.fixture(scope="module")
@@ -36,15 +27,7 @@ def tables():
     """fgb_tables with HOST pointers into the numpy arrays of the compiled 2-D cylinder domain (resolution 8)"""
     from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
     cd = make_cylinder_domain(8).prepare()
-    keep = {}
-    t = native.Tables()
-    t.N, t.NB, t.K_no, t.K_nob, t.viscosity = cd.N, cd.NB, cd.K_no, cd.K_nob, float(cd.visc)
-    for name in FIELDS:
-        a = np.ascontiguousarray(getattr(cd, name))
-        if name == "b_face":
-            a = np.ascontiguousarray(a.astype(np.int8))
-        keep[name] = a
-        setattr(t, name, a.ctypes.data)
+    t, keep = host_tables(cd)
     return cd, t, keep
 
 
@@ -92,66 +75,6 @@ def test_cell_functions_match_reference_trace_and_specification(harness, tables,
     rhs2 = np.zeros((3, nz, N2), f32)
     harness.xh_setup_advection(C.byref(t), nz, C.c_float(hz), _p(u), _p(ustar), _p(bvel), C.c_float(dt), None, None, _p(rhs2), 0)
     assert rel_l2(rhs2, ee.adv_rhs(cd, u, ustar, bvel, dt)) < 5e-7
-
-
-def _csr(nbr6, coff, diag):
-    import scipy.sparse as sp
-    n = diag.size
-    rows, cols, vals = [np.arange(n)], [np.arange(n)], [diag.reshape(-1)]
-    for f in range(6):
-        ok = nbr6[f] >= 0
-        rows.append(np.nonzero(ok)[0]); cols.append(nbr6[f][ok]); vals.append(coff[f].reshape(-1)[ok])
-    return sp.csr_matrix((np.concatenate(vals).astype(f32), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
-
-
-def _bicgstab(M, b, tol, maxit=500):
-    """unpreconditioned BiCGStab, zero start, stop on ||r|| / sqrt(N) < tol (BICG.cu:237-376)"""
-    n = b.size
-    x = np.zeros(n, f32); r = b.copy(); rw = r.copy(); p = r.copy()
-    rho = alpha = omega = f32(1)
-    v = np.zeros(n, f32)
-    for i in range(maxit):
-        if np.sqrt(np.dot(r, r)) / np.sqrt(n) < tol:
-            return x, i
-        rho_new = np.dot(rw, r)
-        if i > 0:
-            p = r + (rho_new / rho) * (alpha / omega) * (p - omega * v)
-        rho = rho_new
-        v = M @ p
-        alpha = rho / np.dot(rw, v)
-        x = x + alpha * p
-        r = r - alpha * v
-        if np.sqrt(np.dot(r, r)) / np.sqrt(n) < tol:
-            return x, i + 1
-        tt = M @ r
-        omega = np.dot(tt, r) / np.dot(tt, tt)
-        x = x + omega * r
-        r = r - omega * tt
-    return x, maxit
-
-
-def _cg(M, b, x0, tol, reset=100, maxit=5000):
-    """CG with residual reset and mean removal (CG.cu:225-446, SIM.py:1908-1925)"""
-    n = b.size
-    x = x0.copy()
-    r = b - M @ x
-    p = r.copy()
-    rho = np.dot(r, r)
-    it = 0
-    for i in range(maxit):
-        if reset and (i + 1) % reset == 0:
-            r = b - M @ x; p = r.copy(); rho = np.dot(r, r)
-        Ap = M @ p
-        alpha = rho / np.dot(p, Ap)
-        x = x + alpha * p
-        r = r - alpha * Ap
-        rr = np.dot(r, r)
-        it = i + 1
-        if np.sqrt(rr) / np.sqrt(n) < tol:
-            break
-        p = r + (rr / rho) * p
-        rho = rr
-    return (x - x.mean()).astype(f32), it
 
 
 def test_substep_orchestration_reaches_the_reference_result(harness, tables, golden):
