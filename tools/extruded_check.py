@@ -1,10 +1,17 @@
-"""FIRST GPU RUN of the extruded D = 3 path (fluidgym_b200/extruded3d.py): one PISO substep from the state the unmodified
-reference traced on CylinderJet3D-easy (resolution 8; tests/golden/cyl3d_substep*.npz) against the reference's result.
-    python tools/extruded_check.py
-Expected: u within the CG tolerance ball (~1e-5), BiCGStab iterations 3,3,1 / CG iterations within a few percent of the reference."""
+"""FIRST GPU RUN of the extruded D = 3 path (fluidgym_b200/extruded3d.py, envs/cylinder3d.py) against the UNMODIFIED reference's
+CylinderJet3D-easy run at resolution 8 (tests/golden/cyl3d_substep*.npz, cyl3d_env.npz):
+  1. one PISO substep from the reference's traced state (twice, two environments per launch),
+  2. environment reset (projection with A = 1) against the reference's reset state,
+  3. one env.step (25 solver steps) from the reference's reset state with its action: state, reward, drag / lift, observations,
+  4. timing of env.step next to the reference's (tests/golden/cyl3d_meta.json: 1.08 substeps/s).
+    python tools/extruded_check.py [--json out.json]
+Prints one JSON line per stage and a final {"ok": bool, ...} verdict; exit code 0 iff every bar holds.  The bars are the ones of
+the CPU stand-in tests (tests/test_cylinder3d_cpu.py), where the same kernel cell code runs on the host."""
+import argparse
 import json
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -19,10 +26,14 @@ def rel(a, b):
     return float(np.linalg.norm(np.asarray(a, np.float64) - b) / np.linalg.norm(np.asarray(b, np.float64)))
 
 
-def main():
-    cd = make_cylinder_domain(8).prepare()
+def golden(name):
+    return np.load(os.path.join(ROOT, "tests", "golden", name))
+
+
+def check_substeps(cd, out):
+    ok = True
     for s in (0, 1):
-        fx = np.load(os.path.join(ROOT, "tests", "golden", f"cyl3d_substep{s}.npz"))
+        fx = golden(f"cyl3d_substep{s}.npz")
         nz, N2 = fx["A"].shape
         sol = ExtrudedPISO3D(cd, nz, float(fx["hz"][0]), n_envs=2)
         sol.u.copy_(torch.from_numpy(fx["u_in"]).reshape(1, 3, -1).cuda().expand_as(sol.u))
@@ -31,8 +42,82 @@ def main():
         sol.piso_substep(float(fx["dt"][0]))
         torch.cuda.synchronize()
         u, p = sol.u[0].cpu().numpy().reshape(3, nz, N2), sol.p[0].cpu().numpy().reshape(nz, N2)
-        print(json.dumps({"substep": s, "rel_l2_u": rel(u, fx["u1"]), "rel_l2_p": rel(p, fx["p1"]), "ref_bicg_iters": fx["bicg_iters"].tolist(),
-                          "ref_cg_iters": fx["cg_iters"].tolist(), "envs_equal": bool(torch.equal(sol.u[0], sol.u[1]))}))
+        line = {"stage": "substep", "substep": s, "rel_l2_u": rel(u, fx["u1"]), "rel_l2_p": rel(p, fx["p1"]),
+                "ref_bicg_iters": fx["bicg_iters"].tolist(), "ref_cg_iters": fx["cg_iters"].tolist(),
+                "envs_equal": bool(torch.equal(sol.u[0], sol.u[1]))}
+        line["ok"] = bool(np.isfinite(u).all() and line["rel_l2_u"] < 2e-5 and line["rel_l2_p"] < 5e-4 and line["envs_equal"])
+        ok &= line["ok"]
+        out.append(line)
+        print(json.dumps(line), flush=True)
+        del sol
+    return ok
+
+
+def check_env(compiled, out):
+    from fluidgym_b200.envs.cylinder3d import CylinderJet3DEnv
+    fx = golden("cyl3d_env.npz")
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "cyl3d_meta.json")))
+    env = CylinderJet3DEnv(n_envs=2, resolution=8, n_jets=8, compiled=compiled)
+    t0 = time.perf_counter()
+    obs, _ = env.reset(seed=42)
+    torch.cuda.synchronize()
+    t_reset = time.perf_counter() - t0
+    s = env.solver
+    line = {"stage": "reset", "seconds": t_reset, "bvel_abs": float(np.abs(s.bvel[0].cpu().numpy() - fx["reset_bvel"]).max()),
+            "rel_l2_u": rel(s.u[0].cpu().numpy().reshape(3, 8, -1), fx["reset_u"]), "rel_l2_p": rel(s.p[0].cpu().numpy().reshape(8, -1), fx["reset_p"]),
+            "obs_velocity_abs": float(np.abs(obs["velocity"][0].cpu().numpy() - fx["reset_obs_velocity"]).max()),
+            "obs_pressure_abs": float(np.abs(obs["pressure"][0].cpu().numpy() - fx["reset_obs_pressure"]).max())}
+    line["ok"] = bool(line["bvel_abs"] < 2e-6 and line["rel_l2_u"] < 3e-4 and line["rel_l2_p"] < 3e-4 and line["obs_velocity_abs"] < 1e-3
+                      and line["obs_pressure_abs"] < 2e-3)
+    ok = line["ok"]
+    out.append(line)
+    print(json.dumps(line), flush=True)
+
+    env.set_state(fx["reset_u"], fx["reset_p"], fx["reset_bvel"], last_control=0.0)
+    a = torch.from_numpy(fx["actions"][0])[None].expand(2, -1, -1).cuda()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    obs, reward, _, _, info = env.step(a)
+    torch.cuda.synchronize()
+    t_step = time.perf_counter() - t0
+    line = {"stage": "env.step", "seconds": t_step, "substeps": env.last_substeps, "substeps_per_s_x_envs": 2 * env.last_substeps / t_step,
+            "reference_substeps_per_s": meta["timing"]["substeps_per_s"],
+            "rel_l2_u": rel(s.u[0].cpu().numpy().reshape(3, 8, -1), fx["env0_u"]), "rel_l2_p": rel(s.p[0].cpu().numpy().reshape(8, -1), fx["env0_p"]),
+            "reward": float(reward[0]), "ref_reward": float(fx["step0_reward"]), "drag": float(info["drag"][0]), "ref_drag": float(fx["step0_info_drag"]),
+            "lift": float(info["lift"][0]), "ref_lift": float(fx["step0_info_lift"]),
+            "all_cds_abs": float(np.abs(info["all_cds"][0].cpu().numpy() - fx["step0_info_all_cds"]).max()),
+            "obs_velocity_abs": float(np.abs(obs["velocity"][0].cpu().numpy() - fx["step0_obs_velocity"]).max()),
+            "obs_pressure_abs": float(np.abs(obs["pressure"][0].cpu().numpy() - fx["step0_obs_pressure"]).max()),
+            "envs_equal": bool(torch.allclose(s.u[0], s.u[1], atol=1e-6))}
+    line["ok"] = bool(env.last_substeps == 25 and line["rel_l2_u"] < 1e-4 and line["rel_l2_p"] < 2e-3 and abs(line["reward"] - line["ref_reward"]) < 1e-3
+                      and abs(line["drag"] - line["ref_drag"]) < 1e-3 and abs(line["lift"] - line["ref_lift"]) < 1e-4 and line["all_cds_abs"] < 1e-3
+                      and line["obs_velocity_abs"] < 2e-4 and line["obs_pressure_abs"] < 2e-2)
+    ok &= line["ok"]
+    out.append(line)
+    print(json.dumps(line), flush=True)
+    return ok
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    spec = make_cylinder_domain(8)
+    cd = spec.prepare()
+    out, ok = [], True
+    try:
+        ok &= check_substeps(cd, out)
+        ok &= check_env((spec, cd), out)
+    except Exception as e:                                              # report, do not hide: this is a bring-up tool
+        out.append({"stage": "exception", "error": f"{type(e).__name__}: {e}"})
+        print(json.dumps(out[-1]), flush=True)
+        ok = False
+    verdict = {"ok": bool(ok), "stages": out}
+    print(json.dumps({"ok": bool(ok)}))
+    if args.json:
+        os.makedirs(os.path.dirname(os.path.abspath(args.json)), exist_ok=True)
+        json.dump(verdict, open(args.json, "w"), indent=1)
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

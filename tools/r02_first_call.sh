@@ -1,0 +1,14 @@
+# First gpurun call of the next round (ONE GPU): the checks that could not run when round 1's GPU budget was spent.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/r02_first_call.sh'
+# 1. first GPU run of the extruded D = 3 launch path + CylinderJet3D environment against the reference's goldens
+# 2. the whole GPU suite
+# 3. the default bench line
+# 4. reference goldens for Airfoil3D at a small resolution (op trace + env.step), for the next extruded environment
+set -x
+mkdir -p gpurun_out/r02
+timeout 900 python tools/extruded_check.py --json gpurun_out/r02/extruded_check.json > gpurun_out/r02/extruded_check.log 2>&1
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r02/gpu_tests.log 2>&1
+timeout 600 python bench.py > gpurun_out/r02/bench.json 2> gpurun_out/r02/bench.err
+timeout 900 python oracle/ref_harness.py --env Airfoil3D-easy-v0 --tag airfoil3d --out gpurun_out/r02/airfoil3d --env-steps 1 --time-steps 1 \
+    --trace-substeps 2 > gpurun_out/r02/airfoil3d.log 2>&1
+tail -3 gpurun_out/r02/*.log
