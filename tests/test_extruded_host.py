@@ -124,3 +124,58 @@ def test_substep_orchestration_reaches_the_reference_result(harness, tables, gol
     assert rel_l2(ures, fx["u1"]) < 1e-5 and rel_l2(p, fx["p1"]) < 3e-4
     ref = fx["cg_iters"].astype(np.float64) + 1
     assert np.all(np.abs(np.array(cg_its) - ref) <= 0.02 * ref)
+
+
+def test_cell_code_reduces_to_the_2d_operators_on_the_airfoil_mesh(harness):
+    """Size-independent property on the mesh of the next extruded environment (Airfoil3D: 6 blocks, 46 806 cells per plane, other
+    block connections / corner rules than the cylinder): on a z-INVARIANT state with w = 0 every in-plane coefficient the extruded
+    cell code produces must equal the 2-D operator of oracle/table_eval.py (the specification of the GPU-verified 2-D kernels), and
+    the z faces must contribute exactly -nu / hz^2 (matrix), det / (hz A) (pressure) and nothing to right-hand sides, divergence and
+    the in-plane velocity correction."""
+    import table_eval as te
+    from fluidgym_b200.envs.airfoil_domain import make_airfoil_domain
+    cd = make_airfoil_domain().prepare()
+    t, _keep = host_tables(cd)
+    N, NB, nz, hz, dt = cd.N, cd.NB, 3, 0.37, 0.004
+    rng = np.random.default_rng(5)
+    u2 = (0.3 + 0.1 * rng.standard_normal((2, N))).astype(f32)
+    us2 = (u2 + 0.01 * rng.standard_normal((2, N))).astype(f32)
+    b2 = np.ascontiguousarray(cd.bvel0[:, :NB] + 0.05 * rng.standard_normal((2, NB))).astype(f32)
+    p2 = rng.standard_normal(N).astype(f32)
+
+    def ext(a, comps):                                       # [c, N] -> z-invariant [comps, nz, N] (missing components zero)
+        out = np.zeros((comps, nz) + a.shape[1:], f32)
+        out[:a.shape[0]] = a[:, None]
+        return np.ascontiguousarray(out)
+
+    u3, us3, b3 = ext(u2, 3), ext(us2, 3), ext(b2, 3)
+    p3 = np.ascontiguousarray(np.broadcast_to(p2, (nz, N))).astype(f32)
+    hzc, dtc, nu = C.c_float(hz), C.c_float(dt), f32(cd.visc)
+    dz = nu / f32(hz * hz)
+    coff, A3, rhs = np.zeros((6, nz, N), f32), np.zeros((nz, N), f32), np.zeros((3, nz, N), f32)
+    harness.xh_setup_advection(C.byref(t), nz, hzc, _p(u3), _p(us3), _p(b3), dtc, _p(coff), _p(A3), _p(rhs), 1)
+    off2, A2 = te.assemble_C(cd, u2, b2, dt)
+    rhs2 = te.adv_rhs(cd, u2, us2, b2, dt)
+    for k in range(nz):
+        assert rel_l2(coff[:4, k], off2) < 1e-6
+        assert np.abs(coff[4:, k] + dz).max() < 1e-6 * dz
+        assert rel_l2(A3[k] - 2 * dz, A2) < 1e-6
+        assert rel_l2(rhs[:2, k], rhs2) < 1e-6 and not rhs[2, k].any()
+    poff, pdiag = np.zeros((6, nz, N), f32), np.zeros((nz, N), f32)
+    harness.xh_pressure_matrix(C.byref(t), nz, hzc, _p(A3), _p(poff), _p(pdiag))
+    Po2, Pd2 = te.build_P(cd, A3[0])
+    assert rel_l2(poff[:4, 1], Po2 * f32(hz)) < 1e-6
+    assert rel_l2(poff[4, 1], cd.det / f32(hz) / A3[0]) < 1e-6 and rel_l2(poff[5, 1], poff[4, 1]) < 1e-7
+    assert rel_l2(pdiag[1] + poff[4, 1] + poff[5, 1], Pd2 * f32(hz)) < 1e-5
+    hb = np.zeros((3, nz, N), f32)
+    harness.xh_hbya(C.byref(t), nz, hzc, _p(u3), _p(us3), _p(b3), _p(coff), _p(A3), dtc, _p(hb))
+    hb2 = te.hbya(cd, u2, us2, off2, A3[0], b2, dt)          # in-plane part with the same diagonal ...
+    assert rel_l2(hb[:2, 2], hb2 + 2 * dz * us2 / A3[0]) < 2e-6    # ... plus the two z neighbours of a z-invariant iterate
+    assert not hb[2].any()
+    div = np.zeros((nz, N), f32)
+    harness.xh_divergence(C.byref(t), nz, hzc, _p(hb), _p(b3), _p(p3), _p(A3), _p(div))
+    d2 = te.divergence(cd, hb[:2, 0], b2, pres=p2, A=A3[0])
+    assert rel_l2(div[1], d2 * f32(hz)) < 2e-5
+    out = np.zeros((3, nz, N), f32)
+    harness.xh_correct(C.byref(t), nz, hzc, _p(hb), _p(p3), _p(A3), _p(out))
+    assert rel_l2(out[:2, 1], te.correct(cd, hb[:2, 0], p2, A3[0])) < 1e-6 and not out[2].any()
