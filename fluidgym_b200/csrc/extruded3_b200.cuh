@@ -4,8 +4,9 @@
 // STATUS: operator layer.  The per-cell functions below are __host__ __device__ so that tests/test_extruded_host.py can
 // execute exactly this code on the CPU (through tests/cpu_harness/extruded_host.cu) and compare it with the numpy
 // specification oracle/extruded_eval.py, which is pinned to an op trace of the unmodified reference on CylinderJet3D-easy
-// (tests/golden/cyl3d_substep*.npz).  The launch glue at the end of this file has NOT run on a GPU yet: no environment is
-// registered on it and no GPU test depends on it.
+// (tests/golden/cyl3d_substep*.npz).  The launch glue at the end of this file has NOT run on a GPU yet
+// (DESIGN.md section 9): envs/cylinder3d.py (CylinderJet3D) is built on it and verified on the CPU
+// through the same cell code (tests/test_cylinder3d_cpu.py); tools/extruded_check.py is its first GPU run.
 //
 // The metric tensor of an extruded cell is block diagonal, M3 = diag(M2, hz): every in-plane coefficient of a row / det3
 // equals the 2-D one from the compiled tables (fgb_tables), the z faces add  -+1/4 (u_z,P + u_z,N) / hz - nu / hz^2  off

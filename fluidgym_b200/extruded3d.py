@@ -2,8 +2,9 @@
 planes, ``envs/cylinder/grid.py:298``, ``shapes.py:641-676``) -- host side of ``csrc/extruded3_b200.cuh``.
 
 STATUS: the operator arithmetic is verified on the CPU against an op trace of the unmodified reference
-(``tests/test_extruded_host.py``, ``tests/test_extruded_cpu.py``); ``ExtrudedPISO3D`` (the launch path) has not run on a GPU yet,
-so no environment is registered on it.  ``tools/extruded_check.py`` is the first thing to run on a GPU: one substep from the
+(``tests/test_extruded_host.py``, ``tests/test_extruded_cpu.py``); ``ExtrudedPISO3D`` (the launch path) has not run on a GPU yet;
+``envs/cylinder3d.py`` is built on it and verified on the CPU through a stand-in that executes the same cell code on the host
+(``tests/test_cylinder3d_cpu.py``).  ``tools/extruded_check.py`` is the first thing to run on a GPU: one substep from the
 reference's traced state, compared with the reference's result.
 """
 from __future__ import annotations

@@ -346,7 +346,7 @@ long long fgb_launch_count(fgb_batch *b);
  * boundary velocities [B][3][nz][NB].  The handle is an fgb_ortho3 created on the 6-face neighbour table of the extruded domain
  * (faces 0..3 in plane, 4 = -z, 5 = +z), whose cooperative Krylov kernels solve the ELL(7) systems.  Operator arithmetic is
  * verified on the CPU against a trace of the reference (tests/test_extruded_host.py); the launch path has not run on a GPU yet
- * and no environment uses it. */
+ * (envs/cylinder3d.py is built on it and verified on the CPU through the same cell code, tests/test_cylinder3d_cpu.py). */
 typedef struct fgb_extruded3_tables {
     fgb_tables plane;
     int32_t nz;
