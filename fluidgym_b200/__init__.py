@@ -28,7 +28,10 @@ def make(env_id: str, n_envs: int = 1, **kwargs):
     # reference-only constructor flags that have no meaning here are accepted and ignored
     import inspect
     params = inspect.signature(entry.__init__).parameters
-    for k in ("load_initial_domain", "load_domain_statistics", "dtype"):
+    # load_domain_statistics (fluid_env.py:234-238): read after construction; False unless asked for (the files come from the
+    # reference's HuggingFace dataset, envs/common.py::DomainStatistics)
+    load_stats = bool(kwargs.pop("load_domain_statistics", False)) if "load_domain_statistics" not in params else False
+    for k in ("load_initial_domain", "dtype"):
         if k not in params:
             kwargs.pop(k, None)
     if "differentiable" in kwargs:
@@ -36,7 +39,10 @@ def make(env_id: str, n_envs: int = 1, **kwargs):
             if kwargs.pop("differentiable"):
                 raise NotImplementedError(f"{env_id}: differentiable=True is not available for this environment family yet")
     cfg.update(kwargs)
-    return entry(n_envs=n_envs, **cfg)
+    env = entry(n_envs=n_envs, **cfg)
+    if load_stats:
+        env.load_domain_statistics()
+    return env
 
 
 def _register_defaults():

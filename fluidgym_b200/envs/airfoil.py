@@ -47,6 +47,7 @@ class Airfoil2DEnv(DifferentiableRollout, InitialDomains):
     action_smoothing_alpha = 0.1
     render_shape = (600, 150)
     metrics = ["drag", "lift"]
+    reference_values = {"cl_cd_ref": ("lift", "mean", "drag", "mean")}
     use_marl = False
 
     def __init__(self, n_envs: int = 1, reynolds_number=3e3, dt=0.05, step_length=0.25, adaptive_cfl=0.8, episode_length=300,

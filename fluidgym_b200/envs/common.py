@@ -5,6 +5,8 @@ kernels use -- so gradients flow from the reward to the action, the cell velocit
 the reference, where those parts are torch code as well (SIM.py:188-393, forces.py:193-275)."""
 from __future__ import annotations
 
+from typing import NamedTuple
+
 import numpy as np
 import torch
 
@@ -169,7 +171,66 @@ def default_initial_domains_path() -> str:
     return os.environ.get("FLUIDGYM_INITIAL_DOMAINS", os.path.join(os.path.expanduser("~"), ".local", "share", "FluidGym", "initial_domains"))
 
 
-class InitialDomains:
+class Stats(NamedTuple):
+    """envs/fluid_env.py:33-44"""
+    mean: float
+    min: float
+    max: float
+    p5: float
+    p25: float
+    p50: float
+    p75: float
+    p95: float
+
+
+STATISTICS_FILENAME = "domain_statistics.json"        # util/data_utils.py:19
+
+
+class DomainStatistics:
+    """Mixin: ``load_domain_statistics=True`` of the reference (envs/fluid_env.py:234-238, 1205-1221; util/data_utils.py:82-98):
+    ``<initial_domains_path>/<initial_domain_id>/domain_statistics.json`` holds the Stats of the velocity magnitude, the pressure
+    and every metric of the uncontrolled flow; the reward normalisers are read from it (``reference_values``).  Needs
+    ``initial_domain_id`` and ``metrics``; ``initial_domains_path`` optional."""
+
+    metrics_stats: dict = {}
+    velocity_stats = None
+    pressure_stats = None
+    # attribute <- (metric, field) or (metric, field, metric2, field2) for a ratio; per family, as in the reference:
+    # cylinder_env_base.py:271-275, rbc_env_base.py:407-416, airfoil_env_base.py:166-172, tcf_env.py:556-562, 1131-1137
+    reference_values: dict = {}
+
+    def domain_statistics_file(self) -> str:
+        import os
+        root = getattr(self, "initial_domains_path", None) or default_initial_domains_path()
+        return os.path.join(root, self.initial_domain_id, STATISTICS_FILENAME)
+
+    def load_domain_statistics(self) -> dict:
+        import json
+        with open(self.domain_statistics_file()) as f:
+            stats = json.load(f)
+        self.velocity_stats = Stats(**stats["velocity_magnitude"])
+        self.pressure_stats = Stats(**stats["pressure"])
+        self.metrics_stats = {key: Stats(**stats[key]) for key in self.metrics}
+        for attr, rule in self.reference_values.items():
+            if all(m in self.metrics_stats for m in rule[0::2]):
+                v = getattr(self.metrics_stats[rule[0]], rule[1])
+                if len(rule) == 4:
+                    v = v / getattr(self.metrics_stats[rule[2]], rule[3])
+                setattr(self, attr, float(v))
+        return stats
+
+    def save_domain_statistics(self, statistics: dict) -> str:
+        """fluid_env.py:1191-1203"""
+        import json
+        import os
+        path = self.domain_statistics_file()
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "w") as f:
+            json.dump(statistics, f, indent=4)
+        return path
+
+
+class InitialDomains(DomainStatistics):
     """Mixin: the published initial-domain splits (``initial_domains/<initial_domain_id>/<idx>/<mode>.{json,npz}``,
     envs/fluid_env.py:507-551, 1040-1112) for batched environments.  Files are read once into a device-resident pool; every
     environment of the batch draws its own index on ``reset`` (the reference draws one per process).

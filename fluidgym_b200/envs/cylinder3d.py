@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from ..sensors import sensor_tables_extruded
-from .common import DifferentiableRollout, build_wall_tables
+from .common import DifferentiableRollout, DomainStatistics, build_wall_tables
 from .cylinder import CylinderJet2DEnv
 from .cylinder_domain import BOTTOM, LEFT, RIGHT, TOP, WAKE, make_cylinder_domain
 from .spanwise import global_obs_from_samples, local_obs_windows, spanwise_sensor_voxels
@@ -26,11 +26,12 @@ CYLINDER_JET_3D_DEFAULT_CONFIG = {
 }
 
 
-class CylinderJet3DEnv:
+class CylinderJet3DEnv(DomainStatistics):
     H, L, D, cylinder_diameter, U_mean, cylinder_offset_y = 4.1, 22.0, 4.0, 1.0, 1.0, 0.05
     action_smoothing_alpha = 0.1
     jet_angle = 10.0
     metrics = ["drag", "lift"]
+    reference_values = {"cd_ref": ("drag", "mean")}
 
     def __init__(self, n_envs: int = 1, n_jets=8, reynolds_number=1e2, resolution=24, dt=1e-2, adaptive_cfl=0.8, step_length=0.25,
                  episode_length=80, lift_penalty=1.0, local_obs_window=3, use_marl=False, local_reward_weight=0.8, local_2d_obs=False,

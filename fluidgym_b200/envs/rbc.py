@@ -43,6 +43,7 @@ class RBC2DEnv(InitialDomains):
     n_sensors_y, n_sensors_per_heater = 8, 4
     buoyancy_factor = 1.0
     metrics = ["nusselt"]
+    reference_values = {"nu_ref": ("nusselt", "p50")}
 
     def __init__(self, n_envs: int = 1, rayleigh_number=8e4, prandtl_number=0.7, n_heaters=12, resolution=8, dt=0.05,
                  adaptive_cfl=0.8, step_length=1.0, episode_length=200, local_obs_window=11, local_reward_weight=0.2,

@@ -61,6 +61,7 @@ class RBC3DEnv(InitialDomains3D):
     H = 1.0
     resolution_scale_y, grid_base = 2.0, 1.02
     metrics = ["nusselt"]
+    reference_values = {"nu_ref": ("nusselt", "mean")}
 
     def __init__(self, n_envs: int = 1, rayleigh_number=2e3, prandtl_number=0.7, n_heaters=8, resolution=8, dt=0.05,
                  adaptive_cfl=0.8, step_length=1.0, episode_length=200, local_obs_window=3, local_reward_weight=0.0015,

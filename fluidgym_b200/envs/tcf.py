@@ -280,7 +280,9 @@ class TCF3DEnv(InitialDomains3D):
 
 class TCF3DBottomEnv(TCF3DEnv):
     both_walls = False
+    reference_values = {"tau_ref": ("wall_stress_bottom", "mean")}           # tcf_env.py:556-562
 
 
 class TCF3DBothEnv(TCF3DEnv):
     both_walls = True
+    reference_values = {"tau_ref": ("wall_stress", "mean")}                  # tcf_env.py:1131-1137

@@ -118,3 +118,52 @@ def test_2d_initial_domain_pool_glue_without_a_gpu(tmp_path):
     from fluidgym_b200.domain_io import load_domain
     spec, st = load_domain(path)
     assert np.array_equal(st["u"], S.u[1].numpy()) and len(spec.blocks) == 5
+
+
+def test_domain_statistics_set_the_reward_normalisers(tmp_path):
+    """load_domain_statistics (fluid_env.py:1205-1221): domain_statistics.json next to the initial domains -> Stats of velocity
+    magnitude / pressure / every metric, and the family's reward normaliser (cd_ref = drag mean; nu_ref = Nusselt median in 2-D,
+    mean in 3-D; lift / drag ratio for the airfoil; bottom or total wall stress for the channel)."""
+    import json
+    import pytest
+    from fluidgym_b200.envs.airfoil import Airfoil2DEnv
+    from fluidgym_b200.envs.common import STATISTICS_FILENAME, Stats
+    from fluidgym_b200.envs.cylinder import CylinderJet2DEnv
+    from fluidgym_b200.envs.cylinder3d import CylinderJet3DEnv
+    from fluidgym_b200.envs.rbc import RBC2DEnv
+    from fluidgym_b200.envs.rbc3d import RBC3DEnv
+    from fluidgym_b200.envs.tcf import TCF3DBothEnv, TCF3DBottomEnv
+
+    def st(mean, p50=None):
+        return dict(mean=mean, min=0.0, max=9.0, p5=0.1, p25=0.2, p50=mean if p50 is None else p50, p75=0.8, p95=0.9)
+
+    cases = [(CylinderJet2DEnv, "cd_ref", {"drag": st(3.2), "lift": st(0.1)}, 3.2),
+             (CylinderJet3DEnv, "cd_ref", {"drag": st(1.3), "lift": st(0.0)}, 1.3),
+             (Airfoil2DEnv, "cl_cd_ref", {"drag": st(0.5), "lift": st(1.5)}, 3.0),
+             (RBC2DEnv, "nu_ref", {"nusselt": st(4.0, p50=3.5)}, 3.5),
+             (RBC3DEnv, "nu_ref", {"nusselt": st(4.0, p50=3.5)}, 4.0),
+             (TCF3DBottomEnv, "tau_ref", {"wall_stress": st(2.0), "wall_stress_bottom": st(1.1), "wall_stress_top": st(0.9)}, 1.1),
+             (TCF3DBothEnv, "tau_ref", {"wall_stress": st(2.0), "wall_stress_bottom": st(1.1), "wall_stress_top": st(0.9)}, 2.0)]
+    for k, (cls, attr, metrics, want) in enumerate(cases):
+        env = object.__new__(cls)
+        env.initial_domains_path = str(tmp_path)
+        env_id = f"case{k}"
+        d = tmp_path / env_id
+        d.mkdir()
+        stats = {"velocity_magnitude": st(0.7), "pressure": st(0.2), **metrics}
+        (d / STATISTICS_FILENAME).write_text(json.dumps(stats))
+        env.__class__ = type("Stub", (cls,), {"initial_domain_id": env_id})
+        out = env.load_domain_statistics()
+        assert out == stats and isinstance(env.velocity_stats, Stats) and env.velocity_stats.mean == 0.7 and env.pressure_stats.p95 == 0.9
+        assert set(env.metrics_stats) == set(cls.metrics)
+        assert abs(getattr(env, attr) - want) < 1e-12, (cls.__name__, attr)
+    # missing file: the reference's open() error surfaces
+    env = object.__new__(type("Stub", (CylinderJet2DEnv,), {"initial_domain_id": "nowhere"}))
+    env.initial_domains_path = str(tmp_path)
+    with pytest.raises(FileNotFoundError):
+        env.load_domain_statistics()
+    # round trip through save_domain_statistics
+    path = env.save_domain_statistics({"velocity_magnitude": st(1.0), "pressure": st(0.0), "drag": st(2.5), "lift": st(0.0)})
+    assert path.endswith(STATISTICS_FILENAME)
+    env.load_domain_statistics()
+    assert env.cd_ref == 2.5
