@@ -1,5 +1,5 @@
 # First gpurun call of the next round (ONE GPU): the checks that could not run when round 1's GPU budget was spent.
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/r02_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 3600 -- 'bash tools/r02_first_call.sh'
 # 1. first GPU run of the extruded D = 3 launch path + CylinderJet3D environment against the reference's goldens
 # 2. the whole GPU suite
 # 3. the default bench line
@@ -9,6 +9,7 @@ mkdir -p gpurun_out/r02
 timeout 900 python tools/extruded_check.py --json gpurun_out/r02/extruded_check.json > gpurun_out/r02/extruded_check.log 2>&1
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r02/gpu_tests.log 2>&1
 timeout 600 python bench.py > gpurun_out/r02/bench.json 2> gpurun_out/r02/bench.err
-timeout 900 python oracle/ref_harness.py --env Airfoil3D-easy-v0 --tag airfoil3d --out gpurun_out/r02/airfoil3d --env-steps 1 --time-steps 1 \
-    --trace-substeps 2 > gpurun_out/r02/airfoil3d.log 2>&1
+# (res_z = 96: 46 806 x 96 = 4.5 M cells, the reference needs minutes per env.step -> lean trace, one env.step, generous limit)
+timeout 1700 python oracle/ref_harness.py --env Airfoil3D-easy-v0 --tag airfoil3d --out gpurun_out/r02/airfoil3d --env-steps 1 --time-steps 0 \
+    --trace-substeps 1 --lean --kw '{"init_from_2d": false}' > gpurun_out/r02/airfoil3d.log 2>&1
 tail -3 gpurun_out/r02/*.log
