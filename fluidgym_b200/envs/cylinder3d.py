@@ -35,7 +35,11 @@ class CylinderJet3DEnv(DomainStatistics):
 
     def __init__(self, n_envs: int = 1, n_jets=8, reynolds_number=1e2, resolution=24, dt=1e-2, adaptive_cfl=0.8, step_length=0.25,
                  episode_length=80, lift_penalty=1.0, local_obs_window=3, use_marl=False, local_reward_weight=0.8, local_2d_obs=False,
-                 device="cuda:0", cd_ref=0.0, randomize_initial_state=False, enable_actions=True, compiled=None, solver_cls=None):
+                 device="cuda:0", cd_ref=0.0, randomize_initial_state=False, enable_actions=True, load_initial_domain=False,
+                 compiled=None, solver_cls=None):
+        if load_initial_domain:
+            raise NotImplementedError("CylinderJet3D: on-disk initial domains of the extruded multi-block grids are not read yet "
+                                      "(fluidgym_b200/domain_io.py handles the 2-D multi-block and the 3-D box formats)")
         if n_jets < 1 or resolution % n_jets != 0:
             raise ValueError("n_agents must be a positive integer that evenly dividescircle_resolution_angular.")
         if local_2d_obs and not use_marl:

@@ -196,3 +196,15 @@ def test_adaptive_plan_splits_per_environment(compiled, golden):
     assert abs(sum(float(d[1]) for d in dts) - 0.01) < 1e-8 and abs(float(dts[0][0]) - 0.01) < 1e-9
     assert torch.equal(s.u[0], u0) and float(s.p[0, 0]) == 1.0 and float(s.p[1, 0]) == 3.0
     s.piso_substep = orig
+
+
+def test_unsupported_options_fail_loudly(compiled):
+    import fluidgym_b200
+    from extruded_standin import HostExtrudedPISO3D
+    kw = dict(resolution=8, device="cpu", compiled=compiled, solver_cls=HostExtrudedPISO3D)
+    with pytest.raises(NotImplementedError, match="initial domains"):
+        fluidgym_b200.make("CylinderJet3D-easy-v0", load_initial_domain=True, **kw)
+    with pytest.raises(NotImplementedError, match="differentiable"):
+        fluidgym_b200.make("CylinderJet3D-easy-v0", differentiable=True, **kw)
+    env = fluidgym_b200.make("CylinderJet3D-medium-v0", load_initial_domain=False, load_domain_statistics=False, **kw)
+    assert env.reynolds_number == 250.0 and env.initial_domain_id == "cylinder_3D_Re250_Res8"
