@@ -186,6 +186,23 @@ class ExtrudedPISO3D(ExtrudedStepping):
     def stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def buffer(self, name):
+        """workspace views of the Krylov handle (as BatchedPISO3D.buffer): "iters" [B, 8], "resid" [B, 8], "iter_total" [B, 2] (CG,
+        BiCGStab iterations summed since creation), "Coff", "A", "rhs", "ures", "Poff", "Pdiag", "hbya", "div"."""
+        B, N = self.B, self.N
+        shapes = {"Coff": ((B, 6, N), torch.float32), "A": ((B, N), torch.float32), "rhs": ((B, 3, N), torch.float32),
+                  "ures": ((B, 3, N), torch.float32), "Poff": ((B, 6, N), torch.float32), "Pdiag": ((B, N), torch.float32),
+                  "hbya": ((B, 3, N), torch.float32), "div": ((B, N), torch.float32), "iters": ((B, 8), torch.int32),
+                  "resid": ((B, 8), torch.float32), "iter_total": ((B, 2), torch.int64)}
+        shape, dtype = shapes[name]
+        ptr = self.lib.fgb_ortho3_buffer(self.handle, name.encode())
+        o = ptr - self.workspace.data_ptr()
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        return self.workspace[o:o + n].view(dtype).view(shape)
+
+    def launch_count(self) -> int:
+        return int(self.lib.fgb_ortho3_launch_count(self.handle))
+
     def piso_substep(self, dt):
         dtc = dt.to(self.device, torch.float32).contiguous() if isinstance(dt, torch.Tensor) else torch.full((self.B,), float(dt), device=self.device)
         native.check(self.lib.fgb_extruded3_piso_substep(self.handle, C.byref(self.xtables), _ptr(self.u), _ptr(self.p), _ptr(self.bvel),

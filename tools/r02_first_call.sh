@@ -7,6 +7,7 @@
 set -x
 mkdir -p gpurun_out/r02
 timeout 900 python tools/extruded_check.py --json gpurun_out/r02/extruded_check.json > gpurun_out/r02/extruded_check.log 2>&1
+timeout 900 python tools/cyl3d_bench.py --resolutions 8 24 --steps 1 --out gpurun_out/r02/cyl3d_bench.json > gpurun_out/r02/cyl3d_bench.log 2>&1
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r02/gpu_tests.log 2>&1
 timeout 600 python bench.py > gpurun_out/r02/bench.json 2> gpurun_out/r02/bench.err
 # (res_z = 96: 46 806 x 96 = 4.5 M cells, the reference needs minutes per env.step -> lean trace, one env.step, generous limit)
