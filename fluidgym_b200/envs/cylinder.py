@@ -16,7 +16,6 @@ import numpy as np
 import torch
 
 from .. import native
-from ..domain import FIXED
 from ..sensors import sensor_tables
 from ..solver import BatchedPISO, _ptr
 from .common import DifferentiableRollout, InitialDomains, build_wall_tables
@@ -30,6 +29,57 @@ CYLINDER_JET_2D_DEFAULT_CONFIG = {
     "reynolds_number": 1e2, "resolution": 24, "dt": 1e-2, "adaptive_cfl": 0.8, "step_length": 0.25,
     "episode_length": 80, "lift_penalty": 1.0,
 }
+
+
+def cylinder_jet_templates(spec, cd, jet_angle: float):
+    """Jet velocity templates on the cylinder faces of the top / bottom blocks (jet_cylinder_env_2d.py:136-183; the 3-D
+    environment repeats them in every z plane, jet_cylinder_env_3d.py:328-396) -> (face indices int32 [nf], template float32 [2, nf])."""
+
+    def coords_to_velocities(coords_boundary, direction):
+        cb = torch.from_numpy(np.ascontiguousarray(coords_boundary))
+        centers = 0.5 * (cb[:, :-1] + cb[:, 1:])
+        if direction == "top":
+            angles = torch.pi / 2 - torch.atan2(centers[1, :], centers[0, :])
+        else:
+            angles = -torch.pi / 2 - torch.atan2(centers[1, :], centers[0, :])
+        angles_deg = torch.rad2deg(angles)
+        angles_deg_abs = torch.abs(angles_deg)
+        angles_deg_abs[angles_deg_abs > jet_angle] = 0.0
+        min_idx, max_idx = torch.where(angles_deg_abs > 0.0)[0][[0, -1]]
+        min_idx, max_idx = int(min_idx) - 1, int(max_idx) + 1
+        prof = torch.from_numpy(jet_profile(max_idx - min_idx + 1))
+        vel = torch.zeros_like(centers)
+        for i, um in zip(range(min_idx, max_idx + 1), prof):
+            a = angles_deg[i]
+            vel[0, i] = um * torch.sin(torch.deg2rad(a))
+            vel[1, i] = um * torch.cos(torch.deg2rad(a))
+        return vel.numpy()
+
+    top_v = coords_to_velocities(spec.blocks[TOP].vertex[:, 0, :], "top")
+    bot_v = coords_to_velocities(spec.blocks[BOTTOM].vertex[:, -1, :], "bottom")
+    nx = spec.blocks[TOP].nx
+    faces = np.concatenate([cd.boff[TOP, 2] + np.arange(nx), cd.boff[BOTTOM, 3] + np.arange(nx)]).astype(np.int32)
+    templ = np.ascontiguousarray(np.concatenate([top_v, bot_v], axis=1).astype(np.float32))
+    return faces, templ
+
+
+def cylinder_sensor_locations(cylinder_diameter: float = 1.0) -> torch.Tensor:
+    """[2, 151] physical sensor positions of the cylinder environments (CYL.py:457-516; shared by the 2-D and 3-D variants)"""
+    x_idx = torch.arange(1.0, 5.0, step=0.5)
+    y_idx = torch.arange(-1.5, 1.75, step=0.5)
+    xy = torch.meshgrid(x_idx, y_idx, indexing="ij")
+    loc = torch.stack([xy[0].ravel(), xy[1].ravel()], dim=0)
+    x_1 = torch.arange(-0.25, 1, 0.25)
+    y_1a, y_1b = torch.full_like(x_1, -1.5), torch.full_like(x_1, 1.5)
+    x_2 = torch.concatenate([torch.tensor([-0.25]), torch.arange(0.25, 1.25, 0.25)])
+    y_2a, y_2b = torch.full_like(x_2, cylinder_diameter), torch.full_like(x_2, -cylinder_diameter)
+    x_3, y_3 = torch.tensor([0.75] * 3), torch.tensor([-0.5, 0, 0.5])
+    add = torch.stack([torch.concatenate([x_1, x_1, x_2, x_2, x_3]), torch.concatenate([y_1a, y_1b, y_2a, y_2b, y_3])], dim=0)
+    ang = torch.linspace(0, 2 * torch.pi, steps=36)
+    r1, r2 = 2 * 0.5, 1.25 * 0.5
+    c1 = torch.stack([r1 * torch.cos(ang), r1 * torch.sin(ang)], dim=0)
+    c2 = torch.stack([r2 * torch.cos(ang), r2 * torch.sin(ang)], dim=0)
+    return torch.concatenate([loc, c1, c2, add], dim=1)
 
 
 class CylinderJet2DEnv(DifferentiableRollout, InitialDomains):
@@ -85,37 +135,9 @@ class CylinderJet2DEnv(DifferentiableRollout, InitialDomains):
 
     # ---- static tables ---------------------------------------------------------------------------
     def _setup_jets(self):
-        """Jet velocity templates on the cylinder faces of the top / bottom blocks
-        (jet_cylinder_env_2d.py:136-183)."""
-        cd, spec = self.cd, self.spec
-
-        def coords_to_velocities(coords_boundary, direction):
-            cb = torch.from_numpy(np.ascontiguousarray(coords_boundary))
-            centers = 0.5 * (cb[:, :-1] + cb[:, 1:])
-            if direction == "top":
-                angles = torch.pi / 2 - torch.atan2(centers[1, :], centers[0, :])
-            else:
-                angles = -torch.pi / 2 - torch.atan2(centers[1, :], centers[0, :])
-            angles_deg = torch.rad2deg(angles)
-            angles_deg_abs = torch.abs(angles_deg)
-            angles_deg_abs[angles_deg_abs > self.jet_angle] = 0.0
-            min_idx, max_idx = torch.where(angles_deg_abs > 0.0)[0][[0, -1]]
-            min_idx, max_idx = int(min_idx) - 1, int(max_idx) + 1
-            prof = torch.from_numpy(jet_profile(max_idx - min_idx + 1))
-            vel = torch.zeros_like(centers)
-            for i, um in zip(range(min_idx, max_idx + 1), prof):
-                a = angles_deg[i]
-                vel[0, i] = um * torch.sin(torch.deg2rad(a))
-                vel[1, i] = um * torch.cos(torch.deg2rad(a))
-            return vel.numpy()
-
-        top_v = coords_to_velocities(spec.blocks[TOP].vertex[:, 0, :], "top")
-        bot_v = coords_to_velocities(spec.blocks[BOTTOM].vertex[:, -1, :], "bottom")
-        nx = spec.blocks[TOP].nx
-        faces = np.concatenate([cd.boff[TOP, 2] + np.arange(nx), cd.boff[BOTTOM, 3] + np.arange(nx)]).astype(np.int32)
-        templ = np.concatenate([top_v, bot_v], axis=1).astype(np.float32)
+        faces, templ = cylinder_jet_templates(self.spec, self.cd, self.jet_angle)
         self.jet_faces = torch.from_numpy(faces).to(self.device)
-        self.jet_templ = torch.from_numpy(np.ascontiguousarray(templ)).to(self.device)
+        self.jet_templ = torch.from_numpy(templ).to(self.device)
 
     def _setup_wall(self):
         """Ring of wall-adjacent cells around the cylinder and its geometry (CYL.py:548-655,
@@ -130,22 +152,7 @@ class CylinderJet2DEnv(DifferentiableRollout, InitialDomains):
         return (int(z / self.H * self.L), z)
 
     def sensor_locations_physical(self) -> torch.Tensor:
-        """CYL.py:457-516"""
-        x_idx = torch.arange(1.0, 5.0, step=0.5)
-        y_idx = torch.arange(-1.5, 1.75, step=0.5)
-        xy = torch.meshgrid(x_idx, y_idx, indexing="ij")
-        loc = torch.stack([xy[0].ravel(), xy[1].ravel()], dim=0)
-        x_1 = torch.arange(-0.25, 1, 0.25)
-        y_1a, y_1b = torch.full_like(x_1, -1.5), torch.full_like(x_1, 1.5)
-        x_2 = torch.concatenate([torch.tensor([-0.25]), torch.arange(0.25, 1.25, 0.25)])
-        y_2a, y_2b = torch.full_like(x_2, self.cylinder_diameter), torch.full_like(x_2, -self.cylinder_diameter)
-        x_3, y_3 = torch.tensor([0.75] * 3), torch.tensor([-0.5, 0, 0.5])
-        add = torch.stack([torch.concatenate([x_1, x_1, x_2, x_2, x_3]), torch.concatenate([y_1a, y_1b, y_2a, y_2b, y_3])], dim=0)
-        ang = torch.linspace(0, 2 * torch.pi, steps=36)
-        r1, r2 = 2 * 0.5, 1.25 * 0.5
-        c1 = torch.stack([r1 * torch.cos(ang), r1 * torch.sin(ang)], dim=0)
-        c2 = torch.stack([r2 * torch.cos(ang), r2 * torch.sin(ang)], dim=0)
-        return torch.concatenate([loc, c1, c2, add], dim=1)
+        return cylinder_sensor_locations(self.cylinder_diameter)
 
     def _setup_sensors(self):
         pc = self.sensor_locations_physical()

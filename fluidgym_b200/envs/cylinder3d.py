@@ -16,7 +16,7 @@ import torch
 
 from ..sensors import sensor_tables_extruded
 from .common import DifferentiableRollout, DomainStatistics, build_wall_tables
-from .cylinder import CylinderJet2DEnv
+from .cylinder import cylinder_jet_templates, cylinder_sensor_locations
 from .cylinder_domain import BOTTOM, LEFT, RIGHT, TOP, WAKE, make_cylinder_domain
 from .spanwise import global_obs_from_samples, local_obs_windows, spanwise_sensor_voxels
 
@@ -72,7 +72,9 @@ class CylinderJet3DEnv(DomainStatistics):
         o = cd.boff[WAKE, 1]
         out_mask[o:o + spec.blocks[WAKE].ny] = True
         self.solver.setup_stepping(out_mask, (self.U_mean, 0.0))
-        CylinderJet2DEnv._setup_jets(self)                          # the 2-D templates, repeated in every plane (:328-396)
+        faces, templ = cylinder_jet_templates(spec, cd, self.jet_angle)     # the 2-D templates, repeated in every plane (:328-396)
+        self.jet_faces = torch.from_numpy(faces).to(self.device)
+        self.jet_templ = torch.from_numpy(templ).to(self.device)
         free = out_mask.copy()
         free[self.jet_faces.cpu().numpy()] = True
         self._free_jets = torch.from_numpy(free).to(self.device)
@@ -96,7 +98,7 @@ class CylinderJet3DEnv(DomainStatistics):
         return self.n_jets * self.n_sensors_per_agent
 
     def _setup_sensors(self):
-        xy = CylinderJet2DEnv.sensor_locations_physical(self)
+        xy = cylinder_sensor_locations(self.cylinder_diameter)
         self.n_sensors_xy = int(xy.shape[1])
         rs = self.render_shape
         self.sensor_px = spanwise_sensor_voxels(xy, self.n_sensors_z, self.H, self.L, rs).numpy()
