@@ -208,3 +208,33 @@ def test_unsupported_options_fail_loudly(compiled):
         fluidgym_b200.make("CylinderJet3D-easy-v0", differentiable=True, **kw)
     env = fluidgym_b200.make("CylinderJet3D-medium-v0", load_initial_domain=False, load_domain_statistics=False, **kw)
     assert env.reynolds_number == 250.0 and env.initial_domain_id == "cylinder_3D_Re250_Res8"
+
+
+def test_rl_library_adapters_accept_the_spanwise_environment(compiled):
+    """integration.py on CylinderJet3D (host logic only, the solver calls are stubbed out): SB3 VecEnv slots = environments x
+    agents, PettingZoo per-agent dictionaries, gymnasium single-environment view."""
+    from fluidgym_b200.integration import GymFluidEnv, PettingZooFluidEnv, VecFluidEnv
+
+    def mk(**kw):
+        e = _env(compiled, step_length=0.01, **kw)
+        e.solver.piso_substep = lambda dt: None
+        e.solver.make_divergence_free = lambda max_iter=1000: None
+        return e
+
+    for marl, slots, lead in ((False, 2, (8, 2)), (True, 16, (3, 2))):
+        v = VecFluidEnv(mk(n_envs=2, use_marl=marl))
+        v.seed(1)
+        obs = v.reset()
+        assert v.num_envs == slots and obs["velocity"].shape == (slots,) + lead + (3, 151) and obs["pressure"].shape == (slots,) + lead + (151,)
+        o, r, d, info = v.step(np.zeros((slots,) + v.action_space.shape, np.float32))
+        assert r.shape == (slots,) and d.shape == (slots,) and len(info) == slots
+    pz = PettingZooFluidEnv(mk(n_envs=1, use_marl=True))
+    o, _ = pz.reset(seed=3)
+    assert len(pz.agents) == 8 and o[pz.agents[0]]["velocity"].shape == (3, 2, 3, 151)
+    o, r, t, tr, _ = pz.step({a: np.zeros(1, np.float32) for a in pz.agents})
+    assert set(r) == set(pz.agents)
+    g = GymFluidEnv(mk(n_envs=1))
+    o, _ = g.reset(seed=1)
+    assert o["velocity"].shape == (8, 2, 3, 151)
+    o, r, t, tr, _ = g.step(np.zeros((8, 1), np.float32))
+    assert np.isfinite(float(r))
