@@ -16,7 +16,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 def lib_is_fresh() -> bool:
     if not os.path.exists(LIB):
         return False
-    deps = [SRC, os.path.join(PKG, "csrc", "ortho3_b200.cuh"), os.path.join(REPO, "include", "fluidgym_b200.h")]
+    deps = [SRC, os.path.join(PKG, "csrc", "ortho3_b200.cuh"), os.path.join(PKG, "csrc", "extruded3_b200.cuh"),
+            os.path.join(REPO, "include", "fluidgym_b200.h")]
     return all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps if os.path.exists(d))
 
 

@@ -10,6 +10,7 @@
 #include <cooperative_groups.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <new>
@@ -50,6 +51,7 @@ struct fgb_batch {
     int32_t *h_counters;  // pinned host mirror
     unsigned long long *iter_total;   // [B][2] accumulated Krylov iterations (cg, bicgstab)
     long long launches;               // kernels launched through this handle
+    int asm_envs;                     // environments per thread in the table-heavy assembly kernels (FGB_ASM_ENVS; 1 = default kernels)
     // optional CUDA-event profiling of the solver launches (bench.py roofline)
     int prof_on;
     static const int PROF_MAX = 8192;
@@ -118,6 +120,8 @@ extern "C" int fgb_batch_create(const fgb_tables *t, int32_t B, void *workspace,
     memset(b, 0, sizeof(*b));
     b->t = *t; b->B = B; b->opt = opt ? *opt : default_options();
     b->ws = (char *)workspace; b->ws_bytes = workspace_bytes;
+    b->asm_envs = 1;
+    if (const char *ev = getenv("FGB_ASM_ENVS")) { const int v = atoi(ev); if (v == 2 || v == 4 || v == 8) b->asm_envs = v; }
     size_t total; carve(b, b->ws, &total);
     ce = cudaMallocHost(&b->h_counters, 64 * sizeof(int32_t));
     if (ce != cudaSuccess) { delete b; return set_err(FGB_E_CUDA, "cudaMallocHost", ce); }
@@ -412,6 +416,139 @@ __global__ void __launch_bounds__(256) k_pressure_div(Tab t, const float *__rest
         d += S;
     }
     Div[(size_t)b * N + g] = d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// OPT-IN variants (FGB_ASM_ENVS = 2 / 4 / 8, default 1 = the kernels above): one thread handles the same cell of E
+// consecutive environments.  The geometry tables are shared by all environments, and the two kernels below read 29 / 45
+// table values per cell for 6 / 5 values of per-environment state (profiles/r01_assembly_kernel_roofline_cylinder_B256.md),
+// i.e. they are bound by re-reading the tables from L2 once per environment.  Here every table value is loaded once per
+// thread (all loads precede the first store; the deferred-correction loop runs over the table entries outside and the
+// environments inside) and the per-environment arithmetic is the same expression, statement by statement, as in
+// k_setup_pressure_matrix / k_pressure_div, so results are expected to be bit-identical.  NOT yet run on a GPU: selected only
+// when the environment variable is set; tests/test_gpu_parity.py::test_multi_env_assembly_variants_are_bit_identical is the check.
+template <int E>
+__global__ void __launch_bounds__(256) k_setup_pressure_matrix_multi(Tab t, int B, const float *__restrict__ A,
+                                                                      const int32_t *__restrict__ active, float *__restrict__ Poff,
+                                                                      float *__restrict__ Pdiag) {
+    const int b0 = blockIdx.y * E;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N;
+    if (g >= N) return;
+    int nb[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) nb[f] = t.nbr[f * N + g];
+    float W[25];
+#pragma unroll
+    for (int q = 0; q < 25; ++q) W[q] = t.Wp[q * N + g];
+    float P[E][5];
+    bool on[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int b = b0 + e;
+        on[e] = b < B && !(active && !active[b]);
+        if (!on[e]) continue;
+        const float *a = A + (size_t)b * N;
+        float rA[5];
+        rA[0] = 1.0f / a[g];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) rA[f + 1] = nb[f] >= 0 ? 1.0f / a[nb[f]] : rA[0];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) sacc += W[5 * q + j] * rA[j];
+            P[e][q] = sacc;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        if (!on[e]) continue;
+        const int b = b0 + e;
+        Pdiag[(size_t)b * N + g] = P[e][0];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) Poff[(size_t)b * 4 * N + f * N + g] = P[e][f + 1];
+    }
+}
+
+template <int E>
+__global__ void __launch_bounds__(256) k_pressure_div_multi(Tab t, int B, const float *__restrict__ Hbya, const float *__restrict__ Bvel,
+                                                             const float *__restrict__ Pprev, const float *__restrict__ A,
+                                                             const int32_t *__restrict__ active, int nonortho, float *__restrict__ Div) {
+    const int b0 = blockIdx.y * E;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N, NB = t.NB;
+    if (g >= N) return;
+    // tables of this cell, loaded once for all E environments (the arithmetic below is face_fluxes / contra_cell / bflux verbatim)
+    int nb[4], src[4], fcm[4];
+    float fdet[4], fma[4], fmb[4];
+    const float det_g = t.det[g], m0 = t.minv[g], m1 = t.minv[N + g], m2 = t.minv[2 * N + g], m3 = t.minv[3 * N + g];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        nb[f] = t.nbr[f * N + g];
+        if (nb[f] >= 0) {
+            const int fc = t.fl_comp[f * N + g], k = fc & 1, n = nb[f];
+            fcm[f] = fc; src[f] = n;
+            fdet[f] = t.det[n]; fma[f] = t.minv[(2 * k) * N + n]; fmb[f] = t.minv[(2 * k + 1) * N + n];
+        } else {
+            const int j = -1 - nb[f], ax = f >> 1;
+            fcm[f] = 0; src[f] = j;
+            fdet[f] = t.b_det[j]; fma[f] = t.b_minv[(2 * ax) * NB + j]; fmb[f] = t.b_minv[(2 * ax + 1) * NB + j];
+        }
+    }
+    float d[E], rA[E][5];
+    bool on[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int b = b0 + e;
+        on[e] = b < B && !(active && !active[b]);
+        d[e] = 0.f;
+        if (!on[e]) continue;
+        const float *vel = Hbya + (size_t)b * 2 * N, *bv = Bvel + (size_t)b * 2 * NB;
+        const float ux = vel[g], uy = vel[N + g];
+        const float Uc[2] = {det_g * (m0 * ux + m1 * uy), det_g * (m2 * ux + m3 * uy)};
+        float fl[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            if (nb[f] >= 0) {
+                float velN = fdet[f] * (fma[f] * vel[src[f]] + fmb[f] * vel[N + src[f]]);
+                if (fcm[f] & 2) velN = -velN;
+                fl[f] = (velN + Uc[f >> 1]) * 0.5f;
+            } else {
+                fl[f] = fdet[f] * (fma[f] * bv[src[f]] + fmb[f] * bv[NB + src[f]]);
+            }
+        }
+        d[e] = (fl[1] - fl[0]) + (fl[3] - fl[2]);
+        if (nonortho) {
+            const float *a = A + (size_t)b * N;
+            rA[e][0] = 1.0f / a[g];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) rA[e][f + 1] = nb[f] >= 0 ? 1.0f / a[nb[f]] : rA[e][0];
+        }
+    }
+    if (nonortho) {
+        float S[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) S[e] = 0.f;
+        for (int k = 0; k < t.K_no; ++k) {
+            const float gP = t.no_gP[k * N + g], gN = t.no_gN[k * N + g];
+            if (gP != 0.f || gN != 0.f) {
+                const int fc = t.no_face[k * N + g];
+                const int j = t.no_idx[k * N + g];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if (!on[e]) continue;
+                    const float rn = fc == 0 ? rA[e][1] : fc == 1 ? rA[e][2] : fc == 2 ? rA[e][3] : rA[e][4];
+                    S[e] += (gP * rA[e][0] + gN * rn) * Pprev[(size_t)(b0 + e) * N + j];
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) d[e] += S[e];
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (on[e]) Div[(size_t)(b0 + e) * N + g] = d[e];
 }
 
 // PISO_update_velocity (K.cu:816-849, 5962-5995)
@@ -2250,7 +2387,12 @@ extern "C" int fgb_solve_advection(fgb_batch *b, int zero_init, const int32_t *a
 extern "C" int fgb_setup_pressure_matrix(fgb_batch *b, const int32_t *active, fgb_stream_t s) {
     if (!b) return set_err(FGB_E_ARG, "fgb_setup_pressure_matrix: null argument");
     ProfScope ps(b, CLS_ASM, STREAM(s));
-    k_setup_pressure_matrix<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, b->A, active, b->Poff, b->Pdiag);
+    const int ae = b->asm_envs > 1 ? b->asm_envs : 1;
+    const dim3 gm((b->t.N + 255) / 256, (b->B + ae - 1) / ae);
+    if (ae == 8) k_setup_pressure_matrix_multi<8><<<gm, 256, 0, STREAM(s)>>>(b->t, b->B, b->A, active, b->Poff, b->Pdiag);
+    else if (ae == 4) k_setup_pressure_matrix_multi<4><<<gm, 256, 0, STREAM(s)>>>(b->t, b->B, b->A, active, b->Poff, b->Pdiag);
+    else if (ae == 2) k_setup_pressure_matrix_multi<2><<<gm, 256, 0, STREAM(s)>>>(b->t, b->B, b->A, active, b->Poff, b->Pdiag);
+    else k_setup_pressure_matrix<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, b->A, active, b->Poff, b->Pdiag);
     LAUNCH_CHECK("k_setup_pressure_matrix");
     return FGB_OK;
 }
@@ -2265,7 +2407,12 @@ extern "C" int fgb_setup_pressure_rhs(fgb_batch *b, const float *u, const float 
         LAUNCH_CHECK("k_hbya");
     }
     const int no = b->opt.nonortho && p_prev;
-    k_pressure_div<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, b->hbya, bvel, p_prev, b->A, active, no, b->div);
+    const int ae = b->asm_envs > 1 ? b->asm_envs : 1;
+    const dim3 gm((b->t.N + 255) / 256, (b->B + ae - 1) / ae);
+    if (ae == 8) k_pressure_div_multi<8><<<gm, 256, 0, STREAM(s)>>>(b->t, b->B, b->hbya, bvel, p_prev, b->A, active, no, b->div);
+    else if (ae == 4) k_pressure_div_multi<4><<<gm, 256, 0, STREAM(s)>>>(b->t, b->B, b->hbya, bvel, p_prev, b->A, active, no, b->div);
+    else if (ae == 2) k_pressure_div_multi<2><<<gm, 256, 0, STREAM(s)>>>(b->t, b->B, b->hbya, bvel, p_prev, b->A, active, no, b->div);
+    else k_pressure_div<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, b->hbya, bvel, p_prev, b->A, active, no, b->div);
     LAUNCH_CHECK("k_pressure_div");
     return FGB_OK;
 }

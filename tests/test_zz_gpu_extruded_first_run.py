@@ -1,4 +1,8 @@
-"""CylinderJet3D / extruded D = 3 launch path on the GPU (tools/extruded_check.py: substep, reset and env.step against the
+"""Code paths that had NEVER run on a GPU when they were committed (the round's GPU budget was spent).  They run LAST (file name) and as
+non-strict xfails, so that a fault in them cannot disturb the verified suites: XPASS = verified on this box.
+
+1. Opt-in multi-environment assembly kernels (FGB_ASM_ENVS): bit-identity with the default kernels.
+2. CylinderJet3D / extruded D = 3 launch path on the GPU (tools/extruded_check.py: substep, reset and env.step against the
 unmodified reference's goldens).  When this file was committed the round's GPU budget was spent and the launch path had NEVER run
 on a GPU -- everything around it is verified on the CPU (tests/test_cylinder3d_cpu.py, test_extruded_host.py).  The check therefore
 runs LAST (file name), in its OWN PROCESS with a time limit, so that a fault in the new path cannot disturb the verified suites,
@@ -13,6 +17,42 @@ import pytest
 from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.xfail(strict=False, reason="first GPU run of the opt-in multi-environment assembly kernels")
+@pytest.mark.parametrize("E", [2, 4, 8])
+def test_multi_env_assembly_variants_are_bit_identical(cyl24, golden, E, monkeypatch):
+    """k_setup_pressure_matrix_multi<E> / k_pressure_div_multi<E> (one thread = the same cell of E environments, tables loaded once)
+    against the default one-thread-per-(cell, environment) kernels on 11 noisy environments (a batch that is not a multiple of E),
+    with the deferred non-orthogonal pressure term switched on."""
+    import numpy as np
+    import torch
+    from fluidgym_b200.solver import BatchedPISO
+    spec, cd = cyl24
+    fx = golden("cyl24_substep1.npz")
+    B, dt = 11, float(fx["dt"][0])
+    res = {}
+    for tag, env in (("base", None), ("multi", str(E))):
+        if env is None:
+            monkeypatch.delenv("FGB_ASM_ENVS", raising=False)
+        else:
+            monkeypatch.setenv("FGB_ASM_ENVS", env)
+        sol = BatchedPISO(cd, B, cg_impl=0)
+        gen = torch.Generator(device="cuda").manual_seed(7)
+        sol.u.copy_(torch.from_numpy(fx["u_in"]).cuda().unsqueeze(0).expand_as(sol.u))
+        sol.u += 0.05 * torch.randn(sol.u.shape, device="cuda", generator=gen)
+        sol.bvel.copy_(torch.from_numpy(fx["bvel_in"]).cuda().unsqueeze(0).expand_as(sol.bvel))
+        sol.p.copy_(torch.randn(sol.p.shape, device="cuda", generator=gen))
+        sol.setup_advection(dt)
+        sol.solve_advection(zero_init=True)
+        sol.setup_pressure_matrix()
+        sol.setup_pressure_rhs(dt, p_prev=sol.p)
+        torch.cuda.synchronize()
+        res[tag] = {k: sol.buffer(k).clone() for k in ("Poff", "Pdiag", "hbya", "div")}
+        del sol
+    for k in res["base"]:
+        assert torch.isfinite(res["multi"][k]).all()
+        assert torch.equal(res["base"][k], res["multi"][k]), (E, k, float((res["base"][k] - res["multi"][k]).abs().max()))
 
 
 @pytest.mark.xfail(strict=False, reason="first GPU run of the extruded launch path (never executed on a GPU when committed)")

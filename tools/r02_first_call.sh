@@ -10,6 +10,8 @@ timeout 900 python tools/extruded_check.py --json gpurun_out/r02/extruded_check.
 timeout 900 python tools/cyl3d_bench.py --resolutions 8 24 --steps 1 --out gpurun_out/r02/cyl3d_bench.json > gpurun_out/r02/cyl3d_bench.log 2>&1
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r02/gpu_tests.log 2>&1
 timeout 600 python bench.py > gpurun_out/r02/bench.json 2> gpurun_out/r02/bench.err
+FGB_ASM_ENVS=4 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/r02/bench_asm4.json 2> gpurun_out/r02/bench_asm4.err
+FGB_ASM_ENVS=8 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/r02/bench_asm8.json 2> gpurun_out/r02/bench_asm8.err
 # (res_z = 96: 46 806 x 96 = 4.5 M cells, the reference needs minutes per env.step -> lean trace, one env.step, generous limit)
 timeout 1700 python oracle/ref_harness.py --env Airfoil3D-easy-v0 --tag airfoil3d --out gpurun_out/r02/airfoil3d --env-steps 1 --time-steps 0 \
     --trace-substeps 1 --lean --kw '{"init_from_2d": false}' > gpurun_out/r02/airfoil3d.log 2>&1
