@@ -551,6 +551,110 @@ __global__ void __launch_bounds__(256) k_pressure_div_multi(Tab t, int B, const 
         if (on[e]) Div[(size_t)(b0 + e) * N + g] = d[e];
 }
 
+// k_setup_advection for E environments per thread (opt-in, see above): 30 table values per cell for 9 values of state.
+template <int E>
+__global__ void __launch_bounds__(256) k_setup_advection_multi(Tab t, int B, const float *__restrict__ U, const float *__restrict__ Ures,
+                                                                const float *__restrict__ Bvel, const float *__restrict__ Src,
+                                                                const float *__restrict__ dtv, const int32_t *__restrict__ active,
+                                                                float *__restrict__ Coff, float *__restrict__ A, float *__restrict__ Rhs,
+                                                                int with_matrix) {
+    const int b0 = blockIdx.y * E;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = t.N, NB = t.NB;
+    if (g >= N) return;
+    int nb[4], src[4], fcm[4];
+    float fdet[4], fma[4], fmb[4], falpha[4], cd[5];
+    const float det = t.det[g], m0 = t.minv[g], m1 = t.minv[N + g], m2 = t.minv[2 * N + g], m3 = t.minv[3 * N + g];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) cd[q] = with_matrix ? t.Cd[q * N + g] : 0.f;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        nb[f] = t.nbr[f * N + g];
+        falpha[f] = 0.f;
+        if (nb[f] >= 0) {
+            const int fc = with_matrix ? t.fl_comp[f * N + g] : 0, k = fc & 1, n = nb[f];
+            fcm[f] = fc; src[f] = n;
+            fdet[f] = with_matrix ? t.det[n] : 0.f;
+            fma[f] = with_matrix ? t.minv[(2 * k) * N + n] : 0.f; fmb[f] = with_matrix ? t.minv[(2 * k + 1) * N + n] : 0.f;
+        } else {
+            const int j = -1 - nb[f], ax = f >> 1;
+            fcm[f] = 0; src[f] = j;
+            fdet[f] = t.b_det[j]; fma[f] = t.b_minv[(2 * ax) * NB + j]; fmb[f] = t.b_minv[(2 * ax + 1) * NB + j];
+            falpha[f] = t.b_alpha[j];
+        }
+    }
+    bool on[E];
+    float dt[E], S0[E], S1[E], no0[E], no1[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int b = b0 + e;
+        on[e] = b < B && !(active && !active[b]);
+        no0[e] = 0.f; no1[e] = 0.f; S0[e] = 0.f; S1[e] = 0.f; dt[e] = 1.f;
+        if (!on[e]) continue;
+        const float *u = U + (size_t)b * 2 * N, *bv = Bvel + (size_t)b * 2 * NB;
+        dt[e] = dtv[b];
+        if (with_matrix) {                                                             // face_fluxes + matrix rows, verbatim
+            const float ux = u[g], uy = u[N + g];
+            const float Uc[2] = {det * (m0 * ux + m1 * uy), det * (m2 * ux + m3 * uy)};
+            float diag = det / dt[e] + cd[0];
+            float *co = Coff + (size_t)b * 4 * N;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                float o = 0.f;
+                if (nb[f] >= 0) {
+                    float velN = fdet[f] * (fma[f] * u[src[f]] + fmb[f] * u[N + src[f]]);
+                    if (fcm[f] & 2) velN = -velN;
+                    const float flf = (velN + Uc[f >> 1]) * 0.5f;
+                    const float ff = ((f & 1) ? 0.5f : -0.5f) * flf;
+                    diag += ff;
+                    o = (ff + cd[f + 1]) / det;
+                }
+                co[f * N + g] = o;
+            }
+            A[(size_t)b * N + g] = diag / det;
+        }
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {                                                  // boundary_source, verbatim
+            if (nb[f] < 0) {
+                const float bu = bv[src[f]], bw = bv[NB + src[f]];
+                const float flux = fdet[f] * (fma[f] * bu + fmb[f] * bw) * ((f & 1) ? 1.f : -1.f);
+                const float visc2a = t.viscosity * 2.f * falpha[f];
+                S0[e] -= bu * flux; S0[e] += bu * visc2a;
+                S1[e] -= bw * flux; S1[e] += bw * visc2a;
+            }
+        }
+    }
+    for (int k = 0; k < t.K_no; ++k) {
+        const float w = t.no_wv[k * N + g];
+        if (w != 0.f) {
+            const int j = t.no_idx[k * N + g];
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                if (on[e]) { const float *ur = Ures + (size_t)(b0 + e) * 2 * N; no0[e] += w * ur[j]; no1[e] += w * ur[N + j]; }
+        }
+    }
+    for (int k = 0; k < t.K_nob; ++k) {
+        const float w = t.nob_w[k * N + g];
+        if (w != 0.f) {
+            const int j = t.nob_idx[k * N + g];
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                if (on[e]) { const float *bv = Bvel + (size_t)(b0 + e) * 2 * NB; no0[e] += w * bv[j]; no1[e] += w * bv[NB + j]; }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        if (!on[e]) continue;
+        const int b = b0 + e;
+        const float *u = U + (size_t)b * 2 * N;
+        float r0 = (det * u[g] / dt[e] + S0[e] - no0[e]) / det;
+        float r1 = (det * u[N + g] / dt[e] + S1[e] - no1[e]) / det;
+        if (Src) { r0 += Src[(size_t)b * 2 * N + g]; r1 += Src[(size_t)b * 2 * N + N + g]; }
+        Rhs[(size_t)b * 2 * N + g] = r0;
+        Rhs[(size_t)b * 2 * N + N + g] = r1;
+    }
+}
+
 // PISO_update_velocity (K.cu:816-849, 5962-5995)
 __global__ void __launch_bounds__(256) k_correct_velocity(Tab t, const float *__restrict__ Hbya, const float *__restrict__ P,
                                                            const float *__restrict__ A, const int32_t *__restrict__ active,
@@ -2371,11 +2475,21 @@ __global__ void __launch_bounds__(256) k_adj_scalar(Tab t, const float *__restri
 static inline dim3 cell_grid(const fgb_batch *b) { return dim3((b->t.N + 255) / 256, b->B); }
 #define STREAM(s) ((cudaStream_t)(s))
 
+static inline void launch_setup_advection(fgb_batch *b, cudaStream_t st, const float *u, const float *ures, const float *bvel, const float *src,
+                                          const float *dt, const int32_t *active, int with_matrix) {
+    const int ae = b->asm_envs > 1 ? b->asm_envs : 1;
+    const dim3 gm((b->t.N + 255) / 256, (b->B + ae - 1) / ae);
+    if (ae == 8) k_setup_advection_multi<8><<<gm, 256, 0, st>>>(b->t, b->B, u, ures, bvel, src, dt, active, b->Coff, b->A, b->rhs, with_matrix);
+    else if (ae == 4) k_setup_advection_multi<4><<<gm, 256, 0, st>>>(b->t, b->B, u, ures, bvel, src, dt, active, b->Coff, b->A, b->rhs, with_matrix);
+    else if (ae == 2) k_setup_advection_multi<2><<<gm, 256, 0, st>>>(b->t, b->B, u, ures, bvel, src, dt, active, b->Coff, b->A, b->rhs, with_matrix);
+    else k_setup_advection<<<cell_grid(b), 256, 0, st>>>(b->t, u, ures, bvel, src, dt, active, b->Coff, b->A, b->rhs, with_matrix);
+}
+
 extern "C" int fgb_setup_advection(fgb_batch *b, const float *u, const float *ures, const float *bvel, const float *src,
                                    const float *dt, const int32_t *active, fgb_stream_t s) {
     if (!b || !u || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_setup_advection: null argument");
     ProfScope ps(b, CLS_ASM, STREAM(s));
-    k_setup_advection<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, u, ures ? ures : u, bvel, src, dt, active, b->Coff, b->A, b->rhs, 1);
+    launch_setup_advection(b, STREAM(s), u, ures ? ures : u, bvel, src, dt, active, 1);
     LAUNCH_CHECK("k_setup_advection");
     return FGB_OK;
 }
@@ -2607,7 +2721,7 @@ extern "C" int fgb_piso_substep(fgb_batch *b, float *u, float *p, const float *b
     const int n_adv = o.nonortho ? o.adv_nonortho_steps : 1;
     for (int ns = 0; ns < n_adv; ++ns) {
         b->launches++;
-        k_setup_advection<<<cell_grid(b), 256, 0, st>>>(b->t, u, ns == 0 ? u : b->ures, bvel, src, dt, active, b->Coff, b->A, b->rhs, ns == 0);
+        launch_setup_advection(b, st, u, ns == 0 ? u : b->ures, bvel, src, dt, active, ns == 0);
         LAUNCH_CHECK("k_setup_advection");
         if ((rc = fgb_solve_advection(b, o.nonortho ? (ns == 0) : 0, active, s))) return rc;
     }

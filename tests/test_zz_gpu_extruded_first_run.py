@@ -48,7 +48,16 @@ def test_multi_env_assembly_variants_are_bit_identical(cyl24, golden, E, monkeyp
         sol.setup_pressure_matrix()
         sol.setup_pressure_rhs(dt, p_prev=sol.p)
         torch.cuda.synchronize()
-        res[tag] = {k: sol.buffer(k).clone() for k in ("Poff", "Pdiag", "hbya", "div")}
+        res[tag] = {k: sol.buffer(k).clone() for k in ("Coff", "A", "rhs", "ures", "Poff", "Pdiag", "hbya", "div")}
+        del sol
+        # a whole substep with two deferred-correction iterations of the predictor (the right-hand-side-only launch) and two of the pressure
+        sol = BatchedPISO(cd, B, cg_impl=6, advect_non_ortho_steps=2, pressure_non_ortho_steps=2)
+        sol.u.copy_(torch.from_numpy(fx["u_in"]).cuda().unsqueeze(0).expand_as(sol.u))
+        sol.u += 0.05 * torch.randn(sol.u.shape, device="cuda", generator=gen)
+        sol.bvel.copy_(torch.from_numpy(fx["bvel_in"]).cuda().unsqueeze(0).expand_as(sol.bvel))
+        sol.piso_substep(dt)
+        torch.cuda.synchronize()
+        res[tag].update(u_substep=sol.u.clone(), p_substep=sol.p.clone())
         del sol
     for k in res["base"]:
         assert torch.isfinite(res["multi"][k]).all()
