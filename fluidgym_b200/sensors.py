@@ -170,9 +170,99 @@ def _ell_rows_at_voxels(R, out_shape, sensor_px):
 
 
 def sensor_tables_extruded(vertex2d_list, z_vertices: np.ndarray, out_shape, sensor_px: np.ndarray, fill_max_steps: int):
-    """sensor_tables_3d for a z-extruded multi-block domain (columns = plane * N2 + g)."""
-    R, _ = pixel_map_extruded(vertex2d_list, z_vertices, out_shape, fill_max_steps)
-    return _ell_rows_at_voxels(R, out_shape, sensor_px)
+    """sensor_tables_3d for a z-extruded multi-block domain (columns = plane * N2 + g).  Only the rows of the sensor voxels are
+    built (``_sensor_rows_localized``): the full voxel map of the registered sizes has 10^7 ... 10^8 rows."""
+    centres, lower, upper = _extruded_centres(vertex2d_list, z_vertices)
+    W, H, Z = (int(s) for s in out_shape)
+    flat = sensor_px[0].astype(np.int64) + W * (sensor_px[1].astype(np.int64) + H * sensor_px[2].astype(np.int64))
+    rows = _sensor_rows_localized(centres, lower, upper, (W, H, Z), fill_max_steps, 3 << 1, flat)
+    ns = flat.size
+    K = max(1, max(len(r[0]) for r in rows))
+    idx = np.zeros((K, ns), dtype=np.int32)
+    w = np.zeros((K, ns), dtype=f32)
+    for s_, (ci, cw) in enumerate(rows):
+        idx[:len(ci), s_] = ci
+        w[:len(ci), s_] = cw
+    return idx, w
+
+
+def _sensor_rows_localized(centres, lower, upper, out_shape, fill_max_steps, n_corners, sensor_flat):
+    """Rows of the rendered-voxel map (``_pixel_map_from_centres``: splat + normalise + hole-fill sweeps) for the voxels
+    ``sensor_flat`` only -> list of (cell indices sorted, weights float64).  The fill level of every voxel is found with dense boolean
+    sweeps; the row of a voxel filled in sweep k is the mean of the rows of its face neighbours that were valid before that sweep,
+    evaluated recursively (memoised) -- identical to the matrix recurrence R <- R + A R restricted to the rows that are needed."""
+    W, H, Z = out_shape
+    S, wsum = _splat_matrix(centres, lower, upper, out_shape, n_corners)
+    npx = W * H * Z
+    valid = (wsum > 1e-8).reshape(Z, H, W)
+    level = np.where(valid, 0, -1).astype(np.int32)
+    for k in range(1, int(fill_max_steps) + 1):
+        if valid.all():
+            break
+        nbv = np.zeros_like(valid)
+        nbv[1:] |= valid[:-1]; nbv[:-1] |= valid[1:]
+        nbv[:, 1:] |= valid[:, :-1]; nbv[:, :-1] |= valid[:, 1:]
+        nbv[:, :, 1:] |= valid[:, :, :-1]; nbv[:, :, :-1] |= valid[:, :, 1:]
+        newly = nbv & ~valid
+        if not newly.any():
+            break
+        level[newly] = k
+        valid = valid | newly
+    level = level.reshape(-1)
+    strides = (1, W, W * H)
+    dims = (W, H, Z)
+    memo = {}
+
+    def neighbours(v):
+        x, y, z = v % W, (v // W) % H, v // (W * H)
+        pos = (x, y, z)
+        for ax in range(3):
+            if pos[ax] > 0:
+                yield v - strides[ax]
+            if pos[ax] < dims[ax] - 1:
+                yield v + strides[ax]
+
+    def row(v0):
+        stack = [v0]
+        while stack:
+            v = stack[-1]
+            if v in memo:
+                stack.pop()
+                continue
+            lv = level[v]
+            if lv < 0:                                       # never filled: zero row
+                memo[v] = {}
+                stack.pop()
+                continue
+            if lv == 0:
+                a, b = S.indptr[v], S.indptr[v + 1]
+                inv = 1.0 / wsum[v]
+                d = {}
+                for c, x in zip(S.indices[a:b], S.data[a:b]):
+                    d[int(c)] = d.get(int(c), 0.0) + x * inv
+                memo[v] = d
+                stack.pop()
+                continue
+            srcs = [n for n in neighbours(v) if 0 <= level[n] < lv]
+            missing = [n for n in srcs if n not in memo]
+            if missing:
+                stack.extend(missing)
+                continue
+            d = {}
+            f = 1.0 / len(srcs)
+            for n in srcs:
+                for c, x in memo[n].items():
+                    d[c] = d.get(c, 0.0) + x * f
+            memo[v] = d
+            stack.pop()
+        return memo[v0]
+
+    out = []
+    for v in np.asarray(sensor_flat, dtype=np.int64):
+        d = row(int(v))
+        ci = np.array(sorted(d), dtype=np.int64)
+        out.append((ci, np.array([d[c] for c in ci], dtype=np.float64)))
+    return out
 
 
 def pixel_map_extruded(vertex2d_list, z_vertices: np.ndarray, out_shape, fill_max_steps: int, n_corners: int = 3 << 1):
@@ -180,6 +270,11 @@ def pixel_map_extruded(vertex2d_list, z_vertices: np.ndarray, out_shape, fill_ma
     the blocks [2, ny+1, nx+1], ``z_vertices`` [nz+1].  Columns are the cells in plane-major order (plane * N2 + g, g = block-major
     2-D cell index), the layout of fluidgym_b200/extruded3d.py."""
     W, H, Z = (int(s) for s in out_shape)
+    centres, lower, upper = _extruded_centres(vertex2d_list, z_vertices)
+    return _pixel_map_from_centres(centres, lower, upper, (W, H, Z), fill_max_steps, n_corners)
+
+
+def _extruded_centres(vertex2d_list, z_vertices):
     z_vertices = np.asarray(z_vertices, dtype=f32)
     allxy = np.concatenate([v.reshape(2, -1) for v in vertex2d_list], axis=1).astype(f32)
     lower = np.array([allxy[0].min(), allxy[1].min(), z_vertices.min()], dtype=f32)
@@ -188,10 +283,11 @@ def pixel_map_extruded(vertex2d_list, z_vertices: np.ndarray, out_shape, fill_ma
     zc = ((z_vertices[:-1] + z_vertices[1:]) * f32(0.5)).astype(f32)
     nz, N2 = zc.size, c2.shape[1]
     centres = np.stack([np.tile(c2[0], nz), np.tile(c2[1], nz), np.repeat(zc, N2)]).astype(f32)     # [3, nz * N2]
-    return _pixel_map_from_centres(centres, lower, upper, (W, H, Z), fill_max_steps, n_corners)
+    return centres, lower, upper
 
 
-def _pixel_map_from_centres(centres, lower, upper, out_shape, fill_max_steps, n_corners):
+def _splat_matrix(centres, lower, upper, out_shape, n_corners):
+    """(S csr [voxels, cells] of the raw splat weights, row sums) -- the first stage of ``_pixel_map_from_centres``"""
     W, H, Z = out_shape
     size = (upper - lower).astype(f32)
     centre = (lower + size * f32(0.5)).astype(f32)
@@ -218,6 +314,13 @@ def _pixel_map_from_centres(centres, lower, upper, out_shape, fill_max_steps, n_
     npx = W * H * Z
     S = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(npx, N))
     wsum = np.asarray(S.sum(axis=1)).ravel()
+    return S, wsum
+
+
+def _pixel_map_from_centres(centres, lower, upper, out_shape, fill_max_steps, n_corners):
+    W, H, Z = out_shape
+    S, wsum = _splat_matrix(centres, lower, upper, out_shape, n_corners)
+    npx = W * H * Z
     valid = wsum > 1e-8
     level = np.where(valid, 0, -1).astype(np.int32)
     inv = np.zeros(npx)

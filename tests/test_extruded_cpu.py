@@ -180,3 +180,25 @@ def test_cylinder3d_boundary_hooks_reproduce_the_reference_boundary_values(cyl3d
     bv = ee.update_outflow(cd, s0["u_in"], bv, float(s0["dt"][0]), out, hz)
     assert np.abs(bv[:, :, jf] - s0["bvel"][:, :, jf]).max() < 1e-7
     assert np.abs(bv - s0["bvel"]).max() < 1e-6
+
+
+def test_localized_sensor_rows_equal_the_full_voxel_map():
+    """sensors.sensor_tables_extruded builds only the rows of the sensor voxels (memoised recursion over the fill levels); they must
+    equal the rows of the full rendered-voxel map (matrix recurrence over all 175 104 voxels) entry by entry."""
+    from fluidgym_b200 import sensors as S
+    from fluidgym_b200.envs.cylinder import cylinder_sensor_locations
+    from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
+    from fluidgym_b200.envs.spanwise import spanwise_sensor_voxels
+    spec = make_cylinder_domain(8)
+    rs = (171, 32, 32)
+    px = spanwise_sensor_voxels(cylinder_sensor_locations(1.0), 16, 4.1, 22.0, rs).numpy()
+    zv = np.linspace(-2.0, 2.0, 9, dtype=np.float32)
+    vs = [b.vertex for b in spec.blocks]
+    idx, w = S.sensor_tables_extruded(vs, zv, rs, px, 16)
+    R, level = S.pixel_map_extruded(vs, zv, rs, 16)
+    flat = px[0].astype(np.int64) + rs[0] * (px[1].astype(np.int64) + rs[1] * px[2].astype(np.int64))
+    assert level[flat].max() >= 1                                    # some sensors sit in voxels that only the fill sweeps reach
+    dense = np.zeros((flat.size, R.shape[1]))
+    np.add.at(dense, (np.repeat(np.arange(flat.size), idx.shape[0]), idx.T.reshape(-1)), w.T.reshape(-1).astype(np.float64))
+    ref = R[flat].toarray()
+    assert np.abs(dense - ref).max() < 1e-7 and ((dense != 0) == (np.abs(ref) > 1e-12)).all()
