@@ -88,4 +88,9 @@ def _register_defaults():
     register("CylinderJet3D-easy-v0", CylinderJet3DEnv, **{**CYLINDER_JET_3D_DEFAULT_CONFIG, "reynolds_number": 100.0, "resolution": 24})
     register("CylinderJet3D-medium-v0", CylinderJet3DEnv, **{**CYLINDER_JET_3D_DEFAULT_CONFIG, "reynolds_number": 250.0, "resolution": 32})
     register("CylinderJet3D-hard-v0", CylinderJet3DEnv, **{**CYLINDER_JET_3D_DEFAULT_CONFIG, "reynolds_number": 500.0, "resolution": 48})
+    from .envs.airfoil3d import AIRFOIL_3D_DEFAULT_CONFIG, Airfoil3DEnv
+    # fluidgym/__init__.py:333-352.  Assembled from pinned parts, environment-level parity unpinned (no reference golden yet), never run
+    # on a GPU (envs/airfoil3d.py) -- not part of tests/test_gpu_all_envs.py.
+    for level, re in (("easy", 1e3), ("medium", 3e3), ("hard", 5e3)):
+        register(f"Airfoil3D-{level}-v0", Airfoil3DEnv, **{**AIRFOIL_3D_DEFAULT_CONFIG, "reynolds_number": re})
     register("CylinderJet2D-hard-v0", CylinderJet2DEnv, **{**CYLINDER_JET_2D_DEFAULT_CONFIG, "reynolds_number": 500.0, "resolution": 32})

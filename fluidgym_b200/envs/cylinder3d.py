@@ -30,6 +30,7 @@ class CylinderJet3DEnv(DomainStatistics):
     H, L, D, cylinder_diameter, U_mean, cylinder_offset_y = 4.1, 22.0, 4.0, 1.0, 1.0, 0.05
     action_smoothing_alpha = 0.1
     jet_angle = 10.0
+    bc_tol = 5e-6                                                       # tolerance of the outflow update's flux balance (:295)
     metrics = ["drag", "lift"]
     reference_values = {"cd_ref": ("drag", "mean")}
 
@@ -45,6 +46,7 @@ class CylinderJet3DEnv(DomainStatistics):
         if local_2d_obs and not use_marl:
             raise ValueError("Local 2D observations are only supported in multi-agent mode.")
         self.n_envs, self.n_jets = int(n_envs), int(n_jets)
+        self.n_span = self.n_jets                                   # agents lined up along the span
         self.resolution, self.dt, self.cfl = int(resolution), float(dt), float(adaptive_cfl)
         self.step_length, self.episode_length = float(step_length), int(episode_length)
         self.lift_penalty, self.cd_ref = float(lift_penalty), float(cd_ref)
@@ -95,7 +97,7 @@ class CylinderJet3DEnv(DomainStatistics):
 
     @property
     def n_sensors_z(self):
-        return self.n_jets * self.n_sensors_per_agent
+        return self.n_span * self.n_sensors_per_agent
 
     def _setup_sensors(self):
         xy = cylinder_sensor_locations(self.cylinder_diameter)
@@ -110,7 +112,7 @@ class CylinderJet3DEnv(DomainStatistics):
     # ---- reference-shaped API --------------------------------------------------------------------------------------------
     @property
     def n_agents(self):
-        return self.n_jets if self.use_marl else 1
+        return self.n_span if self.use_marl else 1
 
     @property
     def id(self):
@@ -134,7 +136,7 @@ class CylinderJet3DEnv(DomainStatistics):
         elif self.use_marl:
             vs, ps = (self.local_obs_window, spa, 3, nxy), (self.local_obs_window, spa, nxy)
         else:
-            vs, ps = (self.n_jets, spa, 3, nxy), (self.n_jets, spa, nxy)
+            vs, ps = (self.n_span, spa, 3, nxy), (self.n_span, spa, nxy)
         return spaces.Dict({"velocity": spaces.Box(-inf, inf, shape=vs), "pressure": spaces.Box(-inf, inf, shape=ps)})
 
     @property
@@ -150,7 +152,7 @@ class CylinderJet3DEnv(DomainStatistics):
     def sample_action(self):
         if self._seed is None:
             raise RuntimeError("Environment must be seeded before sampling actions")
-        return torch.rand(self.n_envs, self.n_jets, 1, device=self.device, generator=self._torch_rng) * 2 - 1
+        return torch.rand(self._zero_action.shape, device=self.device, generator=self._torch_rng) * 2 - 1
 
     def set_state(self, u, p, bvel, last_control=None):
         s = self.solver
@@ -178,7 +180,7 @@ class CylinderJet3DEnv(DomainStatistics):
         s.p.zero_()
         s.bvel.zero_()
         s.bvel[:, :2] = self._bvel0[None, :, None, :]
-        s.make_divergence_free_with_hook(max_iter=1000)              # cylinder_env_base.py:325; SIM.py:1320-1430
+        s.make_divergence_free_with_hook(max_iter=1000, bc_tol=self.bc_tol)      # cylinder_env_base.py:325; SIM.py:1320-1430
         self.last_control.zero_()
         if randomize:
             self._randomize_domain()
@@ -196,7 +198,7 @@ class CylinderJet3DEnv(DomainStatistics):
         s.u += torch.randn(s.u.shape, device=self.device, generator=self._torch_rng) * 0.025
         s.p += torch.randn(s.p.shape, device=self.device, generator=self._torch_rng) * 0.025
         for _ in range(n_steps):
-            s.single_step(self.dt, self.cfl)
+            s.single_step(self.dt, self.cfl, bc_tol=self.bc_tol)
 
     def _apply_action(self, control: torch.Tensor):
         """jet_cylinder_env_3d.py:399-424: every jet drives its ``nz_per_agent`` planes with the 2-D template (no spanwise
@@ -207,6 +209,10 @@ class CylinderJet3DEnv(DomainStatistics):
         s.bvel[:, :2, :, jf] = self.jet_templ[None, :, None, :] * per_plane[:, None, :, None]
         s.bvel[:, 2, :, jf] = 0.0
         s.balance_fluxes(self._free_jets, 1e-7)
+
+    def _reward(self, cd, cl):
+        """cylinder_env_base.py:769, jet_cylinder_env_3d.py:436, 470-472"""
+        return self.cd_ref - cd - self.lift_penalty * torch.abs(cl)
 
     def _drag_and_lift(self):
         """Per-plane drag / lift coefficients [B, nz] each (cylinder_env_base.py:657-700, forces.py:278-377: the 2-D wall
@@ -227,7 +233,7 @@ class CylinderJet3DEnv(DomainStatistics):
         s = self.solver
         us = self._sample(s.u).permute(0, 2, 1)                                                   # [B, sensors, 3]
         ps = self._sample(s.p[:, None])[:, 0]
-        return global_obs_from_samples(us, ps, self.n_jets, self.n_sensors_per_agent, local_2d_obs=self.local_2d_obs)
+        return global_obs_from_samples(us, ps, self.n_span, self.n_sensors_per_agent, local_2d_obs=self.local_2d_obs)
 
     def _get_local_obs(self):
         loc = local_obs_windows(self._get_global_obs(), self.local_obs_window)
@@ -249,7 +255,7 @@ class CylinderJet3DEnv(DomainStatistics):
         if self.use_marl and self.local_reward_weight is None:
             raise ValueError("local_reward_weight must be set for multi-agent step.")
         s = self.solver
-        a = action.reshape(self.n_envs, self.n_jets)
+        a = action.reshape(self.last_control.shape)
         cds = torch.zeros(self.n_envs, self.nz, device=self.device)
         cls_ = torch.zeros_like(cds)
         nsub = 0
@@ -257,24 +263,24 @@ class CylinderJet3DEnv(DomainStatistics):
             self.last_control = self.last_control + self.action_smoothing_alpha * (a - self.last_control)
             if self.enable_actions:
                 self._apply_action(self.last_control)
-            nsub += s.single_step(self.dt, self.cfl)
+            nsub += s.single_step(self.dt, self.cfl, bc_tol=self.bc_tol)
             cd_k, cl_k = self._drag_and_lift()
             cds += cd_k
             cls_ += cl_k
         self.last_substeps = nsub
         all_cds, all_cls = cds / self.n_sim_steps, cls_ / self.n_sim_steps
         cd, cl = all_cds.sum(dim=1) / self.D, all_cls.sum(dim=1) / self.D                        # jet_cylinder_env_3d.py:431-452
-        reward = self.cd_ref - cd - self.lift_penalty * torch.abs(cl)
+        reward = self._reward(cd, cl)
         self._n_steps += 1
         truncated = self._n_steps >= self.episode_length
         info = {"drag": cd, "lift": cl}
         if not self.use_marl:
             info["all_cds"], info["all_cls"] = all_cds, all_cls
             return self._get_global_obs(), reward, False, truncated, info
-        per = self.D / self.n_jets                                                                # :454-486
-        local_cd = all_cds.view(self.n_envs, self.n_jets, -1).sum(dim=2) / per
-        local_cl = all_cls.view(self.n_envs, self.n_jets, -1).sum(dim=2) / per
-        local = self.cd_ref - local_cd - self.lift_penalty * torch.abs(local_cl)
+        per = self.D / self.n_span                                                                # :454-486
+        local_cd = all_cds.view(self.n_envs, self.n_span, -1).sum(dim=2) / per
+        local_cl = all_cls.view(self.n_envs, self.n_span, -1).sum(dim=2) / per
+        local = self._reward(local_cd, local_cl)
         lw = float(self.local_reward_weight)
         info["global_reward"] = reward
         return self._get_local_obs(), lw * local + (1 - lw) * reward[:, None], False, truncated, info

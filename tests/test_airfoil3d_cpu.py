@@ -1,0 +1,112 @@
+"""Airfoil3D environment (fluidgym_b200/envs/airfoil3d.py): host logic on the CPU with the solver calls stubbed out, at a reduced
+number of z planes (8 instead of 96; the plane mesh is the real 46 806-cell airfoil grid).  The environment is assembled from pinned
+parts (extruded solver path + spanwise machinery: tests/test_cylinder3d_cpu.py; 2-D airfoil tables: tests/test_gpu_airfoil.py,
+test_airfoil_cpu.py); ENVIRONMENT-LEVEL PARITY IS UNPINNED until a golden run of the reference's Airfoil3D exists -- these tests
+check the reference's formulas (airfoil_env_3d.py, cited per assertion), not its outputs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+torch = pytest.importorskip("torch")
+sys.path.insert(0, os.path.join(ROOT, "tests", "cpu_harness"))
+
+
+@pytest.fixture(scope="module")
+def compiled():
+    from fluidgym_b200.envs.airfoil_domain import make_airfoil_domain
+    spec = make_airfoil_domain()
+    return spec, spec.prepare()
+
+
+def _env(compiled, **kw):
+    from extruded_standin import HostExtrudedPISO3D
+    from fluidgym_b200.envs.airfoil3d import Airfoil3DEnv
+    e = Airfoil3DEnv(res_z=8, device="cpu", compiled=compiled, solver_cls=HostExtrudedPISO3D, **kw)
+    e.solver.piso_substep = lambda dt: None                      # host logic only: 374 448 cells are too many for numpy Krylov solvers
+    e.solver.make_divergence_free = lambda max_iter=1000: None
+    return e
+
+
+def test_actions_become_per_plane_jet_profiles_with_zero_net_flux(compiled):
+    """airfoil_env_3d.py:383-407, airfoil_env_base.py:709-718: per agent zero-mean / clamped amplitudes times the 2-D unit-flux jet
+    profiles in the agent's planes, no spanwise component, outflow + airfoil top wall rescaled to a zero net boundary flux."""
+    from fluidgym_b200.envs.airfoil import Airfoil2DEnv
+    env = _env(compiled, n_envs=2, n_agents=4)
+    env.reset(seed=0)
+    s = env.solver
+    ctrl = torch.tensor([[[0.5, -0.2, 0.1], [2.0, -3.0, 0.4], [0.0, 0.0, 0.0], [1.0, 1.0, 1.0]]]).repeat(2, 1, 1)
+    ctrl[1] *= -0.5
+    before = s.bvel.clone()
+    env._apply_action(ctrl)
+    jf = env.jet_faces.long()
+    for b in range(2):
+        for a in range(4):
+            want = Airfoil2DEnv._control_to_profile(env, ctrl[b, a][None])[0]              # [2, n_top], the 2-D formula
+            for k in (2 * a, 2 * a + 1):
+                got = s.bvel[b, :2, k, jf]
+                scale = float((got * want).sum() / (want * want).sum()) if float(want.abs().max()) > 0 else 1.0
+                assert torch.allclose(got, want * scale, atol=1e-7)                          # same shape, common flux-balance factor
+                assert not s.bvel[b, 2, k, jf].any()
+    fl = (s.bvel[:, 0] * s._st["fw"][0] + s.bvel[:, 1] * s._st["fw"][1]) * s.hz
+    assert fl.double().sum(dim=(1, 2)).abs().max() < 1e-7
+    fixed = ~env._free_jets
+    assert torch.equal(s.bvel[:, :, :, fixed], before[:, :, :, fixed])                      # inflow / walls untouched
+    # agents 2 (zero) and 3 (constant = zero-mean zero): no blowing
+    assert float(s.bvel[0, :2, 4:8][:, :, jf].abs().max()) == 0.0
+
+
+def test_sensor_layout_spaces_and_multi_agent_rewards(compiled):
+    from fluidgym_b200.envs.airfoil import Airfoil2DEnv
+    env = _env(compiled, n_envs=2, n_agents=4, use_marl=True, local_reward_weight=0.5, cl_cd_ref=1.5, step_length=0.05)   # one solver step
+    # the (x, y) sensor columns are the 2-D environment's, repeated at 4 span positions (airfoil_env_3d.py:303-344)
+    e2 = object.__new__(Airfoil2DEnv)
+    e2.attack_angle_deg = 10.0
+    px2 = Airfoil2DEnv._to_pixels(e2, Airfoil2DEnv.sensor_locations_physical(e2)).numpy()
+    px = env.sensor_px.reshape(3, 4, -1)
+    assert env.n_sensors_xy == px.shape[2] and env.n_sensors_xy <= px2.shape[1]
+    assert all(np.array_equal(px[:2, k], px[:2, 0]) for k in range(4)) and len(set(px[2, :, 0].tolist())) == 4
+    assert set(map(tuple, px[:2, 0].T.tolist())) <= set(map(tuple, px2.T.tolist()))
+    assert not env.airfoil_mask[px[1], px[0]].any()
+    zs = np.round((np.linspace(-0.7, 0.7, 5)[:-1] + 0.175 + 0.7) * 150 / 1.4).astype(int)   # :331-337 with airfoil_env_base.py:581-583
+    assert px[2, :, 0].tolist() == zs.tolist()
+    assert env.n_agents == 4 and env.action_space.shape == (3,)
+    assert env.observation_space.spaces["velocity"].shape == (1, 1, 3, env.n_sensors_xy)
+    env.seed(3)
+    with pytest.raises(RuntimeError, match="must be reset"):
+        env.step(env.sample_action())
+    obs, _ = env.reset()
+    assert obs["velocity"].shape == (2, 4, 1, 1, 3, env.n_sensors_xy) and obs["pressure"].shape == (2, 4, 1, 1, env.n_sensors_xy)
+    env.solver.u[:, 0] = 0.3
+    env.solver.u[:, 0] += 0.01 * torch.randn(env.solver.u[:, 0].shape, generator=torch.Generator().manual_seed(1))
+    a = env.sample_action()
+    assert a.shape == (2, 4, 3)
+    obs, reward, term, trunc, info = env.step(a)
+    cds, cls_ = env._drag_and_lift()                              # one (stubbed) solver step: the mean over the step = the final value
+    cd, cl = cds.sum(1) / 1.4, cls_.sum(1) / 1.4
+    assert torch.allclose(info["drag"], cd, rtol=1e-5) and torch.allclose(info["lift"], cl, rtol=1e-5)
+    glob = cl / cd - 1.5                                         # airfoil_env_3d.py:420
+    lcd, lcl = cds.view(2, 4, -1).sum(2) / 0.35, cls_.view(2, 4, -1).sum(2) / 0.35          # :441-448
+    assert torch.allclose(info["global_reward"], glob, rtol=1e-5, atol=1e-6)
+    assert reward.shape == (2, 4) and torch.allclose(reward, 0.5 * (lcl / lcd - 1.5) + 0.5 * glob[:, None], rtol=1e-4, atol=1e-5)
+    sarl = _env(compiled, n_agents=2)
+    assert sarl.action_space.shape == (2, 3) and sarl.observation_space.spaces["pressure"].shape == (2, 1, sarl.n_sensors_xy)
+
+
+def test_constructor_checks_and_registry(compiled):
+    import fluidgym_b200
+    from extruded_standin import HostExtrudedPISO3D
+    from fluidgym_b200.envs.airfoil3d import Airfoil3DEnv
+    with pytest.raises(ValueError, match="evenly divides"):
+        Airfoil3DEnv(n_agents=5, device="cpu", compiled=compiled)
+    with pytest.raises(ValueError, match="Attack angle"):
+        Airfoil3DEnv(attack_angle_deg=25.0, device="cpu", compiled=compiled)
+    with pytest.raises(NotImplementedError):
+        Airfoil3DEnv(init_from_2d=True, device="cpu", compiled=compiled)
+    env = fluidgym_b200.make("Airfoil3D-hard-v0", res_z=8, device="cpu", compiled=compiled, solver_cls=HostExtrudedPISO3D,
+                             load_domain_statistics=False)
+    assert env.reynolds_number == 5e3 and env.initial_domain_id == "airfoil_3D_Re5000" and env.nz_per_agent == 2
+    assert env.solver.opt["ans"] == 2 and env.solver.opt["pns"] == 4 and env.solver.opt["ptol"] == 1e-8      # airfoil_env_base.py:262-283
