@@ -22,11 +22,15 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--settle", type=int, default=1)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--airfoil3d", action="store_true", help="also time Airfoil3D-easy-v0 (4.5 M cells; first run: finite-ness + timing only)")
     a = ap.parse_args()
     ref = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "cyl3d_meta.json")))
     rows = []
-    for res in a.resolutions:
-        env = fg.make("CylinderJet3D-easy-v0", n_envs=a.envs, resolution=res)
+    cases = [("CylinderJet3D-easy-v0", dict(resolution=res), res) for res in a.resolutions]
+    if a.airfoil3d:
+        cases.append(("Airfoil3D-easy-v0", {}, 96))
+    for env_id, kw, res in cases:
+        env = fg.make(env_id, n_envs=a.envs, **kw)
         t0 = time.time()
         env.reset(seed=42)
         torch.cuda.synchronize()
@@ -46,7 +50,7 @@ def main():
         torch.cuda.synchronize()
         dt = e0.elapsed_time(e1) * 1e-3
         it = (s.buffer("iter_total") - it0)[0].tolist()
-        row = dict(env="CylinderJet3D-easy-v0", resolution=res, cells=s.N, n_envs=a.envs, reset_seconds=t_reset,
+        row = dict(env=env_id, finite=bool(torch.isfinite(s.u).all() and torch.isfinite(s.p).all()), resolution=res, cells=s.N, n_envs=a.envs, reset_seconds=t_reset,
                    env_steps_per_s=a.envs * a.steps / dt, substeps_per_s=a.envs * nsub / dt, ms_per_substep=1e3 * dt / max(nsub, 1),
                    cg_iters_per_solve=it[0] / max(8 * nsub, 1), bicg_iters_per_rhs=it[1] / max(3 * nsub, 1),
                    us_per_cg_iteration_upper_bound=1e6 * dt / max(it[0], 1),
