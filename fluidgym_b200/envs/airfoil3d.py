@@ -38,7 +38,7 @@ class Airfoil3DEnv(CylinderJet3DEnv):
     def __init__(self, n_envs: int = 1, n_agents=4, reynolds_number=3e3, dt=0.05, adaptive_cfl=0.8, step_length=0.25, episode_length=200,
                  attack_angle_deg=10.0, local_obs_window=1, use_marl=False, local_reward_weight=0.5, local_2d_obs=False, init_from_2d=False,
                  device="cuda:0", cl_cd_ref=0.0, randomize_initial_state=False, enable_actions=True, load_initial_domain=False,
-                 compiled=None, solver_cls=None, res_z=None):
+                 initial_domains_path=None, compiled=None, solver_cls=None, res_z=None):
         if res_z is not None:
             self.res_z = int(res_z)                                     # tests only: the reference's value is fixed
         if n_agents < 1 or self.res_z % n_agents != 0:
@@ -47,8 +47,10 @@ class Airfoil3DEnv(CylinderJet3DEnv):
             raise ValueError("Local 2D observations are only supported in multi-agent mode.")
         if attack_angle_deg < 0.0 or attack_angle_deg > 20.0:
             raise ValueError("Attack angle must be between 0 and 20 degrees.")
-        if load_initial_domain or init_from_2d:
-            raise NotImplementedError("Airfoil3D: initial domains from disk (load_initial_domain / init_from_2d) are not read yet")
+        if load_initial_domain:
+            raise NotImplementedError("Airfoil3D: on-disk initial domains of the extruded multi-block grids are not read yet "
+                                      "(init_from_2d=True reads the 2-D airfoil files)")
+        self.init_from_2d, self.initial_domains_path = bool(init_from_2d), initial_domains_path
         self.n_envs, self.n_span = int(n_envs), int(n_agents)
         self.reynolds_number, self.attack_angle_deg = float(reynolds_number), float(attack_angle_deg)
         self.dt, self.cfl = float(dt), float(adaptive_cfl)
@@ -144,6 +146,29 @@ class Airfoil3DEnv(CylinderJet3DEnv):
     def action_space(self):
         from .. import spaces
         return spaces.Box(-1.0, 1.0, shape=(self.n_jets,) if self.use_marl else (self.n_span, self.n_jets))
+
+    def _initial_velocity(self):
+        """``init_from_2d`` (airfoil_env_3d.py:524-593): one random 2-D initial domain of the training split (every
+        environment of the batch draws its own index here), its velocity copied into every plane with a zero spanwise component;
+        pressure and boundary values stay those of the fresh 3-D domain.  A file whose grid differs is skipped, as in the reference."""
+        if not self.init_from_2d:
+            return
+        import os
+        from ..domain_io import load_domain
+        from .common import N_INITIAL_DOMAINS, default_initial_domains_path
+        root = self.initial_domains_path or default_initial_domains_path()
+        dom_id = self.initial_domain_id.replace("airfoil_3D", "airfoil_2D").replace("Re10000", "Re3000")
+        u4 = self.solver.u.view(self.n_envs, 3, self.nz, self.solver.N2)
+        for e in range(self.n_envs):
+            idx = int(self._np_rng.integers(0, N_INITIAL_DOMAINS))
+            path = os.path.join(root, dom_id, str(idx), "train")
+            if not os.path.exists(path + ".json"):
+                raise FileNotFoundError(f"2D initial domain not found on disk but attempting to init from 2D: {path}")
+            spec2, st = load_domain(path)
+            if [b.vertex.shape for b in spec2.blocks] != [b.vertex.shape for b in self.spec.blocks]:
+                continue                                                # "Using 3D initial domain as fallback." (:549-556)
+            u4[e, :2] = torch.from_numpy(np.ascontiguousarray(st["u"])).to(self.device)[:, None, :]
+            u4[e, 2] = 0.0
 
     def _randomize_domain(self):
         """airfoil_env_base.py:302-339"""

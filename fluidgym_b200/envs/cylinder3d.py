@@ -180,6 +180,7 @@ class CylinderJet3DEnv(DomainStatistics):
         s.p.zero_()
         s.bvel.zero_()
         s.bvel[:, :2] = self._bvel0[None, :, None, :]
+        self._initial_velocity()
         s.make_divergence_free_with_hook(max_iter=1000, bc_tol=self.bc_tol)      # cylinder_env_base.py:325; SIM.py:1320-1430
         self.last_control.zero_()
         if randomize:
@@ -188,6 +189,9 @@ class CylinderJet3DEnv(DomainStatistics):
         self._n_steps = 0
         self._reset_called = True
         return self._get_obs(), {}
+
+    def _initial_velocity(self):
+        """hook between the zero field and the projection (Airfoil3D: ``init_from_2d``)"""
 
     def _randomize_domain(self):
         """cylinder_env_base.py:364-404 (per-environment noise, common number of settling steps)"""

@@ -110,3 +110,32 @@ def test_constructor_checks_and_registry(compiled):
                              load_domain_statistics=False)
     assert env.reynolds_number == 5e3 and env.initial_domain_id == "airfoil_3D_Re5000" and env.nz_per_agent == 2
     assert env.solver.opt["ans"] == 2 and env.solver.opt["pns"] == 4 and env.solver.opt["ptol"] == 1e-8      # airfoil_env_base.py:262-283
+
+
+def test_init_from_2d_copies_the_2d_velocity_into_every_plane(compiled, tmp_path):
+    """airfoil_env_3d.py:524-593: a 2-D airfoil initial domain (the reference's on-disk format, fluidgym_b200/domain_io.py) of the
+    training split seeds the 3-D velocity plane by plane with a zero spanwise component; a missing file raises."""
+    from fluidgym_b200.domain_io import save_domain
+    spec, cd = compiled
+    rng = np.random.default_rng(2)
+    files = {}
+    for idx in range(10):
+        st = dict(u=rng.standard_normal((2, cd.N)).astype(np.float32), p=np.zeros(cd.N, np.float32), bvel=cd.bvel0[:, :cd.NB].astype(np.float32))
+        d = tmp_path / "airfoil_2D_Re3000" / str(idx)
+        d.mkdir(parents=True)
+        save_domain(spec, st, str(d / "train"))
+        files[idx] = st["u"]
+    env = _env(compiled, n_envs=3, n_agents=4, init_from_2d=True, initial_domains_path=str(tmp_path))
+    env.reset(seed=5)                                            # projection and solver are stubbed: the seeded field survives
+    u4 = env.solver.u.view(3, 3, 8, cd.N)
+    picks = []
+    for e in range(3):
+        match = [i for i, u in files.items() if np.array_equal(u4[e, :2, 0].numpy(), u)]
+        assert len(match) == 1
+        picks.append(match[0])
+        assert all(torch.equal(u4[e, :2, k], u4[e, :2, 0]) for k in range(8)) and not u4[e, 2].any()
+    rng2 = np.random.default_rng(5)
+    assert picks == [int(rng2.integers(0, 10)) for _ in range(3)]
+    missing = _env(compiled, init_from_2d=True, initial_domains_path=str(tmp_path / "nowhere"))
+    with pytest.raises(FileNotFoundError, match="2D initial domain not found"):
+        missing.reset(seed=1)
