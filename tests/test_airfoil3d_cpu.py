@@ -105,7 +105,11 @@ def test_constructor_checks_and_registry(compiled):
     with pytest.raises(ValueError, match="Attack angle"):
         Airfoil3DEnv(attack_angle_deg=25.0, device="cpu", compiled=compiled)
     with pytest.raises(NotImplementedError):
-        Airfoil3DEnv(init_from_2d=True, device="cpu", compiled=compiled)
+        Airfoil3DEnv(load_initial_domain=True, device="cpu", compiled=compiled)
+    if not torch.cuda.is_available():
+        from fluidgym_b200 import native
+        with pytest.raises(native.FGBError, match="no CPU fallback"):        # the product path has no CPU solver
+            Airfoil3DEnv(device="cpu", compiled=compiled)
     env = fluidgym_b200.make("Airfoil3D-hard-v0", res_z=8, device="cpu", compiled=compiled, solver_cls=HostExtrudedPISO3D,
                              load_domain_statistics=False)
     assert env.reynolds_number == 5e3 and env.initial_domain_id == "airfoil_3D_Re5000" and env.nz_per_agent == 2
