@@ -233,3 +233,127 @@ def save_box_domain(vertex, closed, viscosity: float, state: dict, path: str, sc
     np.savez_compressed(path + ".npz", **{str(i): a for i, a in enumerate(data)})
     with open(path + ".json", "w") as fh:
         json.dump(d, fh)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# D = 3: z-extruded multi-block domains (CylinderJet3D, Airfoil3D).  The reference's writer is generic over the dimension
+# (util/domain_io.py:64-122): tensors carry one more spatial axis as for the boxes above, every block lists six boundaries (the
+# z pair PERIODIC), and a CONNECTED boundary stores ``axes = [otherFace, axis1, axis2]`` where axis1 / axis2 are the faces of the
+# other block that the block's axes (face/2 + 1) % 3 and (face/2 + 2) % 3 are aligned with (envs/cylinder/grid.py:376-415): for an
+# x face the in-plane tangential axis y comes first and z second, for a y face z comes first and x second.  Read into the layout
+# of fluidgym_b200/extruded3d.py: the 2-D DomainSpec of the plane, u [3, nz, N2], p [nz, N2], bvel [3, nz, NB2].
+# PARITY NOTE: the 2-D multi-block and 3-D box formats are pinned to files written by the reference; no reference-written file of a
+# 3-D multi-block domain exists in this repository yet, so the axes triple above follows the reference's source, not a fixture.
+# ---------------------------------------------------------------------------------------------------------------------
+def load_extruded_domain(path: str):
+    """-> (DomainSpec of the plane, z_vertices [nz+1], state = dict(u [3,nz,N2], p [nz,N2], bvel [3,nz,NB2]))"""
+    with open(path + ".json") as fh:
+        d = json.load(fh)
+    with np.load(path + ".npz") as z:
+        data = {k: z[k] for k in z.files}
+
+    def get(dct, name):
+        return data[dct[name]] if name in dct else None
+    if d["spatialDims"] != 3:
+        raise NotImplementedError("load_extruded_domain reads 3-D multi-block domains (2-D: load_domain)")
+    if d.get("passiveScalarChannels", 0):
+        raise NotImplementedError("passive scalars on extruded multi-block domains")
+    spec = DomainSpec(float(np.asarray(get(d, "viscosity")).ravel()[0]), d.get("name", "domain"))
+    zv = None
+    for blk in d["blocks"]:
+        v = get(blk, "vertexCoordinates")
+        if v is None:
+            raise NotImplementedError("blocks stored by transform only (no vertex coordinates)")
+        v = np.asarray(v[0], dtype=np.float32)                                     # [3, nz+1, ny+1, nx+1]
+        if not (np.array_equal(v[:2], np.broadcast_to(v[:2, :1], v[:2].shape)) and np.array_equal(v[2], np.broadcast_to(v[2, :, :1, :1], v[2].shape))):
+            raise NotImplementedError("the block is not a z-extrusion of a 2-D grid")
+        bz = v[2, :, 0, 0]
+        if zv is None:
+            zv = bz
+        elif not np.array_equal(zv, bz):
+            raise NotImplementedError("blocks with different z planes")
+        spec.create_block(np.ascontiguousarray(v[:2, 0]), blk.get("name", ""))
+    nz = zv.size - 1
+    us, ps = [], []
+    for bi, blk in enumerate(d["blocks"]):
+        b = spec.blocks[bi]
+        us.append(np.asarray(get(blk, "velocity"), dtype=np.float32)[0].reshape(3, nz, -1))
+        ps.append(np.asarray(get(blk, "pressure"), dtype=np.float32)[0].reshape(nz, -1))
+        if len(blk["boundaries"]) != 6 or any(blk["boundaries"][f]["type"] != "PERIODIC" for f in (4, 5)):
+            raise NotImplementedError("extruded blocks must be periodic in z")
+        for f in range(4):
+            bd = blk["boundaries"][f]
+            kind = bd["type"]
+            if kind == "FIXED":
+                if bd.get("velocityType", "DIRICHLET") != "DIRICHLET":
+                    raise NotImplementedError(f"boundary velocity type {bd.get('velocityType')}")
+                n = b.size(1 - (f >> 1))
+                vel = np.asarray(get(bd, "velocity"), dtype=np.float32)
+                vfull = np.zeros((3, nz, n), dtype=np.float32)
+                vfull[:] = vel.reshape(3, nz, n) if vel.ndim > 2 else vel.reshape(3, 1, 1)
+                bnd = Boundary(FIXED, velocity=np.ascontiguousarray(vfull[:2, 0]), scalar=np.zeros(n, dtype=np.float32))
+                bnd.velocity3 = vfull
+                b.bounds[f] = bnd
+            elif kind == "CONNECTED":
+                of, a1, a2 = (int(x) for x in bd["axes"])
+                tang, zal = (a1, a2) if (f >> 1) == 0 else (a2, a1)
+                if zal != 4:
+                    raise NotImplementedError("block connections that flip or permute the z axis")
+                b.bounds[f] = Boundary(CONNECTED, int(bd["connectedBlock"]), (of, tang))
+            elif kind == "PERIODIC":
+                b.bounds[f] = Boundary(PERIODIC)
+            else:
+                raise NotImplementedError(f"boundary type {kind}")
+    bvel = [b.bounds[f].velocity3 for b in spec.blocks for f in range(4) if b.bounds[f].type == FIXED]
+    state = dict(u=np.concatenate(us, axis=2), p=np.concatenate(ps, axis=1),
+                 bvel=np.concatenate(bvel, axis=2) if bvel else np.zeros((3, nz, 0), np.float32))
+    return spec, np.asarray(zv, dtype=np.float32), state
+
+
+def save_extruded_domain(spec: DomainSpec, z_vertices, state: dict, path: str):
+    """Write the z-extrusion of ``spec`` over ``z_vertices`` with state u [3,nz,N2], p [nz,N2], bvel [3,nz,NB2] in the reference's
+    format (see the parity note above)."""
+    zv = np.asarray(z_vertices, dtype=np.float32)
+    nz = zv.size - 1
+    data = []
+
+    def add(arr, dct, name):
+        dct[name] = str(len(data))
+        data.append(np.ascontiguousarray(arr, dtype=np.float32))
+    d = {"name": spec.name, "spatialDims": 3}
+    add(np.array([spec.viscosity]), d, "viscosity")
+    d["passiveScalarChannels"] = 0
+    d["blocks"] = []
+    u, p, bv = (np.asarray(state[k], dtype=np.float32) for k in ("u", "p", "bvel"))
+    o = ob = 0
+    for b in spec.blocks:
+        n = b.nx * b.ny
+        bd = {"name": b.name}
+        add(u[:, :, o:o + n].reshape(1, 3, nz, b.ny, b.nx), bd, "velocity")
+        add(p[:, o:o + n].reshape(1, 1, nz, b.ny, b.nx), bd, "pressure")
+        v3 = np.zeros((1, 3, nz + 1, b.ny + 1, b.nx + 1), dtype=np.float32)
+        v3[0, :2] = b.vertex[:, None]
+        v3[0, 2] = zv[:, None, None]
+        add(v3, bd, "vertexCoordinates")
+        o += n
+        bd["boundaries"] = []
+        for f in range(4):
+            bn = b.bounds[f]
+            if bn.type == FIXED:
+                m = b.size(1 - (f >> 1))
+                e = {"type": "FIXED", "velocityType": "DIRICHLET"}
+                shape = (1, 3, nz, m, 1) if (f >> 1) == 0 else (1, 3, nz, 1, m)
+                add(bv[:, :, ob:ob + m].reshape(shape), e, "velocity")
+                ob += m
+            elif bn.type == CONNECTED:
+                of, tang = int(bn.axes[0]), int(bn.axes[1])
+                e = {"type": "CONNECTED", "connectedBlock": int(bn.other), "axes": [of, tang, 4] if (f >> 1) == 0 else [of, 4, tang]}
+            else:
+                e = {"type": "PERIODIC"}
+            bd["boundaries"].append(e)
+        bd["boundaries"] += [{"type": "PERIODIC"}, {"type": "PERIODIC"}]
+        d["blocks"].append(bd)
+    d["data_info"] = {str(i): {"shape": list(a.shape), "dtype": "float32", "device": "cpu"} for i, a in enumerate(data)}
+    np.savez_compressed(path + ".npz", **{str(i): a for i, a in enumerate(data)})
+    with open(path + ".json", "w") as fh:
+        json.dump(d, fh)

@@ -47,9 +47,7 @@ class Airfoil3DEnv(CylinderJet3DEnv):
             raise ValueError("Local 2D observations are only supported in multi-agent mode.")
         if attack_angle_deg < 0.0 or attack_angle_deg > 20.0:
             raise ValueError("Attack angle must be between 0 and 20 degrees.")
-        if load_initial_domain:
-            raise NotImplementedError("Airfoil3D: on-disk initial domains of the extruded multi-block grids are not read yet "
-                                      "(init_from_2d=True reads the 2-D airfoil files)")
+        self.load_domain_on_reset = bool(load_initial_domain)
         self.init_from_2d, self.initial_domains_path = bool(init_from_2d), initial_domains_path
         self.n_envs, self.n_span = int(n_envs), int(n_agents)
         self.reynolds_number, self.attack_angle_deg = float(reynolds_number), float(attack_angle_deg)
@@ -71,6 +69,7 @@ class Airfoil3DEnv(CylinderJet3DEnv):
         self.spec, self.cd = spec, cd
         self.nz = self.res_z
         self.hz = self.D / self.nz
+        self.z_vertices = np.linspace(-self.H / 2, self.H / 2, self.nz + 1, dtype=np.float32)                 # grid.py:609-614
         self.nz_per_agent = self.nz // self.n_span
         if solver_cls is None:
             from ..extruded3d import ExtrudedPISO3D as solver_cls      # raises without a CUDA device: there is no CPU path
@@ -124,8 +123,7 @@ class Airfoil3DEnv(CylinderJet3DEnv):
         gc = gc[:, :, keep]
         self.n_sensors_xy = len(keep)
         self.sensor_px = gc.flatten(start_dim=1).numpy()                                   # z-major
-        zv = np.linspace(-self.H / 2, self.H / 2, self.nz + 1, dtype=np.float32)           # grid.py:609-614
-        idx, w = sensor_tables_extruded([b.vertex for b in self.spec.blocks], zv, rs, self.sensor_px, fill_max_steps=128)
+        idx, w = sensor_tables_extruded([b.vertex for b in self.spec.blocks], self.z_vertices, rs, self.sensor_px, fill_max_steps=128)
         self.sens_idx = torch.from_numpy(idx.astype(np.int64)).to(self.device)
         self.sens_w = torch.from_numpy(w).to(self.device)
 

@@ -336,3 +336,21 @@ class InitialDomains3D(InitialDomains):
         save_box_domain(self.dom.vertex, self.dom.closed, self.dom.visc, st, path,
                         scalar_viscosity=getattr(s, "kappa", None) if getattr(s, "has_scalar", False) else None,
                         name=type(self).__name__)
+
+
+class InitialDomainsExtruded(InitialDomains):
+    """The same for the z-extruded multi-block environments (CylinderJet3D, Airfoil3D): needs ``spec`` (plane), ``nz``, ``z_vertices``."""
+
+    def _read_domain_file(self, path: str) -> dict:
+        from ..domain_io import load_extruded_domain
+        spec, zv, st = load_extruded_domain(path)
+        if [b.vertex.shape for b in spec.blocks] != [b.vertex.shape for b in self.spec.blocks] or any(
+                not np.array_equal(a.vertex, b.vertex) for a, b in zip(spec.blocks, self.spec.blocks)) or zv.size != self.nz + 1 or \
+                not np.allclose(zv, self.z_vertices, atol=1e-6):
+            raise ValueError(f"{path}: the stored grid is not the grid of this environment")
+        return dict(u=st["u"].reshape(3, -1), p=st["p"].reshape(-1), bvel=st["bvel"])
+
+    def _write_domain_file(self, st: dict, path: str):
+        from ..domain_io import save_extruded_domain
+        N2 = self.solver.N2
+        save_extruded_domain(self.spec, self.z_vertices, dict(u=st["u"].reshape(3, self.nz, N2), p=st["p"].reshape(self.nz, N2), bvel=st["bvel"]), path)

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from ..sensors import sensor_tables_extruded
-from .common import DifferentiableRollout, DomainStatistics, build_wall_tables
+from .common import DifferentiableRollout, InitialDomainsExtruded, build_wall_tables
 from .cylinder import cylinder_jet_templates, cylinder_sensor_locations
 from .cylinder_domain import BOTTOM, LEFT, RIGHT, TOP, WAKE, make_cylinder_domain
 from .spanwise import global_obs_from_samples, local_obs_windows, spanwise_sensor_voxels
@@ -26,7 +26,7 @@ CYLINDER_JET_3D_DEFAULT_CONFIG = {
 }
 
 
-class CylinderJet3DEnv(DomainStatistics):
+class CylinderJet3DEnv(InitialDomainsExtruded):
     H, L, D, cylinder_diameter, U_mean, cylinder_offset_y = 4.1, 22.0, 4.0, 1.0, 1.0, 0.05
     action_smoothing_alpha = 0.1
     jet_angle = 10.0
@@ -37,10 +37,8 @@ class CylinderJet3DEnv(DomainStatistics):
     def __init__(self, n_envs: int = 1, n_jets=8, reynolds_number=1e2, resolution=24, dt=1e-2, adaptive_cfl=0.8, step_length=0.25,
                  episode_length=80, lift_penalty=1.0, local_obs_window=3, use_marl=False, local_reward_weight=0.8, local_2d_obs=False,
                  device="cuda:0", cd_ref=0.0, randomize_initial_state=False, enable_actions=True, load_initial_domain=False,
-                 compiled=None, solver_cls=None):
-        if load_initial_domain:
-            raise NotImplementedError("CylinderJet3D: on-disk initial domains of the extruded multi-block grids are not read yet "
-                                      "(fluidgym_b200/domain_io.py handles the 2-D multi-block and the 3-D box formats)")
+                 initial_domains_path=None, compiled=None, solver_cls=None):
+        self.load_domain_on_reset, self.initial_domains_path = bool(load_initial_domain), initial_domains_path
         if n_jets < 1 or resolution % n_jets != 0:
             raise ValueError("n_agents must be a positive integer that evenly dividescircle_resolution_angular.")
         if local_2d_obs and not use_marl:
@@ -64,6 +62,7 @@ class CylinderJet3DEnv(DomainStatistics):
         self.spec, self.cd = spec, cd
         self.nz = self.resolution                                   # grid.py:291-298: res_z = angular resolution, z in [-2, 2]
         self.hz = self.D / self.nz
+        self.z_vertices = np.linspace(-2.0, 2.0, self.nz + 1, dtype=np.float32)
         self.nz_per_agent = self.nz // self.n_jets
         if solver_cls is None:
             from ..extruded3d import ExtrudedPISO3D as solver_cls   # raises without a CUDA device: there is no CPU path
@@ -104,8 +103,7 @@ class CylinderJet3DEnv(DomainStatistics):
         self.n_sensors_xy = int(xy.shape[1])
         rs = self.render_shape
         self.sensor_px = spanwise_sensor_voxels(xy, self.n_sensors_z, self.H, self.L, rs).numpy()
-        zv = np.linspace(-2.0, 2.0, self.nz + 1, dtype=np.float32)
-        idx, w = sensor_tables_extruded([b.vertex for b in self.spec.blocks], zv, rs, self.sensor_px, fill_max_steps=16)
+        idx, w = sensor_tables_extruded([b.vertex for b in self.spec.blocks], self.z_vertices, rs, self.sensor_px, fill_max_steps=16)
         self.sens_idx = torch.from_numpy(idx.astype(np.int64)).to(self.device)
         self.sens_w = torch.from_numpy(w).to(self.device)
 
@@ -176,11 +174,14 @@ class CylinderJet3DEnv(DomainStatistics):
             self.seed(seed)
         s = self.solver
         randomize = self.randomize_initial_state if randomize is None else randomize
-        s.u.zero_()
-        s.p.zero_()
-        s.bvel.zero_()
-        s.bvel[:, :2] = self._bvel0[None, :, None, :]
-        self._initial_velocity()
+        if self.load_domain_on_reset:
+            self._load_initial_domains_on_reset(randomize)          # fluid_env.py:519-539
+        else:
+            s.u.zero_()
+            s.p.zero_()
+            s.bvel.zero_()
+            s.bvel[:, :2] = self._bvel0[None, :, None, :]
+            self._initial_velocity()
         s.make_divergence_free_with_hook(max_iter=1000, bc_tol=self.bc_tol)      # cylinder_env_base.py:325; SIM.py:1320-1430
         self.last_control.zero_()
         if randomize:

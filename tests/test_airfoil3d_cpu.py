@@ -104,8 +104,6 @@ def test_constructor_checks_and_registry(compiled):
         Airfoil3DEnv(n_agents=5, device="cpu", compiled=compiled)
     with pytest.raises(ValueError, match="Attack angle"):
         Airfoil3DEnv(attack_angle_deg=25.0, device="cpu", compiled=compiled)
-    with pytest.raises(NotImplementedError):
-        Airfoil3DEnv(load_initial_domain=True, device="cpu", compiled=compiled)
     if not torch.cuda.is_available():
         from fluidgym_b200 import native
         with pytest.raises(native.FGBError, match="no CPU fallback"):        # the product path has no CPU solver

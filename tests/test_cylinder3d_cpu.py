@@ -202,8 +202,9 @@ def test_unsupported_options_fail_loudly(compiled):
     import fluidgym_b200
     from extruded_standin import HostExtrudedPISO3D
     kw = dict(resolution=8, device="cpu", compiled=compiled, solver_cls=HostExtrudedPISO3D)
-    with pytest.raises(NotImplementedError, match="initial domains"):
-        fluidgym_b200.make("CylinderJet3D-easy-v0", load_initial_domain=True, **kw)
+    env = fluidgym_b200.make("CylinderJet3D-easy-v0", load_initial_domain=True, initial_domains_path="/nonexistent", **kw)
+    with pytest.raises(RuntimeError, match="Initial domain not found"):          # the reference's message (fluid_env.py:1076-1079)
+        env.reset(seed=0)
     with pytest.raises(NotImplementedError, match="differentiable"):
         fluidgym_b200.make("CylinderJet3D-easy-v0", differentiable=True, **kw)
     env = fluidgym_b200.make("CylinderJet3D-medium-v0", load_initial_domain=False, load_domain_statistics=False, **kw)
@@ -238,3 +239,37 @@ def test_rl_library_adapters_accept_the_spanwise_environment(compiled):
     assert o["velocity"].shape == (8, 2, 3, 151)
     o, r, t, tr, _ = g.step(np.zeros((8, 1), np.float32))
     assert np.isfinite(float(r))
+
+
+def test_on_disk_initial_domains_of_the_extruded_grid(compiled, golden, tmp_path):
+    """load_initial_domain=True for CylinderJet3D: the reference's domain format with one more spatial axis, six boundaries per
+    block (z pair PERIODIC) and the axes triple of the block connections (fluidgym_b200/domain_io.py::load_extruded_domain /
+    save_extruded_domain).  Round trip of the reference's traced 3-D state through a file, and reset() loading it per environment.
+    (The 3-D specifics of the format follow the reference's writer source; no reference-written 3-D multi-block file exists yet.)"""
+    import json
+    from fluidgym_b200.domain_io import load_extruded_domain
+    fx = golden("cyl3d_env.npz")
+    env = _env(compiled, n_envs=2, load_initial_domain=True, initial_domains_path=str(tmp_path))
+    env.solver.make_divergence_free = lambda max_iter=1000: None                    # keep the loaded state recognisable
+    env.set_state(fx["env0_u"], fx["env0_p"], fx["env0_bvel"])
+    env.solver.u[1] *= 0.5
+    p0 = env.save_initial_domain(0, env_index=0)
+    p3 = env.save_initial_domain(3, env_index=1)
+    assert p0.endswith(os.path.join("cylinder_3D_Re100_Res8", "0", "train"))
+    d = json.load(open(p0 + ".json"))
+    assert d["spatialDims"] == 3 and len(d["blocks"]) == 5 and all(len(b["boundaries"]) == 6 for b in d["blocks"])
+    conn = [bd for b in d["blocks"] for bd in b["boundaries"] if bd["type"] == "CONNECTED"]
+    assert len(conn) == 10 and all(len(c["axes"]) == 3 and 4 in c["axes"][1:] for c in conn)
+    spec, zv, st = load_extruded_domain(p0)
+    assert np.array_equal(st["u"], fx["env0_u"]) and np.array_equal(st["p"], fx["env0_p"]) and np.array_equal(st["bvel"], fx["env0_bvel"])
+    assert np.allclose(zv, np.linspace(-2, 2, 9)) and all(np.array_equal(a.vertex, b.vertex) for a, b in zip(spec.blocks, env.spec.blocks))
+    cd2 = spec.prepare()                                                            # the file compiles into the same tables
+    assert np.array_equal(cd2.nbr, env.cd.nbr) and np.array_equal(cd2.fl_comp, env.cd.fl_comp)
+    env.solver.u.zero_()
+    env.reset(seed=1, randomize=False)                                              # index 0 for every environment
+    u4 = env.solver.u.view(2, 3, 8, -1)
+    assert torch.equal(u4[0], torch.from_numpy(fx["env0_u"])) and torch.equal(u4[1], u4[0])
+    env.load_initial_domain(3, env_index=[1])
+    assert torch.allclose(env.solver.u.view(2, 3, 8, -1)[1], 0.5 * torch.from_numpy(fx["env0_u"]))
+    with pytest.raises(RuntimeError, match="Initial domain not found"):
+        env.load_initial_domain(7)
