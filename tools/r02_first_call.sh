@@ -15,4 +15,7 @@ FGB_ASM_ENVS=8 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/r02/be
 # (res_z = 96: 46 806 x 96 = 4.5 M cells, the reference needs minutes per env.step -> lean trace, one env.step, generous limit)
 timeout 1700 python oracle/ref_harness.py --env Airfoil3D-easy-v0 --tag airfoil3d --out gpurun_out/r02/airfoil3d --env-steps 1 --time-steps 0 \
     --trace-substeps 1 --lean --kw '{"init_from_2d": false}' > gpurun_out/r02/airfoil3d.log 2>&1
+# a reference-written 3-D multi-block domain file, to pin fluidgym_b200/domain_io.py::load_extruded_domain
+timeout 600 python oracle/ref_harness.py --env CylinderJet3D-easy-v0 --tag cyl3d --out gpurun_out/r02/dom_cyl3d --save-domain-only --env-steps 0 \
+    --kw '{"resolution": 8, "n_jets": 8}' > gpurun_out/r02/dom_cyl3d.log 2>&1
 tail -3 gpurun_out/r02/*.log
