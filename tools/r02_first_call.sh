@@ -12,6 +12,11 @@ timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r02/gpu_tests.log 2
 timeout 600 python bench.py > gpurun_out/r02/bench.json 2> gpurun_out/r02/bench.err
 FGB_ASM_ENVS=4 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/r02/bench_asm4.json 2> gpurun_out/r02/bench_asm4.err
 FGB_ASM_ENVS=8 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/r02/bench_asm8.json 2> gpurun_out/r02/bench_asm8.err
+# launch list + one full capture of the pressure CG of the extruded path (CylinderJet3D res 24), for profiles/
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02/launches_cyl3d_res24.csv \
+    python tools/cyl3d_bench.py --resolutions 24 --steps 1 --settle 0 > gpurun_out/r02/ncu_cyl3d_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k3_cg -s 6 -c 1 -f -o gpurun_out/r02/k3_cg_cyl3d \
+    python tools/cyl3d_bench.py --resolutions 24 --steps 1 --settle 0 > gpurun_out/r02/ncu_cyl3d_cg.log 2>&1
 # (res_z = 96: 46 806 x 96 = 4.5 M cells, the reference needs minutes per env.step -> lean trace, one env.step, generous limit)
 timeout 1700 python oracle/ref_harness.py --env Airfoil3D-easy-v0 --tag airfoil3d --out gpurun_out/r02/airfoil3d --env-steps 1 --time-steps 0 \
     --trace-substeps 1 --lean --kw '{"init_from_2d": false}' > gpurun_out/r02/airfoil3d.log 2>&1
