@@ -273,3 +273,16 @@ def test_on_disk_initial_domains_of_the_extruded_grid(compiled, golden, tmp_path
     assert torch.allclose(env.solver.u.view(2, 3, 8, -1)[1], 0.5 * torch.from_numpy(fx["env0_u"]))
     with pytest.raises(RuntimeError, match="Initial domain not found"):
         env.load_initial_domain(7)
+
+
+def test_first_gpu_run_tool_dry_run_on_the_stand_in(tmp_path):
+    """tools/extruded_check.py (the first GPU run of the extruded path, tests/test_zz_gpu_extruded_first_run.py) executed here
+    on the CPU stand-in: the tool's own code paths and bars are exercised before it ever meets a GPU."""
+    import json
+    import subprocess
+    out = tmp_path / "check.json"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "extruded_check.py"), "--standin", "--skip-env-step", "--json", str(out)],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    v = json.load(open(out))
+    assert v["ok"] and [s["stage"] for s in v["stages"]] == ["substep", "substep", "reset"]

@@ -21,6 +21,30 @@ sys.path.insert(0, ROOT)
 from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain  # noqa: E402
 from fluidgym_b200.extruded3d import ExtrudedPISO3D  # noqa: E402
 
+DEV = "cuda:0"
+SOLVER = ExtrudedPISO3D          # --standin swaps in the CPU stand-in of the tests (a dry run of THIS TOOL without a GPU, not a product path)
+
+
+def sync():
+    if DEV != "cpu":
+        torch.cuda.synchronize()
+
+
+class _Counters:
+    """iteration counters: the Krylov handle's on the GPU, the stand-in's lists in a dry run"""
+
+    def __init__(self, s):
+        self.s = s
+        self.c0 = self.read()
+
+    def read(self):
+        if hasattr(self.s, "cg_iters"):
+            return float(sum(self.s.cg_iters)) / max(self.s.B, 1)
+        return float(self.s.buffer("iter_total")[0, 0])
+
+    def delta(self):
+        return self.read() - self.c0
+
 
 def rel(a, b):
     return float(np.linalg.norm(np.asarray(a, np.float64) - b) / np.linalg.norm(np.asarray(b, np.float64)))
@@ -35,12 +59,12 @@ def check_substeps(cd, out):
     for s in (0, 1):
         fx = golden(f"cyl3d_substep{s}.npz")
         nz, N2 = fx["A"].shape
-        sol = ExtrudedPISO3D(cd, nz, float(fx["hz"][0]), n_envs=2)
-        sol.u.copy_(torch.from_numpy(fx["u_in"]).reshape(1, 3, -1).cuda().expand_as(sol.u))
-        sol.p.copy_(torch.from_numpy(fx["p_in"]).reshape(1, -1).cuda().expand_as(sol.p))
-        sol.bvel.copy_(torch.from_numpy(fx["bvel"]).cuda().unsqueeze(0).expand_as(sol.bvel))
-        sol.piso_substep(float(fx["dt"][0]))
-        torch.cuda.synchronize()
+        sol = SOLVER(cd, nz, float(fx["hz"][0]), n_envs=2, device=DEV)
+        sol.u.copy_(torch.from_numpy(fx["u_in"]).reshape(1, 3, -1).to(DEV).expand_as(sol.u))
+        sol.p.copy_(torch.from_numpy(fx["p_in"]).reshape(1, -1).to(DEV).expand_as(sol.p))
+        sol.bvel.copy_(torch.from_numpy(fx["bvel"]).to(DEV).unsqueeze(0).expand_as(sol.bvel))
+        sol.piso_substep(torch.full((2,), float(fx["dt"][0])))
+        sync()
         u, p = sol.u[0].cpu().numpy().reshape(3, nz, N2), sol.p[0].cpu().numpy().reshape(nz, N2)
         line = {"stage": "substep", "substep": s, "rel_l2_u": rel(u, fx["u1"]), "rel_l2_p": rel(p, fx["p1"]),
                 "ref_bicg_iters": fx["bicg_iters"].tolist(), "ref_cg_iters": fx["cg_iters"].tolist(),
@@ -53,14 +77,14 @@ def check_substeps(cd, out):
     return ok
 
 
-def check_env(compiled, out):
+def check_env(compiled, out, with_step=True):
     from fluidgym_b200.envs.cylinder3d import CylinderJet3DEnv
     fx = golden("cyl3d_env.npz")
     meta = json.load(open(os.path.join(ROOT, "tests", "golden", "cyl3d_meta.json")))
-    env = CylinderJet3DEnv(n_envs=2, resolution=8, n_jets=8, compiled=compiled)
+    env = CylinderJet3DEnv(n_envs=2, resolution=8, n_jets=8, compiled=compiled, device=DEV, solver_cls=None if SOLVER is ExtrudedPISO3D else SOLVER)
     t0 = time.perf_counter()
     obs, _ = env.reset(seed=42)
-    torch.cuda.synchronize()
+    sync()
     t_reset = time.perf_counter() - t0
     s = env.solver
     line = {"stage": "reset", "seconds": t_reset, "bvel_abs": float(np.abs(s.bvel[0].cpu().numpy() - fx["reset_bvel"]).max()),
@@ -72,14 +96,16 @@ def check_env(compiled, out):
     ok = line["ok"]
     out.append(line)
     print(json.dumps(line), flush=True)
+    if not with_step:
+        return ok
 
     env.set_state(fx["reset_u"], fx["reset_p"], fx["reset_bvel"], last_control=0.0)
-    a = torch.from_numpy(fx["actions"][0])[None].expand(2, -1, -1).cuda()
-    it0 = s.buffer("iter_total").clone()
-    torch.cuda.synchronize()
+    a = torch.from_numpy(fx["actions"][0])[None].expand(2, -1, -1).to(DEV)
+    counters = _Counters(s)
+    sync()
     t0 = time.perf_counter()
     obs, reward, _, _, info = env.step(a)
-    torch.cuda.synchronize()
+    sync()
     t_step = time.perf_counter() - t0
     line = {"stage": "env.step", "seconds": t_step, "substeps": env.last_substeps, "substeps_per_s_x_envs": 2 * env.last_substeps / t_step,
             "reference_substeps_per_s": meta["timing"]["substeps_per_s"],
@@ -91,7 +117,7 @@ def check_env(compiled, out):
             "obs_pressure_abs": float(np.abs(obs["pressure"][0].cpu().numpy() - fx["step0_obs_pressure"]).max()),
             "envs_equal": bool(torch.allclose(s.u[0], s.u[1], atol=1e-6)),
             # the reference reports the index of the last iteration (one less than the count); CPU stand-in: 1016.6 vs 1014.7 + 1
-            "cg_iters_per_solve": float((s.buffer("iter_total") - it0)[0, 0]) / (8 * max(env.last_substeps, 1)),
+            "cg_iters_per_solve": counters.delta() / (8 * max(env.last_substeps, 1)),
             "ref_cg_iters_per_solve": meta["mean_iters"]["cg"] + 1.0}
     line["ok"] = bool(env.last_substeps == 25 and line["rel_l2_u"] < 1e-4 and line["rel_l2_p"] < 2e-3 and abs(line["reward"] - line["ref_reward"]) < 1e-3
                       and abs(line["drag"] - line["ref_drag"]) < 1e-3 and abs(line["lift"] - line["ref_lift"]) < 1e-4 and line["all_cds_abs"] < 1e-3
@@ -106,13 +132,20 @@ def check_env(compiled, out):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
+    ap.add_argument("--skip-env-step", action="store_true", help="substep and reset stages only")
+    ap.add_argument("--standin", action="store_true", help="dry run of this tool on the CPU stand-in solver of the tests (no GPU)")
     args = ap.parse_args()
+    if args.standin:
+        global DEV, SOLVER
+        sys.path.insert(0, os.path.join(ROOT, "tests", "cpu_harness"))
+        from extruded_standin import HostExtrudedPISO3D
+        DEV, SOLVER = "cpu", HostExtrudedPISO3D
     spec = make_cylinder_domain(8)
     cd = spec.prepare()
     out, ok = [], True
     try:
         ok &= check_substeps(cd, out)
-        ok &= check_env((spec, cd), out)
+        ok &= check_env((spec, cd), out, with_step=not args.skip_env_step)
     except Exception as e:                                              # report, do not hide: this is a bring-up tool
         out.append({"stage": "exception", "error": f"{type(e).__name__}: {e}"})
         print(json.dumps(out[-1]), flush=True)
