@@ -18,7 +18,7 @@ from ..sensors import sensor_tables_extruded
 from .airfoil import Airfoil2DEnv, polygon_mask
 from .airfoil_domain import BOT, FRONT, TAIL_LOWER, TAIL_UPPER, TOP, airfoil_polyline, make_airfoil_domain
 from .common import build_wall_tables
-from .cylinder3d import CylinderJet3DEnv
+from .cylinder3d import SpanwiseExtrudedEnv
 
 AIRFOIL_3D_DEFAULT_CONFIG = {
     "n_agents": 4, "reynolds_number": 3e3, "dt": 0.05, "adaptive_cfl": 0.8, "step_length": 0.25, "episode_length": 200,
@@ -26,7 +26,7 @@ AIRFOIL_3D_DEFAULT_CONFIG = {
 }
 
 
-class Airfoil3DEnv(CylinderJet3DEnv):
+class Airfoil3DEnv(SpanwiseExtrudedEnv):
     H, L, D, U_mean, airfoil_length = 1.4, 4.5, 1.4, 0.3, 1.0
     res_z = 96                                                          # airfoil_env_base.py:69
     n_jets = 3                                                          # jets per agent (airfoil_env_base.py:68)

@@ -26,99 +26,24 @@ CYLINDER_JET_3D_DEFAULT_CONFIG = {
 }
 
 
-class CylinderJet3DEnv(InitialDomainsExtruded):
-    H, L, D, cylinder_diameter, U_mean, cylinder_offset_y = 4.1, 22.0, 4.0, 1.0, 1.0, 0.05
+class SpanwiseExtrudedEnv(InitialDomainsExtruded):
+    """What the environments on z-extruded domains with agents lined up along the span share (CylinderJet3D, Airfoil3D): the
+    reference-shaped API, reset (zero field + inflow -> projection, or an on-disk initial domain), the solver-step loop with action
+    smoothing, per-plane wall forces, voxel sensors, multi-agent windows and the local / global reward mix.  A subclass provides the
+    tables (``spec, cd, nz, hz, z_vertices, n_span, nz_per_agent, solver, jet_*, _wall_t, wall, sens_idx, sens_w, last_control,
+    _zero_action, _bvel0``), ``_apply_action(control)``, ``_reward(cd, cl)``, ``_randomize_domain()`` and the spaces' shapes."""
+
     action_smoothing_alpha = 0.1
-    jet_angle = 10.0
-    bc_tol = 5e-6                                                       # tolerance of the outflow update's flux balance (:295)
+    bc_tol = 5e-6
     metrics = ["drag", "lift"]
-    reference_values = {"cd_ref": ("drag", "mean")}
-
-    def __init__(self, n_envs: int = 1, n_jets=8, reynolds_number=1e2, resolution=24, dt=1e-2, adaptive_cfl=0.8, step_length=0.25,
-                 episode_length=80, lift_penalty=1.0, local_obs_window=3, use_marl=False, local_reward_weight=0.8, local_2d_obs=False,
-                 device="cuda:0", cd_ref=0.0, randomize_initial_state=False, enable_actions=True, load_initial_domain=False,
-                 initial_domains_path=None, compiled=None, solver_cls=None):
-        self.load_domain_on_reset, self.initial_domains_path = bool(load_initial_domain), initial_domains_path
-        if n_jets < 1 or resolution % n_jets != 0:
-            raise ValueError("n_agents must be a positive integer that evenly dividescircle_resolution_angular.")
-        if local_2d_obs and not use_marl:
-            raise ValueError("Local 2D observations are only supported in multi-agent mode.")
-        self.n_envs, self.n_jets = int(n_envs), int(n_jets)
-        self.n_span = self.n_jets                                   # agents lined up along the span
-        self.resolution, self.dt, self.cfl = int(resolution), float(dt), float(adaptive_cfl)
-        self.step_length, self.episode_length = float(step_length), int(episode_length)
-        self.lift_penalty, self.cd_ref = float(lift_penalty), float(cd_ref)
-        self.use_marl, self.local_reward_weight, self.local_2d_obs = bool(use_marl), local_reward_weight, bool(local_2d_obs)
-        self.local_obs_window = 1 if local_2d_obs else int(local_obs_window)
-        self.n_sensors_per_agent = 1 if local_2d_obs else 2
-        self.randomize_initial_state, self.enable_actions = randomize_initial_state, enable_actions
-        self.reynolds_number = float(reynolds_number)
-        self.device = torch.device(device)
-        if compiled is None:
-            spec = make_cylinder_domain(resolution, reynolds_number, self.U_mean, self.H, self.L, self.cylinder_offset_y)
-            cd = spec.prepare()
-        else:
-            spec, cd = compiled
-        self.spec, self.cd = spec, cd
-        self.nz = self.resolution                                   # grid.py:291-298: res_z = angular resolution, z in [-2, 2]
-        self.hz = self.D / self.nz
-        self.z_vertices = np.linspace(-2.0, 2.0, self.nz + 1, dtype=np.float32)
-        self.nz_per_agent = self.nz // self.n_jets
-        if solver_cls is None:
-            from ..extruded3d import ExtrudedPISO3D as solver_cls   # raises without a CUDA device: there is no CPU path
-        # cylinder_env_base.py:305-323: 2 correctors, 1 + 4 deferred non-orthogonal iterations, tolerances 1e-5 / 5e-7
-        self.solver = solver_cls(cd, self.nz, self.hz, self.n_envs, device=device, corrector_steps=2, advect_non_ortho_steps=1,
-                                 pressure_non_ortho_steps=4, advection_tol=1e-5, pressure_tol=5e-7, max_iter=5000)
-        out_mask = np.zeros(cd.NB, dtype=bool)
-        o = cd.boff[WAKE, 1]
-        out_mask[o:o + spec.blocks[WAKE].ny] = True
-        self.solver.setup_stepping(out_mask, (self.U_mean, 0.0))
-        faces, templ = cylinder_jet_templates(spec, cd, self.jet_angle)     # the 2-D templates, repeated in every plane (:328-396)
-        self.jet_faces = torch.from_numpy(faces).to(self.device)
-        self.jet_templ = torch.from_numpy(templ).to(self.device)
-        free = out_mask.copy()
-        free[self.jet_faces.cpu().numpy()] = True
-        self._free_jets = torch.from_numpy(free).to(self.device)
-        ring = [(LEFT, 1, False), (TOP, 2, False), (RIGHT, 0, True), (BOTTOM, 3, True)]
-        self._wall_t, self.wall = build_wall_tables(cd, spec, ring, self.device, 1.0 / (0.5 * self.U_mean ** 2 * self.cylinder_diameter))
-        self._setup_sensors()
-        B, dev = self.n_envs, self.device
-        self.last_control = torch.zeros(B, self.n_jets, device=dev)
-        self._zero_action = torch.zeros(B, self.n_jets, 1, device=dev)
-        self._bvel0 = torch.from_numpy(np.ascontiguousarray(cd.bvel0[:, :cd.NB])).to(dev)
-        self._reset_called, self._seed, self._n_steps, self.last_substeps = False, None, 0, 0
-
-    # ---- static tables ---------------------------------------------------------------------------------------------------
-    @property
-    def render_shape(self):
-        z = self.resolution * 4
-        return (int(z / self.H * self.L), z, z)
 
     @property
     def n_sensors_z(self):
         return self.n_span * self.n_sensors_per_agent
 
-    def _setup_sensors(self):
-        xy = cylinder_sensor_locations(self.cylinder_diameter)
-        self.n_sensors_xy = int(xy.shape[1])
-        rs = self.render_shape
-        self.sensor_px = spanwise_sensor_voxels(xy, self.n_sensors_z, self.H, self.L, rs).numpy()
-        idx, w = sensor_tables_extruded([b.vertex for b in self.spec.blocks], self.z_vertices, rs, self.sensor_px, fill_max_steps=16)
-        self.sens_idx = torch.from_numpy(idx.astype(np.int64)).to(self.device)
-        self.sens_w = torch.from_numpy(w).to(self.device)
-
-    # ---- reference-shaped API --------------------------------------------------------------------------------------------
     @property
     def n_agents(self):
         return self.n_span if self.use_marl else 1
-
-    @property
-    def id(self):
-        return f"JetCylinder3D_Re{self.reynolds_number}"
-
-    @property
-    def initial_domain_id(self):
-        return f"cylinder_3D_Re{int(self.reynolds_number)}_Res{self.resolution}"
 
     @property
     def n_sim_steps(self):
@@ -136,11 +61,6 @@ class CylinderJet3DEnv(InitialDomainsExtruded):
         else:
             vs, ps = (self.n_span, spa, 3, nxy), (self.n_span, spa, nxy)
         return spaces.Dict({"velocity": spaces.Box(-inf, inf, shape=vs), "pressure": spaces.Box(-inf, inf, shape=ps)})
-
-    @property
-    def action_space(self):
-        from .. import spaces
-        return spaces.Box(-1.0, 1.0, shape=(1,) if self.use_marl else (self.n_jets, 1))
 
     def seed(self, seed: int):
         self._seed = seed
@@ -193,31 +113,6 @@ class CylinderJet3DEnv(InitialDomainsExtruded):
 
     def _initial_velocity(self):
         """hook between the zero field and the projection (Airfoil3D: ``init_from_2d``)"""
-
-    def _randomize_domain(self):
-        """cylinder_env_base.py:364-404 (per-environment noise, common number of settling steps)"""
-        period = 1 / (0.3 * self.U_mean / self.cylinder_diameter)
-        max_n = 2 * int(period / self.step_length) - 1
-        n_steps = int(self._np_rng.integers(int(0.5 * max_n), max_n)) + 1
-        s = self.solver
-        s.u += torch.randn(s.u.shape, device=self.device, generator=self._torch_rng) * 0.025
-        s.p += torch.randn(s.p.shape, device=self.device, generator=self._torch_rng) * 0.025
-        for _ in range(n_steps):
-            s.single_step(self.dt, self.cfl, bc_tol=self.bc_tol)
-
-    def _apply_action(self, control: torch.Tensor):
-        """jet_cylinder_env_3d.py:399-424: every jet drives its ``nz_per_agent`` planes with the 2-D template (no spanwise
-        component), then jets and outflow are rescaled for a zero net boundary flux (tol 1e-7)."""
-        s = self.solver
-        per_plane = control.repeat_interleave(self.nz_per_agent, dim=1)                           # [B, nz]
-        jf = self.jet_faces.long()
-        s.bvel[:, :2, :, jf] = self.jet_templ[None, :, None, :] * per_plane[:, None, :, None]
-        s.bvel[:, 2, :, jf] = 0.0
-        s.balance_fluxes(self._free_jets, 1e-7)
-
-    def _reward(self, cd, cl):
-        """cylinder_env_base.py:769, jet_cylinder_env_3d.py:436, 470-472"""
-        return self.cd_ref - cd - self.lift_penalty * torch.abs(cl)
 
     def _drag_and_lift(self):
         """Per-plane drag / lift coefficients [B, nz] each (cylinder_env_base.py:657-700, forces.py:278-377: the 2-D wall
@@ -289,3 +184,118 @@ class CylinderJet3DEnv(InitialDomainsExtruded):
         lw = float(self.local_reward_weight)
         info["global_reward"] = reward
         return self._get_local_obs(), lw * local + (1 - lw) * reward[:, None], False, truncated, info
+
+
+class CylinderJet3DEnv(SpanwiseExtrudedEnv):
+    H, L, D, cylinder_diameter, U_mean, cylinder_offset_y = 4.1, 22.0, 4.0, 1.0, 1.0, 0.05
+    action_smoothing_alpha = 0.1
+    jet_angle = 10.0
+    bc_tol = 5e-6                                                       # tolerance of the outflow update's flux balance (:295)
+    metrics = ["drag", "lift"]
+    reference_values = {"cd_ref": ("drag", "mean")}
+
+    def __init__(self, n_envs: int = 1, n_jets=8, reynolds_number=1e2, resolution=24, dt=1e-2, adaptive_cfl=0.8, step_length=0.25,
+                 episode_length=80, lift_penalty=1.0, local_obs_window=3, use_marl=False, local_reward_weight=0.8, local_2d_obs=False,
+                 device="cuda:0", cd_ref=0.0, randomize_initial_state=False, enable_actions=True, load_initial_domain=False,
+                 initial_domains_path=None, compiled=None, solver_cls=None):
+        self.load_domain_on_reset, self.initial_domains_path = bool(load_initial_domain), initial_domains_path
+        if n_jets < 1 or resolution % n_jets != 0:
+            raise ValueError("n_agents must be a positive integer that evenly dividescircle_resolution_angular.")
+        if local_2d_obs and not use_marl:
+            raise ValueError("Local 2D observations are only supported in multi-agent mode.")
+        self.n_envs, self.n_jets = int(n_envs), int(n_jets)
+        self.n_span = self.n_jets                                   # agents lined up along the span
+        self.resolution, self.dt, self.cfl = int(resolution), float(dt), float(adaptive_cfl)
+        self.step_length, self.episode_length = float(step_length), int(episode_length)
+        self.lift_penalty, self.cd_ref = float(lift_penalty), float(cd_ref)
+        self.use_marl, self.local_reward_weight, self.local_2d_obs = bool(use_marl), local_reward_weight, bool(local_2d_obs)
+        self.local_obs_window = 1 if local_2d_obs else int(local_obs_window)
+        self.n_sensors_per_agent = 1 if local_2d_obs else 2
+        self.randomize_initial_state, self.enable_actions = randomize_initial_state, enable_actions
+        self.reynolds_number = float(reynolds_number)
+        self.device = torch.device(device)
+        if compiled is None:
+            spec = make_cylinder_domain(resolution, reynolds_number, self.U_mean, self.H, self.L, self.cylinder_offset_y)
+            cd = spec.prepare()
+        else:
+            spec, cd = compiled
+        self.spec, self.cd = spec, cd
+        self.nz = self.resolution                                   # grid.py:291-298: res_z = angular resolution, z in [-2, 2]
+        self.hz = self.D / self.nz
+        self.z_vertices = np.linspace(-2.0, 2.0, self.nz + 1, dtype=np.float32)
+        self.nz_per_agent = self.nz // self.n_jets
+        if solver_cls is None:
+            from ..extruded3d import ExtrudedPISO3D as solver_cls   # raises without a CUDA device: there is no CPU path
+        # cylinder_env_base.py:305-323: 2 correctors, 1 + 4 deferred non-orthogonal iterations, tolerances 1e-5 / 5e-7
+        self.solver = solver_cls(cd, self.nz, self.hz, self.n_envs, device=device, corrector_steps=2, advect_non_ortho_steps=1,
+                                 pressure_non_ortho_steps=4, advection_tol=1e-5, pressure_tol=5e-7, max_iter=5000)
+        out_mask = np.zeros(cd.NB, dtype=bool)
+        o = cd.boff[WAKE, 1]
+        out_mask[o:o + spec.blocks[WAKE].ny] = True
+        self.solver.setup_stepping(out_mask, (self.U_mean, 0.0))
+        faces, templ = cylinder_jet_templates(spec, cd, self.jet_angle)     # the 2-D templates, repeated in every plane (:328-396)
+        self.jet_faces = torch.from_numpy(faces).to(self.device)
+        self.jet_templ = torch.from_numpy(templ).to(self.device)
+        free = out_mask.copy()
+        free[self.jet_faces.cpu().numpy()] = True
+        self._free_jets = torch.from_numpy(free).to(self.device)
+        ring = [(LEFT, 1, False), (TOP, 2, False), (RIGHT, 0, True), (BOTTOM, 3, True)]
+        self._wall_t, self.wall = build_wall_tables(cd, spec, ring, self.device, 1.0 / (0.5 * self.U_mean ** 2 * self.cylinder_diameter))
+        self._setup_sensors()
+        B, dev = self.n_envs, self.device
+        self.last_control = torch.zeros(B, self.n_jets, device=dev)
+        self._zero_action = torch.zeros(B, self.n_jets, 1, device=dev)
+        self._bvel0 = torch.from_numpy(np.ascontiguousarray(cd.bvel0[:, :cd.NB])).to(dev)
+        self._reset_called, self._seed, self._n_steps, self.last_substeps = False, None, 0, 0
+
+    @property
+    def render_shape(self):
+        z = self.resolution * 4
+        return (int(z / self.H * self.L), z, z)
+
+    def _setup_sensors(self):
+        xy = cylinder_sensor_locations(self.cylinder_diameter)
+        self.n_sensors_xy = int(xy.shape[1])
+        rs = self.render_shape
+        self.sensor_px = spanwise_sensor_voxels(xy, self.n_sensors_z, self.H, self.L, rs).numpy()
+        idx, w = sensor_tables_extruded([b.vertex for b in self.spec.blocks], self.z_vertices, rs, self.sensor_px, fill_max_steps=16)
+        self.sens_idx = torch.from_numpy(idx.astype(np.int64)).to(self.device)
+        self.sens_w = torch.from_numpy(w).to(self.device)
+
+    @property
+    def id(self):
+        return f"JetCylinder3D_Re{self.reynolds_number}"
+
+    @property
+    def initial_domain_id(self):
+        return f"cylinder_3D_Re{int(self.reynolds_number)}_Res{self.resolution}"
+
+    @property
+    def action_space(self):
+        from .. import spaces
+        return spaces.Box(-1.0, 1.0, shape=(1,) if self.use_marl else (self.n_jets, 1))
+
+    def _randomize_domain(self):
+        """cylinder_env_base.py:364-404 (per-environment noise, common number of settling steps)"""
+        period = 1 / (0.3 * self.U_mean / self.cylinder_diameter)
+        max_n = 2 * int(period / self.step_length) - 1
+        n_steps = int(self._np_rng.integers(int(0.5 * max_n), max_n)) + 1
+        s = self.solver
+        s.u += torch.randn(s.u.shape, device=self.device, generator=self._torch_rng) * 0.025
+        s.p += torch.randn(s.p.shape, device=self.device, generator=self._torch_rng) * 0.025
+        for _ in range(n_steps):
+            s.single_step(self.dt, self.cfl, bc_tol=self.bc_tol)
+
+    def _apply_action(self, control: torch.Tensor):
+        """jet_cylinder_env_3d.py:399-424: every jet drives its ``nz_per_agent`` planes with the 2-D template (no spanwise
+        component), then jets and outflow are rescaled for a zero net boundary flux (tol 1e-7)."""
+        s = self.solver
+        per_plane = control.repeat_interleave(self.nz_per_agent, dim=1)                           # [B, nz]
+        jf = self.jet_faces.long()
+        s.bvel[:, :2, :, jf] = self.jet_templ[None, :, None, :] * per_plane[:, None, :, None]
+        s.bvel[:, 2, :, jf] = 0.0
+        s.balance_fluxes(self._free_jets, 1e-7)
+
+    def _reward(self, cd, cl):
+        """cylinder_env_base.py:769, jet_cylinder_env_3d.py:436, 470-472"""
+        return self.cd_ref - cd - self.lift_penalty * torch.abs(cl)
