@@ -317,5 +317,129 @@ extern "C" int fgb_extruded3_make_divergence_free(fgb_ortho3 *b, const fgb_extru
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "fgb_extruded3_make_divergence_free: copy", ce);
     return FGB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Boundary hooks of the extruded environments as kernels (OPT-IN: FGB_X3_HOOKS=cuda in extruded3d.py; default = the torch
+// expressions of ExtrudedStepping, which are what the CPU tests pin to the reference).  Same formulas, statement by statement:
+// balance_boundary_fluxes (SIM.py:188-224), update_advective_boundaries (SIM.py:228-393), Domain.getMaxVelocity (DS.cpp:1580-1612).
+// One CTA per environment for the boundary kernels (a few thousand faces), flux sums accumulated in double.  NOT yet run on a GPU.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void x3_block_sum2(double &a, double &b, double *sm /* [66] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane == 0) { sm[2 * warp] = a; sm[2 * warp + 1] = b; }
+    __syncthreads();
+    if (warp == 0) {
+        double x = lane < nw ? sm[2 * lane] : 0.0, y = lane < nw ? sm[2 * lane + 1] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { x += __shfl_xor_sync(0xffffffffu, x, o); y += __shfl_xor_sync(0xffffffffu, y, o); }
+        if (lane == 0) { sm[64] = x; sm[65] = y; }
+    }
+    __syncthreads();
+    a = sm[64]; b = sm[65];
+    __syncthreads();
+}
+// scale all components of the free faces by -(flux through the other prescribed faces) / (flux through the free faces)
+__device__ void x3_balance(int NB, int nz, float hz, float *bv /* [3][nz][NB] */, const float *__restrict__ fw /* [2][NB] */,
+                           const int8_t *__restrict__ free_mask, float tol, double *sm) {
+    const int n = nz * NB;
+    double fixed = 0.0, var = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int j = i % NB;
+        const float fl = (bv[i] * fw[j] + bv[n + i] * fw[NB + j]) * hz;
+        if (free_mask[j]) var += (double)fl; else fixed += (double)fl;
+    }
+    x3_block_sum2(fixed, var, sm);
+    if (!(fabs(fixed + var) <= (double)tol * 0.01)) {
+        const float sc = (float)(-fixed / var);
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            if (free_mask[i % NB]) { bv[i] *= sc; bv[n + i] *= sc; bv[2 * n + i] *= sc; }
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(512) kx3_balance_fluxes(int NB, int nz, float hz, float *Bvel, const float *__restrict__ fw,
+                                                          const int8_t *__restrict__ free_mask, float tol) {
+    __shared__ double sm[66];
+    x3_balance(NB, nz, hz, Bvel + (size_t)blockIdx.x * 3 * nz * NB, fw, free_mask, tol, sm);
+}
+__global__ void __launch_bounds__(512) kx3_update_outflow(int N2, int NB, int nz, float hz, const float *__restrict__ U, float *Bvel,
+                                                          const float *__restrict__ dtv, const float *__restrict__ fw,
+                                                          const int8_t *__restrict__ out_mask, int n_out, const int32_t *__restrict__ out_face,
+                                                          const int32_t *__restrict__ out_cell, const float *__restrict__ out_adv, float tol) {
+    __shared__ double sm[66];
+    const int b = blockIdx.x, n = nz * NB;
+    const size_t N3 = (size_t)N2 * nz;
+    const float *u = U + (size_t)b * 3 * N3;
+    float *bv = Bvel + (size_t)b * 3 * n;
+    const float dt = dtv[b];
+    for (int i = threadIdx.x; i < nz * n_out; i += blockDim.x) {
+        const int k = i / n_out, q = i % n_out, j = out_face[q], c = out_cell[q];
+        const float w = 1.0f - 1.0f / (1.0f + 2.0f * dt * out_adv[q]);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float bo = bv[(size_t)d * n + k * NB + j];
+            bv[(size_t)d * n + k * NB + j] = bo - w * (bo - u[(size_t)d * N3 + (size_t)k * N2 + c]);
+        }
+    }
+    __syncthreads();
+    x3_balance(NB, nz, hz, bv, fw, out_mask, tol, sm);
+}
+__global__ void __launch_bounds__(256) kx3_max_velocity(X3Tab x, const float *__restrict__ U, const float *__restrict__ Bvel, float *__restrict__ maxvel) {
+    __shared__ float smf[33];
+    const int b = blockIdx.y, N2 = x.t.N, NB = x.t.NB, nz = x.nz;
+    const size_t N3 = (size_t)N2 * nz;
+    const float *u = U + (size_t)b * 3 * N3, *bv = Bvel + (size_t)b * 3 * nz * NB;
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N3; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % N2);
+        const float ux = u[i], uy = u[N3 + i];
+        m = fmaxf(m, fabsf(x.t.minv[g] * ux + x.t.minv[N2 + g] * uy));
+        m = fmaxf(m, fabsf(x.t.minv[2 * N2 + g] * ux + x.t.minv[3 * N2 + g] * uy));
+        m = fmaxf(m, fabsf(u[2 * N3 + i]) / x.hz);
+    }
+    const int nb = nz * NB;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) {
+        const int j = i % NB;
+        const float bx = bv[i], by = bv[nb + i];
+        m = fmaxf(m, fabsf(x.t.b_minv[j] * bx + x.t.b_minv[NB + j] * by));
+        m = fmaxf(m, fabsf(x.t.b_minv[2 * NB + j] * bx + x.t.b_minv[3 * NB + j] * by));
+        m = fmaxf(m, fabsf(bv[2 * nb + i]) / x.hz);
+    }
+    const float mv = block_reduce_max(m, smf);
+    if (threadIdx.x == 0) atomicMax((int *)&maxvel[b], __float_as_int(mv));
+}
+
+extern "C" int fgb_extruded3_balance_fluxes(const fgb_extruded3_tables *xt, int32_t B, float *bvel, const float *fw, const int8_t *free_mask,
+                                            float tol, fgb_stream_t s) {
+    if (!xt || !bvel || !fw || !free_mask || B <= 0) return set_err(FGB_E_ARG, "fgb_extruded3_balance_fluxes: bad argument");
+    kx3_balance_fluxes<<<B, 512, 0, STREAM(s)>>>(xt->plane.NB, xt->nz, xt->hz, bvel, fw, free_mask, tol);
+    LAUNCH_CHECK("kx3_balance_fluxes");
+    return FGB_OK;
+}
+extern "C" int fgb_extruded3_update_outflow(const fgb_extruded3_tables *xt, int32_t B, const float *u, float *bvel, const float *dt, const float *fw,
+                                            const int8_t *out_mask, int32_t n_out, const int32_t *out_face, const int32_t *out_cell,
+                                            const float *out_adv, float tol, fgb_stream_t s) {
+    if (!xt || !u || !bvel || !dt || !fw || !out_mask || !out_face || !out_cell || !out_adv || B <= 0 || n_out <= 0)
+        return set_err(FGB_E_ARG, "fgb_extruded3_update_outflow: bad argument");
+    kx3_update_outflow<<<B, 512, 0, STREAM(s)>>>(xt->plane.N, xt->plane.NB, xt->nz, xt->hz, u, bvel, dt, fw, out_mask, n_out, out_face, out_cell,
+                                                 out_adv, tol);
+    LAUNCH_CHECK("kx3_update_outflow");
+    return FGB_OK;
+}
+extern "C" int fgb_extruded3_max_velocity(const fgb_extruded3_tables *xt, int32_t B, const float *u, const float *bvel, float *maxvel,
+                                          fgb_stream_t s) {
+    if (!xt || !u || !bvel || !maxvel || B <= 0) return set_err(FGB_E_ARG, "fgb_extruded3_max_velocity: bad argument");
+    cudaStream_t st = STREAM(s);
+    cudaError_t ce = cudaMemsetAsync(maxvel, 0, (size_t)B * sizeof(float), st);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "fgb_extruded3_max_velocity: memset", ce);
+    X3Tab x; x.t = xt->plane; x.nz = xt->nz; x.hz = xt->hz;
+    const size_t N3 = (size_t)x.t.N * x.nz;
+    unsigned blocks = (unsigned)((N3 + 255) / 256);
+    if (blocks > 592) blocks = 592;
+    kx3_max_velocity<<<dim3(blocks, (unsigned)B), 256, 0, st>>>(x, u, bvel, maxvel);
+    LAUNCH_CHECK("kx3_max_velocity");
+    return FGB_OK;
+}
 #endif  // X3_HOST_ONLY
 #endif  // __CUDACC__

@@ -211,3 +211,43 @@ class ExtrudedPISO3D(ExtrudedStepping):
     def make_divergence_free(self, max_iter: int = 1000):
         native.check(self.lib.fgb_extruded3_make_divergence_free(self.handle, C.byref(self.xtables), _ptr(self.u), _ptr(self.p), _ptr(self.bvel),
                                                                  int(max_iter), self.stream), "fgb_extruded3_make_divergence_free")
+
+    # ---- opt-in: the boundary hooks as kernels (FGB_X3_HOOKS=cuda) instead of the torch expressions of ExtrudedStepping ----
+    # Not yet run on a GPU; tests/test_zz_gpu_extruded_first_run.py compares the two paths.  Default stays torch until then.
+    def _cuda_hooks(self) -> bool:
+        import os
+        return os.environ.get("FGB_X3_HOOKS", "") == "cuda"
+
+    def _hook_tables(self):
+        if "out32" not in self._st:
+            st = self._st
+            st["out32"] = st["out"].to(torch.int32).contiguous()
+            st["out_cells32"] = st["out_cells"].to(torch.int32).contiguous()
+            st["is_out8"] = st["is_out"].to(torch.int8).contiguous()
+            st["fw"] = st["fw"].contiguous()
+        return self._st
+
+    def balance_fluxes(self, free: torch.Tensor, tol: float):
+        if not self._cuda_hooks():
+            return ExtrudedStepping.balance_fluxes(self, free, tol)
+        st = self._hook_tables()
+        mask = free.to(torch.int8).contiguous()
+        native.check(self.lib.fgb_extruded3_balance_fluxes(C.byref(self.xtables), self.B, _ptr(self.bvel), _ptr(st["fw"]), _ptr(mask), float(tol),
+                                                           self.stream), "fgb_extruded3_balance_fluxes")
+
+    def update_outflow(self, dt: torch.Tensor, tol: float = 5e-6):
+        if not self._cuda_hooks():
+            return ExtrudedStepping.update_outflow(self, dt, tol)
+        st = self._hook_tables()
+        dtc = dt.to(self.device, torch.float32).contiguous()
+        native.check(self.lib.fgb_extruded3_update_outflow(C.byref(self.xtables), self.B, _ptr(self.u), _ptr(self.bvel), _ptr(dtc), _ptr(st["fw"]),
+                                                           _ptr(st["is_out8"]), int(st["out32"].numel()), _ptr(st["out32"]), _ptr(st["out_cells32"]),
+                                                           _ptr(st["adv"]), float(tol), self.stream), "fgb_extruded3_update_outflow")
+
+    def max_velocity(self) -> torch.Tensor:
+        if not self._cuda_hooks():
+            return ExtrudedStepping.max_velocity(self)
+        out = torch.empty(self.B, device=self.device)
+        native.check(self.lib.fgb_extruded3_max_velocity(C.byref(self.xtables), self.B, _ptr(self.u), _ptr(self.bvel), _ptr(out), self.stream),
+                     "fgb_extruded3_max_velocity")
+        return out

@@ -359,6 +359,17 @@ int fgb_extruded3_piso_substep(fgb_ortho3 *b, const fgb_extruded3_tables *x, flo
  * corrections; max_iter <= 0 takes the handle's option.  The outflow update of its "PRE" hook is the caller's. */
 int fgb_extruded3_make_divergence_free(fgb_ortho3 *b, const fgb_extruded3_tables *x, float *u, float *p, const float *bvel, int max_iter,
                                        fgb_stream_t s);
+/* Boundary hooks of the extruded environments (opt-in, FGB_X3_HOOKS=cuda; default: the torch expressions of extruded3d.py):
+ * balance_boundary_fluxes (SIM.py:188-224) with an explicit set of free faces (all planes), update_advective_boundaries
+ * (SIM.py:228-393) of the outflow faces followed by their balance, Domain.getMaxVelocity(True, True) (DS.cpp:1580-1612).
+ * fw [2][NB]: signed in-plane flux weights per unit plane spacing; out_face / out_cell / out_adv [n_out]: outflow faces of the plane,
+ * their adjacent cells and advective speeds M^-1 . u_char. */
+int fgb_extruded3_balance_fluxes(const fgb_extruded3_tables *x, int32_t B, float *bvel, const float *fw, const int8_t *free_mask, float tol,
+                                 fgb_stream_t s);
+int fgb_extruded3_update_outflow(const fgb_extruded3_tables *x, int32_t B, const float *u, float *bvel, const float *dt, const float *fw,
+                                 const int8_t *out_mask, int32_t n_out, const int32_t *out_face, const int32_t *out_cell, const float *out_adv,
+                                 float tol, fgb_stream_t s);
+int fgb_extruded3_max_velocity(const fgb_extruded3_tables *x, int32_t B, const float *u, const float *bvel, float *maxvel, fgb_stream_t s);
 
 #ifdef __cplusplus
 }
