@@ -7,6 +7,7 @@
 set -x
 mkdir -p gpurun_out/r02
 timeout 900 python tools/extruded_check.py --json gpurun_out/r02/extruded_check.json > gpurun_out/r02/extruded_check.log 2>&1
+FGB_X3_HOOKS=cuda timeout 900 python tools/extruded_check.py --json gpurun_out/r02/extruded_check_cuda_hooks.json > gpurun_out/r02/extruded_check_cuda_hooks.log 2>&1
 timeout 1200 python tools/cyl3d_bench.py --resolutions 8 24 --steps 1 --airfoil3d --out gpurun_out/r02/cyl3d_bench.json > gpurun_out/r02/cyl3d_bench.log 2>&1
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r02/gpu_tests.log 2>&1
 timeout 600 python bench.py > gpurun_out/r02/bench.json 2> gpurun_out/r02/bench.err
