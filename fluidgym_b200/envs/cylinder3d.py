@@ -127,6 +127,18 @@ class SpanwiseExtrudedEnv(InitialDomainsExtruded):
 
     def _sample(self, field: torch.Tensor) -> torch.Tensor:
         """[B, C, N3] -> [B, C, n_sensors]: the rendered-voxel map evaluated at the sensor voxels only (static ELL rows)"""
+        s = self.solver
+        if field.is_cuda and getattr(s, "_cuda_hooks", lambda: False)():                         # opt-in kernel path (FGB_X3_HOOKS=cuda)
+            from .. import native
+            from ..solver import _ptr
+            if not hasattr(self, "_sens_idx32"):
+                self._sens_idx32 = self.sens_idx.to(torch.int32).contiguous()
+            f = field.contiguous()
+            K, ns = self.sens_idx.shape
+            out = torch.empty(f.shape[0], f.shape[1], ns, device=f.device)
+            native.check(s.lib.fgb_sample_sensors_n(_ptr(f), f.shape[0], f.shape[1], s.N, _ptr(self._sens_idx32), _ptr(self.sens_w), K, ns,
+                                                    _ptr(out), s.stream), "fgb_sample_sensors_n")
+            return out
         return (field[:, :, self.sens_idx] * self.sens_w).sum(dim=2)
 
     def _get_global_obs(self):
