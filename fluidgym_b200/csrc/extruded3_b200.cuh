@@ -410,6 +410,42 @@ __global__ void __launch_bounds__(256) kx3_max_velocity(X3Tab x, const float *__
     if (threadIdx.x == 0) atomicMax((int *)&maxvel[b], __float_as_int(mv));
 }
 
+// per-plane wall forces (forces.py:278-377 = the 2-D wall traction of every plane times the plane spacing; same statements as
+// k_wall_forces with the extruded strides): out[B][nz][2] (drag, lift coefficient contributions), overwritten
+__global__ void __launch_bounds__(128) kx3_wall_forces(fgb_wall w, float visc, int N2, int NB, int nz, float hz, const float *__restrict__ U,
+                                                        const float *__restrict__ P, const float *__restrict__ Bvel, float *__restrict__ out) {
+    __shared__ double red[32 * 2 + 2];
+    const int k = blockIdx.x, b = blockIdx.y;
+    const size_t N3 = (size_t)N2 * nz, nb3 = (size_t)nz * NB;
+    const float *u = U + (size_t)b * 3 * N3 + (size_t)k * N2, *p = P + (size_t)b * N3 + (size_t)k * N2;
+    const float *bv = Bvel + (size_t)b * 3 * nb3 + (size_t)k * NB;
+    const int n = w.n_wall;
+    float f[2] = {0.f, 0.f};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = w.cell[i], j = w.bface[i];
+        const int il = w.cell[(i + 1) % n], ir = w.cell[(i + n - 1) % n];
+        const float nx = w.normal[i], ny = w.normal[n + i];
+        const float tx = ny, ty = -nx;
+        const float du_dn = (u[c] - bv[j]) / w.dist[i], dv_dn = (u[N3 + c] - bv[nb3 + j]) / w.dist[i];
+        const float du_dt = (u[ir] - u[il]) / (2.f * w.tlen[i]), dv_dt = (u[N3 + ir] - u[N3 + il]) / (2.f * w.tlen[i]);
+        const float du_dx = du_dn * nx + du_dt * tx, du_dy = du_dn * ny + du_dt * ty;
+        const float dv_dx = dv_dn * nx + dv_dt * tx, dv_dy = dv_dn * ny + dv_dt * ty;
+        const float sxx = 2.f * visc * du_dx - p[c], syy = 2.f * visc * dv_dy - p[c];
+        const float sxy = 2.f * visc * (0.5f * (du_dy + dv_dx));
+        f[0] += (sxx * nx + sxy * ny) * w.flen[i];
+        f[1] += (sxy * nx + syy * ny) * w.flen[i];
+    }
+    block_reduce_sum<2>(f, red);
+    if (threadIdx.x == 0) { out[((size_t)b * nz + k) * 2] = f[0] * w.scale * hz; out[((size_t)b * nz + k) * 2 + 1] = f[1] * w.scale * hz; }
+}
+extern "C" int fgb_extruded3_wall_forces(const fgb_extruded3_tables *xt, int32_t B, const fgb_wall *w, const float *u, const float *p,
+                                         const float *bvel, float *out, fgb_stream_t s) {
+    if (!xt || !w || !u || !p || !bvel || !out || B <= 0) return set_err(FGB_E_ARG, "fgb_extruded3_wall_forces: bad argument");
+    kx3_wall_forces<<<dim3((unsigned)xt->nz, (unsigned)B), 128, 0, STREAM(s)>>>(*w, xt->plane.viscosity, xt->plane.N, xt->plane.NB, xt->nz, xt->hz,
+                                                                               u, p, bvel, out);
+    LAUNCH_CHECK("kx3_wall_forces");
+    return FGB_OK;
+}
 extern "C" int fgb_extruded3_balance_fluxes(const fgb_extruded3_tables *xt, int32_t B, float *bvel, const float *fw, const int8_t *free_mask,
                                             float tol, fgb_stream_t s) {
     if (!xt || !bvel || !fw || !free_mask || B <= 0) return set_err(FGB_E_ARG, "fgb_extruded3_balance_fluxes: bad argument");

@@ -119,6 +119,14 @@ class SpanwiseExtrudedEnv(InitialDomainsExtruded):
         traction of every plane times the plane spacing)."""
         s = self.solver
         B, nz, N2 = self.n_envs, self.nz, s.N2
+        if s.u.is_cuda and getattr(s, "_cuda_hooks", lambda: False)():                           # opt-in kernel path (FGB_X3_HOOKS=cuda)
+            import ctypes as C
+            from .. import native
+            from ..solver import _ptr
+            out = torch.empty(B, nz, 2, device=self.device)
+            native.check(s.lib.fgb_extruded3_wall_forces(C.byref(s.xtables), B, C.byref(self.wall), _ptr(s.u), _ptr(s.p), _ptr(s.bvel), _ptr(out),
+                                                         s.stream), "fgb_extruded3_wall_forces")
+            return out[:, :, 0], out[:, :, 1]
         u2 = s.u.view(B, 3, nz, N2)[:, :2].permute(0, 2, 1, 3).reshape(B * nz, 2, N2)
         p2 = s.p.view(B * nz, N2)
         b2 = s.bvel[:, :2].permute(0, 2, 1, 3).reshape(B * nz, 2, -1)

@@ -370,6 +370,9 @@ int fgb_extruded3_update_outflow(const fgb_extruded3_tables *x, int32_t B, const
                                  const int8_t *out_mask, int32_t n_out, const int32_t *out_face, const int32_t *out_cell, const float *out_adv,
                                  float tol, fgb_stream_t s);
 int fgb_extruded3_max_velocity(const fgb_extruded3_tables *x, int32_t B, const float *u, const float *bvel, float *maxvel, fgb_stream_t s);
+/* per-plane drag / lift coefficient contributions out[B][nz][2] (forces.py:278-377: 2-D wall traction x plane spacing) */
+int fgb_extruded3_wall_forces(const fgb_extruded3_tables *x, int32_t B, const fgb_wall *w, const float *u, const float *p, const float *bvel,
+                              float *out, fgb_stream_t s);
 
 #ifdef __cplusplus
 }
