@@ -1,0 +1,149 @@
+"""Worker of tests/test_zz_gpu_extruded_first_run.py: each case runs in its OWN PROCESS (a fault in code that has never run on a
+GPU must not take the pytest process, and with it the report of the verified suites, down).
+    python tests/zz_first_run_worker.py asm2|asm4|asm8|hooks|forces
+Exit code 0 = the comparison holds."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+
+
+class _Env:
+    """the two monkeypatch calls the cases use"""
+
+    @staticmethod
+    def setenv(k, v):
+        os.environ[k] = v
+
+    @staticmethod
+    def delenv(k, raising=False):
+        os.environ.pop(k, None)
+
+
+def _cyl24():
+    from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
+    spec = make_cylinder_domain(24)
+    return spec, spec.prepare()
+
+
+def _golden(name):
+    return np.load(os.path.join(HERE, "golden", name))
+
+
+def case_asm(E, monkeypatch=_Env):
+    cyl24, golden = _cyl24(), _golden
+    """k_setup_pressure_matrix_multi<E> / k_pressure_div_multi<E> (one thread = the same cell of E environments, tables loaded once)
+    against the default one-thread-per-(cell, environment) kernels on 11 noisy environments (a batch that is not a multiple of E),
+    with the deferred non-orthogonal pressure term switched on."""
+    import torch
+    from fluidgym_b200.solver import BatchedPISO
+    spec, cd = cyl24
+    fx = golden("cyl24_substep1.npz")
+    B, dt = 11, float(fx["dt"][0])
+    res = {}
+    for tag, env in (("base", None), ("multi", str(E))):
+        if env is None:
+            monkeypatch.delenv("FGB_ASM_ENVS", raising=False)
+        else:
+            monkeypatch.setenv("FGB_ASM_ENVS", env)
+        sol = BatchedPISO(cd, B, cg_impl=0)
+        gen = torch.Generator(device="cuda").manual_seed(7)
+        sol.u.copy_(torch.from_numpy(fx["u_in"]).cuda().unsqueeze(0).expand_as(sol.u))
+        sol.u += 0.05 * torch.randn(sol.u.shape, device="cuda", generator=gen)
+        sol.bvel.copy_(torch.from_numpy(fx["bvel_in"]).cuda().unsqueeze(0).expand_as(sol.bvel))
+        sol.p.copy_(torch.randn(sol.p.shape, device="cuda", generator=gen))
+        sol.setup_advection(dt)
+        sol.solve_advection(zero_init=True)
+        sol.setup_pressure_matrix()
+        sol.setup_pressure_rhs(dt, p_prev=sol.p)
+        torch.cuda.synchronize()
+        res[tag] = {k: sol.buffer(k).clone() for k in ("Coff", "A", "rhs", "ures", "Poff", "Pdiag", "hbya", "div")}
+        del sol
+        # a whole substep with two deferred-correction iterations of the predictor (the right-hand-side-only launch) and two of the pressure
+        sol = BatchedPISO(cd, B, cg_impl=6, advect_non_ortho_steps=2, pressure_non_ortho_steps=2)
+        sol.u.copy_(torch.from_numpy(fx["u_in"]).cuda().unsqueeze(0).expand_as(sol.u))
+        sol.u += 0.05 * torch.randn(sol.u.shape, device="cuda", generator=gen)
+        sol.bvel.copy_(torch.from_numpy(fx["bvel_in"]).cuda().unsqueeze(0).expand_as(sol.bvel))
+        sol.piso_substep(dt)
+        torch.cuda.synchronize()
+        res[tag].update(u_substep=sol.u.clone(), p_substep=sol.p.clone())
+        del sol
+    for k in res["base"]:
+        assert torch.isfinite(res["multi"][k]).all()
+        assert torch.equal(res["base"][k], res["multi"][k]), (E, k, float((res["base"][k] - res["multi"][k]).abs().max()))
+
+
+def case_hooks(monkeypatch=_Env):
+    """FGB_X3_HOOKS=cuda (kx3_balance_fluxes / kx3_update_outflow / kx3_max_velocity) against the default torch expressions of
+    ExtrudedStepping (which the CPU tests pin to the reference's boundary values) on a random state of three environments."""
+    import torch
+    from fluidgym_b200.envs.cylinder_domain import WAKE, make_cylinder_domain
+    from fluidgym_b200.extruded3d import ExtrudedPISO3D
+    spec = make_cylinder_domain(8)
+    cd = spec.prepare()
+    out = np.zeros(cd.NB, dtype=bool)
+    o = cd.boff[WAKE, 1]
+    out[o:o + spec.blocks[WAKE].ny] = True
+    sol = ExtrudedPISO3D(cd, 8, 0.5, n_envs=3)
+    sol.setup_stepping(out, (1.0, 0.0))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    u0 = torch.randn(sol.u.shape, device="cuda", generator=g)
+    b0 = torch.randn(sol.bvel.shape, device="cuda", generator=g)
+    free = torch.from_numpy(out).cuda()
+    free[:7] = True
+    dt = torch.tensor([0.01, 0.004, 0.02])
+    res = {}
+    for mode in ("torch", "cuda"):
+        monkeypatch.setenv("FGB_X3_HOOKS", mode)
+        sol.u.copy_(u0); sol.bvel.copy_(b0)
+        mv = sol.max_velocity().clone()
+        sol.balance_fluxes(free, 1e-7)
+        b1 = sol.bvel.clone()
+        sol.update_outflow(dt, 5e-6)
+        torch.cuda.synchronize()
+        res[mode] = (mv, b1, sol.bvel.clone())
+    assert torch.allclose(res["torch"][0], res["cuda"][0], rtol=1e-6)           # fused multiply-add vs separate roundings
+    for a, b in zip(res["torch"][1:], res["cuda"][1:]):
+        assert torch.isfinite(b).all() and torch.allclose(a, b, rtol=2e-6, atol=1e-7), float((a - b).abs().max())
+    assert not torch.equal(res["cuda"][1], b0)
+
+
+def case_forces(monkeypatch=_Env):
+    """FGB_X3_HOOKS=cuda: kx3_wall_forces and k_sample_sensors on the extruded layout against the torch expressions the CPU tests
+    pin to the reference (per-plane drag / lift, global observation) on a random CylinderJet3D state."""
+    import torch
+    from fluidgym_b200.envs.cylinder3d import CylinderJet3DEnv
+    env = CylinderJet3DEnv(n_envs=2, resolution=8, n_jets=8)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    s = env.solver
+    s.u.copy_(torch.randn(s.u.shape, device="cuda", generator=g))
+    s.p.copy_(torch.randn(s.p.shape, device="cuda", generator=g))
+    s.bvel.copy_(0.1 * torch.randn(s.bvel.shape, device="cuda", generator=g))
+    res = {}
+    for mode in ("torch", "cuda"):
+        monkeypatch.setenv("FGB_X3_HOOKS", mode)
+        cd_, cl_ = env._drag_and_lift()
+        obs = env._get_global_obs()
+        torch.cuda.synchronize()
+        res[mode] = (cd_.clone(), cl_.clone(), obs["velocity"].clone(), obs["pressure"].clone())
+    for a, b in zip(res["torch"], res["cuda"]):
+        assert a.shape == b.shape and torch.isfinite(b).all()
+        assert torch.allclose(a, b, rtol=2e-5, atol=2e-5 * float(a.abs().max())), float((a - b).abs().max())
+
+
+if __name__ == "__main__":
+    case = sys.argv[1]
+    if case.startswith("asm"):
+        case_asm(int(case[3:]))
+    elif case == "hooks":
+        case_hooks()
+    elif case == "forces":
+        case_forces()
+    else:
+        raise SystemExit(f"unknown case {case}")
+    print("OK", case)
