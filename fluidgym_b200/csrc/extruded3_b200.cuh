@@ -446,6 +446,32 @@ extern "C" int fgb_extruded3_wall_forces(const fgb_extruded3_tables *xt, int32_t
     LAUNCH_CHECK("kx3_wall_forces");
     return FGB_OK;
 }
+// actuation (jet_cylinder_env_3d.py:399-424, airfoil_env_3d.py:383-407): bvel[0..1][k][face q] = sum_j amp[b][k][j] * templ[j][0..1][q],
+// spanwise component 0, then the flux balance over the free faces (jets + outflow)
+__global__ void __launch_bounds__(512) kx3_apply_jets(int NB, int nz, float hz, float *Bvel, const float *__restrict__ amp, int J,
+                                                      const int32_t *__restrict__ jet_face, const float *__restrict__ templ, int nf,
+                                                      const float *__restrict__ fw, const int8_t *__restrict__ free_mask, float tol) {
+    __shared__ double sm[66];
+    const int b = blockIdx.x, n = nz * NB;
+    float *bv = Bvel + (size_t)b * 3 * n;
+    const float *a = amp + (size_t)b * nz * J;
+    for (int i = threadIdx.x; i < nz * nf; i += blockDim.x) {
+        const int k = i / nf, q = i % nf, j = jet_face[q];
+        float v0 = 0.f, v1 = 0.f;
+        for (int jj = 0; jj < J; ++jj) { const float am = a[k * J + jj]; v0 += am * templ[(jj * 2) * nf + q]; v1 += am * templ[(jj * 2 + 1) * nf + q]; }
+        bv[k * NB + j] = v0; bv[n + k * NB + j] = v1; bv[2 * n + k * NB + j] = 0.f;
+    }
+    __syncthreads();
+    x3_balance(NB, nz, hz, bv, fw, free_mask, tol, sm);
+}
+extern "C" int fgb_extruded3_apply_jets(const fgb_extruded3_tables *xt, int32_t B, float *bvel, const float *amp, int32_t J, const int32_t *jet_face,
+                                        const float *templ, int32_t nf, const float *fw, const int8_t *free_mask, float tol, fgb_stream_t s) {
+    if (!xt || !bvel || !amp || !jet_face || !templ || !fw || !free_mask || B <= 0 || J <= 0 || nf <= 0)
+        return set_err(FGB_E_ARG, "fgb_extruded3_apply_jets: bad argument");
+    kx3_apply_jets<<<B, 512, 0, STREAM(s)>>>(xt->plane.NB, xt->nz, xt->hz, bvel, amp, J, jet_face, templ, nf, fw, free_mask, tol);
+    LAUNCH_CHECK("kx3_apply_jets");
+    return FGB_OK;
+}
 extern "C" int fgb_extruded3_balance_fluxes(const fgb_extruded3_tables *xt, int32_t B, float *bvel, const float *fw, const int8_t *free_mask,
                                             float tol, fgb_stream_t s) {
     if (!xt || !bvel || !fw || !free_mask || B <= 0) return set_err(FGB_E_ARG, "fgb_extruded3_balance_fluxes: bad argument");

@@ -311,6 +311,8 @@ class CylinderJet3DEnv(SpanwiseExtrudedEnv):
         component), then jets and outflow are rescaled for a zero net boundary flux (tol 1e-7)."""
         s = self.solver
         per_plane = control.repeat_interleave(self.nz_per_agent, dim=1)                           # [B, nz]
+        if getattr(s, "apply_jets", None) and s.apply_jets(per_plane[:, :, None], self.jet_templ[None], self.jet_faces, self._free_jets, 1e-7):
+            return                                                                                # opt-in kernel path (FGB_X3_HOOKS=cuda)
         jf = self.jet_faces.long()
         s.bvel[:, :2, :, jf] = self.jet_templ[None, :, None, :] * per_plane[:, None, :, None]
         s.bvel[:, 2, :, jf] = 0.0

@@ -251,3 +251,15 @@ class ExtrudedPISO3D(ExtrudedStepping):
         native.check(self.lib.fgb_extruded3_max_velocity(C.byref(self.xtables), self.B, _ptr(self.u), _ptr(self.bvel), _ptr(out), self.stream),
                      "fgb_extruded3_max_velocity")
         return out
+
+    def apply_jets(self, amp: torch.Tensor, templ: torch.Tensor, jet_faces: torch.Tensor, free: torch.Tensor, tol: float) -> bool:
+        """amp [B, nz, J], templ [J, 2, nf]: one launch for actuation + flux balance when the kernel hooks are on; returns False (nothing
+        done) otherwise, the caller then uses its torch expressions."""
+        if not self._cuda_hooks():
+            return False
+        st = self._hook_tables()
+        a, t = amp.to(self.device, torch.float32).contiguous(), templ.to(self.device, torch.float32).contiguous()
+        jf, mask = jet_faces.to(torch.int32).contiguous(), free.to(torch.int8).contiguous()
+        native.check(self.lib.fgb_extruded3_apply_jets(C.byref(self.xtables), self.B, _ptr(self.bvel), _ptr(a), int(a.shape[2]), _ptr(jf), _ptr(t),
+                                                       int(jf.numel()), _ptr(st["fw"]), _ptr(mask), float(tol), self.stream), "fgb_extruded3_apply_jets")
+        return True

@@ -77,7 +77,7 @@ EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_cr
            "fgb_ortho3_solve_pressure", "fgb_ortho3_correct_velocity", "fgb_ortho3_piso_substep", "fgb_ortho3_make_divergence_free",
            "fgb_ortho3_sim_step", "fgb_ortho3_wall_rows", "fgb_ipc_alloc", "fgb_ipc_open", "fgb_ipc_close", "fgb_ipc_free",
            "fgb_ortho3_set_slab", "fgb_ortho3_slab_error", "fgb_ortho3_set_scalar", "fgb_ortho3_advect_scalar", "fgb_sample_sensors_n", "fgb_extruded3_piso_substep", "fgb_extruded3_make_divergence_free",
-           "fgb_extruded3_balance_fluxes", "fgb_extruded3_update_outflow", "fgb_extruded3_max_velocity", "fgb_extruded3_wall_forces"]
+           "fgb_extruded3_balance_fluxes", "fgb_extruded3_update_outflow", "fgb_extruded3_max_velocity", "fgb_extruded3_wall_forces", "fgb_extruded3_apply_jets"]
 
 
 def lib_path() -> str:
@@ -158,6 +158,7 @@ def load():
     L.fgb_extruded3_balance_fluxes.argtypes = [C.POINTER(Extruded3Tables), i32, vp, vp, vp, f32, vp]
     L.fgb_extruded3_update_outflow.argtypes = [C.POINTER(Extruded3Tables), i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, f32, vp]
     L.fgb_extruded3_max_velocity.argtypes = [C.POINTER(Extruded3Tables), i32, vp, vp, vp, vp]
+    L.fgb_extruded3_apply_jets.argtypes = [C.POINTER(Extruded3Tables), i32, vp, vp, i32, vp, vp, i32, vp, vp, f32, vp]
     L.fgb_extruded3_wall_forces.argtypes = [C.POINTER(Extruded3Tables), i32, C.POINTER(Wall), vp, vp, vp, vp, vp]
     L.fgb_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
     L.fgb_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]

@@ -370,6 +370,10 @@ int fgb_extruded3_update_outflow(const fgb_extruded3_tables *x, int32_t B, const
                                  const int8_t *out_mask, int32_t n_out, const int32_t *out_face, const int32_t *out_cell, const float *out_adv,
                                  float tol, fgb_stream_t s);
 int fgb_extruded3_max_velocity(const fgb_extruded3_tables *x, int32_t B, const float *u, const float *bvel, float *maxvel, fgb_stream_t s);
+/* actuation: bvel[0..1][plane k][jet_face q] = sum_j amp[b][k][j] * templ[j][0..1][q] (amp [B][nz][J], templ [J][2][nf]), spanwise component 0,
+ * then the flux balance over free_mask (jet_cylinder_env_3d.py:399-424, airfoil_env_3d.py:383-407) */
+int fgb_extruded3_apply_jets(const fgb_extruded3_tables *x, int32_t B, float *bvel, const float *amp, int32_t J, const int32_t *jet_face,
+                             const float *templ, int32_t nf, const float *fw, const int8_t *free_mask, float tol, fgb_stream_t s);
 /* per-plane drag / lift coefficient contributions out[B][nz][2] (forces.py:278-377: 2-D wall traction x plane spacing) */
 int fgb_extruded3_wall_forces(const fgb_extruded3_tables *x, int32_t B, const fgb_wall *w, const float *u, const float *p, const float *bvel,
                               float *out, fgb_stream_t s);

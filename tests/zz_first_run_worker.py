@@ -129,8 +129,12 @@ def case_forces(monkeypatch=_Env):
         monkeypatch.setenv("FGB_X3_HOOKS", mode)
         cd_, cl_ = env._drag_and_lift()
         obs = env._get_global_obs()
+        keep = s.bvel.clone()
+        env._apply_action(torch.linspace(-1, 1, 16, device="cuda").reshape(2, 8))         # actuation + flux balance (kx3_apply_jets)
+        jets = s.bvel.clone()
+        s.bvel.copy_(keep)
         torch.cuda.synchronize()
-        res[mode] = (cd_.clone(), cl_.clone(), obs["velocity"].clone(), obs["pressure"].clone())
+        res[mode] = (cd_.clone(), cl_.clone(), obs["velocity"].clone(), obs["pressure"].clone(), jets)
     for a, b in zip(res["torch"], res["cuda"]):
         assert a.shape == b.shape and torch.isfinite(b).all()
         assert torch.allclose(a, b, rtol=2e-5, atol=2e-5 * float(a.abs().max())), float((a - b).abs().max())
