@@ -63,6 +63,7 @@ struct fgb_ortho3 {
     unsigned long long *slab_ctr;     // [4] device-side sequence counters of the slab protocol
     fgb_ortho3_scalar sc;             // passive scalar + buoyancy (RBC3D); sc.T == nullptr: none
     int grid_blocks;
+    int cg_fused;                     // FGB_K3_CG_FUSED=1: k3_cg_fused (2 grid.sync per CG iteration) on a single GPU; default 0 = k3_cg
     long long launches;
 };
 
@@ -117,6 +118,8 @@ extern "C" int fgb_ortho3_create(const fgb_ortho3_tables *t, int32_t B, void *wo
     ce = cudaMemset(workspace, 0, fgb_ortho3_workspace_bytes(t, B));
     if (ce != cudaSuccess) { cudaFreeHost(b->h_counters); delete b; return set_err(FGB_E_CUDA, "cudaMemset workspace", ce); }
     b->grid_blocks = 0;
+    b->cg_fused = 0;
+    if (const char *ev = getenv("FGB_K3_CG_FUSED")) b->cg_fused = atoi(ev) == 1;
     *out = b;
     return FGB_OK;
 }
@@ -611,6 +614,113 @@ __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, O3Slab sl, int B, const flo
     if (sl.on && blockIdx.x == 0 && threadIdx.x == 0) { sl.ctr[0] = arc; sl.ctr[1] = hc; }
 }
 
+// OPT-IN variant of k3_cg (FGB_K3_CG_FUSED=1, single GPU only; NOT yet run on a GPU): the search-direction update p <- r + beta p is
+// folded into the next matrix-vector product.  Every row forms r[n] + beta * p_old[n] for itself and its six neighbours on the fly and
+// stores its own new value into a second buffer, so the grid-wide synchronisation that separated the update from the product
+// disappears: 2 instead of 3 grid.sync per iteration -- the solves of the extruded environments (1 000 - 2 000 iterations on 10^4 -
+// 10^5 cells) are bound by exactly these synchronisations.  The expression and the summation order of every value are those of
+// k3_cg, so iterates, iteration counts and results are expected to be BIT-IDENTICAL (tests/zz_first_run_worker.py cg_fused).
+__device__ __forceinline__ float o3_pnew(const float *r, const float *pold, float beta, int i) { return __ldcg(&r[i]) + beta * __ldcg(&pold[i]); }
+__global__ void __launch_bounds__(O3_CT) k3_cg_fused(T3 t, O3Slab sl, int B, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
+                                                    const float *__restrict__ Rhs, float *Xout, float *work, float *part, int maxit, float tol,
+                                                    int zero_init, int reset_steps, int slot, const int32_t *__restrict__ active,
+                                                    int32_t *__restrict__ iters, float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red[32 * 2 + 8];
+    const int N = t.N, NS = t.NS;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const float norm = 1.0f / sqrtf((float)t.N_global);
+    unsigned rcount = 0;
+    unsigned long long arc = 0ull;
+    bool dirty = false;
+    for (int b = 0; b < B; ++b) {
+        if (active && !active[b]) continue;
+        const float *off = Poff + (size_t)b * 6 * NS, *dg = Pdiag + (size_t)b * NS, *f = Rhs + (size_t)b * NS;
+        float *wb = work + (size_t)b * O3_KRY * NS;
+        float *r = wb, *p = wb + NS, *ap = wb + 2 * (size_t)NS, *best = wb + 3 * (size_t)NS, *x = wb + 4 * (size_t)NS, *p2 = wb + 5 * (size_t)NS;
+        float *xo = Xout + (size_t)b * NS;
+        float acc[2] = {0.f, 0.f};
+        for (int g = tid; g < N; g += nth) { x[g] = zero_init ? 0.f : xo[g]; acc[1] += (f[g] != 0.f) ? 1.f : 0.f; }
+        o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
+        int used = -1; float fin = 0.f;
+        if (!(acc[1] > 0.f)) {
+            for (int g = tid; g < N; g += nth) x[g] = 0.f;
+        } else {
+            acc[0] = acc[1] = 0.f;
+            for (int g = tid; g < N; g += nth) {
+                const float rr = f[g] - (zero_init ? 0.f : o3_row(t, g, off, dg, x));
+                r[g] = rr; p[g] = rr; acc[0] += rr * rr;
+            }
+            o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
+            float rho = acc[0], bestc = 0.f, lastc = 0.f, beta = 0.f; int best_it = -1, rising = 0;
+            bool fresh = true;                       // p holds the search direction itself (first iteration, after a residual reset)
+            int until_reset = reset_steps > 0 ? reset_steps - 1 : -1;
+            for (int i = 0; i < maxit; ++i) {
+                const bool do_reset = until_reset == 0;
+                if (until_reset >= 0) until_reset = do_reset ? reset_steps - 1 : until_reset - 1;
+                if (do_reset) {
+                    __threadfence(); grid.sync();                                    // x of the previous iteration is complete
+                    acc[0] = acc[1] = 0.f;
+                    for (int g = tid; g < N; g += nth) { const float rr = f[g] - o3_row(t, g, off, dg, x); r[g] = rr; p[g] = rr; acc[0] += rr * rr; }
+                    o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
+                    rho = acc[0];
+                    fresh = true;
+                }
+                acc[0] = acc[1] = 0.f;
+                float *pc = p;                                                        // buffer that holds this iteration's direction
+                if (fresh) {
+                    for (int g = tid; g < N; g += nth) { const float a = o3_row(t, g, off, dg, p); ap[g] = a; acc[0] += p[g] * a; }
+                } else {
+                    for (int g = tid; g < N; g += nth) {
+                        const float pg = o3_pnew(r, p, beta, g);
+                        float a = dg[g] * pg;
+#pragma unroll
+                        for (int fc = 0; fc < 6; ++fc) { const int n = t.nbr[fc * NS + g]; if (n >= 0) a += off[fc * NS + g] * o3_pnew(r, p, beta, n); }
+                        p2[g] = pg; ap[g] = a; acc[0] += pg * a;
+                    }
+                    pc = p2;
+                }
+                o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
+                const float alpha = rho / acc[0];
+                acc[0] = acc[1] = 0.f;
+                for (int g = tid; g < N; g += nth) {
+                    x[g] += alpha * pc[g];
+                    const float rr = r[g] - alpha * ap[g];
+                    r[g] = rr; acc[0] += rr * rr;
+                }
+                o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
+                if (!fresh) { float *tmp = p; p = p2; p2 = tmp; }                   // the new direction becomes "p old" of the next iteration
+                fresh = false;
+                const float crit = sqrtf(acc[0]) * norm;
+                if (!isfinite(crit)) { used = i; fin = crit; break; }
+                if (i == 0 || crit < bestc) {
+                    bestc = crit; best_it = i;
+                    for (int g = tid; g < N; g += nth) best[g] = x[g];
+                }
+                if (i > 0 && crit >= lastc) ++rising; else rising = 0;
+                lastc = crit; used = i; fin = crit;
+                if (crit < tol) break;
+                if (i == maxit - 1 || rising >= 100) {
+                    for (int g = tid; g < N; g += nth) x[g] = best[g];
+                    used = best_it; fin = bestc;
+                    break;
+                }
+                const float rhop = rho; rho = acc[0];
+                beta = rho / rhop;
+            }
+        }
+        acc[0] = acc[1] = 0.f;
+        for (int g = tid; g < N; g += nth) acc[0] += x[g];
+        o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
+        const float mean = acc[0] / (float)t.N_global;
+        for (int g = tid; g < N; g += nth) { const float xv = x[g] - mean; xo[g] = xv; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            iters[b * 8 + 3 + slot] = used; resid[b * 8 + 3 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1);
+        }
+        __threadfence(); grid.sync();
+    }
+}
+
 // ---- stream-level slab helpers ---------------------------------------------------------------------------------------
 // copy the two owned boundary planes of `ncomp` components of a field into the z-neighbours' halo planes
 __global__ void __launch_bounds__(256) k3_halo_push(O3Slab sl, T3 t, float *field, int ncomp) {
@@ -743,6 +853,7 @@ static int o3_coop_blocks(fgb_ortho3 *b) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_a, k3_cg, O3_CT, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_b, k3_bicgstab<3>, O3_CT, 0);
+    if (b->cg_fused) { int per_c = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_c, k3_cg_fused, O3_CT, 0); if (per_c < per_a) per_a = per_c; }
     int blocks = (per_a > 0 && per_b > 0) ? sms : 1;     // one CTA per SM (co-residency is what a cooperative launch needs)
     const int need = (b->t.N + O3_CT - 1) / O3_CT;
     if (blocks > need) blocks = need;
@@ -826,8 +937,9 @@ extern "C" int fgb_ortho3_solve_pressure(fgb_ortho3 *b, float *p_out, int zero_i
     int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
     void *args[] = {&t, &sl, &B, &poff, &pd, &rhs, &p_out, &work, &part, &max_iter, &tol, &zero_init, &reset_steps, &slot, &active, &iters, &resid, &itot};
     b->launches++;
-    cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_cg, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
-    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_cg)", ce);
+    const bool fused = b->cg_fused && !b->slab.on;
+    cudaError_t ce = cudaLaunchCooperativeKernel(fused ? (void *)k3_cg_fused : (void *)k3_cg, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, fused ? "cudaLaunchCooperativeKernel(k3_cg_fused)" : "cudaLaunchCooperativeKernel(k3_cg)", ce);
     return FGB_OK;
 }
 

@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.xfail(strict=False, reason="first GPU run of opt-in kernels (never executed on a GPU when committed)")
-@pytest.mark.parametrize("case", ["asm2", "asm4", "asm8", "hooks", "forces"])
+@pytest.mark.parametrize("case", ["asm2", "asm4", "asm8", "hooks", "forces", "cg_fused"])
 def test_opt_in_kernels_first_gpu_run(case):
     """tests/zz_first_run_worker.py, one process per case:
     asm<E>  -- k_setup_advection_multi / k_setup_pressure_matrix_multi / k_pressure_div_multi<E> (FGB_ASM_ENVS; one thread = the same
@@ -30,7 +30,9 @@ def test_opt_in_kernels_first_gpu_run(case):
     hooks   -- kx3_balance_fluxes / kx3_update_outflow / kx3_max_velocity (FGB_X3_HOOKS=cuda) against the default torch expressions of
                ExtrudedStepping (which the CPU tests pin to the reference's boundary values);
     forces  -- kx3_wall_forces and k_sample_sensors on the extruded layout against the torch expressions (per-plane drag / lift, global
-               observation of CylinderJet3D)."""
+               observation of CylinderJet3D);
+    cg_fused -- k3_cg_fused (FGB_K3_CG_FUSED=1: 2 instead of 3 grid.sync per CG iteration) is BIT-IDENTICAL to k3_cg on an extruded substep
+               (8 solves of 1 400 - 2 300 iterations) and on the reset projection."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "zz_first_run_worker.py"), case], capture_output=True, text=True,
                        timeout=600, cwd=ROOT)
     print(r.stdout[-3000:])

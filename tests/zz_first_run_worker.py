@@ -1,6 +1,6 @@
 """Worker of tests/test_zz_gpu_extruded_first_run.py: each case runs in its OWN PROCESS (a fault in code that has never run on a
 GPU must not take the pytest process, and with it the report of the verified suites, down).
-    python tests/zz_first_run_worker.py asm2|asm4|asm8|hooks|forces
+    python tests/zz_first_run_worker.py asm2|asm4|asm8|hooks|forces|cg_fused
 Exit code 0 = the comparison holds."""
 import os
 import sys
@@ -140,6 +140,37 @@ def case_forces(monkeypatch=_Env):
         assert torch.allclose(a, b, rtol=2e-5, atol=2e-5 * float(a.abs().max())), float((a - b).abs().max())
 
 
+def case_cg_fused(monkeypatch=_Env):
+    """FGB_K3_CG_FUSED=1 (k3_cg_fused: search-direction update folded into the matrix-vector product, 2 instead of 3 grid.sync per
+    iteration) against k3_cg on one extruded substep from the reference's traced CylinderJet3D state (8 pressure solves of
+    1 400 - 2 300 iterations) and on the reset projection (no residual reset, 1 000-iteration cap, best iterate): velocity, pressure
+    and iteration counts must be bit-identical."""
+    import torch
+    from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
+    from fluidgym_b200.extruded3d import ExtrudedPISO3D
+    cd = make_cylinder_domain(8).prepare()
+    fx = _golden("cyl3d_substep0.npz")
+    nz, N2 = fx["A"].shape
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("FGB_K3_CG_FUSED", mode)
+        sol = ExtrudedPISO3D(cd, nz, float(fx["hz"][0]), n_envs=2)
+        sol.u.copy_(torch.from_numpy(fx["u_in"]).reshape(1, 3, -1).cuda().expand_as(sol.u))
+        sol.p.copy_(torch.from_numpy(fx["p_in"]).reshape(1, -1).cuda().expand_as(sol.p))
+        sol.bvel.copy_(torch.from_numpy(fx["bvel"]).cuda().unsqueeze(0).expand_as(sol.bvel))
+        sol.u[1] *= 1.1
+        sol.piso_substep(float(fx["dt"][0]))
+        torch.cuda.synchronize()
+        a = (sol.u.clone(), sol.p.clone(), sol.buffer("iter_total").clone(), sol.buffer("iters").clone())
+        sol.make_divergence_free(1000)
+        torch.cuda.synchronize()
+        res[mode] = a + (sol.u.clone(), sol.p.clone(), sol.buffer("iter_total").clone())
+        del sol
+    assert int(res["0"][2][0, 0]) > 8000                                            # the solves really iterate
+    for a, b in zip(res["0"], res["1"]):
+        assert torch.equal(a, b), float((a.double() - b.double()).abs().max())
+
+
 if __name__ == "__main__":
     case = sys.argv[1]
     if case.startswith("asm"):
@@ -148,6 +179,8 @@ if __name__ == "__main__":
         case_hooks()
     elif case == "forces":
         case_forces()
+    elif case == "cg_fused":
+        case_cg_fused()
     else:
         raise SystemExit(f"unknown case {case}")
     print("OK", case)

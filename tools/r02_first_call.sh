@@ -13,6 +13,10 @@ timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r02/gpu_tests.log 2
 timeout 600 python bench.py > gpurun_out/r02/bench.json 2> gpurun_out/r02/bench.err
 FGB_ASM_ENVS=4 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/r02/bench_asm4.json 2> gpurun_out/r02/bench_asm4.err
 FGB_ASM_ENVS=8 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/r02/bench_asm8.json 2> gpurun_out/r02/bench_asm8.err
+# A/B of the fused-update cooperative CG (bit-identical, one grid.sync less per iteration)
+FGB_K3_CG_FUSED=1 timeout 900 python tools/cyl3d_bench.py --resolutions 8 24 --steps 1 --out gpurun_out/r02/cyl3d_bench_cg_fused.json > gpurun_out/r02/cyl3d_bench_cg_fused.log 2>&1
+timeout 600 python tools/tcf_bench.py --ids TCFSmall3D-both-easy-v0 RBC3D-easy-v0 --steps 2 --out gpurun_out/r02/tcf_bench.json > gpurun_out/r02/tcf_bench.log 2>&1
+FGB_K3_CG_FUSED=1 timeout 600 python tools/tcf_bench.py --ids TCFSmall3D-both-easy-v0 RBC3D-easy-v0 --steps 2 --out gpurun_out/r02/tcf_bench_cg_fused.json > gpurun_out/r02/tcf_bench_cg_fused.log 2>&1
 # launch list + one full capture of the pressure CG of the extruded path (CylinderJet3D res 24), for profiles/
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02/launches_cyl3d_res24.csv \
     python tools/cyl3d_bench.py --resolutions 24 --steps 1 --settle 0 > gpurun_out/r02/ncu_cyl3d_launches.log 2>&1
