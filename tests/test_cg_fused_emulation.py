@@ -120,3 +120,29 @@ def test_fused_direction_update_is_bit_identical(n, tol, reset_steps, maxit):
     x1, it1 = cg_fused(A, b, f32(tol), reset_steps, maxit)
     assert it0 == it1 and it0 > 20
     assert np.array_equal(x0, x1)
+
+
+def test_fused_update_on_the_extruded_pressure_system_of_the_reference_trace(golden):
+    """The same comparison on the real thing: pressure matrix (kernel cell code on the host) and right-hand side of the first
+    pressure solve the unmodified reference traced on CylinderJet3D -- 1 576 iterations with a residual reset every 100, the
+    reference's own count."""
+    import ctypes as C
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cpu_harness"))
+    from extruded_standin import _p, build_harness, csr, host_tables
+    from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
+    from fluidgym_b200.extruded3d import extruded_neighbours
+    cd = make_cylinder_domain(8).prepare()
+    t, _keep = host_tables(cd)
+    fx = golden("cyl3d_substep0.npz")
+    nz, N2 = fx["A"].shape
+    A = np.ascontiguousarray(fx["A"])
+    poff, pd = np.zeros((6, nz, N2), f32), np.zeros((nz, N2), f32)
+    build_harness().xh_pressure_matrix(C.byref(t), nz, C.c_float(float(fx["hz"][0])), _p(A), _p(poff), _p(pd))
+    P = csr(extruded_neighbours(np.asarray(cd.nbr), nz), poff, pd)
+    b = np.ascontiguousarray(fx["div0"]).reshape(-1)
+    x0, i0 = cg_reference(P, b, f32(5e-7), 100, 5000)
+    x1, i1 = cg_fused(P, b, f32(5e-7), 100, 5000)
+    assert i0 == i1 == int(fx["cg_iters"][0]) and np.array_equal(x0, x1)
