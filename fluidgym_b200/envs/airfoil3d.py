@@ -7,7 +7,8 @@ machinery of ``envs/cylinder3d.py`` (reference trace / ``env.step`` of CylinderJ
 2-D airfoil tables -- grid, jet slots and profiles, wall ring, sensor positions, airfoil mask -- of ``envs/airfoil.py`` (GPU parity
 with the reference's Airfoil2D), and the extruded cell code on this very plane mesh (``tests/test_extruded_host.py``).  Host logic
 (action -> jet profiles per plane, flux balance, sensor layout, rewards, multi-agent interface) is exercised on the CPU with the
-solver calls stubbed out (``tests/test_airfoil3d_cpu.py``).  One environment is 46 806 x 96 = 4.5 M cells.
+solver calls stubbed out, and sensor layout / airfoil mask / action mapping / reward mix equal the reference's own pure-torch methods
+run from the installed reference on stub objects (``tests/test_airfoil3d_cpu.py``).  One environment is 46 806 x 96 = 4.5 M cells.
 """
 from __future__ import annotations
 

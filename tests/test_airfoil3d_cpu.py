@@ -141,3 +141,105 @@ def test_init_from_2d_copies_the_2d_velocity_into_every_plane(compiled, tmp_path
     missing = _env(compiled, init_from_2d=True, initial_domains_path=str(tmp_path / "nowhere"))
     with pytest.raises(FileNotFoundError, match="2D initial domain not found"):
         missing.reset(seed=1)
+
+
+def _reference_stub(env):
+    """an object carrying just the attributes the reference's pure-torch methods read, so that they run on the CPU"""
+    from fluidgym.envs.airfoil.airfoil_env_3d import AirfoilEnv3D
+    from fluidgym.envs.airfoil.airfoil_env_base import AirfoilEnvBase
+    from fluidgym_b200.envs.airfoil_domain import airfoil_polyline
+
+    class Stub:
+        pass
+    st = Stub()
+    st.H, st.L, st.D, st.airfoil_length = env.H, env.L, env.D, env.airfoil_length
+    st.render_shape, st._ndims = env.render_shape, 3
+    st._n_agents, st._n_sensors_per_agent, st._n_sensors_z = env.n_span, env.n_sensors_per_agent, env.n_sensors_z
+    st._n_jets, st._nz_per_agent = env.n_jets, env.nz_per_agent
+    st._get_sensor_locations_2d = lambda: AirfoilEnvBase._get_sensor_locations_2d(st)
+    st._get_sensor_locations_3d = lambda: AirfoilEnv3D._get_sensor_locations_3d(st)
+    st._physical_locations_to_grid_coords = lambda c: AirfoilEnvBase._physical_locations_to_grid_coords(st, c)
+    st._airfoil_coords = airfoil_polyline(env.attack_angle_deg)
+    return st, AirfoilEnv3D, AirfoilEnvBase
+
+
+def test_sensor_layout_and_action_mapping_equal_the_reference_methods(compiled):
+    """The reference's own pure-torch methods -- AirfoilEnvBase._get_airfoil_mask, AirfoilEnv3D._get_sensor_locations (z-major voxel
+    coordinates, columns touching the airfoil mask dropped) and AirfoilEnv3D._action_to_control (zero-mean clamped amplitudes repeated
+    over the agents' planes) -- executed on the CPU from the installed reference on a stub object, against this environment."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "fluidgym")):
+        pytest.skip("unmodified reference not installed (baseline/_ref)")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shims
+    ref_shims.install()
+    try:
+        import fluidgym  # noqa: F401
+        env = _env(compiled, n_envs=1, n_agents=4)
+        st, Ref3D, RefBase = _reference_stub(env)
+    except Exception as e:
+        pytest.skip(f"reference not importable here: {e}")
+    mask = RefBase._get_airfoil_mask(st)
+    st._airfoil_mask = mask
+    assert np.array_equal(env.airfoil_mask, mask[0])
+    gc = Ref3D._get_sensor_locations(st)
+    assert tuple(gc.shape) == (3, 4, env.n_sensors_xy) and np.array_equal(env.sensor_px.reshape(3, 4, -1), gc.numpy())
+    # action -> jet wall velocity (before the flux balance, which rescales jets and outflow by one common factor)
+    nz, n_top = env.nz, env.jet_base.shape[2]
+    base = torch.zeros(1, 3, nz, 1, n_top)
+    base[0, :2, :, 0, :] = env.jet_base.sum(dim=0)[:, None, :]                       # the three slots do not overlap
+    st._top_base_profile, st._jet_locations_top = base, [list(ab) for ab in env.jet_slots]
+    action = torch.tensor([[0.5, -0.2, 0.1], [2.0, -3.0, 0.4], [0.0, 0.3, 0.0], [1.0, 1.0, 1.0]])
+    ref = Ref3D._action_to_control(st, action)[0, :, :, 0, :]                         # [3, nz, n_top]
+    env.reset(seed=0)
+    env._apply_action(action[None])
+    got = env.solver.bvel[0][:, :, env.jet_faces.long()]
+    scale = float((got[:2] * ref[:2]).sum() / (ref[:2] * ref[:2]).sum())
+    assert 0.5 < scale < 2.0 and torch.allclose(got, ref * scale, atol=1e-7) and not got[2].any()
+
+
+def test_multi_agent_reward_mix_equals_the_reference_methods(compiled):
+    """AirfoilEnv3D._step_marl_impl and CylinderJetEnv3D._step_marl_impl (pure torch once the solver step is stubbed: they receive the
+    per-plane coefficients from ``_step_impl``) executed from the installed reference, against ``SpanwiseExtrudedEnv.step``'s mix."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "fluidgym")):
+        pytest.skip("unmodified reference not installed (baseline/_ref)")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shims
+    ref_shims.install()
+    try:
+        from fluidgym.envs.airfoil.airfoil_env_3d import AirfoilEnv3D
+        from fluidgym.envs.cylinder.jet_cylinder_env_3d import CylinderJetEnv3D
+    except Exception as e:
+        pytest.skip(f"reference not importable here: {e}")
+    g = torch.Generator().manual_seed(4)
+    cds, cls_ = 1.0 + torch.rand(8, generator=g), torch.randn(8, generator=g)
+
+    class Stub:
+        pass
+    from extruded_standin import HostExtrudedPISO3D
+    from fluidgym_b200.envs.cylinder3d import CylinderJet3DEnv
+    from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
+    cspec = make_cylinder_domain(8)
+    cyl = CylinderJet3DEnv(resolution=8, n_jets=8, device="cpu", compiled=(cspec, cspec.prepare()), solver_cls=HostExtrudedPISO3D, use_marl=True,
+                           local_reward_weight=0.3, cd_ref=3.0, lift_penalty=0.7, step_length=0.01)
+    air = _env(compiled, n_agents=4, use_marl=True, local_reward_weight=0.3, cl_cd_ref=1.5, step_length=0.05)
+    for ref_cls, env, n_agents, D, extra, formula in (
+            (AirfoilEnv3D, air, 4, 1.4, dict(_cl_cd_ref=1.5), lambda cd, cl: cl / cd - 1.5),
+            (CylinderJetEnv3D, cyl, 8, 4.0, dict(_cd_ref=3.0, _lift_penalty=0.7), lambda cd, cl: 3.0 - cd - 0.7 * torch.abs(cl))):
+        st = Stub()
+        st.D, st._n_agents, st._n_jets, st._local_reward_weight = D, n_agents, n_agents, 0.3
+        for k, v in extra.items():
+            setattr(st, k, v)
+        cd, cl = cds.sum() / D, cls_.sum() / D
+        glob = formula(cd, cl)                                                       # the reference's _step_impl result (:420 / :436)
+        st._step_impl = lambda a: (None, glob, False, {"drag": cd, "lift": cl, "all_cds": cds.clone(), "all_cls": cls_.clone()})
+        st._get_local_obs = lambda: {}
+        _, ref_rewards, _, ref_info = ref_cls._step_marl_impl(st, None)
+        # this repository: one (stubbed) solver step whose per-plane coefficients are the same numbers
+        env.solver.piso_substep = lambda dt: None
+        env.solver.make_divergence_free = lambda max_iter=1000: None
+        env.reset(seed=0)
+        env._drag_and_lift = lambda: (cds[None].clone(), cls_[None].clone())
+        _, reward, _, _, info = env.step(torch.zeros_like(env._zero_action))
+        assert reward.shape == (1, n_agents) and torch.allclose(reward[0], ref_rewards, rtol=1e-6, atol=1e-6)
+        assert torch.allclose(info["global_reward"][0], ref_info["global_reward"], rtol=1e-6) and "all_cds" not in info and "all_cds" not in ref_info
+        assert torch.allclose(info["drag"][0], cd) and torch.allclose(info["lift"][0], cl)
