@@ -243,3 +243,36 @@ def test_multi_agent_reward_mix_equals_the_reference_methods(compiled):
         assert reward.shape == (1, n_agents) and torch.allclose(reward[0], ref_rewards, rtol=1e-6, atol=1e-6)
         assert torch.allclose(info["global_reward"][0], ref_info["global_reward"], rtol=1e-6) and "all_cds" not in info and "all_cds" not in ref_info
         assert torch.allclose(info["drag"][0], cd) and torch.allclose(info["lift"][0], cl)
+
+
+def test_per_plane_forces_equal_the_reference_force_function(compiled):
+    """Airfoil3D drag / lift per plane (airfoil_env_base.py:452-476: compute_forces_3d with face areas = wall face length x D / res_z)
+    evaluated by the reference's own function on the CPU, against ``SpanwiseExtrudedEnv._drag_and_lift`` on a random state."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "fluidgym")):
+        pytest.skip("unmodified reference not installed (baseline/_ref)")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shims
+    ref_shims.install()
+    try:
+        import fluidgym  # noqa: F401  (first: the package resolves its circular imports from the top)
+        from fluidgym.envs.util.forces import compute_forces_3d
+    except Exception as e:
+        pytest.skip(f"reference not importable here: {e}")
+    env = _env(compiled, n_envs=1, n_agents=4)
+    s, tab = env.solver, env._wall_t
+    g = torch.Generator().manual_seed(9)
+    s.u.copy_(torch.randn(s.u.shape, generator=g))
+    s.p.copy_(torch.randn(s.p.shape, generator=g))
+    s.bvel.copy_(0.1 * torch.randn(s.bvel.shape, generator=g))
+    nz, N2 = env.nz, s.N2
+    u = s.u[0].view(3, nz, N2)
+    p = s.p[0].view(nz, N2)
+    bv = s.bvel[0]
+    cell, bface = tab["cell"].long(), tab["bface"].long()
+    ref = compute_forces_3d(u[:, :, cell], bv[:, :, bface], p[:, cell], tab["normal"][:, :, None], tab["tlen"][:, None], tab["dist"][:, None],
+                            tab["flen"] * env.hz, torch.tensor(float(env.cd.visc)))                          # [2, nz] forces
+    cds, cls_ = env._drag_and_lift()
+    scale = 1.0 / (0.5 * env.U_mean ** 2 * env.airfoil_length)
+    assert float(ref.abs().max()) > 1e-3
+    assert torch.allclose(cds[0], ref[0] * scale, rtol=2e-4, atol=1e-5 * float((ref * scale).abs().max()))
+    assert torch.allclose(cls_[0], ref[1] * scale, rtol=2e-4, atol=1e-5 * float((ref * scale).abs().max()))
