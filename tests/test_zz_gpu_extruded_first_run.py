@@ -1,13 +1,12 @@
 """Code paths that had NEVER run on a GPU when they were committed (the round's GPU budget was spent).  They run LAST (file name) and as
 non-strict xfails, so that a fault in them cannot disturb the verified suites: XPASS = verified on this box.
 
-1. Opt-in multi-environment assembly kernels (FGB_ASM_ENVS): bit-identity with the default kernels.
-2. Opt-in boundary-hook kernels of the extruded environments (FGB_X3_HOOKS=cuda) against the default torch expressions.
-3. CylinderJet3D / extruded D = 3 launch path on the GPU (tools/extruded_check.py: substep, reset and env.step against the
-unmodified reference's goldens).  When this file was committed the round's GPU budget was spent and the launch path had NEVER run
-on a GPU -- everything around it is verified on the CPU (tests/test_cylinder3d_cpu.py, test_extruded_host.py).  The check therefore
-runs LAST (file name), in its OWN PROCESS with a time limit, so that a fault in the new path cannot disturb the verified suites,
-and it is a non-strict xfail: XPASS = the path is verified on this box, XFAIL = see the JSON lines it prints."""
+1. CylinderJet3D / extruded D = 3 launch path (tools/extruded_check.py: substep, reset and env.step against the unmodified reference's
+   goldens); everything around it is verified on the CPU (tests/test_cylinder3d_cpu.py, test_extruded_host.py).
+2. Opt-in kernels (tests/zz_first_run_worker.py): multi-environment assembly kernels (FGB_ASM_ENVS) and the fused-update cooperative CG
+   (FGB_K3_CG_FUSED) -- bit-identity with the default kernels; hook / force / sensor kernels of the extruded environments
+   (FGB_X3_HOOKS=cuda) against the default torch expressions.
+Every case runs in its OWN PROCESS with a time limit: XPASS = verified on this box, XFAIL = see the output it prints."""
 import json
 import os
 import subprocess
@@ -18,6 +17,24 @@ import pytest
 from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.xfail(strict=False, reason="first GPU run of the extruded launch path (never executed on a GPU when committed)")
+def test_extruded_path_first_gpu_run(tmp_path):
+    out = tmp_path / "extruded_check.json"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "extruded_check.py"), "--json", str(out)], capture_output=True, text=True,
+                       timeout=900, cwd=ROOT)
+    print(r.stdout[-4000:])
+    print(r.stderr[-2000:], file=sys.stderr)
+    try:                                                       # keep the evidence where gpurun brings it back
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "extruded_check.log"), "w") as f:
+            f.write(r.stdout + "\n--- stderr ---\n" + r.stderr)
+    except OSError:
+        pass
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    verdict = json.load(open(out))
+    assert verdict["ok"]
 
 
 @pytest.mark.xfail(strict=False, reason="first GPU run of opt-in kernels (never executed on a GPU when committed)")
@@ -38,21 +55,3 @@ def test_opt_in_kernels_first_gpu_run(case):
     print(r.stdout[-3000:])
     print(r.stderr[-3000:], file=sys.stderr)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
-
-
-@pytest.mark.xfail(strict=False, reason="first GPU run of the extruded launch path (never executed on a GPU when committed)")
-def test_extruded_path_first_gpu_run(tmp_path):
-    out = tmp_path / "extruded_check.json"
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "extruded_check.py"), "--json", str(out)], capture_output=True, text=True,
-                       timeout=900, cwd=ROOT)
-    print(r.stdout[-4000:])
-    print(r.stderr[-2000:], file=sys.stderr)
-    try:                                                       # keep the evidence where gpurun brings it back
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", "extruded_check.log"), "w") as f:
-            f.write(r.stdout + "\n--- stderr ---\n" + r.stderr)
-    except OSError:
-        pass
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    verdict = json.load(open(out))
-    assert verdict["ok"]
