@@ -1235,6 +1235,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t a, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) { while (!mbar_try_wait(a, parity)) {} }
+// as mbar_wait, with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~1 us passes) instead
+// of re-issuing the test -- spinning warps otherwise take issue slots and shared-memory pipe cycles from the working ones
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred P1;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+                     "selp.b32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity), "r"(1000u) : "memory");
+    } while (!ok);
+}
 __device__ __forceinline__ void st_async_f32(uint32_t cluster_addr, float v, uint32_t cluster_mbar) {
     asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];"
                  ::"r"(cluster_addr), "r"(__float_as_uint(v)), "r"(cluster_mbar) : "memory");
@@ -1474,6 +1485,285 @@ __global__ void __launch_bounds__(T, MINB) k_cg_cluster_mb(Tab t, const float *_
 #pragma unroll
     for (int k = 0; k < CPT; ++k) { const int l = threadIdx.x + k * T; if (l < cnt) xo[start + l] = xr[k] - mean; }
     if (threadIdx.x == 0 && rank == 0) { iters[b * 8 + 2 + slot] = used; resid[b * 8 + 2 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1); }
+    cluster_sync_all();   // keep peer shared memory (and in-flight st.async targets) alive until everyone is done
+}
+
+// ------------------------------------------------------------------------------------------------
+// Krylov solvers, implementation 11: register-blocked strip layout (fluidgym_b200/strip_plan.py, tables.st_*).
+// Same recurrence and stopping rules as above (CG.cu:225-446), different data layout and hand-shakes:
+//   * the cells of a CTA are padded 2-D arrays in shared memory, the stencil neighbours of slot s are s-1, s+1,
+//     s-S, s+S: no per-cell neighbour addresses (k_cg_cluster_mb keeps 4 address registers per cell);
+//   * a thread owns CPT = 9 consecutive rows of one column, so the south / north neighbours of its cells are its own
+//     registers: per cell and iteration 2 + 2/CPT shared-memory loads of the search direction instead of 5, all of
+//     them conflict free (S is a multiple of 4, so a warp that runs from one band of rows into the next continues
+//     on the next bank);
+//   * x, r, p, A p live in registers, the five stencil coefficients in shared memory (thread-major, one LDS.128 + one
+//     LDS.32 per row): 72 registers per thread, 896 threads per CTA, 8 064 cells per CTA -- HALF the cluster size of
+//     k_cg_cluster_mb for every domain (cylinder-24: 2 CTAs instead of 4, RBC: 1 instead of 2, airfoil: 8 instead of
+//     16), so twice the environments are in flight and a 2-CTA cluster packs onto all 148 SMs;
+//   * cells that are not array-adjacent are GHOST slots.  Remote ghosts (owner in another CTA) are replicas that run
+//     the same x / p updates with the same scalars as their owner (bit-identical by construction); the only vector
+//     data exchanged per iteration is the residual of the mirrored cells, pushed (st.async) by the owning thread onto
+//     the SAME transaction barrier as the partial sums of <r,r>: an iteration has TWO cross-CTA exchanges (<p,Ap>;
+//     <r,r> + ghost residuals), the separate "search direction published" hand-shake of k_cg_cluster_mb is gone.
+//     Local ghosts (owner in the same CTA: block connections, periodic wrap) are mirror slots the owner stores its new
+//     search direction into before the CTA barrier that publishes the direction anyway.
+// Barrier A (mb[0]) collects NP partials, barrier B (mb[1]) NP partials + the ghost residuals of this CTA; they are
+// used strictly alternately (a reset iteration inserts an empty A), which is what makes the single-buffered slot
+// arrays safe: a CTA can only start exchange n+1 after every warp of every CTA has contributed to exchange n, i.e.
+// has consumed exchange n-1.  The best iterate (CG.cu:335-352) is kept in global scratch (written, never read, unless
+// the solve fails), thread-major and coalesced.
+// ------------------------------------------------------------------------------------------------
+template <int T, int CPT, int CS, int MINB>
+__global__ void __launch_bounds__(T, MINB) k_cg_strip(Tab t, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
+                                                    const float *__restrict__ Rhs, float *__restrict__ Xout,
+                                                    int maxit, float tol, int zero_init, int reset_steps, int slot,
+                                                    const int32_t *__restrict__ active, int32_t *__restrict__ iters,
+                                                    float *__restrict__ resid, unsigned long long *__restrict__ iter_total,
+                                                    int flags, float *__restrict__ mean_out, float *__restrict__ best) {
+    static_assert(T % 32 == 0, "whole warps only: every warp contributes exactly one partial sum per exchange");
+    constexpr int NW = T / 32;
+    constexpr int NP = NW * CS;
+    const int b = blockIdx.x / CS;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if (active && !active[b]) return;
+    extern __shared__ __align__(16) float smem[];
+    const int N = t.N, SL = t.st_slots, G = t.st_gmax;
+    float4 *co4 = reinterpret_cast<float4 *>(smem);    // [CPT][T] off-diagonal coefficients (W, E, S, N)
+    float *cdg = smem + 4 * CPT * T;                   // [CPT][T] diagonal
+    float *vs = cdg + CPT * T;                         // [SL] exposed vector (search direction; x at residual resets)
+    float *rs = vs + SL;                               // [G] residuals received for the remote ghost rows
+    float *red = rs + G;                               // [2][CS] totals of every CTA: A, B ; then [2][NW] warp partials of this CTA
+    float *wpart = red + 2 * CS + (2 * CS & 1 ? 1 : 0);
+    unsigned long long *mb = (unsigned long long *)(wpart + 2 * NW + (2 * NW & 1 ? 1 : 0));   // [0]: A, [1]: B, [2]: A local, [3]: B local
+    uint2 *rex = (uint2 *)(mb + 4);                    // [st_remax] {k | dest rank << 8, cluster address of the destination in rs}
+    uint2 *lex = rex + t.st_remax;                     // [st_lemax] {owner's slot, mirror slot} in vs
+    const float *off = Poff + (size_t)b * 4 * N, *dg = Pdiag + (size_t)b * N, *f = Rhs + (size_t)b * N;
+    float *xo = Xout + (size_t)b * N;
+    const float norm = 1.0f / sqrtf((float)N);
+    const uint32_t red_addr = smem_u32(red), mb_addr = smem_u32(mb), rs_addr = smem_u32(rs);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const int4 th0 = reinterpret_cast<const int4 *>(t.st_thread)[((size_t)rank * T + tid) * 2];
+    const int4 th1 = reinterpret_cast<const int4 *>(t.st_thread)[((size_t)rank * T + tid) * 2 + 1];
+    const int S = th0.y;
+    float *vp = vs + th0.x;                            // slot of row 0 of this thread
+    const int re_off = th0.w & 0xffff, re_cnt = (th0.w >> 16) & 0xff;
+    const int n_lex = t.st_cnt[4 * rank + 2];
+    const float *rgp = rs + th1.y;                     // first remote ghost row of this thread in the receive buffer
+    const uint32_t rm = (uint32_t)th1.z;               // remote ghost rows of this thread (bit k)
+    const int32_t *cellp = t.st_cell + ((size_t)rank * T + tid) * CPT;
+    float *bestp = best + ((size_t)b * CS + rank) * T * CPT + tid;
+    const uint32_t bytesA = CS * 4u, bytesB = CS * 4u + 4u * (uint32_t)t.st_cnt[4 * rank];
+    if (tid == 0) {
+        mbar_init(mb_addr, 1); mbar_init(mb_addr + 8, 1);
+        mbar_init(mb_addr + 16, NW); mbar_init(mb_addr + 24, NW);   // "warp partials of this CTA are in shared memory"
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arrive_expect_tx(mb_addr, bytesA);
+        mbar_arrive_expect_tx(mb_addr + 8, bytesB);
+    }
+    for (int e = tid; e < t.st_cnt[4 * rank + 1]; e += T) {
+        const int32_t a = t.st_rexp[((size_t)rank * t.st_remax + e) * 2], d = t.st_rexp[((size_t)rank * t.st_remax + e) * 2 + 1];
+        rex[e] = make_uint2((uint32_t)a, mapa_u32(rs_addr + 4u * (uint32_t)d, (uint32_t)a >> 8));
+    }
+    for (int e = tid; e < n_lex; e += T)
+        lex[e] = make_uint2((uint32_t)t.st_lexp[((size_t)rank * t.st_lemax + e) * 2], (uint32_t)t.st_lexp[((size_t)rank * t.st_lemax + e) * 2 + 1]);
+    for (int i = tid; i < SL + G; i += T) vs[i] = 0.f;   // vs and rs (pads, dead slots)
+
+    float x[CPT], r[CPT], ap[CPT];                     // the search direction itself lives in vs only
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int c = cellp[k];
+        const bool real = c >= 0;
+        const int g = real ? c : (c <= -2 ? -2 - c : 0);
+        float co[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int ff = (th0.z >> (2 * d)) & 3;
+            const int nb = real ? t.nbr[ff * N + g] : -1;
+            if (flags & 1) co[d] = nb >= 0 ? off[(int)t.rev[ff * N + g] * N + nb] : 0.f;
+            else co[d] = nb >= 0 ? off[ff * N + g] : 0.f;
+        }
+        co4[k * T + tid] = make_float4(co[0], co[1], co[2], co[3]);
+        cdg[k * T + tid] = real ? dg[g] : 0.f;
+        x[k] = (c != -1 && !zero_init) ? xo[g] : 0.f;  // ghost replicas start from their owner's value
+        r[k] = real ? f[g] : 0.f;
+        ap[k] = 0.f;
+    }
+    const uint32_t peer_red = mapa_u32(red_addr, (uint32_t)(lane < CS ? lane : 0));
+    const uint32_t peer_mb = mapa_u32(mb_addr, (uint32_t)(lane < CS ? lane : 0));
+    cluster_sync_all();                                // barriers initialised, shared memory filled everywhere
+
+    // Two-level sum over the cluster: warp shuffle -> one partial per warp in this CTA's shared memory -> warp 0 adds them in
+    // fixed order and pushes ONE value to every CTA of the cluster (CS st.async per CTA and exchange instead of NW * CS:
+    // the transaction-count updates of the receiving barrier serialise) -> every thread adds the CS totals in rank order.
+    uint32_t parA = 0, parB = 0;
+    auto exchange = [&](float a0, const uint32_t which, uint32_t &par, const uint32_t bytes) -> float {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        if (lane == 0) {
+            wpart[which * NW + warp] = a0;
+            asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(mb_addr + 16u + 8u * which) : "memory");
+        }
+        if (warp == 0) {
+            mbar_wait_sleep(mb_addr + 16u + 8u * which, par);
+            float s1 = lane < NW ? wpart[which * NW + lane] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            if (lane < CS) st_async_f32(peer_red + 4u * (which * CS + rank), s1, peer_mb + 8u * which);
+        }
+        mbar_wait_sleep(mb_addr + 8u * which, par); par ^= 1u;
+        float s0 = 0.f;
+#pragma unroll
+        for (int q = 0; q < CS; ++q) s0 += red[which * CS + q];
+        if (tid == 0) mbar_arrive_expect_tx(mb_addr + 8u * which, bytes);   // re-arm (see k_cg_cluster_mb)
+        return s0;
+    };
+    auto row_of = [&](const float (&v)[CPT], int kk) -> float {
+        float s = v[0];
+#pragma unroll
+        for (int k = 1; k < CPT; ++k) s = (kk == k) ? v[k] : s;
+        return s;
+    };
+    // ap = P v for the vector v published in vs (own column: a sliding window of CPT + 2 loads, east / west: 2 per row);
+    // returns this thread's part of <v, P v>
+    auto spmv = [&]() -> float {
+        float a0 = 0.f, a1 = 0.f;                      // two chains: the sum is on the critical path of the iteration
+        float vsouth = vp[-S], vc = vp[0];
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const float *row = vp + k * S;
+            const float vnorth = row[S];
+            const float4 o = co4[k * T + tid];
+            float s = cdg[k * T + tid] * vc;
+            s = fmaf(o.x, row[-1], s);
+            s = fmaf(o.y, row[1], s);
+            s = fmaf(o.z, vsouth, s);
+            s = fmaf(o.w, vnorth, s);
+            ap[k] = s;
+            if (k & 1) a1 = fmaf(vc, s, a1); else a0 = fmaf(vc, s, a0);
+            vsouth = vc; vc = vnorth;
+        }
+        return a0 + a1;
+    };
+    auto mirror_local_ghosts = [&]() {                 // after the vector has been stored: owners' values -> local ghost slots
+        __syncthreads();
+        if (n_lex) {                                   // (uniform over the CTA)
+            for (int e = tid; e < n_lex; e += T) { const uint2 ex = lex[e]; vs[ex.y] = vs[ex.x]; }
+            __syncthreads();
+        }
+    };
+    auto publish_x = [&]() {
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) vp[k * S] = x[k];
+        mirror_local_ghosts();
+    };
+    auto new_direction = [&](float beta) {             // p = r + beta p in place in vs; remote ghost rows use the residual they received
+        if (rm) {                                      // (r of a ghost row is zero otherwise: its coefficients are)
+            int n = 0;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) if (rm & (1u << k)) r[k] = rgp[n++];
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) ap[k] = vp[k * S];   // (loads first: the stores below would otherwise serialise them; A p is dead here)
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) vp[k * S] = fmaf(beta, ap[k], r[k]);
+        if (rm) {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) if (rm & (1u << k)) r[k] = 0.f;
+        }
+        mirror_local_ghosts();
+    };
+    auto residual_norm2 = [&]() -> float {             // exchange B: <r,r> + residuals of the remotely mirrored rows
+        for (int j = 0; j < re_cnt; ++j) {
+            const uint2 ex = rex[re_off + j];
+            st_async_f32(ex.y, row_of(r, (int)(ex.x & 0xff)), mapa_u32(mb_addr + 8, ex.x >> 8));
+        }
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPT; k += 2) { a0 = fmaf(r[k], r[k], a0); if (k + 1 < CPT) a1 = fmaf(r[k + 1], r[k + 1], a1); }
+        return exchange(a0 + a1, 1u, parB, bytesB);
+    };
+
+    float nz = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) nz += (r[k] != 0.f) ? 1.f : 0.f;
+    const float nzt = exchange(nz, 0u, parA, bytesA);
+    int used = -1; float fin = 0.f;
+    bool solved = false;
+    if (!(nzt > 0.f)) {
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) x[k] = 0.f;
+    } else {
+        solved = true;
+        if (!zero_init) {                              // r = f - P x0
+            publish_x();
+            (void)spmv();
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) r[k] -= ap[k];
+            __syncthreads();                           // everyone is done reading vs (= x) before it becomes p
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) bestp[k * T] = x[k];
+        float rho = residual_norm2();
+        new_direction(0.f);                            // p = r (vs holds zeros or x0: 0 * finite + r)
+        float bestc = 0.f, lastc = 0.f; int best_it = -1, rising = 0;
+        int until_reset = reset_steps > 0 ? reset_steps - 1 : -1;   // iterations left before the next residual reset
+        for (int i = 0; i < maxit; ++i) {
+            if (until_reset == 0) {
+                // r = f - P x ; p = r ; rho = <r,r>   (CG.cu:281-302).  x of the ghost rows is already there.
+                until_reset = reset_steps;
+                (void)exchange(0.f, 0u, parA, bytesA);  // keeps A / B alternating
+                publish_x();
+                (void)spmv();
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) { const int c = cellp[k]; r[k] = (c >= 0 ? f[c] : 0.f) - ap[k]; }
+                __syncthreads();
+                rho = residual_norm2();
+                new_direction(0.f);
+            }
+            --until_reset;
+            const float pap = exchange(spmv(), 0u, parA, bytesA);
+            const float alpha = rho / pap;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                x[k] = fmaf(alpha, vp[k * S], x[k]);
+                r[k] = fmaf(-alpha, ap[k], r[k]);
+            }
+            const float rr2 = residual_norm2();
+            const float crit = sqrtf(rr2) * norm;
+            if (!isfinite(crit)) { used = i; fin = crit; break; }
+            if (i == 0 || crit < bestc) {
+                bestc = crit; best_it = i;
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) bestp[k * T] = x[k];
+            }
+            if (i > 0 && crit >= lastc) ++rising; else rising = 0;
+            lastc = crit; used = i; fin = crit;
+            if (crit < tol) break;
+            if (i == maxit - 1 || rising >= 100) {
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) x[k] = bestp[k * T];
+                used = best_it; fin = bestc;
+                break;
+            }
+            const float beta = rr2 / rho;
+            rho = rr2;
+            new_direction(beta);
+        }
+    }
+    float mean = 0.f;
+    if (solved && !(flags & 2)) {
+        float sx = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) sx += (cellp[k] >= 0) ? x[k] : 0.f;
+        mean = exchange(sx, 0u, parA, bytesA) / (float)N;
+    }
+    if (mean_out && tid == 0 && rank == 0) mean_out[b] = mean;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) { const int c = cellp[k]; if (c >= 0) xo[c] = x[k] - mean; }
+    if (tid == 0 && rank == 0) { iters[b * 8 + 2 + slot] = used; resid[b * 8 + 2 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1); }
     cluster_sync_all();   // keep peer shared memory (and in-flight st.async targets) alive until everyone is done
 }
 
@@ -2585,8 +2875,65 @@ static int launch_cg_cluster_mb(fgb_batch *b, const float *poff, const float *pd
     return FGB_OK;
 }
 
+template <int T, int CPT, int CS, int MINB>
+static int launch_cg_strip(fgb_batch *b, const float *poff, const float *pdiag, const float *rhs, float *p_out, int zero_init,
+                           int reset_steps, int max_iter, int slot, const int32_t *active, int flags, float *mean_out,
+                           cudaStream_t st) {
+    if (b->t.st_cs != CS || b->t.st_T != T || b->t.st_cpt != CPT) return 1;
+    if ((size_t)CS * T * CPT > (size_t)KRY_VECS * b->t.N)
+        return set_err(FGB_E_ARG, "cg_impl 11: domain too small for the best-iterate scratch (use cg_impl 6)");
+    const size_t smem = ((size_t)5 * CPT * T + (size_t)b->t.st_slots + (size_t)b->t.st_gmax + (size_t)2 * CS + 2 * (T / 32) + 2) * sizeof(float) + 4 * 8 +
+                        ((size_t)b->t.st_remax + (size_t)b->t.st_lemax) * 8;
+    if (smem > 227 * 1024 || (b->t.st_slots & 3) || (b->t.st_gmax & 1))
+        return set_err(FGB_E_ARG, "cg_impl 11: strip plan does not fit in shared memory");
+    auto kern = k_cg_strip<T, CPT, CS, MINB>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_cg_strip)", ce);
+    if (CS > 8) {
+        ce = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_cg_strip, non-portable cluster)", ce);
+    }
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(b->B * CS); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ce = cudaLaunchKernelEx(&cfg, kern, b->t, poff, pdiag, rhs, p_out, max_iter, b->opt.p_tol, zero_init, reset_steps, slot, active,
+                            b->iters, b->resid, b->iter_total, flags, mean_out, b->kry);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchKernelEx(k_cg_strip)", ce);
+    return FGB_OK;
+}
+
+template <int T, int CPT, int MINB>
+static int cg_strip_cs(fgb_batch *b, const float *poff, const float *pdiag, const float *rhs, float *p_out, int zero_init,
+                       int reset_steps, int max_iter, int slot, const int32_t *active, int flags, float *mean_out, cudaStream_t st) {
+    int rc = launch_cg_strip<T, CPT, 1, MINB>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    if (rc == 1) rc = launch_cg_strip<T, CPT, 2, MINB>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    if (rc == 1) rc = launch_cg_strip<T, CPT, 4, MINB>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    if (rc == 1) rc = launch_cg_strip<T, CPT, 8, MINB>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    if (rc == 1) rc = launch_cg_strip<T, CPT, 16, MINB>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    return rc;
+}
+// instantiated shapes = fluidgym_b200/strip_plan.py::SHAPES: 4 / 2 / 1 co-resident CTAs per SM, 8 320 cells per SM in every case
+static int cg_strip_any(fgb_batch *b, const float *poff, const float *pdiag, const float *rhs, float *p_out, int zero_init,
+                        int reset_steps, int max_iter, int slot, const int32_t *active, int flags, float *mean_out, cudaStream_t st) {
+    int rc = cg_strip_cs<480, 17, 1>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    if (rc == 1) rc = cg_strip_cs<256, 17, 2>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    if (rc == 1) rc = cg_strip_cs<896, 9, 1>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    if (rc == 1) rc = cg_strip_cs<640, 13, 1>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    return rc;
+}
+
+static inline bool uses_halo_plan(int cg_impl) { return cg_impl == 6 || cg_impl == 11; }
+
 static int cg_cluster_mb_any(fgb_batch *b, const float *poff, const float *pdiag, const float *rhs, float *p_out, int zero_init,
                              int reset_steps, int max_iter, int slot, const int32_t *active, int flags, float *mean_out, cudaStream_t st) {
+    if (b->opt.cg_impl == 11 && b->t.st_thread && b->t.st_cell && b->t.st_rexp && b->t.st_lexp && b->t.st_cnt) {
+        const int rc = cg_strip_any(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        if (rc == 1) return set_err(FGB_E_ARG, "cg_impl 11: no k_cg_strip instantiation for the shape (st_T, st_cpt, st_cs) of this strip plan");
+        return rc;
+    }
     if (b->opt.cg_impl == 8) {       // as 6 with 256-thread CTAs of 1792 cells, TWO co-resident CTAs per SM (of different environments):
                                      // while one waits for a cluster hand-shake the other one computes
         int rc = launch_cg_cluster_mb<2, 7, true, 256, 2>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
@@ -2602,7 +2949,7 @@ static int cg_cluster_mb_any(fgb_batch *b, const float *poff, const float *pdiag
         if (rc == 1) rc = launch_cg_cluster_mb<16, 12, true, 256>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
         return rc;
     }
-    if (b->opt.cg_impl == 6) {       // pushed halos: same cluster-size rule, gathers from local shared memory
+    if (uses_halo_plan(b->opt.cg_impl)) {   // pushed halos: same cluster-size rule, gathers from local shared memory (11 without a strip plan = 6)
         int rc = launch_cg_cluster_mb<2, 6, true>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
         if (rc == 1) rc = launch_cg_cluster_mb<4, 7, true>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
         if (rc == 1) rc = launch_cg_cluster_mb<8, 7, true>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
@@ -2657,7 +3004,7 @@ static int solve_pressure_slot(fgb_batch *b, float *p_out, int zero_init, int re
         if (rc == 1) rc = launch_cg_smem<8, 7, 2>(b, p_out, zero_init, reset_steps, max_iter, slot, active, STREAM(s));
         if (rc <= 0) return rc;
     }
-    if (b->opt.cg_impl == 3 || b->opt.cg_impl == 6 || b->opt.cg_impl == 7 || b->opt.cg_impl == 8) {
+    if (b->opt.cg_impl == 3 || uses_halo_plan(b->opt.cg_impl) || b->opt.cg_impl == 7 || b->opt.cg_impl == 8) {
         int rc = cg_cluster_mb_any(b, b->Poff, b->Pdiag, b->div, p_out, zero_init, reset_steps, max_iter, slot, active, 0,
                                    b->pmean + (size_t)mean_slot * b->B, STREAM(s));
         if (rc <= 0) return rc;
@@ -2757,7 +3104,7 @@ static int record_impl(fgb_batch *b, float *u, float *p, const float *bvel, cons
     const fgb_options &o = b->opt;
     const int C = o.corrector_steps, n_adv = o.nonortho ? o.adv_nonortho_steps : 1, n_p = o.nonortho ? o.p_nonortho_steps : 1;
     const int reset = o.nonortho ? 100 : 0;
-    if ((o.cg_impl != 3 && o.cg_impl != 6 && o.cg_impl != 7 && o.cg_impl != 8) || C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8)
+    if ((o.cg_impl != 3 && !uses_halo_plan(o.cg_impl) && o.cg_impl != 7 && o.cg_impl != 8) || C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8)
         return set_err(FGB_E_ARG, "fgb_piso_substep_record: needs cg_impl 3 or 6 and correctors x pressure iterations <= 8");
     cudaStream_t st = STREAM(s);
     const size_t B = b->B, N = b->t.N, NB = b->t.NB;

@@ -24,7 +24,10 @@ class Tables(C.Structure):
                     "nob_idx", "nob_w", "b_minv", "b_det", "b_alpha", "b_cell", "b_face", "b_out")] + [
                     ("scalar_viscosity", C.c_float), ("Cd_s", C.c_void_p), ("sb_neumann", C.c_void_p), ("rev", C.c_void_p),
                     ("cg_slot", C.c_void_p), ("cg_exp", C.c_void_p), ("cg_cnt", C.c_void_p),
-                    ("cg_cs", C.c_int32), ("cg_emax", C.c_int32), ("cg_hmax", C.c_int32), ("cg_pad", C.c_int32)]
+                    ("cg_cs", C.c_int32), ("cg_emax", C.c_int32), ("cg_hmax", C.c_int32), ("cg_pad", C.c_int32),
+                    ("st_thread", C.c_void_p), ("st_cell", C.c_void_p), ("st_rexp", C.c_void_p), ("st_lexp", C.c_void_p),
+                    ("st_cnt", C.c_void_p), ("st_cs", C.c_int32), ("st_T", C.c_int32), ("st_cpt", C.c_int32), ("st_slots", C.c_int32),
+                    ("st_remax", C.c_int32), ("st_lemax", C.c_int32), ("st_gmax", C.c_int32)]
 
 
 class Tape(C.Structure):

@@ -8,6 +8,7 @@ only to own device memory and streams.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -93,6 +94,8 @@ class BatchedPISO:
                  max_iter=5000, cg_impl=6, out_mask=None):
         if not torch.cuda.is_available():
             raise native.FGBError("fluidgym_b200 needs a CUDA device (there is no CPU fallback)")
+        if os.environ.get("FGB_CG_IMPL"):     # A/B runs: overrides the pressure-CG implementation of every solver
+            cg_impl = int(os.environ["FGB_CG_IMPL"])
         self.lib = native.load()
         self.cd = cd
         self.B = int(n_envs)
@@ -117,8 +120,19 @@ class BatchedPISO:
             self.tables.scalar_viscosity = float(cd.scalar_visc)
         else:
             self._tab["Cd_s"] = self._tab["sb_neumann"] = None
-        plan = halo_plan(np.asarray(cd.nbr), cd.N, cg_impl)
+        plan = halo_plan(np.asarray(cd.nbr), cd.N, 6 if cg_impl == 11 else cg_impl)
         self.halo = plan
+        self.strip = None
+        if cg_impl == 11:                    # register-blocked strip layout of the pressure CG (strip_plan.py); 6 when it does not apply
+            from .strip_plan import plan_for_domain
+            sp = self.strip = plan_for_domain(cd)
+            if sp is not None:
+                for k, arr in (("st_thread", sp.thread), ("st_cell", sp.cell), ("st_rexp", sp.rexp), ("st_lexp", sp.lexp), ("st_cnt", sp.cnt)):
+                    self._tab[k] = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int32)).to(dev)
+                    setattr(self.tables, k, self._tab[k].data_ptr())
+                self.tables.st_cs, self.tables.st_T, self.tables.st_cpt = sp.cs, sp.T, sp.cpt
+                self.tables.st_slots, self.tables.st_remax, self.tables.st_lemax = sp.slots, sp.remax, sp.lemax
+                self.tables.st_gmax = sp.gmax + (sp.gmax & 1)
         if plan is not None:
             self._tab["cg_slot"] = torch.from_numpy(plan["slot"]).to(dev)
             self._tab["cg_exp"] = torch.from_numpy(plan["exp"]).to(dev)

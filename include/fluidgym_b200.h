@@ -76,6 +76,20 @@ typedef struct fgb_tables {
     const int32_t *cg_exp;  /* [cg_cs][cg_emax][2]  export list of each CTA: {own slot | dest rank << 24, dest slot} */
     const int32_t *cg_cnt;  /* [cg_cs][2]  {exports, halo cells} of each CTA                                     */
     int32_t cg_cs, cg_emax, cg_hmax, cg_pad;
+    /* optional strip plan of the register-blocked on-chip CG (cg_impl 11), built by fluidgym_b200/strip_plan.py for ONE
+     * cluster size st_cs: the cells of every CTA are laid out as padded 2-D arrays so that the stencil neighbours of
+     * shared-memory slot s are s-1, s+1, s-S, s+S; a thread owns st_cpt consecutive rows of one column; cells that are
+     * not array-adjacent (block connections, periodic wrap, cuts between CTAs) are GHOST slots: replicas that receive the
+     * residual of the mirrored cell every iteration (owner in another CTA) or mirror slots the owner writes itself (same
+     * CTA).  NULL = not available. */
+    const int32_t *st_thread; /* [st_cs][st_T][8]  {first slot, row stride S, face map (2 bits per W,E,S,N), remote exports
+                                 (offset | count << 16), 0, first index in the receive buffer, remote ghost rows (bit k),
+                                 local ghost rows (bit k)}                                               */
+    const int32_t *st_cell;   /* [st_cs][st_T][st_cpt]  cell id of the thread's k-th row, -1 dead, -2-g ghost of cell g      */
+    const int32_t *st_rexp;   /* [st_cs][st_remax][2]  {k | destination rank << 8, index in the destination's receive buffer} */
+    const int32_t *st_lexp;   /* [st_cs][st_lemax][2]  {owner's slot, mirror slot} copy list of the local ghosts              */
+    const int32_t *st_cnt;    /* [st_cs][4]  {remote ghosts, remote exports, local exports, 0} of each CTA                    */
+    int32_t st_cs, st_T, st_cpt, st_slots, st_remax, st_lemax, st_gmax;
 } fgb_tables;
 
 /* Passive scalar + buoyancy coupling of one batch (RBC: temperature; rbc_env_base.py:190-304).  With the
@@ -110,7 +124,12 @@ typedef struct fgb_options {
                                        5: as 4 with two co-resident CTAs per SM
                                        6: as 3 with PUSHED halos (tables.cg_slot/cg_exp): after updating the
                                           search direction every CTA st.async-es the cells its neighbours need into
-                                          their shared memory, all stencil gathers become plain ld.shared      */
+                                          their shared memory, all stencil gathers become plain ld.shared
+                                       11: register-blocked strip layout (tables.st_*): TWO cross-CTA exchanges per
+                                          iteration instead of three (the residual of the ghost cells travels with the
+                                          partial sums of <r,r>, ghost replicas update p and x themselves), no per-cell
+                                          neighbour addresses, north/south neighbours in registers (default where the
+                                          domain has a strip plan; 6 otherwise)                                 */
 } fgb_options;
 
 const char *fgb_last_error(void);

@@ -201,6 +201,9 @@ def main():
     ap.add_argument("--kw", default="{}", help="JSON dict of extra fluidgym.make keyword arguments")
     ap.add_argument("--perturb", type=float, default=0.0, help="std of Gaussian noise added to the block velocities after reset")
     ap.add_argument("--lean", action="store_true", help="do not record the CSR matrices (large 3-D grids)")
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"], help="fluidgym.make(dtype=...)")
+    ap.add_argument("--pressure-tol", type=float, default=None, help="override Simulation.pressure_tol after reset (tight-tolerance goldens)")
+    ap.add_argument("--advection-tol", type=float, default=None, help="override Simulation.advection_tol after reset")
     ap.add_argument("--save-domain-only", action="store_true",
                     help="reset, advance --env-steps steps, write the domain with the reference's own save_domain() and exit")
     args = ap.parse_args()
@@ -215,12 +218,21 @@ def main():
     assert torch.cuda.is_available(), "the reference needs a GPU"
     meta = {"env": args.env, "seed": args.seed, "torch": torch.__version__, "gpu": torch.cuda.get_device_name(0)}
 
+    kw = json.loads(args.kw)
+    if args.dtype == "float64":
+        kw["dtype"] = torch.float64
     env = fluidgym.make(args.env, load_initial_domain=False, load_domain_statistics=False,
-                        randomize_initial_state=False, **json.loads(args.kw))
+                        randomize_initial_state=False, **kw)
+    meta["dtype"] = args.dtype
     t0 = time.time()
     obs0, _ = env.reset(seed=args.seed)
     torch.cuda.synchronize()
     meta["reset_seconds"] = time.time() - t0
+    for name, val in (("pressure_tol", args.pressure_tol), ("advection_tol", args.advection_tol)):
+        if val is not None:
+            assert hasattr(env._sim, name), name
+            setattr(env._sim, name, val)
+            meta[name] = val
     if args.perturb > 0:
         g = torch.Generator(device="cuda").manual_seed(args.seed)
         for blk in env._domain.getBlocks():
@@ -306,6 +318,11 @@ def main():
     meta["max_iters"] = {k: (int(np.max(v)) if v else None) for k, v in its.items()}
     meta["n_solves"] = {k: len(v) for k, v in its.items()}
 
+    if args.time_steps <= 0:
+        with open(os.path.join(args.out, f"{tag}_meta.json"), "w") as f:
+            json.dump(meta, f, indent=1)
+        print(json.dumps({k: meta[k] for k in ("mean_iters", "max_iters", "n_solves", "substeps_in_env_steps")}))
+        return
     # timing of the reference CUDA path (B=1): env.step wall clock
     tracer.uninstall()
     sim.single_step = orig_single
