@@ -109,7 +109,7 @@ class BatchedPISO3D:
         residual reset every 100 iterations (TCF), False = predictor started from the previous result, no reset (RBC)."""
         if not torch.cuda.is_available():
             raise native.FGBError("fluidgym_b200 needs a CUDA device (there is no CPU fallback)")
-        self.lib = native.load()
+        self.lib = native.load_for(device)
         self.dom, self.B, self.N, self.NB = dom, int(n_envs), dom.N, dom.NB
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
@@ -323,7 +323,7 @@ class SlabPISO3D:
     def __init__(self, dom: Box3DDomain, rank: int, world: int, device, group=None, corrector_steps=2, advection_tol=1e-6,
                  pressure_tol=1e-6, max_iter=5000):
         import torch.distributed as dist
-        self.lib = native.load()
+        self.lib = native.load_for(device)
         self.tabs = tb = SlabTables(dom, rank, world)
         self.rank, self.world = rank, world
         self.device = torch.device(device)

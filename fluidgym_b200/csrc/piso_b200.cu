@@ -58,12 +58,22 @@ struct fgb_batch {
     cudaEvent_t *prof_ev;             // [PROF_MAX][2]
     int *prof_cls;                    // class of each recorded pair
     int prof_n;
+    // environment groups (fgb_batch_set_groups / FGB_GROUPS): fgb_piso_substep runs the groups on their own streams, so that the
+    // ragged end of one group's Krylov launch (environments need different iteration counts; a launch only ends with its
+    // slowest environment) is filled by the other groups' kernels and the HBM-bound assembly kernels overlap the
+    // latency-bound solves.  A group is a VIEW of the batch: same tables and options, per-environment pointers advanced.
+    static const int MAX_GROUPS = 8;
+    int groups;
+    fgb_batch *parent;                // view -> the batch that owns the profiling state
+    int pmean_stride;                 // row stride of pmean (= B of the owning batch)
+    cudaStream_t gstream[MAX_GROUPS];
+    cudaEvent_t gfork, gjoin[MAX_GROUPS];
 };
 enum { CLS_CG = 0, CLS_BICG = 1, CLS_ASM = 2, CLS_OTHER = 3 };
 struct ProfScope {
     fgb_batch *b; cudaStream_t st; int idx;
-    ProfScope(fgb_batch *b_, int cls, cudaStream_t st_) : b(b_), st(st_), idx(-1) {
-        b->launches++;
+    ProfScope(fgb_batch *b_, int cls, cudaStream_t st_) : b(b_->parent ? b_->parent : b_), st(st_), idx(-1) {
+        b_->launches++;
         if (b->prof_on && b->prof_n < fgb_batch::PROF_MAX) {
             idx = b->prof_n++;
             b->prof_cls[idx] = cls;
@@ -122,6 +132,8 @@ extern "C" int fgb_batch_create(const fgb_tables *t, int32_t B, void *workspace,
     b->ws = (char *)workspace; b->ws_bytes = workspace_bytes;
     b->asm_envs = 1;
     if (const char *ev = getenv("FGB_ASM_ENVS")) { const int v = atoi(ev); if (v == 2 || v == 4 || v == 8) b->asm_envs = v; }
+    b->groups = 1; b->pmean_stride = B;
+    if (const char *ev = getenv("FGB_GROUPS")) { const int v = atoi(ev); if (v >= 1 && v <= fgb_batch::MAX_GROUPS) b->groups = v; }
     size_t total; carve(b, b->ws, &total);
     ce = cudaMallocHost(&b->h_counters, 64 * sizeof(int32_t));
     if (ce != cudaSuccess) { delete b; return set_err(FGB_E_CUDA, "cudaMallocHost", ce); }
@@ -130,8 +142,17 @@ extern "C" int fgb_batch_create(const fgb_tables *t, int32_t B, void *workspace,
     *out = b;
     return FGB_OK;
 }
+extern "C" int fgb_batch_set_groups(fgb_batch *b, int32_t groups) {
+    if (!b || groups < 1 || groups > fgb_batch::MAX_GROUPS) return set_err(FGB_E_ARG, "fgb_batch_set_groups: 1 <= groups <= 8");
+    b->groups = groups;
+    return FGB_OK;
+}
 extern "C" void fgb_batch_destroy(fgb_batch *b) {
     if (!b) return;
+    if (b->gfork) {
+        cudaEventDestroy(b->gfork);
+        for (int g = 0; g < fgb_batch::MAX_GROUPS; ++g) { cudaEventDestroy(b->gjoin[g]); cudaStreamDestroy(b->gstream[g]); }
+    }
     if (b->h_counters) cudaFreeHost(b->h_counters);
     if (b->prof_ev) { for (int i = 0; i < 2 * fgb_batch::PROF_MAX; ++i) cudaEventDestroy(b->prof_ev[i]); delete[] b->prof_ev; delete[] b->prof_cls; }
     delete b;
@@ -1523,7 +1544,6 @@ __global__ void __launch_bounds__(T, MINB) k_cg_strip(Tab t, const float *__rest
                                                     int flags, float *__restrict__ mean_out, float *__restrict__ best) {
     static_assert(T % 32 == 0, "whole warps only: every warp contributes exactly one partial sum per exchange");
     constexpr int NW = T / 32;
-    constexpr int NP = NW * CS;
     const int b = blockIdx.x / CS;
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -3006,7 +3026,7 @@ static int solve_pressure_slot(fgb_batch *b, float *p_out, int zero_init, int re
     }
     if (b->opt.cg_impl == 3 || uses_halo_plan(b->opt.cg_impl) || b->opt.cg_impl == 7 || b->opt.cg_impl == 8) {
         int rc = cg_cluster_mb_any(b, b->Poff, b->Pdiag, b->div, p_out, zero_init, reset_steps, max_iter, slot, active, 0,
-                                   b->pmean + (size_t)mean_slot * b->B, STREAM(s));
+                                   b->pmean + (size_t)mean_slot * b->pmean_stride, STREAM(s));
         if (rc <= 0) return rc;
     }
     if (b->opt.cg_impl == 1 || b->opt.cg_impl == 2) {
@@ -3038,9 +3058,57 @@ extern "C" int fgb_correct_velocity(fgb_batch *b, const float *p, float *u_out, 
     return FGB_OK;
 }
 
+static int piso_substep_impl(fgb_batch *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
+                             const int32_t *active, const fgb_scalar *sc, fgb_stream_t s);
+
+// view of environments [g0, g0 + cnt) of a batch
+static fgb_batch group_view(fgb_batch *b, int g0, int cnt) {
+    fgb_batch v = *b;
+    const size_t N = b->t.N, o = (size_t)g0;
+    v.B = cnt; v.groups = 1; v.parent = b->parent ? b->parent : b; v.launches = 0;
+    v.Coff += 4 * o * N; v.A += o * N; v.rhs += 2 * o * N; v.ures += 2 * o * N; v.Poff += 4 * o * N; v.Pdiag += o * N;
+    v.hbya += 2 * o * N; v.div += o * N; v.pres += o * N; v.kry += (size_t)KRY_VECS * o * N;
+    v.resid += 8 * o; v.dt += o; v.maxvel += o; v.fluxbal += o; v.pmean += o; v.remaining += o;
+    v.iters += 8 * o; v.active += o; v.nsub += o; v.iter_total += 2 * o;
+    return v;
+}
+
 extern "C" int fgb_piso_substep(fgb_batch *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
                                 const int32_t *active, const fgb_scalar *sc, fgb_stream_t s) {
     if (!b || !u || !p || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_piso_substep: null argument");
+    const int G = b->groups;
+    if (G <= 1 || b->B < 2 * G) return piso_substep_impl(b, u, p, bvel, src, dt, active, sc, s);
+    cudaStream_t st = STREAM(s);
+    cudaError_t ce;
+    if (!b->gfork) {
+        if ((ce = cudaEventCreateWithFlags(&b->gfork, cudaEventDisableTiming)) != cudaSuccess) return set_err(FGB_E_CUDA, "group event", ce);
+        for (int g = 0; g < fgb_batch::MAX_GROUPS; ++g) {
+            if ((ce = cudaEventCreateWithFlags(&b->gjoin[g], cudaEventDisableTiming)) != cudaSuccess) return set_err(FGB_E_CUDA, "group event", ce);
+            if ((ce = cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking)) != cudaSuccess) return set_err(FGB_E_CUDA, "group stream", ce);
+        }
+    }
+    const size_t N = b->t.N, NB = b->t.NB;
+    if ((ce = cudaEventRecord(b->gfork, st)) != cudaSuccess) return set_err(FGB_E_CUDA, "group fork", ce);
+    for (int g = 0; g < G; ++g) {
+        const int g0 = (int)(((long long)b->B * g) / G), g1 = (int)(((long long)b->B * (g + 1)) / G);
+        fgb_batch v = group_view(b, g0, g1 - g0);
+        fgb_scalar scv;
+        if (sc) { scv = *sc; scv.T += (size_t)g0 * N; scv.sbval += (size_t)g0 * NB; scv.src += 2 * (size_t)g0 * N; }
+        cudaStreamWaitEvent(b->gstream[g], b->gfork, 0);
+        const int rc = piso_substep_impl(&v, u + 2 * (size_t)g0 * N, p + (size_t)g0 * N, bvel + 2 * (size_t)g0 * NB,
+                                         src ? src + 2 * (size_t)g0 * N : nullptr, dt + g0, active ? active + g0 : nullptr,
+                                         sc ? &scv : nullptr, (fgb_stream_t)b->gstream[g]);
+        b->launches += v.launches;
+        // the join is recorded even after an error so that the caller's stream never runs ahead of a group
+        cudaEventRecord(b->gjoin[g], b->gstream[g]);
+        cudaStreamWaitEvent(st, b->gjoin[g], 0);
+        if (rc) return rc;
+    }
+    return FGB_OK;
+}
+
+static int piso_substep_impl(fgb_batch *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
+                             const int32_t *active, const fgb_scalar *sc, fgb_stream_t s) {
     int rc;
     const fgb_options &o = b->opt;
     cudaStream_t st = STREAM(s);
@@ -3134,9 +3202,13 @@ static int record_impl(fgb_batch *b, float *u, float *p, const float *bvel, cons
         LAUNCH_CHECK("k_buoyancy");
         src = sc->src;
     }
+    // The reference's differentiable mode starts EVERY linear solve from zero (advect_use_prev_result, advect_non_ortho_reuse_result and
+    // pressure_reuse_result are all "True and not self.differentiable", SIM.py:1436-1440): the recorded forward pass does the same,
+    // so that env.step(differentiable=True) reproduces the reference's differentiable run, which on the airfoil differs visibly from
+    // its plain run (the deferred-correction pressure solves restart from zero and stop at residual ~4e-4).
     for (int k = 0; k < n_adv; ++k) {
         if ((rc = fgb_setup_advection(b, u, k == 0 ? u : b->ures, bvel, src, dt, nullptr, s))) return rc;
-        if ((rc = fgb_solve_advection(b, o.nonortho ? (k == 0) : 0, nullptr, s))) return rc;
+        if ((rc = fgb_solve_advection(b, 1, nullptr, s))) return rc;
         if ((rc = copy_async(tp->ustar + (size_t)k * 2 * B * N, b->ures, 2 * B * N * 4, st))) return rc;
     }
     if ((rc = copy_async(tp->Coff, b->Coff, 4 * B * N * 4, st))) return rc;
@@ -3146,7 +3218,7 @@ static int record_impl(fgb_batch *b, float *u, float *p, const float *bvel, cons
         for (int ps = 0; ps < n_p; ++ps) {
             const int q = cs * n_p + ps;
             if ((rc = fgb_setup_pressure_rhs(b, u, bvel, src, p, dt, ps == 0, nullptr, s))) return rc;
-            if ((rc = solve_pressure_slot(b, p, ps == 0, reset, o.max_iter, q, nullptr, s))) return rc;
+            if ((rc = solve_pressure_slot(b, p, 1, reset, o.max_iter, q, nullptr, s))) return rc;
             if ((rc = copy_async(tp->p + (size_t)q * B * N, p, B * N * 4, st))) return rc;
             if ((rc = copy_async(tp->pmean + (size_t)q * B, b->pmean + (size_t)q * B, B * 4, st))) return rc;
         }

@@ -91,7 +91,7 @@ class CylinderJet2DEnv(DifferentiableRollout, InitialDomains):
     reference_values = {"cd_ref": ("drag", "mean")}
 
     def __init__(self, n_envs: int = 1, reynolds_number=1e2, resolution=24, dt=1e-2, adaptive_cfl=0.8, step_length=0.25,
-                 episode_length=80, lift_penalty=1.0, device="cuda:0", cg_impl=6, compiled=None, cd_ref=0.0,
+                 episode_length=80, lift_penalty=1.0, device="cuda:0", cg_impl=11, compiled=None, cd_ref=0.0,
                  randomize_initial_state=False, enable_actions=True, use_marl=False, differentiable=False, load_initial_domain=False,
                  initial_domains_path=None):
         if use_marl:

@@ -139,7 +139,7 @@ class ExtrudedPISO3D(ExtrudedStepping):
                  advect_non_ortho_steps=1, pressure_non_ortho_steps=4, advection_tol=1e-5, pressure_tol=5e-7, max_iter=5000):
         if not torch.cuda.is_available():
             raise native.FGBError("fluidgym_b200 needs a CUDA device (there is no CPU fallback)")
-        self.lib = native.load()
+        self.lib = native.load_for(device)
         self.cd, self.nz, self.hz, self.B = cd, int(nz), float(hz), int(n_envs)
         self.N2, self.NB2, self.N = cd.N, cd.NB, cd.N * int(nz)
         self.device = torch.device(device)

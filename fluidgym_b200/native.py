@@ -68,7 +68,7 @@ class Wall(C.Structure):
 
 
 EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_create", "fgb_batch_destroy",
-           "fgb_batch_set_options", "fgb_batch_buffer", "fgb_setup_advection", "fgb_solve_advection",
+           "fgb_batch_set_options", "fgb_batch_set_groups", "fgb_batch_buffer", "fgb_setup_advection", "fgb_solve_advection",
            "fgb_setup_pressure_matrix", "fgb_setup_pressure_rhs", "fgb_solve_pressure", "fgb_correct_velocity",
            "fgb_piso_substep", "fgb_make_divergence_free", "fgb_sim_step", "fgb_update_outflow", "fgb_flux_balance", "fgb_balance_fluxes",
            "fgb_max_velocity", "fgb_apply_jet_action", "fgb_wall_forces", "fgb_column_sums", "fgb_sample_sensors",
@@ -85,6 +85,41 @@ EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_cr
 
 def lib_path() -> str:
     return _build.LIB
+
+
+class DeviceLib:
+    """The loaded library bound to ONE CUDA device: every ``fgb_*`` call is issued with that device current.
+
+    The C entry points launch on the stream they are given and allocate nothing, but a launch (and cudaEvent / IPC calls)
+    needs the stream's device to be the calling thread's current device.  A solver on cuda:1 stepped from a thread whose current
+    device is cuda:0 (``ParallelFluidEnv`` worker threads, or simply after constructing another solver on cuda:0) would otherwise
+    launch into the wrong context.  The guard costs one ``cudaGetDevice`` when the device is already current."""
+
+    def __init__(self, lib, device):
+        import torch
+        self._lib = lib
+        self._torch = torch
+        self._index = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._lib, name)
+            torch, index = self._torch, self._index
+
+            def fn(*a, _raw=raw):
+                if torch.cuda.current_device() == index:
+                    return _raw(*a)
+                with torch.cuda.device(index):
+                    return _raw(*a)
+            self._cache[name] = fn
+        return fn
+
+
+def load_for(device):
+    """``load()`` bound to a device (see DeviceLib)."""
+    return DeviceLib(load(), device)
 
 
 def load():
@@ -104,6 +139,7 @@ def load():
     L.fgb_batch_destroy.argtypes = [vp]
     L.fgb_batch_destroy.restype = None
     L.fgb_batch_set_options.argtypes = [vp, C.POINTER(Options)]
+    L.fgb_batch_set_groups.argtypes = [vp, i32]
     L.fgb_batch_buffer.restype = vp
     L.fgb_batch_buffer.argtypes = [vp, C.c_char_p]
     L.fgb_setup_advection.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]

@@ -142,6 +142,11 @@ int fgb_batch_create(const fgb_tables *t, int32_t B, void *workspace, size_t wor
                      const fgb_options *opt, fgb_batch **out);
 void fgb_batch_destroy(fgb_batch *b);
 int fgb_batch_set_options(fgb_batch *b, const fgb_options *opt);
+/* Environment groups, 1 (default) .. 8: fgb_piso_substep / fgb_sim_step run contiguous groups of the batch on streams of their
+ * own (forked from and joined with the caller's stream), so that one group's assembly kernels and the ragged end of its Krylov
+ * launches overlap the other groups' solves.  Results are bit-identical to groups = 1: environments are independent
+ * (the reference runs one OS process per environment, envs/parallel_env.py:162-175).  Also settable with FGB_GROUPS. */
+int fgb_batch_set_groups(fgb_batch *b, int32_t groups);
 
 /* Device pointer of a named intermediate inside the workspace (for parity tests and autograd glue):
  * "Coff"[B][4][N] "A"[B][N] "rhs"[B][2][N] "ures"[B][2][N] "Poff"[B][4][N] "Pdiag"[B][N]

@@ -1,0 +1,86 @@
+"""Reduces the gradient dumps of oracle/ref_grad_harness.py (gpurun_out/r02/golden/, produced by the UNMODIFIED reference with
+differentiable=True on a B200, tools/r02_goldens.sh) and its tight-tolerance trace to the flat fixtures committed next to this script.
+
+    python tests/golden/extract_grad_fixtures.py [gpurun_out/r02/golden]
+
+Layout = layout of the product (see extract_fixtures.py): cells of all blocks concatenated, fields component-major.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from extract_fixtures import _multiblock_helpers  # noqa: E402
+
+
+def multiblock(src, tag, out, spec, with_vjp=True):
+    nb, faces, cells, bfaces = _multiblock_helpers(spec)
+    d = np.load(os.path.join(src, f"{tag}_grad.npz"))
+    meta = json.load(open(os.path.join(src, f"{tag}_grad_meta.json")))
+    fx = dict(action=d["action"], reward=d["reward"], dreward_daction=d["dreward_daction"],
+              pre_u=cells(d, "pre_b{}_u", 2), pre_p=d["pre_pressureResult"].ravel().astype(np.float32), pre_bvel=bfaces(d, "pre_b{}_f{}_velocity"),
+              post_u=cells(d, "post_b{}_u", 2), dreward_du=cells(d, "dreward_db{}_u", 2),
+              info_drag=d["info_drag"] if "info_drag" in d.files else np.zeros(0), info_lift=d["info_lift"] if "info_lift" in d.files else np.zeros(0),
+              forward_cg_mean=np.array(meta["forward_iters"]["cg"]["mean"]), forward_cg_max=np.array(meta["forward_iters"]["cg"]["max"]))
+    if with_vjp:
+        fx.update(vjp_daction=d["vjp_daction"], vjp_du=cells(d, "vjp_db{}_u", 2),
+                  cotangent_u=np.concatenate([d[f"cotangent{bi}"].reshape(2, -1) for bi in range(nb)], axis=1).astype(np.float32))
+    np.savez_compressed(os.path.join(HERE, f"{out}_grad.npz"), **fx)
+    print(out, {k: (v.shape, float(np.abs(v).max()) if v.size else None) for k, v in fx.items()})
+
+
+def rbc(src, tag="rbc", out="rbc"):
+    d = np.load(os.path.join(src, f"{tag}_grad.npz"))
+
+    def sb(pre):
+        return np.concatenate([np.broadcast_to(d[pre + "f2_scalar"].ravel(), (96,)), np.broadcast_to(d[pre + "f3_scalar"].ravel(), (96,))]).astype(np.float32)
+
+    fx = dict(action=d["action"], reward=d["reward"], dreward_daction=d["dreward_daction"], vjp_daction=d["vjp_daction"],
+              pre_u=d["pre_b0_u"].reshape(2, -1), pre_p=d["pre_pressureResult"].ravel(), pre_T=d["pre_b0_s"].ravel(), pre_sbval=sb("pre_b0_"),
+              pre_ures=d["pre_velocityResult"].reshape(2, -1),
+              post_u=d["post_b0_u"].reshape(2, -1), post_T=d["post_b0_s"].ravel(),
+              dreward_du=d["dreward_db0_u"].reshape(2, -1), dreward_dT=d["dreward_db0_s"].ravel(),
+              vjp_du=d["vjp_db0_u"].reshape(2, -1), vjp_dT=d["vjp_db0_s"].ravel(),
+              cotangent_u=d["cotangent0"].reshape(2, -1), cotangent_T=d["cotangent1"].ravel())
+    np.savez_compressed(os.path.join(HERE, f"{out}_grad.npz"), **{k: np.asarray(v, dtype=np.float32) for k, v in fx.items()})
+    print(out, {k: (np.asarray(v).shape, float(np.abs(v).max())) for k, v in fx.items()})
+
+
+def tight_trace(src, tag="cyl24_t32", out="cyl24_tight"):
+    """First two substeps of the reference run with pressure / advection tolerance 1e-7 (its CG then returns the best iterate after
+    5000 iterations at residual ~1.6e-7): input state, dt, u / p after the substep, iteration counts."""
+    from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
+    spec = make_cylinder_domain(24)
+    nb, faces, cells, bfaces = _multiblock_helpers(spec)
+    tr = np.load(os.path.join(src, f"{tag}_trace.npz"))
+    meta = json.load(open(os.path.join(src, f"{tag}_meta.json")))
+    for k in (0, 1):
+        pre = f"s{k}_"
+        its = [m for m in meta["trace_meta"] if m["substep"] == k]
+        fx = dict(dt=tr[pre + "dt"], u_in=cells(tr, pre + "in_b{}_u", 2), bvel_in=bfaces(tr, pre + "in_b{}_f{}_velocity"),
+                  presres_in=tr[pre + "in_pressureResult"].ravel(), ures_in=tr[pre + "in_velocityResult"].reshape(2, -1),
+                  u1=tr[pre + "velocityResult1"].reshape(2, -1), p1=tr[pre + "pressureResult1"].ravel(),
+                  p0=tr[pre + "pressureResult0"].ravel(),
+                  cg_iters=np.array([m["infos"][0][1] for m in its if not m["bicg"]]), cg_resid=np.array([m["infos"][0][0] for m in its if not m["bicg"]]),
+                  bicg_iters=np.array([[i[1] for i in m["infos"]] for m in its if m["bicg"]]),
+                  pressure_tol=np.array(meta["pressure_tol"]), advection_tol=np.array(meta["advection_tol"]))
+        np.savez_compressed(os.path.join(HERE, f"{out}_substep{k}.npz"), **fx)
+        print(out, k, fx["cg_iters"], fx["cg_resid"], fx["bicg_iters"])
+
+
+def main():
+    src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/r02/golden"
+    from fluidgym_b200.envs.airfoil_domain import make_airfoil_domain
+    from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
+    multiblock(src, "cyl24", "cyl24", make_cylinder_domain(24))
+    multiblock(src, "cyl24_tight", "cyl24_tight", make_cylinder_domain(24))
+    multiblock(src, "airfoil", "airfoil", make_airfoil_domain(), with_vjp=False)
+    rbc(src)
+    tight_trace(src)
+
+
+if __name__ == "__main__":
+    main()

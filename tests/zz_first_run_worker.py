@@ -107,9 +107,34 @@ def case_hooks(monkeypatch=_Env):
         sol.update_outflow(dt, 5e-6)
         torch.cuda.synchronize()
         res[mode] = (mv, b1, sol.bvel.clone())
-    assert torch.allclose(res["torch"][0], res["cuda"][0], rtol=1e-6)           # fused multiply-add vs separate roundings
-    for a, b in zip(res["torch"][1:], res["cuda"][1:]):
-        assert torch.isfinite(b).all() and torch.allclose(a, b, rtol=2e-6, atol=1e-7), float((a - b).abs().max())
+    # float64 evaluation of the same expressions (ExtrudedStepping is plain torch): on random +- data the flux sums cancel, so the
+    # scale factor -fixed / var amplifies fp32 round-off; both fp32 paths are judged by their distance from the fp64 result
+    # (round 1 compared them with each other at 2e-6 and failed at 7e-6 abs on values of magnitude ~10: tolerance, not a bug;
+    # log kept in profiles/r02_first_run_checks.md)
+    from fluidgym_b200.extruded3d import ExtrudedStepping
+
+    class Stepping64(ExtrudedStepping):
+        def __init__(self, src):
+            self.B, self.nz, self.N2, self.hz, self.device = src.B, src.nz, src.N2, src.hz, src.device
+            self._st = {k: (v.double() if v.is_floating_point() else v) for k, v in src._st.items()}
+            self.u, self.bvel = u0.double().clone(), b0.double().clone()
+
+    monkeypatch.setenv("FGB_X3_HOOKS", "torch")
+    ref = Stepping64(sol)
+    mv64 = ExtrudedStepping.max_velocity(ref)
+    ExtrudedStepping.balance_fluxes(ref, free, 1e-7)
+    b1_64 = ref.bvel.clone()
+    ExtrudedStepping.update_outflow(ref, dt.double(), 5e-6)
+    b2_64 = ref.bvel.clone()
+    report = {}
+    for name, truth, k in (("max_velocity", mv64, 0), ("balance_fluxes", b1_64, 1), ("update_outflow", b2_64, 2)):
+        et = float((res["torch"][k].double() - truth).abs().max())
+        ec = float((res["cuda"][k].double() - truth).abs().max())
+        scale = float(truth.abs().max())
+        report[name] = dict(err_torch=et, err_cuda=ec, scale=scale)
+        assert torch.isfinite(res["cuda"][k]).all()
+        assert ec <= 4.0 * et + 2e-6 * scale, (name, report[name])
+    print("hooks vs float64:", report)
     assert not torch.equal(res["cuda"][1], b0)
 
 

@@ -20,17 +20,9 @@ from fluidgym_b200.envs.tcf import LARGE_TCF_3D_DEFAULT_CONFIG, SMALL_TCF_3D_DEF
 from fluidgym_b200.grids import channel_vertex_grid  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--large", action="store_true")
-    ap.add_argument("--nz-mult", type=int, default=1, help="repeat the domain along z (weak-scaling style sizes)")
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--plain", action="store_true", help="world 1 only: the plain single-GPU solver on the same state (baseline of the protocol overhead)")
-    a = ap.parse_args()
-    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+def run(large=True, nz_mult=1, steps=20, warmup=5, plain=False, rank=0, world=1, local=0):
+    """One strong-scaling point (needs an initialised NCCL process group when world > 1); returns the record on every rank."""
+    a = argparse.Namespace(large=large, nz_mult=nz_mult, steps=steps, warmup=warmup, plain=plain)
     cfg = LARGE_TCF_3D_DEFAULT_CONFIG if a.large else SMALL_TCF_3D_DEFAULT_CONFIG
     x = z = cfg["resolution_x_z"]
     z *= a.nz_mult
@@ -77,7 +69,8 @@ def main():
     for _ in range(a.warmup):
         slab.single_step(dt, cfl, rows, d_lo, d_hi)
     torch.cuda.synchronize()
-    dist.barrier()
+    if world > 1:
+        dist.barrier()
     it0 = slab.buffer("iter_total").clone()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -87,19 +80,39 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     it = (slab.buffer("iter_total") - it0)[0].tolist()
     err = slab.error()
     chk = float(slab.owned(slab.u).double().pow(2).sum())
     chk_t = torch.tensor([chk], device="cuda", dtype=torch.float64)
-    dist.all_reduce(chk_t)
-    if rank == 0:
-        print(json.dumps({"workload": f"TCF {'Large' if a.large else 'Small'} {dom.nx}x{dom.ny}x{dom.nz} = {dom.N} cells, 1 environment", "n_gpus": world, "mode": "plain" if a.plain else "slab",
-                          "solver_steps": a.steps, "substeps": nsub, "ms_total": float(ms), "ms_per_substep": float(ms) / max(nsub, 1),
-                          "substeps_per_s": nsub / (float(ms) / 1e3), "cg_iters_per_solve": it[0] / max(2 * nsub, 1),
-                          "bicg_iters_per_rhs": it[1] / max(3 * nsub, 1), "slab_error": err, "checksum_u2": float(chk_t)}), flush=True)
+    if world > 1:
+        dist.all_reduce(chk_t)
+    rec = {"workload": f"TCF {'Large' if a.large else 'Small'} {dom.nx}x{dom.ny}x{dom.nz} = {dom.N} cells, 1 environment", "n_gpus": world,
+           "mode": "plain" if a.plain else "slab", "solver_steps": a.steps, "substeps": nsub, "ms_total": float(ms),
+           "ms_per_substep": float(ms) / max(nsub, 1), "substeps_per_s": nsub / (float(ms) / 1e3),
+           "cg_iters_per_solve": it[0] / max(2 * nsub, 1), "bicg_iters_per_rhs": it[1] / max(3 * nsub, 1), "slab_error": err,
+           "checksum_u2": float(chk_t)}
     slab.close()
-    dist.barrier()
+    if world > 1:
+        dist.barrier()
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--large", action="store_true")
+    ap.add_argument("--nz-mult", type=int, default=1, help="repeat the domain along z (weak-scaling style sizes)")
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--plain", action="store_true", help="world 1 only: the plain single-GPU solver on the same state (baseline of the protocol overhead)")
+    a = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    rec = run(a.large, a.nz_mult, a.steps, a.warmup, a.plain, rank, world, local)
+    if rank == 0:
+        print(json.dumps(rec), flush=True)
     dist.destroy_process_group()
 
 
