@@ -3171,7 +3171,10 @@ static int record_impl(fgb_batch *b, float *u, float *p, const float *bvel, cons
                        const fgb_scalar *sc, const fgb_tape_scalar *stp, fgb_stream_t s) {
     const fgb_options &o = b->opt;
     const int C = o.corrector_steps, n_adv = o.nonortho ? o.adv_nonortho_steps : 1, n_p = o.nonortho ? o.p_nonortho_steps : 1;
-    const int reset = o.nonortho ? 100 : 0;
+    // no residual reset in the differentiable backend: its LinearSolveFunction passes residualResetSteps = 0 in both directions
+    // (DIFF.py:527-545, 574-590), unlike the plain backend's 100 (SIM.py:1908); on the singular pressure system the fp32 recurrence
+    // residual then drifts and many solves end with "residual rising for 100 iterations -> best iterate", in the reference and here
+    const int reset = 0;
     if ((o.cg_impl != 3 && !uses_halo_plan(o.cg_impl) && o.cg_impl != 7 && o.cg_impl != 8) || C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8)
         return set_err(FGB_E_ARG, "fgb_piso_substep_record: needs cg_impl 3 or 6 and correctors x pressure iterations <= 8");
     cudaStream_t st = STREAM(s);
@@ -3293,7 +3296,7 @@ static int backward_impl(fgb_batch *b, const fgb_tape *tp, const fgb_tape_scalar
             LAUNCH_CHECK("k_adj_remove_mean");
             {   // lam = P^-T x_bar
                 ProfScope psc(b, CLS_CG, st);
-                rc = cg_cluster_mb_any(b, b->Poff, b->Pdiag, xb, lam, 1, o.nonortho ? 100 : 0, b->opt.max_iter, 5, nullptr, 1 | 2, nullptr, st);
+                rc = cg_cluster_mb_any(b, b->Poff, b->Pdiag, xb, lam, 1, 0, b->opt.max_iter, 5, nullptr, 1 | 2, nullptr, st);
                 if (rc == 1) return set_err(FGB_E_ARG, "fgb_piso_substep_backward: grid too large for the on-chip transposed solve");
                 if (rc) return rc;
             }

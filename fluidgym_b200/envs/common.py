@@ -98,24 +98,31 @@ class DifferentiableRollout:
         return self._dt_tab
 
     def _balance_torch(self, bv, free, bc_tol=1e-5):
-        """balance_boundary_fluxes (SIM.py:188-224): ``free`` is a bool mask [NB] of the faces that are rescaled."""
+        """balance_boundary_fluxes (SIM.py:188-224): ``free`` is a bool mask [NB] of the faces that are rescaled.  As in the
+        reference the flux scale is computed under ``no_grad`` (SIM.py:191-211) and applied as a constant factor outside of it
+        (:212-224): gradients flow through the rescaled boundary values, not through the scale."""
         tb = self._diff_tables()
-        fl = (bv * tb["fw"]).sum(dim=1)
-        fx = (fl * (~free)).sum(dim=1)
-        vr = (fl * free).sum(dim=1)
-        need = ~((fx + vr).abs() <= bc_tol * 0.01)
-        sc = torch.where(need, -fx / vr, torch.ones_like(fx))
-        scale = torch.where(free[None, :], sc[:, None], torch.ones_like(fl))
+        with torch.no_grad():
+            fl = (bv * tb["fw"]).sum(dim=1)
+            fx = (fl * (~free)).sum(dim=1)
+            vr = (fl * free).sum(dim=1)
+            need = ~((fx + vr).abs() <= bc_tol * 0.01)
+            sc = torch.where(need, -fx / vr, torch.ones_like(fx))
+            scale = torch.where(free[None, :], sc[:, None], torch.ones_like(fl))
         return bv * scale[:, None, :]
 
     def _outflow_torch(self, u, bv, dt, bc_tol=1e-5):
-        """k_plan_substep's boundary part (SIM.py:188-224, 282-393) as differentiable torch ops."""
+        """k_plan_substep's boundary part (SIM.py:188-224, 282-393).  The reference runs update_advective_boundaries entirely
+        under ``torch.no_grad()`` (SIM.py:232), including the setVelocity of the relaxed and rescaled outflow values: the outflow
+        faces carry no gradient (neither to the adjacent cells nor to their previous values), all other faces keep theirs."""
         tb = self._diff_tables()
-        w = 1.0 - 1.0 / (1.0 + 2.0 * dt * tb["adv"])
-        bo = bv[:, :, tb["out"]]
-        bo = bo - w * (bo - u[:, :, tb["out_cell"]])
-        bv = bv.index_copy(2, tb["out"], bo)
-        return self._balance_torch(bv, tb["is_out"], bc_tol)
+        with torch.no_grad():
+            w = 1.0 - 1.0 / (1.0 + 2.0 * dt * tb["adv"])
+            bo = bv[:, :, tb["out"]]
+            bo = bo - w * (bo - u[:, :, tb["out_cell"]])
+            bvn = self._balance_torch(bv.index_copy(2, tb["out"], bo), tb["is_out"], bc_tol)
+            bo = bvn[:, :, tb["out"]]
+        return bv.index_copy(2, tb["out"], bo)
 
     def _forces_torch(self, u, p, bv):
         """k_wall_forces (forces.py:193-275) as differentiable torch ops -> [B,2] (drag, lift coefficients)."""

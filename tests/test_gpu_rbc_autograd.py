@@ -34,6 +34,9 @@ def _tensors(arrs):
 
 
 def test_forward_record_equals_plain_substep(setup):
+    """The recorded forward pass is the plain substep up to the reference's own difference between its two backends: the
+    differentiable one starts every solve from zero and never resets the CG residual (DIFF.py:527-545, SIM.py:1436-1440), so the
+    two agree to solver tolerance, not bit for bit."""
     from fluidgym_b200.autograd import piso_substep_scalar
     cd, sol, u, p0, bvel, T, sb = setup
     tu, tp, tb, tT, ts = _tensors((u, p0, bvel, T, sb))
@@ -44,8 +47,10 @@ def test_forward_record_equals_plain_substep(setup):
     sol.set_buoyancy(BETA)
     sol.piso_substep(DT)
     torch.cuda.synchronize()
-    assert torch.equal(sol.T, To.detach())
-    assert torch.equal(sol.u, uo.detach()) and torch.equal(sol.p, po.detach())
+    def rel(a, b):
+        return float((a - b).norm() / b.norm())
+    assert rel(To.detach(), sol.T) < 2e-6
+    assert rel(uo.detach(), sol.u) < 2e-4 and rel(po.detach(), sol.p) < 2e-3
 
 
 def test_vjp_matches_numpy_specification(setup):
