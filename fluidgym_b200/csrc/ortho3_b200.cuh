@@ -63,7 +63,8 @@ struct fgb_ortho3 {
     unsigned long long *slab_ctr;     // [4] device-side sequence counters of the slab protocol
     fgb_ortho3_scalar sc;             // passive scalar + buoyancy (RBC3D); sc.T == nullptr: none
     int grid_blocks;
-    int cg_fused;                     // FGB_K3_CG_FUSED=1: k3_cg_fused (2 grid.sync per CG iteration) on a single GPU; default 0 = k3_cg
+    int cg_fused;                     // k3_cg_fused (2 grid.sync per CG iteration, bit-identical to k3_cg) on a single GPU; default 1,
+                                      // FGB_K3_CG_FUSED=0 selects k3_cg
     long long launches;
 };
 
@@ -118,8 +119,8 @@ extern "C" int fgb_ortho3_create(const fgb_ortho3_tables *t, int32_t B, void *wo
     ce = cudaMemset(workspace, 0, fgb_ortho3_workspace_bytes(t, B));
     if (ce != cudaSuccess) { cudaFreeHost(b->h_counters); delete b; return set_err(FGB_E_CUDA, "cudaMemset workspace", ce); }
     b->grid_blocks = 0;
-    b->cg_fused = 0;
-    if (const char *ev = getenv("FGB_K3_CG_FUSED")) b->cg_fused = atoi(ev) == 1;
+    b->cg_fused = 1;                  // measured on a B200 (profiles/r02_k3_cg_fused_ab.txt): CylinderJet3D res 24 26.5 -> 21.2 ms / substep
+    if (const char *ev = getenv("FGB_K3_CG_FUSED")) b->cg_fused = atoi(ev) != 0;
     *out = b;
     return FGB_OK;
 }
@@ -614,12 +615,12 @@ __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, O3Slab sl, int B, const flo
     if (sl.on && blockIdx.x == 0 && threadIdx.x == 0) { sl.ctr[0] = arc; sl.ctr[1] = hc; }
 }
 
-// OPT-IN variant of k3_cg (FGB_K3_CG_FUSED=1, single GPU only; NOT yet run on a GPU): the search-direction update p <- r + beta p is
+// Default variant of k3_cg on a single GPU (FGB_K3_CG_FUSED=0 switches it off): the search-direction update p <- r + beta p is
 // folded into the next matrix-vector product.  Every row forms r[n] + beta * p_old[n] for itself and its six neighbours on the fly and
 // stores its own new value into a second buffer, so the grid-wide synchronisation that separated the update from the product
 // disappears: 2 instead of 3 grid.sync per iteration -- the solves of the extruded environments (1 000 - 2 000 iterations on 10^4 -
 // 10^5 cells) are bound by exactly these synchronisations.  The expression and the summation order of every value are those of
-// k3_cg, so iterates, iteration counts and results are expected to be BIT-IDENTICAL (tests/zz_first_run_worker.py cg_fused).
+// k3_cg, so iterates, iteration counts and results are BIT-IDENTICAL (tests/zz_first_run_worker.py cg_fused, green on a B200).
 __device__ __forceinline__ float o3_pnew(const float *r, const float *pold, float beta, int i) { return __ldcg(&r[i]) + beta * __ldcg(&pold[i]); }
 __global__ void __launch_bounds__(O3_CT) k3_cg_fused(T3 t, O3Slab sl, int B, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
                                                     const float *__restrict__ Rhs, float *Xout, float *work, float *part, int maxit, float tol,

@@ -12,6 +12,14 @@ import numpy as np
 from .domain import CONNECTED, FIXED, PERIODIC, Boundary, DomainSpec
 
 
+def _scalar_type(bd) -> str:
+    """``passiveScalarType`` of a boundary entry: the reference writes a list (one entry per channel, domain_io.py:145-148) and
+    reads a list or a plain string (:291-302)."""
+    t = bd.get("passiveScalarType", "DIRICHLET")
+    t = t[0] if isinstance(t, (list, tuple)) else t
+    return str(t)
+
+
 def load_domain(path: str):
     """-> (DomainSpec, state) with state = dict(u [2,N], p [N], bvel [2,NB], T [N] | None, sbval [NB] | None) in the flat
     layout of the solver (cells of all blocks concatenated, x fastest; prescribed faces in (block, face) order)."""
@@ -24,7 +32,7 @@ def load_domain(path: str):
         return data[dct[name]] if name in dct else None
     if d["spatialDims"] != 2:
         raise NotImplementedError("domain files of 3-D domains: use fluidgym_b200.box3d (only 2-D multi-block domains are read here)")
-    n_scalar = d.get("passiveScalarChannels", 0)
+    n_scalar = d.get("passiveScalarChannels", 1)           # the reference's loader defaults to one channel (domain_io.py:207-209)
     svisc = get(d, "passiveScalarViscosity")
     spec = DomainSpec(float(np.asarray(get(d, "viscosity")).ravel()[0]), d.get("name", "domain"),
                       scalar_viscosity=None if (n_scalar == 0 or svisc is None) else float(np.asarray(svisc).ravel()[0]))
@@ -50,7 +58,7 @@ def load_domain(path: str):
                 sc, neumann = None, False
                 if "scalar" in bd and n_scalar:
                     sc = np.asarray(get(bd, "scalar"), dtype=np.float32).reshape(-1)
-                    neumann = bd.get("passiveScalarType", ["DIRICHLET"])[0] == "NEUMANN"
+                    neumann = _scalar_type(bd) == "NEUMANN"
                 # the file lists every face explicitly: set it directly (close_boundary would also re-close the partner face)
                 n = b.size(1 - (f >> 1))
                 vfull = np.zeros((2, n), dtype=np.float32)
@@ -152,7 +160,7 @@ def load_box_domain(path: str):
     vertex = np.ascontiguousarray(v[0], dtype=np.float32)
     nz, ny, nx = (s - 1 for s in vertex.shape[1:])
     N = nx * ny * nz
-    n_scalar = d.get("passiveScalarChannels", 0)
+    n_scalar = d.get("passiveScalarChannels", 1)           # the reference's loader defaults to one channel (domain_io.py:207-209)
     svisc = get(d, "passiveScalarViscosity")
     u = np.asarray(get(blk, "velocity"), dtype=np.float32)[0].reshape(3, N)
     p = np.asarray(get(blk, "pressure"), dtype=np.float32)[0].reshape(N)
@@ -175,7 +183,7 @@ def load_box_domain(path: str):
         bvel.append(vfull)
         sfull = np.zeros(n_face, dtype=np.float32)
         if "scalar" in bd and n_scalar:
-            if bd.get("passiveScalarType", ["DIRICHLET"])[0] != "DIRICHLET":
+            if _scalar_type(bd) != "DIRICHLET":
                 raise NotImplementedError("Neumann scalar boundaries on the 3-D box")
             sfull[:] = np.asarray(get(bd, "scalar"), dtype=np.float32).reshape(-1)
         sbval.append(sfull)

@@ -189,7 +189,7 @@ class Airfoil3DEnv(SpanwiseExtrudedEnv):
         v = torch.where(mx > 1.0, v / mx, v)
         per_plane = v.repeat_interleave(self.nz_per_agent, dim=1)                          # [B, nz, n_jets]
         if getattr(s, "apply_jets", None) and s.apply_jets(per_plane, self.jet_base, self.jet_faces, self._free_jets, 1e-5):
-            return                                                                         # opt-in kernel path (FGB_X3_HOOKS=cuda)
+            return                                                                         # kernel path (default; FGB_X3_HOOKS=torch: torch expressions)
         prof = torch.einsum("bkj,jcx->bckx", per_plane, self.jet_base)                     # [B, 2, nz, n_top]
         jf = self.jet_faces.long()
         s.bvel[:, :2, :, jf] = prof

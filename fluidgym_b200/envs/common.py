@@ -162,7 +162,7 @@ class DifferentiableRollout:
                 mts = np.float32(self.cfl) / np.float32(mv)
                 ts = remaining if float(mts) >= remaining else remaining / float(np.ceil(np.float32(remaining) / mts))
             remaining -= ts
-            bv = self._outflow_torch(u, bv, float(np.float32(ts)))
+            bv = self._outflow_torch(u, bv, float(np.float32(ts)), getattr(self, "bc_tol", 1e-5))
             u, p = piso_substep(s, u, p, bv, float(np.float32(ts)))
             nsub += 1
         return u, p, bv, nsub

@@ -89,6 +89,7 @@ class CylinderJet2DEnv(DifferentiableRollout, InitialDomains):
     jet_angle = 10.0
     metrics = ["drag", "lift"]
     reference_values = {"cd_ref": ("drag", "mean")}
+    bc_tol = 5e-6            # flux-balance tolerance of the cylinder's outflow hook (cylinder_env_base.py:293-295: tol=5e-6, 2-D and 3-D)
 
     def __init__(self, n_envs: int = 1, reynolds_number=1e2, resolution=24, dt=1e-2, adaptive_cfl=0.8, step_length=0.25,
                  episode_length=80, lift_penalty=1.0, device="cuda:0", cg_impl=11, compiled=None, cd_ref=0.0,
@@ -234,7 +235,7 @@ class CylinderJet2DEnv(DifferentiableRollout, InitialDomains):
             s.p.zero_()
             s.bvel.copy_(torch.from_numpy(self.cd.bvel0[:, :self.cd.NB].copy()).to(self.device).unsqueeze(0).expand_as(s.bvel))
         # Simulation.make_divergence_free incl. its "PRE" hook with time step 1 (SIM.py:1335-1347)
-        s.update_outflow(1.0, self.char_vel, tol=1e-5)
+        s.update_outflow(1.0, self.char_vel, tol=self.bc_tol)
         s.make_divergence_free(max_iter=1000)
         self.last_control.zero_()
         if randomize:
@@ -254,7 +255,7 @@ class CylinderJet2DEnv(DifferentiableRollout, InitialDomains):
         s.u += torch.randn(s.u.shape, device=self.device, generator=self._torch_rng) * 0.025
         s.p += torch.randn(s.p.shape, device=self.device, generator=self._torch_rng) * 0.025
         for _ in range(n_steps):
-            s.single_step(self.dt, self.cfl, char_vel=self.char_vel)
+            s.single_step(self.dt, self.cfl, char_vel=self.char_vel, bc_tol=self.bc_tol)
 
     def _apply_action(self, action, smooth=True):
         """jet_cylinder_env_2d.py:185-188 with the exponential smoothing of CYL.py:748-751."""
@@ -294,7 +295,7 @@ class CylinderJet2DEnv(DifferentiableRollout, InitialDomains):
         for _ in range(self.n_sim_steps):
             if self.enable_actions:
                 self._apply_action(action)
-            nsub += s.single_step(self.dt, self.cfl, char_vel=self.char_vel)
+            nsub += s.single_step(self.dt, self.cfl, char_vel=self.char_vel, bc_tol=self.bc_tol)
             native.check(self.lib.fgb_wall_forces(s.handle, C.byref(self.wall), _ptr(s.u), _ptr(s.p), _ptr(s.bvel), _ptr(self._acc),
                                                   s.stream), "fgb_wall_forces")
         self.last_substeps = nsub

@@ -119,7 +119,7 @@ class SpanwiseExtrudedEnv(InitialDomainsExtruded):
         traction of every plane times the plane spacing)."""
         s = self.solver
         B, nz, N2 = self.n_envs, self.nz, s.N2
-        if s.u.is_cuda and getattr(s, "_cuda_hooks", lambda: False)():                           # opt-in kernel path (FGB_X3_HOOKS=cuda)
+        if s.u.is_cuda and getattr(s, "_cuda_hooks", lambda: False)():                           # kernel path (default; FGB_X3_HOOKS=torch: torch expressions)
             import ctypes as C
             from .. import native
             from ..solver import _ptr
@@ -136,7 +136,7 @@ class SpanwiseExtrudedEnv(InitialDomainsExtruded):
     def _sample(self, field: torch.Tensor) -> torch.Tensor:
         """[B, C, N3] -> [B, C, n_sensors]: the rendered-voxel map evaluated at the sensor voxels only (static ELL rows)"""
         s = self.solver
-        if field.is_cuda and getattr(s, "_cuda_hooks", lambda: False)():                         # opt-in kernel path (FGB_X3_HOOKS=cuda)
+        if field.is_cuda and getattr(s, "_cuda_hooks", lambda: False)():                         # kernel path (default; FGB_X3_HOOKS=torch: torch expressions)
             from .. import native
             from ..solver import _ptr
             if not hasattr(self, "_sens_idx32"):
@@ -312,7 +312,7 @@ class CylinderJet3DEnv(SpanwiseExtrudedEnv):
         s = self.solver
         per_plane = control.repeat_interleave(self.nz_per_agent, dim=1)                           # [B, nz]
         if getattr(s, "apply_jets", None) and s.apply_jets(per_plane[:, :, None], self.jet_templ[None], self.jet_faces, self._free_jets, 1e-7):
-            return                                                                                # opt-in kernel path (FGB_X3_HOOKS=cuda)
+            return                                                                                # kernel path (default; FGB_X3_HOOKS=torch: torch expressions)
         jf = self.jet_faces.long()
         s.bvel[:, :2, :, jf] = self.jet_templ[None, :, None, :] * per_plane[:, None, :, None]
         s.bvel[:, 2, :, jf] = 0.0

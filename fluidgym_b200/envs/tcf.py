@@ -163,6 +163,9 @@ class TCF3DEnv(InitialDomains3D):
         randomize = self.randomize_initial_state if randomize is None else randomize
         if self.load_domain_on_reset:                      # fluid_env.py:519-551
             self._load_initial_domains_on_reset(randomize)
+            # the reference projects loaded domains as well: _get_simulation always ends with CopyVelocityResultFromBlocks +
+            # make_divergence_free (tcf_env.py:478-511), which also replaces the stored pressure by the projection pressure
+            s.make_divergence_free(max_iter=1000)
         else:
             u0 = torch.zeros(3, self.z, self.ny, self.x)
             u0[0] = self.u_init[None, :, None]

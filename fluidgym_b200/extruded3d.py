@@ -212,11 +212,11 @@ class ExtrudedPISO3D(ExtrudedStepping):
         native.check(self.lib.fgb_extruded3_make_divergence_free(self.handle, C.byref(self.xtables), _ptr(self.u), _ptr(self.p), _ptr(self.bvel),
                                                                  int(max_iter), self.stream), "fgb_extruded3_make_divergence_free")
 
-    # ---- opt-in: the boundary hooks as kernels (FGB_X3_HOOKS=cuda) instead of the torch expressions of ExtrudedStepping ----
-    # Not yet run on a GPU; tests/test_zz_gpu_extruded_first_run.py compares the two paths.  Default stays torch until then.
+    # ---- the boundary hooks as kernels (default; FGB_X3_HOOKS=torch selects the torch expressions of ExtrudedStepping) ----
+    # tests/test_gpu_extruded.py compares the two paths with each other and with a float64 evaluation (green on a B200, round 2).
     def _cuda_hooks(self) -> bool:
         import os
-        return os.environ.get("FGB_X3_HOOKS", "") == "cuda"
+        return os.environ.get("FGB_X3_HOOKS", "cuda") != "torch"
 
     def _hook_tables(self):
         if "out32" not in self._st:

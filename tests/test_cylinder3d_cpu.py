@@ -276,7 +276,7 @@ def test_on_disk_initial_domains_of_the_extruded_grid(compiled, golden, tmp_path
 
 
 def test_first_gpu_run_tool_dry_run_on_the_stand_in(tmp_path):
-    """tools/extruded_check.py (the first GPU run of the extruded path, tests/test_zz_gpu_extruded_first_run.py) executed here
+    """tools/extruded_check.py (the first GPU run of the extruded path, tests/test_gpu_extruded.py) executed here
     on the CPU stand-in: the tool's own code paths and bars are exercised before it ever meets a GPU."""
     import json
     import subprocess

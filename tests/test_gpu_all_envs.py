@@ -8,7 +8,8 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 ENV_IDS = ["CylinderJet2D-easy-v0", "CylinderJet2D-medium-v0", "CylinderRot2D-easy-v0", "RBC2D-easy-v0", "RBC2D-wide-easy-v0",
-           "Airfoil2D-easy-v0", "TCFSmall3D-bottom-easy-v0", "TCFSmall3D-both-easy-v0", "RBC3D-easy-v0"]
+           "Airfoil2D-easy-v0", "TCFSmall3D-bottom-easy-v0", "TCFSmall3D-both-easy-v0", "RBC3D-easy-v0", "CylinderJet3D-easy-v0"]
+ENV_KW = {"CylinderJet3D-easy-v0": {"resolution": 8}}      # the reference's own smallest test grid (res 8: 15 872 cells)
 B = 2
 
 
@@ -35,7 +36,7 @@ def _check_action(env, action, marl):
 @pytest.mark.parametrize("env_id", ENV_IDS)
 def test_env_sarl(env_id):
     import fluidgym_b200
-    env = fluidgym_b200.make(env_id, n_envs=B, use_marl=False)
+    env = fluidgym_b200.make(env_id, n_envs=B, use_marl=False, **ENV_KW.get(env_id, {}))
     env.seed(42)
     obs, info = env.reset()
     _check_obs(env, obs, marl=False)
@@ -52,7 +53,7 @@ def test_env_sarl(env_id):
 def test_env_marl(env_id):
     import fluidgym_b200
     try:
-        env = fluidgym_b200.make(env_id, n_envs=B, use_marl=True)
+        env = fluidgym_b200.make(env_id, n_envs=B, use_marl=True, **ENV_KW.get(env_id, {}))
     except ValueError:
         return                                     # single-agent family (cylinder, airfoil in 2-D), as in the reference
     env.seed(42)

@@ -1,4 +1,4 @@
-"""Worker of tests/test_zz_gpu_extruded_first_run.py: each case runs in its OWN PROCESS (a fault in code that has never run on a
+"""Worker of tests/test_gpu_extruded.py: each case runs in its OWN PROCESS (a fault in code that has never run on a
 GPU must not take the pytest process, and with it the report of the verified suites, down).
     python tests/zz_first_run_worker.py asm2|asm4|asm8|hooks|forces|cg_fused
 Exit code 0 = the comparison holds."""
