@@ -166,7 +166,8 @@ def test_reset_matches_reference(cyl24, golden):
     assert rel_l2(env.solver.p[0].cpu().numpy(), rs["presres"]) < 5e-3
 
 
-def test_env_step_matches_reference(cyl24, golden):
+@pytest.mark.parametrize("cg_impl", [6, 11])
+def test_env_step_matches_reference(cyl24, golden, cg_impl):
     """env.step from the reference's reset state: drag/lift, reward, sensors after 25 sim steps."""
     spec, cd = cyl24
     from fluidgym_b200.envs.cylinder import CylinderJet2DEnv
