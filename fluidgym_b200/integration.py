@@ -242,3 +242,116 @@ class PettingZooFluidEnv:
     @property
     def unwrapped(self):
         return getattr(self._env, "unwrapped", self._env)
+
+
+# ------------------------------------------------------------------------------------------------
+# TorchRL (reference: fluidgym/integration/torchrl.py:87-278)
+# ------------------------------------------------------------------------------------------------
+try:                                                     # pragma: no cover - not installed in the build image
+    from tensordict import TensorDict as _TensorDict
+    from torchrl.data.tensor_specs import Bounded as _Bounded, Categorical as _Categorical, Composite as _Composite, \
+        Unbounded as _Unbounded
+    from torchrl.envs import EnvBase as _TorchRLEnvBase
+    _HAVE_TORCHRL = True
+except Exception:                                        # noqa: BLE001
+    _HAVE_TORCHRL = False
+
+    class _TorchRLEnvBase:                               # the part of EnvBase's constructor contract this adapter uses
+        def __init__(self, device=None, batch_size=()):
+            self.device, self.batch_size = device, torch.Size(batch_size)
+
+
+class SpecLike:
+    """Stand-in for a TorchRL tensor spec when torchrl is not installed: shape / dtype / bounds, nothing else."""
+
+    def __init__(self, shape, dtype=torch.float32, low=None, high=None, device=None):
+        self.shape, self.dtype, self.low, self.high, self.device = torch.Size(shape), dtype, low, high, device
+
+    def __repr__(self):
+        return f"SpecLike(shape={tuple(self.shape)}, dtype={self.dtype})"
+
+
+class TorchRLFluidEnv(_TorchRLEnvBase):
+    """TorchRL ``EnvBase`` over a batched environment.
+
+    The reference exposes ONE environment: batch size ``()`` single-agent, ``(n_agents,)`` multi-agent (the agents as a virtual
+    batch, torchrl.py:87-100).  A batched environment is a real batch: batch size ``(n_envs,)`` or ``(n_envs, n_agents)``, all
+    tensors stay on the environment's device (no numpy round trip).  Same ``_step / _reset / _set_seed`` protocol and the same
+    spec layout (observation keys as a Composite, reward / done / terminated / truncated with a trailing unit dimension).
+    ``from_pixels`` needs the reference's renderer and is not supported (rendering is outside the solver path)."""
+
+    def __init__(self, env, from_pixels: bool = False):
+        if from_pixels:
+            raise NotImplementedError("from_pixels: rendering is not part of fluidgym_b200")
+        n_envs = int(getattr(env, "n_envs", 1))
+        self._n_agents = int(env.n_agents) if getattr(env, "use_marl", False) else None
+        batch = (n_envs,) if self._n_agents is None else (n_envs, self._n_agents)
+        super().__init__(device=_device(env), batch_size=torch.Size(batch))
+        self._env = env
+        self._make_spec()
+
+    def _box(self, space, lead):
+        low = torch.as_tensor(np.broadcast_to(space.low, space.shape).copy(), dtype=torch.float32, device=self.device)
+        high = torch.as_tensor(np.broadcast_to(space.high, space.shape).copy(), dtype=torch.float32, device=self.device)
+        shape = torch.Size((*lead, *space.shape))
+        unbounded = bool(np.all(np.isinf(space.low)) and np.all(np.isinf(space.high)))
+        if not _HAVE_TORCHRL:
+            return SpecLike(shape, low=None if unbounded else low.expand(shape), high=None if unbounded else high.expand(shape), device=self.device)
+        if unbounded:
+            return _Unbounded(shape=shape, dtype=torch.float32, device=self.device)
+        return _Bounded(low=low.expand(shape).clone(), high=high.expand(shape).clone(), shape=shape, dtype=torch.float32, device=self.device)
+
+    def _make_spec(self) -> None:                         # torchrl.py:128-190
+        lead = tuple(self.batch_size)
+        obs_space = self._env.observation_space
+        sub = obs_space.spaces if hasattr(obs_space, "spaces") else {"observation": obs_space}
+        obs = {k: self._box(v, lead) for k, v in sub.items()}
+        flag = (lambda: SpecLike((*lead, 1), dtype=torch.bool, device=self.device)) if not _HAVE_TORCHRL else \
+            (lambda: _Categorical(n=2, shape=torch.Size((*lead, 1)), dtype=torch.bool, device=self.device))
+        if _HAVE_TORCHRL:                                # pragma: no cover
+            self.observation_spec = _Composite(obs, shape=self.batch_size)
+            self.state_spec = self.observation_spec.clone()
+            self.reward_spec = _Unbounded(shape=torch.Size((*lead, 1)), dtype=torch.float32, device=self.device)
+            self.done_spec = _Composite(done=flag(), terminated=flag(), truncated=flag(), shape=self.batch_size)
+        else:
+            self.observation_spec = obs
+            self.state_spec = dict(obs)
+            self.reward_spec = SpecLike((*lead, 1), device=self.device)
+            self.done_spec = {"done": flag(), "terminated": flag(), "truncated": flag()}
+        self.action_spec = self._box(self._env.action_space, lead)
+
+    def _td(self, data: dict):
+        return _TensorDict(data, batch_size=self.batch_size) if _HAVE_TORCHRL else dict(data)
+
+    def _flag(self, flag: bool) -> torch.Tensor:
+        return torch.full((*self.batch_size, 1), bool(flag), dtype=torch.bool, device=self.device)
+
+    def _step(self, tensordict):                          # torchrl.py:205-244
+        with torch.no_grad():
+            obs, reward, term, trunc, _ = self._env.step(tensordict["action"])
+        if not isinstance(obs, dict):
+            obs = {"observation": obs}
+        reward = reward.reshape(*self.batch_size, 1)
+        return self._td({**obs, "reward": reward, "done": self._flag(term or trunc), "terminated": self._flag(term),
+                         "truncated": self._flag(trunc)})
+
+    def _reset(self, tensordict=None, **kwargs):          # torchrl.py:246-268
+        obs, _ = self._env.reset()
+        if not isinstance(obs, dict):
+            obs = {"observation": obs}
+        return self._td(obs)
+
+    def _set_seed(self, seed: int) -> None:               # torchrl.py:270-278
+        self._env.seed(seed)
+
+    if not _HAVE_TORCHRL:                                 # EnvBase provides these when torchrl is installed
+        def reset(self, tensordict=None, **kwargs):
+            return self._reset(tensordict, **kwargs)
+
+        def step(self, tensordict):
+            out = self._step(tensordict)
+            return {**tensordict, "next": out}
+
+        def set_seed(self, seed: int):
+            self._set_seed(seed)
+            return seed

@@ -106,3 +106,30 @@ def test_gym_and_pettingzoo_views_and_their_checks():
     assert list(obs) == ["agent_0", "agent_1", "agent_2"] and obs["agent_2"]["pressure"][0] == 2.0
     obs, rew, terms, truncs, infos = pz.step({a: np.array([i], dtype=np.float32) for i, a in enumerate(pz.possible_agents)})
     assert rew == {"agent_0": 0.0, "agent_1": 1.0, "agent_2": 2.0} and all(truncs.values()) and pz.agents == []
+
+
+@pytest.mark.parametrize("marl", [False, True])
+def test_torchrl_adapter_protocol(marl):
+    """TorchRLFluidEnv (reference: integration/torchrl.py:87-278): batch size (n_envs,) / (n_envs, n_agents), spec shapes with the
+    trailing unit dimension of reward / done flags, _step / _reset / _set_seed."""
+    from fluidgym_b200.integration import TorchRLFluidEnv
+    env = FakeEnv(3, n_agents=4, use_marl=marl, episode_length=2)
+    tenv = TorchRLFluidEnv(env)
+    lead = (3, 4) if marl else (3,)
+    assert tuple(tenv.batch_size) == lead
+    assert tuple(tenv.action_spec.shape) == (*lead, 1)
+    assert tuple(tenv.reward_spec.shape) == (*lead, 1)
+    assert tuple(tenv.observation_spec["velocity"].shape) == (*lead, 2, 4)
+    assert tuple(tenv.done_spec["truncated"].shape) == (*lead, 1)
+    tenv.set_seed(7)
+    assert env._seed == 7
+    td = tenv.reset()
+    assert tuple(td["pressure"].shape) == (*lead, 4)
+    a = torch.ones(*lead, 1)
+    out = tenv.step({"action": a})["next"]
+    assert tuple(out["reward"].shape) == (*lead, 1) and out["reward"].dtype == torch.float32
+    assert not bool(out["done"].any()) and out["done"].dtype == torch.bool and tuple(out["done"].shape) == (*lead, 1)
+    out = tenv.step({"action": a})["next"]
+    assert bool(out["truncated"].all()) and bool(out["done"].all()) and not bool(out["terminated"].any())
+    with pytest.raises(NotImplementedError):
+        TorchRLFluidEnv(env, from_pixels=True)
