@@ -2942,6 +2942,7 @@ static int cg_strip_any(fgb_batch *b, const float *poff, const float *pdiag, con
     if (rc == 1) rc = cg_strip_cs<256, 17, 2>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
     if (rc == 1) rc = cg_strip_cs<896, 9, 1>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
     if (rc == 1) rc = cg_strip_cs<640, 13, 1>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    if (rc == 1) rc = cg_strip_cs<320, 13, 2>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
     return rc;
 }
 

@@ -30,7 +30,7 @@ import math
 import os
 
 CS_CHOICES = (1, 2, 4, 8, 16)
-SHAPES = ((480, 17), (256, 17), (896, 9), (640, 13))   # (threads per CTA, rows per thread) the kernel is instantiated for (1 / 2 co-resident
+SHAPES = ((480, 17), (256, 17), (896, 9), (640, 13), (320, 13))   # (threads per CTA, rows per thread) the kernel is instantiated for (1 / 2 co-resident
 #                                   CTAs per SM); the first that fits is the default.  Threads per CTA: a multiple of 32.
 
 

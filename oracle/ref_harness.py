@@ -204,6 +204,9 @@ def main():
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"], help="fluidgym.make(dtype=...)")
     ap.add_argument("--pressure-tol", type=float, default=None, help="override Simulation.pressure_tol after reset (tight-tolerance goldens)")
     ap.add_argument("--advection-tol", type=float, default=None, help="override Simulation.advection_tol after reset")
+    ap.add_argument("--res-z", type=int, default=None,
+                    help="Airfoil3D: spanwise resolution (class attribute AirfoilEnvBase._res_z, 96 in the reference) -- a smaller value "
+                         "makes the golden run affordable; the reference's code is untouched")
     ap.add_argument("--save-domain-only", action="store_true",
                     help="reset, advance --env-steps steps, write the domain with the reference's own save_domain() and exit")
     args = ap.parse_args()
@@ -219,6 +222,10 @@ def main():
     meta = {"env": args.env, "seed": args.seed, "torch": torch.__version__, "gpu": torch.cuda.get_device_name(0)}
 
     kw = json.loads(args.kw)
+    if args.res_z is not None:
+        from fluidgym.envs.airfoil.airfoil_env_base import AirfoilEnvBase
+        AirfoilEnvBase._res_z = int(args.res_z)
+        meta["res_z"] = int(args.res_z)
     if args.dtype == "float64":
         kw["dtype"] = torch.float64
     env = fluidgym.make(args.env, load_initial_domain=False, load_domain_statistics=False,

@@ -1,0 +1,8 @@
+# Airfoil3D golden of the unmodified reference at a reduced spanwise resolution (res_z 8: 46 806 x 8 = 374 448 cells)
+set -x
+O=gpurun_out/r02/airfoil3d
+mkdir -p $O
+timeout 2400 python oracle/ref_harness.py --env Airfoil3D-easy-v0 --tag airfoil3d --out $O --res-z 8 --env-steps 1 --time-steps 0 \
+    --trace-substeps 1 --lean --kw '{"init_from_2d": false, "n_agents": 4}' > $O/airfoil3d.log 2>&1
+tail -n 5 $O/airfoil3d.log | cut -c1-400
+ls -la $O
