@@ -147,6 +147,34 @@ class BatchedPISO3D:
         self._scalar = native.Ortho3Scalar(self.T.data_ptr(), self.sbval.data_ptr(), self.kappa, self.beta)
         native.check(self.lib.fgb_ortho3_set_scalar(self.handle, C.byref(self._scalar)), "fgb_ortho3_set_scalar")
 
+    # ---- sub-grid-scale viscosity + velocity gradients ---------------------------------------------------------------------
+    def set_sgs(self, coefficient: float, damping=None):
+        """Smagorinsky model (tcf_env.py:441-472): per-cell viscosity nu + C delta |S| damping, refreshed before every substep.
+        ``damping``: [N] squared van Driest factor (envs/tcf/grid.py:101-125) or None; coefficient 0 switches the model off."""
+        self._sgs_damp = None if damping is None else torch.as_tensor(np.asarray(damping, dtype=np.float32).reshape(-1), device=self.device).contiguous()
+        if self._sgs_damp is not None and self._sgs_damp.numel() != self.N:
+            raise ValueError(f"set_sgs: damping has {self._sgs_damp.numel()} entries for {self.N} cells")
+        native.check(self.lib.fgb_ortho3_set_sgs(self.handle, float(coefficient), _ptr(self._sgs_damp)), "fgb_ortho3_set_sgs")
+
+    def sgs_viscosity(self):
+        """PISOtorch.SGSviscosityIncompressibleSmagorinsky + the prep function's damping and base viscosity -> ``visc [B,N]``"""
+        native.check(self.lib.fgb_ortho3_sgs_viscosity(self.handle, _ptr(self.u), _ptr(self.bvel), None, self.stream), "fgb_ortho3_sgs_viscosity")
+        return self.buffer("visc")
+
+    def velocity_gradients(self):
+        """PISOtorch.ComputeSpatialVelocityGradients: ``[B, 3 (component c), 3 (direction d), N]`` = d u_c / d x_d; ``out[:, i]`` is the
+        i-th tensor of the reference's list (K.cu:6470-6480: list index = component, channel = direction)"""
+        out = torch.empty(self.B, 3, 3, self.N, device=self.device)
+        native.check(self.lib.fgb_ortho3_velocity_gradients(self.handle, _ptr(self.u), _ptr(self.bvel), _ptr(out), self.stream),
+                     "fgb_ortho3_velocity_gradients")
+        return out
+
+    def q_criterion(self):
+        """Q = (|Omega|^2 - |S|^2) / 2 (tcf_env.py:586-644, before the reference's resampling to the output grid) -> [B, N]"""
+        g = self.velocity_gradients()                                # [B, c, d, N]
+        s, o = 0.5 * (g + g.transpose(1, 2)), 0.5 * (g - g.transpose(1, 2))
+        return 0.5 * ((o * o).sum(dim=(1, 2)) - (s * s).sum(dim=(1, 2)))
+
     def advect_scalar(self, dt):
         self._dtc = self._dt(dt)
         native.check(self.lib.fgb_ortho3_advect_scalar(self.handle, _ptr(self.u), _ptr(self.bvel), _ptr(self._dtc), None, self.stream),
@@ -168,7 +196,7 @@ class BatchedPISO3D:
         B, N = self.B, self.N
         shapes = {"Coff": ((B, 6, N), torch.float32), "A": ((B, N), torch.float32), "rhs": ((B, 3, N), torch.float32),
                   "ures": ((B, 3, N), torch.float32), "Poff": ((B, 6, N), torch.float32), "Pdiag": ((B, N), torch.float32),
-                  "hbya": ((B, 3, N), torch.float32), "div": ((B, N), torch.float32), "iters": ((B, 8), torch.int32),
+                  "hbya": ((B, 3, N), torch.float32), "div": ((B, N), torch.float32), "visc": ((B, N), torch.float32), "iters": ((B, 8), torch.int32),
                   "resid": ((B, 8), torch.float32), "dt": ((B,), torch.float32), "nsub": ((B,), torch.int32), "maxvel": ((B,), torch.float32),
                   "src": ((B, 4), torch.float32), "rowmean": ((B, 4), torch.float32), "iter_total": ((B, 2), torch.int64)}
         shape, dtype = shapes[name]
@@ -398,6 +426,14 @@ class SlabPISO3D:
 
     def owned(self, t):
         return t[..., :self.tabs.N]
+
+    def set_sgs(self, coefficient: float, damping_global=None):
+        """as BatchedPISO3D.set_sgs; ``damping_global``: [N_global] (this rank keeps its slab's cells)"""
+        self._sgs_damp = None
+        if damping_global is not None:
+            loc = self.tabs.take_cells(np.asarray(damping_global, dtype=f32).reshape(-1))[..., :self.tabs.N]
+            self._sgs_damp = torch.from_numpy(np.ascontiguousarray(loc)).to(self.device)
+        native.check(self.lib.fgb_ortho3_set_sgs(self.handle, float(coefficient), _ptr(self._sgs_damp)), "fgb_ortho3_set_sgs")
 
     def piso_substep(self, dt, src=None):
         dtc = torch.full((1,), float(dt), device=self.device)

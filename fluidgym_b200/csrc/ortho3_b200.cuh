@@ -63,6 +63,8 @@ struct fgb_ortho3 {
     unsigned long long *slab_ctr;     // [4] device-side sequence counters of the slab protocol
     fgb_ortho3_scalar sc;             // passive scalar + buoyancy (RBC3D); sc.T == nullptr: none
     int grid_blocks;
+    float *visc;                      // [B][NS] per-cell viscosity nu + nu_sgs (fgb_ortho3_set_sgs), refreshed before every substep
+    float sgs_coef; const float *sgs_damp;
     int cg_fused;                     // k3_cg_fused (2 grid.sync per CG iteration, bit-identical to k3_cg) on a single GPU; default 1,
                                       // FGB_K3_CG_FUSED=0 selects k3_cg
     long long launches;
@@ -99,11 +101,12 @@ extern "C" int fgb_ortho3_create(const fgb_ortho3_tables *t, int32_t B, void *wo
     if (b->t.N_global <= 0) b->t.N_global = b->t.N;
     memset(&b->slab, 0, sizeof(b->slab)); b->slab.world = 1;
     memset(&b->sc, 0, sizeof(b->sc));
+    b->sgs_coef = 0.f; b->sgs_damp = nullptr;
     const size_t BN = (size_t)B * b->t.NS;
     Carver c{(char *)workspace, 0};
     b->Coff = c.take<float>(6 * BN); b->Poff = c.take<float>(6 * BN);
     b->A = c.take<float>(BN); b->Pdiag = c.take<float>(BN); b->div = c.take<float>(BN);
-    (void)c.take<float>(BN);
+    b->visc = c.take<float>(BN);
     b->rhs = c.take<float>(3 * BN); b->ures = c.take<float>(3 * BN); b->hbya = c.take<float>(3 * BN);
     b->kry = c.take<float>((size_t)O3_KRY * BN);
     b->part = c.take<float>((size_t)2 * 4096 * O3_PART);
@@ -138,7 +141,7 @@ extern "C" void *fgb_ortho3_buffer(fgb_ortho3 *b, const char *name) {
     if (!b || !name) return nullptr;
     struct { const char *n; void *p; } tab[] = {
         {"Coff", b->Coff}, {"A", b->A}, {"rhs", b->rhs}, {"ures", b->ures}, {"Poff", b->Poff}, {"Pdiag", b->Pdiag}, {"hbya", b->hbya},
-        {"div", b->div}, {"iters", b->iters}, {"resid", b->resid}, {"dt", b->dt}, {"active", b->active}, {"nsub", b->nsub},
+        {"div", b->div}, {"visc", b->visc}, {"iters", b->iters}, {"resid", b->resid}, {"dt", b->dt}, {"active", b->active}, {"nsub", b->nsub},
         {"maxvel", b->maxvel}, {"src", b->src}, {"rowmean", b->rowmean}, {"iter_total", b->iter_total}, {"remaining", b->remaining}};
     for (auto &e : tab) if (!strcmp(e.n, name)) return e.p;
     return nullptr;
@@ -158,11 +161,12 @@ __device__ __forceinline__ float o3_bflux(const T3 &t, int j, int d, const float
 __global__ void __launch_bounds__(O3_T) k3_setup_advection(T3 t, O3Slab sl, const float *__restrict__ U, const float *__restrict__ Bvel,
                                                            const float *__restrict__ Src /* [B][4] or null */, const float *__restrict__ dtv,
                                                            const int32_t *__restrict__ active, float *__restrict__ Coff, float *__restrict__ A,
-                                                           float *__restrict__ Rhs, const float *__restrict__ Tbuoy /* [B][NS] or null */, float beta) {
+                                                           float *__restrict__ Rhs, const float *__restrict__ Tbuoy /* [B][NS] or null */, float beta,
+                                                           const float *__restrict__ Visc /* [B][NS] per-cell viscosity (SGS) or null */) {
     const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS, NB = t.NB;
     if (g >= N || (active && !active[b])) return;
-    const float *u = U + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB;
-    const float dt = dtv[b], det = t.det[g], visc = t.viscosity;
+    const float *u = U + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB, *vv = Visc ? Visc + (size_t)b * NS : nullptr;
+    const float dt = dtv[b], det = t.det[g], visc = vv ? vv[g] : t.viscosity;
     float uo[3], mi[3], al[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) { uo[d] = u[d * NS + g]; mi[d] = t.minv[d * NS + g]; al[d] = det * mi[d] * mi[d]; }
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(O3_T) k3_setup_advection(T3 t, O3Slab sl, cons
         if (n >= 0) {
             const float dn = t.det[n], mn = t.minv[d * NS + n];
             const float fl = 0.5f * (det * mi[d] * uo[d] + dn * mn * u[d * NS + n]);
-            const float vc = (al[d] * visc + (dn * mn * mn) * visc) * 0.5f;
+            const float vc = (al[d] * visc + (dn * mn * mn) * (vv ? vv[n] : visc)) * 0.5f;   // K.cu:3741-3750
             const float ff = sig * 0.5f * fl;
             diag += ff + vc;
             off = (ff - vc) / det;
@@ -236,6 +240,66 @@ __global__ void __launch_bounds__(O3_T) k3_setup_scalar(T3 t, const float *__res
     Rhs[(size_t)b * NS + g] = r / det;
 }
 
+// Cell-centred velocity gradients (getBlockDataGradient, K.cu:2997-3043): central differences in computational space -- one-sided
+// with distance 1.5 against a prescribed (Dirichlet) face, whose value sits half a cell away -- times the diagonal inverse metric.
+// G[c][d] = d u_c / d x_d
+__device__ __forceinline__ void o3_velocity_gradient(const T3 &t, const float *__restrict__ u, const float *__restrict__ bv, int g, float G[3][3]) {
+    const int NS = t.NS, NB = t.NB;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int nl = t.nbr[(2 * d) * NS + g], nh = t.nbr[(2 * d + 1) * NS + g];
+        const float dist = 2.0f - (nl < 0 ? 0.5f : 0.f) - (nh < 0 ? 0.5f : 0.f), mi = t.minv[d * NS + g];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float lo = nl >= 0 ? u[c * NS + nl] : bv[c * NB + (-1 - nl)];
+            const float hi = nh >= 0 ? u[c * NS + nh] : bv[c * NB + (-1 - nh)];
+            G[c][d] = ((hi - lo) / dist) * mi;
+        }
+    }
+}
+// ComputeSpatialVelocityGradients (K.cu:6460-6550): Gout[b][c][d][NS] = d u_c / d x_d -- the reference returns one NCDHW tensor per
+// velocity COMPONENT c whose channel is the DIRECTION d (its Python callers name them d_dx, d_dy, d_dz, i.e. read them transposed)
+__global__ void __launch_bounds__(O3_T) k3_velocity_gradients(T3 t, const float *__restrict__ U, const float *__restrict__ Bvel, float *__restrict__ Gout) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, NS = t.NS;
+    if (g >= t.N) return;
+    float G[3][3];
+    o3_velocity_gradient(t, U + (size_t)b * 3 * NS, Bvel + (size_t)b * 3 * t.NB, g, G);
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Gout[(((size_t)b * 3 + c) * 3 + d) * NS + g] = G[c][d];
+}
+// Smagorinsky sub-grid viscosity (k_SGSviscosityIncompressibleSmagorinsky, K.cu:6913-6966) + the environment's prep function
+// (tcf_env.py:441-472): Visc = nu + C delta |S| f_vd^2, |S| = sqrt(2 S_ij S_ij), delta = max_d h_d^2 (the squared longest cell edge),
+// f_vd^2 the squared van Driest damping (envs/tcf/grid.py:101-125) or 1.
+__global__ void __launch_bounds__(O3_T) k3_sgs_viscosity(T3 t, O3Slab sl, const float *__restrict__ U, const float *__restrict__ Bvel, float coef,
+                                                         const float *__restrict__ damp /* [N] or null */, const int32_t *__restrict__ active,
+                                                         float *__restrict__ Visc) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, NS = t.NS;
+    if (g >= t.N || (active && !active[b])) return;
+    float G[3][3];
+    o3_velocity_gradient(t, U + (size_t)b * 3 * NS, Bvel + (size_t)b * 3 * t.NB, g, G);
+    float dsum = 0.f, delta = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = i; j < 3; ++j) {
+            float sij = 0.5f * (G[i][j] + G[j][i]);
+            sij *= sij;
+            dsum += (i != j) ? 2.f * sij : sij;
+        }
+        const float h = 1.0f / t.minv[i * NS + g];
+        delta = fmaxf(delta, h * h);
+    }
+    float v = coef * delta * sqrtf(2.f * dsum);
+    if (damp) v *= damp[g];
+    v += t.viscosity;
+    Visc[(size_t)b * NS + g] = v;
+    bool dirty = false;
+    o3_push(sl, t, Visc, g, v, dirty);            // slabs (B == 1): the assembly reads the z-neighbours' viscosity
+    if (dirty) __threadfence_system();
+}
+
 // P: off = 1/2 (alpha_P / A_P + alpha_N / A_N), diag = -sum (K.cu:4812-4978)
 __global__ void __launch_bounds__(O3_T) k3_pressure_matrix(T3 t, const float *__restrict__ A, const int32_t *__restrict__ active,
                                                            float *__restrict__ Poff, float *__restrict__ Pdiag) {
@@ -262,11 +326,12 @@ __global__ void __launch_bounds__(O3_T) k3_pressure_matrix(T3 t, const float *__
 __global__ void __launch_bounds__(O3_T) k3_hbya(T3 t, O3Slab sl, const float *__restrict__ U, const float *__restrict__ Uprev, const float *__restrict__ Bvel,
                                                 const float *__restrict__ Src, const float *__restrict__ dtv, const int32_t *__restrict__ active,
                                                 const float *__restrict__ Coff, const float *__restrict__ A, float *__restrict__ Hb,
-                                                const float *__restrict__ Tbuoy /* [B][NS] or null */, float beta) {
+                                                const float *__restrict__ Tbuoy /* [B][NS] or null */, float beta,
+                                                const float *__restrict__ Visc /* [B][NS] or null */) {
     const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS, NB = t.NB;
     if (g >= N || (active && !active[b])) return;
     const float *u = U + (size_t)b * 3 * NS, *up = Uprev + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB;
-    const float dt = dtv[b], det = t.det[g], visc = t.viscosity, Ag = A[(size_t)b * NS + g];
+    const float dt = dtv[b], det = t.det[g], visc = Visc ? Visc[(size_t)b * NS + g] : t.viscosity, Ag = A[(size_t)b * NS + g];
     float H[3] = {0.f, 0.f, 0.f}, Sb[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
@@ -864,11 +929,36 @@ static int o3_coop_blocks(fgb_ortho3 *b) {
     return blocks;
 }
 
+// Smagorinsky model on / off (coefficient 0 = off).  `damping`: [N] device floats (squared van Driest factor per owned cell) or NULL;
+// the pointer is kept, not copied.  tcf_env.py:441-472.
+extern "C" int fgb_ortho3_set_sgs(fgb_ortho3 *b, float coefficient, const float *damping) {
+    if (!b) return set_err(FGB_E_ARG, "fgb_ortho3_set_sgs: null argument");
+    b->sgs_coef = coefficient; b->sgs_damp = coefficient != 0.f ? damping : nullptr;
+    return FGB_OK;
+}
+// Refresh the per-cell viscosity from the velocity (the reference's "PRE" prep function); u's halo planes must be current on slabs.
+extern "C" int fgb_ortho3_sgs_viscosity(fgb_ortho3 *b, const float *u, const float *bvel, const int32_t *active, fgb_stream_t s) {
+    if (!b || !u || !bvel) return set_err(FGB_E_ARG, "fgb_ortho3_sgs_viscosity: null argument");
+    if (b->sgs_coef == 0.f) return set_err(FGB_E_ARG, "fgb_ortho3_sgs_viscosity: no model set (fgb_ortho3_set_sgs)");
+    b->launches++;
+    k3_sgs_viscosity<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, b->slab, u, bvel, b->sgs_coef, b->sgs_damp, active, b->visc);
+    LAUNCH_CHECK("k3_sgs_viscosity");
+    return o3_barrier(b, STREAM(s));
+}
+// PISOtorch.ComputeSpatialVelocityGradients (K.cu:6460-6550): grad_out[B][3 (component c)][3 (direction d)][NS] = d u_c / d x_d
+extern "C" int fgb_ortho3_velocity_gradients(fgb_ortho3 *b, const float *u, const float *bvel, float *grad_out, fgb_stream_t s) {
+    if (!b || !u || !bvel || !grad_out) return set_err(FGB_E_ARG, "fgb_ortho3_velocity_gradients: null argument");
+    b->launches++;
+    k3_velocity_gradients<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, u, bvel, grad_out);
+    LAUNCH_CHECK("k3_velocity_gradients");
+    return FGB_OK;
+}
+
 extern "C" int fgb_ortho3_setup_advection(fgb_ortho3 *b, const float *u, const float *bvel, const float *src, const float *dt,
                                           const int32_t *active, fgb_stream_t s) {
     if (!b || !u || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_ortho3_setup_advection: null argument");
     b->launches++;
-    k3_setup_advection<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, b->slab, u, bvel, src, dt, active, b->Coff, b->A, b->rhs, b->sc.T, b->sc.beta);
+    k3_setup_advection<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, b->slab, u, bvel, src, dt, active, b->Coff, b->A, b->rhs, b->sc.T, b->sc.beta, b->sgs_coef != 0.f ? b->visc : nullptr);
     LAUNCH_CHECK("k3_setup_advection");
     return FGB_OK;
 }
@@ -921,7 +1011,7 @@ extern "C" int fgb_ortho3_setup_pressure(fgb_ortho3 *b, const float *u, const fl
         LAUNCH_CHECK("k3_pressure_matrix");
     }
     b->launches += 2;
-    k3_hbya<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->slab, u, b->ures, bvel, src, dt, active, b->Coff, b->A, b->hbya, b->sc.T, b->sc.beta);
+    k3_hbya<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->slab, u, b->ures, bvel, src, dt, active, b->Coff, b->A, b->hbya, b->sc.T, b->sc.beta, b->sgs_coef != 0.f ? b->visc : nullptr);
     LAUNCH_CHECK("k3_hbya");
     { int rc = o3_barrier(b, st); if (rc) return rc; }          // k3_hbya pushed its boundary planes itself
     k3_divergence<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->hbya, bvel, active, b->div);
@@ -964,6 +1054,7 @@ extern "C" int fgb_ortho3_piso_substep(fgb_ortho3 *b, float *u, float *p, const 
     // their end), HbyA and the corrected velocity by their kernels followed by a flag-only barrier.
     if ((rc = o3_exchange(b, u, 3, st))) return rc;
     if (b->sc.T && (rc = fgb_ortho3_advect_scalar(b, u, bvel, dt, active, s))) return rc;
+    if (b->sgs_coef != 0.f && (rc = fgb_ortho3_sgs_viscosity(b, u, bvel, active, s))) return rc;
     if ((rc = fgb_ortho3_setup_advection(b, u, bvel, src, dt, active, s))) return rc;
     // non-orthogonal code path (TCF): zero start; orthogonal path (RBC, non_orthogonal=False): previous velocityResult ("ures")
     if ((rc = fgb_ortho3_solve_advection(b, b->opt.nonortho ? 1 : 0, active, s))) return rc;

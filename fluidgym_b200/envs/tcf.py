@@ -49,8 +49,6 @@ class TCF3DEnv(InitialDomains3D):
                  adaptive_cfl=0.1, step_length=0.6, episode_length=1000, local_obs_window=1, local_reward_weight=0.0, use_marl=True,
                  C_smag=0.0, use_van_driest=False, init_with_noise=False, device="cuda:0", tau_ref=1.0, randomize_initial_state=False,
                  enable_actions=True, domain=None, load_initial_domain=False, initial_domains_path=None):
-        if C_smag != 0.0 or use_van_driest:
-            raise NotImplementedError("sub-grid-scale viscosity (C_smag != 0) is not built; the registered TCF configurations use C_smag = 0")
         if init_with_noise:
             raise NotImplementedError("init_with_noise needs the reference's optional simplex-noise extension; start from a state instead")
         self.n_envs = int(n_envs)
@@ -91,6 +89,15 @@ class TCF3DEnv(InitialDomains3D):
         self.y_obs_bottom_idx = int(torch.argmin(torch.abs(cc[1, 0, :, 0] - y_obs)))
         self.y_obs_top_idx = self.y - self.y_obs_bottom_idx                # tcf_env.py:1141 (uses resolution_y, as the reference)
         self.cell_size = torch.from_numpy(domain.det.copy()).to(dev)      # [nz, ny, nx]
+        # Smagorinsky sub-grid viscosity with optional van Driest wall damping (tcf_env.py:441-472, envs/tcf/grid.py:75-125)
+        self.C_smag, self.use_van_driest = float(C_smag), bool(use_van_driest)
+        if self.C_smag != 0.0:
+            damp = None
+            if self.use_van_driest:
+                wd_cells = (1 - torch.abs(cc[1].to(torch.float32))) * self.u_wall / torch.tensor([self.viscosity], dtype=torch.float32)
+                vd = 1 - torch.exp(-wd_cells * (1.0 / 25.0))
+                damp = (vd * vd).numpy()
+            self.solver.set_sgs(self.C_smag, damp)
         # initial state: Reichardt mean profile (envs/tcf/grid.py:83-98)
         wd = (1 - torch.abs(cc[1, 0, :, 0])) * self.u_wall / torch.tensor([self.viscosity], dtype=torch.float32)
         k = 0.41

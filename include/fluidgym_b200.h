@@ -333,6 +333,17 @@ typedef struct fgb_ortho3_scalar {
 int fgb_ortho3_set_scalar(fgb_ortho3 *b, const fgb_ortho3_scalar *sc);
 /* SetupAdvectionMatrix(forPassiveScalar) + SetupAdvectionScalar + SolveLinear(BiCGStab, zero start): T <- C_s(u)^-1 rhs_s(T) */
 int fgb_ortho3_advect_scalar(fgb_ortho3 *b, const float *u, const float *bvel, const float *dt, const int32_t *active, fgb_stream_t s);
+/* Smagorinsky sub-grid viscosity (PISOtorch.SGSviscosityIncompressibleSmagorinsky, PISO_multiblock_cuda_kernel.cu:6913-7035, as
+ * used by the channel-flow "PRE" prep function, envs/tcf/tcf_env.py:441-472): nu_cell = nu + coefficient * delta * |S| * damping,
+ * delta = squared longest cell edge, |S| = sqrt(2 S_ij S_ij).  coefficient 0 switches the model off.  damping: [N] device floats
+ * (squared van Driest factor, envs/tcf/grid.py:101-125) or NULL; kept by pointer.  With a model set, fgb_ortho3_piso_substep /
+ * _sim_step refresh the per-cell viscosity (buffer "visc") from the incoming velocity before every substep. */
+int fgb_ortho3_set_sgs(fgb_ortho3 *b, float coefficient, const float *damping);
+int fgb_ortho3_sgs_viscosity(fgb_ortho3 *b, const float *u, const float *bvel, const int32_t *active, fgb_stream_t s);
+/* PISOtorch.ComputeSpatialVelocityGradients (PISO_multiblock_cuda_kernel.cu:6460-6550; Q criterion tcf_env.py:586-644, vorticity
+ * fluid_env.py:577-656): grad_out [B][3 component c][3 direction d][NS] = d u_c / d x_d -- the reference's list index is the
+ * component and the tensor channel the direction (its kernel, K.cu:6470-6480), the layout kept here */
+int fgb_ortho3_velocity_gradients(fgb_ortho3 *b, const float *u, const float *bvel, float *grad_out, fgb_stream_t s);
 int fgb_ortho3_make_divergence_free(fgb_ortho3 *b, float *u, float *p, const float *bvel, int max_iter, fgb_stream_t s);
 /* rows: [2][n_row] cells of the first / last wall-normal layer; d_lo, d_hi their wall distances.  With rows != NULL the
  * channel forcing G_x = nu/2 (<u>_lo/d_lo + <u>_hi/d_hi) (envs/tcf/grid.py:128-163) is refreshed before every substep. */

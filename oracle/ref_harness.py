@@ -123,6 +123,8 @@ class OpTracer:
                     for bi, blk in enumerate(dom.getBlocks()):
                         self._rec(f"in_b{bi}_u", blk.velocity)
                         self._rec(f"in_b{bi}_p", blk.pressure)
+                        if blk.hasViscosity():                       # per-cell viscosity set by a "PRE" prep function (SGS model)
+                            self._rec(f"in_b{bi}_viscosity", blk.viscosity)
                         if dom.hasPassiveScalar():
                             self._rec(f"in_b{bi}_s", blk.passiveScalar)
                         for f in range(2 * dom.getSpatialDims()):
@@ -207,6 +209,7 @@ def main():
     ap.add_argument("--res-z", type=int, default=None,
                     help="Airfoil3D: spanwise resolution (class attribute AirfoilEnvBase._res_z, 96 in the reference) -- a smaller value "
                          "makes the golden run affordable; the reference's code is untouched")
+    ap.add_argument("--gradients", action="store_true", help="also record ComputeSpatialVelocityGradients of the state after the env steps")
     ap.add_argument("--save-domain-only", action="store_true",
                     help="reset, advance --env-steps steps, write the domain with the reference's own save_domain() and exit")
     args = ap.parse_args()
@@ -310,6 +313,11 @@ def main():
         sst = snapshot_state(env)
         np.savez_compressed(os.path.join(args.out, f"{tag}_state_step{i}.npz"), **sst)
     step_out["actions"] = np.stack(actions)
+    if args.gradients:                                   # PISOtorch.ComputeSpatialVelocityGradients of the final state
+        env._domain.UpdateDomainData()
+        grads = PISOtorch.ComputeSpatialVelocityGradients(env._domain)
+        np.savez_compressed(os.path.join(args.out, f"{tag}_gradients.npz"),
+                            **{f"b{bi}_d{d}": t2n(g) for bi, gb in enumerate(grads) for d, g in enumerate(gb)})
     np.savez_compressed(os.path.join(args.out, f"{tag}_steps.npz"), **step_out)
     np.savez_compressed(os.path.join(args.out, f"{tag}_trace.npz"), **tracer.records)
     for j in (0, 1, len(per_sim) - 1):

@@ -18,6 +18,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    sgs = len(sys.argv) > 2 and sys.argv[2] == "sgs"          # Smagorinsky model with wall damping on: the viscosity halo exchange
     G = os.path.join(ROOT, "tests", "golden")
     g, fx = np.load(os.path.join(G, "tcf32_geometry.npz")), np.load(os.path.join(G, "tcf32_substep0.npz"))
     visc = json.load(open(os.path.join(G, "tcf32_meta.json")))["viscosity"]
@@ -25,6 +26,11 @@ def main():
     dt = float(fx["dt"][0])
     slab = SlabPISO3D(dom, rank, world, f"cuda:{local}")
     slab.load_global(fx["u_in"], fx["p_in"], {2: fx["bvel2"], 3: fx["bvel3"]})
+    damp = None
+    if sgs:
+        vd = 1 - np.exp(-(1 - np.abs(dom.cell_centres()[1].astype(np.float32))) * np.float32(180.0 / 25.0))
+        damp = (vd * vd).astype(np.float32).reshape(-1)
+        slab.set_sgs(0.1, damp)
     src = torch.zeros(1, 4, device="cuda")
     src[0, :3] = torch.from_numpy(fx["src"]).cuda()
     for _ in range(steps):
@@ -48,13 +54,15 @@ def main():
         ref.u.copy_(torch.from_numpy(fx["u_in"]).cuda().unsqueeze(0))
         ref.p.copy_(torch.from_numpy(fx["p_in"]).cuda().unsqueeze(0))
         ref.bvel.copy_(torch.from_numpy(np.concatenate([fx["bvel2"], fx["bvel3"]], axis=1)).cuda().unsqueeze(0))
+        if sgs:
+            ref.set_sgs(0.1, damp)
         for _ in range(steps):
             ref.piso_substep(dt, src)
         torch.cuda.synchronize()
         eu = float((u_all - ref.u[0]).norm() / ref.u[0].norm())
         ep = float((p_all - ref.p[0]).norm() / ref.p[0].norm())
         its_ref = ref.buffer("iters")[0].tolist()
-        print(json.dumps({"world": world, "steps": steps, "rel_err_u": eu, "rel_err_p": ep, "iters": its, "iters_single": its_ref, "slab_error": err}))
+        print(json.dumps({"world": world, "steps": steps, "sgs": sgs, "rel_err_u": eu, "rel_err_p": ep, "iters": its, "iters_single": its_ref, "slab_error": err}))
         ok = ok and eu < 1e-5 and ep < 1e-3 and its[:5] == its_ref[:5]
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

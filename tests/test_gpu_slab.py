@@ -12,9 +12,9 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-def _run(nproc, port):
+def _run(nproc, port, *extra):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tests", "slab_worker.py"), "3"]
+           "--master-port", str(port), os.path.join(ROOT, "tests", "slab_worker.py"), "3", *extra]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     print(out.stdout[-2000:], out.stderr[-2000:])
     return out.stdout
@@ -26,7 +26,13 @@ def test_slab_protocol_on_one_rank_matches_plain_solver():
     assert "SLAB_OK" in _run(1, 29630)
 
 
+def test_slab_protocol_with_sgs_viscosity_matches_plain_solver():
+    """Smagorinsky model on: the per-cell viscosity is pushed into the z-neighbours' halo planes before the assembly reads it"""
+    assert "SLAB_OK" in _run(1, 29632, "sgs")
+
+
 def test_two_slabs_match_single_gpu():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     assert "SLAB_OK" in _run(2, 29631)
+    assert "SLAB_OK" in _run(2, 29633, "sgs")
