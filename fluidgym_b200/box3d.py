@@ -8,6 +8,7 @@ periodic or closed (``envs/tcf/grid.py:166-272``), compiled into the flat tables
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -100,6 +101,24 @@ class Box3DDomain:
         return (c * f32(0.125)).astype(f32)
 
 
+def structured_neighbours(nx, ny, nz, closed, halo=False):
+    """The neighbour arithmetic of the Krylov kernels (``o3_nbrs``, csrc/ortho3_b200.cuh) on the (z, y, x) cell ordering:
+    [6, N] indices, -1 for a prescribed face, halo planes at N.. / N + P.. for slabs.  Host mirror used by the tests to pin
+    the formula to the tables (``Box3DDomain.nbr`` / ``SlabTables.nbr``)."""
+    P, N = nx * ny, nx * ny * nz
+    g = np.arange(N, dtype=np.int64)
+    i, j, k = g % nx, (g // nx) % ny, g // P
+    cx, cy, cz = (bool(c) for c in closed)
+    n = np.empty((6, N), dtype=np.int64)
+    n[0] = np.where(i > 0, g - 1, -1 if cx else g + (nx - 1))
+    n[1] = np.where(i < nx - 1, g + 1, -1 if cx else g - (nx - 1))
+    n[2] = np.where(j > 0, g - nx, -1 if cy else g + (ny - 1) * nx)
+    n[3] = np.where(j < ny - 1, g + nx, -1 if cy else g - (ny - 1) * nx)
+    n[4] = np.where(k > 0, g - P, N + (g - k * P) if halo else (-1 if cz else g + (nz - 1) * P))
+    n[5] = np.where(k < nz - 1, g + P, N + P + (g - k * P) if halo else (-1 if cz else g - (nz - 1) * P))
+    return n
+
+
 class BatchedPISO3D:
     """State + solver for ``n_envs`` copies of one Box3DDomain: ``u [B,3,N]``, ``p [B,N]``, ``bvel [B,3,NB]``."""
 
@@ -118,6 +137,9 @@ class BatchedPISO3D:
         self._tab["minv"] = torch.from_numpy(np.ascontiguousarray(dom.minv.reshape(3, -1))).to(dev)
         self._tab["det"] = torch.from_numpy(np.ascontiguousarray(dom.det.reshape(-1))).to(dev)
         self.tables = native.Ortho3Tables(dom.N, dom.NB, dom.visc, *[self._tab[k].data_ptr() for k in ("nbr", "minv", "det", "b_minv", "b_det")])
+        if os.environ.get("FGB_O3_BOX", "1") != "0":          # structured neighbour arithmetic in the Krylov kernels (0: nbr table)
+            self.tables.nx, self.tables.ny, self.tables.nz = dom.nx, dom.ny, dom.nz
+            self.tables.closed = sum(1 << d for d in range(3) if dom.closed[d])
         self.options = native.Options(corrector_steps, 1, 1, int(bool(non_orthogonal)), advection_tol, pressure_tol, max_iter, 0)
         nbytes = self.lib.fgb_ortho3_workspace_bytes(C.byref(self.tables), self.B)
         self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
@@ -360,6 +382,9 @@ class SlabPISO3D:
         self._tab = {k: torch.from_numpy(np.ascontiguousarray(getattr(tb, k))).to(dev) for k in ("nbr", "minv", "det", "b_minv", "b_det")}
         self.tables = native.Ortho3Tables(tb.N, tb.NB, dom.visc, *[self._tab[k].data_ptr() for k in ("nbr", "minv", "det", "b_minv", "b_det")],
                                           tb.NS, dom.N, tb.P)
+        if os.environ.get("FGB_O3_BOX", "1") != "0":
+            self.tables.nx, self.tables.ny, self.tables.nz = dom.nx, dom.ny, tb.nzl
+            self.tables.closed = sum(1 << d for d in range(2) if dom.closed[d])      # z: slab halo planes
         self.options = native.Options(corrector_steps, 1, 1, 1, advection_tol, pressure_tol, max_iter, 0)
         ws_bytes = self.lib.fgb_ortho3_workspace_bytes(C.byref(self.tables), 1)
 

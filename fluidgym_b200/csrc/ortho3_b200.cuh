@@ -406,11 +406,32 @@ __global__ void k3_copy_active(const float *__restrict__ src, float *__restrict_
 // ------------------------------------------------------------------------------------------------
 // cooperative Krylov kernels
 // ------------------------------------------------------------------------------------------------
+// neighbour cells of g across the six faces (< 0: prescribed face).  Structured boxes (t.nx > 0): index arithmetic on the
+// (z, y, x) ordering -- periodic wrap, closed ends, slab halo planes [N, N + P) / [N + P, NS) -- instead of six table loads that
+// every gather would depend on.
+__device__ __forceinline__ void o3_nbrs(const T3 &t, int g, int (&n)[6]) {
+    if (t.nx > 0) {
+        const int nx = t.nx, ny = t.ny, P = nx * ny;
+        const int q = g / nx, i = g - q * nx, k = q / ny, j = q - k * ny;
+        const bool cx = t.closed & 1, cy = t.closed & 2, cz = t.closed & 4, halo = t.NS > t.N;
+        n[0] = i > 0 ? g - 1 : (cx ? -1 : g + (nx - 1));
+        n[1] = i < nx - 1 ? g + 1 : (cx ? -1 : g - (nx - 1));
+        n[2] = j > 0 ? g - nx : (cy ? -1 : g + (ny - 1) * nx);
+        n[3] = j < ny - 1 ? g + nx : (cy ? -1 : g - (ny - 1) * nx);
+        n[4] = k > 0 ? g - P : (halo ? t.N + (g - k * P) : (cz ? -1 : g + (t.nz - 1) * P));
+        n[5] = k < t.nz - 1 ? g + P : (halo ? t.N + P + (g - k * P) : (cz ? -1 : g - (t.nz - 1) * P));
+    } else {
+#pragma unroll
+        for (int f = 0; f < 6; ++f) n[f] = t.nbr[f * t.NS + g];
+    }
+}
 __device__ __forceinline__ float o3_row(const T3 &t, int g, const float *__restrict__ off, const float *__restrict__ dg, const float *x) {
     const int NS = t.NS;
+    int n[6];
+    o3_nbrs(t, g, n);
     float s = dg[g] * x[g];
 #pragma unroll
-    for (int f = 0; f < 6; ++f) { const int n = t.nbr[f * NS + g]; if (n >= 0) s += off[f * NS + g] * __ldcg(&x[n]); }
+    for (int f = 0; f < 6; ++f) if (n[f] >= 0) s += off[f * NS + g] * __ldcg(&x[n[f]]);
     return s;
 }
 
@@ -518,13 +539,12 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
         o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, dirty, red);
         bool done[3] = {true, true, true}; int used[3] = {-1, -1, -1}; float fin[3] = {0.f, 0.f, 0.f}, rho[3] = {1.f, 1.f, 1.f}, alpha[3] = {1.f, 1.f, 1.f}, omega[3] = {1.f, 1.f, 1.f};
         for (int c = 0; c < NC; ++c) { fin[c] = sqrtf(acc[c]) * norm; used[c] = -1; done[c] = fin[c] < tol; }
+        // rho_0 = <r^, r> = <r, r> (r^ = r at the start: the same products in the same order as the sum above); later rho is reduced
+        // together with the residual norm that closes the previous iteration (same operands): 5 grid-wide exchanges per iteration
+        float rho_next[3] = {acc[0], acc[1], acc[2]};
         for (int i = 0; i < maxit && !(done[0] && done[1] && done[2]); ++i) {
-            for (int k = 0; k < 6; ++k) acc[k] = 0.f;
-            for (int c = 0; c < NC; ++c) if (!done[c])
-                for (int g = tid; g < N; g += nth) acc[c] += rw[c][g] * r[c][g];
-            o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, dirty, red);
             for (int c = 0; c < NC; ++c) if (!done[c]) {
-                const float rhop = rho[c]; rho[c] = acc[c];
+                const float rhop = rho[c]; rho[c] = rho_next[c];
                 if (i > 0) {
                     const float beta = (rho[c] / rhop) * (alpha[c] / omega[c]);
                     for (int g = tid; g < N; g += nth) { const float pn = r[c][g] + beta * (p[c][g] - omega[c] * v[c][g]); p[c][g] = pn; o3_push(sl, t, p[c], g, pn, dirty); }
@@ -566,12 +586,14 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
                     x[c][g] += omega[c] * rg;
                     const float rr = rg - omega[c] * tt[c][g];
                     acc2[c] += rr * rr;
+                    acc2[3 + c] += rw[c][g] * rr;
                     r[c][g] = rr;
                 }
             }
             o3_grid_sum<6>(grid, sl, acc2, part, rcount, arc, dirty, red);
             for (int c = 0; c < NC; ++c) if (!done[c]) {
                 const float nr = sqrtf(acc2[c]) * norm;
+                rho_next[c] = acc2[3 + c];
                 fin[c] = nr;
                 if (nr < tol) { done[c] = true; used[c] = i + 1; }
             }
@@ -740,8 +762,10 @@ __global__ void __launch_bounds__(O3_CT) k3_cg_fused(T3 t, O3Slab sl, int B, con
                     for (int g = tid; g < N; g += nth) {
                         const float pg = o3_pnew(r, p, beta, g);
                         float a = dg[g] * pg;
+                        int nb6[6];
+                        o3_nbrs(t, g, nb6);
 #pragma unroll
-                        for (int fc = 0; fc < 6; ++fc) { const int n = t.nbr[fc * NS + g]; if (n >= 0) a += off[fc * NS + g] * o3_pnew(r, p, beta, n); }
+                        for (int fc = 0; fc < 6; ++fc) if (nb6[fc] >= 0) a += off[fc * NS + g] * o3_pnew(r, p, beta, nb6[fc]);
                         p2[g] = pg; ap[g] = a; acc[0] += pg * a;
                     }
                     pc = p2;

@@ -1788,6 +1788,388 @@ __global__ void __launch_bounds__(T, MINB) k_cg_strip(Tab t, const float *__rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// Krylov solvers, implementation 12: the strip kernel with TWO environments per cluster, software-interleaved.
+// k_cg_strip is one dependent chain per iteration (SpMV -> all-reduce -> update -> all-reduce -> direction): while a CTA waits
+// for a cluster exchange (~850 cycles, twice per iteration) its SM idles, and co-resident CTAs do not fix that (their compute
+// phases collide as often as they interleave, profiles/r02_cg_strip_development.md).  Here every CTA holds the strips of two
+// independent systems (half the rows per thread each, so a cluster spans twice the CTAs) and runs them in a fixed order:
+//     SpMV(e0) -> start <p,Ap>(e0) -> SpMV(e1) -> start <p,Ap>(e1) -> finish(e0), x/r update, start <r,r>(e0) -> finish(e1), ...
+// An exchange is split in a non-blocking start (warp partials -> the LAST arriving warp of the CTA adds them in fixed order and
+// pushes one value to every CTA of the cluster) and a finish (wait on the transaction barrier, add the CS totals in rank
+// order), so the flight time of one system's reduction is covered by the other system's arithmetic.  Arithmetic, operation
+// order and stopping rules per system are those of k_cg_strip (bit-identical results); the two systems converge independently,
+// the faster one idles until both are done.  Same tables (strip_plan.py) with the shape (T, CPT) of this kernel.
+// ------------------------------------------------------------------------------------------------
+template <int E> struct EnvTag { static constexpr int value = E; };
+
+template <int T, int CPT, int CS>
+__global__ void __launch_bounds__(T, 1) k_cg_strip2(Tab t, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
+                                                    const float *__restrict__ Rhs, float *__restrict__ Xout, int B,
+                                                    int maxit, float tol, int zero_init, int reset_steps, int slot,
+                                                    const int32_t *__restrict__ active, int32_t *__restrict__ iters,
+                                                    float *__restrict__ resid, unsigned long long *__restrict__ iter_total,
+                                                    int flags, float *__restrict__ mean_out, float *__restrict__ best) {
+    static_assert(T % 32 == 0, "whole warps only");
+    constexpr int NW = T / 32;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const int b0 = 2 * (int)(blockIdx.x / CS);
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    bool on[2];
+    on[0] = !active || active[b0];
+    on[1] = b0 + 1 < B && (!active || active[b0 + 1]);
+    if (!on[0] && !on[1]) return;                      // (uniform over the cluster)
+    extern __shared__ __align__(16) float smem[];
+    const int N = t.N, SL = t.st_slots, G = t.st_gmax;
+    // per environment: co4 [CPT][T] float4 | cdg [CPT][T] | vs [SL] | rs [G] | red [2][CS] | wpart [2][NW]   (ENVF floats, multiple of 4)
+    const int ENVF = (5 * CPT * T + SL + G + 2 * CS + 2 * NW + 3) & ~3;
+    unsigned long long *mb = (unsigned long long *)(smem + 2 * ENVF);      // [e][which]: cluster transaction barriers
+    unsigned int *cnt = (unsigned int *)(mb + 4);                          // [e][which]: warps of this CTA that have delivered their partial
+    uint2 *rex = (uint2 *)(cnt + 4);                   // [st_remax] {k | dest rank << 8, cluster address of the destination in rs of environment 0}
+    uint2 *lex = rex + t.st_remax;                     // [st_lemax] {owner's slot, mirror slot} in vs
+    const float norm = 1.0f / sqrtf((float)N);
+    const uint32_t mb_addr = smem_u32(mb);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const int4 th0 = reinterpret_cast<const int4 *>(t.st_thread)[((size_t)rank * T + tid) * 2];
+    const int4 th1 = reinterpret_cast<const int4 *>(t.st_thread)[((size_t)rank * T + tid) * 2 + 1];
+    const int S = th0.y;
+    const int vp_off = 5 * CPT * T + th0.x;            // slot of row 0 of this thread, relative to the environment's base
+    const int re_off = th0.w & 0xffff, re_cnt = (th0.w >> 16) & 0xff;
+    const int n_lex = t.st_cnt[4 * rank + 2];
+    const int rg_off = 5 * CPT * T + SL + th1.y;       // first remote ghost row of this thread in the receive buffer
+    const uint32_t rm = (uint32_t)th1.z;               // remote ghost rows of this thread (bit k)
+    const int32_t *cellp = t.st_cell + ((size_t)rank * T + tid) * CPT;
+    const uint32_t bytesA = CS * 4u, bytesB = CS * 4u + 4u * (uint32_t)t.st_cnt[4 * rank];
+    if (tid == 0) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            mbar_init(mb_addr + 16u * e, 1); mbar_init(mb_addr + 16u * e + 8u, 1);
+            cnt[2 * e] = 0u; cnt[2 * e + 1] = 0u;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { mbar_arrive_expect_tx(mb_addr + 16u * e, bytesA); mbar_arrive_expect_tx(mb_addr + 16u * e + 8u, bytesB); }
+    }
+    {
+        const uint32_t rs_addr = smem_u32(smem + 5 * CPT * T + SL);
+        for (int e = tid; e < t.st_cnt[4 * rank + 1]; e += T) {
+            const int32_t a = t.st_rexp[((size_t)rank * t.st_remax + e) * 2], d = t.st_rexp[((size_t)rank * t.st_remax + e) * 2 + 1];
+            rex[e] = make_uint2((uint32_t)a, mapa_u32(rs_addr + 4u * (uint32_t)d, (uint32_t)a >> 8));
+        }
+    }
+    for (int e = tid; e < n_lex; e += T)
+        lex[e] = make_uint2((uint32_t)t.st_lexp[((size_t)rank * t.st_lemax + e) * 2], (uint32_t)t.st_lexp[((size_t)rank * t.st_lemax + e) * 2 + 1]);
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+        for (int i = tid; i < SL + G; i += T) smem[e * ENVF + 5 * CPT * T + i] = 0.f;   // vs and rs (pads, dead slots)
+
+    float x[2][CPT], r[2][CPT], ap[2][CPT];            // the search directions live in vs only
+    uint32_t par[2][2] = {{0u, 0u}, {0u, 0u}};
+    auto load_env = [&](auto E) {
+        constexpr int e = decltype(E)::value;
+        const int b = b0 + e;
+        const float *off = Poff + (size_t)b * 4 * N, *dg = Pdiag + (size_t)b * N, *f = Rhs + (size_t)b * N;
+        const float *xo = Xout + (size_t)b * N;
+        float4 *co4 = reinterpret_cast<float4 *>(smem + e * ENVF);
+        float *cdg = smem + e * ENVF + 4 * CPT * T;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const int c = cellp[k];
+            const bool real = c >= 0;
+            const int g = real ? c : (c <= -2 ? -2 - c : 0);
+            float co[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int ff = (th0.z >> (2 * d)) & 3;
+                const int nb = real ? t.nbr[ff * N + g] : -1;
+                if (flags & 1) co[d] = nb >= 0 ? off[(int)t.rev[ff * N + g] * N + nb] : 0.f;
+                else co[d] = nb >= 0 ? off[ff * N + g] : 0.f;
+            }
+            co4[k * T + tid] = make_float4(co[0], co[1], co[2], co[3]);
+            cdg[k * T + tid] = real ? dg[g] : 0.f;
+            x[e][k] = (c != -1 && !zero_init) ? xo[g] : 0.f;   // ghost replicas start from their owner's value
+            r[e][k] = real ? f[g] : 0.f;
+            ap[e][k] = 0.f;
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) { x[0][k] = r[0][k] = ap[0][k] = 0.f; x[1][k] = r[1][k] = ap[1][k] = 0.f; }
+    if (on[0]) load_env(EnvTag<0>{});
+    if (on[1]) load_env(EnvTag<1>{});
+    const uint32_t peer_smem = mapa_u32(smem_u32(smem), (uint32_t)(lane < CS ? lane : 0));
+    const uint32_t peer_mb = mapa_u32(mb_addr, (uint32_t)(lane < CS ? lane : 0));
+    cluster_sync_all();                                // barriers initialised, shared memory filled everywhere
+
+    // ---- exchange, split.  which: 0 = A (<p,Ap>, also non-zero count, mean), 1 = B (<r,r> + ghost residuals) ----------------------
+    auto xstart = [&](auto E, auto W, float a0) {
+        constexpr int e = decltype(E)::value;
+        constexpr uint32_t which = decltype(W)::value;
+        float *red = smem + e * ENVF + 5 * CPT * T + SL + G;
+        volatile float *wpart = red + 2 * CS;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(FULL, a0, o);
+        unsigned int last = 0u;
+        if (lane == 0) {
+            wpart[which * NW + warp] = a0;
+            __threadfence_block();
+            last = atomicInc(&cnt[2 * e + which], (unsigned int)(NW - 1)) == (unsigned int)(NW - 1);
+        }
+        last = __shfl_sync(FULL, last, 0);
+        if (last) {                                    // every warp of this CTA has delivered: add in fixed order, one value to every CTA
+            __threadfence_block();
+            float s1 = lane < NW ? wpart[which * NW + lane] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(FULL, s1, o);
+            if (lane < CS)
+                st_async_f32(peer_smem + 4u * (uint32_t)(e * ENVF + 5 * CPT * T + SL + G + which * CS + rank), s1, peer_mb + 16u * e + 8u * which);
+        }
+    };
+    auto xfinish = [&](auto E, auto W) -> float {
+        constexpr int e = decltype(E)::value;
+        constexpr uint32_t which = decltype(W)::value;
+        const float *red = smem + e * ENVF + 5 * CPT * T + SL + G;
+        mbar_wait_sleep(mb_addr + 16u * e + 8u * which, par[e][which]); par[e][which] ^= 1u;
+        float s0 = 0.f;
+#pragma unroll
+        for (int q = 0; q < CS; ++q) s0 += red[which * CS + q];
+        if (tid == 0) mbar_arrive_expect_tx(mb_addr + 16u * e + 8u * which, which ? bytesB : bytesA);   // re-arm (see k_cg_cluster_mb)
+        return s0;
+    };
+    auto spmv = [&](auto E) -> float {                 // ap = P v for the vector published in vs; returns this thread's part of <v, P v>
+        constexpr int e = decltype(E)::value;
+        const float4 *co4 = reinterpret_cast<const float4 *>(smem + e * ENVF);
+        const float *cdg = smem + e * ENVF + 4 * CPT * T, *vp = smem + e * ENVF + vp_off;
+        float a0 = 0.f, a1 = 0.f;
+        float vsouth = vp[-S], vc = vp[0];
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const float *row = vp + k * S;
+            const float vnorth = row[S];
+            const float4 o = co4[k * T + tid];
+            float s = cdg[k * T + tid] * vc;
+            s = fmaf(o.x, row[-1], s);
+            s = fmaf(o.y, row[1], s);
+            s = fmaf(o.z, vsouth, s);
+            s = fmaf(o.w, vnorth, s);
+            ap[e][k] = s;
+            if (k & 1) a1 = fmaf(vc, s, a1); else a0 = fmaf(vc, s, a0);
+            vsouth = vc; vc = vnorth;
+        }
+        return a0 + a1;
+    };
+    auto mirror = [&]() {                              // after vectors have been stored: owners' values -> local ghost slots, both environments
+        __syncthreads();
+        if (n_lex) {                                   // (uniform over the CTA)
+            for (int i = tid; i < n_lex; i += T) {
+                const uint2 ex = lex[i];
+                float *v0 = smem + 5 * CPT * T, *v1 = v0 + ENVF;
+                v0[ex.y] = v0[ex.x]; v1[ex.y] = v1[ex.x];
+            }
+            __syncthreads();
+        }
+    };
+    auto store_x = [&](auto E) {
+        constexpr int e = decltype(E)::value;
+        float *vp = smem + e * ENVF + vp_off;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) vp[k * S] = x[e][k];
+    };
+    auto store_direction = [&](auto E, float beta) {   // p = r + beta p in place in vs; remote ghost rows use the residual they received
+        constexpr int e = decltype(E)::value;
+        float *vp = smem + e * ENVF + vp_off;
+        if (rm) {
+            const float *rgp = smem + e * ENVF + rg_off;
+            int n = 0;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) if (rm & (1u << k)) r[e][k] = rgp[n++];
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) ap[e][k] = vp[k * S];      // (loads first; A p is dead here)
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) vp[k * S] = fmaf(beta, ap[e][k], r[e][k]);
+        if (rm) {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) if (rm & (1u << k)) r[e][k] = 0.f;
+        }
+    };
+    auto residual_start = [&](auto E) {                // exchange B: <r,r> + residuals of the remotely mirrored rows
+        constexpr int e = decltype(E)::value;
+        if (re_cnt) {                                  // the export list of a thread is sorted by row: rows stay compile-time indices (registers)
+            int j = 0;
+            uint2 ex = rex[re_off];
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                while (j < re_cnt && (int)(ex.x & 0xff) == k) {
+                    st_async_f32(ex.y + 4u * (uint32_t)(e * ENVF), r[e][k], mapa_u32(mb_addr + 16u * e + 8u, ex.x >> 8));
+                    if (++j < re_cnt) ex = rex[re_off + j];
+                }
+            }
+        }
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPT; k += 2) { a0 = fmaf(r[e][k], r[e][k], a0); if (k + 1 < CPT) a1 = fmaf(r[e][k + 1], r[e][k + 1], a1); }
+        xstart(E, EnvTag<1>{}, a0 + a1);
+    };
+
+    bool run[2] = {false, false}, solved[2] = {false, false};
+    int used[2] = {-1, -1}, it[2] = {0, 0}, best_it[2] = {-1, -1}, rising[2] = {0, 0}, until_reset[2];
+    float fin[2] = {0.f, 0.f}, rho[2] = {0.f, 0.f}, bestc[2] = {0.f, 0.f}, lastc[2] = {0.f, 0.f};
+    until_reset[0] = until_reset[1] = reset_steps > 0 ? reset_steps - 1 : -1;   // iterations left before the next residual reset
+
+    auto count_start = [&](auto E) {
+        constexpr int e = decltype(E)::value;
+        float nz = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) nz += (r[e][k] != 0.f) ? 1.f : 0.f;
+        xstart(E, EnvTag<0>{}, nz);
+    };
+    auto count_finish = [&](auto E) {
+        constexpr int e = decltype(E)::value;
+        const float nzt = xfinish(E, EnvTag<0>{});
+        run[e] = solved[e] = nzt > 0.f;
+        if (!run[e]) {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) x[e][k] = 0.f;
+        }
+    };
+    if (on[0]) count_start(EnvTag<0>{});
+    if (on[1]) count_start(EnvTag<1>{});
+    if (on[0]) count_finish(EnvTag<0>{});
+    if (on[1]) count_finish(EnvTag<1>{});
+
+    auto initial_residual = [&](auto E) {              // r = f - P x0 (x0 published in vs)
+        constexpr int e = decltype(E)::value;
+        (void)spmv(E);
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) r[e][k] -= ap[e][k];
+    };
+    auto save_best = [&](auto E) {
+        constexpr int e = decltype(E)::value;
+        float *bestp = best + ((size_t)(b0 + e) * CS + rank) * T * CPT + tid;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) bestp[k * T] = x[e][k];
+    };
+    if (run[0] || run[1]) {
+        if (!zero_init) {
+            if (run[0]) store_x(EnvTag<0>{});
+            if (run[1]) store_x(EnvTag<1>{});
+            mirror();
+            if (run[0]) initial_residual(EnvTag<0>{});
+            if (run[1]) initial_residual(EnvTag<1>{});
+            __syncthreads();                           // everyone is done reading vs (= x) before it becomes p
+        }
+        if (run[0]) { save_best(EnvTag<0>{}); residual_start(EnvTag<0>{}); }
+        if (run[1]) { save_best(EnvTag<1>{}); residual_start(EnvTag<1>{}); }
+        if (run[0]) { rho[0] = xfinish(EnvTag<0>{}, EnvTag<1>{}); store_direction(EnvTag<0>{}, 0.f); }   // p = r (vs holds zeros or x0: 0 * finite + r)
+        if (run[1]) { rho[1] = xfinish(EnvTag<1>{}, EnvTag<1>{}); store_direction(EnvTag<1>{}, 0.f); }
+        mirror();
+    }
+
+    // one system's share of the three phases of an iteration
+    auto phase1 = [&](auto E) { xstart(E, EnvTag<0>{}, spmv(E)); };
+    auto phase2 = [&](auto E) {
+        constexpr int e = decltype(E)::value;
+        const float pap = xfinish(E, EnvTag<0>{});
+        const float alpha = rho[e] / pap;
+        const float *vp = smem + e * ENVF + vp_off;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            x[e][k] = fmaf(alpha, vp[k * S], x[e][k]);
+            r[e][k] = fmaf(-alpha, ap[e][k], r[e][k]);
+        }
+        residual_start(E);
+    };
+    auto phase3 = [&](auto E) {
+        constexpr int e = decltype(E)::value;
+        const float rr2 = xfinish(E, EnvTag<1>{});
+        const float crit = sqrtf(rr2) * norm;
+        const int i = it[e];
+        if (!isfinite(crit)) { used[e] = i; fin[e] = crit; run[e] = false; return; }
+        if (i == 0 || crit < bestc[e]) { bestc[e] = crit; best_it[e] = i; save_best(E); }
+        if (i > 0 && crit >= lastc[e]) ++rising[e]; else rising[e] = 0;
+        lastc[e] = crit; used[e] = i; fin[e] = crit;
+        if (crit < tol) { run[e] = false; return; }
+        if (i == maxit - 1 || rising[e] >= 100) {
+            const float *bestp = best + ((size_t)(b0 + e) * CS + rank) * T * CPT + tid;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) x[e][k] = bestp[k * T];
+            used[e] = best_it[e]; fin[e] = bestc[e];
+            run[e] = false; return;
+        }
+        const float beta = rr2 / rho[e];
+        rho[e] = rr2;
+        store_direction(E, beta);
+        it[e] = i + 1;
+    };
+    auto reset_a = [&](auto E) { constexpr int e = decltype(E)::value; until_reset[e] = reset_steps; xstart(E, EnvTag<0>{}, 0.f); };   // keeps A / B alternating
+    auto reset_b = [&](auto E) { (void)xfinish(E, EnvTag<0>{}); store_x(E); };
+    auto reset_c = [&](auto E) {                       // r = f - P x ; rho = <r,r>   (CG.cu:281-302).  x of the ghost rows is already there.
+        constexpr int e = decltype(E)::value;
+        const float *f = Rhs + (size_t)(b0 + e) * N;
+        (void)spmv(E);
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) { const int c = cellp[k]; r[e][k] = (c >= 0 ? f[c] : 0.f) - ap[e][k]; }
+    };
+    auto reset_d = [&](auto E) { constexpr int e = decltype(E)::value; rho[e] = xfinish(E, EnvTag<1>{}); store_direction(E, 0.f); };
+
+    if (maxit <= 0) run[0] = run[1] = false;
+    while (run[0] || run[1]) {
+        const bool rs0 = run[0] && until_reset[0] == 0, rs1 = run[1] && until_reset[1] == 0;
+        if (rs0 || rs1) {
+            if (rs0) reset_a(EnvTag<0>{});
+            if (rs1) reset_a(EnvTag<1>{});
+            if (rs0) reset_b(EnvTag<0>{});
+            if (rs1) reset_b(EnvTag<1>{});
+            mirror();
+            if (rs0) reset_c(EnvTag<0>{});
+            if (rs1) reset_c(EnvTag<1>{});
+            __syncthreads();
+            if (rs0) residual_start(EnvTag<0>{});
+            if (rs1) residual_start(EnvTag<1>{});
+            if (rs0) reset_d(EnvTag<0>{});
+            if (rs1) reset_d(EnvTag<1>{});
+            mirror();
+        }
+        if (run[0]) --until_reset[0];
+        if (run[1]) --until_reset[1];
+        if (run[0]) phase1(EnvTag<0>{});
+        if (run[1]) phase1(EnvTag<1>{});
+        const bool r0 = run[0], r1 = run[1];
+        if (r0) phase2(EnvTag<0>{});
+        if (r1) phase2(EnvTag<1>{});
+        if (r0) phase3(EnvTag<0>{});
+        if (r1) phase3(EnvTag<1>{});
+        if (run[0] || run[1]) mirror();
+    }
+
+    auto mean_start = [&](auto E) {
+        constexpr int e = decltype(E)::value;
+        float sx = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) sx += (cellp[k] >= 0) ? x[e][k] : 0.f;
+        xstart(E, EnvTag<0>{}, sx);
+    };
+    auto finish_env = [&](auto E, bool with_mean) {
+        constexpr int e = decltype(E)::value;
+        const int b = b0 + e;
+        float mean = 0.f;
+        if (with_mean) mean = xfinish(E, EnvTag<0>{}) / (float)N;
+        if (mean_out && tid == 0 && rank == 0) mean_out[b] = mean;
+        float *xo = Xout + (size_t)b * N;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) { const int c = cellp[k]; if (c >= 0) xo[c] = x[e][k] - mean; }
+        if (tid == 0 && rank == 0) { iters[b * 8 + 2 + slot] = used[e]; resid[b * 8 + 2 + slot] = fin[e]; iter_total[b * 2] += (unsigned long long)(used[e] + 1); }
+    };
+    const bool m0 = on[0] && solved[0] && !(flags & 2), m1 = on[1] && solved[1] && !(flags & 2);
+    if (m0) mean_start(EnvTag<0>{});
+    if (m1) mean_start(EnvTag<1>{});
+    if (on[0]) finish_env(EnvTag<0>{}, m0);
+    if (on[1]) finish_env(EnvTag<1>{}, m1);
+    cluster_sync_all();   // keep peer shared memory (and in-flight st.async targets) alive until everyone is done
+}
+
+// ------------------------------------------------------------------------------------------------
 // BiCGStab on chip: one cluster per environment, same mbarrier protocol as the CG above.  r, p, x and the
 // shadow residual live in shared memory (r and p are the two vectors the neighbours gather), v, t and the
 // stencil in registers.  Operation order follows BICG.cu:276-366; rho of the next iteration is reduced
@@ -2946,10 +3328,56 @@ static int cg_strip_any(fgb_batch *b, const float *poff, const float *pdiag, con
     return rc;
 }
 
-static inline bool uses_halo_plan(int cg_impl) { return cg_impl == 6 || cg_impl == 11; }
+
+// cg_impl 12: two environments per cluster (k_cg_strip2); rc 1 = this instantiation does not match the plan
+template <int T, int CPT, int CS>
+static int launch_cg_strip2(fgb_batch *b, const float *poff, const float *pdiag, const float *rhs, float *p_out, int zero_init,
+                            int reset_steps, int max_iter, int slot, const int32_t *active, int flags, float *mean_out,
+                            cudaStream_t st) {
+    if (b->t.st_cs != CS || b->t.st_T != T || b->t.st_cpt != CPT) return 1;
+    if ((size_t)CS * T * CPT > (size_t)KRY_VECS * b->t.N)
+        return set_err(FGB_E_ARG, "cg_impl 12: domain too small for the best-iterate scratch (use cg_impl 6)");
+    const size_t envf = ((size_t)5 * CPT * T + (size_t)b->t.st_slots + (size_t)b->t.st_gmax + (size_t)2 * CS + 2 * (T / 32) + 3) & ~(size_t)3;
+    const size_t smem = 2 * envf * sizeof(float) + 4 * 8 + 4 * 4 + ((size_t)b->t.st_remax + (size_t)b->t.st_lemax) * 8;
+    if (smem > 227 * 1024 || (b->t.st_slots & 3) || (b->t.st_gmax & 1))
+        return set_err(FGB_E_ARG, "cg_impl 12: strip plan does not fit in shared memory");
+    auto kern = k_cg_strip2<T, CPT, CS>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_cg_strip2)", ce);
+    if (CS > 8) {
+        ce = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaFuncSetAttribute(k_cg_strip2, non-portable cluster)", ce);
+    }
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(((b->B + 1) / 2) * CS); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ce = cudaLaunchKernelEx(&cfg, kern, b->t, poff, pdiag, rhs, p_out, b->B, max_iter, b->opt.p_tol, zero_init, reset_steps, slot, active,
+                            b->iters, b->resid, b->iter_total, flags, mean_out, b->kry);
+    if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchKernelEx(k_cg_strip2)", ce);
+    return FGB_OK;
+}
+// instantiated: the shape of fluidgym_b200/strip_plan.py::SHAPES2 for 2 / 4 / 8-CTA clusters (an opt-in kernel kept for the measured
+// comparison of profiles/r02_cg_strip_development.md: slower than k_cg_strip, see there)
+static int cg_strip2_any(fgb_batch *b, const float *poff, const float *pdiag, const float *rhs, float *p_out, int zero_init,
+                         int reset_steps, int max_iter, int slot, const int32_t *active, int flags, float *mean_out, cudaStream_t st) {
+    int rc = launch_cg_strip2<480, 9, 2>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    if (rc == 1) rc = launch_cg_strip2<480, 9, 4>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    if (rc == 1) rc = launch_cg_strip2<480, 9, 8>(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+    return rc;
+}
+
+static inline bool uses_halo_plan(int cg_impl) { return cg_impl == 6 || cg_impl == 11 || cg_impl == 12; }
 
 static int cg_cluster_mb_any(fgb_batch *b, const float *poff, const float *pdiag, const float *rhs, float *p_out, int zero_init,
                              int reset_steps, int max_iter, int slot, const int32_t *active, int flags, float *mean_out, cudaStream_t st) {
+    if (b->opt.cg_impl == 12 && b->t.st_thread && b->t.st_cell && b->t.st_rexp && b->t.st_lexp && b->t.st_cnt) {
+        const int rc = cg_strip2_any(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
+        if (rc == 1) return set_err(FGB_E_ARG, "cg_impl 12: no k_cg_strip2 instantiation for the shape (st_T, st_cpt, st_cs) of this strip plan");
+        return rc;
+    }
     if (b->opt.cg_impl == 11 && b->t.st_thread && b->t.st_cell && b->t.st_rexp && b->t.st_lexp && b->t.st_cnt) {
         const int rc = cg_strip_any(b, poff, pdiag, rhs, p_out, zero_init, reset_steps, max_iter, slot, active, flags, mean_out, st);
         if (rc == 1) return set_err(FGB_E_ARG, "cg_impl 11: no k_cg_strip instantiation for the shape (st_T, st_cpt, st_cs) of this strip plan");

@@ -34,6 +34,19 @@ SHAPES = ((480, 17), (256, 17), (896, 9), (640, 13), (320, 13))   # (threads per
 #                                   CTAs per SM); the first that fits is the default.  Threads per CTA: a multiple of 32.
 
 
+SHAPES2 = ((480, 9),)       # shapes of k_cg_strip2 (cg_impl 12: two environments per cluster, each with these rows per thread)
+
+
+def pair_shape():
+    """(T, CPT) of the two-environment kernel; FGB_STRIP2_SHAPE="T,CPT" selects another instantiated shape."""
+    v = os.environ.get("FGB_STRIP2_SHAPE")
+    if v:
+        T, cpt = (int(x) for x in v.split(","))
+        assert (T, cpt) in SHAPES2, f"FGB_STRIP2_SHAPE must be one of {SHAPES2}"
+        return T, cpt
+    return SHAPES2[0]
+
+
 def default_shape():
     """(T, CPT) of the plan; FGB_STRIP_SHAPE="T,CPT" selects another instantiated shape (A/B runs)."""
     v = os.environ.get("FGB_STRIP_SHAPE")
@@ -232,7 +245,7 @@ def build_strip_plan(sizes, offsets, nbr, N, cs=None, T=None, cpt=None):
     for r in range(cs):
         e = 0
         for st in sorted(rexports[r]):
-            lst = rexports[r][st]
+            lst = sorted(rexports[r][st])                # by row k: the kernels walk the list with compile-time row indices
             assert len(lst) < 256 and e < 65536
             thread[r, st, 3] = e | (len(lst) << 16)
             for (sk, dr, di) in lst:

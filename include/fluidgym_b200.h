@@ -297,6 +297,10 @@ typedef struct fgb_ortho3_tables {
     /* slab decomposition (0 = single GPU): per-cell arrays are strided by NS = N + 2 * plane cells -- owned cells [0, N),
      * lower halo plane [N, N + plane), upper halo plane [N + plane, NS); N_global = cells of the whole domain (norms) */
     int32_t NS, N_global, plane;
+    /* structured box (0 = unknown: the kernels read nbr): cells are ordered (z, y, x) with nx * ny * nz = N owned cells and
+     * `closed` has bit d set where direction d ends in prescribed faces (periodic otherwise).  The Krylov kernels then compute
+     * the neighbour indices instead of loading them (24 bytes per cell and product less, one dependent load less per gather). */
+    int32_t nx, ny, nz, closed;
 } fgb_ortho3_tables;
 typedef struct fgb_ortho3 fgb_ortho3;
 size_t fgb_ortho3_workspace_bytes(const fgb_ortho3_tables *t, int32_t B);

@@ -175,3 +175,22 @@ def test_env_step_with_sgs_matches_reference(golden):
         assert abs(float(info[k][0]) - float(st[f"step0_info_{k}"])) < 1e-3 * abs(float(st[f"step0_info_{k}"]))
     assert np.abs(reward[0].cpu().numpy() - st["step0_reward"]).max() < 1e-3 * np.abs(st["step0_reward"]).max() + 1e-6
     assert torch.equal(s.u[0], s.u[1])
+
+
+def test_structured_neighbour_path_is_bit_identical_to_the_table_path(setup, monkeypatch):
+    """The Krylov kernels compute the neighbour indices of a structured box (tables.nx > 0) instead of loading them: same cells,
+    same operation order -> the same bits as with FGB_O3_BOX=0 (neighbour table)."""
+    from fluidgym_b200.box3d import BatchedPISO3D
+    dom, sol, fx, meta = setup
+    assert sol.tables.nx == dom.nx and sol.tables.closed == 2
+    monkeypatch.setenv("FGB_O3_BOX", "0")
+    tab = BatchedPISO3D(dom, 2)
+    assert tab.tables.nx == 0
+    outs = []
+    for s in (sol, tab):
+        src = _load(s, fx)
+        for _ in range(2):
+            s.piso_substep(float(fx["dt"][0]), src)
+        torch.cuda.synchronize()
+        outs.append((s.u.clone(), s.p.clone(), s.buffer("iters").clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
