@@ -101,21 +101,25 @@ class Box3DDomain:
         return (c * f32(0.125)).astype(f32)
 
 
-def structured_neighbours(nx, ny, nz, closed, halo=False):
-    """The neighbour arithmetic of the Krylov kernels (``o3_nbrs``, csrc/ortho3_b200.cuh) on the (z, y, x) cell ordering:
-    [6, N] indices, -1 for a prescribed face, halo planes at N.. / N + P.. for slabs.  Host mirror used by the tests to pin
-    the formula to the tables (``Box3DDomain.nbr`` / ``SlabTables.nbr``)."""
+def structured_neighbours(nx, ny, nz, closed, halo=False, boff=None):
+    """The neighbour arithmetic of the kernels (``o3_nbrs``, csrc/ortho3_b200.cuh) on the (z, y, x) cell ordering: [6, N]
+    indices, -1 - j for the prescribed face j (``boff``: first face index per cell face; all -1 without it), halo planes at
+    N.. / N + P.. for slabs.  Host mirror used by the tests to pin the formula to the tables (``Box3DDomain.nbr`` / ``SlabTables.nbr``)."""
     P, N = nx * ny, nx * ny * nz
     g = np.arange(N, dtype=np.int64)
-    i, j, k = g % nx, (g // nx) % ny, g // P
+    q = g // nx
+    i, j, k = g % nx, q % ny, g // P
     cx, cy, cz = (bool(c) for c in closed)
+
+    def face(f, idx):
+        return -1 - (boff[f] + idx) if boff is not None else np.full(N, -1, dtype=np.int64)
     n = np.empty((6, N), dtype=np.int64)
-    n[0] = np.where(i > 0, g - 1, -1 if cx else g + (nx - 1))
-    n[1] = np.where(i < nx - 1, g + 1, -1 if cx else g - (nx - 1))
-    n[2] = np.where(j > 0, g - nx, -1 if cy else g + (ny - 1) * nx)
-    n[3] = np.where(j < ny - 1, g + nx, -1 if cy else g - (ny - 1) * nx)
-    n[4] = np.where(k > 0, g - P, N + (g - k * P) if halo else (-1 if cz else g + (nz - 1) * P))
-    n[5] = np.where(k < nz - 1, g + P, N + P + (g - k * P) if halo else (-1 if cz else g - (nz - 1) * P))
+    n[0] = np.where(i > 0, g - 1, face(0, q) if cx else g + (nx - 1))
+    n[1] = np.where(i < nx - 1, g + 1, face(1, q) if cx else g - (nx - 1))
+    n[2] = np.where(j > 0, g - nx, face(2, k * nx + i) if cy else g + (ny - 1) * nx)
+    n[3] = np.where(j < ny - 1, g + nx, face(3, k * nx + i) if cy else g - (ny - 1) * nx)
+    n[4] = np.where(k > 0, g - P, N + (g - k * P) if halo else (face(4, g - k * P) if cz else g + (nz - 1) * P))
+    n[5] = np.where(k < nz - 1, g + P, N + P + (g - k * P) if halo else (face(5, g - k * P) if cz else g - (nz - 1) * P))
     return n
 
 
@@ -140,6 +144,8 @@ class BatchedPISO3D:
         if os.environ.get("FGB_O3_BOX", "1") != "0":          # structured neighbour arithmetic in the Krylov kernels (0: nbr table)
             self.tables.nx, self.tables.ny, self.tables.nz = dom.nx, dom.ny, dom.nz
             self.tables.closed = sum(1 << d for d in range(3) if dom.closed[d])
+            for f, o in dom.boff.items():
+                self.tables.boff[f] = int(o)
         self.options = native.Options(corrector_steps, 1, 1, int(bool(non_orthogonal)), advection_tol, pressure_tol, max_iter, 0)
         nbytes = self.lib.fgb_ortho3_workspace_bytes(C.byref(self.tables), self.B)
         self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
@@ -385,6 +391,8 @@ class SlabPISO3D:
         if os.environ.get("FGB_O3_BOX", "1") != "0":
             self.tables.nx, self.tables.ny, self.tables.nz = dom.nx, dom.ny, tb.nzl
             self.tables.closed = sum(1 << d for d in range(2) if dom.closed[d])      # z: slab halo planes
+            for f, o in tb.boff.items():
+                self.tables.boff[f] = int(o)
         self.options = native.Options(corrector_steps, 1, 1, 1, advection_tol, pressure_tol, max_iter, 0)
         ws_bytes = self.lib.fgb_ortho3_workspace_bytes(C.byref(self.tables), 1)
 

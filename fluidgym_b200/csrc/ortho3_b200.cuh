@@ -153,6 +153,26 @@ extern "C" long long fgb_ortho3_launch_count(fgb_ortho3 *b) { return b ? b->laun
 // ------------------------------------------------------------------------------------------------
 static inline dim3 o3_grid(const fgb_ortho3 *b) { return dim3((unsigned)((b->t.N + O3_T - 1) / O3_T), (unsigned)b->B); }
 
+// neighbour cells of g across the six faces, or -1 - j for the prescribed face j, exactly as tables.nbr holds them.  Structured boxes
+// (t.nx > 0): index arithmetic on the (z, y, x) ordering -- periodic wrap, closed ends (boundary faces of face f are numbered
+// boff[f] + the flattened position in the face layer), slab halo planes [N, N + P) / [N + P, NS) -- instead of six table loads that
+// every gather would depend on.
+__device__ __forceinline__ void o3_nbrs(const T3 &t, int g, int (&n)[6]) {
+    if (t.nx > 0) {
+        const int nx = t.nx, ny = t.ny, P = nx * ny;
+        const int q = g / nx, i = g - q * nx, k = q / ny, j = q - k * ny;
+        const bool cx = t.closed & 1, cy = t.closed & 2, cz = t.closed & 4, halo = t.NS > t.N;
+        n[0] = i > 0 ? g - 1 : (cx ? -1 - (t.boff[0] + q) : g + (nx - 1));
+        n[1] = i < nx - 1 ? g + 1 : (cx ? -1 - (t.boff[1] + q) : g - (nx - 1));
+        n[2] = j > 0 ? g - nx : (cy ? -1 - (t.boff[2] + k * nx + i) : g + (ny - 1) * nx);
+        n[3] = j < ny - 1 ? g + nx : (cy ? -1 - (t.boff[3] + k * nx + i) : g - (ny - 1) * nx);
+        n[4] = k > 0 ? g - P : (halo ? t.N + (g - k * P) : (cz ? -1 - (t.boff[4] + g - k * P) : g + (t.nz - 1) * P));
+        n[5] = k < t.nz - 1 ? g + P : (halo ? t.N + P + (g - k * P) : (cz ? -1 - (t.boff[5] + g - k * P) : g - (t.nz - 1) * P));
+    } else {
+#pragma unroll
+        for (int f = 0; f < 6; ++f) n[f] = t.nbr[f * t.NS + g];
+    }
+}
 __device__ __forceinline__ float o3_bflux(const T3 &t, int j, int d, const float *bv /* [3][NB] of this env */) {
     return t.b_det[j] * t.b_minv[d * t.NB + j] * bv[d * t.NB + j];
 }
@@ -171,9 +191,11 @@ __global__ void __launch_bounds__(O3_T) k3_setup_advection(T3 t, O3Slab sl, cons
 #pragma unroll
     for (int d = 0; d < 3; ++d) { uo[d] = u[d * NS + g]; mi[d] = t.minv[d * NS + g]; al[d] = det * mi[d] * mi[d]; }
     float diag = det / dt, Sb[3] = {0.f, 0.f, 0.f};
+int nb6[6];
+o3_nbrs(t, g, nb6);
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
-        const int d = f >> 1, n = t.nbr[f * NS + g];
+        const int d = f >> 1, n = nb6[f];
         const float sig = (f & 1) ? 1.f : -1.f;
         float off = 0.f;
         if (n >= 0) {
@@ -215,9 +237,11 @@ __global__ void __launch_bounds__(O3_T) k3_setup_scalar(T3 t, const float *__res
     const float *u = U + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB, *sb = Sbval + (size_t)b * NB;
     const float dt = dtv[b], det = t.det[g];
     float diag = det / dt, r = det * Tin[(size_t)b * NS + g] / dt;
+int nb6[6];
+o3_nbrs(t, g, nb6);
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
-        const int d = f >> 1, n = t.nbr[f * NS + g];
+        const int d = f >> 1, n = nb6[f];
         const float sig = (f & 1) ? 1.f : -1.f;
         const float mi = t.minv[d * NS + g], al = det * mi * mi;
         float off = 0.f;
@@ -245,9 +269,11 @@ __global__ void __launch_bounds__(O3_T) k3_setup_scalar(T3 t, const float *__res
 // G[c][d] = d u_c / d x_d
 __device__ __forceinline__ void o3_velocity_gradient(const T3 &t, const float *__restrict__ u, const float *__restrict__ bv, int g, float G[3][3]) {
     const int NS = t.NS, NB = t.NB;
+    int nb6[6];
+    o3_nbrs(t, g, nb6);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        const int nl = t.nbr[(2 * d) * NS + g], nh = t.nbr[(2 * d + 1) * NS + g];
+        const int nl = nb6[2 * d], nh = nb6[2 * d + 1];
         const float dist = 2.0f - (nl < 0 ? 0.5f : 0.f) - (nh < 0 ? 0.5f : 0.f), mi = t.minv[d * NS + g];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -308,9 +334,11 @@ __global__ void __launch_bounds__(O3_T) k3_pressure_matrix(T3 t, const float *__
     const float *a = A + (size_t)b * NS;
     const float det = t.det[g], rA = 1.0f / a[g];
     float diag = 0.f;
+int nb6[6];
+o3_nbrs(t, g, nb6);
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
-        const int d = f >> 1, n = t.nbr[f * NS + g];
+        const int d = f >> 1, n = nb6[f];
         float c = 0.f;
         if (n >= 0) {
             const float mi = t.minv[d * NS + g], mn = t.minv[d * NS + n];
@@ -333,9 +361,11 @@ __global__ void __launch_bounds__(O3_T) k3_hbya(T3 t, O3Slab sl, const float *__
     const float *u = U + (size_t)b * 3 * NS, *up = Uprev + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB;
     const float dt = dtv[b], det = t.det[g], visc = Visc ? Visc[(size_t)b * NS + g] : t.viscosity, Ag = A[(size_t)b * NS + g];
     float H[3] = {0.f, 0.f, 0.f}, Sb[3] = {0.f, 0.f, 0.f};
+int nb6[6];
+o3_nbrs(t, g, nb6);
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
-        const int d = f >> 1, n = t.nbr[f * NS + g];
+        const int d = f >> 1, n = nb6[f];
         if (n >= 0) {
             const float c = Coff[((size_t)b * 6 + f) * NS + g];
 #pragma unroll
@@ -367,9 +397,11 @@ __global__ void __launch_bounds__(O3_T) k3_divergence(T3 t, const float *__restr
     const float *v = V + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB;
     const float det = t.det[g];
     float fl[6];
+int nb6[6];
+o3_nbrs(t, g, nb6);
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
-        const int d = f >> 1, n = t.nbr[f * NS + g];
+        const int d = f >> 1, n = nb6[f];
         if (n >= 0) fl[f] = 0.5f * (det * t.minv[d * NS + g] * v[d * NS + g] + t.det[n] * t.minv[d * NS + n] * v[d * NS + n]);
         else fl[f] = o3_bflux(t, -1 - n, d, bv);
     }
@@ -384,9 +416,11 @@ __global__ void __launch_bounds__(O3_T) k3_correct(T3 t, O3Slab sl, const float 
     const float *p = P + (size_t)b * NS;
     const float pc = p[g], rA = 1.0f / A[(size_t)b * NS + g];
     bool dirty = false;
+    int nb6[6];
+    o3_nbrs(t, g, nb6);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        const int nl = t.nbr[(2 * d) * NS + g], nu = t.nbr[(2 * d + 1) * NS + g];
+        const int nl = nb6[2 * d], nu = nb6[2 * d + 1];
         const float fac = (nl < 0 || nu < 0) ? 1.0f : 0.5f;
         const float pg = ((nu >= 0 ? p[nu] : pc) - (nl >= 0 ? p[nl] : pc)) * fac;
         const float uv = Hb[((size_t)b * 3 + d) * NS + g] - pg * t.minv[d * NS + g] * rA;
@@ -406,25 +440,6 @@ __global__ void k3_copy_active(const float *__restrict__ src, float *__restrict_
 // ------------------------------------------------------------------------------------------------
 // cooperative Krylov kernels
 // ------------------------------------------------------------------------------------------------
-// neighbour cells of g across the six faces (< 0: prescribed face).  Structured boxes (t.nx > 0): index arithmetic on the
-// (z, y, x) ordering -- periodic wrap, closed ends, slab halo planes [N, N + P) / [N + P, NS) -- instead of six table loads that
-// every gather would depend on.
-__device__ __forceinline__ void o3_nbrs(const T3 &t, int g, int (&n)[6]) {
-    if (t.nx > 0) {
-        const int nx = t.nx, ny = t.ny, P = nx * ny;
-        const int q = g / nx, i = g - q * nx, k = q / ny, j = q - k * ny;
-        const bool cx = t.closed & 1, cy = t.closed & 2, cz = t.closed & 4, halo = t.NS > t.N;
-        n[0] = i > 0 ? g - 1 : (cx ? -1 : g + (nx - 1));
-        n[1] = i < nx - 1 ? g + 1 : (cx ? -1 : g - (nx - 1));
-        n[2] = j > 0 ? g - nx : (cy ? -1 : g + (ny - 1) * nx);
-        n[3] = j < ny - 1 ? g + nx : (cy ? -1 : g - (ny - 1) * nx);
-        n[4] = k > 0 ? g - P : (halo ? t.N + (g - k * P) : (cz ? -1 : g + (t.nz - 1) * P));
-        n[5] = k < t.nz - 1 ? g + P : (halo ? t.N + P + (g - k * P) : (cz ? -1 : g - (t.nz - 1) * P));
-    } else {
-#pragma unroll
-        for (int f = 0; f < 6; ++f) n[f] = t.nbr[f * t.NS + g];
-    }
-}
 __device__ __forceinline__ float o3_row(const T3 &t, int g, const float *__restrict__ off, const float *__restrict__ dg, const float *x) {
     const int NS = t.NS;
     int n[6];
@@ -1163,15 +1178,23 @@ __global__ void k3_plan_substep(int B, double *__restrict__ remaining, float *__
 
 // mean streamwise velocity of the first and last wall-normal cell layers -> wall shear stresses and the dynamic
 // forcing G_x = nu/2 (u_lo/d_lo + u_hi/d_hi) (envs/tcf/grid.py:128-163, tcf_env.py:564-584).  rows: [2][n_row] cell lists.
+// (two stages, both in fixed order: a single CTA per environment walking 2 x 16 384 indexed cells took 37 us on the 1 M-cell channel)
 __global__ void __launch_bounds__(512) k3_wall_rows_sum(T3 t, const float *__restrict__ U, const int32_t *__restrict__ rows, int n_row,
-                                                        float *__restrict__ rowmean /* [B][4]: [0..1] = sums over this rank's rows */) {
+                                                        float *__restrict__ part /* [B][gridDim.x][2] */) {
     __shared__ double red[32 * 2 + 2];
-    const int b = blockIdx.x, NS = t.NS;
+    const int b = blockIdx.y, NS = t.NS;
     const float *u = U + (size_t)b * 3 * NS;
     float a[2] = {0.f, 0.f};
-    for (int i = threadIdx.x; i < n_row; i += blockDim.x) { a[0] += u[rows[i]]; a[1] += u[rows[n_row + i]]; }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_row; i += gridDim.x * blockDim.x) { a[0] += u[rows[i]]; a[1] += u[rows[n_row + i]]; }
     block_reduce_sum<2>(a, red);
-    if (threadIdx.x == 0) { rowmean[b * 4 + 0] = a[0]; rowmean[b * 4 + 1] = a[1]; }
+    if (threadIdx.x == 0) { part[((size_t)b * gridDim.x + blockIdx.x) * 2 + 0] = a[0]; part[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = a[1]; }
+}
+__global__ void k3_wall_rows_collect(int B, int nchunk, const float *__restrict__ part, float *__restrict__ rowmean /* [B][4]: [0..1] = sums over this rank's rows */) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double s0 = 0.0, s1 = 0.0;
+    for (int c = 0; c < nchunk; ++c) { s0 += (double)part[((size_t)b * nchunk + c) * 2]; s1 += (double)part[((size_t)b * nchunk + c) * 2 + 1]; }
+    rowmean[b * 4 + 0] = (float)s0; rowmean[b * 4 + 1] = (float)s1;
 }
 __global__ void k3_wall_rows_finish(int B, float visc, int n_row_global, float d_lo, float d_hi, float *__restrict__ rowmean,
                                     float *__restrict__ src /* [B][4] or null */, float *__restrict__ acc /* [B][2] += tau, or null */) {
@@ -1189,9 +1212,15 @@ extern "C" int fgb_ortho3_wall_rows(fgb_ortho3 *b, const float *u, const int32_t
     if (!b || !u || !rows || n_row <= 0) return set_err(FGB_E_ARG, "fgb_ortho3_wall_rows: bad argument");
     cudaStream_t st = STREAM(s);
     int rc;
-    b->launches += 2;
-    k3_wall_rows_sum<<<b->B, 512, 0, st>>>(b->t, u, rows, n_row, b->rowmean);
+    b->launches += 3;
+    int nchunk = (n_row + 511) / 512;
+    if (nchunk > 64) nchunk = 64;
+    while (nchunk > 1 && (size_t)b->B * nchunk * 2 > (size_t)2 * 4096 * O3_PART) nchunk >>= 1;     // partials live in the reduction scratch
+    if ((size_t)b->B * nchunk * 2 > (size_t)2 * 4096 * O3_PART) return set_err(FGB_E_ARG, "fgb_ortho3_wall_rows: too many environments");
+    k3_wall_rows_sum<<<dim3((unsigned)nchunk, (unsigned)b->B), 512, 0, st>>>(b->t, u, rows, n_row, b->part);
     LAUNCH_CHECK("k3_wall_rows_sum");
+    k3_wall_rows_collect<<<(b->B + 127) / 128, 128, 0, st>>>(b->B, nchunk, b->part, b->rowmean);
+    LAUNCH_CHECK("k3_wall_rows_collect");
     if ((rc = o3_allreduce(b, b->rowmean, 2, 0, st))) return rc;       // slabs: every rank holds a part of both wall layers
     k3_wall_rows_finish<<<(b->B + 127) / 128, 128, 0, st>>>(b->B, b->t.viscosity, n_row * b->slab.world, d_lo, d_hi, b->rowmean,
                                                            set_forcing ? b->src : nullptr, acc);

@@ -1438,6 +1438,7 @@ __global__ void __launch_bounds__(T, MINB) k_cg_cluster_mb(Tab t, const float *_
         publish();
         float rho = cluster_sum(a0);
         float bestc = 0.f, lastc = 0.f; int best_it = -1, rising = 0;
+        bool take_best = false;
         float pk[CPT], apk[CPT];
         for (int i = 0; i < maxit; ++i) {
             if (reset_steps > 0 && (i + 1) % reset_steps == 0) {
@@ -1476,26 +1477,32 @@ __global__ void __launch_bounds__(T, MINB) k_cg_cluster_mb(Tab t, const float *_
             }
             const float rr2 = cluster_sum(a0);
             const float crit = sqrtf(rr2) * norm;
-            if (!isfinite(crit)) { used = i; fin = crit; break; }
-            if (i == 0 || crit < bestc) {
-                bestc = crit; best_it = i;
+            // ONE loop exit (see k_cg_strip: several `break`s made the compiler copy the iterate's registers before every test)
+            int stop = isfinite(crit) ? 0 : 1;   // 1: leave with the current iterate, 2: leave with the best one
+            used = i; fin = crit;
+            if (!stop) {
+                if (i == 0 || crit < bestc) {
+                    bestc = crit; best_it = i;
 #pragma unroll
-                for (int k = 0; k < CPT; ++k) bs[threadIdx.x + k * T] = xr[k];
+                    for (int k = 0; k < CPT; ++k) bs[threadIdx.x + k * T] = xr[k];
+                }
+                if (i > 0 && crit >= lastc) ++rising; else rising = 0;
+                lastc = crit;
+                if (crit < tol) stop = 1;
+                else if (i == maxit - 1 || rising >= 100) stop = 2;
             }
-            if (i > 0 && crit >= lastc) ++rising; else rising = 0;
-            lastc = crit; used = i; fin = crit;
-            if (crit < tol) break;
-            if (i == maxit - 1 || rising >= 100) {
-#pragma unroll
-                for (int k = 0; k < CPT; ++k) xr[k] = bs[threadIdx.x + k * T];
-                used = best_it; fin = bestc;
-                break;
-            }
+            asm volatile("" : "+r"(stop));             // opaque: keeps the compiler from threading the exits apart again
+            if (stop) { take_best = stop == 2; break; }
             const float beta = rr2 / rho;
             rho = rr2;
 #pragma unroll
             for (int k = 0; k < CPT; ++k) vs[threadIdx.x + k * T] = rr[k] + beta * pk[k];
             publish();
+        }
+        if (take_best) {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) xr[k] = bs[threadIdx.x + k * T];
+            used = best_it; fin = bestc;
         }
     }
     float sx = 0.f;
@@ -1729,6 +1736,7 @@ __global__ void __launch_bounds__(T, MINB) k_cg_strip(Tab t, const float *__rest
         float rho = residual_norm2();
         new_direction(0.f);                            // p = r (vs holds zeros or x0: 0 * finite + r)
         float bestc = 0.f, lastc = 0.f; int best_it = -1, rising = 0;
+        bool take_best = false;
         int until_reset = reset_steps > 0 ? reset_steps - 1 : -1;   // iterations left before the next residual reset
         for (int i = 0; i < maxit; ++i) {
             if (until_reset == 0) {
@@ -1753,24 +1761,31 @@ __global__ void __launch_bounds__(T, MINB) k_cg_strip(Tab t, const float *__rest
             }
             const float rr2 = residual_norm2();
             const float crit = sqrtf(rr2) * norm;
-            if (!isfinite(crit)) { used = i; fin = crit; break; }
-            if (i == 0 || crit < bestc) {
-                bestc = crit; best_it = i;
+            // ONE loop exit: with several `break`s (each with its own live iterate) the compiler copied all CPT registers of x in front
+            // of every test, 70 of the 625 instructions of an iteration (profiles/r02_cg_strip_development.md)
+            int stop = isfinite(crit) ? 0 : 1;         // 1: leave with the current iterate, 2: leave with the best one
+            used = i; fin = crit;
+            if (!stop) {
+                if (i == 0 || crit < bestc) {
+                    bestc = crit; best_it = i;
 #pragma unroll
-                for (int k = 0; k < CPT; ++k) bestp[k * T] = x[k];
+                    for (int k = 0; k < CPT; ++k) bestp[k * T] = x[k];
+                }
+                if (i > 0 && crit >= lastc) ++rising; else rising = 0;
+                lastc = crit;
+                if (crit < tol) stop = 1;
+                else if (i == maxit - 1 || rising >= 100) stop = 2;
             }
-            if (i > 0 && crit >= lastc) ++rising; else rising = 0;
-            lastc = crit; used = i; fin = crit;
-            if (crit < tol) break;
-            if (i == maxit - 1 || rising >= 100) {
-#pragma unroll
-                for (int k = 0; k < CPT; ++k) x[k] = bestp[k * T];
-                used = best_it; fin = bestc;
-                break;
-            }
+            asm volatile("" : "+r"(stop));             // opaque: keeps the compiler from threading the exits apart again
+            if (stop) { take_best = stop == 2; break; }
             const float beta = rr2 / rho;
             rho = rr2;
             new_direction(beta);
+        }
+        if (take_best) {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) x[k] = bestp[k * T];
+            used = best_it; fin = bestc;
         }
     }
     float mean = 0.f;

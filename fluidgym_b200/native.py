@@ -51,7 +51,8 @@ class Options(C.Structure):
 class Ortho3Tables(C.Structure):
     _fields_ = [("N", C.c_int32), ("NB", C.c_int32), ("viscosity", C.c_float), ("nbr", C.c_void_p), ("minv", C.c_void_p),
                 ("det", C.c_void_p), ("b_minv", C.c_void_p), ("b_det", C.c_void_p), ("NS", C.c_int32), ("N_global", C.c_int32),
-                ("plane", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("closed", C.c_int32)]
+                ("plane", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("closed", C.c_int32),
+                ("boff", C.c_int32 * 6)]
 
 
 class Ortho3Scalar(C.Structure):

@@ -298,9 +298,11 @@ typedef struct fgb_ortho3_tables {
      * lower halo plane [N, N + plane), upper halo plane [N + plane, NS); N_global = cells of the whole domain (norms) */
     int32_t NS, N_global, plane;
     /* structured box (0 = unknown: the kernels read nbr): cells are ordered (z, y, x) with nx * ny * nz = N owned cells and
-     * `closed` has bit d set where direction d ends in prescribed faces (periodic otherwise).  The Krylov kernels then compute
-     * the neighbour indices instead of loading them (24 bytes per cell and product less, one dependent load less per gather). */
+     * `closed` has bit d set where direction d ends in prescribed faces (periodic otherwise), boff[f] = index of the first
+     * prescribed face of cell face f in the [NB] arrays (faces of a layer in (z,y) / (z,x) / (y,x) order).  The kernels then compute
+     * the neighbour indices instead of loading them (24 bytes per cell less, one dependent load less per gather). */
     int32_t nx, ny, nz, closed;
+    int32_t boff[6];
 } fgb_ortho3_tables;
 typedef struct fgb_ortho3 fgb_ortho3;
 size_t fgb_ortho3_workspace_bytes(const fgb_ortho3_tables *t, int32_t B);
