@@ -120,3 +120,59 @@ def piso_substep_scalar(solver: BatchedPISO, u, p, bvel, T, sbval, dt, beta=1.0)
 def piso_substep(solver: BatchedPISO, u, p, bvel, dt):
     """Differentiable PISO substep (functional form: inputs are not modified)."""
     return PISOSubstep.apply(u, p, bvel, solver, dt)
+
+
+# ---- D = 3 structured boxes (turbulent channel): fgb_ortho3_piso_substep_record / _backward ------------------------------------------
+def _new_tape3(solver):
+    B, N, NB = solver.B, solver.N, max(solver.NB, 1)
+    f32 = dict(device=solver.device, dtype=torch.float32)
+    C_ = int(solver.options.corrector_steps)
+    return dict(u_in=torch.empty(B, 3, N, **f32), bvel_in=torch.empty(B, 3, NB, **f32), dt=torch.empty(B, **f32),
+                Coff=torch.empty(B, 6, N, **f32), A=torch.empty(B, N, **f32), ustar=torch.empty(B, 3, N, **f32),
+                hb=torch.empty(C_, B, 3, N, **f32), p=torch.empty(C_, B, N, **f32), u1=torch.empty(max(C_ - 1, 1), B, 3, N, **f32))
+
+
+def _adjoint_workspace3(solver):
+    nbytes = solver.lib.fgb_ortho3_adjoint_workspace_bytes(C.byref(solver.tables), solver.B)
+    ws = getattr(solver, "_adj_ws", None)
+    if ws is None or ws.numel() < nbytes + 256:
+        ws = solver._adj_ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=solver.device)
+    return C.c_void_p(ws.data_ptr() + (-ws.data_ptr()) % 256), nbytes
+
+
+class PISOSubstep3D(torch.autograd.Function):
+    """(u [B,3,N], p [B,N], bvel [B,3,NB]) -> (u_next, p_next) for one substep of a structured 3-D box (``BatchedPISO3D``); ``src``
+    [B,4] (channel forcing) is a constant of the graph, as in the reference (envs/tcf/grid.py:147-161 rebuilds it with
+    ``torch.tensor``).  The previous pressure gets no gradient: every recorded solve starts from zero."""
+
+    @staticmethod
+    def forward(ctx, u, p, bvel, solver, dt, src):
+        dtc = solver._dt(dt)
+        tape = _new_tape3(solver)
+        ct = native.Ortho3Tape(*[tape[k].data_ptr() for k, _ in native.Ortho3Tape._fields_])
+        u_out, p_out = u.detach().clone().contiguous(), p.detach().clone().contiguous()
+        bv = bvel.detach().contiguous()
+        srcc = None if src is None else src.detach().contiguous()
+        native.check(solver.lib.fgb_ortho3_piso_substep_record(solver.handle, _ptr(u_out), _ptr(p_out), _ptr(bv), _ptr(srcc), _ptr(dtc),
+                                                               C.byref(ct), solver.stream), "fgb_ortho3_piso_substep_record")
+        ctx.solver, ctx.tape = solver, tape
+        return u_out, p_out
+
+    @staticmethod
+    def backward(ctx, u_out_bar, p_out_bar):
+        solver, tape = ctx.solver, ctx.tape
+        B, N, NB = solver.B, solver.N, max(solver.NB, 1)
+        f32 = dict(device=solver.device, dtype=torch.float32)
+        ct = native.Ortho3Tape(*[tape[k].data_ptr() for k, _ in native.Ortho3Tape._fields_])
+        ub, bvb = torch.empty(B, 3, N, **f32), torch.empty(B, 3, NB, **f32)
+        ws, nbytes = _adjoint_workspace3(solver)
+        uo = (u_out_bar if u_out_bar is not None else torch.zeros(B, 3, N, **f32)).contiguous()
+        po = (p_out_bar if p_out_bar is not None else torch.zeros(B, N, **f32)).contiguous()
+        native.check(solver.lib.fgb_ortho3_piso_substep_backward(solver.handle, C.byref(ct), _ptr(uo), _ptr(po), _ptr(ub), _ptr(bvb), ws, nbytes,
+                                                                 solver.stream), "fgb_ortho3_piso_substep_backward")
+        return ub, None, bvb, None, None, None
+
+
+def piso_substep_3d(solver, u, p, bvel, dt, src=None):
+    """Differentiable substep of a structured 3-D box (functional form: inputs are not modified)."""
+    return PISOSubstep3D.apply(u, p, bvel, solver, dt, src)

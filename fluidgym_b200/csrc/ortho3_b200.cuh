@@ -449,6 +449,16 @@ __device__ __forceinline__ float o3_row(const T3 &t, int g, const float *__restr
     for (int f = 0; f < 6; ++f) if (n[f] >= 0) s += off[f * NS + g] * __ldcg(&x[n[f]]);
     return s;
 }
+// row g of the TRANSPOSED operator: the entry (n, g) is the coefficient of neighbour n's opposite face (adjoint solves, single GPU)
+__device__ __forceinline__ float o3_row_t(const T3 &t, int g, const float *__restrict__ off, const float *__restrict__ dg, const float *x) {
+    const int NS = t.NS;
+    int n[6];
+    o3_nbrs(t, g, n);
+    float s = dg[g] * x[g];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) if (n[f] >= 0) s += off[(f ^ 1) * NS + n[f]] * __ldcg(&x[n[f]]);
+    return s;
+}
 
 // (measured: batching four rows per thread to get more loads in flight made these kernels SLOWER -- 1.12 vs 1.01 ms per
 //  substep on 1 M cells -- because the 64-register cap of 1024-thread CTAs turns the batch into local-memory spills)
@@ -522,7 +532,7 @@ template <int NC>
 __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, const float *__restrict__ Coff, const float *__restrict__ Adiag,
                                                     const float *__restrict__ Rhs, float *X, float *work, float *part, int maxit, float tol,
                                                     int zero_init, const int32_t *__restrict__ active, int32_t *__restrict__ iters,
-                                                    float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
+                                                    float *__restrict__ resid, unsigned long long *__restrict__ iter_total, int transposed) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double red[32 * 6 + 8];
     const int N = t.N, NS = t.NS;
@@ -546,7 +556,7 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int c = 0; c < NC; ++c)
             for (int g = tid; g < N; g += nth) {
-                const float rr = f[c][g] - (zero_init ? 0.f : o3_row(t, g, off, dg, x[c]));
+                const float rr = f[c][g] - (zero_init ? 0.f : (transposed ? o3_row_t(t, g, off, dg, x[c]) : o3_row(t, g, off, dg, x[c])));
                 r[c][g] = rr; rw[c][g] = rr; p[c][g] = rr;
                 o3_push(sl, t, p[c], g, rr, dirty);
                 acc[c] += rr * rr;
@@ -568,7 +578,7 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
             o3_halo_sync(grid, sl, hc, dirty);
             for (int k = 0; k < 6; ++k) acc[k] = 0.f;
             for (int c = 0; c < NC; ++c) if (!done[c])
-                for (int g = tid; g < N; g += nth) { const float vv = o3_row(t, g, off, dg, p[c]); v[c][g] = vv; acc[c] += rw[c][g] * vv; }
+                for (int g = tid; g < N; g += nth) { const float vv = transposed ? o3_row_t(t, g, off, dg, p[c]) : o3_row(t, g, off, dg, p[c]); v[c][g] = vv; acc[c] += rw[c][g] * vv; }
             o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, dirty, red);
             float acc2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int c = 0; c < NC; ++c) if (!done[c]) {
@@ -589,7 +599,7 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
             for (int k = 0; k < 6; ++k) acc[k] = 0.f;
             for (int c = 0; c < NC; ++c) if (!done[c])
                 for (int g = tid; g < N; g += nth) {
-                    const float tv = o3_row(t, g, off, dg, r[c]); tt[c][g] = tv;
+                    const float tv = transposed ? o3_row_t(t, g, off, dg, r[c]) : o3_row(t, g, off, dg, r[c]); tt[c][g] = tv;
                     acc[c] += tv * r[c][g]; acc[3 + c] += tv * tv;
                 }
             o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, dirty, red);      // every row of t = C r is complete before r is overwritten
@@ -1007,7 +1017,8 @@ extern "C" int fgb_ortho3_solve_advection(fgb_ortho3 *b, int zero_init, const in
     T3 t = b->t; O3Slab sl = b->slab; int B = b->B; const float *coff = b->Coff, *a = b->A, *rhs = b->rhs; float *x = b->ures, *work = b->kry, *part = b->part;
     int maxit = b->opt.max_iter; float tol = b->opt.adv_tol;
     int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
-    void *args[] = {&t, &sl, &B, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot};
+    int transposed = 0;
+    void *args[] = {&t, &sl, &B, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot, &transposed};
     b->launches++;
     cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab<3>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab)", ce);
@@ -1034,7 +1045,8 @@ extern "C" int fgb_ortho3_advect_scalar(fgb_ortho3 *b, const float *u, const flo
     T3 t = b->t; O3Slab sl = b->slab; int B = b->B; const float *coff = b->Coff, *a = b->A, *rhs = b->rhs; float *x = b->sc.T, *work = b->kry, *part = b->part;
     int maxit = b->opt.max_iter, zero_init = 1; float tol = b->opt.adv_tol;
     int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
-    void *args[] = {&t, &sl, &B, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot};
+    int transposed = 0;
+    void *args[] = {&t, &sl, &B, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot, &transposed};
     cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab<1>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab<1>)", ce);
     return FGB_OK;
@@ -1107,6 +1119,305 @@ extern "C" int fgb_ortho3_piso_substep(fgb_ortho3 *b, float *u, float *p, const 
     const size_t n = (size_t)3 * b->t.NS;
     k3_copy_active<<<dim3((unsigned)((n + 255) / 256), b->B), 256, 0, STREAM(s)>>>(b->ures, u, n, active);
     LAUNCH_CHECK("k3_copy_active");
+    return FGB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Reverse mode of the D = 3 substep (single GPU, structured box, no passive scalar / SGS).  Same construction as the 2-D adjoint
+// (piso_b200.cu: k_adj_*): the forward call records a tape, the backward call runs hand-written adjoint kernels and the two
+// Krylov solves with the transposed operator; the reference differentiates these grids through the same dimension-generic
+// _GRAD kernels as 2-D (K.cu:3884-4090, 4403-4491, 6265-6309).  As in its differentiable backend every recorded solve starts
+// from zero and the CG never resets its residual (DIFF.py:527-545, SIM.py:1436-1440).  On these orthogonal grids the previous
+// pressure does not enter a substep (no deferred non-orthogonal term), so its gradient is zero.  One thread per (cell, env).
+// ------------------------------------------------------------------------------------------------
+// scatter of a flux-divergence adjoint: flb[f] = adjoint of face flux f of cell g;  flux_f = 1/2 (det mi_d v_d |g + det mi_d v_d |n)
+__device__ __forceinline__ void o3_fluxes_adjoint(const T3 &t, int g, const int (&nb)[6], const float (&flb)[6], float *__restrict__ vb /*[3][NS]*/,
+                                                  float *__restrict__ Fbb /*[NB] or null*/) {
+    const int NS = t.NS;
+    const float det = t.det[g];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float own = 0.f;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int f = 2 * d + s, n = nb[f];
+            if (n >= 0) {
+                const float gq = 0.5f * flb[f];
+                own += gq;
+                atomicAdd(&vb[d * NS + n], gq * t.det[n] * t.minv[d * NS + n]);
+            } else if (Fbb) atomicAdd(&Fbb[-1 - n], flb[f]);
+        }
+        atomicAdd(&vb[d * NS + g], own * det * t.minv[d * NS + g]);
+    }
+}
+// adjoint of the corrector u_next = hb - rA * minv_d * dp_d:  hbb = unb ; rAb -= sum_d dp_d minv_d unb_d ; pb += D^T(-rA minv_d unb_d)
+__global__ void __launch_bounds__(O3_T) k3_adj_correct(T3 t, const float *__restrict__ Unb, const float *__restrict__ P, const float *__restrict__ A,
+                                                       float *__restrict__ Hbb, float *__restrict__ rAb, float *__restrict__ Pb) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, NS = t.NS;
+    if (g >= t.N) return;
+    const float *p = P + (size_t)b * NS;
+    float *pb = Pb + (size_t)b * NS;
+    const float pc = p[g], rA = 1.0f / A[(size_t)b * NS + g];
+    int nb6[6];
+    o3_nbrs(t, g, nb6);
+    float accr = 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float ub = Unb[((size_t)b * 3 + d) * NS + g];
+        Hbb[((size_t)b * 3 + d) * NS + g] = ub;
+        const int nl = nb6[2 * d], nu = nb6[2 * d + 1];
+        const float fac = (nl < 0 || nu < 0) ? 1.0f : 0.5f, mi = t.minv[d * NS + g];
+        const float pg = ((nu >= 0 ? p[nu] : pc) - (nl >= 0 ? p[nl] : pc)) * fac;
+        accr -= pg * mi * ub;
+        const float w = -rA * mi * ub * fac;
+        atomicAdd(&pb[nu >= 0 ? nu : g], w);
+        atomicAdd(&pb[nl >= 0 ? nl : g], -w);
+    }
+    atomicAdd(&rAb[(size_t)b * NS + g], accr);
+}
+// x_bar = p_bar - mean(p_bar)   (adjoint of the mean removal), one CTA per environment
+__global__ void __launch_bounds__(1024) k3_adj_remove_mean(int N, int NS, const float *__restrict__ Pb, float *__restrict__ Xb) {
+    __shared__ double red[32 * 2 + 2];
+    const int b = blockIdx.x;
+    float acc[2] = {0.f, 0.f};
+    for (int g = threadIdx.x; g < N; g += 1024) acc[0] += Pb[(size_t)b * NS + g];
+    block_reduce_sum<2>(acc, red);
+    const float m = acc[0] / (float)N;
+    for (int g = threadIdx.x; g < N; g += 1024) Xb[(size_t)b * NS + g] = Pb[(size_t)b * NS + g] - m;
+}
+// adjoint of  div = fluxdiv(hb)  and of  x = P^-1 div  w.r.t. P(rA):  given lam = P^-1 x_bar (P is symmetric on these grids)
+//   P_ij = 1/2 (alpha_i rA_i + alpha_j rA_j) across face (i, j), P_ii = - sum_j P_ij,  P_bar_ij = -lam_i x_j
+__global__ void __launch_bounds__(O3_T) k3_adj_pressure_rhs(T3 t, const float *__restrict__ Lam, const float *__restrict__ X, float *__restrict__ Hbb,
+                                                            float *__restrict__ Fbb, float *__restrict__ rAb) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, NS = t.NS;
+    if (g >= t.N) return;
+    const float lam = Lam[(size_t)b * NS + g];
+    const float *x = X + (size_t)b * NS;
+    float *ra = rAb + (size_t)b * NS;
+    int nb6[6];
+    o3_nbrs(t, g, nb6);
+    const float det = t.det[g], xg = x[g];
+    float own = 0.f, flb[6];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const int d = f >> 1, n = nb6[f];
+        flb[f] = (f & 1) ? lam : -lam;
+        if (n >= 0) {
+            const float w = 0.5f * (-lam) * (x[n] - xg);                 // P_bar_f - P_bar_diag
+            const float mi = t.minv[d * NS + g], mn = t.minv[d * NS + n];
+            own += w * (det * mi * mi);
+            atomicAdd(&ra[n], w * (t.det[n] * mn * mn));
+        }
+    }
+    atomicAdd(&ra[g], own);
+    o3_fluxes_adjoint(t, g, nb6, flb, Hbb + (size_t)b * 3 * NS, Fbb + (size_t)b * t.NB);
+}
+// adjoint of  hb = rA * (u/dt - H + Sb/det + src),  H_c = sum_f Coff_f * uprev_c[nb_f]
+__global__ void __launch_bounds__(O3_T) k3_adj_hbya(T3 t, const float *__restrict__ Hbb, const float *__restrict__ Hb /*saved hb*/,
+                                                    const float *__restrict__ A, const float *__restrict__ Coff, const float *__restrict__ Uprev,
+                                                    const float *__restrict__ dtv, float *__restrict__ rAb, float *__restrict__ Ub,
+                                                    float *__restrict__ Sbb, float *__restrict__ Coffb, float *__restrict__ Uprevb) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, NS = t.NS;
+    if (g >= t.N) return;
+    const float dt = dtv[b], Ag = A[(size_t)b * NS + g], rA = 1.0f / Ag, det = t.det[g];
+    int nb6[6];
+    o3_nbrs(t, g, nb6);
+    float accr = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const size_t o = ((size_t)b * 3 + c) * NS;
+        const float hbb = Hbb[o + g];
+        accr += hbb * (Hb[o + g] * Ag);
+        const float ib = rA * hbb;
+        atomicAdd(&Ub[o + g], ib / dt);
+        Sbb[o + g] += ib / det;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) {
+            const int n = nb6[f];
+            if (n >= 0) {
+                Coffb[((size_t)b * 6 + f) * NS + g] += -ib * Uprev[o + n];
+                atomicAdd(&Uprevb[o + n], -ib * Coff[((size_t)b * 6 + f) * NS + g]);
+            }
+        }
+    }
+    atomicAdd(&rAb[(size_t)b * NS + g], accr);
+}
+// adjoint of the predictor  C ustar = rhs,  rhs = u/dt + Sb/det + src,  C = A I + Coff:  given mu = C^-T ustar_bar
+__global__ void __launch_bounds__(O3_T) k3_adj_advection(T3 t, const float *__restrict__ Mu, const float *__restrict__ Ustar, const float *__restrict__ rAb,
+                                                         const float *__restrict__ A, const float *__restrict__ dtv, float *__restrict__ Ab,
+                                                         float *__restrict__ Coffb, float *__restrict__ Ub, float *__restrict__ Sbb) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, NS = t.NS;
+    if (g >= t.N) return;
+    const float dt = dtv[b], det = t.det[g], Ag = A[(size_t)b * NS + g];
+    int nb6[6];
+    o3_nbrs(t, g, nb6);
+    float ab = -rAb[(size_t)b * NS + g] / (Ag * Ag);                      // A_bar from rA_bar (rA = 1 / A)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const size_t o = ((size_t)b * 3 + c) * NS;
+        const float mu = Mu[o + g];
+        ab += -mu * Ustar[o + g];
+#pragma unroll
+        for (int f = 0; f < 6; ++f) if (nb6[f] >= 0) Coffb[((size_t)b * 6 + f) * NS + g] += -mu * Ustar[o + nb6[f]];
+        atomicAdd(&Ub[o + g], mu / dt);
+        Sbb[o + g] += mu / det;
+    }
+    Ab[(size_t)b * NS + g] = ab;
+}
+// adjoint of the assembly (A, Coff from the face fluxes; constant viscosity) and of the boundary sources Sb
+__global__ void __launch_bounds__(O3_T) k3_adj_assemble(T3 t, const float *__restrict__ Ab, const float *__restrict__ Coffb, const float *__restrict__ Sbb,
+                                                        const float *__restrict__ Bvel, float *__restrict__ Ub, float *__restrict__ Bvb, float *__restrict__ Fbb) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, NS = t.NS, NB = t.NB;
+    if (g >= t.N) return;
+    const float det = t.det[g], diagb = Ab[(size_t)b * NS + g] / det;
+    const float *bv = Bvel + (size_t)b * 3 * NB;
+    int nb6[6];
+    o3_nbrs(t, g, nb6);
+    float flb[6];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const float sig = (f & 1) ? 1.f : -1.f;
+        flb[f] = 0.f;
+        if (nb6[f] >= 0) flb[f] = 0.5f * sig * (Coffb[((size_t)b * 6 + f) * NS + g] / det + diagb);
+        else {
+            const int j = -1 - nb6[f], d = f >> 1;
+            const float bm = t.b_minv[d * NB + j];
+            const float k = -(sig * o3_bflux(t, j, d, bv)) + 2.f * t.viscosity * (t.b_det[j] * bm * bm);
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float sb = Sbb[((size_t)b * 3 + c) * NS + g];
+                atomicAdd(&Bvb[((size_t)b * 3 + c) * NB + j], sb * k);
+                dot += sb * bv[c * NB + j];
+            }
+            atomicAdd(&Fbb[(size_t)b * NB + j], -dot * sig);
+        }
+    }
+    o3_fluxes_adjoint(t, g, nb6, flb, Ub + (size_t)b * 3 * NS, nullptr);
+}
+// adjoint of the boundary flux Fb_j = b_det minv_d bv_d (d = axis of the face): one thread per (boundary face, environment)
+__global__ void k3_adj_bflux(T3 t, const float *__restrict__ Fbb, float *__restrict__ Bvb) {
+    const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x, NB = t.NB;
+    if (j >= NB) return;
+    const int cnt[3] = {t.ny * t.nz, t.nx * t.nz, t.nx * t.ny};
+    int d = -1;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) if ((t.closed >> (f >> 1)) & 1) { if (j >= t.boff[f] && j < t.boff[f] + cnt[f >> 1]) d = f >> 1; }
+    if (d < 0) return;
+    Bvb[((size_t)b * 3 + d) * NB + j] += Fbb[(size_t)b * NB + j] * t.b_det[j] * t.b_minv[d * NB + j];
+}
+
+static int o3_copy(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    cudaError_t ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st);
+    return ce == cudaSuccess ? FGB_OK : set_err(FGB_E_CUDA, "cudaMemcpyAsync (D = 3 tape)", ce);
+}
+static int o3_adjoint_supported(const fgb_ortho3 *b, const char *who) {
+    if (b->slab.on || b->t.NS != b->t.N) return set_err(FGB_E_ARG, "D = 3 reverse mode: single GPU only (no slabs)");
+    if (b->t.nx <= 0) return set_err(FGB_E_ARG, "D = 3 reverse mode: needs the structured-box description (tables.nx/ny/nz/closed/boff)");
+    if (b->sc.T || b->sgs_coef != 0.f) return set_err(FGB_E_ARG, "D = 3 reverse mode: passive scalar / sub-grid viscosity are not differentiated");
+    if (b->opt.corrector_steps < 1 || b->opt.corrector_steps > 8) return set_err(FGB_E_ARG, "D = 3 reverse mode: 1..8 corrector steps");
+    (void)who;
+    return FGB_OK;
+}
+// fgb_ortho3_piso_substep (all environments active) that additionally records the tape of the backward pass
+extern "C" int fgb_ortho3_piso_substep_record(fgb_ortho3 *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
+                                              const fgb_ortho3_tape *tp, fgb_stream_t s) {
+    if (!b || !u || !p || !bvel || !dt || !tp) return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep_record: null argument");
+    int rc;
+    if ((rc = o3_adjoint_supported(b, "record"))) return rc;
+    cudaStream_t st = STREAM(s);
+    const size_t BN = (size_t)b->B * b->t.NS, BNB = (size_t)b->B * (b->t.NB > 0 ? b->t.NB : 1);
+    const int C = b->opt.corrector_steps;
+    if ((rc = o3_copy(tp->u_in, u, 3 * BN * 4, st))) return rc;
+    if ((rc = o3_copy(tp->bvel_in, bvel, 3 * BNB * 4, st))) return rc;
+    if ((rc = o3_copy(tp->dt, dt, (size_t)b->B * 4, st))) return rc;
+    if ((rc = fgb_ortho3_setup_advection(b, u, bvel, src, dt, nullptr, s))) return rc;
+    if ((rc = fgb_ortho3_solve_advection(b, 1, nullptr, s))) return rc;
+    if ((rc = o3_copy(tp->ustar, b->ures, 3 * BN * 4, st))) return rc;
+    if ((rc = o3_copy(tp->Coff, b->Coff, 6 * BN * 4, st))) return rc;
+    if ((rc = o3_copy(tp->A, b->A, BN * 4, st))) return rc;
+    for (int cs = 0; cs < C; ++cs) {
+        if ((rc = fgb_ortho3_setup_pressure(b, u, bvel, src, dt, cs == 0, nullptr, s))) return rc;
+        if ((rc = o3_copy(tp->hb + (size_t)cs * 3 * BN, b->hbya, 3 * BN * 4, st))) return rc;
+        if ((rc = fgb_ortho3_solve_pressure(b, p, 1, 0, b->opt.max_iter, cs, nullptr, s))) return rc;      // zero start, no residual reset
+        if ((rc = o3_copy(tp->p + (size_t)cs * BN, p, BN * 4, st))) return rc;
+        if ((rc = fgb_ortho3_correct_velocity(b, p, b->ures, nullptr, s))) return rc;
+        if (cs + 1 < C && (rc = o3_copy(tp->u1 + (size_t)cs * 3 * BN, b->ures, 3 * BN * 4, st))) return rc;
+    }
+    return o3_copy(u, b->ures, 3 * BN * 4, st);
+}
+extern "C" size_t fgb_ortho3_adjoint_workspace_bytes(const fgb_ortho3_tables *t, int32_t B) {
+    const size_t BN = (size_t)B * (t->NS > 0 ? t->NS : t->N), BNB = (size_t)B * (t->NB > 0 ? t->NB : 1);
+    return (size_t)(3 + 3 + 1 + 6 + 3 + 1 + 1 + 1 + 3 + 1 + 3) * align_up(BN * 4) + align_up(BNB * 4) + 8192;
+}
+// vector-Jacobian product of that substep: (u_out_bar, p_out_bar) -> (u_bar, bvel_bar), both overwritten
+extern "C" int fgb_ortho3_piso_substep_backward(fgb_ortho3 *b, const fgb_ortho3_tape *tp, const float *u_out_bar, const float *p_out_bar,
+                                                float *u_bar, float *bvel_bar, void *ws, size_t ws_bytes, fgb_stream_t s) {
+    if (!b || !tp || !u_out_bar || !p_out_bar || !u_bar || !bvel_bar || !ws) return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep_backward: null argument");
+    int rc;
+    if ((rc = o3_adjoint_supported(b, "backward"))) return rc;
+    if (ws_bytes < fgb_ortho3_adjoint_workspace_bytes(&b->t, b->B)) return set_err(FGB_E_WORKSPACE, "fgb_ortho3_piso_substep_backward: workspace too small");
+    cudaStream_t st = STREAM(s);
+    const size_t B = b->B, NB = b->t.NB > 0 ? b->t.NB : 1, BN = B * b->t.NS;
+    Carver c{(char *)ws, 0};
+    float *unb = c.take<float>(3 * BN), *hbb = c.take<float>(3 * BN), *rAb = c.take<float>(BN), *Coffb = c.take<float>(6 * BN);
+    float *Sbb = c.take<float>(3 * BN), *pb = c.take<float>(BN), *xb = c.take<float>(BN), *lam = c.take<float>(BN);
+    float *uprevb = c.take<float>(3 * BN), *Ab = c.take<float>(BN), *mu = c.take<float>(3 * BN), *Fbb = c.take<float>(B * NB);
+    const int C = b->opt.corrector_steps;
+    const dim3 grid = o3_grid(b);
+    cudaError_t ce;
+#define ZERO3(ptr, n) do { ce = cudaMemsetAsync(ptr, 0, (n) * sizeof(float), st); if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "memset", ce); } while (0)
+    ZERO3(rAb, BN); ZERO3(Coffb, 6 * BN); ZERO3(Sbb, 3 * BN); ZERO3(Fbb, B * NB); ZERO3(u_bar, 3 * BN); ZERO3(bvel_bar, 3 * B * NB);
+    if ((rc = o3_copy(unb, u_out_bar, 3 * BN * 4, st))) return rc;
+    if ((rc = o3_copy(pb, p_out_bar, BN * 4, st))) return rc;
+    b->launches++;
+    k3_pressure_matrix<<<grid, O3_T, 0, st>>>(b->t, tp->A, nullptr, b->Poff, b->Pdiag);      // the pressure matrix of this substep (function of A only)
+    LAUNCH_CHECK("k3_pressure_matrix (backward)");
+    for (int cs = C - 1; cs >= 0; --cs) {
+        const float *hb_c = tp->hb + (size_t)cs * 3 * BN, *p_c = tp->p + (size_t)cs * BN;
+        const float *uprev = cs == 0 ? tp->ustar : tp->u1 + (size_t)(cs - 1) * 3 * BN;
+        b->launches += 4;
+        k3_adj_correct<<<grid, O3_T, 0, st>>>(b->t, unb, p_c, tp->A, hbb, rAb, pb);
+        LAUNCH_CHECK("k3_adj_correct");
+        k3_adj_remove_mean<<<b->B, 1024, 0, st>>>(b->t.N, b->t.NS, pb, xb);
+        LAUNCH_CHECK("k3_adj_remove_mean");
+        {   // lam = P^-1 x_bar (P symmetric): the forward CG kernel, zero start, no residual reset, right-hand side xb
+            T3 t = b->t; O3Slab sl = b->slab; int Bi = b->B; const float *poff = b->Poff, *pd = b->Pdiag, *rhs = xb; float *work = b->kry, *part = b->part;
+            float tol = b->opt.p_tol; int max_iter = b->opt.max_iter, zero_init = 1, reset_steps = 0, slot = 4; const int32_t *active = nullptr;
+            int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total; float *out = lam;
+            void *args[] = {&t, &sl, &Bi, &poff, &pd, &rhs, &out, &work, &part, &max_iter, &tol, &zero_init, &reset_steps, &slot, &active, &iters, &resid, &itot};
+            ce = cudaLaunchCooperativeKernel(b->cg_fused ? (void *)k3_cg_fused : (void *)k3_cg, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, st);
+            if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_cg, backward)", ce);
+        }
+        k3_adj_pressure_rhs<<<grid, O3_T, 0, st>>>(b->t, lam, p_c, hbb, Fbb, rAb);
+        LAUNCH_CHECK("k3_adj_pressure_rhs");
+        ZERO3(pb, BN);                         // the previous pressure does not enter this corrector (zero-started solve, orthogonal grid)
+        ZERO3(uprevb, 3 * BN);
+        b->launches++;
+        k3_adj_hbya<<<grid, O3_T, 0, st>>>(b->t, hbb, hb_c, tp->A, tp->Coff, uprev, tp->dt, rAb, u_bar, Sbb, Coffb, uprevb);
+        LAUNCH_CHECK("k3_adj_hbya");
+        float *tmp = unb; unb = uprevb; uprevb = tmp;       // gradient w.r.t. the velocity entering this corrector
+    }
+    {   // mu = C^-T ustar_bar
+        T3 t = b->t; O3Slab sl = b->slab; int Bi = b->B; const float *coff = tp->Coff, *a = tp->A, *rhs = unb; float *x = mu, *work = b->kry, *part = b->part;
+        int maxit = b->opt.max_iter, zero_init = 1, transposed = 1; float tol = b->opt.adv_tol; const int32_t *active = nullptr;
+        int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
+        void *args[] = {&t, &sl, &Bi, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot, &transposed};
+        b->launches++;
+        ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab<3>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, st);
+        if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab, transposed)", ce);
+    }
+    b->launches += 3;
+    k3_adj_advection<<<grid, O3_T, 0, st>>>(b->t, mu, tp->ustar, rAb, tp->A, tp->dt, Ab, Coffb, u_bar, Sbb);
+    LAUNCH_CHECK("k3_adj_advection");
+    k3_adj_assemble<<<grid, O3_T, 0, st>>>(b->t, Ab, Coffb, Sbb, tp->bvel_in, u_bar, bvel_bar, Fbb);
+    LAUNCH_CHECK("k3_adj_assemble");
+    if (b->t.NB > 0) {
+        k3_adj_bflux<<<dim3((unsigned)((b->t.NB + 127) / 128), b->B), 128, 0, st>>>(b->t, Fbb, bvel_bar);
+        LAUNCH_CHECK("k3_adj_bflux");
+    }
+#undef ZERO3
     return FGB_OK;
 }
 

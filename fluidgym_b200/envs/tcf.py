@@ -48,10 +48,13 @@ class TCF3DEnv(InitialDomains3D):
     def __init__(self, n_envs: int = 1, resolution_y=65, resolution_x_z=64, actor_size=2, L=np.pi, D=np.pi / 2, reynolds_number_wall=180,
                  adaptive_cfl=0.1, step_length=0.6, episode_length=1000, local_obs_window=1, local_reward_weight=0.0, use_marl=True,
                  C_smag=0.0, use_van_driest=False, init_with_noise=False, device="cuda:0", tau_ref=1.0, randomize_initial_state=False,
-                 enable_actions=True, domain=None, load_initial_domain=False, initial_domains_path=None):
+                 enable_actions=True, domain=None, load_initial_domain=False, initial_domains_path=None, differentiable=False):
         if init_with_noise:
             raise NotImplementedError("init_with_noise needs the reference's optional simplex-noise extension; start from a state instead")
         self.n_envs = int(n_envs)
+        self.differentiable = bool(differentiable)
+        if self.differentiable and C_smag != 0.0:
+            raise NotImplementedError("differentiable=True with the sub-grid-scale model: the per-cell viscosity is not differentiated")
         self.load_domain_on_reset, self.initial_domains_path = bool(load_initial_domain), initial_domains_path
         self.L, self.D = float(L), float(D)
         self.re_wall = float(reynolds_number_wall)
@@ -257,6 +260,80 @@ class TCF3DEnv(InitialDomains3D):
         t = self._global_obs_at(self.y_obs_top_idx)
         return {k: torch.stack((b[k], t[k]), dim=1) for k in b}
 
+    # ---- differentiable mode (fluidgym.make(..., differentiable=True); reverse mode of the D = 3 substep, autograd.PISOSubstep3D) -------
+    def _forcing_torch(self, u):
+        """set_dynamic_forcing (envs/tcf/grid.py:128-163): G_x = nu / 2 (<u>_lo / d_lo + <u>_hi / d_hi); the reference rebuilds G with
+        ``torch.tensor``: no gradient flows through it"""
+        with torch.no_grad():
+            ux = u[:, 0].reshape(self.n_envs, self.z, self.ny, self.x)
+            tlo = self.viscosity * ux[:, :, 0, :].mean(dim=(1, 2)) / self.d_lo
+            thi = self.viscosity * ux[:, :, -1, :].mean(dim=(1, 2)) / self.d_hi
+            src = torch.zeros(self.n_envs, 4, device=self.device)
+            src[:, 0] = 0.5 * (tlo + thi)
+        return src
+
+    def _wall_stress_torch(self, u):
+        """_get_wall_stress (tcf_env.py:564-584) as differentiable torch ops -> (tau_bottom, tau_top) [B]"""
+        ux = u[:, 0].reshape(self.n_envs, self.z, self.ny, self.x)
+        return (self.viscosity * ux[:, :, 0, :].mean(dim=(1, 2)) / self.d_lo, self.viscosity * ux[:, :, -1, :].mean(dim=(1, 2)) / self.d_hi)
+
+    def _single_step_differentiable(self, u, p, bv):
+        """Simulation.single_step with the adaptive CFL plan (SIM.py:2004-2031, k3_plan_substep); the plan is not differentiated.
+        One common substep size for the batch (the most restrictive environment decides)."""
+        from ..autograd import piso_substep_3d
+        s = self.solver
+        minv = s._tab["minv"].reshape(1, 3, -1)
+        b_minv = s._tab["b_minv"].reshape(1, 3, -1)
+        remaining, nsub = float(self.dt), 0
+        while remaining > 0.0 and not abs(remaining) <= 1e-8:
+            with torch.no_grad():
+                mv = float(torch.maximum((minv * u).abs().max(), (b_minv * bv).abs().max()))
+            if abs(mv) <= 1e-8:
+                ts = remaining
+            else:
+                mts = np.float32(self.cfl) / np.float32(mv)
+                ts = remaining if float(mts) >= remaining else remaining / float(int(np.ceil(np.float32(remaining) / mts)))
+            remaining -= ts
+            u, p = piso_substep_3d(s, u, p, bv, float(np.float32(ts)), self._forcing_torch(u))
+            nsub += 1
+        return u, p, nsub
+
+    def mark_state_differentiable(self):
+        """envs/util/diff_tools.py:8-22: returns the velocity leaf of the incoming state [B, 3, N]"""
+        self._du = self.solver.u.detach().clone().requires_grad_(True)
+        return self._du
+
+    def detach(self):
+        self._du = None
+
+    def _step_differentiable(self, action):
+        s = self.solver
+        u = self._du if getattr(self, "_du", None) is not None else s.u.detach().clone()
+        p = s.p.detach().clone()
+        bv = s.bvel.detach().clone()
+        if self.enable_actions:
+            a = action.reshape(self.n_envs, -1)
+            half = self.nax * self.naz
+            lo = torch.zeros(self.n_envs, 3, self.x * self.z, device=self.device)
+            lo = torch.stack([lo[:, 0], self._action_to_control(a[:, :half].reshape(self.n_envs, self.nax, self.naz)), lo[:, 2]], dim=1)
+            bv = torch.cat([bv[:, :, :self._face_lo.start], lo, bv[:, :, self._face_lo.stop:]], dim=2)
+            if self.both_walls:
+                hi = torch.zeros(self.n_envs, 3, self.x * self.z, device=self.device)
+                hi = torch.stack([hi[:, 0], -1 * self._action_to_control(a[:, half:].reshape(self.n_envs, self.nax, self.naz)), hi[:, 2]], dim=1)
+                bv = torch.cat([bv[:, :, :self._face_hi.start], hi, bv[:, :, self._face_hi.stop:]], dim=2)
+        tb, tt, nsub = [], [], 0
+        for _ in range(self.n_sim_steps):
+            u, p, n = self._single_step_differentiable(u, p, bv)
+            nsub += n
+            lo_, hi_ = self._wall_stress_torch(u)
+            tb.append(lo_); tt.append(hi_)
+        self.last_substeps = nsub
+        with torch.no_grad():                      # the solver buffers mirror the state (observations read them)
+            s.u.copy_(u); s.p.copy_(p); s.bvel.copy_(bv)
+        self._du = u
+        tau_bottom, tau_top = torch.stack(tb).mean(dim=0), torch.stack(tt).mean(dim=0)
+        return tau_bottom, tau_top
+
     def step(self, action):
         if not self._reset_called:
             raise RuntimeError("Environment must be reset before stepping. Call 'reset()' before'step()'.")
@@ -265,6 +342,17 @@ class TCF3DEnv(InitialDomains3D):
             raise ValueError(f"Action shape {action.shape} does not match expected shape {self._zero_action.shape}.")
         if self._n_steps >= self.episode_length:
             raise RuntimeError("Episode has already terminated. Call 'reset()' first.")
+        if self.differentiable:
+            tau_bottom, tau_top = self._step_differentiable(action)
+            tau_total = 0.5 * (tau_bottom + tau_top)
+            reward = 1 - (tau_total if self.both_walls else tau_bottom) / self.tau_ref
+            info = {"wall_stress": tau_total, "wall_stress_bottom": tau_bottom, "wall_stress_top": tau_top}
+            self._n_steps += 1
+            obs = self._get_obs()
+            if self.use_marl:
+                info["global_reward"] = reward
+                reward = reward[:, None] * torch.ones(self.n_envs, self.n_agents, device=self.device)
+            return obs, reward, False, self._n_steps >= self.episode_length, info
         if self.enable_actions:
             self._apply_action(action)
         s = self.solver

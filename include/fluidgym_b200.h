@@ -350,6 +350,29 @@ int fgb_ortho3_sgs_viscosity(fgb_ortho3 *b, const float *u, const float *bvel, c
  * fluid_env.py:577-656): grad_out [B][3 component c][3 direction d][NS] = d u_c / d x_d -- the reference's list index is the
  * component and the tensor channel the direction (its kernel, K.cu:6470-6480), the layout kept here */
 int fgb_ortho3_velocity_gradients(fgb_ortho3 *b, const float *u, const float *bvel, float *grad_out, fgb_stream_t s);
+/* Reverse mode of the D = 3 substep (single GPU, structured box, no scalar / SGS): tape filled by the recording forward call,
+ * vector-Jacobian product by hand-written adjoint kernels + the Krylov solves with the transposed operator.  Replaces the
+ * dimension-generic _GRAD kernels the reference differentiates these grids with (PISO_multiblock_cuda_kernel.cu:3884-4090,
+ * 4403-4491, 6265-6309; PISOtorch_diff.py:624-1808).  As in the reference's differentiable backend every recorded solve starts
+ * from zero and the CG does not reset its residual.  C = corrector_steps. */
+typedef struct fgb_ortho3_tape {
+    float *u_in;     /* [B][3][N]  */
+    float *bvel_in;  /* [B][3][NB] */
+    float *dt;       /* [B]        */
+    float *Coff;     /* [B][6][N]  */
+    float *A;        /* [B][N]     */
+    float *ustar;    /* [B][3][N]       predictor result */
+    float *hb;       /* [C][B][3][N]    HbyA of every corrector */
+    float *p;        /* [C][B][N]       pressure of every corrector (mean removed) */
+    float *u1;       /* [max(C-1,1)][B][3][N]  velocity after every corrector but the last */
+} fgb_ortho3_tape;
+int fgb_ortho3_piso_substep_record(fgb_ortho3 *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
+                                   const fgb_ortho3_tape *tape, fgb_stream_t s);
+size_t fgb_ortho3_adjoint_workspace_bytes(const fgb_ortho3_tables *t, int32_t B);
+/* (u_out_bar, p_out_bar) -> (u_bar, bvel_bar), both overwritten; the previous pressure and the source do not receive gradients
+ * (zero-started solves on an orthogonal grid; the channel forcing is detached in the reference, envs/tcf/grid.py:147-161) */
+int fgb_ortho3_piso_substep_backward(fgb_ortho3 *b, const fgb_ortho3_tape *tape, const float *u_out_bar, const float *p_out_bar,
+                                     float *u_bar, float *bvel_bar, void *workspace, size_t workspace_bytes, fgb_stream_t s);
 int fgb_ortho3_make_divergence_free(fgb_ortho3 *b, float *u, float *p, const float *bvel, int max_iter, fgb_stream_t s);
 /* rows: [2][n_row] cells of the first / last wall-normal layer; d_lo, d_hi their wall distances.  With rows != NULL the
  * channel forcing G_x = nu/2 (<u>_lo/d_lo + <u>_hi/d_hi) (envs/tcf/grid.py:128-163) is refreshed before every substep. */

@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--kw", default="{}")
     ap.add_argument("--pressure-tol", type=float, default=None)
     ap.add_argument("--advection-tol", type=float, default=None)
+    ap.add_argument("--perturb", type=float, default=0.0, help="std of Gaussian noise added to the block velocities after reset (as ref_harness.py)")
     args = ap.parse_args()
     tag = args.tag or args.env.replace("-", "_")
     os.makedirs(args.out, exist_ok=True)
@@ -69,6 +70,13 @@ def main():
         if val is not None:
             setattr(env._sim, name, val)
             meta[name] = val
+    if args.perturb > 0:
+        gen = torch.Generator(device="cuda").manual_seed(args.seed)
+        for blk in env._domain.getBlocks():
+            u = blk.velocity
+            blk.setVelocity((u + args.perturb * torch.randn(u.shape, device=u.device, generator=gen)).contiguous())
+        env._domain.UpdateDomainData()
+        meta["perturb"] = args.perturb
     for _ in range(args.develop):
         with torch.no_grad():
             env.step(torch.zeros_like(env._zero_action))

@@ -71,8 +71,25 @@ def tight_trace(src, tag="cyl24_t32", out="cyl24_tight"):
         print(out, k, fx["cg_iters"], fx["cg_resid"], fx["bicg_iters"])
 
 
+def tcf(src, tag="tcf32", out="tcf32"):
+    """3-D channel, 32 x 33 x 32 (tools/r02_tcf_grad_golden.sh; the grid of tcf32_geometry.npz): one env.step = 10 solver steps.
+    The cotangent of the state vjp is sin(0.37 i + 0) over the flat index (ref_grad_harness.cotangent_like), not stored."""
+    d = np.load(os.path.join(src, f"{tag}_grad.npz"))
+    meta = json.load(open(os.path.join(src, f"{tag}_grad_meta.json")))
+    fx = dict(action=d["action"].reshape(-1), reward=d["reward"].reshape(-1)[:1], dreward_daction=d["dreward_daction"].reshape(-1),
+              vjp_daction=d["vjp_daction"].reshape(-1), pre_u=d["pre_b0_u"].reshape(3, -1), post_u=d["post_b0_u"].reshape(3, -1),
+              dreward_du=d["dreward_db0_u"].reshape(3, -1), vjp_du=d["vjp_db0_u"].reshape(3, -1),
+              info_wall_stress=d["info_wall_stress"].reshape(-1), forward_cg_mean=np.array(meta["forward_iters"]["cg"]["mean"]),
+              forward_cg_n=np.array(meta["forward_iters"]["cg"]["n"]))
+    assert np.abs(d["cotangent0"].reshape(-1) - np.sin(0.37 * np.arange(d["cotangent0"].size)).astype(np.float32)).max() < 1e-6
+    np.savez_compressed(os.path.join(HERE, f"{out}_grad.npz"), **{k: np.asarray(v, dtype=np.float32) for k, v in fx.items()})
+    print(out, {k: (np.asarray(v).shape, float(np.abs(v).max())) for k, v in fx.items()})
+
+
 def main():
     src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/r02/golden"
+    if len(sys.argv) > 2 and sys.argv[2] == "tcf":
+        return tcf(src)
     from fluidgym_b200.envs.airfoil_domain import make_airfoil_domain
     from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
     multiblock(src, "cyl24", "cyl24", make_cylinder_domain(24))
