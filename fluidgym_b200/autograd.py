@@ -176,3 +176,47 @@ class PISOSubstep3D(torch.autograd.Function):
 def piso_substep_3d(solver, u, p, bvel, dt, src=None):
     """Differentiable substep of a structured 3-D box (functional form: inputs are not modified)."""
     return PISOSubstep3D.apply(u, p, bvel, solver, dt, src)
+
+
+class PISOSubstepScalar3D(torch.autograd.Function):
+    """(u [B,3,N], p [B,N], bvel [B,3,NB], T [B,N], sbval [B,NB]) -> (u_next, p_next, T_next) on a structured 3-D box with an attached
+    passive scalar + buoyancy (RBC3D; ``BatchedPISO3D.attach_scalar``).  The solver's own scalar buffers are used as scratch."""
+
+    @staticmethod
+    def forward(ctx, u, p, bvel, T, sbval, solver, dt):
+        dtc = solver._dt(dt)
+        tape = _new_tape3(solver)
+        f32 = dict(device=solver.device, dtype=torch.float32)
+        stape = dict(T_in=torch.empty(solver.B, solver.N, **f32), T_out=torch.empty(solver.B, solver.N, **f32),
+                     sbval_in=torch.empty(solver.B, max(solver.NB, 1), **f32))
+        ct = native.Ortho3Tape(*[tape[k].data_ptr() for k, _ in native.Ortho3Tape._fields_])
+        cs = native.ScalarTape(*[stape[k].data_ptr() for k, _ in native.ScalarTape._fields_])
+        u_out, p_out = u.detach().clone().contiguous(), p.detach().clone().contiguous()
+        bv = bvel.detach().contiguous()
+        solver.T.copy_(T.detach()); solver.sbval.copy_(sbval.detach())
+        native.check(solver.lib.fgb_ortho3_piso_substep_record_scalar(solver.handle, _ptr(u_out), _ptr(p_out), _ptr(bv), None, _ptr(dtc), C.byref(ct),
+                                                                      C.byref(cs), solver.stream), "fgb_ortho3_piso_substep_record_scalar")
+        ctx.solver, ctx.tape, ctx.stape = solver, tape, stape
+        return u_out, p_out, solver.T.clone()
+
+    @staticmethod
+    def backward(ctx, u_out_bar, p_out_bar, T_out_bar):
+        solver, tape, stape = ctx.solver, ctx.tape, ctx.stape
+        B, N, NB = solver.B, solver.N, max(solver.NB, 1)
+        f32 = dict(device=solver.device, dtype=torch.float32)
+        ct = native.Ortho3Tape(*[tape[k].data_ptr() for k, _ in native.Ortho3Tape._fields_])
+        cs = native.ScalarTape(*[stape[k].data_ptr() for k, _ in native.ScalarTape._fields_])
+        ub, bvb, Tb, sbb = torch.empty(B, 3, N, **f32), torch.empty(B, 3, NB, **f32), torch.empty(B, N, **f32), torch.empty(B, NB, **f32)
+        ws, nbytes = _adjoint_workspace3(solver)
+        uo = (u_out_bar if u_out_bar is not None else torch.zeros(B, 3, N, **f32)).contiguous()
+        po = (p_out_bar if p_out_bar is not None else torch.zeros(B, N, **f32)).contiguous()
+        To = (T_out_bar if T_out_bar is not None else torch.zeros(B, N, **f32)).contiguous()
+        native.check(solver.lib.fgb_ortho3_piso_substep_backward_scalar(solver.handle, C.byref(ct), C.byref(cs), _ptr(uo), _ptr(po), _ptr(To), _ptr(ub),
+                                                                        _ptr(bvb), _ptr(Tb), _ptr(sbb), ws, nbytes, solver.stream),
+                     "fgb_ortho3_piso_substep_backward_scalar")
+        return ub, None, bvb, Tb, sbb, None, None
+
+
+def piso_substep_scalar_3d(solver, u, p, bvel, T, sbval, dt):
+    """Differentiable substep of a structured 3-D box with passive scalar + buoyancy (functional form)."""
+    return PISOSubstepScalar3D.apply(u, p, bvel, T, sbval, solver, dt)

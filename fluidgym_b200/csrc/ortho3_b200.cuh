@@ -1296,6 +1296,41 @@ __global__ void __launch_bounds__(O3_T) k3_adj_assemble(T3 t, const float *__res
     }
     o3_fluxes_adjoint(t, g, nb6, flb, Ub + (size_t)b * 3 * NS, nullptr);
 }
+// Passive scalar + buoyancy (RBC3D).  The source (0, beta T_new, 0) enters the predictor right-hand side and HbyA next to S_b / det, so
+// its adjoint is det * S_b_bar:  T_new_bar = T_out_bar + beta * det * S_b_bar[1]
+__global__ void __launch_bounds__(O3_T) k3_adj_buoyancy(T3 t, const float *__restrict__ Sbb, const float *__restrict__ Toutb, float beta, float *__restrict__ Tnb) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, NS = t.NS;
+    if (g >= t.N) return;
+    Tnb[(size_t)b * NS + g] = Toutb[(size_t)b * NS + g] + beta * t.det[g] * Sbb[((size_t)b * 3 + 1) * NS + g];
+}
+// adjoint of k3_setup_scalar + the scalar solve, given lam = C_s^-T T_new_bar:  A_s_bar = -lam T_new, Coff_s_bar[f] = -lam T_new[nb_f];
+// rhs_s = r / det with r = det T_in / dt + sum_{prescribed f} sb (-(sig F_b) + 2 kappa alpha_b)
+__global__ void __launch_bounds__(O3_T) k3_adj_scalar(T3 t, const float *__restrict__ Lam, const float *__restrict__ Tnew, const float *__restrict__ Bvel,
+                                                      const float *__restrict__ Sbval, float kappa, const float *__restrict__ dtv,
+                                                      float *__restrict__ Tinb, float *__restrict__ Sbvalb, float *__restrict__ Fbb, float *__restrict__ Ub) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, NS = t.NS, NB = t.NB;
+    if (g >= t.N) return;
+    const float *tn = Tnew + (size_t)b * NS, *bv = Bvel + (size_t)b * 3 * NB, *sb = Sbval + (size_t)b * NB;
+    const float lam = Lam[(size_t)b * NS + g], det = t.det[g], rb = lam / det;
+    Tinb[(size_t)b * NS + g] = lam / dtv[b];
+    const float diagb = -lam * tn[g] / det;                   // A_s = diag / det
+    int nb6[6];
+    o3_nbrs(t, g, nb6);
+    float flb[6];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const float sig = (f & 1) ? 1.f : -1.f;
+        flb[f] = 0.f;
+        if (nb6[f] >= 0) flb[f] = 0.5f * sig * (-lam * tn[nb6[f]] / det + diagb);
+        else {
+            const int j = -1 - nb6[f], d = f >> 1;
+            const float bm = t.b_minv[d * NB + j];
+            atomicAdd(&Sbvalb[(size_t)b * NB + j], rb * (-(sig * o3_bflux(t, j, d, bv)) + 2.f * kappa * (t.b_det[j] * bm * bm)));
+            atomicAdd(&Fbb[(size_t)b * NB + j], -rb * sb[j] * sig);
+        }
+    }
+    o3_fluxes_adjoint(t, g, nb6, flb, Ub + (size_t)b * 3 * NS, nullptr);
+}
 // adjoint of the boundary flux Fb_j = b_det minv_d bv_d (d = axis of the face): one thread per (boundary face, environment)
 __global__ void k3_adj_bflux(T3 t, const float *__restrict__ Fbb, float *__restrict__ Bvb) {
     const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x, NB = t.NB;
@@ -1312,26 +1347,35 @@ static int o3_copy(void *dst, const void *src, size_t bytes, cudaStream_t st) {
     cudaError_t ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st);
     return ce == cudaSuccess ? FGB_OK : set_err(FGB_E_CUDA, "cudaMemcpyAsync (D = 3 tape)", ce);
 }
-static int o3_adjoint_supported(const fgb_ortho3 *b, const char *who) {
+static int o3_adjoint_supported(const fgb_ortho3 *b, bool with_scalar) {
     if (b->slab.on || b->t.NS != b->t.N) return set_err(FGB_E_ARG, "D = 3 reverse mode: single GPU only (no slabs)");
     if (b->t.nx <= 0) return set_err(FGB_E_ARG, "D = 3 reverse mode: needs the structured-box description (tables.nx/ny/nz/closed/boff)");
-    if (b->sc.T || b->sgs_coef != 0.f) return set_err(FGB_E_ARG, "D = 3 reverse mode: passive scalar / sub-grid viscosity are not differentiated");
+    if (b->sgs_coef != 0.f) return set_err(FGB_E_ARG, "D = 3 reverse mode: the sub-grid viscosity is not differentiated");
+    if (with_scalar != (b->sc.T != nullptr))
+        return set_err(FGB_E_ARG, with_scalar ? "D = 3 reverse mode (scalar): no scalar attached (fgb_ortho3_set_scalar)"
+                                              : "D = 3 reverse mode: a scalar is attached, use the _scalar entry points");
     if (b->opt.corrector_steps < 1 || b->opt.corrector_steps > 8) return set_err(FGB_E_ARG, "D = 3 reverse mode: 1..8 corrector steps");
-    (void)who;
     return FGB_OK;
 }
 // fgb_ortho3_piso_substep (all environments active) that additionally records the tape of the backward pass
-extern "C" int fgb_ortho3_piso_substep_record(fgb_ortho3 *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
-                                              const fgb_ortho3_tape *tp, fgb_stream_t s) {
+static int o3_record_impl(fgb_ortho3 *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
+                          const fgb_ortho3_tape *tp, const fgb_tape_scalar *stp, fgb_stream_t s) {
     if (!b || !u || !p || !bvel || !dt || !tp) return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep_record: null argument");
     int rc;
-    if ((rc = o3_adjoint_supported(b, "record"))) return rc;
+    if ((rc = o3_adjoint_supported(b, stp != nullptr))) return rc;
+    if (stp && (!stp->T_in || !stp->T_out || !stp->sbval_in)) return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep_record_scalar: incomplete scalar tape");
     cudaStream_t st = STREAM(s);
     const size_t BN = (size_t)b->B * b->t.NS, BNB = (size_t)b->B * (b->t.NB > 0 ? b->t.NB : 1);
     const int C = b->opt.corrector_steps;
     if ((rc = o3_copy(tp->u_in, u, 3 * BN * 4, st))) return rc;
     if ((rc = o3_copy(tp->bvel_in, bvel, 3 * BNB * 4, st))) return rc;
     if ((rc = o3_copy(tp->dt, dt, (size_t)b->B * 4, st))) return rc;
+    if (stp) {      // scalar transport with the incoming velocity first; the predictor / HbyA then read the new temperature (buoyancy)
+        if ((rc = o3_copy(stp->T_in, b->sc.T, BN * 4, st))) return rc;
+        if ((rc = o3_copy(stp->sbval_in, b->sc.sbval, BNB * 4, st))) return rc;
+        if ((rc = fgb_ortho3_advect_scalar(b, u, bvel, dt, nullptr, s))) return rc;
+        if ((rc = o3_copy(stp->T_out, b->sc.T, BN * 4, st))) return rc;
+    }
     if ((rc = fgb_ortho3_setup_advection(b, u, bvel, src, dt, nullptr, s))) return rc;
     if ((rc = fgb_ortho3_solve_advection(b, 1, nullptr, s))) return rc;
     if ((rc = o3_copy(tp->ustar, b->ures, 3 * BN * 4, st))) return rc;
@@ -1347,16 +1391,29 @@ extern "C" int fgb_ortho3_piso_substep_record(fgb_ortho3 *b, float *u, float *p,
     }
     return o3_copy(u, b->ures, 3 * BN * 4, st);
 }
+extern "C" int fgb_ortho3_piso_substep_record(fgb_ortho3 *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
+                                              const fgb_ortho3_tape *tp, fgb_stream_t s) {
+    return o3_record_impl(b, u, p, bvel, src, dt, tp, nullptr, s);
+}
+// with an attached scalar (RBC3D): the scalar buffer (fgb_ortho3_scalar.T) is advanced in place, as in fgb_ortho3_piso_substep
+extern "C" int fgb_ortho3_piso_substep_record_scalar(fgb_ortho3 *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
+                                                     const fgb_ortho3_tape *tp, const fgb_tape_scalar *stp, fgb_stream_t s) {
+    if (!stp) return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep_record_scalar: null scalar tape");
+    return o3_record_impl(b, u, p, bvel, src, dt, tp, stp, s);
+}
 extern "C" size_t fgb_ortho3_adjoint_workspace_bytes(const fgb_ortho3_tables *t, int32_t B) {
     const size_t BN = (size_t)B * (t->NS > 0 ? t->NS : t->N), BNB = (size_t)B * (t->NB > 0 ? t->NB : 1);
     return (size_t)(3 + 3 + 1 + 6 + 3 + 1 + 1 + 1 + 3 + 1 + 3) * align_up(BN * 4) + align_up(BNB * 4) + 8192;
 }
 // vector-Jacobian product of that substep: (u_out_bar, p_out_bar) -> (u_bar, bvel_bar), both overwritten
-extern "C" int fgb_ortho3_piso_substep_backward(fgb_ortho3 *b, const fgb_ortho3_tape *tp, const float *u_out_bar, const float *p_out_bar,
-                                                float *u_bar, float *bvel_bar, void *ws, size_t ws_bytes, fgb_stream_t s) {
+static int o3_backward_impl(fgb_ortho3 *b, const fgb_ortho3_tape *tp, const fgb_tape_scalar *stp, const float *u_out_bar, const float *p_out_bar,
+                            const float *T_out_bar, float *u_bar, float *bvel_bar, float *T_bar, float *sbval_bar, void *ws, size_t ws_bytes,
+                            fgb_stream_t s) {
     if (!b || !tp || !u_out_bar || !p_out_bar || !u_bar || !bvel_bar || !ws) return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep_backward: null argument");
     int rc;
-    if ((rc = o3_adjoint_supported(b, "backward"))) return rc;
+    if ((rc = o3_adjoint_supported(b, stp != nullptr))) return rc;
+    if (stp && (!T_out_bar || !T_bar || !sbval_bar || !stp->T_in || !stp->T_out || !stp->sbval_in))
+        return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep_backward_scalar: incomplete scalar arguments");
     if (ws_bytes < fgb_ortho3_adjoint_workspace_bytes(&b->t, b->B)) return set_err(FGB_E_WORKSPACE, "fgb_ortho3_piso_substep_backward: workspace too small");
     cudaStream_t st = STREAM(s);
     const size_t B = b->B, NB = b->t.NB > 0 ? b->t.NB : 1, BN = B * b->t.NS;
@@ -1413,12 +1470,45 @@ extern "C" int fgb_ortho3_piso_substep_backward(fgb_ortho3 *b, const fgb_ortho3_
     LAUNCH_CHECK("k3_adj_advection");
     k3_adj_assemble<<<grid, O3_T, 0, st>>>(b->t, Ab, Coffb, Sbb, tp->bvel_in, u_bar, bvel_bar, Fbb);
     LAUNCH_CHECK("k3_adj_assemble");
+    if (stp) {
+        // buoyancy + scalar transport (they ran BEFORE the predictor): T_new_bar from the source adjoint, one transposed scalar solve,
+        // then the adjoint of the scalar assembly.  xb / lam are free again; the scalar matrix is rebuilt from the taped inputs into
+        // the forward workspace (Coff / A / rhs are not read by this pass any more).
+        float *Tnb = xb;
+        b->launches += 4;
+        k3_adj_buoyancy<<<grid, O3_T, 0, st>>>(b->t, Sbb, T_out_bar, b->sc.beta, Tnb);
+        LAUNCH_CHECK("k3_adj_buoyancy");
+        k3_setup_scalar<<<grid, O3_T, 0, st>>>(b->t, tp->u_in, stp->T_in, tp->bvel_in, stp->sbval_in, b->sc.kappa, tp->dt, nullptr, b->Coff, b->A, b->rhs);
+        LAUNCH_CHECK("k3_setup_scalar (backward)");
+        {   // lam = C_s^-T T_new_bar
+            T3 t = b->t; O3Slab sl = b->slab; int Bi = b->B; const float *coff = b->Coff, *a = b->A, *rhs = Tnb; float *x = lam, *work = b->kry, *part = b->part;
+            int maxit = b->opt.max_iter, zero_init = 1, transposed = 1; float tol = b->opt.adv_tol; const int32_t *active = nullptr;
+            int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
+            void *args[] = {&t, &sl, &Bi, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot, &transposed};
+            ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab<1>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, st);
+            if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab<1>, transposed)", ce);
+        }
+        ZERO3(sbval_bar, B * NB);
+        k3_adj_scalar<<<grid, O3_T, 0, st>>>(b->t, lam, stp->T_out, tp->bvel_in, stp->sbval_in, b->sc.kappa, tp->dt, T_bar, sbval_bar, Fbb, u_bar);
+        LAUNCH_CHECK("k3_adj_scalar");
+    }
     if (b->t.NB > 0) {
         k3_adj_bflux<<<dim3((unsigned)((b->t.NB + 127) / 128), b->B), 128, 0, st>>>(b->t, Fbb, bvel_bar);
         LAUNCH_CHECK("k3_adj_bflux");
     }
 #undef ZERO3
     return FGB_OK;
+}
+extern "C" int fgb_ortho3_piso_substep_backward(fgb_ortho3 *b, const fgb_ortho3_tape *tp, const float *u_out_bar, const float *p_out_bar,
+                                                float *u_bar, float *bvel_bar, void *ws, size_t ws_bytes, fgb_stream_t s) {
+    return o3_backward_impl(b, tp, nullptr, u_out_bar, p_out_bar, nullptr, u_bar, bvel_bar, nullptr, nullptr, ws, ws_bytes, s);
+}
+// (u_out_bar, p_out_bar, T_out_bar) -> (u_bar, bvel_bar, T_bar, sbval_bar), all overwritten
+extern "C" int fgb_ortho3_piso_substep_backward_scalar(fgb_ortho3 *b, const fgb_ortho3_tape *tp, const fgb_tape_scalar *stp, const float *u_out_bar,
+                                                       const float *p_out_bar, const float *T_out_bar, float *u_bar, float *bvel_bar, float *T_bar,
+                                                       float *sbval_bar, void *ws, size_t ws_bytes, fgb_stream_t s) {
+    if (!stp) return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep_backward_scalar: null scalar tape");
+    return o3_backward_impl(b, tp, stp, u_out_bar, p_out_bar, T_out_bar, u_bar, bvel_bar, T_bar, sbval_bar, ws, ws_bytes, s);
 }
 
 // make_divergence_free (SIM.py:1320-1429): A = 1, one projection of the current velocity

@@ -66,8 +66,11 @@ class RBC3DEnv(InitialDomains3D):
     def __init__(self, n_envs: int = 1, rayleigh_number=2e3, prandtl_number=0.7, n_heaters=8, resolution=8, dt=0.05,
                  adaptive_cfl=0.8, step_length=1.0, episode_length=200, local_obs_window=3, local_reward_weight=0.0015,
                  uniform_grid=False, aspect_ratio=1.0, use_marl=True, device="cuda:0", nu_ref=0.0, randomize_initial_state=False,
-                 enable_actions=True, load_initial_domain=False, initial_domains_path=None, transforms=None, btransforms=None):
+                 enable_actions=True, load_initial_domain=False, initial_domains_path=None, transforms=None, btransforms=None,
+                 differentiable=False):
         self.n_envs = int(n_envs)
+        self.differentiable = bool(differentiable)
+        self._dstate = None          # (u, p, T, sbval) carried with their autograd history in differentiable mode
         self.load_domain_on_reset, self.initial_domains_path = bool(load_initial_domain), initial_domains_path
         self.rayleigh_number, self.prandtl_number = rayleigh_number, prandtl_number
         self.Ra, self.Pr = float(rayleigh_number), float(prandtl_number)
@@ -301,7 +304,8 @@ class RBC3DEnv(InitialDomains3D):
     def _fields(self):
         s = self.solver
         B = self.n_envs
-        return s.T.reshape(B, self.nz, self.ny, self.nx), s.u[:, 1].reshape(B, self.nz, self.ny, self.nx)
+        u, T = getattr(self, "_dfields", None) or (s.u, s.T)      # differentiable mode: the tensors that carry the graph
+        return T.reshape(B, self.nz, self.ny, self.nx), u[:, 1].reshape(B, self.nz, self.ny, self.nx)
 
     def compute_global_nusselt(self):
         """rbc_env_base.py:491-539: Nu = 1 + sqrt(Ra Pr) <u_y T>_V"""
@@ -320,6 +324,51 @@ class RBC3DEnv(InitialDomains3D):
         q = (lu * lT * cs).sum(dim=(2, 3, 4)) / cs.sum()
         return self.nu_ref - (1.0 + (self.Ra * self.Pr) ** 0.5 * q)
 
+    # ---- differentiable mode: one autograd node per substep (autograd.PISOSubstepScalar3D, CUDA adjoint of the D = 3 box path); the
+    # heater profile and the Nusselt integrals around it are torch expressions, as in the reference.  The CFL plan is taken from
+    # detached maxima with one common substep size for the batch (the most restrictive environment decides).
+    def detach(self):
+        if self._dstate is not None:
+            self._dstate = tuple(t.detach() for t in self._dstate)
+
+    def mark_state_differentiable(self):
+        """envs/util/diff_tools.py:8-22: (velocity, temperature) leaves of the incoming state"""
+        s = self.solver
+        u, T = s.u.detach().clone().requires_grad_(True), s.T.detach().clone().requires_grad_(True)
+        self._dstate = (u, s.p.detach().clone(), T, s.sbval.detach().clone())
+        return u, T
+
+    def _advance_differentiable(self, action):
+        from ..autograd import piso_substep_scalar_3d
+        s = self.solver
+        if self._dstate is None:
+            self._dstate = (s.u.clone(), s.p.clone(), s.T.clone(), s.sbval.clone())
+        u, p, T, sb = self._dstate
+        if self.enable_actions:
+            ctrl = self._action_to_control(action.reshape(self.n_envs, self.n_heaters, self.n_heaters)).reshape(self.n_envs, -1)
+            sb = sb.index_copy(1, torch.arange(self._bottom.start, self._bottom.stop, device=self.device), ctrl)
+        bv = s.bvel
+        minv, b_minv = s._tab["minv"].reshape(1, 3, -1), s._tab["b_minv"].reshape(1, 3, -1)
+        nsub = 0
+        for _ in range(self.n_sim_steps):
+            remaining = float(self.dt)
+            while remaining > 0.0 and not abs(remaining) <= 1e-8:            # SIM.py:2004-2031
+                with torch.no_grad():
+                    mv = float(torch.maximum((minv * u).abs().max(), (b_minv * bv).abs().max()))
+                if abs(mv) <= 1e-8:
+                    ts = remaining
+                else:
+                    mts = np.float32(self.cfl) / np.float32(mv)
+                    ts = remaining if float(mts) >= remaining else remaining / float(int(np.ceil(np.float32(remaining) / mts)))
+                remaining -= ts
+                u, p, T = piso_substep_scalar_3d(s, u, p, bv, T, sb, float(np.float32(ts)))
+                nsub += 1
+        self._dstate = (u, p, T, sb)
+        with torch.no_grad():                      # keep the solver's own state in step for observations / get_state
+            s.u.copy_(u); s.p.copy_(p); s.T.copy_(T); s.sbval.copy_(sb)
+        self.last_substeps = nsub
+        return u, T
+
     def step(self, action):
         if not self._reset_called:
             raise RuntimeError("Environment must be reset before stepping. Call 'reset()' before'step()'.")
@@ -328,12 +377,16 @@ class RBC3DEnv(InitialDomains3D):
             raise ValueError(f"Action shape {action.shape} does not match expected shape {self._zero_action.shape}.")
         if self._n_steps >= self.episode_length:
             raise RuntimeError("Episode has already terminated. Call 'reset()' first.")
-        if self.enable_actions:
-            self._apply_action(action)
-        nsub = 0
-        for _ in range(self.n_sim_steps):
-            nsub += self.solver.single_step(self.dt, self.cfl)
-        self.last_substeps = nsub
+        if self.differentiable:
+            self._dfields = self._advance_differentiable(action)
+        else:
+            self._dfields = None
+            if self.enable_actions:
+                self._apply_action(action)
+            nsub = 0
+            for _ in range(self.n_sim_steps):
+                nsub += self.solver.single_step(self.dt, self.cfl)
+            self.last_substeps = nsub
         nu = self.compute_global_nusselt()
         reward = self.nu_ref - nu
         info = {"nusselt": nu.detach()}

@@ -373,6 +373,13 @@ size_t fgb_ortho3_adjoint_workspace_bytes(const fgb_ortho3_tables *t, int32_t B)
  * (zero-started solves on an orthogonal grid; the channel forcing is detached in the reference, envs/tcf/grid.py:147-161) */
 int fgb_ortho3_piso_substep_backward(fgb_ortho3 *b, const fgb_ortho3_tape *tape, const float *u_out_bar, const float *p_out_bar,
                                      float *u_bar, float *bvel_bar, void *workspace, size_t workspace_bytes, fgb_stream_t s);
+/* the same with an attached passive scalar + buoyancy (RBC3D; fgb_ortho3_set_scalar): the scalar buffer is advanced in place by the
+ * forward call; additional gradients: temperature field and boundary temperatures (heaters).  fgb_tape_scalar as in 2-D. */
+int fgb_ortho3_piso_substep_record_scalar(fgb_ortho3 *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
+                                          const fgb_ortho3_tape *tape, const fgb_tape_scalar *stape, fgb_stream_t s);
+int fgb_ortho3_piso_substep_backward_scalar(fgb_ortho3 *b, const fgb_ortho3_tape *tape, const fgb_tape_scalar *stape, const float *u_out_bar,
+                                            const float *p_out_bar, const float *T_out_bar, float *u_bar, float *bvel_bar, float *T_bar,
+                                            float *sbval_bar, void *workspace, size_t workspace_bytes, fgb_stream_t s);
 int fgb_ortho3_make_divergence_free(fgb_ortho3 *b, float *u, float *p, const float *bvel, int max_iter, fgb_stream_t s);
 /* rows: [2][n_row] cells of the first / last wall-normal layer; d_lo, d_hi their wall distances.  With rows != NULL the
  * channel forcing G_x = nu/2 (<u>_lo/d_lo + <u>_hi/d_hi) (envs/tcf/grid.py:128-163) is refreshed before every substep. */

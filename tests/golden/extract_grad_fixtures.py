@@ -86,10 +86,32 @@ def tcf(src, tag="tcf32", out="tcf32"):
     print(out, {k: (np.asarray(v).shape, float(np.abs(v).max())) for k, v in fx.items()})
 
 
+def rbc3d(src, tag="rbc3d", out="rbc3d"):
+    """RBC3D-easy with n_heaters 2, resolution 8, step_length 0.25, use_marl False (16 x 10 x 16 cells; the grid of rbc3d_geometry.npz): one
+    env.step = 5 solver steps.  Cotangents: sin(0.37 i) (velocity), sin(0.37 i + 0.3) (temperature)."""
+    d = np.load(os.path.join(src, f"{tag}_grad.npz"))
+    meta = json.load(open(os.path.join(src, f"{tag}_grad_meta.json")))
+    N = d["pre_b0_s"].size
+    nface = d["pre_b0_f2_scalar"].size
+
+    def sb(pre):
+        return np.concatenate([np.broadcast_to(d[pre + "f2_scalar"].ravel(), (nface,)), np.broadcast_to(d[pre + "f3_scalar"].ravel(), (nface,))])
+
+    fx = dict(action=d["action"].reshape(-1), reward=d["reward"].reshape(-1), dreward_daction=d["dreward_daction"].reshape(-1),
+              vjp_daction=d["vjp_daction"].reshape(-1), pre_u=d["pre_b0_u"].reshape(3, N), pre_p=d["pre_pressureResult"].reshape(N),
+              pre_T=d["pre_b0_s"].reshape(N), pre_sbval=sb("pre_b0_"), post_u=d["post_b0_u"].reshape(3, N), post_T=d["post_b0_s"].reshape(N),
+              dreward_du=d["dreward_db0_u"].reshape(3, N), dreward_dT=d["dreward_db0_s"].reshape(N), vjp_du=d["vjp_db0_u"].reshape(3, N),
+              vjp_dT=d["vjp_db0_s"].reshape(N), forward_cg_n=np.array(meta["forward_iters"]["cg"]["n"]))
+    np.savez_compressed(os.path.join(HERE, f"{out}_grad.npz"), **{k: np.asarray(v, dtype=np.float32) for k, v in fx.items()})
+    print(out, {k: (np.asarray(v).shape, float(np.abs(v).max())) for k, v in fx.items()})
+
+
 def main():
     src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/r02/golden"
     if len(sys.argv) > 2 and sys.argv[2] == "tcf":
         return tcf(src)
+    if len(sys.argv) > 2 and sys.argv[2] == "rbc3d":
+        return rbc3d(src)
     from fluidgym_b200.envs.airfoil_domain import make_airfoil_domain
     from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
     multiblock(src, "cyl24", "cyl24", make_cylinder_domain(24))

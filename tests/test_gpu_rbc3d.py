@@ -152,3 +152,40 @@ def test_initial_domain_file_written_by_the_reference_drives_reset(golden, tmp_p
     from fluidgym_b200.domain_io import load_box_domain
     back = load_box_domain(path)
     assert np.array_equal(back["state"]["T"], env.solver.T[1].cpu().numpy())
+
+
+def test_rbc3d_gradients_match_reference(golden):
+    """Reverse mode of the D = 3 box substep with passive scalar + buoyancy against the UNMODIFIED reference run with differentiable=True
+    (tools/r02_rbc3d_grad_golden.sh -> tests/golden/rbc3d_grad.npz; 16 x 10 x 16 cells, 2 x 2 heaters of 8 cells, single agent): one env.step = 5 solver
+    steps, d sum(reward) / d (action, u0, T0) and the vector-Jacobian product of the outgoing (velocity, temperature) with sin cotangents.
+    (With 4-cell heaters -- the grid of the other RBC3D fixtures -- the reference's own action gradient is NaN: its heater blend divides
+    by round(0.1 * 4) = 0 in the branch torch.where does not select, rbc_env_3d.py:205-247; the state gradients agree there as well.)"""
+    import fluidgym_b200 as fg
+    fx = golden("rbc3d_grad.npz")
+    T, bT = _ref_transforms(golden)
+    env = fg.make("RBC3D-easy-v0", n_envs=1, n_heaters=2, resolution=8, step_length=0.25, use_marl=False, transforms=T, btransforms=bT,
+                  differentiable=True)
+    env.reset(seed=1)
+    env.set_state(fx["pre_u"], fx["pre_p"], fx["pre_T"], sbval=fx["pre_sbval"])
+    u0, T0 = env.mark_state_differentiable()
+    act = torch.from_numpy(fx["action"]).cuda().reshape(1, 2, 2, 1).clone().requires_grad_(True)
+    obs, reward, term, trunc, info = env.step(act)
+    g_a, g_u, g_T = torch.autograd.grad(reward.sum(), [act, u0, T0], retain_graph=True)
+    u1, T1 = env._dstate[0], env._dstate[2]
+    cu = torch.sin(0.37 * torch.arange(u1.numel(), device="cuda", dtype=torch.float64)).to(torch.float32).reshape(u1.shape)
+    cT = torch.sin(0.37 * torch.arange(T1.numel(), device="cuda", dtype=torch.float64) + 0.3).to(torch.float32).reshape(T1.shape)
+    v_a, v_u, v_T = torch.autograd.grad([u1, T1], [act, u0, T0], grad_outputs=[cu, cT])
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        a, b = a.detach().cpu().numpy().ravel().astype(np.float64), np.asarray(b, dtype=np.float64).ravel()
+        return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    e = dict(reward=float(np.abs(reward.detach().cpu().numpy().ravel() - fx["reward"].ravel()).max()), u=rel(u1[0], fx["post_u"]), T=rel(T1[0], fx["post_T"]),
+             dr_da=rel(g_a, fx["dreward_daction"]), dr_du=rel(g_u[0], fx["dreward_du"]), dr_dT=rel(g_T[0], fx["dreward_dT"]),
+             vjp_da=rel(v_a, fx["vjp_daction"]), vjp_du=rel(v_u[0], fx["vjp_du"]), vjp_dT=rel(v_T[0], fx["vjp_dT"]), substeps=env.last_substeps)
+    print("rbc3d gradients vs reference:", e)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(e, open("gpurun_out/rbc3d_gradients.json", "w"))
+    assert e["reward"] < 1e-5 and e["u"] < 1e-4 and e["T"] < 1e-5
+    for k in ("dr_da", "dr_du", "dr_dT", "vjp_da", "vjp_du", "vjp_dT"):          # north_star: gradients within 1e-3 relative
+        assert e[k] < 1e-3, (k, e[k])
