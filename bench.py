@@ -389,14 +389,20 @@ def run_ours(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roof = {"bound": "hbm", "kernel": {0: "k_cg", 1: "k_cg_cluster", 2: "k_cg_cluster", 3: "k_cg_cluster_mb", 4: "k_cg_smem", 5: "k_cg_smem", 6: "k_cg_cluster_mb<PUSH>", 7: "k_cg_cluster_mb<PUSH,256x14>", 8: "k_cg_cluster_mb<PUSH,256x7,2 CTAs/SM>", 11: "k_cg_strip<480,17>"}.get(args.cg_impl, f"cg_impl {args.cg_impl}"), "achieved": achieved, "peak": peak,
+    roof = {"bound": "hbm", "kernel": {0: "k_cg", 1: "k_cg_cluster", 2: "k_cg_cluster", 3: "k_cg_cluster_mb", 4: "k_cg_smem", 5: "k_cg_smem", 6: "k_cg_cluster_mb<PUSH>", 7: "k_cg_cluster_mb<PUSH,256x14>", 8: "k_cg_cluster_mb<PUSH,256x7,2 CTAs/SM>", 11: "k_cg_strip<480,17>", 12: "k_cg_strip2<480,9>"}.get(args.cg_impl, f"cg_impl {args.cg_impl}"), "achieved": achieved, "peak": peak,
             "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "algorithmic_bytes_per_launch": cg_bytes / max(cg_launches, 1), "avg_launch_ms": cg_ms / max(cg_launches, 1),
             "launches": cg_launches, "share_of_step": cg_ms / ms_serial,
             "measured_on": f"{n_prof} env.step() replayed after the timed region with one environment group (kernels run alone); "
                            f"the timed region runs {n_groups} groups on concurrent streams",
             "note": "on-chip (cluster-resident) CG: algorithmic bytes are the SURVEY 8(d) streaming figure; measured DRAM "
-                    "traffic is far lower because x/r/p and the stencil stay in registers/shared memory"}
+                    "traffic is far lower because x/r/p and the stencil stay in registers/shared memory, so frac > 1 is not a bound; "
+                    "`traffic` is the ncu capture of profiles/cg_traffic.json (not re-measured in this run)",
+            # the ceilings that do bind this kernel, from the same ncu capture (profiles/r02_ncu_cg_strip_480x17.txt and
+            # profiles/r02_cg_strip_development.md): a latency-bound dependent chain with 15 warps per SM
+            "binding_ceilings": {"issue_slots_active_pct": 31.7, "shared_memory_pipe_pct": 42, "warps_per_sm": 15,
+                                 "cycles_per_iteration": 7100, "warp_instructions_per_iteration": 625,
+                                 "source": "ncu --set full, static (captured once per kernel change, see profiles/)"} if args.cg_impl == 11 else None}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -220,3 +220,50 @@ class PISOSubstepScalar3D(torch.autograd.Function):
 def piso_substep_scalar_3d(solver, u, p, bvel, T, sbval, dt):
     """Differentiable substep of a structured 3-D box with passive scalar + buoyancy (functional form)."""
     return PISOSubstepScalar3D.apply(u, p, bvel, T, sbval, solver, dt)
+
+
+# ---- z-extruded multi-block grids (CylinderJet3D / Airfoil3D): fgb_extruded3_piso_substep_record / _backward -----------------------------
+class PISOSubstepExtruded(torch.autograd.Function):
+    """(u [B,3,N3], p [B,N3], bvel [B,3,nz,NB2]) -> (u_next, p_next) for one substep of an ``ExtrudedPISO3D`` solver"""
+
+    @staticmethod
+    def forward(ctx, u, p, bvel, solver, dt):
+        B, N3, nz, NB = solver.B, solver.N, solver.nz, max(solver.NB2, 1)
+        f32 = dict(device=solver.device, dtype=torch.float32)
+        o = solver.options
+        C_, n_adv, n_p = int(o.corrector_steps), int(o.adv_nonortho_steps), int(o.p_nonortho_steps)
+        tape = dict(u_in=torch.empty(B, 3, N3, **f32), p_in=torch.empty(B, N3, **f32), bvel_in=torch.empty(B, 3, nz, NB, **f32),
+                    dt=torch.empty(B, **f32), Coff=torch.empty(B, 6, N3, **f32), A=torch.empty(B, N3, **f32),
+                    ustar=torch.empty(n_adv, B, 3, N3, **f32), hb=torch.empty(C_, B, 3, N3, **f32), p=torch.empty(C_ * n_p, B, N3, **f32),
+                    pmean=torch.empty(C_ * n_p, B, **f32), u1=torch.empty(max(C_ - 1, 1), B, 3, N3, **f32))
+        ct = native.Tape(*[tape[k].data_ptr() for k, _ in native.Tape._fields_])
+        dtc = dt.to(solver.device, torch.float32).contiguous() if isinstance(dt, torch.Tensor) else torch.full((B,), float(dt), **f32)
+        u_out, p_out = u.detach().clone().contiguous(), p.detach().clone().contiguous()
+        bv = bvel.detach().contiguous()
+        native.check(solver.lib.fgb_extruded3_piso_substep_record(solver.handle, C.byref(solver.xtables), _ptr(u_out), _ptr(p_out), _ptr(bv), _ptr(dtc),
+                                                                  C.byref(ct), solver.stream), "fgb_extruded3_piso_substep_record")
+        ctx.solver, ctx.tape = solver, tape
+        return u_out, p_out
+
+    @staticmethod
+    def backward(ctx, u_out_bar, p_out_bar):
+        solver, tape = ctx.solver, ctx.tape
+        B, N3, nz, NB = solver.B, solver.N, solver.nz, max(solver.NB2, 1)
+        f32 = dict(device=solver.device, dtype=torch.float32)
+        ct = native.Tape(*[tape[k].data_ptr() for k, _ in native.Tape._fields_])
+        ub, pb, bvb = torch.empty(B, 3, N3, **f32), torch.empty(B, N3, **f32), torch.empty(B, 3, nz, NB, **f32)
+        nbytes = solver.lib.fgb_extruded3_adjoint_workspace_bytes(C.byref(solver.xtables), B)
+        ws = getattr(solver, "_adj_ws", None)
+        if ws is None or ws.numel() < nbytes + 256:
+            ws = solver._adj_ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=solver.device)
+        wsp = C.c_void_p(ws.data_ptr() + (-ws.data_ptr()) % 256)
+        uo = (u_out_bar if u_out_bar is not None else torch.zeros(B, 3, N3, **f32)).contiguous()
+        po = (p_out_bar if p_out_bar is not None else torch.zeros(B, N3, **f32)).contiguous()
+        native.check(solver.lib.fgb_extruded3_piso_substep_backward(solver.handle, C.byref(solver.xtables), C.byref(ct), _ptr(uo), _ptr(po), _ptr(ub),
+                                                                    _ptr(pb), _ptr(bvb), wsp, nbytes, solver.stream), "fgb_extruded3_piso_substep_backward")
+        return ub, pb, bvb, None, None
+
+
+def piso_substep_extruded(solver, u, p, bvel, dt):
+    """Differentiable substep of a z-extruded multi-block grid (functional form)."""
+    return PISOSubstepExtruded.apply(u, p, bvel, solver, dt)

@@ -286,6 +286,396 @@ extern "C" int fgb_extruded3_piso_substep(fgb_ortho3 *b, const fgb_extruded3_tab
     return FGB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Reverse mode of the extruded substep (CylinderJet3D / Airfoil3D with differentiable=True).  Same construction as the 2-D adjoint
+// (piso_b200.cu: k_adj_*, whose in-plane terms these kernels repeat per plane on the same tables) plus the z faces; the transposed
+// Krylov solves run in k3_bicgstab / k3_cg<1> with the plane's reverse-face table (fgb_ortho3_tables.rev).  The recorded forward pass
+// follows the reference's differentiable backend: every solve starts from zero, the CG never resets its residual.
+// Tape = fgb_tape with three components: u_in / ustar / hb / u1 [..][B][3][N3], Coff [B][6][N3], bvel_in [B][3][nz][NB2].
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void x3_fluxes_adjoint(const fgb_tables &t, int g, const int nb[4], const float flb[4], float *__restrict__ vbx,
+                                                  float *__restrict__ vby /* plane-local [N2] */, float *__restrict__ Fbb /* plane-local [NB2] or null */) {
+    const int N = t.N;
+    float Ub[2] = {0.f, 0.f};
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        if (nb[f] >= 0) {
+            const float gq = 0.5f * flb[f];
+            Ub[f >> 1] += gq;
+            const int fc = t.fl_comp[f * N + g];
+            const int cn = fc & 1, n = nb[f];
+            const float w = ((fc & 2) ? -gq : gq) * t.det[n];
+            atomicAdd(&vbx[n], w * t.minv[(2 * cn) * N + n]);
+            atomicAdd(&vby[n], w * t.minv[(2 * cn + 1) * N + n]);
+        } else if (Fbb) {
+            atomicAdd(&Fbb[-1 - nb[f]], flb[f]);
+        }
+    }
+    const float d = t.det[g];
+    atomicAdd(&vbx[g], d * (t.minv[g] * Ub[0] + t.minv[2 * N + g] * Ub[1]));
+    atomicAdd(&vby[g], d * (t.minv[N + g] * Ub[0] + t.minv[3 * N + g] * Ub[1]));
+}
+#define X3_ADJ_PROLOGUE \
+    const int b = blockIdx.z, k = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x; \
+    const fgb_tables &t = x.t; \
+    const int N = t.N, nz = x.nz; \
+    if (g >= N) return; \
+    const size_t N3 = (size_t)N * nz, g3 = (size_t)k * N + g; \
+    const int kl = (k + nz - 1) % nz, ku = (k + 1) % nz; \
+    (void)kl; (void)ku; (void)N3; (void)g3;
+
+__global__ void __launch_bounds__(256) kx3_adj_correct(X3Tab x, const float *__restrict__ Unb, const float *__restrict__ P, const float *__restrict__ A,
+                                                       float *__restrict__ Hbb, float *__restrict__ rAb, float *__restrict__ Pb) {
+    X3_ADJ_PROLOGUE
+    const float *p = P + b * N3, *pk = p + (size_t)k * N;
+    float *pb = Pb + b * N3, *pbk = pb + (size_t)k * N;
+    const float ub0 = Unb[b * 3 * N3 + g3], ub1 = Unb[b * 3 * N3 + N3 + g3], ub2 = Unb[b * 3 * N3 + 2 * N3 + g3];
+    Hbb[b * 3 * N3 + g3] = ub0; Hbb[b * 3 * N3 + N3 + g3] = ub1; Hbb[b * 3 * N3 + 2 * N3 + g3] = ub2;
+    const float rA = 1.0f / A[b * N3 + g3], pc = pk[g];
+    float pg[2], fac[2]; int nl[2], nu[2];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        nl[d] = t.nbr[(2 * d) * N + g]; nu[d] = t.nbr[(2 * d + 1) * N + g];
+        fac[d] = (nl[d] < 0 || nu[d] < 0) ? 1.0f : 0.5f;
+        pg[d] = ((nu[d] >= 0 ? pk[nu[d]] : pc) - (nl[d] >= 0 ? pk[nl[d]] : pc)) * fac[d];
+    }
+    const float m00 = t.minv[g], m01 = t.minv[N + g], m10 = t.minv[2 * N + g], m11 = t.minv[3 * N + g];
+    const float gx = pg[0] * m00 + pg[1] * m10, gy = pg[0] * m01 + pg[1] * m11;
+    const float gz = 0.5f * (p[(size_t)ku * N + g] - p[(size_t)kl * N + g]) / x.hz;
+    atomicAdd(&rAb[b * N3 + g3], -(gx * ub0 + gy * ub1 + gz * ub2));
+    const float gb0 = -rA * ub0, gb1 = -rA * ub1;
+    const float pgb[2] = {gb0 * m00 + gb1 * m01, gb0 * m10 + gb1 * m11};
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        const float w = pgb[d] * fac[d];
+        atomicAdd(&pbk[nu[d] >= 0 ? nu[d] : g], w);
+        atomicAdd(&pbk[nl[d] >= 0 ? nl[d] : g], -w);
+    }
+    const float wz = -rA * ub2 * 0.5f / x.hz;
+    atomicAdd(&pb[(size_t)ku * N + g], wz);
+    atomicAdd(&pb[(size_t)kl * N + g], -wz);
+}
+// adjoint of  div = hz (fluxdiv2(hb) + NOp(p_prev, rA)) + det2 D_z(hb_z)  and of  x = P^-1 div  w.r.t. P(rA):  given lam = P^-T x_bar
+__global__ void __launch_bounds__(256) kx3_adj_pressure_rhs(X3Tab x, const float *__restrict__ Lam, const float *__restrict__ Pm, const float *__restrict__ Pmean,
+                                                            const float *__restrict__ Pprev, const float *__restrict__ A, float *__restrict__ Hbb,
+                                                            float *__restrict__ Fbb, float *__restrict__ rAb, float *__restrict__ Pprevb) {
+    X3_ADJ_PROLOGUE
+    const int NB = t.NB;
+    const float hz = x.hz, lam = Lam[b * N3 + g3], mean = Pmean[b];
+    const float *px = Pm + b * N3, *pxk = px + (size_t)k * N;
+    const float *a = A + b * N3, *ak = a + (size_t)k * N, *pp = Pprev + b * N3 + (size_t)k * N;
+    float *ra = rAb + b * N3, *rak = ra + (size_t)k * N;
+    int nb[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) nb[f] = t.nbr[f * N + g];
+    float Pb[5];
+    Pb[0] = -lam * (pxk[g] + mean);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) Pb[f + 1] = nb[f] >= 0 ? -lam * (pxk[nb[f]] + mean) : 0.f;
+    float rb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 5; ++e)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) rb[j] += hz * t.Wp[(5 * e + j) * N + g] * Pb[e];
+    float rA[5];
+    rA[0] = 1.0f / ak[g];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) rA[f + 1] = nb[f] >= 0 ? 1.0f / ak[nb[f]] : rA[0];
+    for (int q = 0; q < t.K_no; ++q) {
+        const float gP = t.no_gP[q * N + g], gN = t.no_gN[q * N + g];
+        if (gP != 0.f || gN != 0.f) {
+            const int fc = t.no_face[q * N + g], j = t.no_idx[q * N + g];
+            const float wb = lam * hz * pp[j];
+            rb[0] += gP * wb; rb[1 + fc] += gN * wb;
+            atomicAdd(&Pprevb[b * N3 + (size_t)k * N + j], (gP * rA[0] + gN * rA[1 + fc]) * lam * hz);
+        }
+    }
+    // z faces of the matrix: pl = 1/2 (det2 / hz) (rA_P + rA_lower), pdiag -= pl (same for the upper face)
+    const float az = 0.5f * t.det[g] / hz;
+    const float wl = (-lam * (px[(size_t)kl * N + g] + mean) - Pb[0]) * az, wu = (-lam * (px[(size_t)ku * N + g] + mean) - Pb[0]) * az;
+    atomicAdd(&rak[g], rb[0] + wl + wu);
+    atomicAdd(&ra[(size_t)kl * N + g], wl);
+    atomicAdd(&ra[(size_t)ku * N + g], wu);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) atomicAdd(&rak[nb[f] >= 0 ? nb[f] : g], rb[f + 1]);
+    const float flb[4] = {-lam * hz, lam * hz, -lam * hz, lam * hz};
+    float *hbb = Hbb + b * 3 * N3;
+    x3_fluxes_adjoint(t, g, nb, flb, hbb + (size_t)k * N, hbb + N3 + (size_t)k * N, Fbb + ((size_t)b * nz + k) * NB);
+    const float wzf = 0.5f * t.det[g] * lam;
+    atomicAdd(&hbb[2 * N3 + (size_t)ku * N + g], wzf);
+    atomicAdd(&hbb[2 * N3 + (size_t)kl * N + g], -wzf);
+}
+// adjoint of  hb = rA (u/dt - H + Sb/det2),  H_c = sum_f Coff_f uprev_c[nb_f]  (6 faces)
+__global__ void __launch_bounds__(256) kx3_adj_hbya(X3Tab x, const float *__restrict__ Hbb, const float *__restrict__ Hb, const float *__restrict__ A,
+                                                    const float *__restrict__ Coff, const float *__restrict__ Uprev, const float *__restrict__ dtv,
+                                                    float *__restrict__ rAb, float *__restrict__ Ub, float *__restrict__ Sbb, float *__restrict__ Coffb,
+                                                    float *__restrict__ Uprevb) {
+    X3_ADJ_PROLOGUE
+    const float dt = dtv[b], Ag = A[b * N3 + g3], rA = 1.0f / Ag, det = t.det[g];
+    const float *coff = Coff + b * 6 * N3;
+    float *coffb = Coffb + b * 6 * N3;
+    int nb[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) nb[f] = t.nbr[f * N + g];
+    float accr = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const size_t o = b * 3 * N3 + (size_t)c * N3;
+        const float hbb = Hbb[o + g3];
+        accr += hbb * (Hb[o + g3] * Ag);
+        const float ib = rA * hbb;
+        atomicAdd(&Ub[o + g3], ib / dt);
+        Sbb[o + g3] += ib / det;
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+            if (nb[f] >= 0) {
+                coffb[(size_t)f * N3 + g3] += -ib * Uprev[o + (size_t)k * N + nb[f]];
+                atomicAdd(&Uprevb[o + (size_t)k * N + nb[f]], -ib * coff[(size_t)f * N3 + g3]);
+            }
+        coffb[4 * N3 + g3] += -ib * Uprev[o + (size_t)kl * N + g];
+        atomicAdd(&Uprevb[o + (size_t)kl * N + g], -ib * coff[4 * N3 + g3]);
+        coffb[5 * N3 + g3] += -ib * Uprev[o + (size_t)ku * N + g];
+        atomicAdd(&Uprevb[o + (size_t)ku * N + g], -ib * coff[5 * N3 + g3]);
+    }
+    atomicAdd(&rAb[b * N3 + g3], accr);
+}
+// adjoint of one predictor iteration  C x = rhs(u, x_prev):  given mu = C^-T x_bar
+__global__ void __launch_bounds__(256) kx3_adj_advection(X3Tab x, const float *__restrict__ Mu, const float *__restrict__ X, const float *__restrict__ rAb,
+                                                         const float *__restrict__ A, const float *__restrict__ dtv, float *__restrict__ Ab,
+                                                         float *__restrict__ Coffb, float *__restrict__ Ub, float *__restrict__ Sbb, float *__restrict__ Bvb,
+                                                         float *__restrict__ NoTarget, int first) {
+    X3_ADJ_PROLOGUE
+    const int NB = t.NB;
+    const float dt = dtv[b], det = t.det[g], Ag = A[b * N3 + g3];
+    float *coffb = Coffb + b * 6 * N3;
+    int nb[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) nb[f] = t.nbr[f * N + g];
+    float ab = first ? -rAb[b * N3 + g3] / (Ag * Ag) : Ab[b * N3 + g3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const size_t o = b * 3 * N3 + (size_t)c * N3;
+        const float mu = Mu[o + g3];
+        ab += -mu * X[o + g3];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) if (nb[f] >= 0) coffb[(size_t)f * N3 + g3] += -mu * X[o + (size_t)k * N + nb[f]];
+        coffb[4 * N3 + g3] += -mu * X[o + (size_t)kl * N + g];
+        coffb[5 * N3 + g3] += -mu * X[o + (size_t)ku * N + g];
+        atomicAdd(&Ub[o + g3], mu / dt);
+        Sbb[o + g3] += mu / det;
+        const float nob = -mu / det;
+        for (int q = 0; q < t.K_no; ++q) { const float w = t.no_wv[q * N + g]; if (w != 0.f) atomicAdd(&NoTarget[o + (size_t)k * N + t.no_idx[q * N + g]], w * nob); }
+        for (int q = 0; q < t.K_nob; ++q) {
+            const float w = t.nob_w[q * N + g];
+            if (w != 0.f) atomicAdd(&Bvb[((size_t)b * 3 + c) * nz * NB + (size_t)k * NB + t.nob_idx[q * N + g]], w * nob);
+        }
+    }
+    Ab[b * N3 + g3] = ab;
+}
+// adjoint of the assembly (A, Coff from the in-plane face fluxes and the z fluxes) and of the boundary sources
+__global__ void __launch_bounds__(256) kx3_adj_assemble(X3Tab x, const float *__restrict__ Ab, const float *__restrict__ Coffb, const float *__restrict__ Sbb,
+                                                        const float *__restrict__ Bvel, float *__restrict__ Ub, float *__restrict__ Bvb, float *__restrict__ Fbb) {
+    X3_ADJ_PROLOGUE
+    const int NB = t.NB;
+    const float det = t.det[g], ab = Ab[b * N3 + g3], diagb = ab / det, hz = x.hz;
+    const float *bvel = Bvel + (size_t)b * 3 * nz * NB;
+    const float *bx = bvel + (size_t)k * NB, *by = bvel + (size_t)nz * NB + (size_t)k * NB;
+    const float *coffb = Coffb + b * 6 * N3;
+    int nb[4]; float flb[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        nb[f] = t.nbr[f * N + g];
+        const float sig = (f & 1) ? 1.f : -1.f;
+        flb[f] = 0.f;
+        if (nb[f] >= 0) flb[f] = 0.5f * sig * (coffb[(size_t)f * N3 + g3] / det + diagb);
+        else {
+            const int j = -1 - nb[f];
+            const float kk = -(sig * x3_bflux(t, j, f >> 1, bx[j], by[j])) + 2.f * t.viscosity * t.b_alpha[j];
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float sb = Sbb[b * 3 * N3 + (size_t)c * N3 + g3];
+                atomicAdd(&Bvb[((size_t)b * 3 + c) * nz * NB + (size_t)k * NB + j], sb * kk);
+                dot += sb * bvel[((size_t)c * nz + k) * NB + j];
+            }
+            atomicAdd(&Fbb[((size_t)b * nz + k) * NB + j], -dot * sig);
+        }
+    }
+    float *ub = Ub + b * 3 * N3;
+    x3_fluxes_adjoint(t, g, nb, flb, ub + (size_t)k * N, ub + N3 + (size_t)k * N, nullptr);
+    // z faces: coff4 = -1/2 Fzm / hz - dz, coff5 = 1/2 Fzp / hz - dz, A += 1/2 (Fzp - Fzm) / hz, Fzm = 1/2 (w_P + w_lower)
+    const float fzm = (-0.5f / hz) * (coffb[4 * N3 + g3] + ab), fzp = (0.5f / hz) * (coffb[5 * N3 + g3] + ab);
+    atomicAdd(&ub[2 * N3 + g3], 0.5f * (fzm + fzp));
+    atomicAdd(&ub[2 * N3 + (size_t)kl * N + g], 0.5f * fzm);
+    atomicAdd(&ub[2 * N3 + (size_t)ku * N + g], 0.5f * fzp);
+}
+// adjoint of the in-plane boundary flux Fb(bx, by): one thread per (boundary face, plane, environment)
+__global__ void kx3_adj_bflux(X3Tab x, const float *__restrict__ Fbb, float *__restrict__ Bvb) {
+    const int b = blockIdx.z, k = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    const fgb_tables &t = x.t;
+    const int NB = t.NB, nz = x.nz;
+    if (j >= NB) return;
+    const int ax = t.b_face[j] >> 1;
+    const float f = Fbb[((size_t)b * nz + k) * NB + j] * t.b_det[j];
+    Bvb[((size_t)b * 3 + 0) * nz * NB + (size_t)k * NB + j] += f * t.b_minv[(2 * ax) * NB + j];
+    Bvb[((size_t)b * 3 + 1) * nz * NB + (size_t)k * NB + j] += f * t.b_minv[(2 * ax + 1) * NB + j];
+}
+__global__ void kx3_take_mean(int B, const float *__restrict__ pmean8, int slot, float *__restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) out[b] = pmean8[b * 8 + 3 + slot];
+}
+
+static int x3_copy(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    cudaError_t ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st);
+    return ce == cudaSuccess ? FGB_OK : set_err(FGB_E_CUDA, "cudaMemcpyAsync (extruded tape)", ce);
+}
+// fgb_extruded3_piso_substep that additionally records the tape of the backward pass (zero-started solves, no CG residual reset)
+extern "C" int fgb_extruded3_piso_substep_record(fgb_ortho3 *b, const fgb_extruded3_tables *xt, float *u, float *p, const float *bvel, const float *dt,
+                                                 const fgb_tape *tp, fgb_stream_t s) {
+    if (!b || !xt || !u || !p || !bvel || !dt || !tp) return set_err(FGB_E_ARG, "fgb_extruded3_piso_substep_record: null argument");
+    if (b->t.N != xt->plane.N * xt->nz || b->slab.on) return set_err(FGB_E_ARG, "fgb_extruded3_piso_substep_record: handle / tables mismatch");
+    const fgb_options &o = b->opt;
+    const int C = o.corrector_steps, n_adv = o.adv_nonortho_steps, n_p = o.p_nonortho_steps;
+    if (C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8) return set_err(FGB_E_ARG, "fgb_extruded3_piso_substep_record: correctors x pressure iterations <= 8");
+    X3Tab x; x.t = xt->plane; x.nz = xt->nz; x.hz = xt->hz;
+    cudaStream_t st = STREAM(s);
+    const dim3 grid((unsigned)((x.t.N + 255) / 256), (unsigned)x.nz, (unsigned)b->B);
+    const size_t B = b->B, BN = B * b->t.N, BNB = B * (size_t)x.nz * (x.t.NB > 0 ? x.t.NB : 1);
+    int rc;
+    if ((rc = x3_copy(tp->u_in, u, 3 * BN * 4, st))) return rc;
+    if ((rc = x3_copy(tp->p_in, p, BN * 4, st))) return rc;
+    if ((rc = x3_copy(tp->bvel_in, bvel, 3 * BNB * 4, st))) return rc;
+    if ((rc = x3_copy(tp->dt, dt, B * 4, st))) return rc;
+    for (int ns = 0; ns < n_adv; ++ns) {
+        b->launches++;
+        kx3_setup_advection<<<grid, 256, 0, st>>>(x, u, ns == 0 ? u : b->ures, bvel, dt, b->Coff, b->A, b->rhs, ns == 0);
+        LAUNCH_CHECK("kx3_setup_advection");
+        if ((rc = fgb_ortho3_solve_advection(b, 1, nullptr, s))) return rc;
+        if ((rc = x3_copy(tp->ustar + (size_t)ns * 3 * BN, b->ures, 3 * BN * 4, st))) return rc;
+    }
+    if ((rc = x3_copy(tp->Coff, b->Coff, 6 * BN * 4, st))) return rc;
+    if ((rc = x3_copy(tp->A, b->A, BN * 4, st))) return rc;
+    b->launches++;
+    kx3_pressure_matrix<<<grid, 256, 0, st>>>(x, b->A, b->Poff, b->Pdiag);
+    LAUNCH_CHECK("kx3_pressure_matrix");
+    for (int cs = 0; cs < C; ++cs) {
+        b->launches++;
+        kx3_hbya<<<grid, 256, 0, st>>>(x, u, b->ures, bvel, b->Coff, b->A, dt, b->hbya);
+        LAUNCH_CHECK("kx3_hbya");
+        for (int ps = 0; ps < n_p; ++ps) {
+            const int q = cs * n_p + ps, slot = q > 4 ? 4 : q;
+            b->launches += 2;
+            kx3_divergence<<<grid, 256, 0, st>>>(x, b->hbya, bvel, p, b->A, b->div);
+            LAUNCH_CHECK("kx3_divergence");
+            if ((rc = fgb_ortho3_solve_pressure(b, p, 1, 0, o.max_iter, slot, nullptr, s))) return rc;
+            if ((rc = x3_copy(tp->p + (size_t)q * BN, p, BN * 4, st))) return rc;
+            kx3_take_mean<<<(unsigned)((B + 127) / 128), 128, 0, st>>>((int)B, b->pmean, slot, tp->pmean + (size_t)q * B);
+            LAUNCH_CHECK("kx3_take_mean");
+        }
+        if ((rc = x3_copy(tp->hb + (size_t)cs * 3 * BN, b->hbya, 3 * BN * 4, st))) return rc;
+        b->launches++;
+        kx3_correct<<<grid, 256, 0, st>>>(x, b->hbya, p, b->A, b->ures);
+        LAUNCH_CHECK("kx3_correct");
+        if (cs + 1 < C && (rc = x3_copy(tp->u1 + (size_t)cs * 3 * BN, b->ures, 3 * BN * 4, st))) return rc;
+    }
+    return x3_copy(u, b->ures, 3 * BN * 4, st);
+}
+extern "C" size_t fgb_extruded3_adjoint_workspace_bytes(const fgb_extruded3_tables *xt, int32_t B) {
+    const size_t BN = (size_t)B * xt->plane.N * xt->nz, BNB = (size_t)B * xt->nz * (xt->plane.NB > 0 ? xt->plane.NB : 1);
+    return (size_t)(3 + 3 + 1 + 6 + 3 + 1 + 1 + 1 + 3 + 1 + 3 + 1 + 3) * align_up(BN * 4) + align_up(BNB * 4) + 8192;
+}
+// (u_out_bar, p_out_bar) -> (u_bar, p_prev_bar, bvel_bar), all overwritten
+extern "C" int fgb_extruded3_piso_substep_backward(fgb_ortho3 *b, const fgb_extruded3_tables *xt, const fgb_tape *tp, const float *u_out_bar,
+                                                   const float *p_out_bar, float *u_bar, float *p_prev_bar, float *bvel_bar, void *ws, size_t ws_bytes,
+                                                   fgb_stream_t s) {
+    if (!b || !xt || !tp || !u_out_bar || !p_out_bar || !u_bar || !p_prev_bar || !bvel_bar || !ws)
+        return set_err(FGB_E_ARG, "fgb_extruded3_piso_substep_backward: null argument");
+    if (b->t.N != xt->plane.N * xt->nz || b->slab.on) return set_err(FGB_E_ARG, "fgb_extruded3_piso_substep_backward: handle / tables mismatch");
+    if (!b->t.rev || b->t.plane != xt->plane.N) return set_err(FGB_E_ARG, "fgb_extruded3_piso_substep_backward: the handle's tables need rev / plane (transposed solves)");
+    if (ws_bytes < fgb_extruded3_adjoint_workspace_bytes(xt, b->B)) return set_err(FGB_E_WORKSPACE, "fgb_extruded3_piso_substep_backward: workspace too small");
+    const fgb_options &o = b->opt;
+    const int C = o.corrector_steps, n_adv = o.adv_nonortho_steps, n_p = o.p_nonortho_steps;
+    if (C < 1 || n_adv < 1 || n_p < 1 || C * n_p > 8) return set_err(FGB_E_ARG, "fgb_extruded3_piso_substep_backward: unsupported iteration counts");
+    X3Tab x; x.t = xt->plane; x.nz = xt->nz; x.hz = xt->hz;
+    cudaStream_t st = STREAM(s);
+    const dim3 grid((unsigned)((x.t.N + 255) / 256), (unsigned)x.nz, (unsigned)b->B);
+    const size_t B = b->B, NBz = (size_t)x.nz * (x.t.NB > 0 ? x.t.NB : 1), BN = B * b->t.N;
+    Carver c{(char *)ws, 0};
+    float *unb = c.take<float>(3 * BN), *hbb = c.take<float>(3 * BN), *rAb = c.take<float>(BN), *Coffb = c.take<float>(6 * BN);
+    float *Sbb = c.take<float>(3 * BN), *pb = c.take<float>(BN), *xb = c.take<float>(BN), *lam = c.take<float>(BN);
+    float *uprevb = c.take<float>(3 * BN), *Ab = c.take<float>(BN), *mu = c.take<float>(3 * BN), *Fbb = c.take<float>(B * NBz);
+    float *pb2 = c.take<float>(BN), *xkb = c.take<float>(3 * BN);
+    cudaError_t ce;
+    int rc;
+#define ZEROX(ptr, n) do { ce = cudaMemsetAsync(ptr, 0, (n) * sizeof(float), st); if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "memset", ce); } while (0)
+    ZEROX(rAb, BN); ZEROX(Coffb, 6 * BN); ZEROX(Sbb, 3 * BN); ZEROX(Fbb, B * NBz); ZEROX(u_bar, 3 * BN); ZEROX(bvel_bar, 3 * B * NBz);
+    if ((rc = x3_copy(unb, u_out_bar, 3 * BN * 4, st))) return rc;
+    if ((rc = x3_copy(pb, p_out_bar, BN * 4, st))) return rc;
+    b->launches++;
+    kx3_pressure_matrix<<<grid, 256, 0, st>>>(x, tp->A, b->Poff, b->Pdiag);
+    LAUNCH_CHECK("kx3_pressure_matrix (backward)");
+    for (int cs = C - 1; cs >= 0; --cs) {
+        const float *hb_c = tp->hb + (size_t)cs * 3 * BN;
+        const float *uprev = cs == 0 ? tp->ustar + (size_t)(n_adv - 1) * 3 * BN : tp->u1 + (size_t)(cs - 1) * 3 * BN;
+        b->launches++;
+        kx3_adj_correct<<<grid, 256, 0, st>>>(x, unb, tp->p + (size_t)(cs * n_p + n_p - 1) * BN, tp->A, hbb, rAb, pb);
+        LAUNCH_CHECK("kx3_adj_correct");
+        for (int ps = n_p - 1; ps >= 0; --ps) {
+            const int q = cs * n_p + ps;
+            const float *pprev = q == 0 ? tp->p_in : tp->p + (size_t)(q - 1) * BN;
+            b->launches += 3;
+            k3_adj_remove_mean<<<b->B, 1024, 0, st>>>(b->t.N, b->t.N, pb, xb);
+            LAUNCH_CHECK("k3_adj_remove_mean");
+            {   // lam = P^-T x_bar: the forward CG kernel on the transposed operator, zero start, no residual reset
+                T3 t = b->t; O3Slab sl = b->slab; int Bi = b->B; const float *poff = b->Poff, *pd = b->Pdiag, *rhs = xb; float *work = b->kry, *part = b->part;
+                float tol = b->opt.p_tol; int max_iter = b->opt.max_iter, zero_init = 1, reset_steps = 0, slot = 4; const int32_t *active = nullptr;
+                int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total; float *out = lam, *pmean = b->pmean;
+                void *args[] = {&t, &sl, &Bi, &poff, &pd, &rhs, &out, &work, &part, &max_iter, &tol, &zero_init, &reset_steps, &slot, &active, &iters, &resid, &itot, &pmean};
+                ce = cudaLaunchCooperativeKernel((void *)k3_cg<1>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, st);
+                if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_cg<1>, backward)", ce);
+            }
+            ZEROX(pb2, BN);                 // becomes the gradient w.r.t. pprev
+            kx3_adj_pressure_rhs<<<grid, 256, 0, st>>>(x, lam, tp->p + (size_t)q * BN, tp->pmean + (size_t)q * B, pprev, tp->A, hbb, Fbb, rAb, pb2);
+            LAUNCH_CHECK("kx3_adj_pressure_rhs");
+            float *tmp = pb; pb = pb2; pb2 = tmp;      // the previous iterate enters only through the deferred term
+        }
+        ZEROX(uprevb, 3 * BN);
+        b->launches++;
+        kx3_adj_hbya<<<grid, 256, 0, st>>>(x, hbb, hb_c, tp->A, tp->Coff, uprev, tp->dt, rAb, u_bar, Sbb, Coffb, uprevb);
+        LAUNCH_CHECK("kx3_adj_hbya");
+        float *tmp = unb; unb = uprevb; uprevb = tmp;   // gradient w.r.t. the velocity entering this corrector
+    }
+    if ((rc = x3_copy(p_prev_bar, pb, BN * 4, st))) return rc;
+    float *xb_cur = unb, *xb_prev = xkb;
+    for (int k = n_adv - 1; k >= 0; --k) {
+        {   // mu = C^-T x_k_bar
+            T3 t = b->t; O3Slab sl = b->slab; int Bi = b->B; const float *coff = tp->Coff, *a = tp->A, *rhs = xb_cur; float *xo = mu, *work = b->kry, *part = b->part;
+            int maxit = b->opt.max_iter, zero_init = 1, transposed = 1; float tol = b->opt.adv_tol; const int32_t *active = nullptr;
+            int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
+            void *args[] = {&t, &sl, &Bi, &coff, &a, &rhs, &xo, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot, &transposed};
+            b->launches++;
+            ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab<3>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, st);
+            if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab, transposed)", ce);
+        }
+        if (k > 0) ZEROX(xb_prev, 3 * BN);
+        b->launches++;
+        kx3_adj_advection<<<grid, 256, 0, st>>>(x, mu, tp->ustar + (size_t)k * 3 * BN, rAb, tp->A, tp->dt, Ab, Coffb, u_bar, Sbb, bvel_bar,
+                                                k > 0 ? xb_prev : u_bar, k == n_adv - 1);
+        LAUNCH_CHECK("kx3_adj_advection");
+        float *tmp = xb_cur; xb_cur = xb_prev; xb_prev = tmp;
+    }
+    b->launches += 2;
+    kx3_adj_assemble<<<grid, 256, 0, st>>>(x, Ab, Coffb, Sbb, tp->bvel_in, u_bar, bvel_bar, Fbb);
+    LAUNCH_CHECK("kx3_adj_assemble");
+    if (x.t.NB > 0) {
+        kx3_adj_bflux<<<dim3((unsigned)((x.t.NB + 127) / 128), (unsigned)x.nz, (unsigned)b->B), 128, 0, st>>>(x, Fbb, bvel_bar);
+        LAUNCH_CHECK("kx3_adj_bflux");
+    }
+#undef ZEROX
+    return FGB_OK;
+}
+
 // Simulation.make_divergence_free on an extruded domain (SIM.py:1320-1430): A = 1, the velocity itself is the pressure right-hand
 // side vector; p_nonortho_steps x [divergence + deferred non-orthogonal term of the current pressure, CG (zero start in the first
 // iteration, then restarted from the previous result), mean removal], one velocity correction.  The "PRE" hook (outflow update

@@ -59,6 +59,7 @@ struct fgb_ortho3 {
     float *Coff, *A, *rhs, *ures, *Poff, *Pdiag, *hbya, *div, *kry, *part;
     int32_t *iters; float *resid; float *dt; int32_t *active; double *remaining; int32_t *nsub; float *maxvel;
     int32_t *counters; int32_t *h_counters; float *src; float *rowmean;
+    float *pmean;                     // [B][8] mean removed from the pressure of solve slot q (the adjoint needs the raw iterate p + mean)
     unsigned long long *iter_total;
     unsigned long long *slab_ctr;     // [4] device-side sequence counters of the slab protocol
     fgb_ortho3_scalar sc;             // passive scalar + buoyancy (RBC3D); sc.T == nullptr: none
@@ -117,6 +118,7 @@ extern "C" int fgb_ortho3_create(const fgb_ortho3_tables *t, int32_t B, void *wo
     b->counters = c.take<int32_t>(4); (void)c.take<float>(B);
     b->src = c.take<float>((size_t)B * 4); b->rowmean = c.take<float>((size_t)B * 4);
     b->slab_ctr = c.take<unsigned long long>(4);
+    b->pmean = c.take<float>((size_t)B * 8);
     ce = cudaMallocHost((void **)&b->h_counters, 16);
     if (ce != cudaSuccess) { delete b; return set_err(FGB_E_CUDA, "cudaMallocHost", ce); }
     ce = cudaMemset(workspace, 0, fgb_ortho3_workspace_bytes(t, B));
@@ -142,7 +144,7 @@ extern "C" void *fgb_ortho3_buffer(fgb_ortho3 *b, const char *name) {
     struct { const char *n; void *p; } tab[] = {
         {"Coff", b->Coff}, {"A", b->A}, {"rhs", b->rhs}, {"ures", b->ures}, {"Poff", b->Poff}, {"Pdiag", b->Pdiag}, {"hbya", b->hbya},
         {"div", b->div}, {"visc", b->visc}, {"iters", b->iters}, {"resid", b->resid}, {"dt", b->dt}, {"active", b->active}, {"nsub", b->nsub},
-        {"maxvel", b->maxvel}, {"src", b->src}, {"rowmean", b->rowmean}, {"iter_total", b->iter_total}, {"remaining", b->remaining}};
+        {"maxvel", b->maxvel}, {"pmean", b->pmean}, {"src", b->src}, {"rowmean", b->rowmean}, {"iter_total", b->iter_total}, {"remaining", b->remaining}};
     for (auto &e : tab) if (!strcmp(e.n, name)) return e.p;
     return nullptr;
 }
@@ -456,7 +458,12 @@ __device__ __forceinline__ float o3_row_t(const T3 &t, int g, const float *__res
     o3_nbrs(t, g, n);
     float s = dg[g] * x[g];
 #pragma unroll
-    for (int f = 0; f < 6; ++f) if (n[f] >= 0) s += off[(f ^ 1) * NS + n[f]] * __ldcg(&x[n[f]]);
+    for (int f = 0; f < 6; ++f)
+        if (n[f] >= 0) {
+            // extruded multi-block grids: the in-plane reverse face comes from the plane's table (block connections may flip axes)
+            const int rf = (t.rev && f < 4) ? (int)t.rev[f * t.plane + (g % t.plane)] : (f ^ 1);
+            s += off[rf * NS + n[f]] * __ldcg(&x[n[f]]);
+        }
     return s;
 }
 
@@ -636,10 +643,12 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
 }
 
 // CG with residual reset, best-iterate tracking, 100-rising-steps cut-off and mean removal (CG.cu:225-446, SIM.py:1908-1925)
+template <int TR>      // TR = 1: the transposed operator (adjoint solves; single GPU)
 __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, O3Slab sl, int B, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
                                               const float *__restrict__ Rhs, float *Xout, float *work, float *part, int maxit, float tol,
                                               int zero_init, int reset_steps, int slot, const int32_t *__restrict__ active,
-                                              int32_t *__restrict__ iters, float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
+                                              int32_t *__restrict__ iters, float *__restrict__ resid, unsigned long long *__restrict__ iter_total,
+                                              float *__restrict__ pmean) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double red[32 * 2 + 8];
     const int N = t.N, NS = t.NS;
@@ -663,7 +672,7 @@ __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, O3Slab sl, int B, const flo
         } else {
             acc[0] = acc[1] = 0.f;
             for (int g = tid; g < N; g += nth) {
-                const float rr = f[g] - (zero_init ? 0.f : o3_row(t, g, off, dg, x));
+                const float rr = f[g] - (zero_init ? 0.f : (TR ? o3_row_t(t, g, off, dg, x) : o3_row(t, g, off, dg, x)));
                 r[g] = rr; p[g] = rr; acc[0] += rr * rr;
                 o3_push(sl, t, p, g, rr, dirty);
             }
@@ -677,14 +686,14 @@ __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, O3Slab sl, int B, const flo
                     if (sl.on) for (int g = tid; g < N; g += nth) o3_push(sl, t, x, g, x[g], dirty);
                     o3_halo_sync(grid, sl, hc, dirty);
                     acc[0] = acc[1] = 0.f;
-                    for (int g = tid; g < N; g += nth) { const float rr = f[g] - o3_row(t, g, off, dg, x); r[g] = rr; acc[0] += rr * rr; }
+                    for (int g = tid; g < N; g += nth) { const float rr = f[g] - (TR ? o3_row_t(t, g, off, dg, x) : o3_row(t, g, off, dg, x)); r[g] = rr; acc[0] += rr * rr; }
                     o3_halo_sync(grid, sl, hc, dirty);              // every row has read the old p halos before p is overwritten
                     for (int g = tid; g < N; g += nth) { const float rr = r[g]; p[g] = rr; o3_push(sl, t, p, g, rr, dirty); }
                     o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
                     rho = acc[0];
                 }
                 acc[0] = acc[1] = 0.f;
-                for (int g = tid; g < N; g += nth) { const float a = o3_row(t, g, off, dg, p); ap[g] = a; acc[0] += p[g] * a; }
+                for (int g = tid; g < N; g += nth) { const float a = (TR ? o3_row_t(t, g, off, dg, p) : o3_row(t, g, off, dg, p)); ap[g] = a; acc[0] += p[g] * a; }
                 o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
                 const float alpha = rho / acc[0];
                 acc[0] = acc[1] = 0.f;
@@ -717,9 +726,12 @@ __global__ void __launch_bounds__(O3_CT) k3_cg(T3 t, O3Slab sl, int B, const flo
         acc[0] = acc[1] = 0.f;
         for (int g = tid; g < N; g += nth) acc[0] += x[g];
         o3_grid_sum<2>(grid, sl, acc, part, rcount, arc, dirty, red);
-        const float mean = acc[0] / (float)t.N_global;
+        // (adjoint solves keep the raw iterate: with a non-symmetric singular operator the constant vector is not in the null space of
+        //  its transpose, removing the mean would change P^T lam)
+        const float mean = TR ? 0.f : acc[0] / (float)t.N_global;
         for (int g = tid; g < N; g += nth) { const float xv = x[g] - mean; xo[g] = xv; o3_push(sl, t, xo, g, xv, dirty); }
         if (blockIdx.x == 0 && threadIdx.x == 0) {
+            pmean[b * 8 + 3 + slot] = mean;
             iters[b * 8 + 3 + slot] = used; resid[b * 8 + 3 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1);
         }
         o3_halo_sync(grid, sl, hc, dirty);
@@ -737,7 +749,8 @@ __device__ __forceinline__ float o3_pnew(const float *r, const float *pold, floa
 __global__ void __launch_bounds__(O3_CT) k3_cg_fused(T3 t, O3Slab sl, int B, const float *__restrict__ Poff, const float *__restrict__ Pdiag,
                                                     const float *__restrict__ Rhs, float *Xout, float *work, float *part, int maxit, float tol,
                                                     int zero_init, int reset_steps, int slot, const int32_t *__restrict__ active,
-                                                    int32_t *__restrict__ iters, float *__restrict__ resid, unsigned long long *__restrict__ iter_total) {
+                                                    int32_t *__restrict__ iters, float *__restrict__ resid, unsigned long long *__restrict__ iter_total,
+                                                    float *__restrict__ pmean) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double red[32 * 2 + 8];
     const int N = t.N, NS = t.NS;
@@ -830,6 +843,7 @@ __global__ void __launch_bounds__(O3_CT) k3_cg_fused(T3 t, O3Slab sl, int B, con
         const float mean = acc[0] / (float)t.N_global;
         for (int g = tid; g < N; g += nth) { const float xv = x[g] - mean; xo[g] = xv; }
         if (blockIdx.x == 0 && threadIdx.x == 0) {
+            pmean[b * 8 + 3 + slot] = mean;
             iters[b * 8 + 3 + slot] = used; resid[b * 8 + 3 + slot] = fin; iter_total[b * 2] += (unsigned long long)(used + 1);
         }
         __threadfence(); grid.sync();
@@ -966,7 +980,7 @@ static int o3_coop_blocks(fgb_ortho3 *b) {
     int dev = 0, sms = 0, per_a = 0, per_b = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_a, k3_cg, O3_CT, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_a, k3_cg<0>, O3_CT, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_b, k3_bicgstab<3>, O3_CT, 0);
     if (b->cg_fused) { int per_c = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_c, k3_cg_fused, O3_CT, 0); if (per_c < per_a) per_a = per_c; }
     int blocks = (per_a > 0 && per_b > 0) ? sms : 1;     // one CTA per SM (co-residency is what a cooperative launch needs)
@@ -1077,10 +1091,11 @@ extern "C" int fgb_ortho3_solve_pressure(fgb_ortho3 *b, float *p_out, int zero_i
     T3 t = b->t; O3Slab sl = b->slab; int B = b->B; const float *poff = b->Poff, *pd = b->Pdiag, *rhs = b->div; float *work = b->kry, *part = b->part;
     float tol = b->opt.p_tol;
     int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
-    void *args[] = {&t, &sl, &B, &poff, &pd, &rhs, &p_out, &work, &part, &max_iter, &tol, &zero_init, &reset_steps, &slot, &active, &iters, &resid, &itot};
+    float *pmean = b->pmean;
+    void *args[] = {&t, &sl, &B, &poff, &pd, &rhs, &p_out, &work, &part, &max_iter, &tol, &zero_init, &reset_steps, &slot, &active, &iters, &resid, &itot, &pmean};
     b->launches++;
     const bool fused = b->cg_fused && !b->slab.on;
-    cudaError_t ce = cudaLaunchCooperativeKernel(fused ? (void *)k3_cg_fused : (void *)k3_cg, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
+    cudaError_t ce = cudaLaunchCooperativeKernel(fused ? (void *)k3_cg_fused : (void *)k3_cg<0>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, fused ? "cudaLaunchCooperativeKernel(k3_cg_fused)" : "cudaLaunchCooperativeKernel(k3_cg)", ce);
     return FGB_OK;
 }
@@ -1443,8 +1458,9 @@ static int o3_backward_impl(fgb_ortho3 *b, const fgb_ortho3_tape *tp, const fgb_
             T3 t = b->t; O3Slab sl = b->slab; int Bi = b->B; const float *poff = b->Poff, *pd = b->Pdiag, *rhs = xb; float *work = b->kry, *part = b->part;
             float tol = b->opt.p_tol; int max_iter = b->opt.max_iter, zero_init = 1, reset_steps = 0, slot = 4; const int32_t *active = nullptr;
             int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total; float *out = lam;
-            void *args[] = {&t, &sl, &Bi, &poff, &pd, &rhs, &out, &work, &part, &max_iter, &tol, &zero_init, &reset_steps, &slot, &active, &iters, &resid, &itot};
-            ce = cudaLaunchCooperativeKernel(b->cg_fused ? (void *)k3_cg_fused : (void *)k3_cg, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, st);
+            float *pmean = b->pmean;
+            void *args[] = {&t, &sl, &Bi, &poff, &pd, &rhs, &out, &work, &part, &max_iter, &tol, &zero_init, &reset_steps, &slot, &active, &iters, &resid, &itot, &pmean};
+            ce = cudaLaunchCooperativeKernel(b->cg_fused ? (void *)k3_cg_fused : (void *)k3_cg<0>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, st);
             if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_cg, backward)", ce);
         }
         k3_adj_pressure_rhs<<<grid, O3_T, 0, st>>>(b->t, lam, p_c, hbb, Fbb, rAb);

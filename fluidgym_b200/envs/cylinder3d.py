@@ -164,6 +164,99 @@ class SpanwiseExtrudedEnv(InitialDomainsExtruded):
     def _get_obs(self):
         return self._get_local_obs() if self.use_marl else self._get_global_obs()
 
+    # ---- differentiable mode: one autograd node per substep (autograd.PISOSubstepExtruded, CUDA adjoint of the extruded path); the
+    # boundary hooks, the jets and the wall forces around it are functional torch expressions with the graph cut where the reference
+    # cuts it: update_advective_boundaries runs entirely under no_grad (SIM.py:232), balance_boundary_fluxes computes its scale under
+    # no_grad and applies it outside (SIM.py:191-224).  One common substep size for the batch (the most restrictive environment decides).
+    differentiable = False
+    _dstate = None
+
+    def detach(self):
+        if self._dstate is not None:
+            self._dstate = tuple(t.detach() for t in self._dstate)
+
+    def mark_state_differentiable(self):
+        """envs/util/diff_tools.py:8-22: the velocity leaf of the incoming state [B, 3, nz * N2]"""
+        s = self.solver
+        u = s.u.detach().clone().requires_grad_(True)
+        self._dstate = (u, s.p.detach().clone(), s.bvel.detach().clone(), self.last_control.detach().clone())
+        return u
+
+    def _balance_fn(self, bv, free, tol):
+        s = self.solver
+        fw = s._st["fw"]
+        with torch.no_grad():
+            fl = (bv[:, 0] * fw[0] + bv[:, 1] * fw[1]) * s.hz                                     # [B, nz, NB2]
+            var = fl[:, :, free].double().sum(dim=(1, 2))
+            fixed = fl[:, :, ~free].double().sum(dim=(1, 2))
+            ok = (fixed + var).abs() <= tol * 0.01
+            sc = torch.where(ok, torch.ones_like(var), -fixed / torch.where(ok, torch.ones_like(var), var)).float()
+            scale = torch.where(free[None, None, None, :], sc[:, None, None, None], torch.ones((), device=bv.device))
+        return bv * scale
+
+    def _outflow_fn(self, u, bv, dtv, tol):
+        s = self.solver
+        st = s._st
+        with torch.no_grad():
+            w = 1.0 - 1.0 / (1.0 + 2.0 * dtv[:, None] * st["adv"][None])                          # [B, n_out]
+            u4 = u.view(self.n_envs, 3, self.nz, s.N2)
+            bo = bv[:, :, :, st["out"]]
+            bo = bo - w[:, None, None, :] * (bo - u4[:, :, :, st["out_cells"]])
+            bo = self._balance_fn(bv.index_copy(3, st["out"], bo), st["is_out"], tol)[:, :, :, st["out"]]
+        return bv.index_copy(3, st["out"], bo)
+
+    def _single_step_differentiable(self, u, p, bv):
+        from ..autograd import piso_substep_extruded
+        s = self.solver
+        st = s._st
+        remaining, nsub = float(self.dt), 0
+        while remaining > 0.0 and not abs(remaining) <= 1e-8:                                     # SIM.py:2004-2031
+            with torch.no_grad():
+                u4, mi, bm = u.view(self.n_envs, 3, self.nz, s.N2), st["minv"], st["b_minv"]
+                mv = float(torch.stack([(mi[0] * u4[:, 0] + mi[1] * u4[:, 1]).abs().max(), (mi[2] * u4[:, 0] + mi[3] * u4[:, 1]).abs().max(),
+                                        u4[:, 2].abs().max() / s.hz, (bm[0] * bv[:, 0] + bm[1] * bv[:, 1]).abs().max(),
+                                        (bm[2] * bv[:, 0] + bm[3] * bv[:, 1]).abs().max(), bv[:, 2].abs().max() / s.hz]).max())
+            if abs(mv) <= 1e-8:
+                ts = remaining
+            else:
+                mts = np.float32(self.cfl) / np.float32(mv)
+                ts = remaining if float(mts) >= remaining else remaining / float(int(np.ceil(np.float32(remaining) / mts)))
+            remaining -= ts
+            dtv = torch.full((self.n_envs,), float(np.float32(ts)), device=self.device)
+            bv = self._outflow_fn(u, bv, dtv, self.bc_tol)
+            u, p = piso_substep_extruded(s, u, p, bv, dtv)
+            nsub += 1
+        return u, p, bv, nsub
+
+    def _advance_differentiable(self, a):
+        s = self.solver
+        B, nz, N2 = self.n_envs, self.nz, s.N2
+        if self._dstate is None:
+            self._dstate = (s.u.clone(), s.p.clone(), s.bvel.clone(), self.last_control.clone())
+        u, p, bv, last = self._dstate
+        cds = torch.zeros(B, nz, device=self.device)
+        cls_ = torch.zeros_like(cds)
+        jf = self.jet_faces.long()
+        nsub = 0
+        for _ in range(self.n_sim_steps):
+            last = last + self.action_smoothing_alpha * (a - last)
+            if self.enable_actions:
+                per_plane = last.repeat_interleave(self.nz_per_agent, dim=1)                       # [B, nz]
+                jets = self.jet_templ[None, :, None, :] * per_plane[:, None, :, None]             # [B, 2, nz, n_jet_faces]
+                bv = bv.index_copy(3, jf, torch.cat([jets, torch.zeros_like(jets[:, :1])], dim=1))
+                bv = self._balance_fn(bv, self._free_jets, 1e-7)
+            u, p, bv, k = self._single_step_differentiable(u, p, bv)
+            nsub += k
+            u2 = u.view(B, 3, nz, N2)[:, :2].permute(0, 2, 1, 3).reshape(B * nz, 2, N2)
+            f = DifferentiableRollout._forces_torch(self, u2, p.view(B * nz, N2), bv[:, :2].permute(0, 2, 1, 3).reshape(B * nz, 2, -1))
+            f = f.view(B, nz, 2) * self.hz
+            cds, cls_ = cds + f[:, :, 0], cls_ + f[:, :, 1]
+        self._dstate = (u, p, bv, last)
+        with torch.no_grad():                      # keep the solver's own state in step for observations / get_state
+            s.u.copy_(u); s.p.copy_(p); s.bvel.copy_(bv); self.last_control = last.detach().clone()
+        self.last_substeps = nsub
+        return cds, cls_
+
     def step(self, action):
         if not self._reset_called:
             raise RuntimeError("Environment must be reset before stepping. Call 'reset()' before'step()'.")
@@ -176,18 +269,21 @@ class SpanwiseExtrudedEnv(InitialDomainsExtruded):
             raise ValueError("local_reward_weight must be set for multi-agent step.")
         s = self.solver
         a = action.reshape(self.last_control.shape)
-        cds = torch.zeros(self.n_envs, self.nz, device=self.device)
-        cls_ = torch.zeros_like(cds)
-        nsub = 0
-        for _ in range(self.n_sim_steps):                                                         # cylinder_env_base.py:741-776
-            self.last_control = self.last_control + self.action_smoothing_alpha * (a - self.last_control)
-            if self.enable_actions:
-                self._apply_action(self.last_control)
-            nsub += s.single_step(self.dt, self.cfl, bc_tol=self.bc_tol)
-            cd_k, cl_k = self._drag_and_lift()
-            cds += cd_k
-            cls_ += cl_k
-        self.last_substeps = nsub
+        if self.differentiable:
+            cds, cls_ = self._advance_differentiable(a)
+        else:
+            cds = torch.zeros(self.n_envs, self.nz, device=self.device)
+            cls_ = torch.zeros_like(cds)
+            nsub = 0
+            for _ in range(self.n_sim_steps):                                                     # cylinder_env_base.py:741-776
+                self.last_control = self.last_control + self.action_smoothing_alpha * (a - self.last_control)
+                if self.enable_actions:
+                    self._apply_action(self.last_control)
+                nsub += s.single_step(self.dt, self.cfl, bc_tol=self.bc_tol)
+                cd_k, cl_k = self._drag_and_lift()
+                cds += cd_k
+                cls_ += cl_k
+            self.last_substeps = nsub
         all_cds, all_cls = cds / self.n_sim_steps, cls_ / self.n_sim_steps
         cd, cl = all_cds.sum(dim=1) / self.D, all_cls.sum(dim=1) / self.D                        # jet_cylinder_env_3d.py:431-452
         reward = self._reward(cd, cl)
@@ -217,8 +313,9 @@ class CylinderJet3DEnv(SpanwiseExtrudedEnv):
     def __init__(self, n_envs: int = 1, n_jets=8, reynolds_number=1e2, resolution=24, dt=1e-2, adaptive_cfl=0.8, step_length=0.25,
                  episode_length=80, lift_penalty=1.0, local_obs_window=3, use_marl=False, local_reward_weight=0.8, local_2d_obs=False,
                  device="cuda:0", cd_ref=0.0, randomize_initial_state=False, enable_actions=True, load_initial_domain=False,
-                 initial_domains_path=None, compiled=None, solver_cls=None):
+                 initial_domains_path=None, compiled=None, solver_cls=None, differentiable=False):
         self.load_domain_on_reset, self.initial_domains_path = bool(load_initial_domain), initial_domains_path
+        self.differentiable = bool(differentiable)
         if n_jets < 1 or resolution % n_jets != 0:
             raise ValueError("n_agents must be a positive integer that evenly dividescircle_resolution_angular.")
         if local_2d_obs and not use_marl:

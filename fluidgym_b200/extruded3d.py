@@ -160,6 +160,7 @@ class ExtrudedPISO3D(ExtrudedStepping):
         self._tab["ones"] = torch.ones(3 * self.N, device=dev)
         t3 = native.Ortho3Tables(self.N, 0, float(cd.visc), self._tab["nbr6"].data_ptr(), self._tab["ones"].data_ptr(),
                                  self._tab["ones"].data_ptr(), self._tab["ones"].data_ptr(), self._tab["ones"].data_ptr(), 0, 0, 0)
+        t3.plane, t3.rev = cd.N, self._tab["rev"].data_ptr()     # transposed Krylov solves of the reverse mode (o3_row_t)
         self.tables3 = t3
         self.options = native.Options(corrector_steps, advect_non_ortho_steps, pressure_non_ortho_steps, 1, advection_tol, pressure_tol,
                                       max_iter, 0)

@@ -56,7 +56,7 @@ class Ortho3Tables(C.Structure):
     _fields_ = [("N", C.c_int32), ("NB", C.c_int32), ("viscosity", C.c_float), ("nbr", C.c_void_p), ("minv", C.c_void_p),
                 ("det", C.c_void_p), ("b_minv", C.c_void_p), ("b_det", C.c_void_p), ("NS", C.c_int32), ("N_global", C.c_int32),
                 ("plane", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("closed", C.c_int32),
-                ("boff", C.c_int32 * 6)]
+                ("boff", C.c_int32 * 6), ("rev", C.c_void_p)]
 
 
 class Ortho3Scalar(C.Structure):
@@ -84,7 +84,7 @@ EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_cr
            "fgb_ortho3_launch_count", "fgb_ortho3_setup_advection", "fgb_ortho3_solve_advection", "fgb_ortho3_setup_pressure",
            "fgb_ortho3_solve_pressure", "fgb_ortho3_correct_velocity", "fgb_ortho3_piso_substep", "fgb_ortho3_make_divergence_free",
            "fgb_ortho3_sim_step", "fgb_ortho3_wall_rows", "fgb_ipc_alloc", "fgb_ipc_open", "fgb_ipc_close", "fgb_ipc_free",
-           "fgb_ortho3_set_slab", "fgb_ortho3_slab_error", "fgb_ortho3_set_scalar", "fgb_ortho3_advect_scalar", "fgb_ortho3_set_sgs", "fgb_ortho3_sgs_viscosity", "fgb_ortho3_velocity_gradients", "fgb_ortho3_piso_substep_record", "fgb_ortho3_adjoint_workspace_bytes", "fgb_ortho3_piso_substep_backward", "fgb_ortho3_piso_substep_record_scalar", "fgb_ortho3_piso_substep_backward_scalar", "fgb_sample_sensors_n", "fgb_extruded3_piso_substep", "fgb_extruded3_make_divergence_free",
+           "fgb_ortho3_set_slab", "fgb_ortho3_slab_error", "fgb_ortho3_set_scalar", "fgb_ortho3_advect_scalar", "fgb_ortho3_set_sgs", "fgb_ortho3_sgs_viscosity", "fgb_ortho3_velocity_gradients", "fgb_ortho3_piso_substep_record", "fgb_ortho3_adjoint_workspace_bytes", "fgb_ortho3_piso_substep_backward", "fgb_ortho3_piso_substep_record_scalar", "fgb_ortho3_piso_substep_backward_scalar", "fgb_extruded3_piso_substep_record", "fgb_extruded3_adjoint_workspace_bytes", "fgb_extruded3_piso_substep_backward", "fgb_sample_sensors_n", "fgb_extruded3_piso_substep", "fgb_extruded3_make_divergence_free",
            "fgb_extruded3_balance_fluxes", "fgb_extruded3_update_outflow", "fgb_extruded3_max_velocity", "fgb_extruded3_wall_forces", "fgb_extruded3_apply_jets"]
 
 
@@ -207,6 +207,10 @@ def load():
     L.fgb_ortho3_sgs_viscosity.argtypes = [vp, vp, vp, vp, vp]
     L.fgb_ortho3_velocity_gradients.argtypes = [vp, vp, vp, vp, vp]
     L.fgb_extruded3_piso_substep.argtypes = [vp, C.POINTER(Extruded3Tables), vp, vp, vp, vp, vp]
+    L.fgb_extruded3_piso_substep_record.argtypes = [vp, C.POINTER(Extruded3Tables), vp, vp, vp, vp, C.POINTER(Tape), vp]
+    L.fgb_extruded3_adjoint_workspace_bytes.argtypes = [C.POINTER(Extruded3Tables), i32]
+    L.fgb_extruded3_adjoint_workspace_bytes.restype = C.c_size_t
+    L.fgb_extruded3_piso_substep_backward.argtypes = [vp, C.POINTER(Extruded3Tables), C.POINTER(Tape), vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     L.fgb_extruded3_make_divergence_free.argtypes = [vp, C.POINTER(Extruded3Tables), vp, vp, vp, i32, vp]
     L.fgb_extruded3_balance_fluxes.argtypes = [C.POINTER(Extruded3Tables), i32, vp, vp, vp, f32, vp]
     L.fgb_extruded3_update_outflow.argtypes = [C.POINTER(Extruded3Tables), i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, f32, vp]

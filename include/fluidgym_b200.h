@@ -303,6 +303,10 @@ typedef struct fgb_ortho3_tables {
      * the neighbour indices instead of loading them (24 bytes per cell less, one dependent load less per gather). */
     int32_t nx, ny, nz, closed;
     int32_t boff[6];
+    /* z-extruded multi-block grids (nx = 0, nbr = the 6-face table of the extruded domain): rev [4][plane] = the in-plane face of
+     * neighbour nbr[f] that points back (tables.rev of the 2-D plane), plane = cells per plane; NULL: the opposite face.  Only the
+     * transposed Krylov solves of the reverse mode read it. */
+    const int8_t *rev;
 } fgb_ortho3_tables;
 typedef struct fgb_ortho3 fgb_ortho3;
 size_t fgb_ortho3_workspace_bytes(const fgb_ortho3_tables *t, int32_t B);
@@ -426,6 +430,16 @@ typedef struct fgb_extruded3_tables {
 /* Simulation._PISO_split_step (SIM.py:1431-2002, non-orthogonal path; pressure_non_ortho_steps = 4 in 3-D, cylinder_env_base.py:317) */
 int fgb_extruded3_piso_substep(fgb_ortho3 *b, const fgb_extruded3_tables *x, float *u, float *p, const float *bvel, const float *dt,
                                fgb_stream_t s);
+/* Reverse mode of the extruded substep (CylinderJet3D / Airfoil3D, differentiable=True): as fgb_piso_substep_record / _backward with three
+ * velocity components -- tape fields u_in / ustar / hb / u1 [..][B][3][N3], Coff [B][6][N3], A / p_in / p [..][B][N3], bvel_in
+ * [B][3][nz][NB2], pmean [C*n_p][B].  The handle's tables need rev (in-plane reverse faces) and plane = N2 for the transposed solves.
+ * Replaces the dimension-generic _GRAD kernels of the reference on these grids (PISO_multiblock_cuda_kernel.cu:3884-4090, 4403-4491). */
+int fgb_extruded3_piso_substep_record(fgb_ortho3 *b, const fgb_extruded3_tables *x, float *u, float *p, const float *bvel, const float *dt,
+                                      const fgb_tape *tape, fgb_stream_t s);
+size_t fgb_extruded3_adjoint_workspace_bytes(const fgb_extruded3_tables *x, int32_t B);
+int fgb_extruded3_piso_substep_backward(fgb_ortho3 *b, const fgb_extruded3_tables *x, const fgb_tape *tape, const float *u_out_bar,
+                                        const float *p_out_bar, float *u_bar, float *p_prev_bar, float *bvel_bar, void *workspace,
+                                        size_t workspace_bytes, fgb_stream_t s);
 /* Simulation.make_divergence_free (SIM.py:1320-1430) on an extruded domain: projection with A = 1, p_nonortho_steps deferred
  * corrections; max_iter <= 0 takes the handle's option.  The outflow update of its "PRE" hook is the caller's. */
 int fgb_extruded3_make_divergence_free(fgb_ortho3 *b, const fgb_extruded3_tables *x, float *u, float *p, const float *bvel, int max_iter,

@@ -106,8 +106,49 @@ def rbc3d(src, tag="rbc3d", out="rbc3d"):
     print(out, {k: (np.asarray(v).shape, float(np.abs(v).max())) for k, v in fx.items()})
 
 
+def cyl3d(src, tag="cyl3d", out="cyl3d"):
+    """CylinderJet3D-easy at resolution 8 (5 blocks x 8 planes = 15 872 cells, 8 jets; tools/r02_cyl3d_grad_golden.sh): one env.step =
+    25 solver steps.  Fields in the "planes" layout [C, nz, N2] of extract_cyl3d_fixtures.py; the cotangent is stored (per block
+    sin(0.37 i + 0.1 block) over the block's flat index)."""
+    from fluidgym_b200.domain import FIXED
+    from fluidgym_b200.envs.cylinder_domain import make_cylinder_domain
+    d = np.load(os.path.join(src, f"{tag}_grad.npz"))
+    meta = json.load(open(os.path.join(src, f"{tag}_grad_meta.json")))
+    spec = make_cylinder_domain(8)
+    cd = spec.prepare()
+    nz, N2 = 8, cd.N
+    offs = np.concatenate([[0], np.cumsum([b.nx * b.ny for b in spec.blocks])])
+
+    def blocks(fmt, comps):
+        o = np.zeros((comps, nz, N2), np.float32)
+        for bi in range(len(spec.blocks)):
+            o[:, :, offs[bi]:offs[bi + 1]] = d[fmt.format(bi)][0].reshape(comps, nz, -1)
+        return o
+
+    def bvel(pre):
+        o, k = np.zeros((3, nz, cd.NB), np.float32), 0
+        for bi, b in enumerate(spec.blocks):
+            for f in range(4):
+                if b.bounds[f].type == FIXED:
+                    n = b.size(1 - (f >> 1))
+                    v = d[f"{pre}b{bi}_f{f}_velocity"][0]
+                    o[:, :, k:k + n] = v.reshape(3, nz, n) if v.size == 3 * nz * n else np.broadcast_to(v.reshape(3, 1, -1), (3, nz, n))
+                    k += n
+        return o
+
+    fx = dict(action=d["action"].reshape(-1), reward=d["reward"].reshape(-1), dreward_daction=d["dreward_daction"].reshape(-1),
+              vjp_daction=d["vjp_daction"].reshape(-1), pre_u=blocks("pre_b{}_u", 3), pre_p=blocks("pre_b{}_p", 1)[0], pre_bvel=bvel("pre_"),
+              post_u=blocks("post_b{}_u", 3), dreward_du=blocks("dreward_db{}_u", 3), vjp_du=blocks("vjp_db{}_u", 3),
+              cotangent_u=blocks("cotangent{}", 3), info_drag=d["info_drag"].reshape(-1), info_lift=d["info_lift"].reshape(-1),
+              forward_cg_n=np.array(meta["forward_iters"]["cg"]["n"]), forward_cg_mean=np.array(meta["forward_iters"]["cg"]["mean"]))
+    np.savez_compressed(os.path.join(HERE, f"{out}_grad.npz"), **{k: np.asarray(v, dtype=np.float32) for k, v in fx.items()})
+    print(out, {k: (np.asarray(v).shape, float(np.abs(v).max())) for k, v in fx.items()})
+
+
 def main():
     src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/r02/golden"
+    if len(sys.argv) > 2 and sys.argv[2] == "cyl3d":
+        return cyl3d(src)
     if len(sys.argv) > 2 and sys.argv[2] == "tcf":
         return tcf(src)
     if len(sys.argv) > 2 and sys.argv[2] == "rbc3d":
