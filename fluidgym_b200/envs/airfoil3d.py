@@ -39,7 +39,8 @@ class Airfoil3DEnv(SpanwiseExtrudedEnv):
     def __init__(self, n_envs: int = 1, n_agents=4, reynolds_number=3e3, dt=0.05, adaptive_cfl=0.8, step_length=0.25, episode_length=200,
                  attack_angle_deg=10.0, local_obs_window=1, use_marl=False, local_reward_weight=0.5, local_2d_obs=False, init_from_2d=False,
                  device="cuda:0", cl_cd_ref=0.0, randomize_initial_state=False, enable_actions=True, load_initial_domain=False,
-                 initial_domains_path=None, compiled=None, solver_cls=None, res_z=None):
+                 initial_domains_path=None, compiled=None, solver_cls=None, res_z=None, differentiable=False):
+        self.differentiable = bool(differentiable)       # reverse mode of the extruded substep (SpanwiseExtrudedEnv._advance_differentiable)
         if res_z is not None:
             self.res_z = int(res_z)                                     # tests only: the reference's value is fixed
         if n_agents < 1 or self.res_z % n_agents != 0:
@@ -195,6 +196,14 @@ class Airfoil3DEnv(SpanwiseExtrudedEnv):
         s.bvel[:, :2, :, jf] = prof
         s.bvel[:, 2, :, jf] = 0.0
         s.balance_fluxes(self._free_jets, 1e-5)
+
+    def _jet_profiles(self, control):
+        """functional form of _apply_action for the differentiable mode"""
+        v = control - control.mean(dim=2, keepdim=True)
+        mx = v.abs().max(dim=2, keepdim=True).values
+        v = torch.where(mx > 1.0, v / mx, v)
+        per_plane = v.repeat_interleave(self.nz_per_agent, dim=1)                          # [B, nz, n_jets]
+        return torch.einsum("bkj,jcx->bckx", per_plane, self.jet_base), 1e-5
 
     def _reward(self, cd, cl):
         """airfoil_env_3d.py:420, 450"""

@@ -241,10 +241,9 @@ class SpanwiseExtrudedEnv(InitialDomainsExtruded):
         for _ in range(self.n_sim_steps):
             last = last + self.action_smoothing_alpha * (a - last)
             if self.enable_actions:
-                per_plane = last.repeat_interleave(self.nz_per_agent, dim=1)                       # [B, nz]
-                jets = self.jet_templ[None, :, None, :] * per_plane[:, None, :, None]             # [B, 2, nz, n_jet_faces]
+                jets, tol = self._jet_profiles(last)                                              # [B, 2, nz, n_jet_faces] (no spanwise component)
                 bv = bv.index_copy(3, jf, torch.cat([jets, torch.zeros_like(jets[:, :1])], dim=1))
-                bv = self._balance_fn(bv, self._free_jets, 1e-7)
+                bv = self._balance_fn(bv, self._free_jets, tol)
             u, p, bv, k = self._single_step_differentiable(u, p, bv)
             nsub += k
             u2 = u.view(B, 3, nz, N2)[:, :2].permute(0, 2, 1, 3).reshape(B * nz, 2, N2)
@@ -414,6 +413,11 @@ class CylinderJet3DEnv(SpanwiseExtrudedEnv):
         s.bvel[:, :2, :, jf] = self.jet_templ[None, :, None, :] * per_plane[:, None, :, None]
         s.bvel[:, 2, :, jf] = 0.0
         s.balance_fluxes(self._free_jets, 1e-7)
+
+    def _jet_profiles(self, control):
+        """functional form of _apply_action for the differentiable mode -> (in-plane jet velocities [B, 2, nz, n_faces], balance tolerance)"""
+        per_plane = control.repeat_interleave(self.nz_per_agent, dim=1)                           # [B, nz]
+        return self.jet_templ[None, :, None, :] * per_plane[:, None, :, None], 1e-7
 
     def _reward(self, cd, cl):
         """cylinder_env_base.py:769, jet_cylinder_env_3d.py:436, 470-472"""

@@ -205,8 +205,9 @@ def test_unsupported_options_fail_loudly(compiled):
     env = fluidgym_b200.make("CylinderJet3D-easy-v0", load_initial_domain=True, initial_domains_path="/nonexistent", **kw)
     with pytest.raises(RuntimeError, match="Initial domain not found"):          # the reference's message (fluid_env.py:1076-1079)
         env.reset(seed=0)
-    with pytest.raises(NotImplementedError, match="differentiable"):
-        fluidgym_b200.make("CylinderJet3D-easy-v0", differentiable=True, **kw)
+    # differentiable=True is a supported option since round 2 (reverse mode of the extruded substep, GPU-tested against the reference's
+    # gradients in tests/test_gpu_extruded.py); the constructor only records it
+    assert fluidgym_b200.make("CylinderJet3D-easy-v0", differentiable=True, **kw).differentiable is True
     env = fluidgym_b200.make("CylinderJet3D-medium-v0", load_initial_domain=False, load_domain_statistics=False, **kw)
     assert env.reynolds_number == 250.0 and env.initial_domain_id == "cylinder_3D_Re250_Res8"
 
