@@ -129,7 +129,8 @@ def _new_tape3(solver):
     C_ = int(solver.options.corrector_steps)
     return dict(u_in=torch.empty(B, 3, N, **f32), bvel_in=torch.empty(B, 3, NB, **f32), dt=torch.empty(B, **f32),
                 Coff=torch.empty(B, 6, N, **f32), A=torch.empty(B, N, **f32), ustar=torch.empty(B, 3, N, **f32),
-                hb=torch.empty(C_, B, 3, N, **f32), p=torch.empty(C_, B, N, **f32), u1=torch.empty(max(C_ - 1, 1), B, 3, N, **f32))
+                hb=torch.empty(C_, B, 3, N, **f32), p=torch.empty(C_, B, N, **f32), u1=torch.empty(max(C_ - 1, 1), B, 3, N, **f32),
+                visc=torch.empty(B, N, **f32))          # read only when a sub-grid model is set
 
 
 def _adjoint_workspace3(solver):

@@ -1282,7 +1282,8 @@ __global__ void __launch_bounds__(O3_T) k3_adj_advection(T3 t, const float *__re
 }
 // adjoint of the assembly (A, Coff from the face fluxes; constant viscosity) and of the boundary sources Sb
 __global__ void __launch_bounds__(O3_T) k3_adj_assemble(T3 t, const float *__restrict__ Ab, const float *__restrict__ Coffb, const float *__restrict__ Sbb,
-                                                        const float *__restrict__ Bvel, float *__restrict__ Ub, float *__restrict__ Bvb, float *__restrict__ Fbb) {
+                                                        const float *__restrict__ Bvel, float *__restrict__ Ub, float *__restrict__ Bvb, float *__restrict__ Fbb,
+                                                        const float *__restrict__ Visc /* [B][NS] taped per-cell viscosity or null */) {
     const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, NS = t.NS, NB = t.NB;
     if (g >= t.N) return;
     const float det = t.det[g], diagb = Ab[(size_t)b * NS + g] / det;
@@ -1298,7 +1299,7 @@ __global__ void __launch_bounds__(O3_T) k3_adj_assemble(T3 t, const float *__res
         else {
             const int j = -1 - nb6[f], d = f >> 1;
             const float bm = t.b_minv[d * NB + j];
-            const float k = -(sig * o3_bflux(t, j, d, bv)) + 2.f * t.viscosity * (t.b_det[j] * bm * bm);
+            const float k = -(sig * o3_bflux(t, j, d, bv)) + 2.f * (Visc ? Visc[(size_t)b * NS + g] : t.viscosity) * (t.b_det[j] * bm * bm);
             float dot = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -1365,7 +1366,6 @@ static int o3_copy(void *dst, const void *src, size_t bytes, cudaStream_t st) {
 static int o3_adjoint_supported(const fgb_ortho3 *b, bool with_scalar) {
     if (b->slab.on || b->t.NS != b->t.N) return set_err(FGB_E_ARG, "D = 3 reverse mode: single GPU only (no slabs)");
     if (b->t.nx <= 0) return set_err(FGB_E_ARG, "D = 3 reverse mode: needs the structured-box description (tables.nx/ny/nz/closed/boff)");
-    if (b->sgs_coef != 0.f) return set_err(FGB_E_ARG, "D = 3 reverse mode: the sub-grid viscosity is not differentiated");
     if (with_scalar != (b->sc.T != nullptr))
         return set_err(FGB_E_ARG, with_scalar ? "D = 3 reverse mode (scalar): no scalar attached (fgb_ortho3_set_scalar)"
                                               : "D = 3 reverse mode: a scalar is attached, use the _scalar entry points");
@@ -1390,6 +1390,12 @@ static int o3_record_impl(fgb_ortho3 *b, float *u, float *p, const float *bvel, 
         if ((rc = o3_copy(stp->sbval_in, b->sc.sbval, BNB * 4, st))) return rc;
         if ((rc = fgb_ortho3_advect_scalar(b, u, bvel, dt, nullptr, s))) return rc;
         if ((rc = o3_copy(stp->T_out, b->sc.T, BN * 4, st))) return rc;
+    }
+    if (b->sgs_coef != 0.f) {     // per-cell viscosity of this substep: a CONSTANT of the graph, as in the reference (its Smagorinsky op has no
+                                  // autograd wrapper: tcf_env.py:456-470 sets the block viscosity from a raw extension call)
+        if (!tp->visc) return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep_record: sub-grid model set, the tape needs a visc buffer");
+        if ((rc = fgb_ortho3_sgs_viscosity(b, u, bvel, nullptr, s))) return rc;
+        if ((rc = o3_copy(tp->visc, b->visc, BN * 4, st))) return rc;
     }
     if ((rc = fgb_ortho3_setup_advection(b, u, bvel, src, dt, nullptr, s))) return rc;
     if ((rc = fgb_ortho3_solve_advection(b, 1, nullptr, s))) return rc;
@@ -1430,6 +1436,7 @@ static int o3_backward_impl(fgb_ortho3 *b, const fgb_ortho3_tape *tp, const fgb_
     if (stp && (!T_out_bar || !T_bar || !sbval_bar || !stp->T_in || !stp->T_out || !stp->sbval_in))
         return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep_backward_scalar: incomplete scalar arguments");
     if (ws_bytes < fgb_ortho3_adjoint_workspace_bytes(&b->t, b->B)) return set_err(FGB_E_WORKSPACE, "fgb_ortho3_piso_substep_backward: workspace too small");
+    if (b->sgs_coef != 0.f && !tp->visc) return set_err(FGB_E_ARG, "fgb_ortho3_piso_substep_backward: sub-grid model set, the tape needs its visc buffer");
     cudaStream_t st = STREAM(s);
     const size_t B = b->B, NB = b->t.NB > 0 ? b->t.NB : 1, BN = B * b->t.NS;
     Carver c{(char *)ws, 0};
@@ -1484,7 +1491,7 @@ static int o3_backward_impl(fgb_ortho3 *b, const fgb_ortho3_tape *tp, const fgb_
     b->launches += 3;
     k3_adj_advection<<<grid, O3_T, 0, st>>>(b->t, mu, tp->ustar, rAb, tp->A, tp->dt, Ab, Coffb, u_bar, Sbb);
     LAUNCH_CHECK("k3_adj_advection");
-    k3_adj_assemble<<<grid, O3_T, 0, st>>>(b->t, Ab, Coffb, Sbb, tp->bvel_in, u_bar, bvel_bar, Fbb);
+    k3_adj_assemble<<<grid, O3_T, 0, st>>>(b->t, Ab, Coffb, Sbb, tp->bvel_in, u_bar, bvel_bar, Fbb, b->sgs_coef != 0.f ? tp->visc : nullptr);
     LAUNCH_CHECK("k3_adj_assemble");
     if (stp) {
         // buoyancy + scalar transport (they ran BEFORE the predictor): T_new_bar from the source adjoint, one transposed scalar solve,

@@ -53,8 +53,6 @@ class TCF3DEnv(InitialDomains3D):
             raise NotImplementedError("init_with_noise needs the reference's optional simplex-noise extension; start from a state instead")
         self.n_envs = int(n_envs)
         self.differentiable = bool(differentiable)
-        if self.differentiable and C_smag != 0.0:
-            raise NotImplementedError("differentiable=True with the sub-grid-scale model: the per-cell viscosity is not differentiated")
         self.load_domain_on_reset, self.initial_domains_path = bool(load_initial_domain), initial_domains_path
         self.L, self.D = float(L), float(D)
         self.re_wall = float(reynolds_number_wall)

@@ -35,7 +35,7 @@ class Tape(C.Structure):
 
 
 class Ortho3Tape(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ("u_in", "bvel_in", "dt", "Coff", "A", "ustar", "hb", "p", "u1")]
+    _fields_ = [(k, C.c_void_p) for k in ("u_in", "bvel_in", "dt", "Coff", "A", "ustar", "hb", "p", "u1", "visc")]
 
 
 class ScalarTape(C.Structure):

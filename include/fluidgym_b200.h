@@ -369,6 +369,8 @@ typedef struct fgb_ortho3_tape {
     float *hb;       /* [C][B][3][N]    HbyA of every corrector */
     float *p;        /* [C][B][N]       pressure of every corrector (mean removed) */
     float *u1;       /* [max(C-1,1)][B][3][N]  velocity after every corrector but the last */
+    float *visc;     /* [B][N] per-cell viscosity of the substep when a sub-grid model is set (fgb_ortho3_set_sgs), else NULL: a constant of
+                      * the graph, as in the reference, whose Smagorinsky op has no autograd wrapper */
 } fgb_ortho3_tape;
 int fgb_ortho3_piso_substep_record(fgb_ortho3 *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
                                    const fgb_ortho3_tape *tape, fgb_stream_t s);

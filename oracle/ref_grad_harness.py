@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--kw", default="{}")
     ap.add_argument("--pressure-tol", type=float, default=None)
     ap.add_argument("--advection-tol", type=float, default=None)
+    ap.add_argument("--res-z", type=int, default=None, help="Airfoil3D: spanwise resolution (class attribute AirfoilEnvBase._res_z), as ref_harness.py")
     ap.add_argument("--perturb", type=float, default=0.0, help="std of Gaussian noise added to the block velocities after reset (as ref_harness.py)")
     args = ap.parse_args()
     tag = args.tag or args.env.replace("-", "_")
@@ -63,6 +64,10 @@ def main():
     assert torch.cuda.is_available(), "the reference needs a GPU"
     meta = {"env": args.env, "seed": args.seed, "torch": torch.__version__, "gpu": torch.cuda.get_device_name(0),
             "develop": args.develop, "action": args.action}
+    if args.res_z is not None:
+        from fluidgym.envs.airfoil.airfoil_env_base import AirfoilEnvBase
+        AirfoilEnvBase._res_z = int(args.res_z)
+        meta["res_z"] = int(args.res_z)
     env = fluidgym.make(args.env, differentiable=True, load_initial_domain=False, load_domain_statistics=False,
                         randomize_initial_state=False, **json.loads(args.kw))
     env.reset(seed=args.seed)

@@ -145,12 +145,61 @@ def cyl3d(src, tag="cyl3d", out="cyl3d"):
     print(out, {k: (np.asarray(v).shape, float(np.abs(v).max())) for k, v in fx.items()})
 
 
+def airfoil3d(src, tag="airfoil3d", out="airfoil3d"):
+    """Airfoil3D-easy at res_z 8 (6 blocks x 8 planes = 374 448 cells, 4 agents x 3 jets; tools/r02_airfoil3d_grad_golden.sh): one
+    env.step = 5 solver steps.  The incoming state (the differentiable backend's own reset) is stored completely; of the field gradients
+    the planes 0 and 5 and the per-plane norms are kept (4.5 MB per full field)."""
+    from fluidgym_b200.envs.airfoil_domain import make_airfoil_domain
+    d = np.load(os.path.join(src, f"{tag}_grad.npz"))
+    meta = json.load(open(os.path.join(src, f"{tag}_grad_meta.json")))
+    spec = make_airfoil_domain()
+    cd = spec.prepare()
+    nz, N2 = int(meta.get("res_z", 8)), cd.N
+    offs = np.concatenate([[0], np.cumsum([b.nx * b.ny for b in spec.blocks])])
+
+    def blocks(fmt, comps):
+        o = np.zeros((comps, nz, N2), np.float32)
+        for bi in range(len(spec.blocks)):
+            o[:, :, offs[bi]:offs[bi + 1]] = d[fmt.format(bi)][0].reshape(comps, nz, -1)
+        return o
+
+    from fluidgym_b200.domain import FIXED
+    # the incoming state is stored: the reset of the differentiable backend (zero-started projection solves without residual reset)
+    # differs from the plain backend's reset state in airfoil3d_env.npz by 27 % in the velocity
+    pre_u, pre_p = blocks("pre_b{}_u", 3), blocks("pre_b{}_p", 1)[0]
+    pre_bvel, k = np.zeros((3, nz, cd.NB), np.float32), 0
+    for bi, b in enumerate(spec.blocks):
+        for f in range(4):
+            if b.bounds[f].type == FIXED:
+                n = b.size(1 - (f >> 1))
+                v = d[f"pre_b{bi}_f{f}_velocity"][0]
+                pre_bvel[:, :, k:k + n] = v.reshape(3, nz, n) if v.size == 3 * nz * n else np.broadcast_to(v.reshape(3, 1, -1), (3, nz, n))
+                k += n
+    gu, vu, cot, post = blocks("dreward_db{}_u", 3), blocks("vjp_db{}_u", 3), blocks("cotangent{}", 3), blocks("post_b{}_u", 3)
+    fx = dict(action=d["action"].reshape(-1), reward=d["reward"].reshape(-1), dreward_daction=d["dreward_daction"].reshape(-1),
+              vjp_daction=d["vjp_daction"].reshape(-1), pre_u=pre_u, pre_p=pre_p, pre_bvel=pre_bvel, planes=np.array([0, 5]), dreward_du_planes=gu[:, [0, 5]], vjp_du_planes=vu[:, [0, 5]],
+              dreward_du_norms=np.sqrt((gu.astype(np.float64) ** 2).sum(axis=(0, 2))), vjp_du_norms=np.sqrt((vu.astype(np.float64) ** 2).sum(axis=(0, 2))),
+              post_u_planes=post[:, [0, 5]], cot_phase=np.array([0.1 * bi for bi in range(len(spec.blocks))]),
+              info_drag=d["info_drag"].reshape(-1), info_lift=d["info_lift"].reshape(-1), forward_cg_n=np.array(meta["forward_iters"]["cg"]["n"]),
+              forward_cg_mean=np.array(meta["forward_iters"]["cg"]["mean"]), forward_seconds=np.array(meta["forward_seconds"]),
+              backward_seconds=np.array(meta["backward_seconds"]))
+    # the cotangent is sin(0.37 i + 0.1 block) over every block's flat index: reproducible from the block sizes, check one block
+    b0 = d["cotangent0"].reshape(-1)
+    assert np.abs(b0 - np.sin(0.37 * np.arange(b0.size)).astype(np.float32)).max() < 1e-6
+    np.savez_compressed(os.path.join(HERE, f"{out}_grad.npz"), **{k: np.asarray(v, dtype=np.float32) for k, v in fx.items()})
+    print(out, {k: (np.asarray(v).shape, float(np.abs(v).max())) for k, v in fx.items()})
+
+
 def main():
     src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/r02/golden"
+    if len(sys.argv) > 2 and sys.argv[2] == "airfoil3d":
+        return airfoil3d(src)
     if len(sys.argv) > 2 and sys.argv[2] == "cyl3d":
         return cyl3d(src)
     if len(sys.argv) > 2 and sys.argv[2] == "tcf":
         return tcf(src)
+    if len(sys.argv) > 2 and sys.argv[2] == "tcf_sgs":          # the same channel with C_smag = 0.1 + van Driest damping
+        return tcf(src, tag="tcf32_sgs", out="tcf32_sgs")
     if len(sys.argv) > 2 and sys.argv[2] == "rbc3d":
         return rbc3d(src)
     from fluidgym_b200.envs.airfoil_domain import make_airfoil_domain

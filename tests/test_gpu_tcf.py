@@ -227,3 +227,32 @@ def test_tcf_gradients_match_reference(golden):
     # north_star: gradients within 1e-3 relative; observed on a B200 (profiles/r02_tcf32_gradients.json): 1.0e-5 / 4e-7 / 1.0e-5 / 1.1e-6
     assert e["dr_da"] < 1e-4 and e["vjp_da"] < 1e-4
     assert e["dr_du"] < 1e-4 and e["vjp_du"] < 1e-4
+
+
+def test_tcf_gradients_with_sgs_match_reference(golden):
+    """As test_tcf_gradients_match_reference with the Smagorinsky model on (C_smag = 0.1, van Driest damping; golden tcf32_sgs_grad.npz).
+    In the reference the sub-grid viscosity is a constant of the graph (its Smagorinsky op has no autograd wrapper): the per-cell viscosity
+    of every substep is taped, not differentiated."""
+    import fluidgym_b200 as fg
+    fx = golden("tcf32_sgs_grad.npz")
+    env = fg.make("TCFSmall3D-both-easy-v0", n_envs=1, resolution_x_z=32, resolution_y=33, C_smag=0.1, use_van_driest=True, differentiable=True)
+    env.reset(seed=42)
+    env.set_state(fx["pre_u"], np.zeros(32768, np.float32), np.zeros((3, 2048), np.float32))
+    u0 = env.mark_state_differentiable()
+    act = torch.from_numpy(fx["action"]).cuda().reshape(1, 512, 1).clone().requires_grad_(True)
+    obs, reward, term, trunc, info = env.step(act)
+    g_a, g_u = torch.autograd.grad(reward.sum(), [act, u0], retain_graph=True)
+    u1 = env._du
+    cot = torch.sin(0.37 * torch.arange(u1.numel(), device="cuda", dtype=torch.float64)).to(torch.float32).reshape(u1.shape)
+    v_a, v_u = torch.autograd.grad([u1], [act, u0], grad_outputs=[cot])
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        a, b = a.detach().cpu().numpy().ravel().astype(np.float64), np.asarray(b, dtype=np.float64).ravel()
+        return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    e = dict(reward=abs(float(reward[0, 0].detach()) - float(fx["reward"][0])) / abs(float(fx["reward"][0])), u=rel(u1[0], fx["post_u"]),
+             dr_da=rel(g_a, fx["dreward_daction"]), dr_du=rel(g_u[0], fx["dreward_du"]), vjp_da=rel(v_a, fx["vjp_daction"]), vjp_du=rel(v_u[0], fx["vjp_du"]))
+    print("tcf32 + SGS gradients vs reference:", e)
+    json.dump(e, open("gpurun_out/tcf32_sgs_gradients.json", "w"))
+    assert e["reward"] < 1e-5 and e["u"] < 1e-4
+    assert e["dr_da"] < 1e-3 and e["vjp_da"] < 1e-3 and e["dr_du"] < 1e-3 and e["vjp_du"] < 1e-3
