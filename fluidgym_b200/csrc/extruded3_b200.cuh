@@ -1,12 +1,11 @@
 // D = 3 operators on z-EXTRUDED multi-block domains (CylinderJet3D, Airfoil3D: the 2-D multi-block grid repeated over nz
 // uniform, periodic z planes; envs/cylinder/grid.py:298, shapes.py:641-676; reference: the K.cu kernels with DIMS = 3).
 //
-// STATUS: operator layer.  The per-cell functions below are __host__ __device__ so that tests/test_extruded_host.py can
-// execute exactly this code on the CPU (through tests/cpu_harness/extruded_host.cu) and compare it with the numpy
-// specification oracle/extruded_eval.py, which is pinned to an op trace of the unmodified reference on CylinderJet3D-easy
-// (tests/golden/cyl3d_substep*.npz).  The launch glue at the end of this file has NOT run on a GPU yet
-// (DESIGN.md section 9): envs/cylinder3d.py (CylinderJet3D) is built on it and verified on the CPU
-// through the same cell code (tests/test_cylinder3d_cpu.py); tools/extruded_check.py is its first GPU run.
+// The per-cell functions below are __host__ __device__ so that tests/test_extruded_host.py can execute exactly this code on the
+// CPU (through tests/cpu_harness/extruded_host.cu) and compare it with the numpy specification oracle/extruded_eval.py, which is
+// pinned to an op trace of the unmodified reference on CylinderJet3D-easy (tests/golden/cyl3d_substep*.npz).  The launch glue at
+// the end of this file is verified on a B200 against the same goldens (tests/test_gpu_extruded.py, profiles/r02_extruded_check.json):
+// substep u 1.7e-6 / p 5.6e-5 with the reference's iteration counts, a whole env.step inside the bars of tools/extruded_check.py.
 //
 // The metric tensor of an extruded cell is block diagonal, M3 = diag(M2, hz): every in-plane coefficient of a row / det3
 // equals the 2-D one from the compiled tables (fgb_tables), the z faces add  -+1/4 (u_z,P + u_z,N) / hz - nu / hz^2  off
@@ -213,7 +212,7 @@ X3_HD void x3_correct_cell(const X3Tab &x, int k, int g, const float *hb, const 
 // ------------------------------------------------------------------------------------------------------------------
 // launch glue (one thread per (cell, plane, environment)); matrices / vectors live in the workspace of an fgb_ortho3
 // handle created on the 6-face neighbour table of the extruded domain, so fgb_ortho3_solve_advection / _solve_pressure
-// run the Krylov iterations.  NOT yet run on a GPU (see the header of this file).
+// run the Krylov iterations.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) kx3_setup_advection(X3Tab x, const float *U, const float *Ures, const float *Bvel, const float *dtv,
                                                           float *Coff, float *A, float *Rhs, int with_matrix) {
@@ -709,10 +708,11 @@ extern "C" int fgb_extruded3_make_divergence_free(fgb_ortho3 *b, const fgb_extru
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Boundary hooks of the extruded environments as kernels (OPT-IN: FGB_X3_HOOKS=cuda in extruded3d.py; default = the torch
-// expressions of ExtrudedStepping, which are what the CPU tests pin to the reference).  Same formulas, statement by statement:
+// Boundary hooks of the extruded environments as kernels (the default on a GPU; FGB_X3_HOOKS=torch selects the torch expressions of
+// ExtrudedStepping, which are what the CPU tests pin to the reference).  Same formulas, statement by statement:
 // balance_boundary_fluxes (SIM.py:188-224), update_advective_boundaries (SIM.py:228-393), Domain.getMaxVelocity (DS.cpp:1580-1612).
-// One CTA per environment for the boundary kernels (a few thousand faces), flux sums accumulated in double.  NOT yet run on a GPU.
+// One CTA per environment for the boundary kernels (a few thousand faces), flux sums accumulated in double.  Checked on a B200 against
+// the torch expressions and a float64 evaluation of them (tests/zz_first_run_worker.py, profiles/r02_hooks_vs_float64.log).
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void x3_block_sum2(double &a, double &b, double *sm /* [66] */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;

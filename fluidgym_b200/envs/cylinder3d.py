@@ -5,9 +5,10 @@ along the span -- one agent per jet with ``use_marl=True`` --, drag / lift per p
 STATUS: every host-side piece of this class (jets, flux balances, outflow update, CFL plan, forces, observations, rewards,
 multi-agent windows) runs on the CPU in tests/test_cylinder3d_cpu.py on top of a stand-in solver that executes the per-cell code
 of the CUDA kernels on the host, and reproduces the unmodified reference's first ``env.step`` (tests/golden/cyl3d_env.npz).  The
-CUDA launch path underneath (``ExtrudedPISO3D`` -> ``fgb_extruded3_*``) has NOT run on a GPU yet; the
-boundary / reward formulas here are torch expressions over a few thousand boundary values, to be fused into kernels once that
-path is measured.  All tensors carry a leading environment dimension.
+CUDA path underneath (``ExtrudedPISO3D`` -> ``fgb_extruded3_*``) is verified on a B200 against the same goldens
+(tests/test_gpu_extruded.py: substep, reset, ``env.step``; boundary hooks / forces / jets as kernels by default), and so is the
+differentiable mode (reverse mode of the extruded substep against the reference's own gradients).  All tensors carry a leading
+environment dimension.
 """
 from __future__ import annotations
 
