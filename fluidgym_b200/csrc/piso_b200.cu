@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) k_pressure_div(Tab t, const float *__rest
 // i.e. they are bound by re-reading the tables from L2 once per environment.  Here every table value is loaded once per
 // thread (all loads precede the first store; the deferred-correction loop runs over the table entries outside and the
 // environments inside) and the per-environment arithmetic is the same expression, statement by statement, as in
-// k_setup_pressure_matrix / k_pressure_div, so results are bit-identical (tests/test_gpu_extruded.py::test_opt_in_kernels[multi_env_assembly] on a B200).  Selected only
+// k_setup_pressure_matrix / k_pressure_div, so results are bit-identical (tests/test_gpu_extruded.py::test_opt_in_kernels[asm2|asm4|asm8] on a B200).  Selected only
 // when the environment variable FGB_ASM_ENVS is set: measured without gain on the headline batch.
 template <int E>
 __global__ void __launch_bounds__(256) k_setup_pressure_matrix_multi(Tab t, int B, const float *__restrict__ A,
