@@ -654,7 +654,7 @@ extern "C" int fgb_extruded3_piso_substep_backward(fgb_ortho3 *b, const fgb_extr
             int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
             void *args[] = {&t, &sl, &Bi, &coff, &a, &rhs, &xo, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot, &transposed};
             b->launches++;
-            ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab<3>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, st);
+            ce = cudaLaunchCooperativeKernel((b->bicg_fused ? (void *)k3_bicgstab<3, 1> : (void *)k3_bicgstab<3, 0>), dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, st);
             if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab, transposed)", ce);
         }
         if (k > 0) ZEROX(xb_prev, 3 * BN);

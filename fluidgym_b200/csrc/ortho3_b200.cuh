@@ -66,6 +66,7 @@ struct fgb_ortho3 {
     int grid_blocks;
     float *visc;                      // [B][NS] per-cell viscosity nu + nu_sgs (fgb_ortho3_set_sgs), refreshed before every substep
     float sgs_coef; const float *sgs_damp;
+    int bicg_fused;                   // k3_bicgstab<.,1>: search-direction update folded into the product (4 instead of 5 exchanges per iteration); opt-in
     int cg_fused;                     // k3_cg_fused (2 grid.sync per CG iteration, bit-identical to k3_cg) on a single GPU; default 1,
                                       // FGB_K3_CG_FUSED=0 selects k3_cg
     long long launches;
@@ -74,7 +75,8 @@ struct fgb_ortho3 {
 static constexpr int O3_T = 256;          // threads per CTA of the one-thread-per-cell kernels
 static constexpr int O3_CT = 1024;        // threads per CTA of the cooperative Krylov kernels (one CTA per SM: a grid.sync over
                                           // 148 CTAs costs ~2 us, over 592 CTAs ~5 us, and there are 3-7 of them per iteration)
-static constexpr int O3_KRY = 15;         // Krylov work vectors per environment (BiCGStab: 5 per component)
+static constexpr int O3_KRY = 21;         // Krylov work vectors per environment (BiCGStab: 7 per component -- r, r^, p, v, t and the second
+                                          // copies of p and v of the fused search-direction update)
 static constexpr int O3_PART = 8;         // floats per CTA per reduction slot
 
 extern "C" size_t fgb_ortho3_workspace_bytes(const fgb_ortho3_tables *t, int32_t B) {
@@ -126,6 +128,9 @@ extern "C" int fgb_ortho3_create(const fgb_ortho3_tables *t, int32_t B, void *wo
     b->grid_blocks = 0;
     b->cg_fused = 1;                  // measured on a B200 (profiles/r02_k3_cg_fused_ab.txt): CylinderJet3D res 24 26.5 -> 21.2 ms / substep
     if (const char *ev = getenv("FGB_K3_CG_FUSED")) b->cg_fused = atoi(ev) != 0;
+    b->bicg_fused = 0;                // opt-in (FGB_K3_BICG_FUSED=1): bit-identical, one exchange less per iteration, but measured SLOWER on one GPU (TCFLarge 1.11 vs
+                                      // 1.04 ms / substep: 21 instead of 7 gathers per cell and 600 bytes of spills at the 64-register cap), profiles/r02_k3_kernels.md
+    if (const char *ev = getenv("FGB_K3_BICG_FUSED")) b->bicg_fused = atoi(ev) != 0;
     *out = b;
     return FGB_OK;
 }
@@ -533,15 +538,21 @@ __device__ __forceinline__ void o3_halo_sync(cg::grid_group &grid, const O3Slab 
     }
 }
 
+// new BiCGStab search direction of cell i from (r, p_old, v_old): one expression for the separate update pass and for the fused product
+__device__ __forceinline__ float o3_bpnew(const float *r, const float *p, const float *v, float beta, float omega, int i) {
+    return fmaf(beta, fmaf(-omega, __ldcg(&v[i]), __ldcg(&p[i])), __ldcg(&r[i]));
+}
 // BiCGStab for NC right-hand sides in lock step (3 velocity components, or 1 passive scalar) (BICG.cu:237-376; same
 // operation order as k_bicgstab)
-template <int NC>
+template <int NC, int FUSED>
 __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, const float *__restrict__ Coff, const float *__restrict__ Adiag,
                                                     const float *__restrict__ Rhs, float *X, float *work, float *part, int maxit, float tol,
                                                     int zero_init, const int32_t *__restrict__ active, int32_t *__restrict__ iters,
-                                                    float *__restrict__ resid, unsigned long long *__restrict__ iter_total, int transposed) {
+                                                    float *__restrict__ resid, unsigned long long *__restrict__ iter_total, int mode /* bit 0: transposed operator */) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double red[32 * 6 + 8];
+    const int transposed = mode & 1;
+    constexpr bool fused = FUSED != 0;            // search-direction update folded into the product (4 exchanges per iteration)
     const int N = t.N, NS = t.NS;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const float norm = 1.0f / sqrtf((float)t.N_global);
@@ -552,10 +563,11 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
         if (active && !active[b]) continue;
         const float *off = Coff + (size_t)b * 6 * NS, *dg = Adiag + (size_t)b * NS;
         float *wb = work + (size_t)b * O3_KRY * NS;
-        float *r[3], *rw[3], *p[3], *v[3], *tt[3], *x[3];
+        float *r[3], *rw[3], *p[3], *v[3], *tt[3], *x[3], *p2[3], *v2[3];
         const float *f[3];
         for (int c = 0; c < NC; ++c) {
-            r[c] = wb + (size_t)(5 * c) * NS; rw[c] = r[c] + NS; p[c] = r[c] + 2 * (size_t)NS; v[c] = r[c] + 3 * (size_t)NS; tt[c] = r[c] + 4 * (size_t)NS;
+            r[c] = wb + (size_t)(7 * c) * NS; rw[c] = r[c] + NS; p[c] = r[c] + 2 * (size_t)NS; v[c] = r[c] + 3 * (size_t)NS; tt[c] = r[c] + 4 * (size_t)NS;
+            p2[c] = r[c] + 5 * (size_t)NS; v2[c] = r[c] + 6 * (size_t)NS;
             x[c] = X + ((size_t)b * NC + c) * NS; f[c] = Rhs + ((size_t)b * NC + c) * NS;
         }
         if (zero_init) { for (int c = 0; c < NC; ++c) for (int g = tid; g < N; g += nth) x[c][g] = 0.f; }
@@ -575,17 +587,50 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
         // together with the residual norm that closes the previous iteration (same operands): 5 grid-wide exchanges per iteration
         float rho_next[3] = {acc[0], acc[1], acc[2]};
         for (int i = 0; i < maxit && !(done[0] && done[1] && done[2]); ++i) {
+            float beta[3] = {0.f, 0.f, 0.f};
             for (int c = 0; c < NC; ++c) if (!done[c]) {
                 const float rhop = rho[c]; rho[c] = rho_next[c];
-                if (i > 0) {
-                    const float beta = (rho[c] / rhop) * (alpha[c] / omega[c]);
-                    for (int g = tid; g < N; g += nth) { const float pn = r[c][g] + beta * (p[c][g] - omega[c] * v[c][g]); p[c][g] = pn; o3_push(sl, t, p[c], g, pn, dirty); }
-                }
+                if (i > 0) beta[c] = (rho[c] / rhop) * (alpha[c] / omega[c]);
             }
-            o3_halo_sync(grid, sl, hc, dirty);
             for (int k = 0; k < 6; ++k) acc[k] = 0.f;
-            for (int c = 0; c < NC; ++c) if (!done[c])
-                for (int g = tid; g < N; g += nth) { const float vv = transposed ? o3_row_t(t, g, off, dg, p[c]) : o3_row(t, g, off, dg, p[c]); v[c][g] = vv; acc[c] += rw[c][g] * vv; }
+            if (FUSED && i > 0) {
+                // p = r + beta (p - omega v) folded into the product: every thread forms the new direction of its cell AND of the six
+                // neighbours from (r, p_old, v_old) -- the same fp32 expression, so the same bits -- and writes p, v = C p into the second
+                // copies; the separate pass over (r, p, v) and its grid-wide "p is complete" hand-shake are gone (4 exchanges per iteration)
+                for (int c = 0; c < NC; ++c) if (!done[c]) {
+                    const float bt = beta[c], om = omega[c];
+                    const float *rc = r[c], *pc = p[c], *vc = v[c];
+                    for (int g = tid; g < N; g += nth) {
+                        int nb6[6];
+                        o3_nbrs(t, g, nb6);
+                        const float pg = o3_bpnew(rc, pc, vc, bt, om, g);
+                        float vv = dg[g] * pg;
+#pragma unroll
+                        for (int fc = 0; fc < 6; ++fc)
+                            if (nb6[fc] >= 0) {
+                                const int n = nb6[fc];
+                                const float cf = transposed ? off[((t.rev && fc < 4) ? (int)t.rev[fc * t.plane + (g % t.plane)] : (fc ^ 1)) * NS + n] : off[fc * NS + g];
+                                vv += cf * o3_bpnew(rc, pc, vc, bt, om, n);
+                            }
+                        p2[c][g] = pg; v2[c][g] = vv; acc[c] += rw[c][g] * vv;
+                        o3_push(sl, t, p2[c], g, pg, dirty); o3_push(sl, t, v2[c], g, vv, dirty);
+                    }
+                    float *tp_ = p[c]; p[c] = p2[c]; p2[c] = tp_;
+                    float *tv_ = v[c]; v[c] = v2[c]; v2[c] = tv_;
+                }
+            } else {
+                if (i > 0) {
+                    for (int c = 0; c < NC; ++c) if (!done[c])
+                        for (int g = tid; g < N; g += nth) { const float pn = o3_bpnew(r[c], p[c], v[c], beta[c], omega[c], g); p[c][g] = pn; o3_push(sl, t, p[c], g, pn, dirty); }
+                }
+                o3_halo_sync(grid, sl, hc, dirty);
+                for (int c = 0; c < NC; ++c) if (!done[c])
+                    for (int g = tid; g < N; g += nth) {
+                        const float vv = transposed ? o3_row_t(t, g, off, dg, p[c]) : o3_row(t, g, off, dg, p[c]);
+                        v[c][g] = vv; acc[c] += rw[c][g] * vv;
+                        if (fused) o3_push(sl, t, v[c], g, vv, dirty);        // the next iteration's fused product reads the neighbours' v
+                    }
+            }
             o3_grid_sum<6>(grid, sl, acc, part, rcount, arc, dirty, red);
             float acc2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int c = 0; c < NC; ++c) if (!done[c]) {
@@ -620,6 +665,7 @@ __global__ void __launch_bounds__(O3_CT) k3_bicgstab(T3 t, O3Slab sl, int B, con
                     acc2[c] += rr * rr;
                     acc2[3 + c] += rw[c][g] * rr;
                     r[c][g] = rr;
+                    if (fused) o3_push(sl, t, r[c], g, rr, dirty);          // the fused product forms the neighbours' new direction from r
                 }
             }
             o3_grid_sum<6>(grid, sl, acc2, part, rcount, arc, dirty, red);
@@ -981,7 +1027,7 @@ static int o3_coop_blocks(fgb_ortho3 *b) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_a, k3_cg<0>, O3_CT, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_b, k3_bicgstab<3>, O3_CT, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_b, k3_bicgstab<3, 0>, O3_CT, 0);
     if (b->cg_fused) { int per_c = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_c, k3_cg_fused, O3_CT, 0); if (per_c < per_a) per_a = per_c; }
     int blocks = (per_a > 0 && per_b > 0) ? sms : 1;     // one CTA per SM (co-residency is what a cooperative launch needs)
     const int need = (b->t.N + O3_CT - 1) / O3_CT;
@@ -1034,7 +1080,7 @@ extern "C" int fgb_ortho3_solve_advection(fgb_ortho3 *b, int zero_init, const in
     int transposed = 0;
     void *args[] = {&t, &sl, &B, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot, &transposed};
     b->launches++;
-    cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab<3>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
+    cudaError_t ce = cudaLaunchCooperativeKernel((b->bicg_fused ? (void *)k3_bicgstab<3, 1> : (void *)k3_bicgstab<3, 0>), dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab)", ce);
     return FGB_OK;
 }
@@ -1061,7 +1107,7 @@ extern "C" int fgb_ortho3_advect_scalar(fgb_ortho3 *b, const float *u, const flo
     int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
     int transposed = 0;
     void *args[] = {&t, &sl, &B, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot, &transposed};
-    cudaError_t ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab<1>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
+    cudaError_t ce = cudaLaunchCooperativeKernel((b->bicg_fused ? (void *)k3_bicgstab<1, 1> : (void *)k3_bicgstab<1, 0>), dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, STREAM(s));
     if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab<1>)", ce);
     return FGB_OK;
 }
@@ -1485,7 +1531,7 @@ static int o3_backward_impl(fgb_ortho3 *b, const fgb_ortho3_tape *tp, const fgb_
         int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
         void *args[] = {&t, &sl, &Bi, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot, &transposed};
         b->launches++;
-        ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab<3>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, st);
+        ce = cudaLaunchCooperativeKernel((b->bicg_fused ? (void *)k3_bicgstab<3, 1> : (void *)k3_bicgstab<3, 0>), dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, st);
         if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab, transposed)", ce);
     }
     b->launches += 3;
@@ -1508,7 +1554,7 @@ static int o3_backward_impl(fgb_ortho3 *b, const fgb_ortho3_tape *tp, const fgb_
             int maxit = b->opt.max_iter, zero_init = 1, transposed = 1; float tol = b->opt.adv_tol; const int32_t *active = nullptr;
             int32_t *iters = b->iters; float *resid = b->resid; unsigned long long *itot = b->iter_total;
             void *args[] = {&t, &sl, &Bi, &coff, &a, &rhs, &x, &work, &part, &maxit, &tol, &zero_init, &active, &iters, &resid, &itot, &transposed};
-            ce = cudaLaunchCooperativeKernel((void *)k3_bicgstab<1>, dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, st);
+            ce = cudaLaunchCooperativeKernel((b->bicg_fused ? (void *)k3_bicgstab<1, 1> : (void *)k3_bicgstab<1, 0>), dim3(o3_coop_blocks(b)), dim3(O3_CT), args, 0, st);
             if (ce != cudaSuccess) return set_err(FGB_E_CUDA, "cudaLaunchCooperativeKernel(k3_bicgstab<1>, transposed)", ce);
         }
         ZERO3(sbval_bar, B * NB);

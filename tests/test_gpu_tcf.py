@@ -256,3 +256,23 @@ def test_tcf_gradients_with_sgs_match_reference(golden):
     json.dump(e, open("gpurun_out/tcf32_sgs_gradients.json", "w"))
     assert e["reward"] < 1e-5 and e["u"] < 1e-4
     assert e["dr_da"] < 1e-3 and e["vjp_da"] < 1e-3 and e["dr_du"] < 1e-3 and e["vjp_du"] < 1e-3
+
+
+def test_fused_bicgstab_direction_update_is_bit_identical(setup, monkeypatch):
+    """k3_bicgstab with the search-direction update folded into the matrix-vector product (opt-in, FGB_K3_BICG_FUSED=1; 4 grid-wide
+    exchanges per iteration) against the default separate update pass (5 exchanges): the same fp32 expression per cell -> the same bits."""
+    from fluidgym_b200.box3d import BatchedPISO3D
+    dom, sol, fx, meta = setup
+    monkeypatch.setenv("FGB_K3_BICG_FUSED", "1")
+    plain = BatchedPISO3D(dom, 2)
+    outs = []
+    for s in (sol, plain):
+        src = _load(s, fx)
+        s.u += 0.05 * torch.sin(torch.arange(s.u.numel(), device="cuda", dtype=torch.float32)).reshape(s.u.shape)     # a few more BiCGStab iterations
+        for _ in range(2):
+            s.piso_substep(float(fx["dt"][0]), src)
+        torch.cuda.synchronize()
+        outs.append((s.u.clone(), s.p.clone(), s.buffer("iters").clone()))
+    print("bicgstab iterations", outs[0][2][0].tolist())
+    assert int(outs[0][2][0, :3].max()) >= 2
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])

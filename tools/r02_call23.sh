@@ -1,0 +1,5 @@
+set -x
+O=gpurun_out/r02/bicgf; mkdir -p $O
+timeout 600 python tools/tcf_bench.py --ids TCFSmall3D-both-easy-v0 TCFLarge3D-both-easy-v0 RBC3D-easy-v0 --steps 2 --out $O/tcf_bench_default.json > $O/tcf_bench_default.log 2>&1; grep -o '"env": "[^"]*"\|"ms_per_substep": [0-9.]*' $O/tcf_bench_default.log | paste - -
+timeout 600 python tools/tcf_bench.py --ids TCFSmall3D-both-easy-v0 TCFLarge3D-both-easy-v0 RBC3D-easy-v0 --steps 2 --out $O/tcf_bench_default2.json > $O/tcf_bench_default2.log 2>&1; grep -o '"env": "[^"]*"\|"ms_per_substep": [0-9.]*' $O/tcf_bench_default2.log | paste - -
+timeout 600 python -m pytest tests/test_gpu_tcf.py -m gpu -x -q -k "fused_bicgstab or substep_matches" > $O/pytest2.log 2>&1; tail -n 3 $O/pytest2.log | cut -c1-200
