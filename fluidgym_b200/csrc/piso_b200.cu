@@ -3883,6 +3883,41 @@ extern "C" int fgb_balance_fluxes(fgb_batch *b, float *bvel, const int8_t *free_
     return FGB_OK;
 }
 
+// PISOtorch.ComputeSpatialVelocityGradients on the 2-D multi-block domains (getBlockDataGradient, K.cu:2997-3043, 6460-6550; vorticity of
+// envs/fluid_env.py:577-656): central differences in computational space -- against a prescribed (Dirichlet) face the face value with
+// distance 1.5 -- times M^-1 (row vector x matrix).  Gout[b][c][d][N] = d u_c / d x_d: as in the reference the outer index is the velocity
+// component and the inner one the direction.
+__global__ void __launch_bounds__(256) k_velocity_gradients(Tab t, const float *__restrict__ U, const float *__restrict__ Bvel, float *__restrict__ Gout) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NB = t.NB;
+    if (g >= N) return;
+    const float *u = U + (size_t)b * 2 * N, *bv = Bvel + (size_t)b * 2 * NB;
+    int nl[2], nu[2]; float dist[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        nl[i] = t.nbr[(2 * i) * N + g]; nu[i] = t.nbr[(2 * i + 1) * N + g];
+        dist[i] = 2.0f - (nl[i] < 0 ? 0.5f : 0.f) - (nu[i] < 0 ? 0.5f : 0.f);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        float dG[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float lo = nl[i] >= 0 ? u[c * N + nl[i]] : bv[c * NB + (-1 - nl[i])];
+            const float hi = nu[i] >= 0 ? u[c * N + nu[i]] : bv[c * NB + (-1 - nu[i])];
+            dG[i] = (hi - lo) / dist[i];
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            Gout[(((size_t)b * 2 + c) * 2 + j) * N + g] = dG[0] * t.minv[j * N + g] + dG[1] * t.minv[(2 + j) * N + g];
+    }
+}
+extern "C" int fgb_velocity_gradients(fgb_batch *b, const float *u, const float *bvel, float *grad_out, fgb_stream_t s) {
+    if (!b || !u || !bvel || !grad_out) return set_err(FGB_E_ARG, "fgb_velocity_gradients: null argument");
+    b->launches++;
+    k_velocity_gradients<<<cell_grid(b), 256, 0, STREAM(s)>>>(b->t, u, bvel, grad_out);
+    LAUNCH_CHECK("k_velocity_gradients");
+    return FGB_OK;
+}
 extern "C" int fgb_max_velocity(fgb_batch *b, const float *u, const float *bvel, float *out, fgb_stream_t s) {
     if (!b || !u || !bvel || !out) return set_err(FGB_E_ARG, "fgb_max_velocity: null argument");
     b->launches++;

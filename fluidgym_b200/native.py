@@ -78,7 +78,7 @@ EXPORTS = ["fgb_last_error", "fgb_version", "fgb_workspace_bytes", "fgb_batch_cr
            "fgb_piso_substep", "fgb_make_divergence_free", "fgb_sim_step", "fgb_update_outflow", "fgb_flux_balance", "fgb_balance_fluxes",
            "fgb_max_velocity", "fgb_apply_jet_action", "fgb_wall_forces", "fgb_column_sums", "fgb_sample_sensors",
            "fgb_profile_enable",
-           "fgb_profile_read", "fgb_launch_count", "fgb_piso_substep_record", "fgb_adjoint_workspace_bytes",
+           "fgb_profile_read", "fgb_launch_count", "fgb_velocity_gradients", "fgb_piso_substep_record", "fgb_adjoint_workspace_bytes",
            "fgb_piso_substep_backward", "fgb_piso_substep_record_scalar", "fgb_piso_substep_backward_scalar",
            "fgb_ortho3_workspace_bytes", "fgb_ortho3_create", "fgb_ortho3_destroy", "fgb_ortho3_set_options", "fgb_ortho3_buffer",
            "fgb_ortho3_launch_count", "fgb_ortho3_setup_advection", "fgb_ortho3_solve_advection", "fgb_ortho3_setup_pressure",
@@ -169,6 +169,7 @@ def load():
     L.fgb_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), i32]
     L.fgb_launch_count.argtypes = [vp]
     L.fgb_launch_count.restype = C.c_longlong
+    L.fgb_velocity_gradients.argtypes = [vp, vp, vp, vp, vp]
     L.fgb_piso_substep_record.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Tape), vp]
     L.fgb_adjoint_workspace_bytes.restype = C.c_size_t
     L.fgb_adjoint_workspace_bytes.argtypes = [C.POINTER(Tables), i32]

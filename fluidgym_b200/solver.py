@@ -283,6 +283,18 @@ class BatchedPISO:
         native.check(self.lib.fgb_column_sums(self.handle, _ptr(fa), _ptr(fb), nx, ny, _ptr(out), self.stream), "fgb_column_sums")
         return out
 
+    def velocity_gradients(self) -> torch.Tensor:
+        """PISOtorch.ComputeSpatialVelocityGradients: ``[B, 2 (component c), 2 (direction d), N]`` = d u_c / d x_d (K.cu:6460-6550)"""
+        out = torch.empty(self.B, 2, 2, self.N, device=self.device)
+        native.check(self.lib.fgb_velocity_gradients(self.handle, _ptr(self.u), _ptr(self.bvel), _ptr(out), self.stream), "fgb_velocity_gradients")
+        return out
+
+    def vorticity(self) -> torch.Tensor:
+        """omega = d v / d x - d u / d y per cell [B, N].  (The reference's renderer, fluid_env.py:577-606, unpacks the per-component
+        tensors as if they were per-direction and therefore shows - omega.)"""
+        g = self.velocity_gradients()
+        return g[:, 1, 0] - g[:, 0, 1]
+
     def max_velocity(self) -> torch.Tensor:
         out = torch.empty(self.B, device=self.device)
         native.check(self.lib.fgb_max_velocity(self.handle, _ptr(self.u), _ptr(self.bvel), _ptr(out), self.stream), "fgb_max_velocity")

@@ -202,6 +202,9 @@ int fgb_flux_balance(fgb_batch *b, const float *bvel, float *out, fgb_stream_t s
  * by the airfoil actuation, whose free set is outflow + jet wall (airfoil_env_base.py:709-718). */
 int fgb_balance_fluxes(fgb_batch *b, float *bvel, const int8_t *free_mask, float bc_tol, fgb_stream_t s);
 /* Domain.getMaxVelocity(True, True) (DS.cpp:1580-1611, 2403-2411) */
+/* PISOtorch.ComputeSpatialVelocityGradients (PISO_multiblock_cuda_kernel.cu:2997-3043, 6460-6550; used for the vorticity of
+ * envs/fluid_env.py:577-656): grad_out [B][2 component c][2 direction d][N] = d u_c / d x_d */
+int fgb_velocity_gradients(fgb_batch *b, const float *u, const float *bvel, float *grad_out, fgb_stream_t s);
 int fgb_max_velocity(fgb_batch *b, const float *u, const float *bvel, float *out, fgb_stream_t s);
 
 /* ---- environment glue ---------------------------------------------------------------------------- */

@@ -393,3 +393,23 @@ def test_environment_groups_are_bit_identical(cyl24, golden, groups):
     assert out[0][4] == out[1][4]
     for a, b in zip(out[0][:4], out[1][:4]):
         assert torch.equal(a, b)
+
+
+def test_velocity_gradients_match_reference(cyl24, golden):
+    """PISOtorch.ComputeSpatialVelocityGradients of the reference's state after an env.step (5 connected blocks with flipped axes,
+    prescribed faces with the one-sided 1.5-cell difference); golden tests/golden/cyl24_velocity_gradients.npz."""
+    spec, cd = cyl24
+    fx = golden("cyl24_velocity_gradients.npz")
+    sol = _solver(cd, 2)
+    sol.u.copy_(torch.from_numpy(fx["u"]).cuda().unsqueeze(0).expand_as(sol.u))
+    sol.bvel.copy_(torch.from_numpy(fx["bvel"]).cuda().unsqueeze(0).expand_as(sol.bvel))
+    g = sol.velocity_gradients()
+    torch.cuda.synchronize()
+    assert g.shape == (2, 2, 2, cd.N) and torch.equal(g[0], g[1])
+    for c in range(2):
+        for d in range(2):
+            e = rel_l2(g[0, c, d].cpu().numpy(), fx["grad"][c, d])
+            print(f"d u_{c} / d x_{d}: rel L2 {e:.2e}")
+            assert e < 5e-6
+    w = sol.vorticity()[0].cpu().numpy()
+    assert rel_l2(w, fx["grad"][1, 0] - fx["grad"][0, 1]) < 1e-5
