@@ -14,6 +14,7 @@ data path.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import ctypes as C
 import json
 import os
@@ -635,10 +636,20 @@ def main():
     ap.add_argument("--extra-tcf-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # ONE line on stdout: libraries write banners to file descriptor 1 behind python's back (NCCL prints "NCCL version ..." there when
+    # the process group comes up), so fd 1 points to stderr while the run is in progress and the JSON line goes to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
+    try:
+        with contextlib.redirect_stdout(out):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_ours(args)
+    finally:
+        out.flush()
 
 
 if __name__ == "__main__":
