@@ -202,18 +202,23 @@ def test_tcf_gradients_match_reference(golden):
     d sum(reward) / d u0 and the vector-Jacobian product of the outgoing velocity with the reference's sin cotangent."""
     import fluidgym_b200 as fg
     fx = golden("tcf32_grad.npz")
-    env = fg.make("TCFSmall3D-both-easy-v0", n_envs=1, resolution_x_z=32, resolution_y=33, differentiable=True)
+    env = fg.make("TCFSmall3D-both-easy-v0", n_envs=2, resolution_x_z=32, resolution_y=33, differentiable=True)     # two identical environments
     env.reset(seed=42)
     env.set_state(fx["pre_u"], np.zeros(32768, np.float32), np.zeros((3, 2048), np.float32))
     u0 = env.mark_state_differentiable()
-    act = torch.from_numpy(fx["action"]).cuda().reshape(1, 512, 1).clone().requires_grad_(True)
+    act = torch.from_numpy(fx["action"]).cuda().reshape(1, 512, 1).repeat(2, 1, 1).clone().requires_grad_(True)
     obs, reward, term, trunc, info = env.step(act)
     assert env.last_substeps == int(fx["forward_cg_n"]) // 2
     g_a, g_u = torch.autograd.grad(reward.sum(), [act, u0], retain_graph=True)
     u1 = env._du
-    cot = torch.sin(0.37 * torch.arange(u1.numel(), device="cuda", dtype=torch.float64)).to(torch.float32).reshape(u1.shape)
+    cot = torch.sin(0.37 * torch.arange(u1[0].numel(), device="cuda", dtype=torch.float64)).to(torch.float32).reshape(u1[:1].shape).repeat(2, 1, 1)
     v_a, v_u = torch.autograd.grad([u1], [act, u0], grad_outputs=[cot])
     torch.cuda.synchronize()
+    # the batch entries are independent: identical inputs give the same outputs (the adjoint scatters with atomics, so up to summation order)
+    assert torch.equal(u1[0], u1[1])
+    for t_ in (g_a, g_u, v_a, v_u):
+        assert float((t_[0] - t_[1]).abs().max()) <= 1e-4 * float(t_[0].abs().max())
+    g_a, v_a = g_a[:1], v_a[:1]
 
     def rel(a, b):
         a, b = a.detach().cpu().numpy().ravel().astype(np.float64), np.asarray(b, dtype=np.float64).ravel()
