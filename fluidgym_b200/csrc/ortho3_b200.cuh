@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(O3_T) k3_setup_advection(T3 t, O3Slab sl, cons
 #pragma unroll
     for (int d = 0; d < 3; ++d) { uo[d] = u[d * NS + g]; mi[d] = t.minv[d * NS + g]; al[d] = det * mi[d] * mi[d]; }
     float diag = det / dt, Sb[3] = {0.f, 0.f, 0.f};
-int nb6[6];
-o3_nbrs(t, g, nb6);
+    int nb6[6];
+    o3_nbrs(t, g, nb6);
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
         const int d = f >> 1, n = nb6[f];
@@ -244,8 +244,8 @@ __global__ void __launch_bounds__(O3_T) k3_setup_scalar(T3 t, const float *__res
     const float *u = U + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB, *sb = Sbval + (size_t)b * NB;
     const float dt = dtv[b], det = t.det[g];
     float diag = det / dt, r = det * Tin[(size_t)b * NS + g] / dt;
-int nb6[6];
-o3_nbrs(t, g, nb6);
+    int nb6[6];
+    o3_nbrs(t, g, nb6);
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
         const int d = f >> 1, n = nb6[f];
@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(O3_T) k3_pressure_matrix(T3 t, const float *__
     const float *a = A + (size_t)b * NS;
     const float det = t.det[g], rA = 1.0f / a[g];
     float diag = 0.f;
-int nb6[6];
-o3_nbrs(t, g, nb6);
+    int nb6[6];
+    o3_nbrs(t, g, nb6);
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
         const int d = f >> 1, n = nb6[f];
@@ -362,14 +362,16 @@ __global__ void __launch_bounds__(O3_T) k3_hbya(T3 t, O3Slab sl, const float *__
                                                 const float *__restrict__ Src, const float *__restrict__ dtv, const int32_t *__restrict__ active,
                                                 const float *__restrict__ Coff, const float *__restrict__ A, float *__restrict__ Hb,
                                                 const float *__restrict__ Tbuoy /* [B][NS] or null */, float beta,
-                                                const float *__restrict__ Visc /* [B][NS] or null */) {
+                                                const float *__restrict__ Visc /* [B][NS] or null */,
+                                                float *__restrict__ Poff /* with Pdiag: also assemble the pressure matrix (first corrector), or null */,
+                                                float *__restrict__ Pdiag) {
     const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS, NB = t.NB;
     if (g >= N || (active && !active[b])) return;
     const float *u = U + (size_t)b * 3 * NS, *up = Uprev + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB;
     const float dt = dtv[b], det = t.det[g], visc = Visc ? Visc[(size_t)b * NS + g] : t.viscosity, Ag = A[(size_t)b * NS + g];
     float H[3] = {0.f, 0.f, 0.f}, Sb[3] = {0.f, 0.f, 0.f};
-int nb6[6];
-o3_nbrs(t, g, nb6);
+    int nb6[6];
+    o3_nbrs(t, g, nb6);
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
         const int d = f >> 1, n = nb6[f];
@@ -384,6 +386,23 @@ o3_nbrs(t, g, nb6);
 #pragma unroll
             for (int c = 0; c < 3; ++c) Sb[c] += bv[c * NB + j] * k;
         }
+    }
+    if (Poff) {                                 // k3_pressure_matrix for this cell (same expressions, same order: bit-identical)
+        const float *a = A + (size_t)b * NS;
+        const float rA = 1.0f / Ag;
+        float pdiag = 0.f;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) {
+            const int d = f >> 1, n = nb6[f];
+            float c = 0.f;
+            if (n >= 0) {
+                const float mi = t.minv[d * NS + g], mn = t.minv[d * NS + n];
+                c = 0.5f * ((det * mi * mi) * rA + (t.det[n] * mn * mn) * (1.0f / a[n]));
+            }
+            Poff[((size_t)b * 6 + f) * NS + g] = c;
+            pdiag -= c;
+        }
+        Pdiag[(size_t)b * NS + g] = pdiag;
     }
     bool dirty = false;
 #pragma unroll
@@ -404,8 +423,8 @@ __global__ void __launch_bounds__(O3_T) k3_divergence(T3 t, const float *__restr
     const float *v = V + (size_t)b * 3 * NS, *bv = Bvel + (size_t)b * 3 * NB;
     const float det = t.det[g];
     float fl[6];
-int nb6[6];
-o3_nbrs(t, g, nb6);
+    int nb6[6];
+    o3_nbrs(t, g, nb6);
 #pragma unroll
     for (int f = 0; f < 6; ++f) {
         const int d = f >> 1, n = nb6[f];
@@ -417,7 +436,8 @@ o3_nbrs(t, g, nb6);
 
 // u = HbyA - (1/A) M^-T grad(p), central differences, one-sided at prescribed boundaries (K.cu:816-849, 5962-5995)
 __global__ void __launch_bounds__(O3_T) k3_correct(T3 t, O3Slab sl, const float *__restrict__ Hb, const float *__restrict__ P, const float *__restrict__ A,
-                                                   const int32_t *__restrict__ active, float *__restrict__ Uout) {
+                                                   const int32_t *__restrict__ active, float *__restrict__ Uout,
+                                                   float *__restrict__ Uout2 /* second destination (the state buffer after the last corrector) or null */) {
     const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x, N = t.N, NS = t.NS;
     if (g >= N || (active && !active[b])) return;
     const float *p = P + (size_t)b * NS;
@@ -433,6 +453,7 @@ __global__ void __launch_bounds__(O3_T) k3_correct(T3 t, O3Slab sl, const float 
         const float uv = Hb[((size_t)b * 3 + d) * NS + g] - pg * t.minv[d * NS + g] * rA;
         Uout[((size_t)b * 3 + d) * NS + g] = uv;
         o3_push(sl, t, Uout + (size_t)d * NS, g, uv, dirty);
+        if (Uout2) { Uout2[((size_t)b * 3 + d) * NS + g] = uv; o3_push(sl, t, Uout2 + (size_t)d * NS, g, uv, dirty); }
     }
     if (dirty) __threadfence_system();
 }
@@ -1116,13 +1137,9 @@ extern "C" int fgb_ortho3_setup_pressure(fgb_ortho3 *b, const float *u, const fl
                                          int with_matrix, const int32_t *active, fgb_stream_t s) {
     if (!b || !u || !bvel || !dt) return set_err(FGB_E_ARG, "fgb_ortho3_setup_pressure: null argument");
     cudaStream_t st = STREAM(s);
-    if (with_matrix) {
-        b->launches++;
-        k3_pressure_matrix<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->A, active, b->Poff, b->Pdiag);
-        LAUNCH_CHECK("k3_pressure_matrix");
-    }
-    b->launches += 2;
-    k3_hbya<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->slab, u, b->ures, bvel, src, dt, active, b->Coff, b->A, b->hbya, b->sc.T, b->sc.beta, b->sgs_coef != 0.f ? b->visc : nullptr);
+    b->launches += 2;           // (the pressure matrix of the first corrector is assembled by k3_hbya: one launch and one pass over the metrics less)
+    k3_hbya<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->slab, u, b->ures, bvel, src, dt, active, b->Coff, b->A, b->hbya, b->sc.T, b->sc.beta, b->sgs_coef != 0.f ? b->visc : nullptr,
+                                         with_matrix ? b->Poff : nullptr, with_matrix ? b->Pdiag : nullptr);
     LAUNCH_CHECK("k3_hbya");
     { int rc = o3_barrier(b, st); if (rc) return rc; }          // k3_hbya pushed its boundary planes itself
     k3_divergence<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->hbya, bvel, active, b->div);
@@ -1149,7 +1166,7 @@ extern "C" int fgb_ortho3_solve_pressure(fgb_ortho3 *b, float *p_out, int zero_i
 extern "C" int fgb_ortho3_correct_velocity(fgb_ortho3 *b, const float *p, float *u_out, const int32_t *active, fgb_stream_t s) {
     if (!b || !p || !u_out) return set_err(FGB_E_ARG, "fgb_ortho3_correct_velocity: null argument");
     b->launches++;
-    k3_correct<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, b->slab, b->hbya, p, b->A, active, u_out);
+    k3_correct<<<o3_grid(b), O3_T, 0, STREAM(s)>>>(b->t, b->slab, b->hbya, p, b->A, active, u_out, nullptr);
     LAUNCH_CHECK("k3_correct");
     return FGB_OK;
 }
@@ -1173,13 +1190,13 @@ extern "C" int fgb_ortho3_piso_substep(fgb_ortho3 *b, float *u, float *p, const 
     for (int cs = 0; cs < b->opt.corrector_steps; ++cs) {
         if ((rc = fgb_ortho3_setup_pressure(b, u, bvel, src, dt, cs == 0, active, s))) return rc;
         if ((rc = fgb_ortho3_solve_pressure(b, p, 1, b->opt.nonortho ? 100 : 0, b->opt.max_iter, cs, active, s))) return rc;
-        if ((rc = fgb_ortho3_correct_velocity(b, p, b->ures, active, s))) return rc;
+        // the last corrector writes the new velocity into the result buffer AND into the state (both incl. the neighbours' halo planes):
+        // no separate copy kernel
+        b->launches++;
+        k3_correct<<<o3_grid(b), O3_T, 0, st>>>(b->t, b->slab, b->hbya, p, b->A, active, b->ures, cs + 1 == b->opt.corrector_steps ? u : nullptr);
+        LAUNCH_CHECK("k3_correct");
         if ((rc = o3_barrier(b, st))) return rc;
     }
-    b->launches++;
-    const size_t n = (size_t)3 * b->t.NS;
-    k3_copy_active<<<dim3((unsigned)((n + 255) / 256), b->B), 256, 0, STREAM(s)>>>(b->ures, u, n, active);
-    LAUNCH_CHECK("k3_copy_active");
     return FGB_OK;
 }
 
