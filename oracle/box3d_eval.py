@@ -129,24 +129,28 @@ def face_fluxes(g: Box3D, u, bvel):
     return fl
 
 
-def assemble(g: Box3D, u, bvel, dt):
-    """off [6, ...], A [...] of C/det (K.cu:3617-3880)"""
+def assemble(g: Box3D, u, bvel, dt, visc=None):
+    """off [6, ...], A [...] of C/det (K.cu:3617-3880).  visc: optional per-cell viscosity [nz, ny, nx] (block viscosity set by a prep
+    function, e.g. the Smagorinsky model): face coefficient (alpha_P nu_P + alpha_N nu_N) / 2, wall term 2 alpha_P nu_P (K.cu:3697-3750, 3845)"""
     fl = face_fluxes(g, u, bvel)
     diag = (g.det / f32(dt)).astype(f32)
     off = np.zeros((6,) + g.shape, dtype=f32)
+    nuP = g.visc if visc is None else np.asarray(visc, f32).reshape(g.shape)
     for f in range(6):
         d, up = f >> 1, f & 1
         sig = f32(1.0 if up else -1.0)
         inner = g.inner(f)
         aN = g.shift(g.alpha[d], d, 1 if up else -1)
-        vc = ((g.alpha[d] * g.visc + aN * g.visc) * f32(0.5)).astype(f32)
+        nuN = g.visc if visc is None else g.shift(nuP, d, 1 if up else -1)
+        vc = ((g.alpha[d] * nuP + aN * nuN) * f32(0.5)).astype(f32)
         ff = (sig * f32(0.5) * fl[f]).astype(f32)
-        diag = diag + np.where(inner, ff + vc, f32(2.0) * g.visc * g.alpha[d])
+        diag = diag + np.where(inner, ff + vc, f32(2.0) * nuP * g.alpha[d])
         off[f] = np.where(inner, (ff - vc) / g.det, 0).astype(f32)
     return off.astype(f32), (diag / g.det).astype(f32), fl
 
 
-def boundary_source(g: Box3D, bvel, fl):
+def boundary_source(g: Box3D, bvel, fl, visc=None):
+    """visc: optional per-cell viscosity; the wall term uses the viscosity of the adjacent cell (getViscosityFixedBoundary, K.cu:1840-1843)"""
     Sb = np.zeros((3,) + g.shape, dtype=f32)
     for f in range(6):
         d, up = f >> 1, f & 1
@@ -155,15 +159,21 @@ def boundary_source(g: Box3D, bvel, fl):
         sig = f32(1.0 if up else -1.0)
         b = g.b[f]
         Fb = (b["det"] * b["minv"][d] * bvel[f][d]).astype(f32)
-        k = (-(sig * Fb) + f32(2.0) * g.visc * b["alpha"]).astype(f32)
+        if visc is None:
+            nu_b = g.visc
+        else:
+            sl = [slice(None)] * 3
+            sl[2 - d] = -1 if up else 0
+            nu_b = np.asarray(visc, f32).reshape(g.shape)[tuple(sl)].reshape(b["alpha"].shape)
+        k = (-(sig * Fb) + f32(2.0) * nu_b * b["alpha"]).astype(f32)
         Sb += g.bexpand(f, (bvel[f] * k).astype(f32))
     return Sb
 
 
-def adv_rhs(g: Box3D, u, bvel, dt, src=None):
+def adv_rhs(g: Box3D, u, bvel, dt, src=None, visc=None):
     u = g.field(u)
     fl = face_fluxes(g, u, bvel)
-    Sb = boundary_source(g, bvel, fl)
+    Sb = boundary_source(g, bvel, fl, visc)
     rhs = ((g.det * u / f32(dt) + Sb) / g.det).astype(f32)
     if src is not None:
         src = np.asarray(src, dtype=f32)

@@ -207,3 +207,22 @@ def test_channel_initial_domain_glue_without_a_gpu(tmp_path):
     e.test()
     with pytest.raises(RuntimeError, match="Initial domain not found"):
         e._load_initial_domains_on_reset(False)                    # no "test" split was written
+
+
+def test_specification_with_per_cell_viscosity_matches_reference(tcf, golden):
+    """Smagorinsky model on (C_smag = 0.1, van Driest): the reference's per-cell viscosity of the first substep (golden
+    tcf32_sgs_substep0.npz) fed into the specification reproduces its predictor matrix diagonal, right-hand side and HbyA -- the diffusive
+    face coefficient (alpha_P nu_P + alpha_N nu_N) / 2 and the wall term 2 alpha_b nu_P (K.cu:3697-3750, 3845, 4342, 5204)."""
+    box = tcf[0]
+    fx = golden("tcf32_sgs_substep0.npz")
+    bvel = {2: fx["bvel2"].reshape(3, 32, 1, 32), 3: fx["bvel3"].reshape(3, 32, 1, 32)}
+    dt, u, visc = float(fx["dt"][0]), fx["u_in"], fx["visc"]
+    off, A, fl = be.assemble(box, u, bvel, dt, visc=visc)
+    assert rel_l2(A, fx["A"]) < 5e-7
+    rhs, Sb = be.adv_rhs(box, u, bvel, dt, fx["src"], visc=visc)
+    assert rel_l2(rhs, fx["rhs"]) < 5e-7
+    hb = be.hbya(box, u, fx["ustar"].reshape(3, *box.shape), off, A, Sb, dt, fx["src"])
+    assert rel_l2(hb, fx["hbya0"]) < 5e-7
+    # with the constant viscosity the same inputs are far from this golden: the test sees the term
+    off0, A0, _ = be.assemble(box, u, bvel, dt)
+    assert rel_l2(A0, fx["A"]) > 1e-3
