@@ -245,6 +245,11 @@ class TCF3DEnv(InitialDomains3D):
             op = torch.flip(op, dims=[2])
         return {"velocity": torch.stack((ox, oy), dim=-1), "pressure": op}
 
+    def q_criterion(self):
+        """_get_q_criterion (tcf_env.py:586-644) on the cell grid [B, nz, ny, nx]: Q = (|Omega|^2 - |S|^2) / 2 from
+        ComputeSpatialVelocityGradients (the reference then resamples it to its rendering grid, which is out of scope here)"""
+        return self.solver.q_criterion().view(self.n_envs, self.z, self.ny, self.x)
+
     def _get_obs(self):
         if self.use_marl:
             b = self._local_obs_at(self.y_obs_bottom_idx, False)
