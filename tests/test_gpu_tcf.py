@@ -173,6 +173,9 @@ def test_env_step_with_sgs_matches_reference(golden):
     assert eu < 1e-3
     for k in ("wall_stress", "wall_stress_bottom", "wall_stress_top"):
         assert abs(float(info[k][0]) - float(st[f"step0_info_{k}"])) < 1e-3 * abs(float(st[f"step0_info_{k}"]))
+    q = env.q_criterion()
+    assert q.shape == (2, env.z, env.ny, env.x) and torch.equal(q.reshape(2, -1), s.q_criterion())
+    assert torch.isfinite(q).all() and float(q.abs().max()) > 0
     assert np.abs(reward[0].cpu().numpy() - st["step0_reward"]).max() < 1e-3 * np.abs(st["step0_reward"]).max() + 1e-6
     assert torch.equal(s.u[0], s.u[1])
 
