@@ -284,6 +284,7 @@ class Airfoil2DEnv(DifferentiableRollout, InitialDomains):
         cd, cl = mean[:, 0], mean[:, 1]
         reward = cl / cd - self.cl_cd_ref
         self._n_steps += 1
+        self._watch_linear_solves()
         truncated = self._n_steps >= self.episode_length
         return obs, reward, False, truncated, {"drag": cd.detach(), "lift": cl.detach()}
 

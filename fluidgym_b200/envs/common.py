@@ -237,7 +237,55 @@ class DomainStatistics:
         return path
 
 
-class InitialDomains(DomainStatistics):
+class LinsolveError(RuntimeError):
+    """A linear solve reported a non-finite residual (PISOtorch_diff.py: LinsolveError)."""
+
+
+class LinearSolveWatch:
+    """Error behaviour of ``_check_solver_return_infos`` (PISOtorch_diff.py:266-301): a non-finite residual of any
+    linear solve raises ``LinsolveError``.  (Its fp64 / preconditioned retries, :418-476, fire on the same condition
+    only, because the environments solve with return_best_result; they are not built -- DESIGN.md §8.)
+
+    The reference inspects the solver infos on the host after every solve.  Here the final residuals of the last
+    substep stay in the solver's ``resid`` table [B, 8]; every ``env.step`` ends with a non-blocking copy of that table
+    into pinned memory and the table of step k is examined when step k+1 ends (or on ``check_linear_solves()``), when
+    the copy has long landed -- no stall.  A state that went non-finite stays so, hence the one-step delay loses nothing
+    but promptness.  ``check_solves = False`` switches the watch off.  Needs ``solver`` with ``buffer("resid")``."""
+
+    check_solves = True
+    _ls_pending = False
+
+    def _watch_linear_solves(self):
+        if not self.check_solves or not hasattr(self.solver, "buffer"):    # (host stand-ins of the CPU tests keep no residual table)
+            return
+        self.check_linear_solves()
+        resid = self.solver.buffer("resid")
+        if getattr(self, "_ls_host", None) is None or self._ls_host.shape != resid.shape:
+            self._ls_host = torch.empty(resid.shape, dtype=resid.dtype, pin_memory=resid.is_cuda)
+            self._ls_event = torch.cuda.Event() if resid.is_cuda else None
+        self._ls_host.copy_(resid, non_blocking=True)
+        if self._ls_event is not None:
+            self._ls_event.record()
+        self._ls_pending, self._ls_step = True, getattr(self, "_n_steps", 0)
+
+    def check_linear_solves(self):
+        """Raise LinsolveError if the last watched step left a non-finite residual; returns the residual table otherwise."""
+        if not self._ls_pending:
+            return None
+        if self._ls_event is not None:
+            self._ls_event.synchronize()
+        self._ls_pending = False
+        table = self._ls_host.numpy()
+        bad = ~np.isfinite(table)
+        if bad.any():
+            envs = np.nonzero(bad.any(axis=-1))[0].tolist()
+            raise LinsolveError("Linear solve reported non-finite residual in env.step %d for environment(s) %s of %d "
+                                "(residual slots %s)." % (self._ls_step, envs[:16], table.shape[0],
+                                                         np.nonzero(bad.any(axis=0))[0].tolist()))
+        return table
+
+
+class InitialDomains(LinearSolveWatch, DomainStatistics):
     """Mixin: the published initial-domain splits (``initial_domains/<initial_domain_id>/<idx>/<mode>.{json,npz}``,
     envs/fluid_env.py:507-551, 1040-1112) for batched environments.  Files are read once into a device-resident pool; every
     environment of the batch draws its own index on ``reset`` (the reference draws one per process).

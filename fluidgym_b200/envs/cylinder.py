@@ -304,6 +304,7 @@ class CylinderJet2DEnv(DifferentiableRollout, InitialDomains):
         cd, cl = mean[:, 0], mean[:, 1]
         reward = self.cd_ref - cd - self.lift_penalty * torch.abs(cl)
         self._n_steps += 1
+        self._watch_linear_solves()
         truncated = self._n_steps >= self.episode_length
         return obs, reward, False, truncated, {"drag": cd.detach(), "lift": cl.detach()}
 
@@ -336,6 +337,7 @@ class CylinderJet2DEnv(DifferentiableRollout, InitialDomains):
         cd, cl = mean[:, 0], mean[:, 1]
         reward = self.cd_ref - cd - self.lift_penalty * torch.abs(cl)
         self._n_steps += 1
+        self._watch_linear_solves()
         truncated = self._n_steps >= self.episode_length
         return obs, reward, False, truncated, {"drag": cd.detach(), "lift": cl.detach()}
 

@@ -288,6 +288,7 @@ class SpanwiseExtrudedEnv(InitialDomainsExtruded):
         cd, cl = all_cds.sum(dim=1) / self.D, all_cls.sum(dim=1) / self.D                        # jet_cylinder_env_3d.py:431-452
         reward = self._reward(cd, cl)
         self._n_steps += 1
+        self._watch_linear_solves()
         truncated = self._n_steps >= self.episode_length
         info = {"drag": cd, "lift": cl}
         if not self.use_marl:

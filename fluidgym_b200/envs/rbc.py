@@ -348,6 +348,7 @@ class RBC2DEnv(InitialDomains):
         reward = self.nu_ref - nu
         info = {"nusselt": nu.detach()}
         self._n_steps += 1
+        self._watch_linear_solves()
         truncated = self._n_steps >= self.episode_length
         if not self.use_marl:
             return self._get_global_obs(), reward, False, truncated, info

@@ -391,6 +391,7 @@ class RBC3DEnv(InitialDomains3D):
         reward = self.nu_ref - nu
         info = {"nusselt": nu.detach()}
         self._n_steps += 1
+        self._watch_linear_solves()
         truncated = self._n_steps >= self.episode_length
         if not self.use_marl:
             return self._get_global_obs(), reward, False, truncated, info

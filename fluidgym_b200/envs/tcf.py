@@ -351,6 +351,7 @@ class TCF3DEnv(InitialDomains3D):
             reward = 1 - (tau_total if self.both_walls else tau_bottom) / self.tau_ref
             info = {"wall_stress": tau_total, "wall_stress_bottom": tau_bottom, "wall_stress_top": tau_top}
             self._n_steps += 1
+            self._watch_linear_solves()
             obs = self._get_obs()
             if self.use_marl:
                 info["global_reward"] = reward
@@ -371,6 +372,7 @@ class TCF3DEnv(InitialDomains3D):
         reward = 1 - (tau_total if self.both_walls else tau_bottom) / self.tau_ref
         info = {"wall_stress": tau_total, "wall_stress_bottom": tau_bottom, "wall_stress_top": tau_top}
         self._n_steps += 1
+        self._watch_linear_solves()
         truncated = self._n_steps >= self.episode_length
         obs = self._get_obs()
         if self.use_marl:

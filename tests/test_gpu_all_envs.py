@@ -63,3 +63,26 @@ def test_env_marl(env_id):
     _check_obs(env, obs, marl=True)
     assert reward.shape[:2] == (B, env.n_agents)
     assert "global_reward" in info and isinstance(info["global_reward"], torch.Tensor)
+
+
+@pytest.mark.parametrize("env_id", ["CylinderJet2D-easy-v0", "TCFSmall3D-both-easy-v0", "CylinderJet3D-easy-v0"])
+def test_non_finite_solve_raises_linsolve_error(env_id):
+    """_check_solver_return_infos (PISOtorch_diff.py:280-300): a non-finite residual raises LinsolveError.  Here the table of
+    final residuals is examined one env.step late (envs/common.py::LinearSolveWatch) and names the environment."""
+    import fluidgym_b200
+    from fluidgym_b200.envs.common import LinsolveError
+    env = fluidgym_b200.make(env_id, n_envs=B, use_marl=False, **ENV_KW.get(env_id, {}))
+    env.reset(seed=42)
+    env.step(env.sample_action())
+    table = env.check_linear_solves()                                      # a healthy step: finite residuals, some solves ran
+    assert table is not None and table.shape[0] == B and (table > 0).any()
+    env.step(env.sample_action())
+    env.solver.u[1].view(-1)[5::97] = float("nan")                         # poison environment 1 only
+    env.step(env.sample_action())                                          # examines the healthy previous step: no error
+    with pytest.raises(LinsolveError) as err:
+        env.check_linear_solves()
+    assert "[1]" in str(err.value)
+    assert env.check_linear_solves() is None                               # reported once
+    with pytest.raises(LinsolveError):                                     # left unattended it surfaces when the next step ends
+        env.step(env.sample_action())
+        env.step(env.sample_action())
