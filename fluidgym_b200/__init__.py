@@ -83,14 +83,14 @@ def _register_defaults():
         register(f"RBC3D-wide-{level}-v0", RBC3DEnv, **{**RBC_3D_DEFAULT_CONFIG, "aspect_ratio": 2, "n_heaters": 16, "rayleigh_number": ra,
                                                         "adaptive_cfl": 0.5})
     from .envs.cylinder3d import CYLINDER_JET_3D_DEFAULT_CONFIG, CylinderJet3DEnv
-    # fluidgym/__init__.py:79-101.  Host side verified on the CPU against the reference's env.step; the CUDA launch path of the
-    # extruded domains has not run on a GPU yet -- not part of tests/test_gpu_all_envs.py until it has.
+    # fluidgym/__init__.py:79-101.  Host side verified on the CPU against the reference's env.step, the CUDA path on a B200 against the
+    # reference's substep, reset, env.step and gradients (tests/test_gpu_extruded.py); res 8 is part of tests/test_gpu_all_envs.py.
     register("CylinderJet3D-easy-v0", CylinderJet3DEnv, **{**CYLINDER_JET_3D_DEFAULT_CONFIG, "reynolds_number": 100.0, "resolution": 24})
     register("CylinderJet3D-medium-v0", CylinderJet3DEnv, **{**CYLINDER_JET_3D_DEFAULT_CONFIG, "reynolds_number": 250.0, "resolution": 32})
     register("CylinderJet3D-hard-v0", CylinderJet3DEnv, **{**CYLINDER_JET_3D_DEFAULT_CONFIG, "reynolds_number": 500.0, "resolution": 48})
     from .envs.airfoil3d import AIRFOIL_3D_DEFAULT_CONFIG, Airfoil3DEnv
-    # fluidgym/__init__.py:333-352.  Assembled from pinned parts, environment-level parity unpinned (no reference golden yet), never run
-    # on a GPU (envs/airfoil3d.py) -- not part of tests/test_gpu_all_envs.py.
+    # fluidgym/__init__.py:333-352.  env.step and gradients pinned on a B200 to the reference's at res_z = 8 (tests/test_gpu_extruded.py,
+    # tests/golden/airfoil3d_{env,grad}.npz); 4.5 M cells per environment at the default 96 planes, so not in tests/test_gpu_all_envs.py.
     for level, re in (("easy", 1e3), ("medium", 3e3), ("hard", 5e3)):
         register(f"Airfoil3D-{level}-v0", Airfoil3DEnv, **{**AIRFOIL_3D_DEFAULT_CONFIG, "reynolds_number": re})
     register("CylinderJet2D-hard-v0", CylinderJet2DEnv, **{**CYLINDER_JET_2D_DEFAULT_CONFIG, "reynolds_number": 500.0, "resolution": 32})

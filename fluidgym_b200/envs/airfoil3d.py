@@ -1,8 +1,11 @@
 """Batched ``Airfoil3D`` environment (``envs/airfoil/airfoil_env_3d.py`` + ``airfoil_env_base.py`` with ``ndims = 3``): the 6-block
 airfoil grid extruded over 96 periodic z planes (span 1.4), ``n_agents`` groups of three suction-side jets lined up along the span.
 
-STATUS: **parity unpinned at the environment level** -- no golden run of the reference's Airfoil3D exists yet (``tools/r02_first_call.sh``
-generates one), and the class has not run on a GPU.  What it is assembled from IS pinned: the extruded solver path and the spanwise
+STATUS: pinned on a B200 to the unmodified reference's Airfoil3D at the reduced spanwise resolution res_z = 8 -- one ``env.step`` from
+the reference's own reset state (56 substeps: plane velocities 8e-4, drag 1e-3, lift 1.3e-2, observations 5e-4; ``tests/golden/
+airfoil3d_env.npz``) and the reverse-mode gradients through it (state vjp 1e-4, reward gradients 6 - 8 % with the reference's capped
+solves; ``tests/golden/airfoil3d_grad.npz``), both in ``tests/test_gpu_extruded.py``.  What it is assembled from is pinned separately:
+the extruded solver path and the spanwise
 machinery of ``envs/cylinder3d.py`` (reference trace / ``env.step`` of CylinderJet3D through the kernels' cell code on the CPU), the
 2-D airfoil tables -- grid, jet slots and profiles, wall ring, sensor positions, airfoil mask -- of ``envs/airfoil.py`` (GPU parity
 with the reference's Airfoil2D), and the extruded cell code on this very plane mesh (``tests/test_extruded_host.py``).  Host logic

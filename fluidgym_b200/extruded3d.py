@@ -2,10 +2,10 @@
 planes, ``envs/cylinder/grid.py:298``, ``shapes.py:641-676``) -- host side of ``csrc/extruded3_b200.cuh``.
 
 STATUS: the operator arithmetic is verified on the CPU against an op trace of the unmodified reference
-(``tests/test_extruded_host.py``, ``tests/test_extruded_cpu.py``); ``ExtrudedPISO3D`` (the launch path) has not run on a GPU yet;
-``envs/cylinder3d.py`` is built on it and verified on the CPU through a stand-in that executes the same cell code on the host
-(``tests/test_cylinder3d_cpu.py``).  ``tools/extruded_check.py`` is the first thing to run on a GPU: one substep from the
-reference's traced state, compared with the reference's result.
+(``tests/test_extruded_host.py``, ``tests/test_extruded_cpu.py``; ``envs/cylinder3d.py`` runs on the CPU through a stand-in that
+executes the same cell code on the host, ``tests/test_cylinder3d_cpu.py``), and ``ExtrudedPISO3D`` (the launch path) on a B200
+against the reference's substep, reset state, ``env.step`` and reverse-mode gradients of CylinderJet3D and Airfoil3D
+(``tests/test_gpu_extruded.py``, ``tools/extruded_check.py``).
 """
 from __future__ import annotations
 

@@ -6,6 +6,11 @@
  *   BIND.cpp  = simulation/extensions/PISOtorch.cpp        (pybind11 module `PISOtorch`)
  *   K.cu      = simulation/extensions/PISO_multiblock_cuda_kernel.cu
  *   SIM.py    = simulation/pict/PISOtorch_simulation.py
+ *   DIFF.py   = simulation/pict/PISOtorch_diff.py          (autograd Functions, linear-solve wrapper)
+ *   FGSIM.py  = simulation/simulation.py                   (FluidGym's Simulation subclass: single_step)
+ *   DS.cpp    = simulation/extensions/domain_structs.cpp   (Domain / Block / boundaries)
+ *   CG.cu     = simulation/extensions/cg_solver_kernel.cu,  BICG.cu = simulation/extensions/bicgstab_solver_kernel.cu
+ *   CYL.py    = envs/cylinder/cylinder_env_base.py
  *
  * Differences by design: the reference ops work on ONE mutable Domain object (batch size 1,
  * DS.cpp:1136) and synchronise the device around every launch; here every op advances B independent
@@ -132,7 +137,9 @@ typedef struct fgb_options {
                                           domain has a strip plan; 6 otherwise)                                 */
 } fgb_options;
 
+/* message of the last failed fgb_* call of the calling thread (the analogue of the reference's TORCH_CHECK text, BIND.cpp) */
 const char *fgb_last_error(void);
+/* ABI version of this header (1) */
 int fgb_version(void);
 
 /* bytes of device workspace fgb_batch_create needs for B environments */
@@ -201,10 +208,10 @@ int fgb_flux_balance(fgb_batch *b, const float *bvel, float *out, fgb_stream_t s
  * (free_mask[NB], device, int8): their velocities are scaled so that the net boundary flux vanishes.  Used
  * by the airfoil actuation, whose free set is outflow + jet wall (airfoil_env_base.py:709-718). */
 int fgb_balance_fluxes(fgb_batch *b, float *bvel, const int8_t *free_mask, float bc_tol, fgb_stream_t s);
-/* Domain.getMaxVelocity(True, True) (DS.cpp:1580-1611, 2403-2411) */
 /* PISOtorch.ComputeSpatialVelocityGradients (PISO_multiblock_cuda_kernel.cu:2997-3043, 6460-6550; used for the vorticity of
  * envs/fluid_env.py:577-656): grad_out [B][2 component c][2 direction d][N] = d u_c / d x_d */
 int fgb_velocity_gradients(fgb_batch *b, const float *u, const float *bvel, float *grad_out, fgb_stream_t s);
+/* Domain.getMaxVelocity(True, True) (DS.cpp:1580-1611, 2403-2411) */
 int fgb_max_velocity(fgb_batch *b, const float *u, const float *bvel, float *out, fgb_stream_t s);
 
 /* ---- environment glue ---------------------------------------------------------------------------- */
@@ -224,6 +231,7 @@ typedef struct fgb_wall {
     const float *flen;     /* [n] wall face length     */
     float scale;           /* 1 / (0.5 U^2 D)          */
 } fgb_wall;
+/* compute_forces (forces.py:193-275) over the ring w + the drag / lift coefficients of CYL.py:657-698, added to acc[B][2] */
 int fgb_wall_forces(fgb_batch *b, const fgb_wall *w, const float *u, const float *p, const float *bvel,
                     float *acc, fgb_stream_t s);
 /* column sums over y of fa*fb*det and of det for a single structured nx x ny block (Nusselt number,
@@ -257,6 +265,7 @@ typedef struct fgb_tape {      /* C = corrector_steps, n_adv / n_p = advect / pr
 /* forward substep (non-orthogonal path, no passive scalar, all environments active, C * n_p <= 8) + tape */
 int fgb_piso_substep_record(fgb_batch *b, float *u, float *p, const float *bvel, const float *dt, const fgb_tape *tape,
                             fgb_stream_t s);
+/* bytes of scratch fgb_piso_substep_backward[_scalar] needs */
 size_t fgb_adjoint_workspace_bytes(const fgb_tables *t, int32_t B);
 /* vector-Jacobian product of that substep: (u_out_bar, p_out_bar) -> (u_bar, p_prev_bar, bvel_bar), all overwritten.
  * Linear-solve adjoints are solves with the transposed operator (DIFF.py:572-590) by the same on-chip kernels;
@@ -312,6 +321,8 @@ typedef struct fgb_ortho3_tables {
     const int8_t *rev;
 } fgb_ortho3_tables;
 typedef struct fgb_ortho3 fgb_ortho3;
+/* D = 3 handle over caller-owned device memory, as fgb_workspace_bytes / fgb_batch_create / fgb_batch_destroy / fgb_batch_set_options
+ * (stands for the reference's Domain + PISOtorch block set-up of a box grid, domain_structs.cpp, envs/tcf/grid.py) */
 size_t fgb_ortho3_workspace_bytes(const fgb_ortho3_tables *t, int32_t B);
 int fgb_ortho3_create(const fgb_ortho3_tables *t, int32_t B, void *workspace, size_t workspace_bytes, const fgb_options *opt,
                       fgb_ortho3 **out);
@@ -320,6 +331,7 @@ int fgb_ortho3_set_options(fgb_ortho3 *b, const fgb_options *opt);
 /* named workspace buffers: "Coff" [B][6][N], "A", "rhs" [B][3][N], "ures", "Poff", "Pdiag", "hbya", "div", "iters" [B][8]
  * (0..2 BiCGStab per component, 3.. CG per corrector), "resid", "dt", "active", "nsub", "maxvel", "src" [B][4], "rowmean" [B][4] */
 void *fgb_ortho3_buffer(fgb_ortho3 *b, const char *name);
+/* number of kernel launches issued through this handle since creation */
 long long fgb_ortho3_launch_count(fgb_ortho3 *b);
 /* per-op entry points (SetupAdvectionMatrix + SetupAdvectionVelocity | SolveLinear(BiCGStab) | SetupPressureMatrix +
  * SetupPressureRHS + SetupPressureRHSdiv | SolveLinear(CG) + mean removal | CorrectVelocity), cf. the 2-D table above.
@@ -375,6 +387,8 @@ typedef struct fgb_ortho3_tape {
     float *visc;     /* [B][N] per-cell viscosity of the substep when a sub-grid model is set (fgb_ortho3_set_sgs), else NULL: a constant of
                       * the graph, as in the reference, whose Smagorinsky op has no autograd wrapper */
 } fgb_ortho3_tape;
+/* forward substep of the D = 3 box (as fgb_ortho3_piso_substep) that also fills the tape (the forward() of the reference's autograd
+ * Functions, PISOtorch_diff.py:624-1808) + bytes of scratch the backward needs */
 int fgb_ortho3_piso_substep_record(fgb_ortho3 *b, float *u, float *p, const float *bvel, const float *src, const float *dt,
                                    const fgb_ortho3_tape *tape, fgb_stream_t s);
 size_t fgb_ortho3_adjoint_workspace_bytes(const fgb_ortho3_tables *t, int32_t B);
@@ -389,8 +403,10 @@ int fgb_ortho3_piso_substep_record_scalar(fgb_ortho3 *b, float *u, float *p, con
 int fgb_ortho3_piso_substep_backward_scalar(fgb_ortho3 *b, const fgb_ortho3_tape *tape, const fgb_tape_scalar *stape, const float *u_out_bar,
                                             const float *p_out_bar, const float *T_out_bar, float *u_bar, float *bvel_bar, float *T_bar,
                                             float *sbval_bar, void *workspace, size_t workspace_bytes, fgb_stream_t s);
+/* Simulation.make_divergence_free (SIM.py:1320-1429) on the box: A = 1, dt = 1 projection of u; p receives the projection pressure */
 int fgb_ortho3_make_divergence_free(fgb_ortho3 *b, float *u, float *p, const float *bvel, int max_iter, fgb_stream_t s);
-/* rows: [2][n_row] cells of the first / last wall-normal layer; d_lo, d_hi their wall distances.  With rows != NULL the
+/* Simulation.single_step with adaptive CFL substeps (FGSIM.py:210-280, SIM.py:2004-2064) for D = 3.
+ * rows: [2][n_row] cells of the first / last wall-normal layer; d_lo, d_hi their wall distances.  With rows != NULL the
  * channel forcing G_x = nu/2 (<u>_lo/d_lo + <u>_hi/d_hi) (envs/tcf/grid.py:128-163) is refreshed before every substep. */
 int fgb_ortho3_sim_step(fgb_ortho3 *b, float *u, float *p, const float *bvel, float dt_target, float cfl, const int32_t *rows,
                         int n_row, float d_lo, float d_hi, int32_t *substeps_max, fgb_stream_t s);
@@ -404,10 +420,13 @@ int fgb_ortho3_wall_rows(fgb_ortho3 *b, const float *u, const int32_t *rows, int
  * (fgb_ipc_alloc) that every peer maps with CUDA IPC (fgb_ipc_open): halo planes and reduction partials are written
  * straight into the peer's memory over NVLink from inside the persistent Krylov kernels, sequence-numbered flags replace
  * collectives (no NCCL call on the solver path).  The first 4 KiB of the region are reserved for the flag pad. */
+/* symmetric allocation of one rank + its CUDA IPC handle / map, unmap a peer's / release the own one (no reference counterpart: the
+ * reference runs one domain on one GPU) */
 int fgb_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle_out /* [64] */);
 int fgb_ipc_open(const unsigned char *handle /* [64] */, void **peer_ptr);
 int fgb_ipc_close(void *peer_ptr);
 int fgb_ipc_free(void *ptr);
+/* bind a handle created on the rank's slab tables (NS, N_global, plane) to its place among the peers' mapped regions */
 int fgb_ortho3_set_slab(fgb_ortho3 *b, int32_t rank, int32_t world, void *local_base, void *const *peer_bases);
 /* non-zero in *out when a wait on a peer timed out (results invalid) */
 int fgb_ortho3_slab_error(fgb_ortho3 *b, int32_t *out);
@@ -425,8 +444,8 @@ long long fgb_launch_count(fgb_batch *b);
  * The 2-D tables of the compiled plane + nz uniform periodic planes of spacing hz.  Fields [B][3][nz*N], cell = plane * N + g;
  * boundary velocities [B][3][nz][NB].  The handle is an fgb_ortho3 created on the 6-face neighbour table of the extruded domain
  * (faces 0..3 in plane, 4 = -z, 5 = +z), whose cooperative Krylov kernels solve the ELL(7) systems.  Operator arithmetic is
- * verified on the CPU against a trace of the reference (tests/test_extruded_host.py); the launch path has not run on a GPU yet
- * (envs/cylinder3d.py is built on it and verified on the CPU through the same cell code, tests/test_cylinder3d_cpu.py). */
+ * verified on the CPU against a trace of the reference (tests/test_extruded_host.py, tests/test_cylinder3d_cpu.py run the same
+ * cell code) and on a B200 against the reference's env.step and gradients (tests/test_gpu_extruded.py). */
 typedef struct fgb_extruded3_tables {
     fgb_tables plane;
     int32_t nz;
