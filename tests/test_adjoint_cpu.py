@@ -77,3 +77,36 @@ def test_scalar_substep_vjp_matches_finite_differences():
             fd = (J(*hi) - J(*lo)) / (2 * eps)
             an = float((grad * d).sum())
             assert abs(fd - an) <= 2e-5 * max(abs(fd), abs(an)) + 5e-6, (name, trial, fd, an)
+
+
+def test_substep_vjp_is_exact_at_the_junction_cells(small):
+    """Single-cell derivatives at the cells where a block connection ends on a prescribed boundary (domain corner left|top at
+    inflow + wall; right|bottom|wake at the lower wall): these are the cells that carry 88 % of the remaining difference to the
+    REFERENCE's d reward / d u0 (profiles/r02_cyl24_gradient_difference_map.md).  The hand-written adjoint equals central
+    differences of the forward substep there, so that difference is not an error of the adjoint."""
+    cd, t = small
+    offs, sizes = np.array(cd.offsets), cd.sizes
+
+    def cell(bi, x, y):
+        return int(offs[bi] + (y % sizes[bi][1]) * sizes[bi][0] + (x % sizes[bi][0]))
+
+    junction = [cell(0, 0, -1), cell(1, 0, -1), cell(2, -1, 0), cell(3, -1, 0), cell(4, 0, 0), cell(0, 1, -2)]
+    rng = np.random.default_rng(3)
+    u = 0.3 * rng.standard_normal((2, t.N)); u[0] += 1.0
+    p0 = 0.1 * rng.standard_normal(t.N)
+    bvel = cd.bvel0[:, :t.NB].astype(np.float64) + 0.05 * rng.standard_normal((2, t.NB))
+    dt = 0.01
+    wu, wp = rng.standard_normal((2, t.N)), rng.standard_normal(t.N)
+
+    def J(u_):
+        uo, po, _ = ae.substep(t, u_, p0, bvel, dt, n_adv=2, n_p=3)
+        return float((wu * uo).sum() + (wp * po).sum())
+
+    uo, po, tape = ae.substep(t, u, p0, bvel, dt, n_adv=2, n_p=3)
+    ub, _, _ = ae.substep_vjp(t, u, p0, bvel, dt, tape, wu, wp)
+    scale = np.abs(ub).max()
+    for c in junction:
+        for comp in (0, 1):
+            d = np.zeros_like(u); d[comp, c] = 1.0
+            fd = (J(u + 1e-6 * d) - J(u - 1e-6 * d)) / 2e-6
+            assert abs(ub[comp, c] - fd) < 2e-5 * scale, (c, comp, ub[comp, c], fd)
